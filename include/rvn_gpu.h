@@ -1,0 +1,310 @@
+/* rvn_gpu.h -- thin C ABI between Raven-surface host code and the sm_100a CUDA engine.
+ *
+ * This is the drop-in boundary of the B200 build.  The reference has no
+ * binary plugin loader: its hot path is the free function
+ *     void MassEnergyBalance(CModel*, const optStruct&, const time_struct&)   (reference src/Solvers.cpp:19-21)
+ * fed by CModel::UpdateHRUForcingFunctions (src/UpdateForcings.cpp:30) and followed by
+ * IncrementCumulInput/IncrementCumOutflow (src/Model.cpp:2458,2493) and the WriteMinorOutput reductions
+ * (src/StandardOutput.cpp:745-785).  The host side (ravenhydroframework_b200/host, C++) keeps those
+ * signatures and flattens the model it parsed from .rvi/.rvh/.rvp/.rvt/.rvc into the plain-C descriptor
+ * below; everything that happens per timestep then runs on the GPU behind these entry points.
+ *
+ * Conventions: plain pointers + sizes, no C++/torch types; every function returns 0 on success or a
+ * negative rvn_status and leaves a message readable through rvn_gpu_last_error().  A handle owns one
+ * CUDA stream and is thread-compatible (not thread-safe), like the reference (one model per process).
+ * All floating point on this path is IEEE FP64.  There is NO CPU fallback: if no CUDA device is present
+ * rvn_gpu_create fails with RVN_ERR_NO_DEVICE.
+ */
+#ifndef RVN_GPU_H
+#define RVN_GPU_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVN_ABI_VERSION 1
+#define RVN_DOESNT_EXIST (-1)
+#define RVN_CONV_STORES 50   /* MAX_CONVOL_STORES, reference src/RavenInclude.h / Convolution.cpp:17 */
+#define RVN_MAX_CONN 24      /* max connections of a non-convolution process (Precipitation: 13..19) */
+#define RVN_MAX_SOIL_LAYERS 8
+#define RVN_MAX_RIVER_SEGS 50 /* MAX_RIVER_SEGS, reference src/SubBasin.h */
+
+typedef enum {
+  RVN_OK = 0, RVN_ERR_NO_DEVICE = -1, RVN_ERR_BAD_ARG = -2, RVN_ERR_CUDA = -3, RVN_ERR_UNSUPPORTED = -4,
+  RVN_ERR_NOMEM = -5
+} rvn_status;
+
+/* ---- state-variable types: numbering == reference enum sv_type (src/RavenInclude.h:876-951) so that the
+ *      SV catalogue can be compared as integers against the reference build. ---- */
+typedef enum {
+  RVN_SV_SURFACE_WATER = 0, RVN_SV_ATMOSPHERE = 1, RVN_SV_ATMOS_PRECIP = 2, RVN_SV_PONDED_WATER = 3,
+  RVN_SV_SOIL = 4, RVN_SV_CANOPY = 5, RVN_SV_CANOPY_SNOW = 6, RVN_SV_TRUNK = 7, RVN_SV_ROOT = 8,
+  RVN_SV_GROUNDWATER = 9, RVN_SV_DEPRESSION = 10, RVN_SV_SNOW = 11, RVN_SV_NEW_SNOW = 12, RVN_SV_SNOW_LIQ = 13,
+  RVN_SV_TOTAL_SWE = 14, RVN_SV_WETLAND = 15, RVN_SV_GLACIER = 16, RVN_SV_GLACIER_ICE = 17, RVN_SV_FIRN = 18,
+  RVN_SV_LAKE_STORAGE = 19, RVN_SV_GLACIER_MB = 20, RVN_SV_CONVOLUTION = 21, RVN_SV_CONV_STOR = 22,
+  RVN_SV_MIN_DEP_DEFICIT = 23, RVN_SV_CONTRIB_FRAC = 24, RVN_SV_INFIL_CORR = 25, RVN_SV_CUM_INFIL = 26,
+  RVN_SV_GA_MOISTURE_INIT = 27, RVN_SV_CUM_SNOWMELT = 28, RVN_SV_AET = 29, RVN_SV_RUNOFF = 30,
+  RVN_SV_ENERGY_LOSSES = 31, RVN_SV_SURFACE_WATER_TEMP = 32, RVN_SV_SNOW_TEMP = 33, RVN_SV_COLD_CONTENT = 34,
+  RVN_SV_SOIL_TEMP = 35, RVN_SV_CANOPY_TEMP = 36, RVN_SV_SOIL_PCT_FROZ = 37, RVN_SV_SNOW_DEPTH = 38,
+  RVN_SV_FIRN_GRAVITY = 39, RVN_SV_PERMAFROST_DEPTH = 40, RVN_SV_THAW_DEPTH = 41, RVN_SV_SNOW_DEPTH_STDDEV = 42,
+  RVN_SV_SNOW_COVER = 43, RVN_SV_GLACIER_CC = 44, RVN_SV_SNOW_DEFICIT = 45, RVN_SV_SNOW_AGE = 46,
+  RVN_SV_SNODRIFT_TEMP = 47, RVN_SV_SNOW_DRIFT = 48, RVN_SV_ICE_THICKNESS = 49, RVN_SV_SNOW_ALBEDO = 50,
+  RVN_SV_NTYPES = 64
+} rvn_sv_type;
+
+/* HRU types: numbering == reference enum HRU_type (src/RavenInclude.h:599-609) */
+typedef enum {
+  RVN_HRU_STANDARD = 0, RVN_HRU_LAKE = 1, RVN_HRU_WATER = 2, RVN_HRU_GLACIER = 3, RVN_HRU_WETLAND = 4,
+  RVN_HRU_MASKED_GLACIER = 5, RVN_HRU_ROCK = 6
+} rvn_hru_type;
+
+/* ---- process opcodes: one per (process class, algorithm) the device interpreter implements.
+ *      Each cites the reference GetRatesOfChange/ApplyConstraints it replaces. ---- */
+typedef enum {
+  RVN_OP_NOP = 0,
+  RVN_OP_PRECIPITATION,        /* CmvPrecipitation        src/PartitionPrecip.cpp:135-358          */
+  RVN_OP_SNOBAL_HMETS,         /* CmvSnowBalance          src/SnowBalance.cpp:472-522              */
+  RVN_OP_SNOBAL_SIMPLE_MELT,   /* CmvSnowBalance          src/SnowBalance.cpp:393-396,1311-1317    */
+  RVN_OP_SNOBAL_CEMA_NEIGE,    /* CmvSnowBalance          src/SnowBalance.cpp:398-413              */
+  RVN_OP_SNOBAL_HBV,           /* CmvSnowBalance          src/SnowBalance.cpp:430-465              */
+  RVN_OP_SNOWREFREEZE_DD,      /* CmvSnowRefreeze         src/SnowMeltRefreeze.cpp:324-365         */
+  RVN_OP_SNOTEMP_NEWTONS,      /* CmvSnowTempEvolve       src/SnowTempEvolve.cpp:42-77             */
+  RVN_OP_INF_HMETS,            /* CmvInfiltration         src/Infiltration.cpp:491-514,605-626     */
+  RVN_OP_INF_HBV,              /* CmvInfiltration         src/Infiltration.cpp:384-398             */
+  RVN_OP_INF_GR4J,             /* CmvInfiltration         src/Infiltration.cpp:477-489             */
+  RVN_OP_OVERFLOW,             /* CmvOverflow             src/Flush.cpp:259-295                    */
+  RVN_OP_FLUSH,                /* CmvFlush                src/Flush.cpp:75-110                     */
+  RVN_OP_SPLIT,                /* CmvSplit                src/Flush.cpp:178-210                    */
+  RVN_OP_BASE_LINEAR,          /* CmvBaseflow             src/Baseflow.cpp:180-186,297-310         */
+  RVN_OP_BASE_POWER_LAW,       /* CmvBaseflow             src/Baseflow.cpp                          */
+  RVN_OP_BASE_GR4J,            /* CmvBaseflow             src/Baseflow.cpp                          */
+  RVN_OP_PERC_LINEAR,          /* CmvPercolation          src/Percolation.cpp:237-243,339-360      */
+  RVN_OP_PERC_CONSTANT,        /* CmvPercolation          src/Percolation.cpp:199-202              */
+  RVN_OP_PERC_GR4J,            /* CmvPercolation          src/Percolation.cpp                       */
+  RVN_OP_PERC_GR4JEXCH,        /* CmvPercolation          src/Percolation.cpp                       */
+  RVN_OP_PERC_GR4JEXCH2,       /* CmvPercolation          src/Percolation.cpp                       */
+  RVN_OP_SOILEVAP_ALL,         /* CmvSoilEvap             src/SoilEvaporation.cpp:379-383,767-783  */
+  RVN_OP_SOILEVAP_HBV,         /* CmvSoilEvap             src/SoilEvaporation.cpp:385-...          */
+  RVN_OP_SOILEVAP_GR4J,        /* CmvSoilEvap             src/SoilEvaporation.cpp                   */
+  RVN_OP_CONVOLVE,             /* CmvConvolution          src/Convolution.cpp:245-303              */
+  RVN_OP_CANEVP_ALL,           /* CmvCanopyEvap           src/VegetationMovers.cpp                  */
+  RVN_OP_CANSNOWEVP_ALL,       /* CmvCanopySublimation    src/VegetationMovers.cpp                  */
+  RVN_OP_OPEN_WATER_EVAP,      /* CmvOWEvaporation        src/OpenWaterEvap.cpp                     */
+  RVN_OP_LAKE_EVAP_BASIC,      /* CmvLakeEvaporation      src/OpenWaterEvap.cpp                     */
+  RVN_OP_CAPRISE_HBV,          /* CmvCapillaryRise        src/CapillaryRise.cpp:103-147,160-179    */
+  RVN_OP_GLACIERMELT_HBV,      /* CmvGlacierMelt          src/GlacierProcesses.cpp                  */
+  RVN_OP_GLACIERRELEASE_HBVEC, /* CmvGlacierRelease       src/GlacierProcesses.cpp                  */
+  RVN_OP_COUNT
+} rvn_opcode;
+
+/* model-wide method switches; numbering is local to this ABI (the host maps Raven's keywords) */
+typedef enum { RVN_RAINSNOW_DATA = 0, RVN_RAINSNOW_DINGMAN, RVN_RAINSNOW_HBV, RVN_RAINSNOW_UBCWM, RVN_RAINSNOW_THRESHOLD } rvn_rainsnow;
+typedef enum { RVN_POTMELT_NONE = 0, RVN_POTMELT_DATA, RVN_POTMELT_DEGREE_DAY, RVN_POTMELT_HBV, RVN_POTMELT_HMETS } rvn_potmelt;
+typedef enum { RVN_PET_DATA = 0, RVN_PET_FROMMONTHLY, RVN_PET_CONSTANT, RVN_PET_NONE, RVN_PET_HARGREAVES_1985, RVN_PET_OUDIN } rvn_pet;
+typedef enum { RVN_OROCORR_NONE = 0, RVN_OROCORR_SIMPLELAPSE, RVN_OROCORR_HBV } rvn_orocorr;
+typedef enum { RVN_ROUTE_NONE = 0, RVN_ROUTE_MUSKINGUM, RVN_ROUTE_MUSKINGUM_CUNGE, RVN_ROUTE_STORAGECOEFF,
+               RVN_ROUTE_PLUG_FLOW, RVN_ROUTE_DIFFUSIVE_WAVE } rvn_routing;
+typedef enum { RVN_CONVOL_GR4J_1 = 0, RVN_CONVOL_GR4J_2, RVN_CONVOL_GAMMA, RVN_CONVOL_GAMMA_2 } rvn_convol_type;
+
+/* ---- per-member parameter table ------------------------------------------------------------------
+ * ptab[member][..] = [ globals | land-use classes | vegetation classes | soil classes ], every class
+ * a fixed-stride row of the fields below (names follow reference src/Properties.h).  Members of an
+ * ensemble differ only in this table (reference CModel::UpdateParameter, src/Model.cpp:2692-2750). */
+typedef enum {
+  RVN_G_SNOW_SWI = 0, RVN_G_SNOW_SWI_MIN, RVN_G_SNOW_SWI_MAX, RVN_G_SWI_REDUCT_COEFF, RVN_G_ADIABATIC_LAPSE,
+  RVN_G_PRECIP_LAPSE, RVN_G_RAINSNOW_TEMP, RVN_G_RAINSNOW_DELTA, RVN_G_AVG_ANNUAL_SNOW, RVN_G_SNOW_TEMPERATURE,
+  RVN_G_HBVEC_LAPSE_UPPER, RVN_G_HBVEC_LAPSE_RATE, RVN_G_HBVEC_LAPSE_ELEV, RVN_G_AIRSNOW_COEFF,
+  RVN_G_AVG_ANNUAL_RUNOFF, RVN_G_MAX_SWE_SURFACE, RVN_G_TOC_MULTIPLIER, RVN_G_TIME_TO_PEAK_MULTIPLIER,
+  RVN_G_GAMMA_SHAPE_MULTIPLIER, RVN_G_GAMMA_SCALE_MULTIPLIER, RVN_G_COUNT
+} rvn_global_field;
+typedef enum {
+  RVN_LU_IMPERMEABLE_FRAC = 0, RVN_LU_FOREST_COVERAGE, RVN_LU_FOREST_SPARSENESS, RVN_LU_MELT_FACTOR,
+  RVN_LU_MIN_MELT_FACTOR, RVN_LU_MAX_MELT_FACTOR, RVN_LU_DD_MELT_TEMP, RVN_LU_DD_AGGRADATION,
+  RVN_LU_REFREEZE_FACTOR, RVN_LU_DD_REFREEZE_TEMP, RVN_LU_REFREEZE_EXP, RVN_LU_HMETS_RUNOFF_COEFF,
+  RVN_LU_GAMMA_SHAPE, RVN_LU_GAMMA_SCALE, RVN_LU_GAMMA_SHAPE2, RVN_LU_GAMMA_SCALE2, RVN_LU_GR4J_X4,
+  RVN_LU_HBV_MELT_FOR_CORR, RVN_LU_HBV_MELT_ASP_CORR, RVN_LU_HBV_MELT_GLACIER_CORR, RVN_LU_HBV_GLACIER_KMIN,
+  RVN_LU_GLAC_STORAGE_COEFF, RVN_LU_HBV_GLACIER_AG, RVN_LU_DEP_MAX, RVN_LU_LAKE_PET_CORR, RVN_LU_OW_PET_CORR,
+  RVN_LU_PARTITION_COEFF, RVN_LU_CC_DECAY_COEFF, RVN_LU_COUNT
+} rvn_landuse_field;
+typedef enum {
+  RVN_V_MAX_HEIGHT = 0, RVN_V_MAX_LAI, RVN_V_SAI_HT_RATIO, RVN_V_MAX_CAPACITY, RVN_V_MAX_SNOW_CAPACITY,
+  RVN_V_RAIN_ICEPT_PCT, RVN_V_SNOW_ICEPT_PCT, RVN_V_PET_VEG_CORR,
+  /* derived canopy variables (reference veg_var_struct; CVegetationClass::RecalculateCanopyParams,
+   * src/VegetationParams.cpp:85-200), refreshed by the host for the current step when date-dependent */
+  RVN_V_VAR_CAPACITY, RVN_V_VAR_SNOW_CAPACITY, RVN_V_VAR_RAIN_ICEPT_PCT, RVN_V_VAR_SNOW_ICEPT_PCT,
+  RVN_V_COUNT
+} rvn_veg_field;
+typedef enum {
+  RVN_S_POROSITY = 0, RVN_S_CAP_RATIO, RVN_S_PERC_COEFF, RVN_S_PET_CORRECTION, RVN_S_BASEFLOW_COEFF,
+  RVN_S_BASEFLOW_N, RVN_S_FIELD_CAPACITY, RVN_S_SAT_WILT, RVN_S_HBV_BETA, RVN_S_MAX_CAP_RISE_RATE,
+  RVN_S_MAX_PERC_RATE, RVN_S_GR4J_X2, RVN_S_GR4J_X3, RVN_S_COUNT
+} rvn_soil_field;
+
+/* forcing series the host uploads per gauge, already sampled on the model step
+ * (reference CGauge::GetForcingValue(ftype,nn), src/Gauge.cpp:533-540) */
+typedef enum {
+  RVN_GF_PRECIP = 0, RVN_GF_SNOW_FRAC, RVN_GF_TEMP_AVE, RVN_GF_TEMP_DAILY_AVE, RVN_GF_TEMP_DAILY_MIN,
+  RVN_GF_TEMP_DAILY_MAX, RVN_GF_PET, RVN_GF_OW_PET, RVN_GF_POTENTIAL_MELT, RVN_GF_COUNT
+} rvn_gauge_series;
+/* per-gauge constants */
+typedef enum {
+  RVN_GC_ELEVATION = 0, RVN_GC_RAIN_CORR, RVN_GC_SNOW_CORR, RVN_GC_TEMP_CORR,
+  RVN_GC_MONTHLY_AVE_TEMP0 /*..+11*/ = 4, RVN_GC_MONTHLY_AVE_PET0 /*..+11*/ = 16,
+  RVN_GC_MONTHLY_MIN_TEMP0 = 28, RVN_GC_MONTHLY_MAX_TEMP0 = 40, RVN_GC_COUNT = 52
+} rvn_gauge_const;
+
+/* derived per-HRU forcings kept on the device (subset of reference force_struct, src/RavenInclude.h:1294-1343) */
+typedef enum {
+  RVN_F_PRECIP = 0, RVN_F_SNOW_FRAC, RVN_F_TEMP_AVE, RVN_F_TEMP_DAILY_AVE, RVN_F_TEMP_DAILY_MIN,
+  RVN_F_TEMP_DAILY_MAX, RVN_F_PET, RVN_F_OW_PET, RVN_F_POTENTIAL_MELT, RVN_F_TEMP_MONTH_AVE, RVN_F_PET_MONTH_AVE,
+  RVN_F_COUNT
+} rvn_forcing_field;
+
+/* per-step calendar record (reference time_struct, filled by JulianConvert, src/CommonFunctions.cpp:300-380) */
+typedef struct rvn_time {
+  double model_time;   /* [d] since start */
+  double julian_day;   /* [d] fractional day of year, 0 = Jan 1 00:00 */
+  double day_angle;    /* CRadiation::DayAngle(mid_day,year) [rad] */
+  int32_t month;       /* 1..12 */
+  int32_t day_of_month;
+  int32_t year;
+  int32_t day_changed; /* tt.day_changed */
+  int32_t nn;          /* sample index into the gauge series */
+  int32_t pad_;
+} rvn_time;
+
+typedef struct rvn_process {
+  int32_t op;       /* rvn_opcode */
+  int32_t nconn;    /* reference GetNumConnections() (101 for a convolution) */
+  int32_t conn0;    /* offset of this process' first connection in conn_from/conn_to (convolutions store none) */
+  int32_t ia[5];    /* op-specific ints:
+                       CONVOLVE: ia[0]=conv index, ia[1]=target SV, ia[2]=first CONV_STOR SV, ia[3]=CONVOLUTION SV,
+                                 ia[4]=rvn_convol_type
+                       soil ops: ia[0]=soil layer of 'from', ia[1]=soil layer of 'to' (or -1)           */
+  double  da[2];    /* op-specific doubles (SPLIT: da[0] = fraction to first target) */
+} rvn_process;
+
+typedef struct rvn_options {
+  double  timestep;               /* Options.timestep [d] */
+  int32_t rainsnow, pot_melt, evaporation, ow_evaporation;
+  int32_t orocorr_temp, orocorr_precip, orocorr_pet;
+  int32_t routing, suppress_competitive_ET, snow_suppress_PET, allow_soil_overfill, direct_evap;
+  int32_t lake_sv;                /* CModel::GetLakeStorageIndex() */
+  int32_t keep_flux_balance;      /* 0: skip per-connection cumulative flux arrays */
+  int32_t pad_[2];
+} rvn_options;
+
+/* Flattened model (all pointers are HOST memory, copied by rvn_gpu_create). */
+typedef struct rvn_model_desc {
+  int32_t abi_version;
+  int32_t nHRU, nSB, nMembers, nGauges, nSteps;
+  rvn_options opt;
+
+  /* state-variable catalogue, order == reference CModel::AddStateVariables (src/Model.cpp:1561-1612) */
+  int32_t NS, nSoilLayers;
+  const int32_t *sv_type;     /* [NS] */
+  const int32_t *sv_layer;    /* [NS] */
+
+  /* process program (reference CModel::_pProcesses order) */
+  int32_t nProc, nConn;
+  const rvn_process *proc;    /* [nProc] */
+  const int32_t *conn_from;   /* [nConn] */
+  const int32_t *conn_to;     /* [nConn] */
+  const uint64_t *apply_mask; /* [nHRU] bit j = _aShouldApplyProcess[j][k] (src/ModelInitialize.cpp:252-263) */
+
+  /* HRU statics (shared by all members) */
+  const double *hru_area, *hru_elev, *hru_lat_rad, *hru_slope, *hru_aspect;   /* [nHRU] */
+  const int32_t *hru_type, *hru_lu, *hru_veg, *hru_profile, *hru_sb, *hru_enabled; /* [nHRU] */
+
+  /* soil profiles: layer m of profile r has class prof_class[r*RVN_MAX_SOIL_LAYERS+m], thickness [m] likewise */
+  int32_t nProfiles, nLU, nVeg, nSoilClasses;
+  const int32_t *prof_class;
+  const double  *prof_thick;
+
+  /* parameter tables [nMembers][ptab_stride]; offsets of the class blocks inside one member's table */
+  int32_t ptab_stride, glob_off, lu_off, veg_off, soil_off;
+  const double *ptab;
+  /* convolution unit hydrographs, hoisted out of the per-HRU-per-step loop (reference rebuilds them in
+   * CmvConvolution::GenerateUnitHydrograph, src/Convolution.cpp:107-154): [nMembers][nLU][nConvProc] */
+  int32_t nConvProc;
+  const int32_t *conv_n;      /* N of each UH */
+  const double  *conv_uh;     /* [..][RVN_CONV_STORES] */
+
+  /* forcings */
+  const double *gauge_series; /* [RVN_GF_COUNT][nGauges][nSteps] */
+  const double *gauge_const;  /* [nGauges][RVN_GC_COUNT] */
+  const double *wt_precip, *wt_temp, *wt_all;  /* [nHRU][nGauges] (src/Model.h:104-106) */
+  const rvn_time *times;      /* [nSteps] */
+
+  /* routing network (reference CSubBasin + CModel::InitializeRoutingNetwork, src/ModelInitialize.cpp:505-619) */
+  const int32_t *sb_down;     /* [nSB] downstream index or -1 */
+  const int32_t *sb_order;    /* [nSB] _aOrderedSBind: processing order, upstream first */
+  const int32_t *sb_level;    /* [nSB] _aSubBasinOrder: hops to outlet */
+  const int32_t *sb_headwater;/* [nSB] */
+  const int32_t *sb_nseg, *sb_nqin, *sb_nqlat; /* [nSB] */
+  const double *sb_area;      /* [nSB] km2 */
+  const double *sb_rain_corr, *sb_snow_corr, *sb_temp_corr; /* [nSB] */
+  const double *sb_musk_K, *sb_musk_X;        /* [nSB] per-segment Muskingum K [d], X (src/SubBasin.cpp:2429-2452) */
+  const double *sb_K_reach;   /* [nSB] GetMuskingumK(dx) for STORAGECOEFF */
+  int32_t max_nqin, max_nqlat;
+  const double *sb_unit_hydro;   /* [nSB][max_nqlat] _aUnitHydro */
+  const double *sb_route_hydro;  /* [nSB][max_nqin]  _aRouteHydro */
+  double watershed_area;         /* km2 */
+} rvn_model_desc;
+
+typedef struct rvn_gpu_model rvn_gpu_model; /* opaque */
+
+/* ---- entry points ------------------------------------------------------------------------------- */
+const char *rvn_gpu_last_error(void);
+int rvn_gpu_abi_version(void);
+int rvn_gpu_device_count(void);
+
+/* build device-resident model; `device` = CUDA ordinal */
+int rvn_gpu_create(const rvn_model_desc *desc, int device, rvn_gpu_model **out);
+void rvn_gpu_destroy(rvn_gpu_model *m);
+
+/* HRU state, host layout [member][hru][sv] (the reference's aPhi[k][i] per member); device is SoA */
+int rvn_gpu_upload_state(rvn_gpu_model *m, const double *state, int member0, int nmembers);
+int rvn_gpu_download_state(rvn_gpu_model *m, double *state, int member0, int nmembers);
+/* basin routing state, host layout per member: qin_hist[nSB][max_nqin], qlat_hist[nSB][max_nqlat],
+ * qout[nSB][RVN_MAX_RIVER_SEGS], scalars[nSB][8] = {QoutLast,QlatLast,Qlocal,QlocLast,channel_storage,rivulet_storage,0,0} */
+int rvn_gpu_upload_basin_state(rvn_gpu_model *m, const double *qin_hist, const double *qlat_hist,
+                               const double *qout, const double *scalars, int member0, int nmembers);
+int rvn_gpu_download_basin_state(rvn_gpu_model *m, double *qin_hist, double *qlat_hist, double *qout,
+                                 double *scalars, int member0, int nmembers);
+/* replace parameter tables / convolution UHs of a member range (ensemble UpdateModel) */
+int rvn_gpu_upload_params(rvn_gpu_model *m, const double *ptab, const int32_t *conv_n, const double *conv_uh,
+                          int member0, int nmembers);
+/* replace forcing series (streaming long runs / BMI SetValue): same layout as desc, nsteps samples from step0 */
+int rvn_gpu_upload_forcings(rvn_gpu_model *m, const double *gauge_series, const rvn_time *times, int step0, int nsteps);
+
+/* advance all members by nsteps model steps starting at step index `step0`:
+ * forcing update -> HRU process sweep -> HRU->basin aggregation -> ordered routing -> balance reductions
+ * (= UpdateHRUForcingFunctions + MassEnergyBalance + IncrementCumulInput/CumOutflow of the reference loop,
+ * src/RavenMain.cpp:151-160).  Asynchronous on the handle's stream; rvn_gpu_sync waits. */
+int rvn_gpu_run(rvn_gpu_model *m, int step0, int nsteps);
+int rvn_gpu_sync(rvn_gpu_model *m);
+
+/* per-step outputs recorded on the device during rvn_gpu_run:
+ *   qout    [nsteps][member][nSB]    CSubBasin::GetOutflowRate() after the step
+ *   wshed   [nsteps][member][4]      {_CumulInput, _CumulOutput, avg precip, total water storage [mm]}
+ * record_every = 0 disables recording. */
+int rvn_gpu_set_recording(rvn_gpu_model *m, int max_steps);
+int rvn_gpu_download_hydrographs(rvn_gpu_model *m, double *qout, int rec0, int nrec, int member0, int nmembers);
+int rvn_gpu_download_watershed(rvn_gpu_model *m, double *wshed, int rec0, int nrec, int member0, int nmembers);
+/* derived per-HRU forcings of the last executed step, host layout [member][hru][RVN_F_COUNT] */
+int rvn_gpu_download_forcings(rvn_gpu_model *m, double *forc, int member0, int nmembers);
+
+/* area-weighted watershed average of every state variable (reference CModel::GetAvgStateVar,
+ * src/Model.cpp:1159-1174): out[member][NS] */
+int rvn_gpu_avg_state(rvn_gpu_model *m, double *out, int member0, int nmembers);
+
+/* raw device pointers for zero-copy callers that already live on the GPU (bench, NCCL EnKF gather) */
+int rvn_gpu_device_state_ptr(rvn_gpu_model *m, void **dptr, int64_t *member_stride, int64_t *sv_stride);
+/* CUDA-event time (ms) spent in kernels of the last rvn_gpu_run, and number of kernel launches it made */
+int rvn_gpu_last_run_stats(rvn_gpu_model *m, double *sweep_ms, double *total_ms, int64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RVN_GPU_H */

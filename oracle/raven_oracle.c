@@ -1,0 +1,716 @@
+/* oracle/raven_oracle.c -- TEST INFRASTRUCTURE ONLY.  CPU restatement, in plain C, of the reference's
+ * per-timestep water balance for the supported option/process subset.  It consumes the same flattened
+ * rvn_model_desc as the CUDA engine and follows the REFERENCE's loop structure (one HRU after another,
+ * one process after another, per-connection state update), so that tests can compare the GPU path
+ * against it on seeded inputs of any size.  Nothing under ravenhydroframework_b200/ may link or call
+ * this file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg do.
+ *
+ * Parity pin: tests/test_oracle_vs_reference.py checks this oracle against in-memory FP64 dumps of the
+ * unmodified reference (oracle/_ref/ref_dump, built from /root/reference by oracle/build_ref.sh) and
+ * against the committed fixtures under tests/golden/ that the same driver generated.
+ *
+ * Each function cites the reference file:line it restates (paths relative to the reference tree).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include "rvn_gpu.h"
+
+#define O_ALMOST_INF 1e99
+#define O_REAL_SMALL 1e-12
+#define O_PI 3.1415926535898
+#define O_SEC_PER_DAY 86400.0
+#define O_MM_PER_METER 1000.0
+#define O_M2_PER_KM2 1e6
+#define O_FREEZING_TEMP 0.0
+#define O_NEGLIGBLE_SNOW 0.1
+#define O_TYPICAL_SNOW_DENS 0.250e3
+#define O_DENSITY_WATER 1.000e3
+#define O_DENSITY_ICE 0.917e3
+#define O_HCP_ICE 1.938
+#define O_WINTER_SOLSTICE_ANG 6.111043
+#define O_HBV_PET_ELEV_CORR 0.0005
+#define O_HBV_PET_TEMP_CORR 0.5
+#define O_GLOBAL_PET_CORR 1.0
+#define O_MAXCONN 256
+
+/* src/RavenInclude.h:1456-1464 -- ties return the FIRST argument */
+static double omax(double r, double l) { return (r >= l) ? r : l; }
+static double omin(double r, double l) { return (r <= l) ? r : l; }
+
+typedef struct {
+  const rvn_model_desc *d;
+  int member;
+  const double *ptab;     /* this member's parameter row */
+  int k;                  /* HRU */
+  const double *F;        /* derived forcings of this HRU [RVN_F_COUNT] */
+  const double *phi_old;  /* stored (start-of-step) state: what pHRU->GetStateVarValue returns */
+  int iSV[RVN_SV_NTYPES]; /* first index of each SV type, or -1 */
+} octx;
+
+static int sv_index(const rvn_model_desc *d, int type, int layer) {
+  for (int i = 0; i < d->NS; i++) if (d->sv_type[i] == type && (layer < 0 || d->sv_layer[i] == layer)) return i;
+  return -1;
+}
+static double P_G(const octx *c, int f) { return c->ptab[c->d->glob_off + f]; }
+static double P_LU(const octx *c, int f) { return c->ptab[c->d->lu_off + c->d->hru_lu[c->k] * RVN_LU_COUNT + f]; }
+static double P_V(const octx *c, int f) { return c->ptab[c->d->veg_off + c->d->hru_veg[c->k] * RVN_V_COUNT + f]; }
+static double P_S(const octx *c, int m, int f) {
+  int cls = c->d->prof_class[c->d->hru_profile[c->k] * RVN_MAX_SOIL_LAYERS + m];
+  return c->ptab[c->d->soil_off + cls * RVN_S_COUNT + f];
+}
+/* CHydroUnit::GetSoilCapacity, src/HydroUnits.cpp:260-267 */
+static double soil_capacity(const octx *c, int m) {
+  double thick = c->d->prof_thick[c->d->hru_profile[c->k] * RVN_MAX_SOIL_LAYERS + m];
+  return thick * O_MM_PER_METER * P_S(c, m, RVN_S_CAP_RATIO);
+}
+/* CHydroUnit::GetSoilTensionStorageCapacity, src/HydroUnits.cpp:275-286 */
+static double soil_tension_capacity(const octx *c, int m) {
+  double thick = c->d->prof_thick[c->d->hru_profile[c->k] * RVN_MAX_SOIL_LAYERS + m];
+  return thick * O_MM_PER_METER * P_S(c, m, RVN_S_CAP_RATIO) * (P_S(c, m, RVN_S_FIELD_CAPACITY) - P_S(c, m, RVN_S_SAT_WILT));
+}
+/* CHydroUnit::GetSnowCover, src/HydroUnits.cpp:679-705 (SNOWCOV_NONE), lagged */
+static double snow_cover(const octx *c) {
+  int iSn = c->iSV[RVN_SV_SNOW], iSC = c->iSV[RVN_SV_SNOW_COVER];
+  if (iSn < 0) return 0.0;
+  if (iSC >= 0) return c->phi_old[iSC];
+  if (c->phi_old[iSn] < O_NEGLIGBLE_SNOW) return 0.0;
+  return 1.0;
+}
+/* CHydroUnit::GetSnowDepth, src/HydroUnits.cpp:626-636, lagged */
+static double snow_depth(const octx *c) {
+  int iSn = c->iSV[RVN_SV_SNOW], iSD = c->iSV[RVN_SV_SNOW_DEPTH];
+  if (iSn < 0) return 0.0;
+  if (iSD >= 0) return c->phi_old[iSD];
+  return (c->phi_old[iSn] / O_TYPICAL_SNOW_DENS) * O_DENSITY_WATER;
+}
+/* CHydroUnit::GetSnowTemperature, src/HydroUnits.cpp:645-658, lagged */
+static double snow_temperature(const octx *c) {
+  int i = c->iSV[RVN_SV_SNOW_TEMP];
+  if (i < 0) {
+    double t = P_G(c, RVN_G_SNOW_TEMPERATURE);
+    if (t < -60000.0) return 0.0; /* NOT_NEEDED_AUTO / unspecified */
+    return t;
+  }
+  return c->phi_old[i];
+}
+/* CHydroUnit::GetStateVarMax, src/HydroUnits.cpp:559-606 */
+static double state_var_max(const octx *c, int i, const double *sv) {
+  const rvn_model_desc *d = c->d;
+  switch (d->sv_type[i]) {
+    case RVN_SV_SOIL: return soil_capacity(c, d->sv_layer[i]);
+    case RVN_SV_CANOPY: return P_V(c, RVN_V_VAR_CAPACITY);
+    case RVN_SV_CANOPY_SNOW: return P_V(c, RVN_V_VAR_SNOW_CAPACITY);
+    case RVN_SV_DEPRESSION: { double dm = P_LU(c, RVN_LU_DEP_MAX); return (dm >= 0) ? dm : O_ALMOST_INF; }
+    case RVN_SV_SNOW_COVER: return 1.0;
+    case RVN_SV_SNOW_LIQ: { double SWE = sv[c->iSV[RVN_SV_SNOW]]; (void)snow_depth; return P_G(c, RVN_G_SNOW_SWI) * SWE; } /* CalculateSnowLiquidCapacity, src/SnowParams.cpp:79-88 */
+    default: return O_ALMOST_INF;
+  }
+}
+/* CStateVariable::IsWaterStorage(typ), src/StateVariables.cpp:612-645 (conv_coverup=true) */
+static int is_water_storage(int t) {
+  switch (t) {
+    case RVN_SV_SURFACE_WATER: case RVN_SV_PONDED_WATER: case RVN_SV_ATMOSPHERE: case RVN_SV_ATMOS_PRECIP: case RVN_SV_SNOW:
+    case RVN_SV_GROUNDWATER: case RVN_SV_SOIL: case RVN_SV_CANOPY: case RVN_SV_CANOPY_SNOW: case RVN_SV_ROOT: case RVN_SV_TRUNK:
+    case RVN_SV_DEPRESSION: case RVN_SV_SNOW_LIQ: case RVN_SV_WETLAND: case RVN_SV_GLACIER: case RVN_SV_GLACIER_ICE: case RVN_SV_FIRN:
+    case RVN_SV_CONVOLUTION: case RVN_SV_NEW_SNOW: case RVN_SV_SNOW_DRIFT: case RVN_SV_LAKE_STORAGE: return 1;
+    default: return 0;
+  }
+}
+
+/* ======================================================================== forcings ============= */
+/* CModel::UpdateHRUForcingFunctions, src/UpdateForcings.cpp:30-668, for gauge-based inputs and the
+ * option subset {RAINSNOW_DATA|DINGMAN|HBV|UBCWM|THRESHOLD, POTMELT_*, PET_DATA|FROMMONTHLY|CONSTANT|NONE,
+ * OROCORR_NONE|SIMPLELAPSE|HBV}, daily-or-longer... (timestep>=1 => subdaily_corr = 1, :949-958). */
+static void update_forcings(const rvn_model_desc *d, const double *ptab, int k, int step, const double *phi_old, const int *iSV, double *F) {
+  const rvn_time *tt = &d->times[step];
+  const int nG = d->nGauges, nS = d->nSteps, mo = tt->month;
+  octx c; c.d = d; c.ptab = ptab; c.k = k; c.F = F; c.phi_old = phi_old; memcpy(c.iSV, iSV, sizeof(c.iSV));
+  const double elev = d->hru_elev[k];
+  double ref_elev_temp = 0.0, ref_elev_precip = 0.0;
+  double temp_month_min = 0, temp_month_max = 0, temp_month_ave = 0, PET_month_ave = 0;
+  for (int f = 0; f < RVN_F_COUNT; f++) F[f] = 0.0;
+  if (!d->hru_enabled[k]) return;
+#define GS(f, g) d->gauge_series[((size_t)(f) * nG + (g)) * nS + step]
+#define GC(g, f) d->gauge_const[(size_t)(g) * RVN_GC_COUNT + (f)]
+  for (int g = 0; g < nG; g++) { /* :184-235 */
+    double wt = d->wt_precip[(size_t)k * nG + g];
+    if (wt != 0.0) { F[RVN_F_PRECIP] += wt * GS(RVN_GF_PRECIP, g); F[RVN_F_SNOW_FRAC] += wt * GS(RVN_GF_SNOW_FRAC, g); ref_elev_precip += wt * GC(g, RVN_GC_ELEVATION); }
+    wt = d->wt_temp[(size_t)k * nG + g];
+    if (wt != 0.0) {
+      F[RVN_F_TEMP_AVE] += wt * GS(RVN_GF_TEMP_AVE, g); F[RVN_F_TEMP_DAILY_AVE] += wt * GS(RVN_GF_TEMP_DAILY_AVE, g);
+      F[RVN_F_TEMP_DAILY_MIN] += wt * GS(RVN_GF_TEMP_DAILY_MIN, g); F[RVN_F_TEMP_DAILY_MAX] += wt * GS(RVN_GF_TEMP_DAILY_MAX, g);
+      temp_month_min += wt * GC(g, RVN_GC_MONTHLY_MIN_TEMP0 + mo - 1); temp_month_max += wt * GC(g, RVN_GC_MONTHLY_MAX_TEMP0 + mo - 1);
+      temp_month_ave += wt * GC(g, RVN_GC_MONTHLY_AVE_TEMP0 + mo - 1);
+      ref_elev_temp += wt * GC(g, RVN_GC_ELEVATION);
+    }
+    wt = d->wt_all[(size_t)k * nG + g];
+    if (wt != 0.0) {
+      PET_month_ave += wt * GC(g, RVN_GC_MONTHLY_AVE_PET0 + mo - 1);
+      F[RVN_F_POTENTIAL_MELT] += wt * GS(RVN_GF_POTENTIAL_MELT, g);
+      F[RVN_F_PET] += wt * GS(RVN_GF_PET, g); F[RVN_F_OW_PET] += wt * GS(RVN_GF_OW_PET, g);
+    }
+  }
+  const int p = d->hru_sb[k];
+  { /* temperature gauge corrections :441-455 -- sums are recomputed over ALL gauges */
+    double tc = d->sb_temp_corr[p];
+    F[RVN_F_TEMP_AVE] = F[RVN_F_TEMP_DAILY_AVE] = F[RVN_F_TEMP_DAILY_MAX] = F[RVN_F_TEMP_DAILY_MIN] = 0.0;
+    for (int g = 0; g < nG; g++) {
+      double gauge_corr = tc + GC(g, RVN_GC_TEMP_CORR), wt = d->wt_temp[(size_t)k * nG + g];
+      F[RVN_F_TEMP_AVE] += wt * (gauge_corr + GS(RVN_GF_TEMP_AVE, g));
+      F[RVN_F_TEMP_DAILY_AVE] += wt * (gauge_corr + GS(RVN_GF_TEMP_DAILY_AVE, g));
+      F[RVN_F_TEMP_DAILY_MAX] += wt * (gauge_corr + GS(RVN_GF_TEMP_DAILY_MAX, g));
+      F[RVN_F_TEMP_DAILY_MIN] += wt * (gauge_corr + GS(RVN_GF_TEMP_DAILY_MIN, g));
+    }
+  }
+  const double temp_ave_unc = F[RVN_F_TEMP_DAILY_AVE]; /* :468 */
+  /* CModel::CorrectTemp, src/OrographicCorrections.cpp:24-58 */
+  if (d->opt.orocorr_temp == RVN_OROCORR_SIMPLELAPSE || d->opt.orocorr_temp == RVN_OROCORR_HBV) {
+    double lapse = P_G(&c, RVN_G_ADIABATIC_LAPSE);
+    lapse /= 1000.0;
+    F[RVN_F_TEMP_AVE] -= lapse * (elev - ref_elev_temp);
+    if (tt->day_changed) {
+      F[RVN_F_TEMP_DAILY_AVE] -= lapse * (elev - ref_elev_temp);
+      F[RVN_F_TEMP_DAILY_MIN] -= lapse * (elev - ref_elev_temp);
+      F[RVN_F_TEMP_DAILY_MAX] -= lapse * (elev - ref_elev_temp);
+      temp_month_max -= lapse * (elev - ref_elev_temp);
+      temp_month_min -= lapse * (elev - ref_elev_temp);
+      if (d->opt.orocorr_temp != RVN_OROCORR_HBV) temp_month_ave -= lapse * (elev - ref_elev_temp);
+    }
+  }
+  F[RVN_F_TEMP_MONTH_AVE] = temp_month_ave; F[RVN_F_PET_MONTH_AVE] = PET_month_ave;
+  const double subdaily_corr = 1.0;
+  /* CModel::EstimateSnowFraction, src/UpdateForcings.cpp:1068-1197 */
+  {
+    double sf = F[RVN_F_SNOW_FRAC];
+    if (d->opt.rainsnow == RVN_RAINSNOW_DINGMAN) {
+      double temp = P_G(&c, RVN_G_RAINSNOW_TEMP);
+      if (F[RVN_F_TEMP_DAILY_MAX] <= temp) sf = 1.0;
+      else if (F[RVN_F_TEMP_DAILY_MIN] >= temp) sf = 0.0;
+      else sf = (temp - F[RVN_F_TEMP_DAILY_MIN]) / (F[RVN_F_TEMP_DAILY_MAX] - F[RVN_F_TEMP_DAILY_MIN]);
+    } else if (d->opt.rainsnow == RVN_RAINSNOW_THRESHOLD) {
+      sf = (F[RVN_F_TEMP_AVE] <= P_G(&c, RVN_G_RAINSNOW_TEMP)) ? 1.0 : 0.0;
+    } else if (d->opt.rainsnow == RVN_RAINSNOW_HBV || d->opt.rainsnow == RVN_RAINSNOW_UBCWM) {
+      double frac, delta = P_G(&c, RVN_G_RAINSNOW_DELTA), temp = P_G(&c, RVN_G_RAINSNOW_TEMP);
+      if (F[RVN_F_TEMP_DAILY_AVE] <= (temp - 0.5 * delta)) frac = 1.0;
+      else if (F[RVN_F_TEMP_DAILY_AVE] >= (temp + 0.5 * delta)) frac = 0.0;
+      else frac = 0.5 + (temp - F[RVN_F_TEMP_DAILY_AVE]) / delta;
+      sf = (d->opt.rainsnow == RVN_RAINSNOW_UBCWM) ? frac : frac * (1.0 - F[RVN_F_SNOW_FRAC]) + F[RVN_F_SNOW_FRAC];
+    }
+    F[RVN_F_SNOW_FRAC] = sf;
+  }
+  { /* precip gauge corrections :507-527 */
+    double rc = d->sb_rain_corr[p], sc = d->sb_snow_corr[p];
+    F[RVN_F_PRECIP] = 0.0;
+    for (int g = 0; g < nG; g++) {
+      double gauge_corr = F[RVN_F_SNOW_FRAC] * sc * GC(g, RVN_GC_SNOW_CORR) + (1.0 - F[RVN_F_SNOW_FRAC]) * rc * GC(g, RVN_GC_RAIN_CORR);
+      double wt = d->wt_precip[(size_t)k * nG + g];
+      F[RVN_F_PRECIP] += wt * gauge_corr * GS(RVN_GF_PRECIP, g);
+    }
+  }
+  /* CModel::CorrectPrecip, src/OrographicCorrections.cpp:213-245 */
+  if (d->opt.orocorr_precip == RVN_OROCORR_SIMPLELAPSE) {
+    double lapse = P_G(&c, RVN_G_PRECIP_LAPSE);
+    lapse /= 1000;
+    if (F[RVN_F_PRECIP] > O_REAL_SMALL) F[RVN_F_PRECIP] = omax(F[RVN_F_PRECIP] + lapse * (elev - ref_elev_precip), 0.0);
+  } else if (d->opt.orocorr_precip == RVN_OROCORR_HBV) {
+    double corr_upper = P_G(&c, RVN_G_HBVEC_LAPSE_UPPER) / 1000.0, corr = P_G(&c, RVN_G_HBVEC_LAPSE_RATE) / 1000.0;
+    double lapse_elev = P_G(&c, RVN_G_HBVEC_LAPSE_ELEV), add = 0.0;
+    if (elev > lapse_elev) add = (corr_upper - corr) * (elev - lapse_elev);
+    F[RVN_F_PRECIP] *= omax(1.0 + corr * (elev - ref_elev_precip) + add, 0.0);
+  }
+  if (d->hru_type[k] == RVN_HRU_MASKED_GLACIER) F[RVN_F_PRECIP] = 0;
+  /* CModel::EstimatePotentialMelt, src/PotentialMelt.cpp:20-246 */
+  {
+    double pm = F[RVN_F_POTENTIAL_MELT];
+    if (d->opt.pot_melt == RVN_POTMELT_DEGREE_DAY) {
+      pm = P_LU(&c, RVN_LU_MELT_FACTOR) * (F[RVN_F_TEMP_DAILY_AVE] - P_LU(&c, RVN_LU_DD_MELT_TEMP)) * subdaily_corr;
+    } else if (d->opt.pot_melt == RVN_POTMELT_HBV) {
+      double Ma = P_LU(&c, RVN_LU_MELT_FACTOR), Ma_min = P_LU(&c, RVN_LU_MIN_MELT_FACTOR), AM = P_LU(&c, RVN_LU_HBV_MELT_ASP_CORR);
+      double MRF = P_LU(&c, RVN_LU_HBV_MELT_FOR_CORR), Fc = P_LU(&c, RVN_LU_FOREST_COVERAGE), melt_temp = P_LU(&c, RVN_LU_DD_MELT_TEMP);
+      double adj = 0, slope_corr;
+      if (d->hru_lat_rad[k] < 0.0) adj = O_PI;
+      Ma = Ma_min + (Ma - Ma_min) * 0.5 * (1.0 - cos(tt->day_angle - O_WINTER_SOLSTICE_ANG - adj));
+      Ma *= ((1.0 - Fc) * 1.0 + (Fc)*MRF);
+      slope_corr = ((1.0 - Fc) * 1.0 + (Fc)*sin(d->hru_slope[k]));
+      Ma *= omax(1.0 - AM * slope_corr * cos(d->hru_aspect[k] - adj), 0.0);
+      pm = Ma * (F[RVN_F_TEMP_DAILY_AVE] - melt_temp) * subdaily_corr + 0.0;
+    } else if (d->opt.pot_melt == RVN_POTMELT_HMETS) {
+      double Ma_min = P_LU(&c, RVN_LU_MIN_MELT_FACTOR), Ma_max = P_LU(&c, RVN_LU_MAX_MELT_FACTOR);
+      double melt_temp = P_LU(&c, RVN_LU_DD_MELT_TEMP), Kcum = P_LU(&c, RVN_LU_DD_AGGRADATION);
+      double cum_melt = 0.0, Ma;
+      if (iSV[RVN_SV_CUM_SNOWMELT] >= 0) cum_melt = phi_old[iSV[RVN_SV_CUM_SNOWMELT]];
+      Ma = omin(Ma_max, Ma_min * (1 + Kcum * cum_melt));
+      pm = Ma * (F[RVN_F_TEMP_DAILY_AVE] - melt_temp) * subdaily_corr;
+    } else if (d->opt.pot_melt == RVN_POTMELT_NONE) {
+      pm = 0.0;
+    }
+    F[RVN_F_POTENTIAL_MELT] = pm;
+  }
+  /* CModel::EstimatePET, src/Evaporation.cpp:282-540 (PET_DATA / PET_FROMMONTHLY / PET_CONSTANT / PET_NONE) */
+  for (int ow = 0; ow < 2; ow++) {
+    int method = ow ? d->opt.ow_evaporation : d->opt.evaporation;
+    double PET = ow ? F[RVN_F_OW_PET] : F[RVN_F_PET];
+    if (method == RVN_PET_CONSTANT) PET = 3.0;
+    else if (method == RVN_PET_NONE) PET = 0.0;
+    else if (method == RVN_PET_FROMMONTHLY) { /* src/Evaporation.cpp:349-355 */
+      double peRatio = 1.0 + O_HBV_PET_TEMP_CORR * (temp_ave_unc - temp_month_ave);
+      peRatio = omax(0.0, omin(2.0, peRatio));
+      PET = PET_month_ave * peRatio;
+    }
+    PET = omax(PET, 0.0);                 /* src/Evaporation.cpp:534-537 */
+    PET = PET * P_V(&c, RVN_V_PET_VEG_CORR);
+    if (ow) F[RVN_F_OW_PET] = PET; else F[RVN_F_PET] = PET;
+  }
+  /* CModel::CorrectPET, src/OrographicCorrections.cpp:350-440 */
+  if (d->opt.orocorr_pet == RVN_OROCORR_HBV) {
+    double factor = O_GLOBAL_PET_CORR * omax(1.0 - O_HBV_PET_ELEV_CORR * (elev - ref_elev_temp), 0.0);
+    F[RVN_F_PET] *= factor; F[RVN_F_OW_PET] *= factor;
+  }
+  if (d->opt.evaporation == RVN_PET_FROMMONTHLY || d->opt.evaporation == RVN_PET_CONSTANT) /* IsDailyPETmethod, src/Evaporation.cpp:540-556 */
+    F[RVN_F_PET] *= subdaily_corr;
+  if (d->opt.snow_suppress_PET) {
+    double SWE = 0.0, sc = 1.0;
+    if (iSV[RVN_SV_SNOW] >= 0) SWE = phi_old[iSV[RVN_SV_SNOW]];
+    if (iSV[RVN_SV_SNOW_COVER] >= 0) sc = phi_old[iSV[RVN_SV_SNOW_COVER]];
+    if (SWE > 0.1) { F[RVN_F_PET] *= (1.0 - sc); F[RVN_F_OW_PET] *= (1.0 - sc); }
+  }
+  if (d->hru_type[k] == RVN_HRU_STANDARD) F[RVN_F_PET] *= P_S(&c, 0, RVN_S_PET_CORRECTION);
+  if (d->hru_type[k] == RVN_HRU_MASKED_GLACIER) F[RVN_F_PET] = F[RVN_F_OW_PET] = 0.0;
+  if (d->opt.direct_evap) { /* :640-650 */
+    double rainfall = F[RVN_F_PRECIP] * (1.0 - F[RVN_F_SNOW_FRAC]);
+    double reduce = omin(F[RVN_F_PET], rainfall + 0.0);
+    double rainfrac = rainfall / (rainfall + 0.0);
+    if ((rainfall + 0.0) == 0) rainfrac = 1.0;
+    if (F[RVN_F_PRECIP] + 0.0 - reduce > 0.0) F[RVN_F_SNOW_FRAC] = 1.0 - (rainfall - reduce * rainfrac) / (F[RVN_F_PRECIP] - reduce * rainfrac);
+    F[RVN_F_PRECIP] -= reduce * rainfrac;
+    F[RVN_F_PET] -= reduce * rainfrac;
+  }
+#undef GS
+#undef GC
+}
+
+/* ======================================================================== processes ============ */
+/* each op restates GetRatesOfChange followed by ApplyConstraints; rates[] arrives zeroed
+ * (CModel::ApplyProcess, src/Model.cpp:3066-3071) */
+static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, const int *iTo, const double *sv, double *rates) {
+  const rvn_model_desc *d = c->d;
+  const double tstep = d->opt.timestep;
+  const int type = d->hru_type[c->k];
+  const double *F = c->F;
+  switch (pr->op) {
+    case RVN_OP_PRECIPITATION: { /* src/PartitionPrecip.cpp:135-355 (no ICE_THICKNESS) */
+      enum { qPond = 0, qCan, qCanSnow, qDep, qAtmos, qSnow, qSnowLiq, qSnowDef, qNewSnow, qLake, qSW, qColdContent, qSnowDepth };
+      const int iCan = c->iSV[RVN_SV_CANOPY], iSCan = c->iSV[RVN_SV_CANOPY_SNOW], iSnLiq = c->iSV[RVN_SV_SNOW_LIQ], iSWE = c->iSV[RVN_SV_SNOW];
+      double total_precip = F[RVN_F_PRECIP], Fsnow = F[RVN_F_SNOW_FRAC], air_temp = F[RVN_F_TEMP_AVE];
+      double snowfall, rainfall, rain_int, snow_int, rainthru, snowthru;
+      if (iSWE < 0) Fsnow = 0;
+      snowfall = (Fsnow)*total_precip;
+      rainfall = (1.0 - Fsnow) * total_precip;
+      rainfall += 0.0; /* irrigation */
+      double SWE = 0.0;
+      if (iSWE >= 0) SWE = sv[iSWE];
+      double Fs = snow_cover(c);
+      const int is_lake = (type == RVN_HRU_LAKE);
+      if (!is_lake) {
+        double Fcan = P_LU(c, RVN_LU_FOREST_COVERAGE);
+        double rain_pct = P_V(c, RVN_V_VAR_RAIN_ICEPT_PCT);
+        rain_int = rainfall * rain_pct;
+        if (iCan >= 0) {
+          double capacity = P_V(c, RVN_V_VAR_CAPACITY);
+          rain_int = omin(rain_int, omax((capacity - sv[iCan]) / tstep, 0.0));
+          rates[qCan] = Fcan * rain_int;
+        } else rates[qAtmos] += Fcan * rain_int;
+        rainthru = rainfall - Fcan * rain_int;
+        double snow_pct = P_V(c, RVN_V_VAR_SNOW_ICEPT_PCT);
+        snow_int = snowfall * snow_pct;
+        if (iSCan >= 0) {
+          double snow_capacity = P_V(c, RVN_V_VAR_SNOW_CAPACITY);
+          snow_int = omax(omin(snow_int, omax((snow_capacity - sv[iSCan]) / tstep, 0.0)), 0.0);
+          rates[qCanSnow] = Fcan * snow_int;
+        } else rates[qAtmos] += Fcan * snow_int;
+        snowthru = snowfall - Fcan * snow_int;
+      } else { snowthru = snowfall; rainthru = rainfall; }
+      if (is_lake) rates[qLake] = snowthru + rainthru;
+      else if (type == RVN_HRU_WETLAND) rates[qDep] = snowthru + rainthru;
+      else if (type == RVN_HRU_WATER) rates[qSW] = snowthru + rainthru;
+      else {
+        if (c->iSV[RVN_SV_NEW_SNOW] < 0) {
+          if (iSWE >= 0) {
+            rates[qSnow] = snowthru;
+            if (c->iSV[RVN_SV_SNOW_DEPTH] >= 0) { /* CalcFreshSnowDensity, src/SnowParams.cpp */
+              double rho = (air_temp <= O_FREEZING_TEMP) ? 67.92 + 51.25 * exp((air_temp - O_FREEZING_TEMP) / 2.59)
+                                                         : omin((119.17 + 20.0 * (air_temp - O_FREEZING_TEMP)), 200.0); /* src/SnowParams.cpp:37-47 */
+              rates[qSnowDepth] = snowthru * O_DENSITY_ICE / rho;
+            }
+            if (c->iSV[RVN_SV_COLD_CONTENT] >= 0) rates[qColdContent] = snowthru * omax(O_FREEZING_TEMP - air_temp, 0.0) * O_HCP_ICE / O_MM_PER_METER;
+            if ((iSnLiq >= 0) && (c->iSV[RVN_SV_SNOW_DEFICIT] < 0) && (SWE > 0.0)) {
+              double melt_cap = state_var_max(c, iSnLiq, sv);
+              double fill_rate = Fs * omin(omax(melt_cap - sv[iSnLiq], 0.0) / tstep, rainthru);
+              rates[qSnowLiq] = fill_rate;
+              rainthru -= fill_rate;
+            }
+            if ((c->iSV[RVN_SV_SNOW_DEFICIT] >= 0) && (SWE > 0.0)) rates[qSnowDef] = P_G(c, RVN_G_SNOW_SWI) * snowthru;
+          }
+        } else rates[qNewSnow] = snowthru;
+        rates[qPond] = rainthru; /* lake/wetland branches unreachable here */
+      }
+      break;
+    }
+    case RVN_OP_SNOBAL_HMETS: { /* src/SnowBalance.cpp:472-522 */
+      double SWE = sv[iFrom[0]], SL = sv[iFrom[3]], cum_melt = sv[iFrom[4]];
+      double Kf = P_LU(c, RVN_LU_REFREEZE_FACTOR), Tbf = P_LU(c, RVN_LU_DD_REFREEZE_TEMP), exp_fe = P_LU(c, RVN_LU_REFREEZE_EXP);
+      double fcmin = P_G(c, RVN_G_SNOW_SWI_MIN), fcmax = P_G(c, RVN_G_SNOW_SWI_MAX), Ccum = P_G(c, RVN_G_SWI_REDUCT_COEFF);
+      double potmelt = omax(F[RVN_F_POTENTIAL_MELT], 0.0);
+      double Tdiurnal = 0.5 * (F[RVN_F_TEMP_DAILY_AVE] + F[RVN_F_TEMP_DAILY_MIN]);
+      double pot_freeze, freeze, melt, SWI, deficit, to_liq, ripe;
+      SL = omax(SL, 0.0);
+      pot_freeze = Kf * pow(omax(Tbf - Tdiurnal, 0.0), exp_fe);
+      freeze = omin(pot_freeze * tstep, SL);
+      SL -= freeze; SWE += freeze;
+      melt = omin(potmelt * tstep, SWE);
+      SWE -= melt; cum_melt += melt;
+      if (SWE <= 0.0) cum_melt = 0.0;
+      SWI = omax(fcmin, fcmax * (1 - Ccum * cum_melt));
+      deficit = omax(SWI * SWE - SL, 0.0);
+      to_liq = omin(melt, deficit);
+      melt -= to_liq; SL += to_liq;
+      ripe = omax(SL - SWI * SWE, 0.0);
+      SL -= ripe;
+      rates[0] = to_liq / tstep; rates[1] = melt / tstep; rates[2] = ripe; rates[3] = freeze / tstep; rates[4] = (melt + to_liq) / tstep;
+      if (SWE <= 0.0) rates[4] = -sv[iFrom[4]] / tstep;
+      break;
+    }
+    case RVN_OP_INF_HMETS: { /* src/Infiltration.cpp:304-330,491-514 + constraints :605-626 */
+      if (type != RVN_HRU_STANDARD && type != RVN_HRU_ROCK && type != RVN_HRU_MASKED_GLACIER) break;
+      double Fimp = P_LU(c, RVN_LU_IMPERMEABLE_FRAC);
+      double ponded = omax(sv[c->iSV[RVN_SV_PONDED_WATER]], 0.0);
+      double rainthru = (ponded / tstep);
+      if (type == RVN_HRU_ROCK) { rates[0] = 0.0; rates[1] = rainthru; }
+      else {
+        double stor = sv[iTo[0]], max_stor = soil_capacity(c, 0), coef = P_LU(c, RVN_LU_HMETS_RUNOFF_COEFF);
+        double sat = omin(omax(stor / max_stor, 0.0), 1.0);
+        double direct = Fimp * rainthru;
+        double runoff = coef * (sat) * (1.0 - Fimp) * rainthru;
+        double infil = (1.0 - Fimp) * rainthru - runoff;
+        double delayed = coef * pow(sat, 2.0) * infil;
+        infil -= delayed;
+        rates[0] = infil; rates[1] = direct; rates[2] = runoff; rates[3] = delayed;
+      }
+      if (type != RVN_HRU_STANDARD && type != RVN_HRU_MASKED_GLACIER) break; /* ApplyConstraints guard */
+      rates[0] = omin(rates[0], sv[iFrom[0]] / tstep);
+      double inf = rates[0];
+      if (!d->opt.allow_soil_overfill) {
+        double max_stor = state_var_max(c, iTo[0], sv);
+        inf = omin(rates[0], omax(max_stor - sv[iTo[0]], 0.0) / tstep);
+      }
+      rates[1] += (rates[0] - inf);
+      rates[0] = inf;
+      break;
+    }
+    case RVN_OP_OVERFLOW: { /* src/Flush.cpp:259-279 */
+      double max_storage = omax(state_var_max(c, iFrom[0], sv), 0.0);
+      rates[0] = omax(sv[iFrom[0]] - max_storage, 0.0) / tstep;
+      break;
+    }
+    case RVN_OP_FLUSH: rates[0] = pr->da[0] * sv[iFrom[0]] / tstep; break; /* src/Flush.cpp:75-86 */
+    case RVN_OP_SPLIT: /* src/Flush.cpp:178-186 */
+      rates[0] = (pr->da[0]) * sv[iFrom[0]] / tstep;
+      rates[1] = (1.0 - pr->da[0]) * sv[iFrom[0]] / tstep;
+      break;
+    case RVN_OP_BASE_LINEAR: { /* src/Baseflow.cpp:152-186 + :297-310 */
+      if (type == RVN_HRU_LAKE || type == RVN_HRU_WATER || type == RVN_HRU_ROCK) { /* GetRatesOfChange returns; constraints still run */ }
+      else {
+        int m = pr->ia[0];
+        double stor = sv[iFrom[0]], max_stor = (m >= 0) ? soil_capacity(c, m) : 0.0;
+        stor = omin(omax(stor, 0.0), max_stor);
+        rates[0] = P_S(c, m, RVN_S_BASEFLOW_COEFF) * stor;
+      }
+      rates[0] = omin(rates[0], omax(sv[iFrom[0]], 0.0) / tstep);
+      rates[0] = omax(rates[0], 0.0);
+      break;
+    }
+    case RVN_OP_PERC_LINEAR: { /* src/Percolation.cpp:183-243 + :339-360 */
+      if (type == RVN_HRU_LAKE || type == RVN_HRU_WATER || type == RVN_HRU_ROCK) break;
+      int m = pr->ia[0];
+      double stor = sv[iFrom[0]], max_stor = soil_capacity(c, m);
+      if (max_stor > 0.0) rates[0] = P_S(c, m, RVN_S_PERC_COEFF) * stor;
+      rates[0] = omin(rates[0], omax(sv[iFrom[0]] - 0.0, 0.0) / tstep);
+      if (!d->opt.allow_soil_overfill) {
+        double room = omax(state_var_max(c, iTo[0], sv) - sv[iTo[0]], 0.0);
+        rates[0] = omin(rates[0], room / tstep);
+      }
+      break;
+    }
+    case RVN_OP_SOILEVAP_ALL: { /* src/SoilEvaporation.cpp:325-343,379-383 + :767-783 */
+      if (type != RVN_HRU_STANDARD) break;
+      double PET = F[RVN_F_PET];
+      if (!d->opt.suppress_competitive_ET) { PET -= (sv[c->iSV[RVN_SV_AET]] / tstep); PET = omax(PET, 0.0); }
+      rates[0] = PET;
+      rates[pr->nconn - 1] = rates[0]; /* PETused -> AET (src/SoilEvaporation.cpp end of GetRatesOfChange) */
+      double corr = 0, oldrate;
+      for (int q = 0; q < pr->nconn - 1; q++) {
+        oldrate = rates[q];
+        rates[q] = omin(rates[q], sv[iFrom[q]] / tstep);
+        corr += oldrate - rates[q];
+      }
+      rates[pr->nconn - 1] -= corr;
+      break;
+    }
+    default: break; /* unsupported ops are rejected in rvo_run before the time loop */
+  }
+}
+
+/* CmvConvolution::GetRatesOfChange, src/Convolution.cpp:245-303, with the hoisted unit hydrograph */
+static void convolution_rates(const octx *c, const rvn_process *pr, const double *sv, double *rates) {
+  const rvn_model_desc *d = c->d;
+  const int NST = RVN_CONV_STORES, i0 = pr->ia[2], iTS = pr->ia[3];
+  const double tstep = d->opt.timestep;
+  size_t slot = ((size_t)c->member * d->nLU + d->hru_lu[c->k]) * d->nConvProc + pr->ia[0];
+  const int N = d->conv_n[slot];
+  const double *UH = &d->conv_uh[slot * RVN_CONV_STORES];
+  double S[RVN_CONV_STORES];
+  double TS_old = sv[iTS], sum = 0.0;
+  for (int i = 0; i < N; i++) { S[i] = sv[i0 + i]; sum += S[i]; }
+  S[0] += (TS_old - sum);
+  rates[0] += (TS_old - sum) / tstep;
+  double sumrem = 1.0, orig;
+  for (int i = 0; i < N; i++) {
+    if (sumrem < O_REAL_SMALL) orig = 0.0; else orig = S[i] / sumrem;
+    rates[i + 1] = UH[i] * orig / tstep;
+    S[i] -= rates[i + 1] * tstep;
+    sumrem -= UH[i];
+  }
+  for (int i = N - 2; i >= 0; i--) {
+    double move = S[i];
+    rates[NST + i + 1] = move / tstep;
+    S[i] -= move; S[i + 1] += move;
+  }
+  double TS_new = 0;
+  for (int i = 1; i < N; i++) TS_new += S[i];
+  rates[2 * NST] = (TS_new - TS_old) / tstep;
+}
+
+static int op_supported(int op) {
+  switch (op) {
+    case RVN_OP_PRECIPITATION: case RVN_OP_SNOBAL_HMETS: case RVN_OP_INF_HMETS: case RVN_OP_OVERFLOW: case RVN_OP_FLUSH: case RVN_OP_SPLIT:
+    case RVN_OP_BASE_LINEAR: case RVN_OP_PERC_LINEAR: case RVN_OP_SOILEVAP_ALL: case RVN_OP_CONVOLVE: return 1;
+    default: return 0;
+  }
+}
+
+/* ======================================================================== routing ============== */
+typedef struct { double *qin, *qlat, *qout, *scal; } obasin; /* one member; layouts of rvn_gpu_upload_basin_state */
+
+/* CSubBasin::RouteWater, src/SubBasin.cpp:2584-2863 */
+static void route_water(const rvn_model_desc *d, int p, const obasin *B, double *aQout_new) {
+  const int nSeg = d->sb_nseg[p], nQin = d->sb_nqin[p], nQlat = d->sb_nqlat[p];
+  const double tstep = d->opt.timestep;
+  const double *QinHist = &B->qin[(size_t)p * d->max_nqin], *QlatHist = &B->qlat[(size_t)p * d->max_nqlat];
+  double *aQout = &B->qout[(size_t)p * RVN_MAX_RIVER_SEGS];
+  const double *UH = &d->sb_unit_hydro[(size_t)p * d->max_nqlat], *RH = &d->sb_route_hydro[(size_t)p * d->max_nqin];
+  const double seg_fraction = 1.0 / (double)(nSeg);
+  double Qlat_new = 0.0;
+  for (int n = 0; n < nQlat; n++) Qlat_new += UH[n] * QlatHist[n];
+  int method = d->opt.routing;
+  if (d->sb_headwater[p]) method = RVN_ROUTE_NONE;
+  if (method == RVN_ROUTE_MUSKINGUM || method == RVN_ROUTE_MUSKINGUM_CUNGE) {
+    double K = d->sb_musk_K[p], X = d->sb_musk_X[p], c1, c2, c3, c4, denom, cunge, dt, Qin, Qin_new;
+    double stored[RVN_MAX_RIVER_SEGS];
+    dt = omin(K, tstep);
+    for (int s = 0; s < nSeg; s++) stored[s] = aQout[s];
+    for (double t = 0; t < tstep; t += dt) {
+      if (dt > (tstep - t)) dt = tstep - t;
+      cunge = (method == RVN_ROUTE_MUSKINGUM_CUNGE) ? 1 : 0;
+      denom = (2 * K * (1.0 - X) + dt);
+      c1 = (dt - 2 * K * (X)) / denom; c2 = (dt + 2 * K * (X)) / denom; c3 = (-dt + 2 * K * (1 - X)) / denom; c4 = (dt) / denom;
+      Qin = QinHist[1] + ((t) / tstep) * (QinHist[0] - QinHist[1]);
+      Qin_new = QinHist[1] + ((t + dt) / tstep) * (QinHist[0] - QinHist[1]);
+      for (int s = 0; s < nSeg; s++) {
+        aQout_new[s] = c1 * Qin_new + c2 * Qin + c3 * aQout[s] + cunge * c4 * (Qlat_new * seg_fraction);
+        Qin = aQout[s]; Qin_new = aQout_new[s];
+        aQout[s] = aQout_new[s];
+      }
+    }
+    for (int s = 0; s < nSeg; s++) aQout[s] = stored[s];
+  } else if (method == RVN_ROUTE_STORAGECOEFF) {
+    double Qin_new = QinHist[0], Qin = QinHist[1], Qlocal = B->scal[(size_t)p * 8 + 2];
+    for (int s = 0; s < nSeg; s++) {
+      double ttime = d->sb_K_reach[p] * seg_fraction;
+      double sc = omin(1.0 / (ttime / tstep + 0.5), 1.0);
+      double c1 = sc / 2, c2 = sc / 2, c3 = (1.0 - sc), corr = 1.0;
+      aQout_new[s] = c1 * Qin + c2 * Qin_new + c3 * (aQout[s] - corr * Qlocal);
+      Qin = aQout[s]; Qin_new = aQout_new[s];
+    }
+  } else if (method == RVN_ROUTE_PLUG_FLOW || method == RVN_ROUTE_DIFFUSIVE_WAVE) {
+    aQout_new[nSeg - 1] = 0.0;
+    for (int n = 0; n < nQin; n++) aQout_new[nSeg - 1] += RH[n] * QinHist[n];
+  } else { /* ROUTE_NONE */
+    for (int s = 0; s < nSeg; s++) aQout_new[s] = 0.0;
+    aQout_new[nSeg - 1] = QinHist[0];
+  }
+  aQout_new[nSeg - 1] += Qlat_new;
+}
+/* CSubBasin::UpdateOutflows, src/SubBasin.cpp:2320-2421 (no irrigation/diversion/reservoir) */
+static void update_outflows(const rvn_model_desc *d, int p, const obasin *B, const double *aQo) {
+  const int nSeg = d->sb_nseg[p], nQlat = d->sb_nqlat[p];
+  double *aQout = &B->qout[(size_t)p * RVN_MAX_RIVER_SEGS], *sc = &B->scal[(size_t)p * 8];
+  const double *QinHist = &B->qin[(size_t)p * d->max_nqin], *QlatHist = &B->qlat[(size_t)p * d->max_nqlat];
+  const double *UH = &d->sb_unit_hydro[(size_t)p * d->max_nqlat];
+  sc[0] = aQout[nSeg - 1]; /* _QoutLast */
+  for (int s = 0; s < nSeg; s++) aQout[s] = aQo[s];
+  double irrQ_act = omin(0.0, aQout[nSeg - 1]); aQout[nSeg - 1] -= irrQ_act;
+  double divQ_act = omin(0.0, aQout[nSeg - 1]); aQout[nSeg - 1] -= divQ_act;
+  double dt = d->opt.timestep * O_SEC_PER_DAY, dV = 0.0, Qlat_new = 0.0;
+  for (int n = 0; n < nQlat; n++) Qlat_new += UH[n] * QlatHist[n];
+  sc[3] = sc[2]; sc[2] = Qlat_new; /* _QlocLast=_Qlocal; _Qlocal=Qlat_new */
+  dV += 0.5 * (QinHist[0] + QinHist[1]) * dt;
+  dV -= 0.5 * (aQout[nSeg - 1] + sc[0]) * dt;
+  dV += 0.5 * (Qlat_new + sc[1]) * dt;
+  dV -= 0.5 * (irrQ_act + 0.0) * dt;
+  dV -= 0.5 * (divQ_act + 0.0) * dt;
+  sc[4] += dV;
+  dV = 0.0;
+  dV += QlatHist[0] * dt;
+  dV -= 0.5 * (Qlat_new + sc[1]) * dt;
+  sc[5] += dV;
+  sc[1] = Qlat_new; /* _QlatLast */
+}
+
+/* ======================================================================== one member, n steps === */
+/* state   [nHRU][NS]   in/out
+ * basin   qin[nSB][max_nqin] qlat[nSB][max_nqlat] qout[nSB][50] scal[nSB][8]  in/out
+ * cumul   [2] {_CumulInput,_CumulOutput} in/out
+ * optional records (NULL to skip): qout_rec[nsteps][nSB], wshed_rec[nsteps][4], state_rec[nsteps][nHRU][NS],
+ *                                  forc_rec[nsteps][nHRU][RVN_F_COUNT]
+ * returns 0, or -1 if the model uses an op the oracle does not implement. */
+int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *qin, double *qlat, double *qout, double *scal, double *cumul,
+                   int step0, int nsteps, double *qout_rec, double *wshed_rec, double *state_rec, double *forc_rec) {
+  const int nH = d->nHRU, NS = d->NS, NB = d->nSB, NP = d->nProc;
+  const double tstep = d->opt.timestep;
+  for (int j = 0; j < NP; j++) if (!op_supported(d->proc[j].op)) return -1;
+  octx c; memset(&c, 0, sizeof(c));
+  c.d = d; c.member = member; c.ptab = d->ptab + (size_t)member * d->ptab_stride;
+  for (int t = 0; t < RVN_SV_NTYPES; t++) c.iSV[t] = sv_index(d, t, -1);
+  const int iSW = c.iSV[RVN_SV_SURFACE_WATER], iAET = c.iSV[RVN_SV_AET], iRO = c.iSV[RVN_SV_RUNOFF], iGW = c.iSV[RVN_SV_GROUNDWATER];
+  const int iTotalSWE = c.iSV[RVN_SV_TOTAL_SWE], iGlacierMB = c.iSV[RVN_SV_GLACIER_MB];
+  double *F = (double *)malloc(sizeof(double) * (size_t)nH * RVN_F_COUNT);
+  double *phinew = (double *)malloc(sizeof(double) * NS);
+  double *aRouted = (double *)malloc(sizeof(double) * NB), *aQinnew = (double *)malloc(sizeof(double) * NB);
+  double rates[O_MAXCONN]; int cf[O_MAXCONN], ct[O_MAXCONN];
+  obasin B; B.qin = qin; B.qlat = qlat; B.qout = qout; B.scal = scal;
+  for (int s = 0; s < nsteps; s++) {
+    const int step = step0 + s;
+    /* ---- UpdateHRUForcingFunctions (all HRUs, on the stored state) */
+    for (int k = 0; k < nH; k++) update_forcings(d, c.ptab, k, step, state + (size_t)k * NS, c.iSV, F + (size_t)k * RVN_F_COUNT);
+    if (forc_rec) memcpy(forc_rec + (size_t)s * nH * RVN_F_COUNT, F, sizeof(double) * (size_t)nH * RVN_F_COUNT);
+    /* ---- MassEnergyBalance, ORDERED_SERIES (src/Solvers.cpp:155-251) */
+    for (int p = 0; p < NB; p++) { aRouted[p] = 0.0; aQinnew[p] = 0.0; }
+    for (int k = 0; k < nH; k++) {
+      double *phi_old = state + (size_t)k * NS;
+      memcpy(phinew, phi_old, sizeof(double) * NS);
+      if (iAET >= 0) phinew[iAET] = 0.0;
+      if (iRO >= 0) phinew[iRO] = 0.0;
+      if (iGW >= 0) phinew[iGW] = 0.0;
+      if (d->hru_enabled[k]) {
+        c.k = k; c.F = F + (size_t)k * RVN_F_COUNT; c.phi_old = phi_old;
+        for (int j = 0; j < NP; j++) {
+          const rvn_process *pr = &d->proc[j];
+          if (!((d->apply_mask[k] >> j) & 1ull)) continue; /* CModel::ApplyProcess gate, src/Model.cpp:3061 */
+          int nconn = pr->nconn;
+          for (int q = 0; q < nconn; q++) rates[q] = 0.0;
+          if (pr->op == RVN_OP_CONVOLVE) {
+            const int NST = RVN_CONV_STORES;
+            cf[0] = ct[0] = pr->ia[2];
+            for (int i = 0; i < NST; i++) {
+              cf[i + 1] = pr->ia[2] + i; ct[i + 1] = pr->ia[1];
+              if (i < NST - 1) { cf[NST + i + 1] = pr->ia[2] + i; ct[NST + i + 1] = pr->ia[2] + i + 1; }
+            }
+            cf[2 * NST] = ct[2 * NST] = pr->ia[3];
+            convolution_rates(&c, pr, phinew, rates);
+          } else {
+            for (int q = 0; q < nconn; q++) { cf[q] = d->conn_from[pr->conn0 + q]; ct[q] = d->conn_to[pr->conn0 + q]; }
+            op_rates(&c, pr, cf, ct, phinew, rates);
+          }
+          for (int q = 0; q < nconn; q++) { /* src/Solvers.cpp:220-236 */
+            int typ = d->sv_type[cf[q]];
+            if (ct[q] != cf[q]) { phinew[cf[q]] -= rates[q] * tstep; phinew[ct[q]] += rates[q] * tstep; }
+            else if (is_water_storage(typ) && (typ != RVN_SV_CONVOLUTION) && (typ != RVN_SV_CONV_STOR)) { rates[q] = 0.0; phinew[ct[q]] += 0.0; }
+            else phinew[ct[q]] += rates[q] * tstep;
+          }
+        }
+        /* routing prep :495-511 */
+        int p = d->hru_sb[k];
+        double SWvol = (phinew[iSW] / O_MM_PER_METER) * (d->hru_area[k] * O_M2_PER_KM2);
+        aRouted[p] += SWvol;
+        phinew[iRO] = phinew[iSW];
+        phinew[iSW] = 0.0;
+        /* write-back :697-729 */
+        if (iTotalSWE >= 0) {
+          phinew[iTotalSWE] = 0.0;
+          for (int i = 0; i < NS; i++) if (d->sv_type[i] == RVN_SV_SNOW || d->sv_type[i] == RVN_SV_SNOW_LIQ) phinew[iTotalSWE] += phinew[i];
+        }
+        if (iGlacierMB >= 0) {
+          phinew[iGlacierMB] = 0.0;
+          for (int i = 0; i < NS; i++) {
+            int t = d->sv_type[i];
+            if (t == RVN_SV_SNOW || t == RVN_SV_SNOW_LIQ || t == RVN_SV_FIRN || t == RVN_SV_GLACIER_ICE || t == RVN_SV_GLACIER) phinew[iGlacierMB] += phinew[i];
+          }
+        }
+        memcpy(phi_old, phinew, sizeof(double) * NS);
+      }
+    }
+    /* ---- routing, upstream to downstream (src/Solvers.cpp:565-615) */
+    for (int pp = 0; pp < NB; pp++) {
+      int p = d->sb_order[pp];
+      double aQoutnew[RVN_MAX_RIVER_SEGS];
+      double *QinHist = &qin[(size_t)p * d->max_nqin], *QlatHist = &qlat[(size_t)p * d->max_nqlat];
+      for (int n = d->sb_nqin[p] - 1; n > 0; n--) QinHist[n] = QinHist[n - 1];   /* UpdateInflow, src/SubBasin.cpp:1531-1537 */
+      QinHist[0] = aQinnew[p];
+      for (int n = d->sb_nqlat[p] - 1; n > 0; n--) QlatHist[n] = QlatHist[n - 1]; /* UpdateLateralInflow :1547-1553 */
+      QlatHist[0] = aRouted[p] / (tstep * O_SEC_PER_DAY);
+      route_water(d, p, &B, aQoutnew);
+      aQoutnew[d->sb_nseg[p] - 1] += 0.0; /* down_Q */
+      update_outflows(d, p, &B, aQoutnew);
+      int pTo = d->sb_down[p];
+      if (pTo >= 0) aQinnew[pTo] += qout[(size_t)p * RVN_MAX_RIVER_SEGS + d->sb_nseg[p] - 1];
+    }
+    /* ---- IncrementCumulInput / IncrementCumOutflow (src/Model.cpp:2458-2539) */
+    {
+      double area = d->watershed_area * O_M2_PER_KM2, sum = 0.0;
+      for (int k = 0; k < nH; k++) if (d->hru_enabled[k]) sum += F[(size_t)k * RVN_F_COUNT + RVN_F_PRECIP] * d->hru_area[k]; /* GetAveragePrecip :1048-1060 */
+      double avg_precip = sum / d->watershed_area;
+      cumul[0] += avg_precip * tstep;
+      cumul[0] += 0.0 * tstep; /* recharge */
+      for (int p = 0; p < NB; p++) cumul[0] += 0.0 / area * O_MM_PER_METER; /* specified inflows */
+      for (int p = 0; p < NB; p++) {
+        int pd = d->sb_down[p];
+        if (d->sb_level[p] == 0 || pd < 0) {
+          double integ = 0.5 * (qout[(size_t)p * RVN_MAX_RIVER_SEGS + d->sb_nseg[p] - 1] + scal[(size_t)p * 8 + 0]) * (tstep * O_SEC_PER_DAY);
+          cumul[1] += integ / area * O_MM_PER_METER;
+        }
+        cumul[1] += 0.0 / area * O_MM_PER_METER; cumul[1] += 0.0 / area * O_MM_PER_METER; cumul[1] += 0.0 / area * O_MM_PER_METER;
+      }
+      if (wshed_rec) {
+        double *w = wshed_rec + (size_t)s * 4;
+        w[0] = cumul[0]; w[1] = cumul[1]; w[2] = avg_precip;
+        /* total water storage [mm]: area-weighted water-storage SVs + channel + rivulet (StandardOutput.cpp:745-785) */
+        double tot = 0.0;
+        for (int i = 0; i < NS; i++) {
+          if (!is_water_storage(d->sv_type[i]) || i == c.iSV[RVN_SV_ATMOS_PRECIP]) continue;
+          double a = 0.0;
+          for (int k = 0; k < nH; k++) if (d->hru_enabled[k]) a += state[(size_t)k * NS + i] * d->hru_area[k];
+          tot += a / d->watershed_area;
+        }
+        double ch = 0, rv = 0;
+        for (int p = 0; p < NB; p++) { ch += scal[(size_t)p * 8 + 4]; rv += scal[(size_t)p * 8 + 5]; }
+        tot += ch / (d->watershed_area * O_M2_PER_KM2) * O_MM_PER_METER + rv / (d->watershed_area * O_M2_PER_KM2) * O_MM_PER_METER + 0.0;
+        w[3] = tot;
+      }
+    }
+    if (qout_rec) for (int p = 0; p < NB; p++) qout_rec[(size_t)s * NB + p] = qout[(size_t)p * RVN_MAX_RIVER_SEGS + d->sb_nseg[p] - 1];
+    if (state_rec) memcpy(state_rec + (size_t)s * nH * NS, state, sizeof(double) * (size_t)nH * NS);
+  }
+  free(F); free(phinew); free(aRouted); free(aQinnew);
+  return 0;
+}

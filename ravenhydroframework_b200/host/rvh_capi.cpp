@@ -1,0 +1,101 @@
+// rvh_capi.cpp -- plain-C surface of the host layer (for ctypes-based tests/bench and foreign callers).
+// It exposes: parse+initialise a model from Raven input files, obtain the flattened rvn_model_desc
+// (to feed rvn_gpu_create or, in tests only, the CPU oracle), initial state, and name/meta lookups.
+#include "rvh_model.h"
+#include "rvh_process.h"
+#include "rvh_solver.h"
+
+struct rvh_model {
+  CModel *pModel;
+  optStruct Options;
+  rvh_model() : pModel(NULL) {}
+};
+static std::string g_err;
+#define RVH_TRY try {
+#define RVH_CATCH(ret) } catch (const std::exception &e) { g_err = e.what(); return ret; }
+
+extern "C" {
+const char *rvh_last_error() { return g_err.c_str(); }
+
+// base: path prefix of the input set ("dir/name" -> dir/name.rvi, .rvh, .rvp, .rvt, .rvc, .rve), like `Raven.exe base`
+// duration_override > 0 shortens the run (the BMI config 'duration:' does the same, src/Raven_BMI.cpp:341-345)
+rvh_model *rvh_model_load(const char *base, double duration_override) {
+  RVH_TRY
+  rvh_model *h = new rvh_model();
+  std::string b(base);
+  h->Options.rvi_filename = b + ".rvi"; h->Options.rvh_filename = b + ".rvh"; h->Options.rvp_filename = b + ".rvp";
+  h->Options.rvt_filename = b + ".rvt"; h->Options.rvc_filename = b + ".rvc"; h->Options.rve_filename = b + ".rve";
+  try {
+    ParseInputFiles(h->pModel, h->Options);
+    if (duration_override > 0) {
+      if (duration_override > h->Options.duration) throw RavenError("rvh_model_load: duration override exceeds :Duration of the .rvi file");
+      h->Options.duration = duration_override;
+    }
+    h->pModel->Initialize(h->Options);
+    ParseInitialConditions(h->pModel, h->Options);
+  } catch (...) { delete h->pModel; delete h; throw; }
+  return h;
+  RVH_CATCH(NULL)
+}
+void rvh_model_free(rvh_model *h) { if (h) { delete h->pModel; delete h; } }
+const rvn_model_desc *rvh_model_flatten(rvh_model *h, int nMembers) {
+  RVH_TRY
+  return h->pModel->Flatten(h->Options, nMembers);
+  RVH_CATCH(NULL)
+}
+int rvh_model_dims(rvh_model *h, int *nHRU, int *NS, int *nSB, int *nProc, int *nGauges) {
+  *nHRU = h->pModel->GetNumHRUs(); *NS = h->pModel->GetNumStateVars(); *nSB = h->pModel->GetNumSubBasins();
+  *nProc = h->pModel->GetNumProcesses(); *nGauges = h->pModel->GetNumGauges();
+  return 0;
+}
+int rvh_model_initial_state(rvh_model *h, double *out) {
+  memcpy(out, h->pModel->initial_state.data(), h->pModel->initial_state.size() * sizeof(double));
+  return 0;
+}
+int rvh_model_basin_state(rvh_model *h, double *qin, double *qlat, double *qout, double *scal) {
+  RVH_TRY
+  std::vector<double> a, b, c, d;
+  h->pModel->PackBasinState(a, b, c, d);
+  memcpy(qin, a.data(), a.size() * 8); memcpy(qlat, b.data(), b.size() * 8); memcpy(qout, c.data(), c.size() * 8); memcpy(scal, d.data(), d.size() * 8);
+  return 0;
+  RVH_CATCH(-1)
+}
+int rvh_model_sv_name(rvh_model *h, int i, char *buf, int buflen) {
+  std::string n = h->pModel->GetStateVarName(i);
+  snprintf(buf, buflen, "%s", n.c_str());
+  return 0;
+}
+int rvh_model_process_info(rvh_model *h, int j, char *name, int buflen, int *nconn, int *from8, int *to8) {
+  const CHydroProcessABC *p = h->pModel->GetProcess(j);
+  snprintf(name, buflen, "%s", p->GetProcessName().c_str());
+  *nconn = p->GetNumConnections();
+  for (int q = 0; q < 8; q++) { from8[q] = (q < *nconn) ? p->GetFromIndices()[q] : -1; to8[q] = (q < *nconn) ? p->GetToIndices()[q] : -1; }
+  return 0;
+}
+// ensemble support: overwrite a class parameter (CModel::UpdateParameter) and refresh one member's flattened row
+int rvh_model_update_parameter(rvh_model *h, int class_type, const char *pname, const char *cname, double value) {
+  RVH_TRY
+  h->pModel->UpdateParameter(class_type, pname, cname, value);
+  return 0;
+  RVH_CATCH(-1)
+}
+int rvh_model_flatten_member(rvh_model *h, int member, const double **ptab, const int32_t **conv_n, const double **conv_uh) {
+  RVH_TRY
+  h->pModel->FlattenMemberParams(member);
+  *ptab = h->pModel->MemberParams(member); *conv_n = h->pModel->MemberConvN(member); *conv_uh = h->pModel->MemberConvUH(member);
+  return 0;
+  RVH_CATCH(-1)
+}
+int rvh_model_num_param_dists(rvh_model *h) { return (int)h->pModel->param_dists.size(); }
+int rvh_model_param_dist(rvh_model *h, int i, char *pname, char *cname, int buflen, int *ctype, int *dist, double *par3) {
+  const param_dist &d = h->pModel->param_dists[i];
+  snprintf(pname, buflen, "%s", d.param_name.c_str()); snprintf(cname, buflen, "%s", d.class_group.c_str());
+  *ctype = d.param_class; *dist = d.distribution; par3[0] = d.distpar[0]; par3[1] = d.distpar[1]; par3[2] = d.distpar[2];
+  return 0;
+}
+int rvh_model_options(rvh_model *h, double *timestep, double *duration, unsigned *seed, int *ensemble, int *num_members) {
+  *timestep = h->Options.timestep; *duration = h->Options.duration; *seed = h->Options.random_seed; *ensemble = (int)h->Options.ensemble;
+  *num_members = h->pModel->num_members;
+  return 0;
+}
+}  // extern "C"

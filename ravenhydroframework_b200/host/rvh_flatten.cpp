@@ -1,0 +1,221 @@
+// rvh_flatten.cpp -- "compile" the parsed model into the flat, device-ready rvn_model_desc.
+// This is where per-(class,date) work the reference repeats for every HRU and step is hoisted:
+// convolution unit hydrographs (reference rebuilds them per HRU per step, src/Convolution.cpp:258),
+// the calendar table (JulianConvert per step, src/RavenMain.cpp:162) and gauge sampling.
+#include "rvh_model.h"
+#include "rvh_process.h"
+
+void CModel::FlattenMemberParams(int member) {
+  double *row = _f_ptab.data() + (size_t)member * _f_ptab_stride;
+  for (int f = 0; f < RVN_G_COUNT; f++) row[_desc.glob_off + f] = globals.v[f];
+  for (size_t c = 0; c < lu_classes.size(); c++)
+    for (int f = 0; f < RVN_LU_COUNT; f++) row[_desc.lu_off + c * RVN_LU_COUNT + f] = lu_classes[c].S.v[f];
+  for (size_t c = 0; c < veg_classes.size(); c++) {
+    veg_struct V = veg_classes[c].V;
+    // PRECIP_ICEPT_USER: canopy interception fractions come straight from the class (src/VegetationParams.cpp:150-154)
+    V.v[RVN_V_VAR_RAIN_ICEPT_PCT] = V.v[RVN_V_RAIN_ICEPT_PCT];
+    V.v[RVN_V_VAR_SNOW_ICEPT_PCT] = V.v[RVN_V_SNOW_ICEPT_PCT];
+    for (int f = 0; f < RVN_V_COUNT; f++) row[_desc.veg_off + c * RVN_V_COUNT + f] = V.v[f];
+  }
+  for (size_t c = 0; c < soil_classes.size(); c++)
+    for (int f = 0; f < RVN_S_COUNT; f++) row[_desc.soil_off + c * RVN_S_COUNT + f] = soil_classes[c].S.v[f];
+  // convolution unit hydrographs for this member, per land-use class
+  const int nLU = (int)lu_classes.size();
+  int ci = 0;
+  for (int j = 0; j < GetNumProcesses(); j++) {
+    const CmvConvolution *cv = dynamic_cast<const CmvConvolution *>(_pProcesses[j]);
+    if (!cv) continue;
+    for (int c = 0; c < nLU; c++) {
+      size_t slot = ((size_t)member * nLU + c) * _f_nconv + ci;
+      int N = 0;
+      cv->GenerateUnitHydrograph(lu_classes[c].S, *_pOpt, &_f_conv_uh[slot * RVN_CONV_STORES], N);
+      _f_conv_n[slot] = N;
+    }
+    ci++;
+  }
+}
+const int32_t *CModel::MemberConvN(int member) const { return _f_conv_n.data() + (size_t)member * lu_classes.size() * _f_nconv; }
+const double *CModel::MemberConvUH(int member) const { return _f_conv_uh.data() + (size_t)member * lu_classes.size() * _f_nconv * RVN_CONV_STORES; }
+
+const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
+  ExitGracefullyIf(_pOpt == NULL, "CModel::Flatten: model must be initialized first");
+  rvn_model_desc &d = _desc;
+  memset(&d, 0, sizeof(d));
+  const int nH = GetNumHRUs(), NB = GetNumSubBasins(), NS = GetNumStateVars(), nG = GetNumGauges();
+  d.abi_version = RVN_ABI_VERSION;
+  d.nHRU = nH; d.nSB = NB; d.nMembers = nMembers; d.nGauges = nG;
+  // ---- options
+  d.opt.timestep = O.timestep;
+  d.opt.rainsnow = O.rainsnow; d.opt.pot_melt = O.pot_melt; d.opt.evaporation = O.evaporation; d.opt.ow_evaporation = O.ow_evaporation;
+  d.opt.orocorr_temp = O.orocorr_temp; d.opt.orocorr_precip = O.orocorr_precip; d.opt.orocorr_pet = O.orocorr_PET;
+  d.opt.routing = O.routing; d.opt.suppress_competitive_ET = O.suppressCompetitiveET; d.opt.snow_suppress_PET = O.snow_suppressPET;
+  d.opt.allow_soil_overfill = O.allow_soil_overfill; d.opt.direct_evap = O.direct_evap; d.opt.lake_sv = _lake_sv; d.opt.keep_flux_balance = 0;
+  // ---- state variables
+  d.NS = NS; d.nSoilLayers = _nSoilVars;
+  _f_svtype.resize(NS); _f_svlayer.resize(NS);
+  for (int i = 0; i < NS; i++) { _f_svtype[i] = (int32_t)GetStateVarType(i); _f_svlayer[i] = GetStateVarLayer(i); }
+  d.sv_type = _f_svtype.data(); d.sv_layer = _f_svlayer.data();
+  // ---- process program
+  const int NP = GetNumProcesses();
+  _f_proc.resize(NP); _f_from.clear(); _f_to.clear();
+  _f_nconv = 0;
+  for (int j = 0; j < NP; j++) {
+    const CHydroProcessABC *pr = _pProcesses[j];
+    pr->Compile(_f_proc[j]);
+    if (_f_proc[j].op == RVN_OP_CONVOLVE) { _f_proc[j].conn0 = -1; _f_nconv++; continue; }
+    ExitGracefullyIf(pr->GetNumConnections() > RVN_MAX_CONN, "CModel::Flatten: process has too many connections");
+    _f_proc[j].conn0 = (int32_t)_f_from.size();
+    for (int q = 0; q < pr->GetNumConnections(); q++) {
+      ExitGracefullyIf(pr->GetFromIndices()[q] < 0 || pr->GetToIndices()[q] < 0, "CModel::Flatten: process " + pr->GetProcessName() + " has an unconnected state variable");
+      _f_from.push_back(pr->GetFromIndices()[q]); _f_to.push_back(pr->GetToIndices()[q]);
+    }
+  }
+  d.nProc = NP; d.nConn = (int32_t)_f_from.size(); d.proc = _f_proc.data(); d.conn_from = _f_from.data(); d.conn_to = _f_to.data();
+  _f_mask.assign(nH, 0);
+  for (int k = 0; k < nH; k++)
+    for (int j = 0; j < NP; j++) if (_pProcesses[j]->ShouldApply(_pHydroUnits[k])) _f_mask[k] |= (1ull << j);
+  d.apply_mask = _f_mask.data();
+  // ---- HRUs
+  for (int a = 0; a < 5; a++) _f_hru_d[a].resize(nH);
+  for (int a = 0; a < 6; a++) _f_hru_i[a].resize(nH);
+  for (int k = 0; k < nH; k++) {
+    const CHydroUnit *h = _pHydroUnits[k];
+    _f_hru_d[0][k] = h->GetArea(); _f_hru_d[1][k] = h->GetElevation(); _f_hru_d[2][k] = h->GetLatRad();
+    _f_hru_d[3][k] = h->GetSlope(); _f_hru_d[4][k] = h->GetAspect();
+    _f_hru_i[0][k] = (int32_t)h->GetHRUType(); _f_hru_i[1][k] = h->lu_class; _f_hru_i[2][k] = h->veg_class;
+    _f_hru_i[3][k] = h->soil_profile; _f_hru_i[4][k] = h->subbasin_index; _f_hru_i[5][k] = h->enabled ? 1 : 0;
+  }
+  d.hru_area = _f_hru_d[0].data(); d.hru_elev = _f_hru_d[1].data(); d.hru_lat_rad = _f_hru_d[2].data();
+  d.hru_slope = _f_hru_d[3].data(); d.hru_aspect = _f_hru_d[4].data();
+  d.hru_type = _f_hru_i[0].data(); d.hru_lu = _f_hru_i[1].data(); d.hru_veg = _f_hru_i[2].data();
+  d.hru_profile = _f_hru_i[3].data(); d.hru_sb = _f_hru_i[4].data(); d.hru_enabled = _f_hru_i[5].data();
+  // ---- profiles / classes
+  d.nProfiles = (int32_t)soil_profiles.size(); d.nLU = (int32_t)lu_classes.size(); d.nVeg = (int32_t)veg_classes.size(); d.nSoilClasses = (int32_t)soil_classes.size();
+  _f_prof_class.assign((size_t)d.nProfiles * RVN_MAX_SOIL_LAYERS, 0); _f_prof_thick.assign((size_t)d.nProfiles * RVN_MAX_SOIL_LAYERS, 0.0);
+  ExitGracefullyIf(_nSoilVars > RVN_MAX_SOIL_LAYERS, "CModel::Flatten: too many soil layers");
+  for (int r = 0; r < d.nProfiles; r++)
+    for (int m = 0; m < soil_profiles[r].nHorizons && m < RVN_MAX_SOIL_LAYERS; m++) {
+      _f_prof_class[(size_t)r * RVN_MAX_SOIL_LAYERS + m] = soil_profiles[r].soil_class[m];
+      _f_prof_thick[(size_t)r * RVN_MAX_SOIL_LAYERS + m] = soil_profiles[r].thickness[m];
+    }
+  d.prof_class = _f_prof_class.data(); d.prof_thick = _f_prof_thick.data();
+  d.glob_off = 0; d.lu_off = RVN_G_COUNT; d.veg_off = d.lu_off + d.nLU * RVN_LU_COUNT; d.soil_off = d.veg_off + d.nVeg * RVN_V_COUNT;
+  _f_ptab_stride = d.soil_off + d.nSoilClasses * RVN_S_COUNT;
+  d.ptab_stride = _f_ptab_stride;
+  _f_ptab.assign((size_t)nMembers * _f_ptab_stride, 0.0);
+  d.nConvProc = _f_nconv;
+  _f_conv_n.assign((size_t)nMembers * d.nLU * (_f_nconv > 0 ? _f_nconv : 1), 0);
+  _f_conv_uh.assign((size_t)nMembers * d.nLU * (_f_nconv > 0 ? _f_nconv : 1) * RVN_CONV_STORES, 0.0);
+  for (int e = 0; e < nMembers; e++) {
+    if (e == 0) FlattenMemberParams(0);
+    else {  // identical until the ensemble sampler overwrites them
+      std::copy(_f_ptab.begin(), _f_ptab.begin() + _f_ptab_stride, _f_ptab.begin() + (size_t)e * _f_ptab_stride);
+      size_t nn = (size_t)d.nLU * _f_nconv;
+      std::copy(_f_conv_n.begin(), _f_conv_n.begin() + nn, _f_conv_n.begin() + e * nn);
+      std::copy(_f_conv_uh.begin(), _f_conv_uh.begin() + nn * RVN_CONV_STORES, _f_conv_uh.begin() + e * nn * RVN_CONV_STORES);
+    }
+  }
+  d.ptab = _f_ptab.data(); d.conv_n = _f_conv_n.data(); d.conv_uh = _f_conv_uh.data();
+  // ---- calendar: replay the reference time loop  for(t=0; t<duration-TIME_CORRECTION; t+=timestep)  (src/RavenMain.cpp:145)
+  _f_times.clear();
+  {
+    time_struct tt;
+    JulianConvert(0.0, O.julian_start_day, O.julian_start_year, O.calendar, tt);
+    double last_angle = 0.0;
+    for (double t = 0.0; t < O.duration - TIME_CORRECTION; t += O.timestep) {
+      rvn_time r; memset(&r, 0, sizeof(r));
+      r.model_time = tt.model_time; r.julian_day = tt.julian_day; r.month = tt.month; r.day_of_month = tt.day_of_month; r.year = tt.year;
+      r.day_changed = tt.day_changed ? 1 : 0;
+      r.nn = (int)((tt.model_time + TIME_CORRECTION) / O.timestep);
+      if (tt.day_changed) {  // src/UpdateForcings.cpp:55,172-176
+        double mid_day = floor(tt.julian_day + TIME_CORRECTION) + 0.5;
+        last_angle = DayAngle(mid_day, tt.year, O.calendar);
+      }
+      r.day_angle = last_angle;
+      _f_times.push_back(r);
+      JulianConvert(t + O.timestep, O.julian_start_day, O.julian_start_year, O.calendar, tt);
+    }
+  }
+  const int nSteps = (int)_f_times.size();
+  d.nSteps = nSteps; d.times = _f_times.data();
+  // ---- gauge series sampled on the model step (src/UpdateForcings.cpp:98-155)
+  _f_series.assign((size_t)RVN_GF_COUNT * nG * nSteps, 0.0);
+  _f_gconst.assign((size_t)nG * RVN_GC_COUNT, 0.0);
+  for (int g = 0; g < nG; g++) {
+    const CGauge *G = _pGauges[g];
+    ExitGracefullyIf(!G->GetTimeSeries(F_PRECIP) || !G->GetTimeSeries(F_TEMP_AVE),
+                     "CModel::Flatten: every gauge must carry precipitation and temperature series in the B200 build");
+    for (int n = 0; n < nSteps; n++) {
+      const int nn = _f_times[n].nn;
+      double *S = _f_series.data();
+#define SER(f) S[((size_t)(f) * nG + g) * nSteps + n]
+      SER(RVN_GF_PRECIP) = G->GetForcingValue(F_PRECIP, nn);
+      SER(RVN_GF_SNOW_FRAC) = G->GetAverageSnowFrac(nn);
+      SER(RVN_GF_TEMP_AVE) = G->GetForcingValue(F_TEMP_AVE, nn);
+      SER(RVN_GF_TEMP_DAILY_AVE) = G->GetForcingValue(F_TEMP_DAILY_AVE, nn);
+      SER(RVN_GF_TEMP_DAILY_MIN) = G->GetForcingValue(F_TEMP_DAILY_MIN, nn);
+      SER(RVN_GF_TEMP_DAILY_MAX) = G->GetForcingValue(F_TEMP_DAILY_MAX, nn);
+      SER(RVN_GF_PET) = G->GetForcingValue(F_PET, nn);
+      SER(RVN_GF_OW_PET) = G->GetForcingValue(F_OW_PET, nn);
+      SER(RVN_GF_POTENTIAL_MELT) = G->GetForcingValue(F_POTENTIAL_MELT, nn);
+#undef SER
+    }
+    double *C = &_f_gconst[(size_t)g * RVN_GC_COUNT];
+    C[RVN_GC_ELEVATION] = G->elevation; C[RVN_GC_RAIN_CORR] = G->rainfall_corr; C[RVN_GC_SNOW_CORR] = G->snowfall_corr; C[RVN_GC_TEMP_CORR] = G->temperature_corr;
+    for (int m = 0; m < 12; m++) {
+      C[RVN_GC_MONTHLY_AVE_TEMP0 + m] = G->aAveTemp[m]; C[RVN_GC_MONTHLY_AVE_PET0 + m] = G->aAvePET[m];
+      C[RVN_GC_MONTHLY_MIN_TEMP0 + m] = G->aMinTemp[m]; C[RVN_GC_MONTHLY_MAX_TEMP0 + m] = G->aMaxTemp[m];
+    }
+  }
+  d.gauge_series = _f_series.data(); d.gauge_const = _f_gconst.data();
+  _f_wt = _aGaugeWeights;
+  d.wt_precip = d.wt_temp = d.wt_all = _f_wt.data();
+  // ---- routing network
+  for (int a = 0; a < 7; a++) _f_sb_i[a].resize(NB);
+  for (int a = 0; a < 7; a++) _f_sb_d[a].resize(NB);
+  int maxqin = 1, maxqlat = 1;
+  for (int p = 0; p < NB; p++) {
+    const CSubBasin *b = _pSubBasins[p];
+    if (b->GetInflowHistorySize() > maxqin) maxqin = b->GetInflowHistorySize();
+    if (b->GetLatHistorySize() > maxqlat) maxqlat = b->GetLatHistorySize();
+  }
+  _f_uh.assign((size_t)NB * maxqlat, 0.0); _f_rh.assign((size_t)NB * maxqin, 0.0);
+  for (int p = 0; p < NB; p++) {
+    const CSubBasin *b = _pSubBasins[p];
+    _f_sb_i[0][p] = _aDownstreamInds[p]; _f_sb_i[1][p] = _aOrderedSBind[p]; _f_sb_i[2][p] = _aSubBasinOrder[p];
+    _f_sb_i[3][p] = b->is_headwater ? 1 : 0; _f_sb_i[4][p] = b->nSegments; _f_sb_i[5][p] = b->GetInflowHistorySize();
+    _f_sb_d[0][p] = b->basin_area; _f_sb_d[1][p] = b->rain_corr; _f_sb_d[2][p] = b->snow_corr; _f_sb_d[3][p] = b->temperature_corr;
+    double K = 0, X = 0;
+    if ((O.routing == RVN_ROUTE_MUSKINGUM || O.routing == RVN_ROUTE_MUSKINGUM_CUNGE || O.routing == RVN_ROUTE_STORAGECOEFF) && b->pChannel) {
+      double dx = b->reach_length / (double)(b->nSegments);
+      K = b->GetMuskingumK(dx);
+      if (O.routing != RVN_ROUTE_STORAGECOEFF) X = b->GetMuskingumX(dx);
+    }
+    _f_sb_d[4][p] = K; _f_sb_d[5][p] = X; _f_sb_d[6][p] = K;
+    for (int n = 0; n < b->GetLatHistorySize(); n++) _f_uh[(size_t)p * maxqlat + n] = b->aUnitHydro[n];
+    for (int n = 0; n < b->GetInflowHistorySize(); n++) _f_rh[(size_t)p * maxqin + n] = b->aRouteHydro[n];
+  }
+  d.sb_down = _f_sb_i[0].data(); d.sb_order = _f_sb_i[1].data(); d.sb_level = _f_sb_i[2].data(); d.sb_headwater = _f_sb_i[3].data();
+  d.sb_nseg = _f_sb_i[4].data(); d.sb_nqin = _f_sb_i[5].data();
+  for (int p = 0; p < NB; p++) _f_sb_i[6][p] = _pSubBasins[p]->GetLatHistorySize();
+  d.sb_nqlat = _f_sb_i[6].data();
+  d.sb_area = _f_sb_d[0].data(); d.sb_rain_corr = _f_sb_d[1].data(); d.sb_snow_corr = _f_sb_d[2].data(); d.sb_temp_corr = _f_sb_d[3].data();
+  d.sb_musk_K = _f_sb_d[4].data(); d.sb_musk_X = _f_sb_d[5].data(); d.sb_K_reach = _f_sb_d[6].data();
+  d.max_nqin = maxqin; d.max_nqlat = maxqlat; d.sb_unit_hydro = _f_uh.data(); d.sb_route_hydro = _f_rh.data();
+  d.watershed_area = _WatershedArea;
+  return &d;
+}
+
+void CModel::PackBasinState(std::vector<double> &qin, std::vector<double> &qlat, std::vector<double> &qout, std::vector<double> &scal) const {
+  const int NB = GetNumSubBasins();
+  qin.assign((size_t)NB * _desc.max_nqin, 0.0); qlat.assign((size_t)NB * _desc.max_nqlat, 0.0);
+  qout.assign((size_t)NB * RVN_MAX_RIVER_SEGS, 0.0); scal.assign((size_t)NB * 8, 0.0);
+  for (int p = 0; p < NB; p++) {
+    const CSubBasin *b = _pSubBasins[p];
+    for (int n = 0; n < b->GetInflowHistorySize(); n++) qin[(size_t)p * _desc.max_nqin + n] = b->aQinHist[n];
+    for (int n = 0; n < b->GetLatHistorySize(); n++) qlat[(size_t)p * _desc.max_nqlat + n] = b->aQlatHist[n];
+    for (int sgm = 0; sgm < b->nSegments; sgm++) qout[(size_t)p * RVN_MAX_RIVER_SEGS + sgm] = b->aQout[sgm];
+    double *s = &scal[(size_t)p * 8];
+    s[0] = b->QoutLast; s[1] = b->QlatLast; s[2] = b->Qlocal; s[3] = b->QlocLast; s[4] = b->channel_storage; s[5] = b->rivulet_storage;
+  }
+}

@@ -1,0 +1,598 @@
+// rvh_model.cpp -- model container, time series/gauges, subbasins and initialisation of the host layer.
+// Everything here runs once (or once per ensemble member): it prepares the tables the GPU consumes.
+#include "rvh_model.h"
+#include "rvh_process.h"
+#include <fstream>
+
+// ---------------------------------------------------------------------------------- field name tables
+static const char *kSoilNames[RVN_S_COUNT] = {"POROSITY", "CAP_RATIO", "PERC_COEFF", "PET_CORRECTION", "BASEFLOW_COEFF", "BASEFLOW_N",
+  "FIELD_CAPACITY", "SAT_WILT", "HBV_BETA", "MAX_CAP_RISE_RATE", "MAX_PERC_RATE", "GR4J_X2", "GR4J_X3"};
+static const char *kLUNames[RVN_LU_COUNT] = {"IMPERMEABLE_FRAC", "FOREST_COVERAGE", "FOREST_SPARSENESS", "MELT_FACTOR", "MIN_MELT_FACTOR",
+  "MAX_MELT_FACTOR", "DD_MELT_TEMP", "DD_AGGRADATION", "REFREEZE_FACTOR", "DD_REFREEZE_TEMP", "REFREEZE_EXP", "HMETS_RUNOFF_COEFF",
+  "GAMMA_SHAPE", "GAMMA_SCALE", "GAMMA_SHAPE2", "GAMMA_SCALE2", "GR4J_X4", "HBV_MELT_FOR_CORR", "HBV_MELT_ASP_CORR",
+  "HBV_MELT_GLACIER_CORR", "HBV_GLACIER_KMIN", "GLAC_STORAGE_COEFF", "HBV_GLACIER_AG", "DEP_MAX", "LAKE_PET_CORR", "OW_PET_CORR",
+  "PARTITION_COEFF", "CC_DECAY_COEFF"};
+static const char *kVegNames[RVN_V_COUNT] = {"MAX_HEIGHT", "MAX_LAI", "SAI_HT_RATIO", "MAX_CAPACITY", "MAX_SNOW_CAPACITY", "RAIN_ICEPT_PCT",
+  "SNOW_ICEPT_PCT", "PET_VEG_CORR", "VAR_CAPACITY", "VAR_SNOW_CAPACITY", "VAR_RAIN_ICEPT_PCT", "VAR_SNOW_ICEPT_PCT"};
+static const char *kGlobalNames[RVN_G_COUNT] = {"SNOW_SWI", "SNOW_SWI_MIN", "SNOW_SWI_MAX", "SWI_REDUCT_COEFF", "ADIABATIC_LAPSE", "PRECIP_LAPSE",
+  "RAINSNOW_TEMP", "RAINSNOW_DELTA", "AVG_ANNUAL_SNOW", "SNOW_TEMPERATURE", "HBVEC_LAPSE_UPPER", "HBVEC_LAPSE_RATE", "HBVEC_LAPSE_ELEV",
+  "AIRSNOW_COEFF", "AVG_ANNUAL_RUNOFF", "MAX_SWE_SURFACE", "TOC_MULTIPLIER", "TIME_TO_PEAK_MULTIPLIER", "GAMMA_SHAPE_MULTIPLIER",
+  "GAMMA_SCALE_MULTIPLIER"};
+static int FindName(const char *const *tab, int n, const std::string &name) {
+  for (int i = 0; i < n; i++) if (name == tab[i]) return i;
+  return -1;
+}
+int SoilFieldFromName(const std::string &n) { return FindName(kSoilNames, RVN_S_COUNT, n); }
+int LandUseFieldFromName(const std::string &n) {
+  if (n == "IMPERM") return RVN_LU_IMPERMEABLE_FRAC;
+  if (n == "FOREST_COV") return RVN_LU_FOREST_COVERAGE;
+  return FindName(kLUNames, RVN_LU_COUNT, n);
+}
+int VegFieldFromName(const std::string &n) {
+  if (n == "MAX_HT") return RVN_V_MAX_HEIGHT;
+  int f = FindName(kVegNames, RVN_V_COUNT, n);
+  return (f >= RVN_V_VAR_CAPACITY) ? -1 : f;
+}
+int GlobalFieldFromName(const std::string &n) { return FindName(kGlobalNames, RVN_G_COUNT, n); }
+const char *SoilFieldName(int f) { return kSoilNames[f]; }
+const char *LandUseFieldName(int f) { return kLUNames[f]; }
+const char *VegFieldName(int f) { return kVegNames[f]; }
+const char *GlobalFieldName(int f) { return kGlobalNames[f]; }
+
+// ---------------------------------------------------------------------------------- CTimeSeries
+int CTimeSeries::GetTimeIndex(double t_loc) const {
+  int n = (int)(rvh_max(floor(t_loc / _interval), 0.0));
+  int last = (int)_aVal.size() - 1;
+  return (n <= last) ? n : last;
+}
+double CTimeSeries::GetValue(double t) const { return _aVal[GetTimeIndex(t + _t_corr)]; }
+double CTimeSeries::GetAvgValue(double t, double tstep) const {
+  // pulse-type series only (all forcing series of the supported subset): reference src/TimeSeries.cpp:343-405
+  double t_loc = t + _t_corr;
+  int n1 = GetTimeIndex(t_loc), n2 = GetTimeIndex(t_loc + tstep);
+  const int nP = (int)_aVal.size();
+  if (t_loc < -TIME_CORRECTION) return RAV_BLANK_DATA;
+  if (t_loc > nP * _interval) return RAV_BLANK_DATA;
+  if (n1 == n2) return _aVal[n1];
+  double sum = 0, blank = 0, inc;
+  inc = ((double)(n1 + 1) * _interval - t_loc);
+  if (_aVal[n1] == RAV_BLANK_DATA) blank += inc; else sum += _aVal[n1] * inc;
+  for (int n = n1 + 1; n < n2; n++) { if (_aVal[n] == RAV_BLANK_DATA) blank += _interval; else sum += _aVal[n] * _interval; }
+  inc = ((t_loc + tstep) - (double)(n2) * _interval);
+  if (_aVal[n2] == RAV_BLANK_DATA) blank += inc; else sum += _aVal[n2] * inc;
+  if (blank / tstep > 0.001) return RAV_BLANK_DATA;
+  return sum / tstep;
+}
+void CTimeSeries::Initialize(double model_start_day, int model_start_year, double model_duration, double timestep, int calendar) {
+  _t_corr = -TimeDifference(model_start_day, model_start_year, _start_day, _start_year, calendar);
+  double duration = (double)_aVal.size() * _interval;
+  double lstart = _t_corr, lend = _t_corr + model_duration;
+  ExitGracefullyIf(duration < lstart, "CTimeSeries::Initialize: time series forcing data not available for entire model simulation duration (" + _name + ")");
+  ExitGracefullyIf(duration + TIME_CORRECTION < lend, "CTimeSeries::Initialize: time series forcing data not available at end of model simulation (" + _name + ")");
+  ExitGracefullyIf((lstart < 0) || (_start_year > model_start_year), "CTimeSeries::Initialize: time series forcing data not available at beginning of model simulation (" + _name + ")");
+  int nSampVal = (int)(ceil(model_duration / timestep - TIME_CORRECTION));
+  _aSampVal.assign(nSampVal, 0.0);
+  _sampInterval = timestep;
+  double t = 0;
+  for (int nn = 0; nn < nSampVal; nn++) { _aSampVal[nn] = GetAvgValue(t, timestep); t += timestep; }
+}
+double CTimeSeries::GetSampledValue(int nn) const {
+  if (nn >= (int)_aSampVal.size()) return RAV_BLANK_DATA;
+  return _aSampVal[nn];
+}
+
+// ---------------------------------------------------------------------------------- CGauge
+CGauge::CGauge(const std::string &nm) : name(nm), latitude(0), longitude(0), elevation(0), rainfall_corr(1.0), snowfall_corr(1.0), temperature_corr(0.0) {
+  for (int i = 0; i < F_NTYPES; i++) { _pTS[i] = NULL; _owned[i] = false; }
+  for (int m = 0; m < 12; m++) aAveTemp[m] = aMinTemp[m] = aMaxTemp[m] = aAvePET[m] = NOT_SPECIFIED;
+}
+CGauge::~CGauge() { for (int i = 0; i < F_NTYPES; i++) if (_owned[i]) delete _pTS[i]; }
+void CGauge::AddTimeSeries(CTimeSeries *pTS, forcing_type f) {
+  if (_owned[f]) delete _pTS[f];
+  _pTS[f] = pTS; _owned[f] = true;
+}
+double CGauge::GetForcingValue(forcing_type f, int nn) const { return _pTS[f] ? _pTS[f]->GetSampledValue(nn) : 0.0; }
+double CGauge::GetAverageSnowFrac(int nn) const {
+  double rain = _pTS[F_RAINFALL]->GetSampledValue(nn), snow = _pTS[F_SNOWFALL]->GetSampledValue(nn);
+  if ((snow + rain) == 0) return 0.0;
+  return snow / (snow + rain);
+}
+void CGauge::Initialize(const optStruct &O) {
+  // temperature series (reference src/Gauge.cpp:78-101, 647-706); daily data on a daily-or-finer model step
+  CTimeSeries *Tave = _pTS[F_TEMP_AVE], *Tmin = _pTS[F_TEMP_DAILY_MIN], *Tmax = _pTS[F_TEMP_DAILY_MAX];
+  if (Tave || _pTS[F_TEMP_DAILY_AVE] || (Tmin && Tmax)) {
+    if (Tave && Tave->IsDaily()) AddTimeSeries(new CTimeSeries("TEMP_DAILY_AVE", Tave->GetStartDay(), Tave->GetStartYear(), 1.0, Tave->Values()), F_TEMP_DAILY_AVE);
+    if (Tave && !Tave->IsDaily()) {
+      ExitGracefully("CGauge::Initialize: sub-daily temperature input is not supported by the B200 build yet");
+    } else if (Tmin && Tmax) {
+      Tmin->Initialize(O.julian_start_day, O.julian_start_year, O.duration, O.timestep, O.calendar);
+      Tmax->Initialize(O.julian_start_day, O.julian_start_year, O.duration, O.timestep, O.calendar);
+      if (!_pTS[F_TEMP_DAILY_AVE]) {
+        int nVals = (int)ceil(O.duration);
+        std::vector<double> aAvg(nVals);
+        double t = 0.0;
+        for (int n = 0; n < nVals; n++) { aAvg[n] = 0.5 * (Tmin->GetValue(t + 0.5) + Tmax->GetValue(t + 0.5)); t += 1.0; }
+        AddTimeSeries(new CTimeSeries("TEMP_DAILY_AVE", O.julian_start_day, O.julian_start_year, 1.0, aAvg), F_TEMP_DAILY_AVE);
+      }
+      if (O.timestep < (1.0 - TIME_CORRECTION)) {
+        ExitGracefully("CGauge::Initialize: sub-daily temperature downscaling is not supported by the B200 build yet");
+      } else {
+        CTimeSeries *T = _pTS[F_TEMP_DAILY_AVE];
+        AddTimeSeries(new CTimeSeries("TEMP_AVE", T->GetStartDay(), T->GetStartYear(), T->GetInterval(), T->Values()), F_TEMP_AVE);
+      }
+    } else if (_pTS[F_TEMP_DAILY_AVE]) {
+      ExitGracefully("CGauge::Initialize: min/max generation from daily average temperature is not supported by the B200 build yet");
+    }
+  }
+  bool hasPrecip = _pTS[F_PRECIP] != NULL, hasSnow = _pTS[F_SNOWFALL] != NULL, hasRain = _pTS[F_RAINFALL] != NULL;
+  ExitGracefullyIf((hasPrecip || hasRain) && (!hasSnow) && (O.rainsnow == RVN_RAINSNOW_DATA),
+                   "CGauge::Initialize: snow autogeneration is off at gauge with precip data, but no snow data has been supplied.");
+  if (hasSnow && hasRain) {  // CTimeSeries::Sum
+    const CTimeSeries *a = _pTS[F_RAINFALL], *b = _pTS[F_SNOWFALL];
+    ExitGracefullyIf(a->Values().size() != b->Values().size() || a->GetInterval() != b->GetInterval() || a->GetStartDay() != b->GetStartDay() ||
+                     a->GetStartYear() != b->GetStartYear(), "CTimeSeries::Sum: time series must have same start, interval and length");
+    std::vector<double> v(a->Values().size());
+    for (size_t i = 0; i < v.size(); i++) {
+      double x = a->Values()[i], y = b->Values()[i];
+      v[i] = (x == RAV_BLANK_DATA || y == RAV_BLANK_DATA) ? RAV_BLANK_DATA : x + y;
+    }
+    AddTimeSeries(new CTimeSeries("PRECIP", a->GetStartDay(), a->GetStartYear(), a->GetInterval(), v), F_PRECIP);
+  }
+  if (!hasRain && !hasSnow && hasPrecip) {
+    const CTimeSeries *a = _pTS[F_PRECIP];
+    AddTimeSeries(new CTimeSeries("RAINFALL", a->GetStartDay(), a->GetStartYear(), a->GetInterval(), a->Values()), F_RAINFALL);
+  }
+  if (!hasSnow && (hasRain || hasPrecip)) {
+    const CTimeSeries *a = _pTS[F_PRECIP] ? _pTS[F_PRECIP] : _pTS[F_RAINFALL];
+    std::vector<double> z(a->Values().size(), 0.0);
+    AddTimeSeries(new CTimeSeries("SNOWFALL", a->GetStartDay(), a->GetStartYear(), a->GetInterval(), z), F_SNOWFALL);
+  }
+  for (int i = 0; i < F_NTYPES; i++) if (_pTS[i]) _pTS[i]->Initialize(O.julian_start_day, O.julian_start_year, O.duration, O.timestep, O.calendar);
+  // if OW_PET requests data but only PET is provided, use PET (src/Gauge.cpp:189-195)
+  if (_pTS[F_PET] && !_pTS[F_OW_PET] && O.ow_evaporation == RVN_PET_DATA) {
+    const CTimeSeries *a = _pTS[F_PET];
+    CTimeSeries *c = new CTimeSeries("OW_PET", a->GetStartDay(), a->GetStartYear(), a->GetInterval(), a->Values());
+    c->Initialize(O.julian_start_day, O.julian_start_year, O.duration, O.timestep, O.calendar);
+    AddTimeSeries(c, F_OW_PET);
+  }
+  ExitGracefullyIf((aAveTemp[0] == NOT_SPECIFIED) && (O.evaporation == RVN_PET_FROMMONTHLY),
+                   "CGauge::Initialize: monthly temperatures for gauge not specified (using :MonthlyAveTemperature command) , but are needed");
+  ExitGracefullyIf((aAvePET[0] == NOT_SPECIFIED) && (O.evaporation == RVN_PET_FROMMONTHLY),
+                   "CGauge::Initialize: monthly PET values for gauge not specified (using :MonthlyAveEvaporation command), but are needed");
+}
+
+// ---------------------------------------------------------------------------------- channel
+void CChannelXSect::GenerateTrapezoid(double bottom_w, double bottom_elev, double sidewall_ratio) {
+  // 50-point rating curve of the reference trapezoid constructor (src/ChannelXSect.cpp:134-168),
+  // including its area formula (bottom_w+sidewall_ratio)*h
+  ExitGracefullyIf(bedslope <= 0.0, "CChannelXSect Constructor: channel profile bedslope must be greater than zero");
+  ExitGracefullyIf(mannings_n <= 0.0, "CChannelXSect Constructor: Manning's n must be greater than zero");
+  min_mannings = mannings_n;
+  const int nP = 50;
+  aQ.resize(nP); aStage.resize(nP); aTopWidth.resize(nP); aXArea.resize(nP); aPerim.resize(nP);
+  double dh = 0.1, h;
+  for (int i = 0; i < nP; i++) {
+    h = i * dh;
+    if (i == nP - 1) h = 20;
+    aStage[i] = bottom_elev + h;
+    aTopWidth[i] = bottom_w + 2.0 * sidewall_ratio * h;
+    aXArea[i] = (bottom_w + sidewall_ratio) * h;
+    aPerim[i] = bottom_w + 2 * sqrt(h * h * (1 + sidewall_ratio * sidewall_ratio));
+    aQ[i] = sqrt(bedslope) * aXArea[i] * pow(aXArea[i] / aPerim[i], 2.0 / 3.0) / min_mannings;
+  }
+}
+static void FlowCorrections(double bedslope, double min_n, double SB_slope, double SB_n, double &Q_mult) {
+  Q_mult = 1.0;
+  if (SB_slope != AUTO_COMPUTE) Q_mult = pow(SB_slope / bedslope, 0.5);
+  if (SB_n != AUTO_COMPUTE) Q_mult *= (min_n / SB_n);
+}
+double CChannelXSect::GetCelerity(double Q, double SB_slope, double SB_n) const {
+  double Q_mult; FlowCorrections(bedslope, min_mannings, SB_slope, SB_n, Q_mult);
+  if (Q < 0) return 0.0;
+  const int nP = (int)aQ.size();
+  int i = 0; while ((Q > Q_mult * aQ[i + 1]) && (i < (nP - 2))) i++;
+  return Q_mult * (aQ[i + 1] - aQ[i]) / (aXArea[i + 1] - aXArea[i]);
+}
+double CChannelXSect::GetTopWidth(double Qin, double SB_slope, double SB_n) const {
+  double Q_mult; FlowCorrections(bedslope, min_mannings, SB_slope, SB_n, Q_mult);
+  // InterpolateCurve(x,xx,y,N,extrapbottom=true), src/CommonFunctions.cpp:1982-2004
+  const double x = Qin / Q_mult;
+  const std::vector<double> &xx = aQ, &y = aTopWidth;
+  const int N = (int)xx.size();
+  if (x <= xx[0]) return y[0] + (y[1] - y[0]) / (xx[1] - xx[0]) * (x - xx[0]);
+  if (x >= xx[N - 1]) return y[N - 1] + (y[N - 1] - y[N - 2]) / (xx[N - 1] - xx[N - 2]) * (x - xx[N - 1]);
+  int i = 0; while ((x > xx[i + 1]) && (i < (N - 2))) i++;
+  if (fabs(xx[i + 1] - xx[i]) < REAL_SMALL) return (y[i] + y[i + 1]) / 2;
+  return y[i] + (y[i + 1] - y[i]) / (xx[i + 1] - xx[i]) * (x - xx[i]);
+}
+
+// ---------------------------------------------------------------------------------- HRU / subbasin
+double CHydroUnit::GetLatRad() const { return latitude * RVH_PI / 180.0; }
+double CHydroUnit::GetSlope() const { return slope * RVH_PI / 180.0; }
+double CHydroUnit::GetAspect() const { return aspect * RVH_PI / 180.0; }
+
+CSubBasin::CSubBasin()
+    : ID(0), downstream_ID(DOESNT_EXIST), pChannel(NULL), reach_length(AUTO_COMPUTE), gauged(false), is_headwater(true), disabled(false),
+      nSegments(1), basin_area(0), drainage_area(0), t_conc(AUTO_COMPUTE), t_peak(AUTO_COMPUTE), t_lag(AUTO_COMPUTE),
+      gamma_shape(AUTO_COMPUTE), gamma_scale(AUTO_COMPUTE), Q_ref(AUTO_COMPUTE), c_ref(AUTO_COMPUTE), w_ref(AUTO_COMPUTE),
+      mannings_n(AUTO_COMPUTE), slope(AUTO_COMPUTE), rain_corr(1.0), snow_corr(1.0), temperature_corr(0.0), QoutLast(0), QlatLast(0),
+      Qlocal(0), QlocLast(0), channel_storage(0), rivulet_storage(0) { aQout.assign(1, AUTO_COMPUTE); }
+
+bool CSubBasin::SetBasinProperties(const std::string &label_in, double value) {
+  std::string l = StringToUppercase(label_in);
+  if (l == "TIME_CONC") t_conc = value;
+  else if (l == "TIME_TO_PEAK") t_peak = value;
+  else if (l == "TIME_LAG") t_lag = value;
+  else if (l == "GAMMA_SHAPE") gamma_shape = value;
+  else if (l == "GAMMA_SCALE") gamma_scale = value;
+  else if (l == "Q_REFERENCE") Q_ref = value;
+  else if (l == "MANNINGS_N") mannings_n = value;
+  else if (l == "SLOPE") slope = value;
+  else if (l == "CELERITY") c_ref = value;
+  else if (l == "RAIN_CORR") rain_corr = value;
+  else if (l == "SNOW_CORR") snow_corr = value;
+  else if (l == "TEMP_CORR") temperature_corr = value;
+  else if (l == "REACH_LENGTH") reach_length = value * M_PER_KM;
+  else return false;
+  return true;
+}
+double CSubBasin::GetMuskingumK(double dx) const { return dx / (c_ref * SEC_PER_DAY); }
+double CSubBasin::GetMuskingumX(double dx) const {
+  ExitGracefullyIf(!pChannel, "CSubBasin::GetMuskingumX");
+  double bedslope = slope;
+  if (slope == AUTO_COMPUTE) bedslope = pChannel->bedslope;
+  return rvh_max(0.0, 0.5 * (1.0 - Q_ref / bedslope / w_ref / c_ref / dx));
+}
+void CSubBasin::ResetReferenceFlow(double Qreference) {
+  Q_ref = Qreference;
+  if ((Q_ref != AUTO_COMPUTE) && (pChannel != NULL)) {
+    ExitGracefullyIf((Q_ref <= 0.0) && (!is_headwater), "CSubBasin::ResetReferenceFlow: invalid (negative or zero) reference flow rate in non-headwater basin");
+    if (c_ref == AUTO_COMPUTE) {
+      c_ref = pChannel->GetCelerity(Q_ref, slope, mannings_n);
+      ExitGracefullyIf(c_ref <= 0.0, "CSubBasin::ResetReferenceFlow: negative or zero celerity");
+    }
+    w_ref = pChannel->GetTopWidth(Q_ref, slope, mannings_n);
+  } else {
+    c_ref = AUTO_COMPUTE; w_ref = AUTO_COMPUTE;
+  }
+}
+double CSubBasin::CalculateTOC() const {  // TOC_MCDERMOTT_PILGRIM (reference default, src/SubBasin.cpp:1742-1745)
+  double A = rvh_max(basin_area, 0.001);
+  return 0.76 * pow(A, 0.38) / HR_PER_DAY;
+}
+void CSubBasin::GenerateCatchmentHydrograph(double Qlat_avg, const optStruct &O) {
+  const double tstep = O.timestep;
+  int n, nQlat = 0;
+  if (O.catchment_routing == ROUTE_TRI_CONVOLUTION) nQlat = (int)(ceil((t_conc) / tstep)) + 3;
+  else if (O.catchment_routing == ROUTE_GAMMA_CONVOLUTION) nQlat = (int)(ceil(4.5 * pow(gamma_shape, 0.6) / gamma_scale / tstep)) + 1;
+  else if (O.catchment_routing == ROUTE_DELAYED_FIRST_ORDER) nQlat = 2;
+  else if (O.catchment_routing == ROUTE_DUMP) nQlat = 3;
+  nQlat += (int)(ceil(t_lag / tstep));
+  ExitGracefullyIf(nQlat <= 0, "GenerateCatchmentHydrograph: negative or zero inflow history");
+  aQlatHist.assign(nQlat, Qlat_avg);
+  aUnitHydro.assign(nQlat, 0.0);
+  double sum, t;
+  if (O.catchment_routing == ROUTE_GAMMA_CONVOLUTION) {
+    sum = 0;
+    for (n = 0; n < nQlat; n++) { t = n * tstep - t_lag; aUnitHydro[n] = GammaCumDist(t + tstep, gamma_shape, gamma_scale) - sum; sum += aUnitHydro[n]; }
+    aUnitHydro[nQlat - 1] = 0.0;
+  } else if (O.catchment_routing == ROUTE_TRI_CONVOLUTION) {
+    sum = 0.0;
+    for (n = 0; n < nQlat; n++) { t = n * tstep - t_lag; aUnitHydro[n] = TriCumDist(t + tstep, t_conc, t_peak) - sum; sum += aUnitHydro[n]; }
+  } else if (O.catchment_routing == ROUTE_DUMP) {
+    aUnitHydro[0] = 1.0;
+  } else {
+    ExitGracefully("GenerateCatchmentHydrograph: catchment routing method not implemented in the B200 build");
+  }
+  sum = 0.0;
+  for (n = 0; n < nQlat; n++) sum += aUnitHydro[n];
+  ExitGracefullyIf(sum == 0.0, "CSubBasin::GenerateCatchmentHydrograph: bad unit hydrograph constructed");
+  for (n = 0; n < nQlat; n++) aUnitHydro[n] /= sum;
+}
+void CSubBasin::GenerateRoutingHydrograph(double Qin_avg, const optStruct &O) {
+  const double tstep = O.timestep;
+  double travel_time = reach_length / c_ref / SEC_PER_DAY;
+  int nQin;
+  if (O.routing == RVN_ROUTE_PLUG_FLOW) nQin = (int)(ceil(travel_time / tstep)) + 2;
+  else if (O.routing == RVN_ROUTE_DIFFUSIVE_WAVE) { ExitGracefully("ROUTE_DIFFUSIVE_WAVE hydrograph generation is not implemented in the B200 build yet"); nQin = 0; }
+  else nQin = 20;
+  aQinHist.assign(nQin, Qin_avg);
+  aRouteHydro.assign(nQin, 0.0);
+  if (O.routing == RVN_ROUTE_PLUG_FLOW) {
+    for (int n = 0; n < nQin - 1; n++) {
+      double ts = (travel_time - n * tstep) / tstep;
+      if ((ts >= 0.0) && (ts < 1.0)) { aRouteHydro[n] = 1 - ts; aRouteHydro[n + 1] = ts; }
+    }
+  } else {
+    aRouteHydro[0] = 1.0;
+  }
+  double sum = 0.0;
+  for (int n = 0; n < nQin; n++) sum += aRouteHydro[n];
+  ExitGracefullyIf(sum < 0.2, "CSubBasin::GenerateRoutingHydrograph: bad routing hydrograph constructed");
+  for (int n = 0; n < nQin; n++) aRouteHydro[n] /= sum;
+}
+void CSubBasin::InitializeFlowStates(double Qin_avg, double Qlat_avg, const optStruct &O) {
+  if (disabled) return;
+  for (int seg = 0; seg < nSegments; seg++) aQout[seg] = Qin_avg + Qlat_avg * (double)(seg + 1) / (double)(nSegments);
+  QoutLast = aQout[nSegments - 1];
+  QlatLast = Qlat_avg;
+  channel_storage = 0.0;
+  if (O.routing == RVN_ROUTE_NONE) channel_storage = 0.0;
+  else if (O.routing == RVN_ROUTE_PLUG_FLOW || O.routing == RVN_ROUTE_DIFFUSIVE_WAVE) {
+    double sum = 0;
+    for (int n = (int)aQinHist.size() - 1; n > 0; n--) { sum += aRouteHydro[n]; channel_storage += aQinHist[n] * sum * (O.timestep * SEC_PER_DAY); }
+  } else if (O.routing == RVN_ROUTE_MUSKINGUM || O.routing == RVN_ROUTE_MUSKINGUM_CUNGE) {
+    double dx = reach_length / (double)(nSegments);
+    double K = GetMuskingumK(dx), X = GetMuskingumX(dx);
+    channel_storage = K * (X * Qin_avg + (1.0 - X) * aQout[0]);
+    for (int seg = 1; seg < nSegments; seg++) channel_storage += K * (X * aQout[seg - 1] + (1.0 - X) * aQout[seg]);
+  }
+  channel_storage += aQout[nSegments - 1] * (O.timestep * SEC_PER_DAY);
+  channel_storage -= Qlat_avg * (O.timestep * SEC_PER_DAY);
+  double sum = 0.0;
+  for (int n = (int)aQlatHist.size() - 1; n > 0; n--) { sum += aUnitHydro[n]; rivulet_storage += sum * Qlat_avg * (O.timestep * SEC_PER_DAY); }
+  rivulet_storage += Qlat_avg * O.timestep * (O.timestep * SEC_PER_DAY);
+}
+void CSubBasin::Initialize(double Qin_avg, double Qlat_avg, double total_drain_area, const CModel *pModel, const optStruct &O) {
+  ExitGracefullyIf((pChannel == NULL) && (O.routing != RVN_ROUTE_NONE),
+                   "CSubBasin::Initialize: channel profile for basin " + std::to_string(ID) + " may only be 'NONE' if Routing=ROUTE_NONE or ROUTE_EXTERNAL");
+  drainage_area = total_drain_area;
+  if (disabled) return;
+  const global_struct *G = pModel->GetGlobalParams();
+  if (Q_ref == AUTO_COMPUTE) {
+    ExitGracefullyIf(((Qin_avg + Qlat_avg) <= 0) && (!is_headwater),
+                     "CSubBasin::Initialize: negative or zero average flow specified in initialization (basin " + std::to_string(ID) + ")");
+    ResetReferenceFlow(1.0 * (Qin_avg + Qlat_avg));  // reference_flow_mult default 1.0
+  } else {
+    ResetReferenceFlow(Q_ref);
+  }
+  if (reach_length == AUTO_COMPUTE) reach_length = pow(basin_area, 0.67) * M_PER_KM;
+  if (t_conc == AUTO_COMPUTE) { t_conc = CalculateTOC(); t_conc *= G->v[RVN_G_TOC_MULTIPLIER]; }
+  if (O.catchment_routing == ROUTE_GAMMA_CONVOLUTION) t_peak = AUTO_COMPUTE;
+  if (O.catchment_routing == ROUTE_DUMP) t_peak = AUTO_COMPUTE;
+  if (t_peak == AUTO_COMPUTE) { t_peak = 0.3 * t_conc; t_peak *= G->v[RVN_G_TIME_TO_PEAK_MULTIPLIER]; }
+  if (t_lag == AUTO_COMPUTE) t_lag = 0.0;
+  if (gamma_shape == AUTO_COMPUTE) { gamma_shape = 3.0; gamma_shape *= G->v[RVN_G_GAMMA_SHAPE_MULTIPLIER]; }
+  if (gamma_scale == AUTO_COMPUTE) { gamma_scale = rvh_max((gamma_shape - 1.0) / t_peak, 0.01); gamma_scale *= G->v[RVN_G_GAMMA_SCALE_MULTIPLIER]; }
+  ExitGracefullyIf(t_conc < t_peak, "CSubBasin::Initialize: time of concentration must be greater than time to peak");
+  ExitGracefullyIf(t_peak <= 0, "CSubBasin::Initialize: time to peak must be greater than zero");
+  aQout.assign(nSegments, 0.0);
+  GenerateCatchmentHydrograph(Qlat_avg, O);
+  GenerateRoutingHydrograph(Qin_avg, O);
+  InitializeFlowStates(Qin_avg, Qlat_avg, O);
+}
+void CSubBasin::SetQout(double Q) {
+  for (int i = 0; i < nSegments; i++) aQout[i] = Q;
+  QoutLast = Q;
+}
+
+// ---------------------------------------------------------------------------------- CModel: catalogue
+CModel::CModel(int nsoillayers) : num_members(1), _nSoilVars(nsoillayers), _lake_sv(0), _nConvVariables(0), _WatershedArea(0), _pOpt(NULL),
+                                  _f_ptab_stride(0), _f_nconv(0) {
+  ExitGracefullyIf(nsoillayers < 1, "CModel constructor::improper number of soil layers. SoilModel not specified?");
+  // constructor defaults of the reference (src/Model.cpp:104-117)
+  const sv_type base[5] = {RVN_SV_SURFACE_WATER, RVN_SV_ATMOSPHERE, RVN_SV_ATMOS_PRECIP, RVN_SV_PONDED_WATER, RVN_SV_RUNOFF};
+  for (int i = 0; i < 5; i++) { _aStateVarType.push_back(base[i]); _aStateVarLayer.push_back(i == 4 ? (int)RVN_SV_RUNOFF : DOESNT_EXIST); }
+  for (int m = 0; m < nsoillayers; m++) { _aStateVarType.push_back(RVN_SV_SOIL); _aStateVarLayer.push_back(m); }
+  memset(&_desc, 0, sizeof(_desc));
+}
+CModel::~CModel() {
+  for (size_t i = 0; i < _pHydroUnits.size(); i++) delete _pHydroUnits[i];
+  for (size_t i = 0; i < _pSubBasins.size(); i++) delete _pSubBasins[i];
+  for (size_t i = 0; i < _pProcesses.size(); i++) delete _pProcesses[i];
+  for (size_t i = 0; i < _pGauges.size(); i++) delete _pGauges[i];
+  for (size_t i = 0; i < channels.size(); i++) delete channels[i];
+}
+int CModel::GetStateVarIndex(sv_type typ) const { return GetStateVarIndex(typ, DOESNT_EXIST); }
+int CModel::GetStateVarLayer(int ii) const {
+  int count = 0;
+  for (int i = 0; i < ii; i++) if (_aStateVarType[i] == _aStateVarType[ii]) count++;
+  return count;
+}
+int CModel::GetStateVarIndex(sv_type typ, int layer) const {
+  // reference _aStateVarIndices[type][layer] table: layer DOESNT_EXIST maps to slot 0 (src/Model.cpp:789-797)
+  int want = (layer == DOESNT_EXIST) ? 0 : layer;
+  for (size_t i = 0; i < _aStateVarType.size(); i++) {
+    if (_aStateVarType[i] != typ) continue;
+    int have = (_aStateVarLayer[i] == DOESNT_EXIST || typ == RVN_SV_RUNOFF) ? 0 : _aStateVarLayer[i];
+    if (have == want) return (int)i;
+  }
+  return DOESNT_EXIST;
+}
+void CModel::AddStateVariables(const sv_type *aSV, const int *aLev, int nSV) {
+  for (int ii = 0; ii < nSV; ii++) {
+    bool found = false;
+    for (size_t i = 0; i < _aStateVarType.size(); i++)
+      if ((_aStateVarType[i] == aSV[ii]) && (_aStateVarLayer[i] == aLev[ii])) found = true;
+    if (!found) { _aStateVarType.push_back(aSV[ii]); _aStateVarLayer.push_back(aLev[ii]); }
+  }
+}
+bool CModel::IsWaterStorage(sv_type typ) {
+  switch (typ) {
+    case RVN_SV_SURFACE_WATER: case RVN_SV_PONDED_WATER: case RVN_SV_ATMOSPHERE: case RVN_SV_ATMOS_PRECIP: case RVN_SV_SNOW:
+    case RVN_SV_GROUNDWATER: case RVN_SV_SOIL: case RVN_SV_CANOPY: case RVN_SV_CANOPY_SNOW: case RVN_SV_ROOT: case RVN_SV_TRUNK:
+    case RVN_SV_DEPRESSION: case RVN_SV_SNOW_LIQ: case RVN_SV_WETLAND: case RVN_SV_GLACIER: case RVN_SV_GLACIER_ICE: case RVN_SV_FIRN:
+    case RVN_SV_CONVOLUTION: case RVN_SV_NEW_SNOW: case RVN_SV_SNOW_DRIFT: case RVN_SV_LAKE_STORAGE:
+      return true;
+    default: return false;
+  }
+}
+static const struct { const char *name; sv_type t; } kSVNames[] = {
+  {"SURFACE_WATER", RVN_SV_SURFACE_WATER}, {"ATMOSPHERE", RVN_SV_ATMOSPHERE}, {"ATMOS_PRECIP", RVN_SV_ATMOS_PRECIP},
+  {"PONDED_WATER", RVN_SV_PONDED_WATER}, {"SOIL", RVN_SV_SOIL}, {"CANOPY", RVN_SV_CANOPY}, {"CANOPY_SNOW", RVN_SV_CANOPY_SNOW},
+  {"GROUNDWATER", RVN_SV_GROUNDWATER}, {"DEPRESSION", RVN_SV_DEPRESSION}, {"SNOW", RVN_SV_SNOW}, {"NEW_SNOW", RVN_SV_NEW_SNOW},
+  {"SNOW_LIQ", RVN_SV_SNOW_LIQ}, {"TOTAL_SWE", RVN_SV_TOTAL_SWE}, {"WETLAND", RVN_SV_WETLAND}, {"GLACIER", RVN_SV_GLACIER},
+  {"GLACIER_ICE", RVN_SV_GLACIER_ICE}, {"LAKE_STORAGE", RVN_SV_LAKE_STORAGE}, {"GLACIER_MB", RVN_SV_GLACIER_MB},
+  {"CONVOLUTION", RVN_SV_CONVOLUTION}, {"CONV_STOR", RVN_SV_CONV_STOR}, {"CUM_INFIL", RVN_SV_CUM_INFIL}, {"CUM_SNOWMELT", RVN_SV_CUM_SNOWMELT},
+  {"AET", RVN_SV_AET}, {"RUNOFF", RVN_SV_RUNOFF}, {"SNOW_TEMP", RVN_SV_SNOW_TEMP}, {"COLD_CONTENT", RVN_SV_COLD_CONTENT},
+  {"SNOW_DEPTH", RVN_SV_SNOW_DEPTH}, {"SNOW_COVER", RVN_SV_SNOW_COVER}, {"SNOW_DEFICIT", RVN_SV_SNOW_DEFICIT}, {"SNOW_AGE", RVN_SV_SNOW_AGE},
+  {"SNOW_ALBEDO", RVN_SV_SNOW_ALBEDO}, {"ICE_THICKNESS", RVN_SV_ICE_THICKNESS}, {NULL, RVN_SV_NTYPES}};
+sv_type CModel::StringToSVType(const std::string &sin, int &layer, bool strict) const {
+  std::string s = sin;
+  std::map<std::string, std::string>::const_iterator it = _aliases.find(s);
+  if (it != _aliases.end()) s = it->second;
+  layer = DOESNT_EXIST;
+  size_t b = s.find('[');
+  std::string base = s;
+  if (b != std::string::npos) {
+    size_t e = s.find(']', b);
+    ExitGracefullyIf(e == std::string::npos, "StringToSVType: malformed state variable name " + sin);
+    layer = s_to_i(s.substr(b + 1, e - b - 1));
+    base = s.substr(0, b);
+  }
+  for (int i = 0; kSVNames[i].name; i++) if (base == kSVNames[i].name) return kSVNames[i].t;
+  ExitGracefullyIf(strict, "StringToSVType: unrecognized state variable name " + sin);
+  return RVN_SV_NTYPES;
+}
+int CModel::ParseSVTypeIndex(const std::string &s) {
+  int layer; sv_type t = StringToSVType(s, layer, true);
+  AddStateVariables(&t, &layer, 1);
+  int i = GetStateVarIndex(t, layer);
+  ExitGracefullyIf(i == DOESNT_EXIST, "ParseSVTypeIndex: invalid state variable " + s);
+  return i;
+}
+std::string CModel::GetStateVarName(int i) const {
+  sv_type t = _aStateVarType[i];
+  std::string nm = "SV" + std::to_string((int)t);
+  for (int q = 0; kSVNames[q].name; q++) if (kSVNames[q].t == t) nm = kSVNames[q].name;
+  if (t == RVN_SV_SOIL || t == RVN_SV_CONVOLUTION || t == RVN_SV_CONV_STOR) nm += "[" + std::to_string(_aStateVarLayer[i]) + "]";
+  return nm;
+}
+int CModel::FindSoilClass(const std::string &t) const { for (size_t i = 0; i < soil_classes.size(); i++) if (soil_classes[i].tag == t) return (int)i; return -1; }
+int CModel::FindVegClass(const std::string &t) const { for (size_t i = 0; i < veg_classes.size(); i++) if (veg_classes[i].tag == t) return (int)i; return -1; }
+int CModel::FindLUClass(const std::string &t) const { for (size_t i = 0; i < lu_classes.size(); i++) if (lu_classes[i].tag == t) return (int)i; return -1; }
+int CModel::FindTerrainClass(const std::string &t) const { for (size_t i = 0; i < terrain_classes.size(); i++) if (terrain_classes[i].tag == t) return (int)i; return -1; }
+int CModel::FindSoilProfile(const std::string &t) const { for (size_t i = 0; i < soil_profiles.size(); i++) if (soil_profiles[i].tag == t) return (int)i; return -1; }
+const CChannelXSect *CModel::FindChannel(const std::string &t) const { for (size_t i = 0; i < channels.size(); i++) if (channels[i]->name == t) return channels[i]; return NULL; }
+int CModel::GetSubBasinIndex(long long SBID) const {
+  if (SBID < 0) return DOESNT_EXIST;
+  for (size_t p = 0; p < _pSubBasins.size(); p++) if (_pSubBasins[p]->ID == SBID) return (int)p;
+  return -2;  // INDEX_NOT_FOUND
+}
+void CModel::UpdateParameter(int ctype, const std::string &pname, const std::string &cname, double value) {
+  // sets the raw field only; derived fields (e.g. cap_ratio) are NOT refreshed, like the reference
+  if (ctype == CLASS_SOIL) {
+    int f = SoilFieldFromName(pname), c = FindSoilClass(cname);
+    ExitGracefullyIf(f < 0 || c < 0, "CModel::UpdateParameter: unknown soil parameter/class " + pname + "/" + cname);
+    soil_classes[c].S.v[f] = value;
+  } else if (ctype == CLASS_VEGETATION) {
+    int f = VegFieldFromName(pname), c = FindVegClass(cname);
+    ExitGracefullyIf(f < 0 || c < 0, "CModel::UpdateParameter: unknown vegetation parameter/class " + pname + "/" + cname);
+    veg_classes[c].V.v[f] = value;
+  } else if (ctype == CLASS_LANDUSE) {
+    int f = LandUseFieldFromName(pname), c = FindLUClass(cname);
+    ExitGracefullyIf(f < 0 || c < 0, "CModel::UpdateParameter: unknown land use parameter/class " + pname + "/" + cname);
+    lu_classes[c].S.v[f] = value;
+  } else if (ctype == CLASS_GLOBAL) {
+    int f = GlobalFieldFromName(pname);
+    ExitGracefullyIf(f < 0, "CModel::UpdateParameter: unknown global parameter " + pname);
+    globals.v[f] = value;
+  } else ExitGracefully("CModel::UpdateParameter: unsupported class type");
+}
+void CModel::AllocateInitialState() { initial_state.assign((size_t)GetNumHRUs() * GetNumStateVars(), 0.0); }
+
+// ---------------------------------------------------------------------------------- CModel: initialisation
+void CModel::InitializeRoutingNetwork() {
+  const int NB = GetNumSubBasins();
+  _aSubBasinOrder.assign(NB, 0); _aDownstreamInds.assign(NB, DOESNT_EXIST); _aOrderedSBind.assign(NB, 0);
+  std::vector<int> inflow(NB, 0);
+  for (int p = 0; p < NB; p++) {
+    int pp = GetSubBasinIndex(_pSubBasins[p]->downstream_ID);
+    ExitGracefullyIf(pp == -2, "CModel::InitializeRoutingNetwork: downstream basin ID not found");
+    ExitGracefullyIf(pp == p, "CModel::InitializeRoutingNetwork: subbasin empties into itself: circular reference!");
+    _aDownstreamInds[p] = pp;
+  }
+  for (int p = 0; p < NB; p++) if (_aDownstreamInds[p] != DOESNT_EXIST) inflow[_aDownstreamInds[p]]++;
+  const int MAX_ITER = 1000;
+  int last_ordersum, iter = 0, ordersum = 0, maxorder = 0;
+  do {
+    last_ordersum = ordersum;
+    for (int p = 0; p < NB; p++) {
+      int pTo = _aDownstreamInds[p];
+      _aSubBasinOrder[p] = (pTo == DOESNT_EXIST) ? 0 : _aSubBasinOrder[pTo] + 1;
+    }
+    ordersum = 0;
+    for (int p = 0; p < NB; p++) { ordersum += _aSubBasinOrder[p]; if (_aSubBasinOrder[p] > maxorder) maxorder = _aSubBasinOrder[p]; }
+    iter++;
+  } while ((ordersum > last_ordersum) && (iter < MAX_ITER));
+  ExitGracefullyIf(iter >= MAX_ITER, "CModel::InitializeRoutingNetwork: exceeded maximum iterations. Circular reference in basin connections?");
+  int pp = 0;
+  for (int ord = maxorder; ord >= 0; ord--)
+    for (int p = 0; p < NB; p++) if (_aSubBasinOrder[p] == ord) _aOrderedSBind[pp++] = p;
+  for (int p = 0; p < NB; p++) _pSubBasins[p]->is_headwater = (inflow[p] == 0);
+}
+void CModel::InitializeBasins(const optStruct &O) {
+  const int NB = GetNumSubBasins();
+  std::vector<double> aSBArea(NB), aSBQin(NB), aSBQlat(NB);
+  double runoff_est = 0.0;
+  for (int p = 0; p < NB; p++) {
+    aSBArea[p] = _pSubBasins[p]->GetBasinArea();
+    if (globals.v[RVN_G_AVG_ANNUAL_RUNOFF] > 0) runoff_est = globals.v[RVN_G_AVG_ANNUAL_RUNOFF] / DAYS_PER_YEAR;
+    aSBQlat[p] = runoff_est / MM_PER_METER * (aSBArea[p] * M2_PER_KM2) / SEC_PER_DAY;
+    aSBQin[p] = 0.0;
+  }
+  for (int pp = 0; pp < NB; pp++) {
+    int p = GetOrderedSubBasinIndex(pp);
+    int pTo = _aDownstreamInds[p];
+    if ((pTo != DOESNT_EXIST) && (!_pSubBasins[pTo]->disabled)) aSBQin[pTo] += aSBQlat[p] + aSBQin[p];
+    if (pTo != DOESNT_EXIST) aSBArea[pTo] += aSBArea[p];
+    _pSubBasins[p]->Initialize(aSBQin[p], aSBQlat[p], aSBArea[p], this, O);
+  }
+}
+void CModel::GenerateGaugeWeights(const optStruct &O) {
+  const int nH = GetNumHRUs(), nG = GetNumGauges();
+  _aGaugeWeights.assign((size_t)nH * nG, 0.0);
+  ExitGracefullyIf(nG == 0, "GenerateGaugeWeights: no gauges present");
+  if (O.interpolation == INTERP_FROM_FILE) {
+    // first line "nGauges nHRUs", then one row of nGauges weights per HRU (src/ModelInitialize.cpp:977-1060)
+    CParser p(O.interp_file);
+    ExitGracefullyIf(!p.ok(), "GenerateGaugeWeights:: Cannot find gauge weighting file " + O.interp_file);
+    std::vector<std::string> s;
+    bool have_dims = false; int k = 0;
+    while (p.Tokenize(s)) {
+      if (s.empty() || s[0] == ":GaugeWeightTable") continue;
+      if (s[0] == ":EndGaugeWeightTable") break;
+      if (!have_dims) {
+        ExitGracefullyIf(s.size() < 2 || s_to_i(s[0]) != nG || s_to_i(s[1]) != nH, "GenerateGaugeWeights: improper number of gauges/HRUs in gauge weighting file");
+        have_dims = true; continue;
+      }
+      ExitGracefullyIf((int)s.size() != nG || k >= nH, "GenerateGaugeWeights: incorrect number of columns/rows in gauge weighting file");
+      double sum = 0;
+      for (int g = 0; g < nG; g++) { _aGaugeWeights[(size_t)k * nG + g] = s_to_d(s[g]); sum += _aGaugeWeights[(size_t)k * nG + g]; }
+      ExitGracefullyIf(fabs(sum - 1.0) > 1e-4, "GenerateGaugeWeights: user-specified weights for gauge don't add up to 1.0");
+      k++;
+    }
+    ExitGracefullyIf(k != nH, "GenerateGaugeWeights: too few rows in gauge weighting file");
+  } else if (O.interpolation == INTERP_AVERAGE_ALL) {
+    for (int k = 0; k < nH; k++) for (int g = 0; g < nG; g++) _aGaugeWeights[(size_t)k * nG + g] = 1.0 / (double)(nG);
+  } else {
+    ExitGracefullyIf(nG != 1, "GenerateGaugeWeights: distance-based gauge interpolation with several gauges needs the UTM projection, which the "
+                              "B200 build does not implement yet; use INTERP_FROM_FILE or INTERP_AVERAGE_ALL");
+    for (int k = 0; k < nH; k++) _aGaugeWeights[k] = 1.0;
+  }
+}
+void CModel::Initialize(optStruct &O) {
+  _pOpt = &O;
+  ExitGracefullyIf(GetNumHRUs() == 0, "CModel::Initialize: Must have at least one hydrologic unit");
+  ExitGracefullyIf(GetNumSubBasins() == 0, "CModel::Initialize: Must have at least one SubBasin");
+  ExitGracefullyIf(GetNumProcesses() == 0, "CModel::Initialize: must have at least one hydrological process included in model");
+  ExitGracefullyIf(GetNumProcesses() > 64, "CModel::Initialize: the B200 build supports at most 64 processes");
+  _WatershedArea = 0.0;
+  for (int p = 0; p < GetNumSubBasins(); p++) {
+    CSubBasin *b = _pSubBasins[p];
+    b->basin_area = 0.0;
+    for (size_t i = 0; i < b->hru_index.size(); i++) b->basin_area += _pHydroUnits[b->hru_index[i]]->GetArea();
+    _WatershedArea += b->basin_area;
+  }
+  for (int k = 0; k < GetNumHRUs(); k++) {
+    const CHydroUnit *h = _pHydroUnits[k];
+    ExitGracefullyIf(soil_profiles[h->soil_profile].nHorizons != _nSoilVars && h->type == RVN_HRU_STANDARD,
+                     "CModel::Initialize: soil profile " + soil_profiles[h->soil_profile].tag + " does not have one horizon per model soil layer");
+  }
+  for (int g = 0; g < GetNumGauges(); g++) _pGauges[g]->Initialize(O);
+  GenerateGaugeWeights(O);
+  InitializeRoutingNetwork();
+  ExitGracefullyIf(GetNumSubBasins() > 1 && !(globals.v[RVN_G_AVG_ANNUAL_RUNOFF] > 0) && O.routing != RVN_ROUTE_NONE,
+                   "CModel::Initialize: :AvgAnnualRunoff is required in the .rvp file when more than one subbasin is routed");
+  InitializeBasins(O);
+}

@@ -1,0 +1,278 @@
+// rvh_model.h -- the Raven model container as seen by the hot path, re-authored for the B200 build.
+//
+// Class and method names mirror the reference so that Raven front ends and user code read the same
+// (CModel src/Model.h, CHydroUnit src/HydroUnits.h:21-161, CSubBasin src/SubBasin.h:43-348,
+// CGauge src/Gauge.h, CTimeSeries src/TimeSeries.h, class structs src/Properties.h), but the objects
+// here are *descriptions*: the numerical state lives on the GPU in SoA form and these objects are
+// flattened into rvn_model_desc (include/rvn_gpu.h) by CModel::Flatten().
+#ifndef RVH_MODEL_H
+#define RVH_MODEL_H
+#include "rvh_common.h"
+
+class CModel;
+class CHydroProcessABC;
+
+// ---- parameter classes (fixed-stride rows; see rvn_*_field enums) --------------------------------
+struct soil_struct    { double v[RVN_S_COUNT]; };
+struct surface_struct { double v[RVN_LU_COUNT]; };
+struct veg_struct     { double v[RVN_V_COUNT]; double relative_ht[12]; double relative_LAI[12]; };
+struct global_struct  { double v[RVN_G_COUNT]; };
+int SoilFieldFromName(const std::string &name);     // "POROSITY" -> RVN_S_POROSITY, -1 if unknown
+int LandUseFieldFromName(const std::string &name);
+int VegFieldFromName(const std::string &name);
+int GlobalFieldFromName(const std::string &name);
+const char *SoilFieldName(int f);
+const char *LandUseFieldName(int f);
+const char *VegFieldName(int f);
+const char *GlobalFieldName(int f);
+
+struct CSoilClass    { std::string tag; soil_struct S; };
+struct CVegetationClass { std::string tag; veg_struct V; };
+struct CLandUseClass { std::string tag; surface_struct S; };
+struct CTerrainClass { std::string tag; };
+struct CSoilProfile  { std::string tag; int nHorizons; std::vector<int> soil_class; std::vector<double> thickness; };
+
+// trapezoidal / surveyed channel cross-section with the reference's tabulated rating curve
+// (CChannelXSect, src/ChannelXSect.cpp): only what Muskingum K/X needs (celerity + top width at Q_ref)
+class CChannelXSect {
+public:
+  std::string name;
+  double bedslope, mannings_n;
+  std::vector<double> aQ, aStage, aTopWidth, aXArea, aPerim;
+  void GenerateTrapezoid(double bottom_w, double bottom_elev, double incline_ratio);
+  double GetCelerity(double Q, double SB_slope, double SB_n) const;
+  double GetTopWidth(double Q, double SB_slope, double SB_n) const;
+private:
+  double GetQfromQref(double Q, double SB_slope, double SB_n) const;
+  void   Interp(double Q, int &i, double &wt) const;
+  double min_mannings;
+};
+
+// ---- time series & gauges -------------------------------------------------------------------------
+class CTimeSeries {
+public:
+  CTimeSeries(const std::string &name, double start_day, int start_yr, double interval, const std::vector<double> &vals)
+      : _name(name), _start_day(start_day), _start_year(start_yr), _interval(interval), _aVal(vals), _t_corr(0), _sampInterval(1) {}
+  void   Initialize(double model_start_day, int model_start_year, double model_duration, double timestep, int calendar);
+  double GetValue(double t) const;                  // pulse-type point value at model time t
+  double GetAvgValue(double t, double tstep) const;
+  double GetSampledValue(int nn) const;
+  int    GetNumSampledValues() const { return (int)_aSampVal.size(); }
+  bool   IsDaily() const { return _interval == 1.0; }
+  double GetInterval() const { return _interval; }
+  double GetStartDay() const { return _start_day; }
+  int    GetStartYear() const { return _start_year; }
+  const std::vector<double> &Values() const { return _aVal; }
+  const std::string &GetName() const { return _name; }
+private:
+  int GetTimeIndex(double t_loc) const;
+  std::string _name;
+  double _start_day; int _start_year; double _interval;
+  std::vector<double> _aVal;
+  double _t_corr;
+  std::vector<double> _aSampVal; double _sampInterval;
+};
+
+enum forcing_type { F_PRECIP, F_RAINFALL, F_SNOWFALL, F_TEMP_AVE, F_TEMP_DAILY_MIN, F_TEMP_DAILY_MAX, F_TEMP_DAILY_AVE,
+                    F_PET, F_OW_PET, F_POTENTIAL_MELT, F_NTYPES };
+forcing_type ForcingFromString(const std::string &s);  // F_NTYPES if unsupported
+
+class CGauge {
+public:
+  explicit CGauge(const std::string &name);
+  ~CGauge();
+  void Initialize(const optStruct &Options);       // reference CGauge::Initialize, src/Gauge.cpp:70-270
+  void AddTimeSeries(CTimeSeries *pTS, forcing_type f);
+  CTimeSeries *GetTimeSeries(forcing_type f) const { return _pTS[f]; }
+  double GetForcingValue(forcing_type f, int nn) const;   // src/Gauge.cpp:533-540
+  double GetAverageSnowFrac(int nn) const;                // src/Gauge.cpp:486-492
+  std::string name;
+  double latitude, longitude, elevation;
+  double rainfall_corr, snowfall_corr, temperature_corr;
+  double aAveTemp[12], aMinTemp[12], aMaxTemp[12], aAvePET[12];
+private:
+  CTimeSeries *_pTS[F_NTYPES];
+  bool _owned[F_NTYPES];
+};
+
+// ---- HRUs and subbasins ---------------------------------------------------------------------------
+class CHydroUnit {
+public:
+  long long ID; int global_k;
+  double area, elevation, latitude, longitude, slope, aspect;  // deg in file; GetLatRad()/GetSlope()/GetAspect() in rad
+  long long SBID; int subbasin_index;
+  int lu_class, veg_class, soil_profile, terrain_class;
+  rvn_hru_type type;
+  bool enabled;
+  double GetArea() const { return area; }
+  double GetElevation() const { return elevation; }
+  double GetLatRad() const;
+  double GetSlope() const;
+  double GetAspect() const;
+  int    GetSubBasinIndex() const { return subbasin_index; }
+  rvn_hru_type GetHRUType() const { return type; }
+  bool   IsEnabled() const { return enabled; }
+};
+
+class CSubBasin {
+public:
+  CSubBasin();
+  long long ID; std::string name; long long downstream_ID; std::string profile_name;
+  const CChannelXSect *pChannel;
+  double reach_length;      // [m] or AUTO_COMPUTE
+  bool gauged, is_headwater, disabled;
+  int  nSegments;
+  double basin_area, drainage_area;  // [km2]
+  double t_conc, t_peak, t_lag, gamma_shape, gamma_scale, Q_ref, c_ref, w_ref, mannings_n, slope;
+  double rain_corr, snow_corr, temperature_corr;
+  std::vector<int> hru_index;
+  // routing arrays (reference _aUnitHydro/_aRouteHydro/_aQlatHist/_aQinHist/_aQout)
+  std::vector<double> aUnitHydro, aRouteHydro, aQlatHist, aQinHist, aQout;
+  double QoutLast, QlatLast, Qlocal, QlocLast, channel_storage, rivulet_storage;
+  // reference-surface accessors
+  long long GetID() const { return ID; }
+  double GetBasinArea() const { return basin_area; }
+  double GetReachLength() const { return reach_length; }
+  int    GetNumSegments() const { return nSegments; }
+  int    GetLatHistorySize() const { return (int)aQlatHist.size(); }
+  int    GetInflowHistorySize() const { return (int)aQinHist.size(); }
+  const double *GetUnitHydrograph() const { return aUnitHydro.data(); }
+  const double *GetRoutingHydrograph() const { return aRouteHydro.data(); }
+  double GetOutflowRate() const { return aQout[nSegments - 1]; }
+  double GetMuskingumK(double dx) const;    // src/SubBasin.cpp:2429-2437
+  double GetMuskingumX(double dx) const;    // src/SubBasin.cpp:2443-2452
+  bool   SetBasinProperties(const std::string &label, double value);  // src/SubBasin.cpp SetBasinProperties
+  void   Initialize(double Qin_avg, double Qlat_avg, double total_drain_area, const CModel *pModel, const optStruct &Options);
+  void   InitializeFlowStates(double Qin_avg, double Qlat_avg, const optStruct &Options);
+  void   SetQout(double Q);                 // :BasinInitialConditions (src/SubBasin.cpp SetQout)
+private:
+  void   GenerateCatchmentHydrograph(double Qlat_avg, const optStruct &Options);
+  void   GenerateRoutingHydrograph(double Qin_avg, const optStruct &Options);
+  void   ResetReferenceFlow(double Qreference);
+  double CalculateTOC() const;
+};
+
+struct param_dist {  // reference ModelEnsemble.h:20-32
+  std::string param_name; int param_class; std::string class_group; int distribution; double distpar[3]; double default_val;
+};
+
+// ---- the model ------------------------------------------------------------------------------------
+class CModel {
+public:
+  explicit CModel(int nsoillayers);
+  ~CModel();
+  // state-variable catalogue (reference CModelABC surface, src/ModelABC.h:18-52)
+  int     GetNumStateVars() const { return (int)_aStateVarType.size(); }
+  sv_type GetStateVarType(int i) const { return _aStateVarType[i]; }
+  int     GetStateVarLayer(int i) const;   // count of earlier SVs of the same type (src/Model.cpp:805-812)
+  int     GetStateVarRawLayer(int i) const { return _aStateVarLayer[i]; }
+  int     GetStateVarIndex(sv_type typ) const;
+  int     GetStateVarIndex(sv_type typ, int layer) const;
+  bool    StateVarExists(sv_type typ) const { return GetStateVarIndex(typ) != DOESNT_EXIST; }
+  int     GetNumSoilLayers() const { return _nSoilVars; }
+  int     GetLakeStorageIndex() const { return _lake_sv; }
+  void    SetLakeStorage(int i) { _lake_sv = i; }
+  void    AddStateVariables(const sv_type *aSV, const int *aLev, int nSV);  // src/Model.cpp:1561-1612
+  std::string GetStateVarName(int i) const;
+  // parse "SOIL[1]" / aliases into (type, layer); adds nothing
+  sv_type StringToSVType(const std::string &s, int &layer, bool strict) const;
+  int     ParseSVTypeIndex(const std::string &s);  // adds the SV if missing, returns its index
+  void    AddAlias(const std::string &alias, const std::string &target) { _aliases[alias] = target; }
+  static bool IsWaterStorage(sv_type typ);          // src/StateVariables.cpp:612-645 (conv_coverup=true)
+
+  // containers
+  int  GetNumHRUs() const { return (int)_pHydroUnits.size(); }
+  int  GetNumSubBasins() const { return (int)_pSubBasins.size(); }
+  int  GetNumProcesses() const { return (int)_pProcesses.size(); }
+  int  GetNumGauges() const { return (int)_pGauges.size(); }
+  CHydroUnit *GetHydroUnit(int k) const { return _pHydroUnits[k]; }
+  CSubBasin  *GetSubBasin(int p) const { return _pSubBasins[p]; }
+  CHydroProcessABC *GetProcess(int j) const { return _pProcesses[j]; }
+  CGauge *GetGauge(int g) const { return _pGauges[g]; }
+  int  GetSubBasinIndex(long long SBID) const;
+  int  GetOrderedSubBasinIndex(int pp) const { return _aOrderedSBind[pp]; }
+  int  GetDownstreamBasin(int p) const { return _aDownstreamInds[p]; }
+  int  GetSubBasinOrder(int p) const { return _aSubBasinOrder[p]; }
+  void AddHRU(CHydroUnit *p) { p->global_k = (int)_pHydroUnits.size(); _pHydroUnits.push_back(p); }
+  void AddSubBasin(CSubBasin *p) { _pSubBasins.push_back(p); }
+  void AddProcess(CHydroProcessABC *p) { _pProcesses.push_back(p); }
+  void AddGauge(CGauge *p) { _pGauges.push_back(p); }
+  int  IncrementConvolutionCount() { return _nConvVariables++; }
+  int  GetNumConvolutionVariables() const { return _nConvVariables; }
+
+  // classes
+  std::vector<CSoilClass> soil_classes;
+  std::vector<CVegetationClass> veg_classes;
+  std::vector<CLandUseClass> lu_classes;
+  std::vector<CTerrainClass> terrain_classes;
+  std::vector<CSoilProfile> soil_profiles;
+  std::vector<CChannelXSect *> channels;
+  global_struct globals;
+  int FindSoilClass(const std::string &t) const;
+  int FindVegClass(const std::string &t) const;
+  int FindLUClass(const std::string &t) const;
+  int FindTerrainClass(const std::string &t) const;
+  int FindSoilProfile(const std::string &t) const;
+  const CChannelXSect *FindChannel(const std::string &t) const;
+  const global_struct *GetGlobalParams() const { return &globals; }
+  const optStruct *GetOptStruct() const { return _pOpt; }
+
+  // reference CModel::UpdateParameter (src/Model.cpp:2692-2750): class 0=soil 1=veg 2=landuse 3=terrain 4=global
+  void UpdateParameter(int ctype, const std::string &pname, const std::string &cname, double value);
+
+  // initial conditions (per HRU rows of NS doubles; filled by the .rvc reader)
+  std::vector<double> initial_state;   // [nHRU][NS]
+  void   AllocateInitialState();
+  void   SetInitialStateVar(int k, int i, double v) { initial_state[(size_t)k * GetNumStateVars() + i] = v; }
+
+  // initialisation (reference CModel::Initialize, src/ModelInitialize.cpp:29-400)
+  void Initialize(optStruct &Options);
+  double GetWatershedArea() const { return _WatershedArea; }
+  const std::vector<double> &GetGaugeWeights() const { return _aGaugeWeights; }  // [nHRU][nGauges]
+
+  // ensemble description (.rve)
+  std::vector<param_dist> param_dists;
+  int num_members;
+
+  // ---- compile to the device ABI --------------------------------------------------------------
+  // Owns every buffer referenced by the returned descriptor until the next Flatten()/destruction.
+  const rvn_model_desc *Flatten(const optStruct &Options, int nMembers);
+  // refresh one member's parameter row + convolution UHs from the *current* class structs (after
+  // UpdateParameter); writes into the flattened buffers and returns pointers for rvn_gpu_upload_params.
+  void FlattenMemberParams(int member);
+  const double *MemberParams(int member) const { return _f_ptab.data() + (size_t)member * _f_ptab_stride; }
+  const int32_t *MemberConvN(int member) const;
+  const double *MemberConvUH(int member) const;
+  // initial basin routing state in the layout of rvn_gpu_upload_basin_state (one member)
+  void PackBasinState(std::vector<double> &qin, std::vector<double> &qlat, std::vector<double> &qout, std::vector<double> &scal) const;
+
+private:
+  void InitializeRoutingNetwork();
+  void InitializeBasins(const optStruct &Options);
+  void GenerateGaugeWeights(const optStruct &Options);
+  std::vector<sv_type> _aStateVarType;
+  std::vector<int> _aStateVarLayer;
+  int _nSoilVars, _lake_sv, _nConvVariables;
+  std::map<std::string, std::string> _aliases;
+  std::vector<CHydroUnit *> _pHydroUnits;
+  std::vector<CSubBasin *> _pSubBasins;
+  std::vector<CHydroProcessABC *> _pProcesses;
+  std::vector<CGauge *> _pGauges;
+  std::vector<int> _aOrderedSBind, _aDownstreamInds, _aSubBasinOrder;
+  std::vector<double> _aGaugeWeights;
+  double _WatershedArea;
+  const optStruct *_pOpt;
+  // flattened storage
+  rvn_model_desc _desc;
+  std::vector<int32_t> _f_svtype, _f_svlayer, _f_from, _f_to, _f_hru_i[6], _f_prof_class, _f_conv_n, _f_sb_i[7];
+  std::vector<rvn_process> _f_proc;
+  std::vector<uint64_t> _f_mask;
+  std::vector<double> _f_hru_d[5], _f_prof_thick, _f_ptab, _f_conv_uh, _f_series, _f_gconst, _f_wt, _f_sb_d[7], _f_uh, _f_rh;
+  std::vector<rvn_time> _f_times;
+  int _f_ptab_stride, _f_nconv;
+};
+
+// front-end entry points that keep the reference names/signatures (src/RavenMain.h)
+bool ParseInputFiles(CModel *&pModel, optStruct &Options);           // .rvi -> .rvp -> .rvh -> .rvt (-> .rve)
+bool ParseInitialConditions(CModel *&pModel, const optStruct &Options); // .rvc
+#endif

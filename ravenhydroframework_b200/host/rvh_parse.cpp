@@ -1,0 +1,806 @@
+// rvh_parse.cpp -- readers for the Raven input subset the hot path needs:
+//   .rvi  model options + :HydrologicProcesses      (reference src/ParseInput.cpp)
+//   .rvp  classes + parameter lists                 (reference src/ParsePropertyFile.cpp)
+//   .rvh  subbasins + HRUs                          (reference src/ParseHRUFile.cpp)
+//   .rvt  gauges + forcing series                   (reference src/ParseTimeSeriesFile.cpp, src/TimeSeries.cpp)
+//   .rvc  initial conditions                        (reference src/ParseInitialConditionFile.cpp)
+//   .rve  ensemble description                      (reference src/ParseEnsembleFile.cpp)
+// Anything outside the subset fails loudly (RavenError) instead of being silently ignored, except for
+// the output/diagnostic commands listed in kIgnoredRVI which do not influence the water balance.
+#include "rvh_model.h"
+#include "rvh_process.h"
+#include <set>
+
+// decimal reader with the arithmetic of the reference's time-series reader (fast_s_to_d,
+// src/CommonFunctions.cpp:1267-1342): digits are accumulated in floating point, so the result can
+// differ from strtod in the last bit.  Forcing values must be the same doubles the reference sees.
+static double ts_s_to_d(const char *p) {
+  while (*p == ' ' || *p == '\t') p++;
+  double sign = 1.0;
+  if (*p == '-') { sign = -1.0; p++; } else if (*p == '+') { p++; }
+  double value = 0.0;
+  for (; *p >= '0' && *p <= '9'; p++) value = value * 10.0 + (*p - '0');
+  if (*p == '.') {
+    double pow10 = 10.0;
+    p++;
+    while (*p >= '0' && *p <= '9') { value += (*p - '0') / pow10; pow10 *= 10.0; p++; }
+  }
+  int frac = 0;
+  double scale = 1.0;
+  if (*p == 'e' || *p == 'E') {
+    unsigned int expon = 0;
+    p++;
+    if (*p == '-') { frac = 1; p++; } else if (*p == '+') { p++; }
+    for (; *p >= '0' && *p <= '9'; p++) expon = expon * 10 + (unsigned)(*p - '0');
+    if (expon > 308) expon = 308;
+    while (expon >= 50) { scale *= 1E50; expon -= 50; }
+    while (expon >= 8) { scale *= 1E8; expon -= 8; }
+    while (expon > 0) { scale *= 10.0; expon -= 1; }
+  }
+  return sign * (frac ? (value / scale) : (value * scale));
+}
+
+static double FixTimestep(double tstep) {
+  double tmp = floor(1.0 / tstep + 0.5);
+  ExitGracefullyIf(fabs(tstep * tmp - 1.0) > 0.1, "FixTimestep: timesteps and time intervals must evenly divide into one day");
+  return 1.0 / tmp;
+}
+static bool IsValidDateString(const std::string &s) {
+  return (s.length() == 10) && (s[4] == '/' || s[4] == '-') && (s[7] == '/' || s[7] == '-');
+}
+static bool LooksLikeClock(const std::string &t) { return t.length() >= 3 && (t[2] == ':' || t[1] == ':'); }
+static double ParseIntervalToken(const std::string &t, int calendar) {
+  if (LooksLikeClock(t)) return FixTimestep(DateStringToTimeStruct("0000-01-01", t, calendar).julian_day);
+  return FixTimestep(s_to_d(t));
+}
+
+// ================================================================================================ .rvi
+static const char *kIgnoredRVI[] = {":FileType", ":WrittenBy", ":CreationDate", ":Description", ":SilentMode", ":NoisyMode", ":QuietMode",
+  ":EvaluationMetrics", ":CustomOutput", ":WriteForcingFunctions", ":WriteMassBalanceFile", ":WriteEnsimFormat", ":WriteNetCDFFormat",
+  ":RunName", ":OutputDirectory", ":OutputInterval", ":SuppressOutput", ":DontWriteWatershedStorage", ":EvaluationPeriod", ":SnapshotHydrograph",
+  ":SWRadiationMethod", ":SWCloudCorrect", ":SWCanopyCorrect", ":LWRadiationMethod", ":LWIncomingMethod", ":CloudCoverMethod", ":WindspeedMethod",
+  ":RelativeHumidityMethod", ":AirPressureMethod", ":PavicsMode", ":DebugMode", ":WriteExhaustiveMB", ":HydrologicProcesses", ":EndHydrologicProcesses",
+  ":DefineHRUGroups", ":WriteSubbasinFile", ":NetCDFAttribute", ":rvh_Filename", NULL};
+
+static rvn_pet ParsePET(const std::string &s) {
+  if (s == "PET_DATA") return RVN_PET_DATA;
+  if (s == "PET_FROMMONTHLY") return RVN_PET_FROMMONTHLY;
+  if (s == "PET_CONSTANT") return RVN_PET_CONSTANT;
+  if (s == "PET_NONE") return RVN_PET_NONE;
+  if (s == "PET_HARGREAVES_1985") return RVN_PET_HARGREAVES_1985;
+  if (s == "PET_OUDIN") return RVN_PET_OUDIN;
+  ExitGracefully("ParseMainInputFile: evaporation method " + s + " is not implemented in the B200 build");
+  return RVN_PET_NONE;
+}
+static rvn_orocorr ParseOro(const std::string &s) {
+  if (s == "OROCORR_NONE") return RVN_OROCORR_NONE;
+  if (s == "OROCORR_SIMPLELAPSE") return RVN_OROCORR_SIMPLELAPSE;
+  if (s == "OROCORR_HBV") return RVN_OROCORR_HBV;
+  ExitGracefully("ParseMainInputFile: orographic correction " + s + " is not implemented in the B200 build");
+  return RVN_OROCORR_NONE;
+}
+
+static void ParseMainInputFile(CModel *&pModel, optStruct &Options) {
+  CParser p(Options.rvi_filename);
+  ExitGracefullyIf(!p.ok(), "ParseMainInputFile: cannot open " + Options.rvi_filename);
+  std::vector<std::string> s;
+  CHydroProcessABC *pLast = NULL;
+  std::set<std::string> ignored;
+  for (int i = 0; kIgnoredRVI[i]; i++) ignored.insert(kIgnoredRVI[i]);
+  std::vector<std::pair<std::string, std::string> > pending_alias;
+  while (p.Tokenize(s)) {
+    if (s.empty()) continue;
+    const std::string &c = s[0];
+    const int Len = (int)s.size();
+    if (c[0] != ':') continue;  // stray table rows of ignored blocks
+    if (ignored.count(c)) continue;
+    if (c == ":BenchmarkingMode") { Options.benchmarking = true; continue; }
+    if (c == ":StartDate") {
+      time_struct tt = DateStringToTimeStruct(s[1], Len == 2 ? "00:00:00" : s[2], Options.calendar);
+      Options.julian_start_day = tt.julian_day; Options.julian_start_year = tt.year; continue;
+    }
+    if (c == ":JulianStartDay") { Options.julian_start_day = s_to_d(s[1]); continue; }
+    if (c == ":JulianStartYear") { Options.julian_start_year = s_to_i(s[1]); continue; }
+    if (c == ":Duration") {
+      double part = 0.0;
+      if (Len >= 3 && !IsComment(s[2]) && LooksLikeClock(s[2])) part = DateStringToTimeStruct("0000-01-01", s[2], Options.calendar).julian_day;
+      Options.duration = s_to_d(s[1]) + part; continue;
+    }
+    if (c == ":EndDate") {
+      time_struct tt = DateStringToTimeStruct(s[1], Len == 2 ? "00:00:00" : s[2], Options.calendar);
+      Options.duration = TimeDifference(Options.julian_start_day, Options.julian_start_year, tt.julian_day, tt.year, Options.calendar); continue;
+    }
+    if (c == ":TimeStep") { Options.timestep = ParseIntervalToken(s[1], Options.calendar); continue; }
+    if (c == ":Method" || c == ":NumericalMethod") {
+      ExitGracefullyIf(s[1] != "ORDERED_SERIES", "ParseMainInputFile: only :Method ORDERED_SERIES is implemented in the B200 build"); continue;
+    }
+    if (c == ":SoilModel") {
+      if (s[1] == "SOIL_ONE_LAYER") Options.num_soillayers = 1;
+      else if (s[1] == "SOIL_TWO_LAYER") Options.num_soillayers = 2;
+      else if (s[1] == "SOIL_MULTILAYER") Options.num_soillayers = s_to_i(s[2]);
+      else ExitGracefully("ParseMainInputFile: Unrecognized Soil model");
+      pModel = new CModel(Options.num_soillayers);
+      for (size_t i = 0; i < pending_alias.size(); i++) pModel->AddAlias(pending_alias[i].first, pending_alias[i].second);
+      continue;
+    }
+    if (c == ":Routing") {
+      if (s[1] == "ROUTE_NONE") Options.routing = RVN_ROUTE_NONE;
+      else if (s[1] == "ROUTE_MUSKINGUM") Options.routing = RVN_ROUTE_MUSKINGUM;
+      else if (s[1] == "ROUTE_MUSKINGUM_CUNGE") Options.routing = RVN_ROUTE_MUSKINGUM_CUNGE;
+      else if (s[1] == "ROUTE_STORAGECOEFF") Options.routing = RVN_ROUTE_STORAGECOEFF;
+      else if (s[1] == "ROUTE_PLUG_FLOW") Options.routing = RVN_ROUTE_PLUG_FLOW;
+      else if (s[1] == "ROUTE_DIFFUSIVE_WAVE") Options.routing = RVN_ROUTE_DIFFUSIVE_WAVE;
+      else ExitGracefully("ParseMainInputFile: routing method " + s[1] + " is not implemented in the B200 build (SURVEY 8f)");
+      continue;
+    }
+    if (c == ":CatchmentRoute" || c == ":CatchmentRouting") {
+      if (s[1] == "ROUTE_DUMP" || s[1] == "DUMP") Options.catchment_routing = ROUTE_DUMP;
+      else if (s[1] == "TRIANGULAR_UH" || s[1] == "ROUTE_TRI_CONVOLUTION" || s[1] == "TRI_CONVOLUTION") Options.catchment_routing = ROUTE_TRI_CONVOLUTION;
+      else if (s[1] == "GAMMA_UH" || s[1] == "ROUTE_GAMMA_CONVOLUTION" || s[1] == "GAMMA_CONVOLUTION") Options.catchment_routing = ROUTE_GAMMA_CONVOLUTION;
+      else if (s[1] == "ROUTE_DELAYED_FIRST_ORDER" || s[1] == "DELAYED_FIRST_ORDER") Options.catchment_routing = ROUTE_DELAYED_FIRST_ORDER;
+      else ExitGracefully("ParseMainInputFile: catchment routing method " + s[1] + " is not implemented in the B200 build");
+      continue;
+    }
+    if (c == ":Evaporation") { Options.evaporation = ParsePET(s[1]); continue; }
+    if (c == ":OW_Evaporation") { Options.ow_evaporation = ParsePET(s[1]); continue; }
+    if (c == ":OroTempCorrect") { Options.orocorr_temp = ParseOro(s[1]); continue; }
+    if (c == ":OroPrecipCorrect") { Options.orocorr_precip = ParseOro(s[1]); continue; }
+    if (c == ":OroPETCorrect") { Options.orocorr_PET = ParseOro(s[1]); continue; }
+    if (c == ":RainSnowFraction" || c == ":RainSnowMethod") {
+      if (s[1] == "RAINSNOW_DATA") Options.rainsnow = RVN_RAINSNOW_DATA;
+      else if (s[1] == "RAINSNOW_DINGMAN") Options.rainsnow = RVN_RAINSNOW_DINGMAN;
+      else if (s[1] == "RAINSNOW_HBV") Options.rainsnow = RVN_RAINSNOW_HBV;
+      else if (s[1] == "RAINSNOW_UBC" || s[1] == "RAINSNOW_UBCWM") Options.rainsnow = RVN_RAINSNOW_UBCWM;
+      else if (s[1] == "RAINSNOW_THRESHOLD") Options.rainsnow = RVN_RAINSNOW_THRESHOLD;
+      else ExitGracefully("ParseMainInputFile: rain/snow method " + s[1] + " is not implemented in the B200 build");
+      continue;
+    }
+    if (c == ":PotentialMeltMethod" || c == ":PotentialMelt") {
+      if (s[1] == "POTMELT_DEGREE_DAY") Options.pot_melt = RVN_POTMELT_DEGREE_DAY;
+      else if (s[1] == "POTMELT_HBV") Options.pot_melt = RVN_POTMELT_HBV;
+      else if (s[1] == "POTMELT_HMETS") Options.pot_melt = RVN_POTMELT_HMETS;
+      else if (s[1] == "POTMELT_DATA") Options.pot_melt = RVN_POTMELT_DATA;
+      else if (s[1] == "POTMELT_NONE") Options.pot_melt = RVN_POTMELT_NONE;
+      else ExitGracefully("ParseMainInputFile: potential melt method " + s[1] + " is not implemented in the B200 build");
+      continue;
+    }
+    if (c == ":PrecipIceptFract") {
+      ExitGracefullyIf(s[1] != "PRECIP_ICEPT_USER", "ParseMainInputFile: only PRECIP_ICEPT_USER is implemented in the B200 build"); continue;
+    }
+    if (c == ":SubdailyMethod" || c == ":SubDailyMethod") {
+      ExitGracefullyIf(s[1] != "SUBDAILY_NONE", "ParseMainInputFile: only SUBDAILY_NONE is implemented in the B200 build"); continue;
+    }
+    if (c == ":MonthlyInterpolationMethod") {
+      if (s[1] == "UNIFORM") Options.month_interp_method = MONTHINT_UNIFORM;
+      else if (s[1] == "LINEAR_START_OF_MONTH" || s[1] == "LINEAR_FOM") Options.month_interp_method = MONTHINT_LINEAR_FOM;
+      else if (s[1] == "LINEAR_21" || s[1] == "MONTHINT_LINEAR_21") Options.month_interp_method = MONTHINT_LINEAR_21;
+      else if (s[1] == "LINEAR_MID" || s[1] == "MONTHINT_LINEAR_MID") Options.month_interp_method = MONTHINT_LINEAR_MID;
+      else ExitGracefully("ParseMainInputFile: Unrecognized monthly interpolation");
+      continue;
+    }
+    if (c == ":InterpolationMethod" || c == ":Interpolation" || c == ":MetGaugeInterpolation") {
+      if (s[1] == "NEAREST_NEIGHBOR" || s[1] == "INTERP_NEAREST_NEIGHBOR") Options.interpolation = INTERP_NEAREST_NEIGHBOR;
+      else if (s[1] == "AVERAGE_ALL" || s[1] == "INTERP_AVERAGE_ALL") Options.interpolation = INTERP_AVERAGE_ALL;
+      else if (s[1] == "INVERSE_DISTANCE" || s[1] == "INTERP_INVERSE_DISTANCE") Options.interpolation = INTERP_INVERSE_DISTANCE;
+      else if (s[1] == "INTERP_FROM_FILE") { Options.interpolation = INTERP_FROM_FILE; Options.interp_file = CorrectForRelativePath(s[2], Options.rvi_filename); }
+      else ExitGracefully("ParseMainInputFile: Unrecognized interpolation method");
+      continue;
+    }
+    if (c == ":Alias") {
+      if (pModel) pModel->AddAlias(s[1], s[2]); else pending_alias.push_back(std::make_pair(s[1], s[2]));
+      continue;
+    }
+    if (c == ":LakeStorage") {
+      ExitGracefullyIf(!pModel, ":LakeStorage command must be after :SoilModel command in .rvi file");
+      pModel->SetLakeStorage(pModel->ParseSVTypeIndex(s[1])); continue;
+    }
+    if (c == ":SuppressCompetitiveET") { Options.suppressCompetitiveET = true; continue; }
+    if (c == ":SnowSuppressesPET") { Options.snow_suppressPET = true; continue; }
+    if (c == ":AllowSoilOverfill") { Options.allow_soil_overfill = true; continue; }
+    if (c == ":DirectEvaporation") { Options.direct_evap = true; continue; }
+    if (c == ":EnsembleMode") {
+      if (s[1] == "ENSEMBLE_MONTECARLO") Options.ensemble = ENSEMBLE_MONTECARLO;
+      else if (s[1] == "ENSEMBLE_NONE") Options.ensemble = ENSEMBLE_NONE;
+      else if (s[1] == "ENSEMBLE_ENKF") Options.ensemble = ENSEMBLE_ENKF;
+      else if (s[1] == "ENSEMBLE_DDS") Options.ensemble = ENSEMBLE_DDS;
+      else ExitGracefully("ParseMainInputFile: unrecognized ensemble mode");
+      if (pModel && Len >= 3) pModel->num_members = s_to_i(s[2]);
+      continue;
+    }
+    if (c == ":RandomSeed") { Options.random_seed = (unsigned)s_to_i(s[1]); Options.random_seed_set = true; continue; }
+    // ---- process list -----------------------------------------------------------------------------
+    if (c == ":-->Conditional" || c == ":Conditional") {
+      ExitGracefullyIf(!pLast || Len < 4, "ParseMainInputFile: :-->Conditional must follow a process");
+      condition_basis basis; comparison cmp;
+      if (s[1] == "HRU_TYPE") basis = BASIS_HRU_TYPE;
+      else if (s[1] == "LAND_CLASS") basis = BASIS_LANDCLASS;
+      else if (s[1] == "VEGETATION") basis = BASIS_VEGETATION;
+      else if (s[1] == "HRU_GROUP") basis = BASIS_HRU_GROUP;
+      else { ExitGracefully("ParseMainInputFile: unrecognized condition basis"); basis = BASIS_HRU_TYPE; }
+      if (s[2] == "IS") cmp = COMPARE_IS_EQUAL;
+      else if (s[2] == "IS_NOT") cmp = COMPARE_NOT_EQUAL;
+      else { ExitGracefully("ParseMainInputFile: unrecognized comparison in :-->Conditional"); cmp = COMPARE_IS_EQUAL; }
+      pLast->AddCondition(basis, cmp, s[3]);
+      continue;
+    }
+    if (c == ":-->RedirectFlow") {
+      ExitGracefullyIf(!pLast || Len < 3, "ParseMainInputFile: :-->RedirectFlow must follow a process");
+      pLast->Redirect(pModel->ParseSVTypeIndex(s[1]), pModel->ParseSVTypeIndex(s[2]));
+      continue;
+    }
+    ExitGracefullyIf(!pModel && c != ":FileType", "ParseMainInputFile: " + c + " appears before :SoilModel, or is not supported by the B200 build");
+    CHydroProcessABC *pMover = CreateProcessFromRVI(s, pModel, Options);
+    if (pMover) { pModel->AddProcess(pMover); pLast = pMover; continue; }
+    ExitGracefully("ParseMainInputFile: command " + c + " (line " + std::to_string(p.line()) + " of " + Options.rvi_filename +
+                   ") is not supported by the B200 build");
+  }
+  ExitGracefullyIf(!pModel, "ParseMainInputFile: :SoilModel command missing from .rvi file");
+  // Add TOTAL_SWE state variable if any snow is simulated (src/ParseInput.cpp:3775-3779)
+  if (pModel->StateVarExists(RVN_SV_SNOW)) { sv_type t = RVN_SV_TOTAL_SWE; int l = 0; pModel->AddStateVariables(&t, &l, 1); }
+  if (pModel->StateVarExists(RVN_SV_GLACIER_ICE)) { sv_type t = RVN_SV_GLACIER_MB; int l = 0; pModel->AddStateVariables(&t, &l, 1); }
+}
+
+// ================================================================================================ .rvp
+struct ParamTable {  // [DEFAULT] row + per-class explicit cells for one class family
+  std::map<int, double> def;                              // field -> default
+  std::map<std::pair<int, int>, double> cell;             // (class, field) -> explicit value
+};
+template <class FieldFn>
+static void ParseParameterList(CParser &p, const char *endtok, FieldFn field_of, int (CModel::*find)(const std::string &) const,
+                               CModel *pModel, ParamTable &T, const char *family) {
+  std::vector<std::string> s;
+  std::vector<int> fields;
+  while (p.Tokenize(s)) {
+    if (s.empty()) continue;
+    if (s[0] == endtok) return;
+    if (s[0] == ":Parameters") {
+      fields.clear();
+      for (size_t i = 1; i < s.size(); i++) {
+        int f = field_of(s[i]);
+        ExitGracefullyIf(f == -2, std::string("ParsePropertyFile: ") + family + " parameter " + s[i] + " is not supported by the B200 build");
+        fields.push_back(f);
+      }
+      continue;
+    }
+    if (s[0] == ":Units") continue;
+    ExitGracefullyIf(s.size() != fields.size() + 1, std::string("ParsePropertyFile: wrong number of columns in ") + family + " parameter list row " + s[0]);
+    bool is_default = (s[0] == "[DEFAULT]");
+    int c = -1;
+    if (!is_default) {
+      c = (pModel->*find)(s[0]);
+      ExitGracefullyIf(c < 0, std::string("ParsePropertyFile: unknown ") + family + " class " + s[0]);
+    }
+    for (size_t i = 0; i < fields.size(); i++) {
+      if (fields[i] < 0) continue;  // recognised but irrelevant to the hot path
+      const std::string &v = s[i + 1];
+      if (v == "_DEFAULT" || v == "_DEF") continue;
+      ExitGracefullyIf(v == "_AUTO", std::string("ParsePropertyFile: _AUTO values are not supported by the B200 build (") + family + ")");
+      if (is_default) T.def[fields[i]] = s_to_d(v);
+      else T.cell[std::make_pair(c, fields[i])] = s_to_d(v);
+    }
+  }
+}
+
+// name -> field, with -1 = "known to the reference, irrelevant here" and -2 = unknown
+static int SoilFieldOrIgnore(const std::string &n) {
+  int f = SoilFieldFromName(n);
+  if (f >= 0) return f;
+  static const char *ign[] = {"SAND_CON", "CLAY_CON", "SILT_CON", "ORG_CON", "STONE_FRAC", "BULK_DENSITY", "HYDRAUL_COND", "ALBEDO_WET", "ALBEDO_DRY", NULL};
+  for (int i = 0; ign[i]; i++) if (n == ign[i]) return -1;
+  return -2;
+}
+static int LUFieldOrIgnore(const std::string &n) {
+  int f = LandUseFieldFromName(n);
+  if (f >= 0) return f;
+  static const char *ign[] = {"ROUGHNESS", "FOREST_PET_CORR", NULL};
+  for (int i = 0; ign[i]; i++) if (n == ign[i]) return -1;
+  return -2;
+}
+static int VegFieldOrIgnore(const std::string &n) {
+  if (n == "TFRAIN") return 1000 + RVN_V_RAIN_ICEPT_PCT;   // throughfall fractions: icept = 1 - value (src/ParsePropertyFile.cpp)
+  if (n == "TFSNOW") return 1000 + RVN_V_SNOW_ICEPT_PCT;
+  int f = VegFieldFromName(n);
+  if (f >= 0) return f;
+  static const char *ign[] = {"MAX_LEAF_COND", "ALBEDO", "ALBEDO_WET", "SVF_EXTINCTION", "MAX_INTERCEPT_RATE", "RAIN_ICEPT_FACT", "SNOW_ICEPT_FACT", NULL};
+  for (int i = 0; ign[i]; i++) if (n == ign[i]) return -1;
+  return -2;
+}
+
+static void ParseClassPropertiesFile(CModel *pModel, const optStruct &Options) {
+  CParser p(Options.rvp_filename);
+  ExitGracefullyIf(!p.ok(), "ParseClassPropertiesFile: cannot open " + Options.rvp_filename);
+  std::vector<std::string> s;
+  ParamTable Tsoil, Tlu, Tveg;
+  for (int f = 0; f < RVN_G_COUNT; f++) pModel->globals.v[f] = NOT_SPECIFIED;
+  pModel->globals.v[RVN_G_TOC_MULTIPLIER] = pModel->globals.v[RVN_G_TIME_TO_PEAK_MULTIPLIER] = 1.0;
+  pModel->globals.v[RVN_G_GAMMA_SHAPE_MULTIPLIER] = pModel->globals.v[RVN_G_GAMMA_SCALE_MULTIPLIER] = 1.0;
+  std::map<int, double> veg_lai_set;
+  while (p.Tokenize(s)) {
+    if (s.empty()) continue;
+    const std::string &c = s[0];
+    if (c == ":FileType" || c == ":WrittenBy" || c == ":CreationDate") continue;
+    if (c == ":SoilClasses") {
+      while (p.Tokenize(s)) {
+        if (s.empty() || s[0] == ":Attributes" || s[0] == ":Units") continue;
+        if (s[0] == ":EndSoilClasses") break;
+        CSoilClass sc; sc.tag = s[0];
+        for (int f = 0; f < RVN_S_COUNT; f++) sc.S.v[f] = NOT_SPECIFIED;
+        pModel->soil_classes.push_back(sc);
+      }
+      continue;
+    }
+    if (c == ":VegetationClasses") {
+      while (p.Tokenize(s)) {
+        if (s.empty() || s[0] == ":Attributes" || s[0] == ":Units") continue;
+        if (s[0] == ":EndVegetationClasses") break;
+        ExitGracefullyIf(s.size() < 4, "ParseClassPropertiesFile: :VegetationClasses rows need NAME MAX_HT MAX_LAI MAX_LEAF_COND");
+        CVegetationClass vc; vc.tag = s[0];
+        for (int f = 0; f < RVN_V_COUNT; f++) vc.V.v[f] = NOT_SPECIFIED;
+        vc.V.v[RVN_V_MAX_HEIGHT] = s_to_d(s[1]);
+        vc.V.v[RVN_V_MAX_LAI] = s_to_d(s[2]);
+        for (int m = 0; m < 12; m++) { vc.V.relative_ht[m] = 1.0; vc.V.relative_LAI[m] = 1.0; }
+        pModel->veg_classes.push_back(vc);
+      }
+      continue;
+    }
+    if (c == ":LandUseClasses") {
+      while (p.Tokenize(s)) {
+        if (s.empty() || s[0] == ":Attributes" || s[0] == ":Units") continue;
+        if (s[0] == ":EndLandUseClasses") break;
+        ExitGracefullyIf(s.size() < 3, "ParseClassPropertiesFile: :LandUseClasses rows need NAME IMPERM FOREST_COV");
+        CLandUseClass lc; lc.tag = s[0];
+        for (int f = 0; f < RVN_LU_COUNT; f++) lc.S.v[f] = NOT_SPECIFIED;
+        lc.S.v[RVN_LU_IMPERMEABLE_FRAC] = s_to_d(s[1]);
+        lc.S.v[RVN_LU_FOREST_COVERAGE] = s_to_d(s[2]);
+        pModel->lu_classes.push_back(lc);
+      }
+      continue;
+    }
+    if (c == ":TerrainClasses") {
+      while (p.Tokenize(s)) {
+        if (s.empty() || s[0] == ":Attributes" || s[0] == ":Units") continue;
+        if (s[0] == ":EndTerrainClasses") break;
+        CTerrainClass tc; tc.tag = s[0]; pModel->terrain_classes.push_back(tc);
+      }
+      continue;
+    }
+    if (c == ":SoilProfiles") {
+      while (p.Tokenize(s)) {
+        if (s.empty() || s[0] == ":Attributes" || s[0] == ":Units") continue;
+        if (s[0] == ":EndSoilProfiles") break;
+        ExitGracefullyIf(s.size() < 2, "ParseClassPropertiesFile: bad :SoilProfiles row");
+        CSoilProfile sp; sp.tag = s[0]; sp.nHorizons = s_to_i(s[1]);
+        ExitGracefullyIf((int)s.size() < 2 + 2 * sp.nHorizons, "ParseClassPropertiesFile: :SoilProfiles row " + s[0] + " has too few horizon entries");
+        for (int m = 0; m < sp.nHorizons; m++) {
+          int sc = pModel->FindSoilClass(s[2 + 2 * m]);
+          ExitGracefullyIf(sc < 0, "ParseClassPropertiesFile: bad soiltype code '" + s[2 + 2 * m] + "' in soil profile " + sp.tag);
+          sp.soil_class.push_back(sc);
+          sp.thickness.push_back(s_to_d(s[3 + 2 * m]));
+        }
+        pModel->soil_profiles.push_back(sp);
+      }
+      continue;
+    }
+    if (c == ":SoilParameterList") { ParseParameterList(p, ":EndSoilParameterList", SoilFieldOrIgnore, &CModel::FindSoilClass, pModel, Tsoil, "soil"); continue; }
+    if (c == ":LandUseParameterList") { ParseParameterList(p, ":EndLandUseParameterList", LUFieldOrIgnore, &CModel::FindLUClass, pModel, Tlu, "land use"); continue; }
+    if (c == ":VegetationParameterList") { ParseParameterList(p, ":EndVegetationParameterList", VegFieldOrIgnore, &CModel::FindVegClass, pModel, Tveg, "vegetation"); continue; }
+    if (c == ":GlobalParameter") {
+      int f = GlobalFieldFromName(s[1]);
+      ExitGracefullyIf(f < 0, "ParseClassPropertiesFile: global parameter " + s[1] + " is not supported by the B200 build");
+      pModel->globals.v[f] = s_to_d(s[2]);
+      continue;
+    }
+    if (c == ":AvgAnnualRunoff") { pModel->globals.v[RVN_G_AVG_ANNUAL_RUNOFF] = s_to_d(s[1]); continue; }
+    if (c == ":AvgAnnualSnow") { pModel->globals.v[RVN_G_AVG_ANNUAL_SNOW] = s_to_d(s[1]); continue; }
+    if (c == ":AdiabaticLapseRate") { pModel->globals.v[RVN_G_ADIABATIC_LAPSE] = s_to_d(s[1]); continue; }
+    if (c == ":RainSnowTransition") { pModel->globals.v[RVN_G_RAINSNOW_TEMP] = s_to_d(s[1]); pModel->globals.v[RVN_G_RAINSNOW_DELTA] = s_to_d(s[2]); continue; }
+    if (c == ":IrreducibleSnowSaturation") { pModel->globals.v[RVN_G_SNOW_SWI] = s_to_d(s[1]); continue; }
+    if (c == ":PrecipitationLapseRate") { pModel->globals.v[RVN_G_PRECIP_LAPSE] = s_to_d(s[1]); continue; }
+    if (c == ":AirSnowCoeff") { pModel->globals.v[RVN_G_AIRSNOW_COEFF] = s_to_d(s[1]); continue; }
+    if (c == ":SeasonalRelativeLAI" || c == ":SeasonalRelativeHeight") {
+      const bool lai = (c == ":SeasonalRelativeLAI");
+      const char *endt = lai ? ":EndSeasonalRelativeLAI" : ":EndSeasonalRelativeHeight";
+      while (p.Tokenize(s)) {
+        if (s.empty() || s[0] == ":Attributes" || s[0] == ":Units") continue;
+        if (s[0] == endt) break;
+        ExitGracefullyIf(s.size() < 13, "ParseClassPropertiesFile: seasonal vegetation rows need 12 monthly values");
+        if (s[0] == "[DEFAULT]") {
+          for (size_t v = 0; v < pModel->veg_classes.size(); v++)
+            for (int m = 0; m < 12; m++) (lai ? pModel->veg_classes[v].V.relative_LAI : pModel->veg_classes[v].V.relative_ht)[m] = s_to_d(s[1 + m]);
+        } else {
+          int v = pModel->FindVegClass(s[0]);
+          ExitGracefullyIf(v < 0, "ParseClassPropertiesFile: unknown vegetation class " + s[0]);
+          for (int m = 0; m < 12; m++) (lai ? pModel->veg_classes[v].V.relative_LAI : pModel->veg_classes[v].V.relative_ht)[m] = s_to_d(s[1 + m]);
+        }
+      }
+      continue;
+    }
+    if (c == ":TrapezoidalChannel") {  // name bot_width bot_elev incline mannings_n bedslope (src/ParsePropertyFile.cpp:982-988)
+      ExitGracefullyIf(s.size() < 7, "ParseClassPropertiesFile: :TrapezoidalChannel needs 6 arguments");
+      CChannelXSect *ch = new CChannelXSect();
+      ch->name = s[1]; ch->mannings_n = s_to_d(s[5]); ch->bedslope = s_to_d(s[6]);
+      ch->GenerateTrapezoid(s_to_d(s[2]), s_to_d(s[3]), s_to_d(s[4]));
+      pModel->channels.push_back(ch);
+      continue;
+    }
+    if (c == ":RedirectToFile") ExitGracefully("ParseClassPropertiesFile: :RedirectToFile inside .rvp is not supported by the B200 build");
+    ExitGracefully("ParseClassPropertiesFile: command " + c + " (line " + std::to_string(p.line()) + ") is not supported by the B200 build");
+  }
+  // resolve [DEFAULT] rows into the classes
+  for (size_t k = 0; k < pModel->soil_classes.size(); k++)
+    for (int f = 0; f < RVN_S_COUNT; f++) {
+      std::map<std::pair<int, int>, double>::iterator it = Tsoil.cell.find(std::make_pair((int)k, f));
+      if (it != Tsoil.cell.end()) pModel->soil_classes[k].S.v[f] = it->second;
+      else if (Tsoil.def.count(f)) pModel->soil_classes[k].S.v[f] = Tsoil.def[f];
+    }
+  for (size_t k = 0; k < pModel->lu_classes.size(); k++)
+    for (int f = 0; f < RVN_LU_COUNT; f++) {
+      std::map<std::pair<int, int>, double>::iterator it = Tlu.cell.find(std::make_pair((int)k, f));
+      if (it != Tlu.cell.end()) pModel->lu_classes[k].S.v[f] = it->second;
+      else if (Tlu.def.count(f)) pModel->lu_classes[k].S.v[f] = Tlu.def[f];
+    }
+  for (size_t k = 0; k < pModel->veg_classes.size(); k++) {
+    for (int f = 0; f < RVN_V_COUNT; f++) {
+      for (int alt = 0; alt < 2; alt++) {  // alt=1: throughfall aliases (1 - value)
+        int key = f + 1000 * alt;
+        std::map<std::pair<int, int>, double>::iterator it = Tveg.cell.find(std::make_pair((int)k, key));
+        double val = NOT_SPECIFIED; bool have = false;
+        if (it != Tveg.cell.end()) { val = it->second; have = true; }
+        else if (Tveg.def.count(key)) { val = Tveg.def[key]; have = true; }
+        if (have) pModel->veg_classes[k].V.v[f] = alt ? (1.0 - val) : val;
+      }
+    }
+  }
+  // derived / autogenerated values the hot path reads
+  for (size_t k = 0; k < pModel->soil_classes.size(); k++) {
+    soil_struct &S = pModel->soil_classes[k].S;
+    // conceptual-model default: POROSITY autogenerates to 1.0 when no sand content is given (src/SoilClass.cpp:84-88)
+    if (S.v[RVN_S_POROSITY] == NOT_SPECIFIED) S.v[RVN_S_POROSITY] = 1.0;
+    S.v[RVN_S_CAP_RATIO] = S.v[RVN_S_POROSITY] * (1.0 - 0.0);  // stone_frac autogenerates to 0 (src/SoilClass.cpp:93-99,113)
+    if (S.v[RVN_S_PET_CORRECTION] == NOT_SPECIFIED) S.v[RVN_S_PET_CORRECTION] = 1.0;  // src/SoilClass.cpp PET_CORRECTION default
+  }
+  for (size_t k = 0; k < pModel->lu_classes.size(); k++) {
+    surface_struct &S = pModel->lu_classes[k].S;
+    if (S.v[RVN_LU_FOREST_SPARSENESS] == NOT_SPECIFIED) S.v[RVN_LU_FOREST_SPARSENESS] = 0.0;  // src/LandUseClass.cpp autocalc
+    if (S.v[RVN_LU_LAKE_PET_CORR] == NOT_SPECIFIED) S.v[RVN_LU_LAKE_PET_CORR] = 1.0;
+    if (S.v[RVN_LU_OW_PET_CORR] == NOT_SPECIFIED) S.v[RVN_LU_OW_PET_CORR] = 1.0;
+  }
+  for (size_t k = 0; k < pModel->veg_classes.size(); k++) {
+    veg_struct &V = pModel->veg_classes[k].V;
+    if (V.v[RVN_V_SAI_HT_RATIO] == NOT_SPECIFIED) V.v[RVN_V_SAI_HT_RATIO] = 0.0;
+    if (V.v[RVN_V_PET_VEG_CORR] == NOT_SPECIFIED) V.v[RVN_V_PET_VEG_CORR] = 1.0;
+  }
+}
+
+// ================================================================================================ .rvh
+static void ParseHRUPropsFile(CModel *pModel, const optStruct &Options) {
+  CParser p(Options.rvh_filename);
+  ExitGracefullyIf(!p.ok(), "ParseHRUPropsFile: cannot open " + Options.rvh_filename);
+  std::vector<std::string> s;
+  while (p.Tokenize(s)) {
+    if (s.empty()) continue;
+    const std::string &c = s[0];
+    if (c == ":FileType" || c == ":WrittenBy" || c == ":CreationDate") continue;
+    if (c == ":SubBasins") {
+      while (p.Tokenize(s)) {
+        if (s.empty() || s[0] == ":Attributes" || s[0] == ":Units") continue;
+        if (s[0] == ":EndSubBasins") break;
+        ExitGracefullyIf(s.size() < 6, "ParseHRUPropsFile: :SubBasins rows need ID NAME DOWNSTREAM_ID PROFILE REACH_LENGTH GAUGED");
+        CSubBasin *b = new CSubBasin();
+        b->ID = s_to_ll(s[0]); b->name = s[1]; b->downstream_ID = s_to_ll(s[2]); b->profile_name = s[3];
+        if (b->downstream_ID < 0) b->downstream_ID = DOESNT_EXIST;
+        b->pChannel = NULL;
+        if (StringToUppercase(s[3]) != "NONE") {
+          b->pChannel = pModel->FindChannel(s[3]);
+          ExitGracefullyIf(!b->pChannel, "ParseHRUPropsFile: Unrecognized Channel profile code (" + s[3] + ") in SubBasins command");
+        }
+        if (s[4] == "_AUTO" || StringToUppercase(s[4]) == "AUTO") b->reach_length = AUTO_COMPUTE;
+        else b->reach_length = s_to_d(s[4]) * M_PER_KM;
+        b->gauged = s_to_i(s[5]) != 0;
+        pModel->AddSubBasin(b);
+      }
+      continue;
+    }
+    if (c == ":HRUs") {
+      while (p.Tokenize(s)) {
+        if (s.empty() || s[0] == ":Attributes" || s[0] == ":Units") continue;
+        if (s[0] == ":EndHRUs") break;
+        ExitGracefullyIf(s.size() < 13, "ParseHRUPropsFile: :HRUs rows need 13 columns");
+        CHydroUnit *h = new CHydroUnit();
+        h->ID = s_to_ll(s[0]); h->area = s_to_d(s[1]); h->elevation = s_to_d(s[2]);
+        h->latitude = s_to_d(s[3]); h->longitude = s_to_d(s[4]); h->SBID = s_to_ll(s[5]);
+        h->lu_class = pModel->FindLUClass(s[6]);
+        ExitGracefullyIf(h->lu_class < 0, "ParseHRUPropsFile: Unrecognized Land Use Code/index in HRU definition: " + s[6]);
+        h->veg_class = pModel->FindVegClass(s[7]);
+        ExitGracefullyIf(h->veg_class < 0, "ParseHRUPropsFile: Unrecognized Vegetation Code/index in HRU definition: " + s[7]);
+        h->soil_profile = pModel->FindSoilProfile(s[8]);
+        ExitGracefullyIf(h->soil_profile < 0, "ParseHRUPropsFile: Unrecognized Soil Profile Code/index in HRU definition: " + s[8]);
+        h->terrain_class = (s[10] == "[NONE]") ? DOESNT_EXIST : pModel->FindTerrainClass(s[10]);
+        // HRU type from the soil-profile tag (reference src/ParseHRUFile.cpp: LAKE/GLACIER/ROCK/WATER/WETLAND prefixes)
+        std::string tag = pModel->soil_profiles[h->soil_profile].tag;
+        h->type = RVN_HRU_STANDARD;
+        if (tag.substr(0, 4) == "LAKE") h->type = RVN_HRU_LAKE;
+        else if (tag.substr(0, 7) == "GLACIER") h->type = RVN_HRU_GLACIER;
+        else if (tag.substr(0, 5) == "WATER") h->type = RVN_HRU_WATER;
+        else if (tag.substr(0, 4) == "ROCK") h->type = RVN_HRU_ROCK;
+        else if (tag.substr(0, 8) == "PAVEMENT") h->type = RVN_HRU_ROCK;
+        else if (tag.substr(0, 7) == "WETLAND") h->type = RVN_HRU_WETLAND;
+        h->slope = (s[11] == "[NONE]") ? 0.0 : s_to_d(s[11]);
+        h->aspect = (s[12] == "[NONE]") ? 0.0 : s_to_d(s[12]);
+        h->enabled = true;
+        h->subbasin_index = pModel->GetSubBasinIndex(h->SBID);
+        ExitGracefullyIf(h->subbasin_index < 0, "ParseHRUPropsFile: HRU " + s[0] + " references unknown subbasin " + s[5]);
+        ExitGracefullyIf(h->area <= 0.0, "ParseHRUPropsFile: HRU area must be positive");
+        pModel->GetSubBasin(h->subbasin_index)->hru_index.push_back(pModel->GetNumHRUs());
+        pModel->AddHRU(h);
+      }
+      continue;
+    }
+    if (c == ":SubBasinProperties") {
+      std::vector<std::string> names;
+      while (p.Tokenize(s)) {
+        if (s.empty() || s[0] == ":Units") continue;
+        if (s[0] == ":EndSubBasinProperties") break;
+        if (s[0] == ":Parameters" || s[0] == ":Attributes") { names.assign(s.begin() + 1, s.end()); continue; }
+        int pb = pModel->GetSubBasinIndex(s_to_ll(s[0]));
+        ExitGracefullyIf(pb < 0, "ParseHRUPropsFile: bad subbasin ID in :SubBasinProperties");
+        for (size_t i = 0; i < names.size() && i + 1 < s.size(); i++)
+          ExitGracefullyIf(!pModel->GetSubBasin(pb)->SetBasinProperties(names[i], s_to_d(s[i + 1])),
+                           "ParseHRUPropsFile: subbasin property " + names[i] + " is not supported by the B200 build");
+      }
+      continue;
+    }
+    if (c == ":HRUGroup" || c == ":SubBasinGroup" || c == ":PopulateHRUGroup" || c == ":PopulateSubBasinGroup") {
+      // groups only matter for outputs / HRU_GROUP conditions (unsupported, fails in ShouldApply)
+      if (c == ":HRUGroup") while (p.Tokenize(s)) { if (!s.empty() && s[0] == ":EndHRUGroup") break; }
+      if (c == ":SubBasinGroup") while (p.Tokenize(s)) { if (!s.empty() && s[0] == ":EndSubBasinGroup") break; }
+      continue;
+    }
+    ExitGracefully("ParseHRUPropsFile: command " + c + " (line " + std::to_string(p.line()) + ") is not supported by the B200 build");
+  }
+}
+
+// ================================================================================================ .rvt
+forcing_type ForcingFromString(const std::string &s) {
+  if (s == "PRECIP") return F_PRECIP;
+  if (s == "RAINFALL") return F_RAINFALL;
+  if (s == "SNOWFALL") return F_SNOWFALL;
+  if (s == "TEMP_AVE") return F_TEMP_AVE;
+  if (s == "TEMP_DAILY_MIN" || s == "TEMP_MIN") return F_TEMP_DAILY_MIN;
+  if (s == "TEMP_DAILY_MAX" || s == "TEMP_MAX") return F_TEMP_DAILY_MAX;
+  if (s == "TEMP_DAILY_AVE") return F_TEMP_DAILY_AVE;
+  if (s == "PET") return F_PET;
+  if (s == "OW_PET") return F_OW_PET;
+  if (s == "POTENTIAL_MELT") return F_POTENTIAL_MELT;
+  return F_NTYPES;
+}
+
+static void ReadSeriesHeader(CParser &p, const optStruct &Options, double &start_day, int &start_yr, double &interval, int &n) {
+  std::vector<std::string> s;
+  do { ExitGracefullyIf(!p.Tokenize(s), "ParseTimeSeriesFile: unexpected end of file in time series header"); } while (s.empty());
+  ExitGracefullyIf(s.size() < 4, "ParseTimeSeriesFile: time series header needs [date] [time] [interval] [N]");
+  if (IsValidDateString(s[0])) {
+    time_struct tt = DateStringToTimeStruct(s[0], s[1], Options.calendar);
+    start_day = tt.julian_day; start_yr = tt.year;
+    interval = ParseIntervalToken(s[2], Options.calendar);
+    n = s_to_i(s[3]);
+  } else {
+    n = s_to_i(s[0]); start_day = s_to_d(s[1]); start_yr = s_to_i(s[2]); interval = FixTimestep(s_to_d(s[3]));
+  }
+}
+
+static void ParseGaugeBody(CParser &p, CGauge *g, const optStruct &Options, const std::string &thisfile);
+static void ParseMultiData(CParser &p, CGauge *g, const optStruct &Options) {
+  double start_day, interval; int start_yr, n;
+  ReadSeriesHeader(p, Options, start_day, start_yr, interval, n);
+  std::vector<std::string> s;
+  do { ExitGracefullyIf(!p.Tokenize(s), "ParseTimeSeriesFile: truncated :MultiData"); } while (s.empty());
+  ExitGracefullyIf(s[0] != ":Parameters", "CTimeSeries::ParseMultiple : MultiData command improperly formatted");
+  std::vector<forcing_type> types;
+  for (size_t i = 1; i < s.size(); i++) {
+    forcing_type f = ForcingFromString(s[i]);
+    ExitGracefullyIf(f == F_NTYPES, "CTimeSeries::ParseMultiple : time series type " + s[i] + " is not supported by the B200 build");
+    types.push_back(f);
+  }
+  do { ExitGracefullyIf(!p.Tokenize(s), "ParseTimeSeriesFile: truncated :MultiData"); } while (s.empty());
+  ExitGracefullyIf(s[0] != ":Units", "CTimeSeries::ParseMultiple : MultiData command improperly formatted");
+  std::vector<std::vector<double> > vals(types.size());
+  for (size_t i = 0; i < types.size(); i++) vals[i].reserve(n);
+  int cnt = 0;
+  while (p.Tokenize(s)) {
+    if (s.empty()) continue;
+    if (s[0] == ":EndMultiData") break;
+    ExitGracefullyIf(s.size() != types.size(), "CTimeSeries:ParseMultiple: wrong number of columns in :MultiData data. File: " + p.filename());
+    ExitGracefullyIf(cnt >= n, "CTimeSeries::ParseMultiple: Bad number of time series points. File: " + p.filename());
+    for (size_t i = 0; i < types.size(); i++) vals[i].push_back(ts_s_to_d(s[i].c_str()));
+    cnt++;
+  }
+  ExitGracefullyIf(cnt != n, "CTimeSeries::ParseMultiple: Insufficient number of time series points. File: " + p.filename());
+  static const char *nm[F_NTYPES] = {"PRECIP", "RAINFALL", "SNOWFALL", "TEMP_AVE", "TEMP_DAILY_MIN", "TEMP_DAILY_MAX", "TEMP_DAILY_AVE", "PET", "OW_PET", "POTENTIAL_MELT"};
+  for (size_t i = 0; i < types.size(); i++) g->AddTimeSeries(new CTimeSeries(nm[types[i]], start_day, start_yr, interval, vals[i]), types[i]);
+}
+static void ParseData(CParser &p, CGauge *g, const std::vector<std::string> &hdr, const optStruct &Options) {
+  forcing_type f = ForcingFromString(hdr[1]);
+  ExitGracefullyIf(f == F_NTYPES, "ParseTimeSeriesFile: :Data type " + hdr[1] + " is not supported by the B200 build");
+  double start_day, interval; int start_yr, n;
+  ReadSeriesHeader(p, Options, start_day, start_yr, interval, n);
+  std::vector<double> v; v.reserve(n);
+  std::vector<std::string> s;
+  while (p.Tokenize(s)) {
+    if (s.empty()) continue;
+    if (s[0] == ":EndData") break;
+    for (size_t i = 0; i < s.size(); i++) v.push_back(ts_s_to_d(s[i].c_str()));
+  }
+  ExitGracefullyIf((int)v.size() != n, "CTimeSeries::Parse: wrong number of data points in :Data block. File: " + p.filename());
+  g->AddTimeSeries(new CTimeSeries(hdr[1], start_day, start_yr, interval, v), f);
+}
+static void ParseGaugeBody(CParser &p, CGauge *g, const optStruct &Options, const std::string &thisfile) {
+  std::vector<std::string> s;
+  while (p.Tokenize(s)) {
+    if (s.empty()) continue;
+    const std::string &c = s[0];
+    if (c == ":EndGauge") return;
+    if (c == ":Latitude") g->latitude = s_to_d(s[1]);
+    else if (c == ":Longitude") g->longitude = s_to_d(s[1]);
+    else if (c == ":Elevation") g->elevation = s_to_d(s[1]);
+    else if (c == ":RainCorrection") g->rainfall_corr = s_to_d(s[1]);
+    else if (c == ":SnowCorrection") g->snowfall_corr = s_to_d(s[1]);
+    else if (c == ":TemperatureCorrection") g->temperature_corr = s_to_d(s[1]);
+    else if (c == ":MonthlyAveEvaporation") { for (int m = 0; m < 12; m++) g->aAvePET[m] = s_to_d(s[1 + m]); }
+    else if (c == ":MonthlyAveTemperature") { for (int m = 0; m < 12; m++) g->aAveTemp[m] = s_to_d(s[1 + m]); }
+    else if (c == ":MonthlyMinTemperature") { for (int m = 0; m < 12; m++) g->aMinTemp[m] = s_to_d(s[1 + m]); }
+    else if (c == ":MonthlyMaxTemperature") { for (int m = 0; m < 12; m++) g->aMaxTemp[m] = s_to_d(s[1 + m]); }
+    else if (c == ":MultiData") ParseMultiData(p, g, Options);
+    else if (c == ":Data") ParseData(p, g, s, Options);
+    else if (c == ":RedirectToFile") {
+      std::string f = CorrectForRelativePath(s[1], thisfile);
+      CParser q(f);
+      ExitGracefullyIf(!q.ok(), "ParseTimeSeriesFile: cannot open redirect file " + f);
+      ParseGaugeBody(q, g, Options, f);  // returns at EOF
+    } else if (c == ":FileType" || c == ":WrittenBy" || c == ":CreationDate") {
+    } else ExitGracefully("ParseTimeSeriesFile: command " + c + " inside :Gauge is not supported by the B200 build");
+  }
+}
+static void SkipBlock(CParser &p, const char *endtok) {
+  std::vector<std::string> s;
+  while (p.Tokenize(s)) if (!s.empty() && s[0] == endtok) return;
+}
+static void ParseTimeSeriesFile(CModel *pModel, const optStruct &Options, const std::string &filename, bool top) {
+  CParser p(filename);
+  ExitGracefullyIf(!p.ok(), "ParseTimeSeriesFile: cannot open " + filename);
+  std::vector<std::string> s;
+  while (p.Tokenize(s)) {
+    if (s.empty()) continue;
+    const std::string &c = s[0];
+    if (c == ":FileType" || c == ":WrittenBy" || c == ":CreationDate") continue;
+    if (c == ":Gauge") {
+      CGauge *g = new CGauge(s.size() > 1 ? s[1] : ("Gauge" + std::to_string(pModel->GetNumGauges() + 1)));
+      ParseGaugeBody(p, g, Options, filename);
+      pModel->AddGauge(g);
+      continue;
+    }
+    if (c == ":RedirectToFile") { ParseTimeSeriesFile(pModel, Options, CorrectForRelativePath(s[1], filename), false); continue; }
+    if (c == ":ObservationData") { SkipBlock(p, ":EndObservationData"); continue; }   // observations do not enter the balance
+    if (c == ":ObservationWeights") { SkipBlock(p, ":EndObservationWeights"); continue; }
+    ExitGracefully("ParseTimeSeriesFile: command " + c + " (line " + std::to_string(p.line()) + " of " + filename + ") is not supported by the B200 build");
+  }
+  (void)top;
+}
+
+// ================================================================================================ .rve
+static void ParseEnsembleFile(CModel *pModel, optStruct &Options) {
+  if (Options.rve_filename.empty()) return;
+  CParser p(Options.rve_filename);
+  if (!p.ok()) { ExitGracefullyIf(Options.ensemble != ENSEMBLE_NONE, "ParseEnsembleFile: cannot open " + Options.rve_filename); return; }
+  std::vector<std::string> s;
+  while (p.Tokenize(s)) {
+    if (s.empty()) continue;
+    const std::string &c = s[0];
+    if (c == ":FileType" || c == ":WrittenBy" || c == ":CreationDate" || c == ":OutputDirectoryFormat" || c == ":RunNameFormat") continue;
+    if (c == ":ParameterDistributions") {  // src/ParseEnsembleFile.cpp:150-215
+      while (p.Tokenize(s)) {
+        if (s.empty() || s[0] == ":Attributes" || s[0] == ":Units") continue;
+        if (s[0] == ":EndParameterDistributions") break;
+        // [param_name] [class_type] [class_name] [dist_type] [distpar1] [distpar2] {distpar3}
+        ExitGracefullyIf(s.size() < 6, "ParseEnsembleFile: bad :ParameterDistributions row");
+        param_dist d; d.param_name = s[0];
+        std::string ct = StringToUppercase(s[1]);
+        if (ct == "SOIL") d.param_class = CLASS_SOIL; else if (ct == "VEGETATION") d.param_class = CLASS_VEGETATION;
+        else if (ct == "LANDUSE") d.param_class = CLASS_LANDUSE; else if (ct == "TERRAIN") d.param_class = CLASS_TERRAIN;
+        else if (ct == "GLOBALS" || ct == "GLOBAL") d.param_class = CLASS_GLOBAL;
+        else { ExitGracefully("ParseEnsembleFile: invalid parameter class in :ParameterDistributions"); d.param_class = CLASS_GLOBAL; }
+        d.class_group = s[2];
+        std::string dt = StringToUppercase(s[3]);
+        if (dt == "DIST_UNIFORM" || dt == "UNIFORM") d.distribution = 0;
+        else if (dt == "DIST_NORMAL" || dt == "NORMAL" || dt == "DIST_GAUSSIAN") d.distribution = 1;
+        else if (dt == "DIST_LOGNORMAL" || dt == "LOGNORMAL") d.distribution = 2;
+        else if (dt == "DIST_GAMMA" || dt == "GAMMA") d.distribution = 3;
+        else { ExitGracefully("ParseEnsembleFile: invalid distribution type"); d.distribution = 0; }
+        d.distpar[0] = s_to_d(s[4]); d.distpar[1] = s_to_d(s[5]); d.distpar[2] = (s.size() > 6) ? s_to_d(s[6]) : 0.0;
+        d.default_val = 0.0;
+        pModel->param_dists.push_back(d);
+      }
+      continue;
+    }
+    ExitGracefully("ParseEnsembleFile: command " + c + " is not supported by the B200 build");
+  }
+}
+
+// ================================================================================================ drivers
+bool ParseInputFiles(CModel *&pModel, optStruct &Options) {
+  pModel = NULL;
+  ParseMainInputFile(pModel, Options);
+  ParseClassPropertiesFile(pModel, Options);
+  ParseHRUPropsFile(pModel, Options);
+  ParseTimeSeriesFile(pModel, Options, Options.rvt_filename, true);
+  if (Options.ensemble != ENSEMBLE_NONE) ParseEnsembleFile(pModel, Options);
+  for (int j = 0; j < pModel->GetNumProcesses(); j++) pModel->GetProcess(j)->Initialize();
+  return true;
+}
+
+bool ParseInitialConditions(CModel *&pModel, const optStruct &Options) {
+  pModel->AllocateInitialState();
+  if (Options.rvc_filename.empty()) return true;
+  CParser p(Options.rvc_filename);
+  if (!p.ok()) return true;  // reference: .rvc is optional (all-zero initial state)
+  const int NS = pModel->GetNumStateVars(), nH = pModel->GetNumHRUs();
+  std::vector<std::string> s;
+  while (p.Tokenize(s)) {
+    if (s.empty()) continue;
+    const std::string &c = s[0];
+    if (c == ":FileType" || c == ":WrittenBy" || c == ":CreationDate" || c == ":TimeStamp") continue;
+    if (c == ":UniformInitialConditions") {
+      int lay; sv_type t = pModel->StringToSVType(s[1], lay, false);
+      int i = (t == RVN_SV_NTYPES) ? DOESNT_EXIST : pModel->GetStateVarIndex(t, lay);
+      if (i == DOESNT_EXIST) { WriteWarning("Initial conditions specified for state variable not in model (" + s[1] + ")"); continue; }
+      for (int k = 0; k < nH; k++) pModel->SetInitialStateVar(k, i, s_to_d(s[2]));
+      continue;
+    }
+    if (c == ":HRUStateVariableTable") {
+      std::vector<int> idx;
+      while (p.Tokenize(s)) {
+        if (s.empty() || s[0] == ":Units") continue;
+        if (s[0] == ":EndHRUStateVariableTable") break;
+        if (s[0] == ":Attributes") {
+          idx.clear();
+          for (size_t i = 1; i < s.size(); i++) {
+            int lay; sv_type t = pModel->StringToSVType(s[i], lay, false);
+            idx.push_back((t == RVN_SV_NTYPES) ? DOESNT_EXIST : pModel->GetStateVarIndex(t, lay));
+          }
+          continue;
+        }
+        long long id = s_to_ll(s[0]);
+        int k = -1;
+        for (int kk = 0; kk < nH; kk++) if (pModel->GetHydroUnit(kk)->ID == id) { k = kk; break; }
+        if (k < 0) continue;
+        for (size_t i = 0; i < idx.size() && i + 1 < s.size(); i++) if (idx[i] >= 0) pModel->SetInitialStateVar(k, idx[i], s_to_d(s[i + 1]));
+      }
+      continue;
+    }
+    if (c == ":InitialConditions") {  // one value per HRU (or a single value for all)
+      int lay; sv_type t = pModel->StringToSVType(s[1], lay, false);
+      int i = (t == RVN_SV_NTYPES) ? DOESNT_EXIST : pModel->GetStateVarIndex(t, lay);
+      std::vector<double> v;
+      while (p.Tokenize(s)) {
+        if (s.empty()) continue;
+        if (s[0] == ":EndInitialConditions") break;
+        for (size_t q = 0; q < s.size(); q++) v.push_back(s_to_d(s[q]));
+      }
+      if (i >= 0) for (int k = 0; k < nH && k < (int)v.size(); k++) pModel->SetInitialStateVar(k, i, v[k]);
+      continue;
+    }
+    if (c == ":BasinInitialConditions") {
+      while (p.Tokenize(s)) {
+        if (s.empty() || s[0] == ":Attributes" || s[0] == ":Units") continue;
+        if (s[0] == ":EndBasinInitialConditions") break;
+        int pb = pModel->GetSubBasinIndex(s_to_ll(s[0]));
+        ExitGracefullyIf(pb < 0, "ParseInitialConditionsFile: bad basin index in :BasinInitialConditions (.rvc file)");
+        pModel->GetSubBasin(pb)->SetQout(s_to_d(s[1]));
+      }
+      continue;
+    }
+    ExitGracefully("ParseInitialConditions: command " + c + " is not supported by the B200 build");
+  }
+  (void)NS;
+  return true;
+}

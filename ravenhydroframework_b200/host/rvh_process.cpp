@@ -1,0 +1,296 @@
+// rvh_process.cpp -- host half of the process plugins: state-variable registration order, connection
+// lists and conditions exactly as the reference constructs them while parsing :HydrologicProcesses
+// (src/ParseInput.cpp case 200..), so that the SV catalogue and connection tables are integer-identical
+// to the reference build.  Rates are computed on the device (csrc/rvn_processes.cuh).
+#include "rvh_process.h"
+
+rvn_hru_type StringToHRUType(const std::string &sin) {
+  std::string s = StringToUppercase(sin);
+  if (s == "GLACIER") return RVN_HRU_GLACIER;
+  if (s == "LAKE") return RVN_HRU_LAKE;
+  if (s == "WATER") return RVN_HRU_WATER;
+  if (s == "ROCK") return RVN_HRU_ROCK;
+  if (s == "WETLAND") return RVN_HRU_WETLAND;
+  if (s == "STANDARD") return RVN_HRU_STANDARD;
+  if (s == "MASKED_GLACIER") return RVN_HRU_MASKED_GLACIER;
+  ExitGracefully("StringToHRUType: unrecognized HRU type " + sin);
+  return RVN_HRU_STANDARD;
+}
+
+bool CHydroProcessABC::ShouldApply(const CHydroUnit *pHRU) const {
+  if (!pHRU->IsEnabled()) return false;
+  for (size_t i = 0; i < _conditions.size(); i++) {
+    const condition &c = _conditions[i];
+    if (c.basis == BASIS_HRU_TYPE) {
+      rvn_hru_type typ2 = StringToHRUType(c.data);
+      if ((c.compare_method == COMPARE_IS_EQUAL) && (pHRU->GetHRUType() != typ2)) return false;
+      if ((c.compare_method == COMPARE_NOT_EQUAL) && (pHRU->GetHRUType() == typ2)) return false;
+    } else if (c.basis == BASIS_LANDCLASS) {
+      const std::string &nm = pModel->lu_classes[pHRU->lu_class].tag;
+      if ((c.data != nm) && (c.compare_method == COMPARE_IS_EQUAL)) return false;
+      if ((c.data == nm) && (c.compare_method == COMPARE_NOT_EQUAL)) return false;
+    } else if (c.basis == BASIS_VEGETATION) {
+      const std::string &nm = pModel->veg_classes[pHRU->veg_class].tag;
+      if ((c.data != nm) && (c.compare_method == COMPARE_IS_EQUAL)) return false;
+      if ((c.data == nm) && (c.compare_method == COMPARE_NOT_EQUAL)) return false;
+    } else {
+      ExitGracefully("CHydroProcessABC::ShouldApply: HRU_GROUP conditions are not supported by the B200 build yet");
+    }
+  }
+  return true;
+}
+void CHydroProcessABC::AddCondition(condition_basis basis, comparison cmp, const std::string &data) {
+  condition c; c.basis = basis; c.compare_method = cmp; c.data = data;
+  _conditions.push_back(c);
+}
+void CHydroProcessABC::Redirect(int toSVindex, int newToSVindex) {
+  bool found = false;
+  for (size_t q = 0; q < iTo.size(); q++)
+    if (iTo[q] == toSVindex) { iTo[q] = newToSVindex; found = true; }
+  ExitGracefullyIf(!found, "CHydroProcessABC::Redirect: state variable in :-->RedirectFlow command not a recipient of the preceding process");
+}
+
+void CmvGeneric::Compile(rvn_process &rec) const {
+  rec.op = (int32_t)_op;
+  rec.nconn = GetNumConnections();
+  rec.conn0 = 0;
+  for (int i = 0; i < 5; i++) rec.ia[i] = _ia[i];
+  rec.da[0] = _da[0]; rec.da[1] = _da[1];
+}
+
+// ---- Precipitation ---------------------------------------------------------------------------------
+void CmvPrecipitation::GetParticipatingStateVarList(sv_type *aSV, int *aLev, int &nSV) {
+  nSV = 1; aSV[0] = RVN_SV_ATMOS_PRECIP; aLev[0] = DOESNT_EXIST;
+}
+void CmvPrecipitation::Initialize() {
+  int iAtmos = pModel->GetStateVarIndex(RVN_SV_ATMOS_PRECIP);
+  ExitGracefullyIf(pModel->StateVarExists(RVN_SV_ICE_THICKNESS), "CmvPrecipitation: ICE_THICKNESS (frozen lake) connections are not supported yet");
+  DynamicSpecifyConnections(13);
+  const sv_type tgt[11] = {RVN_SV_PONDED_WATER, RVN_SV_CANOPY, RVN_SV_CANOPY_SNOW, RVN_SV_DEPRESSION, RVN_SV_ATMOSPHERE, RVN_SV_SNOW,
+                           RVN_SV_SNOW_LIQ, RVN_SV_SNOW_DEFICIT, RVN_SV_NEW_SNOW, RVN_SV_NTYPES /*lake*/, RVN_SV_SURFACE_WATER};
+  for (int q = 0; q < 11; q++) {
+    iFrom[q] = iAtmos;
+    iTo[q] = (q == 9) ? pModel->GetLakeStorageIndex() : pModel->GetStateVarIndex(tgt[q]);
+  }
+  iFrom[11] = iTo[11] = pModel->GetStateVarIndex(RVN_SV_COLD_CONTENT);
+  iFrom[12] = iTo[12] = pModel->GetStateVarIndex(RVN_SV_SNOW_DEPTH);
+  for (int q = 0; q < 13; q++) {  // dummy slots for missing state variables
+    if (iTo[q] == DOESNT_EXIST) iTo[q] = iAtmos;
+    if (iFrom[q] == DOESNT_EXIST) iFrom[q] = iAtmos;
+  }
+}
+
+// ---- Convolution -------------------------------------------------------------------------------------
+CmvConvolution::CmvConvolution(rvn_convol_type type, int to_index, CModel *pM, int conv_index)
+    : CmvGeneric("Convolve", RVN_OP_CONVOLVE, pM), _type(type), _conv_index(conv_index) {
+  const int N = MAX_CONVOL_STORES;
+  DynamicSpecifyConnections(2 * N + 1);
+  iFrom[0] = iTo[0] = pModel->GetStateVarIndex(RVN_SV_CONV_STOR, 0 + conv_index * N);
+  for (int i = 0; i < N; i++) {
+    iFrom[i + 1] = pModel->GetStateVarIndex(RVN_SV_CONV_STOR, i + conv_index * N);
+    iTo[i + 1] = to_index;
+    if (i < N - 1) {
+      iFrom[N + i + 1] = pModel->GetStateVarIndex(RVN_SV_CONV_STOR, i + conv_index * N);
+      iTo[N + i + 1] = pModel->GetStateVarIndex(RVN_SV_CONV_STOR, i + 1 + conv_index * N);
+    }
+  }
+  iFrom[2 * N] = iTo[2 * N] = pModel->GetStateVarIndex(RVN_SV_CONVOLUTION, conv_index);
+  SetIntArg(0, conv_index);
+  SetIntArg(1, to_index);
+  SetIntArg(2, iFrom[1]);
+  SetIntArg(3, iFrom[2 * N]);
+  SetIntArg(4, (int)type);
+  // the device kernel streams the stores; they must be contiguous in the catalogue
+  for (int i = 1; i < N; i++)
+    ExitGracefullyIf(iFrom[i + 1] != iFrom[1] + i, "CmvConvolution: CONV_STOR state variables are not contiguous");
+}
+void CmvConvolution::GetParticipatingStateVarList(rvn_convol_type, sv_type *aSV, int *aLev, int &nSV, int conv_index) {
+  const int N = MAX_CONVOL_STORES;
+  nSV = N + 1;
+  for (int i = 0; i < N; i++) { aSV[i] = RVN_SV_CONV_STOR; aLev[i] = conv_index * N + i; }
+  aSV[N] = RVN_SV_CONVOLUTION; aLev[N] = conv_index;
+}
+double CmvConvolution::LocalCumulDist(double t, const surface_struct &S) const {
+  if (_type == RVN_CONVOL_GR4J_1) {
+    double x4 = S.v[RVN_LU_GR4J_X4];
+    return rvh_min(pow(t / x4, 2.5), 1.0);
+  } else if (_type == RVN_CONVOL_GR4J_2) {
+    double x4 = S.v[RVN_LU_GR4J_X4];
+    if (t / x4 < 1.0) return 0.5 * pow(t / x4, 2.5);
+    else if (t / x4 < 2.0) return 1.0 - 0.5 * pow(2 - t / x4, 2.5);
+    else return 1.0;
+  } else if (_type == RVN_CONVOL_GAMMA) {
+    return GammaCumDist(t, S.v[RVN_LU_GAMMA_SHAPE], S.v[RVN_LU_GAMMA_SCALE]);
+  } else if (_type == RVN_CONVOL_GAMMA_2) {
+    return GammaCumDist(t, S.v[RVN_LU_GAMMA_SHAPE2], S.v[RVN_LU_GAMMA_SCALE2]);
+  }
+  return 1.0;
+}
+void CmvConvolution::GenerateUnitHydrograph(const surface_struct &S, const optStruct &Options, double *aUnitHydro, int &N) const {
+  double tstep = Options.timestep, max_time = 0;
+  if (_type == RVN_CONVOL_GR4J_1) max_time = S.v[RVN_LU_GR4J_X4];
+  else if (_type == RVN_CONVOL_GR4J_2) max_time = 2 * S.v[RVN_LU_GR4J_X4];
+  else if (_type == RVN_CONVOL_GAMMA) max_time = 4.5 * pow(S.v[RVN_LU_GAMMA_SHAPE], 0.6) / S.v[RVN_LU_GAMMA_SCALE];
+  else if (_type == RVN_CONVOL_GAMMA_2) max_time = 4.5 * pow(S.v[RVN_LU_GAMMA_SHAPE2], 0.6) / S.v[RVN_LU_GAMMA_SCALE2];
+  ExitGracefullyIf(!(max_time > 0.0), "CmvConvolution::GenerateUnitHydrograph: negative or zero duration of unit hydrograph (bad GR4J_x4, or GAMMA_SHAPE/GAMMA_SCALE)");
+  double sum = 0;
+  max_time = rvh_min(MAX_CONVOL_STORES * tstep, max_time);
+  N = (int)(ceil(max_time / tstep));
+  if (N == 0) N = 1;
+  for (int n = 0; n < N; n++) {
+    aUnitHydro[n] = LocalCumulDist((n + 1) * tstep, S) - sum;
+    sum += aUnitHydro[n];
+  }
+  ExitGracefullyIf(sum == 0.0, "CmvConvolution::GenerateUnitHydrograph: bad unit hydrograph constructed");
+  for (int n = 0; n < N; n++) aUnitHydro[n] /= sum;
+  for (int n = N; n < MAX_CONVOL_STORES; n++) aUnitHydro[n] = 0.0;
+}
+
+// ---- factory -------------------------------------------------------------------------------------------
+static void AddSV1(CModel *pM, sv_type t, int lev = DOESNT_EXIST) { pM->AddStateVariables(&t, &lev, 1); }
+static void AddSVs(CModel *pM, const std::vector<std::pair<sv_type, int> > &l) {
+  for (size_t i = 0; i < l.size(); i++) AddSV1(pM, l[i].first, l[i].second);
+}
+typedef std::pair<sv_type, int> SVL;
+static int SoilLayerOf(CModel *pM, int i) { return (pM->GetStateVarType(i) == RVN_SV_SOIL) ? pM->GetStateVarLayer(i) : DOESNT_EXIST; }
+
+CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel *pM, const optStruct &Options) {
+  (void)Options;
+  const std::string &cmd = s[0];
+  const int Len = (int)s.size();
+  const int iAtmos = pM->GetStateVarIndex(RVN_SV_ATMOSPHERE);
+  const int iSW = pM->GetStateVarIndex(RVN_SV_SURFACE_WATER);
+  const int iPond = pM->GetStateVarIndex(RVN_SV_PONDED_WATER);
+  auto need = [&](int n) { ExitGracefullyIf(Len < n, "ParseMainInputFile: improper format of " + cmd + " command"); };
+
+  if (cmd == ":Precipitation") {  // src/ParseInput.cpp case 212
+    need(4);
+    AddSV1(pM, RVN_SV_ATMOS_PRECIP);
+    return new CmvPrecipitation(pM);
+  }
+  if (cmd == ":SnowBalance") {  // case 209; connections src/SnowBalance.cpp:31-176
+    need(4);
+    CmvGeneric *p = NULL;
+    if (s[1] == "SNOBAL_HMETS") {
+      AddSVs(pM, {SVL(RVN_SV_SNOW, -1), SVL(RVN_SV_SNOW_LIQ, -1), SVL(RVN_SV_PONDED_WATER, -1), SVL(RVN_SV_CUM_SNOWMELT, -1)});
+      int iSnow = pM->GetStateVarIndex(RVN_SV_SNOW), iSL = pM->GetStateVarIndex(RVN_SV_SNOW_LIQ), iCM = pM->GetStateVarIndex(RVN_SV_CUM_SNOWMELT);
+      p = new CmvGeneric("SnowBalance", RVN_OP_SNOBAL_HMETS, pM);
+      p->Connect(iSnow, iSL); p->Connect(iSnow, iPond); p->Connect(iSL, iPond); p->Connect(iSL, iSnow); p->Connect(iCM, iCM);
+    } else if (s[1] == "SNOBAL_SIMPLE_MELT") {
+      AddSV1(pM, RVN_SV_SNOW);
+      int to = pM->ParseSVTypeIndex(s[3]);
+      p = new CmvGeneric("SnowBalance", RVN_OP_SNOBAL_SIMPLE_MELT, pM);
+      p->Connect(pM->GetStateVarIndex(RVN_SV_SNOW), to);
+    } else if (s[1] == "SNOBAL_CEMA_NIEGE" || s[1] == "SNOBAL_CEMA_NEIGE") {
+      AddSVs(pM, {SVL(RVN_SV_SNOW, -1), SVL(RVN_SV_PONDED_WATER, -1), SVL(RVN_SV_SNOW_COVER, -1)});
+      int iSnow = pM->GetStateVarIndex(RVN_SV_SNOW), iSC = pM->GetStateVarIndex(RVN_SV_SNOW_COVER);
+      p = new CmvGeneric("SnowBalance", RVN_OP_SNOBAL_CEMA_NEIGE, pM);
+      p->Connect(iSnow, iPond); p->Connect(iSC, iSC);
+    } else {
+      ExitGracefully("ParseMainInputFile: snow balance algorithm " + s[1] + " is not implemented in the B200 build");
+    }
+    return p;
+  }
+  if (cmd == ":Infiltration") {  // case 204; src/Infiltration.cpp:19-66
+    need(4);
+    AddSVs(pM, {SVL(RVN_SV_PONDED_WATER, -1), SVL(RVN_SV_SURFACE_WATER, -1)});
+    int iTop = pM->GetStateVarIndex(RVN_SV_SOIL, 0);
+    CmvGeneric *p = NULL;
+    if (s[1] == "INF_HMETS") {
+      AddSVs(pM, {SVL(RVN_SV_CONVOLUTION, 0), SVL(RVN_SV_CONVOLUTION, 1)});
+      p = new CmvGeneric("Infiltration", RVN_OP_INF_HMETS, pM);
+      p->Connect(iPond, iTop); p->Connect(iPond, iSW);
+      p->Connect(iPond, pM->GetStateVarIndex(RVN_SV_CONVOLUTION, 0)); p->Connect(iPond, pM->GetStateVarIndex(RVN_SV_CONVOLUTION, 1));
+    } else if (s[1] == "INF_HBV" || s[1] == "INF_GR4J") {
+      p = new CmvGeneric("Infiltration", s[1] == "INF_HBV" ? RVN_OP_INF_HBV : RVN_OP_INF_GR4J, pM);
+      p->Connect(iPond, iTop); p->Connect(iPond, iSW);
+    } else {
+      ExitGracefully("ParseMainInputFile: infiltration algorithm " + s[1] + " is not implemented in the B200 build");
+    }
+    return p;
+  }
+  if (cmd == ":Overflow" || cmd == ":-->Overflow") {  // case 222
+    need(4);
+    int from = pM->ParseSVTypeIndex(s[2]), to = pM->ParseSVTypeIndex(s[3]);
+    CmvGeneric *p = new CmvGeneric("Overflow", RVN_OP_OVERFLOW, pM);
+    p->Connect(from, to);
+    p->SetIntArg(0, SoilLayerOf(pM, from));
+    return p;
+  }
+  if (cmd == ":Flush") {  // case 221
+    need(4);
+    int from = pM->ParseSVTypeIndex(s[2]), to = pM->ParseSVTypeIndex(s[3]);
+    CmvGeneric *p = new CmvGeneric("Flush", RVN_OP_FLUSH, pM);
+    p->Connect(from, to);
+    p->SetDblArg(0, (Len >= 5) ? s_to_d(s[4]) : 1.0);
+    return p;
+  }
+  if (cmd == ":Split") {  // case 227
+    need(6);
+    int from = pM->ParseSVTypeIndex(s[2]), to1 = pM->ParseSVTypeIndex(s[3]), to2 = pM->ParseSVTypeIndex(s[4]);
+    CmvGeneric *p = new CmvGeneric("Split", RVN_OP_SPLIT, pM);
+    p->Connect(from, to1); p->Connect(from, to2);
+    p->SetDblArg(0, s_to_d(s[5]));
+    return p;
+  }
+  if (cmd == ":Baseflow") {  // case 201
+    need(4);
+    AddSV1(pM, RVN_SV_SURFACE_WATER);
+    int from = pM->ParseSVTypeIndex(s[2]);
+    rvn_opcode op = RVN_OP_NOP;
+    if (s[1] == "BASE_LINEAR") op = RVN_OP_BASE_LINEAR;
+    else if (s[1] == "BASE_POWER_LAW") op = RVN_OP_BASE_POWER_LAW;
+    else if (s[1] == "BASE_GR4J") op = RVN_OP_BASE_GR4J;
+    else ExitGracefully("ParseMainInputFile: baseflow algorithm " + s[1] + " is not implemented in the B200 build");
+    CmvGeneric *p = new CmvGeneric("Baseflow", op, pM);
+    p->Connect(from, iSW);
+    p->SetIntArg(0, SoilLayerOf(pM, from));
+    return p;
+  }
+  if (cmd == ":Percolation") {  // case 205
+    need(4);
+    int from = pM->ParseSVTypeIndex(s[2]), to = pM->ParseSVTypeIndex(s[3]);
+    rvn_opcode op = RVN_OP_NOP;
+    if (s[1] == "PERC_LINEAR") op = RVN_OP_PERC_LINEAR;
+    else if (s[1] == "PERC_CONSTANT") op = RVN_OP_PERC_CONSTANT;
+    else if (s[1] == "PERC_GR4J") op = RVN_OP_PERC_GR4J;
+    else if (s[1] == "PERC_GR4JEXCH") op = RVN_OP_PERC_GR4JEXCH;
+    else if (s[1] == "PERC_GR4JEXCH2") op = RVN_OP_PERC_GR4JEXCH2;
+    else ExitGracefully("ParseMainInputFile: percolation algorithm " + s[1] + " is not implemented in the B200 build");
+    CmvGeneric *p = new CmvGeneric("Percolation", op, pM);
+    p->Connect(from, to);
+    p->SetIntArg(0, SoilLayerOf(pM, from));
+    p->SetIntArg(1, SoilLayerOf(pM, to));
+    return p;
+  }
+  if (cmd == ":SoilEvaporation") {  // case 208; src/SoilEvaporation.cpp:21-100,244-313
+    need(4);
+    rvn_opcode op = RVN_OP_NOP;
+    if (s[1] == "SOILEVAP_ALL") op = RVN_OP_SOILEVAP_ALL;
+    else if (s[1] == "SOILEVAP_HBV") op = RVN_OP_SOILEVAP_HBV;
+    else if (s[1] == "SOILEVAP_GR4J") op = RVN_OP_SOILEVAP_GR4J;
+    else ExitGracefully("ParseMainInputFile: soil evaporation algorithm " + s[1] + " is not implemented in the B200 build");
+    AddSVs(pM, {SVL(RVN_SV_SOIL, 0), SVL(RVN_SV_ATMOSPHERE, -1), SVL(RVN_SV_AET, -1)});
+    CmvGeneric *p = new CmvGeneric("SoilEvaporation", op, pM);
+    int iAET = pM->GetStateVarIndex(RVN_SV_AET);
+    p->Connect(pM->GetStateVarIndex(RVN_SV_SOIL, 0), iAtmos);
+    p->Connect(iAET, iAET);
+    return p;
+  }
+  if (cmd == ":Convolve") {  // case 228
+    need(4);
+    rvn_convol_type ct = RVN_CONVOL_GR4J_1;
+    if (s[1] == "CONVOL_GR4J_1") ct = RVN_CONVOL_GR4J_1;
+    else if (s[1] == "CONVOL_GR4J_2") ct = RVN_CONVOL_GR4J_2;
+    else if (s[1] == "CONVOL_GAMMA") ct = RVN_CONVOL_GAMMA;
+    else if (s[1] == "CONVOL_GAMMA_2") ct = RVN_CONVOL_GAMMA_2;
+    else ExitGracefully("ParseMainInputFile: Unrecognized convolution process representation");
+    pM->IncrementConvolutionCount();
+    int conv_index = pM->GetNumConvolutionVariables() - 1;
+    sv_type tS[MAX_CONVOL_STORES + 1]; int tL[MAX_CONVOL_STORES + 1]; int tN;
+    CmvConvolution::GetParticipatingStateVarList(ct, tS, tL, tN, conv_index);
+    pM->AddStateVariables(tS, tL, tN);
+    return new CmvConvolution(ct, pM->ParseSVTypeIndex(s[3]), pM, conv_index);
+  }
+  return NULL;
+}

@@ -1,0 +1,89 @@
+// rvh_process.h -- host half of the hydrological-process plugin contract.
+//
+// Reference contract (src/HydroProcessABC.h:42-113): a process owns its iFrom[]/iTo[] connection
+// lists, optional conditions (ShouldApply), names the parameters and state variables it needs, and
+// returns rates through GetRatesOfChange()/ApplyConstraints().  In the B200 build the connection
+// lists, conditions and parameter/state lists stay on the host with the same accessors, while the two
+// rate functions are __device__ functions of the same names in csrc/rvn_processes.cuh, selected by the
+// opcode that Compile() emits.  (There is deliberately no host implementation of the rate functions:
+// no CPU fallback exists on the product path.)
+#ifndef RVH_PROCESS_H
+#define RVH_PROCESS_H
+#include "rvh_model.h"
+
+enum condition_basis { BASIS_HRU_TYPE, BASIS_HRU_GROUP, BASIS_LANDCLASS, BASIS_VEGETATION };
+enum comparison { COMPARE_IS_EQUAL, COMPARE_NOT_EQUAL };
+struct condition { condition_basis basis; comparison compare_method; std::string data; };
+enum class_type { CLASS_SOIL = 0, CLASS_VEGETATION = 1, CLASS_LANDUSE = 2, CLASS_TERRAIN = 3, CLASS_GLOBAL = 4 };
+
+rvn_hru_type StringToHRUType(const std::string &s);
+
+class CHydroProcessABC {
+public:
+  CHydroProcessABC(const std::string &process_name, CModel *pM) : _name(process_name), pModel(pM) {}
+  virtual ~CHydroProcessABC() {}
+  const int *GetFromIndices() const { return iFrom.data(); }
+  const int *GetToIndices() const { return iTo.data(); }
+  int  GetNumConnections() const { return (int)iFrom.size(); }
+  const std::string &GetProcessName() const { return _name; }
+  bool ShouldApply(const CHydroUnit *pHRU) const;                       // src/HydroProcessABC.cpp:290-328
+  void AddCondition(condition_basis basis, comparison cmp, const std::string &data);
+  void Redirect(int toSVindex, int newToSVindex);                       // src/HydroProcessABC.cpp:273-283
+  virtual void Initialize() {}
+  virtual void GetParticipatingParamList(std::vector<std::string> &aP, std::vector<class_type> &aPC) const {}
+  // emit the device opcode record; conn arrays are appended by the caller from iFrom/iTo
+  virtual void Compile(rvn_process &rec) const = 0;
+protected:
+  void DynamicSpecifyConnections(int n) { iFrom.assign(n, DOESNT_EXIST); iTo.assign(n, DOESNT_EXIST); }
+  std::string _name;
+  CModel *pModel;
+  std::vector<int> iFrom, iTo;
+  std::vector<condition> _conditions;
+};
+
+// generic single-opcode mover: used for every process whose host half is only "connections + opcode"
+class CmvGeneric : public CHydroProcessABC {
+public:
+  CmvGeneric(const std::string &pname, rvn_opcode op, CModel *pM) : CHydroProcessABC(pname, pM), _op(op) {
+    for (int i = 0; i < 5; i++) _ia[i] = DOESNT_EXIST;
+    _da[0] = _da[1] = 0.0;
+  }
+  void Connect(int from, int to) { iFrom.push_back(from); iTo.push_back(to); }
+  void SetIntArg(int i, int v) { _ia[i] = v; }
+  void SetDblArg(int i, double v) { _da[i] = v; }
+  void Compile(rvn_process &rec) const override;
+  rvn_opcode opcode() const { return _op; }
+protected:
+  rvn_opcode _op;
+  int _ia[5];
+  double _da[2];
+};
+
+// CmvPrecipitation: connections depend on which state variables exist once the whole process list is
+// parsed, so they are built in Initialize() (reference src/PartitionPrecip.cpp:28-73)
+class CmvPrecipitation : public CmvGeneric {
+public:
+  explicit CmvPrecipitation(CModel *pM) : CmvGeneric("Precipitation", RVN_OP_PRECIPITATION, pM) {}
+  void Initialize() override;
+  static void GetParticipatingStateVarList(sv_type *aSV, int *aLev, int &nSV);
+};
+
+// CmvConvolution (reference src/Convolution.cpp:31-64): 2N+1 connections, N=MAX_CONVOL_STORES
+class CmvConvolution : public CmvGeneric {
+public:
+  CmvConvolution(rvn_convol_type type, int to_index, CModel *pM, int conv_index);
+  static void GetParticipatingStateVarList(rvn_convol_type t, sv_type *aSV, int *aLev, int &nSV, int conv_index);
+  rvn_convol_type type() const { return _type; }
+  int conv_index() const { return _conv_index; }
+  // unit hydrograph for one land-use class (reference GenerateUnitHydrograph, src/Convolution.cpp:107-154)
+  void GenerateUnitHydrograph(const surface_struct &S, const optStruct &Options, double *aUnitHydro, int &N) const;
+private:
+  double LocalCumulDist(double t, const surface_struct &S) const;
+  rvn_convol_type _type;
+  int _conv_index;
+};
+
+// factory used by the .rvi reader: builds the process for a ':ProcessName ALGORITHM FROM TO' line,
+// registering its state variables in the reference's order.  Returns NULL for unknown commands.
+CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel *pModel, const optStruct &Options);
+#endif

@@ -1,0 +1,267 @@
+// rvh_util.cpp -- tokenizer, calendar arithmetic and the special functions the host needs to hoist
+// per-(class,date) work out of the per-HRU-per-step loop.  Formulas follow the reference so that the
+// hoisted values are the same doubles the reference recomputes for every HRU and step:
+//   JulianConvert / IsLeapYear / TimeDifference  src/CommonFunctions.cpp:273-380, 673-692
+//   gamma2 / IncompleteGamma / GammaCumDist      src/CommonFunctions.cpp:1588-1688
+//   TriCumDist                                   src/CommonFunctions.cpp:1699-1715
+//   InterpolateMo                                src/CommonFunctions.cpp:865-925
+//   CRadiation::DayAngle                         src/Radiation.cpp:423-430
+#include "rvh_common.h"
+#include <fstream>
+#include <sstream>
+#include <algorithm>
+
+static std::vector<std::string> g_warnings;
+void ExitGracefully(const std::string &statement) { throw RavenError(statement); }
+void WriteWarning(const std::string &warn, bool noisy) {
+  g_warnings.push_back(warn);
+  if (noisy) fprintf(stderr, "WARNING: %s\n", warn.c_str());
+}
+const std::vector<std::string> &RavenWarnings() { return g_warnings; }
+
+optStruct::optStruct()
+    : julian_start_day(0), julian_start_year(1666), duration(365), timestep(1.0), calendar(0), sol_method(0),
+      rainsnow(RVN_RAINSNOW_DINGMAN), pot_melt(RVN_POTMELT_DEGREE_DAY), evaporation(RVN_PET_HARGREAVES_1985),
+      ow_evaporation(RVN_PET_HARGREAVES_1985), evap_infill(RVN_PET_HARGREAVES_1985), ow_evap_infill(RVN_PET_HARGREAVES_1985),
+      orocorr_temp(RVN_OROCORR_NONE), orocorr_precip(RVN_OROCORR_NONE), orocorr_PET(RVN_OROCORR_NONE),
+      routing(RVN_ROUTE_STORAGECOEFF), catchment_routing(ROUTE_DUMP), interpolation(INTERP_NEAREST_NEIGHBOR),
+      month_interp_method(MONTHINT_LINEAR_MID), num_soillayers(-1), suppressCompetitiveET(false), snow_suppressPET(false),
+      allow_soil_overfill(false), direct_evap(false), silent(false), noisy(false), benchmarking(false),
+      ensemble(ENSEMBLE_NONE), random_seed(0), random_seed_set(false) {}
+
+// ---------------------------------------------------------------------------------- strings / files
+std::string StringToUppercase(const std::string &s) {
+  std::string r = s;
+  for (size_t i = 0; i < r.size(); i++) r[i] = (char)toupper((unsigned char)r[i]);
+  return r;
+}
+bool IsComment(const std::string &t) { return !t.empty() && (t[0] == '#' || t[0] == '*'); }
+double s_to_d(const std::string &s) { return atof(s.c_str()); }
+int s_to_i(const std::string &s) { return atoi(s.c_str()); }
+long long s_to_ll(const std::string &s) { return atoll(s.c_str()); }
+std::string DirName(const std::string &path) {
+  size_t p = path.find_last_of("/\\");
+  return (p == std::string::npos) ? std::string("") : path.substr(0, p + 1);
+}
+std::string CorrectForRelativePath(const std::string &filename, const std::string &relfile) {
+  if (!filename.empty() && (filename[0] == '/' || (filename.size() > 1 && filename[1] == ':'))) return filename;
+  return DirName(relfile) + filename;
+}
+
+CParser::CParser(const std::string &filename) : _pos(0), _line(0), _ok(false), _filename(filename) {
+  std::ifstream in(filename.c_str());
+  if (!in.good()) return;
+  _ok = true;
+  std::string l;
+  while (std::getline(in, l)) _lines.push_back(l);
+}
+bool CParser::Tokenize(std::vector<std::string> &tokens) {
+  tokens.clear();
+  if (_pos >= _lines.size()) return false;
+  const std::string &l = _lines[_pos++];
+  _line++;
+  std::string cur;
+  for (size_t i = 0; i <= l.size(); i++) {
+    char c = (i < l.size()) ? l[i] : ' ';
+    if (c == ' ' || c == '\t' || c == ',' || c == '\r' || c == '\n') {
+      if (!cur.empty()) { tokens.push_back(cur); cur.clear(); }
+    } else if ((c == '#' || c == '*') && cur.empty()) {
+      break;  // comment to end of line
+    } else {
+      cur.push_back(c);
+    }
+  }
+  if (!cur.empty()) tokens.push_back(cur);
+  return true;
+}
+
+// ---------------------------------------------------------------------------------- calendar
+bool IsLeapYear(int year, int calendar) {
+  (void)calendar;  // only the proleptic Gregorian calendar (reference default) is supported
+  return (((year % 4 == 0) && (year % 100 != 0)) || (year % 400 == 0));
+}
+
+void JulianConvert(double model_time, double start_date, int start_year, int calendar, time_struct &tt) {
+  // snap daily / hourly round-off exactly as the reference does before splitting the date
+  if ((model_time - floor(model_time)) > (1 - TIME_CORRECTION)) model_time = floor(model_time + TIME_CORRECTION);
+  if (model_time * HR_PER_DAY - floor(model_time * HR_PER_DAY) > (1.0 - TIME_CORRECTION) * HR_PER_DAY)
+    model_time = floor(HR_PER_DAY * (model_time + TIME_CORRECTION)) / HR_PER_DAY;
+
+  double ddate = start_date + model_time;
+  int dyear = start_year;
+  int leap = IsLeapYear(dyear, calendar) ? 1 : 0;
+  while (ddate >= (365 + leap)) {
+    ddate -= (365.0 + leap);
+    dyear++;
+    leap = IsLeapYear(dyear, calendar) ? 1 : 0;
+  }
+  static const int mdays[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+  int dmonth = 1;
+  double days = 31, sum = 31 - TIME_CORRECTION;
+  for (int m = 1; m < 12; m++) {
+    if (ddate >= sum) {
+      dmonth += 1;
+      days = mdays[m] + ((m == 1) ? leap : 0);
+      sum += days;
+    }
+  }
+  double dday = ddate - sum + days;
+  tt.model_time = model_time;
+  tt.julian_day = ddate;
+  tt.day_of_month = (int)(ceil(dday + REAL_SMALL));
+  if (tt.day_of_month == 0) tt.day_of_month = 1;
+  tt.month = dmonth;
+  tt.year = dyear;
+  tt.day_changed = false;
+  if ((model_time <= PRETTY_SMALL) || (tt.julian_day - floor(tt.julian_day + TIME_CORRECTION) < 0.001)) tt.day_changed = true;
+  char out[64];
+  snprintf(out, sizeof(out), "%4.4d-%2.2i-%2.2d", dyear, tt.month, tt.day_of_month);
+  tt.date_string = out;
+  tt.leap_yr = IsLeapYear(tt.year, calendar);
+}
+
+time_struct DateStringToTimeStruct(const std::string &sDate, const std::string &sTimeIn, int calendar) {
+  // yyyy-mm-dd (or yyyy/mm/dd) and hh:mm:ss[.ss]  (reference src/CommonFunctions.cpp:404-470)
+  time_struct tt;
+  std::string sTime = sTimeIn;
+  ExitGracefullyIf(sDate.length() != 10, "DateStringToTimeStruct: Invalid date format used: " + sDate);
+  if (sTime.length() == 7) sTime = "0" + sTime;  // h:mm:ss
+  ExitGracefullyIf(sTime.length() < 8, "DateStringToTimeStruct: Invalid time format used: " + sTime);
+  tt.year = s_to_i(sDate.substr(0, 4));
+  tt.month = s_to_i(sDate.substr(5, 2));
+  tt.day_of_month = s_to_i(sDate.substr(8, 2));
+  ExitGracefullyIf(tt.month > 12 || tt.month < 1, "DateStringToTimeStruct: Invalid month in date " + sDate);
+  static const int mdays[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+  int leap = IsLeapYear(tt.year, calendar) ? 1 : 0;
+  tt.julian_day = tt.day_of_month - 1;
+  for (int m = 0; m < tt.month - 1; m++) tt.julian_day += mdays[m] + ((m == 1) ? leap : 0);
+  int hr = s_to_i(sTime.substr(0, 2));
+  int mn = s_to_i(sTime.substr(3, 2));
+  double sec = s_to_d(sTime.substr(6));
+  tt.julian_day += (double)hr / HR_PER_DAY;
+  tt.julian_day += (double)mn / 1440.0;
+  tt.julian_day += sec / SEC_PER_DAY;
+  tt.model_time = 0.0;
+  tt.leap_yr = leap != 0;
+  tt.date_string = sDate;
+  return tt;
+}
+
+double TimeDifference(double jul_day1, int year1, double jul_day2, int year2, int calendar) {
+  double diff = jul_day2 - jul_day1;
+  int yr = year2 - 1;
+  while (yr >= year1) { diff += 365 + (IsLeapYear(yr, calendar) ? 1 : 0); yr--; }
+  yr = year2;
+  while (yr < year1) { diff -= 365 + (IsLeapYear(yr, calendar) ? 1 : 0); yr++; }
+  return diff;
+}
+
+double DayAngle(double julian_day, int year, int calendar) {
+  double leap = IsLeapYear(year, calendar) ? 1.0 : 0.0;
+  return 2.0 * RVH_PI * (julian_day / (365.0 + leap));
+}
+
+// ---------------------------------------------------------------------------------- special functions
+double gamma2(double x) {
+  // Taylor coefficients of 1/Gamma(z) (Zhang & Jin, "Computation of Special Functions", routine GAMMA),
+  // the same published series the reference uses.
+  static const double g[25] = {1.0, 0.5772156649015329, -0.6558780715202538, -0.420026350340952e-1, 0.1665386113822915,
+                               -0.421977345555443e-1, -0.9621971527877e-2, 0.7218943246663e-2, -0.11651675918591e-2,
+                               -0.2152416741149e-3, 0.1280502823882e-3, -0.201348547807e-4, -0.12504934821e-5,
+                               0.1133027232e-5, -0.2056338417e-6, 0.6116095e-8, 0.50020075e-8, -0.11812746e-8,
+                               0.1043427e-9, 0.77823e-11, -0.36968e-11, 0.51e-12, -0.206e-13, -0.54e-14, 0.14e-14};
+  double ga = 0, gr, r = 0, z;
+  if (x > 171.0) return 0.0;
+  if (x == (int)x) {
+    if (x > 0.0) {
+      ga = 1.0;
+      for (int i = 2; i < x; i++) ga *= i;
+    } else {
+      ExitGracefully("Gamma:negative integer values not allowed");
+    }
+  } else {
+    z = x;
+    r = 1.0;
+    int m = 0;
+    if (fabs(x) > 1.0) {
+      z = fabs(x);
+      m = (int)(z);
+      r = 1.0;
+      for (int k = 1; k <= m; k++) r *= (z - k);
+      z -= m;
+    }
+    gr = g[24];
+    for (int k = 23; k >= 0; k--) gr = gr * z + g[k];
+    ga = 1.0 / (gr * z);
+    if (fabs(x) > 1.0) {
+      ga *= r;
+      if (x < 0.0) ga = -RVH_PI / (x * ga * sin(RVH_PI * x));
+    }
+  }
+  return ga;
+}
+
+double IncompleteGamma(double x, double a) {
+  const int N = 100;
+  if (x <= 0) return 0.0;
+  if (x > 50) return IncompleteGamma(49.9, a);
+  double num = 1.0, sum = 0.0, prod = 1.0;
+  for (int n = 0; n < N; n++) {
+    if (n > 0) num *= x;
+    prod *= (a + n);
+    sum += num / prod;
+  }
+  return sum * pow(x, a) * exp(-x);
+}
+double GammaCumDist(double t, double alpha, double beta) { return IncompleteGamma(beta * t, alpha) / gamma2(alpha); }
+
+double TriCumDist(double t, double tc, double tp) {
+  double b = 2.0 / tc, m;
+  if (t < 0.0) return 0.0;
+  if (t <= tp) {
+    m = (b / tp);
+    return 0.5 * m * t * t;
+  } else if (t <= tc) {
+    m = -b / (tc - tp);
+    return tp / tc + b * (t - tp) + 0.5 * m * (t - tp) * (t - tp);
+  }
+  return 1.0;
+}
+
+double InterpolateMo(const double aVal[12], const time_struct &tt, month_interp method, const optStruct &Options) {
+  static const double DAYS_PER_MONTH[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+  double wt;
+  int leap = 0, mo, nextmo;
+  int day = tt.day_of_month, month = tt.month, year = tt.year;
+  if (method == MONTHINT_UNIFORM) return aVal[month - 1];
+  if (method == MONTHINT_LINEAR_FOM) {
+    mo = month - 1;
+    nextmo = mo + 1;
+    if (nextmo == 12) nextmo = 0;
+    leap = (IsLeapYear(year, Options.calendar) && (mo == 1)) ? 1 : 0;
+    wt = 1.0 - (double)(day) / (DAYS_PER_MONTH[mo] + leap);
+    return wt * aVal[mo] + (1 - wt) * aVal[nextmo];
+  }
+  double pivot = 0.0;
+  if (method == MONTHINT_LINEAR_21) pivot = 21;
+  else {
+    pivot = 0.5 * DAYS_PER_MONTH[month - 1];
+    if (IsLeapYear(year, Options.calendar) && (month == 2)) pivot += 0.5;
+  }
+  if (day <= pivot) {
+    mo = month - 2;
+    nextmo = mo + 1;
+    if (mo == -1) { mo = 11; nextmo = 0; }
+    leap = (IsLeapYear(year, Options.calendar) && (mo == 1)) ? 1 : 0;
+    wt = 1.0 - (double)(day + (DAYS_PER_MONTH[mo] + leap) - pivot) / (double)(DAYS_PER_MONTH[mo] + leap);
+  } else {
+    mo = month - 1;
+    nextmo = mo + 1;
+    int lastmo = mo - 1;
+    if (lastmo == -1) lastmo = 11;
+    if (nextmo == 12) nextmo = 0;
+    leap = (IsLeapYear(year, Options.calendar) && (lastmo == 1)) ? 1 : 0;
+    wt = 1.0 - (double)(day - pivot) / (double)(DAYS_PER_MONTH[lastmo] + leap);
+  }
+  return wt * aVal[mo] + (1 - wt) * aVal[nextmo];
+}
