@@ -285,11 +285,17 @@ int rvn_gpu_upload_forcings(rvn_gpu_model *m, const double *gauge_series, const 
 int rvn_gpu_run(rvn_gpu_model *m, int step0, int nsteps);
 int rvn_gpu_sync(rvn_gpu_model *m);
 
-/* per-step outputs recorded on the device during rvn_gpu_run:
- *   qout    [nsteps][member][nSB]    CSubBasin::GetOutflowRate() after the step
- *   wshed   [nsteps][member][4]      {_CumulInput, _CumulOutput, avg precip, total water storage [mm]}
- * record_every = 0 disables recording. */
-int rvn_gpu_set_recording(rvn_gpu_model *m, int max_steps);
+/* per-step outputs recorded on the device during rvn_gpu_run (max_steps records; 0 disables):
+ *   flags bit 0: qout  [rec][member][nSB]  CSubBasin::GetOutflowRate() after the step
+ *   flags bit 1: wshed [rec][member][4]    {_CumulInput, _CumulOutput, avg precip, total water storage [mm]}
+ *                (the WatershedStorage.csv columns, src/StandardOutput.cpp:745-785) */
+int rvn_gpu_set_recording(rvn_gpu_model *m, int max_steps, int flags);
+/* keep the derived per-HRU forcings of the last step on the device (off by default: 88 B/HRU/step) */
+int rvn_gpu_enable_forcing_output(rvn_gpu_model *m, int on);
+/* bracket every HRU-sweep launch with CUDA events so that rvn_gpu_last_run_stats can report sweep_ms */
+int rvn_gpu_set_kernel_timing(rvn_gpu_model *m, int on);
+/* {_CumulInput,_CumulOutput} [mm] per member: out[member][2] */
+int rvn_gpu_download_cumulative(rvn_gpu_model *m, double *cumul, int member0, int nmembers);
 int rvn_gpu_download_hydrographs(rvn_gpu_model *m, double *qout, int rec0, int nrec, int member0, int nmembers);
 int rvn_gpu_download_watershed(rvn_gpu_model *m, double *wshed, int rec0, int nrec, int member0, int nmembers);
 /* derived per-HRU forcings of the last executed step, host layout [member][hru][RVN_F_COUNT] */

@@ -1,0 +1,312 @@
+"""ctypes front end of the B200 build: host layer (libraven_b200.so) + CUDA engine (librvn_gpu.so).
+
+PyTorch is not needed for the engine itself; bench.py uses torch only for distributed plumbing and
+pinned host buffers.  Nothing here falls back to a CPU implementation: `GpuSimulation` raises if the
+engine reports no CUDA device.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+F_COUNT = 11  # RVN_F_COUNT
+FORCING_NAMES = ["PRECIP", "SNOW_FRAC", "TEMP_AVE", "TEMP_DAILY_AVE", "TEMP_DAILY_MIN", "TEMP_DAILY_MAX", "PET", "OW_PET",
+                 "POTENTIAL_MELT", "TEMP_MONTH_AVE", "PET_MONTH_AVE"]
+MAX_RIVER_SEGS = 50
+
+_engine = None
+_host = None
+
+
+class RavenError(RuntimeError):
+    pass
+
+
+def engine_lib():
+    """librvn_gpu.so (C ABI of include/rvn_gpu.h)."""
+    global _engine
+    if _engine is None:
+        path = os.path.join(HERE, "librvn_gpu.so")
+        if not os.path.exists(path):
+            raise RavenError("librvn_gpu.so is not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
+        lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        lib.rvn_gpu_last_error.restype = C.c_char_p
+        vp, i, dp = C.c_void_p, C.c_int, C.c_void_p
+        lib.rvn_gpu_create.argtypes = [vp, i, C.POINTER(vp)]
+        lib.rvn_gpu_destroy.argtypes = [vp]
+        lib.rvn_gpu_destroy.restype = None
+        lib.rvn_gpu_upload_state.argtypes = [vp, dp, i, i]
+        lib.rvn_gpu_download_state.argtypes = [vp, dp, i, i]
+        lib.rvn_gpu_upload_basin_state.argtypes = [vp, dp, dp, dp, dp, i, i]
+        lib.rvn_gpu_download_basin_state.argtypes = [vp, dp, dp, dp, dp, i, i]
+        lib.rvn_gpu_upload_params.argtypes = [vp, dp, dp, dp, i, i]
+        lib.rvn_gpu_upload_forcings.argtypes = [vp, dp, dp, i, i]
+        lib.rvn_gpu_run.argtypes = [vp, i, i]
+        lib.rvn_gpu_sync.argtypes = [vp]
+        lib.rvn_gpu_set_recording.argtypes = [vp, i, i]
+        lib.rvn_gpu_enable_forcing_output.argtypes = [vp, i]
+        lib.rvn_gpu_set_kernel_timing.argtypes = [vp, i]
+        lib.rvn_gpu_download_hydrographs.argtypes = [vp, dp, i, i, i, i]
+        lib.rvn_gpu_download_watershed.argtypes = [vp, dp, i, i, i, i]
+        lib.rvn_gpu_download_forcings.argtypes = [vp, dp, i, i]
+        lib.rvn_gpu_download_cumulative.argtypes = [vp, dp, i, i]
+        lib.rvn_gpu_avg_state.argtypes = [vp, dp, i, i]
+        lib.rvn_gpu_device_state_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        lib.rvn_gpu_last_run_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+        _engine = lib
+    return _engine
+
+
+def host_lib():
+    """libraven_b200.so (Raven-surface C++ host layer)."""
+    global _host
+    if _host is None:
+        engine_lib()
+        path = os.path.join(HERE, "libraven_b200.so")
+        if not os.path.exists(path):
+            raise RavenError("libraven_b200.so is not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
+        lib = C.CDLL(path)
+        vp = C.c_void_p
+        lib.rvh_last_error.restype = C.c_char_p
+        lib.rvh_model_load.restype = vp
+        lib.rvh_model_load.argtypes = [C.c_char_p, C.c_double]
+        lib.rvh_model_free.argtypes = [vp]
+        lib.rvh_model_free.restype = None
+        lib.rvh_model_flatten.restype = vp
+        lib.rvh_model_flatten.argtypes = [vp, C.c_int]
+        lib.rvh_model_dims.argtypes = [vp] + [C.POINTER(C.c_int)] * 5
+        lib.rvh_model_initial_state.argtypes = [vp, vp]
+        lib.rvh_model_basin_state.argtypes = [vp, vp, vp, vp, vp]
+        lib.rvh_model_sv_name.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
+        lib.rvh_model_process_info.argtypes = [vp, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.rvh_model_update_parameter.argtypes = [vp, C.c_int, C.c_char_p, C.c_char_p, C.c_double]
+        lib.rvh_model_flatten_member.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+        lib.rvh_model_num_param_dists.argtypes = [vp]
+        lib.rvh_model_param_dist.argtypes = [vp, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        lib.rvh_model_options.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.rvh_desc_info.argtypes = [vp, C.POINTER(C.c_int)]
+        _host = lib
+    return _host
+
+
+class RavenModel:
+    """A Raven model parsed from <base>.rvi/.rvh/.rvp/.rvt/.rvc by the C++ host layer (CModel)."""
+
+    def __init__(self, base, duration=0.0):
+        self.lib = host_lib()
+        self.h = self.lib.rvh_model_load(str(base).encode(), float(duration))
+        if not self.h:
+            raise RavenError(self.lib.rvh_last_error().decode())
+        d = [C.c_int() for _ in range(5)]
+        self.lib.rvh_model_dims(self.h, *[C.byref(x) for x in d])
+        self.nHRU, self.NS, self.nSB, self.nProc, self.nGauges = [x.value for x in d]
+        ts, du, seed, ens, nm = C.c_double(), C.c_double(), C.c_uint(), C.c_int(), C.c_int()
+        self.lib.rvh_model_options(self.h, C.byref(ts), C.byref(du), C.byref(seed), C.byref(ens), C.byref(nm))
+        self.timestep, self.duration, self.random_seed, self.ensemble_mode, self.num_members = ts.value, du.value, seed.value, ens.value, nm.value
+        self.desc = None
+        self.nMembers = 0
+
+    def close(self):
+        if self.h:
+            self.lib.rvh_model_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def flatten(self, n_members=1):
+        """Compile to rvn_model_desc (owned by the C++ model). Returns the descriptor pointer."""
+        p = self.lib.rvh_model_flatten(self.h, int(n_members))
+        if not p:
+            raise RavenError(self.lib.rvh_last_error().decode())
+        self.desc = p
+        self.nMembers = int(n_members)
+        info = (C.c_int * 8)()
+        self.lib.rvh_desc_info(p, info)
+        self.nSteps, self.max_nqin, self.max_nqlat, self.nCore, self.nConvProc, self.ptab_stride = [info[i] for i in range(6)]
+        return p
+
+    def sv_names(self):
+        buf = C.create_string_buffer(64)
+        out = []
+        for i in range(self.NS):
+            self.lib.rvh_model_sv_name(self.h, i, buf, 64)
+            out.append(buf.value.decode())
+        return out
+
+    def processes(self):
+        out = []
+        buf = C.create_string_buffer(64)
+        n = C.c_int()
+        f8, t8 = (C.c_int * 8)(), (C.c_int * 8)()
+        for j in range(self.nProc):
+            self.lib.rvh_model_process_info(self.h, j, buf, 64, C.byref(n), f8, t8)
+            m = min(n.value, 8)
+            out.append((buf.value.decode(), n.value, list(f8)[:m], list(t8)[:m]))
+        return out
+
+    def initial_state(self):
+        a = np.zeros((self.nHRU, self.NS))
+        self.lib.rvh_model_initial_state(self.h, a.ctypes.data)
+        return a
+
+    def basin_state(self):
+        assert self.desc, "flatten() first"
+        qin = np.zeros((self.nSB, self.max_nqin))
+        qlat = np.zeros((self.nSB, self.max_nqlat))
+        qout = np.zeros((self.nSB, MAX_RIVER_SEGS))
+        scal = np.zeros((self.nSB, 8))
+        if self.lib.rvh_model_basin_state(self.h, qin.ctypes.data, qlat.ctypes.data, qout.ctypes.data, scal.ctypes.data):
+            raise RavenError(self.lib.rvh_last_error().decode())
+        return qin, qlat, qout, scal
+
+    def update_parameter(self, class_type, pname, cname, value):
+        """CModel::UpdateParameter: class_type 0=soil 1=vegetation 2=landuse 3=terrain 4=global."""
+        if self.lib.rvh_model_update_parameter(self.h, int(class_type), pname.encode(), cname.encode(), float(value)):
+            raise RavenError(self.lib.rvh_last_error().decode())
+
+    def flatten_member(self, member):
+        """Refresh member's parameter row / convolution UHs from the current class values; returns raw pointers."""
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        if self.lib.rvh_model_flatten_member(self.h, int(member), C.byref(a), C.byref(b), C.byref(c)):
+            raise RavenError(self.lib.rvh_last_error().decode())
+        return a, b, c
+
+    def param_dists(self):
+        out = []
+        pn, cn = C.create_string_buffer(64), C.create_string_buffer(64)
+        ct, di = C.c_int(), C.c_int()
+        par = (C.c_double * 3)()
+        for i in range(self.lib.rvh_model_num_param_dists(self.h)):
+            self.lib.rvh_model_param_dist(self.h, i, pn, cn, 64, C.byref(ct), C.byref(di), par)
+            out.append(dict(name=pn.value.decode(), cls=cn.value.decode(), class_type=ct.value, dist=di.value, par=list(par)))
+        return out
+
+
+class GpuSimulation:
+    """Device-resident simulation of all members of a flattened model (rvn_gpu_* C ABI)."""
+
+    def __init__(self, model, n_members=1, device=0, upload_initial=True):
+        self.lib = engine_lib()
+        self.model = model
+        if model.desc is None or model.nMembers != n_members:
+            model.flatten(n_members)
+        self.E, self.nHRU, self.NS, self.nSB = n_members, model.nHRU, model.NS, model.nSB
+        self.nSteps = model.nSteps
+        h = C.c_void_p()
+        rc = self.lib.rvn_gpu_create(model.desc, int(device), C.byref(h))
+        if rc != 0:
+            raise RavenError("rvn_gpu_create: %s" % self.lib.rvn_gpu_last_error().decode())
+        self.h = h
+        self.step = 0
+        if upload_initial:
+            st = model.initial_state()
+            qin, qlat, qout, scal = model.basin_state()
+            for e in range(n_members):
+                self.upload_state(st, e, 1)
+                self._ck(self.lib.rvn_gpu_upload_basin_state(self.h, qin.ctypes.data, qlat.ctypes.data, qout.ctypes.data, scal.ctypes.data, e, 1))
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RavenError(self.lib.rvn_gpu_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rvn_gpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload_state(self, state, member0=0, nmembers=None):
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        if nmembers is None:
+            nmembers = state.shape[0] if state.ndim == 3 else 1
+        assert state.size == nmembers * self.nHRU * self.NS
+        self._ck(self.lib.rvn_gpu_upload_state(self.h, state.ctypes.data, member0, nmembers))
+
+    def download_state(self, member0=0, nmembers=None):
+        nmembers = self.E - member0 if nmembers is None else nmembers
+        out = np.empty((nmembers, self.nHRU, self.NS))
+        self._ck(self.lib.rvn_gpu_download_state(self.h, out.ctypes.data, member0, nmembers))
+        return out
+
+    def download_basin_state(self, member0=0, nmembers=None):
+        nmembers = self.E - member0 if nmembers is None else nmembers
+        m = self.model
+        qin = np.empty((nmembers, self.nSB, m.max_nqin)); qlat = np.empty((nmembers, self.nSB, m.max_nqlat))
+        qout = np.empty((nmembers, self.nSB, MAX_RIVER_SEGS)); scal = np.empty((nmembers, self.nSB, 8))
+        self._ck(self.lib.rvn_gpu_download_basin_state(self.h, qin.ctypes.data, qlat.ctypes.data, qout.ctypes.data, scal.ctypes.data, member0, nmembers))
+        return qin, qlat, qout, scal
+
+    def upload_member_params(self, member):
+        a, b, c = self.model.flatten_member(member)
+        self._ck(self.lib.rvn_gpu_upload_params(self.h, a, b, c, member, 1))
+
+    def upload_forcings(self, gauge_series, step0, nsteps):
+        """gauge_series [RVN_GF_COUNT][nGauges][nsteps] host array replacing steps step0..step0+nsteps."""
+        g = np.ascontiguousarray(gauge_series, dtype=np.float64)
+        self._ck(self.lib.rvn_gpu_upload_forcings(self.h, g.ctypes.data, None, step0, nsteps))
+
+    def set_recording(self, max_steps, hydrographs=True, watershed=True):
+        self._ck(self.lib.rvn_gpu_set_recording(self.h, int(max_steps), (1 if hydrographs else 0) | (2 if watershed else 0)))
+        self._rec = 0
+
+    def enable_forcing_output(self, on=True):
+        self._ck(self.lib.rvn_gpu_enable_forcing_output(self.h, 1 if on else 0))
+
+    def set_kernel_timing(self, on=True):
+        self._ck(self.lib.rvn_gpu_set_kernel_timing(self.h, 1 if on else 0))
+
+    def run(self, nsteps=-1, sync=True):
+        if nsteps < 0:
+            nsteps = self.nSteps - self.step
+        self._ck(self.lib.rvn_gpu_run(self.h, self.step, nsteps))
+        self.step += nsteps
+        if sync:
+            self._ck(self.lib.rvn_gpu_sync(self.h))
+
+    def sync(self):
+        self._ck(self.lib.rvn_gpu_sync(self.h))
+
+    def hydrographs(self, rec0, nrec, member0=0, nmembers=None):
+        nmembers = self.E - member0 if nmembers is None else nmembers
+        out = np.empty((nrec, nmembers, self.nSB))
+        self._ck(self.lib.rvn_gpu_download_hydrographs(self.h, out.ctypes.data, rec0, nrec, member0, nmembers))
+        return out
+
+    def watershed(self, rec0, nrec, member0=0, nmembers=None):
+        nmembers = self.E - member0 if nmembers is None else nmembers
+        out = np.empty((nrec, nmembers, 4))
+        self._ck(self.lib.rvn_gpu_download_watershed(self.h, out.ctypes.data, rec0, nrec, member0, nmembers))
+        return out
+
+    def forcings(self, member0=0, nmembers=None):
+        nmembers = self.E - member0 if nmembers is None else nmembers
+        out = np.empty((nmembers, self.nHRU, F_COUNT))
+        self._ck(self.lib.rvn_gpu_download_forcings(self.h, out.ctypes.data, member0, nmembers))
+        return out
+
+    def cumulative(self, member0=0, nmembers=None):
+        nmembers = self.E - member0 if nmembers is None else nmembers
+        out = np.empty((nmembers, 2))
+        self._ck(self.lib.rvn_gpu_download_cumulative(self.h, out.ctypes.data, member0, nmembers))
+        return out
+
+    def avg_state(self, member0=0, nmembers=None):
+        nmembers = self.E - member0 if nmembers is None else nmembers
+        out = np.empty((nmembers, self.NS))
+        self._ck(self.lib.rvn_gpu_avg_state(self.h, out.ctypes.data, member0, nmembers))
+        return out
+
+    def last_run_stats(self):
+        a, b, n = C.c_double(), C.c_double(), C.c_int64()
+        self._ck(self.lib.rvn_gpu_last_run_stats(self.h, C.byref(a), C.byref(b), C.byref(n)))
+        return dict(sweep_ms=a.value, total_ms=b.value, launches=n.value)

@@ -1,0 +1,69 @@
+// rvn_device.cuh -- device-side data model of the B200 engine (sm_100a, FP64 throughout).
+//
+// HBM layout (all FP64 unless noted; nHp = nHRU rounded up to 32 so that every row starts 256-B aligned):
+//   state   [member][sv][nHp]        SoA: a warp reading one state variable of 32 neighbouring HRUs
+//                                    touches 256 contiguous bytes (8 full sectors)
+//   swvol   [member][nHp]            surface-water volume handed to in-catchment routing [m3]
+//   forc    [member][RVN_F_COUNT][nHp]  derived forcings (written only when forcing output is enabled)
+//   ptab    [member][ptab_stride]    parameter rows (globals | land-use | vegetation | soil classes)
+//   conv_uh [member][nLU][nConv][50] hoisted convolution unit hydrographs, conv_n = their lengths
+//   basin   qin[member][nSB][max_nqin] qlat[..][max_nqlat] qout[..][50] scal[..][8]
+// Static, member-independent tables (HRU attributes, class handles, gauge series/weights, network
+// CSR, calendar) are stored once and shared by all members.
+#ifndef RVN_DEVICE_CUH
+#define RVN_DEVICE_CUH
+#include <stdint.h>
+#include "rvn_gpu.h"
+
+#define RVN_BS 128            // threads per CTA of the HRU sweep: one (member, HRU) pair per thread
+#define RVN_MAX_CORE 40       // max non-CONV_STOR state variables held in shared memory
+#define RVN_MAX_PROC 64
+#define RVN_MAX_PROG_CONN 256
+
+// process program + catalogue, copied into shared memory by every CTA (uniform reads -> broadcasts)
+struct DevProgram {
+  int32_t nProc, nCore, NS, nSoil;
+  rvn_options opt;
+  rvn_process proc[RVN_MAX_PROC];          // SV references translated to core slots (see below)
+  int16_t conn_from[RVN_MAX_PROG_CONN];     // core slots
+  int16_t conn_to[RVN_MAX_PROG_CONN];
+  int16_t slot_sv[RVN_MAX_CORE];            // core slot -> catalogue index
+  int8_t  slot_type[RVN_MAX_CORE];          // sv_type of slot
+  int8_t  slot_layer[RVN_MAX_CORE];
+  int8_t  slot_water[RVN_MAX_CORE];         // IsWaterStorage(type)
+  int16_t iSV[RVN_SV_NTYPES];               // first core slot of each SV type or -1
+  int16_t soil_slot[RVN_MAX_SOIL_LAYERS];   // core slot of SOIL[m]
+  int32_t glob_off, lu_off, veg_off, soil_off, ptab_stride;
+  int32_t nLU, nConv, nGauges, nSteps, record_forcings;
+};
+
+struct DevModel {
+  int32_t nH, nHp, nSB, E, NS, nCore;
+  // per-member arrays
+  double *state, *swvol, *forc, *ptab, *conv_uh;
+  int32_t *conv_n;
+  double *qin, *qlat, *qout, *scal, *cumul;      // cumul [member][2]
+  double *part_precip, *part_storage;             // [member][nBlocksX] block partial sums of the sweep
+  int32_t nBlocksX;
+  // shared static tables
+  const double *hru_area, *hru_elev, *hru_lat, *hru_slope, *hru_aspect;
+  const int32_t *hru_type, *hru_lu, *hru_veg, *hru_profile, *hru_sb, *hru_enabled;
+  const unsigned long long *apply_mask;
+  const int32_t *prof_class; const double *prof_thick;
+  const double *gauge_series, *gauge_const, *wt_precip, *wt_temp, *wt_all;
+  const rvn_time *times;
+  // network
+  const int32_t *sb_down, *sb_level, *sb_headwater, *sb_nseg, *sb_nqin, *sb_nqlat;
+  const int32_t *sb_hru_ptr, *sb_hru_idx;          // CSR: HRUs of each basin in HRU-index order
+  const int32_t *sb_up_ptr, *sb_up_idx;            // CSR: upstream basins, ascending index
+  const int32_t *level_ptr, *level_idx;            // basins grouped by level, deepest level first, ascending index inside
+  int32_t nLevels, max_nqin, max_nqlat;
+  const double *sb_area, *sb_rain_corr, *sb_snow_corr, *sb_temp_corr, *sb_musk_K, *sb_musk_X, *sb_K_reach;
+  const double *sb_unit_hydro, *sb_route_hydro;
+  double watershed_area;
+  // recording
+  double *rec_qout, *rec_wshed;                    // [rec][member][nSB], [rec][member][4]
+  int32_t rec_capacity, rec_flags;
+  const DevProgram *prog;
+};
+#endif

@@ -43,6 +43,16 @@ const rvn_model_desc *rvh_model_flatten(rvh_model *h, int nMembers) {
   return h->pModel->Flatten(h->Options, nMembers);
   RVH_CATCH(NULL)
 }
+// sizes a caller needs to allocate buffers for a flattened model: {nSteps,max_nqin,max_nqlat,nCore,nConvProc,ptab_stride,nMembers,nLU}
+int rvh_desc_info(const rvn_model_desc *d, int *out8) {
+  int ncore = 0;
+  for (int i = 0; i < d->NS; i++) if (d->sv_type[i] != RVN_SV_CONV_STOR) ncore++;
+  out8[0] = d->nSteps; out8[1] = d->max_nqin; out8[2] = d->max_nqlat; out8[3] = ncore; out8[4] = d->nConvProc; out8[5] = d->ptab_stride;
+  out8[6] = d->nMembers; out8[7] = d->nLU;
+  return 0;
+}
+const double *rvh_desc_gauge_series(const rvn_model_desc *d) { return d->gauge_series; }
+const int32_t *rvh_desc_conv_n(const rvn_model_desc *d) { return d->conv_n; }
 int rvh_model_dims(rvh_model *h, int *nHRU, int *NS, int *nSB, int *nProc, int *nGauges) {
   *nHRU = h->pModel->GetNumHRUs(); *NS = h->pModel->GetNumStateVars(); *nSB = h->pModel->GetNumSubBasins();
   *nProc = h->pModel->GetNumProcesses(); *nGauges = h->pModel->GetNumGauges();

@@ -1,0 +1,206 @@
+"""Synthetic Raven input sets (.rvi/.rvh/.rvp/.rvt/.rvc[/.rve]) for the BASELINE.json configurations.
+
+The files are plain Raven inputs: the same set is read by this package's C++ host layer and, in the
+parity tests, by the unmodified reference executable.  Watershed = heap-ordered binary tree of
+subbasins (downstream of p is p//2, outlet p=1) with `hru_per_sb` HRUs each; HRU attributes and the
+daily weather series are drawn from a seeded generator (no reference data is used).
+"""
+import math
+import os
+
+import numpy as np
+
+
+def weather(n_days, seed=1):
+    """Daily RAINFALL, SNOWFALL [mm/d], TEMP_DAILY_MIN, TEMP_DAILY_MAX [C], PET [mm/d] for a cold-region climate."""
+    rng = np.random.RandomState(seed)
+    doy = np.arange(n_days) % 365
+    tmean = 2.5 + 13.0 * np.sin(2 * np.pi * (doy - 110) / 365.0)
+    noise = np.zeros(n_days)
+    eps = rng.normal(0, 3.0, n_days)
+    for i in range(1, n_days):
+        noise[i] = 0.7 * noise[i - 1] + eps[i]
+    tmean = tmean + noise
+    tmin = tmean - rng.uniform(2.5, 8.0, n_days)
+    tmax = tmean + rng.uniform(2.5, 8.0, n_days)
+    wet = rng.uniform(0, 1, n_days) < 0.42
+    amount = rng.gamma(0.8, 6.0, n_days) * wet
+    snow_frac = np.clip((1.5 - tmean) / 3.0, 0.0, 1.0)
+    snow = amount * snow_frac
+    rain = amount - snow
+    pet = np.clip(0.18 * (tmean + 4.0), 0.0, None) * (0.6 + 0.4 * np.sin(2 * np.pi * (doy - 80) / 365.0) ** 2)
+    return np.round(rain, 4), np.round(snow, 4), np.round(tmin, 4), np.round(tmax, 4), np.round(pet, 4)
+
+
+HMETS_RVI = """# HMETS emulation, synthetic watershed (written by ravenhydroframework_b200.synth)
+:StartDate             2000-01-01 00:00:00
+:Duration              {duration}
+:TimeStep              1.0
+:Method                ORDERED_SERIES
+:PotentialMeltMethod   POTMELT_HMETS
+:RainSnowFraction      RAINSNOW_DATA
+:Evaporation           PET_DATA
+:CatchmentRoute        {catchment_route}
+:Routing               {routing}
+:SoilModel             SOIL_TWO_LAYER
+:SilentMode
+{extra}
+:Alias DELAYED_RUNOFF CONVOLUTION[1]
+:HydrologicProcesses
+  :SnowBalance     SNOBAL_HMETS    MULTIPLE       MULTIPLE
+  :Precipitation   RAVEN_DEFAULT   ATMOS_PRECIP   MULTIPLE
+  :Infiltration    INF_HMETS       PONDED_WATER   MULTIPLE
+    :Overflow      OVERFLOW_RAVEN  SOIL[0]        DELAYED_RUNOFF
+  :Baseflow        BASE_LINEAR     SOIL[0]        SURFACE_WATER
+  :Percolation     PERC_LINEAR     SOIL[0]        SOIL[1]
+    :Overflow      OVERFLOW_RAVEN  SOIL[1]        DELAYED_RUNOFF
+  :SoilEvaporation SOILEVAP_ALL    SOIL[0]        ATMOSPHERE
+  :Convolve        CONVOL_GAMMA    CONVOLUTION[0] SURFACE_WATER
+  :Convolve        CONVOL_GAMMA_2  DELAYED_RUNOFF SURFACE_WATER
+  :Baseflow        BASE_LINEAR     SOIL[1]        SURFACE_WATER
+:EndHydrologicProcesses
+"""
+
+HMETS_RVP = """# HMETS parameters (synthetic)
+:SoilClasses
+  :Attributes,
+  :Units,
+  TOPSOIL,
+  PHREATIC,
+:EndSoilClasses
+:LandUseClasses,
+  :Attributes,  IMPERM, FOREST_COV,
+  :Units,         frac,       frac,
+  FOREST,          0.0,        1.0,
+  OPEN,           0.05,        0.1,
+:EndLandUseClasses
+:VegetationClasses,
+  :Attributes,  MAX_HT, MAX_LAI, MAX_LEAF_COND,
+  :Units,            m,    none,      mm_per_s,
+  FOREST,            4,       5,             5,
+  GRASS,           0.5,       2,             5,
+:EndVegetationClasses
+:SoilProfiles
+  LAKE, 0
+  ROCK, 0
+  DEFAULT_P, 2, TOPSOIL, 0.3107, PHREATIC, 0.9162,
+  THIN_P,    2, TOPSOIL, 0.2200, PHREATIC, 0.6100,
+:EndSoilProfiles
+:GlobalParameter     SNOW_SWI_MIN 0.0464
+:GlobalParameter     SNOW_SWI_MAX 0.2462
+:GlobalParameter SWI_REDUCT_COEFF 0.0222
+:GlobalParameter         SNOW_SWI 0.05
+:SoilParameterList
+  :Parameters, POROSITY, PERC_COEFF, PET_CORRECTION, BASEFLOW_COEFF
+  :Units,             -,        1/d,              -,            1/d
+  TOPSOIL,          1.0,     0.0114,            1.0,         0.0243
+  PHREATIC,         1.0,        0.0,            0.0,         0.0069
+:EndSoilParameterList
+:LandUseParameterList
+  :Parameters, MIN_MELT_FACTOR, MAX_MELT_FACTOR, DD_MELT_TEMP, DD_AGGRADATION, REFREEZE_FACTOR, REFREEZE_EXP, DD_REFREEZE_TEMP, HMETS_RUNOFF_COEFF,
+  :Units,               mm/d/C,          mm/d/C,            C,           1/mm,          mm/d/C,            -,                C,                  -,
+  [DEFAULT],            1.2875,          6.7009,       2.3641,         0.0973,          2.6851,       0.3740,          -1.0919,             0.4739,
+  OPEN,                 1.6000,          7.9000,       1.8000,         0.0700,          2.1000,       0.4500,          -0.5000,             0.3900,
+:EndLandUseParameterList
+:LandUseParameterList
+  :Parameters, GAMMA_SHAPE, GAMMA_SCALE, GAMMA_SHAPE2, GAMMA_SCALE2,
+  :Units,                -,         1/d,            -,          1/d,
+  [DEFAULT],        9.5019,      0.2774,       6.3942,       0.6884,
+  OPEN,             5.1000,      0.6100,       4.2000,       0.9500,
+:EndLandUseParameterList
+:VegetationParameterList
+  :Parameters, RAIN_ICEPT_PCT, SNOW_ICEPT_PCT,
+  :Units,                   -,              -,
+  [DEFAULT],              0.0,            0.0,
+  FOREST,                0.06,           0.04,
+:EndVegetationParameterList
+{extra}
+"""
+
+HMETS_RVC = """# half-full soil stores
+:UniformInitialConditions SOIL[0] 155.36055
+:UniformInitialConditions SOIL[1] 458.09735
+"""
+
+# the 19 HMETS parameters CModel::UpdateParameter can reach, uniform +-20 %
+HMETS_DISTS = [
+    ("GAMMA_SHAPE", "LANDUSE", "FOREST", 9.5019), ("GAMMA_SCALE", "LANDUSE", "FOREST", 0.2774),
+    ("GAMMA_SHAPE2", "LANDUSE", "FOREST", 6.3942), ("GAMMA_SCALE2", "LANDUSE", "FOREST", 0.6884),
+    ("MIN_MELT_FACTOR", "LANDUSE", "FOREST", 1.2875), ("MAX_MELT_FACTOR", "LANDUSE", "FOREST", 6.7009),
+    ("DD_MELT_TEMP", "LANDUSE", "FOREST", 2.3641), ("DD_AGGRADATION", "LANDUSE", "FOREST", 0.0973),
+    ("SNOW_SWI_MIN", "GLOBALS", "ALL", 0.0464), ("SNOW_SWI_MAX", "GLOBALS", "ALL", 0.2462),
+    ("SWI_REDUCT_COEFF", "GLOBALS", "ALL", 0.0222), ("DD_REFREEZE_TEMP", "LANDUSE", "FOREST", -1.0919),
+    ("REFREEZE_FACTOR", "LANDUSE", "FOREST", 2.6851), ("REFREEZE_EXP", "LANDUSE", "FOREST", 0.3740),
+    ("PET_CORRECTION", "SOIL", "TOPSOIL", 1.0), ("HMETS_RUNOFF_COEFF", "LANDUSE", "FOREST", 0.4739),
+    ("PERC_COEFF", "SOIL", "TOPSOIL", 0.0114), ("BASEFLOW_COEFF", "SOIL", "TOPSOIL", 0.0243),
+    ("BASEFLOW_COEFF", "SOIL", "PHREATIC", 0.0069),
+]
+
+
+def _write(path, text):
+    with open(path, "w") as f:
+        f.write(text)
+
+
+def write_network(f, n_sb, hru_per_sb, rng, profile, lu_classes, veg_classes, soil_profiles, gauged_all=False):
+    f.write(":SubBasins\n  :Attributes NAME DOWNSTREAM_ID PROFILE REACH_LENGTH GAUGED\n  :Units none none none km none\n")
+    for p in range(1, n_sb + 1):
+        down = -1 if p == 1 else p // 2
+        reach = "_AUTO" if profile == "NONE" else "%.4f" % rng.uniform(5, 15)
+        f.write("  %d, sb%d, %d, %s, %s, %d\n" % (p, p, down, profile, reach, 1 if (p == 1 or gauged_all) else 0))
+    f.write(":EndSubBasins\n:HRUs\n  :Attributes AREA ELEVATION LATITUDE LONGITUDE BASIN_ID LAND_USE_CLASS VEG_CLASS SOIL_PROFILE AQUIFER_PROFILE TERRAIN_CLASS SLOPE ASPECT\n")
+    f.write("  :Units km2 m deg deg none none none none none none deg deg\n")
+    k = 1
+    for p in range(1, n_sb + 1):
+        for _ in range(hru_per_sb):
+            c = rng.randint(0, len(lu_classes))
+            f.write("  %d, %.4f, %.2f, %.5f, %.5f, %d, %s, %s, %s, [NONE], [NONE], %.3f, %.2f\n" % (
+                k, rng.uniform(0.5, 2.5), rng.uniform(600, 1400), rng.uniform(54, 55), rng.uniform(-123.5, -122.5), p,
+                lu_classes[c], veg_classes[c], soil_profiles[rng.randint(0, len(soil_profiles))], rng.uniform(0, 20), rng.uniform(0, 360)))
+            k += 1
+    f.write(":EndHRUs\n")
+
+
+def write_gauge(f, rain, snow, tmin, tmax, pet, elev=843.0, lat=54.4848, lon=-123.3659, extra=""):
+    n = len(rain)
+    f.write(":Gauge met1\n  :Latitude %.4f\n  :Longitude %.4f\n  :Elevation %.1f\n%s" % (lat, lon, elev, extra))
+    f.write("  :MultiData\n    2000-01-01 00:00:00 1 %d\n" % n)
+    f.write("    :Parameters RAINFALL SNOWFALL TEMP_DAILY_MIN TEMP_DAILY_MAX PET\n    :Units mm/d mm/d C C mm/d\n")
+    for i in range(n):
+        f.write("    %.4f %.4f %.4f %.4f %.4f\n" % (rain[i], snow[i], tmin[i], tmax[i], pet[i]))
+    f.write("  :EndMultiData\n:EndGauge\n")
+
+
+def write_hmets(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUTE_NONE", catchment_route="ROUTE_DUMP",
+                single_class=False, ensemble_members=0, name="hmets"):
+    """HMETS template (BASELINE config 3 member): returns the input base path."""
+    os.makedirs(dirpath, exist_ok=True)
+    base = os.path.join(dirpath, name)
+    rng = np.random.RandomState(seed)
+    extra_rvi = ""
+    if ensemble_members > 0:
+        extra_rvi = ":EnsembleMode ENSEMBLE_MONTECARLO %d\n:RandomSeed %d\n" % (ensemble_members, seed)
+    _write(base + ".rvi", HMETS_RVI.format(duration=n_days, routing=routing, catchment_route=catchment_route, extra=extra_rvi))
+    profile = "NONE" if routing == "ROUTE_NONE" else "CHN"
+    extra_rvp = ""
+    if n_sb > 1 or routing != "ROUTE_NONE":
+        extra_rvp += ":AvgAnnualRunoff 400\n"
+    if profile != "NONE":
+        extra_rvp += ":TrapezoidalChannel CHN 10.0 0.0 2.0 0.035 0.001\n"
+    _write(base + ".rvp", HMETS_RVP.format(extra=extra_rvp))
+    with open(base + ".rvh", "w") as f:
+        if single_class:
+            write_network(f, n_sb, hru_per_sb, rng, profile, ["FOREST"], ["FOREST"], ["DEFAULT_P"])
+        else:
+            write_network(f, n_sb, hru_per_sb, rng, profile, ["FOREST", "OPEN"], ["FOREST", "GRASS"], ["DEFAULT_P", "THIN_P"])
+    with open(base + ".rvt", "w") as f:
+        write_gauge(f, *weather(n_days, seed))
+    _write(base + ".rvc", HMETS_RVC)
+    if ensemble_members > 0:
+        with open(base + ".rve", "w") as f:
+            f.write(":OutputDirectoryFormat ./ens_*\n:ParameterDistributions\n  :Attributes NAME CLASS_TYPE CLASS DIST PAR1 PAR2\n")
+            for (pn, ct, cn, v) in HMETS_DISTS:
+                lo, hi = sorted([0.8 * v, 1.2 * v])
+                f.write("  %s %s %s DIST_UNIFORM %.8g %.8g\n" % (pn, ct, cn, lo, hi))
+            f.write(":EndParameterDistributions\n")
+    return base
