@@ -89,7 +89,7 @@ class ClockSampler:
 def write_workload(td, n_days, members=0):
     from ravenhydroframework_b200 import synth
     return synth.write_hmets(td, n_sb=N_SB, hru_per_sb=HRU_PER_SB, n_days=n_days, seed=1, routing="ROUTE_NONE", catchment_route="ROUTE_DUMP",
-                             single_class=True, ensemble_members=members)
+                             single_class=True, ensemble_members=members, season_offset=105)  # timed window = snowmelt season: every store is active
 
 
 def run_reference_cpu(n_days, nproc, td):

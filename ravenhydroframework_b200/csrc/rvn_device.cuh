@@ -38,7 +38,7 @@ struct DevProgram {
 };
 
 struct DevModel {
-  int32_t nH, nHp, nSB, E, NS, nCore;
+  int32_t nH, nHp, nSB, E, NS, nCore, maxConn;
   // per-member arrays
   double *state, *swvol, *forc, *ptab, *conv_uh;
   int32_t *conv_n;

@@ -11,10 +11,10 @@ import os
 import numpy as np
 
 
-def weather(n_days, seed=1):
+def weather(n_days, seed=1, season_offset=0):
     """Daily RAINFALL, SNOWFALL [mm/d], TEMP_DAILY_MIN, TEMP_DAILY_MAX [C], PET [mm/d] for a cold-region climate."""
     rng = np.random.RandomState(seed)
-    doy = np.arange(n_days) % 365
+    doy = (np.arange(n_days) + season_offset) % 365
     tmean = 2.5 + 13.0 * np.sin(2 * np.pi * (doy - 110) / 365.0)
     noise = np.zeros(n_days)
     eps = rng.normal(0, 3.0, n_days)
@@ -172,7 +172,7 @@ def write_gauge(f, rain, snow, tmin, tmax, pet, elev=843.0, lat=54.4848, lon=-12
 
 
 def write_hmets(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUTE_NONE", catchment_route="ROUTE_DUMP",
-                single_class=False, ensemble_members=0, name="hmets"):
+                single_class=False, ensemble_members=0, name="hmets", season_offset=0):
     """HMETS template (BASELINE config 3 member): returns the input base path."""
     os.makedirs(dirpath, exist_ok=True)
     base = os.path.join(dirpath, name)
@@ -194,7 +194,7 @@ def write_hmets(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUT
         else:
             write_network(f, n_sb, hru_per_sb, rng, profile, ["FOREST", "OPEN"], ["FOREST", "GRASS"], ["DEFAULT_P", "THIN_P"])
     with open(base + ".rvt", "w") as f:
-        write_gauge(f, *weather(n_days, seed))
+        write_gauge(f, *weather(n_days, seed, season_offset))
     _write(base + ".rvc", HMETS_RVC)
     if ensemble_members > 0:
         with open(base + ".rve", "w") as f:
