@@ -42,6 +42,8 @@ struct DevModel {
   // per-member arrays
   double *state, *swvol, *forc, *ptab, *conv_uh;
   int32_t *conv_n;
+  double *conv_sum;                               // [member][nConv][nHp] sum of each HRU's live convolution stores
+  int32_t conv_sum_valid;                         // 0 after the state/parameters were replaced from the host
   double *qin, *qlat, *qout, *scal, *cumul;      // cumul [member][2]
   double *part_precip, *part_storage;             // [member][nBlocksX] block partial sums of the sweep
   int32_t nBlocksX;
