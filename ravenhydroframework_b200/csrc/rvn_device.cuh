@@ -1,6 +1,6 @@
 // rvn_device.cuh -- device-side data model of the B200 engine (sm_100a, FP64 throughout).
 //
-// HBM layout (all FP64 unless noted; nHp = nHRU rounded up to 32 so that every row starts 256-B aligned):
+// HBM layout (all FP64 unless noted; nHp = nHRU rounded up to the 128-thread CTA so that every row is a whole number of 1 KB CTA tiles):
 //   state   [member][sv][nHp]        SoA: a warp reading one state variable of 32 neighbouring HRUs
 //                                    touches 256 contiguous bytes (8 full sectors)
 //   swvol   [member][nHp]            surface-water volume handed to in-catchment routing [m3]
