@@ -62,22 +62,9 @@ def build_host(force=False):
     return out
 
 
-def build_oracle(force=False):
-    """Test infrastructure: the C oracle, and (when the reference tree is present) the unmodified reference."""
-    odir = os.path.join(ROOT, "oracle")
-    out = os.path.join(odir, "liboracle.so")
-    src = os.path.join(odir, "raven_oracle.c")
-    if force or _newer(out, [src, os.path.join(ROOT, "include", "rvn_gpu.h")]):
-        _run(["gcc", "-std=c99", "-O2", "-fPIC", "-shared", "-I" + os.path.join(ROOT, "include"), src, "-o", out, "-lm"])
-    if os.path.isdir("/root/reference/src"):
-        _run(["bash", os.path.join(odir, "build_ref.sh")])
-    return out
-
-
 def build_all(force=False, verbose=False):
     build_engine(force, verbose)
     build_host(force)
-    build_oracle(force)
 
 
 if __name__ == "__main__":

@@ -53,6 +53,36 @@ int rvh_desc_info(const rvn_model_desc *d, int *out8) {
 }
 const double *rvh_desc_gauge_series(const rvn_model_desc *d) { return d->gauge_series; }
 const int32_t *rvh_desc_conv_n(const rvn_model_desc *d) { return d->conv_n; }
+int rvh_desc_sv_table(const rvn_model_desc *d, int32_t *type, int32_t *layer) {
+  for (int i = 0; i < d->NS; i++) { type[i] = d->sv_type[i]; layer[i] = d->sv_layer[i]; }
+  return 0;
+}
+int rvh_desc_order(const rvn_model_desc *d, int32_t *order) { for (int p = 0; p < d->nSB; p++) order[p] = d->sb_order[p]; return 0; }
+int rvh_desc_hru_area(const rvn_model_desc *d, double *area) { for (int k = 0; k < d->nHRU; k++) area[k] = d->hru_area[k]; return 0; }
+// resolved class parameter of HRU k as the hot path will see it; kind = "G" | "LU" | "VEG" | "SOIL<m>"
+double rvh_model_param_value(rvh_model *h, const char *kind, int k, const char *name) {
+  const CModel *M = h->pModel;
+  std::string kd(kind), nm(name);
+  if (kd == "G") { int f = GlobalFieldFromName(nm); return f < 0 ? NOT_SPECIFIED : M->globals.v[f]; }
+  const CHydroUnit *u = M->GetHydroUnit(k);
+  if (kd == "LU") { int f = LandUseFieldFromName(nm); return f < 0 ? NOT_SPECIFIED : M->lu_classes[u->lu_class].S.v[f]; }
+  if (kd == "VEG") {
+    for (int f = 0; f < RVN_V_COUNT; f++) if (nm == VegFieldName(f)) {
+      if (f == RVN_V_VAR_RAIN_ICEPT_PCT) f = RVN_V_RAIN_ICEPT_PCT;
+      if (f == RVN_V_VAR_SNOW_ICEPT_PCT) f = RVN_V_SNOW_ICEPT_PCT;
+      return M->veg_classes[u->veg_class].V.v[f];
+    }
+    return NOT_SPECIFIED;
+  }
+  if (kd.substr(0, 4) == "SOIL") {
+    int m = atoi(kd.c_str() + 4);
+    int f = SoilFieldFromName(nm);
+    const CSoilProfile &sp = M->soil_profiles[u->soil_profile];
+    if (f < 0 || m >= sp.nHorizons) return NOT_SPECIFIED;
+    return M->soil_classes[sp.soil_class[m]].S.v[f];
+  }
+  return NOT_SPECIFIED;
+}
 int rvh_model_dims(rvh_model *h, int *nHRU, int *NS, int *nSB, int *nProc, int *nGauges) {
   *nHRU = h->pModel->GetNumHRUs(); *NS = h->pModel->GetNumStateVars(); *nSB = h->pModel->GetNumSubBasins();
   *nProc = h->pModel->GetNumProcesses(); *nGauges = h->pModel->GetNumGauges();

@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures: run the UNMODIFIED reference (oracle/_ref/ref_dump, built from /root/reference by
+oracle/build_ref.sh) on synthetic input sets and store its in-memory FP64 results.
+
+Only runs where the reference tree is available (the build container).  The input files written next to each
+fixture are our own synthetic inputs (ravenhydroframework_b200.synth); the .npz holds reference OUTPUTS:
+  state_steps / state   HRU state [nrec][nHRU][NS] at the recorded steps (1-based step numbers; 0 = initial)
+  qout                  [nsteps][NB] CSubBasin::GetOutflowRate after every step
+  wshed                 [nsteps][3]  _CumulInput, _CumulOutput, GetAveragePrecip
+  forc_steps / forc     force_struct rows at the recorded steps (reference layout, 39 doubles)
+  sv_type / sv_layer    state-variable catalogue (integers, must match exactly)
+  order                 routing order _aOrderedSBind (integers, must match exactly)
+  proc                  per process: reference process_type id, nconn, first <=8 connections
+"""
+import os
+import shutil
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import helpers as H  # noqa: E402
+from ravenhydroframework_b200 import synth  # noqa: E402
+
+CASES = {
+    "hmets_single": dict(kind="hmets", n_sb=1, hru_per_sb=1, n_days=730, seed=5, single_class=True),
+    "hmets_tree": dict(kind="hmets", n_sb=7, hru_per_sb=4, n_days=400, seed=3),
+    "hmets_tree31": dict(kind="hmets", n_sb=31, hru_per_sb=13, n_days=300, seed=7),
+}
+WRITERS = {"hmets": synth.write_hmets}
+if hasattr(synth, "write_hbv"):
+    WRITERS["hbv"] = synth.write_hbv
+    CASES["hbv_single"] = dict(kind="hbv", n_sb=1, hru_per_sb=1, n_days=730, seed=4)
+    CASES["hbv_muskingum"] = dict(kind="hbv", n_sb=15, hru_per_sb=6, n_days=400, seed=6, routing="ROUTE_MUSKINGUM")
+    CASES["hbv_storagecoeff"] = dict(kind="hbv", n_sb=7, hru_per_sb=3, n_days=200, seed=8, routing="ROUTE_STORAGECOEFF")
+if hasattr(synth, "write_gr4j"):
+    WRITERS["gr4j"] = synth.write_gr4j
+    CASES["gr4j_single"] = dict(kind="gr4j", n_sb=1, hru_per_sb=1, n_days=730, seed=9)
+    CASES["gr4j_tree"] = dict(kind="gr4j", n_sb=7, hru_per_sb=5, n_days=300, seed=10)
+
+
+def make(name, spec):
+    spec = dict(spec)
+    kind = spec.pop("kind")
+    d = os.path.join(HERE, name)
+    shutil.rmtree(d, ignore_errors=True)
+    base = WRITERS[kind](d, name="model", **spec)
+    n = spec["n_days"]
+    out = os.path.join(d, "_refout")
+    ref = H.reference_run(base, out, n)
+    rec = sorted(set([1, 2, 3, 10, 50, 100, 150, 200, 250, 300, 365, 400, 500, 600, 700, n]) & set(range(1, n + 1)))
+    np.savez_compressed(os.path.join(d, "reference.npz"),
+                        state_steps=np.array(rec), state=ref["state"][rec], qout=ref["basin"][1:n + 1, :, 0],
+                        basin_last=ref["basin"][n], wshed=ref["wshed"][1:n + 1], forc_steps=np.array(rec), forc=ref["forc"][rec],
+                        sv_type=np.array([t for t, _ in ref["sv"]]), sv_layer=np.array([l for _, l in ref["sv"]]),
+                        order=np.array(ref["order"]), proc=np.array([" ".join(p) for p in ref["proc"]]),
+                        param=np.array([" ".join(p) for p in ref["param"]]))
+    shutil.rmtree(out, ignore_errors=True)
+    print("golden %-18s nHRU=%d NS=%d NB=%d steps=%d" % (name, ref["nHRU"], ref["NS"], ref["NB"], n))
+
+
+if __name__ == "__main__":
+    assert H.have_reference(), "oracle/_ref/ref_dump missing: run oracle/build_ref.sh where /root/reference exists"
+    only = sys.argv[1:]
+    for name, spec in CASES.items():
+        if only and name not in only:
+            continue
+        make(name, spec)

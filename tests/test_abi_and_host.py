@@ -1,0 +1,108 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol include/rvn_gpu.h declares, fails loudly
+without a GPU (no CPU fallback), and the host layer's parsers reject what they do not implement."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import helpers as H
+from ravenhydroframework_b200 import api, synth
+
+ROOT = H.ROOT
+
+
+def test_engine_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "rvn_gpu.h")).read()
+    names = sorted(set(re.findall(r"\b(rvn_gpu_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(names) >= 20
+    lib = api.engine_lib()
+    for n in names:
+        assert hasattr(lib, n), "librvn_gpu.so does not export %s" % n
+    assert lib.rvn_gpu_abi_version() == 1
+
+
+def test_engine_is_sm100a_and_uses_bulk_async_copy():
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    so = os.path.join(ROOT, "ravenhydroframework_b200", "librvn_gpu.so")
+    out = subprocess.run(["cuobjdump", "-sass", so], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
+    assert "sm_100a" in out
+    assert "UBLKCP" in out, "hru_sweep_kernel should stream state tiles with cp.async.bulk (SASS UBLKCP)"
+    assert "SYNCS" in out  # mbarrier
+
+
+def test_no_cpu_fallback(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    base = synth.write_hmets(str(tmp_path), n_sb=1, hru_per_sb=1, n_days=10)
+    m = api.RavenModel(base)
+    with pytest.raises(api.RavenError, match="no CUDA device"):
+        api.GpuSimulation(m)
+
+
+def test_product_path_does_not_touch_the_oracle():
+    pkg = os.path.join(ROOT, "ravenhydroframework_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".h", ".cu", ".cuh")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "liboracle" not in txt and "raven_oracle" not in txt and "rvo_run" not in txt, f
+
+
+def test_unsupported_commands_fail_loudly(tmp_path):
+    base = synth.write_hmets(str(tmp_path), n_sb=1, hru_per_sb=1, n_days=10)
+    rvi = open(base + ".rvi").read()
+    open(base + ".rvi", "w").write(rvi.replace("INF_HMETS", "INF_GREEN_AMPT"))
+    with pytest.raises(api.RavenError, match="not implemented"):
+        api.RavenModel(base)
+    open(base + ".rvi", "w").write(rvi + ":ReservoirDemandAllocation X\n")
+    with pytest.raises(api.RavenError, match="not supported"):
+        api.RavenModel(base)
+    open(base + ".rvi", "w").write(rvi.replace(":Method                ORDERED_SERIES", ":Method EULER"))
+    with pytest.raises(api.RavenError, match="ORDERED_SERIES"):
+        api.RavenModel(base)
+
+
+def test_routing_order_heap_tree(tmp_path):
+    base = synth.write_hmets(str(tmp_path), n_sb=15, hru_per_sb=2, n_days=10)
+    m = api.RavenModel(base)
+    m.flatten(1)
+    o = np.zeros(15, dtype=np.int32)
+    m.lib.rvh_desc_order.argtypes = [C.c_void_p, C.c_void_p]
+    m.lib.rvh_desc_order(m.desc, o.ctypes.data)
+    # deepest level first (subbasins 8..15 -> indices 7..14), ascending inside a level, outlet last
+    assert list(o) == list(range(7, 15)) + list(range(3, 7)) + [1, 2] + [0]
+
+
+def test_timeseries_reader_matches_reference_digit_arithmetic(tmp_path):
+    """Forcing values are parsed with the reference's own decimal accumulation (src/CommonFunctions.cpp:1267-1342)."""
+    base = synth.write_hmets(str(tmp_path), n_sb=1, hru_per_sb=1, n_days=5)
+    txt = open(base + ".rvt").read().split("\n")
+    i = [j for j, l in enumerate(txt) if ":Units" in l][0] + 1
+    txt[i] = "    0.1 0.7 -17.991528 -4.024469 0.3"
+    open(base + ".rvt", "w").write("\n".join(txt))
+    m = api.RavenModel(base)
+    m.flatten(1)
+    m.lib.rvh_desc_gauge_series.restype = C.c_void_p
+    m.lib.rvh_desc_gauge_series.argtypes = [C.c_void_p]
+    s = np.ctypeslib.as_array((C.c_double * (9 * 5)).from_address(m.lib.rvh_desc_gauge_series(m.desc))).reshape(9, 5)
+
+    def ref_parse(t):
+        sign = -1.0 if t.startswith("-") else 1.0
+        t = t.lstrip("+-")
+        ip, fp = (t.split(".") + [""])[:2]
+        v = 0.0
+        for ch in ip:
+            v = v * 10.0 + (ord(ch) - 48)
+        p10 = 10.0
+        for ch in fp:
+            v += (ord(ch) - 48) / p10
+            p10 *= 10.0
+        return sign * v
+    assert s[0, 0] == ref_parse("0.1") + ref_parse("0.7")            # PRECIP = RAINFALL + SNOWFALL
+    assert s[4, 0] == ref_parse("-17.991528") and s[5, 0] == ref_parse("-4.024469")

@@ -1,0 +1,133 @@
+"""CPU tests: the C oracle + the C++ host layer against (a) the committed golden fixtures (outputs of the unmodified
+reference, tests/golden/make_golden.py) and (b), when the reference tree is present, a live run of the reference on
+its own Salmon inputs.  Integer tables (state-variable catalogue, routing order, connections) must match exactly;
+FP64 results within 1e-9 relative (they are in fact bit-identical on the build host)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+from ravenhydroframework_b200 import api
+
+TOL = 1e-9
+CASES = sorted(os.path.basename(os.path.dirname(p)) for p in glob.glob(os.path.join(H.GOLDEN, "*", "reference.npz")))
+
+
+def _load(case):
+    g = np.load(os.path.join(H.GOLDEN, case, "reference.npz"))
+    model = api.RavenModel(os.path.join(H.GOLDEN, case, "model"))
+    model.flatten(1)
+    return g, model
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_integer_tables_match_reference(case):
+    g, model = _load(case)
+    import ctypes as C
+    lib = model.lib
+    # state-variable catalogue: types (reference enum numbering) and layers
+    names = model.sv_names()
+    assert model.NS == len(g["sv_type"]) == len(names)
+    info = (C.c_int * 8)()
+    lib.rvh_desc_info(model.desc, info)
+    lib.rvh_desc_sv_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    t = np.zeros(model.NS, dtype=np.int32); l = np.zeros(model.NS, dtype=np.int32)
+    lib.rvh_desc_sv_table(model.desc, t.ctypes.data, l.ctypes.data)
+    assert np.array_equal(t, g["sv_type"])
+    assert np.array_equal(l, g["sv_layer"])
+    # routing order
+    lib.rvh_desc_order.argtypes = [C.c_void_p, C.c_void_p]
+    o = np.zeros(model.nSB, dtype=np.int32)
+    lib.rvh_desc_order(model.desc, o.ctypes.data)
+    assert np.array_equal(o, g["order"])
+    # process connection tables (reference dump lists nconn and the first <= 8 connections of every process)
+    procs = model.processes()
+    assert len(procs) == len(g["proc"])
+    for (name, nconn, frm, to), ref in zip(procs, g["proc"]):
+        f = str(ref).split()
+        assert int(f[2]) == nconn, (name, f)
+        conns = ["%d>%d" % (a, b) for a, b in zip(frm, to)]
+        assert conns == f[3:3 + len(conns)], (name, conns, f)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_matches_golden(case):
+    g, model = _load(case)
+    n = g["qout"].shape[0]
+    o = H.oracle_run(model, n, record_forcings=True)
+    steps = g["state_steps"]
+    assert H.rel_err(o["state_rec"][steps - 1], g["state"]) < TOL
+    assert H.rel_err(o["qout_rec"], g["qout"]) < TOL
+    assert H.rel_err(o["wshed_rec"][:, :3], g["wshed"]) < TOL
+    # derived forcings the oracle keeps (subset of the reference force_struct; indices from src/RavenInclude.h:1294-1343)
+    ref_f = g["forc"]
+    idx = {"PRECIP": 0, "SNOW_FRAC": 3, "TEMP_AVE": 7, "TEMP_DAILY_MIN": 8, "TEMP_DAILY_MAX": 9, "TEMP_DAILY_AVE": 10,
+           "POTENTIAL_MELT": 32, "PET": 34, "OW_PET": 35}
+    if case.startswith("hmets"):
+        idx.pop("OW_PET")   # :OW_Evaporation defaults to PET_HARGREAVES_1985 there; no HMETS process consumes OW_PET (not derived)
+    for name, j in idx.items():
+        mine = o["forc_rec"][steps - 1][:, :, api.FORCING_NAMES.index(name)]
+        assert H.rel_err(mine, ref_f[:, :, j]) < TOL, name
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_parameters_match_reference(case):
+    """Class parameters as the reference resolved them ([DEFAULT] rows, autogeneration) vs the host layer's tables."""
+    g, model = _load(case)
+    import ctypes as C
+    lib = model.lib
+    lib.rvh_model_param_value.restype = C.c_double
+    lib.rvh_model_param_value.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_char_p]
+    checked = 0
+    for row in g["param"]:
+        kind, k, name, val = str(row).split()
+        val = float(val)
+        if val < -60000:      # reference marks parameters the model does not use
+            continue
+        if name in ("VAR_CAPACITY", "VAR_SNOW_CAPACITY") or (name == "THICKNESS"):
+            continue
+        mine = lib.rvh_model_param_value(model.h, kind.encode(), int(k), name.encode())
+        if mine < -30000 and kind == "VEG" and name in ("MAX_CAPACITY", "MAX_SNOW_CAPACITY"):
+            continue
+        assert abs(mine - val) <= 1e-12 * max(1.0, abs(val)), (kind, k, name, mine, val)
+        checked += 1
+    assert checked > 10
+
+
+@pytest.mark.skipif(not (H.have_reference() and os.path.isdir(H.REFERENCE_INPUTS)), reason="reference tree not present (GPU box)")
+def test_oracle_matches_live_reference_salmon_hmets(tmp_path):
+    """The reference's own Salmon_HMETS inputs (benchmarking/_InputFiles), first 3000 daily steps, run by the unmodified
+    reference here and by host layer + oracle."""
+    base = os.path.join(H.REFERENCE_INPUTS, "Salmon_HMETS", "raven-hmets-salmon")
+    n = 3000
+    ref = H.reference_run(base, str(tmp_path / "out"), n)
+    model = api.RavenModel(base, duration=n)
+    model.flatten(1)
+    o = H.oracle_run(model, n)
+    assert H.rel_err(o["state_rec"], ref["state"][1:n + 1]) < TOL
+    assert H.rel_err(o["qout_rec"], ref["basin"][1:n + 1, :, 0]) < TOL
+    assert H.rel_err(o["wshed_rec"][:, :2], ref["wshed"][1:n + 1, :2]) < TOL
+
+
+def test_mass_balance_closes():
+    """WatershedStorage.csv 'MB Error' column: (S - S0) + (CumulOutput - CumulInput) stays at round-off."""
+    g, model = _load("hmets_tree")
+    n = 400
+    o = H.oracle_run(model, n)
+    st0 = model.initial_state()
+    # initial water: area-weighted SOIL stores (everything else starts empty)
+    w = o["wshed_rec"]
+    names = model.sv_names()
+    import ctypes as C
+    area = np.zeros(model.nHRU)
+    model.lib.rvh_desc_hru_area.argtypes = [C.c_void_p, C.c_void_p]
+    model.lib.rvh_desc_hru_area(model.desc, area.ctypes.data)
+    water = [i for i, nm in enumerate(names) if nm.split("[")[0] in ("SURFACE_WATER", "ATMOSPHERE", "PONDED_WATER", "SOIL", "SNOW", "SNOW_LIQ", "CONVOLUTION")]
+    s0 = float((st0[:, water].sum(axis=1) * area).sum() / area.sum())
+    # + initial channel and rivulet storage [m3 -> mm] (CModel::CalculateInitialWaterStorage, src/ModelInitialize.cpp:412-447)
+    _, _, _, scal = model.basin_state()
+    s0 += float(scal[:, 4].sum() + scal[:, 5].sum()) / (area.sum() * 1e6) * 1000.0
+    mb = (w[:, 3] - s0) + (w[:, 1] - w[:, 0])
+    assert np.max(np.abs(mb)) < 1e-8
