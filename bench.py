@@ -43,7 +43,7 @@ def measured_peak():
 
 
 class ClockSampler:
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
@@ -55,10 +55,12 @@ class ClockSampler:
         fd, self.path = tempfile.mkstemp(suffix=".csv")
         os.close(fd)
         self.f = open(self.path, "w")
-        self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+        self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                   stdout=self.f, stderr=subprocess.DEVNULL)
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Samples taken between wall-clock times t0 and t1 (the timed region); all samples if none fall inside."""
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if not self.p:
             return out
@@ -68,21 +70,27 @@ class ClockSampler:
         except Exception:
             self.p.kill()
         self.f.close()
-        sm, mx, reasons = [], [], set()
+        rows = []
         for line in open(self.path):
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
             try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(c[1]), float(c[2]), c[5:9]))
             except ValueError:
                 continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], c[5:9]):
+        os.unlink(self.path)
+        inside = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
+        use = inside if inside else rows
+        reasons = set()
+        for r in use:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        os.unlink(self.path)
-        if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        if use:
+            out = {"sm_mhz": statistics.median([r[1] for r in use]), "sm_max_mhz": max(r[2] for r in use), "reasons": sorted(reasons),
+                   "samples": len(use), "window": "timed region" if inside else "whole run (no sample fell inside the timed region)"}
         return out
 
 
@@ -122,7 +130,7 @@ def run_reference_cpu(n_days, nproc, td):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--members", type=int, default=MEMBERS_PER_GPU, help="members per GPU (default: the 8-GPU share of config 3)")
@@ -198,16 +206,17 @@ def main():
         # ---- resident pass: W warm-up steps, then exactly K timed steps
         sim.set_recording(n_days, hydrographs=False, watershed=True)
         sim.set_kernel_timing(True)
-        sim.run(W)
         clocks = ClockSampler(local_rank)
+        clocks.start()          # sampling runs from before the warm-up; only samples inside the timed region are reported
+        sim.run(W)
         barrier()
-        clocks.start()
+        tw0 = time.time()
         t0 = time.perf_counter()
         sim.run(K)              # asynchronous launches on the engine's stream ...
         stats = sim.last_run_stats()   # ... synchronises on that stream and reads the CUDA events
         barrier()
         wall_ms = 1000.0 * (time.perf_counter() - t0)
-        clk = clocks.stop()
+        clk = clocks.stop(tw0, time.time())
         dev_ms = stats["total_ms"]
         sweep_ms = stats["sweep_ms"]
         launches = stats["launches"]

@@ -62,3 +62,21 @@ tot = sum(l[0] for l in lines) or 1; stot = sum(l[1] for l in lines) or 1
 print("top source lines by executed warp-instructions:")
 for n, sm, f, ln, txt in sorted(lines, reverse=True)[:28]:
     print("  %5.1f%% inst %5.1f%% stall  %s:%d  %s" % (100.0 * n / tot, 100.0 * sm / stot, f, ln, txt))
+
+# ---- the same, grouped by region of the sweep kernel (line ranges of rvn_engine.cu / whole helper files)
+def region(f, ln):
+    if f == "rvn_engine.cu":
+        for name, lo, hi in (("forcings", 29, 191), ("conv pipeline+div", 194, 264), ("conv loop", 265, 362), ("block_sum", 363, 377),
+                             ("prologue", 378, 485), ("process interpreter", 486, 512), ("epilogue", 513, 571)):
+            if lo <= ln <= hi:
+                return name
+        return "engine other"
+    if f == "rvn_processes.cuh":
+        return "process rate functions"
+    return f
+reg = collections.Counter(); regs = collections.Counter()
+for n, sm, f, ln, txt in lines:
+    reg[region(f, ln)] += n; regs[region(f, ln)] += sm
+print("by region (line ranges valid for the source revision profiled):")
+for r, n in reg.most_common():
+    print("  %-28s %5.1f%% inst %5.1f%% stall" % (r, 100.0 * n / tot, 100.0 * regs[r] / stot))
