@@ -271,7 +271,7 @@ def main():
         sweep_per_launch_ms = sweep_ms / K
         achieved = units_per_step * b_alg_live / (sweep_per_launch_ms / 1000.0) / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "kernel": "hru_sweep_kernel", "kernel_ms_per_launch": sweep_per_launch_ms, "kernel_share_of_step": sweep_ms / dev_ms,
+                    "kernel": sim.kernel_variant(), "kernel_ms_per_launch": sweep_per_launch_ms, "kernel_share_of_step": sweep_ms / dev_ms,
                     "bytes_per_hru_step": b_alg_live, "bytes_per_hru_step_reference_layout": b_alg_full, "live_conv_stores_mean": live,
                     "peak_source": peak_src}
 

@@ -310,6 +310,13 @@ int rvn_gpu_device_state_ptr(rvn_gpu_model *m, void **dptr, int64_t *member_stri
 /* CUDA-event time (ms) spent in kernels of the last rvn_gpu_run, and number of kernel launches it made */
 int rvn_gpu_last_run_stats(rvn_gpu_model *m, double *sweep_ms, double *total_ms, int64_t *launches);
 
+/* which HRU-sweep kernel serves this model: "static:<PROGRAM>" (compile-time specialisation of a known process
+ * program, csrc/rvn_static_programs.cuh) or "interpreter" (any supported process list) */
+int rvn_gpu_kernel_variant(rvn_gpu_model *m, char *buf, int buflen);
+/* build tool (no device needed): text of the compile-time program struct for `desc`'s process list, as written into
+ * csrc/rvn_static_programs.cuh by tools/gen_static_programs.py */
+int rvn_gpu_emit_static_program(const rvn_model_desc *desc, const char *name, char *buf, int64_t buflen);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,7 +27,7 @@ def engine_lib():
     """librvn_gpu.so (C ABI of include/rvn_gpu.h)."""
     global _engine
     if _engine is None:
-        path = os.path.join(HERE, "librvn_gpu.so")
+        path = os.environ.get("RVN_GPU_LIB") or os.path.join(HERE, "librvn_gpu.so")   # override: kernel-variant experiments
         if not os.path.exists(path):
             raise RavenError("librvn_gpu.so is not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
         lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
@@ -54,6 +54,8 @@ def engine_lib():
         lib.rvn_gpu_avg_state.argtypes = [vp, dp, i, i]
         lib.rvn_gpu_device_state_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         lib.rvn_gpu_last_run_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+        lib.rvn_gpu_kernel_variant.argtypes = [vp, C.c_char_p, i]
+        lib.rvn_gpu_emit_static_program.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int64]
         _engine = lib
     return _engine
 
@@ -305,6 +307,12 @@ class GpuSimulation:
         out = np.empty((nmembers, self.NS))
         self._ck(self.lib.rvn_gpu_avg_state(self.h, out.ctypes.data, member0, nmembers))
         return out
+
+    def kernel_variant(self):
+        """'static:<PROGRAM>' or 'interpreter' (which HRU-sweep kernel serves this model)."""
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.rvn_gpu_kernel_variant(self.h, buf, 64))
+        return buf.value.decode()
 
     def last_run_stats(self):
         a, b, n = C.c_double(), C.c_double(), C.c_int64()

@@ -3,10 +3,11 @@
 // HBM layout (all FP64 unless noted; nHp = nHRU rounded up to the 128-thread CTA so that every row is a whole number of 1 KB CTA tiles):
 //   state   [member][sv][nHp]        SoA: a warp reading one state variable of 32 neighbouring HRUs
 //                                    touches 256 contiguous bytes (8 full sectors)
-//   swvol   [member][nHp]            surface-water volume handed to in-catchment routing [m3]
+//   swvol   [2][member][nHp]         surface-water volume handed to in-catchment routing [m3] (double-buffered by step parity
+//                                    so that routing of step s can overlap the HRU sweep of step s+1)
 //   forc    [member][RVN_F_COUNT][nHp]  derived forcings (written only when forcing output is enabled)
 //   ptab    [member][ptab_stride]    parameter rows (globals | land-use | vegetation | soil classes)
-//   conv_uh [member][nLU][nConv][50] hoisted convolution unit hydrographs, conv_n = their lengths
+//   conv_tab[member][nLU][nConv][50] hoisted convolution unit hydrographs as ConvRow records, conv_n = their lengths
 //   basin   qin[member][nSB][max_nqin] qlat[..][max_nqlat] qout[..][50] scal[..][8]
 // Static, member-independent tables (HRU attributes, class handles, gauge series/weights, network
 // CSR, calendar) are stored once and shared by all members.
@@ -16,11 +17,18 @@
 #include "rvn_gpu.h"
 
 #define RVN_BS 128            // threads per CTA of the HRU sweep: one (member, HRU) pair per thread
-#define RVN_MAX_CORE 40       // max non-CONV_STOR state variables held in shared memory
+#define RVN_MAX_CORE 40       // max non-CONV_STOR state variables
 #define RVN_MAX_PROC 64
 #define RVN_MAX_PROG_CONN 256
+#define RVN_MAX_CONVPROC 4
 
-// process program + catalogue, copied into shared memory by every CTA (uniform reads -> broadcasts)
+// One ordinate of a hoisted convolution unit hydrograph (reference CmvConvolution::GenerateUnitHydrograph,
+// src/Convolution.cpp:107-154) together with the two member/class constants the release of store i needs
+// (src/Convolution.cpp:278-283): sumrem = 1 - sum(UH[0..i-1]) accumulated in the reference's order, and its correctly
+// rounded reciprocal (0 where the reference's guard `sumrem < REAL_SMALL` sets the release to zero).
+struct __align__(32) ConvRow { double uh, rcp, sumrem, pad; };
+
+// process program + catalogue, read by the interpreter kernel (uniform reads -> broadcasts)
 struct DevProgram {
   int32_t nProc, nCore, NS, nSoil;
   rvn_options opt;
@@ -30,22 +38,25 @@ struct DevProgram {
   int16_t slot_sv[RVN_MAX_CORE];            // core slot -> catalogue index
   int8_t  slot_type[RVN_MAX_CORE];          // sv_type of slot
   int8_t  slot_layer[RVN_MAX_CORE];
-  int8_t  slot_water[RVN_MAX_CORE];         // IsWaterStorage(type)
+  int8_t  slot_water[RVN_MAX_CORE];         // 1: water storage where a self-connection is a no-op; 2: CONVOLUTION; 0: other
   int16_t iSV[RVN_SV_NTYPES];               // first core slot of each SV type or -1
   int16_t soil_slot[RVN_MAX_SOIL_LAYERS];   // core slot of SOIL[m]
-  int32_t glob_off, lu_off, veg_off, soil_off, ptab_stride;
-  int32_t nLU, nConv, nGauges, nSteps, record_forcings;
+  int32_t maxConn, nConn, nConv;
 };
 
 struct DevModel {
   int32_t nH, nHp, nSB, E, NS, nCore, maxConn;
+  rvn_options opt;
+  int32_t glob_off, lu_off, veg_off, soil_off, ptab_stride;
+  int32_t nLU, nConv, nGauges, nSteps, record_forcings;
   // per-member arrays
-  double *state, *swvol, *forc, *ptab, *conv_uh;
+  double *state, *swvol, *forc, *ptab;
+  ConvRow *conv_tab;
   int32_t *conv_n;
   double *conv_sum;                               // [member][nConv][nHp] sum of each HRU's live convolution stores
   int32_t conv_sum_valid;                         // 0 after the state/parameters were replaced from the host
   double *qin, *qlat, *qout, *scal, *cumul;      // cumul [member][2]
-  double *part_precip, *part_storage;             // [member][nBlocksX] block partial sums of the sweep
+  double *part_precip, *part_storage;             // [2][member][nBlocksX] block partial sums of the sweep (step parity)
   int32_t nBlocksX;
   // shared static tables
   const double *hru_area, *hru_elev, *hru_lat, *hru_slope, *hru_aspect;

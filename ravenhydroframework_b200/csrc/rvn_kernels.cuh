@@ -1,0 +1,824 @@
+// rvn_kernels.cuh -- the sm_100a kernels behind include/rvn_gpu.h.
+//
+// Per model step two kernels run for ALL ensemble members at once:
+//   hru_sweep_*        = CModel::UpdateHRUForcingFunctions (src/UpdateForcings.cpp:30-668, fused in) +
+//                        the ORDERED_SERIES HRU loop of MassEnergyBalance (src/Solvers.cpp:155-251) +
+//                        routing prep / TOTAL_SWE / write-back (:495-511, :697-729) + the per-HRU part
+//                        of the output reductions (src/Model.cpp:1048-1060,1159-1174).
+//                        One thread owns one (member, HRU) pair.  Two forms share every process function:
+//        hru_sweep_static<Prog>   the process list is a compile-time program (rvn_static_programs.cuh): state and rates
+//                                 live in registers, every connection index is a constant, the process loop is unrolled
+//                                 ("one fused FP64 kernel per process group")
+//        hru_sweep_interp         the same sweep as an interpreter over the DevProgram for arbitrary process lists:
+//                                 state and rates live in shared-memory columns indexed at run time
+//                        In both the 50-slot convolution stores are streamed HBM -> registers -> HBM, coalesced over
+//                        neighbouring HRUs, with a register double buffer; no CTA-wide barrier inside the time-critical part.
+//   route_kernel       = HRU->subbasin aggregation (:490-511), the upstream->downstream routing loop
+//                        (:565-615; CSubBasin::RouteWater/UpdateOutflows, src/SubBasin.cpp:2584-2863,
+//                        2320-2421) level by level, IncrementCumulInput/CumOutflow (src/Model.cpp:
+//                        2458-2539) and the watershed-storage total (src/StandardOutput.cpp:745-785).
+//                        One CTA per member walks the precomputed level order with a CTA barrier per level.
+//                        It runs on a second, higher-priority stream: routing of step s overlaps the sweep of step s+1.
+// Bound: HBM bandwidth (state is read once and written once per step, ~0.5 flop/byte); no tensor cores.
+#ifndef RVN_KERNELS_CUH
+#define RVN_KERNELS_CUH
+#include <cuda_runtime.h>
+#include "rvn_device.cuh"
+#include "rvn_processes.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// contexts
+// ------------------------------------------------------------------------------------------------
+struct CtxCommon {
+  double F[RVN_F_COUNT];   // derived forcings of this HRU for this step
+  // lagged (start-of-step) values (what pHRU->GetStateVarValue returns inside processes)
+  double old_snow, old_snow_cover, old_snow_depth, old_snow_temp;
+  double area, elev, lat, slope, aspect;
+  double tstep;
+  int type, lu, veg, profile;
+  const double *ptab;      // member parameter row (shared memory)
+  const rvn_options *popt;
+  int glob_off, lu_base, veg_base, soil_off;
+  RVN_DI double G(int f) const { return ptab[glob_off + f]; }
+  RVN_DI double LU(int f) const { return ptab[lu_base + f]; }
+  RVN_DI double VEG(int f) const { return ptab[veg_base + f]; }
+  RVN_DI const rvn_options &opt() const { return *popt; }
+};
+
+// run-time context of the interpreter: shared-memory columns (column-major over the CTA's threads so that dynamic
+// indexing by state-variable slot is bank-conflict free)
+struct DynCtx : CtxCommon {
+  const DevProgram *P;     // program (shared memory)
+  double *sv;              // &s_sv[tid]; slot i at sv[i*RVN_BS]  -- newest state (aPhinew[k])
+  double *rt;              // &s_rates[tid]; connection q at rt[q*RVN_BS]
+  const int32_t *prof_class; const double *prof_thick;   // global, row of this HRU's soil profile
+  RVN_DI double &SV(int slot) const { return sv[slot * RVN_BS]; }
+  RVN_DI double &R(int q) const { return rt[q * RVN_BS]; }
+  RVN_DI int iSV(int t) const { return P->iSV[t]; }
+  RVN_DI int slot_type(int s) const { return P->slot_type[s]; }
+  RVN_DI int slot_layer(int s) const { return P->slot_layer[s]; }
+  RVN_DI int slot_water(int s) const { return P->slot_water[s]; }
+  RVN_DI double SOIL(int m, int f) const { return ptab[soil_off + prof_class[m] * RVN_S_COUNT + f]; }
+  RVN_DI double thick(int m) const { return prof_thick[m]; }
+};
+struct DynProc {
+  const rvn_process *p; const DevProgram *P;
+  RVN_DI int from(int q) const { return P->conn_from[p->conn0 + q]; }
+  RVN_DI int to(int q) const { return P->conn_to[p->conn0 + q]; }
+  RVN_DI int nconn() const { return p->nconn; }
+  RVN_DI int ia(int i) const { return p->ia[i]; }
+  RVN_DI double da(int i) const { return p->da[i]; }
+};
+
+// compile-time context of the specialised kernels: everything indexed by constants -> registers
+template <class Prog>
+struct StatCtx : CtxCommon {
+  double sv[Prog::nCore];
+  double rt[Prog::maxConn];
+  int sbase[Prog::nSoil > 0 ? Prog::nSoil : 1];
+  double sthick[Prog::nSoil > 0 ? Prog::nSoil : 1];
+  RVN_DI double &SV(int slot) { return sv[slot]; }
+  RVN_DI const double &SV(int slot) const { return sv[slot]; }
+  RVN_DI double &R(int q) { return rt[q]; }
+  static constexpr RVN_DI int iSV(int t) { return Prog::iSV(t); }
+  static constexpr RVN_DI int slot_type(int s) { return Prog::slot_type(s); }
+  static constexpr RVN_DI int slot_layer(int s) { return Prog::slot_layer(s); }
+  static constexpr RVN_DI int slot_water(int s) { return Prog::slot_water(s); }
+  RVN_DI double SOIL(int m, int f) const { return ptab[sbase[m] + f]; }
+  RVN_DI double thick(int m) const { return sthick[m]; }
+};
+template <class Prog, int J>
+struct StatProc {
+  static constexpr RVN_DI int from(int q) { return Prog::conn_from(Prog::conn0(J) + q); }
+  static constexpr RVN_DI int to(int q) { return Prog::conn_to(Prog::conn0(J) + q); }
+  static constexpr RVN_DI int nconn() { return Prog::nconn(J); }
+  static constexpr RVN_DI int ia(int i) { return Prog::ia(J, i); }
+  static constexpr RVN_DI double da(int i) { return Prog::da(J, i); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// forcing derivation for one HRU (restates CModel::UpdateHRUForcingFunctions for gauge-based input)
+// ------------------------------------------------------------------------------------------------
+template <class C>
+RVN_DI void compute_forcings(C &c, const DevModel &M, int k, int step, int sb) {
+  const rvn_options &opt = c.opt();
+  const rvn_time tt = M.times[step];
+  const int nG = M.nGauges, nS = M.nSteps, mo = tt.month;
+  const double elev = c.elev;
+  double *F = c.F;
+  double ref_elev_temp = 0.0, ref_elev_precip = 0.0, temp_month_min = 0, temp_month_max = 0, temp_month_ave = 0, PET_month_ave = 0;
+#pragma unroll
+  for (int f = 0; f < RVN_F_COUNT; f++) F[f] = 0.0;
+#define GS(f, g) M.gauge_series[((size_t)(f) * nG + (g)) * nS + step]
+#define GC(g, f) M.gauge_const[(size_t)(g) * RVN_GC_COUNT + (f)]
+  for (int g = 0; g < nG; g++) {  // src/UpdateForcings.cpp:184-235
+    double wt = M.wt_precip[(size_t)k * nG + g];
+    if (wt != 0.0) { F[RVN_F_PRECIP] += wt * GS(RVN_GF_PRECIP, g); F[RVN_F_SNOW_FRAC] += wt * GS(RVN_GF_SNOW_FRAC, g); ref_elev_precip += wt * GC(g, RVN_GC_ELEVATION); }
+    wt = M.wt_temp[(size_t)k * nG + g];
+    if (wt != 0.0) {
+      temp_month_min += wt * GC(g, RVN_GC_MONTHLY_MIN_TEMP0 + mo - 1); temp_month_max += wt * GC(g, RVN_GC_MONTHLY_MAX_TEMP0 + mo - 1);
+      temp_month_ave += wt * GC(g, RVN_GC_MONTHLY_AVE_TEMP0 + mo - 1);
+      ref_elev_temp += wt * GC(g, RVN_GC_ELEVATION);
+    }
+    wt = M.wt_all[(size_t)k * nG + g];
+    if (wt != 0.0) {
+      PET_month_ave += wt * GC(g, RVN_GC_MONTHLY_AVE_PET0 + mo - 1);
+      F[RVN_F_POTENTIAL_MELT] += wt * GS(RVN_GF_POTENTIAL_MELT, g);
+      F[RVN_F_PET] += wt * GS(RVN_GF_PET, g); F[RVN_F_OW_PET] += wt * GS(RVN_GF_OW_PET, g);
+    }
+  }
+  {  // temperature gauge+basin corrections, recomputed over all gauges (:441-455)
+    const double tc = M.sb_temp_corr[sb];
+    for (int g = 0; g < nG; g++) {
+      double gauge_corr = tc + GC(g, RVN_GC_TEMP_CORR), wt = M.wt_temp[(size_t)k * nG + g];
+      F[RVN_F_TEMP_AVE] += wt * (gauge_corr + GS(RVN_GF_TEMP_AVE, g));
+      F[RVN_F_TEMP_DAILY_AVE] += wt * (gauge_corr + GS(RVN_GF_TEMP_DAILY_AVE, g));
+      F[RVN_F_TEMP_DAILY_MAX] += wt * (gauge_corr + GS(RVN_GF_TEMP_DAILY_MAX, g));
+      F[RVN_F_TEMP_DAILY_MIN] += wt * (gauge_corr + GS(RVN_GF_TEMP_DAILY_MIN, g));
+    }
+  }
+  const double temp_ave_unc = F[RVN_F_TEMP_DAILY_AVE];  // :468
+  // CModel::CorrectTemp  src/OrographicCorrections.cpp:24-58
+  if (opt.orocorr_temp == RVN_OROCORR_SIMPLELAPSE || opt.orocorr_temp == RVN_OROCORR_HBV) {
+    double lapse = c.G(RVN_G_ADIABATIC_LAPSE);
+    lapse /= 1000.0;
+    F[RVN_F_TEMP_AVE] -= lapse * (elev - ref_elev_temp);
+    if (tt.day_changed) {
+      F[RVN_F_TEMP_DAILY_AVE] -= lapse * (elev - ref_elev_temp);
+      F[RVN_F_TEMP_DAILY_MIN] -= lapse * (elev - ref_elev_temp);
+      F[RVN_F_TEMP_DAILY_MAX] -= lapse * (elev - ref_elev_temp);
+      temp_month_max -= lapse * (elev - ref_elev_temp);
+      temp_month_min -= lapse * (elev - ref_elev_temp);
+      if (opt.orocorr_temp != RVN_OROCORR_HBV) temp_month_ave -= lapse * (elev - ref_elev_temp);
+    }
+  }
+  F[RVN_F_TEMP_MONTH_AVE] = temp_month_ave; F[RVN_F_PET_MONTH_AVE] = PET_month_ave;
+  const double subdaily_corr = 1.0;  // CalculateSubDailyCorrection: timestep>=1 (src/UpdateForcings.cpp:949-958)
+  {  // CModel::EstimateSnowFraction  src/UpdateForcings.cpp:1068-1197
+    double sf = F[RVN_F_SNOW_FRAC];
+    const int method = opt.rainsnow;
+    if (method == RVN_RAINSNOW_DINGMAN) {
+      double temp = c.G(RVN_G_RAINSNOW_TEMP);
+      if (F[RVN_F_TEMP_DAILY_MAX] <= temp) sf = 1.0;
+      else if (F[RVN_F_TEMP_DAILY_MIN] >= temp) sf = 0.0;
+      else sf = (temp - F[RVN_F_TEMP_DAILY_MIN]) / (F[RVN_F_TEMP_DAILY_MAX] - F[RVN_F_TEMP_DAILY_MIN]);
+    } else if (method == RVN_RAINSNOW_THRESHOLD) {
+      sf = (F[RVN_F_TEMP_AVE] <= c.G(RVN_G_RAINSNOW_TEMP)) ? 1.0 : 0.0;
+    } else if (method == RVN_RAINSNOW_HBV || method == RVN_RAINSNOW_UBCWM) {
+      double frac, delta = c.G(RVN_G_RAINSNOW_DELTA), temp = c.G(RVN_G_RAINSNOW_TEMP);
+      if (F[RVN_F_TEMP_DAILY_AVE] <= (temp - 0.5 * delta)) frac = 1.0;
+      else if (F[RVN_F_TEMP_DAILY_AVE] >= (temp + 0.5 * delta)) frac = 0.0;
+      else frac = 0.5 + (temp - F[RVN_F_TEMP_DAILY_AVE]) / delta;
+      sf = (method == RVN_RAINSNOW_UBCWM) ? frac : frac * (1.0 - F[RVN_F_SNOW_FRAC]) + F[RVN_F_SNOW_FRAC];
+    }
+    F[RVN_F_SNOW_FRAC] = sf;
+  }
+  {  // precipitation gauge+basin corrections (:507-527)
+    const double rc = M.sb_rain_corr[sb], sc = M.sb_snow_corr[sb];
+    F[RVN_F_PRECIP] = 0.0;
+    for (int g = 0; g < nG; g++) {
+      double gauge_corr = F[RVN_F_SNOW_FRAC] * sc * GC(g, RVN_GC_SNOW_CORR) + (1.0 - F[RVN_F_SNOW_FRAC]) * rc * GC(g, RVN_GC_RAIN_CORR);
+      double wt = M.wt_precip[(size_t)k * nG + g];
+      F[RVN_F_PRECIP] += wt * gauge_corr * GS(RVN_GF_PRECIP, g);
+    }
+  }
+  // CModel::CorrectPrecip  src/OrographicCorrections.cpp:213-245
+  if (opt.orocorr_precip == RVN_OROCORR_SIMPLELAPSE) {
+    double lapse = c.G(RVN_G_PRECIP_LAPSE);
+    lapse /= 1000;
+    if (F[RVN_F_PRECIP] > D_REAL_SMALL) F[RVN_F_PRECIP] = dmax(F[RVN_F_PRECIP] + lapse * (elev - ref_elev_precip), 0.0);
+  } else if (opt.orocorr_precip == RVN_OROCORR_HBV) {
+    double corr_upper = c.G(RVN_G_HBVEC_LAPSE_UPPER) / 1000.0, corr = c.G(RVN_G_HBVEC_LAPSE_RATE) / 1000.0;
+    double lapse_elev = c.G(RVN_G_HBVEC_LAPSE_ELEV), add = 0.0;
+    if (elev > lapse_elev) add = (corr_upper - corr) * (elev - lapse_elev);
+    F[RVN_F_PRECIP] *= dmax(1.0 + corr * (elev - ref_elev_precip) + add, 0.0);
+  }
+  if (c.type == RVN_HRU_MASKED_GLACIER) F[RVN_F_PRECIP] = 0;
+  {  // CModel::EstimatePotentialMelt  src/PotentialMelt.cpp:20-246
+    double pm = F[RVN_F_POTENTIAL_MELT];
+    const int method = opt.pot_melt;
+    if (method == RVN_POTMELT_DEGREE_DAY) {
+      pm = c.LU(RVN_LU_MELT_FACTOR) * (F[RVN_F_TEMP_DAILY_AVE] - c.LU(RVN_LU_DD_MELT_TEMP)) * subdaily_corr;
+    } else if (method == RVN_POTMELT_HBV) {
+      double Ma = c.LU(RVN_LU_MELT_FACTOR), Ma_min = c.LU(RVN_LU_MIN_MELT_FACTOR), AM = c.LU(RVN_LU_HBV_MELT_ASP_CORR);
+      double MRF = c.LU(RVN_LU_HBV_MELT_FOR_CORR), Fc = c.LU(RVN_LU_FOREST_COVERAGE), melt_temp = c.LU(RVN_LU_DD_MELT_TEMP);
+      double adj = 0, slope_corr;
+      if (c.lat < 0.0) adj = D_PI;
+      Ma = Ma_min + (Ma - Ma_min) * 0.5 * (1.0 - cos(tt.day_angle - D_WINTER_SOLSTICE_ANG - adj));
+      Ma *= ((1.0 - Fc) * 1.0 + (Fc)*MRF);
+      slope_corr = ((1.0 - Fc) * 1.0 + (Fc)*sin(c.slope));
+      Ma *= dmax(1.0 - AM * slope_corr * cos(c.aspect - adj), 0.0);
+      pm = Ma * (F[RVN_F_TEMP_DAILY_AVE] - melt_temp) * subdaily_corr + 0.0;
+    } else if (method == RVN_POTMELT_HMETS) {
+      double Ma_min = c.LU(RVN_LU_MIN_MELT_FACTOR), Ma_max = c.LU(RVN_LU_MAX_MELT_FACTOR);
+      double melt_temp = c.LU(RVN_LU_DD_MELT_TEMP), Kcum = c.LU(RVN_LU_DD_AGGRADATION);
+      double cum_melt = 0.0;
+      if (c.iSV(RVN_SV_CUM_SNOWMELT) >= 0) cum_melt = c.SV(c.iSV(RVN_SV_CUM_SNOWMELT));  // still the stored value here
+      double Ma = dmin(Ma_max, Ma_min * (1 + Kcum * cum_melt));
+      pm = Ma * (F[RVN_F_TEMP_DAILY_AVE] - melt_temp) * subdaily_corr;
+    } else if (method == RVN_POTMELT_NONE) {
+      pm = 0.0;
+    }
+    F[RVN_F_POTENTIAL_MELT] = pm;
+  }
+  // CModel::EstimatePET  src/Evaporation.cpp:282-540
+#pragma unroll
+  for (int ow = 0; ow < 2; ow++) {
+    const int method = ow ? opt.ow_evaporation : opt.evaporation;
+    double PET = ow ? F[RVN_F_OW_PET] : F[RVN_F_PET];
+    if (method == RVN_PET_CONSTANT) PET = 3.0;
+    else if (method == RVN_PET_NONE) PET = 0.0;
+    else if (method == RVN_PET_FROMMONTHLY) {
+      double peRatio = 1.0 + D_HBV_PET_TEMP_CORR * (temp_ave_unc - temp_month_ave);
+      peRatio = dmax(0.0, dmin(2.0, peRatio));
+      PET = PET_month_ave * peRatio;
+    }
+    PET = dmax(PET, 0.0);
+    PET = PET * c.VEG(RVN_V_PET_VEG_CORR);
+    if (ow) F[RVN_F_OW_PET] = PET; else F[RVN_F_PET] = PET;
+  }
+  // CModel::CorrectPET  src/OrographicCorrections.cpp:350-440
+  if (opt.orocorr_pet == RVN_OROCORR_HBV) {
+    double factor = D_GLOBAL_PET_CORR * dmax(1.0 - D_HBV_PET_ELEV_CORR * (elev - ref_elev_temp), 0.0);
+    F[RVN_F_PET] *= factor; F[RVN_F_OW_PET] *= factor;
+  }
+  if (opt.evaporation == RVN_PET_FROMMONTHLY || opt.evaporation == RVN_PET_CONSTANT) F[RVN_F_PET] *= subdaily_corr;
+  if (opt.snow_suppress_PET) {
+    double SWE = 0.0, sc = 1.0;
+    if (c.iSV(RVN_SV_SNOW) >= 0) SWE = c.old_snow;
+    if (c.iSV(RVN_SV_SNOW_COVER) >= 0) sc = c.old_snow_cover;
+    if (SWE > 0.1) { F[RVN_F_PET] *= (1.0 - sc); F[RVN_F_OW_PET] *= (1.0 - sc); }
+  }
+  if (c.type == RVN_HRU_STANDARD) F[RVN_F_PET] *= c.SOIL(0, RVN_S_PET_CORRECTION);
+  if (c.type == RVN_HRU_MASKED_GLACIER) F[RVN_F_PET] = F[RVN_F_OW_PET] = 0.0;
+  if (opt.direct_evap) {  // src/UpdateForcings.cpp:640-650
+    double rainfall = F[RVN_F_PRECIP] * (1.0 - F[RVN_F_SNOW_FRAC]);
+    double reduce = dmin(F[RVN_F_PET], rainfall + 0.0);
+    double rainfrac = rainfall / (rainfall + 0.0);
+    if ((rainfall + 0.0) == 0) rainfrac = 1.0;
+    if (F[RVN_F_PRECIP] + 0.0 - reduce > 0.0) F[RVN_F_SNOW_FRAC] = 1.0 - (rainfall - reduce * rainfrac) / (F[RVN_F_PRECIP] - reduce * rainfrac);
+    F[RVN_F_PRECIP] -= reduce * rainfrac;
+    F[RVN_F_PET] -= reduce * rainfrac;
+  }
+#undef GS
+#undef GC
+}
+
+// ------------------------------------------------------------------------------------------------
+// CmvConvolution (src/Convolution.cpp:245-303) + the solver's per-connection update of its 2N+1 connections
+// (src/Solvers.cpp:220-236) in ONE pass over the N live stores of this HRU: store i is loaded, released, shifted and
+// written back.  Only S'[i-1] is carried between rows.  Stores >= N are never touched: their rates are zero in the
+// reference as well.  UNIT_DT: tstep == 1.0, where x/tstep and r*tstep are exact identities (daily models).
+//
+// orig = (sumrem < REAL_SMALL) ? 0 : S/sumrem  (src/Convolution.cpp:280-281).  sumrem depends only on (member, land-use
+// class, row), so the host stores it with its correctly rounded reciprocal y = RN(1/sumrem) in the ConvRow table; the
+// quotient is then one Markstein correction step  q = S*y; r = fma(-sumrem, q, S); q' = fma(r, y, q)  which returns the
+// correctly rounded S/sumrem (the same closing sequence the compiler emits for a/b, without its reciprocal refinement
+// and range scaffolding).  y = 0 encodes the reference's guard (q = 0, r = S, q' = 0).  S = 0 (every dry day leaves one
+// such store) gives 0 like the division.  Outside 1e-290 < |S| < 1e290 the sequence is only faithful, not correctly
+// rounded -- storages are O(1e-12..1e5) mm.
+// ------------------------------------------------------------------------------------------------
+RVN_DI double conv_orig(const double S, const ConvRow &t) {
+  const double q = __dmul_rn(S, t.rcp);
+  const double r = __fma_rn(-t.sumrem, q, S);
+  return __fma_rn(r, t.rcp, q);
+}
+RVN_DI ConvRow ld_row(const ConvRow *__restrict__ tab, int i) {
+  const double2 a = __ldg(reinterpret_cast<const double2 *>(tab + i));
+  ConvRow t; t.uh = a.x; t.rcp = a.y; t.sumrem = __ldg(&tab[i].sumrem); t.pad = 0.0;
+  return t;
+}
+
+#ifndef RVN_CONV_R
+#define RVN_CONV_R 4   // rows per register buffer
+#endif
+
+template <bool UNIT_DT, class C>
+RVN_DI void convolve_direct(C &c, const int iTarget, const int iTS, double *__restrict__ g /*store 0 of this HRU*/, const size_t stride,
+                            const ConvRow *__restrict__ tab, const int N, double *__restrict__ sum_cache, const bool sum_valid) {
+  if (N <= 0) return;
+  const double tstep = c.tstep;
+  // ---- the reference's `sum` of the stores in index order.  The same sum, over the same values in the same order, is
+  // accumulated while the stores are written at the end of the previous step, so it is normally read back from a
+  // one-double-per-HRU cache; only after the state was replaced from outside is it recomputed.
+  double sum = 0.0;
+  if (sum_valid) sum = *sum_cache;
+  else {
+    const double *p = g;
+    for (int i = 0; i < N; i++) { sum += *p; p += stride; }
+  }
+  const double TS_old = c.SV(iTS);
+  const double added = TS_old - sum;
+  double target = c.SV(iTarget), nsum = 0.0, TS_new = 0.0;
+  {
+    // ---- row 0: receives the new water (connection 0), releases, shifts out unless it is the only store
+    const ConvRow t = ld_row(tab, 0);
+    const double g0 = __ldcs(g);
+    const double r0 = UNIT_DT ? added : added / tstep;                         // rates[0]
+    const double Sin = g0 + added;                                             // local S[0]
+    double act = UNIT_DT ? Sin : g0 + r0 * tstep;                              // store 0 after connection 0
+    const double orig = conv_orig(Sin, t);
+    const double r_ = UNIT_DT ? t.uh * orig : t.uh * orig / tstep;             // rates[1]
+    const double rdt = UNIT_DT ? r_ : r_ * tstep;
+    const double Sloc = Sin - rdt;                                             // local S[0] after release
+    act = act - rdt;                                                           // solver: phinew[store 0] -= r*tstep
+    target += rdt;                                                             // solver: phinew[target]  += r*tstep
+    if (N == 1) {
+      __stcs(g, act);
+      nsum = act;
+    } else {
+      const double mv0 = UNIT_DT ? Sloc : (Sloc / tstep) * tstep;              // m_0*tstep
+      const double fin0 = act - mv0;                                           // connection N+1
+      __stcs(g, fin0);
+      nsum = fin0;
+      double prev_move = mv0, prevS = Sloc;
+      // ---- interior rows 1..N-2: every special case is statically decided; the loads of the next RVN_CONV_R rows are in
+      // flight while the current ones are processed
+      const int end = N - 1;
+      double cur[RVN_CONV_R];
+      double *p = g + stride;
+#pragma unroll
+      for (int r = 0; r < RVN_CONV_R; r++) cur[r] = (1 + r < end) ? __ldcs(p + (size_t)r * stride) : 0.0;
+      for (int i = 1; i < end; i += RVN_CONV_R) {
+        double nxt[RVN_CONV_R];
+        const double *pn = p + (size_t)RVN_CONV_R * stride;
+#pragma unroll
+        for (int r = 0; r < RVN_CONV_R; r++) nxt[r] = (i + RVN_CONV_R + r < end) ? __ldcs(pn + (size_t)r * stride) : 0.0;
+#pragma unroll
+        for (int r = 0; r < RVN_CONV_R; r++) {
+          if (i + r < end) {
+            const ConvRow t = ld_row(tab, i + r);
+            const double gi = cur[r];
+            const double orig = conv_orig(gi, t);
+            const double rdt = UNIT_DT ? t.uh * orig : (t.uh * orig / tstep) * tstep;   // rates[i+1]*tstep
+            const double Sloc = gi - rdt;                               // local S[i] after release == store i after release
+            target += rdt;
+            const double mv = UNIT_DT ? Sloc : (Sloc / tstep) * tstep; // m_i*tstep
+            const double fin = (Sloc + prev_move) - mv;                 // connections N+i then N+i+1
+            __stcs(p + (size_t)r * stride, fin);
+            nsum += fin;
+            TS_new += prevS;                                            // local S[i] after the shift loop = S'[i-1]
+            prev_move = mv; prevS = Sloc;
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < RVN_CONV_R; r++) cur[r] = nxt[r];
+        p += (size_t)RVN_CONV_R * stride;
+      }
+      // ---- last row N-1: releases, receives the shift, keeps what is left
+      {
+        double *pl = g + (size_t)(N - 1) * stride;
+        const ConvRow t = ld_row(tab, N - 1);
+        const double gi = __ldcs(pl);
+        const double orig = conv_orig(gi, t);
+        const double r_ = UNIT_DT ? t.uh * orig : t.uh * orig / tstep;
+        const double rdt = UNIT_DT ? r_ : r_ * tstep;
+        const double Sloc = gi - rdt;
+        target += rdt;
+        const double fin = Sloc + prev_move;                            // connection 2N-1
+        __stcs(pl, fin);
+        nsum += fin;
+        // reference TS_new = sum_{j=1..N-1} of the local array after its descending shift loop:
+        //   local S[j] = S'[j-1] for j<=N-2 and S'[N-1]+S'[N-2] for j=N-1
+        TS_new += (Sloc + prevS);
+      }
+    }
+  }
+  *sum_cache = nsum;
+  c.SV(iTarget) = target;
+  const double rTS = UNIT_DT ? (TS_new - TS_old) : (TS_new - TS_old) / tstep;   // rates[2N]
+  c.SV(iTS) += UNIT_DT ? rTS : rTS * tstep;                                     // CONVOLUTION[c]: iTo==iFrom, updated in place
+}
+
+// ------------------------------------------------------------------------------------------------
+// solver pieces shared by both sweeps
+// ------------------------------------------------------------------------------------------------
+// per-connection update of the newest state (src/Solvers.cpp:220-236)
+template <class C, class PR>
+RVN_DI void apply_connections(C &c, const PR &pr) {
+  const double tstep = c.tstep;
+#pragma unroll
+  for (int q = 0; q < pr.nconn(); q++) {
+    const int from = pr.from(q), to = pr.to(q);
+    const double r = c.R(q);
+    if (to != from) { c.SV(from) -= r * tstep; c.SV(to) += r * tstep; }
+    else if (c.slot_water(from) == 1) { c.SV(to) += 0.0; }   // redirect-to-self: rate forced to zero
+    else c.SV(to) += r * tstep;
+  }
+}
+
+RVN_DI double block_sum(double v, double *s_red) {
+  // fixed-shape tree: warp shuffles then the (<=4) warp totals in order -> deterministic
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[w] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int i = 0; i < RVN_BS / 32; i++) t += s_red[i];
+  return t;
+}
+
+template <class C>
+RVN_DI void load_hru_statics(C &c, const DevModel &M, int k, const double *s_ptab) {
+  c.ptab = s_ptab; c.popt = &M.opt;
+  c.tstep = M.opt.timestep;
+  c.area = M.hru_area[k]; c.elev = M.hru_elev[k]; c.lat = M.hru_lat[k]; c.slope = M.hru_slope[k]; c.aspect = M.hru_aspect[k];
+  c.type = M.hru_type[k]; c.lu = M.hru_lu[k]; c.veg = M.hru_veg[k]; c.profile = M.hru_profile[k];
+  c.glob_off = M.glob_off; c.lu_base = M.lu_off + c.lu * RVN_LU_COUNT; c.veg_base = M.veg_off + c.veg * RVN_V_COUNT; c.soil_off = M.soil_off;
+}
+
+// AET / RUNOFF / GROUNDWATER reboot (src/Solvers.cpp:171-200)
+template <class C> RVN_DI void reboot_diagnostics(C &c) {
+  if (c.iSV(RVN_SV_AET) >= 0) c.SV(c.iSV(RVN_SV_AET)) = 0.0;
+  if (c.iSV(RVN_SV_RUNOFF) >= 0) c.SV(c.iSV(RVN_SV_RUNOFF)) = 0.0;
+  if (c.iSV(RVN_SV_GROUNDWATER) >= 0) c.SV(c.iSV(RVN_SV_GROUNDWATER)) = 0.0;
+}
+// routing prep (src/Solvers.cpp:495-511) and diagnostics (:697-729); returns the surface-water volume [m3]
+template <class C> RVN_DI double finish_step(C &c, const int nCore) {
+  const int iSW = c.iSV(RVN_SV_SURFACE_WATER);
+  const double swv = (c.SV(iSW) / D_MM_PER_METER) * (c.area * D_M2_PER_KM2);
+  if (c.iSV(RVN_SV_RUNOFF) >= 0) c.SV(c.iSV(RVN_SV_RUNOFF)) = c.SV(iSW);
+  c.SV(iSW) = 0.0;
+  if (c.iSV(RVN_SV_TOTAL_SWE) >= 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int s = 0; s < nCore; s++) if (c.slot_type(s) == RVN_SV_SNOW || c.slot_type(s) == RVN_SV_SNOW_LIQ) t += c.SV(s);
+    c.SV(c.iSV(RVN_SV_TOTAL_SWE)) = t;
+  }
+  if (c.iSV(RVN_SV_GLACIER_MB) >= 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int s = 0; s < nCore; s++) {
+      const int ty = c.slot_type(s);
+      if (ty == RVN_SV_SNOW || ty == RVN_SV_SNOW_LIQ || ty == RVN_SV_FIRN || ty == RVN_SV_GLACIER_ICE || ty == RVN_SV_GLACIER) t += c.SV(s);
+    }
+    c.SV(c.iSV(RVN_SV_GLACIER_MB)) = t;
+  }
+  return swv;
+}
+// this HRU's water storage [mm] over the non-convolution-store variables (the stores are represented by CONVOLUTION[c])
+template <class C> RVN_DI double hru_storage(C &c, const int nCore) {
+  double stor = 0.0;
+#pragma unroll
+  for (int s = 0; s < nCore; s++)
+    if ((c.slot_water(s) == 1 || c.slot_water(s) == 2) && c.slot_type(s) != RVN_SV_ATMOS_PRECIP) stor += c.SV(s);
+  return stor;
+}
+
+extern __shared__ __align__(16) unsigned char rvn_smem[];
+
+// ------------------------------------------------------------------------------------------------
+// specialised sweep: the process list is the compile-time program Prog
+// ------------------------------------------------------------------------------------------------
+template <class Prog, bool UNIT_DT, int J>
+struct RunProcs {
+  static RVN_DI void run(StatCtx<Prog> &c, const DevModel &M, const bool enabled, const unsigned long long mask, const int e, const int k,
+                         double *gstate) {
+    if constexpr (J < Prog::nProc) {
+      constexpr int op = Prog::op(J);
+      const bool apply = enabled && ((mask >> J) & 1ull);   // CModel::ApplyProcess gate (src/Model.cpp:3061)
+      if constexpr (op == RVN_OP_CONVOLVE) {
+        if (apply) {
+          constexpr int ci = Prog::ia(J, 0);
+          const size_t slot = ((size_t)e * M.nLU + c.lu) * M.nConv + ci;
+          convolve_direct<UNIT_DT>(c, Prog::ia(J, 1), Prog::ia(J, 3), gstate + (size_t)Prog::ia(J, 2) * M.nHp, (size_t)M.nHp,
+                                   M.conv_tab + slot * RVN_CONV_STORES, M.conv_n[slot], M.conv_sum + ((size_t)e * M.nConv + ci) * M.nHp + k,
+                                   M.conv_sum_valid != 0);
+        }
+      } else {
+        if (apply) {
+          const StatProc<Prog, J> pr{};
+#pragma unroll
+          for (int q = 0; q < Prog::nconn(J); q++) c.R(q) = 0.0;          // src/Model.cpp:3066-3071
+          dispatch_rates(c, pr, op);
+          apply_connections(c, pr);
+        }
+      }
+      RunProcs<Prog, UNIT_DT, J + 1>::run(c, M, enabled, mask, e, k, gstate);
+    }
+  }
+};
+
+#ifndef RVN_STATIC_MIN_BLOCKS
+#define RVN_STATIC_MIN_BLOCKS 6   // resident CTAs per SM the specialised sweep is compiled for (caps registers at 80/thread)
+#endif
+template <class Prog, bool UNIT_DT>
+__global__ void __launch_bounds__(RVN_BS, RVN_STATIC_MIN_BLOCKS) hru_sweep_static(const __grid_constant__ DevModel M, const int step) {
+  double *s_ptab = reinterpret_cast<double *>(rvn_smem);
+  double *s_red = s_ptab + ((M.ptab_stride + 1) & ~1);
+  const int tid = threadIdx.x, e = blockIdx.y, k = blockIdx.x * RVN_BS + tid;
+  {
+    const double *prow = M.ptab + (size_t)e * M.ptab_stride;
+    for (int i = tid; i < M.ptab_stride; i += RVN_BS) s_ptab[i] = prow[i];
+  }
+  const size_t nHp = (size_t)M.nHp;
+  const bool in_range = (k < M.nH);
+  const bool enabled = in_range && (M.hru_enabled[k] != 0);
+  StatCtx<Prog> c;
+  load_hru_statics(c, M, k, s_ptab);
+  if (UNIT_DT) c.tstep = 1.0;
+#pragma unroll
+  for (int m = 0; m < Prog::nSoil; m++) {
+    c.sbase[m] = M.soil_off + M.prof_class[c.profile * RVN_MAX_SOIL_LAYERS + m] * RVN_S_COUNT;
+    c.sthick[m] = M.prof_thick[c.profile * RVN_MAX_SOIL_LAYERS + m];
+  }
+  const int sb = M.hru_sb[k];
+  const unsigned long long mask = M.apply_mask[k];
+  // ---- state in: coalesced over k for every state variable (aPhi[k][i] = pHRU->GetStateVarValue(i))
+  double *gstate = M.state + (size_t)e * M.NS * nHp + k;
+#pragma unroll
+  for (int s = 0; s < Prog::nCore; s++) c.sv[s] = __ldcs(gstate + (size_t)Prog::slot_sv(s) * nHp);
+  c.old_snow = (Prog::iSV(RVN_SV_SNOW) >= 0) ? c.sv[Prog::iSV(RVN_SV_SNOW) >= 0 ? Prog::iSV(RVN_SV_SNOW) : 0] : 0.0;
+  c.old_snow_cover = (Prog::iSV(RVN_SV_SNOW_COVER) >= 0) ? c.sv[Prog::iSV(RVN_SV_SNOW_COVER) >= 0 ? Prog::iSV(RVN_SV_SNOW_COVER) : 0] : 0.0;
+  c.old_snow_depth = (Prog::iSV(RVN_SV_SNOW_DEPTH) >= 0) ? c.sv[Prog::iSV(RVN_SV_SNOW_DEPTH) >= 0 ? Prog::iSV(RVN_SV_SNOW_DEPTH) : 0] : 0.0;
+  c.old_snow_temp = (Prog::iSV(RVN_SV_SNOW_TEMP) >= 0) ? c.sv[Prog::iSV(RVN_SV_SNOW_TEMP) >= 0 ? Prog::iSV(RVN_SV_SNOW_TEMP) : 0] : 0.0;
+  __syncthreads();   // parameter row staged
+  // ---- forcings (on the stored state)
+  if (enabled) compute_forcings(c, M, k, step, sb);
+  else {
+#pragma unroll
+    for (int f = 0; f < RVN_F_COUNT; f++) c.F[f] = 0.0;
+  }
+  if (enabled) reboot_diagnostics(c);   // disabled HRUs keep their stored values (the reference never writes them back, :701)
+  // ---- ordered-series process sweep on the newest state
+  RunProcs<Prog, UNIT_DT, 0>::run(c, M, enabled, mask, e, k, gstate);
+  // ---- routing prep, diagnostics, state out + per-HRU part of the output reductions
+  double swv = 0.0, stor = 0.0;
+  if (enabled) {
+    swv = finish_step(c, Prog::nCore);
+    stor = hru_storage(c, Prog::nCore) * c.area;
+#pragma unroll
+    for (int s = 0; s < Prog::nCore; s++) __stcs(gstate + (size_t)Prog::slot_sv(s) * nHp, c.sv[s]);
+    if (M.record_forcings) {
+      double *gf = M.forc + (size_t)e * RVN_F_COUNT * nHp + k;
+#pragma unroll
+      for (int f = 0; f < RVN_F_COUNT; f++) gf[(size_t)f * nHp] = c.F[f];
+    }
+  }
+  const int par = step & 1;
+  if (in_range) M.swvol[((size_t)par * M.E + e) * nHp + k] = swv;
+  const double pa = enabled ? c.F[RVN_F_PRECIP] * c.area : 0.0;
+  const double bp = block_sum(pa, s_red);
+  const double bs = block_sum(stor, s_red);
+  if (tid == 0) {
+    M.part_precip[((size_t)par * M.E + e) * M.nBlocksX + blockIdx.x] = bp;
+    M.part_storage[((size_t)par * M.E + e) * M.nBlocksX + blockIdx.x] = bs;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// interpreter sweep: arbitrary process lists (DevProgram), state/rates in shared-memory columns
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant__ DevModel M, const int step) {
+  // ---- shared memory carve-up
+  DevProgram *P = reinterpret_cast<DevProgram *>(rvn_smem);
+  double *s_ptab = reinterpret_cast<double *>(rvn_smem + ((sizeof(DevProgram) + 15) & ~size_t(15)));
+  double *s_sv = s_ptab + ((M.ptab_stride + 1) & ~1);
+  double *s_rt = s_sv + (size_t)M.nCore * RVN_BS;
+  double *s_red = s_rt + (size_t)M.maxConn * RVN_BS;
+  const int tid = threadIdx.x, e = blockIdx.y, k = blockIdx.x * RVN_BS + tid;
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(M.prog);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(P);
+    for (int i = tid; i < (int)(sizeof(DevProgram) / 4); i += RVN_BS) dst[i] = src[i];
+    const double *prow = M.ptab + (size_t)e * M.ptab_stride;
+    for (int i = tid; i < M.ptab_stride; i += RVN_BS) s_ptab[i] = prow[i];
+  }
+  __syncthreads();
+  const int nCore = P->nCore;
+  const size_t nHp = (size_t)M.nHp;
+  const bool in_range = (k < M.nH);
+  const bool enabled = in_range && (M.hru_enabled[k] != 0);
+  DynCtx c;
+  load_hru_statics(c, M, k, s_ptab);
+  c.P = P; c.sv = s_sv + tid; c.rt = s_rt + tid;
+  c.prof_class = M.prof_class + c.profile * RVN_MAX_SOIL_LAYERS; c.prof_thick = M.prof_thick + c.profile * RVN_MAX_SOIL_LAYERS;
+  const int sb = M.hru_sb[k];
+  const unsigned long long mask = M.apply_mask[k];
+  double *gstate = M.state + (size_t)e * M.NS * nHp + k;
+  for (int s = 0; s < nCore; s++) c.SV(s) = __ldcs(gstate + (size_t)P->slot_sv[s] * nHp);
+  c.old_snow = (P->iSV[RVN_SV_SNOW] >= 0) ? c.SV(P->iSV[RVN_SV_SNOW]) : 0.0;
+  c.old_snow_cover = (P->iSV[RVN_SV_SNOW_COVER] >= 0) ? c.SV(P->iSV[RVN_SV_SNOW_COVER]) : 0.0;
+  c.old_snow_depth = (P->iSV[RVN_SV_SNOW_DEPTH] >= 0) ? c.SV(P->iSV[RVN_SV_SNOW_DEPTH]) : 0.0;
+  c.old_snow_temp = (P->iSV[RVN_SV_SNOW_TEMP] >= 0) ? c.SV(P->iSV[RVN_SV_SNOW_TEMP]) : 0.0;
+  if (enabled) compute_forcings(c, M, k, step, sb);
+  else { for (int f = 0; f < RVN_F_COUNT; f++) c.F[f] = 0.0; }
+  if (enabled) reboot_diagnostics(c);
+  const bool unit_dt = (c.tstep == 1.0);
+  const int nProc = P->nProc;
+  for (int j = 0; j < nProc; j++) {
+    const rvn_process &pr = P->proc[j];
+    const bool apply = enabled && ((mask >> j) & 1ull);   // CModel::ApplyProcess gate (src/Model.cpp:3061)
+    if (!apply) continue;
+    if (pr.op == RVN_OP_CONVOLVE) {
+      const int ci = pr.ia[0];
+      const size_t slot = ((size_t)e * M.nLU + c.lu) * M.nConv + ci;
+      double *g = gstate + (size_t)pr.ia[2] * nHp;
+      double *sc = M.conv_sum + ((size_t)e * M.nConv + ci) * nHp + k;
+      if (unit_dt) convolve_direct<true>(c, pr.ia[1], pr.ia[3], g, nHp, M.conv_tab + slot * RVN_CONV_STORES, M.conv_n[slot], sc, M.conv_sum_valid != 0);
+      else convolve_direct<false>(c, pr.ia[1], pr.ia[3], g, nHp, M.conv_tab + slot * RVN_CONV_STORES, M.conv_n[slot], sc, M.conv_sum_valid != 0);
+      continue;
+    }
+    const DynProc dp = {&pr, P};
+    for (int q = 0; q < pr.nconn; q++) c.R(q) = 0.0;          // src/Model.cpp:3066-3071
+    dispatch_rates(c, dp, pr.op);
+    apply_connections(c, dp);
+  }
+  double swv = 0.0, stor = 0.0;
+  if (enabled) {
+    swv = finish_step(c, nCore);
+    stor = hru_storage(c, nCore) * c.area;
+    for (int s = 0; s < nCore; s++) __stcs(gstate + (size_t)P->slot_sv[s] * nHp, c.SV(s));
+    if (M.record_forcings) {
+      double *gf = M.forc + (size_t)e * RVN_F_COUNT * nHp + k;
+#pragma unroll
+      for (int f = 0; f < RVN_F_COUNT; f++) gf[(size_t)f * nHp] = c.F[f];
+    }
+  }
+  const int par = step & 1;
+  if (in_range) M.swvol[((size_t)par * M.E + e) * nHp + k] = swv;
+  const double pa = enabled ? c.F[RVN_F_PRECIP] * c.area : 0.0;
+  const double bp = block_sum(pa, s_red);
+  const double bs = block_sum(stor, s_red);
+  if (tid == 0) {
+    M.part_precip[((size_t)par * M.E + e) * M.nBlocksX + blockIdx.x] = bp;
+    M.part_storage[((size_t)par * M.E + e) * M.nBlocksX + blockIdx.x] = bs;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// routing + balance: one CTA per member
+// ------------------------------------------------------------------------------------------------
+#define RVN_ROUTE_BS 256
+__device__ void route_one_basin(const DevModel &M, int e, int p) {
+  const double tstep = M.opt.timestep;
+  const int nSeg = M.sb_nseg[p], nQin = M.sb_nqin[p], nQlat = M.sb_nqlat[p];
+  double *QinHist = M.qin + ((size_t)e * M.nSB + p) * M.max_nqin;
+  double *QlatHist = M.qlat + ((size_t)e * M.nSB + p) * M.max_nqlat;
+  double *aQout = M.qout + ((size_t)e * M.nSB + p) * RVN_MAX_RIVER_SEGS;
+  double *sc = M.scal + ((size_t)e * M.nSB + p) * 8;
+  const double *UH = M.sb_unit_hydro + (size_t)p * M.max_nqlat, *RH = M.sb_route_hydro + (size_t)p * M.max_nqin;
+  // inflow from upstream basins, accumulated in the reference's processing order (ascending index inside the
+  // level above; src/Solvers.cpp:602-606), then CSubBasin::UpdateInflow (src/SubBasin.cpp:1531-1537)
+  double Qin_up = 0.0;
+  for (int u = M.sb_up_ptr[p]; u < M.sb_up_ptr[p + 1]; u++) {
+    const int pu = M.sb_up_idx[u];
+    Qin_up += M.qout[((size_t)e * M.nSB + pu) * RVN_MAX_RIVER_SEGS + M.sb_nseg[pu] - 1];
+  }
+  for (int n = nQin - 1; n > 0; n--) QinHist[n] = QinHist[n - 1];
+  QinHist[0] = Qin_up;
+  // CSubBasin::RouteWater  src/SubBasin.cpp:2584-2863
+  double Qlat_new = 0.0;
+  for (int n = 0; n < nQlat; n++) Qlat_new += UH[n] * QlatHist[n];
+  int method = M.opt.routing;
+  if (M.sb_headwater[p]) method = RVN_ROUTE_NONE;
+  const double seg_fraction = 1.0 / (double)(nSeg);
+  const double QoutLast = aQout[nSeg - 1];
+  if (method == RVN_ROUTE_MUSKINGUM || method == RVN_ROUTE_MUSKINGUM_CUNGE) {
+    const double K = M.sb_musk_K[p], X = M.sb_musk_X[p];
+    const double cunge = (method == RVN_ROUTE_MUSKINGUM_CUNGE) ? 1.0 : 0.0;
+    double dt = dmin(K, tstep);
+    // aQout[] is advanced in place over the local sub-steps; the reference restores the stored array and then
+    // overwrites it with the final values in UpdateOutflows, which is the same end state.
+    for (double t = 0; t < tstep; t += dt) {
+      if (dt > (tstep - t)) dt = tstep - t;
+      const double denom = (2 * K * (1.0 - X) + dt);
+      const double c1 = (dt - 2 * K * (X)) / denom, c2 = (dt + 2 * K * (X)) / denom, c3 = (-dt + 2 * K * (1 - X)) / denom, c4 = (dt) / denom;
+      double Qin = QinHist[1] + ((t) / tstep) * (QinHist[0] - QinHist[1]);
+      double Qin_new = QinHist[1] + ((t + dt) / tstep) * (QinHist[0] - QinHist[1]);
+      for (int s = 0; s < nSeg; s++) {
+        const double old = aQout[s];
+        const double qn = c1 * Qin_new + c2 * Qin + c3 * old + cunge * c4 * (Qlat_new * seg_fraction);
+        Qin = old; Qin_new = qn;
+        aQout[s] = qn;
+      }
+    }
+  } else if (method == RVN_ROUTE_STORAGECOEFF) {
+    double Qin_new = QinHist[0], Qin = QinHist[1];
+    const double Qlocal = sc[2];
+    for (int s = 0; s < nSeg; s++) {
+      const double ttime = M.sb_K_reach[p] * seg_fraction;
+      const double stc = dmin(1.0 / (ttime / tstep + 0.5), 1.0);
+      const double c1 = stc / 2, c2 = stc / 2, c3 = (1.0 - stc), corr = 1.0;
+      const double old = aQout[s];
+      const double qn = c1 * Qin + c2 * Qin_new + c3 * (old - corr * Qlocal);
+      Qin = old; Qin_new = qn;
+      aQout[s] = qn;
+    }
+  } else if (method == RVN_ROUTE_PLUG_FLOW || method == RVN_ROUTE_DIFFUSIVE_WAVE) {
+    double q = 0.0;
+    for (int n = 0; n < nQin; n++) q += RH[n] * QinHist[n];
+    aQout[nSeg - 1] = q;
+  } else {  // ROUTE_NONE
+    for (int s = 0; s < nSeg; s++) aQout[s] = 0.0;
+    aQout[nSeg - 1] = QinHist[0];
+  }
+  aQout[nSeg - 1] += Qlat_new;
+  aQout[nSeg - 1] += 0.0;  // down_Q (specified downstream inflows / return flows: none)
+  // CSubBasin::UpdateOutflows  src/SubBasin.cpp:2320-2421 (no irrigation, diversions or reservoirs)
+  sc[0] = QoutLast;
+  const double irrQ = dmin(0.0, aQout[nSeg - 1]); aQout[nSeg - 1] -= irrQ;
+  const double divQ = dmin(0.0, aQout[nSeg - 1]); aQout[nSeg - 1] -= divQ;
+  const double dts = tstep * D_SEC_PER_DAY;
+  sc[3] = sc[2]; sc[2] = Qlat_new;
+  double dV = 0.0;
+  dV += 0.5 * (QinHist[0] + QinHist[1]) * dts;
+  dV -= 0.5 * (aQout[nSeg - 1] + QoutLast) * dts;
+  dV += 0.5 * (Qlat_new + sc[1]) * dts;
+  dV -= 0.5 * (irrQ + 0.0) * dts;
+  dV -= 0.5 * (divQ + 0.0) * dts;
+  sc[4] += dV;
+  dV = 0.0;
+  dV += QlatHist[0] * dts;
+  dV -= 0.5 * (Qlat_new + sc[1]) * dts;
+  sc[5] += dV;
+  sc[1] = Qlat_new;
+}
+
+// fixed-shape CTA tree sum (deterministic)
+RVN_DI double route_block_sum(double v, double *s_red) {
+  const int tid = threadIdx.x;
+  s_red[tid] = v;
+  __syncthreads();
+  for (int o = RVN_ROUTE_BS / 2; o > 0; o >>= 1) { if (tid < o) s_red[tid] += s_red[tid + o]; __syncthreads(); }
+  const double t = s_red[0];
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(RVN_ROUTE_BS) route_kernel(const __grid_constant__ DevModel M, const int step, const int rec) {
+  const int e = blockIdx.x, tid = threadIdx.x, NB = M.nSB;
+  const double tstep = M.opt.timestep;
+  const int par = step & 1;
+  __shared__ double s_red[RVN_ROUTE_BS];
+  // ---- HRU -> subbasin aggregation in HRU-index order (src/Solvers.cpp:490-511) + UpdateLateralInflow
+  const double *swvol = M.swvol + ((size_t)par * M.E + e) * M.nHp;
+  for (int p = tid; p < NB; p += RVN_ROUTE_BS) {
+    double routed = 0.0;
+    for (int i = M.sb_hru_ptr[p]; i < M.sb_hru_ptr[p + 1]; i++) routed += swvol[M.sb_hru_idx[i]];
+    double *QlatHist = M.qlat + ((size_t)e * NB + p) * M.max_nqlat;
+    for (int n = M.sb_nqlat[p] - 1; n > 0; n--) QlatHist[n] = QlatHist[n - 1];
+    QlatHist[0] = routed / (tstep * D_SEC_PER_DAY);
+  }
+  __syncthreads();
+  // ---- level-ordered routing: deepest level first; basins inside a level are independent
+  for (int L = 0; L < M.nLevels; L++) {
+    for (int i = M.level_ptr[L] + tid; i < M.level_ptr[L + 1]; i += RVN_ROUTE_BS) route_one_basin(M, e, M.level_idx[i]);
+    __syncthreads();
+  }
+  // ---- balance: IncrementCumulInput / IncrementCumOutflow + watershed storage
+  const double area = M.watershed_area * D_M2_PER_KM2;
+  double out_part = 0.0, ch_part = 0.0, rv_part = 0.0;
+  for (int p = tid; p < NB; p += RVN_ROUTE_BS) {
+    const double *sc = M.scal + ((size_t)e * NB + p) * 8;
+    const double qo = M.qout[((size_t)e * NB + p) * RVN_MAX_RIVER_SEGS + M.sb_nseg[p] - 1];
+    if (M.sb_level[p] == 0 || M.sb_down[p] < 0) out_part += (0.5 * (qo + sc[0]) * (tstep * D_SEC_PER_DAY)) / area * D_MM_PER_METER;
+    ch_part += sc[4]; rv_part += sc[5];
+    if ((M.rec_flags & 1) && rec >= 0) M.rec_qout[((size_t)rec * M.E + e) * NB + p] = qo;
+  }
+  double pp = 0.0, ps = 0.0;
+  const double *part_p = M.part_precip + ((size_t)par * M.E + e) * M.nBlocksX, *part_s = M.part_storage + ((size_t)par * M.E + e) * M.nBlocksX;
+  for (int b = tid; b < M.nBlocksX; b += RVN_ROUTE_BS) { pp += part_p[b]; ps += part_s[b]; }
+  const double tot_out = route_block_sum(out_part, s_red), tot_ch = route_block_sum(ch_part, s_red), tot_rv = route_block_sum(rv_part, s_red);
+  const double psum = route_block_sum(pp, s_red), ssum = route_block_sum(ps, s_red);
+  if (tid == 0) {
+    const double avg_precip = psum / M.watershed_area;
+    double *cum = M.cumul + (size_t)e * 2;
+    cum[0] += avg_precip * tstep;
+    cum[1] += tot_out;
+    if ((M.rec_flags & 2) && rec >= 0) {
+      double *w = M.rec_wshed + ((size_t)rec * M.E + e) * 4;
+      w[0] = cum[0]; w[1] = cum[1]; w[2] = avg_precip;
+      w[3] = ssum / M.watershed_area + tot_ch / area * D_MM_PER_METER + tot_rv / area * D_MM_PER_METER;
+    }
+  }
+}
+
+// area-weighted watershed average of every state variable (CModel::GetAvgStateVar, src/Model.cpp:1159-1174)
+__global__ void avg_state_kernel(const __grid_constant__ DevModel M, double *out, int member0) {
+  const int e = member0 + blockIdx.y, i = blockIdx.x, tid = threadIdx.x;
+  __shared__ double s_red[256];
+  const double *row = M.state + ((size_t)e * M.NS + i) * M.nHp;
+  double v = 0.0;
+  for (int k = tid; k < M.nH; k += 256) if (M.hru_enabled[k]) v += row[k] * M.hru_area[k];
+  s_red[tid] = v;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (tid < o) s_red[tid] += s_red[tid + o]; __syncthreads(); }
+  if (tid == 0) out[(size_t)blockIdx.y * M.NS + i] = s_red[0] / M.watershed_area;
+}
+
+// [member][hru][sv] (host order) <-> [member][sv][nHp] (device order)
+__global__ void transpose_in_kernel(const double *__restrict__ src, double *__restrict__ dst, int nH, int nHp, int NS) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x, e = blockIdx.y;
+  if (k >= nH) return;
+  for (int i = 0; i < NS; i++) dst[((size_t)e * NS + i) * nHp + k] = src[((size_t)e * nH + k) * NS + i];
+}
+__global__ void transpose_out_kernel(const double *__restrict__ src, double *__restrict__ dst, int nH, int nHp, int NS) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x, e = blockIdx.y;
+  if (k >= nH) return;
+  for (int i = 0; i < NS; i++) dst[((size_t)e * nH + k) * NS + i] = src[((size_t)e * NS + i) * nHp + k];
+}
+#endif

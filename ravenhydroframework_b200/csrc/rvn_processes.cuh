@@ -2,12 +2,19 @@
 //
 // Every process of the reference exposes  GetRatesOfChange(state_vars,pHRU,Options,tt,rates)  and
 // ApplyConstraints(...)  (src/HydroProcessABC.h:102-112).  Here each supported (process, algorithm)
-// pair is one __device__ function  rates_<NAME>(ctx, pr)  that performs both calls back to back on the
-// calling thread's (member, HRU) pair.  `ctx` plays the role of pHRU/Options/tt: it gives access to the
-// newest state vector (shared-memory column of this thread), the lagged start-of-step values the
-// reference reads through pHRU->GetStateVarValue, derived forcings, class parameters
-// and HRU attributes.  Arithmetic order follows the cited reference lines; min/max are the reference's
-// (first argument wins ties), FMA contraction is disabled at compile time (-fmad=false).
+// pair is one __device__ function template  rates_<NAME>(ctx, pr)  that performs both calls back to back on the
+// calling thread's (member, HRU) pair.
+//
+//   ctx  plays the role of pHRU/Options/tt: newest state vector SV(slot), rate vector R(q), the lagged start-of-step
+//        values the reference reads through pHRU->GetStateVarValue, derived forcings, class
+//        parameters and HRU attributes.  Two context types exist (rvn_engine.cu):
+//          DynCtx        state/rates in shared-memory columns, catalogue lookups at run time  (interpreter kernel)
+//          StatCtx<Prog> state/rates in registers, every index a compile-time constant         (specialised kernels)
+//   pr   is the process record: connection slots from(q)/to(q), nconn(), integer/double arguments ia(i)/da(i);
+//        run-time (DynProc) or constexpr (StatProc<Prog,J>).
+//
+// Arithmetic order follows the cited reference lines; min/max are the reference's (first argument wins ties), FMA
+// contraction is disabled at compile time (-fmad=false).
 #ifndef RVN_PROCESSES_CUH
 #define RVN_PROCESSES_CUH
 #include "rvn_device.cuh"
@@ -29,74 +36,47 @@
 #define D_HBV_PET_TEMP_CORR 0.5
 #define D_GLOBAL_PET_CORR 1.0
 
-__device__ __forceinline__ double dmax(double r, double l) { return (r >= l) ? r : l; }   // src/RavenInclude.h:1456
-__device__ __forceinline__ double dmin(double r, double l) { return (r <= l) ? r : l; }   // src/RavenInclude.h:1464
+#define RVN_DI __device__ __forceinline__
+#define RVN_HD __host__ __device__ __forceinline__
 
-// Per-thread view of "its" HRU.  Shared-memory arrays are column-major over the CTA's threads so that
-// dynamic indexing by state-variable slot is bank-conflict free.
-struct HruCtx {
-  const DevProgram *P;     // program (shared memory)
-  double *sv;              // &s_sv[tid]; slot i at sv[i*RVN_BS]  -- newest state (aPhinew[k])
-  double *rt;              // &s_rates[tid]; connection q at rt[q*RVN_BS]
-  const double *ptab;      // member parameter row (shared memory)
-  const int32_t *prof_class; const double *prof_thick;   // global
-  double F[RVN_F_COUNT];   // derived forcings of this HRU for this step
-  // lagged (start-of-step) values (what pHRU->GetStateVarValue returns inside processes)
-  double old_snow, old_snow_cover, old_snow_depth, old_snow_temp;
-  double area, elev, lat, slope, aspect;
-  int type, lu, veg, profile;
-  double tstep;
-  __device__ __forceinline__ double &SV(int slot) const { return sv[slot * RVN_BS]; }
-  __device__ __forceinline__ double &R(int q) const { return rt[q * RVN_BS]; }
-  __device__ __forceinline__ double G(int f) const { return ptab[P->glob_off + f]; }
-  __device__ __forceinline__ double LU(int f) const { return ptab[P->lu_off + lu * RVN_LU_COUNT + f]; }
-  __device__ __forceinline__ double VEG(int f) const { return ptab[P->veg_off + veg * RVN_V_COUNT + f]; }
-  __device__ __forceinline__ double SOIL(int m, int f) const {
-    return ptab[P->soil_off + prof_class[profile * RVN_MAX_SOIL_LAYERS + m] * RVN_S_COUNT + f];
-  }
-  // CHydroUnit::GetSoilCapacity (src/HydroUnits.cpp:260-267)
-  __device__ __forceinline__ double SoilCapacity(int m) const {
-    return prof_thick[profile * RVN_MAX_SOIL_LAYERS + m] * D_MM_PER_METER * SOIL(m, RVN_S_CAP_RATIO);
-  }
-  // CHydroUnit::GetSoilTensionStorageCapacity (src/HydroUnits.cpp:275-286)
-  __device__ __forceinline__ double SoilTensionCapacity(int m) const {
-    return prof_thick[profile * RVN_MAX_SOIL_LAYERS + m] * D_MM_PER_METER * SOIL(m, RVN_S_CAP_RATIO) *
-           (SOIL(m, RVN_S_FIELD_CAPACITY) - SOIL(m, RVN_S_SAT_WILT));
-  }
-  // CHydroUnit::GetSnowCover (src/HydroUnits.cpp:679-705), lagged, SNOWCOV_NONE
-  __device__ __forceinline__ double SnowCover() const {
-    if (P->iSV[RVN_SV_SNOW] < 0) return 0.0;
-    if (P->iSV[RVN_SV_SNOW_COVER] >= 0) return old_snow_cover;
-    return (old_snow < D_NEGLIGBLE_SNOW) ? 0.0 : 1.0;
-  }
-  // CHydroUnit::GetSnowTemperature (src/HydroUnits.cpp:645-658), lagged
-  __device__ __forceinline__ double SnowTemperature() const {
-    if (P->iSV[RVN_SV_SNOW_TEMP] < 0) { double t = G(RVN_G_SNOW_TEMPERATURE); return (t < -60000.0) ? 0.0 : t; }
-    return old_snow_temp;
-  }
-  // CHydroUnit::GetStateVarMax (src/HydroUnits.cpp:559-606); CalculateSnowLiquidCapacity (src/SnowParams.cpp:79-88)
-  __device__ double StateVarMax(int slot) const {
-    switch (P->slot_type[slot]) {
-      case RVN_SV_SOIL: return SoilCapacity(P->slot_layer[slot]);
-      case RVN_SV_CANOPY: return VEG(RVN_V_VAR_CAPACITY);
-      case RVN_SV_CANOPY_SNOW: return VEG(RVN_V_VAR_SNOW_CAPACITY);
-      case RVN_SV_DEPRESSION: { double dm = LU(RVN_LU_DEP_MAX); return (dm >= 0) ? dm : D_ALMOST_INF; }
-      case RVN_SV_SNOW_COVER: return 1.0;
-      case RVN_SV_SNOW_LIQ: return G(RVN_G_SNOW_SWI) * SV(P->iSV[RVN_SV_SNOW]);
-      default: return D_ALMOST_INF;
-    }
-  }
-};
+RVN_DI double dmax(double r, double l) { return (r >= l) ? r : l; }   // src/RavenInclude.h:1456
+RVN_DI double dmin(double r, double l) { return (r <= l) ? r : l; }   // src/RavenInclude.h:1464
 
-// connection slots of process pr
-#define FROM(q) ((int)c.P->conn_from[pr.conn0 + (q)])
-#define TO(q) ((int)c.P->conn_to[pr.conn0 + (q)])
+// ---- helpers shared by both context types (CRTP-free: plain function templates over the context) -------------
+// CHydroUnit::GetSoilCapacity (src/HydroUnits.cpp:260-267)
+template <class C> RVN_DI double SoilCapacity(const C &c, int m) { return c.thick(m) * D_MM_PER_METER * c.SOIL(m, RVN_S_CAP_RATIO); }
+// CHydroUnit::GetSoilTensionStorageCapacity (src/HydroUnits.cpp:275-286)
+template <class C> RVN_DI double SoilTensionCapacity(const C &c, int m) {
+  return c.thick(m) * D_MM_PER_METER * c.SOIL(m, RVN_S_CAP_RATIO) * (c.SOIL(m, RVN_S_FIELD_CAPACITY) - c.SOIL(m, RVN_S_SAT_WILT));
+}
+// CHydroUnit::GetSnowCover (src/HydroUnits.cpp:679-705), lagged, SNOWCOV_NONE
+template <class C> RVN_DI double SnowCover(const C &c) {
+  if (c.iSV(RVN_SV_SNOW) < 0) return 0.0;
+  if (c.iSV(RVN_SV_SNOW_COVER) >= 0) return c.old_snow_cover;
+  return (c.old_snow < D_NEGLIGBLE_SNOW) ? 0.0 : 1.0;
+}
+// CHydroUnit::GetSnowTemperature (src/HydroUnits.cpp:645-658), lagged
+template <class C> RVN_DI double SnowTemperature(const C &c) {
+  if (c.iSV(RVN_SV_SNOW_TEMP) < 0) { double t = c.G(RVN_G_SNOW_TEMPERATURE); return (t < -60000.0) ? 0.0 : t; }
+  return c.old_snow_temp;
+}
+// CHydroUnit::GetStateVarMax (src/HydroUnits.cpp:559-606); CalculateSnowLiquidCapacity (src/SnowParams.cpp:79-88)
+template <class C> RVN_DI double StateVarMax(const C &c, int slot) {
+  switch (c.slot_type(slot)) {
+    case RVN_SV_SOIL: return SoilCapacity(c, c.slot_layer(slot));
+    case RVN_SV_CANOPY: return c.VEG(RVN_V_VAR_CAPACITY);
+    case RVN_SV_CANOPY_SNOW: return c.VEG(RVN_V_VAR_SNOW_CAPACITY);
+    case RVN_SV_DEPRESSION: { double dm = c.LU(RVN_LU_DEP_MAX); return (dm >= 0) ? dm : D_ALMOST_INF; }
+    case RVN_SV_SNOW_COVER: return 1.0;
+    case RVN_SV_SNOW_LIQ: return c.G(RVN_G_SNOW_SWI) * c.SV(c.iSV(RVN_SV_SNOW));
+    default: return D_ALMOST_INF;
+  }
+}
 
 // CmvPrecipitation::GetRatesOfChange  src/PartitionPrecip.cpp:135-355 (models without ICE_THICKNESS)
-__device__ void rates_PRECIPITATION(const HruCtx &c, const rvn_process &pr) {
+template <class C, class PR> RVN_DI void rates_PRECIPITATION(C &c, const PR &pr) {
   enum { qPond = 0, qCan, qCanSnow, qDep, qAtmos, qSnow, qSnowLiq, qSnowDef, qNewSnow, qLake, qSW, qColdContent, qSnowDepth };
-  const DevProgram *P = c.P;
-  const int iCan = P->iSV[RVN_SV_CANOPY], iSCan = P->iSV[RVN_SV_CANOPY_SNOW], iSnLiq = P->iSV[RVN_SV_SNOW_LIQ], iSWE = P->iSV[RVN_SV_SNOW];
+  const int iCan = c.iSV(RVN_SV_CANOPY), iSCan = c.iSV(RVN_SV_CANOPY_SNOW), iSnLiq = c.iSV(RVN_SV_SNOW_LIQ), iSWE = c.iSV(RVN_SV_SNOW);
   const double tstep = c.tstep;
   double total_precip = c.F[RVN_F_PRECIP], Fsnow = c.F[RVN_F_SNOW_FRAC], air_temp = c.F[RVN_F_TEMP_AVE];
   if (iSWE < 0) Fsnow = 0;
@@ -105,7 +85,7 @@ __device__ void rates_PRECIPITATION(const HruCtx &c, const rvn_process &pr) {
   rainfall += 0.0;  // irrigation
   double SWE = 0.0;
   if (iSWE >= 0) SWE = c.SV(iSWE);
-  const double Fs = c.SnowCover();
+  const double Fs = SnowCover(c);
   double rainthru, snowthru;
   const bool is_lake = (c.type == RVN_HRU_LAKE);
   if (!is_lake) {
@@ -129,22 +109,22 @@ __device__ void rates_PRECIPITATION(const HruCtx &c, const rvn_process &pr) {
   else if (c.type == RVN_HRU_WETLAND) c.R(qDep) = snowthru + rainthru;
   else if (c.type == RVN_HRU_WATER) c.R(qSW) = snowthru + rainthru;
   else {
-    if (P->iSV[RVN_SV_NEW_SNOW] < 0) {
+    if (c.iSV(RVN_SV_NEW_SNOW) < 0) {
       if (iSWE >= 0) {
         c.R(qSnow) = snowthru;
-        if (P->iSV[RVN_SV_SNOW_DEPTH] >= 0) {  // CalcFreshSnowDensity, src/SnowParams.cpp:37-47
+        if (c.iSV(RVN_SV_SNOW_DEPTH) >= 0) {  // CalcFreshSnowDensity, src/SnowParams.cpp:37-47
           double rho = (air_temp <= D_FREEZING_TEMP) ? 67.92 + 51.25 * exp((air_temp - D_FREEZING_TEMP) / 2.59)
                                                      : dmin((119.17 + 20.0 * (air_temp - D_FREEZING_TEMP)), 200.0);
           c.R(qSnowDepth) = snowthru * D_DENSITY_ICE / rho;
         }
-        if (P->iSV[RVN_SV_COLD_CONTENT] >= 0) c.R(qColdContent) = snowthru * dmax(D_FREEZING_TEMP - air_temp, 0.0) * D_HCP_ICE / D_MM_PER_METER;
-        if ((iSnLiq >= 0) && (P->iSV[RVN_SV_SNOW_DEFICIT] < 0) && (SWE > 0.0)) {
-          double melt_cap = c.StateVarMax(iSnLiq);
+        if (c.iSV(RVN_SV_COLD_CONTENT) >= 0) c.R(qColdContent) = snowthru * dmax(D_FREEZING_TEMP - air_temp, 0.0) * D_HCP_ICE / D_MM_PER_METER;
+        if ((iSnLiq >= 0) && (c.iSV(RVN_SV_SNOW_DEFICIT) < 0) && (SWE > 0.0)) {
+          double melt_cap = StateVarMax(c, iSnLiq);
           double fill_rate = Fs * dmin(dmax(melt_cap - c.SV(iSnLiq), 0.0) / tstep, rainthru);
           c.R(qSnowLiq) = fill_rate;
           rainthru -= fill_rate;
         }
-        if ((P->iSV[RVN_SV_SNOW_DEFICIT] >= 0) && (SWE > 0.0)) c.R(qSnowDef) = c.G(RVN_G_SNOW_SWI) * snowthru;
+        if ((c.iSV(RVN_SV_SNOW_DEFICIT) >= 0) && (SWE > 0.0)) c.R(qSnowDef) = c.G(RVN_G_SNOW_SWI) * snowthru;
       }
     } else c.R(qNewSnow) = snowthru;
     c.R(qPond) = rainthru;
@@ -153,9 +133,9 @@ __device__ void rates_PRECIPITATION(const HruCtx &c, const rvn_process &pr) {
 }
 
 // CmvSnowBalance SNOBAL_HMETS  src/SnowBalance.cpp:472-522
-__device__ void rates_SNOBAL_HMETS(const HruCtx &c, const rvn_process &pr) {
+template <class C, class PR> RVN_DI void rates_SNOBAL_HMETS(C &c, const PR &pr) {
   const double tstep = c.tstep;
-  double SWE = c.SV(FROM(0)), SL = c.SV(FROM(3)), cum_melt = c.SV(FROM(4));
+  double SWE = c.SV(pr.from(0)), SL = c.SV(pr.from(3)), cum_melt = c.SV(pr.from(4));
   const double Kf = c.LU(RVN_LU_REFREEZE_FACTOR), Tbf = c.LU(RVN_LU_DD_REFREEZE_TEMP), exp_fe = c.LU(RVN_LU_REFREEZE_EXP);
   const double fcmin = c.G(RVN_G_SNOW_SWI_MIN), fcmax = c.G(RVN_G_SNOW_SWI_MAX), Ccum = c.G(RVN_G_SWI_REDUCT_COEFF);
   const double potmelt = dmax(c.F[RVN_F_POTENTIAL_MELT], 0.0);
@@ -174,20 +154,20 @@ __device__ void rates_SNOBAL_HMETS(const HruCtx &c, const rvn_process &pr) {
   double ripe = dmax(SL - SWI * SWE, 0.0);
   SL -= ripe;
   c.R(0) = to_liq / tstep; c.R(1) = melt / tstep; c.R(2) = ripe; c.R(3) = freeze / tstep; c.R(4) = (melt + to_liq) / tstep;
-  if (SWE <= 0.0) c.R(4) = -c.SV(FROM(4)) / tstep;
+  if (SWE <= 0.0) c.R(4) = -c.SV(pr.from(4)) / tstep;
 }
 
 // CmvInfiltration INF_HMETS  src/Infiltration.cpp:304-330,491-514; ApplyConstraints :605-626
-__device__ void rates_INF_HMETS(const HruCtx &c, const rvn_process &pr) {
+template <class C, class PR> RVN_DI void rates_INF_HMETS(C &c, const PR &pr) {
   const double tstep = c.tstep;
   const int type = c.type;
   if (type != RVN_HRU_STANDARD && type != RVN_HRU_ROCK && type != RVN_HRU_MASKED_GLACIER) return;
   const double Fimp = c.LU(RVN_LU_IMPERMEABLE_FRAC);
-  const double ponded = dmax(c.SV(c.P->iSV[RVN_SV_PONDED_WATER]), 0.0);
+  const double ponded = dmax(c.SV(c.iSV(RVN_SV_PONDED_WATER)), 0.0);
   const double rainthru = (ponded / tstep);
   if (type == RVN_HRU_ROCK) { c.R(0) = 0.0; c.R(1) = rainthru; }
   else {
-    double stor = c.SV(TO(0)), max_stor = c.SoilCapacity(0), coef = c.LU(RVN_LU_HMETS_RUNOFF_COEFF);
+    double stor = c.SV(pr.to(0)), max_stor = SoilCapacity(c, 0), coef = c.LU(RVN_LU_HMETS_RUNOFF_COEFF);
     double sat = dmin(dmax(stor / max_stor, 0.0), 1.0);
     double direct = Fimp * rainthru;
     double runoff = coef * (sat) * (1.0 - Fimp) * rainthru;
@@ -197,72 +177,74 @@ __device__ void rates_INF_HMETS(const HruCtx &c, const rvn_process &pr) {
     c.R(0) = infil; c.R(1) = direct; c.R(2) = runoff; c.R(3) = delayed;
   }
   if (type != RVN_HRU_STANDARD && type != RVN_HRU_MASKED_GLACIER) return;
-  c.R(0) = dmin(c.R(0), c.SV(FROM(0)) / tstep);
+  c.R(0) = dmin(c.R(0), c.SV(pr.from(0)) / tstep);
   double inf = c.R(0);
-  if (!c.P->opt.allow_soil_overfill) {
-    double max_stor = c.StateVarMax(TO(0));
-    inf = dmin(c.R(0), dmax(max_stor - c.SV(TO(0)), 0.0) / tstep);
+  if (!c.opt().allow_soil_overfill) {
+    double max_stor = StateVarMax(c, pr.to(0));
+    inf = dmin(c.R(0), dmax(max_stor - c.SV(pr.to(0)), 0.0) / tstep);
   }
   c.R(1) += (c.R(0) - inf);
   c.R(0) = inf;
 }
 
 // CmvOverflow  src/Flush.cpp:259-279
-__device__ void rates_OVERFLOW(const HruCtx &c, const rvn_process &pr) {
-  double max_storage = dmax(c.StateVarMax(FROM(0)), 0.0);
-  c.R(0) = dmax(c.SV(FROM(0)) - max_storage, 0.0) / c.tstep;
+template <class C, class PR> RVN_DI void rates_OVERFLOW(C &c, const PR &pr) {
+  double max_storage = dmax(StateVarMax(c, pr.from(0)), 0.0);
+  c.R(0) = dmax(c.SV(pr.from(0)) - max_storage, 0.0) / c.tstep;
 }
 // CmvFlush  src/Flush.cpp:75-86
-__device__ void rates_FLUSH(const HruCtx &c, const rvn_process &pr) { c.R(0) = pr.da[0] * c.SV(FROM(0)) / c.tstep; }
+template <class C, class PR> RVN_DI void rates_FLUSH(C &c, const PR &pr) { c.R(0) = pr.da(0) * c.SV(pr.from(0)) / c.tstep; }
 // CmvSplit  src/Flush.cpp:178-186
-__device__ void rates_SPLIT(const HruCtx &c, const rvn_process &pr) {
-  c.R(0) = (pr.da[0]) * c.SV(FROM(0)) / c.tstep;
-  c.R(1) = (1.0 - pr.da[0]) * c.SV(FROM(0)) / c.tstep;
+template <class C, class PR> RVN_DI void rates_SPLIT(C &c, const PR &pr) {
+  c.R(0) = (pr.da(0)) * c.SV(pr.from(0)) / c.tstep;
+  c.R(1) = (1.0 - pr.da(0)) * c.SV(pr.from(0)) / c.tstep;
 }
 // CmvBaseflow BASE_LINEAR  src/Baseflow.cpp:152-186; ApplyConstraints :297-310
-__device__ void rates_BASE_LINEAR(const HruCtx &c, const rvn_process &pr) {
+template <class C, class PR> RVN_DI void rates_BASE_LINEAR(C &c, const PR &pr) {
   const int type = c.type;
   if (!(type == RVN_HRU_LAKE || type == RVN_HRU_WATER || type == RVN_HRU_ROCK)) {
-    const int m = pr.ia[0];
-    double stor = c.SV(FROM(0)), max_stor = (m >= 0) ? c.SoilCapacity(m) : 0.0;
+    const int m = pr.ia(0);
+    double stor = c.SV(pr.from(0)), max_stor = (m >= 0) ? SoilCapacity(c, m) : 0.0;
     stor = dmin(dmax(stor, 0.0), max_stor);
     c.R(0) = c.SOIL(m, RVN_S_BASEFLOW_COEFF) * stor;
   }
-  c.R(0) = dmin(c.R(0), dmax(c.SV(FROM(0)), 0.0) / c.tstep);
+  c.R(0) = dmin(c.R(0), dmax(c.SV(pr.from(0)), 0.0) / c.tstep);
   c.R(0) = dmax(c.R(0), 0.0);
 }
 // CmvPercolation PERC_LINEAR  src/Percolation.cpp:183-243; ApplyConstraints :339-360
-__device__ void rates_PERC_LINEAR(const HruCtx &c, const rvn_process &pr) {
+template <class C, class PR> RVN_DI void rates_PERC_LINEAR(C &c, const PR &pr) {
   const int type = c.type;
   if (type == RVN_HRU_LAKE || type == RVN_HRU_WATER || type == RVN_HRU_ROCK) return;
-  const int m = pr.ia[0];
-  double stor = c.SV(FROM(0)), max_stor = c.SoilCapacity(m);
+  const int m = pr.ia(0);
+  double stor = c.SV(pr.from(0)), max_stor = SoilCapacity(c, m);
   if (max_stor > 0.0) c.R(0) = c.SOIL(m, RVN_S_PERC_COEFF) * stor;
-  c.R(0) = dmin(c.R(0), dmax(c.SV(FROM(0)) - 0.0, 0.0) / c.tstep);
-  if (!c.P->opt.allow_soil_overfill) {
-    double room = dmax(c.StateVarMax(TO(0)) - c.SV(TO(0)), 0.0);
+  c.R(0) = dmin(c.R(0), dmax(c.SV(pr.from(0)) - 0.0, 0.0) / c.tstep);
+  if (!c.opt().allow_soil_overfill) {
+    double room = dmax(StateVarMax(c, pr.to(0)) - c.SV(pr.to(0)), 0.0);
     c.R(0) = dmin(c.R(0), room / c.tstep);
   }
 }
 // CmvSoilEvap SOILEVAP_ALL  src/SoilEvaporation.cpp:325-343,379-383,751; ApplyConstraints :767-783
-__device__ void rates_SOILEVAP_ALL(const HruCtx &c, const rvn_process &pr) {
+template <class C, class PR> RVN_DI void rates_SOILEVAP_ALL(C &c, const PR &pr) {
   if (c.type != RVN_HRU_STANDARD) return;
   double PET = c.F[RVN_F_PET];
-  if (!c.P->opt.suppress_competitive_ET) { PET -= (c.SV(c.P->iSV[RVN_SV_AET]) / c.tstep); PET = dmax(PET, 0.0); }
+  if (!c.opt().suppress_competitive_ET) { PET -= (c.SV(c.iSV(RVN_SV_AET)) / c.tstep); PET = dmax(PET, 0.0); }
   c.R(0) = PET;
-  const int last = pr.nconn - 1;
+  const int last = pr.nconn() - 1;
   c.R(last) = c.R(0);
   double corr = 0;
+#pragma unroll
   for (int q = 0; q < last; q++) {
     double oldrate = c.R(q);
-    c.R(q) = dmin(c.R(q), c.SV(FROM(q)) / c.tstep);
+    c.R(q) = dmin(c.R(q), c.SV(pr.from(q)) / c.tstep);
     corr += oldrate - c.R(q);
   }
   c.R(last) -= corr;
 }
 
-__device__ __forceinline__ void dispatch_rates(const HruCtx &c, const rvn_process &pr) {
-  switch (pr.op) {   // uniform across the CTA: every thread runs the same process at the same time
+// GetRatesOfChange + ApplyConstraints of process `pr` (opcode `op`: a compile-time constant in the specialised kernels)
+template <class C, class PR> RVN_DI void dispatch_rates(C &c, const PR &pr, const int op) {
+  switch (op) {   // uniform across the CTA: every thread runs the same process at the same time
     case RVN_OP_PRECIPITATION: rates_PRECIPITATION(c, pr); break;
     case RVN_OP_SNOBAL_HMETS: rates_SNOBAL_HMETS(c, pr); break;
     case RVN_OP_INF_HMETS: rates_INF_HMETS(c, pr); break;
@@ -282,6 +264,4 @@ __host__ __device__ inline bool rvn_op_supported(int op) {
     default: return false;
   }
 }
-#undef FROM
-#undef TO
 #endif

@@ -23,7 +23,7 @@ def test_engine_exports_every_declared_symbol():
     assert lib.rvn_gpu_abi_version() == 1
 
 
-def test_engine_is_sm100a_and_uses_bulk_async_copy():
+def test_engine_is_sm100a_with_specialised_and_interpreter_sweeps():
     import shutil
     import subprocess
     if not shutil.which("cuobjdump"):
@@ -31,8 +31,25 @@ def test_engine_is_sm100a_and_uses_bulk_async_copy():
     so = os.path.join(ROOT, "ravenhydroframework_b200", "librvn_gpu.so")
     out = subprocess.run(["cuobjdump", "-sass", so], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
     assert "sm_100a" in out
-    assert "UBLKCP" in out, "hru_sweep_kernel should stream state tiles with cp.async.bulk (SASS UBLKCP)"
-    assert "SYNCS" in out  # mbarrier
+    assert "hru_sweep_static" in out and "Prog_HMETS" in out, "specialised sweep of the HMETS program missing"
+    assert "hru_sweep_interp" in out and "route_kernel" in out
+    assert "DFMA" in out and "DADD" in out      # FP64 arithmetic
+    assert "LDG.E.64.EF" in out or "LDG.E.EF.64" in out, "state streams should use evict-first loads (__ldcs)"
+
+
+def test_static_program_header_is_current():
+    """csrc/rvn_static_programs.cuh must equal what the engine emits for the current templates (tools/gen_static_programs.py)."""
+    import ctypes as C
+    eng = api.engine_lib()
+    hdr = open(os.path.join(ROOT, "ravenhydroframework_b200", "csrc", "rvn_static_programs.cuh")).read()
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        base = synth.write_hmets(td, n_sb=1, hru_per_sb=1, n_days=5, seed=1)
+        m = api.RavenModel(base)
+        m.flatten(1)
+        buf = C.create_string_buffer(1 << 16)
+        assert eng.rvn_gpu_emit_static_program(m.desc, b"HMETS", buf, len(buf)) == 0
+        assert buf.value.decode() in hdr
 
 
 def test_no_cpu_fallback(tmp_path):
