@@ -13,12 +13,13 @@
 //                                 state and rates live in shared-memory columns indexed at run time
 //                        In both the 50-slot convolution stores are streamed HBM -> registers -> HBM, coalesced over
 //                        neighbouring HRUs, with a register double buffer; no CTA-wide barrier inside the time-critical part.
-//   route_kernel       = HRU->subbasin aggregation (:490-511), the upstream->downstream routing loop
+//   aggregate_kernel, route_level_kernel (one launch per level), balance_kernel
+//                      = HRU->subbasin aggregation (:490-511), the upstream->downstream routing loop
 //                        (:565-615; CSubBasin::RouteWater/UpdateOutflows, src/SubBasin.cpp:2584-2863,
 //                        2320-2421) level by level, IncrementCumulInput/CumOutflow (src/Model.cpp:
 //                        2458-2539) and the watershed-storage total (src/StandardOutput.cpp:745-785).
-//                        One CTA per member walks the precomputed level order with a CTA barrier per level.
-//                        It runs on a second, higher-priority stream: routing of step s overlaps the sweep of step s+1.
+//                        One thread per (member, basin); the level order is the reference's precomputed topological order.
+//                        They run on a second, higher-priority stream: routing of step s overlaps the sweep of step s+1.
 // Bound: HBM bandwidth (state is read once and written once per step, ~0.5 flop/byte); no tensor cores.
 #ifndef RVN_KERNELS_CUH
 #define RVN_KERNELS_CUH
@@ -292,6 +293,15 @@ RVN_DI ConvRow ld_row(const ConvRow *__restrict__ tab, int i) {
 #ifndef RVN_CONV_R
 #define RVN_CONV_R 4   // rows per register buffer
 #endif
+#ifndef RVN_PF_DIST
+#define RVN_PF_DIST 16  // rows of L2 prefetch run-ahead of the store stream (0 = off)
+#endif
+RVN_DI void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// warm L2 with the first rows of a convolution's stores (issued at kernel start, long before they are consumed)
+RVN_DI void conv_prefetch_head(const double *g, const size_t stride) {
+#pragma unroll
+  for (int r = 0; r < RVN_PF_DIST; r++) prefetch_l2(g + (size_t)r * stride);
+}
 
 template <bool UNIT_DT, class C>
 RVN_DI void convolve_direct(C &c, const int iTarget, const int iTS, double *__restrict__ g /*store 0 of this HRU*/, const size_t stride,
@@ -344,6 +354,10 @@ RVN_DI void convolve_direct(C &c, const int iTarget, const int iTS, double *__re
         const double *pn = p + (size_t)RVN_CONV_R * stride;
 #pragma unroll
         for (int r = 0; r < RVN_CONV_R; r++) nxt[r] = (i + RVN_CONV_R + r < end) ? __ldcs(pn + (size_t)r * stride) : 0.0;
+        if (RVN_PF_DIST > 0) {
+#pragma unroll
+          for (int r = 0; r < RVN_CONV_R; r++) if (i + RVN_PF_DIST + r < N) prefetch_l2(p + (size_t)(RVN_PF_DIST - 1 + r) * stride);
+        }
 #pragma unroll
         for (int r = 0; r < RVN_CONV_R; r++) {
           if (i + r < end) {
@@ -473,6 +487,16 @@ extern __shared__ __align__(16) unsigned char rvn_smem[];
 // ------------------------------------------------------------------------------------------------
 // specialised sweep: the process list is the compile-time program Prog
 // ------------------------------------------------------------------------------------------------
+template <class Prog, int J>
+struct PrefetchConvs {
+  static RVN_DI void run(const double *gstate, const size_t nHp) {
+    if constexpr (J < Prog::nProc) {
+      if constexpr (Prog::op(J) == RVN_OP_CONVOLVE) conv_prefetch_head(gstate + (size_t)Prog::ia(J, 2) * nHp, nHp);
+      PrefetchConvs<Prog, J + 1>::run(gstate, nHp);
+    }
+  }
+};
+
 template <class Prog, bool UNIT_DT, int J>
 struct RunProcs {
   static RVN_DI void run(StatCtx<Prog> &c, const DevModel &M, const bool enabled, const unsigned long long mask, const int e, const int k,
@@ -531,6 +555,7 @@ __global__ void __launch_bounds__(RVN_BS, RVN_STATIC_MIN_BLOCKS) hru_sweep_stati
   double *gstate = M.state + (size_t)e * M.NS * nHp + k;
 #pragma unroll
   for (int s = 0; s < Prog::nCore; s++) c.sv[s] = __ldcs(gstate + (size_t)Prog::slot_sv(s) * nHp);
+  if (RVN_PF_DIST > 0 && enabled) PrefetchConvs<Prog, 0>::run(gstate, nHp);
   c.old_snow = (Prog::iSV(RVN_SV_SNOW) >= 0) ? c.sv[Prog::iSV(RVN_SV_SNOW) >= 0 ? Prog::iSV(RVN_SV_SNOW) : 0] : 0.0;
   c.old_snow_cover = (Prog::iSV(RVN_SV_SNOW_COVER) >= 0) ? c.sv[Prog::iSV(RVN_SV_SNOW_COVER) >= 0 ? Prog::iSV(RVN_SV_SNOW_COVER) : 0] : 0.0;
   c.old_snow_depth = (Prog::iSV(RVN_SV_SNOW_DEPTH) >= 0) ? c.sv[Prog::iSV(RVN_SV_SNOW_DEPTH) >= 0 ? Prog::iSV(RVN_SV_SNOW_DEPTH) : 0] : 0.0;
@@ -650,9 +675,8 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
-// routing + balance: one CTA per member
+// routing + balance
 // ------------------------------------------------------------------------------------------------
-#define RVN_ROUTE_BS 256
 __device__ void route_one_basin(const DevModel &M, int e, int p) {
   const double tstep = M.opt.timestep;
   const int nSeg = M.sb_nseg[p], nQin = M.sb_nqin[p], nQlat = M.sb_nqlat[p];
@@ -738,61 +762,67 @@ __device__ void route_one_basin(const DevModel &M, int e, int p) {
   sc[1] = Qlat_new;
 }
 
-// fixed-shape CTA tree sum (deterministic)
-RVN_DI double route_block_sum(double v, double *s_red) {
-  const int tid = threadIdx.x;
-  s_red[tid] = v;
-  __syncthreads();
-  for (int o = RVN_ROUTE_BS / 2; o > 0; o >>= 1) { if (tid < o) s_red[tid] += s_red[tid + o]; __syncthreads(); }
-  const double t = s_red[0];
-  __syncthreads();
-  return t;
+// ---- routing runs as a short sequence of small kernels on its own stream (one thread per (member, basin)), so that it
+// occupies little of the machine while the next step's HRU sweep is running:
+//   aggregate_kernel            HRU -> subbasin aggregation in HRU-index order (src/Solvers.cpp:490-511) + UpdateLateralInflow
+//   route_level_kernel x nLevels  level-ordered routing, deepest level first; basins inside a level are independent
+//   balance_kernel              IncrementCumulInput / IncrementCumOutflow + watershed storage + per-step records
+#define RVN_ROUTE_BS 128
+__global__ void __launch_bounds__(RVN_ROUTE_BS) aggregate_kernel(const __grid_constant__ DevModel M, const int step) {
+  const int NB = M.nSB;
+  const long long idx = (long long)blockIdx.x * RVN_ROUTE_BS + threadIdx.x;
+  if (idx >= (long long)M.E * NB) return;
+  const int e = (int)(idx / NB), p = (int)(idx - (long long)e * NB);
+  const double tstep = M.opt.timestep;
+  const double *swvol = M.swvol + ((size_t)(step & 1) * M.E + e) * M.nHp;
+  double routed = 0.0;
+  for (int i = M.sb_hru_ptr[p]; i < M.sb_hru_ptr[p + 1]; i++) routed += swvol[M.sb_hru_idx[i]];
+  double *QlatHist = M.qlat + ((size_t)e * NB + p) * M.max_nqlat;
+  for (int n = M.sb_nqlat[p] - 1; n > 0; n--) QlatHist[n] = QlatHist[n - 1];
+  QlatHist[0] = routed / (tstep * D_SEC_PER_DAY);
 }
-
-__global__ void __launch_bounds__(RVN_ROUTE_BS) route_kernel(const __grid_constant__ DevModel M, const int step, const int rec) {
+__global__ void __launch_bounds__(RVN_ROUTE_BS) route_level_kernel(const __grid_constant__ DevModel M, const int lev0, const int nlev) {
+  const long long idx = (long long)blockIdx.x * RVN_ROUTE_BS + threadIdx.x;
+  if (idx >= (long long)M.E * nlev) return;
+  const int e = (int)(idx / nlev), i = (int)(idx - (long long)e * nlev);
+  route_one_basin(M, e, M.level_idx[lev0 + i]);
+}
+__global__ void __launch_bounds__(RVN_ROUTE_BS) balance_kernel(const __grid_constant__ DevModel M, const int step, const int rec) {
   const int e = blockIdx.x, tid = threadIdx.x, NB = M.nSB;
   const double tstep = M.opt.timestep;
   const int par = step & 1;
-  __shared__ double s_red[RVN_ROUTE_BS];
-  // ---- HRU -> subbasin aggregation in HRU-index order (src/Solvers.cpp:490-511) + UpdateLateralInflow
-  const double *swvol = M.swvol + ((size_t)par * M.E + e) * M.nHp;
-  for (int p = tid; p < NB; p += RVN_ROUTE_BS) {
-    double routed = 0.0;
-    for (int i = M.sb_hru_ptr[p]; i < M.sb_hru_ptr[p + 1]; i++) routed += swvol[M.sb_hru_idx[i]];
-    double *QlatHist = M.qlat + ((size_t)e * NB + p) * M.max_nqlat;
-    for (int n = M.sb_nqlat[p] - 1; n > 0; n--) QlatHist[n] = QlatHist[n - 1];
-    QlatHist[0] = routed / (tstep * D_SEC_PER_DAY);
-  }
-  __syncthreads();
-  // ---- level-ordered routing: deepest level first; basins inside a level are independent
-  for (int L = 0; L < M.nLevels; L++) {
-    for (int i = M.level_ptr[L] + tid; i < M.level_ptr[L + 1]; i += RVN_ROUTE_BS) route_one_basin(M, e, M.level_idx[i]);
-    __syncthreads();
-  }
-  // ---- balance: IncrementCumulInput / IncrementCumOutflow + watershed storage
+  __shared__ double s_red[RVN_ROUTE_BS / 32][5];
   const double area = M.watershed_area * D_M2_PER_KM2;
-  double out_part = 0.0, ch_part = 0.0, rv_part = 0.0;
+  double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // outflow, channel storage, rivulet storage, precip partials, storage partials
   for (int p = tid; p < NB; p += RVN_ROUTE_BS) {
     const double *sc = M.scal + ((size_t)e * NB + p) * 8;
     const double qo = M.qout[((size_t)e * NB + p) * RVN_MAX_RIVER_SEGS + M.sb_nseg[p] - 1];
-    if (M.sb_level[p] == 0 || M.sb_down[p] < 0) out_part += (0.5 * (qo + sc[0]) * (tstep * D_SEC_PER_DAY)) / area * D_MM_PER_METER;
-    ch_part += sc[4]; rv_part += sc[5];
+    if (M.sb_level[p] == 0 || M.sb_down[p] < 0) v[0] += (0.5 * (qo + sc[0]) * (tstep * D_SEC_PER_DAY)) / area * D_MM_PER_METER;
+    v[1] += sc[4]; v[2] += sc[5];
     if ((M.rec_flags & 1) && rec >= 0) M.rec_qout[((size_t)rec * M.E + e) * NB + p] = qo;
   }
-  double pp = 0.0, ps = 0.0;
   const double *part_p = M.part_precip + ((size_t)par * M.E + e) * M.nBlocksX, *part_s = M.part_storage + ((size_t)par * M.E + e) * M.nBlocksX;
-  for (int b = tid; b < M.nBlocksX; b += RVN_ROUTE_BS) { pp += part_p[b]; ps += part_s[b]; }
-  const double tot_out = route_block_sum(out_part, s_red), tot_ch = route_block_sum(ch_part, s_red), tot_rv = route_block_sum(rv_part, s_red);
-  const double psum = route_block_sum(pp, s_red), ssum = route_block_sum(ps, s_red);
+  for (int b = tid; b < M.nBlocksX; b += RVN_ROUTE_BS) { v[3] += part_p[b]; v[4] += part_s[b]; }
+  // fixed-shape tree (warp shuffles, then the warp totals in order): deterministic
+#pragma unroll
+  for (int w = 0; w < 5; w++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[w] += __shfl_xor_sync(0xffffffffu, v[w], o);
+    if ((tid & 31) == 0) s_red[tid >> 5][w] = v[w];
+  }
+  __syncthreads();
   if (tid == 0) {
-    const double avg_precip = psum / M.watershed_area;
+    double t[5];
+#pragma unroll
+    for (int w = 0; w < 5; w++) { t[w] = 0.0; for (int i = 0; i < RVN_ROUTE_BS / 32; i++) t[w] += s_red[i][w]; }
+    const double avg_precip = t[3] / M.watershed_area;
     double *cum = M.cumul + (size_t)e * 2;
     cum[0] += avg_precip * tstep;
-    cum[1] += tot_out;
+    cum[1] += t[0];
     if ((M.rec_flags & 2) && rec >= 0) {
       double *w = M.rec_wshed + ((size_t)rec * M.E + e) * 4;
       w[0] = cum[0]; w[1] = cum[1]; w[2] = avg_precip;
-      w[3] = ssum / M.watershed_area + tot_ch / area * D_MM_PER_METER + tot_rv / area * D_MM_PER_METER;
+      w[3] = t[4] / M.watershed_area + t[1] / area * D_MM_PER_METER + t[2] / area * D_MM_PER_METER;
     }
   }
 }
