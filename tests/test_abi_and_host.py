@@ -32,7 +32,7 @@ def test_engine_is_sm100a_with_specialised_and_interpreter_sweeps():
     out = subprocess.run(["cuobjdump", "-sass", so], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True).stdout
     assert "sm_100a" in out
     assert "hru_sweep_static" in out and "Prog_HMETS" in out, "specialised sweep of the HMETS program missing"
-    assert "hru_sweep_interp" in out and "route_kernel" in out
+    assert "hru_sweep_interp" in out and "route_level_kernel" in out and "balance_kernel" in out
     assert "DFMA" in out and "DADD" in out      # FP64 arithmetic
     assert "LDG.E.64.EF" in out or "LDG.E.EF.64" in out, "state streams should use evict-first loads (__ldcs)"
 
