@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RVN_ABI_VERSION 1
+#define RVN_ABI_VERSION 2
 #define RVN_DOESNT_EXIST (-1)
 #define RVN_CONV_STORES 50   /* MAX_CONVOL_STORES, reference src/RavenInclude.h / Convolution.cpp:17 */
 #define RVN_MAX_CONN 24      /* max connections of a non-convolution process (Precipitation: 13..19) */
@@ -250,6 +250,15 @@ typedef struct rvn_model_desc {
   const double *sb_unit_hydro;   /* [nSB][max_nqlat] _aUnitHydro */
   const double *sb_route_hydro;  /* [nSB][max_nqin]  _aRouteHydro */
   double watershed_area;         /* km2 */
+  /* month-interpolated relative vegetation height / LAI of every vegetation class at every step
+   * (InterpolateMo(relative_ht|relative_LAI, tt), reference src/VegetationParams.cpp:102-107): [nSteps][nVeg][2] */
+  const double *veg_season;
+  /* extraterrestrial radiation on each HRU's slope [MJ/m2/d] (reference CRadiation::CalcETRadiation2, src/Radiation.cpp:
+   * 637-822) for every distinct (day angle, step interval) of the run: et_radia[nEtRows][nHRU], row of step n = et_row[n].
+   * NULL when no process consumes a PET estimated from it (PET_HARGREAVES_1985). */
+  int32_t nEtRows, pad2_;
+  const double *et_radia;
+  const int32_t *et_row;      /* [nSteps] */
 } rvn_model_desc;
 
 typedef struct rvn_gpu_model rvn_gpu_model; /* opaque */

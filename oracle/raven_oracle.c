@@ -45,6 +45,7 @@ typedef struct {
   int k;                  /* HRU */
   const double *F;        /* derived forcings of this HRU [RVN_F_COUNT] */
   const double *phi_old;  /* stored (start-of-step) state: what pHRU->GetStateVarValue returns */
+  double canopy_cap, canopy_snow_cap; /* veg_var_struct capacity / snow_capacity for this HRU and step */
   int iSV[RVN_SV_NTYPES]; /* first index of each SV type, or -1 */
 } octx;
 
@@ -99,8 +100,8 @@ static double state_var_max(const octx *c, int i, const double *sv) {
   const rvn_model_desc *d = c->d;
   switch (d->sv_type[i]) {
     case RVN_SV_SOIL: return soil_capacity(c, d->sv_layer[i]);
-    case RVN_SV_CANOPY: return P_V(c, RVN_V_VAR_CAPACITY);
-    case RVN_SV_CANOPY_SNOW: return P_V(c, RVN_V_VAR_SNOW_CAPACITY);
+    case RVN_SV_CANOPY: return c->canopy_cap;
+    case RVN_SV_CANOPY_SNOW: return c->canopy_snow_cap;
     case RVN_SV_DEPRESSION: { double dm = P_LU(c, RVN_LU_DEP_MAX); return (dm >= 0) ? dm : O_ALMOST_INF; }
     case RVN_SV_SNOW_COVER: return 1.0;
     case RVN_SV_SNOW_LIQ: { double SWE = sv[c->iSV[RVN_SV_SNOW]]; (void)snow_depth; return P_G(c, RVN_G_SNOW_SWI) * SWE; } /* CalculateSnowLiquidCapacity, src/SnowParams.cpp:79-88 */
@@ -253,6 +254,15 @@ static void update_forcings(const rvn_model_desc *d, const double *ptab, int k, 
     double PET = ow ? F[RVN_F_OW_PET] : F[RVN_F_PET];
     if (method == RVN_PET_CONSTANT) PET = 3.0;
     else if (method == RVN_PET_NONE) PET = 0.0;
+    else if (method == RVN_PET_HARGREAVES_1985) { /* Hargreaves1985Evap, src/Evaporation.cpp:215-228; ET radiation hoisted by the host layer */
+      if (d->et_radia) {
+        double Ra = d->et_radia[(size_t)d->et_row[step] * d->nHRU + k], delT;
+        Ra /= (2.501 * O_DENSITY_WATER / O_MM_PER_METER);
+        delT = F[RVN_F_TEMP_DAILY_MAX] - F[RVN_F_TEMP_DAILY_MIN];
+        delT = omax(delT, 0.0);
+        PET = omax(0.0, 0.0023 * Ra * sqrt(delT) * (F[RVN_F_TEMP_DAILY_AVE] + 17.8));
+      }
+    }
     else if (method == RVN_PET_FROMMONTHLY) { /* src/Evaporation.cpp:349-355 */
       double peRatio = 1.0 + O_HBV_PET_TEMP_CORR * (temp_ave_unc - temp_month_ave);
       peRatio = omax(0.0, omin(2.0, peRatio));
@@ -317,7 +327,7 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
         double rain_pct = P_V(c, RVN_V_VAR_RAIN_ICEPT_PCT);
         rain_int = rainfall * rain_pct;
         if (iCan >= 0) {
-          double capacity = P_V(c, RVN_V_VAR_CAPACITY);
+          double capacity = c->canopy_cap;
           rain_int = omin(rain_int, omax((capacity - sv[iCan]) / tstep, 0.0));
           rates[qCan] = Fcan * rain_int;
         } else rates[qAtmos] += Fcan * rain_int;
@@ -325,7 +335,7 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
         double snow_pct = P_V(c, RVN_V_VAR_SNOW_ICEPT_PCT);
         snow_int = snowfall * snow_pct;
         if (iSCan >= 0) {
-          double snow_capacity = P_V(c, RVN_V_VAR_SNOW_CAPACITY);
+          double snow_capacity = c->canopy_snow_cap;
           snow_int = omax(omin(snow_int, omax((snow_capacity - sv[iSCan]) / tstep, 0.0)), 0.0);
           rates[qCanSnow] = Fcan * snow_int;
         } else rates[qAtmos] += Fcan * snow_int;
@@ -381,13 +391,13 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       if (SWE <= 0.0) rates[4] = -sv[iFrom[4]] / tstep;
       break;
     }
-    case RVN_OP_INF_HMETS: { /* src/Infiltration.cpp:304-330,491-514 + constraints :605-626 */
+    case RVN_OP_INF_HMETS: case RVN_OP_INF_HBV: case RVN_OP_INF_GR4J: { /* src/Infiltration.cpp:304-330,384-398,477-489,491-514 + constraints :605-626 */
       if (type != RVN_HRU_STANDARD && type != RVN_HRU_ROCK && type != RVN_HRU_MASKED_GLACIER) break;
       double Fimp = P_LU(c, RVN_LU_IMPERMEABLE_FRAC);
       double ponded = omax(sv[c->iSV[RVN_SV_PONDED_WATER]], 0.0);
       double rainthru = (ponded / tstep);
       if (type == RVN_HRU_ROCK) { rates[0] = 0.0; rates[1] = rainthru; }
-      else {
+      else if (pr->op == RVN_OP_INF_HMETS) {
         double stor = sv[iTo[0]], max_stor = soil_capacity(c, 0), coef = P_LU(c, RVN_LU_HMETS_RUNOFF_COEFF);
         double sat = omin(omax(stor / max_stor, 0.0), 1.0);
         double direct = Fimp * rainthru;
@@ -396,6 +406,19 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
         double delayed = coef * pow(sat, 2.0) * infil;
         infil -= delayed;
         rates[0] = infil; rates[1] = direct; rates[2] = runoff; rates[3] = delayed;
+      } else if (pr->op == RVN_OP_INF_HBV) {
+        double stor = sv[iTo[0]], max_stor = soil_capacity(c, 0), beta = P_S(c, 0, RVN_S_HBV_BETA);
+        double sat = omax(omin(stor / max_stor, 1.0), 0.0);
+        double runoff = pow(sat, beta) * rainthru;
+        runoff = (Fimp)*rainthru + (1 - Fimp) * runoff;
+        rates[0] = rainthru - runoff; rates[1] = runoff;
+      } else {
+        double x1 = soil_capacity(c, 0), stor = sv[iTo[0]];
+        double sat = stor / x1;
+        double tmp = tanh(ponded / x1);
+        double infil = x1 * (1.0 - (sat * sat)) * tmp / (1.0 + sat * tmp);
+        infil = (1.0 - Fimp) * infil;
+        rates[0] = infil; rates[1] = rainthru - infil;
       }
       if (type != RVN_HRU_STANDARD && type != RVN_HRU_MASKED_GLACIER) break; /* ApplyConstraints guard */
       rates[0] = omin(rates[0], sv[iFrom[0]] / tstep);
@@ -418,23 +441,41 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       rates[0] = (pr->da[0]) * sv[iFrom[0]] / tstep;
       rates[1] = (1.0 - pr->da[0]) * sv[iFrom[0]] / tstep;
       break;
-    case RVN_OP_BASE_LINEAR: { /* src/Baseflow.cpp:152-186 + :297-310 */
+    case RVN_OP_BASE_LINEAR: case RVN_OP_BASE_POWER_LAW: case RVN_OP_BASE_GR4J: { /* src/Baseflow.cpp:152-186,208-215,238-243 + :297-310 */
       if (type == RVN_HRU_LAKE || type == RVN_HRU_WATER || type == RVN_HRU_ROCK) { /* GetRatesOfChange returns; constraints still run */ }
       else {
         int m = pr->ia[0];
         double stor = sv[iFrom[0]], max_stor = (m >= 0) ? soil_capacity(c, m) : 0.0;
         stor = omin(omax(stor, 0.0), max_stor);
-        rates[0] = P_S(c, m, RVN_S_BASEFLOW_COEFF) * stor;
+        if (pr->op == RVN_OP_BASE_LINEAR) rates[0] = P_S(c, m, RVN_S_BASEFLOW_COEFF) * stor;
+        else if (pr->op == RVN_OP_BASE_POWER_LAW) rates[0] = P_S(c, m, RVN_S_BASEFLOW_COEFF) * pow(stor, P_S(c, m, RVN_S_BASEFLOW_N));
+        else {
+          double x3 = P_S(c, m, RVN_S_GR4J_X3);
+          rates[0] = stor * (1.0 - pow(1.0 + pow(omax(stor / x3, 0.0), 4), -0.25)) / tstep;
+        }
       }
       rates[0] = omin(rates[0], omax(sv[iFrom[0]], 0.0) / tstep);
       rates[0] = omax(rates[0], 0.0);
       break;
     }
-    case RVN_OP_PERC_LINEAR: { /* src/Percolation.cpp:183-243 + :339-360 */
+    case RVN_OP_PERC_LINEAR: case RVN_OP_PERC_CONSTANT: case RVN_OP_PERC_GR4J: case RVN_OP_PERC_GR4JEXCH: case RVN_OP_PERC_GR4JEXCH2: {
+      /* src/Percolation.cpp:183-202,237-243,293-316 + :339-360 */
       if (type == RVN_HRU_LAKE || type == RVN_HRU_WATER || type == RVN_HRU_ROCK) break;
       int m = pr->ia[0];
       double stor = sv[iFrom[0]], max_stor = soil_capacity(c, m);
-      if (max_stor > 0.0) rates[0] = P_S(c, m, RVN_S_PERC_COEFF) * stor;
+      if (max_stor > 0.0) {
+        if (pr->op == RVN_OP_PERC_LINEAR) rates[0] = P_S(c, m, RVN_S_PERC_COEFF) * stor;
+        else if (pr->op == RVN_OP_PERC_CONSTANT) rates[0] = P_S(c, m, RVN_S_MAX_PERC_RATE);
+        else if (pr->op == RVN_OP_PERC_GR4J) rates[0] = stor * (1.0 - pow(1.0 + pow(4.0 / 9.0 * omax(stor / max_stor, 0.0), 4), -0.25)) / tstep;
+        else if (pr->op == RVN_OP_PERC_GR4JEXCH) {
+          double x2 = P_S(c, m, RVN_S_GR4J_X2), x3 = P_S(c, m, RVN_S_GR4J_X3);
+          rates[0] = -x2 * pow(omax(omin(stor / x3, 1.0), 0.0), 3.5);
+        } else {
+          double x2 = P_S(c, 1, RVN_S_GR4J_X2), x3 = P_S(c, 1, RVN_S_GR4J_X3);
+          stor = sv[sv_index(d, RVN_SV_SOIL, 1)];
+          rates[0] = -x2 * pow(omax(omin(stor / x3, 1.0), 0.0), 3.5);
+        }
+      }
       rates[0] = omin(rates[0], omax(sv[iFrom[0]] - 0.0, 0.0) / tstep);
       if (!d->opt.allow_soil_overfill) {
         double room = omax(state_var_max(c, iTo[0], sv) - sv[iTo[0]], 0.0);
@@ -442,11 +483,23 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       }
       break;
     }
-    case RVN_OP_SOILEVAP_ALL: { /* src/SoilEvaporation.cpp:325-343,379-383 + :767-783 */
+    case RVN_OP_SOILEVAP_ALL: case RVN_OP_SOILEVAP_HBV: case RVN_OP_SOILEVAP_GR4J: { /* src/SoilEvaporation.cpp:325-343,379-405,640-650 + :767-783 */
       if (type != RVN_HRU_STANDARD) break;
       double PET = F[RVN_F_PET];
       if (!d->opt.suppress_competitive_ET) { PET -= (sv[c->iSV[RVN_SV_AET]] / tstep); PET = omax(PET, 0.0); }
-      rates[0] = PET;
+      if (pr->op == RVN_OP_SOILEVAP_ALL) rates[0] = PET;
+      else if (pr->op == RVN_OP_SOILEVAP_HBV) {
+        double stor = omax(sv[iFrom[0]], 0.0), tens_stor = soil_tension_capacity(c, 0);
+        rates[0] = PET * omin(stor / tens_stor, 1.0);
+        int iSnow = c->iSV[RVN_SV_SNOW];
+        double Fc = P_LU(c, RVN_LU_FOREST_COVERAGE);
+        if ((iSnow >= 0) && (sv[iSnow] > O_REAL_SMALL)) rates[0] = (Fc)*rates[0];
+      } else {
+        double max_stor = soil_capacity(c, 0), stor = sv[iFrom[0]];
+        double sat = stor / max_stor;
+        double tmp = tanh(omax(PET, 0.0) / max_stor);
+        rates[0] = stor * (2.0 - sat) * tmp / (1.0 + (1.0 - sat) * tmp);
+      }
       rates[pr->nconn - 1] = rates[0]; /* PETused -> AET (src/SoilEvaporation.cpp end of GetRatesOfChange) */
       double corr = 0, oldrate;
       for (int q = 0; q < pr->nconn - 1; q++) {
@@ -455,6 +508,92 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
         corr += oldrate - rates[q];
       }
       rates[pr->nconn - 1] -= corr;
+      break;
+    }
+    case RVN_OP_SNOBAL_SIMPLE_MELT: /* src/SnowBalance.cpp:393-396 + :1311-1317 */
+      rates[0] = omax(F[RVN_F_POTENTIAL_MELT], 0.0);
+      if (rates[0] < 0.0) rates[0] = 0.0;
+      rates[0] = omin(rates[0], omax(sv[iFrom[0]] / tstep, 0.0));
+      break;
+    case RVN_OP_SNOBAL_CEMA_NEIGE: { /* src/SnowBalance.cpp:398-413 */
+      double avg_annual_snow = P_G(c, RVN_G_AVG_ANNUAL_SNOW), snotemp = snow_temperature(c), pot_melt = 0.0, SWE, snow_cov;
+      if (snotemp == O_FREEZING_TEMP) pot_melt = omax(F[RVN_F_POTENTIAL_MELT], 0.0);
+      SWE = sv[iFrom[0]];
+      snow_cov = omin(SWE / avg_annual_snow, 1.0);
+      rates[0] = (0.9 * snow_cov + 0.1) * omin(SWE / tstep, pot_melt);
+      rates[1] = (snow_cov - sv[iFrom[1]]) / tstep;
+      break;
+    }
+    case RVN_OP_SNOWREFREEZE_DD: { /* src/SnowMeltRefreeze.cpp:324-365 */
+      double Kf = P_LU(c, RVN_LU_REFREEZE_FACTOR), Ta = F[RVN_F_TEMP_DAILY_AVE];
+      rates[0] = omax(Kf * (O_FREEZING_TEMP - Ta), 0.0);
+      if (sv[iFrom[0]] <= 0) rates[0] = 0.0;
+      rates[0] = omin(rates[0], sv[iFrom[0]] / tstep);
+      if (rates[0] < 0) rates[0] = 0.0;
+      break;
+    }
+    case RVN_OP_SNOTEMP_NEWTONS: { /* src/SnowTempEvolve.cpp:42-77 */
+      double Tsnow = sv[iFrom[0]], Tair = F[RVN_F_TEMP_AVE];
+      rates[0] = P_G(c, RVN_G_AIRSNOW_COEFF) * (Tair - Tsnow);
+      rates[0] = omin(rates[0], (O_FREEZING_TEMP - Tsnow) / tstep);
+      break;
+    }
+    case RVN_OP_CANEVP_ALL: case RVN_OP_CANSNOWEVP_ALL: { /* src/VegetationMovers.cpp:110-190 and :283-346 */
+      if ((type != RVN_HRU_STANDARD) && (type != RVN_HRU_WETLAND)) break;
+      double Fc = P_LU(c, RVN_LU_FOREST_COVERAGE), oldRates;
+      if (Fc != 0) { rates[0] = sv[iFrom[0]] / tstep; rates[1] = rates[0]; }
+      oldRates = rates[0];
+      if (pr->op == RVN_OP_CANEVP_ALL) rates[0] = omax(rates[0], 0.0);
+      rates[0] = omin(rates[0], sv[iFrom[0]] / tstep);
+      rates[1] -= (oldRates - rates[0]);
+      break;
+    }
+    case RVN_OP_OPEN_WATER_EVAP: { /* src/OpenWaterEvap.cpp:113-186 */
+      if (type == RVN_HRU_MASKED_GLACIER) break;
+      double OWPET = F[RVN_F_OW_PET];
+      if (!d->opt.suppress_competitive_ET) { OWPET -= (sv[c->iSV[RVN_SV_AET]] / tstep); OWPET = omax(OWPET, 0.0); }
+      rates[0] = P_LU(c, RVN_LU_OW_PET_CORR) * OWPET;
+      if (rates[0] < 0) rates[0] = 0.0;
+      if (iFrom[0] != c->iSV[RVN_SV_SURFACE_WATER]) {
+        rates[0] = omin(rates[0], sv[iFrom[0]] / tstep);
+        if (sv[iFrom[0]] <= 0) rates[0] = 0.0;
+      }
+      rates[pr->nconn - 1] = rates[0];
+      break;
+    }
+    case RVN_OP_LAKE_EVAP_BASIC: { /* src/OpenWaterEvap.cpp:269-314 */
+      if ((type == RVN_HRU_LAKE) || (d->opt.lake_sv == iFrom[0])) {
+        rates[0] = P_LU(c, RVN_LU_LAKE_PET_CORR) * F[RVN_F_OW_PET];
+        rates[pr->nconn - 1] = rates[0];
+      }
+      if (sv[iFrom[0]] <= 0) rates[0] = 0.0;
+      if (rates[0] < 0) rates[0] = 0.0;
+      rates[0] = omin(rates[0], sv[iFrom[0]] / tstep);
+      rates[pr->nconn - 1] = rates[0];
+      break;
+    }
+    case RVN_OP_CAPRISE_HBV: { /* src/CapillaryRise.cpp:103-179 */
+      if (type == RVN_HRU_LAKE || type == RVN_HRU_WATER || type == RVN_HRU_ROCK) break;
+      int m = d->sv_layer[iTo[0]];
+      double stor = sv[iTo[0]], max_stor = soil_capacity(c, m);
+      stor = omin(omax(stor, 0.0), max_stor);
+      rates[0] = P_S(c, m, RVN_S_MAX_CAP_RISE_RATE) * (1.0 - omin(stor / max_stor, 1.0));
+      rates[0] = omin(rates[0], omax(sv[iFrom[0]], 0.0) / tstep);
+      if (!d->opt.allow_soil_overfill) rates[0] = omin(rates[0], (state_var_max(c, iTo[0], sv) - sv[iTo[0]]) / tstep);
+      break;
+    }
+    case RVN_OP_GLACIERMELT_HBV: /* src/GlacierProcesses.cpp:117-190 */
+      if (type != RVN_HRU_GLACIER) break;
+      if (!(sv[c->iSV[RVN_SV_SNOW]] > O_REAL_SMALL)) rates[0] = P_LU(c, RVN_LU_HBV_MELT_GLACIER_CORR) * omax(F[RVN_F_POTENTIAL_MELT], 0.0);
+      if (rates[0] < 0.0) rates[0] = 0.0;
+      break;
+    case RVN_OP_GLACIERRELEASE_HBVEC: { /* src/GlacierProcesses.cpp:292-350 */
+      if (type != RVN_HRU_GLACIER) break;
+      double glacier_stor = sv[c->iSV[RVN_SV_GLACIER]], snow = sv[c->iSV[RVN_SV_SNOW]], liq_snow = sv[c->iSV[RVN_SV_SNOW_LIQ]];
+      double Kmin = P_LU(c, RVN_LU_HBV_GLACIER_KMIN), Kmax = P_LU(c, RVN_LU_GLAC_STORAGE_COEFF), Ag = P_LU(c, RVN_LU_HBV_GLACIER_AG);
+      double K = Kmin + (Kmax - Kmin) * exp(-Ag * (snow + liq_snow));
+      rates[0] = K * glacier_stor;
+      if (rates[0] < 0.0) rates[0] = 0.0;
       break;
     }
     default: break; /* unsupported ops are rejected in rvo_run before the time loop */
@@ -491,11 +630,25 @@ static void convolution_rates(const octx *c, const rvn_process *pr, const double
   rates[2 * NST] = (TS_new - TS_old) / tstep;
 }
 
-static int op_supported(int op) {
-  switch (op) {
-    case RVN_OP_PRECIPITATION: case RVN_OP_SNOBAL_HMETS: case RVN_OP_INF_HMETS: case RVN_OP_OVERFLOW: case RVN_OP_FLUSH: case RVN_OP_SPLIT:
-    case RVN_OP_BASE_LINEAR: case RVN_OP_PERC_LINEAR: case RVN_OP_SOILEVAP_ALL: case RVN_OP_CONVOLVE: return 1;
-    default: return 0;
+static int op_supported(int op) { return op > RVN_OP_NOP && op < RVN_OP_COUNT; }
+
+/* CVegetationClass::RecalculateCanopyParams, src/VegetationParams.cpp:85-135 (capacities only; the month interpolation
+ * of relative height / LAI arrives hoisted in d->veg_season) */
+static void canopy_capacities(octx *c, int step) {
+  const rvn_model_desc *d = c->d;
+  c->canopy_cap = c->canopy_snow_cap = 0.0;
+  if (c->iSV[RVN_SV_CANOPY] < 0 && c->iSV[RVN_SV_CANOPY_SNOW] < 0) return;
+  int veg = d->hru_veg[c->k];
+  double rel_ht = d->veg_season[((size_t)step * d->nVeg + veg) * 2 + 0], rel_LAI = d->veg_season[((size_t)step * d->nVeg + veg) * 2 + 1];
+  double max_height = P_V(c, RVN_V_MAX_HEIGHT), sparseness = P_LU(c, RVN_LU_FOREST_SPARSENESS), max_LAI = P_V(c, RVN_V_MAX_LAI);
+  double SAI_ht_ratio = P_V(c, RVN_V_SAI_HT_RATIO);
+  double max_SAI = max_height * SAI_ht_ratio;
+  double height = max_height * rel_ht;
+  double LAI = (1.0 - sparseness) * max_LAI * rel_LAI;
+  double SAI = (1.0 - sparseness) * (height * SAI_ht_ratio);
+  if ((max_LAI + max_SAI) > 0) {
+    c->canopy_cap = ((LAI + SAI) / (max_LAI + max_SAI)) * P_V(c, RVN_V_MAX_CAPACITY);
+    c->canopy_snow_cap = ((LAI + SAI) / (max_LAI + max_SAI)) * P_V(c, RVN_V_MAX_SNOW_CAPACITY);
   }
 }
 
@@ -614,6 +767,7 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
       if (iGW >= 0) phinew[iGW] = 0.0;
       if (d->hru_enabled[k]) {
         c.k = k; c.F = F + (size_t)k * RVN_F_COUNT; c.phi_old = phi_old;
+        canopy_capacities(&c, step);
         for (int j = 0; j < NP; j++) {
           const rvn_process *pr = &d->proc[j];
           if (!((d->apply_mask[k] >> j) & 1ull)) continue; /* CModel::ApplyProcess gate, src/Model.cpp:3061 */

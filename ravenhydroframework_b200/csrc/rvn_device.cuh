@@ -48,7 +48,7 @@ struct DevModel {
   int32_t nH, nHp, nSB, E, NS, nCore, maxConn;
   rvn_options opt;
   int32_t glob_off, lu_off, veg_off, soil_off, ptab_stride;
-  int32_t nLU, nConv, nGauges, nSteps, record_forcings;
+  int32_t nLU, nVeg, nConv, nGauges, nSteps, record_forcings;
   // per-member arrays
   double *state, *swvol, *forc, *ptab;
   ConvRow *conv_tab;
@@ -65,6 +65,8 @@ struct DevModel {
   const int32_t *prof_class; const double *prof_thick;
   const double *gauge_series, *gauge_const, *wt_precip, *wt_temp, *wt_all;
   const rvn_time *times;
+  const double *veg_season;                        // [nSteps][nVeg][2] month-interpolated relative height, relative LAI
+  const double *et_radia; const int32_t *et_row;   // [nEtRows][nHp] extraterrestrial radiation on the HRU's slope, row of each step (or NULL)
   // network
   const int32_t *sb_down, *sb_level, *sb_headwater, *sb_nseg, *sb_nqin, *sb_nqlat;
   const int32_t *sb_hru_ptr, *sb_hru_idx;          // CSR: HRUs of each basin in HRU-index order

@@ -36,6 +36,7 @@ struct CtxCommon {
   double old_snow, old_snow_cover, old_snow_depth, old_snow_temp;
   double area, elev, lat, slope, aspect;
   double tstep;
+  double canopy_cap, canopy_snow_cap;   // veg_var_struct capacity / snow_capacity of this HRU for this step
   int type, lu, veg, profile;
   const double *ptab;      // member parameter row (shared memory)
   const rvn_options *popt;
@@ -59,6 +60,7 @@ struct DynCtx : CtxCommon {
   RVN_DI int slot_type(int s) const { return P->slot_type[s]; }
   RVN_DI int slot_layer(int s) const { return P->slot_layer[s]; }
   RVN_DI int slot_water(int s) const { return P->slot_water[s]; }
+  RVN_DI int soil_slot(int m) const { return P->soil_slot[m]; }
   RVN_DI double SOIL(int m, int f) const { return ptab[soil_off + prof_class[m] * RVN_S_COUNT + f]; }
   RVN_DI double thick(int m) const { return prof_thick[m]; }
 };
@@ -85,6 +87,7 @@ struct StatCtx : CtxCommon {
   static constexpr RVN_DI int slot_type(int s) { return Prog::slot_type(s); }
   static constexpr RVN_DI int slot_layer(int s) { return Prog::slot_layer(s); }
   static constexpr RVN_DI int slot_water(int s) { return Prog::slot_water(s); }
+  static constexpr RVN_DI int soil_slot(int m) { return Prog::soil_slot(m); }
   RVN_DI double SOIL(int m, int f) const { return ptab[sbase[m] + f]; }
   RVN_DI double thick(int m) const { return sthick[m]; }
 };
@@ -229,7 +232,15 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int k, int step, int sb) {
     double PET = ow ? F[RVN_F_OW_PET] : F[RVN_F_PET];
     if (method == RVN_PET_CONSTANT) PET = 3.0;
     else if (method == RVN_PET_NONE) PET = 0.0;
-    else if (method == RVN_PET_FROMMONTHLY) {
+    else if (method == RVN_PET_HARGREAVES_1985) {  // Hargreaves1985Evap  src/Evaporation.cpp:215-228
+      if (M.et_radia != nullptr) {
+        double Ra = M.et_radia[(size_t)M.et_row[step] * M.nHp + k];   // F->ET_radia [MJ/m2/d] (hoisted CalcETRadiation2)
+        Ra /= (D_LH_VAPOR * D_DENSITY_WATER / D_MM_PER_METER);
+        double delT = F[RVN_F_TEMP_DAILY_MAX] - F[RVN_F_TEMP_DAILY_MIN];
+        delT = dmax(delT, 0.0);
+        PET = dmax(0.0, 0.0023 * Ra * sqrt(delT) * (F[RVN_F_TEMP_DAILY_AVE] + 17.8));
+      }
+    } else if (method == RVN_PET_FROMMONTHLY) {
       double peRatio = 1.0 + D_HBV_PET_TEMP_CORR * (temp_ave_unc - temp_month_ave);
       peRatio = dmax(0.0, dmin(2.0, peRatio));
       PET = PET_month_ave * peRatio;
@@ -444,6 +455,25 @@ RVN_DI void load_hru_statics(C &c, const DevModel &M, int k, const double *s_pta
   c.glob_off = M.glob_off; c.lu_base = M.lu_off + c.lu * RVN_LU_COUNT; c.veg_base = M.veg_off + c.veg * RVN_V_COUNT; c.soil_off = M.soil_off;
 }
 
+// canopy storage capacities of this HRU for this step: CVegetationClass::RecalculateCanopyParams (src/VegetationParams.cpp:85-135).
+// The month-interpolated relative height / LAI of each vegetation class depend on the date only and are hoisted to the
+// host (veg_season[step][veg][2]); everything else is evaluated here in the reference's order.
+template <class C> RVN_DI void load_canopy(C &c, const DevModel &M, int step) {
+  c.canopy_cap = 0.0; c.canopy_snow_cap = 0.0;
+  if (c.iSV(RVN_SV_CANOPY) < 0 && c.iSV(RVN_SV_CANOPY_SNOW) < 0) return;
+  const double rel_ht = M.veg_season[((size_t)step * M.nVeg + c.veg) * 2 + 0], rel_LAI = M.veg_season[((size_t)step * M.nVeg + c.veg) * 2 + 1];
+  const double max_height = c.VEG(RVN_V_MAX_HEIGHT), sparseness = c.LU(RVN_LU_FOREST_SPARSENESS), max_LAI = c.VEG(RVN_V_MAX_LAI);
+  const double SAI_ht_ratio = c.VEG(RVN_V_SAI_HT_RATIO);
+  const double max_SAI = max_height * SAI_ht_ratio;
+  const double height = max_height * rel_ht;
+  const double LAI = (1.0 - sparseness) * max_LAI * rel_LAI;
+  const double SAI = (1.0 - sparseness) * (height * SAI_ht_ratio);
+  if ((max_LAI + max_SAI) > 0) {
+    c.canopy_cap = ((LAI + SAI) / (max_LAI + max_SAI)) * c.VEG(RVN_V_MAX_CAPACITY);
+    c.canopy_snow_cap = ((LAI + SAI) / (max_LAI + max_SAI)) * c.VEG(RVN_V_MAX_SNOW_CAPACITY);
+  }
+}
+
 // AET / RUNOFF / GROUNDWATER reboot (src/Solvers.cpp:171-200)
 template <class C> RVN_DI void reboot_diagnostics(C &c) {
   if (c.iSV(RVN_SV_AET) >= 0) c.SV(c.iSV(RVN_SV_AET)) = 0.0;
@@ -561,6 +591,7 @@ __global__ void __launch_bounds__(RVN_BS, RVN_STATIC_MIN_BLOCKS) hru_sweep_stati
   c.old_snow_depth = (Prog::iSV(RVN_SV_SNOW_DEPTH) >= 0) ? c.sv[Prog::iSV(RVN_SV_SNOW_DEPTH) >= 0 ? Prog::iSV(RVN_SV_SNOW_DEPTH) : 0] : 0.0;
   c.old_snow_temp = (Prog::iSV(RVN_SV_SNOW_TEMP) >= 0) ? c.sv[Prog::iSV(RVN_SV_SNOW_TEMP) >= 0 ? Prog::iSV(RVN_SV_SNOW_TEMP) : 0] : 0.0;
   __syncthreads();   // parameter row staged
+  load_canopy(c, M, step);
   // ---- forcings (on the stored state)
   if (enabled) compute_forcings(c, M, k, step, sb);
   else {
@@ -629,6 +660,7 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
   c.old_snow_cover = (P->iSV[RVN_SV_SNOW_COVER] >= 0) ? c.SV(P->iSV[RVN_SV_SNOW_COVER]) : 0.0;
   c.old_snow_depth = (P->iSV[RVN_SV_SNOW_DEPTH] >= 0) ? c.SV(P->iSV[RVN_SV_SNOW_DEPTH]) : 0.0;
   c.old_snow_temp = (P->iSV[RVN_SV_SNOW_TEMP] >= 0) ? c.SV(P->iSV[RVN_SV_SNOW_TEMP]) : 0.0;
+  load_canopy(c, M, step);
   if (enabled) compute_forcings(c, M, k, step, sb);
   else { for (int f = 0; f < RVN_F_COUNT; f++) c.F[f] = 0.0; }
   if (enabled) reboot_diagnostics(c);

@@ -31,6 +31,7 @@
 #define D_DENSITY_WATER 1.000e3
 #define D_DENSITY_ICE 0.917e3
 #define D_HCP_ICE 1.938
+#define D_LH_VAPOR 2.501
 #define D_WINTER_SOLSTICE_ANG 6.111043
 #define D_HBV_PET_ELEV_CORR 0.0005
 #define D_HBV_PET_TEMP_CORR 0.5
@@ -64,8 +65,8 @@ template <class C> RVN_DI double SnowTemperature(const C &c) {
 template <class C> RVN_DI double StateVarMax(const C &c, int slot) {
   switch (c.slot_type(slot)) {
     case RVN_SV_SOIL: return SoilCapacity(c, c.slot_layer(slot));
-    case RVN_SV_CANOPY: return c.VEG(RVN_V_VAR_CAPACITY);
-    case RVN_SV_CANOPY_SNOW: return c.VEG(RVN_V_VAR_SNOW_CAPACITY);
+    case RVN_SV_CANOPY: return c.canopy_cap;
+    case RVN_SV_CANOPY_SNOW: return c.canopy_snow_cap;
     case RVN_SV_DEPRESSION: { double dm = c.LU(RVN_LU_DEP_MAX); return (dm >= 0) ? dm : D_ALMOST_INF; }
     case RVN_SV_SNOW_COVER: return 1.0;
     case RVN_SV_SNOW_LIQ: return c.G(RVN_G_SNOW_SWI) * c.SV(c.iSV(RVN_SV_SNOW));
@@ -92,14 +93,14 @@ template <class C, class PR> RVN_DI void rates_PRECIPITATION(C &c, const PR &pr)
     const double Fcan = c.LU(RVN_LU_FOREST_COVERAGE);
     double rain_int = rainfall * c.VEG(RVN_V_VAR_RAIN_ICEPT_PCT);
     if (iCan >= 0) {
-      double capacity = c.VEG(RVN_V_VAR_CAPACITY);
+      double capacity = c.canopy_cap;
       rain_int = dmin(rain_int, dmax((capacity - c.SV(iCan)) / tstep, 0.0));
       c.R(qCan) = Fcan * rain_int;
     } else c.R(qAtmos) += Fcan * rain_int;
     rainthru = rainfall - Fcan * rain_int;
     double snow_int = snowfall * c.VEG(RVN_V_VAR_SNOW_ICEPT_PCT);
     if (iSCan >= 0) {
-      double snow_capacity = c.VEG(RVN_V_VAR_SNOW_CAPACITY);
+      double snow_capacity = c.canopy_snow_cap;
       snow_int = dmax(dmin(snow_int, dmax((snow_capacity - c.SV(iSCan)) / tstep, 0.0)), 0.0);
       c.R(qCanSnow) = Fcan * snow_int;
     } else c.R(qAtmos) += Fcan * snow_int;
@@ -157,8 +158,107 @@ template <class C, class PR> RVN_DI void rates_SNOBAL_HMETS(C &c, const PR &pr) 
   if (SWE <= 0.0) c.R(4) = -c.SV(pr.from(4)) / tstep;
 }
 
-// CmvInfiltration INF_HMETS  src/Infiltration.cpp:304-330,491-514; ApplyConstraints :605-626
-template <class C, class PR> RVN_DI void rates_INF_HMETS(C &c, const PR &pr) {
+// CmvSnowBalance SNOBAL_SIMPLE_MELT  src/SnowBalance.cpp:393-396; ApplyConstraints :1311-1317 (no FIRN)
+template <class C, class PR> RVN_DI void rates_SNOBAL_SIMPLE_MELT(C &c, const PR &pr) {
+  c.R(0) = dmax(c.F[RVN_F_POTENTIAL_MELT], 0.0);
+  if (c.R(0) < 0.0) c.R(0) = 0.0;
+  c.R(0) = dmin(c.R(0), dmax(c.SV(pr.from(0)) / c.tstep, 0.0));
+}
+// CmvSnowBalance SNOBAL_CEMA_NEIGE  src/SnowBalance.cpp:398-413 (snow temperature is the lagged, stored value)
+template <class C, class PR> RVN_DI void rates_SNOBAL_CEMA_NEIGE(C &c, const PR &pr) {
+  const double avg_annual_snow = c.G(RVN_G_AVG_ANNUAL_SNOW);
+  const double snotemp = SnowTemperature(c);
+  double pot_melt = 0.0;
+  if (snotemp == D_FREEZING_TEMP) pot_melt = dmax(c.F[RVN_F_POTENTIAL_MELT], 0.0);
+  const double SWE = c.SV(pr.from(0));
+  const double snow_cov = dmin(SWE / avg_annual_snow, 1.0);
+  c.R(0) = (0.9 * snow_cov + 0.1) * dmin(SWE / c.tstep, pot_melt);
+  c.R(1) = (snow_cov - c.SV(pr.from(1))) / c.tstep;
+}
+// CmvSnowRefreeze FREEZE_DEGREE_DAY  src/SnowMeltRefreeze.cpp:324-341; ApplyConstraints :354-365
+template <class C, class PR> RVN_DI void rates_SNOWREFREEZE_DD(C &c, const PR &pr) {
+  const double Kf = c.LU(RVN_LU_REFREEZE_FACTOR), Ta = c.F[RVN_F_TEMP_DAILY_AVE];
+  c.R(0) = dmax(Kf * (D_FREEZING_TEMP - Ta), 0.0);
+  if (c.SV(pr.from(0)) <= 0) c.R(0) = 0.0;
+  c.R(0) = dmin(c.R(0), c.SV(pr.from(0)) / c.tstep);
+  if (c.R(0) < 0) c.R(0) = 0.0;
+}
+// CmvSnowTempEvolve SNOTEMP_NEWTONS  src/SnowTempEvolve.cpp:42-77
+template <class C, class PR> RVN_DI void rates_SNOTEMP_NEWTONS(C &c, const PR &pr) {
+  const double Tsnow = c.SV(pr.from(0)), Tair = c.F[RVN_F_TEMP_AVE];
+  c.R(0) = c.G(RVN_G_AIRSNOW_COEFF) * (Tair - Tsnow);
+  c.R(0) = dmin(c.R(0), (D_FREEZING_TEMP - Tsnow) / c.tstep);
+}
+// CmvCanopyEvap CANEVP_ALL  src/VegetationMovers.cpp:110-160; ApplyConstraints :176-190
+template <class C, class PR> RVN_DI void rates_CANEVP_ALL(C &c, const PR &pr) {
+  if ((c.type != RVN_HRU_STANDARD) && (c.type != RVN_HRU_WETLAND)) return;
+  const double Fc = c.LU(RVN_LU_FOREST_COVERAGE);
+  if (Fc != 0) {
+    c.R(0) = c.SV(pr.from(0)) / c.tstep;
+    c.R(1) = c.R(0);
+  }
+  const double oldRates = c.R(0);
+  c.R(0) = dmax(c.R(0), 0.0);
+  c.R(0) = dmin(c.R(0), c.SV(pr.from(0)) / c.tstep);
+  c.R(1) -= (oldRates - c.R(0));
+}
+// CmvCanopySublimation SUBLIM_ALL (:CanopySnowEvap CANEVP_ALL)  src/VegetationMovers.cpp:283-346
+template <class C, class PR> RVN_DI void rates_CANSNOWEVP_ALL(C &c, const PR &pr) {
+  if ((c.type != RVN_HRU_STANDARD) && (c.type != RVN_HRU_WETLAND)) return;
+  const double Fc = c.LU(RVN_LU_FOREST_COVERAGE);
+  if (Fc != 0) {
+    c.R(0) = c.SV(pr.from(0)) / c.tstep;
+    c.R(1) = c.R(0);
+  }
+  const double oldRates = c.R(0);
+  c.R(0) = dmin(c.R(0), c.SV(pr.from(0)) / c.tstep);
+  c.R(1) -= (oldRates - c.R(0));
+}
+// CmvOWEvaporation OPEN_WATER_EVAP  src/OpenWaterEvap.cpp:113-160; ApplyConstraints :170-186
+template <class C, class PR> RVN_DI void rates_OPEN_WATER_EVAP(C &c, const PR &pr) {
+  if (c.type == RVN_HRU_MASKED_GLACIER) return;
+  double OWPET = c.F[RVN_F_OW_PET];
+  if (!c.opt().suppress_competitive_ET) { OWPET -= (c.SV(c.iSV(RVN_SV_AET)) / c.tstep); OWPET = dmax(OWPET, 0.0); }
+  c.R(0) = c.LU(RVN_LU_OW_PET_CORR) * OWPET;
+  if (c.R(0) < 0) c.R(0) = 0.0;
+  if (pr.from(0) != c.iSV(RVN_SV_SURFACE_WATER)) {
+    c.R(0) = dmin(c.R(0), c.SV(pr.from(0)) / c.tstep);
+    if (c.SV(pr.from(0)) <= 0) c.R(0) = 0.0;
+  }
+  c.R(pr.nconn() - 1) = c.R(0);
+}
+// CmvLakeEvaporation LAKE_EVAP_BASIC  src/OpenWaterEvap.cpp:269-290; ApplyConstraints :300-314.  ia(0) = 1 when the
+// source is the :LakeStorage variable (then the process applies to every HRU type, not only lakes)
+template <class C, class PR> RVN_DI void rates_LAKE_EVAP_BASIC(C &c, const PR &pr) {
+  if ((c.type == RVN_HRU_LAKE) || (pr.ia(0) == 1)) {
+    c.R(0) = c.LU(RVN_LU_LAKE_PET_CORR) * c.F[RVN_F_OW_PET];
+    c.R(pr.nconn() - 1) = c.R(0);
+  }
+  if (c.SV(pr.from(0)) <= 0) c.R(0) = 0.0;
+  if (c.R(0) < 0) c.R(0) = 0.0;
+  c.R(0) = dmin(c.R(0), c.SV(pr.from(0)) / c.tstep);
+  c.R(pr.nconn() - 1) = c.R(0);
+}
+// CmvGlacierMelt GMELT_HBV  src/GlacierProcesses.cpp:117-160; ApplyConstraints :176-190 (glacier_model_on = false)
+template <class C, class PR> RVN_DI void rates_GLACIERMELT_HBV(C &c, const PR &pr) {
+  if (c.type != RVN_HRU_GLACIER) return;
+  if (!(c.SV(c.iSV(RVN_SV_SNOW)) > D_REAL_SMALL)) c.R(0) = c.LU(RVN_LU_HBV_MELT_GLACIER_CORR) * dmax(c.F[RVN_F_POTENTIAL_MELT], 0.0);
+  if (c.R(0) < 0.0) c.R(0) = 0.0;
+  (void)pr;
+}
+// CmvGlacierRelease GRELEASE_HBV_EC  src/GlacierProcesses.cpp:292-325; ApplyConstraints :340-350
+template <class C, class PR> RVN_DI void rates_GLACIERRELEASE_HBVEC(C &c, const PR &pr) {
+  if (c.type != RVN_HRU_GLACIER) return;
+  const double glacier_stor = c.SV(c.iSV(RVN_SV_GLACIER)), snow = c.SV(c.iSV(RVN_SV_SNOW)), liq_snow = c.SV(c.iSV(RVN_SV_SNOW_LIQ));
+  const double Kmin = c.LU(RVN_LU_HBV_GLACIER_KMIN), Kmax = c.LU(RVN_LU_GLAC_STORAGE_COEFF), Ag = c.LU(RVN_LU_HBV_GLACIER_AG);
+  const double K = Kmin + (Kmax - Kmin) * exp(-Ag * (snow + liq_snow));
+  c.R(0) = K * glacier_stor;
+  if (c.R(0) < 0.0) c.R(0) = 0.0;
+  (void)pr;
+}
+
+// CmvInfiltration INF_HMETS / INF_HBV / INF_GR4J  src/Infiltration.cpp:304-330, 384-398, 477-489, 491-514; ApplyConstraints :605-626
+template <class C, class PR> RVN_DI void rates_INFILTRATION(C &c, const PR &pr, const int op) {
   const double tstep = c.tstep;
   const int type = c.type;
   if (type != RVN_HRU_STANDARD && type != RVN_HRU_ROCK && type != RVN_HRU_MASKED_GLACIER) return;
@@ -166,7 +266,7 @@ template <class C, class PR> RVN_DI void rates_INF_HMETS(C &c, const PR &pr) {
   const double ponded = dmax(c.SV(c.iSV(RVN_SV_PONDED_WATER)), 0.0);
   const double rainthru = (ponded / tstep);
   if (type == RVN_HRU_ROCK) { c.R(0) = 0.0; c.R(1) = rainthru; }
-  else {
+  else if (op == RVN_OP_INF_HMETS) {
     double stor = c.SV(pr.to(0)), max_stor = SoilCapacity(c, 0), coef = c.LU(RVN_LU_HMETS_RUNOFF_COEFF);
     double sat = dmin(dmax(stor / max_stor, 0.0), 1.0);
     double direct = Fimp * rainthru;
@@ -175,6 +275,19 @@ template <class C, class PR> RVN_DI void rates_INF_HMETS(C &c, const PR &pr) {
     double delayed = coef * pow(sat, 2.0) * infil;
     infil -= delayed;
     c.R(0) = infil; c.R(1) = direct; c.R(2) = runoff; c.R(3) = delayed;
+  } else if (op == RVN_OP_INF_HBV) {
+    double stor = c.SV(pr.to(0)), max_stor = SoilCapacity(c, 0), beta = c.SOIL(0, RVN_S_HBV_BETA);
+    double sat = dmax(dmin(stor / max_stor, 1.0), 0.0);
+    double runoff = pow(sat, beta) * rainthru;
+    runoff = (Fimp)*rainthru + (1 - Fimp) * runoff;
+    c.R(0) = rainthru - runoff; c.R(1) = runoff;
+  } else if (op == RVN_OP_INF_GR4J) {
+    double x1 = SoilCapacity(c, 0), stor = c.SV(pr.to(0));
+    double sat = stor / x1;
+    double tmp = tanh(ponded / x1);
+    double infil = x1 * (1.0 - (sat * sat)) * tmp / (1.0 + sat * tmp);
+    infil = (1.0 - Fimp) * infil;
+    c.R(0) = infil; c.R(1) = rainthru - infil;
   }
   if (type != RVN_HRU_STANDARD && type != RVN_HRU_MASKED_GLACIER) return;
   c.R(0) = dmin(c.R(0), c.SV(pr.from(0)) / tstep);
@@ -199,37 +312,77 @@ template <class C, class PR> RVN_DI void rates_SPLIT(C &c, const PR &pr) {
   c.R(0) = (pr.da(0)) * c.SV(pr.from(0)) / c.tstep;
   c.R(1) = (1.0 - pr.da(0)) * c.SV(pr.from(0)) / c.tstep;
 }
-// CmvBaseflow BASE_LINEAR  src/Baseflow.cpp:152-186; ApplyConstraints :297-310
-template <class C, class PR> RVN_DI void rates_BASE_LINEAR(C &c, const PR &pr) {
+// CmvBaseflow BASE_LINEAR / BASE_POWER_LAW / BASE_GR4J  src/Baseflow.cpp:152-186,208-215,238-243; ApplyConstraints :297-310
+template <class C, class PR> RVN_DI void rates_BASEFLOW(C &c, const PR &pr, const int op) {
   const int type = c.type;
   if (!(type == RVN_HRU_LAKE || type == RVN_HRU_WATER || type == RVN_HRU_ROCK)) {
     const int m = pr.ia(0);
     double stor = c.SV(pr.from(0)), max_stor = (m >= 0) ? SoilCapacity(c, m) : 0.0;
     stor = dmin(dmax(stor, 0.0), max_stor);
-    c.R(0) = c.SOIL(m, RVN_S_BASEFLOW_COEFF) * stor;
+    if (op == RVN_OP_BASE_LINEAR) c.R(0) = c.SOIL(m, RVN_S_BASEFLOW_COEFF) * stor;
+    else if (op == RVN_OP_BASE_POWER_LAW) c.R(0) = c.SOIL(m, RVN_S_BASEFLOW_COEFF) * pow(stor, c.SOIL(m, RVN_S_BASEFLOW_N));
+    else if (op == RVN_OP_BASE_GR4J) {
+      const double x3 = c.SOIL(m, RVN_S_GR4J_X3);
+      c.R(0) = stor * (1.0 - pow(1.0 + pow(dmax(stor / x3, 0.0), 4.0), -0.25)) / c.tstep;
+    }
   }
   c.R(0) = dmin(c.R(0), dmax(c.SV(pr.from(0)), 0.0) / c.tstep);
   c.R(0) = dmax(c.R(0), 0.0);
 }
-// CmvPercolation PERC_LINEAR  src/Percolation.cpp:183-243; ApplyConstraints :339-360
-template <class C, class PR> RVN_DI void rates_PERC_LINEAR(C &c, const PR &pr) {
+// CmvPercolation PERC_LINEAR / PERC_CONSTANT / PERC_GR4J / PERC_GR4JEXCH / PERC_GR4JEXCH2
+// src/Percolation.cpp:183-202,237-243,293-316; ApplyConstraints :339-360
+template <class C, class PR> RVN_DI void rates_PERCOLATION(C &c, const PR &pr, const int op) {
   const int type = c.type;
   if (type == RVN_HRU_LAKE || type == RVN_HRU_WATER || type == RVN_HRU_ROCK) return;
   const int m = pr.ia(0);
   double stor = c.SV(pr.from(0)), max_stor = SoilCapacity(c, m);
-  if (max_stor > 0.0) c.R(0) = c.SOIL(m, RVN_S_PERC_COEFF) * stor;
+  if (max_stor > 0.0) {
+    if (op == RVN_OP_PERC_LINEAR) c.R(0) = c.SOIL(m, RVN_S_PERC_COEFF) * stor;
+    else if (op == RVN_OP_PERC_CONSTANT) c.R(0) = c.SOIL(m, RVN_S_MAX_PERC_RATE);
+    else if (op == RVN_OP_PERC_GR4J) c.R(0) = stor * (1.0 - pow(1.0 + pow(4.0 / 9.0 * dmax(stor / max_stor, 0.0), 4.0), -0.25)) / c.tstep;
+    else if (op == RVN_OP_PERC_GR4JEXCH) {
+      const double x2 = c.SOIL(m, RVN_S_GR4J_X2), x3 = c.SOIL(m, RVN_S_GR4J_X3);
+      c.R(0) = -x2 * pow(dmax(dmin(stor / x3, 1.0), 0.0), 3.5);
+    } else if (op == RVN_OP_PERC_GR4JEXCH2) {
+      const double x2 = c.SOIL(1, RVN_S_GR4J_X2), x3 = c.SOIL(1, RVN_S_GR4J_X3);
+      stor = c.SV(c.soil_slot(1));   // SOIL[1]
+      c.R(0) = -x2 * pow(dmax(dmin(stor / x3, 1.0), 0.0), 3.5);
+    }
+  }
   c.R(0) = dmin(c.R(0), dmax(c.SV(pr.from(0)) - 0.0, 0.0) / c.tstep);
   if (!c.opt().allow_soil_overfill) {
     double room = dmax(StateVarMax(c, pr.to(0)) - c.SV(pr.to(0)), 0.0);
     c.R(0) = dmin(c.R(0), room / c.tstep);
   }
 }
-// CmvSoilEvap SOILEVAP_ALL  src/SoilEvaporation.cpp:325-343,379-383,751; ApplyConstraints :767-783
-template <class C, class PR> RVN_DI void rates_SOILEVAP_ALL(C &c, const PR &pr) {
+// CmvCapillaryRise RISE_HBV  src/CapillaryRise.cpp:103-147; ApplyConstraints :160-179
+template <class C, class PR> RVN_DI void rates_CAPRISE_HBV(C &c, const PR &pr) {
+  const int type = c.type;
+  if (type == RVN_HRU_LAKE || type == RVN_HRU_WATER || type == RVN_HRU_ROCK) return;
+  const int m = pr.ia(1);   // soil layer of the receiving store
+  double stor = c.SV(pr.to(0)), max_stor = SoilCapacity(c, m);
+  stor = dmin(dmax(stor, 0.0), max_stor);
+  c.R(0) = c.SOIL(m, RVN_S_MAX_CAP_RISE_RATE) * (1.0 - dmin(stor / max_stor, 1.0));
+  c.R(0) = dmin(c.R(0), dmax(c.SV(pr.from(0)), 0.0) / c.tstep);
+  if (!c.opt().allow_soil_overfill) c.R(0) = dmin(c.R(0), (StateVarMax(c, pr.to(0)) - c.SV(pr.to(0))) / c.tstep);
+}
+// CmvSoilEvap SOILEVAP_ALL / SOILEVAP_HBV / SOILEVAP_GR4J  src/SoilEvaporation.cpp:325-343,379-383,385-405,640-650,751; ApplyConstraints :767-783
+template <class C, class PR> RVN_DI void rates_SOILEVAP(C &c, const PR &pr, const int op) {
   if (c.type != RVN_HRU_STANDARD) return;
   double PET = c.F[RVN_F_PET];
   if (!c.opt().suppress_competitive_ET) { PET -= (c.SV(c.iSV(RVN_SV_AET)) / c.tstep); PET = dmax(PET, 0.0); }
-  c.R(0) = PET;
+  if (op == RVN_OP_SOILEVAP_ALL) c.R(0) = PET;
+  else if (op == RVN_OP_SOILEVAP_HBV) {
+    const double stor = dmax(c.SV(pr.from(0)), 0.0), tens_stor = SoilTensionCapacity(c, 0);
+    c.R(0) = PET * dmin(stor / tens_stor, 1.0);
+    const int iSnow = c.iSV(RVN_SV_SNOW);
+    if (iSnow >= 0) { if (c.SV(iSnow) > D_REAL_SMALL) c.R(0) = (c.LU(RVN_LU_FOREST_COVERAGE)) * c.R(0); }
+  } else if (op == RVN_OP_SOILEVAP_GR4J) {
+    const double max_stor = SoilCapacity(c, 0), stor = c.SV(pr.from(0));
+    const double sat = stor / max_stor;
+    const double tmp = tanh(dmax(PET, 0.0) / max_stor);
+    c.R(0) = stor * (2.0 - sat) * tmp / (1.0 + (1.0 - sat) * tmp);
+  }
   const int last = pr.nconn() - 1;
   c.R(last) = c.R(0);
   double corr = 0;
@@ -247,21 +400,27 @@ template <class C, class PR> RVN_DI void dispatch_rates(C &c, const PR &pr, cons
   switch (op) {   // uniform across the CTA: every thread runs the same process at the same time
     case RVN_OP_PRECIPITATION: rates_PRECIPITATION(c, pr); break;
     case RVN_OP_SNOBAL_HMETS: rates_SNOBAL_HMETS(c, pr); break;
-    case RVN_OP_INF_HMETS: rates_INF_HMETS(c, pr); break;
+    case RVN_OP_SNOBAL_SIMPLE_MELT: rates_SNOBAL_SIMPLE_MELT(c, pr); break;
+    case RVN_OP_SNOBAL_CEMA_NEIGE: rates_SNOBAL_CEMA_NEIGE(c, pr); break;
+    case RVN_OP_SNOWREFREEZE_DD: rates_SNOWREFREEZE_DD(c, pr); break;
+    case RVN_OP_SNOTEMP_NEWTONS: rates_SNOTEMP_NEWTONS(c, pr); break;
+    case RVN_OP_INF_HMETS: case RVN_OP_INF_HBV: case RVN_OP_INF_GR4J: rates_INFILTRATION(c, pr, op); break;
     case RVN_OP_OVERFLOW: rates_OVERFLOW(c, pr); break;
     case RVN_OP_FLUSH: rates_FLUSH(c, pr); break;
     case RVN_OP_SPLIT: rates_SPLIT(c, pr); break;
-    case RVN_OP_BASE_LINEAR: rates_BASE_LINEAR(c, pr); break;
-    case RVN_OP_PERC_LINEAR: rates_PERC_LINEAR(c, pr); break;
-    case RVN_OP_SOILEVAP_ALL: rates_SOILEVAP_ALL(c, pr); break;
+    case RVN_OP_BASE_LINEAR: case RVN_OP_BASE_POWER_LAW: case RVN_OP_BASE_GR4J: rates_BASEFLOW(c, pr, op); break;
+    case RVN_OP_PERC_LINEAR: case RVN_OP_PERC_CONSTANT: case RVN_OP_PERC_GR4J: case RVN_OP_PERC_GR4JEXCH: case RVN_OP_PERC_GR4JEXCH2:
+      rates_PERCOLATION(c, pr, op); break;
+    case RVN_OP_SOILEVAP_ALL: case RVN_OP_SOILEVAP_HBV: case RVN_OP_SOILEVAP_GR4J: rates_SOILEVAP(c, pr, op); break;
+    case RVN_OP_CANEVP_ALL: rates_CANEVP_ALL(c, pr); break;
+    case RVN_OP_CANSNOWEVP_ALL: rates_CANSNOWEVP_ALL(c, pr); break;
+    case RVN_OP_OPEN_WATER_EVAP: rates_OPEN_WATER_EVAP(c, pr); break;
+    case RVN_OP_LAKE_EVAP_BASIC: rates_LAKE_EVAP_BASIC(c, pr); break;
+    case RVN_OP_CAPRISE_HBV: rates_CAPRISE_HBV(c, pr); break;
+    case RVN_OP_GLACIERMELT_HBV: rates_GLACIERMELT_HBV(c, pr); break;
+    case RVN_OP_GLACIERRELEASE_HBVEC: rates_GLACIERRELEASE_HBVEC(c, pr); break;
     default: break;
   }
 }
-__host__ __device__ inline bool rvn_op_supported(int op) {
-  switch (op) {
-    case RVN_OP_PRECIPITATION: case RVN_OP_SNOBAL_HMETS: case RVN_OP_INF_HMETS: case RVN_OP_OVERFLOW: case RVN_OP_FLUSH: case RVN_OP_SPLIT:
-    case RVN_OP_BASE_LINEAR: case RVN_OP_PERC_LINEAR: case RVN_OP_SOILEVAP_ALL: case RVN_OP_CONVOLVE: return true;
-    default: return false;
-  }
-}
+__host__ __device__ inline bool rvn_op_supported(int op) { return op > RVN_OP_NOP && op < RVN_OP_COUNT; }
 #endif

@@ -102,6 +102,9 @@ void   JulianConvert(double model_time, double start_date, int start_year, int c
 time_struct DateStringToTimeStruct(const std::string &sDate, const std::string &sTime, int calendar);
 double TimeDifference(double jul_day1, int year1, double jul_day2, int year2, int calendar);
 double DayAngle(double julian_day, int year, int calendar);
+double SolarDeclination(double day_angle);                         // src/Radiation.cpp:484-497
+double EccentricityCorr(double day_angle);                         // src/Radiation.cpp:505-515
+double CalcETRadiation2(double latrad, double aspect, double declin, double ecc, double slope, double t1, double t2, bool avg_daily);  // src/Radiation.cpp:637-822
 double gamma2(double x);
 double IncompleteGamma(double x, double a);
 double GammaCumDist(double t, double alpha, double beta);

@@ -118,6 +118,7 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
   d.ptab = _f_ptab.data(); d.conv_n = _f_conv_n.data(); d.conv_uh = _f_conv_uh.data();
   // ---- calendar: replay the reference time loop  for(t=0; t<duration-TIME_CORRECTION; t+=timestep)  (src/RavenMain.cpp:145)
   _f_times.clear();
+  _f_veg_season.clear();
   {
     time_struct tt;
     JulianConvert(0.0, O.julian_start_day, O.julian_start_year, O.calendar, tt);
@@ -133,11 +134,51 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
       }
       r.day_angle = last_angle;
       _f_times.push_back(r);
+      // month-interpolated relative vegetation height / LAI (CVegetationClass::RecalculateCanopyParams, src/VegetationParams.cpp:102-107;
+      // the reference repeats this per HRU per step although it depends on (vegetation class, date) only)
+      for (size_t v = 0; v < veg_classes.size(); v++) {
+        _f_veg_season.push_back(InterpolateMo(veg_classes[v].V.relative_ht, tt, O.month_interp_method, O));
+        _f_veg_season.push_back(InterpolateMo(veg_classes[v].V.relative_LAI, tt, O.month_interp_method, O));
+      }
       JulianConvert(t + O.timestep, O.julian_start_day, O.julian_start_year, O.calendar, tt);
     }
   }
   const int nSteps = (int)_f_times.size();
   d.nSteps = nSteps; d.times = _f_times.data();
+  if (_f_veg_season.empty()) _f_veg_season.push_back(0.0);
+  d.veg_season = _f_veg_season.data();
+  // ---- extraterrestrial radiation (CRadiation::EstimateShortwaveRadiation -> ClearSkySolarRadiation -> CalcETRadiation2,
+  // src/Radiation.cpp:24-57,992-1032): needed only when a PET that a process consumes is estimated from it.  It depends on
+  // (HRU geometry, day angle, position of the step inside the day), not on the member: one row per distinct date.
+  d.nEtRows = 0; d.et_radia = NULL; d.et_row = NULL;
+  {
+    bool uses_pet = false, uses_owpet = false;
+    for (int j = 0; j < NP; j++) {
+      const int op = _f_proc[j].op;
+      if (op == RVN_OP_SOILEVAP_ALL || op == RVN_OP_SOILEVAP_HBV || op == RVN_OP_SOILEVAP_GR4J || op == RVN_OP_CANEVP_ALL || op == RVN_OP_CANSNOWEVP_ALL) uses_pet = true;
+      if (op == RVN_OP_OPEN_WATER_EVAP || op == RVN_OP_LAKE_EVAP_BASIC) uses_owpet = true;
+    }
+    const bool need = (uses_pet && O.evaporation == RVN_PET_HARGREAVES_1985) || (uses_owpet && O.ow_evaporation == RVN_PET_HARGREAVES_1985);
+    if (need) {
+      _f_et_row.assign(nSteps, 0);
+      _f_et.clear();
+      std::map<std::pair<double, double>, int> rows;
+      for (int n = 0; n < nSteps; n++) {
+        const double t_sol = _f_times[n].julian_day - floor(_f_times[n].julian_day) - 0.5;
+        const std::pair<double, double> key(_f_times[n].day_angle, t_sol);
+        std::map<std::pair<double, double>, int>::iterator it = rows.find(key);
+        if (it == rows.end()) {
+          const int r = (int)rows.size();
+          rows[key] = r;
+          const double declin = SolarDeclination(_f_times[n].day_angle), ecc = EccentricityCorr(_f_times[n].day_angle);
+          for (int k = 0; k < nH; k++)
+            _f_et.push_back(CalcETRadiation2(_f_hru_d[2][k], _f_hru_d[4][k], declin, ecc, _f_hru_d[3][k], t_sol, t_sol + O.timestep, O.timestep >= 1.0));
+          _f_et_row[n] = r;
+        } else _f_et_row[n] = it->second;
+      }
+      d.nEtRows = (int32_t)rows.size(); d.et_radia = _f_et.data(); d.et_row = _f_et_row.data();
+    }
+  }
   // ---- gauge series sampled on the model step (src/UpdateForcings.cpp:98-155)
   _f_series.assign((size_t)RVN_GF_COUNT * nG * nSteps, 0.0);
   _f_gconst.assign((size_t)nG * RVN_GC_COUNT, 0.0);

@@ -207,9 +207,12 @@ double CChannelXSect::GetTopWidth(double Qin, double SB_slope, double SB_n) cons
 }
 
 // ---------------------------------------------------------------------------------- HRU / subbasin
-double CHydroUnit::GetLatRad() const { return latitude * RVH_PI / 180.0; }
-double CHydroUnit::GetSlope() const { return slope * RVH_PI / 180.0; }
-double CHydroUnit::GetAspect() const { return aspect * RVH_PI / 180.0; }
+// the reference converts with the rounded literal DEGREES_TO_RADIANS = 0.017453293 (src/RavenInclude.h:166; src/ParseHRUFile.cpp:327-328,
+// src/HydroUnits.cpp:95), not with PI/180
+static const double DEGREES_TO_RADIANS = 0.017453293;
+double CHydroUnit::GetLatRad() const { return latitude * DEGREES_TO_RADIANS; }
+double CHydroUnit::GetSlope() const { return slope * DEGREES_TO_RADIANS; }
+double CHydroUnit::GetAspect() const { return aspect * DEGREES_TO_RADIANS; }
 
 CSubBasin::CSubBasin()
     : ID(0), downstream_ID(DOESNT_EXIST), pChannel(NULL), reach_length(AUTO_COMPUTE), gauged(false), is_headwater(true), disabled(false),
@@ -342,7 +345,7 @@ void CSubBasin::Initialize(double Qin_avg, double Qlat_avg, double total_drain_a
   if (Q_ref == AUTO_COMPUTE) {
     ExitGracefullyIf(((Qin_avg + Qlat_avg) <= 0) && (!is_headwater),
                      "CSubBasin::Initialize: negative or zero average flow specified in initialization (basin " + std::to_string(ID) + ")");
-    ResetReferenceFlow(1.0 * (Qin_avg + Qlat_avg));  // reference_flow_mult default 1.0
+    ResetReferenceFlow(10.0 * (Qin_avg + Qlat_avg));  // REFERENCE_FLOW_MULT autogenerates to 10 (src/GlobalParams.cpp:159-163; src/SubBasin.cpp Initialize)
   } else {
     ResetReferenceFlow(Q_ref);
   }

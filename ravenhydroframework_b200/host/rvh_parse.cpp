@@ -464,11 +464,36 @@ static void ParseClassPropertiesFile(CModel *pModel, const optStruct &Options) {
     if (S.v[RVN_LU_FOREST_SPARSENESS] == NOT_SPECIFIED) S.v[RVN_LU_FOREST_SPARSENESS] = 0.0;  // src/LandUseClass.cpp autocalc
     if (S.v[RVN_LU_LAKE_PET_CORR] == NOT_SPECIFIED) S.v[RVN_LU_LAKE_PET_CORR] = 1.0;
     if (S.v[RVN_LU_OW_PET_CORR] == NOT_SPECIFIED) S.v[RVN_LU_OW_PET_CORR] = 1.0;
+    // autogenerated snow parameters (CLandUseClass::AutoCalculateLandUseProps, src/LandUseClass.cpp:100-160)
+    if (S.v[RVN_LU_FOREST_COVERAGE] == NOT_SPECIFIED) S.v[RVN_LU_FOREST_COVERAGE] = 0.0;
+    if (S.v[RVN_LU_MELT_FACTOR] == NOT_SPECIFIED) S.v[RVN_LU_MELT_FACTOR] = 5.04;
+    if (S.v[RVN_LU_DD_MELT_TEMP] == NOT_SPECIFIED) S.v[RVN_LU_DD_MELT_TEMP] = 0.0;
+    if (S.v[RVN_LU_MIN_MELT_FACTOR] == NOT_SPECIFIED) S.v[RVN_LU_MIN_MELT_FACTOR] = S.v[RVN_LU_MELT_FACTOR];
+    if (S.v[RVN_LU_REFREEZE_FACTOR] == NOT_SPECIFIED) S.v[RVN_LU_REFREEZE_FACTOR] = 5.04;
+    if (S.v[RVN_LU_DD_REFREEZE_TEMP] == NOT_SPECIFIED) S.v[RVN_LU_DD_REFREEZE_TEMP] = 0.0;
+    if (S.v[RVN_LU_REFREEZE_EXP] == NOT_SPECIFIED) S.v[RVN_LU_REFREEZE_EXP] = 1.0;
+    if (S.v[RVN_LU_HBV_MELT_FOR_CORR] == NOT_SPECIFIED) S.v[RVN_LU_HBV_MELT_FOR_CORR] = 1.0;
+    if (S.v[RVN_LU_HBV_MELT_ASP_CORR] == NOT_SPECIFIED) S.v[RVN_LU_HBV_MELT_ASP_CORR] = 0.0;
+    if (S.v[RVN_LU_HBV_MELT_GLACIER_CORR] == NOT_SPECIFIED) S.v[RVN_LU_HBV_MELT_GLACIER_CORR] = 1.0;
+  }
+  {  // autogenerated global parameters (CGlobalParams::AutoCalculateGlobalParams, src/GlobalParams.cpp:80-325)
+    global_struct &G = pModel->globals;
+    static const struct { int f; double v; } gd[] = {
+      {RVN_G_SNOW_SWI, 0.05}, {RVN_G_SNOW_SWI_MIN, 0.05}, {RVN_G_SNOW_SWI_MAX, 0.05}, {RVN_G_SNOW_TEMPERATURE, 0.0}, {RVN_G_RAINSNOW_TEMP, 0.15},
+      {RVN_G_RAINSNOW_DELTA, 2.0}, {RVN_G_MAX_SWE_SURFACE, 100.0}, {RVN_G_ADIABATIC_LAPSE, 6.4}, {RVN_G_PRECIP_LAPSE, 0.0},
+      {RVN_G_HBVEC_LAPSE_RATE, 0.08}, {RVN_G_HBVEC_LAPSE_UPPER, 0.0}, {RVN_G_HBVEC_LAPSE_ELEV, 5000.0}};
+    for (size_t i = 0; i < sizeof(gd) / sizeof(gd[0]); i++) if (G.v[gd[i].f] == NOT_SPECIFIED) G.v[gd[i].f] = gd[i].v;
   }
   for (size_t k = 0; k < pModel->veg_classes.size(); k++) {
     veg_struct &V = pModel->veg_classes[k].V;
     if (V.v[RVN_V_SAI_HT_RATIO] == NOT_SPECIFIED) V.v[RVN_V_SAI_HT_RATIO] = 0.0;
     if (V.v[RVN_V_PET_VEG_CORR] == NOT_SPECIFIED) V.v[RVN_V_PET_VEG_CORR] = 1.0;
+    // CVegetationClass::AutoCalculateVegetationProps (src/VegetationClass.cpp:118-195)
+    if (V.v[RVN_V_RAIN_ICEPT_PCT] == NOT_SPECIFIED) V.v[RVN_V_RAIN_ICEPT_PCT] = 0.12;
+    if (V.v[RVN_V_SNOW_ICEPT_PCT] == NOT_SPECIFIED) V.v[RVN_V_SNOW_ICEPT_PCT] = 0.10;
+    const double max_LAI = V.v[RVN_V_MAX_LAI], max_SAI = V.v[RVN_V_SAI_HT_RATIO] * V.v[RVN_V_MAX_HEIGHT];
+    if (V.v[RVN_V_MAX_CAPACITY] == NOT_SPECIFIED) V.v[RVN_V_MAX_CAPACITY] = 0.15 * (max_LAI + max_SAI);
+    if (V.v[RVN_V_MAX_SNOW_CAPACITY] == NOT_SPECIFIED) V.v[RVN_V_MAX_SNOW_CAPACITY] = 0.6 * (max_LAI + max_SAI);
   }
 }
 
@@ -801,6 +826,28 @@ bool ParseInitialConditions(CModel *&pModel, const optStruct &Options) {
     }
     ExitGracefully("ParseInitialConditions: command " + c + " is not supported by the B200 build");
   }
-  (void)NS;
+  // quality check of the initial state (src/ParseInitialConditionFile.cpp:1050-1080): values above the state-independent
+  // capacity (GetStateVarMax with ignorevar=true: SOIL capacity, DEPRESSION dep_max, SNOW_COVER 1) are clipped to it
+  for (int k = 0; k < nH; k++) {
+    const CHydroUnit *h = pModel->GetHydroUnit(k);
+    const CSoilProfile &sp = pModel->soil_profiles[h->soil_profile];
+    for (int i = 0; i < NS; i++) {
+      double maxv = ALMOST_INF;
+      const sv_type t = pModel->GetStateVarType(i);
+      if (t == RVN_SV_SOIL) {
+        const int m = pModel->GetStateVarLayer(i);
+        maxv = (m < sp.nHorizons) ? sp.thickness[m] * MM_PER_METER * pModel->soil_classes[sp.soil_class[m]].S.v[RVN_S_CAP_RATIO] : 0.0;
+      } else if (t == RVN_SV_DEPRESSION) {
+        const double dm = pModel->lu_classes[h->lu_class].S.v[RVN_LU_DEP_MAX];
+        if (dm >= 0) maxv = dm;
+      } else if (t == RVN_SV_SNOW_COVER) maxv = 1.0;
+      maxv = rvh_max(maxv, 0.0);
+      const double v = pModel->initial_state[(size_t)k * NS + i];
+      if ((v - maxv) > 1e-8) {
+        WriteWarning("maximum state variable limit exceeded in initial conditions for " + pModel->GetStateVarName(i) + " (in HRU " + std::to_string(h->ID) + ") in .rvc file");
+        pModel->SetInitialStateVar(k, i, maxv);
+      }
+    }
+  }
   return true;
 }

@@ -277,6 +277,89 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
     p->Connect(iAET, iAET);
     return p;
   }
+  if (cmd == ":SnowRefreeze") {  // case 214; src/SnowMeltRefreeze.cpp:253-267
+    need(4);
+    ExitGracefullyIf(s[1] != "FREEZE_DEGREE_DAY", "ParseMainInputFile: Unrecognized snow refreeze process representation");
+    AddSVs(pM, {SVL(RVN_SV_SNOW_LIQ, -1), SVL(RVN_SV_SNOW, -1)});
+    CmvGeneric *p = new CmvGeneric("SnowRefreeze", RVN_OP_SNOWREFREEZE_DD, pM);
+    p->Connect(pM->GetStateVarIndex(RVN_SV_SNOW_LIQ), pM->GetStateVarIndex(RVN_SV_SNOW));
+    return p;
+  }
+  if (cmd == ":SnowTempEvolve") {  // case 229; src/SnowTempEvolve.cpp:14-22
+    need(3);
+    ExitGracefullyIf(s[1] != "SNOTEMP_NEWTONS", "ParseMainInputFile: Unrecognized snow temp evolution process representation");
+    AddSV1(pM, RVN_SV_SNOW_TEMP);
+    CmvGeneric *p = new CmvGeneric("SnowTempEvolve", RVN_OP_SNOTEMP_NEWTONS, pM);
+    p->Connect(pM->GetStateVarIndex(RVN_SV_SNOW_TEMP), pM->GetStateVarIndex(RVN_SV_SNOW_TEMP));
+    return p;
+  }
+  if (cmd == ":CanopyEvaporation") {  // case 202; src/VegetationMovers.cpp:20-32
+    need(4);
+    ExitGracefullyIf(s[1] != "CANEVP_ALL", "ParseMainInputFile: canopy evaporation algorithm " + s[1] + " is not implemented in the B200 build");
+    AddSVs(pM, {SVL(RVN_SV_CANOPY, -1), SVL(RVN_SV_ATMOSPHERE, -1), SVL(RVN_SV_AET, -1)});
+    CmvGeneric *p = new CmvGeneric("CanopyEvaporation", RVN_OP_CANEVP_ALL, pM);
+    int iAET = pM->GetStateVarIndex(RVN_SV_AET);
+    p->Connect(pM->GetStateVarIndex(RVN_SV_CANOPY), iAtmos); p->Connect(iAET, iAET);
+    return p;
+  }
+  if (cmd == ":CanopySnowEvap" || cmd == ":CanopySnowEvaporation" || cmd == ":CanopySublimation") {  // case 221; src/VegetationMovers.cpp:205-216
+    need(4);
+    ExitGracefullyIf(s[1] != "CANEVP_ALL" && s[1] != "SUBLIM_ALL", "ParseMainInputFile: canopy sublimation algorithm " + s[1] + " is not implemented in the B200 build");
+    AddSVs(pM, {SVL(RVN_SV_CANOPY_SNOW, -1), SVL(RVN_SV_ATMOSPHERE, -1), SVL(RVN_SV_AET, -1)});
+    CmvGeneric *p = new CmvGeneric("CanopySublimation", RVN_OP_CANSNOWEVP_ALL, pM);
+    int iAET = pM->GetStateVarIndex(RVN_SV_AET);
+    p->Connect(pM->GetStateVarIndex(RVN_SV_CANOPY_SNOW), iAtmos); p->Connect(iAET, iAET);
+    return p;
+  }
+  if (cmd == ":OpenWaterEvaporation") {  // case 211; src/OpenWaterEvap.cpp:17-38
+    need(4);
+    ExitGracefullyIf(s[1] != "OPEN_WATER_EVAP", "ParseMainInputFile: open water evaporation algorithm " + s[1] + " is not implemented in the B200 build");
+    AddSVs(pM, {SVL(RVN_SV_ATMOSPHERE, -1), SVL(RVN_SV_AET, -1)});
+    int from = pM->ParseSVTypeIndex(s[2]);
+    CmvGeneric *p = new CmvGeneric("OpenWaterEvaporation", RVN_OP_OPEN_WATER_EVAP, pM);
+    int iAET = pM->GetStateVarIndex(RVN_SV_AET);
+    p->Connect(from, iAtmos); p->Connect(iAET, iAET);
+    return p;
+  }
+  if (cmd == ":LakeEvaporation") {  // case 217; src/OpenWaterEvap.cpp:206-222
+    need(4);
+    ExitGracefullyIf(s[1] != "LAKE_EVAP_BASIC" && s[1] != "BASIC", "ParseMainInputFile: Unrecognized Lake Evaporation process representation");
+    AddSVs(pM, {SVL(RVN_SV_ATMOSPHERE, -1), SVL(RVN_SV_AET, -1)});
+    int lake_ind = pM->GetLakeStorageIndex();   // the 'from' token is ignored by the reference when four tokens are given
+    ExitGracefullyIf(lake_ind == DOESNT_EXIST, "CmvLakeEvaporation Constructor: invalid 'from' compartment specified");
+    CmvGeneric *p = new CmvGeneric("LakeEvaporation", RVN_OP_LAKE_EVAP_BASIC, pM);
+    int iAET = pM->GetStateVarIndex(RVN_SV_AET);
+    p->Connect(lake_ind, iAtmos); p->Connect(iAET, iAET);
+    p->SetIntArg(0, 1);   // source == :LakeStorage variable
+    return p;
+  }
+  if (cmd == ":GlacierMelt") {  // case 219; src/GlacierProcesses.cpp:17-36
+    need(4);
+    ExitGracefullyIf(s[1] != "GMELT_HBV" && s[1] != "HBV", "ParseMainInputFile: glacier melt algorithm " + s[1] + " is not implemented in the B200 build");
+    AddSVs(pM, {SVL(RVN_SV_GLACIER_ICE, -1), SVL(RVN_SV_GLACIER, -1)});
+    CmvGeneric *p = new CmvGeneric("GlacierMelt", RVN_OP_GLACIERMELT_HBV, pM);
+    p->Connect(pM->GetStateVarIndex(RVN_SV_GLACIER_ICE), pM->GetStateVarIndex(RVN_SV_GLACIER));
+    return p;
+  }
+  if (cmd == ":GlacierRelease") {  // case 220; src/GlacierProcesses.cpp:200-211,240-251
+    need(4);
+    ExitGracefullyIf(s[1] != "GRELEASE_HBV_EC" && s[1] != "HBV_EC", "ParseMainInputFile: glacier release algorithm " + s[1] + " is not implemented in the B200 build");
+    AddSVs(pM, {SVL(RVN_SV_GLACIER, -1), SVL(RVN_SV_SNOW, -1), SVL(RVN_SV_SNOW_LIQ, -1)});
+    CmvGeneric *p = new CmvGeneric("GlacierRelease", RVN_OP_GLACIERRELEASE_HBVEC, pM);
+    p->Connect(pM->GetStateVarIndex(RVN_SV_GLACIER), iSW);
+    return p;
+  }
+  if (cmd == ":CapillaryRise") {  // case 216; src/CapillaryRise.cpp:20-35
+    need(4);
+    ExitGracefullyIf(s[1] != "RISE_HBV" && s[1] != "CRISE_HBV", "ParseMainInputFile: Unrecognized capillary rise process representation");
+    int from = pM->ParseSVTypeIndex(s[2]), to = pM->ParseSVTypeIndex(s[3]);
+    ExitGracefullyIf(pM->GetStateVarType(from) != RVN_SV_SOIL || pM->GetStateVarType(to) != RVN_SV_SOIL, "CmvCapillaryRise::Initialize:CapillaryRise must come from and go to soil units");
+    CmvGeneric *p = new CmvGeneric("CapillaryRise", RVN_OP_CAPRISE_HBV, pM);
+    p->Connect(from, to);
+    p->SetIntArg(0, SoilLayerOf(pM, from));
+    p->SetIntArg(1, SoilLayerOf(pM, to));
+    return p;
+  }
   if (cmd == ":Convolve") {  // case 228
     need(4);
     rvn_convol_type ct = RVN_CONVOL_GR4J_1;

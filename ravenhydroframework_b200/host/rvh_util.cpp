@@ -265,3 +265,119 @@ double InterpolateMo(const double aVal[12], const time_struct &tt, month_interp 
   }
   return wt * aVal[mo] + (1 - wt) * aVal[nextmo];
 }
+
+// ---- extraterrestrial radiation on an inclined surface ---------------------------------------------------------
+// Restates CRadiation::SolarDeclination / EccentricityCorr (src/Radiation.cpp:484-515) and CRadiation::CalcETRadiation2
+// (src/Radiation.cpp:637-822; analytical integration of the beam over the sunlit interval after Allen et al. 2006,
+// including the double-sunrise case of steep pole-facing slopes).  The result depends on (HRU geometry, date, step
+// interval) only -- never on an ensemble member -- so the B200 build evaluates it once per distinct date on the host
+// (same libm as the reference) instead of once per HRU per member per step.
+double SolarDeclination(double day_angle) { return 0.40928 * sin(day_angle - 1.384); }
+double EccentricityCorr(double day_angle) {
+  return 1.000110 + 0.034221 * cos(1.0 * day_angle) + 0.001280 * sin(1.0 * day_angle) + 0.000719 * cos(2.0 * day_angle) + 0.000077 * sin(2.0 * day_angle);
+}
+namespace {
+const double PI = RVH_PI;
+const double SOLAR_CONSTANT = 118.1;   // [MJ/m2/d] src/RavenInclude.h:223
+struct BeamGeom {   // Allen et al. (2006) eqn 11 constants + the trigonometric pieces the integral reuses
+  double a, b, c, sd, cd, sl, cl, ss, cs, sr, cr;
+  double cos_at(double w) const { return -a + b * cos(w) + c * sin(w); }   // eqn 14
+  // eqn 5 integrated from w_lo to w_hi, terms in the reference's factored order
+  double integral(double w_lo, double w_hi) const {
+    return (sd * sl * cs - sd * cl * ss * cr) * (w_hi - w_lo) + (cd * cl * cs + cd * sl * ss * cr) * (sin(w_hi) - sin(w_lo)) - (cd * ss * sr) * (cos(w_hi) - cos(w_lo));
+  }
+};
+}  // namespace
+double CalcETRadiation2(double latrad, double aspect, double declin, double ecc, double slope, double t1, double t2, bool avg_daily) {
+  double revasp = -(aspect + PI);
+  if (revasp > 2 * PI) revasp -= 2 * PI;
+  BeamGeom g;
+  g.cs = cos(slope); g.ss = sin(slope); g.cd = cos(declin); g.sd = sin(declin);
+  g.cl = cos(latrad); g.sl = sin(latrad); g.cr = cos(revasp); g.sr = sin(revasp);
+  g.a = g.sd * (g.cl * g.ss * g.cr - g.sl * g.cs);
+  g.b = g.cd * (g.cl * g.cs + g.sl * g.ss * g.cr);
+  g.c = g.cd * g.ss * g.sr;
+  double quad = g.b * g.b + g.c * g.c - g.a * g.a;
+  quad = rvh_max(0.0001, quad);
+  const double noon_cos_theta = (g.sd * g.sl + g.cd * g.cl) * g.cs + (g.cd * g.sl - g.sd * g.cl) * g.ss * g.cr;
+  // horizontal-surface sunset / sunrise hour angles (eqn 8) with polar day / night
+  double ws2 = acos(-g.sd / g.cd * g.sl / g.cl), ws1 = -ws2;
+  if (latrad > 0) {
+    if (declin + latrad > PI / 2.0) { ws1 = -PI; ws2 = PI; }
+    else if (fabs(declin - latrad) > PI / 2.0) { ws1 = 0.0; ws2 = 0.0; }
+  } else if (latrad < 0) {
+    if (declin + latrad < -PI / 2.0) { ws1 = -PI; ws2 = PI; }
+    else if (fabs(declin - latrad) < -PI / 2.0) { ws1 = 0; ws2 = 0; }
+  }
+  const double root = sqrt(quad), den = g.b * g.b + g.c * g.c;
+  // sunrise on the slope (eqn 13a, steps A.2)
+  double w1_24 = 0.0;
+  {
+    double s = (g.a * g.c - g.b * root) / den;
+    s = rvh_max(-1.0, s); s = rvh_min(1.0, s);
+    const double w1 = asin(s), w1x = -PI - w1;
+    const double cos_w1 = g.cos_at(w1), cos_w1x = g.cos_at(w1x), cos_ws1 = g.cos_at(ws1);
+    if ((cos_ws1 <= cos_w1) && (cos_w1 < 0.001)) w1_24 = w1;
+    else if (cos_w1x > 0.001) w1_24 = ws1;
+    else if (w1x <= ws1) w1_24 = ws1;
+    else if (w1x > ws1) w1_24 = w1x;
+    w1_24 = rvh_max(w1_24, ws1);
+  }
+  // sunset on the slope (eqn 13b, steps A.3)
+  double w2_24 = 0.0;
+  {
+    double s = (g.a * g.c + g.b * root) / den;
+    s = rvh_max(-1.0, s); s = rvh_min(1.0, s);
+    const double w2 = asin(s), w2x = PI - w2;
+    const double cos_w2 = g.cos_at(w2), cos_w2x = g.cos_at(w2x), cos_ws2 = g.cos_at(ws2);
+    if ((cos_ws2 <= cos_w2) && (cos_w2 < 0.001)) w2_24 = w2;
+    else if (cos_w2x > 0.001) w2_24 = ws2;
+    else if (w2x >= ws2) w2_24 = ws2;
+    else if (w2x < ws2) w2_24 = w2x;
+    w2_24 = rvh_min(w2_24, ws2);
+  }
+  if (w2_24 < w1_24) w1_24 = w2_24;   // slope always shaded
+  double cos_theta = 0.0;
+  bool two_periods = false;
+  if (noon_cos_theta < 0) {   // the slope may be shaded around noon: two sunlit periods (eqns 44-51)
+    double sA = (g.a * g.c + g.b * root) / den; sA = rvh_max(-1.0, sA); sA = rvh_min(1.0, sA);
+    double sB = (g.a * g.c - g.b * root) / den; sB = rvh_max(-1.0, sB); sB = rvh_min(1.0, sB);
+    const double AA = asin(sA), BB = asin(sB);
+    double w2_24b = rvh_min(AA, BB), w1_24b = rvh_max(AA, BB);
+    const double cos_w2b = g.cos_at(w2_24b), cos_w1b = g.cos_at(w1_24b);
+    if ((cos_w2b < -0.001) || (cos_w2b > 0.001)) w2_24b = -PI - w2_24b;
+    if ((cos_w1b < -0.001) || (cos_w1b > 0.001)) w1_24b = PI - w1_24b;
+    if ((w2_24b >= w1_24) && (w1_24b <= w2_24)) {
+      // the reference evaluates this test integral term by term with un-factored products
+      const double X = sin(declin) * sin(latrad) * cos(slope) * (w1_24b - w2_24b) - sin(declin) * cos(latrad) * sin(slope) * cos(revasp) * (w1_24b - w2_24b) +
+                       cos(declin) * cos(latrad) * cos(slope) * (sin(w1_24b) - sin(w2_24b)) + cos(declin) * sin(latrad) * sin(slope) * cos(revasp) * (sin(w1_24b) - sin(w2_24b)) -
+                       cos(declin) * sin(slope) * sin(revasp) * (cos(w1_24b) - cos(w2_24b));
+      if (X < 0) {
+        if (!avg_daily) {
+          w1_24 = rvh_max(w1_24, t1 * 2.0 * PI); w2_24b = rvh_min(w2_24b, t2 * 2.0 * PI);
+          if (w2_24b < w1_24) w2_24b = w1_24;
+        }
+        const double p1 = sin(declin) * sin(latrad) * cos(slope) * (w2_24b - w1_24) - sin(declin) * cos(latrad) * sin(slope) * cos(revasp) * (w2_24b - w1_24) +
+                          cos(declin) * cos(latrad) * cos(slope) * (sin(w2_24b) - sin(w1_24)) + cos(declin) * sin(latrad) * sin(slope) * cos(revasp) * (sin(w2_24b) - sin(w1_24)) -
+                          cos(declin) * sin(slope) * sin(revasp) * (cos(w2_24b) - cos(w1_24));
+        if (!avg_daily) {
+          w1_24b = rvh_max(w1_24b, t1 * 2.0 * PI); w2_24 = rvh_min(w2_24, t2 * 2.0 * PI);
+          if (w2_24 < w1_24b) w2_24 = w1_24b;
+        }
+        const double p2 = sin(declin) * sin(latrad) * cos(slope) * (w2_24 - w1_24b) - sin(declin) * cos(latrad) * sin(slope) * cos(revasp) * (w2_24 - w1_24b) +
+                          cos(declin) * cos(latrad) * cos(slope) * (sin(w2_24) - sin(w1_24b)) + cos(declin) * sin(latrad) * sin(slope) * cos(revasp) * (sin(w2_24) - sin(w1_24b)) -
+                          cos(declin) * sin(slope) * sin(revasp) * (cos(w2_24) - cos(w1_24b));
+        two_periods = true;
+        cos_theta = p1 + p2;
+      }
+    }
+  }
+  if (!two_periods) {
+    if (!avg_daily) {
+      w1_24 = rvh_max(w1_24, t1 * 2.0 * PI); w2_24 = rvh_min(w2_24, t2 * 2.0 * PI);
+      if (w2_24 <= w1_24) w2_24 = w1_24;
+    }
+    cos_theta = g.integral(w1_24, w2_24);
+  }
+  return rvh_max(0.0, SOLAR_CONSTANT * cos_theta * ecc) / 2.0 / PI / (t2 - t1);
+}

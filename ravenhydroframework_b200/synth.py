@@ -142,7 +142,7 @@ def _write(path, text):
         f.write(text)
 
 
-def write_network(f, n_sb, hru_per_sb, rng, profile, lu_classes, veg_classes, soil_profiles, gauged_all=False):
+def write_network(f, n_sb, hru_per_sb, rng, profile, lu_classes, veg_classes, soil_profiles, gauged_all=False, paired_profiles=False):
     f.write(":SubBasins\n  :Attributes NAME DOWNSTREAM_ID PROFILE REACH_LENGTH GAUGED\n  :Units none none none km none\n")
     for p in range(1, n_sb + 1):
         down = -1 if p == 1 else p // 2
@@ -156,7 +156,8 @@ def write_network(f, n_sb, hru_per_sb, rng, profile, lu_classes, veg_classes, so
             c = rng.randint(0, len(lu_classes))
             f.write("  %d, %.4f, %.2f, %.5f, %.5f, %d, %s, %s, %s, [NONE], [NONE], %.3f, %.2f\n" % (
                 k, rng.uniform(0.5, 2.5), rng.uniform(600, 1400), rng.uniform(54, 55), rng.uniform(-123.5, -122.5), p,
-                lu_classes[c], veg_classes[c], soil_profiles[rng.randint(0, len(soil_profiles))], rng.uniform(0, 20), rng.uniform(0, 360)))
+                lu_classes[c], veg_classes[c], soil_profiles[c if paired_profiles else rng.randint(0, len(soil_profiles))],
+                rng.uniform(0, 20), rng.uniform(0, 360)))
             k += 1
     f.write(":EndHRUs\n")
 
@@ -203,4 +204,273 @@ def write_hmets(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUT
                 lo, hi = sorted([0.8 * v, 1.2 * v])
                 f.write("  %s %s %s DIST_UNIFORM %.8g %.8g\n" % (pn, ct, cn, lo, hi))
             f.write(":EndParameterDistributions\n")
+    return base
+
+
+# ------------------------------------------------------------------------------------------------ HBV-EC
+HBV_RVI = """# HBV-EC emulation, synthetic watershed (written by ravenhydroframework_b200.synth)
+:StartDate             2000-01-01 00:00:00
+:Duration              {duration}
+:TimeStep              1.0
+:Method                ORDERED_SERIES
+:Routing               {routing}
+:CatchmentRoute        {catchment_route}
+:Evaporation           PET_FROMMONTHLY
+:OW_Evaporation        PET_FROMMONTHLY
+:SWRadiationMethod     SW_RAD_DEFAULT
+:SWCloudCorrect        SW_CLOUD_CORR_NONE
+:SWCanopyCorrect       SW_CANOPY_CORR_NONE
+:LWRadiationMethod     LW_RAD_DEFAULT
+:RainSnowFraction      RAINSNOW_HBV
+:PotentialMeltMethod   POTMELT_HBV
+:OroTempCorrect        OROCORR_HBV
+:OroPrecipCorrect      OROCORR_HBV
+:OroPETCorrect         OROCORR_HBV
+:CloudCoverMethod      CLOUDCOV_NONE
+:PrecipIceptFract      PRECIP_ICEPT_USER
+:MonthlyInterpolationMethod MONTHINT_LINEAR_21
+:SoilModel             SOIL_MULTILAYER 3
+:SilentMode
+{extra}
+:Alias       FAST_RESERVOIR SOIL[1]
+:Alias       SLOW_RESERVOIR SOIL[2]
+:LakeStorage SLOW_RESERVOIR
+:HydrologicProcesses
+  :SnowRefreeze      FREEZE_DEGREE_DAY  SNOW_LIQ        SNOW
+  :Precipitation     PRECIP_RAVEN       ATMOS_PRECIP    MULTIPLE
+  :CanopyEvaporation CANEVP_ALL         CANOPY          ATMOSPHERE
+  :CanopySnowEvap    CANEVP_ALL         CANOPY_SNOW     ATMOSPHERE
+  :SnowBalance       SNOBAL_SIMPLE_MELT SNOW            SNOW_LIQ
+    :-->Overflow     RAVEN_DEFAULT      SNOW_LIQ        PONDED_WATER
+  :Flush             RAVEN_DEFAULT      PONDED_WATER    GLACIER
+    :-->Conditional HRU_TYPE IS GLACIER
+  :GlacierMelt       GMELT_HBV          GLACIER_ICE     GLACIER
+  :GlacierRelease    GRELEASE_HBV_EC    GLACIER         SURFACE_WATER
+  :Infiltration      INF_HBV            PONDED_WATER    MULTIPLE
+  :Flush             RAVEN_DEFAULT      SURFACE_WATER   FAST_RESERVOIR
+    :-->Conditional HRU_TYPE IS_NOT GLACIER
+  :SoilEvaporation   SOILEVAP_HBV       SOIL[0]         ATMOSPHERE
+  :CapillaryRise     RISE_HBV           FAST_RESERVOIR  SOIL[0]
+  :LakeEvaporation   LAKE_EVAP_BASIC    SLOW_RESERVOIR  ATMOSPHERE
+  :Percolation       PERC_CONSTANT      FAST_RESERVOIR  SLOW_RESERVOIR
+  :Baseflow          BASE_POWER_LAW     FAST_RESERVOIR  SURFACE_WATER
+  :Baseflow          BASE_LINEAR        SLOW_RESERVOIR  SURFACE_WATER
+:EndHydrologicProcesses
+"""
+
+HBV_RVP = """# HBV-EC parameters (synthetic)
+:SoilClasses
+  :Attributes,
+  :Units,
+  TOPSOIL,
+  SLOW_RES,
+  FAST_RES,
+:EndSoilClasses
+:SoilProfiles
+  DEFAULT_P,  3, TOPSOIL, 2.036937, FAST_RES, 100.0, SLOW_RES, 100.0
+  SHALLOW_P,  3, TOPSOIL, 1.100000, FAST_RES, 100.0, SLOW_RES, 100.0
+  GLACIER_P,  3, TOPSOIL, 0.500000, FAST_RES, 100.0, SLOW_RES, 100.0
+:EndSoilProfiles
+:VegetationClasses
+  :Attributes,  MAX_HT, MAX_LAI, MAX_LEAF_COND
+  :Units,            m,    none,      mm_per_s
+  VEG_ALL,          25,     6.0,           5.3
+  VEG_LOW,           3,     2.5,           5.3
+:EndVegetationClasses
+:VegetationParameterList
+  :Parameters,  MAX_CAPACITY, MAX_SNOW_CAPACITY,  TFRAIN,  TFSNOW,
+  :Units,                 mm,                mm,    frac,    frac,
+  VEG_ALL,             10000,             10000,    0.88,    0.88,
+  VEG_LOW,               2.5,               4.0,    0.95,    0.93,
+:EndVegetationParameterList
+:SeasonalRelativeLAI
+  VEG_LOW, 0.3, 0.3, 0.4, 0.6, 0.9, 1.0, 1.0, 1.0, 0.8, 0.5, 0.3, 0.3
+:EndSeasonalRelativeLAI
+:LandUseClasses
+  :Attributes,  IMPERM, FOREST_COV
+  :Units,         frac,       frac
+  LU_ALL,          0.0,          1
+  LU_OPEN,        0.02,       0.25
+  LU_ICE,          0.0,        0.0
+:EndLandUseClasses
+:GlobalParameter ADIABATIC_LAPSE     0.5718813
+:GlobalParameter RAINSNOW_TEMP       0.05984519
+:GlobalParameter RAINSNOW_DELTA             2.0
+:GlobalParameter SNOW_SWI            0.03473693
+:GlobalParameter PRECIP_LAPSE          4.873686
+:LandUseParameterList
+  :Parameters,   MELT_FACTOR, MIN_MELT_FACTOR,   HBV_MELT_FOR_CORR, REFREEZE_FACTOR, HBV_MELT_ASP_CORR
+  :Units     ,        mm/d/K,          mm/d/K,                none,          mm/d/K,              none
+    [DEFAULT],      4.072232,             2.2,           0.4452843,        2.001574,              0.48
+    LU_OPEN,        4.600000,             2.5,            _DEFAULT,        1.700000,          _DEFAULT
+:EndLandUseParameterList
+:LandUseParameterList
+  :Parameters, HBV_MELT_GLACIER_CORR,   HBV_GLACIER_KMIN, GLAC_STORAGE_COEFF, HBV_GLACIER_AG
+  :Units     ,                  none,                1/d,                1/d,           1/mm
+   [DEFAULT],                  1.64,               0.05,          0.6771759,           0.05
+:EndLandUseParameterList
+:SoilParameterList
+  :Parameters,   POROSITY, FIELD_CAPACITY,   SAT_WILT,  HBV_BETA, MAX_CAP_RISE_RATE, MAX_PERC_RATE, BASEFLOW_COEFF, BASEFLOW_N
+  :Units     ,       none,           none,       none,      none,              mm/d,          mm/d,            1/d,       none
+    [DEFAULT], 0.09985144,      0.5060520, 0.04505643,  3.438486,          18.94145,           0.0,            0.0,        0.0
+     FAST_RES,   _DEFAULT,       _DEFAULT,        0.0,  _DEFAULT,          _DEFAULT,      38.32455,      0.4606565,   1.877607
+     SLOW_RES,   _DEFAULT,       _DEFAULT,        0.0,  _DEFAULT,          _DEFAULT,      _DEFAULT,     0.06303738,        1.0
+:EndSoilParameterList
+{extra}
+"""
+
+HBV_RVC = """# initial lower groundwater storage
+:UniformInitialConditions SOIL[2] 0.50657
+:UniformInitialConditions SOIL[0] 60.0
+"""
+
+MONTHLY_EVAP = [0.028, 0.089, 0.315, 1.003, 2.077, 2.959, 3.190, 2.548, 1.382, 0.520, 0.101, 0.023]
+MONTHLY_TEMP = [-11.4, -7.2, -2.8, 2.8, 8.1, 12.2, 14.4, 13.5, 8.9, 3.4, -4.0, -9.3]
+
+
+def write_hbv(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUTE_NONE", catchment_route="TRIANGULAR_UH",
+              single_class=False, name="hbv", season_offset=0):
+    """HBV-EC template (BASELINE config 2): multi-class, with glacier HRUs unless single_class. Returns the input base path."""
+    os.makedirs(dirpath, exist_ok=True)
+    base = os.path.join(dirpath, name)
+    rng = np.random.RandomState(seed)
+    _write(base + ".rvi", HBV_RVI.format(duration=n_days, routing=routing, catchment_route=catchment_route, extra=""))
+    profile = "NONE" if routing == "ROUTE_NONE" else "CHN"
+    extra_rvp = ""
+    if n_sb > 1 or routing != "ROUTE_NONE":
+        extra_rvp += ":AvgAnnualRunoff 400\n"
+    if profile != "NONE":
+        extra_rvp += ":TrapezoidalChannel CHN 10.0 0.0 2.0 0.035 0.001\n"
+    _write(base + ".rvp", HBV_RVP.format(extra=extra_rvp))
+    with open(base + ".rvh", "w") as f:
+        if single_class:
+            write_network(f, n_sb, hru_per_sb, rng, profile, ["LU_ALL"], ["VEG_ALL"], ["DEFAULT_P"])
+        else:
+            write_network(f, n_sb, hru_per_sb, rng, profile, ["LU_ALL", "LU_OPEN", "LU_ICE"], ["VEG_ALL", "VEG_LOW", "VEG_LOW"],
+                          ["DEFAULT_P", "SHALLOW_P", "GLACIER_P"], paired_profiles=True)
+        f.write(":SubBasinProperties\n  :Parameters, TIME_CONC, TIME_TO_PEAK\n  :Units, d, d\n")
+        for p in range(1, n_sb + 1):
+            tc = rng.uniform(1.2, 3.2)
+            f.write("  %d, %.6f, %.6f\n" % (p, tc, 0.5 * tc))
+        f.write(":EndSubBasinProperties\n")
+    with open(base + ".rvt", "w") as f:
+        gx = "  :RainCorrection 1.141608\n  :SnowCorrection 1.024278\n"
+        gx += "  :MonthlyAveEvaporation, " + ", ".join("%.3f" % v for v in MONTHLY_EVAP) + ",\n"
+        gx += "  :MonthlyAveTemperature, " + ", ".join("%.1f" % v for v in MONTHLY_TEMP) + ",\n"
+        write_gauge(f, *weather(n_days, seed, season_offset), extra=gx)
+    _write(base + ".rvc", HBV_RVC)
+    return base
+
+
+# ------------------------------------------------------------------------------------------------ GR4J
+GR4J_RVI = """# GR4J + Cema-Neige emulation, synthetic watershed (written by ravenhydroframework_b200.synth)
+:StartDate             2000-01-01 00:00:00
+:Duration              {duration}
+:TimeStep              1.0
+:Method                ORDERED_SERIES
+:SoilModel             SOIL_MULTILAYER  4
+:Routing               {routing}
+:CatchmentRoute        {catchment_route}
+:Evaporation           PET_DATA
+:RainSnowFraction      RAINSNOW_DINGMAN
+:PotentialMeltMethod   POTMELT_DEGREE_DAY
+:OroTempCorrect        OROCORR_SIMPLELAPSE
+:OroPrecipCorrect      OROCORR_SIMPLELAPSE
+:SilentMode
+{extra}
+:Alias PRODUCT_STORE      SOIL[0]
+:Alias ROUTING_STORE      SOIL[1]
+:Alias TEMP_STORE         SOIL[2]
+:Alias GW_STORE           SOIL[3]
+:HydrologicProcesses
+ :Precipitation            PRECIP_RAVEN       ATMOS_PRECIP    MULTIPLE
+ :SnowTempEvolve           SNOTEMP_NEWTONS    SNOW_TEMP
+ :SnowBalance              SNOBAL_CEMA_NIEGE  SNOW            PONDED_WATER
+ :OpenWaterEvaporation     OPEN_WATER_EVAP    PONDED_WATER    ATMOSPHERE
+ :Infiltration             INF_GR4J           PONDED_WATER    MULTIPLE
+ :SoilEvaporation          SOILEVAP_GR4J      PRODUCT_STORE   ATMOSPHERE
+ :Percolation              PERC_GR4J          PRODUCT_STORE   TEMP_STORE
+ :Flush                    RAVEN_DEFAULT      SURFACE_WATER   TEMP_STORE
+ :Split                    RAVEN_DEFAULT      TEMP_STORE      CONVOLUTION[0] CONVOLUTION[1] 0.9
+ :Convolve                 CONVOL_GR4J_1      CONVOLUTION[0]  ROUTING_STORE
+ :Convolve                 CONVOL_GR4J_2      CONVOLUTION[1]  TEMP_STORE
+ :Percolation              PERC_GR4JEXCH      ROUTING_STORE   GW_STORE
+ :Percolation              PERC_GR4JEXCH2     TEMP_STORE      GW_STORE
+ :Flush                    RAVEN_DEFAULT      TEMP_STORE      SURFACE_WATER
+ :Baseflow                 BASE_GR4J          ROUTING_STORE   SURFACE_WATER
+:EndHydrologicProcesses
+"""
+
+GR4J_RVP = """# GR4J parameters (synthetic)
+:SoilClasses
+  :Attributes
+  :Units
+   SOIL_PROD
+   SOIL_ROUT
+   SOIL_TEMP
+   SOIL_GW
+:EndSoilClasses
+:SoilProfiles
+  DEFAULT_P,  4, SOIL_PROD, 0.529, SOIL_ROUT, 0.300, SOIL_TEMP, 1.000, SOIL_GW, 1.000,
+  THIN_P,     4, SOIL_PROD, 0.310, SOIL_ROUT, 0.300, SOIL_TEMP, 1.000, SOIL_GW, 1.000,
+:EndSoilProfiles
+:VegetationClasses
+   :Attributes,       MAX_HT,       MAX_LAI,      MAX_LEAF_COND
+        :Units,            m,          none,           mm_per_s
+       VEG_ALL,           0.0,          0.0,                0.0
+:EndVegetationClasses
+:LandUseClasses
+  :Attributes, IMPERM, FOREST_COV
+  :Units     ,   frac,       frac
+       LU_ALL,    0.0,        0.0
+       LU_TOWN,   0.3,        0.0
+:EndLandUseClasses
+:GlobalParameter RAINSNOW_TEMP       0.0
+:GlobalParameter RAINSNOW_DELTA      1.0
+:GlobalParameter AIRSNOW_COEFF     0.053
+:GlobalParameter AVG_ANNUAL_SNOW    16.9
+:GlobalParameter PRECIP_LAPSE     0.0004
+:GlobalParameter ADIABATIC_LAPSE  0.0065
+:SoilParameterList
+ :Parameters, POROSITY ,  GR4J_X3, GR4J_X2
+ :Units     ,     none ,       mm,    mm/d
+   [DEFAULT],      1.0 ,   407.29,  -3.396
+:EndSoilParameterList
+:LandUseParameterList
+ :Parameters, GR4J_X4, MELT_FACTOR
+ :Units     ,       d,      mm/d/C
+   [DEFAULT],   1.072,        7.73
+   LU_TOWN,     2.600,        6.10
+:EndLandUseParameterList
+{extra}
+"""
+
+GR4J_RVC = """:UniformInitialConditions SOIL[0] 150.0
+:UniformInitialConditions SOIL[1] 15.0
+"""
+
+
+def write_gr4j(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUTE_NONE", catchment_route="ROUTE_DUMP",
+               single_class=False, name="gr4j", season_offset=0):
+    """GR4J + Cema-Neige template (BASELINE config 1 process list). :OW_Evaporation is left at the reference's default
+    (PET_HARGREAVES_1985), so the open-water PET that OPEN_WATER_EVAP consumes comes from extraterrestrial radiation."""
+    os.makedirs(dirpath, exist_ok=True)
+    base = os.path.join(dirpath, name)
+    rng = np.random.RandomState(seed)
+    _write(base + ".rvi", GR4J_RVI.format(duration=n_days, routing=routing, catchment_route=catchment_route, extra=""))
+    profile = "NONE" if routing == "ROUTE_NONE" else "CHN"
+    extra_rvp = ""
+    if n_sb > 1 or routing != "ROUTE_NONE":
+        extra_rvp += ":AvgAnnualRunoff 400\n"
+    if profile != "NONE":
+        extra_rvp += ":TrapezoidalChannel CHN 10.0 0.0 2.0 0.035 0.001\n"
+    _write(base + ".rvp", GR4J_RVP.format(extra=extra_rvp))
+    with open(base + ".rvh", "w") as f:
+        if single_class:
+            write_network(f, n_sb, hru_per_sb, rng, profile, ["LU_ALL"], ["VEG_ALL"], ["DEFAULT_P"])
+        else:
+            write_network(f, n_sb, hru_per_sb, rng, profile, ["LU_ALL", "LU_TOWN"], ["VEG_ALL", "VEG_ALL"], ["DEFAULT_P", "THIN_P"])
+    with open(base + ".rvt", "w") as f:
+        write_gauge(f, *weather(n_days, seed, season_offset))
+    _write(base + ".rvc", GR4J_RVC)
     return base

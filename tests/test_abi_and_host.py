@@ -20,7 +20,7 @@ def test_engine_exports_every_declared_symbol():
     lib = api.engine_lib()
     for n in names:
         assert hasattr(lib, n), "librvn_gpu.so does not export %s" % n
-    assert lib.rvn_gpu_abi_version() == 1
+    assert lib.rvn_gpu_abi_version() == 2
 
 
 def test_engine_is_sm100a_with_specialised_and_interpreter_sweeps():
@@ -40,16 +40,17 @@ def test_engine_is_sm100a_with_specialised_and_interpreter_sweeps():
 def test_static_program_header_is_current():
     """csrc/rvn_static_programs.cuh must equal what the engine emits for the current templates (tools/gen_static_programs.py)."""
     import ctypes as C
+    import tempfile
     eng = api.engine_lib()
     hdr = open(os.path.join(ROOT, "ravenhydroframework_b200", "csrc", "rvn_static_programs.cuh")).read()
-    import tempfile
-    with tempfile.TemporaryDirectory() as td:
-        base = synth.write_hmets(td, n_sb=1, hru_per_sb=1, n_days=5, seed=1)
-        m = api.RavenModel(base)
-        m.flatten(1)
-        buf = C.create_string_buffer(1 << 16)
-        assert eng.rvn_gpu_emit_static_program(m.desc, b"HMETS", buf, len(buf)) == 0
-        assert buf.value.decode() in hdr
+    for name, writer in (("HMETS", synth.write_hmets), ("HBVEC", synth.write_hbv), ("GR4J", synth.write_gr4j)):
+        with tempfile.TemporaryDirectory() as td:
+            base = writer(td, n_sb=1, hru_per_sb=1, n_days=5, seed=1)
+            m = api.RavenModel(base)
+            m.flatten(1)
+            buf = C.create_string_buffer(1 << 16)
+            assert eng.rvn_gpu_emit_static_program(m.desc, name.encode(), buf, len(buf)) == 0
+            assert buf.value.decode() in hdr, name
 
 
 def test_no_cpu_fallback(tmp_path):

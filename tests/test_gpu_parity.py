@@ -144,3 +144,80 @@ def test_state_upload_mid_run_invalidates_cached_sums(tmp_path):
                             200, 60, None, None, None, None)
     assert rc == 0
     assert H.rel_err(a.download_state()[0], s2) < TOL
+
+
+# ---- HBV-EC / GR4J templates, channel routing methods, kernel variants ---------------------------------------------
+WRITERS = {"hmets": synth.write_hmets, "hbv": synth.write_hbv, "gr4j": synth.write_gr4j}
+
+
+def _gpu_vs_oracle(tmp_path, kind, n_days, members=1, **kw):
+    base = WRITERS[kind](str(tmp_path), n_days=n_days, **kw)
+    model = api.RavenModel(base)
+    model.flatten(members)
+    sim = api.GpuSimulation(model, n_members=members)
+    sim.set_recording(n_days)
+    sim.enable_forcing_output(True)
+    sim.run(n_days)
+    ref = H.oracle_run(model, n_days, record_forcings=True)
+    e = members - 1
+    assert H.rel_err(sim.download_state()[e], ref["state"]) < TOL
+    assert H.rel_err(sim.hydrographs(0, n_days)[:, e, :], ref["qout_rec"]) < TOL
+    assert H.rel_err(sim.forcings()[e], ref["forc_rec"][-1]) < TOL
+    w = sim.watershed(0, n_days)[:, e, :]
+    assert H.rel_err(w[:, :3], ref["wshed_rec"][:, :3]) < TOL
+    assert H.rel_err(w[:, 3], ref["wshed_rec"][:, 3]) < TOL
+    qin, qlat, qout, scal = sim.download_basin_state()
+    assert H.rel_err(scal[e], ref["scal"]) < TOL
+    return sim
+
+
+@pytest.mark.parametrize("routing,catch", [("ROUTE_MUSKINGUM", "TRIANGULAR_UH"), ("ROUTE_MUSKINGUM_CUNGE", "ROUTE_DUMP"),
+                                           ("ROUTE_STORAGECOEFF", "ROUTE_GAMMA_CONVOLUTION"), ("ROUTE_PLUG_FLOW", "TRIANGULAR_UH"),
+                                           ("ROUTE_NONE", "TRIANGULAR_UH")])
+def test_hbv_routing_methods(tmp_path, routing, catch):
+    """HBV-EC multi-class watershed with glacier HRUs (BASELINE config 2 process list) over every channel routing method."""
+    sim = _gpu_vs_oracle(tmp_path, "hbv", 300, n_sb=15, hru_per_sb=9, seed=21, routing=routing, catchment_route=catch)
+    assert sim.kernel_variant() == "static:HBVEC"
+
+
+def test_hbv_ragged_members(tmp_path):
+    _gpu_vs_oracle(tmp_path, "hbv", 200, members=3, n_sb=31, hru_per_sb=13, seed=5, routing="ROUTE_MUSKINGUM")
+
+
+def test_gr4j_tree(tmp_path):
+    sim = _gpu_vs_oracle(tmp_path, "gr4j", 400, members=2, n_sb=7, hru_per_sb=19, seed=13)
+    assert sim.kernel_variant() == "static:GR4J"
+
+
+@pytest.mark.parametrize("kind", ["hmets", "hbv", "gr4j"])
+def test_specialised_kernel_equals_interpreter(tmp_path, kind, monkeypatch):
+    """The compile-time specialisation and the interpreter run the same process functions: results must be bit-identical."""
+    base = WRITERS[kind](str(tmp_path), n_sb=5, hru_per_sb=31, n_days=150, seed=17)
+    model = api.RavenModel(base)
+    model.flatten(2)
+    a = api.GpuSimulation(model, n_members=2)
+    assert a.kernel_variant().startswith("static:")
+    a.set_recording(150)
+    a.run(150)
+    monkeypatch.setenv("RVN_FORCE_INTERPRETER", "1")
+    b = api.GpuSimulation(model, n_members=2)
+    assert b.kernel_variant() == "interpreter"
+    b.set_recording(150)
+    b.run(150)
+    assert np.array_equal(a.download_state(), b.download_state())
+    assert np.array_equal(a.hydrographs(0, 150), b.hydrographs(0, 150))
+    assert np.array_equal(a.watershed(0, 150), b.watershed(0, 150))
+
+
+def test_non_template_process_list_runs_on_interpreter(tmp_path):
+    """A process list that is not one of the compiled templates (HMETS without the second baseflow) must still run, on the interpreter."""
+    base = synth.write_hmets(str(tmp_path), n_sb=3, hru_per_sb=7, n_days=120, seed=4)
+    rvi = open(base + ".rvi").read().replace("  :Baseflow        BASE_LINEAR     SOIL[1]        SURFACE_WATER\n", "")
+    open(base + ".rvi", "w").write(rvi)
+    model = api.RavenModel(base)
+    model.flatten(1)
+    sim = api.GpuSimulation(model)
+    assert sim.kernel_variant() == "interpreter"
+    sim.run(120)
+    ref = H.oracle_run(model, 120)
+    assert H.rel_err(sim.download_state()[0], ref["state"]) < TOL

@@ -111,6 +111,25 @@ def test_oracle_matches_live_reference_salmon_hmets(tmp_path):
     assert H.rel_err(o["wshed_rec"][:, :2], ref["wshed"][1:n + 1, :2]) < TOL
 
 
+@pytest.mark.skipif(not (H.have_reference() and os.path.isdir(H.REFERENCE_INPUTS)), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("rel", ["Salmon_HBV/raven-hbv-salmon", "Salmon_GR4J/raven-gr4j-salmon"])
+def test_oracle_matches_live_reference_salmon_hbv_gr4j(tmp_path, rel):
+    """The reference's own Salmon_HBV (HBV-EC) and Salmon_GR4J (BASELINE config 1) inputs as shipped, first 2000 daily steps:
+    unmodified reference vs host layer + oracle, HRU state, hydrograph, balance and the derived forcings (incl. the
+    Hargreaves-1985 open-water PET from extraterrestrial radiation that GR4J consumes)."""
+    base = os.path.join(H.REFERENCE_INPUTS, rel)
+    n = 2000
+    ref = H.reference_run(base, str(tmp_path / "out"), n)
+    model = api.RavenModel(base, duration=n)
+    model.flatten(1)
+    o = H.oracle_run(model, n, record_forcings=True)
+    assert H.rel_err(o["state_rec"], ref["state"][1:n + 1]) < TOL
+    assert H.rel_err(o["qout_rec"], ref["basin"][1:n + 1, :, 0]) < TOL
+    assert H.rel_err(o["wshed_rec"][:, :2], ref["wshed"][1:n + 1, :2]) < TOL
+    for name, j in {"PRECIP": 0, "SNOW_FRAC": 3, "TEMP_AVE": 7, "POTENTIAL_MELT": 32, "PET": 34, "OW_PET": 35}.items():
+        assert H.rel_err(o["forc_rec"][:, :, api.FORCING_NAMES.index(name)], ref["forc"][1:n + 1, :, j]) < TOL, name
+
+
 def test_mass_balance_closes():
     """WatershedStorage.csv 'MB Error' column: (S - S0) + (CumulOutput - CumulInput) stays at round-off."""
     g, model = _load("hmets_tree")
