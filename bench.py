@@ -180,20 +180,17 @@ def main():
     n_days = W + K + W + K + 4  # resident pass + end-to-end pass
     td = tempfile.mkdtemp(prefix="rvnbench%d_" % rank)
     try:
-        base = write_workload(td, n_days)
+        base = write_workload(td, n_days, members=E * world)   # .rve: the 19 HMETS parameters, uniform +-20 %
         t_setup = time.time()
         model = api.RavenModel(base)
         model.flatten(E)
         sim = api.GpuSimulation(model, n_members=E, device=local_rank)
-        # Monte-Carlo members: every member gets its own parameter row (+-20 % around the template values)
-        rng = np.random.RandomState(1000 + rank)
-        from ravenhydroframework_b200 import synth
-        ct = {"LANDUSE": 2, "SOIL": 0, "GLOBALS": 4}
-        for e in range(E):
-            for (pn, cls, cn, v) in synth.HMETS_DISTS:
-                lo, hi = sorted([0.8 * v, 1.2 * v])
-                model.update_parameter(ct[cls], pn, cn if cls != "GLOBALS" else "", rng.uniform(lo, hi))
-            sim.upload_member_params(e)
+        # Monte-Carlo members exactly as the reference's member loop would draw them (CMonteCarloEnsemble::UpdateModel,
+        # one shared rand() stream): this rank owns global members rank*E .. rank*E+E-1
+        from ravenhydroframework_b200 import ensemble
+        member0, n_local = ensemble.shard_members(E * world, rank, world)
+        assert n_local == E
+        sim.apply_ensemble(member0)
         setup_s = time.time() - t_setup
         nH, NS, NB = model.nHRU, model.NS, model.nSB
         units_per_step = E * nH  # HRU-steps per step on this rank
@@ -287,6 +284,15 @@ def main():
                 line["cpu_baseline"] = {"value": r["value"], "unit": "HRU-steps/s", "cores": r["nproc"], "kind": "reference",
                                         "sample": "%d concurrent single-threaded Raven.exe processes, one 10k-HRU HMETS member each, 12 daily steps "
                                                   "(%.1f s wall incl. parsing); per-process %.0f HRU-steps/s" % (r["nproc"], r["wall_s"], r["per_proc"])}
+        # ---- final ensemble statistics over ALL members (outside the timed regions): outlet hydrograph of the end-to-end pass,
+        # reduced with one NCCL all-reduce per statistic (sum/sumsq, min, max)
+        q_out = torch.from_numpy(sim.hydrographs(W, K)[:, :, 0].T.copy()).cuda()     # [members, K]
+        torch.cuda.synchronize()
+        ts = time.perf_counter()
+        stats = ensemble.ensemble_statistics(q_out)
+        torch.cuda.synchronize()
+        line["ensemble_statistics"] = {"members": stats["n"], "outlet_q_mean_last_step": float(stats["mean"][-1]), "outlet_q_std_last_step": float(stats["std"][-1]),
+                                       "ms": 1000.0 * (time.perf_counter() - ts), "backend": "nccl" if world > 1 else "local"}
         if rank == 0:
             print(json.dumps(line))
         sim.close()

@@ -70,7 +70,10 @@ int main(int argc, char **argv)
   int nsteps_total = (int)((Options.duration - TIME_CORRECTION) / Options.timestep) + 1;
   (void)nsteps_total;
 
-  int e = 0;
+  // REF_DUMP_MEMBER=m: dump ensemble member m.  Members before it are "updated" in order first so that the shared
+  // rand() stream is where the reference's own member loop (src/RavenMain.cpp:117-120) would have left it.
+  int e = getenv("REF_DUMP_MEMBER") ? atoi(getenv("REF_DUMP_MEMBER")) : 0;
+  for (int ee = 0; ee < e; ee++) pModel->GetEnsemble()->UpdateModel(pModel, Options, ee);
   pModel->GetEnsemble()->UpdateModel(pModel, Options, e);
   PrepareOutputdirectory(Options);
   pModel->WriteOutputFileHeaders(Options);

@@ -88,6 +88,8 @@ def host_lib():
         lib.rvh_model_param_dist.argtypes = [vp, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]
         lib.rvh_model_options.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         lib.rvh_desc_info.argtypes = [vp, C.POINTER(C.c_int)]
+        lib.rvh_ensemble_begin.argtypes = [vp]
+        lib.rvh_ensemble_update_model.argtypes = [vp, C.c_int, vp, C.c_int]
         _host = lib
     return _host
 
@@ -178,6 +180,22 @@ class RavenModel:
             raise RavenError(self.lib.rvh_last_error().decode())
         return a, b, c
 
+    def ensemble_begin(self):
+        """Create and seed the ensemble object the .rvi/.rve describe (CEnsemble::SetRandomSeed + Initialize). Returns #members."""
+        n = self.lib.rvh_ensemble_begin(self.h)
+        if n < 0:
+            raise RavenError(self.lib.rvh_last_error().decode())
+        return n
+
+    def ensemble_update_model(self, e):
+        """CEnsemble::UpdateModel(pModel, Options, e): draws member e's parameters from the shared rand() stream and applies
+        them with CModel::UpdateParameter. Members must be visited in order. Returns the sampled values."""
+        vals = np.zeros(256)
+        n = self.lib.rvh_ensemble_update_model(self.h, int(e), vals.ctypes.data, 256)
+        if n < 0:
+            raise RavenError(self.lib.rvh_last_error().decode())
+        return vals[:n].copy()
+
     def param_dists(self):
         out = []
         pn, cn = C.create_string_buffer(64), C.create_string_buffer(64)
@@ -251,6 +269,19 @@ class GpuSimulation:
     def upload_member_params(self, member):
         a, b, c = self.model.flatten_member(member)
         self._ck(self.lib.rvn_gpu_upload_params(self.h, a, b, c, member, 1))
+
+    def apply_ensemble(self, member0=0):
+        """Give local member i the parameters of global ensemble member member0+i (reference CEnsemble::UpdateModel order):
+        the draws of members 0..member0-1 are replayed and discarded, so any rank of a sharded ensemble sees the same stream."""
+        m = self.model
+        m.ensemble_begin()
+        samples = []
+        for e in range(member0 + self.E):
+            v = m.ensemble_update_model(e)
+            if e >= member0:
+                self.upload_member_params(e - member0)
+                samples.append(v)
+        return np.array(samples)
 
     def upload_forcings(self, gauge_series, step0, nsteps):
         """gauge_series [RVN_GF_COUNT][nGauges][nsteps] host array replacing steps step0..step0+nsteps."""

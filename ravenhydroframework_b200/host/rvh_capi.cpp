@@ -4,11 +4,13 @@
 #include "rvh_model.h"
 #include "rvh_process.h"
 #include "rvh_solver.h"
+#include "rvh_ensemble.h"
 
 struct rvh_model {
   CModel *pModel;
   optStruct Options;
-  rvh_model() : pModel(NULL) {}
+  CEnsemble *pEnsemble;
+  rvh_model() : pModel(NULL), pEnsemble(NULL) {}
 };
 static std::string g_err;
 #define RVH_TRY try {
@@ -37,7 +39,28 @@ rvh_model *rvh_model_load(const char *base, double duration_override) {
   return h;
   RVH_CATCH(NULL)
 }
-void rvh_model_free(rvh_model *h) { if (h) { delete h->pModel; delete h; } }
+void rvh_model_free(rvh_model *h) { if (h) { delete h->pEnsemble; delete h->pModel; delete h; } }
+// ensemble hooks with the reference's call order (src/RavenMain.cpp:110-120): rvh_ensemble_begin = ParseInput's
+// SetRandomSeed + CEnsemble::Initialize; rvh_ensemble_update_model(e) = CEnsemble::UpdateModel(pModel,Options,e).
+// Members must be updated in order 0,1,2,... (one shared rand() stream).  Returns the number of sampled values written.
+int rvh_ensemble_begin(rvh_model *h) {
+  RVH_TRY
+  delete h->pEnsemble;
+  h->pEnsemble = CreateEnsemble(h->pModel, h->Options);
+  h->pEnsemble->Initialize(h->pModel, h->Options);
+  return h->pEnsemble->GetNumMembers();
+  RVH_CATCH(-1)
+}
+int rvh_ensemble_update_model(rvh_model *h, int e, double *values, int nmax) {
+  RVH_TRY
+  if (!h->pEnsemble) throw RavenError("rvh_ensemble_update_model: call rvh_ensemble_begin first");
+  h->pEnsemble->UpdateModel(h->pModel, h->Options, e);
+  const CMonteCarloEnsemble *mc = dynamic_cast<const CMonteCarloEnsemble *>(h->pEnsemble);
+  int n = 0;
+  if (mc && values) for (; n < (int)mc->LastSample().size() && n < nmax; n++) values[n] = mc->LastSample()[n];
+  return n;
+  RVH_CATCH(-1)
+}
 const rvn_model_desc *rvh_model_flatten(rvh_model *h, int nMembers) {
   RVH_TRY
   return h->pModel->Flatten(h->Options, nMembers);

@@ -207,7 +207,10 @@ static void ParseMainInputFile(CModel *&pModel, optStruct &Options) {
       if (pModel && Len >= 3) pModel->num_members = s_to_i(s[2]);
       continue;
     }
-    if (c == ":RandomSeed") { Options.random_seed = (unsigned)s_to_i(s[1]); Options.random_seed_set = true; continue; }
+    if (c == ":RandomSeed") {  // src/ParseInput.cpp:1941-1946: the seed is offset by the start date known at this point of the file
+      int timestamp_corr = Options.julian_start_year + int(round(Options.julian_start_day * 48));
+      Options.random_seed = (unsigned int)(s_to_i(s[1]) + timestamp_corr); Options.random_seed_set = true; continue;
+    }
     // ---- process list -----------------------------------------------------------------------------
     if (c == ":-->Conditional" || c == ":Conditional") {
       ExitGracefullyIf(!pLast || Len < 4, "ParseMainInputFile: :-->Conditional must follow a process");
@@ -726,23 +729,30 @@ static void ParseEnsembleFile(CModel *pModel, optStruct &Options) {
       while (p.Tokenize(s)) {
         if (s.empty() || s[0] == ":Attributes" || s[0] == ":Units") continue;
         if (s[0] == ":EndParameterDistributions") break;
-        // [param_name] [class_type] [class_name] [dist_type] [distpar1] [distpar2] {distpar3}
-        ExitGracefullyIf(s.size() < 6, "ParseEnsembleFile: bad :ParameterDistributions row");
+        // [param_name] [class_type] [class_name] [base_value] [dist_type] [distpar1] [distpar2] {distpar3}   (src/ParseEnsembleFile.cpp:168-220)
+        ExitGracefullyIf(s.size() < 7, "Parse Ensemble File: incorrect number of terms in ParameterDistributions command.");
         param_dist d; d.param_name = s[0];
-        std::string ct = StringToUppercase(s[1]);
+        const std::string &ct = s[1];
         if (ct == "SOIL") d.param_class = CLASS_SOIL; else if (ct == "VEGETATION") d.param_class = CLASS_VEGETATION;
         else if (ct == "LANDUSE") d.param_class = CLASS_LANDUSE; else if (ct == "TERRAIN") d.param_class = CLASS_TERRAIN;
-        else if (ct == "GLOBALS" || ct == "GLOBAL") d.param_class = CLASS_GLOBAL;
-        else { ExitGracefully("ParseEnsembleFile: invalid parameter class in :ParameterDistributions"); d.param_class = CLASS_GLOBAL; }
+        else if (ct == "GLOBALS") d.param_class = CLASS_GLOBAL;
+        else { ExitGracefully("ParseEnsembleFile: invalid parameter class in :ParameterDistributions command"); d.param_class = CLASS_GLOBAL; }
         d.class_group = s[2];
-        std::string dt = StringToUppercase(s[3]);
-        if (dt == "DIST_UNIFORM" || dt == "UNIFORM") d.distribution = 0;
-        else if (dt == "DIST_NORMAL" || dt == "NORMAL" || dt == "DIST_GAUSSIAN") d.distribution = 1;
-        else if (dt == "DIST_LOGNORMAL" || dt == "LOGNORMAL") d.distribution = 2;
-        else if (dt == "DIST_GAMMA" || dt == "GAMMA") d.distribution = 3;
-        else { ExitGracefully("ParseEnsembleFile: invalid distribution type"); d.distribution = 0; }
-        d.distpar[0] = s_to_d(s[4]); d.distpar[1] = s_to_d(s[5]); d.distpar[2] = (s.size() > 6) ? s_to_d(s[6]) : 0.0;
-        d.default_val = 0.0;
+        d.default_val = s_to_d(s[3]);
+        bool fix = false;
+        const std::string &dt = s[4];
+        if (dt == "DIST_UNIFORM") d.distribution = 0;
+        else if (dt == "DIST_NORMAL") d.distribution = 1;
+        else if (dt == "DIST_LOGNORMAL") d.distribution = 2;
+        else if (dt == "DIST_LOGNORMAL2") { d.distribution = 2; fix = true; }
+        else if (dt == "DIST_GAMMA") d.distribution = 3;
+        else { ExitGracefully("ParseEnsembleFile: invalid distribution type in :ParameterDistributions command"); d.distribution = 0; }
+        d.distpar[0] = s_to_d(s[5]); d.distpar[1] = s_to_d(s[6]); d.distpar[2] = (s.size() > 7) ? s_to_d(s[7]) : 0.0;
+        if (fix) {  // mean / std of x -> mu / std of ln(x)
+          const double mean = d.distpar[0], sd = d.distpar[1];
+          d.distpar[0] = log(mean * mean) - log(sqrt(mean * mean + sd * sd));
+          d.distpar[1] = log(1.0 + sd * sd / mean / mean);
+        }
         pModel->param_dists.push_back(d);
       }
       continue;

@@ -173,7 +173,7 @@ def write_gauge(f, rain, snow, tmin, tmax, pet, elev=843.0, lat=54.4848, lon=-12
 
 
 def write_hmets(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUTE_NONE", catchment_route="ROUTE_DUMP",
-                single_class=False, ensemble_members=0, name="hmets", season_offset=0):
+                single_class=False, ensemble_members=0, name="hmets", season_offset=0, mixed_distributions=False):
     """HMETS template (BASELINE config 3 member): returns the input base path."""
     os.makedirs(dirpath, exist_ok=True)
     base = os.path.join(dirpath, name)
@@ -199,10 +199,15 @@ def write_hmets(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUT
     _write(base + ".rvc", HMETS_RVC)
     if ensemble_members > 0:
         with open(base + ".rve", "w") as f:
-            f.write(":OutputDirectoryFormat ./ens_*\n:ParameterDistributions\n  :Attributes NAME CLASS_TYPE CLASS DIST PAR1 PAR2\n")
-            for (pn, ct, cn, v) in HMETS_DISTS:
+            f.write(":OutputDirectoryFormat ./ens_*\n:ParameterDistributions\n  :Attributes NAME CLASS_TYPE CLASS BASE_VALUE DIST PAR1 PAR2\n")
+            for i, (pn, ct, cn, v) in enumerate(HMETS_DISTS):
                 lo, hi = sorted([0.8 * v, 1.2 * v])
-                f.write("  %s %s %s DIST_UNIFORM %.8g %.8g\n" % (pn, ct, cn, lo, hi))
+                if mixed_distributions and i % 4 == 1:
+                    f.write("  %s %s %s %.8g DIST_NORMAL %.8g %.8g\n" % (pn, ct, cn, v, v, 0.03 * abs(v)))
+                elif mixed_distributions and i % 4 == 2:
+                    f.write("  %s %s %s %.8g DIST_GAMMA %.8g %.8g\n" % (pn, ct, cn, v, 40.0, abs(v) / 40.0))
+                else:
+                    f.write("  %s %s %s %.8g DIST_UNIFORM %.8g %.8g\n" % (pn, ct, cn, v, lo, hi))
             f.write(":EndParameterDistributions\n")
     return base
 

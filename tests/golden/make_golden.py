@@ -42,17 +42,28 @@ if hasattr(synth, "write_gr4j"):
     CASES["gr4j_tree"] = dict(kind="gr4j", n_sb=7, hru_per_sb=5, n_days=300, seed=10)
 
 
+# Monte-Carlo ensemble (reference CMonteCarloEnsemble): fixture = ensemble member MEMBER as the reference's own member
+# loop would run it (ref_dump replays UpdateModel for the members before it), stored as reference_member<k>.npz
+MC_CASES = {"hmets_mc": dict(kind="hmets", n_sb=3, hru_per_sb=4, n_days=150, seed=7, ensemble_members=4, mixed_distributions=True, member=2)}
+
+
 def make(name, spec):
     spec = dict(spec)
     kind = spec.pop("kind")
+    member = spec.pop("member", None)
     d = os.path.join(HERE, name)
     shutil.rmtree(d, ignore_errors=True)
     base = WRITERS[kind](d, name="model", **spec)
     n = spec["n_days"]
     out = os.path.join(d, "_refout")
-    ref = H.reference_run(base, out, n)
+    if member is not None:
+        os.environ["REF_DUMP_MEMBER"] = str(member)
+    try:
+        ref = H.reference_run(base, out, n)
+    finally:
+        os.environ.pop("REF_DUMP_MEMBER", None)
     rec = sorted(set([1, 2, 3, 10, 50, 100, 150, 200, 250, 300, 365, 400, 500, 600, 700, n]) & set(range(1, n + 1)))
-    np.savez_compressed(os.path.join(d, "reference.npz"),
+    np.savez_compressed(os.path.join(d, "reference.npz" if member is None else "reference_member%d.npz" % member),
                         state_steps=np.array(rec), state=ref["state"][rec], qout=ref["basin"][1:n + 1, :, 0],
                         basin_last=ref["basin"][n], wshed=ref["wshed"][1:n + 1], forc_steps=np.array(rec), forc=ref["forc"][rec],
                         sv_type=np.array([t for t, _ in ref["sv"]]), sv_layer=np.array([l for _, l in ref["sv"]]),
@@ -65,7 +76,7 @@ def make(name, spec):
 if __name__ == "__main__":
     assert H.have_reference(), "oracle/_ref/ref_dump missing: run oracle/build_ref.sh where /root/reference exists"
     only = sys.argv[1:]
-    for name, spec in CASES.items():
+    for name, spec in list(CASES.items()) + list(MC_CASES.items()):
         if only and name not in only:
             continue
         make(name, spec)

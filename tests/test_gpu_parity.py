@@ -221,3 +221,25 @@ def test_non_template_process_list_runs_on_interpreter(tmp_path):
     sim.run(120)
     ref = H.oracle_run(model, 120)
     assert H.rel_err(sim.download_state()[0], ref["state"]) < TOL
+
+
+def test_monte_carlo_ensemble_matches_reference_member_and_shards():
+    """GPU ensemble (all members at once) vs member 2 of the reference's sequential member loop; a shard that starts at
+    global member 2 (what rank 1 of 2 would hold) reproduces members 2..3 of the full run bit for bit."""
+    d = os.path.join(H.GOLDEN, "hmets_mc")
+    g = np.load(os.path.join(d, "reference_member2.npz"))
+    n = g["qout"].shape[0]
+    model = api.RavenModel(os.path.join(d, "model"))
+    model.flatten(4)
+    full = api.GpuSimulation(model, n_members=4)
+    full.apply_ensemble(0)
+    full.set_recording(n)
+    full.run(n)
+    assert H.rel_err(full.hydrographs(0, n)[:, 2, :], g["qout"]) < TOL
+    st = full.download_state()
+    model2 = api.RavenModel(os.path.join(d, "model"))
+    model2.flatten(2)
+    shard = api.GpuSimulation(model2, n_members=2)
+    shard.apply_ensemble(2)
+    shard.run(n)
+    assert np.array_equal(shard.download_state(), st[2:4])

@@ -150,3 +150,27 @@ def test_mass_balance_closes():
     s0 += float(scal[:, 4].sum() + scal[:, 5].sum()) / (area.sum() * 1e6) * 1000.0
     mb = (w[:, 3] - s0) + (w[:, 1] - w[:, 0])
     assert np.max(np.abs(mb)) < 1e-8
+
+
+def test_monte_carlo_member_matches_reference_golden():
+    """CMonteCarloEnsemble on the host (libc rand() replay, seed offset by the start date, uniform/normal/gamma draws,
+    CModel::UpdateParameter) + oracle vs member 2 of the reference's own ensemble loop."""
+    d = os.path.join(H.GOLDEN, "hmets_mc")
+    g = np.load(os.path.join(d, "reference_member2.npz"))
+    model = api.RavenModel(os.path.join(d, "model"))
+    assert model.ensemble_mode == 1 and model.num_members == 4
+    model.flatten(4)
+    assert model.ensemble_begin() == 4
+    samples = []
+    for e in range(4):
+        samples.append(model.ensemble_update_model(e))
+        model.flatten_member(e)
+    samples = np.array(samples)
+    assert samples.shape == (4, 19) and len(np.unique(samples[:, 0])) == 4
+    n = g["qout"].shape[0]
+    o = H.oracle_run(model, n, member=2)
+    steps = g["state_steps"]
+    assert H.rel_err(o["state_rec"][steps - 1], g["state"]) < TOL
+    assert H.rel_err(o["qout_rec"], g["qout"]) < TOL
+    other = H.oracle_run(model, n, member=1)
+    assert H.rel_err(other["qout_rec"], g["qout"]) > 1e-3     # members really differ
