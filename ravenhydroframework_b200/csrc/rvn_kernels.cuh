@@ -13,7 +13,7 @@
 //                                 state and rates live in shared-memory columns indexed at run time
 //                        In both the 50-slot convolution stores are streamed HBM -> registers -> HBM, coalesced over
 //                        neighbouring HRUs, with a register double buffer; no CTA-wide barrier inside the time-critical part.
-//   aggregate_kernel, route_level_kernel (one launch per level), balance_kernel
+//   route_level_kernel (one launch per level), balance_kernel
 //                      = HRU->subbasin aggregation (:490-511), the upstream->downstream routing loop
 //                        (:565-615; CSubBasin::RouteWater/UpdateOutflows, src/SubBasin.cpp:2584-2863,
 //                        2320-2421) level by level, IncrementCumulInput/CumOutflow (src/Model.cpp:
@@ -557,7 +557,7 @@ struct RunProcs {
 };
 
 #ifndef RVN_STATIC_MIN_BLOCKS
-#define RVN_STATIC_MIN_BLOCKS 6   // resident CTAs per SM the specialised sweep is compiled for (caps registers at 80/thread)
+#define RVN_STATIC_MIN_BLOCKS 7   // resident CTAs per SM the specialised sweep is compiled for (caps registers at 72/thread)
 #endif
 template <class Prog, bool UNIT_DT>
 __global__ void __launch_bounds__(RVN_BS, RVN_STATIC_MIN_BLOCKS) hru_sweep_static(const __grid_constant__ DevModel M, const int step) {
@@ -709,14 +709,33 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
 // ------------------------------------------------------------------------------------------------
 // routing + balance
 // ------------------------------------------------------------------------------------------------
-__device__ void route_one_basin(const DevModel &M, int e, int p) {
+// The inflow / lateral-inflow histories (_aQinHist, _aQlatHist) are ring buffers: the reference shifts every history by one
+// slot per step (src/SubBasin.cpp:1531-1553), here only the newest value is written.  After t pushes since the last upload,
+// history element n (0 = newest) of a basin with nQ slots lives at slot (n - t) mod nQ; uploads/downloads present the
+// reference's ordered arrays (rvn_engine.cu rotates).
+struct Ring {
+  double *buf; int nQ, base;
+  RVN_DI Ring(double *b, int n, int t) : buf(b), nQ(n) { base = n - (t % n); if (base == n) base = 0; }
+  RVN_DI double &operator[](int n) const { int i = base + n; if (i >= nQ) i -= nQ; return buf[i]; }
+};
+
+// one basin, one member, one step: HRU -> subbasin aggregation in HRU-index order (src/Solvers.cpp:490-511),
+// CSubBasin::UpdateLateralInflow / UpdateInflow, RouteWater (src/SubBasin.cpp:2584-2863), UpdateOutflows (:2320-2421).
+// `t` = pushes into the histories before this step.
+__device__ void route_one_basin(const DevModel &M, int e, int p, int step, int t) {
   const double tstep = M.opt.timestep;
   const int nSeg = M.sb_nseg[p], nQin = M.sb_nqin[p], nQlat = M.sb_nqlat[p];
-  double *QinHist = M.qin + ((size_t)e * M.nSB + p) * M.max_nqin;
-  double *QlatHist = M.qlat + ((size_t)e * M.nSB + p) * M.max_nqlat;
+  const Ring QinHist(M.qin + ((size_t)e * M.nSB + p) * M.max_nqin, nQin, t + 1);
+  const Ring QlatHist(M.qlat + ((size_t)e * M.nSB + p) * M.max_nqlat, nQlat, t + 1);
   double *aQout = M.qout + ((size_t)e * M.nSB + p) * RVN_MAX_RIVER_SEGS;
   double *sc = M.scal + ((size_t)e * M.nSB + p) * 8;
   const double *UH = M.sb_unit_hydro + (size_t)p * M.max_nqlat, *RH = M.sb_route_hydro + (size_t)p * M.max_nqin;
+  {
+    const double *swvol = M.swvol + ((size_t)(step & 1) * M.E + e) * M.nHp;
+    double routed = 0.0;
+    for (int i = M.sb_hru_ptr[p]; i < M.sb_hru_ptr[p + 1]; i++) routed += swvol[M.sb_hru_idx[i]];
+    QlatHist[0] = routed / (tstep * D_SEC_PER_DAY);
+  }
   // inflow from upstream basins, accumulated in the reference's processing order (ascending index inside the
   // level above; src/Solvers.cpp:602-606), then CSubBasin::UpdateInflow (src/SubBasin.cpp:1531-1537)
   double Qin_up = 0.0;
@@ -724,8 +743,8 @@ __device__ void route_one_basin(const DevModel &M, int e, int p) {
     const int pu = M.sb_up_idx[u];
     Qin_up += M.qout[((size_t)e * M.nSB + pu) * RVN_MAX_RIVER_SEGS + M.sb_nseg[pu] - 1];
   }
-  for (int n = nQin - 1; n > 0; n--) QinHist[n] = QinHist[n - 1];
   QinHist[0] = Qin_up;
+  const double Qin0 = Qin_up, Qin1 = QinHist[1], Qlat0 = QlatHist[0];
   // CSubBasin::RouteWater  src/SubBasin.cpp:2584-2863
   double Qlat_new = 0.0;
   for (int n = 0; n < nQlat; n++) Qlat_new += UH[n] * QlatHist[n];
@@ -739,12 +758,12 @@ __device__ void route_one_basin(const DevModel &M, int e, int p) {
     double dt = dmin(K, tstep);
     // aQout[] is advanced in place over the local sub-steps; the reference restores the stored array and then
     // overwrites it with the final values in UpdateOutflows, which is the same end state.
-    for (double t = 0; t < tstep; t += dt) {
-      if (dt > (tstep - t)) dt = tstep - t;
+    for (double tt = 0; tt < tstep; tt += dt) {
+      if (dt > (tstep - tt)) dt = tstep - tt;
       const double denom = (2 * K * (1.0 - X) + dt);
       const double c1 = (dt - 2 * K * (X)) / denom, c2 = (dt + 2 * K * (X)) / denom, c3 = (-dt + 2 * K * (1 - X)) / denom, c4 = (dt) / denom;
-      double Qin = QinHist[1] + ((t) / tstep) * (QinHist[0] - QinHist[1]);
-      double Qin_new = QinHist[1] + ((t + dt) / tstep) * (QinHist[0] - QinHist[1]);
+      double Qin = Qin1 + ((tt) / tstep) * (Qin0 - Qin1);
+      double Qin_new = Qin1 + ((tt + dt) / tstep) * (Qin0 - Qin1);
       for (int s = 0; s < nSeg; s++) {
         const double old = aQout[s];
         const double qn = c1 * Qin_new + c2 * Qin + c3 * old + cunge * c4 * (Qlat_new * seg_fraction);
@@ -753,7 +772,7 @@ __device__ void route_one_basin(const DevModel &M, int e, int p) {
       }
     }
   } else if (method == RVN_ROUTE_STORAGECOEFF) {
-    double Qin_new = QinHist[0], Qin = QinHist[1];
+    double Qin_new = Qin0, Qin = Qin1;
     const double Qlocal = sc[2];
     for (int s = 0; s < nSeg; s++) {
       const double ttime = M.sb_K_reach[p] * seg_fraction;
@@ -770,7 +789,7 @@ __device__ void route_one_basin(const DevModel &M, int e, int p) {
     aQout[nSeg - 1] = q;
   } else {  // ROUTE_NONE
     for (int s = 0; s < nSeg; s++) aQout[s] = 0.0;
-    aQout[nSeg - 1] = QinHist[0];
+    aQout[nSeg - 1] = Qin0;
   }
   aQout[nSeg - 1] += Qlat_new;
   aQout[nSeg - 1] += 0.0;  // down_Q (specified downstream inflows / return flows: none)
@@ -781,45 +800,37 @@ __device__ void route_one_basin(const DevModel &M, int e, int p) {
   const double dts = tstep * D_SEC_PER_DAY;
   sc[3] = sc[2]; sc[2] = Qlat_new;
   double dV = 0.0;
-  dV += 0.5 * (QinHist[0] + QinHist[1]) * dts;
+  dV += 0.5 * (Qin0 + Qin1) * dts;
   dV -= 0.5 * (aQout[nSeg - 1] + QoutLast) * dts;
   dV += 0.5 * (Qlat_new + sc[1]) * dts;
   dV -= 0.5 * (irrQ + 0.0) * dts;
   dV -= 0.5 * (divQ + 0.0) * dts;
   sc[4] += dV;
   dV = 0.0;
-  dV += QlatHist[0] * dts;
+  dV += Qlat0 * dts;
   dV -= 0.5 * (Qlat_new + sc[1]) * dts;
   sc[5] += dV;
   sc[1] = Qlat_new;
 }
 
-// ---- routing runs as a short sequence of small kernels on its own stream (one thread per (member, basin)), so that it
-// occupies little of the machine while the next step's HRU sweep is running:
-//   aggregate_kernel            HRU -> subbasin aggregation in HRU-index order (src/Solvers.cpp:490-511) + UpdateLateralInflow
-//   route_level_kernel x nLevels  level-ordered routing, deepest level first; basins inside a level are independent
-//   balance_kernel              IncrementCumulInput / IncrementCumOutflow + watershed storage + per-step records
-#define RVN_ROUTE_BS 128
-__global__ void __launch_bounds__(RVN_ROUTE_BS) aggregate_kernel(const __grid_constant__ DevModel M, const int step) {
-  const int NB = M.nSB;
-  const long long idx = (long long)blockIdx.x * RVN_ROUTE_BS + threadIdx.x;
-  if (idx >= (long long)M.E * NB) return;
-  const int e = (int)(idx / NB), p = (int)(idx - (long long)e * NB);
-  const double tstep = M.opt.timestep;
-  const double *swvol = M.swvol + ((size_t)(step & 1) * M.E + e) * M.nHp;
-  double routed = 0.0;
-  for (int i = M.sb_hru_ptr[p]; i < M.sb_hru_ptr[p + 1]; i++) routed += swvol[M.sb_hru_idx[i]];
-  double *QlatHist = M.qlat + ((size_t)e * NB + p) * M.max_nqlat;
-  for (int n = M.sb_nqlat[p] - 1; n > 0; n--) QlatHist[n] = QlatHist[n - 1];
-  QlatHist[0] = routed / (tstep * D_SEC_PER_DAY);
-}
-__global__ void __launch_bounds__(RVN_ROUTE_BS) route_level_kernel(const __grid_constant__ DevModel M, const int lev0, const int nlev) {
+// ---- routing runs as a short sequence of small kernels on its own stream (one thread per (member, basin)):
+//   route_level_kernel x nLevels  aggregation + level-ordered routing, deepest level first; basins inside a level are independent
+//   balance_kernel                IncrementCumulInput / IncrementCumOutflow + watershed storage + per-step records
+// Small CTAs (64 threads x <=32 registers): routing CTAs slip into the register-file and thread slots the resident sweep
+// CTAs leave free on an SM instead of displacing them (measured: 128 threads x 72 registers cost the sweep 0.2 ms/step)
+#ifndef RVN_ROUTE_BS
+#define RVN_ROUTE_BS 64
+#endif
+#ifndef RVN_ROUTE_MINB
+#define RVN_ROUTE_MINB 32
+#endif
+__global__ void __launch_bounds__(RVN_ROUTE_BS, RVN_ROUTE_MINB) route_level_kernel(const __grid_constant__ DevModel M, const int lev0, const int nlev, const int step, const int t) {
   const long long idx = (long long)blockIdx.x * RVN_ROUTE_BS + threadIdx.x;
   if (idx >= (long long)M.E * nlev) return;
   const int e = (int)(idx / nlev), i = (int)(idx - (long long)e * nlev);
-  route_one_basin(M, e, M.level_idx[lev0 + i]);
+  route_one_basin(M, e, M.level_idx[lev0 + i], step, t);
 }
-__global__ void __launch_bounds__(RVN_ROUTE_BS) balance_kernel(const __grid_constant__ DevModel M, const int step, const int rec) {
+__global__ void __launch_bounds__(RVN_ROUTE_BS, RVN_ROUTE_MINB) balance_kernel(const __grid_constant__ DevModel M, const int step, const int rec) {
   const int e = blockIdx.x, tid = threadIdx.x, NB = M.nSB;
   const double tstep = M.opt.timestep;
   const int par = step & 1;
