@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RVN_ABI_VERSION 2
+#define RVN_ABI_VERSION 3
 #define RVN_DOESNT_EXIST (-1)
 #define RVN_CONV_STORES 50   /* MAX_CONVOL_STORES, reference src/RavenInclude.h / Convolution.cpp:17 */
 #define RVN_MAX_CONN 24      /* max connections of a non-convolution process (Precipitation: 13..19) */
@@ -233,7 +233,14 @@ typedef struct rvn_model_desc {
   /* forcings */
   const double *gauge_series; /* [RVN_GF_COUNT][nGauges][nSteps] */
   const double *gauge_const;  /* [nGauges][RVN_GC_COUNT] */
-  const double *wt_precip, *wt_temp, *wt_all;  /* [nHRU][nGauges] (src/Model.h:104-106) */
+  /* gauge (or grid-cell) interpolation weights as CSR over HRUs, entries in ascending gauge index: entry i of HRU k is
+   * gauge wt_idx[i] with weights wt_val[3*i+{0,1,2}] = {precipitation, temperature, everything else} -- the three dense
+   * [nHRU][nGauges] weight tables of the reference (src/Model.h:104-106, used at src/UpdateForcings.cpp:184-235), or the
+   * sparse grid weights of CForcingGrid::GetWeightedValue (src/ForcingGrid.cpp:1886-1946).  Zero weights are omitted:
+   * they contribute exact zeros to the reference's sums. */
+  const int32_t *wt_ptr;      /* [nHRU+1] */
+  const int32_t *wt_idx;      /* [nnz] */
+  const double  *wt_val;      /* [nnz][3] */
   const rvn_time *times;      /* [nSteps] */
 
   /* routing network (reference CSubBasin + CModel::InitializeRoutingNetwork, src/ModelInitialize.cpp:505-619) */

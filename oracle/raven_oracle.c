@@ -134,10 +134,12 @@ static void update_forcings(const rvn_model_desc *d, const double *ptab, int k, 
   if (!d->hru_enabled[k]) return;
 #define GS(f, g) d->gauge_series[((size_t)(f) * nG + (g)) * nS + step]
 #define GC(g, f) d->gauge_const[(size_t)(g) * RVN_GC_COUNT + (f)]
-  for (int g = 0; g < nG; g++) { /* :184-235 */
-    double wt = d->wt_precip[(size_t)k * nG + g];
+  const int w0 = d->wt_ptr[k], w1 = d->wt_ptr[k + 1]; /* CSR row of this HRU: the reference's dense loops, zero weights omitted */
+  for (int i = w0; i < w1; i++) { /* :184-235 */
+    const int g = d->wt_idx[i];
+    double wt = d->wt_val[3 * (size_t)i + 0];
     if (wt != 0.0) { F[RVN_F_PRECIP] += wt * GS(RVN_GF_PRECIP, g); F[RVN_F_SNOW_FRAC] += wt * GS(RVN_GF_SNOW_FRAC, g); ref_elev_precip += wt * GC(g, RVN_GC_ELEVATION); }
-    wt = d->wt_temp[(size_t)k * nG + g];
+    wt = d->wt_val[3 * (size_t)i + 1];
     if (wt != 0.0) {
       F[RVN_F_TEMP_AVE] += wt * GS(RVN_GF_TEMP_AVE, g); F[RVN_F_TEMP_DAILY_AVE] += wt * GS(RVN_GF_TEMP_DAILY_AVE, g);
       F[RVN_F_TEMP_DAILY_MIN] += wt * GS(RVN_GF_TEMP_DAILY_MIN, g); F[RVN_F_TEMP_DAILY_MAX] += wt * GS(RVN_GF_TEMP_DAILY_MAX, g);
@@ -145,7 +147,7 @@ static void update_forcings(const rvn_model_desc *d, const double *ptab, int k, 
       temp_month_ave += wt * GC(g, RVN_GC_MONTHLY_AVE_TEMP0 + mo - 1);
       ref_elev_temp += wt * GC(g, RVN_GC_ELEVATION);
     }
-    wt = d->wt_all[(size_t)k * nG + g];
+    wt = d->wt_val[3 * (size_t)i + 2];
     if (wt != 0.0) {
       PET_month_ave += wt * GC(g, RVN_GC_MONTHLY_AVE_PET0 + mo - 1);
       F[RVN_F_POTENTIAL_MELT] += wt * GS(RVN_GF_POTENTIAL_MELT, g);
@@ -156,8 +158,9 @@ static void update_forcings(const rvn_model_desc *d, const double *ptab, int k, 
   { /* temperature gauge corrections :441-455 -- sums are recomputed over ALL gauges */
     double tc = d->sb_temp_corr[p];
     F[RVN_F_TEMP_AVE] = F[RVN_F_TEMP_DAILY_AVE] = F[RVN_F_TEMP_DAILY_MAX] = F[RVN_F_TEMP_DAILY_MIN] = 0.0;
-    for (int g = 0; g < nG; g++) {
-      double gauge_corr = tc + GC(g, RVN_GC_TEMP_CORR), wt = d->wt_temp[(size_t)k * nG + g];
+    for (int i = w0; i < w1; i++) {
+      const int g = d->wt_idx[i];
+      double gauge_corr = tc + GC(g, RVN_GC_TEMP_CORR), wt = d->wt_val[3 * (size_t)i + 1];
       F[RVN_F_TEMP_AVE] += wt * (gauge_corr + GS(RVN_GF_TEMP_AVE, g));
       F[RVN_F_TEMP_DAILY_AVE] += wt * (gauge_corr + GS(RVN_GF_TEMP_DAILY_AVE, g));
       F[RVN_F_TEMP_DAILY_MAX] += wt * (gauge_corr + GS(RVN_GF_TEMP_DAILY_MAX, g));
@@ -203,9 +206,10 @@ static void update_forcings(const rvn_model_desc *d, const double *ptab, int k, 
   { /* precip gauge corrections :507-527 */
     double rc = d->sb_rain_corr[p], sc = d->sb_snow_corr[p];
     F[RVN_F_PRECIP] = 0.0;
-    for (int g = 0; g < nG; g++) {
+    for (int i = w0; i < w1; i++) {
+      const int g = d->wt_idx[i];
       double gauge_corr = F[RVN_F_SNOW_FRAC] * sc * GC(g, RVN_GC_SNOW_CORR) + (1.0 - F[RVN_F_SNOW_FRAC]) * rc * GC(g, RVN_GC_RAIN_CORR);
-      double wt = d->wt_precip[(size_t)k * nG + g];
+      double wt = d->wt_val[3 * (size_t)i + 0];
       F[RVN_F_PRECIP] += wt * gauge_corr * GS(RVN_GF_PRECIP, g);
     }
   }

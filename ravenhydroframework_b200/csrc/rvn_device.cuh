@@ -63,7 +63,10 @@ struct DevModel {
   const int32_t *hru_type, *hru_lu, *hru_veg, *hru_profile, *hru_sb, *hru_enabled;
   const unsigned long long *apply_mask;
   const int32_t *prof_class; const double *prof_thick;
-  const double *gauge_series, *gauge_const, *wt_precip, *wt_temp, *wt_all;
+  const double *gauge_series;                      // [step][RVN_GF_COUNT][nGauges]: one contiguous slab per step
+  const double *gauge_const;
+  const int32_t *wt_ptr, *wt_idx; const double *wt_val;   // CSR gauge/grid-cell weights (rvn_gpu.h)
+  int32_t unit_weights;                            // 1: one station, every HRU weight exactly 1.0 (CSR not read)
   const rvn_time *times;
   const double *veg_season;                        // [nSteps][nVeg][2] month-interpolated relative height, relative LAI
   const double *et_radia; const int32_t *et_row;   // [nEtRows][nHp] extraterrestrial radiation on the HRU's slope, row of each step (or NULL)

@@ -107,24 +107,33 @@ template <class C>
 RVN_DI void compute_forcings(C &c, const DevModel &M, int k, int step, int sb) {
   const rvn_options &opt = c.opt();
   const rvn_time tt = M.times[step];
-  const int nG = M.nGauges, nS = M.nSteps, mo = tt.month;
+  const int nG = M.nGauges, mo = tt.month;
   const double elev = c.elev;
   double *F = c.F;
   double ref_elev_temp = 0.0, ref_elev_precip = 0.0, temp_month_min = 0, temp_month_max = 0, temp_month_ave = 0, PET_month_ave = 0;
 #pragma unroll
   for (int f = 0; f < RVN_F_COUNT; f++) F[f] = 0.0;
-#define GS(f, g) M.gauge_series[((size_t)(f) * nG + (g)) * nS + step]
+  // K3: sparse gather over this HRU's gauges / grid cells (CSR, ascending gauge index = the reference's summation order;
+  // omitted zero weights add exact zeros there).  The step's series form one contiguous [forcing][gauge] slab.
+  const double *slab = M.gauge_series + (size_t)step * RVN_GF_COUNT * nG;
+#define GS(f, g) slab[(size_t)(f) * nG + (g)]
 #define GC(g, f) M.gauge_const[(size_t)(g) * RVN_GC_COUNT + (f)]
-  for (int g = 0; g < nG; g++) {  // src/UpdateForcings.cpp:184-235
-    double wt = M.wt_precip[(size_t)k * nG + g];
+  // single-station models (every weight exactly 1.0): no CSR loads at all, the loops below run once with g = 0, wt = 1.0
+  const bool uw = (M.unit_weights != 0);
+  const int w0 = uw ? 0 : M.wt_ptr[k], w1 = uw ? 1 : M.wt_ptr[k + 1];
+#define WT(i, j) (uw ? 1.0 : M.wt_val[3 * (size_t)(i) + (j)])
+#define WG(i) (uw ? 0 : M.wt_idx[i])
+  for (int i = w0; i < w1; i++) {  // src/UpdateForcings.cpp:184-235
+    const int g = WG(i);
+    double wt = WT(i, 0);
     if (wt != 0.0) { F[RVN_F_PRECIP] += wt * GS(RVN_GF_PRECIP, g); F[RVN_F_SNOW_FRAC] += wt * GS(RVN_GF_SNOW_FRAC, g); ref_elev_precip += wt * GC(g, RVN_GC_ELEVATION); }
-    wt = M.wt_temp[(size_t)k * nG + g];
+    wt = WT(i, 1);
     if (wt != 0.0) {
       temp_month_min += wt * GC(g, RVN_GC_MONTHLY_MIN_TEMP0 + mo - 1); temp_month_max += wt * GC(g, RVN_GC_MONTHLY_MAX_TEMP0 + mo - 1);
       temp_month_ave += wt * GC(g, RVN_GC_MONTHLY_AVE_TEMP0 + mo - 1);
       ref_elev_temp += wt * GC(g, RVN_GC_ELEVATION);
     }
-    wt = M.wt_all[(size_t)k * nG + g];
+    wt = WT(i, 2);
     if (wt != 0.0) {
       PET_month_ave += wt * GC(g, RVN_GC_MONTHLY_AVE_PET0 + mo - 1);
       F[RVN_F_POTENTIAL_MELT] += wt * GS(RVN_GF_POTENTIAL_MELT, g);
@@ -133,8 +142,9 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int k, int step, int sb) {
   }
   {  // temperature gauge+basin corrections, recomputed over all gauges (:441-455)
     const double tc = M.sb_temp_corr[sb];
-    for (int g = 0; g < nG; g++) {
-      double gauge_corr = tc + GC(g, RVN_GC_TEMP_CORR), wt = M.wt_temp[(size_t)k * nG + g];
+    for (int i = w0; i < w1; i++) {
+      const int g = WG(i);
+      double gauge_corr = tc + GC(g, RVN_GC_TEMP_CORR), wt = WT(i, 1);
       F[RVN_F_TEMP_AVE] += wt * (gauge_corr + GS(RVN_GF_TEMP_AVE, g));
       F[RVN_F_TEMP_DAILY_AVE] += wt * (gauge_corr + GS(RVN_GF_TEMP_DAILY_AVE, g));
       F[RVN_F_TEMP_DAILY_MAX] += wt * (gauge_corr + GS(RVN_GF_TEMP_DAILY_MAX, g));
@@ -180,9 +190,10 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int k, int step, int sb) {
   {  // precipitation gauge+basin corrections (:507-527)
     const double rc = M.sb_rain_corr[sb], sc = M.sb_snow_corr[sb];
     F[RVN_F_PRECIP] = 0.0;
-    for (int g = 0; g < nG; g++) {
+    for (int i = w0; i < w1; i++) {
+      const int g = WG(i);
       double gauge_corr = F[RVN_F_SNOW_FRAC] * sc * GC(g, RVN_GC_SNOW_CORR) + (1.0 - F[RVN_F_SNOW_FRAC]) * rc * GC(g, RVN_GC_RAIN_CORR);
-      double wt = M.wt_precip[(size_t)k * nG + g];
+      double wt = WT(i, 0);
       F[RVN_F_PRECIP] += wt * gauge_corr * GS(RVN_GF_PRECIP, g);
     }
   }
@@ -274,6 +285,8 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int k, int step, int sb) {
   }
 #undef GS
 #undef GC
+#undef WT
+#undef WG
 }
 
 // ------------------------------------------------------------------------------------------------

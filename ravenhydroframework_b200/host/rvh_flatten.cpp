@@ -209,8 +209,17 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
     }
   }
   d.gauge_series = _f_series.data(); d.gauge_const = _f_gconst.data();
-  _f_wt = _aGaugeWeights;
-  d.wt_precip = d.wt_temp = d.wt_all = _f_wt.data();
+  // gauge weights -> CSR (the reference keeps three dense [nHRU][nGauges] tables; here they hold the same values)
+  _f_wt_ptr.assign(nH + 1, 0); _f_wt_idx.clear(); _f_wt.clear();
+  for (int k = 0; k < nH; k++) {
+    for (int g = 0; g < nG; g++) {
+      const double w = _aGaugeWeights[(size_t)k * nG + g];
+      if (w != 0.0) { _f_wt_idx.push_back(g); _f_wt.push_back(w); _f_wt.push_back(w); _f_wt.push_back(w); }
+    }
+    _f_wt_ptr[k + 1] = (int32_t)_f_wt_idx.size();
+  }
+  if (_f_wt_idx.empty()) { _f_wt_idx.push_back(0); _f_wt.assign(3, 0.0); }
+  d.wt_ptr = _f_wt_ptr.data(); d.wt_idx = _f_wt_idx.data(); d.wt_val = _f_wt.data();
   // ---- routing network
   for (int a = 0; a < 7; a++) _f_sb_i[a].resize(NB);
   for (int a = 0; a < 7; a++) _f_sb_d[a].resize(NB);

@@ -268,7 +268,7 @@ private:
   std::vector<rvn_process> _f_proc;
   std::vector<uint64_t> _f_mask;
   std::vector<double> _f_hru_d[5], _f_prof_thick, _f_ptab, _f_conv_uh, _f_series, _f_gconst, _f_wt, _f_sb_d[7], _f_uh, _f_rh, _f_veg_season, _f_et;
-  std::vector<int32_t> _f_et_row;
+  std::vector<int32_t> _f_et_row, _f_wt_ptr, _f_wt_idx;
   std::vector<rvn_time> _f_times;
   int _f_ptab_stride, _f_nconv;
 };

@@ -172,8 +172,64 @@ def write_gauge(f, rain, snow, tmin, tmax, pet, elev=843.0, lat=54.4848, lon=-12
     f.write("  :EndMultiData\n:EndGauge\n")
 
 
+def write_gauge_grid(base, n_gauges, n_days, seed, season_offset, hru_latlon, extra=""):
+    """n_gauges stations on a regular lat/lon grid over the watershed, each with its own series (base weather x a smooth
+    spatial factor, different elevations), + an INTERP_FROM_FILE weight table giving every HRU its 4 nearest stations with
+    normalised inverse-distance weights: the same sparse weighted sums a gridded forcing (CForcingGrid::GetWeightedValue,
+    src/ForcingGrid.cpp:1886-1946) produces, expressed through the gauge path the reference can run without NetCDF.
+    Returns the .rvi line that selects the table."""
+    rng = np.random.RandomState(seed + 1000)
+    gx = int(math.ceil(math.sqrt(n_gauges)))
+    rain, snow, tmin, tmax, pet = weather(n_days, seed, season_offset)
+    lats, lons = [], []
+    with open(base + ".rvt", "w") as f:
+        for g in range(n_gauges):
+            iy, ix = divmod(g, gx)
+            lat = 54.0 + (iy + 0.5) / gx
+            lon = -123.5 + (ix + 0.5) / gx
+            lats.append(lat); lons.append(lon)
+            fac = 1.0 + 0.25 * math.sin(1.3 * ix + 0.4) * math.cos(0.9 * iy - 0.2)
+            dT = 2.0 * math.sin(0.7 * ix) - 1.5 * math.cos(1.1 * iy)
+            elev = 700.0 + 500.0 * rng.uniform(0, 1)
+            f.write(":Gauge met%d\n  :Latitude %.4f\n  :Longitude %.4f\n  :Elevation %.1f\n%s" % (g + 1, lat, lon, elev, extra))
+            f.write("  :MultiData\n    2000-01-01 00:00:00 1 %d\n" % n_days)
+            f.write("    :Parameters RAINFALL SNOWFALL TEMP_DAILY_MIN TEMP_DAILY_MAX PET\n    :Units mm/d mm/d C C mm/d\n")
+            for i in range(n_days):
+                f.write("    %.4f %.4f %.4f %.4f %.4f\n" % (rain[i] * fac, snow[i] * fac, tmin[i] + dT, tmax[i] + dT, pet[i] * (2.0 - fac)))
+            f.write("  :EndMultiData\n:EndGauge\n")
+    wfile = base + "_gauge_weights.txt"
+    with open(wfile, "w") as f:
+        f.write("%d %d\n" % (n_gauges, len(hru_latlon)))
+        for (la, lo) in hru_latlon:
+            d2 = [(la - a) ** 2 + (lo - b) ** 2 for a, b in zip(lats, lons)]
+            near = sorted(np.argsort(d2)[:min(4, n_gauges)])
+            raw = np.array([1.0 / (d2[g] + 1e-6) for g in near])
+            w = raw / raw.sum()
+            row = [0.0] * n_gauges
+            for g, x in zip(near[:-1], w[:-1]):
+                row[g] = float("%.12g" % x)
+            row[near[-1]] = 1.0 - sum(row[g] for g in near[:-1])
+            f.write(" ".join("%.17g" % x for x in row) + "\n")
+    return ":InterpolationMethod INTERP_FROM_FILE %s\n" % os.path.basename(wfile)
+
+
+def _hru_latlon(rvh_path):
+    out, on = [], False
+    for line in open(rvh_path):
+        t = line.replace(",", " ").split()
+        if not t:
+            continue
+        if t[0] == ":HRUs":
+            on = True; continue
+        if t[0] == ":EndHRUs":
+            break
+        if on and not t[0].startswith(":"):
+            out.append((float(t[3]), float(t[4])))
+    return out
+
+
 def write_hmets(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUTE_NONE", catchment_route="ROUTE_DUMP",
-                single_class=False, ensemble_members=0, name="hmets", season_offset=0, mixed_distributions=False):
+                single_class=False, ensemble_members=0, name="hmets", season_offset=0, mixed_distributions=False, n_gauges=1):
     """HMETS template (BASELINE config 3 member): returns the input base path."""
     os.makedirs(dirpath, exist_ok=True)
     base = os.path.join(dirpath, name)
@@ -181,7 +237,7 @@ def write_hmets(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUT
     extra_rvi = ""
     if ensemble_members > 0:
         extra_rvi = ":EnsembleMode ENSEMBLE_MONTECARLO %d\n:RandomSeed %d\n" % (ensemble_members, seed)
-    _write(base + ".rvi", HMETS_RVI.format(duration=n_days, routing=routing, catchment_route=catchment_route, extra=extra_rvi))
+    hmets_rvi_extra = extra_rvi
     profile = "NONE" if routing == "ROUTE_NONE" else "CHN"
     extra_rvp = ""
     if n_sb > 1 or routing != "ROUTE_NONE":
@@ -194,8 +250,12 @@ def write_hmets(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUT
             write_network(f, n_sb, hru_per_sb, rng, profile, ["FOREST"], ["FOREST"], ["DEFAULT_P"])
         else:
             write_network(f, n_sb, hru_per_sb, rng, profile, ["FOREST", "OPEN"], ["FOREST", "GRASS"], ["DEFAULT_P", "THIN_P"])
-    with open(base + ".rvt", "w") as f:
-        write_gauge(f, *weather(n_days, seed, season_offset))
+    if n_gauges > 1:
+        hmets_rvi_extra += write_gauge_grid(base, n_gauges, n_days, seed, season_offset, _hru_latlon(base + ".rvh"))
+    else:
+        with open(base + ".rvt", "w") as f:
+            write_gauge(f, *weather(n_days, seed, season_offset))
+    _write(base + ".rvi", HMETS_RVI.format(duration=n_days, routing=routing, catchment_route=catchment_route, extra=hmets_rvi_extra))
     _write(base + ".rvc", HMETS_RVC)
     if ensemble_members > 0:
         with open(base + ".rve", "w") as f:
@@ -334,12 +394,11 @@ MONTHLY_TEMP = [-11.4, -7.2, -2.8, 2.8, 8.1, 12.2, 14.4, 13.5, 8.9, 3.4, -4.0, -
 
 
 def write_hbv(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUTE_NONE", catchment_route="TRIANGULAR_UH",
-              single_class=False, name="hbv", season_offset=0):
+              single_class=False, name="hbv", season_offset=0, n_gauges=1):
     """HBV-EC template (BASELINE config 2): multi-class, with glacier HRUs unless single_class. Returns the input base path."""
     os.makedirs(dirpath, exist_ok=True)
     base = os.path.join(dirpath, name)
     rng = np.random.RandomState(seed)
-    _write(base + ".rvi", HBV_RVI.format(duration=n_days, routing=routing, catchment_route=catchment_route, extra=""))
     profile = "NONE" if routing == "ROUTE_NONE" else "CHN"
     extra_rvp = ""
     if n_sb > 1 or routing != "ROUTE_NONE":
@@ -358,11 +417,16 @@ def write_hbv(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUTE_
             tc = rng.uniform(1.2, 3.2)
             f.write("  %d, %.6f, %.6f\n" % (p, tc, 0.5 * tc))
         f.write(":EndSubBasinProperties\n")
-    with open(base + ".rvt", "w") as f:
-        gx = "  :RainCorrection 1.141608\n  :SnowCorrection 1.024278\n"
-        gx += "  :MonthlyAveEvaporation, " + ", ".join("%.3f" % v for v in MONTHLY_EVAP) + ",\n"
-        gx += "  :MonthlyAveTemperature, " + ", ".join("%.1f" % v for v in MONTHLY_TEMP) + ",\n"
-        write_gauge(f, *weather(n_days, seed, season_offset), extra=gx)
+    gx = "  :RainCorrection 1.141608\n  :SnowCorrection 1.024278\n"
+    gx += "  :MonthlyAveEvaporation, " + ", ".join("%.3f" % v for v in MONTHLY_EVAP) + ",\n"
+    gx += "  :MonthlyAveTemperature, " + ", ".join("%.1f" % v for v in MONTHLY_TEMP) + ",\n"
+    extra_rvi = ""
+    if n_gauges > 1:
+        extra_rvi = write_gauge_grid(base, n_gauges, n_days, seed, season_offset, _hru_latlon(base + ".rvh"), extra=gx)
+    else:
+        with open(base + ".rvt", "w") as f:
+            write_gauge(f, *weather(n_days, seed, season_offset), extra=gx)
+    _write(base + ".rvi", HBV_RVI.format(duration=n_days, routing=routing, catchment_route=catchment_route, extra=extra_rvi))
     _write(base + ".rvc", HBV_RVC)
     return base
 

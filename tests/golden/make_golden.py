@@ -36,6 +36,8 @@ if hasattr(synth, "write_hbv"):
     CASES["hbv_single"] = dict(kind="hbv", n_sb=1, hru_per_sb=1, n_days=730, seed=4)
     CASES["hbv_muskingum"] = dict(kind="hbv", n_sb=15, hru_per_sb=6, n_days=400, seed=6, routing="ROUTE_MUSKINGUM")
     CASES["hbv_storagecoeff"] = dict(kind="hbv", n_sb=7, hru_per_sb=3, n_days=200, seed=8, routing="ROUTE_STORAGECOEFF")
+    # sparse multi-station interpolation (INTERP_FROM_FILE: 4 nearest of 9 stations per HRU) = the gridded-forcing gather
+    CASES["hbv_gauges9"] = dict(kind="hbv", n_sb=5, hru_per_sb=4, n_days=150, seed=12, routing="ROUTE_MUSKINGUM", n_gauges=9)
 if hasattr(synth, "write_gr4j"):
     WRITERS["gr4j"] = synth.write_gr4j
     CASES["gr4j_single"] = dict(kind="gr4j", n_sb=1, hru_per_sb=1, n_days=730, seed=9)

@@ -243,3 +243,10 @@ def test_monte_carlo_ensemble_matches_reference_member_and_shards():
     shard.apply_ensemble(2)
     shard.run(n)
     assert np.array_equal(shard.download_state(), st[2:4])
+
+
+def test_sparse_station_interpolation(tmp_path):
+    """K3: every HRU gathers its 4 nearest of 25 stations (CSR weights from an INTERP_FROM_FILE table) -- the sparse weighted
+    sums of a gridded forcing -- with elevation-dependent corrections from the weighted station elevations."""
+    _gpu_vs_oracle(tmp_path, "hbv", 120, members=2, n_sb=9, hru_per_sb=17, seed=31, routing="ROUTE_MUSKINGUM", n_gauges=25)
+    _gpu_vs_oracle(tmp_path / "b", "hmets", 120, n_sb=3, hru_per_sb=50, seed=32, n_gauges=16)
