@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RVN_ABI_VERSION 3
+#define RVN_ABI_VERSION 4
 #define RVN_DOESNT_EXIST (-1)
 #define RVN_CONV_STORES 50   /* MAX_CONVOL_STORES, reference src/RavenInclude.h / Convolution.cpp:17 */
 #define RVN_MAX_CONN 24      /* max connections of a non-convolution process (Precipitation: 13..19) */
@@ -104,6 +104,12 @@ typedef enum { RVN_PET_DATA = 0, RVN_PET_FROMMONTHLY, RVN_PET_CONSTANT, RVN_PET_
 typedef enum { RVN_OROCORR_NONE = 0, RVN_OROCORR_SIMPLELAPSE, RVN_OROCORR_HBV } rvn_orocorr;
 typedef enum { RVN_ROUTE_NONE = 0, RVN_ROUTE_MUSKINGUM, RVN_ROUTE_MUSKINGUM_CUNGE, RVN_ROUTE_STORAGECOEFF,
                RVN_ROUTE_PLUG_FLOW, RVN_ROUTE_DIFFUSIVE_WAVE } rvn_routing;
+/* forcing perturbations of the EnKF members (reference forcing_type / adjustment, src/RavenInclude.h; applied by
+ * CModel::ApplyForcingPerturbation, src/Model.cpp:2856-2879, in the order the reference calls it from
+ * UpdateHRUForcingFunctions: TEMP_AVE after the temperature lapse, then PRECIP, RAINFALL, SNOWFALL after the precipitation lapse) */
+typedef enum { RVN_PF_PRECIP = 0, RVN_PF_RAINFALL, RVN_PF_SNOWFALL, RVN_PF_TEMP_AVE } rvn_pert_forcing;
+typedef enum { RVN_ADJ_ADDITIVE = 0, RVN_ADJ_MULTIPLICATIVE, RVN_ADJ_REPLACE } rvn_adjustment;
+#define RVN_MAX_PERT 8
 typedef enum { RVN_CONVOL_GR4J_1 = 0, RVN_CONVOL_GR4J_2, RVN_CONVOL_GAMMA, RVN_CONVOL_GAMMA_2 } rvn_convol_type;
 
 /* ---- per-member parameter table ------------------------------------------------------------------
@@ -266,7 +272,26 @@ typedef struct rvn_model_desc {
   int32_t nEtRows, pad2_;
   const double *et_radia;
   const int32_t *et_row;      /* [nSteps] */
+  /* forcing perturbations (EnKF members; 0 for every other model).  One sample per perturbation, member and DAY (the
+   * reference draws nStepsPerDay samples at the start of a day, src/Model.cpp:2829-2847; steps here are daily or longer):
+   * pert_eps[member][step][pert].  pert_mask[pert][hru] = 1 where the HRU belongs to the perturbation's HRU group
+   * (NULL = every perturbation applies to every HRU). */
+  int32_t nPert, pad3_;
+  const int32_t *pert_forcing;  /* [nPert] rvn_pert_forcing */
+  const int32_t *pert_adj;      /* [nPert] rvn_adjustment */
+  const uint8_t *pert_mask;     /* [nPert][nHRU] or NULL */
+  const double  *pert_eps;      /* [nMembers][nSteps][nPert] */
 } rvn_model_desc;
+
+/* ---- EnKF state matrix (reference CEnKFEnsemble::AddToStateMatrix / UpdateFromStateMatrix, src/EnKF.cpp:602-747) ------
+ * One record per row of the reference's _state_matrix[e][...], in the reference's row order. */
+typedef enum {
+  RVN_XROW_HRU_SV = 0,   /* index = HRU k, sub = state-variable index i        : pHRU->GetStateVarValue(i)   */
+  RVN_XROW_QIN_HIST,     /* index = subbasin p, sub = n                          : _aQinHist[n]               */
+  RVN_XROW_QOUT,         /* index = subbasin p, sub = segment                    : _aQout[seg]                */
+  RVN_XROW_QOUT_LAST     /* index = subbasin p                                   : _QoutLast                  */
+} rvn_xrow_kind;
+typedef struct rvn_enkf_row { int32_t kind, index, sub, pad_; } rvn_enkf_row;
 
 typedef struct rvn_gpu_model rvn_gpu_model; /* opaque */
 
@@ -320,6 +345,28 @@ int rvn_gpu_download_forcings(rvn_gpu_model *m, double *forc, int member0, int n
 /* area-weighted watershed average of every state variable (reference CModel::GetAvgStateVar,
  * src/Model.cpp:1159-1174): out[member][NS] */
 int rvn_gpu_avg_state(rvn_gpu_model *m, double *out, int member0, int nmembers);
+
+/* replace the forcing-perturbation samples of a member range (next assimilation window): eps[nmembers][nSteps][nPert] */
+int rvn_gpu_upload_perturbations(rvn_gpu_model *m, const double *eps, int member0, int nmembers);
+
+/* ---- EnKF analysis on the device (reference CEnKFEnsemble::AssimilationCalcs, src/EnKF.cpp:478-596) -------------------
+ * rvn_gpu_enkf_configure  declares the M rows of the state matrix.
+ * rvn_gpu_enkf_pack       writes this handle's members into Xlocal[nMembers][M] (DEVICE memory) = AddToStateMatrix.
+ * rvn_gpu_enkf_update     given the state rows of ALL N ensemble members Xall[N][M] (DEVICE memory; on several GPUs the
+ *                         all-gather of every rank's Xlocal, members in global order) and the N x N matrix Z = HA'.inv(P).(D-HA)
+ *                         (HOST memory, row-major, computed from the N x Nobs observation matrices by the host layer),
+ *                         computes for the local members e = member0_global .. +nMembers-1
+ *                             Xa[e][k] = X[e][k] + (1/(N-1)) * sum_i (X[i][k] - mean_i X[.][k]) * Z[i][e]
+ *                         with the reference's summation order (i ascending, no FMA), writes Xa back into the caller's
+ *                         Xall rows of the local members, and stores max(Xa,0) into the model state = UpdateFromStateMatrix. */
+int rvn_gpu_enkf_configure(rvn_gpu_model *m, const rvn_enkf_row *rows, int64_t nrows);
+int rvn_gpu_enkf_pack(rvn_gpu_model *m, double *Xlocal_dev);
+int rvn_gpu_enkf_update(rvn_gpu_model *m, double *Xall_dev, const double *Z_host, int N, int member0_global);
+/* the same two steps with HOST matrices (single-GPU callers, tests): X[nMembers][M] out / Xall[N][M] in-out */
+int rvn_gpu_enkf_pack_host(rvn_gpu_model *m, double *Xlocal_host);
+int rvn_gpu_enkf_update_host(rvn_gpu_model *m, double *Xall_host, const double *Z_host, int N, int member0_global);
+/* CUDA-event time [ms] of the last rvn_gpu_enkf_update's update kernel */
+int rvn_gpu_enkf_last_ms(rvn_gpu_model *m, double *update_ms);
 
 /* raw device pointers for zero-copy callers that already live on the GPU (bench, NCCL EnKF gather) */
 int rvn_gpu_device_state_ptr(rvn_gpu_model *m, void **dptr, int64_t *member_stride, int64_t *sv_stride);

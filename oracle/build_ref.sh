@@ -22,4 +22,8 @@ if [ -f "$HERE/ref_dump.cpp" ]; then
   g++ -std=c++11 -O2 -w -D_BMI_LIBRARY_ -I"$SRC" "$HERE/ref_dump.cpp" -o "$OUT/ref_dump" \
       -L"$OUT" -lravenref -Wl,-rpath,'$ORIGIN'
 fi
+if [ -f "$HERE/ref_enkf_dump.cpp" ]; then
+  g++ -std=c++11 -O2 -w -D_BMI_LIBRARY_ -I"$SRC" "$HERE/ref_enkf_dump.cpp" -o "$OUT/ref_enkf_dump" \
+      -L"$OUT" -lravenref -Wl,-rpath,'$ORIGIN'
+fi
 echo "build_ref: ok -> $OUT"

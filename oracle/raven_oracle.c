@@ -123,7 +123,59 @@ static int is_water_storage(int t) {
 /* CModel::UpdateHRUForcingFunctions, src/UpdateForcings.cpp:30-668, for gauge-based inputs and the
  * option subset {RAINSNOW_DATA|DINGMAN|HBV|UBCWM|THRESHOLD, POTMELT_*, PET_DATA|FROMMONTHLY|CONSTANT|NONE,
  * OROCORR_NONE|SIMPLELAPSE|HBV}, daily-or-longer... (timestep>=1 => subdaily_corr = 1, :949-958). */
-static void update_forcings(const rvn_model_desc *d, const double *ptab, int k, int step, const double *phi_old, const int *iSV, double *F) {
+/* CModel::ApplyForcingPerturbation, src/Model.cpp:2856-2879, with CHydroUnit::AdjustHRUForcing (src/HydroUnits.cpp:461-509)
+ * and AdjustDailyHRUForcings (:513-538).  Daily-or-longer steps: nStepsPerDay = 1, nn = 0, every step starts a day. */
+static void apply_forcing_perturbation(const rvn_model_desc *d, int ftype, int member, int k, int step, double *F) {
+  for (int i = 0; i < d->nPert; i++) {
+    if (d->pert_forcing[i] != ftype) continue;
+    if (d->pert_mask != NULL && !d->pert_mask[(size_t)i * d->nHRU + k]) continue; /* (kk==DOESNT_EXIST) || IsInGroup(k) */
+    const int nStepsPerDay = 1;
+    const double *eps = &d->pert_eps[((size_t)member * d->nSteps + step) * d->nPert + i]; /* eps[n], n < nStepsPerDay */
+    const double epsilon = eps[0];
+    const int adj = d->pert_adj[i];
+    /* AdjustHRUForcing */
+    if (ftype == RVN_PF_PRECIP) {
+      if (adj == RVN_ADJ_MULTIPLICATIVE) F[RVN_F_PRECIP] *= epsilon;
+      else if (adj == RVN_ADJ_ADDITIVE) F[RVN_F_PRECIP] += epsilon;
+      else if (adj == RVN_ADJ_REPLACE) F[RVN_F_PRECIP] = epsilon;
+      if (0.0 > F[RVN_F_PRECIP]) F[RVN_F_PRECIP] = 0.0;
+    } else if (ftype == RVN_PF_RAINFALL) {
+      double sf = F[RVN_F_SNOW_FRAC], Po = F[RVN_F_PRECIP];
+      if (adj == RVN_ADJ_MULTIPLICATIVE) F[RVN_F_PRECIP] += Po * (1.0 - sf) * (epsilon - 1.0);
+      else if (adj == RVN_ADJ_ADDITIVE) F[RVN_F_PRECIP] += epsilon;
+      else if (adj == RVN_ADJ_REPLACE) F[RVN_F_PRECIP] += epsilon - (1 - sf) * Po;
+      if (0.0 > F[RVN_F_PRECIP]) F[RVN_F_PRECIP] = 0.0;
+      if (F[RVN_F_PRECIP] == 0) F[RVN_F_SNOW_FRAC] = 0;
+      else F[RVN_F_SNOW_FRAC] = F[RVN_F_SNOW_FRAC] * Po / F[RVN_F_PRECIP];
+    } else if (ftype == RVN_PF_SNOWFALL) {
+      double sf = F[RVN_F_SNOW_FRAC], Po = F[RVN_F_PRECIP];
+      if (adj == RVN_ADJ_MULTIPLICATIVE) F[RVN_F_PRECIP] += Po * (sf) * (epsilon - 1.0);
+      else if (adj == RVN_ADJ_ADDITIVE) F[RVN_F_PRECIP] += epsilon;
+      else if (adj == RVN_ADJ_REPLACE) F[RVN_F_PRECIP] += epsilon - (sf)*Po;
+      if (0.0 > F[RVN_F_PRECIP]) F[RVN_F_PRECIP] = 0.0;
+      if (F[RVN_F_PRECIP] == 0) F[RVN_F_SNOW_FRAC] = 0;
+      else F[RVN_F_SNOW_FRAC] = 1.0 - (1.0 - F[RVN_F_SNOW_FRAC]) * Po / F[RVN_F_PRECIP];
+    } else if (ftype == RVN_PF_TEMP_AVE) {
+      if (adj == RVN_ADJ_MULTIPLICATIVE) F[RVN_F_TEMP_AVE] *= epsilon;
+      else if (adj == RVN_ADJ_ADDITIVE) F[RVN_F_TEMP_AVE] += epsilon;
+      else if (adj == RVN_ADJ_REPLACE) F[RVN_F_TEMP_AVE] = epsilon;
+    }
+    /* AdjustDailyHRUForcings (start of day) */
+    if (ftype == RVN_PF_TEMP_AVE) {
+      if (adj == RVN_ADJ_MULTIPLICATIVE) {
+        double adjust = 0;
+        for (int n = 0; n < nStepsPerDay; n++) adjust += eps[n] / nStepsPerDay;
+        F[RVN_F_TEMP_DAILY_MIN] *= adjust; F[RVN_F_TEMP_DAILY_MAX] *= adjust; F[RVN_F_TEMP_DAILY_AVE] *= adjust;
+      } else if (adj == RVN_ADJ_ADDITIVE) {
+        double adjust = 0;
+        for (int n = 0; n < nStepsPerDay; n++) adjust += eps[n] / nStepsPerDay;
+        F[RVN_F_TEMP_DAILY_AVE] += adjust; F[RVN_F_TEMP_DAILY_MIN] += adjust; F[RVN_F_TEMP_DAILY_MAX] += adjust;
+      }
+    }
+  }
+}
+
+static void update_forcings(const rvn_model_desc *d, const double *ptab, int member, int k, int step, const double *phi_old, const int *iSV, double *F) {
   const rvn_time *tt = &d->times[step];
   const int nG = d->nGauges, nS = d->nSteps, mo = tt->month;
   octx c; c.d = d; c.ptab = ptab; c.k = k; c.F = F; c.phi_old = phi_old; memcpy(c.iSV, iSV, sizeof(c.iSV));
@@ -182,6 +234,7 @@ static void update_forcings(const rvn_model_desc *d, const double *ptab, int k, 
       if (d->opt.orocorr_temp != RVN_OROCORR_HBV) temp_month_ave -= lapse * (elev - ref_elev_temp);
     }
   }
+  if (d->nPert > 0) apply_forcing_perturbation(d, RVN_PF_TEMP_AVE, member, k, step, F); /* src/UpdateForcings.cpp:474 */
   F[RVN_F_TEMP_MONTH_AVE] = temp_month_ave; F[RVN_F_PET_MONTH_AVE] = PET_month_ave;
   const double subdaily_corr = 1.0;
   /* CModel::EstimateSnowFraction, src/UpdateForcings.cpp:1068-1197 */
@@ -223,6 +276,11 @@ static void update_forcings(const rvn_model_desc *d, const double *ptab, int k, 
     double lapse_elev = P_G(&c, RVN_G_HBVEC_LAPSE_ELEV), add = 0.0;
     if (elev > lapse_elev) add = (corr_upper - corr) * (elev - lapse_elev);
     F[RVN_F_PRECIP] *= omax(1.0 + corr * (elev - ref_elev_precip) + add, 0.0);
+  }
+  if (d->nPert > 0) { /* src/UpdateForcings.cpp:558-560 */
+    apply_forcing_perturbation(d, RVN_PF_PRECIP, member, k, step, F);
+    apply_forcing_perturbation(d, RVN_PF_RAINFALL, member, k, step, F);
+    apply_forcing_perturbation(d, RVN_PF_SNOWFALL, member, k, step, F);
   }
   if (d->hru_type[k] == RVN_HRU_MASKED_GLACIER) F[RVN_F_PRECIP] = 0;
   /* CModel::EstimatePotentialMelt, src/PotentialMelt.cpp:20-246 */
@@ -759,7 +817,7 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
   for (int s = 0; s < nsteps; s++) {
     const int step = step0 + s;
     /* ---- UpdateHRUForcingFunctions (all HRUs, on the stored state) */
-    for (int k = 0; k < nH; k++) update_forcings(d, c.ptab, k, step, state + (size_t)k * NS, c.iSV, F + (size_t)k * RVN_F_COUNT);
+    for (int k = 0; k < nH; k++) update_forcings(d, c.ptab, member, k, step, state + (size_t)k * NS, c.iSV, F + (size_t)k * RVN_F_COUNT);
     if (forc_rec) memcpy(forc_rec + (size_t)s * nH * RVN_F_COUNT, F, sizeof(double) * (size_t)nH * RVN_F_COUNT);
     /* ---- MassEnergyBalance, ORDERED_SERIES (src/Solvers.cpp:155-251) */
     for (int p = 0; p < NB; p++) { aRouted[p] = 0.0; aQinnew[p] = 0.0; }

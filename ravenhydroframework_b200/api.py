@@ -56,6 +56,13 @@ def engine_lib():
         lib.rvn_gpu_last_run_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         lib.rvn_gpu_kernel_variant.argtypes = [vp, C.c_char_p, i]
         lib.rvn_gpu_emit_static_program.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_int64]
+        lib.rvn_gpu_upload_perturbations.argtypes = [vp, dp, i, i]
+        lib.rvn_gpu_enkf_configure.argtypes = [vp, dp, C.c_int64]
+        lib.rvn_gpu_enkf_pack.argtypes = [vp, dp]
+        lib.rvn_gpu_enkf_update.argtypes = [vp, dp, dp, i, i]
+        lib.rvn_gpu_enkf_pack_host.argtypes = [vp, dp]
+        lib.rvn_gpu_enkf_update_host.argtypes = [vp, dp, dp, i, i]
+        lib.rvn_gpu_enkf_last_ms.argtypes = [vp, C.POINTER(C.c_double)]
         _engine = lib
     return _engine
 
@@ -90,6 +97,15 @@ def host_lib():
         lib.rvh_desc_info.argtypes = [vp, C.POINTER(C.c_int)]
         lib.rvh_ensemble_begin.argtypes = [vp]
         lib.rvh_ensemble_update_model.argtypes = [vp, C.c_int, vp, C.c_int]
+        lib.rvh_enkf_begin.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        lib.rvh_enkf_rows.argtypes = [vp, vp]
+        lib.rvh_enkf_row_name.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
+        lib.rvh_enkf_observations.argtypes = [vp, vp, vp, vp, vp]
+        lib.rvh_enkf_member_eps.argtypes = [vp, C.c_int]
+        lib.rvh_enkf_member_eps.restype = vp
+        lib.rvh_enkf_harvest_outputs.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
+        lib.rvh_enkf_compute_Z.argtypes = [vp, vp, vp]
+        lib.rvh_desc_nseg.argtypes = [vp, vp]
         _host = lib
     return _host
 
@@ -195,6 +211,70 @@ class RavenModel:
         if n < 0:
             raise RavenError(self.lib.rvh_last_error().decode())
         return vals[:n].copy()
+
+    # ---- EnKF (reference CEnKFEnsemble) -------------------------------------------------------------------------------
+    def enkf_begin(self, member0=0, nlocal=None):
+        """CEnsemble::SetRandomSeed + CEnKFEnsemble::Initialize + UpdateModel(e) for e < member0+nlocal: observation noise and the
+        forcing-perturbation samples of the local member block are drawn from the shared rand() stream in the reference's order
+        and written into the flattened descriptor (flatten(nlocal) first).  Returns dict(N, M, Nobs, nPert, nsteps, mode)."""
+        nlocal = self.nMembers if nlocal is None else nlocal
+        assert self.desc and self.nMembers == nlocal, "flatten(nlocal) first"
+        info = (C.c_int * 6)()
+        if self.lib.rvh_enkf_begin(self.h, int(member0), int(nlocal), info):
+            raise RavenError(self.lib.rvh_last_error().decode())
+        self.enkf = dict(N=info[0], M=info[1], Nobs=info[2], nPert=info[3], nsteps=info[4], mode=info[5], member0=member0, nlocal=nlocal)
+        return self.enkf
+
+    def enkf_rows(self):
+        """State-matrix rows [M][4] int32 = (kind, index, sub, 0) in the reference's row order (rvn_enkf_row)."""
+        rows = np.zeros((self.enkf["M"], 4), dtype=np.int32)
+        if self.lib.rvh_enkf_rows(self.h, rows.ctypes.data):
+            raise RavenError(self.lib.rvh_last_error().decode())
+        return rows
+
+    def enkf_row_names(self):
+        buf = C.create_string_buffer(96)
+        out = []
+        for i in range(self.enkf["M"]):
+            self.lib.rvh_enkf_row_name(self.h, i, buf, 96)
+            out.append(buf.value.decode())
+        return out
+
+    def enkf_observations(self):
+        """(obs [N][Nobs] perturbed observations, noise [N][Nobs], basin [Nobs], nn [Nobs])."""
+        N, Nobs = self.enkf["N"], self.enkf["Nobs"]
+        obs, noise = np.zeros((N, Nobs)), np.zeros((N, Nobs))
+        basin, nn = np.zeros(Nobs, dtype=np.int32), np.zeros(Nobs, dtype=np.int32)
+        if self.lib.rvh_enkf_observations(self.h, obs.ctypes.data, noise.ctypes.data, basin.ctypes.data, nn.ctypes.data):
+            raise RavenError(self.lib.rvh_last_error().decode())
+        return obs, noise, basin, nn
+
+    def enkf_member_eps(self, member_local):
+        """Forcing-perturbation samples of a local member [nsteps][nPert] (a copy)."""
+        p = self.lib.rvh_enkf_member_eps(self.h, int(member_local))
+        n = self.nSteps * self.enkf["nPert"]
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)), shape=(n,)).reshape(self.nSteps, self.enkf["nPert"]).copy()
+
+    def enkf_harvest_outputs(self, qout_rec, qout_initial):
+        """CloseTimeStepOps: simulated observations [nmembers][Nobs] from recorded outflows qout_rec [nsteps][nmembers][nSB]."""
+        q = np.ascontiguousarray(qout_rec, dtype=np.float64)
+        q0 = np.ascontiguousarray(qout_initial, dtype=np.float64)
+        nsteps, nmem, _ = q.shape
+        out = np.zeros((nmem, self.enkf["Nobs"]))
+        if self.lib.rvh_enkf_harvest_outputs(self.h, q.ctypes.data, q0.ctypes.data, nsteps, nmem, out.ctypes.data):
+            raise RavenError(self.lib.rvh_last_error().decode())
+        return out
+
+    def enkf_compute_Z(self, out_all):
+        """Host part of AssimilationCalcs: Z [N][N] from the simulated observations of all members; None when no analysis is due."""
+        o = np.ascontiguousarray(out_all, dtype=np.float64)
+        N = self.enkf["N"]
+        assert o.shape == (N, self.enkf["Nobs"])
+        Z = np.zeros((N, N))
+        rc = self.lib.rvh_enkf_compute_Z(self.h, o.ctypes.data, Z.ctypes.data)
+        if rc < 0:
+            raise RavenError(self.lib.rvh_last_error().decode())
+        return Z if rc == 1 else None
 
     def param_dists(self):
         out = []
@@ -338,6 +418,46 @@ class GpuSimulation:
         out = np.empty((nmembers, self.NS))
         self._ck(self.lib.rvn_gpu_avg_state(self.h, out.ctypes.data, member0, nmembers))
         return out
+
+    # ---- EnKF analysis on the device ---------------------------------------------------------------------------------
+    def upload_perturbations(self, eps, member0=0, nmembers=None):
+        e = np.ascontiguousarray(eps, dtype=np.float64)
+        nmembers = self.E - member0 if nmembers is None else nmembers
+        self._ck(self.lib.rvn_gpu_upload_perturbations(self.h, e.ctypes.data, member0, nmembers))
+
+    def enkf_configure(self, rows):
+        r = np.ascontiguousarray(rows, dtype=np.int32)
+        self.enkf_M = r.shape[0]
+        self._ck(self.lib.rvn_gpu_enkf_configure(self.h, r.ctypes.data, r.shape[0]))
+
+    def enkf_pack(self):
+        """AddToStateMatrix for the local members: X [E][M] on the host."""
+        X = np.zeros((self.E, self.enkf_M))
+        self._ck(self.lib.rvn_gpu_enkf_pack_host(self.h, X.ctypes.data))
+        return X
+
+    def enkf_update(self, X_all, Z, member0_global=0):
+        """Analysis update + UpdateFromStateMatrix for the local members; X_all [N][M] host array of ALL members (updated in place
+        for the local rows).  Returns the updated local rows."""
+        X = np.ascontiguousarray(X_all, dtype=np.float64)
+        Zc = np.ascontiguousarray(Z, dtype=np.float64)
+        N = X.shape[0]
+        self._ck(self.lib.rvn_gpu_enkf_update_host(self.h, X.ctypes.data, Zc.ctypes.data, N, int(member0_global)))
+        if X is not X_all:
+            X_all[...] = X
+        return X[member0_global:member0_global + self.E]
+
+    def enkf_pack_device(self, dptr):
+        self._ck(self.lib.rvn_gpu_enkf_pack(self.h, C.c_void_p(int(dptr))))
+
+    def enkf_update_device(self, dptr_all, Z, N, member0_global):
+        Zc = np.ascontiguousarray(Z, dtype=np.float64)
+        self._ck(self.lib.rvn_gpu_enkf_update(self.h, C.c_void_p(int(dptr_all)), Zc.ctypes.data, int(N), int(member0_global)))
+
+    def enkf_last_ms(self):
+        v = C.c_double()
+        self._ck(self.lib.rvn_gpu_enkf_last_ms(self.h, C.byref(v)))
+        return v.value
 
     def kernel_variant(self):
         """'static:<PROGRAM>' or 'interpreter' (which HRU-sweep kernel serves this model)."""

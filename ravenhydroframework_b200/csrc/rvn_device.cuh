@@ -83,5 +83,10 @@ struct DevModel {
   double *rec_qout, *rec_wshed;                    // [rec][member][nSB], [rec][member][4]
   int32_t rec_capacity, rec_flags;
   const DevProgram *prog;
+  // forcing perturbations of the EnKF members (0 = none)
+  int32_t nPert;
+  int32_t pert_forcing[RVN_MAX_PERT], pert_adj[RVN_MAX_PERT];
+  const uint8_t *pert_mask;                        // [nPert][nHp] or NULL
+  const double *pert_eps;                          // [member][nSteps][nPert]
 };
 #endif

@@ -1,0 +1,89 @@
+// rvn_enkf.cuh -- EnKF analysis on the device (reference CEnKFEnsemble, src/EnKF.cpp).
+//
+//   enkf_pack_kernel    AddToStateMatrix       (src/EnKF.cpp:679-747): member state -> row of the state matrix X
+//   enkf_update_kernel  AssimilationCalcs      (src/EnKF.cpp:478-596), the O(M N^2) part:
+//                           A = X - mean(X);  X_delta = (A . Z) * 1/(N-1);  Xa = X + X_delta
+//                       The N x Nobs part (HA, P, the N solves, Z = HA'.MM) is tiny and is done by the host layer
+//                       (host/rvh_enkf.cpp); Z arrives as an N x N matrix.
+//   enkf_unpack_kernel  UpdateFromStateMatrix  (src/EnKF.cpp:602-673): max(Xa, 0) -> member state
+//
+// Layout: X is [member][row] (a member's row is contiguous), exactly the reference's _state_matrix[e][i]; on several GPUs it
+// is the NCCL all-gather of every rank's local member rows, so the gathered buffer needs no transposition.
+// The update kernel gives one thread one state row k (coalesced over k for every member i) and a tile of ET local members;
+// the sum over the N ensemble members runs in ascending i with separate multiply and add (-fmad=false), which is the
+// reference's MatMult order (src/Matrix.cpp:38-49) -> bit-identical X_delta for identical Z.  Bound: HBM/L2 streaming of X
+// (N*M*8 bytes read N_local/ET times) and the FP64 pipe (2*N*M*N_local flop).
+#ifndef RVN_ENKF_CUH
+#define RVN_ENKF_CUH
+#include "rvn_device.cuh"
+
+struct EnkfMap {
+  const rvn_enkf_row *rows;   // [M]
+  long long M;
+  int hist_t;                 // pushes into the basin history rings since they were last in reference order
+};
+
+RVN_DI double *enkf_locate(const DevModel &Mo, const EnkfMap &mp, const int e, const long long r) {
+  const rvn_enkf_row row = mp.rows[r];
+  if (row.kind == RVN_XROW_HRU_SV) return Mo.state + ((size_t)e * Mo.NS + row.sub) * Mo.nHp + row.index;
+  const int p = row.index;
+  if (row.kind == RVN_XROW_QIN_HIST) {
+    const int nQ = Mo.sb_nqin[p];
+    int base = nQ - (mp.hist_t % nQ); if (base == nQ) base = 0;   // same ring arithmetic as struct Ring (rvn_kernels.cuh)
+    int i = base + row.sub; if (i >= nQ) i -= nQ;
+    return Mo.qin + ((size_t)e * Mo.nSB + p) * Mo.max_nqin + i;
+  }
+  if (row.kind == RVN_XROW_QOUT) return Mo.qout + ((size_t)e * Mo.nSB + p) * RVN_MAX_RIVER_SEGS + row.sub;
+  return Mo.scal + ((size_t)e * Mo.nSB + p) * 8 + 0;   // RVN_XROW_QOUT_LAST
+}
+
+__global__ void enkf_pack_kernel(const __grid_constant__ DevModel Mo, const EnkfMap mp, double *__restrict__ X) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = blockIdx.y;
+  if (r >= mp.M) return;
+  X[(size_t)e * mp.M + r] = *enkf_locate(Mo, mp, e, r);
+}
+// X points at the first LOCAL member's row
+__global__ void enkf_unpack_kernel(const __grid_constant__ DevModel Mo, const EnkfMap mp, const double *__restrict__ X) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = blockIdx.y;
+  if (r >= mp.M) return;
+  const double v = X[(size_t)e * mp.M + r];
+  *enkf_locate(Mo, mp, e, r) = (v >= 0.0) ? v : 0.0;   // max(_state_matrix[e][ii], 0.0)
+}
+
+#define RVN_ENKF_BS 128
+#define RVN_ENKF_ET 8
+// Xall [N][M] in; Xa [nLocal][M] out (separate buffer: every CTA reads all members' rows).  Zt = Z restricted to the local
+// columns, stored [N][nLocalPad] with nLocalPad a multiple of ET (padding columns zero).
+__global__ void __launch_bounds__(RVN_ENKF_BS) enkf_update_kernel(const double *__restrict__ Xall, const double *__restrict__ Zt, double *__restrict__ Xa,
+                                                                 const long long M, const int N, const int e0, const int nLocal, const int nLocalPad) {
+  extern __shared__ double s_z[];   // [N][ET]
+  const int tile = blockIdx.y;
+  for (int i = threadIdx.x; i < N * RVN_ENKF_ET; i += RVN_ENKF_BS) {
+    const int row = i / RVN_ENKF_ET, col = i - row * RVN_ENKF_ET;
+    s_z[i] = Zt[(size_t)row * nLocalPad + tile * RVN_ENKF_ET + col];
+  }
+  __syncthreads();
+  const long long k = (long long)blockIdx.x * RVN_ENKF_BS + threadIdx.x;
+  if (k >= M) return;
+  // A = X - 1/N*(X*e_N1)*e_1N : Xmean accumulates X[i][k]/N in member order (src/EnKF.cpp:539-546)
+  double Xmean = 0.0;
+  for (int i = 0; i < N; i++) Xmean += Xall[(size_t)i * M + k] / N;
+  double acc[RVN_ENKF_ET];
+#pragma unroll
+  for (int c = 0; c < RVN_ENKF_ET; c++) acc[c] = 0.0;
+  for (int i = 0; i < N; i++) {
+    const double a = Xall[(size_t)i * M + k] - Xmean;
+    const double *z = s_z + i * RVN_ENKF_ET;
+#pragma unroll
+    for (int c = 0; c < RVN_ENKF_ET; c++) acc[c] += a * z[c];   // MatMult(A,Z,...): C[n][p] += A[n][m]*B[m][p]
+  }
+  const double scale = 1.0 / (N - 1);
+#pragma unroll
+  for (int c = 0; c < RVN_ENKF_ET; c++) {
+    const int el = tile * RVN_ENKF_ET + c;
+    if (el < nLocal) Xa[(size_t)el * M + k] = Xall[(size_t)(e0 + el) * M + k] + acc[c] * scale;   // ScalarMatMult, MatAdd
+  }
+}
+#endif

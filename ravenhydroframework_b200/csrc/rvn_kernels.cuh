@@ -103,8 +103,49 @@ struct StatProc {
 // ------------------------------------------------------------------------------------------------
 // forcing derivation for one HRU (restates CModel::UpdateHRUForcingFunctions for gauge-based input)
 // ------------------------------------------------------------------------------------------------
+// CModel::ApplyForcingPerturbation (src/Model.cpp:2856-2879) for forcing type `ftype`: CHydroUnit::AdjustHRUForcing
+// (src/HydroUnits.cpp:461-509) followed, at the start of a day (every step of a daily model), by AdjustDailyHRUForcings
+// (:513-538).  One sample per perturbation and day: eps[nn] = eps[0] and the daily mean adjustment 0.0 + eps/1 = eps.
+RVN_DI void apply_perturbations(double *F, const DevModel &M, const int ftype, const int e, const int k, const int step) {
+  for (int i = 0; i < M.nPert; i++) {
+    if (M.pert_forcing[i] != ftype) continue;
+    if (M.pert_mask != nullptr && M.pert_mask[(size_t)i * M.nHp + k] == 0) continue;
+    const double eps = M.pert_eps[((size_t)e * M.nSteps + step) * M.nPert + i];
+    const int adj = M.pert_adj[i];
+    if (ftype == RVN_PF_PRECIP) {
+      if (adj == RVN_ADJ_MULTIPLICATIVE) F[RVN_F_PRECIP] *= eps;
+      else if (adj == RVN_ADJ_ADDITIVE) F[RVN_F_PRECIP] += eps;
+      else F[RVN_F_PRECIP] = eps;
+      if (0.0 > F[RVN_F_PRECIP]) F[RVN_F_PRECIP] = 0.0;   // upperswap
+    } else if (ftype == RVN_PF_RAINFALL) {
+      const double sf = F[RVN_F_SNOW_FRAC], Po = F[RVN_F_PRECIP];
+      if (adj == RVN_ADJ_MULTIPLICATIVE) F[RVN_F_PRECIP] += Po * (1.0 - sf) * (eps - 1.0);
+      else if (adj == RVN_ADJ_ADDITIVE) F[RVN_F_PRECIP] += eps;
+      else F[RVN_F_PRECIP] += eps - (1 - sf) * Po;
+      if (0.0 > F[RVN_F_PRECIP]) F[RVN_F_PRECIP] = 0.0;
+      if (F[RVN_F_PRECIP] == 0) F[RVN_F_SNOW_FRAC] = 0;
+      else F[RVN_F_SNOW_FRAC] = F[RVN_F_SNOW_FRAC] * Po / F[RVN_F_PRECIP];
+    } else if (ftype == RVN_PF_SNOWFALL) {
+      const double sf = F[RVN_F_SNOW_FRAC], Po = F[RVN_F_PRECIP];
+      if (adj == RVN_ADJ_MULTIPLICATIVE) F[RVN_F_PRECIP] += Po * (sf) * (eps - 1.0);
+      else if (adj == RVN_ADJ_ADDITIVE) F[RVN_F_PRECIP] += eps;
+      else F[RVN_F_PRECIP] += eps - (sf)*Po;
+      if (0.0 > F[RVN_F_PRECIP]) F[RVN_F_PRECIP] = 0.0;
+      if (F[RVN_F_PRECIP] == 0) F[RVN_F_SNOW_FRAC] = 0;
+      else F[RVN_F_SNOW_FRAC] = 1.0 - (1.0 - F[RVN_F_SNOW_FRAC]) * Po / F[RVN_F_PRECIP];
+    } else if (ftype == RVN_PF_TEMP_AVE) {
+      if (adj == RVN_ADJ_MULTIPLICATIVE) F[RVN_F_TEMP_AVE] *= eps;
+      else if (adj == RVN_ADJ_ADDITIVE) F[RVN_F_TEMP_AVE] += eps;
+      else F[RVN_F_TEMP_AVE] = eps;
+      const double adjust = 0.0 + eps / 1;
+      if (adj == RVN_ADJ_MULTIPLICATIVE) { F[RVN_F_TEMP_DAILY_MIN] *= adjust; F[RVN_F_TEMP_DAILY_MAX] *= adjust; F[RVN_F_TEMP_DAILY_AVE] *= adjust; }
+      else if (adj == RVN_ADJ_ADDITIVE) { F[RVN_F_TEMP_DAILY_AVE] += adjust; F[RVN_F_TEMP_DAILY_MIN] += adjust; F[RVN_F_TEMP_DAILY_MAX] += adjust; }
+    }
+  }
+}
+
 template <class C>
-RVN_DI void compute_forcings(C &c, const DevModel &M, int k, int step, int sb) {
+RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, int sb) {
   const rvn_options &opt = c.opt();
   const rvn_time tt = M.times[step];
   const int nG = M.nGauges, mo = tt.month;
@@ -166,6 +207,7 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int k, int step, int sb) {
       if (opt.orocorr_temp != RVN_OROCORR_HBV) temp_month_ave -= lapse * (elev - ref_elev_temp);
     }
   }
+  if (M.nPert > 0) apply_perturbations(F, M, RVN_PF_TEMP_AVE, e, k, step);   // src/UpdateForcings.cpp:474
   F[RVN_F_TEMP_MONTH_AVE] = temp_month_ave; F[RVN_F_PET_MONTH_AVE] = PET_month_ave;
   const double subdaily_corr = 1.0;  // CalculateSubDailyCorrection: timestep>=1 (src/UpdateForcings.cpp:949-958)
   {  // CModel::EstimateSnowFraction  src/UpdateForcings.cpp:1068-1197
@@ -207,6 +249,11 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int k, int step, int sb) {
     double lapse_elev = c.G(RVN_G_HBVEC_LAPSE_ELEV), add = 0.0;
     if (elev > lapse_elev) add = (corr_upper - corr) * (elev - lapse_elev);
     F[RVN_F_PRECIP] *= dmax(1.0 + corr * (elev - ref_elev_precip) + add, 0.0);
+  }
+  if (M.nPert > 0) {   // src/UpdateForcings.cpp:558-560
+    apply_perturbations(F, M, RVN_PF_PRECIP, e, k, step);
+    apply_perturbations(F, M, RVN_PF_RAINFALL, e, k, step);
+    apply_perturbations(F, M, RVN_PF_SNOWFALL, e, k, step);
   }
   if (c.type == RVN_HRU_MASKED_GLACIER) F[RVN_F_PRECIP] = 0;
   {  // CModel::EstimatePotentialMelt  src/PotentialMelt.cpp:20-246
@@ -606,7 +653,7 @@ __global__ void __launch_bounds__(RVN_BS, RVN_STATIC_MIN_BLOCKS) hru_sweep_stati
   __syncthreads();   // parameter row staged
   load_canopy(c, M, step);
   // ---- forcings (on the stored state)
-  if (enabled) compute_forcings(c, M, k, step, sb);
+  if (enabled) compute_forcings(c, M, e, k, step, sb);
   else {
 #pragma unroll
     for (int f = 0; f < RVN_F_COUNT; f++) c.F[f] = 0.0;
@@ -674,7 +721,7 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
   c.old_snow_depth = (P->iSV[RVN_SV_SNOW_DEPTH] >= 0) ? c.SV(P->iSV[RVN_SV_SNOW_DEPTH]) : 0.0;
   c.old_snow_temp = (P->iSV[RVN_SV_SNOW_TEMP] >= 0) ? c.SV(P->iSV[RVN_SV_SNOW_TEMP]) : 0.0;
   load_canopy(c, M, step);
-  if (enabled) compute_forcings(c, M, k, step, sb);
+  if (enabled) compute_forcings(c, M, e, k, step, sb);
   else { for (int f = 0; f < RVN_F_COUNT; f++) c.F[f] = 0.0; }
   if (enabled) reboot_diagnostics(c);
   const bool unit_dt = (c.tstep == 1.0);

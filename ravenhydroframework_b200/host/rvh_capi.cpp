@@ -61,6 +61,78 @@ int rvh_ensemble_update_model(rvh_model *h, int e, double *values, int nmax) {
   return n;
   RVH_CATCH(-1)
 }
+// ---- EnKF (CEnKFEnsemble).  rvh_enkf_begin = SetRandomSeed + Initialize + UpdateModel(e) for e = 0 .. member0+nlocal-1: the
+// observation noise and the forcing-perturbation samples of the local member block [member0, member0+nlocal) come out of the
+// one shared rand() stream at the positions the reference's member loop would use.  The model must have been flattened for
+// nlocal members; the samples land in the descriptor's pert_eps table (rvn_gpu_create / rvn_gpu_upload_perturbations).
+// info[6] = {N members, M state rows, Nobs datapoints, nPert, window steps, EnKF mode}
+static CEnKFEnsemble *enkf_of(rvh_model *h) {
+  CEnKFEnsemble *en = dynamic_cast<CEnKFEnsemble *>(h->pEnsemble);
+  if (!en) throw RavenError("rvh_enkf: the model is not an ENSEMBLE_ENKF model or rvh_enkf_begin was not called");
+  return en;
+}
+int rvh_enkf_begin(rvh_model *h, int member0, int nlocal, int *info) {
+  RVH_TRY
+  if (h->Options.ensemble != ENSEMBLE_ENKF) throw RavenError("rvh_enkf_begin: :EnsembleMode is not ENSEMBLE_ENKF");
+  delete h->pEnsemble;
+  h->pEnsemble = CreateEnsemble(h->pModel, h->Options);
+  CEnKFEnsemble *en = enkf_of(h);
+  if (member0 < 0 || nlocal < 1 || member0 + nlocal > en->GetNumMembers()) throw RavenError("rvh_enkf_begin: bad member block");
+  en->SetLocalMembers(member0, nlocal);
+  en->Initialize(h->pModel, h->Options);
+  for (int e = 0; e < member0 + nlocal; e++) en->UpdateModel(h->pModel, h->Options, e);
+  info[0] = en->GetNumMembers(); info[1] = en->GetNumStateVars(); info[2] = en->GetNumObsDatapoints();
+  info[3] = h->pModel->GetNumForcingPerturbations(); info[4] = (int)((h->Options.duration - TIME_CORRECTION) / h->Options.timestep) + 1;
+  info[5] = (int)en->GetEnKFMode();
+  return 0;
+  RVH_CATCH(-1)
+}
+int rvh_enkf_rows(rvh_model *h, rvn_enkf_row *rows) {
+  RVH_TRY
+  const std::vector<rvn_enkf_row> &r = enkf_of(h)->GetStateRows();
+  memcpy(rows, r.data(), r.size() * sizeof(rvn_enkf_row));
+  return 0;
+  RVH_CATCH(-1)
+}
+int rvh_enkf_row_name(rvh_model *h, int i, char *buf, int buflen) {
+  RVH_TRY
+  snprintf(buf, buflen, "%s", enkf_of(h)->GetStateName(i).c_str());
+  return 0;
+  RVH_CATCH(-1)
+}
+int rvh_enkf_observations(rvh_model *h, double *obs, double *noise, int32_t *basin, int32_t *nn) {
+  RVH_TRY
+  const CEnKFEnsemble *en = enkf_of(h);
+  if (obs) memcpy(obs, en->ObsMatrix().data(), en->ObsMatrix().size() * 8);
+  if (noise) memcpy(noise, en->NoiseMatrix().data(), en->NoiseMatrix().size() * 8);
+  for (int j = 0; j < en->GetNumObsDatapoints(); j++) { if (basin) basin[j] = en->ObsBasins()[j]; if (nn) nn[j] = en->ObsTimeIndices()[j]; }
+  return 0;
+  RVH_CATCH(-1)
+}
+const double *rvh_enkf_member_eps(rvh_model *h, int member_local) { return h->pModel->MemberPerturbations(member_local); }
+// qout_rec[nsteps][nmembers][nSB] (layout of rvn_gpu_download_hydrographs), qout_initial[nSB]; out[nmembers][Nobs]
+int rvh_enkf_harvest_outputs(rvh_model *h, const double *qout_rec, const double *qout_initial, int nsteps, int nmembers, double *out) {
+  RVH_TRY
+  const CEnKFEnsemble *en = enkf_of(h);
+  const int nSB = h->pModel->GetNumSubBasins(), Nobs = en->GetNumObsDatapoints();
+  std::vector<double> one((size_t)nsteps * nSB);
+  for (int e = 0; e < nmembers; e++) {
+    for (int n = 0; n < nsteps; n++) memcpy(&one[(size_t)n * nSB], qout_rec + ((size_t)n * nmembers + e) * nSB, (size_t)nSB * 8);
+    en->HarvestOutputs(one.data(), qout_initial, nSB, h->Options.timestep, out + (size_t)e * Nobs);
+  }
+  return 0;
+  RVH_CATCH(-1)
+}
+// out_all[N][Nobs] -> Z[N][N]; returns 1 when an analysis is due, 0 when there are no observations (Z = 0)
+int rvh_enkf_compute_Z(rvh_model *h, const double *out_all, double *Z) {
+  RVH_TRY
+  const CEnKFEnsemble *en = enkf_of(h);
+  std::vector<double> z;
+  const bool due = en->AssimilationCalcs(out_all, z);
+  memcpy(Z, z.data(), z.size() * 8);
+  return due ? 1 : 0;
+  RVH_CATCH(-1)
+}
 const rvn_model_desc *rvh_model_flatten(rvh_model *h, int nMembers) {
   RVH_TRY
   return h->pModel->Flatten(h->Options, nMembers);
@@ -80,6 +152,7 @@ int rvh_desc_sv_table(const rvn_model_desc *d, int32_t *type, int32_t *layer) {
   for (int i = 0; i < d->NS; i++) { type[i] = d->sv_type[i]; layer[i] = d->sv_layer[i]; }
   return 0;
 }
+int rvh_desc_nseg(const rvn_model_desc *d, int32_t *nseg) { for (int p = 0; p < d->nSB; p++) nseg[p] = d->sb_nseg[p]; return 0; }
 int rvh_desc_order(const rvn_model_desc *d, int32_t *order) { for (int p = 0; p < d->nSB; p++) order[p] = d->sb_order[p]; return 0; }
 int rvh_desc_hru_area(const rvn_model_desc *d, double *area) { for (int k = 0; k < d->nHRU; k++) area[k] = d->hru_area[k]; return 0; }
 // resolved class parameter of HRU k as the hot path will see it; kind = "G" | "LU" | "VEG" | "SOIL<m>"

@@ -55,12 +55,235 @@ void CMonteCarloEnsemble::UpdateModel(CModel *pModel, optStruct &Options, int e)
   // the reference re-reads the .rvc here: every member starts from the same initial state (uploaded once per member by the caller)
 }
 
+// ---------------------------------------------------------------------------------------------------------------- EnKF
+CEnKFEnsemble::CEnKFEnsemble(int num_members, const optStruct &Options)
+    : CEnsemble(num_members, Options), _EnKF_mode(ENKF_UNSPECIFIED), _window_size(1), _nTimeSteps(0), _nObsDatapoints(0), _member0(0), _nLocal(num_members) {
+  _type = ENSEMBLE_ENKF;
+}
+void CEnKFEnsemble::AddObsPerturbation(sv_type type, int distrib, const double *distpars, adjustment adj) {
+  obs_perturb p; p.state = type; p.distribution = distrib; p.kk = DOESNT_EXIST; p.adj_type = adj;
+  for (int i = 0; i < 3; i++) p.distpar[i] = distpars[i];
+  _pObsPerturbations.push_back(p);
+}
+void CEnKFEnsemble::AddAssimilationState(sv_type sv, int lay, int assim_groupID, bool is_streamflow) {
+  assim_state a; a.sv = sv; a.layer = lay; a.group = assim_groupID; a.is_streamflow = is_streamflow;
+  _aAssim.push_back(a);
+}
+void CEnKFEnsemble::Initialize(const CModel *pModel, const optStruct &Options) {   // src/EnKF.cpp:197-418
+  ExitGracefullyIf(_nMembers <= 1, "CEnKFEnsemble::Initialize: number of EnKF ensemble members must be >1");
+  const bool forecast = (_EnKF_mode == ENKF_FORECAST) || (_EnKF_mode == ENKF_OPEN_FORECAST);
+  ExitGracefullyIf((pModel->GetNumForcingPerturbations() == 0) && !forecast,
+                   "CEnKFEnsemble::Initialize: at least one forcing perturbation must be set using :ForcingPerturbation command");
+  ExitGracefullyIf(_aAssim.empty() && !forecast, "CEnKFEnsemble::Initialize: at least one assimilated state must be set in :ForcingPerturbation command");
+  // rows of the state matrix, in the order of AddToStateMatrix / UpdateFromStateMatrix (:602-747)
+  _rows.clear(); _state_names.clear();
+  for (size_t i = 0; i < _aAssim.size(); i++) {
+    const assim_state &a = _aAssim[i];
+    if (a.is_streamflow) {
+      const CSubbasinGroup &G = pModel->sb_groups[a.group];
+      for (size_t pp = 0; pp < G.sb.size(); pp++) {
+        const int p = G.sb[pp];
+        const CSubBasin *pBasin = pModel->GetSubBasin(p);
+        for (int n = 0; n < pBasin->GetInflowHistorySize(); n++) { rvn_enkf_row r = {RVN_XROW_QIN_HIST, p, n, 0}; _rows.push_back(r); _state_names.push_back("inflow_" + std::to_string(pp) + "_" + std::to_string(n)); }
+        for (int n = 0; n < pBasin->GetNumSegments(); n++) { rvn_enkf_row r = {RVN_XROW_QOUT, p, n, 0}; _rows.push_back(r); _state_names.push_back("outflow_" + std::to_string(pp) + "_" + std::to_string(n)); }
+        rvn_enkf_row r = {RVN_XROW_QOUT_LAST, p, 0, 0}; _rows.push_back(r); _state_names.push_back("outflowlast_" + std::to_string(pp));
+      }
+    } else {
+      const CHRUGroup &G = pModel->hru_groups[a.group];
+      const int iii = pModel->GetStateVarIndex(a.sv, a.layer);
+      for (size_t n = 0; n < G.hru.size(); n++) {
+        rvn_enkf_row r = {RVN_XROW_HRU_SV, G.hru[n], iii, 0}; _rows.push_back(r);
+        _state_names.push_back(pModel->GetStateVarName(iii) + "_" + std::to_string(pModel->GetHydroUnit(G.hru[n])->ID));
+      }
+    }
+  }
+  // observations available in the data window
+  _nTimeSteps = (int)(floor((Options.duration + TIME_CORRECTION) / Options.timestep));
+  _window_size = (_window_size <= _nTimeSteps) ? _window_size : _nTimeSteps;
+  std::vector<int> aObsIndices;
+  _obs_basin.clear(); _obs_nn.clear(); _series_basin.clear(); _series_valid.clear();
+  for (int i = 0; i < pModel->GetNumObservedTS(); i++) {
+    const observed_ts &o = pModel->observed[i];
+    const int p = pModel->GetSubBasinIndex(o.loc_ID);
+    const bool good = (p != DOESNT_EXIST) && pModel->GetSubBasin(p)->assimilate;
+    if (good && o.name == "HYDROGRAPH") {
+      aObsIndices.push_back(i);
+      _series_basin.push_back(p);
+      for (int nn = _nTimeSteps - _window_size + 1; nn <= _nTimeSteps; nn++) {
+        const bool valid = (o.pTS->GetSampledValue(nn) != RAV_BLANK_DATA);
+        _series_valid.push_back(valid ? 1 : 0);
+        if (valid) { _obs_basin.push_back(p); _obs_nn.push_back(nn); }
+      }
+    }
+  }
+  _nObsDatapoints = (int)_obs_basin.size();
+  ExitGracefullyIf(aObsIndices.empty() && !forecast,
+                   "EnKF::Initialize : no observations available for assimilation. Use :AssimilateStreamflow command to indicate enabled observation time series");
+  if ((_nObsDatapoints == 0) && !forecast) WriteWarning("EnKF::Initialize : no observations were available for assimilation. EnKF assimilation updates will not be performed.");
+  // perturbed observations: one draw per (member, datapoint) in member-major order (:372-405)
+  _obs_matrix.assign((size_t)_nMembers * _nObsDatapoints, 0.0);
+  _noise_matrix.assign((size_t)_nMembers * _nObsDatapoints, 0.0);
+  for (int e = 0; e < _nMembers; e++) {
+    int j = 0;
+    for (size_t ii = 0; ii < aObsIndices.size(); ii++) {
+      const observed_ts &o = pModel->observed[aObsIndices[ii]];
+      const obs_perturb *pPerturb = NULL;   // HYDROGRAPH observations are perturbed by the STREAMFLOW error model; the last one given wins
+      for (size_t q = 0; q < _pObsPerturbations.size(); q++) if (_pObsPerturbations[q].state == (sv_type)RVN_SV_NTYPES) pPerturb = &_pObsPerturbations[q];
+      for (int nn = _nTimeSteps - _window_size + 1; nn <= _nTimeSteps; nn++) {
+        const double obsval = o.pTS->GetSampledValue(nn);
+        if (obsval != RAV_BLANK_DATA) {
+          double noise = 0;
+          if (pPerturb != NULL) {
+            const double eps = SampleFromDistribution(pPerturb->distribution, pPerturb->distpar);
+            if (pPerturb->adj_type == ADJ_ADDITIVE) noise = eps;
+            else if (pPerturb->adj_type == ADJ_MULTIPLICATIVE) noise = (eps * obsval) - obsval;
+          }
+          _noise_matrix[(size_t)e * _nObsDatapoints + j] = noise;
+          _obs_matrix[(size_t)e * _nObsDatapoints + j] = obsval + noise;
+          j++;
+        }
+      }
+    }
+  }
+}
+void CEnKFEnsemble::UpdateModel(CModel *pModel, optStruct &Options, int e) {
+  CEnsemble::UpdateModel(pModel, Options, e);
+  ExitGracefullyIf(e >= _nMembers, "CEnKFEnsemble::UpdateMode: invalid ensemble member index");
+  if ((_EnKF_mode == ENKF_FORECAST) || (_EnKF_mode == ENKF_OPEN_FORECAST)) return;   // no perturbations drawn (src/EnKF.cpp:428-431)
+  // the window's forcing-perturbation samples of member e, in the order StartTimeStepOps draws them: step by step, perturbation
+  // by perturbation, nStepsPerDay (= 1 for the daily-or-longer steps supported here) samples each
+  const int nP = pModel->GetNumForcingPerturbations();
+  const int nsteps = (int)((Options.duration - TIME_CORRECTION) / Options.timestep) + 1;   // iterations of the reference time loop (src/RavenMain.cpp:147)
+  for (int n = 0; n < nsteps; n++)
+    for (int i = 0; i < nP; i++) {
+      const force_perturb &P = pModel->perturbations[i];
+      const double eps = SampleFromDistribution(P.distribution, P.distpar);
+      const bool matched = !(P.forcing == F_TEMP_DAILY_MIN || P.forcing == F_TEMP_DAILY_MAX);
+      if (matched && e >= _member0 && e < _member0 + _nLocal) pModel->SetPerturbationSample(e - _member0, n, i, eps);
+    }
+}
+void CEnKFEnsemble::HarvestOutputs(const double *qout_rec, const double *qout_initial, int nSB, double timestep, double *out_row) const {
+  // CloseTimeStepOps (src/EnKF.cpp:440-472) replayed for every step of the data window.  The modelled HYDROGRAPH at time index
+  // nn is CSubBasin::GetIntegratedOutflow(tstep)/(tstep*SEC_PER_DAY) after step nn-1 (src/Model.cpp:2929-2936,
+  // src/SubBasin.cpp:929-934; Options.ave_hydrograph is on by default).  The reference's slot counter j stops advancing at the
+  // `break` once the current step is found, so with a window > 1 and several gauges later series land in earlier slots and
+  // some slots keep their initial 0 -- reproduced as is (the analysis is defined on these numbers).
+  for (int j = 0; j < _nObsDatapoints; j++) out_row[j] = 0.0;
+  const int nSeries = (int)_series_basin.size();
+  for (int curr_nn = 1; curr_nn <= _nTimeSteps; curr_nn++) {
+    if (curr_nn < _nTimeSteps - _window_size + 1) continue;
+    int j = 0;
+    for (int ii = 0; ii < nSeries; ii++) {
+      const int p = _series_basin[ii];
+      for (int nn = _nTimeSteps - _window_size + 1; nn <= _nTimeSteps; nn++) {
+        if (_series_valid[(size_t)ii * _window_size + (nn - (_nTimeSteps - _window_size + 1))]) {
+          if (nn == curr_nn) {
+            const double Qout = qout_rec[(size_t)(nn - 1) * nSB + p];
+            const double QoutLast = (nn >= 2) ? qout_rec[(size_t)(nn - 2) * nSB + p] : qout_initial[p];
+            out_row[j] = (0.5 * (Qout + QoutLast) * (timestep * SEC_PER_DAY)) / (timestep * SEC_PER_DAY);
+            j++;
+            break;
+          } else j++;
+        }
+      }
+    }
+  }
+}
+// cyclic Jacobi eigen-decomposition of a symmetric matrix (A is destroyed; V's columns are the eigenvectors)
+static void JacobiEigen(std::vector<double> &A, int n, std::vector<double> &w, std::vector<double> &V) {
+  V.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; i++) V[(size_t)i * n + i] = 1.0;
+  for (int sweep = 0; sweep < 100; sweep++) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) { if (i != j) off += A[(size_t)i * n + j] * A[(size_t)i * n + j]; else diag += A[(size_t)i * n + i] * A[(size_t)i * n + i]; }
+    if (off <= 1e-60 * (diag > 0 ? diag : 1.0) || off == 0.0) break;
+    for (int p = 0; p < n - 1; p++)
+      for (int q = p + 1; q < n; q++) {
+        const double apq = A[(size_t)p * n + q];
+        if (apq == 0.0) continue;
+        const double theta = (A[(size_t)q * n + q] - A[(size_t)p * n + p]) / (2.0 * apq);
+        const double t = ((theta >= 0) ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s_ = t * c;
+        for (int k = 0; k < n; k++) {   // columns p,q
+          const double akp = A[(size_t)k * n + p], akq = A[(size_t)k * n + q];
+          A[(size_t)k * n + p] = c * akp - s_ * akq; A[(size_t)k * n + q] = s_ * akp + c * akq;
+        }
+        for (int k = 0; k < n; k++) {   // rows p,q
+          const double apk = A[(size_t)p * n + k], aqk = A[(size_t)q * n + k];
+          A[(size_t)p * n + k] = c * apk - s_ * aqk; A[(size_t)q * n + k] = s_ * apk + c * aqk;
+        }
+        for (int k = 0; k < n; k++) {
+          const double vkp = V[(size_t)k * n + p], vkq = V[(size_t)k * n + q];
+          V[(size_t)k * n + p] = c * vkp - s_ * vkq; V[(size_t)k * n + q] = s_ * vkp + c * vkq;
+        }
+      }
+  }
+  w.resize(n);
+  for (int i = 0; i < n; i++) w[i] = A[(size_t)i * n + i];
+}
+void SolveSymmetricTruncated(const std::vector<double> &P, int n, double tol, const std::vector<double> &B, int nrhs, std::vector<double> &X) {
+  std::vector<double> A(P), w, V;
+  JacobiEigen(A, n, w, V);
+  double maxw = 0.0;
+  for (int j = 0; j < n; j++) if (fabs(w[j]) > maxw) maxw = fabs(w[j]);
+  std::vector<double> inv(n, 0.0);
+  for (int j = 0; j < n; j++) if (maxw > 0 && !(fabs(w[j] / maxw) < tol)) inv[j] = 1.0 / w[j];
+  X.assign((size_t)n * nrhs, 0.0);
+  std::vector<double> t(n);
+  for (int r = 0; r < nrhs; r++) {   // B, X are [n][nrhs]
+    for (int j = 0; j < n; j++) { double s_ = 0.0; for (int i = 0; i < n; i++) s_ += V[(size_t)i * n + j] * B[(size_t)i * nrhs + r]; t[j] = s_ * inv[j]; }
+    for (int i = 0; i < n; i++) { double s_ = 0.0; for (int j = 0; j < n; j++) s_ += V[(size_t)i * n + j] * t[j]; X[(size_t)i * nrhs + r] = s_; }
+  }
+}
+bool CEnKFEnsemble::AssimilationCalcs(const double *out_all, std::vector<double> &Z) const {   // src/EnKF.cpp:478-575
+  const int N = _nMembers, Nobs = _nObsDatapoints;
+  Z.assign((size_t)N * N, 0.0);
+  if (Nobs == 0) return false;
+  std::vector<double> HA((size_t)Nobs * N), P((size_t)Nobs * Nobs), tmp((size_t)Nobs * Nobs), D((size_t)Nobs * N), MM;
+  for (int j = 0; j < Nobs; j++) {   // HA = O_sim - mean
+    double outMean = 0;
+    for (int i = 0; i < N; i++) outMean += out_all[(size_t)i * Nobs + j] / N;
+    for (int i = 0; i < N; i++) HA[(size_t)j * N + i] = out_all[(size_t)i * Nobs + j] - outMean;
+  }
+  // P = 1/(N-1) * (HA*HA' + eQ*eQ'), each product accumulated over the members in order (MatMult, src/Matrix.cpp:38-49)
+  for (int a = 0; a < Nobs; a++)
+    for (int b = 0; b < Nobs; b++) {
+      double s1 = 0.0, s2 = 0.0;
+      for (int i = 0; i < N; i++) s1 += HA[(size_t)a * N + i] * HA[(size_t)b * N + i];
+      for (int i = 0; i < N; i++) s2 += _noise_matrix[(size_t)i * Nobs + a] * _noise_matrix[(size_t)i * Nobs + b];
+      P[(size_t)a * Nobs + b] = (s1 + s2) * (1.0 / (N - 1));
+    }
+  (void)tmp;
+  for (int i = 0; i < N; i++) for (int j = 0; j < Nobs; j++) D[(size_t)j * N + i] = _obs_matrix[(size_t)i * Nobs + j] - out_all[(size_t)i * Nobs + j];
+  SolveSymmetricTruncated(P, Nobs, 1e-8, D, N, MM);   // MM [Nobs][N] = inv(P)*(O_obs-O_sim)
+  for (int a = 0; a < N; a++)                           // Z = HA' * MM
+    for (int b = 0; b < N; b++) {
+      double s_ = 0.0;
+      for (int j = 0; j < Nobs; j++) s_ += HA[(size_t)j * N + a] * MM[(size_t)j * N + b];
+      Z[(size_t)a * N + b] = s_;
+    }
+  return true;
+}
+
 CEnsemble *CreateEnsemble(CModel *pModel, const optStruct &Options) {
   CEnsemble *pE = NULL;
   if (Options.ensemble == ENSEMBLE_MONTECARLO) {
     CMonteCarloEnsemble *mc = new CMonteCarloEnsemble(pModel->num_members, Options);
     for (size_t i = 0; i < pModel->param_dists.size(); i++) mc->AddParamDist(pModel->param_dists[i]);
     pE = mc;
+  } else if (Options.ensemble == ENSEMBLE_ENKF) {   // src/ParseInput.cpp:3830 + the .rve commands (src/ParseEnsembleFile.cpp)
+    CEnKFEnsemble *en = new CEnKFEnsemble(pModel->num_members, Options);
+    en->SetEnKFMode(pModel->enkf.mode);
+    en->SetWindowSize(pModel->enkf.window_size);
+    for (size_t i = 0; i < pModel->enkf.obs_perturbations.size(); i++) {
+      const obs_perturb &o = pModel->enkf.obs_perturbations[i];
+      en->AddObsPerturbation(o.state, o.distribution, o.distpar, o.adj_type);
+    }
+    for (size_t i = 0; i < pModel->enkf.assim_states.size(); i++) {
+      const assim_state &a = pModel->enkf.assim_states[i];
+      en->AddAssimilationState(a.sv, a.layer, a.group, a.is_streamflow);
+    }
+    pE = en;
   } else if (Options.ensemble == ENSEMBLE_NONE) {
     pE = new CEnsemble(1, Options);
   } else {

@@ -46,6 +46,58 @@ private:
   std::vector<double> _last;
 };
 
+// EnKF ensemble (reference CEnKFEnsemble, src/EnKF.h:31-89, src/EnKF.cpp).  The reference runs the N members one after
+// another over one assimilation window and then updates the state matrix on the host; here
+//   * Initialize() builds the state-row map, finds the observation datapoints of the window and draws the observation
+//     noise (same rand() stream, same order: src/EnKF.cpp:197-418);
+//   * UpdateModel(e) draws member e's forcing-perturbation samples for every step of the window -- what the reference draws
+//     step by step in StartTimeStepOps -> CModel::PrepareForcingPerturbation (src/EnKF.cpp:424-432, src/Model.cpp:2829-2847);
+//     members are visited in order, so the stream position is the reference's;
+//   * the members then advance together on the GPU; HarvestOutputs() = CloseTimeStepOps (:440-472);
+//   * AssimilationCalcs() does the N x Nobs part of the analysis on the host (HA, P, the N solves, Z = HA'.MM, :478-575) and
+//     returns Z; the O(M N^2) update X += A.Z/(N-1) and UpdateFromStateMatrix run on the device (csrc/rvn_enkf.cuh).
+class CEnKFEnsemble : public CEnsemble {
+public:
+  CEnKFEnsemble(int num_members, const optStruct &Options);
+  void SetEnKFMode(EnKF_mode mode) { _EnKF_mode = mode; }
+  EnKF_mode GetEnKFMode() const { return _EnKF_mode; }
+  void SetWindowSize(int nTimesteps) { _window_size = nTimesteps; }
+  void AddObsPerturbation(sv_type type, int distrib, const double *distpars, adjustment adj);
+  void AddAssimilationState(sv_type sv, int lay, int assim_groupID, bool is_streamflow);
+  void SetLocalMembers(int member0, int nlocal) { _member0 = member0; _nLocal = nlocal; }
+  void Initialize(const CModel *pModel, const optStruct &Options) override;
+  void UpdateModel(CModel *pModel, optStruct &Options, int e) override;
+  // state matrix description
+  int  GetNumStateVars() const { return (int)_rows.size(); }
+  const std::vector<rvn_enkf_row> &GetStateRows() const { return _rows; }
+  const std::string &GetStateName(int i) const { return _state_names[i]; }
+  // observations of the window: datapoint j = subbasin _obs_basin[j] at time index _obs_nn[j]
+  int  GetNumObsDatapoints() const { return _nObsDatapoints; }
+  const std::vector<int> &ObsBasins() const { return _obs_basin; }
+  const std::vector<int> &ObsTimeIndices() const { return _obs_nn; }
+  const std::vector<double> &ObsMatrix() const { return _obs_matrix; }       // [N][Nobs]
+  const std::vector<double> &NoiseMatrix() const { return _noise_matrix; }   // [N][Nobs]
+  // CloseTimeStepOps for one member: simulated HYDROGRAPH values of the window from the recorded outflows
+  // qout_rec[nsteps][nSB] (CSubBasin::GetOutflowRate after every step) and the outflows before the first step
+  void HarvestOutputs(const double *qout_rec, const double *qout_initial, int nSB, double timestep, double *out_row) const;
+  // Z [N][N] from the simulated outputs of ALL members out_all[N][Nobs]; false (Z = 0) when there are no observations
+  bool AssimilationCalcs(const double *out_all, std::vector<double> &Z) const;
+private:
+  EnKF_mode _EnKF_mode;
+  int _window_size, _nTimeSteps, _nObsDatapoints, _member0, _nLocal;
+  std::vector<obs_perturb> _pObsPerturbations;
+  std::vector<assim_state> _aAssim;
+  std::vector<rvn_enkf_row> _rows;
+  std::vector<std::string> _state_names;
+  std::vector<int> _obs_basin, _obs_nn;
+  std::vector<int> _series_basin;            // subbasin of every assimilated observation series
+  std::vector<char> _series_valid;           // [series][window step] 1 = a (non-blank) observation exists
+  std::vector<double> _obs_matrix, _noise_matrix;
+};
+// x = pinv(P) b for the symmetric positive semi-definite Nobs x Nobs matrix P, singular values below tol*max dropped
+// (what the reference's SVD(P,b,x,size,tol) returns, src/Matrix.cpp:144-390)
+void SolveSymmetricTruncated(const std::vector<double> &P, int n, double tol, const std::vector<double> &B, int nrhs, std::vector<double> &X);
+
 // factory: the ensemble object the .rvi/.rve files describe (src/ParseInput.cpp:3826-3833), seeded
 CEnsemble *CreateEnsemble(CModel *pModel, const optStruct &Options);
 #endif

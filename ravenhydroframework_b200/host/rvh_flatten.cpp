@@ -253,6 +253,39 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
   d.sb_musk_K = _f_sb_d[4].data(); d.sb_musk_X = _f_sb_d[5].data(); d.sb_K_reach = _f_sb_d[6].data();
   d.max_nqin = maxqin; d.max_nqlat = maxqlat; d.sb_unit_hydro = _f_uh.data(); d.sb_route_hydro = _f_rh.data();
   d.watershed_area = _WatershedArea;
+  // ---- forcing perturbations (EnKF): samples start neutral; CEnKFEnsemble::UpdateModel fills them per member
+  const int nP = (int)perturbations.size();
+  d.nPert = nP; d.pad3_ = 0; d.pert_forcing = NULL; d.pert_adj = NULL; d.pert_mask = NULL; d.pert_eps = NULL;
+  if (nP > 0) {
+    _f_pert_forcing.resize(nP); _f_pert_adj.resize(nP);
+    bool any_group = false;
+    for (int i = 0; i < nP; i++) {
+      const force_perturb &P = perturbations[i];
+      int f = -1;
+      if (P.forcing == F_PRECIP) f = RVN_PF_PRECIP; else if (P.forcing == F_RAINFALL) f = RVN_PF_RAINFALL;
+      else if (P.forcing == F_SNOWFALL) f = RVN_PF_SNOWFALL; else if (P.forcing == F_TEMP_AVE) f = RVN_PF_TEMP_AVE;
+      // the reference only ever applies these four (src/UpdateForcings.cpp:474,558-560); TEMP_DAILY_MIN/MAX perturbations are never matched
+      ExitGracefullyIf(f < 0 && P.forcing != F_TEMP_DAILY_MIN && P.forcing != F_TEMP_DAILY_MAX,
+                       "CHydroUnit::AdjustHRUForcing: Only PRECIP, SNOWFALL, RAINFALL, TEMP_DAILY_MIN, and TEMP_AVE are supported for forcing perturbation. ");
+      _f_pert_forcing[i] = (f < 0) ? RVN_PF_TEMP_AVE : f;
+      _f_pert_adj[i] = (f < 0) ? RVN_ADJ_ADDITIVE : (int)P.adj_type;
+      if (P.kk != DOESNT_EXIST) any_group = true;
+    }
+    if (any_group) {
+      _f_pert_mask.assign((size_t)nP * nH, 0);
+      for (int i = 0; i < nP; i++)
+        for (int k = 0; k < nH; k++) _f_pert_mask[(size_t)i * nH + k] = (perturbations[i].kk == DOESNT_EXIST || hru_groups[perturbations[i].kk].IsInGroup(k)) ? 1 : 0;
+      d.pert_mask = _f_pert_mask.data();
+    }
+    _f_pert_eps.assign((size_t)nMembers * d.nSteps * nP, 0.0);
+    for (int e = 0; e < nMembers; e++)
+      for (int n = 0; n < d.nSteps; n++)
+        for (int i = 0; i < nP; i++) {
+          const bool unmatched = (perturbations[i].forcing == F_TEMP_DAILY_MIN || perturbations[i].forcing == F_TEMP_DAILY_MAX);
+          _f_pert_eps[((size_t)e * d.nSteps + n) * nP + i] = (!unmatched && perturbations[i].adj_type == ADJ_MULTIPLICATIVE) ? 1.0 : 0.0;
+        }
+    d.pert_forcing = _f_pert_forcing.data(); d.pert_adj = _f_pert_adj.data(); d.pert_eps = _f_pert_eps.data();
+  }
   return &d;
 }
 

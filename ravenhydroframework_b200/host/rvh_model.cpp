@@ -63,10 +63,18 @@ double CTimeSeries::GetAvgValue(double t, double tstep) const {
   if (blank / tstep > 0.001) return RAV_BLANK_DATA;
   return sum / tstep;
 }
-void CTimeSeries::Initialize(double model_start_day, int model_start_year, double model_duration, double timestep, int calendar) {
+void CTimeSeries::Initialize(double model_start_day, int model_start_year, double model_duration, double timestep, int calendar, bool is_observation) {
   _t_corr = -TimeDifference(model_start_day, model_start_year, _start_day, _start_year, calendar);
   double duration = (double)_aVal.size() * _interval;
   double lstart = _t_corr, lend = _t_corr + model_duration;
+  if (is_observation) {  // observations need not cover the run; one extra sample for the last period-ending value
+    int nSampVal = (int)(ceil((model_duration + timestep) / timestep - TIME_CORRECTION));
+    _aSampVal.assign(nSampVal, 0.0);
+    _sampInterval = timestep;
+    double t = 0;
+    for (int nn = 0; nn < nSampVal; nn++) { _aSampVal[nn] = GetAvgValue(t, timestep); t += timestep; }
+    return;
+  }
   ExitGracefullyIf(duration < lstart, "CTimeSeries::Initialize: time series forcing data not available for entire model simulation duration (" + _name + ")");
   ExitGracefullyIf(duration + TIME_CORRECTION < lend, "CTimeSeries::Initialize: time series forcing data not available at end of model simulation (" + _name + ")");
   ExitGracefullyIf((lstart < 0) || (_start_year > model_start_year), "CTimeSeries::Initialize: time series forcing data not available at beginning of model simulation (" + _name + ")");
@@ -215,7 +223,7 @@ double CHydroUnit::GetSlope() const { return slope * DEGREES_TO_RADIANS; }
 double CHydroUnit::GetAspect() const { return aspect * DEGREES_TO_RADIANS; }
 
 CSubBasin::CSubBasin()
-    : ID(0), downstream_ID(DOESNT_EXIST), pChannel(NULL), reach_length(AUTO_COMPUTE), gauged(false), is_headwater(true), disabled(false),
+    : ID(0), downstream_ID(DOESNT_EXIST), pChannel(NULL), reach_length(AUTO_COMPUTE), gauged(false), is_headwater(true), disabled(false), assimilate(false),
       nSegments(1), basin_area(0), drainage_area(0), t_conc(AUTO_COMPUTE), t_peak(AUTO_COMPUTE), t_lag(AUTO_COMPUTE),
       gamma_shape(AUTO_COMPUTE), gamma_scale(AUTO_COMPUTE), Q_ref(AUTO_COMPUTE), c_ref(AUTO_COMPUTE), w_ref(AUTO_COMPUTE),
       mannings_n(AUTO_COMPUTE), slope(AUTO_COMPUTE), rain_corr(1.0), snow_corr(1.0), temperature_corr(0.0), QoutLast(0), QlatLast(0),
@@ -385,7 +393,22 @@ CModel::~CModel() {
   for (size_t i = 0; i < _pProcesses.size(); i++) delete _pProcesses[i];
   for (size_t i = 0; i < _pGauges.size(); i++) delete _pGauges[i];
   for (size_t i = 0; i < channels.size(); i++) delete channels[i];
+  for (size_t i = 0; i < observed.size(); i++) delete observed[i].pTS;
 }
+int CModel::FindHRUGroup(const std::string &name) const { for (size_t i = 0; i < hru_groups.size(); i++) if (hru_groups[i].name == name) return (int)i; return DOESNT_EXIST; }
+int CModel::FindSubBasinGroup(const std::string &name) const { for (size_t i = 0; i < sb_groups.size(); i++) if (sb_groups[i].name == name) return (int)i; return DOESNT_EXIST; }
+void CModel::AddForcingPerturbation(forcing_type f, int distribution, const double distpar[3], int kk, adjustment adj) {
+  force_perturb P; P.forcing = f; P.distribution = distribution; P.kk = kk; P.adj_type = adj;
+  for (int i = 0; i < 3; i++) P.distpar[i] = distpar[i];
+  perturbations.push_back(P);
+}
+void CModel::SetPerturbationSample(int member, int step, int i, double eps) {
+  const int nP = (int)perturbations.size();
+  ExitGracefullyIf(member < 0 || member >= _desc.nMembers || step < 0 || step >= _desc.nSteps || i < 0 || i >= nP || _f_pert_eps.empty(),
+                   "CModel::SetPerturbationSample: index outside the flattened perturbation table (call Flatten first)");
+  _f_pert_eps[((size_t)member * _desc.nSteps + step) * nP + i] = eps;
+}
+const double *CModel::MemberPerturbations(int member) const { return _f_pert_eps.data() + (size_t)member * _desc.nSteps * perturbations.size(); }
 int CModel::GetStateVarIndex(sv_type typ) const { return GetStateVarIndex(typ, DOESNT_EXIST); }
 int CModel::GetStateVarLayer(int ii) const {
   int count = 0;
@@ -593,6 +616,7 @@ void CModel::Initialize(optStruct &O) {
                      "CModel::Initialize: soil profile " + soil_profiles[h->soil_profile].tag + " does not have one horizon per model soil layer");
   }
   for (int g = 0; g < GetNumGauges(); g++) _pGauges[g]->Initialize(O);
+  for (size_t i = 0; i < observed.size(); i++) observed[i].pTS->Initialize(O.julian_start_day, O.julian_start_year, O.duration, O.timestep, O.calendar, true);
   GenerateGaugeWeights(O);
   InitializeRoutingNetwork();
   ExitGracefullyIf(GetNumSubBasins() > 1 && !(globals.v[RVN_G_AVG_ANNUAL_RUNOFF] > 0) && O.routing != RVN_ROUTE_NONE,

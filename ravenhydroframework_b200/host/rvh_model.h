@@ -53,7 +53,8 @@ class CTimeSeries {
 public:
   CTimeSeries(const std::string &name, double start_day, int start_yr, double interval, const std::vector<double> &vals)
       : _name(name), _start_day(start_day), _start_year(start_yr), _interval(interval), _aVal(vals), _t_corr(0), _sampInterval(1) {}
-  void   Initialize(double model_start_day, int model_start_year, double model_duration, double timestep, int calendar);
+  // is_observation: no overlap QA, one extra sample for the last period-ending value (src/TimeSeries.cpp:214-262)
+  void   Initialize(double model_start_day, int model_start_year, double model_duration, double timestep, int calendar, bool is_observation = false);
   double GetValue(double t) const;                  // pulse-type point value at model time t
   double GetAvgValue(double t, double tstep) const;
   double GetSampledValue(int nn) const;
@@ -121,6 +122,7 @@ public:
   const CChannelXSect *pChannel;
   double reach_length;      // [m] or AUTO_COMPUTE
   bool gauged, is_headwater, disabled;
+  bool assimilate;          // :AssimilateStreamflow (CSubBasin::IncludeInAssimilation / UseInFlowAssimilation)
   int  nSegments;
   double basin_area, drainage_area;  // [km2]
   double t_conc, t_peak, t_lag, gamma_shape, gamma_scale, Q_ref, c_ref, w_ref, mannings_n, slope;
@@ -150,6 +152,24 @@ private:
   void   GenerateRoutingHydrograph(double Qin_avg, const optStruct &Options);
   void   ResetReferenceFlow(double Qreference);
   double CalculateTOC() const;
+};
+
+// ---- groups, observations, forcing perturbations (what the EnKF ensemble refers to) ---------------------------------------
+struct CHRUGroup      { std::string name; std::vector<int> hru; bool IsInGroup(int k) const { for (size_t i = 0; i < hru.size(); i++) if (hru[i] == k) return true; return false; } };
+struct CSubbasinGroup { std::string name; std::vector<int> sb; };
+struct observed_ts    { std::string name; long long loc_ID; CTimeSeries *pTS; };   // :ObservationData [type] [SBID|HRUID]
+enum adjustment { ADJ_ADDITIVE = 0, ADJ_MULTIPLICATIVE = 1, ADJ_REPLACE = 2 };
+struct force_perturb {  // reference force_perturb (src/Model.h), one :ForcingPerturbation command
+  forcing_type forcing; int distribution; double distpar[3]; int kk; adjustment adj_type;
+};
+enum EnKF_mode { ENKF_SPINUP, ENKF_CLOSED_LOOP, ENKF_OPEN_LOOP, ENKF_FORECAST, ENKF_OPEN_FORECAST, ENKF_UNSPECIFIED };
+struct obs_perturb { sv_type state; int distribution; double distpar[3]; int kk; adjustment adj_type; };   // src/EnKF.h:22-29
+struct assim_state { sv_type sv; int layer; int group; bool is_streamflow; };
+struct enkf_settings {   // what the .rve file says about the EnKF run (src/ParseEnsembleFile.cpp:263-470)
+  EnKF_mode mode; int window_size;
+  std::vector<obs_perturb> obs_perturbations;
+  std::vector<assim_state> assim_states;
+  enkf_settings() : mode(ENKF_UNSPECIFIED), window_size(1) {}
 };
 
 struct param_dist {  // reference ModelEnsemble.h:20-32
@@ -233,6 +253,20 @@ public:
   // ensemble description (.rve)
   std::vector<param_dist> param_dists;
   int num_members;
+  enkf_settings enkf;
+  // groups / observations / forcing perturbations
+  std::vector<CHRUGroup> hru_groups;
+  std::vector<CSubbasinGroup> sb_groups;
+  int  FindHRUGroup(const std::string &name) const;       // DOESNT_EXIST if absent
+  int  FindSubBasinGroup(const std::string &name) const;
+  std::vector<observed_ts> observed;
+  int  GetNumObservedTS() const { return (int)observed.size(); }
+  std::vector<force_perturb> perturbations;
+  int  GetNumForcingPerturbations() const { return (int)perturbations.size(); }
+  void AddForcingPerturbation(forcing_type f, int distribution, const double distpar[3], int kk, adjustment adj);   // src/Model.cpp AddForcingPerturbation
+  // sample of perturbation i for (local member, step) in the flattened table handed to the device (pert_eps)
+  void SetPerturbationSample(int member, int step, int i, double eps);
+  const double *MemberPerturbations(int member) const;
 
   // ---- compile to the device ABI --------------------------------------------------------------
   // Owns every buffer referenced by the returned descriptor until the next Flatten()/destruction.
@@ -268,7 +302,9 @@ private:
   std::vector<rvn_process> _f_proc;
   std::vector<uint64_t> _f_mask;
   std::vector<double> _f_hru_d[5], _f_prof_thick, _f_ptab, _f_conv_uh, _f_series, _f_gconst, _f_wt, _f_sb_d[7], _f_uh, _f_rh, _f_veg_season, _f_et;
-  std::vector<int32_t> _f_et_row, _f_wt_ptr, _f_wt_idx;
+  std::vector<int32_t> _f_et_row, _f_wt_ptr, _f_wt_idx, _f_pert_forcing, _f_pert_adj;
+  std::vector<uint8_t> _f_pert_mask;
+  std::vector<double> _f_pert_eps;
   std::vector<rvn_time> _f_times;
   int _f_ptab_stride, _f_nconv;
 };

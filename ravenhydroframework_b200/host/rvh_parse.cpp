@@ -578,12 +578,43 @@ static void ParseHRUPropsFile(CModel *pModel, const optStruct &Options) {
       }
       continue;
     }
-    if (c == ":HRUGroup" || c == ":SubBasinGroup" || c == ":PopulateHRUGroup" || c == ":PopulateSubBasinGroup") {
-      // groups only matter for outputs / HRU_GROUP conditions (unsupported, fails in ShouldApply)
-      if (c == ":HRUGroup") while (p.Tokenize(s)) { if (!s.empty() && s[0] == ":EndHRUGroup") break; }
-      if (c == ":SubBasinGroup") while (p.Tokenize(s)) { if (!s.empty() && s[0] == ":EndSubBasinGroup") break; }
+    if (c == ":HRUGroup" || c == ":SubBasinGroup") {
+      // {ID1,ID2,a-b,...} lines until :End...; members keep the listed order (src/ParseHRUFile.cpp:472-530, 660-720)
+      const bool hru = (c == ":HRUGroup");
+      ExitGracefullyIf(s.size() < 2, "ParseHRUPropsFile: " + c + " needs a group name");
+      const std::string gname = s[1];
+      std::vector<int> members;
+      while (p.Tokenize(s)) {
+        if (s.empty()) continue;
+        if (s[0] == (hru ? ":EndHRUGroup" : ":EndSubBasinGroup")) break;
+        ExitGracefullyIf(s[0][0] == ':', "ParseHRUPropsFile: command found between " + c + " ... :End commands; only IDs should be in this block");
+        for (size_t i = 0; i < s.size(); i++) {
+          long long a, b;
+          size_t dash = s[i].find('-', 1);
+          if (dash == std::string::npos) a = b = s_to_ll(s[i]);
+          else { a = s_to_ll(s[i].substr(0, dash)); b = s_to_ll(s[i].substr(dash + 1)); }
+          ExitGracefullyIf((b - a) > 10000000, "Parsing " + c + " command: invalid range of indices");
+          for (long long id = a; id <= b; id++) {
+            int idx = DOESNT_EXIST;
+            if (hru) { for (int k = 0; k < pModel->GetNumHRUs(); k++) if (pModel->GetHydroUnit(k)->ID == id) { idx = k; break; } }
+            else idx = pModel->GetSubBasinIndex(id);
+            if (idx == DOESNT_EXIST) { if (a == b) WriteWarning("ID " + std::to_string(id) + " specified in " + c + " command for group " + gname + " does not exist"); continue; }
+            members.push_back(idx);
+          }
+        }
+      }
+      if (hru) {
+        int g = pModel->FindHRUGroup(gname);
+        if (g == DOESNT_EXIST) { CHRUGroup G; G.name = gname; pModel->hru_groups.push_back(G); g = (int)pModel->hru_groups.size() - 1; }
+        pModel->hru_groups[g].hru.insert(pModel->hru_groups[g].hru.end(), members.begin(), members.end());
+      } else {
+        int g = pModel->FindSubBasinGroup(gname);
+        if (g == DOESNT_EXIST) { CSubbasinGroup G; G.name = gname; pModel->sb_groups.push_back(G); g = (int)pModel->sb_groups.size() - 1; }
+        pModel->sb_groups[g].sb.insert(pModel->sb_groups[g].sb.end(), members.begin(), members.end());
+      }
       continue;
     }
+    if (c == ":PopulateHRUGroup" || c == ":PopulateSubBasinGroup") continue;   // output-only groups
     ExitGracefully("ParseHRUPropsFile: command " + c + " (line " + std::to_string(p.line()) + ") is not supported by the B200 build");
   }
 }
@@ -693,6 +724,17 @@ static void SkipBlock(CParser &p, const char *endtok) {
   std::vector<std::string> s;
   while (p.Tokenize(s)) if (!s.empty() && s[0] == endtok) return;
 }
+// :AssimilateStreamflow [SBID] (.rvt or .rve): flags the subbasin when a continuous HYDROGRAPH observation exists for it
+static void AssimilateStreamflowCommand(CModel *pModel, const std::vector<std::string> &s) {
+  ExitGracefullyIf(s.size() < 2, ":AssimilateStreamflow needs a subbasin ID");
+  const long long SBID = s_to_ll(s[1]);
+  const int pb = pModel->GetSubBasinIndex(SBID);
+  if (pb == DOESNT_EXIST) { WriteWarning("ParseTimeSeries::Trying to assimilate streamflow at non-existent subbasin " + std::to_string(SBID)); return; }
+  bool ObsExists = false;
+  for (size_t i = 0; i < pModel->observed.size(); i++) if (pModel->observed[i].name == "HYDROGRAPH" && pModel->observed[i].loc_ID == SBID) ObsExists = true;
+  if (ObsExists) pModel->GetSubBasin(pb)->assimilate = true;
+  else WriteWarning("AssimilateStreamflow: no observation time series associated with subbasin " + std::to_string(SBID) + ". Cannot assimilate flow in this subbasin.");
+}
 static void ParseTimeSeriesFile(CModel *pModel, const optStruct &Options, const std::string &filename, bool top) {
   CParser p(filename);
   ExitGracefullyIf(!p.ok(), "ParseTimeSeriesFile: cannot open " + filename);
@@ -708,7 +750,34 @@ static void ParseTimeSeriesFile(CModel *pModel, const optStruct &Options, const 
       continue;
     }
     if (c == ":RedirectToFile") { ParseTimeSeriesFile(pModel, Options, CorrectForRelativePath(s[1], filename), false); continue; }
-    if (c == ":ObservationData") { SkipBlock(p, ":EndObservationData"); continue; }   // observations do not enter the balance
+    if (c == ":ObservationData") {   // src/ParseTimeSeriesFile.cpp:431-497; used by the EnKF ensemble (HYDROGRAPH observations)
+      ExitGracefullyIf(s.size() < 3, "ParseTimeSeriesFile: :ObservationData needs [data type] [SBID or HRUID]");
+      const std::string dtype = s[1];
+      const long long loc = s_to_ll(s[2]);
+      double start_day, interval; int start_yr, n;
+      ReadSeriesHeader(p, Options, start_day, start_yr, interval, n);
+      if (dtype == "HYDROGRAPH") {   // hydrographs are stored period-ending: shifted by one model step (src/TimeSeries.cpp:1040-1046)
+        start_day += Options.timestep;
+        int leap = IsLeapYear(start_yr, Options.calendar) ? 1 : 0;
+        if (start_day >= 365 + leap) { start_day -= 365 + leap; start_yr++; }
+      }
+      std::vector<double> v; v.reserve(n);
+      std::vector<std::string> t;
+      while (p.Tokenize(t)) {
+        if (t.empty()) continue;
+        if (t[0] == ":EndObservationData") break;
+        for (size_t i = 0; i < t.size(); i++) v.push_back(ts_s_to_d(t[i].c_str()));
+      }
+      ExitGracefullyIf((int)v.size() != n, "CTimeSeries::Parse: wrong number of data points in :ObservationData block. File: " + p.filename());
+      if (dtype == "HYDROGRAPH" && pModel->GetSubBasinIndex(loc) == DOESNT_EXIST) { WriteWarning("ParseTimeSeries:: Invalid subbasin ID in observation hydrograph time series. Will be ignored"); continue; }
+      observed_ts o; o.name = dtype; o.loc_ID = loc; o.pTS = new CTimeSeries(dtype, start_day, start_yr, interval, v);
+      pModel->observed.push_back(o);
+      continue;
+    }
+    if (c == ":AssimilateStreamflow") {   // src/ParseTimeSeriesFile.cpp:1225-1248
+      AssimilateStreamflowCommand(pModel, s);
+      continue;
+    }
     if (c == ":ObservationWeights") { SkipBlock(p, ":EndObservationWeights"); continue; }
     ExitGracefully("ParseTimeSeriesFile: command " + c + " (line " + std::to_string(p.line()) + " of " + filename + ") is not supported by the B200 build");
   }
@@ -757,6 +826,72 @@ static void ParseEnsembleFile(CModel *pModel, optStruct &Options) {
       }
       continue;
     }
+    const bool is_enkf = (Options.ensemble == ENSEMBLE_ENKF);
+    if (c == ":EnKFMode") {   // src/ParseEnsembleFile.cpp:431-450
+      ExitGracefullyIf(s.size() < 2, "ParseEnsembleFile: :EnKFMode needs a mode");
+      EnKF_mode mode = ENKF_UNSPECIFIED;
+      if (s[1] == "ENKF_SPINUP") mode = ENKF_SPINUP; else if (s[1] == "ENKF_CLOSED_LOOP") mode = ENKF_CLOSED_LOOP;
+      else if (s[1] == "ENKF_OPEN_LOOP") mode = ENKF_OPEN_LOOP; else if (s[1] == "ENKF_FORECAST") mode = ENKF_FORECAST;
+      else if (s[1] == "ENKF_OPEN_FORECAST") mode = ENKF_OPEN_FORECAST;
+      else ExitGracefully("ParseEnsembleFile: EnKFMode-  invalid mode specified");
+      if (is_enkf) pModel->enkf.mode = mode;
+      continue;
+    }
+    if (c == ":WindowSize" || c == ":DataHorizon") { if (is_enkf) pModel->enkf.window_size = s_to_i(s[1]); continue; }
+    if (c == ":ForcingPerturbation" || c == ":ObservationErrorModel") {   // src/ParseEnsembleFile.cpp:263-303, 375-420
+      if (!is_enkf) { WriteWarning(c + " command will be ignored; only valid for EnKF ensemble simulation."); continue; }
+      ExitGracefullyIf(s.size() < 6, "ParseEnsembleFile: " + c + " needs [type] [distrib] [par1] [par2] [adj_type]");
+      int distrib = 1; bool fix = false;
+      if (s[2] == "DIST_UNIFORM") distrib = 0; else if (s[2] == "DIST_NORMAL") distrib = 1; else if (s[2] == "DIST_LOGNORMAL") distrib = 2;
+      else if (s[2] == "DIST_LOGNORMAL2") { distrib = 2; fix = true; } else if (s[2] == "DIST_GAMMA") distrib = 3;
+      else ExitGracefully("ParseEnsembleFile: invalid distribution type in " + c + " command");
+      double distpars[3] = {s_to_d(s[3]), s_to_d(s[4]), 0.0};
+      if (fix) {
+        const double mean = distpars[0], sd = distpars[1];
+        distpars[0] = log(mean * mean) - log(sqrt(mean * mean + sd * sd));
+        distpars[1] = log(1.0 + sd * sd / mean / mean);
+        ExitGracefullyIf(mean <= 0.0, "ParseEnsembleFile: invalid (negative or zero) mean of lognormal distribution in " + c + " command");
+      }
+      adjustment adj = ADJ_ADDITIVE;
+      if (s[5] == "ADDITIVE") adj = ADJ_ADDITIVE; else if (s[5] == "MULTIPLICATIVE") adj = ADJ_MULTIPLICATIVE;
+      else ExitGracefully("ParseEnsembleFile: invalid perturbation adjustment type in " + c + " command");
+      if (c == ":ForcingPerturbation") {
+        forcing_type ftyp = ForcingFromString(s[1]);
+        ExitGracefullyIf(ftyp == F_NTYPES, "ParseEnsembleFile: forcing type " + s[1] + " in :ForcingPerturbation is not supported by the B200 build");
+        int kk = DOESNT_EXIST;
+        if (s.size() >= 7) { kk = pModel->FindHRUGroup(s[6]); ExitGracefullyIf(kk == DOESNT_EXIST, "ParseEnsembleFile: :ForcingPerturbation HRU group does not exist"); }
+        pModel->AddForcingPerturbation(ftyp, distrib, distpars, kk, adj);
+      } else {
+        int lay = DOESNT_EXIST;
+        obs_perturb op; op.state = (s[1] == "STREAMFLOW") ? (sv_type)RVN_SV_NTYPES : pModel->StringToSVType(s[1], lay, true);
+        op.distribution = distrib; op.kk = DOESNT_EXIST; op.adj_type = adj;
+        for (int i = 0; i < 3; i++) op.distpar[i] = distpars[i];
+        pModel->enkf.obs_perturbations.push_back(op);
+      }
+      continue;
+    }
+    if (c == ":AssimilatedState") {   // src/ParseEnsembleFile.cpp:305-345
+      if (!is_enkf) { WriteWarning(":AssimilatedState command will be ignored; only valid for EnKF ensemble simulation."); continue; }
+      ExitGracefullyIf(s.size() < 3, "ParseEnsembleFile: :AssimilatedState needs [state] [group]");
+      assim_state a; a.layer = DOESNT_EXIST; a.is_streamflow = (s[1] == "STREAMFLOW");
+      ExitGracefullyIf(s[1] == "RESERVOIR_STAGE", "ParseEnsembleFile: :AssimilatedState RESERVOIR_STAGE is not supported by the B200 build (no reservoirs)");
+      if (a.is_streamflow) {
+        a.sv = (sv_type)RVN_SV_NTYPES;
+        a.group = pModel->FindSubBasinGroup(s[2]);
+        ExitGracefullyIf(a.group == DOESNT_EXIST, "ParseEnsembleFile: :AssimilatedState subbasin/HRU group does not exist");
+      } else {
+        a.sv = pModel->StringToSVType(s[1], a.layer, true);
+        if (pModel->GetStateVarIndex(a.sv, a.layer) == DOESNT_EXIST) {
+          WriteWarning("State variable " + s[1] + " does not exist in this model and will be ignored in the :AssimilatedState command"); continue;
+        }
+        a.group = pModel->FindHRUGroup(s[2]);
+        ExitGracefullyIf(a.group == DOESNT_EXIST, "ParseEnsembleFile: :AssimilatedState subbasin/HRU group does not exist");
+      }
+      pModel->enkf.assim_states.push_back(a);
+      continue;
+    }
+    if (c == ":AssimilateStreamflow") { AssimilateStreamflowCommand(pModel, s); continue; }
+    if (c == ":SolutionRunName" || c == ":EnsembleRVCFormat" || c == ":ExtraRVTFilename" || c == ":ForecastRVTFilename") continue;   // file plumbing of the external EnKF driver
     ExitGracefully("ParseEnsembleFile: command " + c + " is not supported by the B200 build");
   }
 }

@@ -543,3 +543,43 @@ def write_gr4j(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUTE
         write_gauge(f, *weather(n_days, seed, season_offset))
     _write(base + ".rvc", GR4J_RVC)
     return base
+
+
+def add_enkf(base, n_members, n_sb, n_hru, n_days, obs_basins=(1,), seed=3, window=1, mode="ENKF_SPINUP", random_seed=11,
+             assimilated=("SOIL[0]", "SNOW"), start="2000-01-01", obs_level=6.0,
+             perturbations=("RAINFALL DIST_GAMMA 4.0 0.25 MULTIPLICATIVE", "TEMP_AVE DIST_NORMAL 0 1.5 ADDITIVE"),
+             obs_error="STREAMFLOW DIST_NORMAL 1 0.07 MULTIPLICATIVE", hru_group_range=None):
+    """Turn the input set at `base` (written by write_hbv / write_hmets / write_gr4j) into an EnKF ensemble run (BASELINE
+    config 5): `:EnsembleMode ENSEMBLE_ENKF`, HRU / subbasin groups, synthetic HYDROGRAPH observations at `obs_basins`, and the
+    .rve commands of reference src/ParseEnsembleFile.cpp (:EnKFMode, :ForcingPerturbation, :ObservationErrorModel,
+    :AssimilatedState, :AssimilateStreamflow)."""
+    rng = np.random.RandomState(seed)
+    with open(base + ".rvi", "a") as f:
+        f.write(":EnsembleMode ENSEMBLE_ENKF %d\n:RandomSeed %d\n" % (n_members, random_seed))
+    lo, hi = hru_group_range or (1, n_hru)
+    with open(base + ".rvh", "a") as f:
+        f.write(":HRUGroup AssimHRUs\n  %d-%d\n:EndHRUGroup\n" % (lo, hi))
+        f.write(":SubBasinGroup AssimSBs\n")
+        ids = list(range(1, n_sb + 1))
+        for i in range(0, len(ids), 20):
+            f.write("  " + " ".join(str(x) for x in ids[i:i + 20]) + "\n")
+        f.write(":EndSubBasinGroup\n")
+    with open(base + ".rvt", "a") as f:
+        for sb in obs_basins:
+            f.write(":ObservationData HYDROGRAPH %d m3/s\n  %s 00:00:00 1.0 %d\n" % (sb, start, n_days + 1))
+            q = obs_level * (1.0 + 0.5 * rng.uniform(size=n_days + 1))
+            for v in q:
+                f.write("  %.4f\n" % v)
+            f.write(":EndObservationData\n")
+    with open(base + ".rve", "w") as f:
+        f.write(":EnKFMode %s\n:WindowSize %d\n" % (mode, window))
+        for p in perturbations:
+            f.write(":ForcingPerturbation %s\n" % p)
+        if obs_error:
+            f.write(":ObservationErrorModel %s\n" % obs_error)
+        for a in assimilated:
+            f.write(":AssimilatedState %s AssimHRUs\n" % a)
+        f.write(":AssimilatedState STREAMFLOW AssimSBs\n")
+        for sb in obs_basins:
+            f.write(":AssimilateStreamflow %d\n" % sb)
+    return base

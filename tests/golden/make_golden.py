@@ -49,6 +49,47 @@ if hasattr(synth, "write_gr4j"):
 MC_CASES = {"hmets_mc": dict(kind="hmets", n_sb=3, hru_per_sb=4, n_days=150, seed=7, ensemble_members=4, mixed_distributions=True, member=2)}
 
 
+# EnKF ensembles (reference CEnKFEnsemble): one assimilation window run by the UNMODIFIED reference through
+# oracle/_ref/ref_enkf_dump; fixture = reference_enkf.npz with the observation / noise / output matrices, the forcing
+# perturbation samples, every member's final state and the state matrix before and after the reference's AssimilationCalcs.
+ENKF_CASES = {
+    "enkf_hbv": dict(kind="hbv", n_sb=7, hru_per_sb=4, n_days=40, seed=21, routing="ROUTE_MUSKINGUM", season_offset=120,
+                     enkf=dict(n_members=6, obs_basins=(1, 3), window=2)),
+    "enkf_hmets": dict(kind="hmets", n_sb=3, hru_per_sb=5, n_days=30, seed=23, routing="ROUTE_NONE", season_offset=100,
+                       enkf=dict(n_members=5, obs_basins=(1,), window=1, assimilated=("SOIL[1]", "SNOW_LIQ"), hru_group_range=(3, 12),
+                                 perturbations=("PRECIP DIST_NORMAL 0.5 1.0 ADDITIVE", "SNOWFALL DIST_UNIFORM 0.5 1.5 MULTIPLICATIVE",
+                                                "TEMP_AVE DIST_LOGNORMAL 0.0 0.1 MULTIPLICATIVE AssimHRUs"),
+                                 obs_error="STREAMFLOW DIST_GAMMA 2.0 0.3 ADDITIVE", obs_level=3.0)),
+}
+
+
+def make_enkf(name, spec):
+    import subprocess
+    spec = dict(spec)
+    kind = spec.pop("kind")
+    en = spec.pop("enkf")
+    d = os.path.join(HERE, name)
+    shutil.rmtree(d, ignore_errors=True)
+    base = WRITERS[kind](d, name="model", **spec)
+    synth.add_enkf(base, n_sb=spec["n_sb"], n_hru=spec["n_sb"] * spec["hru_per_sb"], n_days=spec["n_days"], **en)
+    out = os.path.join(d, "_refout") + "/"
+    os.makedirs(out, exist_ok=True)
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_enkf_dump"), "model", out], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and os.path.exists(out + "enkf_Xpost.f64"), r.stdout[-3000:]
+    meta = dict(l.split()[:2] for l in open(out + "enkf_meta.txt") if not l.startswith("ROW"))
+    N, M, Nobs, nH, NS, NB, nsteps, nP = [int(meta[k]) for k in ("N", "M", "Nobs", "nHRU", "NS", "NB", "nsteps", "nPert")]
+    ld = lambda f, *shape: np.fromfile(out + f).reshape(*shape)  # noqa: E731
+    np.savez_compressed(os.path.join(d, "reference_enkf.npz"), obs=ld("enkf_obs.f64", N, Nobs), noise=ld("enkf_noise.f64", N, Nobs),
+                        out=ld("enkf_out.f64", N, Nobs), Xpre=ld("enkf_Xpre.f64", N, M), Xpost=ld("enkf_Xpost.f64", N, M),
+                        state=ld("enkf_state.f64", N, nH, NS), qout_member0=ld("enkf_qout.f64", N, nsteps, NB)[0],
+                        qout_last=ld("enkf_qout.f64", N, nsteps, NB)[:, -1, :], eps=ld("enkf_eps.f64", N, nsteps, nP),
+                        row_names=np.array([l.split()[2] for l in open(out + "enkf_meta.txt") if l.startswith("ROW")]))
+    shutil.rmtree(out, ignore_errors=True)
+    for junk in ("ens_1", "ens_2"):
+        shutil.rmtree(os.path.join(d, junk), ignore_errors=True)
+    print("golden %-18s N=%d M=%d Nobs=%d nHRU=%d NB=%d steps=%d nPert=%d" % (name, N, M, Nobs, nH, NB, nsteps, nP))
+
+
 def make(name, spec):
     spec = dict(spec)
     kind = spec.pop("kind")
@@ -82,3 +123,7 @@ if __name__ == "__main__":
         if only and name not in only:
             continue
         make(name, spec)
+    for name, spec in ENKF_CASES.items():
+        if only and name not in only:
+            continue
+        make_enkf(name, spec)
