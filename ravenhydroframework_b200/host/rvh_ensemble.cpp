@@ -105,7 +105,7 @@ void CEnKFEnsemble::Initialize(const CModel *pModel, const optStruct &Options) {
   for (int i = 0; i < pModel->GetNumObservedTS(); i++) {
     const observed_ts &o = pModel->observed[i];
     const int p = pModel->GetSubBasinIndex(o.loc_ID);
-    const bool good = (p != DOESNT_EXIST) && pModel->GetSubBasin(p)->assimilate;
+    const bool good = (p >= 0) && pModel->GetSubBasin(p)->assimilate;
     if (good && o.name == "HYDROGRAPH") {
       aObsIndices.push_back(i);
       _series_basin.push_back(p);

@@ -273,8 +273,11 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
     }
     if (any_group) {
       _f_pert_mask.assign((size_t)nP * nH, 0);
-      for (int i = 0; i < nP; i++)
-        for (int k = 0; k < nH; k++) _f_pert_mask[(size_t)i * nH + k] = (perturbations[i].kk == DOESNT_EXIST || hru_groups[perturbations[i].kk].IsInGroup(k)) ? 1 : 0;
+      for (int i = 0; i < nP; i++) {
+        if (perturbations[i].kk == DOESNT_EXIST) { for (int k = 0; k < nH; k++) _f_pert_mask[(size_t)i * nH + k] = 1; continue; }
+        const std::vector<int> &g = hru_groups[perturbations[i].kk].hru;
+        for (size_t q = 0; q < g.size(); q++) _f_pert_mask[(size_t)i * nH + g[q]] = 1;
+      }
       d.pert_mask = _f_pert_mask.data();
     }
     _f_pert_eps.assign((size_t)nMembers * d.nSteps * nP, 0.0);

@@ -155,7 +155,7 @@ private:
 };
 
 // ---- groups, observations, forcing perturbations (what the EnKF ensemble refers to) ---------------------------------------
-struct CHRUGroup      { std::string name; std::vector<int> hru; bool IsInGroup(int k) const { for (size_t i = 0; i < hru.size(); i++) if (hru[i] == k) return true; return false; } };
+struct CHRUGroup      { std::string name; std::vector<int> hru; bool IsInGroup(int k) const { for (size_t i = 0; i < hru.size(); i++) if (hru[i] == k) return true; return false; } };   // CHRUGroup::IsInGroup (src/HRUGroup.cpp)
 struct CSubbasinGroup { std::string name; std::vector<int> sb; };
 struct observed_ts    { std::string name; long long loc_ID; CTimeSeries *pTS; };   // :ObservationData [type] [SBID|HRUID]
 enum adjustment { ADJ_ADDITIVE = 0, ADJ_MULTIPLICATIVE = 1, ADJ_REPLACE = 2 };

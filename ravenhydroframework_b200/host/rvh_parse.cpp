@@ -584,6 +584,8 @@ static void ParseHRUPropsFile(CModel *pModel, const optStruct &Options) {
       ExitGracefullyIf(s.size() < 2, "ParseHRUPropsFile: " + c + " needs a group name");
       const std::string gname = s[1];
       std::vector<int> members;
+      std::map<long long, int> hru_of_id;
+      if (hru) for (int k = 0; k < pModel->GetNumHRUs(); k++) hru_of_id.insert(std::make_pair(pModel->GetHydroUnit(k)->ID, k));   // first HRU with an ID wins, as in the reference's scan
       while (p.Tokenize(s)) {
         if (s.empty()) continue;
         if (s[0] == (hru ? ":EndHRUGroup" : ":EndSubBasinGroup")) break;
@@ -596,9 +598,9 @@ static void ParseHRUPropsFile(CModel *pModel, const optStruct &Options) {
           ExitGracefullyIf((b - a) > 10000000, "Parsing " + c + " command: invalid range of indices");
           for (long long id = a; id <= b; id++) {
             int idx = DOESNT_EXIST;
-            if (hru) { for (int k = 0; k < pModel->GetNumHRUs(); k++) if (pModel->GetHydroUnit(k)->ID == id) { idx = k; break; } }
+            if (hru) { std::map<long long, int>::const_iterator it = hru_of_id.find(id); if (it != hru_of_id.end()) idx = it->second; }
             else idx = pModel->GetSubBasinIndex(id);
-            if (idx == DOESNT_EXIST) { if (a == b) WriteWarning("ID " + std::to_string(id) + " specified in " + c + " command for group " + gname + " does not exist"); continue; }
+            if (idx < 0) { if (a == b) WriteWarning("ID " + std::to_string(id) + " specified in " + c + " command for group " + gname + " does not exist"); continue; }
             members.push_back(idx);
           }
         }
@@ -729,7 +731,7 @@ static void AssimilateStreamflowCommand(CModel *pModel, const std::vector<std::s
   ExitGracefullyIf(s.size() < 2, ":AssimilateStreamflow needs a subbasin ID");
   const long long SBID = s_to_ll(s[1]);
   const int pb = pModel->GetSubBasinIndex(SBID);
-  if (pb == DOESNT_EXIST) { WriteWarning("ParseTimeSeries::Trying to assimilate streamflow at non-existent subbasin " + std::to_string(SBID)); return; }
+  if (pb < 0) { WriteWarning("ParseTimeSeries::Trying to assimilate streamflow at non-existent subbasin " + std::to_string(SBID)); return; }
   bool ObsExists = false;
   for (size_t i = 0; i < pModel->observed.size(); i++) if (pModel->observed[i].name == "HYDROGRAPH" && pModel->observed[i].loc_ID == SBID) ObsExists = true;
   if (ObsExists) pModel->GetSubBasin(pb)->assimilate = true;
@@ -769,7 +771,7 @@ static void ParseTimeSeriesFile(CModel *pModel, const optStruct &Options, const 
         for (size_t i = 0; i < t.size(); i++) v.push_back(ts_s_to_d(t[i].c_str()));
       }
       ExitGracefullyIf((int)v.size() != n, "CTimeSeries::Parse: wrong number of data points in :ObservationData block. File: " + p.filename());
-      if (dtype == "HYDROGRAPH" && pModel->GetSubBasinIndex(loc) == DOESNT_EXIST) { WriteWarning("ParseTimeSeries:: Invalid subbasin ID in observation hydrograph time series. Will be ignored"); continue; }
+      if (dtype == "HYDROGRAPH" && pModel->GetSubBasinIndex(loc) < 0) { WriteWarning("ParseTimeSeries:: Invalid subbasin ID in observation hydrograph time series. Will be ignored"); continue; }
       observed_ts o; o.name = dtype; o.loc_ID = loc; o.pTS = new CTimeSeries(dtype, start_day, start_yr, interval, v);
       pModel->observed.push_back(o);
       continue;
