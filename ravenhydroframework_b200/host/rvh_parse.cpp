@@ -580,8 +580,9 @@ static void ParseHRUPropsFile(CModel *pModel, const optStruct &Options) {
     }
     if (c == ":HRUGroup" || c == ":SubBasinGroup") {
       // {ID1,ID2,a-b,...} lines until :End...; members keep the listed order (src/ParseHRUFile.cpp:472-530, 660-720)
-      const bool hru = (c == ":HRUGroup");
-      ExitGracefullyIf(s.size() < 2, "ParseHRUPropsFile: " + c + " needs a group name");
+      const std::string cmd = c;   // `c` refers into the token list, which the loop below overwrites
+      const bool hru = (cmd == ":HRUGroup");
+      ExitGracefullyIf(s.size() < 2, "ParseHRUPropsFile: " + cmd + " needs a group name");
       const std::string gname = s[1];
       std::vector<int> members;
       std::map<long long, int> hru_of_id;
@@ -589,18 +590,18 @@ static void ParseHRUPropsFile(CModel *pModel, const optStruct &Options) {
       while (p.Tokenize(s)) {
         if (s.empty()) continue;
         if (s[0] == (hru ? ":EndHRUGroup" : ":EndSubBasinGroup")) break;
-        ExitGracefullyIf(s[0][0] == ':', "ParseHRUPropsFile: command found between " + c + " ... :End commands; only IDs should be in this block");
+        ExitGracefullyIf(s[0][0] == ':', "ParseHRUPropsFile: command found between " + cmd + " ... :End commands; only IDs should be in this block");
         for (size_t i = 0; i < s.size(); i++) {
           long long a, b;
           size_t dash = s[i].find('-', 1);
           if (dash == std::string::npos) a = b = s_to_ll(s[i]);
           else { a = s_to_ll(s[i].substr(0, dash)); b = s_to_ll(s[i].substr(dash + 1)); }
-          ExitGracefullyIf((b - a) > 10000000, "Parsing " + c + " command: invalid range of indices");
+          ExitGracefullyIf((b - a) > 10000000, "Parsing " + cmd + " command: invalid range of indices");
           for (long long id = a; id <= b; id++) {
             int idx = DOESNT_EXIST;
             if (hru) { std::map<long long, int>::const_iterator it = hru_of_id.find(id); if (it != hru_of_id.end()) idx = it->second; }
             else idx = pModel->GetSubBasinIndex(id);
-            if (idx < 0) { if (a == b) WriteWarning("ID " + std::to_string(id) + " specified in " + c + " command for group " + gname + " does not exist"); continue; }
+            if (idx < 0) { if (a == b) WriteWarning("ID " + std::to_string(id) + " specified in " + cmd + " command for group " + gname + " does not exist"); continue; }
             members.push_back(idx);
           }
         }
