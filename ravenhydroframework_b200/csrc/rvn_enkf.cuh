@@ -53,37 +53,63 @@ __global__ void enkf_unpack_kernel(const __grid_constant__ DevModel Mo, const En
 }
 
 #define RVN_ENKF_BS 128
-#define RVN_ENKF_ET 8
+#define RVN_ENKF_ET 16   // local members per CTA tile (accumulators per column)
+#define RVN_ENKF_KT 2    // state rows (columns of X) per thread
 // Xall [N][M] in; Xa [nLocal][M] out (separate buffer: every CTA reads all members' rows).  Zt = Z restricted to the local
-// columns, stored [N][nLocalPad] with nLocalPad a multiple of ET (padding columns zero).
+// columns, stored [N][nLocalPad] with nLocalPad a multiple of ET (padding columns zero).  Per ensemble member i a thread loads
+// KT values of X (coalesced) and ET values of Z (128-bit shared-memory broadcasts) for 2*KT*ET FP64 operations.
 __global__ void __launch_bounds__(RVN_ENKF_BS) enkf_update_kernel(const double *__restrict__ Xall, const double *__restrict__ Zt, double *__restrict__ Xa,
                                                                  const long long M, const int N, const int e0, const int nLocal, const int nLocalPad) {
-  extern __shared__ double s_z[];   // [N][ET]
+  extern __shared__ __align__(16) double s_z[];   // [N][ET]
   const int tile = blockIdx.y;
   for (int i = threadIdx.x; i < N * RVN_ENKF_ET; i += RVN_ENKF_BS) {
     const int row = i / RVN_ENKF_ET, col = i - row * RVN_ENKF_ET;
     s_z[i] = Zt[(size_t)row * nLocalPad + tile * RVN_ENKF_ET + col];
   }
   __syncthreads();
-  const long long k = (long long)blockIdx.x * RVN_ENKF_BS + threadIdx.x;
-  if (k >= M) return;
+  const long long k0 = (long long)blockIdx.x * (RVN_ENKF_BS * RVN_ENKF_KT) + threadIdx.x;
+  bool live[RVN_ENKF_KT];
+  long long kk[RVN_ENKF_KT];
+#pragma unroll
+  for (int j = 0; j < RVN_ENKF_KT; j++) { kk[j] = k0 + (long long)j * RVN_ENKF_BS; live[j] = kk[j] < M; if (!live[j]) kk[j] = M - 1; }
   // A = X - 1/N*(X*e_N1)*e_1N : Xmean accumulates X[i][k]/N in member order (src/EnKF.cpp:539-546)
-  double Xmean = 0.0;
-  for (int i = 0; i < N; i++) Xmean += Xall[(size_t)i * M + k] / N;
-  double acc[RVN_ENKF_ET];
+  double Xmean[RVN_ENKF_KT];
 #pragma unroll
-  for (int c = 0; c < RVN_ENKF_ET; c++) acc[c] = 0.0;
+  for (int j = 0; j < RVN_ENKF_KT; j++) Xmean[j] = 0.0;
   for (int i = 0; i < N; i++) {
-    const double a = Xall[(size_t)i * M + k] - Xmean;
-    const double *z = s_z + i * RVN_ENKF_ET;
 #pragma unroll
-    for (int c = 0; c < RVN_ENKF_ET; c++) acc[c] += a * z[c];   // MatMult(A,Z,...): C[n][p] += A[n][m]*B[m][p]
+    for (int j = 0; j < RVN_ENKF_KT; j++) Xmean[j] += Xall[(size_t)i * M + kk[j]] / N;
+  }
+  double acc[RVN_ENKF_KT][RVN_ENKF_ET];
+#pragma unroll
+  for (int j = 0; j < RVN_ENKF_KT; j++)
+#pragma unroll
+    for (int c = 0; c < RVN_ENKF_ET; c++) acc[j][c] = 0.0;
+#pragma unroll 2
+  for (int i = 0; i < N; i++) {
+    double a[RVN_ENKF_KT];
+#pragma unroll
+    for (int j = 0; j < RVN_ENKF_KT; j++) a[j] = Xall[(size_t)i * M + kk[j]] - Xmean[j];
+    const double2 *z2 = reinterpret_cast<const double2 *>(s_z + i * RVN_ENKF_ET);
+#pragma unroll
+    for (int c = 0; c < RVN_ENKF_ET / 2; c++) {
+      const double2 z = z2[c];
+#pragma unroll
+      for (int j = 0; j < RVN_ENKF_KT; j++) {   // MatMult(A,Z,...): C[n][p] += A[n][m]*B[m][p], m ascending, separate multiply and add
+        acc[j][2 * c] += a[j] * z.x;
+        acc[j][2 * c + 1] += a[j] * z.y;
+      }
+    }
   }
   const double scale = 1.0 / (N - 1);
 #pragma unroll
-  for (int c = 0; c < RVN_ENKF_ET; c++) {
-    const int el = tile * RVN_ENKF_ET + c;
-    if (el < nLocal) Xa[(size_t)el * M + k] = Xall[(size_t)(e0 + el) * M + k] + acc[c] * scale;   // ScalarMatMult, MatAdd
+  for (int j = 0; j < RVN_ENKF_KT; j++) {
+    if (!live[j]) continue;
+#pragma unroll
+    for (int c = 0; c < RVN_ENKF_ET; c++) {
+      const int el = tile * RVN_ENKF_ET + c;
+      if (el < nLocal) Xa[(size_t)el * M + kk[j]] = Xall[(size_t)(e0 + el) * M + kk[j]] + acc[j][c] * scale;   // ScalarMatMult, MatAdd
+    }
   }
 }
 #endif

@@ -118,7 +118,7 @@ def main():
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
     fc_ms, upd_ms, gather_ms, upd_wall_ms = [float(v) for v in vals.cpu()]
     if rank == 0:
-        ntile = (nloc + 7) // 8
+        ntile = (nloc + 15) // 16
         flop = 2.0 * N * M * nloc
         bytes_ = N * M * 8.0 * ntile + N * M * 8.0 + nloc * M * 8.0
         print(json.dumps({
