@@ -94,6 +94,14 @@ typedef enum {
   RVN_OP_CAPRISE_HBV,          /* CmvCapillaryRise        src/CapillaryRise.cpp:103-147,160-179    */
   RVN_OP_GLACIERMELT_HBV,      /* CmvGlacierMelt          src/GlacierProcesses.cpp                  */
   RVN_OP_GLACIERRELEASE_HBVEC, /* CmvGlacierRelease       src/GlacierProcesses.cpp                  */
+  RVN_OP_INF_VIC_ARNO,         /* CmvInfiltration         src/Infiltration.cpp:400-416              */
+  RVN_OP_BASE_LINEAR_ANALYTIC, /* CmvBaseflow             src/Baseflow.cpp:199-205                  */
+  RVN_OP_BASE_VIC,             /* CmvBaseflow             src/Baseflow.cpp:221-228                  */
+  RVN_OP_BASE_TOPMODEL,        /* CmvBaseflow             src/Baseflow.cpp:230-242                  */
+  RVN_OP_SOILEVAP_TOPMODEL,    /* CmvSoilEvap             src/SoilEvaporation.cpp:385-402           */
+  RVN_OP_INTERFLOW_PRMS,       /* CmvInterflow            src/Interflow.cpp:98-124,136-148          */
+  RVN_OP_SNOWMELT_POTMELT,     /* CmvSnowMelt             src/SnowMeltRefreeze.cpp:87-131           */
+  RVN_OP_SNOWSQUEEZE,          /* CmvSnowSqueeze          src/SnowMeltRefreeze.cpp:197-244          */
   RVN_OP_COUNT
 } rvn_opcode;
 
@@ -113,7 +121,7 @@ typedef enum { RVN_ADJ_ADDITIVE = 0, RVN_ADJ_MULTIPLICATIVE, RVN_ADJ_REPLACE } r
 typedef enum { RVN_CONVOL_GR4J_1 = 0, RVN_CONVOL_GR4J_2, RVN_CONVOL_GAMMA, RVN_CONVOL_GAMMA_2 } rvn_convol_type;
 
 /* ---- per-member parameter table ------------------------------------------------------------------
- * ptab[member][..] = [ globals | land-use classes | vegetation classes | soil classes ], every class
+ * ptab[member][..] = [ globals | land-use classes | vegetation classes | soil classes | terrain classes ], every class
  * a fixed-stride row of the fields below (names follow reference src/Properties.h).  Members of an
  * ensemble differ only in this table (reference CModel::UpdateParameter, src/Model.cpp:2692-2750). */
 typedef enum {
@@ -143,8 +151,9 @@ typedef enum {
 typedef enum {
   RVN_S_POROSITY = 0, RVN_S_CAP_RATIO, RVN_S_PERC_COEFF, RVN_S_PET_CORRECTION, RVN_S_BASEFLOW_COEFF,
   RVN_S_BASEFLOW_N, RVN_S_FIELD_CAPACITY, RVN_S_SAT_WILT, RVN_S_HBV_BETA, RVN_S_MAX_CAP_RISE_RATE,
-  RVN_S_MAX_PERC_RATE, RVN_S_GR4J_X2, RVN_S_GR4J_X3, RVN_S_COUNT
+  RVN_S_MAX_PERC_RATE, RVN_S_GR4J_X2, RVN_S_GR4J_X3, RVN_S_VIC_B_EXP, RVN_S_MAX_BASEFLOW_RATE, RVN_S_MAX_INTERFLOW_RATE, RVN_S_COUNT
 } rvn_soil_field;
+typedef enum { RVN_T_TOPMODEL_LAMBDA = 0, RVN_T_COUNT } rvn_terrain_field;   /* reference terrain_struct, src/Properties.h */
 
 /* forcing series the host uploads per gauge, already sampled on the model step
  * (reference CGauge::GetForcingValue(ftype,nn), src/Gauge.cpp:533-540) */
@@ -188,7 +197,17 @@ typedef struct rvn_process {
                                  ia[4]=rvn_convol_type
                        soil ops: ia[0]=soil layer of 'from', ia[1]=soil layer of 'to' (or -1)           */
   double  da[2];    /* op-specific doubles (SPLIT: da[0] = fraction to first target) */
+  /* :ProcessGroup ... :EndProcessGroup (reference CProcessGroup, src/ProcessGroup.cpp:72-99): the members of a group are
+   * consecutive records; every member's rates are evaluated on the SAME state into a shared local rate vector that is zeroed
+   * once per group (the reference's loc_rates), scaled by `weight` into the group's rate vector, and the group's connections
+   * (the concatenation of the members', conn_from/conn_to[gconn0 .. gconn0+gnconn)) are applied after the last member. */
+  int32_t group;    /* 0: ordinary process; bit 0: first member of a group; bit 1: last member; 4: middle member */
+  int32_t gconn0, gnconn, pad_;
+  double  weight;
 } rvn_process;
+#define RVN_GRP_FIRST 1
+#define RVN_GRP_LAST 2
+#define RVN_GRP_MEMBER 4
 
 typedef struct rvn_options {
   double  timestep;               /* Options.timestep [d] */
@@ -230,6 +249,10 @@ typedef struct rvn_model_desc {
   /* parameter tables [nMembers][ptab_stride]; offsets of the class blocks inside one member's table */
   int32_t ptab_stride, glob_off, lu_off, veg_off, soil_off;
   const double *ptab;
+  /* terrain classes: block of nTerrain rows of RVN_T_COUNT fields at terr_off in every member's table; class of each HRU
+   * (-1 = [NONE]) */
+  int32_t terr_off, nTerrain;
+  const int32_t *hru_terrain; /* [nHRU] */
   /* convolution unit hydrographs, hoisted out of the per-HRU-per-step loop (reference rebuilds them in
    * CmvConvolution::GenerateUnitHydrograph, src/Convolution.cpp:107-154): [nMembers][nLU][nConvProc] */
   int32_t nConvProc;

@@ -453,7 +453,7 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       if (SWE <= 0.0) rates[4] = -sv[iFrom[4]] / tstep;
       break;
     }
-    case RVN_OP_INF_HMETS: case RVN_OP_INF_HBV: case RVN_OP_INF_GR4J: { /* src/Infiltration.cpp:304-330,384-398,477-489,491-514 + constraints :605-626 */
+    case RVN_OP_INF_HMETS: case RVN_OP_INF_HBV: case RVN_OP_INF_GR4J: case RVN_OP_INF_VIC_ARNO: { /* src/Infiltration.cpp:304-330,384-398,477-489,491-514 + constraints :605-626 */
       if (type != RVN_HRU_STANDARD && type != RVN_HRU_ROCK && type != RVN_HRU_MASKED_GLACIER) break;
       double Fimp = P_LU(c, RVN_LU_IMPERMEABLE_FRAC);
       double ponded = omax(sv[c->iSV[RVN_SV_PONDED_WATER]], 0.0);
@@ -472,6 +472,13 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
         double stor = sv[iTo[0]], max_stor = soil_capacity(c, 0), beta = P_S(c, 0, RVN_S_HBV_BETA);
         double sat = omax(omin(stor / max_stor, 1.0), 0.0);
         double runoff = pow(sat, beta) * rainthru;
+        runoff = (Fimp)*rainthru + (1 - Fimp) * runoff;
+        rates[0] = rainthru - runoff; rates[1] = runoff;
+      } else if (pr->op == RVN_OP_INF_VIC_ARNO) { /* src/Infiltration.cpp:400-416 */
+        double stor = sv[iTo[0]], max_stor = soil_capacity(c, 0), b = P_S(c, 0, RVN_S_VIC_B_EXP);
+        double sat = omin(stor / max_stor, 1.0);
+        double sat_area = 1.0 - pow(1.0 - sat, b);
+        double runoff = sat_area * rainthru;
         runoff = (Fimp)*rainthru + (1 - Fimp) * runoff;
         rates[0] = rainthru - runoff; rates[1] = runoff;
       } else {
@@ -503,7 +510,8 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       rates[0] = (pr->da[0]) * sv[iFrom[0]] / tstep;
       rates[1] = (1.0 - pr->da[0]) * sv[iFrom[0]] / tstep;
       break;
-    case RVN_OP_BASE_LINEAR: case RVN_OP_BASE_POWER_LAW: case RVN_OP_BASE_GR4J: { /* src/Baseflow.cpp:152-186,208-215,238-243 + :297-310 */
+    case RVN_OP_BASE_LINEAR: case RVN_OP_BASE_POWER_LAW: case RVN_OP_BASE_GR4J: case RVN_OP_BASE_LINEAR_ANALYTIC: case RVN_OP_BASE_VIC:
+    case RVN_OP_BASE_TOPMODEL: { /* src/Baseflow.cpp:152-186,208-215,238-243 + :297-310 */
       if (type == RVN_HRU_LAKE || type == RVN_HRU_WATER || type == RVN_HRU_ROCK) { /* GetRatesOfChange returns; constraints still run */ }
       else {
         int m = pr->ia[0];
@@ -511,7 +519,18 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
         stor = omin(omax(stor, 0.0), max_stor);
         if (pr->op == RVN_OP_BASE_LINEAR) rates[0] = P_S(c, m, RVN_S_BASEFLOW_COEFF) * stor;
         else if (pr->op == RVN_OP_BASE_POWER_LAW) rates[0] = P_S(c, m, RVN_S_BASEFLOW_COEFF) * pow(stor, P_S(c, m, RVN_S_BASEFLOW_N));
-        else {
+        else if (pr->op == RVN_OP_BASE_LINEAR_ANALYTIC) { /* :199-205 */
+          double K = P_S(c, m, RVN_S_BASEFLOW_COEFF);
+          rates[0] = stor * (1 - exp(-K * tstep)) / tstep;
+        } else if (pr->op == RVN_OP_BASE_VIC) { /* :221-228 */
+          double max_rate = P_S(c, m, RVN_S_MAX_BASEFLOW_RATE), n = P_S(c, m, RVN_S_BASEFLOW_N);
+          rates[0] = max_rate * pow(stor / max_stor, n);
+        } else if (pr->op == RVN_OP_BASE_TOPMODEL) { /* :230-242 */
+          double K = P_S(c, m, RVN_S_MAX_BASEFLOW_RATE), n = P_S(c, m, RVN_S_BASEFLOW_N);
+          int terr = d->hru_terrain ? d->hru_terrain[c->k] : -1;
+          double lambda = c->ptab[d->terr_off + (terr >= 0 ? terr : 0) * RVN_T_COUNT + RVN_T_TOPMODEL_LAMBDA];
+          rates[0] = K * (max_stor / n * pow(lambda, -n)) * pow(stor / max_stor, n);
+        } else {
           double x3 = P_S(c, m, RVN_S_GR4J_X3);
           rates[0] = stor * (1.0 - pow(1.0 + pow(omax(stor / x3, 0.0), 4), -0.25)) / tstep;
         }
@@ -545,17 +564,19 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       }
       break;
     }
-    case RVN_OP_SOILEVAP_ALL: case RVN_OP_SOILEVAP_HBV: case RVN_OP_SOILEVAP_GR4J: { /* src/SoilEvaporation.cpp:325-343,379-405,640-650 + :767-783 */
+    case RVN_OP_SOILEVAP_ALL: case RVN_OP_SOILEVAP_HBV: case RVN_OP_SOILEVAP_GR4J: case RVN_OP_SOILEVAP_TOPMODEL: { /* src/SoilEvaporation.cpp:325-343,379-405,640-650 + :767-783 */
       if (type != RVN_HRU_STANDARD) break;
       double PET = F[RVN_F_PET];
       if (!d->opt.suppress_competitive_ET) { PET -= (sv[c->iSV[RVN_SV_AET]] / tstep); PET = omax(PET, 0.0); }
       if (pr->op == RVN_OP_SOILEVAP_ALL) rates[0] = PET;
-      else if (pr->op == RVN_OP_SOILEVAP_HBV) {
+      else if (pr->op == RVN_OP_SOILEVAP_HBV || pr->op == RVN_OP_SOILEVAP_TOPMODEL) {
         double stor = omax(sv[iFrom[0]], 0.0), tens_stor = soil_tension_capacity(c, 0);
         rates[0] = PET * omin(stor / tens_stor, 1.0);
-        int iSnow = c->iSV[RVN_SV_SNOW];
-        double Fc = P_LU(c, RVN_LU_FOREST_COVERAGE);
-        if ((iSnow >= 0) && (sv[iSnow] > O_REAL_SMALL)) rates[0] = (Fc)*rates[0];
+        if (pr->op == RVN_OP_SOILEVAP_HBV) { /* correction for snow in non-forested areas */
+          int iSnow = c->iSV[RVN_SV_SNOW];
+          double Fc = P_LU(c, RVN_LU_FOREST_COVERAGE);
+          if ((iSnow >= 0) && (sv[iSnow] > O_REAL_SMALL)) rates[0] = (Fc)*rates[0];
+        }
       } else {
         double max_stor = soil_capacity(c, 0), stor = sv[iFrom[0]];
         double sat = stor / max_stor;
@@ -570,6 +591,50 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
         corr += oldrate - rates[q];
       }
       rates[pr->nconn - 1] -= corr;
+      break;
+    }
+    case RVN_OP_SNOBAL_HBV: { /* src/SnowBalance.cpp:430-465; liquid capacity src/SnowParams.cpp:79-88 */
+      double Ka = P_LU(c, RVN_LU_REFREEZE_FACTOR), Ta = F[RVN_F_TEMP_DAILY_AVE];
+      double melt, refreeze, liq_cap, to_liq, overflow;
+      double SWE = sv[iFrom[0]], SL = sv[iTo[0]];
+      melt = omax(F[RVN_F_POTENTIAL_MELT], 0.0);
+      melt = omin(melt, SWE / tstep);
+      SWE -= melt * tstep;
+      refreeze = Ka * omax(O_FREEZING_TEMP - Ta, 0.0);
+      refreeze = omax(omin(SL / tstep, refreeze), 0.0);
+      SL -= refreeze * tstep;
+      liq_cap = P_G(c, RVN_G_SNOW_SWI) * SWE;
+      to_liq = omin(melt, omax(liq_cap - SL, 0.0) / tstep);
+      SL += to_liq * tstep;
+      overflow = omax((SL - liq_cap) / tstep, 0.0);
+      rates[0] = -refreeze;
+      rates[0] += to_liq;
+      rates[1] = omax(melt - to_liq, 0.0);
+      rates[2] = overflow;
+      if (type != RVN_HRU_STANDARD) { rates[3] = rates[1]; rates[1] = 0.0; rates[4] = rates[2]; rates[2] = 0.0; }
+      break;
+    }
+    case RVN_OP_INTERFLOW_PRMS: { /* src/Interflow.cpp:98-124 + :136-148 */
+      if (type == RVN_HRU_LAKE || type == RVN_HRU_WATER || type == RVN_HRU_ROCK) break;
+      int m = pr->ia[0];
+      double stor = sv[iFrom[0]];
+      double max_stor = soil_capacity(c, m), tens_stor = soil_tension_capacity(c, m), K = P_S(c, m, RVN_S_MAX_INTERFLOW_RATE);
+      rates[0] = K * omax(stor - tens_stor, 0.0) / (max_stor - tens_stor);
+      rates[0] = omin(rates[0], sv[iFrom[0]] / tstep);
+      break;
+    }
+    case RVN_OP_SNOWMELT_POTMELT: /* src/SnowMeltRefreeze.cpp:87-131 */
+      rates[0] = omax(F[RVN_F_POTENTIAL_MELT], 0.0);
+      if (sv[iFrom[0]] <= 0) rates[0] = 0.0;
+      if (rates[0] < 0.0) rates[0] = 0.0;
+      rates[0] = omin(rates[0], sv[iFrom[0]] / tstep);
+      break;
+    case RVN_OP_SNOWSQUEEZE: { /* src/SnowMeltRefreeze.cpp:197-244 (no SNOW_DEPTH variable) */
+      double S = sv[c->iSV[RVN_SV_SNOW]], SL = sv[c->iSV[RVN_SV_SNOW_LIQ]];
+      double liq_cap = P_G(c, RVN_G_SNOW_SWI) * S;
+      rates[0] = omax(SL - liq_cap, 0.0) / tstep;
+      if (sv[iFrom[0]] <= 0) rates[0] = 0.0;
+      if (rates[0] < 0.0) rates[0] = 0.0;
       break;
     }
     case RVN_OP_SNOBAL_SIMPLE_MELT: /* src/SnowBalance.cpp:393-396 + :1311-1317 */
@@ -834,6 +899,27 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
           const rvn_process *pr = &d->proc[j];
           if (!((d->apply_mask[k] >> j) & 1ull)) continue; /* CModel::ApplyProcess gate, src/Model.cpp:3061 */
           int nconn = pr->nconn;
+          if (pr->group != 0) {
+            /* CProcessGroup::GetRatesOfChange (src/ProcessGroup.cpp:72-99): j is the group's FIRST member (the loop skips the others
+             * below); loc_rates is zeroed once and shared by all members; group rates[q1+qq] = weight * loc_rates[qq]. */
+            if (!(pr->group & RVN_GRP_FIRST)) continue;
+            const int gn = pr->gnconn;
+            double loc_rates[O_MAXCONN];
+            for (int q = 0; q < gn; q++) { rates[q] = 0.0; loc_rates[q] = 0.0; }
+            int q1 = 0, jj = j;
+            for (;;) {
+              const rvn_process *sp = &d->proc[jj];
+              int scf[O_MAXCONN], sct[O_MAXCONN];
+              for (int q = 0; q < sp->nconn; q++) { scf[q] = d->conn_from[sp->conn0 + q]; sct[q] = d->conn_to[sp->conn0 + q]; }
+              op_rates(&c, sp, scf, sct, phinew, loc_rates);
+              for (int qq = 0; qq < sp->nconn; qq++) rates[q1 + qq] = sp->weight * loc_rates[qq];
+              q1 += sp->nconn;
+              if (sp->group & RVN_GRP_LAST) break;
+              jj++;
+            }
+            nconn = gn;
+            for (int q = 0; q < nconn; q++) { cf[q] = d->conn_from[pr->gconn0 + q]; ct[q] = d->conn_to[pr->gconn0 + q]; }
+          } else {
           for (int q = 0; q < nconn; q++) rates[q] = 0.0;
           if (pr->op == RVN_OP_CONVOLVE) {
             const int NST = RVN_CONV_STORES;
@@ -847,6 +933,7 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
           } else {
             for (int q = 0; q < nconn; q++) { cf[q] = d->conn_from[pr->conn0 + q]; ct[q] = d->conn_to[pr->conn0 + q]; }
             op_rates(&c, pr, cf, ct, phinew, rates);
+          }
           }
           for (int q = 0; q < nconn; q++) { /* src/Solvers.cpp:220-236 */
             int typ = d->sv_type[cf[q]];

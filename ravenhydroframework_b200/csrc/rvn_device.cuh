@@ -41,11 +41,11 @@ struct DevProgram {
   int8_t  slot_water[RVN_MAX_CORE];         // 1: water storage where a self-connection is a no-op; 2: CONVOLUTION; 0: other
   int16_t iSV[RVN_SV_NTYPES];               // first core slot of each SV type or -1
   int16_t soil_slot[RVN_MAX_SOIL_LAYERS];   // core slot of SOIL[m]
-  int32_t maxConn, nConn, nConv;
+  int32_t maxConn, nConn, nConv, maxGroupConn;
 };
 
 struct DevModel {
-  int32_t nH, nHp, nSB, E, NS, nCore, maxConn;
+  int32_t nH, nHp, nSB, E, NS, nCore, maxConn, maxGroupConn;
   rvn_options opt;
   int32_t glob_off, lu_off, veg_off, soil_off, ptab_stride;
   int32_t nLU, nVeg, nConv, nGauges, nSteps, record_forcings;
@@ -61,6 +61,7 @@ struct DevModel {
   // shared static tables
   const double *hru_area, *hru_elev, *hru_lat, *hru_slope, *hru_aspect;
   const int32_t *hru_type, *hru_lu, *hru_veg, *hru_profile, *hru_sb, *hru_enabled;
+  const int32_t *hru_terrain; int32_t terr_off;   // terrain class of each HRU (or NULL) and its block in the parameter table
   const unsigned long long *apply_mask;
   const int32_t *prof_class; const double *prof_thick;
   const double *gauge_series;                      // [step][RVN_GF_COUNT][nGauges]: one contiguous slab per step
@@ -83,6 +84,7 @@ struct DevModel {
   double *rec_qout, *rec_wshed;                    // [rec][member][nSB], [rec][member][4]
   int32_t rec_capacity, rec_flags;
   const DevProgram *prog;
+  const double *proc_weight;                       // [nProc] process-group member weights (1.0 outside groups)
   // forcing perturbations of the EnKF members (0 = none)
   int32_t nPert;
   int32_t pert_forcing[RVN_MAX_PERT], pert_adj[RVN_MAX_PERT];

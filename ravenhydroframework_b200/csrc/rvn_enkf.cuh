@@ -55,6 +55,7 @@ __global__ void enkf_unpack_kernel(const __grid_constant__ DevModel Mo, const En
 #define RVN_ENKF_BS 128
 #define RVN_ENKF_ET 16   // local members per CTA tile (accumulators per column)
 #define RVN_ENKF_KT 2    // state rows (columns of X) per thread
+#define RVN_ENKF_U 8     // ensemble members fetched ahead
 // Xall [N][M] in; Xa [nLocal][M] out (separate buffer: every CTA reads all members' rows).  Zt = Z restricted to the local
 // columns, stored [N][nLocalPad] with nLocalPad a multiple of ET (padding columns zero).  Per ensemble member i a thread loads
 // KT values of X (coalesced) and ET values of Z (128-bit shared-memory broadcasts) for 2*KT*ET FP64 operations.
@@ -76,28 +77,39 @@ __global__ void __launch_bounds__(RVN_ENKF_BS) enkf_update_kernel(const double *
   double Xmean[RVN_ENKF_KT];
 #pragma unroll
   for (int j = 0; j < RVN_ENKF_KT; j++) Xmean[j] = 0.0;
+#pragma unroll 8
   for (int i = 0; i < N; i++) {
 #pragma unroll
-    for (int j = 0; j < RVN_ENKF_KT; j++) Xmean[j] += Xall[(size_t)i * M + kk[j]] / N;
+    for (int j = 0; j < RVN_ENKF_KT; j++) Xmean[j] += __ldg(Xall + (size_t)i * M + kk[j]) / N;
   }
   double acc[RVN_ENKF_KT][RVN_ENKF_ET];
 #pragma unroll
   for (int j = 0; j < RVN_ENKF_KT; j++)
 #pragma unroll
     for (int c = 0; c < RVN_ENKF_ET; c++) acc[j][c] = 0.0;
-#pragma unroll 2
-  for (int i = 0; i < N; i++) {
-    double a[RVN_ENKF_KT];
+  // the X values of RVN_ENKF_U members are fetched before they are used: U*KT independent loads in flight per thread
+  for (int i0 = 0; i0 < N; i0 += RVN_ENKF_U) {
+    double xv[RVN_ENKF_U][RVN_ENKF_KT];
 #pragma unroll
-    for (int j = 0; j < RVN_ENKF_KT; j++) a[j] = Xall[(size_t)i * M + kk[j]] - Xmean[j];
-    const double2 *z2 = reinterpret_cast<const double2 *>(s_z + i * RVN_ENKF_ET);
+    for (int u = 0; u < RVN_ENKF_U; u++)
 #pragma unroll
-    for (int c = 0; c < RVN_ENKF_ET / 2; c++) {
-      const double2 z = z2[c];
+      for (int j = 0; j < RVN_ENKF_KT; j++) xv[u][j] = (i0 + u < N) ? __ldg(Xall + (size_t)(i0 + u) * M + kk[j]) : 0.0;
 #pragma unroll
-      for (int j = 0; j < RVN_ENKF_KT; j++) {   // MatMult(A,Z,...): C[n][p] += A[n][m]*B[m][p], m ascending, separate multiply and add
-        acc[j][2 * c] += a[j] * z.x;
-        acc[j][2 * c + 1] += a[j] * z.y;
+    for (int u = 0; u < RVN_ENKF_U; u++) {
+      if (i0 + u < N) {
+        double a[RVN_ENKF_KT];
+#pragma unroll
+        for (int j = 0; j < RVN_ENKF_KT; j++) a[j] = xv[u][j] - Xmean[j];
+        const double2 *z2 = reinterpret_cast<const double2 *>(s_z + (i0 + u) * RVN_ENKF_ET);
+#pragma unroll
+        for (int c = 0; c < RVN_ENKF_ET / 2; c++) {
+          const double2 z = z2[c];
+#pragma unroll
+          for (int j = 0; j < RVN_ENKF_KT; j++) {   // MatMult(A,Z,...): C[n][p] += A[n][m]*B[m][p], m ascending, separate multiply and add
+            acc[j][2 * c] += a[j] * z.x;
+            acc[j][2 * c + 1] += a[j] * z.y;
+          }
+        }
       }
     }
   }

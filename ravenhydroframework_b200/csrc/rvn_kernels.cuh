@@ -40,7 +40,8 @@ struct CtxCommon {
   int type, lu, veg, profile;
   const double *ptab;      // member parameter row (shared memory)
   const rvn_options *popt;
-  int glob_off, lu_base, veg_base, soil_off;
+  int glob_off, lu_base, veg_base, soil_off, terr_base;
+  RVN_DI double TERR(int f) const { return ptab[terr_base + f]; }
   RVN_DI double G(int f) const { return ptab[glob_off + f]; }
   RVN_DI double LU(int f) const { return ptab[lu_base + f]; }
   RVN_DI double VEG(int f) const { return ptab[veg_base + f]; }
@@ -53,9 +54,11 @@ struct DynCtx : CtxCommon {
   const DevProgram *P;     // program (shared memory)
   double *sv;              // &s_sv[tid]; slot i at sv[i*RVN_BS]  -- newest state (aPhinew[k])
   double *rt;              // &s_rates[tid]; connection q at rt[q*RVN_BS]
+  double *grt;             // &s_grates[tid]: rate vector of the current process group
   const int32_t *prof_class; const double *prof_thick;   // global, row of this HRU's soil profile
   RVN_DI double &SV(int slot) const { return sv[slot * RVN_BS]; }
   RVN_DI double &R(int q) const { return rt[q * RVN_BS]; }
+  RVN_DI double &GR(int q) const { return grt[q * RVN_BS]; }
   RVN_DI int iSV(int t) const { return P->iSV[t]; }
   RVN_DI int slot_type(int s) const { return P->slot_type[s]; }
   RVN_DI int slot_layer(int s) const { return P->slot_layer[s]; }
@@ -71,6 +74,12 @@ struct DynProc {
   RVN_DI int nconn() const { return p->nconn; }
   RVN_DI int ia(int i) const { return p->ia[i]; }
   RVN_DI double da(int i) const { return p->da[i]; }
+  RVN_DI int conn0() const { return p->conn0; }
+  RVN_DI int gconn0() const { return p->gconn0; }
+  RVN_DI int gnconn() const { return p->gnconn; }
+  RVN_DI double weight() const { return p->weight; }
+  RVN_DI int gfrom(int q) const { return P->conn_from[p->gconn0 + q]; }
+  RVN_DI int gto(int q) const { return P->conn_to[p->gconn0 + q]; }
 };
 
 // compile-time context of the specialised kernels: everything indexed by constants -> registers
@@ -78,11 +87,13 @@ template <class Prog>
 struct StatCtx : CtxCommon {
   double sv[Prog::nCore];
   double rt[Prog::maxConn];
+  double grt[Prog::maxGroupConn > 0 ? Prog::maxGroupConn : 1];
   int sbase[Prog::nSoil > 0 ? Prog::nSoil : 1];
   double sthick[Prog::nSoil > 0 ? Prog::nSoil : 1];
   RVN_DI double &SV(int slot) { return sv[slot]; }
   RVN_DI const double &SV(int slot) const { return sv[slot]; }
   RVN_DI double &R(int q) { return rt[q]; }
+  RVN_DI double &GR(int q) { return grt[q]; }
   static constexpr RVN_DI int iSV(int t) { return Prog::iSV(t); }
   static constexpr RVN_DI int slot_type(int s) { return Prog::slot_type(s); }
   static constexpr RVN_DI int slot_layer(int s) { return Prog::slot_layer(s); }
@@ -98,6 +109,13 @@ struct StatProc {
   static constexpr RVN_DI int nconn() { return Prog::nconn(J); }
   static constexpr RVN_DI int ia(int i) { return Prog::ia(J, i); }
   static constexpr RVN_DI double da(int i) { return Prog::da(J, i); }
+  static constexpr RVN_DI int conn0() { return Prog::conn0(J); }
+  static constexpr RVN_DI int gconn0() { return Prog::gconn0(J); }
+  static constexpr RVN_DI int gnconn() { return Prog::gnconn(J); }
+  const double *w;   // run-time group weights [nProc] (the only part of a program that is not compile-time: calibration varies them)
+  RVN_DI double weight() const { return __ldg(w + J); }
+  static constexpr RVN_DI int gfrom(int q) { return Prog::conn_from(Prog::gconn0(J) + q); }
+  static constexpr RVN_DI int gto(int q) { return Prog::conn_to(Prog::gconn0(J) + q); }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -492,6 +510,32 @@ RVN_DI void apply_connections(C &c, const PR &pr) {
   }
 }
 
+// one member of a :ProcessGroup (CProcessGroup::GetRatesOfChange, src/ProcessGroup.cpp:72-99): `grp` = the record's group flags.
+// The local rate vector R (the reference's loc_rates) is zeroed once per group and NOT between members; every member's
+// GetRatesOfChange + ApplyConstraints run on the same state; the group's connections are applied after the last member.
+template <class C, class PR>
+RVN_DI void run_group_member(C &c, const PR &pr, const int op, const int grp, const int maxConn) {
+  if (grp & RVN_GRP_FIRST) {
+#pragma unroll
+    for (int q = 0; q < maxConn; q++) c.R(q) = 0.0;
+  }
+  dispatch_rates(c, pr, op);
+  const int off = pr.conn0() - pr.gconn0();
+#pragma unroll
+  for (int q = 0; q < pr.nconn(); q++) c.GR(off + q) = pr.weight() * c.R(q);
+  if (grp & RVN_GRP_LAST) {
+    const double tstep = c.tstep;
+#pragma unroll
+    for (int q = 0; q < pr.gnconn(); q++) {   // src/Solvers.cpp:220-236 over the group's concatenated connections
+      const int from = pr.gfrom(q), to = pr.gto(q);
+      const double r = c.GR(q);
+      if (to != from) { c.SV(from) -= r * tstep; c.SV(to) += r * tstep; }
+      else if (c.slot_water(from) == 1) { c.SV(to) += 0.0; }
+      else c.SV(to) += r * tstep;
+    }
+  }
+}
+
 RVN_DI double block_sum(double v, double *s_red) {
   // fixed-shape tree: warp shuffles then the (<=4) warp totals in order -> deterministic
 #pragma unroll
@@ -513,6 +557,10 @@ RVN_DI void load_hru_statics(C &c, const DevModel &M, int k, const double *s_pta
   c.area = M.hru_area[k]; c.elev = M.hru_elev[k]; c.lat = M.hru_lat[k]; c.slope = M.hru_slope[k]; c.aspect = M.hru_aspect[k];
   c.type = M.hru_type[k]; c.lu = M.hru_lu[k]; c.veg = M.hru_veg[k]; c.profile = M.hru_profile[k];
   c.glob_off = M.glob_off; c.lu_base = M.lu_off + c.lu * RVN_LU_COUNT; c.veg_base = M.veg_off + c.veg * RVN_V_COUNT; c.soil_off = M.soil_off;
+  {
+    const int terr = (M.hru_terrain != nullptr) ? M.hru_terrain[k] : -1;
+    c.terr_base = M.terr_off + ((terr >= 0) ? terr : 0) * RVN_T_COUNT;   // [NONE] terrain: the host rejects models whose processes read terrain parameters
+  }
 }
 
 // canopy storage capacities of this HRU for this step: CVegetationClass::RecalculateCanopyParams (src/VegetationParams.cpp:85-135).
@@ -604,11 +652,14 @@ struct RunProcs {
         }
       } else {
         if (apply) {
-          const StatProc<Prog, J> pr{};
+          const StatProc<Prog, J> pr{M.proc_weight};
+          if constexpr (Prog::grp(J) != 0) run_group_member(c, pr, op, Prog::grp(J), Prog::maxConn);
+          else {
 #pragma unroll
-          for (int q = 0; q < Prog::nconn(J); q++) c.R(q) = 0.0;          // src/Model.cpp:3066-3071
-          dispatch_rates(c, pr, op);
-          apply_connections(c, pr);
+            for (int q = 0; q < Prog::nconn(J); q++) c.R(q) = 0.0;          // src/Model.cpp:3066-3071
+            dispatch_rates(c, pr, op);
+            apply_connections(c, pr);
+          }
         }
       }
       RunProcs<Prog, UNIT_DT, J + 1>::run(c, M, enabled, mask, e, k, gstate);
@@ -694,7 +745,8 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
   double *s_ptab = reinterpret_cast<double *>(rvn_smem + ((sizeof(DevProgram) + 15) & ~size_t(15)));
   double *s_sv = s_ptab + ((M.ptab_stride + 1) & ~1);
   double *s_rt = s_sv + (size_t)M.nCore * RVN_BS;
-  double *s_red = s_rt + (size_t)M.maxConn * RVN_BS;
+  double *s_grt = s_rt + (size_t)M.maxConn * RVN_BS;
+  double *s_red = s_grt + (size_t)M.maxGroupConn * RVN_BS;
   const int tid = threadIdx.x, e = blockIdx.y, k = blockIdx.x * RVN_BS + tid;
   {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(M.prog);
@@ -710,7 +762,7 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
   const bool enabled = in_range && (M.hru_enabled[k] != 0);
   DynCtx c;
   load_hru_statics(c, M, k, s_ptab);
-  c.P = P; c.sv = s_sv + tid; c.rt = s_rt + tid;
+  c.P = P; c.sv = s_sv + tid; c.rt = s_rt + tid; c.grt = s_grt + tid;
   c.prof_class = M.prof_class + c.profile * RVN_MAX_SOIL_LAYERS; c.prof_thick = M.prof_thick + c.profile * RVN_MAX_SOIL_LAYERS;
   const int sb = M.hru_sb[k];
   const unsigned long long mask = M.apply_mask[k];
@@ -740,6 +792,7 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
       continue;
     }
     const DynProc dp = {&pr, P};
+    if (pr.group != 0) { run_group_member(c, dp, pr.op, pr.group, P->maxConn); continue; }
     for (int q = 0; q < pr.nconn; q++) c.R(q) = 0.0;          // src/Model.cpp:3066-3071
     dispatch_rates(c, dp, pr.op);
     apply_connections(c, dp);

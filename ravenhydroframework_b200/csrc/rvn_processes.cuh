@@ -281,6 +281,13 @@ template <class C, class PR> RVN_DI void rates_INFILTRATION(C &c, const PR &pr, 
     double runoff = pow(sat, beta) * rainthru;
     runoff = (Fimp)*rainthru + (1 - Fimp) * runoff;
     c.R(0) = rainthru - runoff; c.R(1) = runoff;
+  } else if (op == RVN_OP_INF_VIC_ARNO) {   // src/Infiltration.cpp:400-416
+    double stor = c.SV(pr.to(0)), max_stor = SoilCapacity(c, 0), b = c.SOIL(0, RVN_S_VIC_B_EXP);
+    double sat = dmin(stor / max_stor, 1.0);
+    double sat_area = 1.0 - pow(1.0 - sat, b);
+    double runoff = sat_area * rainthru;
+    runoff = (Fimp)*rainthru + (1 - Fimp) * runoff;
+    c.R(0) = rainthru - runoff; c.R(1) = runoff;
   } else if (op == RVN_OP_INF_GR4J) {
     double x1 = SoilCapacity(c, 0), stor = c.SV(pr.to(0));
     double sat = stor / x1;
@@ -321,6 +328,12 @@ template <class C, class PR> RVN_DI void rates_BASEFLOW(C &c, const PR &pr, cons
     stor = dmin(dmax(stor, 0.0), max_stor);
     if (op == RVN_OP_BASE_LINEAR) c.R(0) = c.SOIL(m, RVN_S_BASEFLOW_COEFF) * stor;
     else if (op == RVN_OP_BASE_POWER_LAW) c.R(0) = c.SOIL(m, RVN_S_BASEFLOW_COEFF) * pow(stor, c.SOIL(m, RVN_S_BASEFLOW_N));
+    else if (op == RVN_OP_BASE_LINEAR_ANALYTIC) c.R(0) = stor * (1 - exp(-c.SOIL(m, RVN_S_BASEFLOW_COEFF) * c.tstep)) / c.tstep;
+    else if (op == RVN_OP_BASE_VIC) c.R(0) = c.SOIL(m, RVN_S_MAX_BASEFLOW_RATE) * pow(stor / max_stor, c.SOIL(m, RVN_S_BASEFLOW_N));
+    else if (op == RVN_OP_BASE_TOPMODEL) {
+      const double K = c.SOIL(m, RVN_S_MAX_BASEFLOW_RATE), n = c.SOIL(m, RVN_S_BASEFLOW_N), lambda = c.TERR(RVN_T_TOPMODEL_LAMBDA);
+      c.R(0) = K * (max_stor / n * pow(lambda, -n)) * pow(stor / max_stor, n);
+    }
     else if (op == RVN_OP_BASE_GR4J) {
       const double x3 = c.SOIL(m, RVN_S_GR4J_X3);
       c.R(0) = stor * (1.0 - pow(1.0 + pow(dmax(stor / x3, 0.0), 4.0), -0.25)) / c.tstep;
@@ -372,11 +385,11 @@ template <class C, class PR> RVN_DI void rates_SOILEVAP(C &c, const PR &pr, cons
   double PET = c.F[RVN_F_PET];
   if (!c.opt().suppress_competitive_ET) { PET -= (c.SV(c.iSV(RVN_SV_AET)) / c.tstep); PET = dmax(PET, 0.0); }
   if (op == RVN_OP_SOILEVAP_ALL) c.R(0) = PET;
-  else if (op == RVN_OP_SOILEVAP_HBV) {
+  else if (op == RVN_OP_SOILEVAP_HBV || op == RVN_OP_SOILEVAP_TOPMODEL) {
     const double stor = dmax(c.SV(pr.from(0)), 0.0), tens_stor = SoilTensionCapacity(c, 0);
     c.R(0) = PET * dmin(stor / tens_stor, 1.0);
     const int iSnow = c.iSV(RVN_SV_SNOW);
-    if (iSnow >= 0) { if (c.SV(iSnow) > D_REAL_SMALL) c.R(0) = (c.LU(RVN_LU_FOREST_COVERAGE)) * c.R(0); }
+    if (op == RVN_OP_SOILEVAP_HBV && iSnow >= 0) { if (c.SV(iSnow) > D_REAL_SMALL) c.R(0) = (c.LU(RVN_LU_FOREST_COVERAGE)) * c.R(0); }
   } else if (op == RVN_OP_SOILEVAP_GR4J) {
     const double max_stor = SoilCapacity(c, 0), stor = c.SV(pr.from(0));
     const double sat = stor / max_stor;
@@ -395,6 +408,51 @@ template <class C, class PR> RVN_DI void rates_SOILEVAP(C &c, const PR &pr, cons
   c.R(last) -= corr;
 }
 
+// CmvSnowBalance SNOBAL_HBV  src/SnowBalance.cpp:430-465 (connections :56-70; CalculateSnowLiquidCapacity src/SnowParams.cpp:79-88)
+template <class C, class PR> RVN_DI void rates_SNOBAL_HBV(C &c, const PR &pr) {
+  const double Ka = c.LU(RVN_LU_REFREEZE_FACTOR), Ta = c.F[RVN_F_TEMP_DAILY_AVE], tstep = c.tstep;
+  double SWE = c.SV(pr.from(0)), SL = c.SV(pr.to(0));
+  double melt = dmax(c.F[RVN_F_POTENTIAL_MELT], 0.0);
+  melt = dmin(melt, SWE / tstep);
+  SWE -= melt * tstep;
+  double refreeze = Ka * dmax(D_FREEZING_TEMP - Ta, 0.0);
+  refreeze = dmax(dmin(SL / tstep, refreeze), 0.0);
+  SL -= refreeze * tstep;
+  const double liq_cap = c.G(RVN_G_SNOW_SWI) * SWE;
+  const double to_liq = dmin(melt, dmax(liq_cap - SL, 0.0) / tstep);
+  SL += to_liq * tstep;
+  const double overflow = dmax((SL - liq_cap) / tstep, 0.0);
+  c.R(0) = -refreeze;
+  c.R(0) += to_liq;
+  c.R(1) = dmax(melt - to_liq, 0.0);
+  c.R(2) = overflow;
+  if (c.type != RVN_HRU_STANDARD) { c.R(3) = c.R(1); c.R(1) = 0.0; c.R(4) = c.R(2); c.R(2) = 0.0; }
+}
+// CmvInterflow INTERFLOW_PRMS  src/Interflow.cpp:98-124; ApplyConstraints :136-148
+template <class C, class PR> RVN_DI void rates_INTERFLOW_PRMS(C &c, const PR &pr) {
+  const int type = c.type;
+  if (type == RVN_HRU_LAKE || type == RVN_HRU_WATER || type == RVN_HRU_ROCK) return;
+  const int m = pr.ia(0);
+  const double stor = c.SV(pr.from(0)), max_stor = SoilCapacity(c, m), tens_stor = SoilTensionCapacity(c, m);
+  c.R(0) = c.SOIL(m, RVN_S_MAX_INTERFLOW_RATE) * dmax(stor - tens_stor, 0.0) / (max_stor - tens_stor);
+  c.R(0) = dmin(c.R(0), c.SV(pr.from(0)) / c.tstep);
+}
+// CmvSnowMelt MELT_POTMELT  src/SnowMeltRefreeze.cpp:87-131
+template <class C, class PR> RVN_DI void rates_SNOWMELT_POTMELT(C &c, const PR &pr) {
+  c.R(0) = dmax(c.F[RVN_F_POTENTIAL_MELT], 0.0);
+  if (c.SV(pr.from(0)) <= 0) c.R(0) = 0.0;
+  if (c.R(0) < 0.0) c.R(0) = 0.0;
+  c.R(0) = dmin(c.R(0), c.SV(pr.from(0)) / c.tstep);
+}
+// CmvSnowSqueeze  src/SnowMeltRefreeze.cpp:197-244
+template <class C, class PR> RVN_DI void rates_SNOWSQUEEZE(C &c, const PR &pr) {
+  const double S = c.SV(c.iSV(RVN_SV_SNOW)), SL = c.SV(c.iSV(RVN_SV_SNOW_LIQ));
+  const double liq_cap = c.G(RVN_G_SNOW_SWI) * S;
+  c.R(0) = dmax(SL - liq_cap, 0.0) / c.tstep;
+  if (c.SV(pr.from(0)) <= 0) c.R(0) = 0.0;
+  if (c.R(0) < 0.0) c.R(0) = 0.0;
+}
+
 // GetRatesOfChange + ApplyConstraints of process `pr` (opcode `op`: a compile-time constant in the specialised kernels)
 template <class C, class PR> RVN_DI void dispatch_rates(C &c, const PR &pr, const int op) {
   switch (op) {   // uniform across the CTA: every thread runs the same process at the same time
@@ -404,14 +462,19 @@ template <class C, class PR> RVN_DI void dispatch_rates(C &c, const PR &pr, cons
     case RVN_OP_SNOBAL_CEMA_NEIGE: rates_SNOBAL_CEMA_NEIGE(c, pr); break;
     case RVN_OP_SNOWREFREEZE_DD: rates_SNOWREFREEZE_DD(c, pr); break;
     case RVN_OP_SNOTEMP_NEWTONS: rates_SNOTEMP_NEWTONS(c, pr); break;
-    case RVN_OP_INF_HMETS: case RVN_OP_INF_HBV: case RVN_OP_INF_GR4J: rates_INFILTRATION(c, pr, op); break;
+    case RVN_OP_INF_HMETS: case RVN_OP_INF_HBV: case RVN_OP_INF_GR4J: case RVN_OP_INF_VIC_ARNO: rates_INFILTRATION(c, pr, op); break;
+    case RVN_OP_SNOBAL_HBV: rates_SNOBAL_HBV(c, pr); break;
+    case RVN_OP_INTERFLOW_PRMS: rates_INTERFLOW_PRMS(c, pr); break;
+    case RVN_OP_SNOWMELT_POTMELT: rates_SNOWMELT_POTMELT(c, pr); break;
+    case RVN_OP_SNOWSQUEEZE: rates_SNOWSQUEEZE(c, pr); break;
     case RVN_OP_OVERFLOW: rates_OVERFLOW(c, pr); break;
     case RVN_OP_FLUSH: rates_FLUSH(c, pr); break;
     case RVN_OP_SPLIT: rates_SPLIT(c, pr); break;
-    case RVN_OP_BASE_LINEAR: case RVN_OP_BASE_POWER_LAW: case RVN_OP_BASE_GR4J: rates_BASEFLOW(c, pr, op); break;
+    case RVN_OP_BASE_LINEAR: case RVN_OP_BASE_POWER_LAW: case RVN_OP_BASE_GR4J: case RVN_OP_BASE_LINEAR_ANALYTIC: case RVN_OP_BASE_VIC:
+    case RVN_OP_BASE_TOPMODEL: rates_BASEFLOW(c, pr, op); break;
     case RVN_OP_PERC_LINEAR: case RVN_OP_PERC_CONSTANT: case RVN_OP_PERC_GR4J: case RVN_OP_PERC_GR4JEXCH: case RVN_OP_PERC_GR4JEXCH2:
       rates_PERCOLATION(c, pr, op); break;
-    case RVN_OP_SOILEVAP_ALL: case RVN_OP_SOILEVAP_HBV: case RVN_OP_SOILEVAP_GR4J: rates_SOILEVAP(c, pr, op); break;
+    case RVN_OP_SOILEVAP_ALL: case RVN_OP_SOILEVAP_HBV: case RVN_OP_SOILEVAP_GR4J: case RVN_OP_SOILEVAP_TOPMODEL: rates_SOILEVAP(c, pr, op); break;
     case RVN_OP_CANEVP_ALL: rates_CANEVP_ALL(c, pr); break;
     case RVN_OP_CANSNOWEVP_ALL: rates_CANSNOWEVP_ALL(c, pr); break;
     case RVN_OP_OPEN_WATER_EVAP: rates_OPEN_WATER_EVAP(c, pr); break;

@@ -19,6 +19,8 @@ void CModel::FlattenMemberParams(int member) {
   }
   for (size_t c = 0; c < soil_classes.size(); c++)
     for (int f = 0; f < RVN_S_COUNT; f++) row[_desc.soil_off + c * RVN_S_COUNT + f] = soil_classes[c].S.v[f];
+  for (size_t c = 0; c < terrain_classes.size(); c++)
+    for (int f = 0; f < RVN_T_COUNT; f++) row[_desc.terr_off + c * RVN_T_COUNT + f] = terrain_classes[c].T.v[f];
   // convolution unit hydrographs for this member, per land-use class
   const int nLU = (int)lu_classes.size();
   int ci = 0;
@@ -56,24 +58,50 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
   for (int i = 0; i < NS; i++) { _f_svtype[i] = (int32_t)GetStateVarType(i); _f_svlayer[i] = GetStateVarLayer(i); }
   d.sv_type = _f_svtype.data(); d.sv_layer = _f_svlayer.data();
   // ---- process program
+  // A :ProcessGroup is one process of the model (one gate) but one device record per member (include/rvn_gpu.h rvn_process).
   const int NP = GetNumProcesses();
-  _f_proc.resize(NP); _f_from.clear(); _f_to.clear();
+  _f_proc.clear(); _f_from.clear(); _f_to.clear();
+  std::vector<int> rec_owner;   // model process index of every device record
   _f_nconv = 0;
-  for (int j = 0; j < NP; j++) {
-    const CHydroProcessABC *pr = _pProcesses[j];
-    pr->Compile(_f_proc[j]);
-    if (_f_proc[j].op == RVN_OP_CONVOLVE) { _f_proc[j].conn0 = -1; _f_nconv++; continue; }
-    ExitGracefullyIf(pr->GetNumConnections() > RVN_MAX_CONN, "CModel::Flatten: process has too many connections");
-    _f_proc[j].conn0 = (int32_t)_f_from.size();
-    for (int q = 0; q < pr->GetNumConnections(); q++) {
-      ExitGracefullyIf(pr->GetFromIndices()[q] < 0 || pr->GetToIndices()[q] < 0, "CModel::Flatten: process " + pr->GetProcessName() + " has an unconnected state variable");
-      _f_from.push_back(pr->GetFromIndices()[q]); _f_to.push_back(pr->GetToIndices()[q]);
+  auto emit = [&](const CHydroProcessABC *pr, int owner) -> rvn_process & {
+    rvn_process rec; memset(&rec, 0, sizeof(rec));
+    pr->Compile(rec);
+    rec.group = 0; rec.gconn0 = 0; rec.gnconn = 0; rec.pad_ = 0; rec.weight = 1.0;
+    if (rec.op == RVN_OP_CONVOLVE) { rec.conn0 = -1; _f_nconv++; }
+    else {
+      ExitGracefullyIf(pr->GetNumConnections() > RVN_MAX_CONN, "CModel::Flatten: process has too many connections");
+      rec.conn0 = (int32_t)_f_from.size();
+      for (int q = 0; q < pr->GetNumConnections(); q++) {
+        ExitGracefullyIf(pr->GetFromIndices()[q] < 0 || pr->GetToIndices()[q] < 0, "CModel::Flatten: process " + pr->GetProcessName() + " has an unconnected state variable");
+        _f_from.push_back(pr->GetFromIndices()[q]); _f_to.push_back(pr->GetToIndices()[q]);
+      }
     }
+    _f_proc.push_back(rec); rec_owner.push_back(owner);
+    return _f_proc.back();
+  };
+  for (int j = 0; j < NP; j++) {
+    const CProcessGroup *grp = dynamic_cast<const CProcessGroup *>(_pProcesses[j]);
+    if (!grp) { emit(_pProcesses[j], j); continue; }
+    const int n = grp->GetGroupSize();
+    if (n == 0) continue;
+    const int gconn0 = (int32_t)_f_from.size();
+    const size_t first = _f_proc.size();
+    for (int i = 0; i < n; i++) {
+      ExitGracefullyIf(dynamic_cast<const CmvConvolution *>(grp->GetSubProcess(i)) != NULL || dynamic_cast<const CProcessGroup *>(grp->GetSubProcess(i)) != NULL,
+                       "CModel::Flatten: convolutions and nested groups inside a :ProcessGroup are not supported by the B200 build");
+      rvn_process &rec = emit(grp->GetSubProcess(i), j);
+      rec.group = RVN_GRP_MEMBER | (i == 0 ? RVN_GRP_FIRST : 0) | (i == n - 1 ? RVN_GRP_LAST : 0);
+      rec.weight = grp->GetWeight(i);
+    }
+    const int gnconn = (int32_t)_f_from.size() - gconn0;
+    for (size_t r = first; r < _f_proc.size(); r++) { _f_proc[r].gconn0 = gconn0; _f_proc[r].gnconn = gnconn; }
   }
-  d.nProc = NP; d.nConn = (int32_t)_f_from.size(); d.proc = _f_proc.data(); d.conn_from = _f_from.data(); d.conn_to = _f_to.data();
+  const int NR = (int)_f_proc.size();
+  ExitGracefullyIf(NR > 64, "CModel::Flatten: more than 64 process records (the per-HRU process gate is a 64-bit mask)");
+  d.nProc = NR; d.nConn = (int32_t)_f_from.size(); d.proc = _f_proc.data(); d.conn_from = _f_from.data(); d.conn_to = _f_to.data();
   _f_mask.assign(nH, 0);
   for (int k = 0; k < nH; k++)
-    for (int j = 0; j < NP; j++) if (_pProcesses[j]->ShouldApply(_pHydroUnits[k])) _f_mask[k] |= (1ull << j);
+    for (int r = 0; r < NR; r++) if (_pProcesses[rec_owner[r]]->ShouldApply(_pHydroUnits[k])) _f_mask[k] |= (1ull << r);
   d.apply_mask = _f_mask.data();
   // ---- HRUs
   for (int a = 0; a < 5; a++) _f_hru_d[a].resize(nH);
@@ -100,7 +128,15 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
     }
   d.prof_class = _f_prof_class.data(); d.prof_thick = _f_prof_thick.data();
   d.glob_off = 0; d.lu_off = RVN_G_COUNT; d.veg_off = d.lu_off + d.nLU * RVN_LU_COUNT; d.soil_off = d.veg_off + d.nVeg * RVN_V_COUNT;
-  _f_ptab_stride = d.soil_off + d.nSoilClasses * RVN_S_COUNT;
+  d.terr_off = d.soil_off + d.nSoilClasses * RVN_S_COUNT; d.nTerrain = (int32_t)terrain_classes.size();
+  _f_ptab_stride = d.terr_off + (d.nTerrain > 0 ? d.nTerrain : 1) * RVN_T_COUNT;
+  _f_hru_terr.resize(nH);
+  for (int k = 0; k < nH; k++) _f_hru_terr[k] = _pHydroUnits[k]->terrain_class;
+  d.hru_terrain = _f_hru_terr.data();
+  for (int r = 0; r < d.nProc; r++)
+    if (d.proc[r].op == RVN_OP_BASE_TOPMODEL)
+      for (int k = 0; k < nH; k++)
+        ExitGracefullyIf(_pHydroUnits[k]->terrain_class < 0 && ((_f_mask[k] >> r) & 1ull), "CModel::Flatten: BASE_TOPMODEL needs a terrain class (TOPMODEL_LAMBDA) for every HRU it applies to");
   d.ptab_stride = _f_ptab_stride;
   _f_ptab.assign((size_t)nMembers * _f_ptab_stride, 0.0);
   d.nConvProc = _f_nconv;

@@ -29,7 +29,8 @@ const char *GlobalFieldName(int f);
 struct CSoilClass    { std::string tag; soil_struct S; };
 struct CVegetationClass { std::string tag; veg_struct V; };
 struct CLandUseClass { std::string tag; surface_struct S; };
-struct CTerrainClass { std::string tag; };
+struct terrain_struct { double v[RVN_T_COUNT]; };
+struct CTerrainClass { std::string tag; terrain_struct T; };
 struct CSoilProfile  { std::string tag; int nHorizons; std::vector<int> soil_class; std::vector<double> thickness; };
 
 // trapezoidal / surveyed channel cross-section with the reference's tabulated rating curve
@@ -302,7 +303,7 @@ private:
   std::vector<rvn_process> _f_proc;
   std::vector<uint64_t> _f_mask;
   std::vector<double> _f_hru_d[5], _f_prof_thick, _f_ptab, _f_conv_uh, _f_series, _f_gconst, _f_wt, _f_sb_d[7], _f_uh, _f_rh, _f_veg_season, _f_et;
-  std::vector<int32_t> _f_et_row, _f_wt_ptr, _f_wt_idx, _f_pert_forcing, _f_pert_adj;
+  std::vector<int32_t> _f_et_row, _f_wt_ptr, _f_wt_idx, _f_pert_forcing, _f_pert_adj, _f_hru_terr;
   std::vector<uint8_t> _f_pert_mask;
   std::vector<double> _f_pert_eps;
   std::vector<rvn_time> _f_times;

@@ -85,6 +85,7 @@ static void ParseMainInputFile(CModel *&pModel, optStruct &Options) {
   ExitGracefullyIf(!p.ok(), "ParseMainInputFile: cannot open " + Options.rvi_filename);
   std::vector<std::string> s;
   CHydroProcessABC *pLast = NULL;
+  CProcessGroup *pGroup = NULL;   // open :ProcessGroup, if any
   std::set<std::string> ignored;
   for (int i = 0; kIgnoredRVI[i]; i++) ignored.insert(kIgnoredRVI[i]);
   std::vector<std::pair<std::string, std::string> > pending_alias;
@@ -232,8 +233,27 @@ static void ParseMainInputFile(CModel *&pModel, optStruct &Options) {
       continue;
     }
     ExitGracefullyIf(!pModel && c != ":FileType", "ParseMainInputFile: " + c + " appears before :SoilModel, or is not supported by the B200 build");
+    if (c == ":ProcessGroup") {   // src/ParseInput.cpp case 295
+      ExitGracefullyIf(pGroup != NULL, "ParseMainInputFile: nested :ProcessGroup commands are not supported by the B200 build");
+      pGroup = new CProcessGroup(Len > 1 ? s[1] : "", pModel);
+      continue;
+    }
+    if (c == ":EndProcessGroup") {   // case 296: {wt1 .. wtN} | CALCULATE_WTS {r1 .. rN-1}
+      ExitGracefullyIf(pGroup == NULL, "ParseMainInputFile: :EndProcessGroup without :ProcessGroup");
+      const int N = pGroup->GetGroupSize();
+      std::vector<double> aWts(N > 0 ? N : 1, 0.0);
+      if (Len == N + 1) {
+        if (s[1] == "CALCULATE_WTS") { for (int i = 0; i < N - 1; i++) aWts[i] = s_to_d(s[i + 2]); pGroup->CalcWeights(aWts.data(), N - 1); }
+        else { for (int i = 0; i < N; i++) aWts[i] = s_to_d(s[i + 1]); pGroup->SetWeights(aWts.data(), N); }
+      } else if (Len > 1) WriteWarning("ParseMainInputFile: incorrect number of weights in :EndProcessGroup command. Contents ignored.");
+      pModel->AddProcess(pGroup); pLast = pGroup; pGroup = NULL;
+      continue;
+    }
     CHydroProcessABC *pMover = CreateProcessFromRVI(s, pModel, Options);
-    if (pMover) { pModel->AddProcess(pMover); pLast = pMover; continue; }
+    if (pMover) {
+      if (pGroup) pGroup->AddProcess(pMover); else pModel->AddProcess(pMover);
+      pLast = pMover; continue;
+    }
     ExitGracefully("ParseMainInputFile: command " + c + " (line " + std::to_string(p.line()) + " of " + Options.rvi_filename +
                    ") is not supported by the B200 build");
   }
@@ -363,7 +383,9 @@ static void ParseClassPropertiesFile(CModel *pModel, const optStruct &Options) {
       while (p.Tokenize(s)) {
         if (s.empty() || s[0] == ":Attributes" || s[0] == ":Units") continue;
         if (s[0] == ":EndTerrainClasses") break;
-        CTerrainClass tc; tc.tag = s[0]; pModel->terrain_classes.push_back(tc);
+        CTerrainClass tc; tc.tag = s[0];
+        tc.T.v[RVN_T_TOPMODEL_LAMBDA] = (s.size() == 4) ? s_to_d(s[3]) : 7.5;   // CTerrainClass::InitializeTerrainProperties (src/TerrainClass.cpp:83-91), src/ParsePropertyFile.cpp:1019-1024
+        pModel->terrain_classes.push_back(tc);
       }
       continue;
     }

@@ -58,6 +58,34 @@ void CmvGeneric::Compile(rvn_process &rec) const {
   rec.da[0] = _da[0]; rec.da[1] = _da[1];
 }
 
+// ---- ProcessGroup -----------------------------------------------------------------------------------
+void CalcWeightsFromUniformNums(const double *aVals, double *aWeights, int N) {
+  double sum = 0.0;
+  for (int q = 0; q < (N - 1); q++) {
+    aWeights[q] = (1.0 - sum) * (1.0 - pow(1.0 - aVals[q], 1.0 / (N - q - 1)));
+    sum += aWeights[q];
+  }
+  aWeights[N - 1] = 1.0 - sum;
+}
+void CProcessGroup::SetWeights(const double *aWts, int nVal) {
+  if (nVal != GetGroupSize()) { WriteWarning("CProcessGroup::SetWeights: Incorrect number of weights for process group. Weights will be ignored"); return; }
+  double sum = 0.0;
+  for (int q = 0; q < nVal; q++) { _aWeights[q] = aWts[q]; sum += _aWeights[q]; }
+  if (fabs(sum - 1.0) > 0.01) for (int q = 0; q < nVal; q++) _aWeights[q] /= sum;
+  if (fabs(sum - 1.0) > REAL_SMALL) WriteWarning("CProcessGroup::SetWeights: Process group weights do not sum to 1.0");
+}
+void CProcessGroup::CalcWeights(const double *aVals, int nVal) {
+  if (nVal != GetGroupSize() - 1) { WriteWarning("CProcessGroup::SetWeights: Incorrect number of numbers for process group. Weights will be ignored"); return; }
+  CalcWeightsFromUniformNums(aVals, _aWeights.data(), GetGroupSize());
+}
+void CProcessGroup::Initialize() {
+  iFrom.clear(); iTo.clear();
+  for (size_t j = 0; j < _pSubProcesses.size(); j++) {
+    _pSubProcesses[j]->Initialize();
+    for (int q = 0; q < _pSubProcesses[j]->GetNumConnections(); q++) { iFrom.push_back(_pSubProcesses[j]->GetFromIndices()[q]); iTo.push_back(_pSubProcesses[j]->GetToIndices()[q]); }
+  }
+}
+
 // ---- Precipitation ---------------------------------------------------------------------------------
 void CmvPrecipitation::GetParticipatingStateVarList(sv_type *aSV, int *aLev, int &nSV) {
   nSV = 1; aSV[0] = RVN_SV_ATMOS_PRECIP; aLev[0] = DOESNT_EXIST;
@@ -181,6 +209,11 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
       int to = pM->ParseSVTypeIndex(s[3]);
       p = new CmvGeneric("SnowBalance", RVN_OP_SNOBAL_SIMPLE_MELT, pM);
       p->Connect(pM->GetStateVarIndex(RVN_SV_SNOW), to);
+    } else if (s[1] == "SNOBAL_HBV") {   // src/SnowBalance.cpp:56-70, 296-303
+      AddSVs(pM, {SVL(RVN_SV_SNOW, -1), SVL(RVN_SV_SNOW_LIQ, -1), SVL(RVN_SV_SNOW_DEPTH, -1)});
+      int iSnow = pM->GetStateVarIndex(RVN_SV_SNOW), iSL = pM->GetStateVarIndex(RVN_SV_SNOW_LIQ), iSoil = pM->GetStateVarIndex(RVN_SV_SOIL, 0);
+      p = new CmvGeneric("SnowBalance", RVN_OP_SNOBAL_HBV, pM);
+      p->Connect(iSnow, iSL); p->Connect(iSnow, iSoil); p->Connect(iSL, iSoil); p->Connect(iSnow, iPond); p->Connect(iSL, iPond);
     } else if (s[1] == "SNOBAL_CEMA_NIEGE" || s[1] == "SNOBAL_CEMA_NEIGE") {
       AddSVs(pM, {SVL(RVN_SV_SNOW, -1), SVL(RVN_SV_PONDED_WATER, -1), SVL(RVN_SV_SNOW_COVER, -1)});
       int iSnow = pM->GetStateVarIndex(RVN_SV_SNOW), iSC = pM->GetStateVarIndex(RVN_SV_SNOW_COVER);
@@ -201,8 +234,8 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
       p = new CmvGeneric("Infiltration", RVN_OP_INF_HMETS, pM);
       p->Connect(iPond, iTop); p->Connect(iPond, iSW);
       p->Connect(iPond, pM->GetStateVarIndex(RVN_SV_CONVOLUTION, 0)); p->Connect(iPond, pM->GetStateVarIndex(RVN_SV_CONVOLUTION, 1));
-    } else if (s[1] == "INF_HBV" || s[1] == "INF_GR4J") {
-      p = new CmvGeneric("Infiltration", s[1] == "INF_HBV" ? RVN_OP_INF_HBV : RVN_OP_INF_GR4J, pM);
+    } else if (s[1] == "INF_HBV" || s[1] == "INF_GR4J" || s[1] == "INF_VIC_ARNO") {
+      p = new CmvGeneric("Infiltration", s[1] == "INF_HBV" ? RVN_OP_INF_HBV : (s[1] == "INF_GR4J" ? RVN_OP_INF_GR4J : RVN_OP_INF_VIC_ARNO), pM);
       p->Connect(iPond, iTop); p->Connect(iPond, iSW);
     } else {
       ExitGracefully("ParseMainInputFile: infiltration algorithm " + s[1] + " is not implemented in the B200 build");
@@ -241,6 +274,9 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
     if (s[1] == "BASE_LINEAR") op = RVN_OP_BASE_LINEAR;
     else if (s[1] == "BASE_POWER_LAW") op = RVN_OP_BASE_POWER_LAW;
     else if (s[1] == "BASE_GR4J") op = RVN_OP_BASE_GR4J;
+    else if (s[1] == "BASE_LINEAR_ANALYTIC") op = RVN_OP_BASE_LINEAR_ANALYTIC;
+    else if (s[1] == "BASE_VIC") op = RVN_OP_BASE_VIC;
+    else if (s[1] == "BASE_TOPMODEL") op = RVN_OP_BASE_TOPMODEL;
     else ExitGracefully("ParseMainInputFile: baseflow algorithm " + s[1] + " is not implemented in the B200 build");
     CmvGeneric *p = new CmvGeneric("Baseflow", op, pM);
     p->Connect(from, iSW);
@@ -269,12 +305,43 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
     if (s[1] == "SOILEVAP_ALL") op = RVN_OP_SOILEVAP_ALL;
     else if (s[1] == "SOILEVAP_HBV") op = RVN_OP_SOILEVAP_HBV;
     else if (s[1] == "SOILEVAP_GR4J") op = RVN_OP_SOILEVAP_GR4J;
+    else if (s[1] == "SOILEVAP_TOPMODEL") op = RVN_OP_SOILEVAP_TOPMODEL;
     else ExitGracefully("ParseMainInputFile: soil evaporation algorithm " + s[1] + " is not implemented in the B200 build");
     AddSVs(pM, {SVL(RVN_SV_SOIL, 0), SVL(RVN_SV_ATMOSPHERE, -1), SVL(RVN_SV_AET, -1)});
     CmvGeneric *p = new CmvGeneric("SoilEvaporation", op, pM);
     int iAET = pM->GetStateVarIndex(RVN_SV_AET);
     p->Connect(pM->GetStateVarIndex(RVN_SV_SOIL, 0), iAtmos);
     p->Connect(iAET, iAET);
+    return p;
+  }
+  if (cmd == ":Interflow") {  // case 210; src/Interflow.cpp:19-45,78-87
+    need(4);
+    ExitGracefullyIf(s[1] != "INTERFLOW_PRMS" && s[1] != "PRMS", "ParseMainInputFile: Unrecognized interflow process representation");
+    AddSVs(pM, {SVL(RVN_SV_SOIL, 0), SVL(RVN_SV_SURFACE_WATER, -1)});
+    int from = pM->ParseSVTypeIndex(s[2]);
+    ExitGracefullyIf(pM->GetStateVarType(from) != RVN_SV_SOIL, "CmvInterflow Constructor: invalid 'from' compartment specified");
+    CmvGeneric *p = new CmvGeneric("Interflow", RVN_OP_INTERFLOW_PRMS, pM);
+    p->Connect(from, iSW);
+    p->SetIntArg(0, SoilLayerOf(pM, from));
+    return p;
+  }
+  if (cmd == ":SnowMelt") {  // case 213; src/SnowMeltRefreeze.cpp:22-75
+    need(4);
+    ExitGracefullyIf(s[1] != "MELT_POTMELT", "ParseMainInputFile: Unrecognized snow melt process representation");
+    AddSV1(pM, RVN_SV_SNOW);
+    int to = pM->ParseSVTypeIndex(s[3]);
+    CmvGeneric *p = new CmvGeneric("SnowMelt", RVN_OP_SNOWMELT_POTMELT, pM);
+    p->Connect(pM->GetStateVarIndex(RVN_SV_SNOW), to);
+    return p;
+  }
+  if (cmd == ":SnowSqueeze") {  // case 218; src/SnowMeltRefreeze.cpp:137-166
+    need(4);
+    ExitGracefullyIf(s[1] != "SQUEEZE_RAVEN", "ParseMainInputFile: Unrecognized snow squeeze process representation");
+    AddSV1(pM, RVN_SV_SNOW_LIQ);
+    int to = pM->ParseSVTypeIndex(s[3]);
+    ExitGracefullyIf(pM->StateVarExists(RVN_SV_SNOW_DEPTH), "CmvSnowSqueeze: models with a SNOW_DEPTH state variable are not supported by the B200 build");
+    CmvGeneric *p = new CmvGeneric("SnowSqueeze", RVN_OP_SNOWSQUEEZE, pM);
+    p->Connect(pM->GetStateVarIndex(RVN_SV_SNOW_LIQ), to);
     return p;
   }
   if (cmd == ":SnowRefreeze") {  // case 214; src/SnowMeltRefreeze.cpp:253-267

@@ -83,6 +83,27 @@ private:
   int _conv_index;
 };
 
+// CProcessGroup (reference src/ProcessGroup.cpp): weighted blend of sub-process rates.  The group is ONE process of the model
+// (one ShouldApply gate, connections = concatenation of the members'); on the device its members are consecutive records.
+class CProcessGroup : public CHydroProcessABC {
+public:
+  CProcessGroup(const std::string &name, CModel *pM) : CHydroProcessABC("ProcessGroup", pM), _group_name(name) {}
+  ~CProcessGroup() override { for (size_t i = 0; i < _pSubProcesses.size(); i++) delete _pSubProcesses[i]; }
+  void AddProcess(CHydroProcessABC *pProc) { _pSubProcesses.push_back(pProc); _aWeights.assign(_pSubProcesses.size(), 1.0); }   // weights default to 1.0
+  int  GetGroupSize() const { return (int)_pSubProcesses.size(); }
+  const CHydroProcessABC *GetSubProcess(int i) const { return _pSubProcesses[i]; }
+  double GetWeight(int i) const { return _aWeights[i]; }
+  void SetWeights(const double *aWts, int nVal);     // src/ProcessGroup.cpp:180-196
+  void CalcWeights(const double *aVals, int nVal);   // src/ProcessGroup.cpp:203-210 -> CalcWeightsFromUniformNums
+  void Initialize() override;                        // src/ProcessGroup.cpp:32-56
+  void Compile(rvn_process &rec) const override { (void)rec; ExitGracefully("CProcessGroup::Compile: groups are flattened member by member"); }
+private:
+  std::string _group_name;
+  std::vector<CHydroProcessABC *> _pSubProcesses;
+  std::vector<double> _aWeights;
+};
+void CalcWeightsFromUniformNums(const double *aVals, double *aWeights, int N);   // src/CommonFunctions.cpp:1845-1853
+
 // factory used by the .rvi reader: builds the process for a ':ProcessName ALGORITHM FROM TO' line,
 // registering its state variables in the reference's order.  Returns NULL for unknown commands.
 CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel *pModel, const optStruct &Options);

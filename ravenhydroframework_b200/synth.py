@@ -142,7 +142,8 @@ def _write(path, text):
         f.write(text)
 
 
-def write_network(f, n_sb, hru_per_sb, rng, profile, lu_classes, veg_classes, soil_profiles, gauged_all=False, paired_profiles=False):
+def write_network(f, n_sb, hru_per_sb, rng, profile, lu_classes, veg_classes, soil_profiles, gauged_all=False, paired_profiles=False,
+                  terrain_classes=None):
     f.write(":SubBasins\n  :Attributes NAME DOWNSTREAM_ID PROFILE REACH_LENGTH GAUGED\n  :Units none none none km none\n")
     for p in range(1, n_sb + 1):
         down = -1 if p == 1 else p // 2
@@ -154,9 +155,10 @@ def write_network(f, n_sb, hru_per_sb, rng, profile, lu_classes, veg_classes, so
     for p in range(1, n_sb + 1):
         for _ in range(hru_per_sb):
             c = rng.randint(0, len(lu_classes))
-            f.write("  %d, %.4f, %.2f, %.5f, %.5f, %d, %s, %s, %s, [NONE], [NONE], %.3f, %.2f\n" % (
+            f.write("  %d, %.4f, %.2f, %.5f, %.5f, %d, %s, %s, %s, [NONE], %s, %.3f, %.2f\n" % (
                 k, rng.uniform(0.5, 2.5), rng.uniform(600, 1400), rng.uniform(54, 55), rng.uniform(-123.5, -122.5), p,
                 lu_classes[c], veg_classes[c], soil_profiles[c if paired_profiles else rng.randint(0, len(soil_profiles))],
+                "[NONE]" if not terrain_classes else terrain_classes[c % len(terrain_classes)],
                 rng.uniform(0, 20), rng.uniform(0, 360)))
             k += 1
     f.write(":EndHRUs\n")
@@ -394,8 +396,10 @@ MONTHLY_TEMP = [-11.4, -7.2, -2.8, 2.8, 8.1, 12.2, 14.4, 13.5, 8.9, 3.4, -4.0, -
 
 
 def write_hbv(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUTE_NONE", catchment_route="TRIANGULAR_UH",
-              single_class=False, name="hbv", season_offset=0, n_gauges=1):
-    """HBV-EC template (BASELINE config 2): multi-class, with glacier HRUs unless single_class. Returns the input base path."""
+              single_class=False, name="hbv", season_offset=0, n_gauges=1, variant=None):
+    """HBV-EC template (BASELINE config 2): multi-class, with glacier HRUs unless single_class. Returns the input base path.
+    variant="melt_squeeze_interflow": the snow balance is replaced by :SnowMelt + :SnowSqueeze and a PRMS :Interflow drains the
+    fast reservoir (process classes outside the three templates)."""
     os.makedirs(dirpath, exist_ok=True)
     base = os.path.join(dirpath, name)
     rng = np.random.RandomState(seed)
@@ -405,6 +409,8 @@ def write_hbv(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUTE_
         extra_rvp += ":AvgAnnualRunoff 400\n"
     if profile != "NONE":
         extra_rvp += ":TrapezoidalChannel CHN 10.0 0.0 2.0 0.035 0.001\n"
+    if variant == "melt_squeeze_interflow":
+        extra_rvp += ":SoilParameterList\n  :Parameters, MAX_INTERFLOW_RATE\n  :Units, mm/d\n  [DEFAULT], 0.0\n  FAST_RES, 7.25\n:EndSoilParameterList\n"
     _write(base + ".rvp", HBV_RVP.format(extra=extra_rvp))
     with open(base + ".rvh", "w") as f:
         if single_class:
@@ -426,7 +432,16 @@ def write_hbv(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUTE_
     else:
         with open(base + ".rvt", "w") as f:
             write_gauge(f, *weather(n_days, seed, season_offset), extra=gx)
-    _write(base + ".rvi", HBV_RVI.format(duration=n_days, routing=routing, catchment_route=catchment_route, extra=extra_rvi))
+    rvi = HBV_RVI.format(duration=n_days, routing=routing, catchment_route=catchment_route, extra=extra_rvi)
+    if variant == "melt_squeeze_interflow":
+        a = "  :SnowBalance       SNOBAL_SIMPLE_MELT SNOW            SNOW_LIQ\n    :-->Overflow     RAVEN_DEFAULT      SNOW_LIQ        PONDED_WATER\n"
+        b = "  :SnowMelt          MELT_POTMELT       SNOW            SNOW_LIQ\n  :SnowSqueeze       SQUEEZE_RAVEN      SNOW_LIQ        PONDED_WATER\n"
+        assert a in rvi
+        rvi = rvi.replace(a, b)
+        c = "  :LakeEvaporation   LAKE_EVAP_BASIC    SLOW_RESERVOIR  ATMOSPHERE\n"
+        assert c in rvi
+        rvi = rvi.replace(c, "  :Interflow         INTERFLOW_PRMS     FAST_RESERVOIR  SURFACE_WATER\n" + c)
+    _write(base + ".rvi", rvi)
     _write(base + ".rvc", HBV_RVC)
     return base
 
@@ -582,4 +597,152 @@ def add_enkf(base, n_members, n_sb, n_hru, n_days, obs_basins=(1,), seed=3, wind
         f.write(":AssimilatedState STREAMFLOW AssimSBs\n")
         for sb in obs_basins:
             f.write(":AssimilateStreamflow %d\n" % sb)
+    return base
+
+
+# ------------------------------------------------------------------------------------------------ Blended (Mai et al. 2020)
+BLENDED_RVI = """# Blended model emulation (process groups with weights), synthetic watershed (written by ravenhydroframework_b200.synth)
+:StartDate             2000-01-01 00:00:00
+:Duration              {duration}
+:TimeStep              1.0
+:Method                ORDERED_SERIES
+:PotentialMeltMethod   POTMELT_HMETS
+:RainSnowFraction      RAINSNOW_HBV
+:Evaporation           PET_DATA
+:CatchmentRoute        {catchment_route}
+:Routing               {routing}
+:SoilModel             SOIL_MULTILAYER 3
+:SilentMode
+{extra}
+:Alias DELAYED_RUNOFF CONVOLUTION[1]
+:Alias DIRECT_RUNOFF  SURFACE_WATER
+:HydrologicProcesses
+  :Precipitation     RAVEN_DEFAULT         ATMOS_PRECIP   MULTIPLE
+  :ProcessGroup
+    :Infiltration    INF_HMETS             PONDED_WATER   MULTIPLE
+    :Infiltration    INF_VIC_ARNO          PONDED_WATER   MULTIPLE
+    :Infiltration    INF_HBV               PONDED_WATER   MULTIPLE
+  :EndProcessGroup CALCULATE_WTS {r[0]} {r[1]}
+    :Overflow        OVERFLOW_RAVEN        SOIL[0]        DIRECT_RUNOFF
+  :ProcessGroup
+    :Baseflow        BASE_LINEAR_ANALYTIC  SOIL[0]        SURFACE_WATER
+    :Baseflow        BASE_VIC              SOIL[0]        SURFACE_WATER
+    :Baseflow        BASE_TOPMODEL         SOIL[0]        SURFACE_WATER
+  :EndProcessGroup CALCULATE_WTS {r[2]} {r[3]}
+  :Percolation       PERC_LINEAR           SOIL[0]        SOIL[1]
+    :Overflow        OVERFLOW_RAVEN        SOIL[1]        DIRECT_RUNOFF
+  :Percolation       PERC_LINEAR           SOIL[1]        SOIL[2]
+  :ProcessGroup
+    :SoilEvaporation SOILEVAP_ALL          SOIL[0]        ATMOSPHERE
+    :SoilEvaporation SOILEVAP_TOPMODEL     SOIL[0]        ATMOSPHERE
+  :EndProcessGroup CALCULATE_WTS {r[4]}
+  :Convolve          CONVOL_GAMMA          CONVOLUTION[0] SURFACE_WATER
+  :Convolve          CONVOL_GAMMA_2        DELAYED_RUNOFF SURFACE_WATER
+  :ProcessGroup
+    :Baseflow        BASE_LINEAR_ANALYTIC  SOIL[1]        SURFACE_WATER
+    :Baseflow        BASE_POWER_LAW        SOIL[1]        SURFACE_WATER
+  :EndProcessGroup CALCULATE_WTS {r[5]}
+  :ProcessGroup
+    :SnowBalance     SNOBAL_HMETS          MULTIPLE       MULTIPLE
+    :SnowBalance     SNOBAL_SIMPLE_MELT    SNOW           PONDED_WATER
+    :SnowBalance     SNOBAL_HBV            MULTIPLE       MULTIPLE
+  :EndProcessGroup CALCULATE_WTS {r[6]} {r[7]}
+:EndHydrologicProcesses
+"""
+
+BLENDED_RVP = """# Blended model parameters (synthetic)
+:SoilClasses
+  :Attributes,
+  :Units,
+  TOPSOIL,
+  PHREATIC,
+  DEEP_GW,
+:EndSoilClasses
+:LandUseClasses,
+  :Attributes,  IMPERM, FOREST_COV,
+  :Units,         frac,       frac,
+  FOREST,          0.0,        1.0,
+  OPEN,           0.05,        0.1,
+:EndLandUseClasses
+:VegetationClasses,
+  :Attributes,  MAX_HT, MAX_LAI, MAX_LEAF_COND,
+  :Units,            m,    none,      mm_per_s,
+  FOREST,            4,       5,             5,
+  GRASS,           0.5,       2,             5,
+:EndVegetationClasses
+:TerrainClasses
+  :Attributes, HILLSLOPE_LENGTH, DRAINAGE_DENSITY, TOPMODEL_LAMBDA
+  :Units,                     m,             km/km2,            m
+  DEFAULT_T,                1.0,                1.0,       7.0832
+  STEEP_T,                  1.0,                1.0,       5.9000
+:EndTerrainClasses
+:SoilProfiles
+  LAKE, 0
+  ROCK, 0
+  DEFAULT_P, 3, TOPSOIL, 0.4038, PHREATIC, 1.0199, DEEP_GW, 5.0
+  THIN_P,    3, TOPSOIL, 0.2700, PHREATIC, 0.7100, DEEP_GW, 5.0
+:EndSoilProfiles
+:GlobalParameter     SNOW_SWI_MIN 0.0355
+:GlobalParameter     SNOW_SWI_MAX 0.1838
+:GlobalParameter SWI_REDUCT_COEFF 0.0120
+:GlobalParameter         SNOW_SWI 0.0420
+:GlobalParameter    RAINSNOW_TEMP -0.1500
+:GlobalParameter   RAINSNOW_DELTA 1.6500
+:SoilParameterList
+  :Parameters, POROSITY, PERC_COEFF, PET_CORRECTION, BASEFLOW_COEFF, VIC_B_EXP, HBV_BETA, MAX_BASEFLOW_RATE, BASEFLOW_N, FIELD_CAPACITY, SAT_WILT
+  :Units,             -,        1/d,              -,            1/d,     -,        -,              mm/d,          -,              -,        -
+  TOPSOIL,          1.0,     0.0270,         0.8750,         0.0541, 0.1150,   1.9320,           21.200,     2.5400,         0.5314,      0.0
+  PHREATIC,         1.0,     0.0042,            0.0,         0.0117,    0.0,      0.0,              0.0,     1.2200,            0.0,      0.0
+  DEEP_GW,          1.0,        0.0,            0.0,            0.0,    0.0,      0.0,              0.0,        0.0,            0.0,      0.0
+:EndSoilParameterList
+:LandUseParameterList
+  :Parameters, MIN_MELT_FACTOR, MAX_MELT_FACTOR, DD_MELT_TEMP, DD_AGGRADATION, REFREEZE_FACTOR, REFREEZE_EXP, DD_REFREEZE_TEMP, HMETS_RUNOFF_COEFF,
+  :Units,               mm/d/C,          mm/d/C,            C,           1/mm,          mm/d/C,            -,                C,                  -,
+  [DEFAULT],            1.2875,          6.7009,       2.3641,         0.0973,          2.6851,       0.3740,          -1.0919,             0.4739,
+  OPEN,                 1.6000,          7.9000,       1.8000,         0.0700,          2.1000,       0.4500,          -0.5000,             0.3900,
+:EndLandUseParameterList
+:LandUseParameterList
+  :Parameters, GAMMA_SHAPE, GAMMA_SCALE, GAMMA_SHAPE2, GAMMA_SCALE2,
+  :Units,                -,         1/d,            -,          1/d,
+  [DEFAULT],        3.5019,      0.8774,       4.3942,       1.1884,
+  OPEN,             2.1000,      1.1100,       3.2000,       1.4500,
+:EndLandUseParameterList
+:VegetationParameterList
+  :Parameters, RAIN_ICEPT_PCT, SNOW_ICEPT_PCT,
+  :Units,                   -,              -,
+  [DEFAULT],              0.0,            0.0,
+  FOREST,                0.06,           0.04,
+:EndVegetationParameterList
+{extra}
+"""
+
+BLENDED_RVC = """:UniformInitialConditions SOIL[0] 120.0
+:UniformInitialConditions SOIL[1] 300.0
+"""
+
+
+def write_blended(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUTE_NONE", catchment_route="ROUTE_DUMP",
+                  name="blended", season_offset=0, n_gauges=1, r=(0.35, 0.6, 0.2, 0.7, 0.45, 0.8, 0.3, 0.55)):
+    """Blended multi-model template (BASELINE config 4): process groups whose members' rates are blended with the weights
+    CALCULATE_WTS derives from `r` (reference CProcessGroup).  Returns the input base path."""
+    os.makedirs(dirpath, exist_ok=True)
+    base = os.path.join(dirpath, name)
+    rng = np.random.RandomState(seed)
+    profile = "NONE" if routing == "ROUTE_NONE" else "CHN"
+    extra_rvp = ""
+    if n_sb > 1 or routing != "ROUTE_NONE":
+        extra_rvp += ":AvgAnnualRunoff 400\n"
+    if profile != "NONE":
+        extra_rvp += ":TrapezoidalChannel CHN 10.0 0.0 2.0 0.035 0.001\n"
+    _write(base + ".rvp", BLENDED_RVP.format(extra=extra_rvp))
+    with open(base + ".rvh", "w") as f:
+        write_network(f, n_sb, hru_per_sb, rng, profile, ["FOREST", "OPEN"], ["FOREST", "GRASS"], ["DEFAULT_P", "THIN_P"], terrain_classes=["DEFAULT_T", "STEEP_T"])
+    extra_rvi = ""
+    if n_gauges > 1:
+        extra_rvi += write_gauge_grid(base, n_gauges, n_days, seed, season_offset, _hru_latlon(base + ".rvh"))
+    else:
+        with open(base + ".rvt", "w") as f:
+            write_gauge(f, *weather(n_days, seed, season_offset))
+    _write(base + ".rvi", BLENDED_RVI.format(duration=n_days, routing=routing, catchment_route=catchment_route, extra=extra_rvi, r=["%.6f" % x for x in r]))
+    _write(base + ".rvc", BLENDED_RVC)
     return base

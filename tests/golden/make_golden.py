@@ -38,6 +38,13 @@ if hasattr(synth, "write_hbv"):
     CASES["hbv_storagecoeff"] = dict(kind="hbv", n_sb=7, hru_per_sb=3, n_days=200, seed=8, routing="ROUTE_STORAGECOEFF")
     # sparse multi-station interpolation (INTERP_FROM_FILE: 4 nearest of 9 stations per HRU) = the gridded-forcing gather
     CASES["hbv_gauges9"] = dict(kind="hbv", n_sb=5, hru_per_sb=4, n_days=150, seed=12, routing="ROUTE_MUSKINGUM", n_gauges=9)
+    # process classes outside the three templates: :SnowMelt, :SnowSqueeze, :Interflow
+    CASES["hbv_meltsqueeze"] = dict(kind="hbv", n_sb=3, hru_per_sb=5, n_days=300, seed=14, routing="ROUTE_MUSKINGUM", variant="melt_squeeze_interflow")
+if hasattr(synth, "write_blended"):
+    # Blended multi-model template (BASELINE config 4): weighted process groups, VIC/TOPMODEL/analytic algorithms, SNOBAL_HBV
+    WRITERS["blended"] = synth.write_blended
+    CASES["blended_tree"] = dict(kind="blended", n_sb=5, hru_per_sb=4, n_days=300, seed=16, routing="ROUTE_MUSKINGUM", catchment_route="TRIANGULAR_UH")
+    CASES["blended_single"] = dict(kind="blended", n_sb=1, hru_per_sb=1, n_days=500, seed=17)
 if hasattr(synth, "write_gr4j"):
     WRITERS["gr4j"] = synth.write_gr4j
     CASES["gr4j_single"] = dict(kind="gr4j", n_sb=1, hru_per_sb=1, n_days=730, seed=9)

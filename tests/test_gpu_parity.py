@@ -147,7 +147,7 @@ def test_state_upload_mid_run_invalidates_cached_sums(tmp_path):
 
 
 # ---- HBV-EC / GR4J templates, channel routing methods, kernel variants ---------------------------------------------
-WRITERS = {"hmets": synth.write_hmets, "hbv": synth.write_hbv, "gr4j": synth.write_gr4j}
+WRITERS = {"hmets": synth.write_hmets, "hbv": synth.write_hbv, "gr4j": synth.write_gr4j, "blended": synth.write_blended}
 
 
 def _gpu_vs_oracle(tmp_path, kind, n_days, members=1, **kw):
@@ -189,7 +189,7 @@ def test_gr4j_tree(tmp_path):
     assert sim.kernel_variant() == "static:GR4J"
 
 
-@pytest.mark.parametrize("kind", ["hmets", "hbv", "gr4j"])
+@pytest.mark.parametrize("kind", ["hmets", "hbv", "gr4j", "blended"])
 def test_specialised_kernel_equals_interpreter(tmp_path, kind, monkeypatch):
     """The compile-time specialisation and the interpreter run the same process functions: results must be bit-identical."""
     base = WRITERS[kind](str(tmp_path), n_sb=5, hru_per_sb=31, n_days=150, seed=17)
@@ -207,6 +207,24 @@ def test_specialised_kernel_equals_interpreter(tmp_path, kind, monkeypatch):
     assert np.array_equal(a.download_state(), b.download_state())
     assert np.array_equal(a.hydrographs(0, 150), b.hydrographs(0, 150))
     assert np.array_equal(a.watershed(0, 150), b.watershed(0, 150))
+
+
+def test_blended_weights_are_runtime_data(tmp_path):
+    """Different :EndProcessGroup weights keep the specialised Blended kernel (weights are not part of the compiled program) and
+    change the result; both runs equal the oracle."""
+    res = []
+    for i, r in enumerate([(0.35, 0.6, 0.2, 0.7, 0.45, 0.8, 0.3, 0.55), (0.9, 0.1, 0.5, 0.5, 0.05, 0.3, 0.75, 0.2)]):
+        base = synth.write_blended(str(tmp_path / ("w%d" % i)), n_sb=3, hru_per_sb=9, n_days=200, seed=9, season_offset=80, r=r)
+        model = api.RavenModel(base)
+        model.flatten(1)
+        sim = api.GpuSimulation(model)
+        assert sim.kernel_variant() == "static:BLENDED"
+        sim.run(200)
+        ref = H.oracle_run(model, 200)
+        st = sim.download_state()[0]
+        assert H.rel_err(st, ref["state"]) < TOL
+        res.append(st)
+    assert not np.array_equal(res[0], res[1])
 
 
 def test_non_template_process_list_runs_on_interpreter(tmp_path):

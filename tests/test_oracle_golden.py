@@ -65,7 +65,7 @@ def test_oracle_matches_golden(case):
     ref_f = g["forc"]
     idx = {"PRECIP": 0, "SNOW_FRAC": 3, "TEMP_AVE": 7, "TEMP_DAILY_MIN": 8, "TEMP_DAILY_MAX": 9, "TEMP_DAILY_AVE": 10,
            "POTENTIAL_MELT": 32, "PET": 34, "OW_PET": 35}
-    if case.startswith("hmets"):
+    if case.startswith("hmets") or case.startswith("blended"):
         idx.pop("OW_PET")   # :OW_Evaporation defaults to PET_HARGREAVES_1985 there; no HMETS process consumes OW_PET (not derived)
     for name, j in idx.items():
         mine = o["forc_rec"][steps - 1][:, :, api.FORCING_NAMES.index(name)]
