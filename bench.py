@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 MEMBERS_PER_GPU = 512
 N_SB, HRU_PER_SB = 500, 20
 METRIC = "HRU-timesteps/sec (members x HRUs x steps)"
+CPU_SAMPLE_STEPS = 100   # bounded cpu_baseline sample: ~16 s of time loop per reference process at ~6e4 HRU-steps/s
 
 
 def measured_peak():
@@ -40,6 +41,19 @@ def measured_peak():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kernel, units_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed `ncu --set full` capture
+    (profiles/r01/ncu_traffic.json), or None when there is no capture of this kernel at this launch size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01", "ncu_traffic.json")) as f:
+            rec = json.load(f).get(kernel)
+        if rec and int(rec["units_per_launch"]) == int(units_per_launch):
+            return float(rec["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
 
 
 class ClockSampler:
@@ -267,7 +281,8 @@ def main():
         b_alg_full = 16.0 * NS + 8.0                          # reference layout: every state variable in and out
         sweep_per_launch_ms = sweep_ms / K
         achieved = units_per_step * b_alg_live / (sweep_per_launch_ms / 1000.0) / 1e9
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": ncu_traffic(sim.kernel_variant(), units_per_step),
                     "kernel": sim.kernel_variant(), "kernel_ms_per_launch": sweep_per_launch_ms, "kernel_share_of_step": sweep_ms / dev_ms,
                     "bytes_per_hru_step": b_alg_live, "bytes_per_hru_step_reference_layout": b_alg_full, "live_conv_stores_mean": live,
                     "peak_source": peak_src}
@@ -279,11 +294,11 @@ def main():
                 "gpu_launches": int(launches), "clocks": clk, "wall_ms_timed_region": wall_ms, "setup_s": setup_s}
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             with tempfile.TemporaryDirectory() as td2:
-                r = run_reference_cpu(12, min(ncores, 16), td2)
+                r = run_reference_cpu(CPU_SAMPLE_STEPS, min(ncores, 16), td2)
             if r is not None:
                 line["cpu_baseline"] = {"value": r["value"], "unit": "HRU-steps/s", "cores": r["nproc"], "kind": "reference",
-                                        "sample": "%d concurrent single-threaded Raven.exe processes, one 10k-HRU HMETS member each, 12 daily steps "
-                                                  "(%.1f s wall incl. parsing); per-process %.0f HRU-steps/s" % (r["nproc"], r["wall_s"], r["per_proc"])}
+                                        "sample": "%d concurrent single-threaded Raven.exe processes, one 10k-HRU HMETS member each, %d daily steps "
+                                                  "(%.1f s wall incl. parsing); per-process %.0f HRU-steps/s" % (r["nproc"], CPU_SAMPLE_STEPS, r["wall_s"], r["per_proc"])}
         # ---- final ensemble statistics over ALL members (outside the timed regions): outlet hydrograph of the end-to-end pass,
         # reduced with one NCCL all-reduce per statistic (sum/sumsq, min, max)
         q_out = torch.from_numpy(sim.hydrographs(W, K)[:, :, 0].T.copy()).cuda()     # [members, K]

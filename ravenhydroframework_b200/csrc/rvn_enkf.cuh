@@ -56,11 +56,59 @@ __global__ void enkf_unpack_kernel(const __grid_constant__ DevModel Mo, const En
 #define RVN_ENKF_ET 16   // local members per CTA tile (accumulators per column)
 #define RVN_ENKF_KT 2    // state rows (columns of X) per thread
 #define RVN_ENKF_U 8     // ensemble members fetched ahead
+// Xmean[k] = sum_i X[i][k]/N accumulated in member order (src/EnKF.cpp:539-546), once per column (the FP64 division costs ~25
+// instructions; inside the update kernel it was repeated for every member tile and took 65 % of its stall samples).
+// N a power of two: x/N == x*(1/N) exactly (one rounding of the same real number), so the division becomes a multiply.
+__global__ void __launch_bounds__(256) enkf_mean_kernel(const double *__restrict__ Xall, double *__restrict__ Xmean, const long long M, const int N) {
+  const long long k = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (k >= M) return;
+  const bool pow2 = (N & (N - 1)) == 0;
+  const double rN = 1.0 / N;
+  double m = 0.0;
+  int i = 0;
+  for (; i + 8 <= N; i += 8) {
+    double x[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) x[u] = __ldg(Xall + (size_t)(i + u) * M + k);
+#pragma unroll
+    for (int u = 0; u < 8; u++) m += pow2 ? x[u] * rN : x[u] / N;
+  }
+  for (; i < N; i++) { const double x = __ldg(Xall + (size_t)i * M + k); m += pow2 ? x * rN : x / N; }
+  Xmean[k] = m;
+}
 // Xall [N][M] in; Xa [nLocal][M] out (separate buffer: every CTA reads all members' rows).  Zt = Z restricted to the local
 // columns, stored [N][nLocalPad] with nLocalPad a multiple of ET (padding columns zero).  Per ensemble member i a thread loads
 // KT values of X (coalesced) and ET values of Z (128-bit shared-memory broadcasts) for 2*KT*ET FP64 operations.
-__global__ void __launch_bounds__(RVN_ENKF_BS) enkf_update_kernel(const double *__restrict__ Xall, const double *__restrict__ Zt, double *__restrict__ Xa,
-                                                                 const long long M, const int N, const int e0, const int nLocal, const int nLocalPad) {
+template <bool CHECK>
+RVN_DI void enkf_mac_chunk(const double *__restrict__ Xall, const double *s_z, const long long M, const int N, const int i0, const long long (&kk)[RVN_ENKF_KT],
+                           const double (&Xmean)[RVN_ENKF_KT], double (&acc)[RVN_ENKF_KT][RVN_ENKF_ET]) {
+  double xv[RVN_ENKF_U][RVN_ENKF_KT];   // U*KT independent loads in flight per thread
+#pragma unroll
+  for (int u = 0; u < RVN_ENKF_U; u++)
+#pragma unroll
+    for (int j = 0; j < RVN_ENKF_KT; j++) xv[u][j] = (!CHECK || i0 + u < N) ? __ldg(Xall + (size_t)(i0 + u) * M + kk[j]) : 0.0;
+#pragma unroll
+  for (int u = 0; u < RVN_ENKF_U; u++) {
+    if (!CHECK || i0 + u < N) {
+      double a[RVN_ENKF_KT];
+#pragma unroll
+      for (int j = 0; j < RVN_ENKF_KT; j++) a[j] = xv[u][j] - Xmean[j];   // A = X - 1/N*(X*e_N1)*e_1N
+      const double2 *z2 = reinterpret_cast<const double2 *>(s_z + (i0 + u) * RVN_ENKF_ET);
+#pragma unroll
+      for (int c = 0; c < RVN_ENKF_ET / 2; c++) {
+        const double2 z = z2[c];
+#pragma unroll
+        for (int j = 0; j < RVN_ENKF_KT; j++) {   // MatMult(A,Z,...): C[n][p] += A[n][m]*B[m][p], m ascending, separate multiply and add
+          acc[j][2 * c] += a[j] * z.x;
+          acc[j][2 * c + 1] += a[j] * z.y;
+        }
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(RVN_ENKF_BS) enkf_update_kernel(const double *__restrict__ Xall, const double *__restrict__ Zt, const double *__restrict__ mean,
+                                                                 double *__restrict__ Xa, const long long M, const int N, const int e0, const int nLocal,
+                                                                 const int nLocalPad) {
   extern __shared__ __align__(16) double s_z[];   // [N][ET]
   const int tile = blockIdx.y;
   for (int i = threadIdx.x; i < N * RVN_ENKF_ET; i += RVN_ENKF_BS) {
@@ -71,48 +119,20 @@ __global__ void __launch_bounds__(RVN_ENKF_BS) enkf_update_kernel(const double *
   const long long k0 = (long long)blockIdx.x * (RVN_ENKF_BS * RVN_ENKF_KT) + threadIdx.x;
   bool live[RVN_ENKF_KT];
   long long kk[RVN_ENKF_KT];
-#pragma unroll
-  for (int j = 0; j < RVN_ENKF_KT; j++) { kk[j] = k0 + (long long)j * RVN_ENKF_BS; live[j] = kk[j] < M; if (!live[j]) kk[j] = M - 1; }
-  // A = X - 1/N*(X*e_N1)*e_1N : Xmean accumulates X[i][k]/N in member order (src/EnKF.cpp:539-546)
   double Xmean[RVN_ENKF_KT];
 #pragma unroll
-  for (int j = 0; j < RVN_ENKF_KT; j++) Xmean[j] = 0.0;
-#pragma unroll 8
-  for (int i = 0; i < N; i++) {
-#pragma unroll
-    for (int j = 0; j < RVN_ENKF_KT; j++) Xmean[j] += __ldg(Xall + (size_t)i * M + kk[j]) / N;
+  for (int j = 0; j < RVN_ENKF_KT; j++) {
+    kk[j] = k0 + (long long)j * RVN_ENKF_BS; live[j] = kk[j] < M; if (!live[j]) kk[j] = M - 1;
+    Xmean[j] = __ldg(mean + kk[j]);
   }
   double acc[RVN_ENKF_KT][RVN_ENKF_ET];
 #pragma unroll
   for (int j = 0; j < RVN_ENKF_KT; j++)
 #pragma unroll
     for (int c = 0; c < RVN_ENKF_ET; c++) acc[j][c] = 0.0;
-  // the X values of RVN_ENKF_U members are fetched before they are used: U*KT independent loads in flight per thread
-  for (int i0 = 0; i0 < N; i0 += RVN_ENKF_U) {
-    double xv[RVN_ENKF_U][RVN_ENKF_KT];
-#pragma unroll
-    for (int u = 0; u < RVN_ENKF_U; u++)
-#pragma unroll
-      for (int j = 0; j < RVN_ENKF_KT; j++) xv[u][j] = (i0 + u < N) ? __ldg(Xall + (size_t)(i0 + u) * M + kk[j]) : 0.0;
-#pragma unroll
-    for (int u = 0; u < RVN_ENKF_U; u++) {
-      if (i0 + u < N) {
-        double a[RVN_ENKF_KT];
-#pragma unroll
-        for (int j = 0; j < RVN_ENKF_KT; j++) a[j] = xv[u][j] - Xmean[j];
-        const double2 *z2 = reinterpret_cast<const double2 *>(s_z + (i0 + u) * RVN_ENKF_ET);
-#pragma unroll
-        for (int c = 0; c < RVN_ENKF_ET / 2; c++) {
-          const double2 z = z2[c];
-#pragma unroll
-          for (int j = 0; j < RVN_ENKF_KT; j++) {   // MatMult(A,Z,...): C[n][p] += A[n][m]*B[m][p], m ascending, separate multiply and add
-            acc[j][2 * c] += a[j] * z.x;
-            acc[j][2 * c + 1] += a[j] * z.y;
-          }
-        }
-      }
-    }
-  }
+  int i0 = 0;
+  for (; i0 + RVN_ENKF_U <= N; i0 += RVN_ENKF_U) enkf_mac_chunk<false>(Xall, s_z, M, N, i0, kk, Xmean, acc);
+  if (i0 < N) enkf_mac_chunk<true>(Xall, s_z, M, N, i0, kk, Xmean, acc);
   const double scale = 1.0 / (N - 1);
 #pragma unroll
   for (int j = 0; j < RVN_ENKF_KT; j++) {
@@ -120,7 +140,7 @@ __global__ void __launch_bounds__(RVN_ENKF_BS) enkf_update_kernel(const double *
 #pragma unroll
     for (int c = 0; c < RVN_ENKF_ET; c++) {
       const int el = tile * RVN_ENKF_ET + c;
-      if (el < nLocal) Xa[(size_t)el * M + kk[j]] = Xall[(size_t)(e0 + el) * M + kk[j]] + acc[j][c] * scale;   // ScalarMatMult, MatAdd
+      if (el < nLocal) Xa[(size_t)el * M + kk[j]] = __ldg(Xall + (size_t)(e0 + el) * M + kk[j]) + acc[j][c] * scale;   // ScalarMatMult, MatAdd
     }
   }
 }
