@@ -209,6 +209,16 @@ typedef struct rvn_process {
 #define RVN_GRP_LAST 2
 #define RVN_GRP_MEMBER 4
 
+/* one lateral exchange process (LAT_FLUSH: reference CmvLatFlush, src/LatFlush.cpp:55-234) */
+typedef enum { RVN_LAT_FLUSH = 0 } rvn_lateral_kind;
+typedef struct rvn_lateral {
+  int32_t kind;            /* rvn_lateral_kind */
+  int32_t sv_from, sv_to;  /* state-variable indices _iFromLat / _iToLat (the same for every connection of a flush) */
+  int32_t nconn, conn0;    /* connections in lat_kfrom/lat_kto/lat_frac */
+  int32_t nchunks, chunk0; /* chunk offsets in lat_chunk_ptr (nchunks + 1 entries) */
+  int32_t pad_;
+} rvn_lateral;
+
 typedef struct rvn_options {
   double  timestep;               /* Options.timestep [d] */
   int32_t rainsnow, pot_melt, evaporation, ow_evaporation;
@@ -295,6 +305,17 @@ typedef struct rvn_model_desc {
   int32_t nEtRows, pad2_;
   const double *et_radia;
   const int32_t *et_row;      /* [nSteps] */
+  /* lateral exchange processes (reference CLateralExchangeProcessABC; CModel::ApplyLateralProcess, src/Model.cpp:3126-3165,
+   * applied by the solver after ALL vertical processes of ALL HRUs and before the routing prep, src/Solvers.cpp:404-443).
+   * Only processes that apply (gate of the first source HRU, every participating HRU enabled) are listed, in process order.
+   * Connection q of process L: lat_kfrom/lat_kto/lat_frac[L.conn0 + q].  Connections are grouped into chunks of HRUs that no
+   * other chunk touches (one subbasin each; a single chunk for INTERBASIN): chunk c of L = connections
+   * lat_chunk_ptr[L.chunk0 + c] .. lat_chunk_ptr[L.chunk0 + c + 1] (offsets relative to L.conn0). */
+  int32_t nLat, nLatConn;
+  const struct rvn_lateral *lat;   /* [nLat] */
+  const int32_t *lat_kfrom, *lat_kto;
+  const double  *lat_frac;
+  const int32_t *lat_chunk_ptr;
   /* forcing perturbations (EnKF members; 0 for every other model).  One sample per perturbation, member and DAY (the
    * reference draws nStepsPerDay samples at the start of a day, src/Model.cpp:2829-2847; steps here are daily or longer):
    * pert_eps[member][step][pert].  pert_mask[pert][hru] = 1 where the HRU belongs to the perturbation's HRU group

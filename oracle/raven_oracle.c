@@ -858,6 +858,27 @@ static void update_outflows(const rvn_model_desc *d, int p, const obasin *B, con
 }
 
 /* ======================================================================== one member, n steps === */
+/* routing prep (src/Solvers.cpp:495-511) and diagnostics of the write-back (:697-729) for one HRU's newest state vector */
+static void finish_hru(const rvn_model_desc *d, int k, double *phinew, double *aRouted, int iSW, int iRO, int iTotalSWE, int iGlacierMB) {
+  const int NS = d->NS;
+  int p = d->hru_sb[k];
+  double SWvol = (phinew[iSW] / O_MM_PER_METER) * (d->hru_area[k] * O_M2_PER_KM2);
+  aRouted[p] += SWvol;
+  phinew[iRO] = phinew[iSW];
+  phinew[iSW] = 0.0;
+  if (iTotalSWE >= 0) {
+    phinew[iTotalSWE] = 0.0;
+    for (int i = 0; i < NS; i++) if (d->sv_type[i] == RVN_SV_SNOW || d->sv_type[i] == RVN_SV_SNOW_LIQ) phinew[iTotalSWE] += phinew[i];
+  }
+  if (iGlacierMB >= 0) {
+    phinew[iGlacierMB] = 0.0;
+    for (int i = 0; i < NS; i++) {
+      int t = d->sv_type[i];
+      if (t == RVN_SV_SNOW || t == RVN_SV_SNOW_LIQ || t == RVN_SV_FIRN || t == RVN_SV_GLACIER_ICE || t == RVN_SV_GLACIER) phinew[iGlacierMB] += phinew[i];
+    }
+  }
+}
+
 /* state   [nHRU][NS]   in/out
  * basin   qin[nSB][max_nqin] qlat[nSB][max_nqlat] qout[nSB][50] scal[nSB][8]  in/out
  * cumul   [2] {_CumulInput,_CumulOutput} in/out
@@ -942,26 +963,36 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
             else phinew[ct[q]] += rates[q] * tstep;
           }
         }
-        /* routing prep :495-511 */
-        int p = d->hru_sb[k];
-        double SWvol = (phinew[iSW] / O_MM_PER_METER) * (d->hru_area[k] * O_M2_PER_KM2);
-        aRouted[p] += SWvol;
-        phinew[iRO] = phinew[iSW];
-        phinew[iSW] = 0.0;
-        /* write-back :697-729 */
-        if (iTotalSWE >= 0) {
-          phinew[iTotalSWE] = 0.0;
-          for (int i = 0; i < NS; i++) if (d->sv_type[i] == RVN_SV_SNOW || d->sv_type[i] == RVN_SV_SNOW_LIQ) phinew[iTotalSWE] += phinew[i];
-        }
-        if (iGlacierMB >= 0) {
-          phinew[iGlacierMB] = 0.0;
-          for (int i = 0; i < NS; i++) {
-            int t = d->sv_type[i];
-            if (t == RVN_SV_SNOW || t == RVN_SV_SNOW_LIQ || t == RVN_SV_FIRN || t == RVN_SV_GLACIER_ICE || t == RVN_SV_GLACIER) phinew[iGlacierMB] += phinew[i];
-          }
-        }
+        if (d->nLat > 0) { memcpy(phi_old, phinew, sizeof(double) * NS); continue; } /* lateral exchange first: the row now holds aPhinew[k] */
+        finish_hru(d, k, phinew, aRouted, iSW, iRO, iTotalSWE, iGlacierMB);
         memcpy(phi_old, phinew, sizeof(double) * NS);
       }
+    }
+    if (d->nLat > 0) {
+      /* ---- lateral exchange processes on the post-vertical state of ALL HRUs (src/Solvers.cpp:404-443; CModel::ApplyLateralProcess,
+       * src/Model.cpp:3126-3165; CmvLatFlush::GetLateralExchange, src/LatFlush.cpp:204-234).  state[k] is aPhinew[k] here. */
+      for (int l = 0; l < d->nLat; l++) {
+        const rvn_lateral *L = &d->lat[l];
+        double *ex = (double *)malloc(sizeof(double) * (size_t)(L->nconn > 0 ? L->nconn : 1));
+        for (int q = 0; q < L->nconn; q++) {
+          const int kF = d->lat_kfrom[L->conn0 + q], kT = d->lat_kto[L->conn0 + q];
+          double stor = state[(size_t)kF * NS + L->sv_from], to_stor = state[(size_t)kT * NS + L->sv_to];
+          double Afrom = d->hru_area[kF], Ato = d->hru_area[kT];
+          octx cc = c; cc.k = kT;
+          double max_to_stor = state_var_max(&cc, L->sv_to, state + (size_t)kT * NS);
+          double max_rate = omax(max_to_stor - to_stor, 0.0) / tstep * Ato;
+          double mult = 1.0;
+          ex[q] = omax(mult * stor, 0.0) / tstep * Afrom * d->lat_frac[L->conn0 + q];
+          ex[q] = omin(ex[q], max_rate);
+        }
+        for (int q = 0; q < L->nconn; q++) {
+          const int kF = d->lat_kfrom[L->conn0 + q], kT = d->lat_kto[L->conn0 + q];
+          state[(size_t)kF * NS + L->sv_from] -= ex[q] / d->hru_area[kF] * tstep;
+          state[(size_t)kT * NS + L->sv_to] += ex[q] / d->hru_area[kT] * tstep;
+        }
+        free(ex);
+      }
+      for (int k = 0; k < nH; k++) if (d->hru_enabled[k]) finish_hru(d, k, state + (size_t)k * NS, aRouted, iSW, iRO, iTotalSWE, iGlacierMB);
     }
     /* ---- routing, upstream to downstream (src/Solvers.cpp:565-615) */
     for (int pp = 0; pp < NB; pp++) {

@@ -798,9 +798,12 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
     apply_connections(c, dp);
   }
   double swv = 0.0, stor = 0.0;
+  const bool defer = (M.defer_finish != 0);   // lateral exchange processes follow: routing prep / diagnostics move to finish_kernel
   if (enabled) {
-    swv = finish_step(c, nCore);
-    stor = hru_storage(c, nCore) * c.area;
+    if (!defer) {
+      swv = finish_step(c, nCore);
+      stor = hru_storage(c, nCore) * c.area;
+    }
     for (int s = 0; s < nCore; s++) __stcs(gstate + (size_t)P->slot_sv[s] * nHp, c.SV(s));
     if (M.record_forcings) {
       double *gf = M.forc + (size_t)e * RVN_F_COUNT * nHp + k;
@@ -809,13 +812,13 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
     }
   }
   const int par = step & 1;
-  if (in_range) M.swvol[((size_t)par * M.E + e) * nHp + k] = swv;
+  if (in_range && !defer) M.swvol[((size_t)par * M.E + e) * nHp + k] = swv;
   const double pa = enabled ? c.F[RVN_F_PRECIP] * c.area : 0.0;
   const double bp = block_sum(pa, s_red);
   const double bs = block_sum(stor, s_red);
   if (tid == 0) {
     M.part_precip[((size_t)par * M.E + e) * M.nBlocksX + blockIdx.x] = bp;
-    M.part_storage[((size_t)par * M.E + e) * M.nBlocksX + blockIdx.x] = bs;
+    if (!defer) M.part_storage[((size_t)par * M.E + e) * M.nBlocksX + blockIdx.x] = bs;
   }
 }
 

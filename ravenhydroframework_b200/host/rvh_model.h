@@ -305,6 +305,9 @@ private:
   std::vector<double> _f_hru_d[5], _f_prof_thick, _f_ptab, _f_conv_uh, _f_series, _f_gconst, _f_wt, _f_sb_d[7], _f_uh, _f_rh, _f_veg_season, _f_et;
   std::vector<int32_t> _f_et_row, _f_wt_ptr, _f_wt_idx, _f_pert_forcing, _f_pert_adj, _f_hru_terr;
   std::vector<uint8_t> _f_pert_mask;
+  std::vector<rvn_lateral> _f_lat;
+  std::vector<int32_t> _f_lat_kfrom, _f_lat_kto, _f_lat_chunk;
+  std::vector<double> _f_lat_frac;
   std::vector<double> _f_pert_eps;
   std::vector<rvn_time> _f_times;
   int _f_ptab_stride, _f_nconv;

@@ -60,7 +60,7 @@ static const char *kIgnoredRVI[] = {":FileType", ":WrittenBy", ":CreationDate", 
   ":RunName", ":OutputDirectory", ":OutputInterval", ":SuppressOutput", ":DontWriteWatershedStorage", ":EvaluationPeriod", ":SnapshotHydrograph",
   ":SWRadiationMethod", ":SWCloudCorrect", ":SWCanopyCorrect", ":LWRadiationMethod", ":LWIncomingMethod", ":CloudCoverMethod", ":WindspeedMethod",
   ":RelativeHumidityMethod", ":AirPressureMethod", ":PavicsMode", ":DebugMode", ":WriteExhaustiveMB", ":HydrologicProcesses", ":EndHydrologicProcesses",
-  ":DefineHRUGroups", ":WriteSubbasinFile", ":NetCDFAttribute", ":rvh_Filename", NULL};
+  ":WriteSubbasinFile", ":NetCDFAttribute", ":rvh_Filename", NULL};
 
 static rvn_pet ParsePET(const std::string &s) {
   if (s == "PET_DATA") return RVN_PET_DATA;
@@ -233,6 +233,10 @@ static void ParseMainInputFile(CModel *&pModel, optStruct &Options) {
       continue;
     }
     ExitGracefullyIf(!pModel && c != ":FileType", "ParseMainInputFile: " + c + " appears before :SoilModel, or is not supported by the B200 build");
+    if (c == ":DefineHRUGroups" || c == ":DefineHRUGroup") {   // groups are populated by the .rvh file
+      for (int i = 1; i < Len; i++) if (pModel->FindHRUGroup(s[i]) == DOESNT_EXIST) { CHRUGroup G; G.name = s[i]; pModel->hru_groups.push_back(G); }
+      continue;
+    }
     if (c == ":ProcessGroup") {   // src/ParseInput.cpp case 295
       ExitGracefullyIf(pGroup != NULL, "ParseMainInputFile: nested :ProcessGroup commands are not supported by the B200 build");
       pGroup = new CProcessGroup(Len > 1 ? s[1] : "", pModel);

@@ -86,6 +86,61 @@ void CProcessGroup::Initialize() {
   }
 }
 
+// ---- LateralFlush -----------------------------------------------------------------------------------
+CmvLatFlush::CmvLatFlush(int from_sv_ind, int to_sv_ind, int from_HRU_grp, int to_HRU_grp, bool constrain_to_SBs, CModel *pM)
+    : CHydroProcessABC("LateralFlush", pM), _iFlushFrom(from_sv_ind), _iFlushTo(to_sv_ind), _kk_from(from_HRU_grp), _kk_to(to_HRU_grp),
+      _constrain_to_SBs(constrain_to_SBs) {
+  ExitGracefullyIf(to_HRU_grp < 0 || to_HRU_grp >= (int)pM->hru_groups.size(), "CmvLatFlush::unrecognized 'to' HRU group specified in :LateralFlush/:LateralDivert command");
+  ExitGracefullyIf(from_HRU_grp < 0 || from_HRU_grp >= (int)pM->hru_groups.size(), "CmvLatFlush::unrecognized 'from' HRU group specified in :LateralFlush/:LateralDivert command");
+  ExitGracefullyIf(from_sv_ind == DOESNT_EXIST, "CmvLatFlush::unrecognized 'from' state variable specified in :LateralFlush/:LateralDivert command");
+  ExitGracefullyIf(to_sv_ind == DOESNT_EXIST, "CmvLatFlush::unrecognized 'to' state variable specified in :LateralFlush/:LateralDivert command");
+}
+void CmvLatFlush::Initialize() {   // src/LatFlush.cpp:55-177
+  _kFrom.clear(); _kTo.clear(); _aFrac.clear(); _chunk_ptr.assign(1, 0);
+  const int nH = pModel->GetNumHRUs();
+  std::vector<char> inFrom(nH, 0), inTo(nH, 0);
+  { const std::vector<int> &g = pModel->hru_groups[_kk_from].hru; for (size_t i = 0; i < g.size(); i++) inFrom[g[i]] = 1; }
+  { const std::vector<int> &g = pModel->hru_groups[_kk_to].hru; for (size_t i = 0; i < g.size(); i++) inTo[g[i]] = 1; }
+  if (_constrain_to_SBs) {
+    bool source_sink_issue = false;
+    for (int p = 0; p < pModel->GetNumSubBasins(); p++) {
+      const CSubBasin *b = pModel->GetSubBasin(p);
+      if (b->disabled) continue;
+      for (size_t ks = 0; ks < b->hru_index.size(); ks++) {   // sources
+        const int k1 = b->hru_index[ks];
+        if (!inFrom[k1]) continue;
+        double Asum = 0.0;
+        int nRecipients = 0;
+        for (size_t ks2 = 0; ks2 < b->hru_index.size(); ks2++) {   // recipients
+          const int k2 = b->hru_index[ks2];
+          if (!inTo[k2]) continue;
+          if (k1 != k2) {
+            const double area = pModel->GetHydroUnit(k2)->GetArea();
+            _kFrom.push_back(k1); _kTo.push_back(k2); _aFrac.push_back(area);
+            Asum += area; nRecipients++;
+          } else source_sink_issue = true;
+        }
+        const size_t q = _aFrac.size();
+        for (int qq = 0; qq < nRecipients; qq++) _aFrac[q - qq - 1] = _aFrac[q - qq - 1] / Asum;   // fraction of the recipient areas
+      }
+      if ((int)_kFrom.size() > _chunk_ptr.back()) _chunk_ptr.push_back((int)_kFrom.size());
+    }
+    if (_kFrom.empty()) WriteWarning("CmvLatFlush::Initialize: no connections found between from and to HRU groups in any of the basins. if INTERBASIN flag not used, only transfer within basins is supported. ");
+    if (source_sink_issue) WriteWarning("CmvLatFlush::Initialize: one or more HRUs belongs to both source and recipient HRU groups in LateralFlush or LateralDivert process. This may have unintentended consequences. ");
+  } else {
+    int kToSB = DOESNT_EXIST;
+    for (int k = 0; k < nH; k++)
+      if (inTo[k]) {
+        ExitGracefullyIf(kToSB != DOESNT_EXIST, "LatFlush::Initialize - only one HRU in the model can recieve flush output if INTERBASIN is used. More than one recipient HRU found.");
+        kToSB = k;
+      }
+    for (int k = 0; k < nH; k++)
+      if (inFrom[k] && (kToSB != DOESNT_EXIST) && pModel->GetHydroUnit(k)->IsEnabled()) { _kFrom.push_back(k); _kTo.push_back(kToSB); _aFrac.push_back(1.0); }
+    if (!_kFrom.empty()) _chunk_ptr.push_back((int)_kFrom.size());
+    if (_kFrom.empty()) WriteWarning("CmvLatFlush::Initialize: no connections found between from and to HRU groups. HRU Group population of zero?");
+  }
+}
+
 // ---- Precipitation ---------------------------------------------------------------------------------
 void CmvPrecipitation::GetParticipatingStateVarList(sv_type *aSV, int *aLev, int &nSV) {
   nSV = 1; aSV[0] = RVN_SV_ATMOS_PRECIP; aLev[0] = DOESNT_EXIST;
@@ -313,6 +368,14 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
     p->Connect(pM->GetStateVarIndex(RVN_SV_SOIL, 0), iAtmos);
     p->Connect(iAET, iAET);
     return p;
+  }
+  if (cmd == ":LateralFlush") {  // case 232: :LateralFlush RAVEN_DEFAULT [FROM_HRUGroup] [FROM_SV] To [TO_HRUGROUP] [TO_SV] {INTERBASIN}
+    need(7);
+    const int from = pM->ParseSVTypeIndex(s[3]), to = pM->ParseSVTypeIndex(s[6]);
+    const bool interbasin = (Len >= 8) && (s[7] == "INTERBASIN");
+    const int gF = pM->FindHRUGroup(s[2]), gT = pM->FindHRUGroup(s[5]);
+    ExitGracefullyIf(gF == DOESNT_EXIST || gT == DOESNT_EXIST, "ParseInput: Lateral Flush - invalid 'to' or 'from' HRU Group used. Must define using :DefineHRUGroups command.");
+    return new CmvLatFlush(from, to, gF, gT, !interbasin, pM);
   }
   if (cmd == ":Interflow") {  // case 210; src/Interflow.cpp:19-45,78-87
     need(4);

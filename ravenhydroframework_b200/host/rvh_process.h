@@ -102,6 +102,28 @@ private:
   std::vector<CHydroProcessABC *> _pSubProcesses;
   std::vector<double> _aWeights;
 };
+// CmvLatFlush (reference src/LatFlush.cpp:16-177): moves the whole content of one state variable of the 'from' group's HRUs to a
+// state variable of the 'to' group's HRUs -- within each subbasin, split by recipient area, or to one single recipient HRU when
+// INTERBASIN is given.  No vertical connections; the lateral ones are built in Initialize() once the groups are populated.
+class CmvLatFlush : public CHydroProcessABC {
+public:
+  CmvLatFlush(int from_sv_ind, int to_sv_ind, int from_HRU_grp, int to_HRU_grp, bool constrain_to_SBs, CModel *pM);
+  void Initialize() override;
+  void Compile(rvn_process &rec) const override { (void)rec; ExitGracefully("CmvLatFlush::Compile: lateral processes have no vertical record"); }
+  int  GetNumLatConnections() const { return (int)_kFrom.size(); }
+  const int *GetFromHRUIndices() const { return _kFrom.data(); }
+  const int *GetToHRUIndices() const { return _kTo.data(); }
+  const double *GetFractions() const { return _aFrac.data(); }
+  int  GetLateralFromIndex() const { return _iFlushFrom; }
+  int  GetLateralToIndex() const { return _iFlushTo; }
+  bool IsConstrainedToSubBasins() const { return _constrain_to_SBs; }
+  const std::vector<int> &ChunkOffsets() const { return _chunk_ptr; }   // connections grouped by subbasin (one chunk when INTERBASIN)
+private:
+  int _iFlushFrom, _iFlushTo, _kk_from, _kk_to;
+  bool _constrain_to_SBs;
+  std::vector<int> _kFrom, _kTo, _chunk_ptr;
+  std::vector<double> _aFrac;
+};
 void CalcWeightsFromUniformNums(const double *aVals, double *aWeights, int N);   // src/CommonFunctions.cpp:1845-1853
 
 // factory used by the .rvi reader: builds the process for a ':ProcessName ALGORITHM FROM TO' line,

@@ -441,6 +441,21 @@ def write_hbv(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUTE_
         c = "  :LakeEvaporation   LAKE_EVAP_BASIC    SLOW_RESERVOIR  ATMOSPHERE\n"
         assert c in rvi
         rvi = rvi.replace(c, "  :Interflow         INTERFLOW_PRMS     FAST_RESERVOIR  SURFACE_WATER\n" + c)
+    if variant == "lateral":
+        # lateral exchange (reference CmvLatFlush): surface water of the 'UpGroup' HRUs is flushed into the fast reservoir of the
+        # 'LowGroup' HRUs of the same subbasin (limited by the room left there); one more flush moves ponded water to one single
+        # recipient HRU across basins
+        a = ":HydrologicProcesses\n"
+        assert a in rvi
+        rvi = rvi.replace(a, ":DefineHRUGroups UpGroup LowGroup Sink\n" + a)
+        e = ":EndHydrologicProcesses"
+        rvi = rvi.replace(e, "  :LateralFlush      RAVEN_DEFAULT      UpGroup SURFACE_WATER To LowGroup FAST_RESERVOIR\n"
+                             "  :LateralFlush      RAVEN_DEFAULT      LowGroup SNOW_LIQ To Sink SOIL[0] INTERBASIN\n" + e)
+        n_hru = n_sb * hru_per_sb
+        with open(base + ".rvh", "a") as f:
+            f.write(":HRUGroup UpGroup\n  " + " ".join(str(k) for k in range(1, n_hru + 1) if k % 3 != 0) + "\n:EndHRUGroup\n")
+            f.write(":HRUGroup LowGroup\n  " + " ".join(str(k) for k in range(1, n_hru + 1) if k % 3 == 0 or k % 5 == 0) + "\n:EndHRUGroup\n")
+            f.write(":HRUGroup Sink\n  2\n:EndHRUGroup\n")
     _write(base + ".rvi", rvi)
     _write(base + ".rvc", HBV_RVC)
     return base

@@ -40,6 +40,8 @@ if hasattr(synth, "write_hbv"):
     CASES["hbv_gauges9"] = dict(kind="hbv", n_sb=5, hru_per_sb=4, n_days=150, seed=12, routing="ROUTE_MUSKINGUM", n_gauges=9)
     # process classes outside the three templates: :SnowMelt, :SnowSqueeze, :Interflow
     CASES["hbv_meltsqueeze"] = dict(kind="hbv", n_sb=3, hru_per_sb=5, n_days=300, seed=14, routing="ROUTE_MUSKINGUM", variant="melt_squeeze_interflow")
+    # lateral exchange between HRUs (CmvLatFlush): within-subbasin flush limited by the recipient's room + an INTERBASIN flush
+    CASES["hbv_lateral"] = dict(kind="hbv", n_sb=4, hru_per_sb=7, n_days=250, seed=8, routing="ROUTE_MUSKINGUM", season_offset=40, variant="lateral")
 if hasattr(synth, "write_blended"):
     # Blended multi-model template (BASELINE config 4): weighted process groups, VIC/TOPMODEL/analytic algorithms, SNOBAL_HBV
     WRITERS["blended"] = synth.write_blended
