@@ -175,7 +175,9 @@ static void apply_forcing_perturbation(const rvn_model_desc *d, int ftype, int m
   }
 }
 
-static void update_forcings(const rvn_model_desc *d, const double *ptab, int member, int k, int step, const double *phi_old, const int *iSV, double *F) {
+/* daily[7]: the HRU's daily forcing items of the previous step (temp_daily_min/max/ave, temp_month_max/min/ave, PET_month_ave), i.e. the
+ * part of CHydroUnit::_Forcings that CopyDailyForcingItems (src/Forcings.cpp:72-89) carries through the day on sub-daily steps */
+static void update_forcings(const rvn_model_desc *d, const double *ptab, int member, int k, int step, const double *phi_old, const int *iSV, double *F, double *daily) {
   const rvn_time *tt = &d->times[step];
   const int nG = d->nGauges, nS = d->nSteps, mo = tt->month;
   octx c; c.d = d; c.ptab = ptab; c.k = k; c.F = F; c.phi_old = phi_old; memcpy(c.iSV, iSV, sizeof(c.iSV));
@@ -235,6 +237,13 @@ static void update_forcings(const rvn_model_desc *d, const double *ptab, int mem
     }
   }
   if (d->nPert > 0) apply_forcing_perturbation(d, RVN_PF_TEMP_AVE, member, k, step, F); /* src/UpdateForcings.cpp:474 */
+  if (!tt->day_changed) { /* src/UpdateForcings.cpp:480-482: CopyDailyForcings */
+    F[RVN_F_TEMP_DAILY_MIN] = daily[0]; F[RVN_F_TEMP_DAILY_MAX] = daily[1]; F[RVN_F_TEMP_DAILY_AVE] = daily[2];
+    temp_month_max = daily[3]; temp_month_min = daily[4]; temp_month_ave = daily[5];
+    PET_month_ave = daily[6];
+  }
+  daily[0] = F[RVN_F_TEMP_DAILY_MIN]; daily[1] = F[RVN_F_TEMP_DAILY_MAX]; daily[2] = F[RVN_F_TEMP_DAILY_AVE];
+  daily[3] = temp_month_max; daily[4] = temp_month_min; daily[5] = temp_month_ave; daily[6] = PET_month_ave;
   F[RVN_F_TEMP_MONTH_AVE] = temp_month_ave; F[RVN_F_PET_MONTH_AVE] = PET_month_ave;
   const double subdaily_corr = 1.0;
   /* CModel::EstimateSnowFraction, src/UpdateForcings.cpp:1068-1197 */
@@ -896,6 +905,7 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
   const int iSW = c.iSV[RVN_SV_SURFACE_WATER], iAET = c.iSV[RVN_SV_AET], iRO = c.iSV[RVN_SV_RUNOFF], iGW = c.iSV[RVN_SV_GROUNDWATER];
   const int iTotalSWE = c.iSV[RVN_SV_TOTAL_SWE], iGlacierMB = c.iSV[RVN_SV_GLACIER_MB];
   double *F = (double *)malloc(sizeof(double) * (size_t)nH * RVN_F_COUNT);
+  double *daily = (double *)calloc((size_t)nH * 7, sizeof(double)); /* valid from the first step of a day on: runs must start at a day boundary */
   double *phinew = (double *)malloc(sizeof(double) * NS);
   double *aRouted = (double *)malloc(sizeof(double) * NB), *aQinnew = (double *)malloc(sizeof(double) * NB);
   double rates[O_MAXCONN]; int cf[O_MAXCONN], ct[O_MAXCONN];
@@ -903,7 +913,7 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
   for (int s = 0; s < nsteps; s++) {
     const int step = step0 + s;
     /* ---- UpdateHRUForcingFunctions (all HRUs, on the stored state) */
-    for (int k = 0; k < nH; k++) update_forcings(d, c.ptab, member, k, step, state + (size_t)k * NS, c.iSV, F + (size_t)k * RVN_F_COUNT);
+    for (int k = 0; k < nH; k++) update_forcings(d, c.ptab, member, k, step, state + (size_t)k * NS, c.iSV, F + (size_t)k * RVN_F_COUNT, daily + (size_t)k * 7);
     if (forc_rec) memcpy(forc_rec + (size_t)s * nH * RVN_F_COUNT, F, sizeof(double) * (size_t)nH * RVN_F_COUNT);
     /* ---- MassEnergyBalance, ORDERED_SERIES (src/Solvers.cpp:155-251) */
     for (int p = 0; p < NB; p++) { aRouted[p] = 0.0; aQinnew[p] = 0.0; }
@@ -1045,6 +1055,6 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
     if (qout_rec) for (int p = 0; p < NB; p++) qout_rec[(size_t)s * NB + p] = qout[(size_t)p * RVN_MAX_RIVER_SEGS + d->sb_nseg[p] - 1];
     if (state_rec) memcpy(state_rec + (size_t)s * nH * NS, state, sizeof(double) * (size_t)nH * NS);
   }
-  free(F); free(phinew); free(aRouted); free(aQinnew);
+  free(F); free(daily); free(phinew); free(aRouted); free(aQinnew);
   return 0;
 }

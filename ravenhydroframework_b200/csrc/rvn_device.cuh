@@ -84,6 +84,7 @@ struct DevModel {
   double *rec_qout, *rec_wshed;                    // [rec][member][nSB], [rec][member][4]
   int32_t rec_capacity, rec_flags;
   const DevProgram *prog;
+  double *daily;                                   // sub-daily steps only: [member][7][nHp] daily forcing items carried through the day (CopyDailyForcingItems)
   int32_t defer_finish;                            // 1: lateral processes follow the sweep; routing prep / diagnostics run in finish_kernel
   const double *proc_weight;                       // [nProc] process-group member weights (1.0 outside groups)
   // forcing perturbations of the EnKF members (0 = none)

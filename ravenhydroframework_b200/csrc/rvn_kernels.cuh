@@ -226,6 +226,20 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
     }
   }
   if (M.nPert > 0) apply_perturbations(F, M, RVN_PF_TEMP_AVE, e, k, step);   // src/UpdateForcings.cpp:474
+  if (M.daily != nullptr) {
+    // sub-daily steps: within a day the daily items are the ones the HRU got at the first step of the day
+    // (CHydroUnit::CopyDailyForcings -> CopyDailyForcingItems, src/UpdateForcings.cpp:480-482, src/Forcings.cpp:72-89)
+    double *dly = M.daily + (size_t)e * 7 * M.nHp + k;
+    if (!tt.day_changed) {
+      F[RVN_F_TEMP_DAILY_MIN] = dly[0 * (size_t)M.nHp]; F[RVN_F_TEMP_DAILY_MAX] = dly[1 * (size_t)M.nHp]; F[RVN_F_TEMP_DAILY_AVE] = dly[2 * (size_t)M.nHp];
+      temp_month_max = dly[3 * (size_t)M.nHp]; temp_month_min = dly[4 * (size_t)M.nHp]; temp_month_ave = dly[5 * (size_t)M.nHp];
+      PET_month_ave = dly[6 * (size_t)M.nHp];
+    } else {
+      dly[0 * (size_t)M.nHp] = F[RVN_F_TEMP_DAILY_MIN]; dly[1 * (size_t)M.nHp] = F[RVN_F_TEMP_DAILY_MAX]; dly[2 * (size_t)M.nHp] = F[RVN_F_TEMP_DAILY_AVE];
+      dly[3 * (size_t)M.nHp] = temp_month_max; dly[4 * (size_t)M.nHp] = temp_month_min; dly[5 * (size_t)M.nHp] = temp_month_ave;
+      dly[6 * (size_t)M.nHp] = PET_month_ave;
+    }
+  }
   F[RVN_F_TEMP_MONTH_AVE] = temp_month_ave; F[RVN_F_PET_MONTH_AVE] = PET_month_ave;
   const double subdaily_corr = 1.0;  // CalculateSubDailyCorrection: timestep>=1 (src/UpdateForcings.cpp:949-958)
   {  // CModel::EstimateSnowFraction  src/UpdateForcings.cpp:1068-1197

@@ -122,8 +122,18 @@ void CGauge::Initialize(const optStruct &O) {
         for (int n = 0; n < nVals; n++) { aAvg[n] = 0.5 * (Tmin->GetValue(t + 0.5) + Tmax->GetValue(t + 0.5)); t += 1.0; }
         AddTimeSeries(new CTimeSeries("TEMP_DAILY_AVE", O.julian_start_day, O.julian_start_year, 1.0, aAvg), F_TEMP_DAILY_AVE);
       }
-      if (O.timestep < (1.0 - TIME_CORRECTION)) {
-        ExitGracefully("CGauge::Initialize: sub-daily temperature downscaling is not supported by the B200 build yet");
+      if (O.timestep < (1.0 - TIME_CORRECTION)) {   // GenerateAveSubdailyTempFromMinMax, sub-daily branch (src/Gauge.cpp:683-699)
+        const int nVals = (int)ceil(O.duration / O.timestep);
+        std::vector<double> aT(nVals);
+        double t = 0.0;
+        for (int n = 0; n < nVals; n++) {
+          const double Tmax_ = Tmax->GetValue(t + O.timestep / 2.0), Tmin_ = Tmin->GetValue(t + O.timestep / 2.0);
+          // CGauge::DailyTempCorrection (src/Gauge.cpp:468-471): -cos(2*PI*(t - PEAK_TEMP_HR/HR_PER_DAY)), PEAK_TEMP_HR = 3
+          const double c1 = -cos(2.0 * RVH_PI * (t - 3 / HR_PER_DAY)), c2 = -cos(2.0 * RVH_PI * ((t + O.timestep) - 3 / HR_PER_DAY));
+          aT[n] = 0.5 * (Tmax_ + Tmin_) + 0.5 * (Tmax_ - Tmin_) * 0.5 * (c1 + c2);
+          t += O.timestep;
+        }
+        AddTimeSeries(new CTimeSeries("TEMP_AVE", O.julian_start_day, O.julian_start_year, O.timestep, aT), F_TEMP_AVE);
       } else {
         CTimeSeries *T = _pTS[F_TEMP_DAILY_AVE];
         AddTimeSeries(new CTimeSeries("TEMP_AVE", T->GetStartDay(), T->GetStartYear(), T->GetInterval(), T->Values()), F_TEMP_AVE);

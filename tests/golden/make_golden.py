@@ -47,6 +47,12 @@ if hasattr(synth, "write_blended"):
     WRITERS["blended"] = synth.write_blended
     CASES["blended_tree"] = dict(kind="blended", n_sb=5, hru_per_sb=4, n_days=300, seed=16, routing="ROUTE_MUSKINGUM", catchment_route="TRIANGULAR_UH")
     CASES["blended_single"] = dict(kind="blended", n_sb=1, hru_per_sb=1, n_days=500, seed=17)
+    # sub-daily steps (BASELINE config 4 asks for hourly): daily min/max temperatures downscaled by the gauge, daily items
+    # carried through the day, Muskingum routing with sub-daily histories
+    CASES["blended_hourly"] = dict(kind="blended", n_sb=5, hru_per_sb=4, n_days=25, seed=18, routing="ROUTE_MUSKINGUM", catchment_route="TRIANGULAR_UH",
+                                   season_offset=95, n_gauges=9, timestep="01:00:00")
+    CASES["hbv_6hourly"] = dict(kind="hbv", n_sb=7, hru_per_sb=3, n_days=120, seed=19, routing="ROUTE_MUSKINGUM", season_offset=60, timestep="06:00:00")
+    CASES["hmets_3hourly"] = dict(kind="hmets", n_sb=3, hru_per_sb=4, n_days=60, seed=20, season_offset=90, timestep="03:00:00")
 if hasattr(synth, "write_gr4j"):
     WRITERS["gr4j"] = synth.write_gr4j
     CASES["gr4j_single"] = dict(kind="gr4j", n_sb=1, hru_per_sb=1, n_days=730, seed=9)
@@ -103,10 +109,17 @@ def make(name, spec):
     spec = dict(spec)
     kind = spec.pop("kind")
     member = spec.pop("member", None)
+    timestep = spec.pop("timestep", None)     # e.g. "01:00:00": sub-daily model step on the daily forcing series
     d = os.path.join(HERE, name)
     shutil.rmtree(d, ignore_errors=True)
     base = WRITERS[kind](d, name="model", **spec)
     n = spec["n_days"]
+    if timestep is not None:
+        rvi = open(base + ".rvi").read()
+        assert ":TimeStep              1.0" in rvi
+        open(base + ".rvi", "w").write(rvi.replace(":TimeStep              1.0", ":TimeStep              " + timestep))
+        h, mi, se = [float(x) for x in timestep.split(":")]
+        n = int(round(n / ((h + mi / 60.0 + se / 3600.0) / 24.0)))
     out = os.path.join(d, "_refout")
     if member is not None:
         os.environ["REF_DUMP_MEMBER"] = str(member)
