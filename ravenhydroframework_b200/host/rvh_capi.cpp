@@ -56,8 +56,32 @@ int rvh_ensemble_update_model(rvh_model *h, int e, double *values, int nmax) {
   if (!h->pEnsemble) throw RavenError("rvh_ensemble_update_model: call rvh_ensemble_begin first");
   h->pEnsemble->UpdateModel(h->pModel, h->Options, e);
   const CMonteCarloEnsemble *mc = dynamic_cast<const CMonteCarloEnsemble *>(h->pEnsemble);
+  const CDDSEnsemble *dds = dynamic_cast<const CDDSEnsemble *>(h->pEnsemble);
   int n = 0;
   if (mc && values) for (; n < (int)mc->LastSample().size() && n < nmax; n++) values[n] = mc->LastSample()[n];
+  if (dds && values) for (; n < (int)dds->TestParams().size() && n < nmax; n++) values[n] = dds->TestParams()[n];
+  return n;
+  RVH_CATCH(-1)
+}
+// ---- DDS (CDDSEnsemble): rvh_ensemble_begin + rvh_ensemble_update_model(e) perturb the best-so-far vector (the sampled values
+// returned are the trial's parameters); after the trial's GPU run rvh_dds_finish_run(e, hydrographs) evaluates the objective
+// function and updates the best solution.  qout_rec[nsteps][nSB] = CSubBasin::GetOutflowRate after every step of the single member.
+double rvh_dds_finish_run(rvh_model *h, int e, const double *qout_rec, const double *qout_initial, int nsteps, double *Fbest) {
+  RVH_TRY
+  CDDSEnsemble *dds = dynamic_cast<CDDSEnsemble *>(h->pEnsemble);
+  if (!dds) throw RavenError("rvh_dds_finish_run: the model is not an ENSEMBLE_DDS model or rvh_ensemble_begin was not called");
+  const double F = dds->ObjectiveFromHydrograph(h->pModel, h->Options, qout_rec, qout_initial, nsteps, h->pModel->GetNumSubBasins());
+  dds->FinishEnsembleRun(F, e);
+  if (Fbest) *Fbest = dds->BestObjective();
+  return F;
+  RVH_CATCH(-1e300)
+}
+int rvh_dds_best(rvh_model *h, double *best, int nmax) {
+  RVH_TRY
+  CDDSEnsemble *dds = dynamic_cast<CDDSEnsemble *>(h->pEnsemble);
+  if (!dds) throw RavenError("rvh_dds_best: not a DDS ensemble");
+  int n = 0;
+  for (; n < (int)dds->BestParams().size() && n < nmax; n++) best[n] = dds->BestParams()[n];
   return n;
   RVH_CATCH(-1)
 }

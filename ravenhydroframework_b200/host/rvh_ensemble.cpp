@@ -55,6 +55,139 @@ void CMonteCarloEnsemble::UpdateModel(CModel *pModel, optStruct &Options, int e)
   // the reference re-reads the .rvc here: every member starts from the same initial state (uploaded once per member by the caller)
 }
 
+// ----------------------------------------------------------------------------------------------------------------- DDS
+diag_type StringToDiagnostic(const std::string &s) {
+  if (s == "NASH_SUTCLIFFE") return DIAG_NASH_SUTCLIFFE;
+  if (s == "RMSE") return DIAG_RMSE;
+  if (s == "KLING_GUPTA") return DIAG_KLING_GUPTA;
+  return DIAG_UNRECOGNIZED;
+}
+double CalculateDiagnostic(diag_type type, const std::vector<double> &mod, const std::vector<double> &obs, double starttime, double endtime,
+                           double timestep, bool is_hydrograph) {
+  const int nSampVal = (int)obs.size();
+  auto index_of = [&](double t_mod) {   // CTimeSeries::GetTimeIndexFromModelTime (src/TimeSeries.cpp:311-314)
+    int i = (int)(rvh_max(floor((t_mod + TIME_CORRECTION) / timestep), 0.0));
+    return (i < nSampVal - 1) ? i : nSampVal - 1;
+  };
+  const int skip = is_hydrograph ? 1 : 0;   // averaged hydrographs: the value at index 0 is not a period average
+  const int nnstart = index_of(starttime) + skip, nnend = index_of(endtime) + 1;
+  std::vector<double> w(nnend > 0 ? nnend : 1, 0.0);
+  for (int nn = nnstart; nn < nnend; nn++) {
+    w[nn] = 1.0;
+    if (obs[nn] == RAV_BLANK_DATA) w[nn] = 0.0;
+    if (nn >= (int)mod.size() || mod[nn] == RAV_BLANK_DATA) w[nn] = 0.0;
+  }
+  double N = 0;
+  if (type == DIAG_NASH_SUTCLIFFE) {
+    double avgobs = 0.0;
+    for (int nn = nnstart; nn < nnend; nn++) { avgobs += w[nn] * obs[nn]; N += w[nn]; }
+    if (N > 0.0) avgobs /= N;
+    double sum1 = 0.0, sum2 = 0.0;
+    for (int nn = nnstart; nn < nnend; nn++) {
+      const double m = (nn < (int)mod.size()) ? mod[nn] : 0.0;
+      sum1 += w[nn] * pow(obs[nn] - m, 2);
+      sum2 += w[nn] * pow(obs[nn] - avgobs, 2);
+    }
+    return (N > 0) ? 1.0 - (sum1 / sum2) : -ALMOST_INF;
+  }
+  if (type == DIAG_RMSE) {
+    double sum = 0.0;
+    for (int nn = nnstart; nn < nnend; nn++) { const double m = (nn < (int)mod.size()) ? mod[nn] : 0.0; sum += w[nn] * pow(obs[nn] - m, 2); N += w[nn]; }
+    return (N > 0.0) ? sqrt(sum / N) : -ALMOST_INF;
+  }
+  if (type == DIAG_KLING_GUPTA) {
+    double ObsSum = 0, ModSum = 0, ObsStd = 0, ModStd = 0, Cov = 0;
+    for (int nn = nnstart; nn < nnend; nn++) { const double m = (nn < (int)mod.size()) ? mod[nn] : 0.0; ObsSum += obs[nn] * w[nn]; ModSum += m * w[nn]; N += w[nn]; }
+    const double ObsAvg = ObsSum / N, ModAvg = ModSum / N;
+    for (int nn = nnstart; nn < nnend; nn++) {
+      const double m = (nn < (int)mod.size()) ? mod[nn] : 0.0;
+      ObsStd += pow((obs[nn] - ObsAvg), 2) * w[nn];
+      ModStd += pow((m - ModAvg), 2) * w[nn];
+      Cov += (obs[nn] - ObsAvg) * (m - ModAvg) * w[nn];
+    }
+    ObsStd = sqrt(ObsStd / N); ModStd = sqrt(ModStd / N); Cov /= N;
+    const double r = Cov / ObsStd / ModStd, Beta = ModAvg / ObsAvg, Alpha = ModStd / ObsStd;
+    if ((N > 0) && ((ObsAvg != 0.0) || (Beta == 1.0)) && (ObsStd != 0.0) && (ModStd != 0.0)) return 1.0 - sqrt(pow((r - 1), 2) + pow((Alpha - 1), 2) + pow((Beta - 1), 2));
+    return -ALMOST_INF;
+  }
+  ExitGracefully("CalculateDiagnostic: this diagnostic is not implemented in the B200 build");
+  return 0.0;
+}
+CDDSEnsemble::CDDSEnsemble(int num_members, const optStruct &Options)
+    : CEnsemble(num_members, Options), _Fbest(ALMOST_INF), _r_val(0.2), _calib_SBID(DOESNT_EXIST), _calib_Obj(DIAG_NASH_SUTCLIFFE), _calib_Period("ALL") {
+  _type = ENSEMBLE_DDS;
+}
+void CDDSEnsemble::SetPerturbationValue(double perturb) {
+  _r_val = perturb;
+  ExitGracefullyIf((_r_val < 0) || (_r_val > 1.0), "CDDSEnsemble::SetPerturbationValue");
+}
+void CDDSEnsemble::SetCalibrationTarget(long long SBID, diag_type object_diag, const std::string &period) { _calib_SBID = SBID; _calib_Obj = object_diag; _calib_Period = period; }
+void CDDSEnsemble::Initialize(const CModel *pModel, const optStruct &Options) {
+  (void)pModel; (void)Options;
+  ExitGracefullyIf(_calib_SBID == DOESNT_EXIST, "CDDSEnsemble::Initialize: DDS calibration target/objective function must be set");
+  ExitGracefullyIf(_nMembers == 0, "CDDSEnsemble::Initialize: number of DDS iterations/ensemble members must be >0");
+  ExitGracefullyIf(_ParamDists.empty(), "CDDSEnsemble::Initialize: at least one parameter distribution must be set using :ParameterDistributions command");
+  _BestParams.assign(_ParamDists.size(), 0.0); _TestParams.assign(_ParamDists.size(), 0.0);
+  for (size_t i = 0; i < _ParamDists.size(); i++) _BestParams[i] = _TestParams[i] = _ParamDists[i].default_val;
+  _Fbest = ALMOST_INF; _log.clear();
+}
+double CDDSEnsemble::PerturbParam(double x_best, double lowerbound, double upperbound) {   // src/DDS.cpp:121-148, reflecting bounds
+  const double x_min = lowerbound, x_max = upperbound;
+  double x_new = x_best + GaussRandom() * _r_val * (x_max - x_min);
+  if (x_new < x_min) { x_new = x_min + (x_min - x_new); if (x_new > x_max) x_new = x_min; }
+  else if (x_new > x_max) { x_new = x_max - (x_new - x_max); if (x_new < x_min) x_new = x_max; }
+  return x_new;
+}
+void CDDSEnsemble::UpdateModel(CModel *pModel, optStruct &Options, int e) {   // src/DDS.cpp:150-208
+  CEnsemble::UpdateModel(pModel, Options, e);
+  ExitGracefullyIf(e >= _nMembers, "CDDSEnsemble::UpdateMode: invalid ensemble member index");
+  const int nP = (int)_ParamDists.size();
+  const double Pn = 1.0 - log(double(e)) / log(double(_nMembers));   // probability of including a decision variable
+  int dvn_count = 0;
+  for (int k = 0; k < nP; k++) _TestParams[k] = _BestParams[k];
+  for (int k = 0; k < nP; k++) {
+    const double u = UniformRandom();
+    if (u < Pn) { dvn_count++; _TestParams[k] = PerturbParam(_BestParams[k], _ParamDists[k].distpar[0], _ParamDists[k].distpar[1]); }
+  }
+  if (dvn_count == 0) {
+    const double u = UniformRandom();
+    const int dv = (int)(ceil((double)(nP)*u)) - 1;
+    _TestParams[dv] = PerturbParam(_BestParams[dv], _ParamDists[dv].distpar[0], _ParamDists[dv].distpar[1]);
+  }
+  for (int k = 0; k < nP; k++) pModel->UpdateParameter(_ParamDists[k].param_class, _ParamDists[k].param_name, _ParamDists[k].class_group, _TestParams[k]);
+  // the reference re-reads the .rvc here: every trial starts from the same initial state (uploaded by the caller)
+}
+void CDDSEnsemble::FinishEnsembleRun(double Ftest, int e) {   // src/DDS.cpp:210-240; minimisation
+  if (Ftest <= _Fbest) {
+    _Fbest = Ftest;
+    _BestParams = _TestParams;
+    _log.push_back(std::make_pair(e + 1, _Fbest));
+  }
+}
+double CDDSEnsemble::ObjectiveFromHydrograph(const CModel *pModel, const optStruct &Options, const double *qout_rec, const double *qout_initial, int nsteps, int nSB) const {
+  // CModel::GetObjFuncVal (src/StandardOutput.cpp:3282-3322)
+  double starttime = 0.0, endtime = 0.0;
+  for (size_t d = 0; d < pModel->diag_periods.size(); d++)
+    if (pModel->diag_periods[d].name == _calib_Period) { starttime = pModel->diag_periods[d].t_start; endtime = pModel->diag_periods[d].t_end; }
+  const observed_ts *pObs = NULL;
+  for (size_t i = 0; i < pModel->observed.size(); i++) if (pModel->observed[i].name == "HYDROGRAPH" && pModel->observed[i].loc_ID == _calib_SBID) pObs = &pModel->observed[i];
+  ExitGracefullyIf(pObs == NULL, "GetObjFuncVal: unable to find calibration target time series (hydrograph in basin :CalibrationSBID)");
+  ExitGracefullyIf(endtime == 0.0, "GetObjFuncVal: unable to find calibration period with this name ");
+  const int p = pModel->GetSubBasinIndex(_calib_SBID);
+  // modelled HYDROGRAPH at time index nn (CModel::UpdateDiagnostics, src/Model.cpp:2929-2936): period average of the outflow for nn >= 1,
+  // the initial outflow at nn = 0
+  std::vector<double> mod(nsteps + 1), obs(pObs->pTS->GetNumSampledValues());
+  mod[0] = qout_initial[p];
+  for (int nn = 1; nn <= nsteps; nn++) {
+    const double Qout = qout_rec[(size_t)(nn - 1) * nSB + p], QoutLast = (nn >= 2) ? qout_rec[(size_t)(nn - 2) * nSB + p] : qout_initial[p];
+    mod[nn] = (0.5 * (Qout + QoutLast) * (Options.timestep * SEC_PER_DAY)) / (Options.timestep * SEC_PER_DAY);
+  }
+  for (size_t nn = 0; nn < obs.size(); nn++) obs[nn] = pObs->pTS->GetSampledValue((int)nn);
+  double objval = CalculateDiagnostic(_calib_Obj, mod, obs, starttime, endtime, Options.timestep, true);
+  if ((_calib_Obj == DIAG_NASH_SUTCLIFFE) || (_calib_Obj == DIAG_KLING_GUPTA)) objval *= -1;
+  return objval;
+}
+
 // ---------------------------------------------------------------------------------------------------------------- EnKF
 CEnKFEnsemble::CEnKFEnsemble(int num_members, const optStruct &Options)
     : CEnsemble(num_members, Options), _EnKF_mode(ENKF_UNSPECIFIED), _window_size(1), _nTimeSteps(0), _nObsDatapoints(0), _member0(0), _nLocal(num_members) {
@@ -271,6 +404,11 @@ CEnsemble *CreateEnsemble(CModel *pModel, const optStruct &Options) {
     CMonteCarloEnsemble *mc = new CMonteCarloEnsemble(pModel->num_members, Options);
     for (size_t i = 0; i < pModel->param_dists.size(); i++) mc->AddParamDist(pModel->param_dists[i]);
     pE = mc;
+  } else if (Options.ensemble == ENSEMBLE_DDS) {
+    CDDSEnsemble *dds = new CDDSEnsemble(pModel->num_members, Options);
+    for (size_t i = 0; i < pModel->param_dists.size(); i++) dds->AddParamDist(pModel->param_dists[i]);
+    if (pModel->calib_SBID != DOESNT_EXIST) dds->SetCalibrationTarget(pModel->calib_SBID, (diag_type)pModel->calib_obj, pModel->calib_period);
+    pE = dds;
   } else if (Options.ensemble == ENSEMBLE_ENKF) {   // src/ParseInput.cpp:3830 + the .rve commands (src/ParseEnsembleFile.cpp)
     CEnKFEnsemble *en = new CEnKFEnsemble(pModel->num_members, Options);
     en->SetEnKFMode(pModel->enkf.mode);

@@ -46,6 +46,43 @@ private:
   std::vector<double> _last;
 };
 
+// DDS calibration (reference CDDSEnsemble, src/DDS.cpp; Tolson & Shoemaker 2007).  Trial e+1 perturbs the best parameter vector
+// found so far, so the trials are strictly sequential: every trial is one full GPU run of one member.  UpdateModel(e) draws from
+// the same rand() stream in the same order as the reference; FinishEnsembleRun(e) takes the trial's objective function value
+// (CModel::GetObjFuncVal, src/StandardOutput.cpp:3282-3322: the named diagnostic of the HYDROGRAPH observation at the calibration
+// subbasin, negated for NSE / KGE because DDS minimises).
+enum diag_type { DIAG_NASH_SUTCLIFFE = 0, DIAG_RMSE, DIAG_KLING_GUPTA, DIAG_UNRECOGNIZED };
+diag_type StringToDiagnostic(const std::string &s);
+// CDiagnostic::CalculateDiagnostic (src/Diagnostics.cpp:93-200,423-445,1072-1160) for the three objective functions above:
+// mod/obs are sampled values at time indices 0..n-1 (blank = RAV_BLANK_DATA), evaluated over [starttime, endtime] model days
+double CalculateDiagnostic(diag_type type, const std::vector<double> &mod, const std::vector<double> &obs, double starttime, double endtime,
+                           double timestep, bool is_hydrograph);
+class CDDSEnsemble : public CEnsemble {
+public:
+  CDDSEnsemble(int num_members, const optStruct &Options);
+  void AddParamDist(const param_dist &dist) { _ParamDists.push_back(dist); }
+  void SetPerturbationValue(double perturb);
+  void SetCalibrationTarget(long long SBID, diag_type object_diag, const std::string &period);
+  void Initialize(const CModel *pModel, const optStruct &Options) override;
+  void UpdateModel(CModel *pModel, optStruct &Options, int e) override;
+  // the reference signature reads the objective from the model; here the caller hands over the modelled series of the trial
+  void FinishEnsembleRun(double Ftest, int e);
+  double ObjectiveFromHydrograph(const CModel *pModel, const optStruct &Options, const double *qout_rec, const double *qout_initial, int nsteps, int nSB) const;
+  const std::vector<double> &TestParams() const { return _TestParams; }
+  const std::vector<double> &BestParams() const { return _BestParams; }
+  double BestObjective() const { return _Fbest; }
+  const std::vector<std::pair<int, double> > &Improvements() const { return _log; }   // the rows of DDSOutput.csv: (trial e+1, Fbest)
+private:
+  double PerturbParam(double x_best, double lowerbound, double upperbound);
+  std::vector<param_dist> _ParamDists;
+  std::vector<double> _BestParams, _TestParams;
+  std::vector<std::pair<int, double> > _log;
+  double _Fbest, _r_val;
+  long long _calib_SBID;
+  diag_type _calib_Obj;
+  std::string _calib_Period;
+};
+
 // EnKF ensemble (reference CEnKFEnsemble, src/EnKF.h:31-89, src/EnKF.cpp).  The reference runs the N members one after
 // another over one assimilation window and then updates the state matrix on the host; here
 //   * Initialize() builds the state-row map, finds the observation datapoints of the window and draws the observation

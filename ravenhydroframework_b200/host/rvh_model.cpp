@@ -391,6 +391,7 @@ void CSubBasin::SetQout(double Q) {
 CModel::CModel(int nsoillayers) : num_members(1), _nSoilVars(nsoillayers), _lake_sv(0), _nConvVariables(0), _WatershedArea(0), _pOpt(NULL),
                                   _f_ptab_stride(0), _f_nconv(0) {
   ExitGracefullyIf(nsoillayers < 1, "CModel constructor::improper number of soil layers. SoilModel not specified?");
+  calib_SBID = DOESNT_EXIST; calib_obj = 0; calib_period = "ALL";
   // constructor defaults of the reference (src/Model.cpp:104-117)
   const sv_type base[5] = {RVN_SV_SURFACE_WATER, RVN_SV_ATMOSPHERE, RVN_SV_ATMOS_PRECIP, RVN_SV_PONDED_WATER, RVN_SV_RUNOFF};
   for (int i = 0; i < 5; i++) { _aStateVarType.push_back(base[i]); _aStateVarLayer.push_back(i == 4 ? (int)RVN_SV_RUNOFF : DOESNT_EXIST); }
@@ -624,6 +625,15 @@ void CModel::Initialize(optStruct &O) {
     const CHydroUnit *h = _pHydroUnits[k];
     ExitGracefullyIf(soil_profiles[h->soil_profile].nHorizons != _nSoilVars && h->type == RVN_HRU_STANDARD,
                      "CModel::Initialize: soil profile " + soil_profiles[h->soil_profile].tag + " does not have one horizon per model soil layer");
+  }
+  {  // default evaluation period: the whole simulation (CDiagPeriod "ALL", src/ModelInitialize.cpp:287; clipping src/Diagnostics.cpp:1572-1573)
+    bool have_all = false;
+    for (size_t i = 0; i < diag_periods.size(); i++) if (diag_periods[i].name == "ALL") have_all = true;
+    if (!have_all) { diag_period P; P.name = "ALL"; P.t_start = 0.0; P.t_end = O.duration; diag_periods.push_back(P); }
+    for (size_t i = 0; i < diag_periods.size(); i++) {
+      diag_periods[i].t_start = rvh_max(rvh_min(diag_periods[i].t_start, O.duration), 0.0);
+      diag_periods[i].t_end = rvh_max(rvh_min(diag_periods[i].t_end, O.duration), 0.0);
+    }
   }
   for (int g = 0; g < GetNumGauges(); g++) _pGauges[g]->Initialize(O);
   for (size_t i = 0; i < observed.size(); i++) observed[i].pTS->Initialize(O.julian_start_day, O.julian_start_year, O.duration, O.timestep, O.calendar, true);

@@ -255,6 +255,10 @@ public:
   std::vector<param_dist> param_dists;
   int num_members;
   enkf_settings enkf;
+  // DDS calibration target (.rve :ObjectiveFunction) and the evaluation periods of the .rvi (:EvaluationPeriod; "ALL" always exists)
+  long long calib_SBID; int calib_obj; std::string calib_period;
+  struct diag_period { std::string name; double t_start, t_end; };
+  std::vector<diag_period> diag_periods;
   // groups / observations / forcing perturbations
   std::vector<CHRUGroup> hru_groups;
   std::vector<CSubbasinGroup> sb_groups;

@@ -9,6 +9,7 @@
 // the output/diagnostic commands listed in kIgnoredRVI which do not influence the water balance.
 #include "rvh_model.h"
 #include "rvh_process.h"
+#include "rvh_ensemble.h"
 #include <set>
 
 // decimal reader with the arithmetic of the reference's time-series reader (fast_s_to_d,
@@ -57,7 +58,7 @@ static double ParseIntervalToken(const std::string &t, int calendar) {
 // ================================================================================================ .rvi
 static const char *kIgnoredRVI[] = {":FileType", ":WrittenBy", ":CreationDate", ":Description", ":SilentMode", ":NoisyMode", ":QuietMode",
   ":EvaluationMetrics", ":CustomOutput", ":WriteForcingFunctions", ":WriteMassBalanceFile", ":WriteEnsimFormat", ":WriteNetCDFFormat",
-  ":RunName", ":OutputDirectory", ":OutputInterval", ":SuppressOutput", ":DontWriteWatershedStorage", ":EvaluationPeriod", ":SnapshotHydrograph",
+  ":RunName", ":OutputDirectory", ":OutputInterval", ":SuppressOutput", ":DontWriteWatershedStorage", ":SnapshotHydrograph",
   ":SWRadiationMethod", ":SWCloudCorrect", ":SWCanopyCorrect", ":LWRadiationMethod", ":LWIncomingMethod", ":CloudCoverMethod", ":WindspeedMethod",
   ":RelativeHumidityMethod", ":AirPressureMethod", ":PavicsMode", ":DebugMode", ":WriteExhaustiveMB", ":HydrologicProcesses", ":EndHydrologicProcesses",
   ":WriteSubbasinFile", ":NetCDFAttribute", ":rvh_Filename", NULL};
@@ -233,6 +234,16 @@ static void ParseMainInputFile(CModel *&pModel, optStruct &Options) {
       continue;
     }
     ExitGracefullyIf(!pModel && c != ":FileType", "ParseMainInputFile: " + c + " appears before :SoilModel, or is not supported by the B200 build");
+    if (c == ":EvaluationPeriod") {   // :EvaluationPeriod [name] [yyyy-mm-dd start] [yyyy-mm-dd end]  (src/ParseInput.cpp case 73, src/Diagnostics.cpp:1547-1574)
+      ExitGracefullyIf(Len < 4, "ParseMainInputFile: :EvaluationPeriod needs [name] [start] [end]");
+      CModel::diag_period P; P.name = s[1];
+      time_struct t1 = DateStringToTimeStruct(s[2], "00:00:00", Options.calendar), t2 = DateStringToTimeStruct(s[3], "00:00:00", Options.calendar);
+      P.t_start = TimeDifference(Options.julian_start_day, Options.julian_start_year, t1.julian_day, t1.year, Options.calendar);
+      P.t_end = TimeDifference(Options.julian_start_day, Options.julian_start_year, t2.julian_day, t2.year, Options.calendar);
+      ExitGracefullyIf(!pModel, "ParseMainInputFile: :EvaluationPeriod appears before :SoilModel");
+      pModel->diag_periods.push_back(P);
+      continue;
+    }
     if (c == ":DefineHRUGroups" || c == ":DefineHRUGroup") {   // groups are populated by the .rvh file
       for (int i = 1; i < Len; i++) if (pModel->FindHRUGroup(s[i]) == DOESNT_EXIST) { CHRUGroup G; G.name = s[i]; pModel->hru_groups.push_back(G); }
       continue;
@@ -853,6 +864,14 @@ static void ParseEnsembleFile(CModel *pModel, optStruct &Options) {
         }
         pModel->param_dists.push_back(d);
       }
+      continue;
+    }
+    if (c == ":ObjectiveFunction") {   // :ObjectiveFunction [SBID] [Diagnostic] {Period}  (src/ParseEnsembleFile.cpp:232-260)
+      ExitGracefullyIf(s.size() < 3, "ParseEnsembleFile: :ObjectiveFunction needs [SBID] [Diagnostic]");
+      const int diag = (int)StringToDiagnostic(s[2]);
+      ExitGracefullyIf(diag == (int)DIAG_UNRECOGNIZED, "ParseEnsembleFile::unknown diagnostic in :ObjectiveFunction command.");
+      if (Options.ensemble == ENSEMBLE_DDS) { pModel->calib_SBID = s_to_ll(s[1]); pModel->calib_obj = diag; pModel->calib_period = (s.size() >= 4) ? s[3] : "ALL"; }
+      else WriteWarning(":ObjectiveFunction command will be ignored; no calibration method specified.");
       continue;
     }
     const bool is_enkf = (Options.ensemble == ENSEMBLE_ENKF);

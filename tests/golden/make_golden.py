@@ -105,6 +105,39 @@ def make_enkf(name, spec):
     print("golden %-18s N=%d M=%d Nobs=%d nHRU=%d NB=%d steps=%d nPert=%d" % (name, N, M, Nobs, nH, NB, nsteps, nP))
 
 
+def make_dds(name="dds_hmets"):
+    """DDS calibration (reference CDDSEnsemble): the reference EXECUTABLE runs all trials; fixture = every trial's objective function
+    value as printed (6 digits), the rows of DDSOutput.csv and the best parameter vector."""
+    import json
+    import re
+    import subprocess
+    d = os.path.join(HERE, name)
+    shutil.rmtree(d, ignore_errors=True)
+    base = synth.write_hmets(d, n_sb=3, hru_per_sb=4, n_days=200, seed=6, name="model", season_offset=60)
+    rvi = open(base + ".rvi").read().replace(":SilentMode", ":SilentMode\n:EnsembleMode ENSEMBLE_DDS 25\n:RandomSeed 7\n:EvaluationMetrics NASH_SUTCLIFFE")
+    open(base + ".rvi", "w").write(rvi)
+    rng = np.random.RandomState(2)
+    with open(base + ".rvt", "a") as f:
+        f.write(":ObservationData HYDROGRAPH 1 m3/s\n  2000-01-01 00:00:00 1.0 201\n")
+        for i in range(201):
+            f.write("  %.4f\n" % (1.5 + 1.2 * np.sin(i / 20.0) ** 2 + 0.2 * rng.rand()))
+        f.write(":EndObservationData\n")
+    with open(base + ".rve", "w") as f:
+        f.write(":ObjectiveFunction 1 NASH_SUTCLIFFE\n:ParameterDistributions\n")
+        f.write("  GAMMA_SHAPE LANDUSE FOREST 9.5019 DIST_UNIFORM 3.0 15.0\n  GAMMA_SCALE LANDUSE FOREST 0.2774 DIST_UNIFORM 0.1 0.9\n")
+        f.write("  MAX_MELT_FACTOR LANDUSE FOREST 6.7009 DIST_UNIFORM 4.0 9.0\n  PERC_COEFF SOIL TOPSOIL 0.0114 DIST_UNIFORM 0.002 0.05\n")
+        f.write("  BASEFLOW_COEFF SOIL PHREATIC 0.0069 DIST_UNIFORM 0.001 0.03\n:EndParameterDistributions\n")
+    out = os.path.join(d, "_refout") + "/"
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "Raven.exe"), "model", "-o", out], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    trials = [[float(x) for x in re.findall(r"DDS Obj. Function: ([-0-9.eE+]+) \[best: ([-0-9.eE+]+)\]", l)[0]] for l in r.stdout.split("\n") if "DDS Obj" in l]
+    txt = open(out + "DDSOutput.csv").read().split("Best parameter vector:")
+    rows = [[float(x) for x in l.strip().strip(",").split(",")] for l in txt[0].strip().split("\n")]
+    best = [float(l.split(",")[1]) for l in txt[1].strip().split("\n")]
+    json.dump(dict(trials=trials, improvements=rows, best=best), open(os.path.join(d, "reference_dds.json"), "w"), indent=1)
+    shutil.rmtree(out, ignore_errors=True)
+    print("golden %-18s trials=%d improvements=%d" % (name, len(trials), len(rows)))
+
+
 def make(name, spec):
     spec = dict(spec)
     kind = spec.pop("kind")
@@ -145,6 +178,8 @@ if __name__ == "__main__":
         if only and name not in only:
             continue
         make(name, spec)
+    if not only or "dds_hmets" in only:
+        make_dds()
     for name, spec in ENKF_CASES.items():
         if only and name not in only:
             continue

@@ -67,12 +67,15 @@ def test_config2_hbvec_10k_hrus_500_subbasins_muskingum(tmp_path):
 
 def test_config4_blended_distributed_muskingum(tmp_path):
     """BASELINE config 4 shape at a size the oracle finishes in seconds: Blended process groups, 40,000 HRUs / 2,000 subbasins,
-    9-station interpolation (the sparse gridded-forcing gather), Muskingum routing; daily step (sub-daily steps are not built yet)."""
-    n = 20
-    base = synth.write_blended(str(tmp_path), n_sb=2000, hru_per_sb=20, n_days=n, seed=3, routing="ROUTE_MUSKINGUM", catchment_route="TRIANGULAR_UH",
-                               season_offset=110, n_gauges=9)
+    9-station interpolation (the sparse gridded-forcing gather), hourly step, Muskingum routing."""
+    n = 72
+    base = synth.write_blended(str(tmp_path), n_sb=2000, hru_per_sb=20, n_days=3, seed=3, routing="ROUTE_MUSKINGUM", catchment_route="TRIANGULAR_UH",
+                               season_offset=124, n_gauges=9)
+    rvi = open(base + ".rvi").read()
+    open(base + ".rvi", "w").write(rvi.replace(":TimeStep              1.0", ":TimeStep              01:00:00"))
     model = api.RavenModel(base)
     model.flatten(1)
+    assert model.nSteps == n
     sim = api.GpuSimulation(model)
     assert sim.kernel_variant() == "static:BLENDED"
     sim.set_recording(n)
