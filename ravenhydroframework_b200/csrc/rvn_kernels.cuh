@@ -30,8 +30,18 @@
 // ------------------------------------------------------------------------------------------------
 // contexts
 // ------------------------------------------------------------------------------------------------
+#ifndef RVN_F_SMEM
+#define RVN_F_SMEM 0   // 1: the derived forcings of the thread's HRU live in a shared-memory column instead of registers
+#endif
+#if RVN_F_SMEM
+struct FVec { double *p; RVN_DI double &operator[](int f) const { return p[f * RVN_BS]; } };   // forcing f of this thread at p[f * RVN_BS]
+#define RVN_F_SMEM_DOUBLES (RVN_F_COUNT * RVN_BS)
+#else
+struct FVec { double v[RVN_F_COUNT]; RVN_DI double &operator[](int f) { return v[f]; } RVN_DI const double &operator[](int f) const { return v[f]; } };
+#define RVN_F_SMEM_DOUBLES 0
+#endif
 struct CtxCommon {
-  double F[RVN_F_COUNT];   // derived forcings of this HRU for this step
+  FVec F;                  // derived forcings of this HRU for this step
   // lagged (start-of-step) values (what pHRU->GetStateVarValue returns inside processes)
   double old_snow, old_snow_cover, old_snow_depth, old_snow_temp;
   double area, elev, lat, slope, aspect;
@@ -83,15 +93,27 @@ struct DynProc {
 };
 
 // compile-time context of the specialised kernels: everything indexed by constants -> registers
+#ifndef RVN_SV_SMEM
+#define RVN_SV_SMEM 1   // 1: the specialised sweep keeps the core state vector in shared-memory columns instead of registers
+#endif
 template <class Prog>
 struct StatCtx : CtxCommon {
+#if RVN_SV_SMEM
+  double *svp;   // &s_sv[tid]; slot s at svp[s * RVN_BS] (constant offsets; no register pressure, no local-memory spills)
+#else
   double sv[Prog::nCore];
+#endif
   double rt[Prog::maxConn];
   double grt[Prog::maxGroupConn > 0 ? Prog::maxGroupConn : 1];
   int sbase[Prog::nSoil > 0 ? Prog::nSoil : 1];
   double sthick[Prog::nSoil > 0 ? Prog::nSoil : 1];
+#if RVN_SV_SMEM
+  RVN_DI double &SV(int slot) { return svp[slot * RVN_BS]; }
+  RVN_DI const double &SV(int slot) const { return svp[slot * RVN_BS]; }
+#else
   RVN_DI double &SV(int slot) { return sv[slot]; }
   RVN_DI const double &SV(int slot) const { return sv[slot]; }
+#endif
   RVN_DI double &R(int q) { return rt[q]; }
   RVN_DI double &GR(int q) { return grt[q]; }
   static constexpr RVN_DI int iSV(int t) { return Prog::iSV(t); }
@@ -124,7 +146,7 @@ struct StatProc {
 // CModel::ApplyForcingPerturbation (src/Model.cpp:2856-2879) for forcing type `ftype`: CHydroUnit::AdjustHRUForcing
 // (src/HydroUnits.cpp:461-509) followed, at the start of a day (every step of a daily model), by AdjustDailyHRUForcings
 // (:513-538).  One sample per perturbation and day: eps[nn] = eps[0] and the daily mean adjustment 0.0 + eps/1 = eps.
-RVN_DI void apply_perturbations(double *F, const DevModel &M, const int ftype, const int e, const int k, const int step) {
+RVN_DI void apply_perturbations(FVec &F, const DevModel &M, const int ftype, const int e, const int k, const int step) {
   for (int i = 0; i < M.nPert; i++) {
     if (M.pert_forcing[i] != ftype) continue;
     if (M.pert_mask != nullptr && M.pert_mask[(size_t)i * M.nHp + k] == 0) continue;
@@ -168,7 +190,7 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
   const rvn_time tt = M.times[step];
   const int nG = M.nGauges, mo = tt.month;
   const double elev = c.elev;
-  double *F = c.F;
+  FVec &F = c.F;
   double ref_elev_temp = 0.0, ref_elev_precip = 0.0, temp_month_min = 0, temp_month_max = 0, temp_month_ave = 0, PET_month_ave = 0;
 #pragma unroll
   for (int f = 0; f < RVN_F_COUNT; f++) F[f] = 0.0;
@@ -697,6 +719,12 @@ __global__ void __launch_bounds__(RVN_BS, RVN_STATIC_MIN_BLOCKS) hru_sweep_stati
   const bool in_range = (k < M.nH);
   const bool enabled = in_range && (M.hru_enabled[k] != 0);
   StatCtx<Prog> c;
+#if RVN_SV_SMEM
+  c.svp = s_red + 8 + tid;   // after the reduction scratch
+#endif
+#if RVN_F_SMEM
+  c.F.p = s_red + 8 + (RVN_SV_SMEM ? Prog::nCore * RVN_BS : 0) + tid;
+#endif
   load_hru_statics(c, M, k, s_ptab);
   if (UNIT_DT) c.tstep = 1.0;
 #pragma unroll
@@ -709,12 +737,12 @@ __global__ void __launch_bounds__(RVN_BS, RVN_STATIC_MIN_BLOCKS) hru_sweep_stati
   // ---- state in: coalesced over k for every state variable (aPhi[k][i] = pHRU->GetStateVarValue(i))
   double *gstate = M.state + (size_t)e * M.NS * nHp + k;
 #pragma unroll
-  for (int s = 0; s < Prog::nCore; s++) c.sv[s] = __ldcs(gstate + (size_t)Prog::slot_sv(s) * nHp);
+  for (int s = 0; s < Prog::nCore; s++) c.SV(s) = __ldcs(gstate + (size_t)Prog::slot_sv(s) * nHp);
   if (RVN_PF_DIST > 0 && enabled) PrefetchConvs<Prog, 0>::run(gstate, nHp);
-  c.old_snow = (Prog::iSV(RVN_SV_SNOW) >= 0) ? c.sv[Prog::iSV(RVN_SV_SNOW) >= 0 ? Prog::iSV(RVN_SV_SNOW) : 0] : 0.0;
-  c.old_snow_cover = (Prog::iSV(RVN_SV_SNOW_COVER) >= 0) ? c.sv[Prog::iSV(RVN_SV_SNOW_COVER) >= 0 ? Prog::iSV(RVN_SV_SNOW_COVER) : 0] : 0.0;
-  c.old_snow_depth = (Prog::iSV(RVN_SV_SNOW_DEPTH) >= 0) ? c.sv[Prog::iSV(RVN_SV_SNOW_DEPTH) >= 0 ? Prog::iSV(RVN_SV_SNOW_DEPTH) : 0] : 0.0;
-  c.old_snow_temp = (Prog::iSV(RVN_SV_SNOW_TEMP) >= 0) ? c.sv[Prog::iSV(RVN_SV_SNOW_TEMP) >= 0 ? Prog::iSV(RVN_SV_SNOW_TEMP) : 0] : 0.0;
+  c.old_snow = (Prog::iSV(RVN_SV_SNOW) >= 0) ? c.SV(Prog::iSV(RVN_SV_SNOW) >= 0 ? Prog::iSV(RVN_SV_SNOW) : 0) : 0.0;
+  c.old_snow_cover = (Prog::iSV(RVN_SV_SNOW_COVER) >= 0) ? c.SV(Prog::iSV(RVN_SV_SNOW_COVER) >= 0 ? Prog::iSV(RVN_SV_SNOW_COVER) : 0) : 0.0;
+  c.old_snow_depth = (Prog::iSV(RVN_SV_SNOW_DEPTH) >= 0) ? c.SV(Prog::iSV(RVN_SV_SNOW_DEPTH) >= 0 ? Prog::iSV(RVN_SV_SNOW_DEPTH) : 0) : 0.0;
+  c.old_snow_temp = (Prog::iSV(RVN_SV_SNOW_TEMP) >= 0) ? c.SV(Prog::iSV(RVN_SV_SNOW_TEMP) >= 0 ? Prog::iSV(RVN_SV_SNOW_TEMP) : 0) : 0.0;
   __syncthreads();   // parameter row staged
   load_canopy(c, M, step);
   // ---- forcings (on the stored state)
@@ -732,7 +760,7 @@ __global__ void __launch_bounds__(RVN_BS, RVN_STATIC_MIN_BLOCKS) hru_sweep_stati
     swv = finish_step(c, Prog::nCore);
     stor = hru_storage(c, Prog::nCore) * c.area;
 #pragma unroll
-    for (int s = 0; s < Prog::nCore; s++) __stcs(gstate + (size_t)Prog::slot_sv(s) * nHp, c.sv[s]);
+    for (int s = 0; s < Prog::nCore; s++) __stcs(gstate + (size_t)Prog::slot_sv(s) * nHp, c.SV(s));
     if (M.record_forcings) {
       double *gf = M.forc + (size_t)e * RVN_F_COUNT * nHp + k;
 #pragma unroll
@@ -777,6 +805,9 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
   DynCtx c;
   load_hru_statics(c, M, k, s_ptab);
   c.P = P; c.sv = s_sv + tid; c.rt = s_rt + tid; c.grt = s_grt + tid;
+#if RVN_F_SMEM
+  c.F.p = s_red + 8 + tid;
+#endif
   c.prof_class = M.prof_class + c.profile * RVN_MAX_SOIL_LAYERS; c.prof_thick = M.prof_thick + c.profile * RVN_MAX_SOIL_LAYERS;
   const int sb = M.hru_sb[k];
   const unsigned long long mask = M.apply_mask[k];
