@@ -118,6 +118,7 @@ typedef enum { RVN_ROUTE_NONE = 0, RVN_ROUTE_MUSKINGUM, RVN_ROUTE_MUSKINGUM_CUNG
 typedef enum { RVN_PF_PRECIP = 0, RVN_PF_RAINFALL, RVN_PF_SNOWFALL, RVN_PF_TEMP_AVE } rvn_pert_forcing;
 typedef enum { RVN_ADJ_ADDITIVE = 0, RVN_ADJ_MULTIPLICATIVE, RVN_ADJ_REPLACE } rvn_adjustment;
 #define RVN_MAX_PERT 8
+typedef enum { RVN_SOL_ORDERED_SERIES = 0, RVN_SOL_EULER = 1 } rvn_sol_method;
 typedef enum { RVN_CONVOL_GR4J_1 = 0, RVN_CONVOL_GR4J_2, RVN_CONVOL_GAMMA, RVN_CONVOL_GAMMA_2 } rvn_convol_type;
 
 /* ---- per-member parameter table ------------------------------------------------------------------
@@ -226,7 +227,8 @@ typedef struct rvn_options {
   int32_t routing, suppress_competitive_ET, snow_suppress_PET, allow_soil_overfill, direct_evap;
   int32_t lake_sv;                /* CModel::GetLakeStorageIndex() */
   int32_t keep_flux_balance;      /* 0: skip per-connection cumulative flux arrays */
-  int32_t pad_[2];
+  int32_t sol_method;             /* rvn_sol_method: ORDERED_SERIES (default) or EULER (reference src/Solvers.cpp:205-251 / 256-297) */
+  int32_t pad_[1];
 } rvn_options;
 
 /* Flattened model (all pointers are HOST memory, copied by rvn_gpu_create). */

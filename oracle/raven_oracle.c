@@ -899,6 +899,7 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
   const int nH = d->nHRU, NS = d->NS, NB = d->nSB, NP = d->nProc;
   const double tstep = d->opt.timestep;
   for (int j = 0; j < NP; j++) if (!op_supported(d->proc[j].op)) return -1;
+  if (d->opt.sol_method == RVN_SOL_EULER && d->nConvProc > 0) return -1; /* the reference's Euler branch mishandles convolution stores (:279-282) */
   octx c; memset(&c, 0, sizeof(c));
   c.d = d; c.member = member; c.ptab = d->ptab + (size_t)member * d->ptab_stride;
   for (int t = 0; t < RVN_SV_NTYPES; t++) c.iSV[t] = sv_index(d, t, -1);
@@ -906,7 +907,7 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
   const int iTotalSWE = c.iSV[RVN_SV_TOTAL_SWE], iGlacierMB = c.iSV[RVN_SV_GLACIER_MB];
   double *F = (double *)malloc(sizeof(double) * (size_t)nH * RVN_F_COUNT);
   double *daily = (double *)calloc((size_t)nH * 7, sizeof(double)); /* valid from the first step of a day on: runs must start at a day boundary */
-  double *phinew = (double *)malloc(sizeof(double) * NS);
+  double *phinew = (double *)malloc(sizeof(double) * NS), *phiread = (double *)malloc(sizeof(double) * NS);
   double *aRouted = (double *)malloc(sizeof(double) * NB), *aQinnew = (double *)malloc(sizeof(double) * NB);
   double rates[O_MAXCONN]; int cf[O_MAXCONN], ct[O_MAXCONN];
   obasin B; B.qin = qin; B.qlat = qlat; B.qout = qout; B.scal = scal;
@@ -923,6 +924,11 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
       if (iAET >= 0) phinew[iAET] = 0.0;
       if (iRO >= 0) phinew[iRO] = 0.0;
       if (iGW >= 0) phinew[iGW] = 0.0;
+      /* EULER (src/Solvers.cpp:256-297): every process sees aPhi, the start-of-step vector (with the same reboots), and the
+       * changes accumulate in aPhinew; ORDERED_SERIES (:205-251): processes see the newest vector */
+      const int euler = (d->opt.sol_method == RVN_SOL_EULER);
+      if (euler) memcpy(phiread, phinew, sizeof(double) * NS);
+      const double *phisee = euler ? phiread : phinew;
       if (d->hru_enabled[k]) {
         c.k = k; c.F = F + (size_t)k * RVN_F_COUNT; c.phi_old = phi_old;
         canopy_capacities(&c, step);
@@ -942,7 +948,7 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
               const rvn_process *sp = &d->proc[jj];
               int scf[O_MAXCONN], sct[O_MAXCONN];
               for (int q = 0; q < sp->nconn; q++) { scf[q] = d->conn_from[sp->conn0 + q]; sct[q] = d->conn_to[sp->conn0 + q]; }
-              op_rates(&c, sp, scf, sct, phinew, loc_rates);
+              op_rates(&c, sp, scf, sct, phisee, loc_rates);
               for (int qq = 0; qq < sp->nconn; qq++) rates[q1 + qq] = sp->weight * loc_rates[qq];
               q1 += sp->nconn;
               if (sp->group & RVN_GRP_LAST) break;
@@ -960,10 +966,10 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
               if (i < NST - 1) { cf[NST + i + 1] = pr->ia[2] + i; ct[NST + i + 1] = pr->ia[2] + i + 1; }
             }
             cf[2 * NST] = ct[2 * NST] = pr->ia[3];
-            convolution_rates(&c, pr, phinew, rates);
+            convolution_rates(&c, pr, phisee, rates);
           } else {
             for (int q = 0; q < nconn; q++) { cf[q] = d->conn_from[pr->conn0 + q]; ct[q] = d->conn_to[pr->conn0 + q]; }
-            op_rates(&c, pr, cf, ct, phinew, rates);
+            op_rates(&c, pr, cf, ct, phisee, rates);
           }
           }
           for (int q = 0; q < nconn; q++) { /* src/Solvers.cpp:220-236 */
@@ -1055,6 +1061,6 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
     if (qout_rec) for (int p = 0; p < NB; p++) qout_rec[(size_t)s * NB + p] = qout[(size_t)p * RVN_MAX_RIVER_SEGS + d->sb_nseg[p] - 1];
     if (state_rec) memcpy(state_rec + (size_t)s * nH * NS, state, sizeof(double) * (size_t)nH * NS);
   }
-  free(F); free(daily); free(phinew); free(aRouted); free(aQinnew);
+  free(F); free(daily); free(phinew); free(phiread); free(aRouted); free(aQinnew);
   return 0;
 }

@@ -62,11 +62,14 @@ struct CtxCommon {
 // indexing by state-variable slot is bank-conflict free)
 struct DynCtx : CtxCommon {
   const DevProgram *P;     // program (shared memory)
-  double *sv;              // &s_sv[tid]; slot i at sv[i*RVN_BS]  -- newest state (aPhinew[k])
+  double *sv;              // &s_sv[tid]; slot i at sv[i*RVN_BS]  -- the state the processes read: newest (aPhinew[k], ORDERED_SERIES) or
+                           //             start-of-step (aPhi[k], EULER)
+  double *svw;             // the state the solver updates (aPhinew[k]); == sv for ORDERED_SERIES
   double *rt;              // &s_rates[tid]; connection q at rt[q*RVN_BS]
   double *grt;             // &s_grates[tid]: rate vector of the current process group
   const int32_t *prof_class; const double *prof_thick;   // global, row of this HRU's soil profile
   RVN_DI double &SV(int slot) const { return sv[slot * RVN_BS]; }
+  RVN_DI double &SVW(int slot) const { return svw[slot * RVN_BS]; }
   RVN_DI double &R(int q) const { return rt[q * RVN_BS]; }
   RVN_DI double &GR(int q) const { return grt[q * RVN_BS]; }
   RVN_DI int iSV(int t) const { return P->iSV[t]; }
@@ -114,6 +117,7 @@ struct StatCtx : CtxCommon {
   RVN_DI double &SV(int slot) { return sv[slot]; }
   RVN_DI const double &SV(int slot) const { return sv[slot]; }
 #endif
+  RVN_DI double &SVW(int slot) { return SV(slot); }   // specialised kernels are ORDERED_SERIES only
   RVN_DI double &R(int q) { return rt[q]; }
   RVN_DI double &GR(int q) { return grt[q]; }
   static constexpr RVN_DI int iSV(int t) { return Prog::iSV(t); }
@@ -540,9 +544,9 @@ RVN_DI void apply_connections(C &c, const PR &pr) {
   for (int q = 0; q < pr.nconn(); q++) {
     const int from = pr.from(q), to = pr.to(q);
     const double r = c.R(q);
-    if (to != from) { c.SV(from) -= r * tstep; c.SV(to) += r * tstep; }
-    else if (c.slot_water(from) == 1) { c.SV(to) += 0.0; }   // redirect-to-self: rate forced to zero
-    else c.SV(to) += r * tstep;
+    if (to != from) { c.SVW(from) -= r * tstep; c.SVW(to) += r * tstep; }
+    else if (c.slot_water(from) == 1) { c.SVW(to) += 0.0; }   // redirect-to-self: rate forced to zero
+    else c.SVW(to) += r * tstep;
   }
 }
 
@@ -565,9 +569,9 @@ RVN_DI void run_group_member(C &c, const PR &pr, const int op, const int grp, co
     for (int q = 0; q < pr.gnconn(); q++) {   // src/Solvers.cpp:220-236 over the group's concatenated connections
       const int from = pr.gfrom(q), to = pr.gto(q);
       const double r = c.GR(q);
-      if (to != from) { c.SV(from) -= r * tstep; c.SV(to) += r * tstep; }
-      else if (c.slot_water(from) == 1) { c.SV(to) += 0.0; }
-      else c.SV(to) += r * tstep;
+      if (to != from) { c.SVW(from) -= r * tstep; c.SVW(to) += r * tstep; }
+      else if (c.slot_water(from) == 1) { c.SVW(to) += 0.0; }
+      else c.SVW(to) += r * tstep;
     }
   }
 }
@@ -788,7 +792,9 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
   double *s_sv = s_ptab + ((M.ptab_stride + 1) & ~1);
   double *s_rt = s_sv + (size_t)M.nCore * RVN_BS;
   double *s_grt = s_rt + (size_t)M.maxConn * RVN_BS;
-  double *s_red = s_grt + (size_t)M.maxGroupConn * RVN_BS;
+  double *s_svw = s_grt + (size_t)M.maxGroupConn * RVN_BS;                       // EULER only: aPhinew columns
+  const bool euler = (M.opt.sol_method == RVN_SOL_EULER);
+  double *s_red = s_svw + (euler ? (size_t)M.nCore * RVN_BS : 0);
   const int tid = threadIdx.x, e = blockIdx.y, k = blockIdx.x * RVN_BS + tid;
   {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(M.prog);
@@ -805,6 +811,7 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
   DynCtx c;
   load_hru_statics(c, M, k, s_ptab);
   c.P = P; c.sv = s_sv + tid; c.rt = s_rt + tid; c.grt = s_grt + tid;
+  c.svw = euler ? (s_svw + tid) : c.sv;
 #if RVN_F_SMEM
   c.F.p = s_red + 8 + tid;
 #endif
@@ -821,6 +828,7 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
   if (enabled) compute_forcings(c, M, e, k, step, sb);
   else { for (int f = 0; f < RVN_F_COUNT; f++) c.F[f] = 0.0; }
   if (enabled) reboot_diagnostics(c);
+  if (euler) { for (int s = 0; s < nCore; s++) c.SVW(s) = c.SV(s); }   // aPhinew = aPhi (src/Solvers.cpp:155-200); rates come from aPhi
   const bool unit_dt = (c.tstep == 1.0);
   const int nProc = P->nProc;
   for (int j = 0; j < nProc; j++) {
@@ -842,6 +850,7 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
     dispatch_rates(c, dp, pr.op);
     apply_connections(c, dp);
   }
+  c.sv = c.svw;   // from here on "the state" is the updated vector aPhinew
   double swv = 0.0, stor = 0.0;
   const bool defer = (M.defer_finish != 0);   // lateral exchange processes follow: routing prep / diagnostics move to finish_kernel
   if (enabled) {

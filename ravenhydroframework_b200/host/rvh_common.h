@@ -77,7 +77,7 @@ struct optStruct {
   int    calendar;
   std::string rvi_filename, rvh_filename, rvp_filename, rvt_filename, rvc_filename, rve_filename;
   std::string output_dir, main_output_dir, run_name, working_dir;
-  int    sol_method;            // only ORDERED_SERIES (0) is implemented on the device
+  int    sol_method;            // rvn_sol_method: ORDERED_SERIES (0) or EULER (1)
   rvn_rainsnow rainsnow;
   rvn_potmelt  pot_melt;
   rvn_pet      evaporation, ow_evaporation, evap_infill, ow_evap_infill;

@@ -114,7 +114,10 @@ static void ParseMainInputFile(CModel *&pModel, optStruct &Options) {
     }
     if (c == ":TimeStep") { Options.timestep = ParseIntervalToken(s[1], Options.calendar); continue; }
     if (c == ":Method" || c == ":NumericalMethod") {
-      ExitGracefullyIf(s[1] != "ORDERED_SERIES", "ParseMainInputFile: only :Method ORDERED_SERIES is implemented in the B200 build"); continue;
+      if (s[1] == "ORDERED_SERIES" || s[1] == "STANDARD") Options.sol_method = RVN_SOL_ORDERED_SERIES;
+      else if (s[1] == "EULER") Options.sol_method = RVN_SOL_EULER;
+      else ExitGracefully("ParseMainInputFile: only :Method ORDERED_SERIES and EULER are implemented in the B200 build");
+      continue;
     }
     if (c == ":SoilModel") {
       if (s[1] == "SOIL_ONE_LAYER") Options.num_soillayers = 1;

@@ -52,6 +52,8 @@ if hasattr(synth, "write_blended"):
     CASES["blended_hourly"] = dict(kind="blended", n_sb=5, hru_per_sb=4, n_days=25, seed=18, routing="ROUTE_MUSKINGUM", catchment_route="TRIANGULAR_UH",
                                    season_offset=95, n_gauges=9, timestep="01:00:00")
     CASES["hbv_6hourly"] = dict(kind="hbv", n_sb=7, hru_per_sb=3, n_days=120, seed=19, routing="ROUTE_MUSKINGUM", season_offset=60, timestep="06:00:00")
+    # explicit Euler (:Method EULER): every process sees the start-of-step state
+    CASES["hbv_euler"] = dict(kind="hbv", n_sb=4, hru_per_sb=5, n_days=300, seed=9, routing="ROUTE_MUSKINGUM", season_offset=30, method="EULER")
     CASES["hmets_3hourly"] = dict(kind="hmets", n_sb=3, hru_per_sb=4, n_days=60, seed=20, season_offset=90, timestep="03:00:00")
 if hasattr(synth, "write_gr4j"):
     WRITERS["gr4j"] = synth.write_gr4j
@@ -143,10 +145,15 @@ def make(name, spec):
     kind = spec.pop("kind")
     member = spec.pop("member", None)
     timestep = spec.pop("timestep", None)     # e.g. "01:00:00": sub-daily model step on the daily forcing series
+    method = spec.pop("method", None)         # :Method (numerical method) other than ORDERED_SERIES
     d = os.path.join(HERE, name)
     shutil.rmtree(d, ignore_errors=True)
     base = WRITERS[kind](d, name="model", **spec)
     n = spec["n_days"]
+    if method is not None:
+        rvi = open(base + ".rvi").read()
+        assert ":Method                ORDERED_SERIES" in rvi
+        open(base + ".rvi", "w").write(rvi.replace(":Method                ORDERED_SERIES", ":Method                " + method))
     if timestep is not None:
         rvi = open(base + ".rvi").read()
         assert ":TimeStep              1.0" in rvi
