@@ -81,7 +81,7 @@ def test_unsupported_commands_fail_loudly(tmp_path):
     open(base + ".rvi", "w").write(rvi + ":ReservoirDemandAllocation X\n")
     with pytest.raises(api.RavenError, match="not supported"):
         api.RavenModel(base)
-    open(base + ".rvi", "w").write(rvi.replace(":Method                ORDERED_SERIES", ":Method EULER"))
+    open(base + ".rvi", "w").write(rvi.replace(":Method                ORDERED_SERIES", ":Method ITERATED_HEUN"))
     with pytest.raises(api.RavenError, match="ORDERED_SERIES"):
         api.RavenModel(base)
 
