@@ -43,7 +43,7 @@ def test_static_program_header_is_current():
     import tempfile
     eng = api.engine_lib()
     hdr = open(os.path.join(ROOT, "ravenhydroframework_b200", "csrc", "rvn_static_programs.cuh")).read()
-    for name, writer in (("HMETS", synth.write_hmets), ("HBVEC", synth.write_hbv), ("GR4J", synth.write_gr4j)):
+    for name, writer in (("HMETS", synth.write_hmets), ("HBVEC", synth.write_hbv), ("GR4J", synth.write_gr4j), ("BLENDED", synth.write_blended)):
         with tempfile.TemporaryDirectory() as td:
             base = writer(td, n_sb=1, hru_per_sb=1, n_days=5, seed=1)
             m = api.RavenModel(base)
@@ -81,7 +81,7 @@ def test_unsupported_commands_fail_loudly(tmp_path):
     open(base + ".rvi", "w").write(rvi + ":ReservoirDemandAllocation X\n")
     with pytest.raises(api.RavenError, match="not supported"):
         api.RavenModel(base)
-    open(base + ".rvi", "w").write(rvi.replace(":Method                ORDERED_SERIES", ":Method ITERATED_HEUN"))
+    open(base + ".rvi", "w").write(rvi.replace(":Method                ORDERED_SERIES", ":Method ITER_HEUN 0.01 30"))
     with pytest.raises(api.RavenError, match="ORDERED_SERIES"):
         api.RavenModel(base)
 
