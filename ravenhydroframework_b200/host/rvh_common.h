@@ -109,6 +109,7 @@ double gamma2(double x);
 double IncompleteGamma(double x, double a);
 double GammaCumDist(double t, double alpha, double beta);
 double TriCumDist(double t, double tc, double tp);
+double DiffusiveWaveUH(int n, double L, double v, double D, double dt);   // src/CommonFunctions.cpp:1796-1806
 double InterpolateMo(const double aVal[12], const time_struct &tt, month_interp method, const optStruct &Options);
 inline double rvh_max(double r, double l) { return (r >= l) ? r : l; }   // tie -> first argument (src/RavenInclude.h:1456)
 inline double rvh_min(double r, double l) { return (r <= l) ? r : l; }

@@ -315,7 +315,7 @@ void CSubBasin::GenerateRoutingHydrograph(double Qin_avg, const optStruct &O) {
   double travel_time = reach_length / c_ref / SEC_PER_DAY;
   int nQin;
   if (O.routing == RVN_ROUTE_PLUG_FLOW) nQin = (int)(ceil(travel_time / tstep)) + 2;
-  else if (O.routing == RVN_ROUTE_DIFFUSIVE_WAVE) { ExitGracefully("ROUTE_DIFFUSIVE_WAVE hydrograph generation is not implemented in the B200 build yet"); nQin = 0; }
+  else if (O.routing == RVN_ROUTE_DIFFUSIVE_WAVE) nQin = (int)(ceil(2 * travel_time / tstep)) + 2;
   else nQin = 20;
   aQinHist.assign(nQin, Qin_avg);
   aRouteHydro.assign(nQin, 0.0);
@@ -324,6 +324,14 @@ void CSubBasin::GenerateRoutingHydrograph(double Qin_avg, const optStruct &O) {
       double ts = (travel_time - n * tstep) / tstep;
       if ((ts >= 0.0) && (ts < 1.0)) { aRouteHydro[n] = 1 - ts; aRouteHydro[n + 1] = ts; }
     }
+  } else if (O.routing == RVN_ROUTE_DIFFUSIVE_WAVE) {   // src/SubBasin.cpp:2113-2133
+    ExitGracefullyIf(nSegments > 1, "ROUTE_DIFFUSIVE_WAVE only valid for single-segment rivers");
+    // CChannelXSect::GetDiffusivity at the reference flow (src/ChannelXSect.cpp:388-397; Roberson et al. 1995)
+    ExitGracefullyIf(Q_ref <= 0, "CChannelXSect::GetDiffusivity: Invalid channel flowrate");
+    const double slope_mult = (slope != AUTO_COMPUTE) ? (slope / pChannel->bedslope) : 1.0;
+    const double diff_ref = 0.5 * (Q_ref) / pChannel->GetTopWidth(Q_ref, slope, mannings_n) / (slope_mult * pChannel->bedslope);
+    const double cc = c_ref * SEC_PER_DAY, diffusivity = diff_ref * SEC_PER_DAY;   // [m/d], [m2/d]
+    for (int n = 0; n < nQin; n++) aRouteHydro[n] = DiffusiveWaveUH(n, reach_length, cc, diffusivity, tstep);
   } else {
     aRouteHydro[0] = 1.0;
   }
