@@ -111,7 +111,7 @@ typedef enum { RVN_POTMELT_NONE = 0, RVN_POTMELT_DATA, RVN_POTMELT_DEGREE_DAY, R
 typedef enum { RVN_PET_DATA = 0, RVN_PET_FROMMONTHLY, RVN_PET_CONSTANT, RVN_PET_NONE, RVN_PET_HARGREAVES_1985, RVN_PET_OUDIN } rvn_pet;
 typedef enum { RVN_OROCORR_NONE = 0, RVN_OROCORR_SIMPLELAPSE, RVN_OROCORR_HBV } rvn_orocorr;
 typedef enum { RVN_ROUTE_NONE = 0, RVN_ROUTE_MUSKINGUM, RVN_ROUTE_MUSKINGUM_CUNGE, RVN_ROUTE_STORAGECOEFF,
-               RVN_ROUTE_PLUG_FLOW, RVN_ROUTE_DIFFUSIVE_WAVE } rvn_routing;
+               RVN_ROUTE_PLUG_FLOW, RVN_ROUTE_DIFFUSIVE_WAVE, RVN_ROUTE_HYDROLOGIC } rvn_routing;
 /* forcing perturbations of the EnKF members (reference forcing_type / adjustment, src/RavenInclude.h; applied by
  * CModel::ApplyForcingPerturbation, src/Model.cpp:2856-2879, in the order the reference calls it from
  * UpdateHRUForcingFunctions: TEMP_AVE after the temperature lapse, then PRECIP, RAINFALL, SNOWFALL after the precipitation lapse) */
@@ -298,6 +298,13 @@ typedef struct rvn_model_desc {
   const double *sb_unit_hydro;   /* [nSB][max_nqlat] _aUnitHydro */
   const double *sb_route_hydro;  /* [nSB][max_nqin]  _aRouteHydro */
   double watershed_area;         /* km2 */
+  /* ROUTE_HYDROLOGIC (reference src/SubBasin.cpp:2685-2741): rating curves of the channel profiles, flow -> cross-section area
+   * (CChannelXSect::_aQ/_aXArea; GetArea = InterpolateCurve(Q/Q_mult,...), src/ChannelXSect.cpp:297-302), and per basin the
+   * profile index, the Manning/slope flow multiplier (GetFlowCorrections, :345-359) and the reach length [m].  NULL otherwise. */
+  int32_t nChannels, nChanPts;
+  const double *chan_Q, *chan_A;   /* [nChannels][nChanPts] */
+  const int32_t *sb_channel;       /* [nSB] */
+  const double *sb_Qmult, *sb_reach_m; /* [nSB] */
   /* month-interpolated relative vegetation height / LAI of every vegetation class at every step
    * (InterpolateMo(relative_ht|relative_LAI, tt), reference src/VegetationParams.cpp:102-107): [nSteps][nVeg][2] */
   const double *veg_season;

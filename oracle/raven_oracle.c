@@ -792,6 +792,19 @@ static void canopy_capacities(octx *c, int step) {
 typedef struct { double *qin, *qlat, *qout, *scal; } obasin; /* one member; layouts of rvn_gpu_upload_basin_state */
 
 /* CSubBasin::RouteWater, src/SubBasin.cpp:2584-2863 */
+/* CChannelXSect::GetArea (src/ChannelXSect.cpp:297-302) -> InterpolateCurve (src/CommonFunctions.cpp:1982-2004), linear scan for the interval */
+static double channel_get_area(const rvn_model_desc *d, int p, double Q) {
+  const int N = d->nChanPts;
+  const double *xx = d->chan_Q + (size_t)d->sb_channel[p] * N, *y = d->chan_A + (size_t)d->sb_channel[p] * N;
+  const double x = Q / d->sb_Qmult[p];
+  if (x <= xx[0]) return y[0] + (y[1] - y[0]) / (xx[1] - xx[0]) * (x - xx[0]);
+  else if (x >= xx[N - 1]) return y[N - 1] + (y[N - 1] - y[N - 2]) / (xx[N - 1] - xx[N - 2]) * (x - xx[N - 1]);
+  int i = 0;
+  while (!((x >= xx[i]) && (x < xx[i + 1]))) i++;
+  if (fabs(xx[i + 1] - xx[i]) < O_REAL_SMALL) return (y[i] + y[i + 1]) / 2;
+  return y[i] + (y[i + 1] - y[i]) / (xx[i + 1] - xx[i]) * (x - xx[i]);
+}
+
 static void route_water(const rvn_model_desc *d, int p, const obasin *B, double *aQout_new) {
   const int nSeg = d->sb_nseg[p], nQin = d->sb_nqin[p], nQlat = d->sb_nqlat[p];
   const double tstep = d->opt.timestep;
@@ -831,6 +844,29 @@ static void route_water(const rvn_model_desc *d, int p, const obasin *B, double 
       aQout_new[s] = c1 * Qin + c2 * Qin_new + c3 * (aQout[s] - corr * Qlocal);
       Qin = aQout[s]; Qin_new = aQout_new[s];
     }
+  } else if (method == RVN_ROUTE_HYDROLOGIC) { /* src/SubBasin.cpp:2685-2741 */
+    const double ROUTE_MAXITER = 20, ROUTE_TOLERANCE = 0.0001;
+    double reach_length = d->sb_reach_m[p];
+    double Qout_old = aQout[nSeg - 1] - B->scal[(size_t)p * 8 + 2]; /* _aQout[last] - _Qlocal */
+    double Qin_new = QinHist[0], Qin_old = QinHist[1];
+    double V_old = channel_get_area(d, p, Qout_old) * reach_length;
+    int iter = 0;
+    double change = 0;
+    double gamma = V_old + (Qin_old + Qin_new - Qout_old) / 2.0 * (tstep * O_SEC_PER_DAY);
+    double dQ = 0.1, f, dfdQ, Q_guess = Qout_old, relax = 1.0;
+    do {
+      f = (channel_get_area(d, p, Q_guess) * reach_length + (Q_guess) / 2.0 * (tstep * O_SEC_PER_DAY));
+      dfdQ = (channel_get_area(d, p, Q_guess + dQ) * reach_length + (Q_guess + dQ) / 2.0 * (tstep * O_SEC_PER_DAY) - f) / dQ;
+      change = -(f - gamma) / dfdQ;
+      if (dfdQ == 0.0) change = 1e-7;
+      Q_guess += relax * change;
+      if (Q_guess < 0) { Q_guess = 0; change = 0.0; }
+      iter++;
+      if (iter > 3) relax = 0.9;
+      if (iter > 10) relax = 0.7;
+    } while ((iter < ROUTE_MAXITER) && (fabs(change) > ROUTE_TOLERANCE));
+    for (int s = 0; s < nSeg; s++) aQout_new[s] = aQout[s];
+    aQout_new[nSeg - 1] = Q_guess;
   } else if (method == RVN_ROUTE_PLUG_FLOW || method == RVN_ROUTE_DIFFUSIVE_WAVE) {
     aQout_new[nSeg - 1] = 0.0;
     for (int n = 0; n < nQin; n++) aQout_new[nSeg - 1] += RH[n] * QinHist[n];

@@ -79,6 +79,7 @@ struct DevModel {
   int32_t nLevels, max_nqin, max_nqlat;
   const double *sb_area, *sb_rain_corr, *sb_snow_corr, *sb_temp_corr, *sb_musk_K, *sb_musk_X, *sb_K_reach;
   const double *sb_unit_hydro, *sb_route_hydro;
+  const double *chan_Q, *chan_A, *sb_Qmult, *sb_reach_m; const int32_t *sb_channel; int32_t nChanPts;   // ROUTE_HYDROLOGIC rating curves
   double watershed_area;
   // recording
   double *rec_qout, *rec_wshed;                    // [rec][member][nSB], [rec][member][4]

@@ -889,6 +889,20 @@ struct Ring {
   RVN_DI double &operator[](int n) const { int i = base + n; if (i >= nQ) i -= nQ; return buf[i]; }
 };
 
+// CChannelXSect::GetArea (src/ChannelXSect.cpp:297-302): InterpolateCurve(Q/Q_mult, aQ, aXArea, N, extrapbottom=true)
+// (src/CommonFunctions.cpp:1982-2004); the interval is the one with aQ[i] <= x < aQ[i+1]
+RVN_DI double channel_area(const DevModel &M, const int p, const double Q) {
+  const int N = M.nChanPts;
+  const double *xx = M.chan_Q + (size_t)M.sb_channel[p] * N, *y = M.chan_A + (size_t)M.sb_channel[p] * N;
+  const double x = Q / M.sb_Qmult[p];
+  if (x <= xx[0]) return y[0] + (y[1] - y[0]) / (xx[1] - xx[0]) * (x - xx[0]);
+  if (x >= xx[N - 1]) return y[N - 1] + (y[N - 1] - y[N - 2]) / (xx[N - 1] - xx[N - 2]) * (x - xx[N - 1]);
+  int lo = 0, hi = N - 1;   // invariant: xx[lo] <= x < xx[hi]
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (x >= xx[mid]) lo = mid; else hi = mid; }
+  if (fabs(xx[lo + 1] - xx[lo]) < D_REAL_SMALL) return (y[lo] + y[lo + 1]) / 2;
+  return y[lo] + (y[lo + 1] - y[lo]) / (xx[lo + 1] - xx[lo]) * (x - xx[lo]);
+}
+
 // one basin, one member, one step: HRU -> subbasin aggregation in HRU-index order (src/Solvers.cpp:490-511),
 // CSubBasin::UpdateLateralInflow / UpdateInflow, RouteWater (src/SubBasin.cpp:2584-2863), UpdateOutflows (:2320-2421).
 // `t` = pushes into the histories before this step.
@@ -953,6 +967,30 @@ __device__ void route_one_basin(const DevModel &M, int e, int p, int step, int t
       Qin = old; Qin_new = qn;
       aQout[s] = qn;
     }
+  } else if (method == RVN_ROUTE_HYDROLOGIC) {
+    // level-pool routing of the reach with Newton's method on the rating curve (src/SubBasin.cpp:2685-2741): solve
+    // V(Q) + Q/2*dt = V_old + (Qin_old + Qin_new - Qout_old)/2*dt for the new outflow; finite-difference derivative, relaxation
+    // after 3 and 10 iterations, at most 20 iterations
+    const double dts = tstep * D_SEC_PER_DAY, L = M.sb_reach_m[p];
+    const double Qout_old = aQout[nSeg - 1] - sc[2];
+    const double V_old = channel_area(M, p, Qout_old) * L;
+    int iter = 0;
+    double change = 0;
+    const double gamma = V_old + (Qin1 + Qin0 - Qout_old) / 2.0 * dts;
+    const double dQ = 0.1;
+    double Q_guess = Qout_old, relax = 1.0;
+    do {
+      const double f = (channel_area(M, p, Q_guess) * L + (Q_guess) / 2.0 * dts);
+      const double dfdQ = (channel_area(M, p, Q_guess + dQ) * L + (Q_guess + dQ) / 2.0 * dts - f) / dQ;
+      change = -(f - gamma) / dfdQ;
+      if (dfdQ == 0.0) change = 1e-7;
+      Q_guess += relax * change;
+      if (Q_guess < 0) { Q_guess = 0; change = 0.0; }
+      iter++;
+      if (iter > 3) relax = 0.9;
+      if (iter > 10) relax = 0.7;
+    } while ((iter < 20) && (fabs(change) > 0.0001));
+    aQout[nSeg - 1] = Q_guess;
   } else if (method == RVN_ROUTE_PLUG_FLOW || method == RVN_ROUTE_DIFFUSIVE_WAVE) {
     double q = 0.0;
     for (int n = 0; n < nQin; n++) q += RH[n] * QinHist[n];

@@ -2,6 +2,7 @@
 // This is where per-(class,date) work the reference repeats for every HRU and step is hoisted:
 // convolution unit hydrographs (reference rebuilds them per HRU per step, src/Convolution.cpp:258),
 // the calendar table (JulianConvert per step, src/RavenMain.cpp:162) and gauge sampling.
+#include <algorithm>
 #include "rvh_model.h"
 #include "rvh_process.h"
 
@@ -313,6 +314,27 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
   d.sb_musk_K = _f_sb_d[4].data(); d.sb_musk_X = _f_sb_d[5].data(); d.sb_K_reach = _f_sb_d[6].data();
   d.max_nqin = maxqin; d.max_nqlat = maxqlat; d.sb_unit_hydro = _f_uh.data(); d.sb_route_hydro = _f_rh.data();
   d.watershed_area = _WatershedArea;
+  // ---- ROUTE_HYDROLOGIC: rating curves flow -> cross-section area
+  d.nChannels = 0; d.nChanPts = 0; d.chan_Q = d.chan_A = NULL; d.sb_channel = NULL; d.sb_Qmult = d.sb_reach_m = NULL;
+  if (O.routing == RVN_ROUTE_HYDROLOGIC) {
+    int npts = 0;
+    for (size_t c = 0; c < channels.size(); c++) npts = std::max(npts, (int)channels[c]->aQ.size());
+    d.nChannels = (int32_t)channels.size(); d.nChanPts = npts;
+    _f_chan_Q.assign((size_t)d.nChannels * npts, 0.0); _f_chan_A.assign((size_t)d.nChannels * npts, 0.0);
+    for (size_t c = 0; c < channels.size(); c++) {
+      const CChannelXSect *ch = channels[c];
+      ExitGracefullyIf((int)ch->aQ.size() != npts, "CModel::Flatten: channel profiles with different rating-curve lengths are not supported");
+      for (int i = 0; i < npts; i++) { _f_chan_Q[c * npts + i] = ch->aQ[i]; _f_chan_A[c * npts + i] = ch->aXArea[i]; }
+    }
+    _f_sb_channel.assign(NB, -1); _f_sb_Qmult.assign(NB, 1.0); _f_sb_reach.assign(NB, 0.0);
+    for (int p = 0; p < NB; p++) {
+      const CSubBasin *b = _pSubBasins[p];
+      for (size_t c = 0; c < channels.size(); c++) if (channels[c] == b->pChannel) _f_sb_channel[p] = (int32_t)c;
+      if (b->pChannel) _f_sb_Qmult[p] = b->pChannel->GetFlowMultiplier(b->slope, b->mannings_n);
+      _f_sb_reach[p] = b->reach_length;
+    }
+    d.chan_Q = _f_chan_Q.data(); d.chan_A = _f_chan_A.data(); d.sb_channel = _f_sb_channel.data(); d.sb_Qmult = _f_sb_Qmult.data(); d.sb_reach_m = _f_sb_reach.data();
+  }
   // ---- forcing perturbations (EnKF): samples start neutral; CEnKFEnsemble::UpdateModel fills them per member
   const int nP = (int)perturbations.size();
   d.nPert = nP; d.pad3_ = 0; d.pert_forcing = NULL; d.pert_adj = NULL; d.pert_mask = NULL; d.pert_eps = NULL;

@@ -224,6 +224,18 @@ double CChannelXSect::GetTopWidth(double Qin, double SB_slope, double SB_n) cons
   return y[i] + (y[i + 1] - y[i]) / (xx[i + 1] - xx[i]) * (x - xx[i]);
 }
 
+double CChannelXSect::GetFlowMultiplier(double SB_slope, double SB_n) const { double Q_mult; FlowCorrections(bedslope, min_mannings, SB_slope, SB_n, Q_mult); return Q_mult; }
+double CChannelXSect::GetArea(double Qin, double SB_slope, double SB_n) const {
+  const double x = Qin / GetFlowMultiplier(SB_slope, SB_n);
+  const std::vector<double> &xx = aQ, &y = aXArea;
+  const int N = (int)xx.size();
+  if (x <= xx[0]) return y[0] + (y[1] - y[0]) / (xx[1] - xx[0]) * (x - xx[0]);
+  if (x >= xx[N - 1]) return y[N - 1] + (y[N - 1] - y[N - 2]) / (xx[N - 1] - xx[N - 2]) * (x - xx[N - 1]);
+  int i = 0; while (!((x >= xx[i]) && (x < xx[i + 1]))) i++;
+  if (fabs(xx[i + 1] - xx[i]) < REAL_SMALL) return (y[i] + y[i + 1]) / 2;
+  return y[i] + (y[i + 1] - y[i]) / (xx[i + 1] - xx[i]) * (x - xx[i]);
+}
+
 // ---------------------------------------------------------------------------------- HRU / subbasin
 // the reference converts with the rounded literal DEGREES_TO_RADIANS = 0.017453293 (src/RavenInclude.h:166; src/ParseHRUFile.cpp:327-328,
 // src/HydroUnits.cpp:95), not with PI/180
@@ -316,6 +328,7 @@ void CSubBasin::GenerateRoutingHydrograph(double Qin_avg, const optStruct &O) {
   int nQin;
   if (O.routing == RVN_ROUTE_PLUG_FLOW) nQin = (int)(ceil(travel_time / tstep)) + 2;
   else if (O.routing == RVN_ROUTE_DIFFUSIVE_WAVE) nQin = (int)(ceil(2 * travel_time / tstep)) + 2;
+  else if (O.routing == RVN_ROUTE_HYDROLOGIC) nQin = 2;
   else nQin = 20;
   aQinHist.assign(nQin, Qin_avg);
   aRouteHydro.assign(nQin, 0.0);
@@ -347,7 +360,9 @@ void CSubBasin::InitializeFlowStates(double Qin_avg, double Qlat_avg, const optS
   QlatLast = Qlat_avg;
   channel_storage = 0.0;
   if (O.routing == RVN_ROUTE_NONE) channel_storage = 0.0;
-  else if (O.routing == RVN_ROUTE_PLUG_FLOW || O.routing == RVN_ROUTE_DIFFUSIVE_WAVE) {
+  else if (O.routing == RVN_ROUTE_HYDROLOGIC) {   // src/SubBasin.cpp:1983-1989
+    for (int seg = 0; seg < nSegments; seg++) channel_storage += pChannel->GetArea(aQout[seg], slope, mannings_n) * (reach_length / nSegments);
+  } else if (O.routing == RVN_ROUTE_PLUG_FLOW || O.routing == RVN_ROUTE_DIFFUSIVE_WAVE) {
     double sum = 0;
     for (int n = (int)aQinHist.size() - 1; n > 0; n--) { sum += aRouteHydro[n]; channel_storage += aQinHist[n] * sum * (O.timestep * SEC_PER_DAY); }
   } else if (O.routing == RVN_ROUTE_MUSKINGUM || O.routing == RVN_ROUTE_MUSKINGUM_CUNGE) {

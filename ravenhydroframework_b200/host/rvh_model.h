@@ -43,6 +43,8 @@ public:
   void GenerateTrapezoid(double bottom_w, double bottom_elev, double incline_ratio);
   double GetCelerity(double Q, double SB_slope, double SB_n) const;
   double GetTopWidth(double Q, double SB_slope, double SB_n) const;
+  double GetArea(double Q, double SB_slope, double SB_n) const;          // src/ChannelXSect.cpp:297-302
+  double GetFlowMultiplier(double SB_slope, double SB_n) const;           // Q_mult of GetFlowCorrections (src/ChannelXSect.cpp:345-359)
 private:
   double GetQfromQref(double Q, double SB_slope, double SB_n) const;
   void   Interp(double Q, int &i, double &wt) const;
@@ -311,7 +313,8 @@ private:
   std::vector<uint8_t> _f_pert_mask;
   std::vector<rvn_lateral> _f_lat;
   std::vector<int32_t> _f_lat_kfrom, _f_lat_kto, _f_lat_chunk;
-  std::vector<double> _f_lat_frac;
+  std::vector<double> _f_lat_frac, _f_chan_Q, _f_chan_A, _f_sb_Qmult, _f_sb_reach;
+  std::vector<int32_t> _f_sb_channel;
   std::vector<double> _f_pert_eps;
   std::vector<rvn_time> _f_times;
   int _f_ptab_stride, _f_nconv;

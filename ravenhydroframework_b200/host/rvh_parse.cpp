@@ -134,6 +134,7 @@ static void ParseMainInputFile(CModel *&pModel, optStruct &Options) {
       else if (s[1] == "ROUTE_MUSKINGUM_CUNGE") Options.routing = RVN_ROUTE_MUSKINGUM_CUNGE;
       else if (s[1] == "ROUTE_STORAGECOEFF") Options.routing = RVN_ROUTE_STORAGECOEFF;
       else if (s[1] == "ROUTE_PLUG_FLOW") Options.routing = RVN_ROUTE_PLUG_FLOW;
+      else if (s[1] == "ROUTE_HYDROLOGIC") Options.routing = RVN_ROUTE_HYDROLOGIC;
       else if (s[1] == "ROUTE_DIFFUSIVE_WAVE") Options.routing = RVN_ROUTE_DIFFUSIVE_WAVE;
       else ExitGracefully("ParseMainInputFile: routing method " + s[1] + " is not implemented in the B200 build (SURVEY 8f)");
       continue;

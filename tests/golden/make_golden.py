@@ -54,6 +54,7 @@ if hasattr(synth, "write_blended"):
     CASES["hbv_6hourly"] = dict(kind="hbv", n_sb=7, hru_per_sb=3, n_days=120, seed=19, routing="ROUTE_MUSKINGUM", season_offset=60, timestep="06:00:00")
     # explicit Euler (:Method EULER): every process sees the start-of-step state
     CASES["hbv_diffusive"] = dict(kind="hbv", n_sb=7, hru_per_sb=3, n_days=200, seed=22, routing="ROUTE_DIFFUSIVE_WAVE", season_offset=70)
+    CASES["hbv_hydrologic"] = dict(kind="hbv", n_sb=7, hru_per_sb=3, n_days=250, seed=24, routing="ROUTE_HYDROLOGIC", season_offset=50)
     CASES["hbv_euler"] = dict(kind="hbv", n_sb=4, hru_per_sb=5, n_days=300, seed=9, routing="ROUTE_MUSKINGUM", season_offset=30, method="EULER")
     CASES["hmets_3hourly"] = dict(kind="hmets", n_sb=3, hru_per_sb=4, n_days=60, seed=20, season_offset=90, timestep="03:00:00")
 if hasattr(synth, "write_gr4j"):
