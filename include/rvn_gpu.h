@@ -378,6 +378,13 @@ int rvn_gpu_upload_forcings(rvn_gpu_model *m, const double *gauge_series, const 
  * src/RavenMain.cpp:151-160).  Asynchronous on the handle's stream; rvn_gpu_sync waits. */
 int rvn_gpu_run(rvn_gpu_model *m, int step0, int nsteps);
 int rvn_gpu_sync(rvn_gpu_model *m);
+/* streaming form of ONE model step for host-side callers (BMI-style drivers that feed forcings and consume hydrographs step by
+ * step): nothing waits.  Enqueued, in order: copy of this step's forcing slab forcing_host[RVN_GF_COUNT][nGauges] (pinned host
+ * memory, may be NULL to keep the uploaded series) to the device; the step; copies of the step's outflows
+ * qout_host[nMembers][nSB] and watershed record wshed_host[nMembers][4] (pinned, either may be NULL) back to the host.  The
+ * result copies run on the routing stream underneath the next step's sweep.  Host buffers must stay untouched / are valid
+ * after rvn_gpu_sync (or any later synchronising call); steps must be enqueued in order. */
+int rvn_gpu_step_async(rvn_gpu_model *m, int step, const double *forcing_host, double *qout_host, double *wshed_host);
 
 /* per-step outputs recorded on the device during rvn_gpu_run (max_steps records; 0 disables):
  *   flags bit 0: qout  [rec][member][nSB]  CSubBasin::GetOutflowRate() after the step

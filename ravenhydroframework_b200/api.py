@@ -44,6 +44,7 @@ def engine_lib():
         lib.rvn_gpu_upload_forcings.argtypes = [vp, dp, dp, i, i]
         lib.rvn_gpu_run.argtypes = [vp, i, i]
         lib.rvn_gpu_sync.argtypes = [vp]
+        lib.rvn_gpu_step_async.argtypes = [vp, i, dp, dp, dp]
         lib.rvn_gpu_set_recording.argtypes = [vp, i, i]
         lib.rvn_gpu_enable_forcing_output.argtypes = [vp, i]
         lib.rvn_gpu_set_kernel_timing.argtypes = [vp, i]
@@ -388,6 +389,11 @@ class GpuSimulation:
 
     def sync(self):
         self._ck(self.lib.rvn_gpu_sync(self.h))
+
+    def step_async(self, forcing_ptr=None, qout_ptr=None, wshed_ptr=None):
+        """Streaming step (rvn_gpu_step_async): raw addresses of PINNED host buffers (or None); nothing waits, sync() completes."""
+        self._ck(self.lib.rvn_gpu_step_async(self.h, self.step, forcing_ptr, qout_ptr, wshed_ptr))
+        self.step += 1
 
     def hydrographs(self, rec0, nrec, member0=0, nmembers=None):
         nmembers = self.E - member0 if nmembers is None else nmembers

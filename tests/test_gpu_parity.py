@@ -88,6 +88,28 @@ def test_stepwise_equals_batched(tmp_path):
     assert np.array_equal(a.download_state(), b.download_state())
 
 
+def test_streaming_steps_equal_batched(tmp_path):
+    """rvn_gpu_step_async (forcing slab in, outflows + watershed record out, nothing waits) gives the bits of the batched run."""
+    import torch
+    model, sim = _run_pair(tmp_path, 7, 9, 60, 3, members=3)
+    q_ref, w_ref, st_ref = sim.hydrographs(0, 60), sim.watershed(0, 60), sim.download_state()
+    import ctypes as C
+    model.lib.rvh_desc_gauge_series.restype = C.c_void_p
+    model.lib.rvh_desc_gauge_series.argtypes = [C.c_void_p]
+    nG = model.nGauges
+    series = np.ctypeslib.as_array((C.c_double * (9 * nG * model.nSteps)).from_address(model.lib.rvh_desc_gauge_series(model.desc))).reshape(9, nG, model.nSteps)
+    slabs = torch.from_numpy(np.ascontiguousarray(series.transpose(2, 0, 1))).pin_memory()
+    b = api.GpuSimulation(model, n_members=3)
+    b.upload_forcings(np.zeros((9, nG, model.nSteps)), 0, model.nSteps)        # the device copy is wiped: every step must bring its own slab
+    q = torch.zeros((60, 3, model.nSB), dtype=torch.float64).pin_memory()
+    w = torch.zeros((60, 3, 4), dtype=torch.float64).pin_memory()
+    for n in range(60):
+        b.step_async(slabs.data_ptr() + n * 9 * nG * 8, q.data_ptr() + n * 3 * model.nSB * 8, w.data_ptr() + n * 3 * 4 * 8)
+    b.sync()
+    assert np.array_equal(q.numpy(), q_ref) and np.array_equal(w.numpy(), w_ref)
+    assert np.array_equal(b.download_state(), st_ref)
+
+
 def test_state_roundtrip(tmp_path):
     base = synth.write_hmets(str(tmp_path), n_sb=2, hru_per_sb=3, n_days=10, seed=2)
     model = api.RavenModel(base)
