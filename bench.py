@@ -30,7 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 MEMBERS_PER_GPU = 512
-N_SB, HRU_PER_SB = 500, 20
+N_SB, HRU_PER_SB = int(os.environ.get("RVN_BENCH_NSB", 500)), int(os.environ.get("RVN_BENCH_HPS", 20))   # env overrides: layout experiments only
 METRIC = "HRU-timesteps/sec (members x HRUs x steps)"
 CPU_SAMPLE_STEPS = 100   # bounded cpu_baseline sample: ~16 s of time loop per reference process at ~6e4 HRU-steps/s
 

@@ -107,6 +107,7 @@ def host_lib():
         lib.rvh_enkf_harvest_outputs.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
         lib.rvh_enkf_compute_Z.argtypes = [vp, vp, vp]
         lib.rvh_desc_nseg.argtypes = [vp, vp]
+        lib.rvh_model_write_solution.argtypes = [vp, C.c_char_p, C.c_double, vp, vp, vp, vp, vp, C.c_int]
         _host = lib
     return _host
 
@@ -184,6 +185,13 @@ class RavenModel:
         if self.lib.rvh_model_basin_state(self.h, qin.ctypes.data, qlat.ctypes.data, qout.ctypes.data, scal.ctypes.data):
             raise RavenError(self.lib.rvh_last_error().decode())
         return qin, qlat, qout, scal
+
+    def write_solution(self, filename, model_time, state, qin, qlat, qout, scal, full_precision=True):
+        """Checkpoint of one member in the reference's solution.rvc format (CModel::WriteMajorOutput): state [nHRU][NS], basin arrays
+        as returned by GpuSimulation.download_basin_state() for that member.  full_precision writes %.17g so a restart is bit-exact."""
+        a = [np.ascontiguousarray(x, dtype=np.float64) for x in (state, qin, qlat, qout, scal)]
+        if self.lib.rvh_model_write_solution(self.h, str(filename).encode(), float(model_time), *[x.ctypes.data for x in a], 1 if full_precision else 0):
+            raise RavenError(self.lib.rvh_last_error().decode())
 
     def update_parameter(self, class_type, pname, cname, value):
         """CModel::UpdateParameter: class_type 0=soil 1=vegetation 2=landuse 3=terrain 4=global."""
@@ -346,6 +354,12 @@ class GpuSimulation:
         qout = np.empty((nmembers, self.nSB, MAX_RIVER_SEGS)); scal = np.empty((nmembers, self.nSB, 8))
         self._ck(self.lib.rvn_gpu_download_basin_state(self.h, qin.ctypes.data, qlat.ctypes.data, qout.ctypes.data, scal.ctypes.data, member0, nmembers))
         return qin, qlat, qout, scal
+
+    def write_solution(self, filename, member=0, full_precision=True):
+        """solution.rvc of `member` at the current step, straight from the device buffers."""
+        st = self.download_state(member, 1)[0]
+        qin, qlat, qout, scal = [a[0] for a in self.download_basin_state(member, 1)]
+        self.model.write_solution(filename, self.step * self.model.timestep, st, qin, qlat, qout, scal, full_precision)
 
     def upload_member_params(self, member):
         a, b, c = self.model.flatten_member(member)

@@ -63,6 +63,14 @@ int rvh_ensemble_update_model(rvh_model *h, int e, double *values, int nmax) {
   return n;
   RVH_CATCH(-1)
 }
+// checkpoint of one member: the reference's solution.rvc from arrays in the layouts of rvn_gpu_download_state / _basin_state
+int rvh_model_write_solution(rvh_model *h, const char *filename, double model_time, const double *state, const double *qin, const double *qlat,
+                             const double *qout, const double *scal, int full_precision) {
+  RVH_TRY
+  h->pModel->WriteSolutionFile(filename, h->Options, model_time, state, qin, qlat, qout, scal, full_precision != 0);
+  return 0;
+  RVH_CATCH(-1)
+}
 // ---- DDS (CDDSEnsemble): rvh_ensemble_begin + rvh_ensemble_update_model(e) perturb the best-so-far vector (the sampled values
 // returned are the trial's parameters); after the trial's GPU run rvh_dds_finish_run(e, hydrographs) evaluates the objective
 // function and updates the best solution.  qout_rec[nsteps][nSB] = CSubBasin::GetOutflowRate after every step of the single member.

@@ -387,3 +387,57 @@ void CModel::PackBasinState(std::vector<double> &qin, std::vector<double> &qlat,
     s[0] = b->QoutLast; s[1] = b->QlatLast; s[2] = b->Qlocal; s[3] = b->QlocLast; s[4] = b->channel_storage; s[5] = b->rivulet_storage;
   }
 }
+
+static std::string DecDaysToHours(double dec_date) {   // src/CommonFunctions.cpp DecDaysToHours: hh:mm:ss.sss of the fractional day
+  double hours = (dec_date - floor(dec_date)) * 24.0 + 1e-9;
+  int h = (int)floor(hours); double mins = (hours - h) * 60.0; int mi = (int)floor(mins); double sec = (mins - mi) * 60.0;
+  char b[32]; snprintf(b, sizeof b, "%02d:%02d:%06.3f", h, mi, sec < 0 ? 0.0 : sec);
+  return b;
+}
+void CModel::WriteSolutionFile(const std::string &filename, const optStruct &O, double model_time, const double *state, const double *qin, const double *qlat,
+                               const double *qout, const double *scal, bool full_precision) const {
+  FILE *f = fopen(filename.c_str(), "w");
+  ExitGracefullyIf(f == NULL, "CModel::WriteMajorOutput: Unable to open output file " + filename + " for writing.");
+  const char *fmt_s = full_precision ? "%.17g" : "%.5f";   // HRU table: std::fixed, precision 5
+  const char *fmt_b = full_precision ? "%.17g" : "%.5f";   // the stream stays fixed/5 for the basin block as well
+  time_struct tts, tt;
+  JulianConvert(0, O.julian_start_day, O.julian_start_year, O.calendar, tts);
+  JulianConvert(model_time, O.julian_start_day, O.julian_start_year, O.calendar, tt);
+  fprintf(f, ":StartTime %s %s\n", tts.date_string.c_str(), DecDaysToHours(tts.julian_day).c_str());
+  fprintf(f, ":TimeStamp %s %s\n", tt.date_string.c_str(), DecDaysToHours(tt.julian_day).c_str());
+  fprintf(f, ":TimeStep %.17g\n", O.timestep);
+  const int NS = GetNumStateVars(), nH = GetNumHRUs(), NB = GetNumSubBasins(), M = 80;
+  for (int j = 0; j < (int)ceil(NS / (double)(M)); j++) {   // blocks of 80 state variables
+    const int mini = j * M, maxi = (NS < (j + 1) * M) ? NS : (j + 1) * M;
+    fprintf(f, ":HRUStateVariableTable\n  :Attributes,");
+    for (int i = mini; i < maxi; i++) fprintf(f, "%s%s", GetStateVarName(i).c_str(), (i != NS - 1) ? "," : "");
+    fprintf(f, "\n  :Units,");
+    for (int i = mini; i < maxi; i++) fprintf(f, "%s%s", "none", (i != NS - 1) ? "," : "");
+    fprintf(f, "\n");
+    for (int k = 0; k < nH; k++) {
+      fprintf(f, "  %lld,", _pHydroUnits[k]->ID);
+      for (int i = mini; i < maxi; i++) { fprintf(f, fmt_s, state[(size_t)k * NS + i]); if (i != NS - 1) fprintf(f, ","); }
+      fprintf(f, "\n");
+    }
+    fprintf(f, ":EndHRUStateVariableTable\n");
+  }
+  fprintf(f, ":BasinStateVariables\n");
+  for (int p = 0; p < NB; p++) {
+    const CSubBasin *b = _pSubBasins[p];
+    const double *sc = scal + (size_t)p * 8;
+    fprintf(f, "  :BasinIndex %lld,%s\n", b->ID, b->name.c_str());
+    fprintf(f, "    :ChannelStorage, "); fprintf(f, fmt_b, sc[4]); fprintf(f, "\n");
+    fprintf(f, "    :RivuletStorage, "); fprintf(f, fmt_b, sc[5]); fprintf(f, "\n");
+    fprintf(f, "    :Qout,%d", b->nSegments);
+    for (int i = 0; i < b->nSegments; i++) { fprintf(f, ","); fprintf(f, fmt_b, qout[(size_t)p * RVN_MAX_RIVER_SEGS + i]); }
+    fprintf(f, ","); fprintf(f, fmt_b, sc[0]); fprintf(f, "\n");
+    fprintf(f, "    :Qlat,%d", b->GetLatHistorySize());
+    for (int i = 0; i < b->GetLatHistorySize(); i++) { fprintf(f, ","); fprintf(f, fmt_b, qlat[(size_t)p * _desc.max_nqlat + i]); if (i % 200 == 199) fprintf(f, "\n    "); }
+    fprintf(f, ","); fprintf(f, fmt_b, sc[1]); fprintf(f, "\n");
+    fprintf(f, "    :Qin ,%d", b->GetInflowHistorySize());
+    for (int i = 0; i < b->GetInflowHistorySize(); i++) { fprintf(f, ","); fprintf(f, fmt_b, qin[(size_t)p * _desc.max_nqin + i]); if (i % 200 == 199) fprintf(f, "\n    "); }
+    fprintf(f, "\n");
+  }
+  fprintf(f, ":EndBasinStateVariables\n");
+  fclose(f);
+}

@@ -284,6 +284,12 @@ public:
   const double *MemberParams(int member) const { return _f_ptab.data() + (size_t)member * _f_ptab_stride; }
   const int32_t *MemberConvN(int member) const;
   const double *MemberConvUH(int member) const;
+  // checkpoint: the reference's {RunName}_solution.rvc (CModel::WriteMajorOutput, src/StandardOutput.cpp:1388-1451;
+  // CSubBasin::WriteToSolutionFile, src/SubBasin.cpp:2869-2880) for ONE member, from arrays in the layouts of
+  // rvn_gpu_download_state / rvn_gpu_download_basin_state.  full_precision: %.17g instead of the reference's 5 fixed decimals
+  // (6 significant digits for the basin block), so that a restart continues bit-identically.
+  void WriteSolutionFile(const std::string &filename, const optStruct &Options, double model_time, const double *state, const double *qin,
+                         const double *qlat, const double *qout, const double *scal, bool full_precision) const;
   // initial basin routing state in the layout of rvn_gpu_upload_basin_state (one member)
   void PackBasinState(std::vector<double> &qin, std::vector<double> &qlat, std::vector<double> &qout, std::vector<double> &scal) const;
 

@@ -967,10 +967,77 @@ bool ParseInitialConditions(CModel *&pModel, const optStruct &Options) {
   if (!p.ok()) return true;  // reference: .rvc is optional (all-zero initial state)
   const int NS = pModel->GetNumStateVars(), nH = pModel->GetNumHRUs();
   std::vector<std::string> s;
+  double rvc_tstep = Options.timestep;
+  std::map<long long, int> hru_of_id;
+  for (int kk = 0; kk < nH; kk++) hru_of_id.insert(std::make_pair(pModel->GetHydroUnit(kk)->ID, kk));
   while (p.Tokenize(s)) {
     if (s.empty()) continue;
-    const std::string &c = s[0];
-    if (c == ":FileType" || c == ":WrittenBy" || c == ":CreationDate" || c == ":TimeStamp") continue;
+    const std::string c = s[0];   // a copy: several blocks below re-tokenise into s
+    if (c == ":FileType" || c == ":WrittenBy" || c == ":CreationDate" || c == ":TimeStamp" || c == ":StartTime") continue;
+    if (c == ":TimeStep") {   // time step of the run that wrote the file; histories are only taken over at the same step
+      rvc_tstep = ParseIntervalToken(s[1], Options.calendar);
+      continue;
+    }
+    if (c == ":BasinStateVariables") {   // src/ParseInitialConditionFile.cpp:539-660 (no reservoirs)
+      CSubBasin *pBasin = NULL;
+      // values may continue on following lines: pull `need` numbers starting at token i of the current line
+      auto pull = [&](size_t i, int need, std::vector<double> &out) {
+        out.clear();
+        while ((int)out.size() < need) {
+          if (i >= s.size()) { if (!p.Tokenize(s)) break; i = 0; if (s.empty()) continue; }
+          out.push_back(s_to_d(s[i++]));
+        }
+      };
+      while (p.Tokenize(s)) {
+        if (s.empty()) continue;
+        if (s[0] == ":EndBasinStateVariables") break;
+        if (s[0] == ":BasinIndex") {
+          const int pb = pModel->GetSubBasinIndex(s_to_ll(s[1]));
+          ExitGracefullyIf(pb < 0, "ParseInitialConditionsFile: bad basin index in .rvc file");
+          pBasin = pModel->GetSubBasin(pb);
+          continue;
+        }
+        ExitGracefullyIf(pBasin == NULL, "ParseInitialConditionsFile: basin state given before :BasinIndex");
+        ExitGracefullyIf(rvc_tstep != Options.timestep, "ParseInitialConditionsFile: the .rvc file was written with a different time step (history rescaling is not supported by the B200 build)");
+        std::vector<double> v;
+        if (s[0] == ":ChannelStorage") { if (s.size() >= 2) pBasin->channel_storage = s_to_d(s[1]); }
+        else if (s[0] == ":RivuletStorage") { if (s.size() >= 2) pBasin->rivulet_storage = s_to_d(s[1]); }
+        else if (s[0] == ":Qout") {   // [nsegs] [aQout x nsegs] [QoutLast]  -> CSubBasin::SetQoutArray (src/SubBasin.cpp:1407-1417)
+          if (s.size() > 2) {
+            const int nsegs = s_to_i(s[1]);
+            pull(2, nsegs + 1, v);
+            if (nsegs != pBasin->nSegments) WriteWarning("Number of reach segments in state file and input file are inconsistent in basin " + std::to_string(pBasin->ID) + ". Unable to read in-reach flow initial conditions");
+            else if ((int)v.size() == nsegs + 1) { for (int i = 0; i < nsegs; i++) pBasin->aQout[i] = v[i]; pBasin->QoutLast = v[nsegs]; }
+          }
+        } else if (s[0] == ":Qlat") {   // [n] [aQlatHist x n] [QlatLast] -> SetQlatHist (:1435-1476): also recomputes _Qlocal
+          if (s.size() > 2) {
+            const int n = s_to_i(s[1]);
+            pull(2, n + 1, v);
+            if (n != 0 && (int)v.size() == n + 1) {
+              pBasin->QlatLast = v[n];
+              const int m = (n < pBasin->GetLatHistorySize()) ? n : pBasin->GetLatHistorySize();
+              if (n != pBasin->GetLatHistorySize()) WriteWarning("CSubBasin::SetQlatHist: size of lateral flow history differs between current model and initial conditions file. Array will be truncated");
+              for (int i = 0; i < m; i++) pBasin->aQlatHist[i] = v[i];
+              pBasin->Qlocal = 0.0;
+              for (int i = 0; i < pBasin->GetLatHistorySize(); i++) pBasin->Qlocal += pBasin->aUnitHydro[i] * pBasin->aQlatHist[i];
+            }
+          }
+        } else if (s[0] == ":Qin") {   // [n] [aQinHist x n] -> SetQinHist (:1485-1518)
+          if (s.size() > 2) {
+            const int n = s_to_i(s[1]);
+            pull(2, n, v);
+            if (n != 0 && (int)v.size() == n) {
+              const int m = (n < pBasin->GetInflowHistorySize()) ? n : pBasin->GetInflowHistorySize();
+              if (n != pBasin->GetInflowHistorySize()) WriteWarning("CSubBasin::SetQinHist: size of inflow history differs between current model and initial conditions file. Array will be truncated");
+              for (int i = 0; i < m; i++) pBasin->aQinHist[i] = v[i];
+            }
+          }
+        } else if (s[0] == ":ResStage" || s[0] == ":ResFlow") {
+          WriteWarning("ParseInitialConditionsFile: reservoir initial conditions for basin without reservoir will be ignored.");
+        } else ExitGracefully("ParseInitialConditionsFile: command " + s[0] + " inside :BasinStateVariables is not supported by the B200 build");
+      }
+      continue;
+    }
     if (c == ":UniformInitialConditions") {
       int lay; sv_type t = pModel->StringToSVType(s[1], lay, false);
       int i = (t == RVN_SV_NTYPES) ? DOESNT_EXIST : pModel->GetStateVarIndex(t, lay);
@@ -987,14 +1054,18 @@ bool ParseInitialConditions(CModel *&pModel, const optStruct &Options) {
           idx.clear();
           for (size_t i = 1; i < s.size(); i++) {
             int lay; sv_type t = pModel->StringToSVType(s[i], lay, false);
-            idx.push_back((t == RVN_SV_NTYPES) ? DOESNT_EXIST : pModel->GetStateVarIndex(t, lay));
+            int ix = (t == RVN_SV_NTYPES) ? DOESNT_EXIST : pModel->GetStateVarIndex(t, lay);
+            // initial conditions of cumulative precip, evaporation and glacier loss are ignored, left at zero (src/ParseInitialConditionFile.cpp:385-388;
+            // Options.glacier_model_on is off in every model the host layer accepts)
+            if (t == RVN_SV_ATMOS_PRECIP || t == RVN_SV_ATMOSPHERE || t == RVN_SV_GLACIER_ICE) ix = DOESNT_EXIST;
+            idx.push_back(ix);
           }
           continue;
         }
         long long id = s_to_ll(s[0]);
-        int k = -1;
-        for (int kk = 0; kk < nH; kk++) if (pModel->GetHydroUnit(kk)->ID == id) { k = kk; break; }
-        if (k < 0) continue;
+        std::map<long long, int>::const_iterator it = hru_of_id.find(id);
+        if (it == hru_of_id.end()) continue;
+        const int k = it->second;
         for (size_t i = 0; i < idx.size() && i + 1 < s.size(); i++) if (idx[i] >= 0) pModel->SetInitialStateVar(k, idx[i], s_to_d(s[i + 1]));
       }
       continue;

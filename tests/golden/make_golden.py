@@ -109,6 +109,40 @@ def make_enkf(name, spec):
     print("golden %-18s N=%d M=%d Nobs=%d nHRU=%d NB=%d steps=%d nPert=%d" % (name, N, M, Nobs, nH, NB, nsteps, nP))
 
 
+def make_restart(name="hbv_restart", n1=120, n2=100):
+    """Warm start from a checkpoint written by the reference EXECUTABLE: Raven.exe runs n1 days and writes solution.rvc (HRU state
+    table + :BasinStateVariables, 5 decimals); the fixture model starts at day n1 from that file and the reference runs n2 more days."""
+    import datetime
+    import subprocess
+    d = os.path.join(HERE, name)
+    shutil.rmtree(d, ignore_errors=True)
+    base = synth.write_hbv(d, n_sb=7, hru_per_sb=3, n_days=n1 + n2, seed=26, routing="ROUTE_MUSKINGUM", name="model", season_offset=20)
+    rvi0 = open(base + ".rvi").read()
+    open(base + ".rvi", "w").write(rvi0.replace(":Duration              %d" % (n1 + n2), ":Duration              %d" % n1).replace(":SilentMode", ":SilentMode\n:SuppressOutput"))
+    out = os.path.join(d, "_first") + "/"
+    # :SuppressOutput also suppresses the solution file: run without it, quietly
+    open(base + ".rvi", "w").write(rvi0.replace(":Duration              %d" % (n1 + n2), ":Duration              %d" % n1))
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "Raven.exe"), "model", "-o", out], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert os.path.exists(out + "solution.rvc"), r.stdout[-2000:]
+    shutil.copy(out + "solution.rvc", base + ".rvc")
+    shutil.rmtree(out, ignore_errors=True)
+    start = datetime.date(2000, 1, 1) + datetime.timedelta(days=n1)
+    rvi = rvi0.replace(":StartDate             2000-01-01 00:00:00", ":StartDate             %s 00:00:00" % start.isoformat())
+    rvi = rvi.replace(":Duration              %d" % (n1 + n2), ":Duration              %d" % n2)
+    assert rvi != rvi0
+    open(base + ".rvi", "w").write(rvi)
+    outd = os.path.join(d, "_refout")
+    ref = H.reference_run(base, outd, n2)
+    rec = sorted(set([1, 2, 3, 10, 50, n2]))
+    np.savez_compressed(os.path.join(d, "reference.npz"), state_steps=np.array(rec), state=ref["state"][rec], qout=ref["basin"][1:n2 + 1, :, 0],
+                        basin_last=ref["basin"][n2], wshed=ref["wshed"][1:n2 + 1], forc_steps=np.array(rec), forc=ref["forc"][rec],
+                        sv_type=np.array([t for t, _ in ref["sv"]]), sv_layer=np.array([l for _, l in ref["sv"]]),
+                        order=np.array(ref["order"]), proc=np.array([" ".join(p) for p in ref["proc"]]),
+                        param=np.array([" ".join(p) for p in ref["param"]]))
+    shutil.rmtree(outd, ignore_errors=True)
+    print("golden %-18s warm start at day %d, %d steps" % (name, n1, n2))
+
+
 def make_dds(name="dds_hmets"):
     """DDS calibration (reference CDDSEnsemble): the reference EXECUTABLE runs all trials; fixture = every trial's objective function
     value as printed (6 digits), the rows of DDSOutput.csv and the best parameter vector."""
@@ -189,6 +223,8 @@ if __name__ == "__main__":
         make(name, spec)
     if not only or "dds_hmets" in only:
         make_dds()
+    if not only or "hbv_restart" in only:
+        make_restart()
     for name, spec in ENKF_CASES.items():
         if only and name not in only:
             continue
