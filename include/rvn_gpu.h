@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RVN_ABI_VERSION 4
+#define RVN_ABI_VERSION 5
 #define RVN_DOESNT_EXIST (-1)
 #define RVN_CONV_STORES 50   /* MAX_CONVOL_STORES, reference src/RavenInclude.h / Convolution.cpp:17 */
 #define RVN_MAX_CONN 24      /* max connections of a non-convolution process (Precipitation: 13..19) */
@@ -102,6 +102,32 @@ typedef enum {
   RVN_OP_INTERFLOW_PRMS,       /* CmvInterflow            src/Interflow.cpp:98-124,136-148          */
   RVN_OP_SNOWMELT_POTMELT,     /* CmvSnowMelt             src/SnowMeltRefreeze.cpp:87-131           */
   RVN_OP_SNOWSQUEEZE,          /* CmvSnowSqueeze          src/SnowMeltRefreeze.cpp:197-244          */
+  RVN_OP_BASE_LINEAR_CONSTRAIN,/* CmvBaseflow             src/Baseflow.cpp:188-197                  */
+  RVN_OP_BASE_CONSTANT,        /* CmvBaseflow             src/Baseflow.cpp:207-210                  */
+  RVN_OP_BASE_THRESH_POWER,    /* CmvBaseflow             src/Baseflow.cpp:250-266                  */
+  RVN_OP_BASE_THRESH_STOR,     /* CmvBaseflow             src/Baseflow.cpp:268-279                  */
+  RVN_OP_PERC_GAWSER,          /* CmvPercolation          src/Percolation.cpp:204-213               */
+  RVN_OP_PERC_GAWSER_CONSTRAIN,/* CmvPercolation          src/Percolation.cpp:215-226               */
+  RVN_OP_PERC_POWER_LAW,       /* CmvPercolation          src/Percolation.cpp:228-236               */
+  RVN_OP_PERC_LINEAR_ANALYTIC, /* CmvPercolation          src/Percolation.cpp:245-251               */
+  RVN_OP_PERC_PRMS,            /* CmvPercolation          src/Percolation.cpp:253-267               */
+  RVN_OP_PERC_SACRAMENTO,      /* CmvPercolation          src/Percolation.cpp:269-294               */
+  RVN_OP_PERC_ASPEN,           /* CmvPercolation          src/Percolation.cpp:317-321               */
+  RVN_OP_INF_RATIONAL,         /* CmvInfiltration         src/Infiltration.cpp:333-338              */
+  RVN_OP_INF_ALL_INFILTRATES,  /* CmvInfiltration         src/Infiltration.cpp:347-353              */
+  RVN_OP_INF_VIC,              /* CmvInfiltration         src/Infiltration.cpp:361-383              */
+  RVN_OP_INF_PRMS,             /* CmvInfiltration         src/Infiltration.cpp:418-431              */
+  RVN_OP_INF_PDM,              /* CmvInfiltration         src/Infiltration.cpp:540-563              */
+  RVN_OP_SOILEVAP_LINEAR,      /* CmvSoilEvap             src/SoilEvaporation.cpp:370-377           */
+  RVN_OP_SOILEVAP_PDM,         /* CmvSoilEvap             src/SoilEvaporation.cpp:424-437           */
+  RVN_OP_SOILEVAP_HYMOD2,      /* CmvSoilEvap             src/SoilEvaporation.cpp:439-458           */
+  RVN_OP_SOILEVAP_UBC,         /* CmvSoilEvap             src/SoilEvaporation.cpp:470-494           */
+  RVN_OP_SOILEVAP_VIC,         /* CmvSoilEvap             src/SoilEvaporation.cpp:496-515           */
+  RVN_OP_SOILEVAP_HYPR,        /* CmvSoilEvap             src/SoilEvaporation.cpp:385-420           */
+  RVN_OP_SOILEVAP_SEQUEN,      /* CmvSoilEvap             src/SoilEvaporation.cpp:553-568           */
+  RVN_OP_SOILEVAP_ROOT,        /* CmvSoilEvap             src/SoilEvaporation.cpp:570-596           */
+  RVN_OP_SOILEVAP_ROOT_CONSTRAIN, /* CmvSoilEvap          src/SoilEvaporation.cpp:598-622           */
+  RVN_OP_SOILEVAP_AWBM,        /* CmvSoilEvap             src/SoilEvaporation.cpp:716-727           */
   RVN_OP_COUNT
 } rvn_opcode;
 
@@ -139,7 +165,9 @@ typedef enum {
   RVN_LU_GAMMA_SHAPE, RVN_LU_GAMMA_SCALE, RVN_LU_GAMMA_SHAPE2, RVN_LU_GAMMA_SCALE2, RVN_LU_GR4J_X4,
   RVN_LU_HBV_MELT_FOR_CORR, RVN_LU_HBV_MELT_ASP_CORR, RVN_LU_HBV_MELT_GLACIER_CORR, RVN_LU_HBV_GLACIER_KMIN,
   RVN_LU_GLAC_STORAGE_COEFF, RVN_LU_HBV_GLACIER_AG, RVN_LU_DEP_MAX, RVN_LU_LAKE_PET_CORR, RVN_LU_OW_PET_CORR,
-  RVN_LU_PARTITION_COEFF, RVN_LU_CC_DECAY_COEFF, RVN_LU_COUNT
+  RVN_LU_PARTITION_COEFF, RVN_LU_CC_DECAY_COEFF, RVN_LU_MAX_SAT_AREA_FRAC, RVN_LU_PDM_B, RVN_LU_AET_COEFF,
+  RVN_LU_MAX_DEP_AREA_FRAC, RVN_LU_PONDED_EXP, RVN_LU_AWBM_AREAFRAC1, RVN_LU_AWBM_AREAFRAC2, RVN_LU_HYMOD2_G, RVN_LU_HYMOD2_KMAX,
+  RVN_LU_HYMOD2_EXP, RVN_LU_COUNT
 } rvn_landuse_field;
 typedef enum {
   RVN_V_MAX_HEIGHT = 0, RVN_V_MAX_LAI, RVN_V_SAI_HT_RATIO, RVN_V_MAX_CAPACITY, RVN_V_MAX_SNOW_CAPACITY,
@@ -152,7 +180,10 @@ typedef enum {
 typedef enum {
   RVN_S_POROSITY = 0, RVN_S_CAP_RATIO, RVN_S_PERC_COEFF, RVN_S_PET_CORRECTION, RVN_S_BASEFLOW_COEFF,
   RVN_S_BASEFLOW_N, RVN_S_FIELD_CAPACITY, RVN_S_SAT_WILT, RVN_S_HBV_BETA, RVN_S_MAX_CAP_RISE_RATE,
-  RVN_S_MAX_PERC_RATE, RVN_S_GR4J_X2, RVN_S_GR4J_X3, RVN_S_VIC_B_EXP, RVN_S_MAX_BASEFLOW_RATE, RVN_S_MAX_INTERFLOW_RATE, RVN_S_COUNT
+  RVN_S_MAX_PERC_RATE, RVN_S_GR4J_X2, RVN_S_GR4J_X3, RVN_S_VIC_B_EXP, RVN_S_MAX_BASEFLOW_RATE, RVN_S_MAX_INTERFLOW_RATE,
+  RVN_S_PERC_N, RVN_S_SAC_PERC_ALPHA, RVN_S_SAC_PERC_EXPON, RVN_S_PERC_ASPEN, RVN_S_BASEFLOW_THRESH, RVN_S_BASEFLOW_COEFF2,
+  RVN_S_STORAGE_THRESHOLD, RVN_S_VIC_ZMIN, RVN_S_VIC_ZMAX, RVN_S_VIC_ALPHA, RVN_S_VIC_EVAP_GAMMA, RVN_S_UBC_EVAP_SOIL_DEF,
+  RVN_S_UBC_INFIL_SOIL_DEF, RVN_S_COUNT
 } rvn_soil_field;
 typedef enum { RVN_T_TOPMODEL_LAMBDA = 0, RVN_T_COUNT } rvn_terrain_field;   /* reference terrain_struct, src/Properties.h */
 

@@ -462,7 +462,8 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       if (SWE <= 0.0) rates[4] = -sv[iFrom[4]] / tstep;
       break;
     }
-    case RVN_OP_INF_HMETS: case RVN_OP_INF_HBV: case RVN_OP_INF_GR4J: case RVN_OP_INF_VIC_ARNO: { /* src/Infiltration.cpp:304-330,384-398,477-489,491-514 + constraints :605-626 */
+    case RVN_OP_INF_HMETS: case RVN_OP_INF_HBV: case RVN_OP_INF_GR4J: case RVN_OP_INF_VIC_ARNO: case RVN_OP_INF_RATIONAL:
+    case RVN_OP_INF_ALL_INFILTRATES: case RVN_OP_INF_VIC: case RVN_OP_INF_PRMS: case RVN_OP_INF_PDM: { /* src/Infiltration.cpp:304-330,384-398,477-489,491-514 + constraints :605-626 */
       if (type != RVN_HRU_STANDARD && type != RVN_HRU_ROCK && type != RVN_HRU_MASKED_GLACIER) break;
       double Fimp = P_LU(c, RVN_LU_IMPERMEABLE_FRAC);
       double ponded = omax(sv[c->iSV[RVN_SV_PONDED_WATER]], 0.0);
@@ -490,6 +491,39 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
         double runoff = sat_area * rainthru;
         runoff = (Fimp)*rainthru + (1 - Fimp) * runoff;
         rates[0] = rainthru - runoff; rates[1] = runoff;
+      } else if (pr->op == RVN_OP_INF_RATIONAL) { /* :333-338 */
+        double runoff = P_LU(c, RVN_LU_PARTITION_COEFF) * rainthru;
+        rates[0] = rainthru - runoff; rates[1] = runoff;
+      } else if (pr->op == RVN_OP_INF_ALL_INFILTRATES) { /* :347-353 */
+        double runoff = 0.0;
+        runoff = (Fimp)*rainthru + (1 - Fimp) * runoff;
+        rates[0] = rainthru - runoff; rates[1] = runoff;
+      } else if (pr->op == RVN_OP_INF_VIC) { /* :361-383 */
+        int iTop = sv_index(d, RVN_SV_SOIL, 0);
+        double stor = sv[iTop], max_stor = soil_capacity(c, 0);
+        double zmax = P_S(c, 0, RVN_S_VIC_ZMAX), zmin = P_S(c, 0, RVN_S_VIC_ZMIN), alpha = P_S(c, 0, RVN_S_VIC_ALPHA);
+        double sat = omin(stor / max_stor, 1.0);
+        double gamma = 1.0 / (alpha + 1.0);
+        double K1 = pow((zmax - zmin) * alpha * gamma, -gamma);
+        double Smax = gamma * (alpha * zmax + zmin);
+        double runoff = rainthru * omax(1.0 - K1 * pow(Smax - sat, gamma), 1.0); /* threshMax(x,1.0,0.0) */
+        runoff = (Fimp)*rainthru + (1 - Fimp) * runoff;
+        rates[0] = rainthru - runoff; rates[1] = runoff;
+      } else if (pr->op == RVN_OP_INF_PRMS) { /* :418-431 */
+        int iTop = sv_index(d, RVN_SV_SOIL, 0);
+        double sat_frac = P_LU(c, RVN_LU_MAX_SAT_AREA_FRAC), tens_stor = soil_tension_capacity(c, 0), stor = sv[iTop];
+        double runoff = sat_frac * omin(stor / tens_stor, 1.0) * rainthru;
+        runoff = (Fimp)*rainthru + (1 - Fimp) * runoff;
+        rates[0] = rainthru - runoff; rates[1] = runoff;
+      } else if (pr->op == RVN_OP_INF_PDM) { /* :540-563 */
+        int iTop = sv_index(d, RVN_SV_SOIL, 0);
+        double b = P_LU(c, RVN_LU_PDM_B), stor = sv[iTop], max_stor = soil_capacity(c, 0);
+        double c_max = (b + 1) * max_stor;
+        double c_star = c_max * (1.0 - pow(1.0 - (stor / max_stor), 1.0 / (b + 1.0)));
+        double infil = max_stor * (pow(1.0 - (c_star / c_max), b + 1.0) - pow(1.0 - omin(c_star + ponded, c_max) / c_max, b + 1.0));
+        infil = omin(infil, ponded);
+        infil = (1.0 - Fimp) * infil / tstep;
+        rates[0] = infil; rates[1] = rainthru - infil;
       } else {
         double x1 = soil_capacity(c, 0), stor = sv[iTo[0]];
         double sat = stor / x1;
@@ -520,7 +554,8 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       rates[1] = (1.0 - pr->da[0]) * sv[iFrom[0]] / tstep;
       break;
     case RVN_OP_BASE_LINEAR: case RVN_OP_BASE_POWER_LAW: case RVN_OP_BASE_GR4J: case RVN_OP_BASE_LINEAR_ANALYTIC: case RVN_OP_BASE_VIC:
-    case RVN_OP_BASE_TOPMODEL: { /* src/Baseflow.cpp:152-186,208-215,238-243 + :297-310 */
+    case RVN_OP_BASE_TOPMODEL: case RVN_OP_BASE_LINEAR_CONSTRAIN: case RVN_OP_BASE_CONSTANT: case RVN_OP_BASE_THRESH_POWER:
+    case RVN_OP_BASE_THRESH_STOR: { /* src/Baseflow.cpp:152-186,208-215,238-243 + :297-310 */
       if (type == RVN_HRU_LAKE || type == RVN_HRU_WATER || type == RVN_HRU_ROCK) { /* GetRatesOfChange returns; constraints still run */ }
       else {
         int m = pr->ia[0];
@@ -539,6 +574,22 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
           int terr = d->hru_terrain ? d->hru_terrain[c->k] : -1;
           double lambda = c->ptab[d->terr_off + (terr >= 0 ? terr : 0) * RVN_T_COUNT + RVN_T_TOPMODEL_LAMBDA];
           rates[0] = K * (max_stor / n * pow(lambda, -n)) * pow(stor / max_stor, n);
+        } else if (pr->op == RVN_OP_BASE_LINEAR_CONSTRAIN) { /* :188-197 */
+          double K = P_S(c, m, RVN_S_BASEFLOW_COEFF), sat = stor / max_stor;
+          if (sat > P_S(c, m, RVN_S_FIELD_CAPACITY)) rates[0] = K * stor;
+        } else if (pr->op == RVN_OP_BASE_CONSTANT) { rates[0] = P_S(c, m, RVN_S_MAX_BASEFLOW_RATE);
+        } else if (pr->op == RVN_OP_BASE_THRESH_POWER) { /* :250-266 */
+          double K = P_S(c, m, RVN_S_MAX_BASEFLOW_RATE), n = P_S(c, m, RVN_S_BASEFLOW_N), tsat = P_S(c, m, RVN_S_BASEFLOW_THRESH);
+          double sat = stor / max_stor;
+          rates[0] = 0.0;
+          if (sat > tsat) {
+            rates[0] = K * pow((sat - tsat) / (1.0 - tsat), n);
+            rates[0] = omin(rates[0], max_stor * (sat - tsat) / tstep);
+          }
+        } else if (pr->op == RVN_OP_BASE_THRESH_STOR) { /* :268-279 */
+          double K = P_S(c, m, RVN_S_BASEFLOW_COEFF2), tstor = P_S(c, m, RVN_S_STORAGE_THRESHOLD);
+          rates[0] = 0.0;
+          if (stor > tstor) rates[0] = K * (stor - tstor);
         } else {
           double x3 = P_S(c, m, RVN_S_GR4J_X3);
           rates[0] = stor * (1.0 - pow(1.0 + pow(omax(stor / x3, 0.0), 4), -0.25)) / tstep;
@@ -548,7 +599,9 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       rates[0] = omax(rates[0], 0.0);
       break;
     }
-    case RVN_OP_PERC_LINEAR: case RVN_OP_PERC_CONSTANT: case RVN_OP_PERC_GR4J: case RVN_OP_PERC_GR4JEXCH: case RVN_OP_PERC_GR4JEXCH2: {
+    case RVN_OP_PERC_LINEAR: case RVN_OP_PERC_CONSTANT: case RVN_OP_PERC_GR4J: case RVN_OP_PERC_GR4JEXCH: case RVN_OP_PERC_GR4JEXCH2:
+    case RVN_OP_PERC_GAWSER: case RVN_OP_PERC_GAWSER_CONSTRAIN: case RVN_OP_PERC_POWER_LAW: case RVN_OP_PERC_LINEAR_ANALYTIC: case RVN_OP_PERC_PRMS:
+    case RVN_OP_PERC_SACRAMENTO: case RVN_OP_PERC_ASPEN: {
       /* src/Percolation.cpp:183-202,237-243,293-316 + :339-360 */
       if (type == RVN_HRU_LAKE || type == RVN_HRU_WATER || type == RVN_HRU_ROCK) break;
       int m = pr->ia[0];
@@ -557,7 +610,33 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
         if (pr->op == RVN_OP_PERC_LINEAR) rates[0] = P_S(c, m, RVN_S_PERC_COEFF) * stor;
         else if (pr->op == RVN_OP_PERC_CONSTANT) rates[0] = P_S(c, m, RVN_S_MAX_PERC_RATE);
         else if (pr->op == RVN_OP_PERC_GR4J) rates[0] = stor * (1.0 - pow(1.0 + pow(4.0 / 9.0 * omax(stor / max_stor, 0.0), 4), -0.25)) / tstep;
-        else if (pr->op == RVN_OP_PERC_GR4JEXCH) {
+        else if (pr->op == RVN_OP_PERC_GAWSER) { /* :204-213 */
+          double field_cap = P_S(c, m, RVN_S_FIELD_CAPACITY) * max_stor, max_rate = P_S(c, m, RVN_S_MAX_PERC_RATE);
+          rates[0] = max_rate * omax(stor - field_cap, 0.0) / (max_stor - field_cap);
+        } else if (pr->op == RVN_OP_PERC_GAWSER_CONSTRAIN) { /* :215-226 */
+          double field_cap = P_S(c, m, RVN_S_FIELD_CAPACITY) * max_stor, max_rate = P_S(c, m, RVN_S_MAX_PERC_RATE);
+          rates[0] = 0.0;
+          if (stor > field_cap) {
+            rates[0] = max_rate * omax(stor - field_cap, 0.0) / (max_stor - field_cap);
+            rates[0] = omin(rates[0], (stor - field_cap) / tstep);
+          }
+        } else if (pr->op == RVN_OP_PERC_POWER_LAW) { rates[0] = P_S(c, m, RVN_S_MAX_PERC_RATE) * pow(stor / max_stor, P_S(c, m, RVN_S_PERC_N));
+        } else if (pr->op == RVN_OP_PERC_LINEAR_ANALYTIC) { rates[0] = stor * (1 - exp(-P_S(c, m, RVN_S_PERC_COEFF) * tstep)) / tstep;
+        } else if (pr->op == RVN_OP_PERC_PRMS) { /* :253-267 */
+          double tens_stor = soil_tension_capacity(c, m), max_rate = P_S(c, m, RVN_S_MAX_PERC_RATE), n = P_S(c, m, RVN_S_PERC_N);
+          double free_stor = omax(0.0, stor - tens_stor), free_stor_max = (max_stor - tens_stor);
+          rates[0] = max_rate * pow(free_stor / free_stor_max, n);
+        } else if (pr->op == RVN_OP_PERC_SACRAMENTO) { /* :269-294 */
+          int m2 = pr->ia[1];
+          double stor2 = sv[iTo[0]], tens_stor = soil_tension_capacity(c, m);
+          double psi = P_S(c, m2, RVN_S_SAC_PERC_EXPON), alpha = P_S(c, m2, RVN_S_SAC_PERC_ALPHA);
+          double max_stor2 = (m == 0) ? soil_capacity(c, m2) : 1e99;
+          double free_stor = omax(0.0, stor - tens_stor), free_stor_max = (max_stor - tens_stor);
+          double max_baseflow = P_S(c, m, RVN_S_MAX_BASEFLOW_RATE);
+          double lz_perc = 1.0 + alpha * pow((1 - (stor2 / max_stor2)), psi);
+          rates[0] = lz_perc * max_baseflow * (free_stor / free_stor_max);
+        } else if (pr->op == RVN_OP_PERC_ASPEN) { rates[0] = P_S(c, m, RVN_S_PERC_ASPEN);
+        } else if (pr->op == RVN_OP_PERC_GR4JEXCH) {
           double x2 = P_S(c, m, RVN_S_GR4J_X2), x3 = P_S(c, m, RVN_S_GR4J_X3);
           rates[0] = -x2 * pow(omax(omin(stor / x3, 1.0), 0.0), 3.5);
         } else {
@@ -573,10 +652,13 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       }
       break;
     }
-    case RVN_OP_SOILEVAP_ALL: case RVN_OP_SOILEVAP_HBV: case RVN_OP_SOILEVAP_GR4J: case RVN_OP_SOILEVAP_TOPMODEL: { /* src/SoilEvaporation.cpp:325-343,379-405,640-650 + :767-783 */
+    case RVN_OP_SOILEVAP_ALL: case RVN_OP_SOILEVAP_HBV: case RVN_OP_SOILEVAP_GR4J: case RVN_OP_SOILEVAP_TOPMODEL:
+    case RVN_OP_SOILEVAP_LINEAR: case RVN_OP_SOILEVAP_PDM: case RVN_OP_SOILEVAP_HYMOD2: case RVN_OP_SOILEVAP_UBC: case RVN_OP_SOILEVAP_VIC:
+    case RVN_OP_SOILEVAP_HYPR: case RVN_OP_SOILEVAP_SEQUEN: case RVN_OP_SOILEVAP_ROOT: case RVN_OP_SOILEVAP_ROOT_CONSTRAIN: case RVN_OP_SOILEVAP_AWBM: { /* src/SoilEvaporation.cpp:325-343,379-405,640-650 + :767-783 */
       if (type != RVN_HRU_STANDARD) break;
       double PET = F[RVN_F_PET];
       if (!d->opt.suppress_competitive_ET) { PET -= (sv[c->iSV[RVN_SV_AET]] / tstep); PET = omax(PET, 0.0); }
+      double PETused = 0.0; int multi = 0;
       if (pr->op == RVN_OP_SOILEVAP_ALL) rates[0] = PET;
       else if (pr->op == RVN_OP_SOILEVAP_HBV || pr->op == RVN_OP_SOILEVAP_TOPMODEL) {
         double stor = omax(sv[iFrom[0]], 0.0), tens_stor = soil_tension_capacity(c, 0);
@@ -586,13 +668,82 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
           double Fc = P_LU(c, RVN_LU_FOREST_COVERAGE);
           if ((iSnow >= 0) && (sv[iSnow] > O_REAL_SMALL)) rates[0] = (Fc)*rates[0];
         }
-      } else {
+      } else if (pr->op == RVN_OP_SOILEVAP_GR4J) {
         double max_stor = soil_capacity(c, 0), stor = sv[iFrom[0]];
         double sat = stor / max_stor;
         double tmp = tanh(omax(PET, 0.0) / max_stor);
         rates[0] = stor * (2.0 - sat) * tmp / (1.0 + (1.0 - sat) * tmp);
+      } else if (pr->op == RVN_OP_SOILEVAP_HYPR) { /* :385-420 */
+        double stor = omax(sv[iFrom[0]], 0.0), tens_stor = soil_tension_capacity(c, 0);
+        rates[0] = PET * omin(stor / tens_stor, 1.0);
+        int iDep = c->iSV[RVN_SV_DEPRESSION];
+        double maxPondedAreaFrac = P_LU(c, RVN_LU_MAX_DEP_AREA_FRAC), n = P_LU(c, RVN_LU_PONDED_EXP), dep_max = P_LU(c, RVN_LU_DEP_MAX);
+        double area_ponded = maxPondedAreaFrac * pow(omin(sv[iDep] / dep_max, 1.0), n);
+        rates[0] = (1.0 - area_ponded) * rates[0];
+        rates[1] = (area_ponded)*F[RVN_F_OW_PET];
+        PETused = (rates[0] + rates[1]); multi = 1;
+      } else if (pr->op == RVN_OP_SOILEVAP_LINEAR) { /* :370-377 */
+        double stor = sv[iFrom[0]], alpha = P_LU(c, RVN_LU_AET_COEFF);
+        rates[0] = omin(alpha * stor, PET);
+      } else if (pr->op == RVN_OP_SOILEVAP_PDM || pr->op == RVN_OP_SOILEVAP_HYMOD2) { /* :424-458 */
+        double stor = sv[iFrom[0]], max_stor = soil_capacity(c, 0), b = P_LU(c, RVN_LU_PDM_B);
+        double c_max = (b + 1) * max_stor;
+        double c_star = c_max * (1.0 - pow(1.0 - (stor / max_stor), 1.0 / (b + 1.0)));
+        if (pr->op == RVN_OP_SOILEVAP_PDM) rates[0] = omin(c_star, (c_star / c_max) * PET);
+        else {
+          double gp = P_LU(c, RVN_LU_HYMOD2_G), Kmax = P_LU(c, RVN_LU_HYMOD2_KMAX), ce = P_LU(c, RVN_LU_HYMOD2_EXP);
+          double K = Kmax * (gp + (1 - gp) * pow(c_star / c_max, ce));
+          rates[0] = K * omin(c_star, PET);
+        }
+      } else if (pr->op == RVN_OP_SOILEVAP_UBC) { /* :470-494 */
+        double P0AGEN = P_S(c, 0, RVN_S_UBC_INFIL_SOIL_DEF), P0EGEN = P_S(c, 0, RVN_S_UBC_EVAP_SOIL_DEF);
+        double soil_deficit = omax(soil_capacity(c, 0) - sv[iFrom[0]], 0.0);
+        double Fimp = P_LU(c, RVN_LU_IMPERMEABLE_FRAC);
+        double AET = (PET)*pow(10.0, -soil_deficit / P0EGEN);
+        double total_precip = sv[c->iSV[RVN_SV_PONDED_WATER]];
+        double soil_deficit_est = omax(soil_deficit - total_precip + AET * tstep, 0.0);
+        double b1 = 0.0;
+        if (Fimp < 1.0) b1 = Fimp * pow(10.0, -soil_deficit_est / P0AGEN);
+        rates[0] = (PET)*pow(10.0, -soil_deficit_est / P0EGEN) * (1.0 - b1);
+      } else if (pr->op == RVN_OP_SOILEVAP_VIC) { /* :496-515 */
+        double stor = sv[iFrom[0]], stor_max = soil_capacity(c, 0);
+        double alpha = P_S(c, 0, RVN_S_VIC_ALPHA), zmax = P_S(c, 0, RVN_S_VIC_ZMAX), zmin = P_S(c, 0, RVN_S_VIC_ZMIN), gamma2 = P_S(c, 0, RVN_S_VIC_EVAP_GAMMA);
+        double Smax = 1.0 / (alpha + 1.0) * (alpha * zmax + zmin);
+        double Sat = stor / stor_max;
+        rates[0] = PET * (1.0 - pow(1.0 - Sat / Smax, gamma2));
+      } else if (pr->op == RVN_OP_SOILEVAP_SEQUEN) { /* :553-568 */
+        double stor_u = omax(sv[iFrom[0]], 0.0), stor_l = omax(sv[iFrom[1]], 0.0);
+        double tens_stor_u = soil_tension_capacity(c, 0), tens_stor_l = soil_tension_capacity(c, 1);
+        rates[0] = (PET)*omin(stor_u / tens_stor_u, 1.0);
+        rates[1] = (PET - rates[0]) * omin(stor_l / tens_stor_l, 1.0);
+        PETused = rates[0] + rates[1]; multi = 1;
+      } else if (pr->op == RVN_OP_SOILEVAP_ROOT) { /* :570-596 */
+        double rootfrac_u = 0.7, rootfrac_l = 1.0 - rootfrac_u;
+        double stor_u = sv[iFrom[0]];
+        double tens_stor_u = soil_tension_capacity(c, 0); tens_stor_u = omax(0.0001, tens_stor_u);
+        rates[0] = PET * rootfrac_u * omin(stor_u / tens_stor_u, 1.0);
+        double stor_l = sv[iFrom[1]];
+        double tens_stor_l = soil_tension_capacity(c, 1); tens_stor_l = omax(0.0001, tens_stor_l);
+        rates[1] = PET * rootfrac_l * omin(stor_l / tens_stor_l, 1.0);
+        PETused = rates[0] + rates[1]; multi = 1;
+      } else if (pr->op == RVN_OP_SOILEVAP_ROOT_CONSTRAIN) { /* :598-622 */
+        double rootfrac_u = 0.7;
+        double stor_u = sv[iFrom[0]], tens_stor_u = soil_tension_capacity(c, 0);
+        double stor_wilt = P_S(c, 0, RVN_S_SAT_WILT) * soil_capacity(c, 0);
+        rates[0] = PET * rootfrac_u * omin(stor_u / tens_stor_u, 1.0);
+        if (rates[0] > omax(stor_u - stor_wilt, 0.0)) rates[0] = omax(stor_u - stor_wilt, 0.0);
+        double rootfrac_l = 1.0 - rootfrac_u;
+        rates[1] = PET * rootfrac_l * 1;
+        PETused = rates[0] + rates[1]; multi = 1;
+      } else if (pr->op == RVN_OP_SOILEVAP_AWBM) { /* :716-727 */
+        double a1 = P_LU(c, RVN_LU_AWBM_AREAFRAC1), a2 = P_LU(c, RVN_LU_AWBM_AREAFRAC2);
+        double a3 = 1.0 - a1 - a2;
+        rates[0] = omin(a1 * PET, sv[iFrom[0]] / tstep);
+        rates[1] = omin(a2 * PET, sv[iFrom[1]] / tstep);
+        rates[2] = omin(a3 * PET, sv[iFrom[2]] / tstep);
+        PETused = rates[0] + rates[1] + rates[2]; multi = 1;
       }
-      rates[pr->nconn - 1] = rates[0]; /* PETused -> AET (src/SoilEvaporation.cpp end of GetRatesOfChange) */
+      rates[pr->nconn - 1] = multi ? PETused : rates[0]; /* PETused -> AET (src/SoilEvaporation.cpp end of GetRatesOfChange) */
       double corr = 0, oldrate;
       for (int q = 0; q < pr->nconn - 1; q++) {
         oldrate = rates[q];

@@ -288,6 +288,36 @@ template <class C, class PR> RVN_DI void rates_INFILTRATION(C &c, const PR &pr, 
     double runoff = sat_area * rainthru;
     runoff = (Fimp)*rainthru + (1 - Fimp) * runoff;
     c.R(0) = rainthru - runoff; c.R(1) = runoff;
+  } else if (op == RVN_OP_INF_RATIONAL) {   // src/Infiltration.cpp:333-338 (no impermeable-fraction correction in the reference)
+    double runoff = c.LU(RVN_LU_PARTITION_COEFF) * rainthru;
+    c.R(0) = rainthru - runoff; c.R(1) = runoff;
+  } else if (op == RVN_OP_INF_ALL_INFILTRATES) {   // :347-353
+    double runoff = 0.0;
+    runoff = (Fimp)*rainthru + (1 - Fimp) * runoff;
+    c.R(0) = rainthru - runoff; c.R(1) = runoff;
+  } else if (op == RVN_OP_INF_VIC) {   // :361-383
+    double stor = c.SV(c.soil_slot(0)), max_stor = SoilCapacity(c, 0);
+    double zmax = c.SOIL(0, RVN_S_VIC_ZMAX), zmin = c.SOIL(0, RVN_S_VIC_ZMIN), alpha = c.SOIL(0, RVN_S_VIC_ALPHA);
+    double sat = dmin(stor / max_stor, 1.0);
+    double gamma = 1.0 / (alpha + 1.0);
+    double K1 = pow((zmax - zmin) * alpha * gamma, -gamma);
+    double Smax = gamma * (alpha * zmax + zmin);
+    double runoff = rainthru * dmax(1.0 - K1 * pow(Smax - sat, gamma), 1.0);   // threshMax(.,1.0,0.0) as written in the reference
+    runoff = (Fimp)*rainthru + (1 - Fimp) * runoff;
+    c.R(0) = rainthru - runoff; c.R(1) = runoff;
+  } else if (op == RVN_OP_INF_PRMS) {   // :418-431
+    double sat_frac = c.LU(RVN_LU_MAX_SAT_AREA_FRAC), tens_stor = SoilTensionCapacity(c, 0), stor = c.SV(c.soil_slot(0));
+    double runoff = sat_frac * dmin(stor / tens_stor, 1.0) * rainthru;
+    runoff = (Fimp)*rainthru + (1 - Fimp) * runoff;
+    c.R(0) = rainthru - runoff; c.R(1) = runoff;
+  } else if (op == RVN_OP_INF_PDM) {   // :540-563 (Moore 1985)
+    double b = c.LU(RVN_LU_PDM_B), stor = c.SV(c.soil_slot(0)), max_stor = SoilCapacity(c, 0);
+    double c_max = (b + 1) * max_stor;
+    double c_star = c_max * (1.0 - pow(1.0 - (stor / max_stor), 1.0 / (b + 1.0)));
+    double infil = max_stor * (pow(1.0 - (c_star / c_max), b + 1.0) - pow(1.0 - dmin(c_star + ponded, c_max) / c_max, b + 1.0));
+    infil = dmin(infil, ponded);
+    infil = (1.0 - Fimp) * infil / tstep;
+    c.R(0) = infil; c.R(1) = rainthru - infil;
   } else if (op == RVN_OP_INF_GR4J) {
     double x1 = SoilCapacity(c, 0), stor = c.SV(pr.to(0));
     double sat = stor / x1;
@@ -334,6 +364,25 @@ template <class C, class PR> RVN_DI void rates_BASEFLOW(C &c, const PR &pr, cons
       const double K = c.SOIL(m, RVN_S_MAX_BASEFLOW_RATE), n = c.SOIL(m, RVN_S_BASEFLOW_N), lambda = c.TERR(RVN_T_TOPMODEL_LAMBDA);
       c.R(0) = K * (max_stor / n * pow(lambda, -n)) * pow(stor / max_stor, n);
     }
+    else if (op == RVN_OP_BASE_LINEAR_CONSTRAIN) {   // src/Baseflow.cpp:188-197
+      const double sat = stor / max_stor;
+      if (sat > c.SOIL(m, RVN_S_FIELD_CAPACITY)) c.R(0) = c.SOIL(m, RVN_S_BASEFLOW_COEFF) * stor;
+    }
+    else if (op == RVN_OP_BASE_CONSTANT) c.R(0) = c.SOIL(m, RVN_S_MAX_BASEFLOW_RATE);
+    else if (op == RVN_OP_BASE_THRESH_POWER) {   // :250-266
+      const double K = c.SOIL(m, RVN_S_MAX_BASEFLOW_RATE), n = c.SOIL(m, RVN_S_BASEFLOW_N), tsat = c.SOIL(m, RVN_S_BASEFLOW_THRESH);
+      const double sat = stor / max_stor;
+      c.R(0) = 0.0;
+      if (sat > tsat) {
+        c.R(0) = K * pow((sat - tsat) / (1.0 - tsat), n);
+        c.R(0) = dmin(c.R(0), max_stor * (sat - tsat) / c.tstep);
+      }
+    }
+    else if (op == RVN_OP_BASE_THRESH_STOR) {   // :268-279
+      const double K = c.SOIL(m, RVN_S_BASEFLOW_COEFF2), tstor = c.SOIL(m, RVN_S_STORAGE_THRESHOLD);
+      c.R(0) = 0.0;
+      if (stor > tstor) c.R(0) = K * (stor - tstor);
+    }
     else if (op == RVN_OP_BASE_GR4J) {
       const double x3 = c.SOIL(m, RVN_S_GR4J_X3);
       c.R(0) = stor * (1.0 - pow(1.0 + pow(dmax(stor / x3, 0.0), 4.0), -0.25)) / c.tstep;
@@ -353,6 +402,32 @@ template <class C, class PR> RVN_DI void rates_PERCOLATION(C &c, const PR &pr, c
     if (op == RVN_OP_PERC_LINEAR) c.R(0) = c.SOIL(m, RVN_S_PERC_COEFF) * stor;
     else if (op == RVN_OP_PERC_CONSTANT) c.R(0) = c.SOIL(m, RVN_S_MAX_PERC_RATE);
     else if (op == RVN_OP_PERC_GR4J) c.R(0) = stor * (1.0 - pow(1.0 + pow(4.0 / 9.0 * dmax(stor / max_stor, 0.0), 4.0), -0.25)) / c.tstep;
+    else if (op == RVN_OP_PERC_GAWSER) {   // src/Percolation.cpp:204-213
+      const double field_cap = c.SOIL(m, RVN_S_FIELD_CAPACITY) * max_stor, max_rate = c.SOIL(m, RVN_S_MAX_PERC_RATE);
+      c.R(0) = max_rate * dmax(stor - field_cap, 0.0) / (max_stor - field_cap);
+    } else if (op == RVN_OP_PERC_GAWSER_CONSTRAIN) {   // :215-226
+      const double field_cap = c.SOIL(m, RVN_S_FIELD_CAPACITY) * max_stor, max_rate = c.SOIL(m, RVN_S_MAX_PERC_RATE);
+      c.R(0) = 0.0;
+      if (stor > field_cap) {
+        c.R(0) = max_rate * dmax(stor - field_cap, 0.0) / (max_stor - field_cap);
+        c.R(0) = dmin(c.R(0), (stor - field_cap) / c.tstep);
+      }
+    } else if (op == RVN_OP_PERC_POWER_LAW) c.R(0) = c.SOIL(m, RVN_S_MAX_PERC_RATE) * pow(stor / max_stor, c.SOIL(m, RVN_S_PERC_N));
+    else if (op == RVN_OP_PERC_LINEAR_ANALYTIC) c.R(0) = stor * (1 - exp(-c.SOIL(m, RVN_S_PERC_COEFF) * c.tstep)) / c.tstep;
+    else if (op == RVN_OP_PERC_PRMS) {   // :253-267
+      const double tens_stor = SoilTensionCapacity(c, m), max_rate = c.SOIL(m, RVN_S_MAX_PERC_RATE), n = c.SOIL(m, RVN_S_PERC_N);
+      const double free_stor = dmax(0.0, stor - tens_stor), free_stor_max = (max_stor - tens_stor);
+      c.R(0) = max_rate * pow(free_stor / free_stor_max, n);
+    } else if (op == RVN_OP_PERC_SACRAMENTO) {   // :269-294
+      const int m2 = pr.ia(1);
+      const double stor2 = c.SV(pr.to(0)), tens_stor = SoilTensionCapacity(c, m);
+      const double psi = c.SOIL(m2, RVN_S_SAC_PERC_EXPON), alpha = c.SOIL(m2, RVN_S_SAC_PERC_ALPHA);
+      const double max_stor2 = (m == 0) ? SoilCapacity(c, m2) : D_ALMOST_INF;
+      const double free_stor = dmax(0.0, stor - tens_stor), free_stor_max = (max_stor - tens_stor);
+      const double max_baseflow = c.SOIL(m, RVN_S_MAX_BASEFLOW_RATE);
+      const double lz_perc = 1.0 + alpha * pow((1 - (stor2 / max_stor2)), psi);
+      c.R(0) = lz_perc * max_baseflow * (free_stor / free_stor_max);
+    } else if (op == RVN_OP_PERC_ASPEN) c.R(0) = c.SOIL(m, RVN_S_PERC_ASPEN);
     else if (op == RVN_OP_PERC_GR4JEXCH) {
       const double x2 = c.SOIL(m, RVN_S_GR4J_X2), x3 = c.SOIL(m, RVN_S_GR4J_X3);
       c.R(0) = -x2 * pow(dmax(dmin(stor / x3, 1.0), 0.0), 3.5);
@@ -384,6 +459,7 @@ template <class C, class PR> RVN_DI void rates_SOILEVAP(C &c, const PR &pr, cons
   if (c.type != RVN_HRU_STANDARD) return;
   double PET = c.F[RVN_F_PET];
   if (!c.opt().suppress_competitive_ET) { PET -= (c.SV(c.iSV(RVN_SV_AET)) / c.tstep); PET = dmax(PET, 0.0); }
+  double PETused = 0.0; bool multi = false;   // several evaporating stores: PETused is their sum (last connection = AET)
   if (op == RVN_OP_SOILEVAP_ALL) c.R(0) = PET;
   else if (op == RVN_OP_SOILEVAP_HBV || op == RVN_OP_SOILEVAP_TOPMODEL) {
     const double stor = dmax(c.SV(pr.from(0)), 0.0), tens_stor = SoilTensionCapacity(c, 0);
@@ -395,9 +471,76 @@ template <class C, class PR> RVN_DI void rates_SOILEVAP(C &c, const PR &pr, cons
     const double sat = stor / max_stor;
     const double tmp = tanh(dmax(PET, 0.0) / max_stor);
     c.R(0) = stor * (2.0 - sat) * tmp / (1.0 + (1.0 - sat) * tmp);
+  } else if (op == RVN_OP_SOILEVAP_HYPR) {   // src/SoilEvaporation.cpp:385-420 (Ahmed et al. 2020)
+    const double stor = dmax(c.SV(pr.from(0)), 0.0), tens_stor = SoilTensionCapacity(c, 0);
+    c.R(0) = PET * dmin(stor / tens_stor, 1.0);
+    const double maxPondedAreaFrac = c.LU(RVN_LU_MAX_DEP_AREA_FRAC), n = c.LU(RVN_LU_PONDED_EXP), dep_max = c.LU(RVN_LU_DEP_MAX);
+    const double area_ponded = maxPondedAreaFrac * pow(dmin(c.SV(c.iSV(RVN_SV_DEPRESSION)) / dep_max, 1.0), n);
+    c.R(0) = (1.0 - area_ponded) * c.R(0);
+    c.R(1) = (area_ponded)*c.F[RVN_F_OW_PET];
+    PETused = (c.R(0) + c.R(1)); multi = true;
+  } else if (op == RVN_OP_SOILEVAP_LINEAR) {   // :370-377
+    c.R(0) = dmin(c.LU(RVN_LU_AET_COEFF) * c.SV(pr.from(0)), PET);
+  } else if (op == RVN_OP_SOILEVAP_PDM || op == RVN_OP_SOILEVAP_HYMOD2) {   // :424-458
+    const double stor = c.SV(pr.from(0)), max_stor = SoilCapacity(c, 0), b = c.LU(RVN_LU_PDM_B);
+    const double c_max = (b + 1) * max_stor;
+    const double c_star = c_max * (1.0 - pow(1.0 - (stor / max_stor), 1.0 / (b + 1.0)));
+    if (op == RVN_OP_SOILEVAP_PDM) c.R(0) = dmin(c_star, (c_star / c_max) * PET);
+    else {
+      const double gp = c.LU(RVN_LU_HYMOD2_G), Kmax = c.LU(RVN_LU_HYMOD2_KMAX), ce = c.LU(RVN_LU_HYMOD2_EXP);
+      const double K = Kmax * (gp + (1 - gp) * pow(c_star / c_max, ce));
+      c.R(0) = K * dmin(c_star, PET);
+    }
+  } else if (op == RVN_OP_SOILEVAP_UBC) {   // :470-494 (Quick 1995, RFS emulation)
+    const double P0AGEN = c.SOIL(0, RVN_S_UBC_INFIL_SOIL_DEF), P0EGEN = c.SOIL(0, RVN_S_UBC_EVAP_SOIL_DEF);
+    const double soil_deficit = dmax(SoilCapacity(c, 0) - c.SV(pr.from(0)), 0.0);
+    const double Fimp = c.LU(RVN_LU_IMPERMEABLE_FRAC);
+    const double AET = (PET)*pow(10.0, -soil_deficit / P0EGEN);
+    const double total_precip = c.SV(c.iSV(RVN_SV_PONDED_WATER));
+    const double soil_deficit_est = dmax(soil_deficit - total_precip + AET * c.tstep, 0.0);
+    double b1 = 0.0;
+    if (Fimp < 1.0) b1 = Fimp * pow(10.0, -soil_deficit_est / P0AGEN);
+    c.R(0) = (PET)*pow(10.0, -soil_deficit_est / P0EGEN) * (1.0 - b1);
+  } else if (op == RVN_OP_SOILEVAP_VIC) {   // :496-515 (Woods et al. 1992)
+    const double stor = c.SV(pr.from(0)), stor_max = SoilCapacity(c, 0);
+    const double alpha = c.SOIL(0, RVN_S_VIC_ALPHA), zmax = c.SOIL(0, RVN_S_VIC_ZMAX), zmin = c.SOIL(0, RVN_S_VIC_ZMIN), gamma2 = c.SOIL(0, RVN_S_VIC_EVAP_GAMMA);
+    const double Smax = 1.0 / (alpha + 1.0) * (alpha * zmax + zmin);
+    const double Sat = stor / stor_max;
+    c.R(0) = PET * (1.0 - pow(1.0 - Sat / Smax, gamma2));
+  } else if (op == RVN_OP_SOILEVAP_SEQUEN) {   // :553-568
+    const double stor_u = dmax(c.SV(pr.from(0)), 0.0), stor_l = dmax(c.SV(pr.from(1)), 0.0);
+    const double tens_stor_u = SoilTensionCapacity(c, 0), tens_stor_l = SoilTensionCapacity(c, 1);
+    c.R(0) = (PET)*dmin(stor_u / tens_stor_u, 1.0);
+    c.R(1) = (PET - c.R(0)) * dmin(stor_l / tens_stor_l, 1.0);
+    PETused = c.R(0) + c.R(1); multi = true;
+  } else if (op == RVN_OP_SOILEVAP_ROOT) {   // :570-596
+    const double rootfrac_u = 0.7, rootfrac_l = 1.0 - rootfrac_u;
+    const double stor_u = c.SV(pr.from(0));
+    double tens_stor_u = SoilTensionCapacity(c, 0); tens_stor_u = dmax(0.0001, tens_stor_u);
+    c.R(0) = PET * rootfrac_u * dmin(stor_u / tens_stor_u, 1.0);
+    const double stor_l = c.SV(pr.from(1));
+    double tens_stor_l = SoilTensionCapacity(c, 1); tens_stor_l = dmax(0.0001, tens_stor_l);
+    c.R(1) = PET * rootfrac_l * dmin(stor_l / tens_stor_l, 1.0);
+    PETused = c.R(0) + c.R(1); multi = true;
+  } else if (op == RVN_OP_SOILEVAP_ROOT_CONSTRAIN) {   // :598-622
+    const double rootfrac_u = 0.7;
+    const double stor_u = c.SV(pr.from(0)), tens_stor_u = SoilTensionCapacity(c, 0);
+    const double stor_wilt = c.SOIL(0, RVN_S_SAT_WILT) * SoilCapacity(c, 0);
+    c.R(0) = PET * rootfrac_u * dmin(stor_u / tens_stor_u, 1.0);
+    if (c.R(0) > dmax(stor_u - stor_wilt, 0.0)) c.R(0) = dmax(stor_u - stor_wilt, 0.0);
+    const double rootfrac_l = 1.0 - rootfrac_u;
+    c.R(1) = PET * rootfrac_l * 1;
+    PETused = c.R(0) + c.R(1); multi = true;
+  } else if (op == RVN_OP_SOILEVAP_AWBM) {   // :716-727 (Boughton 2004)
+    const double a1 = c.LU(RVN_LU_AWBM_AREAFRAC1), a2 = c.LU(RVN_LU_AWBM_AREAFRAC2);
+    const double a3 = 1.0 - a1 - a2;
+    c.R(0) = dmin(a1 * PET, c.SV(pr.from(0)) / c.tstep);
+    c.R(1) = dmin(a2 * PET, c.SV(pr.from(1)) / c.tstep);
+    c.R(2) = dmin(a3 * PET, c.SV(pr.from(2)) / c.tstep);
+    PETused = c.R(0) + c.R(1) + c.R(2); multi = true;
   }
   const int last = pr.nconn() - 1;
-  c.R(last) = c.R(0);
+  c.R(last) = multi ? PETused : c.R(0);
   double corr = 0;
 #pragma unroll
   for (int q = 0; q < last; q++) {
@@ -462,7 +605,8 @@ template <class C, class PR> RVN_DI void dispatch_rates(C &c, const PR &pr, cons
     case RVN_OP_SNOBAL_CEMA_NEIGE: rates_SNOBAL_CEMA_NEIGE(c, pr); break;
     case RVN_OP_SNOWREFREEZE_DD: rates_SNOWREFREEZE_DD(c, pr); break;
     case RVN_OP_SNOTEMP_NEWTONS: rates_SNOTEMP_NEWTONS(c, pr); break;
-    case RVN_OP_INF_HMETS: case RVN_OP_INF_HBV: case RVN_OP_INF_GR4J: case RVN_OP_INF_VIC_ARNO: rates_INFILTRATION(c, pr, op); break;
+    case RVN_OP_INF_HMETS: case RVN_OP_INF_HBV: case RVN_OP_INF_GR4J: case RVN_OP_INF_VIC_ARNO: case RVN_OP_INF_RATIONAL:
+    case RVN_OP_INF_ALL_INFILTRATES: case RVN_OP_INF_VIC: case RVN_OP_INF_PRMS: case RVN_OP_INF_PDM: rates_INFILTRATION(c, pr, op); break;
     case RVN_OP_SNOBAL_HBV: rates_SNOBAL_HBV(c, pr); break;
     case RVN_OP_INTERFLOW_PRMS: rates_INTERFLOW_PRMS(c, pr); break;
     case RVN_OP_SNOWMELT_POTMELT: rates_SNOWMELT_POTMELT(c, pr); break;
@@ -471,10 +615,15 @@ template <class C, class PR> RVN_DI void dispatch_rates(C &c, const PR &pr, cons
     case RVN_OP_FLUSH: rates_FLUSH(c, pr); break;
     case RVN_OP_SPLIT: rates_SPLIT(c, pr); break;
     case RVN_OP_BASE_LINEAR: case RVN_OP_BASE_POWER_LAW: case RVN_OP_BASE_GR4J: case RVN_OP_BASE_LINEAR_ANALYTIC: case RVN_OP_BASE_VIC:
-    case RVN_OP_BASE_TOPMODEL: rates_BASEFLOW(c, pr, op); break;
+    case RVN_OP_BASE_TOPMODEL: case RVN_OP_BASE_LINEAR_CONSTRAIN: case RVN_OP_BASE_CONSTANT: case RVN_OP_BASE_THRESH_POWER:
+    case RVN_OP_BASE_THRESH_STOR: rates_BASEFLOW(c, pr, op); break;
     case RVN_OP_PERC_LINEAR: case RVN_OP_PERC_CONSTANT: case RVN_OP_PERC_GR4J: case RVN_OP_PERC_GR4JEXCH: case RVN_OP_PERC_GR4JEXCH2:
-      rates_PERCOLATION(c, pr, op); break;
-    case RVN_OP_SOILEVAP_ALL: case RVN_OP_SOILEVAP_HBV: case RVN_OP_SOILEVAP_GR4J: case RVN_OP_SOILEVAP_TOPMODEL: rates_SOILEVAP(c, pr, op); break;
+    case RVN_OP_PERC_GAWSER: case RVN_OP_PERC_GAWSER_CONSTRAIN: case RVN_OP_PERC_POWER_LAW: case RVN_OP_PERC_LINEAR_ANALYTIC: case RVN_OP_PERC_PRMS:
+    case RVN_OP_PERC_SACRAMENTO: case RVN_OP_PERC_ASPEN: rates_PERCOLATION(c, pr, op); break;
+    case RVN_OP_SOILEVAP_ALL: case RVN_OP_SOILEVAP_HBV: case RVN_OP_SOILEVAP_GR4J: case RVN_OP_SOILEVAP_TOPMODEL:
+    case RVN_OP_SOILEVAP_LINEAR: case RVN_OP_SOILEVAP_PDM: case RVN_OP_SOILEVAP_HYMOD2: case RVN_OP_SOILEVAP_UBC: case RVN_OP_SOILEVAP_VIC:
+    case RVN_OP_SOILEVAP_HYPR: case RVN_OP_SOILEVAP_SEQUEN: case RVN_OP_SOILEVAP_ROOT: case RVN_OP_SOILEVAP_ROOT_CONSTRAIN: case RVN_OP_SOILEVAP_AWBM:
+      rates_SOILEVAP(c, pr, op); break;
     case RVN_OP_CANEVP_ALL: rates_CANEVP_ALL(c, pr); break;
     case RVN_OP_CANSNOWEVP_ALL: rates_CANSNOWEVP_ALL(c, pr); break;
     case RVN_OP_OPEN_WATER_EVAP: rates_OPEN_WATER_EVAP(c, pr); break;

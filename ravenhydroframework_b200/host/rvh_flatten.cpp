@@ -162,6 +162,45 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
     if (d.proc[r].op == RVN_OP_BASE_TOPMODEL)
       for (int k = 0; k < nH; k++)
         ExitGracefullyIf(_pHydroUnits[k]->terrain_class < 0 && ((_f_mask[k] >> r) & 1ull), "CModel::Flatten: BASE_TOPMODEL needs a terrain class (TOPMODEL_LAMBDA) for every HRU it applies to");
+  // class parameters an algorithm needs must have been given (reference: "required parameter not specified" from
+  // CSoilClass / CLandUseClass::AutoCalculate*Props fed by each process's GetParticipatingParamList)
+  {
+    struct Need { int op; char cls; int f[5]; };
+    static const Need needs[] = {
+      {RVN_OP_BASE_CONSTANT, 'S', {RVN_S_MAX_BASEFLOW_RATE, -1}}, {RVN_OP_BASE_LINEAR_CONSTRAIN, 'S', {RVN_S_BASEFLOW_COEFF, RVN_S_FIELD_CAPACITY, -1}},
+      {RVN_OP_BASE_THRESH_POWER, 'S', {RVN_S_MAX_BASEFLOW_RATE, RVN_S_BASEFLOW_N, RVN_S_BASEFLOW_THRESH, -1}},
+      {RVN_OP_BASE_THRESH_STOR, 'S', {RVN_S_BASEFLOW_COEFF2, RVN_S_STORAGE_THRESHOLD, -1}},
+      {RVN_OP_PERC_GAWSER, 'S', {RVN_S_MAX_PERC_RATE, RVN_S_FIELD_CAPACITY, -1}}, {RVN_OP_PERC_GAWSER_CONSTRAIN, 'S', {RVN_S_MAX_PERC_RATE, RVN_S_FIELD_CAPACITY, -1}},
+      {RVN_OP_PERC_POWER_LAW, 'S', {RVN_S_MAX_PERC_RATE, RVN_S_PERC_N, -1}}, {RVN_OP_PERC_LINEAR_ANALYTIC, 'S', {RVN_S_PERC_COEFF, -1}},
+      {RVN_OP_PERC_PRMS, 'S', {RVN_S_MAX_PERC_RATE, RVN_S_PERC_N, RVN_S_FIELD_CAPACITY, RVN_S_SAT_WILT, -1}},
+      {RVN_OP_PERC_SACRAMENTO, 'S', {RVN_S_MAX_BASEFLOW_RATE, RVN_S_SAC_PERC_ALPHA, RVN_S_SAC_PERC_EXPON, RVN_S_FIELD_CAPACITY, RVN_S_SAT_WILT}},
+      {RVN_OP_PERC_ASPEN, 'S', {RVN_S_PERC_ASPEN, -1}},
+      {RVN_OP_INF_RATIONAL, 'L', {RVN_LU_PARTITION_COEFF, -1}}, {RVN_OP_INF_PDM, 'L', {RVN_LU_PDM_B, -1}},
+      {RVN_OP_INF_VIC, 'S', {RVN_S_VIC_ZMAX, RVN_S_VIC_ZMIN, RVN_S_VIC_ALPHA, -1}}, {RVN_OP_INF_PRMS, 'S', {RVN_S_FIELD_CAPACITY, RVN_S_SAT_WILT, -1}},
+      {RVN_OP_SOILEVAP_LINEAR, 'L', {RVN_LU_AET_COEFF, -1}}, {RVN_OP_SOILEVAP_PDM, 'L', {RVN_LU_PDM_B, -1}},
+      {RVN_OP_SOILEVAP_HYMOD2, 'L', {RVN_LU_PDM_B, RVN_LU_HYMOD2_G, RVN_LU_HYMOD2_KMAX, RVN_LU_HYMOD2_EXP, -1}},
+      {RVN_OP_SOILEVAP_UBC, 'S', {RVN_S_UBC_EVAP_SOIL_DEF, RVN_S_UBC_INFIL_SOIL_DEF, -1}},
+      {RVN_OP_SOILEVAP_VIC, 'S', {RVN_S_VIC_ZMAX, RVN_S_VIC_ZMIN, RVN_S_VIC_ALPHA, RVN_S_VIC_EVAP_GAMMA, -1}},
+      {RVN_OP_SOILEVAP_HYPR, 'L', {RVN_LU_MAX_DEP_AREA_FRAC, RVN_LU_PONDED_EXP, RVN_LU_DEP_MAX, -1}},
+      {RVN_OP_SOILEVAP_SEQUEN, 'S', {RVN_S_FIELD_CAPACITY, RVN_S_SAT_WILT, -1}}, {RVN_OP_SOILEVAP_ROOT, 'S', {RVN_S_FIELD_CAPACITY, RVN_S_SAT_WILT, -1}},
+      {RVN_OP_SOILEVAP_ROOT_CONSTRAIN, 'S', {RVN_S_FIELD_CAPACITY, RVN_S_SAT_WILT, -1}},
+      {RVN_OP_SOILEVAP_AWBM, 'L', {RVN_LU_AWBM_AREAFRAC1, RVN_LU_AWBM_AREAFRAC2, -1}},
+    };
+    for (int r = 0; r < d.nProc; r++)
+      for (size_t q = 0; q < sizeof(needs) / sizeof(needs[0]); q++) {
+        if (needs[q].op != d.proc[r].op) continue;
+        for (int j = 0; j < 5 && needs[q].f[j] >= 0; j++) {
+          const int f = needs[q].f[j];
+          if (needs[q].cls == 'S') {
+            for (size_t c = 0; c < soil_classes.size(); c++)
+              ExitGracefullyIf(soil_classes[c].S.v[f] == NOT_SPECIFIED, std::string("CSoilClass::AutoCalculateSoilProps: required parameter ") + SoilFieldName(f) + " not specified for soil class " + soil_classes[c].tag);
+          } else {
+            for (size_t c = 0; c < lu_classes.size(); c++)
+              ExitGracefullyIf(lu_classes[c].S.v[f] == NOT_SPECIFIED, std::string("CLandUseClass::AutoCalculateLandUseProps: required parameter ") + LandUseFieldName(f) + " not specified for land use class " + lu_classes[c].tag);
+          }
+        }
+      }
+  }
   d.ptab_stride = _f_ptab_stride;
   _f_ptab.assign((size_t)nMembers * _f_ptab_stride, 0.0);
   d.nConvProc = _f_nconv;

@@ -6,12 +6,15 @@
 
 // ---------------------------------------------------------------------------------- field name tables
 static const char *kSoilNames[RVN_S_COUNT] = {"POROSITY", "CAP_RATIO", "PERC_COEFF", "PET_CORRECTION", "BASEFLOW_COEFF", "BASEFLOW_N",
-  "FIELD_CAPACITY", "SAT_WILT", "HBV_BETA", "MAX_CAP_RISE_RATE", "MAX_PERC_RATE", "GR4J_X2", "GR4J_X3", "VIC_B_EXP", "MAX_BASEFLOW_RATE", "MAX_INTERFLOW_RATE"};
+  "FIELD_CAPACITY", "SAT_WILT", "HBV_BETA", "MAX_CAP_RISE_RATE", "MAX_PERC_RATE", "GR4J_X2", "GR4J_X3", "VIC_B_EXP", "MAX_BASEFLOW_RATE", "MAX_INTERFLOW_RATE",
+  "PERC_N", "SAC_PERC_ALPHA", "SAC_PERC_EXPON", "PERC_ASPEN", "BASEFLOW_THRESH", "BASEFLOW_COEFF2", "STORAGE_THRESHOLD", "VIC_ZMIN", "VIC_ZMAX",
+  "VIC_ALPHA", "VIC_EVAP_GAMMA", "UBC_EVAP_SOIL_DEF", "UBC_INFIL_SOIL_DEF"};
 static const char *kLUNames[RVN_LU_COUNT] = {"IMPERMEABLE_FRAC", "FOREST_COVERAGE", "FOREST_SPARSENESS", "MELT_FACTOR", "MIN_MELT_FACTOR",
   "MAX_MELT_FACTOR", "DD_MELT_TEMP", "DD_AGGRADATION", "REFREEZE_FACTOR", "DD_REFREEZE_TEMP", "REFREEZE_EXP", "HMETS_RUNOFF_COEFF",
   "GAMMA_SHAPE", "GAMMA_SCALE", "GAMMA_SHAPE2", "GAMMA_SCALE2", "GR4J_X4", "HBV_MELT_FOR_CORR", "HBV_MELT_ASP_CORR",
   "HBV_MELT_GLACIER_CORR", "HBV_GLACIER_KMIN", "GLAC_STORAGE_COEFF", "HBV_GLACIER_AG", "DEP_MAX", "LAKE_PET_CORR", "OW_PET_CORR",
-  "PARTITION_COEFF", "CC_DECAY_COEFF"};
+  "PARTITION_COEFF", "CC_DECAY_COEFF", "MAX_SAT_AREA_FRAC", "PDM_B", "AET_COEFF", "MAX_DEP_AREA_FRAC", "PONDED_EXP", "AWBM_AREAFRAC1",
+  "AWBM_AREAFRAC2", "HYMOD2_G", "HYMOD2_KMAX", "HYMOD2_EXP"};
 static const char *kVegNames[RVN_V_COUNT] = {"MAX_HEIGHT", "MAX_LAI", "SAI_HT_RATIO", "MAX_CAPACITY", "MAX_SNOW_CAPACITY", "RAIN_ICEPT_PCT",
   "SNOW_ICEPT_PCT", "PET_VEG_CORR", "VAR_CAPACITY", "VAR_SNOW_CAPACITY", "VAR_RAIN_ICEPT_PCT", "VAR_SNOW_ICEPT_PCT"};
 static const char *kGlobalNames[RVN_G_COUNT] = {"SNOW_SWI", "SNOW_SWI_MIN", "SNOW_SWI_MAX", "SWI_REDUCT_COEFF", "ADIABATIC_LAPSE", "PRECIP_LAPSE",

@@ -334,7 +334,7 @@ static int SoilFieldOrIgnore(const std::string &n) {
 static int LUFieldOrIgnore(const std::string &n) {
   int f = LandUseFieldFromName(n);
   if (f >= 0) return f;
-  static const char *ign[] = {"ROUGHNESS", "FOREST_PET_CORR", NULL};
+  static const char *ign[] = {"ROUGHNESS", "FOREST_PET_CORR", "PDMROF_B", NULL};
   for (int i = 0; ign[i]; i++) if (n == ign[i]) return -1;
   return -2;
 }
@@ -507,6 +507,7 @@ static void ParseClassPropertiesFile(CModel *pModel, const optStruct &Options) {
     surface_struct &S = pModel->lu_classes[k].S;
     if (S.v[RVN_LU_FOREST_SPARSENESS] == NOT_SPECIFIED) S.v[RVN_LU_FOREST_SPARSENESS] = 0.0;  // src/LandUseClass.cpp autocalc
     if (S.v[RVN_LU_LAKE_PET_CORR] == NOT_SPECIFIED) S.v[RVN_LU_LAKE_PET_CORR] = 1.0;
+    if (S.v[RVN_LU_MAX_SAT_AREA_FRAC] == NOT_SPECIFIED) S.v[RVN_LU_MAX_SAT_AREA_FRAC] = 1.0;  // src/LandUseClass.cpp:93-98
     if (S.v[RVN_LU_OW_PET_CORR] == NOT_SPECIFIED) S.v[RVN_LU_OW_PET_CORR] = 1.0;
     // autogenerated snow parameters (CLandUseClass::AutoCalculateLandUseProps, src/LandUseClass.cpp:100-160)
     if (S.v[RVN_LU_FOREST_COVERAGE] == NOT_SPECIFIED) S.v[RVN_LU_FOREST_COVERAGE] = 0.0;

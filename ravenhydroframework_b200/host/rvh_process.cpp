@@ -292,6 +292,11 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
     } else if (s[1] == "INF_HBV" || s[1] == "INF_GR4J" || s[1] == "INF_VIC_ARNO") {
       p = new CmvGeneric("Infiltration", s[1] == "INF_HBV" ? RVN_OP_INF_HBV : (s[1] == "INF_GR4J" ? RVN_OP_INF_GR4J : RVN_OP_INF_VIC_ARNO), pM);
       p->Connect(iPond, iTop); p->Connect(iPond, iSW);
+    } else if (s[1] == "INF_RATIONAL" || s[1] == "INF_PARTITION" || s[1] == "INF_ALL_INFILTRATES" || s[1] == "INF_VIC" || s[1] == "INF_PRMS" || s[1] == "INF_PDM") {
+      const rvn_opcode op = (s[1] == "INF_ALL_INFILTRATES") ? RVN_OP_INF_ALL_INFILTRATES : (s[1] == "INF_VIC") ? RVN_OP_INF_VIC
+                          : (s[1] == "INF_PRMS") ? RVN_OP_INF_PRMS : (s[1] == "INF_PDM") ? RVN_OP_INF_PDM : RVN_OP_INF_RATIONAL;
+      p = new CmvGeneric("Infiltration", op, pM);
+      p->Connect(iPond, iTop); p->Connect(iPond, iSW);
     } else {
       ExitGracefully("ParseMainInputFile: infiltration algorithm " + s[1] + " is not implemented in the B200 build");
     }
@@ -332,6 +337,10 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
     else if (s[1] == "BASE_LINEAR_ANALYTIC") op = RVN_OP_BASE_LINEAR_ANALYTIC;
     else if (s[1] == "BASE_VIC") op = RVN_OP_BASE_VIC;
     else if (s[1] == "BASE_TOPMODEL") op = RVN_OP_BASE_TOPMODEL;
+    else if (s[1] == "BASE_LINEAR_CONSTRAIN") op = RVN_OP_BASE_LINEAR_CONSTRAIN;
+    else if (s[1] == "BASE_CONSTANT") op = RVN_OP_BASE_CONSTANT;
+    else if (s[1] == "BASE_THRESH_POWER") op = RVN_OP_BASE_THRESH_POWER;
+    else if (s[1] == "BASE_THRESH_STOR") op = RVN_OP_BASE_THRESH_STOR;
     else ExitGracefully("ParseMainInputFile: baseflow algorithm " + s[1] + " is not implemented in the B200 build");
     CmvGeneric *p = new CmvGeneric("Baseflow", op, pM);
     p->Connect(from, iSW);
@@ -347,6 +356,13 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
     else if (s[1] == "PERC_GR4J") op = RVN_OP_PERC_GR4J;
     else if (s[1] == "PERC_GR4JEXCH") op = RVN_OP_PERC_GR4JEXCH;
     else if (s[1] == "PERC_GR4JEXCH2") op = RVN_OP_PERC_GR4JEXCH2;
+    else if (s[1] == "PERC_GAWSER") op = RVN_OP_PERC_GAWSER;
+    else if (s[1] == "PERC_GAWSER_CONSTRAIN") op = RVN_OP_PERC_GAWSER_CONSTRAIN;
+    else if (s[1] == "PERC_POWER_LAW") op = RVN_OP_PERC_POWER_LAW;
+    else if (s[1] == "PERC_LINEAR_ANALYTIC") op = RVN_OP_PERC_LINEAR_ANALYTIC;
+    else if (s[1] == "PERC_PRMS") op = RVN_OP_PERC_PRMS;
+    else if (s[1] == "PERC_SACRAMENTO") op = RVN_OP_PERC_SACRAMENTO;
+    else if (s[1] == "PERC_ASPEN") op = RVN_OP_PERC_ASPEN;
     else ExitGracefully("ParseMainInputFile: percolation algorithm " + s[1] + " is not implemented in the B200 build");
     CmvGeneric *p = new CmvGeneric("Percolation", op, pM);
     p->Connect(from, to);
@@ -361,11 +377,32 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
     else if (s[1] == "SOILEVAP_HBV") op = RVN_OP_SOILEVAP_HBV;
     else if (s[1] == "SOILEVAP_GR4J") op = RVN_OP_SOILEVAP_GR4J;
     else if (s[1] == "SOILEVAP_TOPMODEL") op = RVN_OP_SOILEVAP_TOPMODEL;
+    else if (s[1] == "SOILEVAP_LINEAR") op = RVN_OP_SOILEVAP_LINEAR;
+    else if (s[1] == "SOILEVAP_PDM") op = RVN_OP_SOILEVAP_PDM;
+    else if (s[1] == "SOILEVAP_HYMOD2") op = RVN_OP_SOILEVAP_HYMOD2;
+    else if (s[1] == "SOILEVAP_UBC") op = RVN_OP_SOILEVAP_UBC;
+    else if (s[1] == "SOILEVAP_VIC") op = RVN_OP_SOILEVAP_VIC;
+    else if (s[1] == "SOILEVAP_HYPR") op = RVN_OP_SOILEVAP_HYPR;
+    else if (s[1] == "SOILEVAP_SEQUEN") op = RVN_OP_SOILEVAP_SEQUEN;
+    else if (s[1] == "SOILEVAP_ROOT") op = RVN_OP_SOILEVAP_ROOT;
+    else if (s[1] == "SOILEVAP_ROOT_CONSTRAIN") op = RVN_OP_SOILEVAP_ROOT_CONSTRAIN;
+    else if (s[1] == "SOILEVAP_AWBM") op = RVN_OP_SOILEVAP_AWBM;
     else ExitGracefully("ParseMainInputFile: soil evaporation algorithm " + s[1] + " is not implemented in the B200 build");
-    AddSVs(pM, {SVL(RVN_SV_SOIL, 0), SVL(RVN_SV_ATMOSPHERE, -1), SVL(RVN_SV_AET, -1)});
+    // state variables and connections: src/SoilEvaporation.cpp:21-100 and :244-313
+    const bool two = (op == RVN_OP_SOILEVAP_SEQUEN || op == RVN_OP_SOILEVAP_ROOT || op == RVN_OP_SOILEVAP_ROOT_CONSTRAIN);
+    AddSV1(pM, RVN_SV_SOIL, 0);
+    if (two || op == RVN_OP_SOILEVAP_AWBM) AddSV1(pM, RVN_SV_SOIL, 1);
+    if (op == RVN_OP_SOILEVAP_AWBM) AddSV1(pM, RVN_SV_SOIL, 2);
+    AddSV1(pM, RVN_SV_ATMOSPHERE);
+    if (op == RVN_OP_SOILEVAP_HYPR) AddSV1(pM, RVN_SV_DEPRESSION);
+    if (op == RVN_OP_SOILEVAP_UBC) AddSV1(pM, RVN_SV_SNOW);
+    AddSV1(pM, RVN_SV_AET);
     CmvGeneric *p = new CmvGeneric("SoilEvaporation", op, pM);
     int iAET = pM->GetStateVarIndex(RVN_SV_AET);
     p->Connect(pM->GetStateVarIndex(RVN_SV_SOIL, 0), iAtmos);
+    if (two || op == RVN_OP_SOILEVAP_AWBM) p->Connect(pM->GetStateVarIndex(RVN_SV_SOIL, 1), iAtmos);
+    if (op == RVN_OP_SOILEVAP_AWBM) p->Connect(pM->GetStateVarIndex(RVN_SV_SOIL, 2), iAtmos);
+    if (op == RVN_OP_SOILEVAP_HYPR) p->Connect(pM->GetStateVarIndex(RVN_SV_DEPRESSION), iAtmos);
     p->Connect(iAET, iAET);
     return p;
   }

@@ -395,6 +395,45 @@ MONTHLY_EVAP = [0.028, 0.089, 0.315, 1.003, 2.077, 2.959, 3.190, 2.548, 1.382, 0
 MONTHLY_TEMP = [-11.4, -7.2, -2.8, 2.8, 8.1, 12.2, 14.4, 13.5, 8.9, 3.4, -4.0, -9.3]
 
 
+# Algorithm sets for write_hbv(variant="algo:<key>"): each swaps the infiltration / soil evaporation / percolation / baseflow
+# algorithms of the HBV-EC process list for other members of the same process classes.
+ALGO_SETS = {
+    "a": dict(inf="INF_RATIONAL", sevap="SOILEVAP_LINEAR", perc="PERC_GAWSER", base_fast="BASE_LINEAR_CONSTRAIN", base_slow="BASE_CONSTANT"),
+    "b": dict(inf="INF_ALL_INFILTRATES", sevap="SOILEVAP_PDM", perc="PERC_GAWSER_CONSTRAIN", base_fast="BASE_THRESH_POWER", base_slow="BASE_THRESH_STOR"),
+    "c": dict(inf="INF_VIC", sevap="SOILEVAP_VIC", perc="PERC_POWER_LAW", base_fast="BASE_VIC"),
+    "d": dict(inf="INF_PRMS", sevap="SOILEVAP_SEQUEN", perc="PERC_PRMS"),
+    "e": dict(inf="INF_PDM", sevap="SOILEVAP_HYMOD2", perc="PERC_LINEAR_ANALYTIC"),
+    "f": dict(sevap="SOILEVAP_ROOT", perc="PERC_SACRAMENTO", perc_top="PERC_SACRAMENTO"),
+    "g": dict(sevap="SOILEVAP_ROOT_CONSTRAIN", perc="PERC_ASPEN"),
+    "h": dict(sevap="SOILEVAP_AWBM", inf="INF_PDM"),
+    "i": dict(sevap="SOILEVAP_UBC"),
+    "j": dict(sevap="SOILEVAP_HYPR", depression=True),
+}
+ALGO_RVP = """:SoilParameterList
+  :Parameters, PERC_N, SAC_PERC_ALPHA, SAC_PERC_EXPON, PERC_ASPEN, BASEFLOW_THRESH, BASEFLOW_COEFF2, STORAGE_THRESHOLD, MAX_BASEFLOW_RATE, PERC_COEFF
+  :Units     ,   none,           none,           none,       mm/d,            none,             1/d,                mm,              mm/d,        1/d
+    [DEFAULT],    1.7,           35.0,            2.4,        1.9,            0.22,           0.083,              12.5,              3.25,      0.061
+     FAST_RES,    2.2,           28.0,            3.1,        2.3,            0.15,           0.120,               9.0,              9.75,      0.143
+:EndSoilParameterList
+:SoilParameterList
+  :Parameters, VIC_ZMIN, VIC_ZMAX, VIC_ALPHA, VIC_EVAP_GAMMA, UBC_EVAP_SOIL_DEF, UBC_INFIL_SOIL_DEF
+  :Units     ,       mm,       mm,      none,           none,                mm,                 mm
+    [DEFAULT],     0.05,     1.35,       0.8,            1.6,             105.0,               85.0
+:EndSoilParameterList
+:LandUseParameterList
+  :Parameters, PARTITION_COEFF, MAX_SAT_AREA_FRAC, PDM_B, AET_COEFF, MAX_DEP_AREA_FRAC, PONDED_EXP, DEP_MAX, AWBM_AREAFRAC1, AWBM_AREAFRAC2
+  :Units     ,            none,              none,  none,       1/d,              none,       none,      mm,           none,           none
+    [DEFAULT],            0.37,              0.62,   1.4,     0.031,              0.45,        1.8,    40.0,          0.134,          0.433
+    LU_OPEN,              0.52,              0.48,   0.9,     0.044,              0.30,        2.2,    25.0,          0.210,          0.390
+:EndLandUseParameterList
+:LandUseParameterList
+  :Parameters, HYMOD2_G, HYMOD2_KMAX, HYMOD2_EXP, PDMROF_B
+  :Units     ,     none,        none,       none,     none
+    [DEFAULT],     0.28,        0.91,        1.3,      0.5
+:EndLandUseParameterList
+"""
+
+
 def write_hbv(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUTE_NONE", catchment_route="TRIANGULAR_UH",
               single_class=False, name="hbv", season_offset=0, n_gauges=1, variant=None):
     """HBV-EC template (BASELINE config 2): multi-class, with glacier HRUs unless single_class. Returns the input base path.
@@ -411,6 +450,9 @@ def write_hbv(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUTE_
         extra_rvp += ":TrapezoidalChannel CHN 10.0 0.0 2.0 0.035 0.001\n"
     if variant == "melt_squeeze_interflow":
         extra_rvp += ":SoilParameterList\n  :Parameters, MAX_INTERFLOW_RATE\n  :Units, mm/d\n  [DEFAULT], 0.0\n  FAST_RES, 7.25\n:EndSoilParameterList\n"
+    algo = ALGO_SETS[variant[5:]] if (variant or "").startswith("algo:") else None
+    if algo is not None:
+        extra_rvp += ALGO_RVP
     _write(base + ".rvp", HBV_RVP.format(extra=extra_rvp))
     with open(base + ".rvh", "w") as f:
         if single_class:
@@ -441,6 +483,22 @@ def write_hbv(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUTE_
         c = "  :LakeEvaporation   LAKE_EVAP_BASIC    SLOW_RESERVOIR  ATMOSPHERE\n"
         assert c in rvi
         rvi = rvi.replace(c, "  :Interflow         INTERFLOW_PRMS     FAST_RESERVOIR  SURFACE_WATER\n" + c)
+    if algo is not None:
+        def swap(line_old, line_new):
+            nonlocal rvi
+            assert line_old in rvi, line_old
+            rvi = rvi.replace(line_old, line_new)
+        if "inf" in algo:
+            swap("  :Infiltration      INF_HBV            PONDED_WATER    MULTIPLE\n", "  :Infiltration      %s PONDED_WATER MULTIPLE\n" % algo["inf"])
+        if "sevap" in algo:
+            swap("  :SoilEvaporation   SOILEVAP_HBV       SOIL[0]         ATMOSPHERE\n", "  :SoilEvaporation   %s SOIL[0] ATMOSPHERE\n" % algo["sevap"])
+        if "perc" in algo:
+            swap("  :Percolation       PERC_CONSTANT      FAST_RESERVOIR  SLOW_RESERVOIR\n", ("  :Percolation       %s SOIL[0] FAST_RESERVOIR\n" % algo["perc_top"] if "perc_top" in algo else "")
+                 + "  :Percolation       %s FAST_RESERVOIR SLOW_RESERVOIR\n" % algo["perc"])
+        if "base_fast" in algo:
+            swap("  :Baseflow          BASE_POWER_LAW     FAST_RESERVOIR  SURFACE_WATER\n", "  :Baseflow          %s FAST_RESERVOIR SURFACE_WATER\n" % algo["base_fast"])
+        if "base_slow" in algo:
+            swap("  :Baseflow          BASE_LINEAR        SLOW_RESERVOIR  SURFACE_WATER\n", "  :Baseflow          %s SLOW_RESERVOIR SURFACE_WATER\n" % algo["base_slow"])
     if variant == "lateral":
         # lateral exchange (reference CmvLatFlush): surface water of the 'UpGroup' HRUs is flushed into the fast reservoir of the
         # 'LowGroup' HRUs of the same subbasin (limited by the room left there); one more flush moves ponded water to one single
@@ -457,7 +515,7 @@ def write_hbv(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUTE_
             f.write(":HRUGroup LowGroup\n  " + " ".join(str(k) for k in range(1, n_hru + 1) if k % 3 == 0 or k % 5 == 0) + "\n:EndHRUGroup\n")
             f.write(":HRUGroup Sink\n  2\n:EndHRUGroup\n")
     _write(base + ".rvi", rvi)
-    _write(base + ".rvc", HBV_RVC)
+    _write(base + ".rvc", HBV_RVC + (":UniformInitialConditions DEPRESSION 18.0\n" if (algo or {}).get("depression") else ""))
     return base
 
 

@@ -41,6 +41,9 @@ if hasattr(synth, "write_hbv"):
     # process classes outside the three templates: :SnowMelt, :SnowSqueeze, :Interflow
     CASES["hbv_meltsqueeze"] = dict(kind="hbv", n_sb=3, hru_per_sb=5, n_days=300, seed=14, routing="ROUTE_MUSKINGUM", variant="melt_squeeze_interflow")
     # lateral exchange between HRUs (CmvLatFlush): within-subbasin flush limited by the recipient's room + an INTERBASIN flush
+    for _k in "abcdefghij":   # other members of the infiltration / soil evaporation / percolation / baseflow process classes
+        CASES["hbv_algo_" + _k] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=220, seed=30 + ord(_k), routing="ROUTE_MUSKINGUM", season_offset=80,
+                                       variant="algo:" + _k)
     CASES["hbv_lateral"] = dict(kind="hbv", n_sb=4, hru_per_sb=7, n_days=250, seed=8, routing="ROUTE_MUSKINGUM", season_offset=40, variant="lateral")
 if hasattr(synth, "write_blended"):
     # Blended multi-model template (BASELINE config 4): weighted process groups, VIC/TOPMODEL/analytic algorithms, SNOBAL_HBV
