@@ -1177,7 +1177,29 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
       for (int l = 0; l < d->nLat; l++) {
         const rvn_lateral *L = &d->lat[l];
         double *ex = (double *)malloc(sizeof(double) * (size_t)(L->nconn > 0 ? L->nconn : 1));
-        for (int q = 0; q < L->nconn; q++) {
+        if (L->kind == RVN_LAT_EQUILIBRATE) {
+          /* CmvLatEquilibrate::GetLateralExchange (src/LatEquilibrate.cpp:168-212).  The reference walks all connections with one
+           * pool sum[p] per subbasin; the list here is the same connections grouped by subbasin (chunks) in the same relative
+           * order, and the p/plast/qstart bookkeeping, which depends on the list only, arrives as lat_flag. */
+          double mix = omin(L->mixing_rate * tstep, 1.0);
+          const int32_t *cp = d->lat_chunk_ptr + L->chunk0;
+          for (int ch = 0; ch < L->nchunks; ch++) {
+            double sum = 0.0;
+            for (int q = cp[ch]; q < cp[ch + 1]; q++) {
+              const int kF = d->lat_kfrom[L->conn0 + q], kT = d->lat_kto[L->conn0 + q], flag = d->lat_flag[L->conn0 + q];
+              double stor = state[(size_t)kF * NS + L->sv_from], to_stor = state[(size_t)kT * NS + L->sv_to];
+              double Afrom = d->hru_area[kF], Ato = d->hru_area[kT];
+              if (flag & 1) sum += mix * omax(to_stor, 0.0) * Ato;
+              if (flag & 2) { /* step 1: a fraction of the storage moves to the mixing unit */
+                ex[q] = mix * omax(stor, 0.0) / tstep * Afrom;
+                sum += ex[q] * tstep;
+              } else {        /* step 2: the mixed water goes back by area */
+                ex[q] = sum * d->lat_frac[L->conn0 + q] / tstep;
+              }
+            }
+          }
+        }
+        else for (int q = 0; q < L->nconn; q++) {
           const int kF = d->lat_kfrom[L->conn0 + q], kT = d->lat_kto[L->conn0 + q];
           double stor = state[(size_t)kF * NS + L->sv_from], to_stor = state[(size_t)kT * NS + L->sv_to];
           double Afrom = d->hru_area[kF], Ato = d->hru_area[kT];

@@ -2,7 +2,8 @@
 // the solver after the vertical processes of ALL HRUs, src/Solvers.cpp:404-443) and the end-of-step pieces the sweep defers
 // when lateral processes exist.
 //
-//   lateral_flush_kernel  CmvLatFlush::GetLateralExchange (src/LatFlush.cpp:204-234) + the solver's sequential application
+//   lateral_flush_kernel  CmvLatFlush::GetLateralExchange (src/LatFlush.cpp:204-234) or CmvLatEquilibrate::GetLateralExchange
+//                         (src/LatEquilibrate.cpp:168-212) + the solver's sequential application
 //                         aPhinew[kFrom][iFrom] -= rate/Afrom*tstep; aPhinew[kTo][iTo] += rate/Ato*tstep (src/Solvers.cpp:424-430).
 //                         All rates of a process are computed from the same post-vertical state, then applied in connection
 //                         order.  Connections are grouped into chunks whose HRUs no other chunk touches (one subbasin each:
@@ -21,6 +22,9 @@ struct DevLateral {
   double *rates;             // scratch [member][nconn]
   int32_t to_type, to_layer; // sv_type / layer of the receiving state variable (CHydroUnit::GetStateVarMax, src/HydroUnits.cpp:559-606)
   int32_t sv_snow;           // index of SNOW (for a SNOW_LIQ recipient) or -1
+  int32_t kind;              // rvn_lateral_kind
+  const int32_t *flag;       // LAT_EQUILIBRATE control-flow flags per connection
+  double mixing_rate;        // LAT_EQUILIBRATE [1/d]
 };
 
 // GetStateVarMax of the recipient for the state-variable types a flush may target here; CANOPY / CANOPY_SNOW recipients (date
@@ -46,7 +50,21 @@ __global__ void lateral_flush_kernel(const __grid_constant__ DevModel M, const D
   double *from_row = M.state + ((size_t)e * M.NS + L.sv_from) * M.nHp, *to_row = M.state + ((size_t)e * M.NS + L.sv_to) * M.nHp;
   double *rates = L.rates + (size_t)e * L.nconn;
   const int q0 = L.chunk_ptr[c], q1 = L.chunk_ptr[c + 1];
-  for (int q = q0; q < q1; q++) {   // GetLateralExchange: every rate from the state before any of them is applied
+  if (L.kind == RVN_LAT_EQUILIBRATE) {   // CmvLatEquilibrate::GetLateralExchange, src/LatEquilibrate.cpp:168-212; one chunk = one subbasin's pool
+    const double mix = dmin(L.mixing_rate * tstep, 1.0);
+    double sum = 0.0;
+    for (int q = q0; q < q1; q++) {
+      const int kF = L.kfrom[q], kT = L.kto[q], flag = L.flag[q];
+      const double stor = from_row[kF], to_stor = to_row[kT];
+      const double Afrom = M.hru_area[kF], Ato = M.hru_area[kT];
+      if (flag & 1) sum += mix * dmax(to_stor, 0.0) * Ato;
+      double r;
+      if (flag & 2) { r = mix * dmax(stor, 0.0) / tstep * Afrom; sum += r * tstep; }   // step 1: into the mixing unit
+      else r = sum * L.frac[q] / tstep;                                                // step 2: back out by area
+      rates[q] = r;
+    }
+  }
+  else for (int q = q0; q < q1; q++) {   // GetLateralExchange: every rate from the state before any of them is applied
     const int kF = L.kfrom[q], kT = L.kto[q];
     const double stor = from_row[kF], to_stor = to_row[kT];
     const double Afrom = M.hru_area[kF], Ato = M.hru_area[kT];

@@ -80,9 +80,9 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
     _f_proc.push_back(rec); rec_owner.push_back(owner);
     return _f_proc.back();
   };
-  _f_lat.clear(); _f_lat_kfrom.clear(); _f_lat_kto.clear(); _f_lat_frac.clear(); _f_lat_chunk.clear();
+  _f_lat.clear(); _f_lat_kfrom.clear(); _f_lat_kto.clear(); _f_lat_frac.clear(); _f_lat_flag.clear(); _f_lat_chunk.clear();
   for (int j = 0; j < NP; j++) {
-    if (const CmvLatFlush *lf = dynamic_cast<const CmvLatFlush *>(_pProcesses[j])) {
+    if (const CLateralExchangeProcessABC *lf = dynamic_cast<const CLateralExchangeProcessABC *>(_pProcesses[j])) {
       // CModel::ApplyLateralProcess (src/Model.cpp:3126-3165): no connections -> nothing; gate of the FIRST source HRU; every
       // participating HRU must be enabled.  All of it is static, so a process that does not apply is simply not listed.
       const int nc = lf->GetNumLatConnections();
@@ -92,10 +92,11 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
       for (int q = 0; q < nc; q++) if (!_pHydroUnits[lf->GetFromHRUIndices()[q]]->IsEnabled() || !_pHydroUnits[lf->GetToHRUIndices()[q]]->IsEnabled()) all_enabled = false;
       if (!all_enabled) continue;
       rvn_lateral L; memset(&L, 0, sizeof(L));
-      L.kind = RVN_LAT_FLUSH; L.sv_from = lf->GetLateralFromIndex(); L.sv_to = lf->GetLateralToIndex();
+      L.kind = lf->GetLateralKind(); L.sv_from = lf->GetLateralFromIndex(); L.sv_to = lf->GetLateralToIndex(); L.mixing_rate = lf->GetMixingRate();
       L.nconn = nc; L.conn0 = (int32_t)_f_lat_kfrom.size();
       L.nchunks = (int32_t)lf->ChunkOffsets().size() - 1; L.chunk0 = (int32_t)_f_lat_chunk.size();
-      for (int q = 0; q < nc; q++) { _f_lat_kfrom.push_back(lf->GetFromHRUIndices()[q]); _f_lat_kto.push_back(lf->GetToHRUIndices()[q]); _f_lat_frac.push_back(lf->GetFractions()[q]); }
+      for (int q = 0; q < nc; q++) { _f_lat_kfrom.push_back(lf->GetFromHRUIndices()[q]); _f_lat_kto.push_back(lf->GetToHRUIndices()[q]); _f_lat_frac.push_back(lf->GetFractions()[q]);
+        _f_lat_flag.push_back(lf->GetLateralKind() == RVN_LAT_EQUILIBRATE ? lf->GetFlags()[q] : 0); }
       for (size_t c = 0; c < lf->ChunkOffsets().size(); c++) _f_lat_chunk.push_back(lf->ChunkOffsets()[c]);
       _f_lat.push_back(L);
       continue;
@@ -117,9 +118,9 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
     for (size_t r = first; r < _f_proc.size(); r++) { _f_proc[r].gconn0 = gconn0; _f_proc[r].gnconn = gnconn; }
   }
   d.nLat = (int32_t)_f_lat.size(); d.nLatConn = (int32_t)_f_lat_kfrom.size();
-  if (_f_lat_kfrom.empty()) { _f_lat_kfrom.push_back(0); _f_lat_kto.push_back(0); _f_lat_frac.push_back(0.0); }
+  if (_f_lat_kfrom.empty()) { _f_lat_kfrom.push_back(0); _f_lat_kto.push_back(0); _f_lat_frac.push_back(0.0); _f_lat_flag.push_back(0); }
   if (_f_lat_chunk.empty()) _f_lat_chunk.push_back(0);
-  d.lat = _f_lat.empty() ? NULL : _f_lat.data(); d.lat_kfrom = _f_lat_kfrom.data(); d.lat_kto = _f_lat_kto.data(); d.lat_frac = _f_lat_frac.data();
+  d.lat = _f_lat.empty() ? NULL : _f_lat.data(); d.lat_kfrom = _f_lat_kfrom.data(); d.lat_kto = _f_lat_kto.data(); d.lat_frac = _f_lat_frac.data(); d.lat_flag = _f_lat_flag.data();
   d.lat_chunk_ptr = _f_lat_chunk.data();
   const int NR = (int)_f_proc.size();
   ExitGracefullyIf(NR > 64, "CModel::Flatten: more than 64 process records (the per-HRU process gate is a 64-bit mask)");

@@ -3,6 +3,8 @@
 // (src/ParseInput.cpp case 200..), so that the SV catalogue and connection tables are integer-identical
 // to the reference build.  Rates are computed on the device (csrc/rvn_processes.cuh).
 #include "rvh_process.h"
+#include <algorithm>
+#include <map>
 
 rvn_hru_type StringToHRUType(const std::string &sin) {
   std::string s = StringToUppercase(sin);
@@ -88,15 +90,15 @@ void CProcessGroup::Initialize() {
 
 // ---- LateralFlush -----------------------------------------------------------------------------------
 CmvLatFlush::CmvLatFlush(int from_sv_ind, int to_sv_ind, int from_HRU_grp, int to_HRU_grp, bool constrain_to_SBs, CModel *pM)
-    : CHydroProcessABC("LateralFlush", pM), _iFlushFrom(from_sv_ind), _iFlushTo(to_sv_ind), _kk_from(from_HRU_grp), _kk_to(to_HRU_grp),
-      _constrain_to_SBs(constrain_to_SBs) {
+    : CLateralExchangeProcessABC("LateralFlush", RVN_LAT_FLUSH, pM), _kk_from(from_HRU_grp), _kk_to(to_HRU_grp), _constrain_to_SBs(constrain_to_SBs) {
+  _iFromLat = from_sv_ind; _iToLat = to_sv_ind;
   ExitGracefullyIf(to_HRU_grp < 0 || to_HRU_grp >= (int)pM->hru_groups.size(), "CmvLatFlush::unrecognized 'to' HRU group specified in :LateralFlush/:LateralDivert command");
   ExitGracefullyIf(from_HRU_grp < 0 || from_HRU_grp >= (int)pM->hru_groups.size(), "CmvLatFlush::unrecognized 'from' HRU group specified in :LateralFlush/:LateralDivert command");
   ExitGracefullyIf(from_sv_ind == DOESNT_EXIST, "CmvLatFlush::unrecognized 'from' state variable specified in :LateralFlush/:LateralDivert command");
   ExitGracefullyIf(to_sv_ind == DOESNT_EXIST, "CmvLatFlush::unrecognized 'to' state variable specified in :LateralFlush/:LateralDivert command");
 }
 void CmvLatFlush::Initialize() {   // src/LatFlush.cpp:55-177
-  _kFrom.clear(); _kTo.clear(); _aFrac.clear(); _chunk_ptr.assign(1, 0);
+  _kFrom.clear(); _kTo.clear(); _aFrac.clear(); _aFlag.clear(); _chunk_ptr.assign(1, 0);
   const int nH = pModel->GetNumHRUs();
   std::vector<char> inFrom(nH, 0), inTo(nH, 0);
   { const std::vector<int> &g = pModel->hru_groups[_kk_from].hru; for (size_t i = 0; i < g.size(); i++) inFrom[g[i]] = 1; }
@@ -138,6 +140,72 @@ void CmvLatFlush::Initialize() {   // src/LatFlush.cpp:55-177
       if (inFrom[k] && (kToSB != DOESNT_EXIST) && pModel->GetHydroUnit(k)->IsEnabled()) { _kFrom.push_back(k); _kTo.push_back(kToSB); _aFrac.push_back(1.0); }
     if (!_kFrom.empty()) _chunk_ptr.push_back((int)_kFrom.size());
     if (_kFrom.empty()) WriteWarning("CmvLatFlush::Initialize: no connections found between from and to HRU groups. HRU Group population of zero?");
+  }
+}
+
+CmvLatEquilibrate::CmvLatEquilibrate(int sv_ind, int HRU_grp, double mixing_rate, bool constrain_to_SBs, CModel *pM)
+    : CLateralExchangeProcessABC("LateralEquilibrate", RVN_LAT_EQUILIBRATE, pM), _kk(HRU_grp), _constrain_to_SBs(constrain_to_SBs) {
+  _iFromLat = _iToLat = sv_ind; _mixing_rate = mixing_rate;
+  ExitGracefullyIf(HRU_grp < 0 || HRU_grp >= (int)pM->hru_groups.size(), "CmvLatEquilibrate::unrecognized HRU group specified in :LatEquilibrate command");
+  ExitGracefullyIf(sv_ind == DOESNT_EXIST, "CmvLatEquilibrate::unrecognized state variable specified in :LatEquilibrate command");
+}
+void CmvLatEquilibrate::Initialize() {   // src/LatEquilibrate.cpp:49-148 (connections) and the control flow of :176-210 (flags)
+  _kFrom.clear(); _kTo.clear(); _aFrac.clear(); _aFlag.clear(); _chunk_ptr.assign(1, 0);
+  const int nH = pModel->GetNumHRUs(), NB = pModel->GetNumSubBasins();
+  std::vector<char> inGrp(nH, 0);
+  { const std::vector<int> &g = pModel->hru_groups[_kk].hru; for (size_t i = 0; i < g.size(); i++) inGrp[g[i]] = 1; }
+  std::vector<int> kFrom, kTo, halfconn(NB > 0 ? NB : 1, 0);
+  std::vector<double> Asum(NB > 0 ? NB : 1, 0.0);
+  if (_constrain_to_SBs) {
+    for (int p = 0; p < NB; p++) {
+      const CSubBasin *b = pModel->GetSubBasin(p);
+      int kToSB = DOESNT_EXIST;
+      for (size_t ks = 0; ks < b->hru_index.size(); ks++) {
+        const int k = b->hru_index[ks];
+        if (inGrp[k] && (kToSB == DOESNT_EXIST)) { kToSB = k; Asum[p] += pModel->GetHydroUnit(k)->GetArea(); }   // first found is the mixing unit
+        else if (inGrp[k] && (kToSB != DOESNT_EXIST)) {
+          kFrom.push_back(k); kTo.push_back(kToSB);
+          Asum[p] += pModel->GetHydroUnit(k)->GetArea(); halfconn[p]++;
+        }
+      }
+    }
+    if (kFrom.empty()) WriteWarning("CmvLatEquilibrate::Initialize: no connections found between from and to HRU groups in any of the basins. if INTERBASIN flag not used, only transfer within basins is supported. ");
+  } else {
+    int kToSB = DOESNT_EXIST;
+    for (int k = 0; k < nH; k++)
+      if (inGrp[k] && (kToSB == DOESNT_EXIST)) { kToSB = k; Asum[0] += pModel->GetHydroUnit(k)->GetArea(); }
+    for (int k = 0; k < nH; k++)   // includes the mixing unit itself, whose area is counted twice (as in the reference)
+      if (inGrp[k] && (kToSB != DOESNT_EXIST)) { kFrom.push_back(k); kTo.push_back(kToSB); Asum[0] += pModel->GetHydroUnit(k)->GetArea(); halfconn[0]++; }
+  }
+  const int half = (int)kFrom.size(), nConn = 2 * half;
+  std::vector<int> qF(nConn), qT(nConn), qP(nConn), qFlag(nConn);
+  for (int q = 0; q < nConn; q++) {
+    if (q < half) { qF[q] = kFrom[q]; qT[q] = kTo[q]; }
+    else { qF[q] = kTo[q - half]; qT[q] = kFrom[q - half]; }
+  }
+  // GetLateralExchange's bookkeeping (p, plast, qstart) depends on the connection list only: replay it once
+  int plast = -1, qstart = 0;
+  for (int q = 0; q < nConn; q++) {
+    int p = pModel->GetHydroUnit(qF[q])->GetSubBasinIndex();
+    if (!_constrain_to_SBs) p = 0;
+    int flag = 0;
+    if (p != plast) { flag |= 1; plast = p; qstart = q; }                 // bit 0: add the recipient's share to the pool first
+    if ((q >= qstart) && (q < qstart + halfconn[p])) flag |= 2;            // bit 1: step 1 (mix into the pool); else step 2 (hand back)
+    qP[q] = p; qFlag[q] = flag;
+  }
+  // chunks: one per subbasin (its connections in the reference's order), a single one with INTERBASIN
+  std::vector<int> plist;
+  for (int q = 0; q < nConn; q++) if (std::find(plist.begin(), plist.end(), qP[q]) == plist.end()) plist.push_back(qP[q]);
+  std::map<int, std::vector<int> > byp;
+  for (int q = 0; q < nConn; q++) byp[qP[q]].push_back(q);
+  for (size_t i = 0; i < plist.size(); i++) {
+    const std::vector<int> &v = byp[plist[i]];
+    for (size_t j = 0; j < v.size(); j++) {
+      const int q = v[j];
+      _kFrom.push_back(qF[q]); _kTo.push_back(qT[q]); _aFlag.push_back(qFlag[q]);
+      _aFrac.push_back(pModel->GetHydroUnit(qT[q])->GetArea() / Asum[qP[q]]);   // (Ato / _Asum[p])
+    }
+    _chunk_ptr.push_back((int)_kFrom.size());
   }
 }
 
@@ -413,6 +481,14 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
     const int gF = pM->FindHRUGroup(s[2]), gT = pM->FindHRUGroup(s[5]);
     ExitGracefullyIf(gF == DOESNT_EXIST || gT == DOESNT_EXIST, "ParseInput: Lateral Flush - invalid 'to' or 'from' HRU Group used. Must define using :DefineHRUGroups command.");
     return new CmvLatFlush(from, to, gF, gT, !interbasin, pM);
+  }
+  if (cmd == ":LateralEquilibrate") {  // case 238: :LateralEquilibrate RAVEN_DEFAULT [HRUGroup] [SV] [mixing_rate] {INTERBASIN}
+    need(5);
+    const int sv = pM->ParseSVTypeIndex(s[3]);
+    const bool interbasin = (Len >= 6) && (s[5] == "INTERBASIN");
+    const int g = pM->FindHRUGroup(s[2]);
+    ExitGracefullyIf(g == DOESNT_EXIST, "ParseInput: Lateral Equilibrate - invalid HRU Group used. Must define using :DefineHRUGroups command.");
+    return new CmvLatEquilibrate(sv, g, s_to_d(s[4]), !interbasin, pM);
   }
   if (cmd == ":Interflow") {  // case 210; src/Interflow.cpp:19-45,78-87
     need(4);

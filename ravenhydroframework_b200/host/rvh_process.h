@@ -102,27 +102,51 @@ private:
   std::vector<CHydroProcessABC *> _pSubProcesses;
   std::vector<double> _aWeights;
 };
-// CmvLatFlush (reference src/LatFlush.cpp:16-177): moves the whole content of one state variable of the 'from' group's HRUs to a
-// state variable of the 'to' group's HRUs -- within each subbasin, split by recipient area, or to one single recipient HRU when
-// INTERBASIN is given.  No vertical connections; the lateral ones are built in Initialize() once the groups are populated.
-class CmvLatFlush : public CHydroProcessABC {
+// CLateralExchangeProcessABC (reference src/LateralExchangeABC.h:20-75): a process that moves water between HRUs.  No vertical
+// connections; the lateral ones (_kFrom/_kTo with one state variable on either side) are built in Initialize() once the HRU
+// groups are populated.  Connections are stored grouped into chunks of HRUs no other chunk touches (see rvn_model_desc.lat*).
+class CLateralExchangeProcessABC : public CHydroProcessABC {
 public:
-  CmvLatFlush(int from_sv_ind, int to_sv_ind, int from_HRU_grp, int to_HRU_grp, bool constrain_to_SBs, CModel *pM);
-  void Initialize() override;
-  void Compile(rvn_process &rec) const override { (void)rec; ExitGracefully("CmvLatFlush::Compile: lateral processes have no vertical record"); }
+  CLateralExchangeProcessABC(const char *name, int kind, CModel *pM) : CHydroProcessABC(name, pM), _kind(kind), _iFromLat(DOESNT_EXIST), _iToLat(DOESNT_EXIST), _mixing_rate(0.0) {}
+  void Compile(rvn_process &rec) const override { (void)rec; ExitGracefully("CLateralExchangeProcessABC::Compile: lateral processes have no vertical record"); }
+  int  GetLateralKind() const { return _kind; }
   int  GetNumLatConnections() const { return (int)_kFrom.size(); }
   const int *GetFromHRUIndices() const { return _kFrom.data(); }
   const int *GetToHRUIndices() const { return _kTo.data(); }
   const double *GetFractions() const { return _aFrac.data(); }
-  int  GetLateralFromIndex() const { return _iFlushFrom; }
-  int  GetLateralToIndex() const { return _iFlushTo; }
-  bool IsConstrainedToSubBasins() const { return _constrain_to_SBs; }
-  const std::vector<int> &ChunkOffsets() const { return _chunk_ptr; }   // connections grouped by subbasin (one chunk when INTERBASIN)
-private:
-  int _iFlushFrom, _iFlushTo, _kk_from, _kk_to;
-  bool _constrain_to_SBs;
-  std::vector<int> _kFrom, _kTo, _chunk_ptr;
+  const int *GetFlags() const { return _aFlag.data(); }
+  int  GetLateralFromIndex() const { return _iFromLat; }
+  int  GetLateralToIndex() const { return _iToLat; }
+  double GetMixingRate() const { return _mixing_rate; }
+  const std::vector<int> &ChunkOffsets() const { return _chunk_ptr; }
+protected:
+  int _kind, _iFromLat, _iToLat;
+  double _mixing_rate;
+  std::vector<int> _kFrom, _kTo, _aFlag, _chunk_ptr;
   std::vector<double> _aFrac;
+};
+// CmvLatFlush (reference src/LatFlush.cpp:16-177): moves the whole content of one state variable of the 'from' group's HRUs to a
+// state variable of the 'to' group's HRUs -- within each subbasin, split by recipient area, or to one single recipient HRU when
+// INTERBASIN is given.
+class CmvLatFlush : public CLateralExchangeProcessABC {
+public:
+  CmvLatFlush(int from_sv_ind, int to_sv_ind, int from_HRU_grp, int to_HRU_grp, bool constrain_to_SBs, CModel *pM);
+  void Initialize() override;
+  bool IsConstrainedToSubBasins() const { return _constrain_to_SBs; }
+private:
+  int _kk_from, _kk_to;
+  bool _constrain_to_SBs;
+};
+// CmvLatEquilibrate (reference src/LatEquilibrate.cpp:14-212): partially mixes one state variable among the HRUs of a group, within
+// each subbasin (or across the whole model with INTERBASIN): a fraction min(mixing_rate*dt,1) of every member's storage is pooled
+// in the group's first HRU of the basin and handed back in proportion to area.
+class CmvLatEquilibrate : public CLateralExchangeProcessABC {
+public:
+  CmvLatEquilibrate(int sv_ind, int HRU_grp, double mixing_rate, bool constrain_to_SBs, CModel *pM);
+  void Initialize() override;
+private:
+  int _kk;
+  bool _constrain_to_SBs;
 };
 void CalcWeightsFromUniformNums(const double *aVals, double *aWeights, int N);   // src/CommonFunctions.cpp:1845-1853
 

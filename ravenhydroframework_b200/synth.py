@@ -514,6 +514,19 @@ def write_hbv(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUTE_
             f.write(":HRUGroup UpGroup\n  " + " ".join(str(k) for k in range(1, n_hru + 1) if k % 3 != 0) + "\n:EndHRUGroup\n")
             f.write(":HRUGroup LowGroup\n  " + " ".join(str(k) for k in range(1, n_hru + 1) if k % 3 == 0 or k % 5 == 0) + "\n:EndHRUGroup\n")
             f.write(":HRUGroup Sink\n  2\n:EndHRUGroup\n")
+    if variant in ("equilibrate", "equilibrate_interbasin"):
+        # lateral mixing (reference CmvLatEquilibrate): the fast reservoirs of the 'MixGroup' HRUs of a subbasin are partially
+        # mixed each step; with INTERBASIN the snow packs of the 'Wet' HRUs are mixed across the whole model
+        a = ":HydrologicProcesses\n"
+        assert a in rvi
+        rvi = rvi.replace(a, ":DefineHRUGroups MixGroup Wet\n" + a)
+        e = ":EndHydrologicProcesses"
+        rvi = rvi.replace(e, "  :LateralEquilibrate RAVEN_DEFAULT     MixGroup FAST_RESERVOIR 0.35\n"
+                          + ("  :LateralEquilibrate RAVEN_DEFAULT     Wet SNOW 0.6 INTERBASIN\n" if variant == "equilibrate_interbasin" else "") + e)
+        n_hru = n_sb * hru_per_sb
+        with open(base + ".rvh", "a") as f:
+            f.write(":HRUGroup MixGroup\n  " + " ".join(str(k) for k in range(1, n_hru + 1) if k % 4 != 0) + "\n:EndHRUGroup\n")
+            f.write(":HRUGroup Wet\n  " + " ".join(str(k) for k in range(1, n_hru + 1) if k % 2 == 0) + "\n:EndHRUGroup\n")
     _write(base + ".rvi", rvi)
     _write(base + ".rvc", HBV_RVC + (":UniformInitialConditions DEPRESSION 18.0\n" if (algo or {}).get("depression") else ""))
     return base

@@ -44,6 +44,10 @@ if hasattr(synth, "write_hbv"):
     for _k in "abcdefghij":   # other members of the infiltration / soil evaporation / percolation / baseflow process classes
         CASES["hbv_algo_" + _k] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=220, seed=30 + ord(_k), routing="ROUTE_MUSKINGUM", season_offset=80,
                                        variant="algo:" + _k)
+    # lateral mixing (CmvLatEquilibrate): several subbasins (where the reference's pool bookkeeping never reaches its hand-back step) and
+    # one subbasin (where it does), the latter with an INTERBASIN mixing of the snow packs as well
+    CASES["hbv_equil"] = dict(kind="hbv", n_sb=4, hru_per_sb=7, n_days=200, seed=41, routing="ROUTE_MUSKINGUM", season_offset=60, variant="equilibrate")
+    CASES["hbv_equil_1sb"] = dict(kind="hbv", n_sb=1, hru_per_sb=9, n_days=200, seed=42, season_offset=20, variant="equilibrate_interbasin")
     CASES["hbv_lateral"] = dict(kind="hbv", n_sb=4, hru_per_sb=7, n_days=250, seed=8, routing="ROUTE_MUSKINGUM", season_offset=40, variant="lateral")
 if hasattr(synth, "write_blended"):
     # Blended multi-model template (BASELINE config 4): weighted process groups, VIC/TOPMODEL/analytic algorithms, SNOBAL_HBV
