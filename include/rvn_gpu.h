@@ -242,14 +242,17 @@ typedef struct rvn_process {
 #define RVN_GRP_MEMBER 4
 
 /* one lateral exchange process (LAT_FLUSH: reference CmvLatFlush, src/LatFlush.cpp:55-234) */
-typedef enum { RVN_LAT_FLUSH = 0, RVN_LAT_EQUILIBRATE = 1 /* CmvLatEquilibrate, src/LatEquilibrate.cpp:49-212 */ } rvn_lateral_kind;
+typedef enum { RVN_LAT_FLUSH = 0, RVN_LAT_EQUILIBRATE = 1 /* CmvLatEquilibrate, src/LatEquilibrate.cpp:49-212 */,
+               RVN_LAT_REDISTRIBUTE = 2 /* CmvLatRedistribute, src/SnowRedistribute.cpp:59-215 */ } rvn_lateral_kind;
+typedef enum { RVN_REDIST_CONTINUOUS = 0, RVN_REDIST_THRESHOLD = 1 } rvn_redist_method;
 typedef struct rvn_lateral {
   int32_t kind;            /* rvn_lateral_kind */
   int32_t sv_from, sv_to;  /* state-variable indices _iFromLat / _iToLat (the same for every connection of a flush) */
   int32_t nconn, conn0;    /* connections in lat_kfrom/lat_kto/lat_frac */
   int32_t nchunks, chunk0; /* chunk offsets in lat_chunk_ptr (nchunks + 1 entries) */
-  int32_t pad_;
-  double  mixing_rate;     /* LAT_EQUILIBRATE: fraction mixed per day; the step mixes min(mixing_rate*dt, 1) */
+  int32_t method;          /* LAT_REDISTRIBUTE: rvn_redist_method */
+  double  mixing_rate;     /* LAT_EQUILIBRATE: fraction mixed per day, the step mixes min(mixing_rate*dt, 1);
+                            * LAT_REDISTRIBUTE: _max_snow_height [mm] */
 } rvn_lateral;
 
 typedef struct rvn_options {
@@ -355,7 +358,8 @@ typedef struct rvn_model_desc {
   int32_t nLat, nLatConn;
   const struct rvn_lateral *lat;   /* [nLat] */
   const int32_t *lat_kfrom, *lat_kto;
-  const double  *lat_frac;         /* FLUSH: share of the source's water this recipient gets; EQUILIBRATE: A_to / A_sum of its subbasin */
+  const double  *lat_frac;         /* FLUSH: share of the source's water this recipient gets; EQUILIBRATE: A_to / A_sum of its subbasin;
+                                    * REDISTRIBUTE: the connection weight of :LateralConnections */
   const int32_t *lat_flag;         /* EQUILIBRATE (the control flow of src/LatEquilibrate.cpp:190-207, which depends on the connection
                                     * list only): bit 0 = first add mix*max(S_to,0)*A_to to the subbasin's pool; bit 1 = step 1 (mix the
                                     * source into the pool), else step 2 (hand the pool back by area) */

@@ -1199,6 +1199,33 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
             }
           }
         }
+        else if (L->kind == RVN_LAT_REDISTRIBUTE) { /* CmvLatRedistribute::GetLateralExchange, src/SnowRedistribute.cpp:114-215 */
+          const double TAN_80_DEGREES = tan(80.0 * O_PI / 180.0), RAD_TO_DEG = 180.0 / O_PI;
+          const double SWE_TO_DEPTH_FACTOR = 1000.0 / 250.0;
+          for (int q = 0; q < L->nconn; q++) {
+            const int kF = d->lat_kfrom[L->conn0 + q];
+            double weight = d->lat_frac[L->conn0 + q];
+            double areaFrom = d->hru_area[kF], slope_rad = d->hru_slope[kF];
+            double slope_deg = slope_rad * RAD_TO_DEG;
+            double snowSWE = state[(size_t)kF * NS + L->sv_from], snowMoved = 0.0;
+            if (L->method == RVN_REDIST_CONTINUOUS) {
+              double snowTransport = omin(0.5, slope_deg / TAN_80_DEGREES) * omin(1.0, snowSWE / L->mixing_rate);
+              snowMoved = snowTransport * snowSWE;
+            } else {
+              double snowDepth = snowSWE * SWE_TO_DEPTH_FACTOR;
+              double slope_thres = slope_deg;
+              if (slope_thres < 10.0) slope_thres = 10.0;
+              double threshold_snow_height_m = 3178.4 * pow(slope_thres, -1.998);
+              double threshold_snow_height = threshold_snow_height_m * 1000;
+              if (slope_deg > 60.0) threshold_snow_height = 0.0;
+              if (snowDepth > threshold_snow_height) {
+                double excessSnowDepth = snowDepth - threshold_snow_height;
+                snowMoved = excessSnowDepth / SWE_TO_DEPTH_FACTOR;
+              }
+            }
+            ex[q] = (snowMoved * weight * areaFrom) / tstep;
+          }
+        }
         else for (int q = 0; q < L->nconn; q++) {
           const int kF = d->lat_kfrom[L->conn0 + q], kT = d->lat_kto[L->conn0 + q];
           double stor = state[(size_t)kF * NS + L->sv_from], to_stor = state[(size_t)kT * NS + L->sv_to];

@@ -24,7 +24,9 @@ struct DevLateral {
   int32_t sv_snow;           // index of SNOW (for a SNOW_LIQ recipient) or -1
   int32_t kind;              // rvn_lateral_kind
   const int32_t *flag;       // LAT_EQUILIBRATE control-flow flags per connection
-  double mixing_rate;        // LAT_EQUILIBRATE [1/d]
+  double mixing_rate;        // LAT_EQUILIBRATE [1/d]; LAT_REDISTRIBUTE: max snow height [mm]
+  int32_t method;            // LAT_REDISTRIBUTE: rvn_redist_method
+  double tan80;              // tan(80 deg) from the host's libm (the reference's TAN_80_DEGREES)
 };
 
 // GetStateVarMax of the recipient for the state-variable types a flush may target here; CANOPY / CANOPY_SNOW recipients (date
@@ -62,6 +64,29 @@ __global__ void lateral_flush_kernel(const __grid_constant__ DevModel M, const D
       if (flag & 2) { r = mix * dmax(stor, 0.0) / tstep * Afrom; sum += r * tstep; }   // step 1: into the mixing unit
       else r = sum * L.frac[q] / tstep;                                                // step 2: back out by area
       rates[q] = r;
+    }
+  }
+  else if (L.kind == RVN_LAT_REDISTRIBUTE) {   // CmvLatRedistribute::GetLateralExchange, src/SnowRedistribute.cpp:114-215
+    const double RAD_TO_DEG = 180.0 / D_PI, SWE_TO_DEPTH_FACTOR = 1000.0 / 250.0;
+    for (int q = q0; q < q1; q++) {
+      const int kF = L.kfrom[q];
+      const double weight = L.frac[q], areaFrom = M.hru_area[kF];
+      const double slope_deg = M.hru_slope[kF] * RAD_TO_DEG;
+      const double snowSWE = from_row[kF];
+      double snowMoved = 0.0;
+      if (L.method == RVN_REDIST_CONTINUOUS) {
+        const double snowTransport = dmin(0.5, slope_deg / L.tan80) * dmin(1.0, snowSWE / L.mixing_rate);
+        snowMoved = snowTransport * snowSWE;
+      } else {   // Bernhardt & Schulz (2010) threshold with the FSM2 holding depth
+        const double snowDepth = snowSWE * SWE_TO_DEPTH_FACTOR;
+        double slope_thres = slope_deg;
+        if (slope_thres < 10.0) slope_thres = 10.0;
+        const double threshold_snow_height_m = 3178.4 * pow(slope_thres, -1.998);
+        double threshold_snow_height = threshold_snow_height_m * D_MM_PER_METER;
+        if (slope_deg > 60.0) threshold_snow_height = 0.0;
+        if (snowDepth > threshold_snow_height) { const double excessSnowDepth = snowDepth - threshold_snow_height; snowMoved = excessSnowDepth / SWE_TO_DEPTH_FACTOR; }
+      }
+      rates[q] = (snowMoved * weight * areaFrom) / tstep;
     }
   }
   else for (int q = q0; q < q1; q++) {   // GetLateralExchange: every rate from the state before any of them is applied

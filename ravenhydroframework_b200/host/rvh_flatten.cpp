@@ -92,7 +92,7 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
       for (int q = 0; q < nc; q++) if (!_pHydroUnits[lf->GetFromHRUIndices()[q]]->IsEnabled() || !_pHydroUnits[lf->GetToHRUIndices()[q]]->IsEnabled()) all_enabled = false;
       if (!all_enabled) continue;
       rvn_lateral L; memset(&L, 0, sizeof(L));
-      L.kind = lf->GetLateralKind(); L.sv_from = lf->GetLateralFromIndex(); L.sv_to = lf->GetLateralToIndex(); L.mixing_rate = lf->GetMixingRate();
+      L.kind = lf->GetLateralKind(); L.sv_from = lf->GetLateralFromIndex(); L.sv_to = lf->GetLateralToIndex(); L.mixing_rate = lf->GetMixingRate(); L.method = lf->GetMethod();
       L.nconn = nc; L.conn0 = (int32_t)_f_lat_kfrom.size();
       L.nchunks = (int32_t)lf->ChunkOffsets().size() - 1; L.chunk0 = (int32_t)_f_lat_chunk.size();
       for (int q = 0; q < nc; q++) { _f_lat_kfrom.push_back(lf->GetFromHRUIndices()[q]); _f_lat_kto.push_back(lf->GetToHRUIndices()[q]); _f_lat_frac.push_back(lf->GetFractions()[q]);

@@ -659,6 +659,20 @@ static void ParseHRUPropsFile(CModel *pModel, const optStruct &Options) {
       }
       continue;
     }
+    if (c == ":LateralConnections") {   // src/ParseHRUFile.cpp:1134-1200: {source HRU ID} {recipient HRU ID} {weight} rows
+      ExitGracefullyIf(s.size() < 2, "ParseHRUPropsFile: :LateralConnections needs a process name");
+      ExitGracefullyIf(s[1] != "SNOW_REDISTRIBUTE", "ParseHRUPropsFile: :LateralConnections " + s[1] + " is not supported by the B200 build");
+      std::vector<CmvLatRedistribute *> targets;
+      for (int j = 0; j < pModel->GetNumProcesses(); j++)
+        if (CmvLatRedistribute *r = dynamic_cast<CmvLatRedistribute *>(pModel->GetProcess(j))) { r->ClearConnections(); targets.push_back(r); }
+      while (p.Tokenize(s)) {
+        if (s.empty()) continue;
+        if (s[0] == ":EndLateralConnections") break;
+        ExitGracefullyIf(s.size() < 3, "ParseHRUPropsFile: improper format of a :LateralConnections row");
+        for (size_t t = 0; t < targets.size(); t++) targets[t]->AddConnection(s_to_ll(s[0]), s_to_ll(s[1]), s_to_d(s[2]));
+      }
+      continue;
+    }
     if (c == ":PopulateHRUGroup" || c == ":PopulateSubBasinGroup") continue;   // output-only groups
     ExitGracefully("ParseHRUPropsFile: command " + c + " (line " + std::to_string(p.line()) + ") is not supported by the B200 build");
   }

@@ -209,6 +209,42 @@ void CmvLatEquilibrate::Initialize() {   // src/LatEquilibrate.cpp:49-148 (conne
   }
 }
 
+CmvLatRedistribute::CmvLatRedistribute(int sv_ind, double max_snow_height, int method, CModel *pM)
+    : CLateralExchangeProcessABC("SnowRedistribute", RVN_LAT_REDISTRIBUTE, pM) {
+  _iFromLat = _iToLat = sv_ind; _mixing_rate = max_snow_height; _method = method;
+  ExitGracefullyIf(sv_ind == DOESNT_EXIST, "CmvLatRedistribute::unrecognized state variable specified in :SnowRedistribute command");
+}
+void CmvLatRedistribute::Initialize() {   // src/SnowRedistribute.cpp:59-93
+  _kFrom.clear(); _kTo.clear(); _aFrac.clear(); _aFlag.clear(); _chunk_ptr.assign(1, 0);
+  ExitGracefullyIf(_src.empty(), "CmvLatRedistribute::Initialize(): no lateral connections specified. Missing the :LateralConnections command?");
+  const int nH = pModel->GetNumHRUs(), nC = (int)_src.size();
+  std::map<long long, int> hru_of_id;
+  for (int k = 0; k < nH; k++) hru_of_id.insert(std::make_pair(pModel->GetHydroUnit(k)->ID, k));
+  std::vector<int> kF(nC), kT(nC);
+  for (int q = 0; q < nC; q++) {
+    std::map<long long, int>::const_iterator a = hru_of_id.find(_src[q]), b = hru_of_id.find(_dst[q]);
+    ExitGracefullyIf(a == hru_of_id.end() || b == hru_of_id.end(), "CmvLatRedistribute::Initialize: HRU ID in :LateralConnections does not exist");
+    kF[q] = a->second; kT[q] = b->second;
+  }
+  // chunks = connected components of the connection graph (HRUs no other chunk touches), each in the table's order
+  std::vector<int> parent(nH);
+  for (int k = 0; k < nH; k++) parent[k] = k;
+  struct UF { static int find(std::vector<int> &p, int x) { while (p[x] != x) { p[x] = p[p[x]]; x = p[x]; } return x; } };
+  for (int q = 0; q < nC; q++) { int a = UF::find(parent, kF[q]), b = UF::find(parent, kT[q]); if (a != b) parent[a] = b; }
+  std::vector<int> roots;
+  std::map<int, std::vector<int> > byroot;
+  for (int q = 0; q < nC; q++) {
+    const int r = UF::find(parent, kF[q]);
+    if (!byroot.count(r)) roots.push_back(r);
+    byroot[r].push_back(q);
+  }
+  for (size_t i = 0; i < roots.size(); i++) {
+    const std::vector<int> &v = byroot[roots[i]];
+    for (size_t j = 0; j < v.size(); j++) { _kFrom.push_back(kF[v[j]]); _kTo.push_back(kT[v[j]]); _aFrac.push_back(_w[v[j]]); _aFlag.push_back(0); }
+    _chunk_ptr.push_back((int)_kFrom.size());
+  }
+}
+
 // ---- Precipitation ---------------------------------------------------------------------------------
 void CmvPrecipitation::GetParticipatingStateVarList(sv_type *aSV, int *aLev, int &nSV) {
   nSV = 1; aSV[0] = RVN_SV_ATMOS_PRECIP; aLev[0] = DOESNT_EXIST;
@@ -489,6 +525,14 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
     const int g = pM->FindHRUGroup(s[2]);
     ExitGracefullyIf(g == DOESNT_EXIST, "ParseInput: Lateral Equilibrate - invalid HRU Group used. Must define using :DefineHRUGroups command.");
     return new CmvLatEquilibrate(sv, g, s_to_d(s[4]), !interbasin, pM);
+  }
+  if (cmd == ":SnowRedistribute") {  // case 241: :SnowRedistribute [method] [SV] [max_snow_height]
+    need(4);
+    int method = RVN_REDIST_CONTINUOUS;
+    if (s[1] == "CONTINUOUS") method = RVN_REDIST_CONTINUOUS;
+    else if (s[1] == "THRESHOLD") method = RVN_REDIST_THRESHOLD;
+    else ExitGracefully("ParseMainInputFile: Unrecognized snow redistribution method");
+    return new CmvLatRedistribute(pM->ParseSVTypeIndex(s[2]), s_to_d(s[3]), method, pM);
   }
   if (cmd == ":Interflow") {  // case 210; src/Interflow.cpp:19-45,78-87
     need(4);

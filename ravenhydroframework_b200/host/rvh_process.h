@@ -107,7 +107,7 @@ private:
 // groups are populated.  Connections are stored grouped into chunks of HRUs no other chunk touches (see rvn_model_desc.lat*).
 class CLateralExchangeProcessABC : public CHydroProcessABC {
 public:
-  CLateralExchangeProcessABC(const char *name, int kind, CModel *pM) : CHydroProcessABC(name, pM), _kind(kind), _iFromLat(DOESNT_EXIST), _iToLat(DOESNT_EXIST), _mixing_rate(0.0) {}
+  CLateralExchangeProcessABC(const char *name, int kind, CModel *pM) : CHydroProcessABC(name, pM), _kind(kind), _iFromLat(DOESNT_EXIST), _iToLat(DOESNT_EXIST), _method(0), _mixing_rate(0.0) {}
   void Compile(rvn_process &rec) const override { (void)rec; ExitGracefully("CLateralExchangeProcessABC::Compile: lateral processes have no vertical record"); }
   int  GetLateralKind() const { return _kind; }
   int  GetNumLatConnections() const { return (int)_kFrom.size(); }
@@ -118,9 +118,10 @@ public:
   int  GetLateralFromIndex() const { return _iFromLat; }
   int  GetLateralToIndex() const { return _iToLat; }
   double GetMixingRate() const { return _mixing_rate; }
+  int  GetMethod() const { return _method; }
   const std::vector<int> &ChunkOffsets() const { return _chunk_ptr; }
 protected:
-  int _kind, _iFromLat, _iToLat;
+  int _kind, _iFromLat, _iToLat, _method;
   double _mixing_rate;
   std::vector<int> _kFrom, _kTo, _aFlag, _chunk_ptr;
   std::vector<double> _aFrac;
@@ -147,6 +148,18 @@ public:
 private:
   int _kk;
   bool _constrain_to_SBs;
+};
+// CmvLatRedistribute (reference src/SnowRedistribute.cpp:14-215): gravitational snow redistribution along the user's
+// :LateralConnections SNOW_REDISTRIBUTE table (source HRU ID, recipient HRU ID, weight) of the .rvh file.
+class CmvLatRedistribute : public CLateralExchangeProcessABC {
+public:
+  CmvLatRedistribute(int sv_ind, double max_snow_height, int method, CModel *pM);
+  void AddConnection(long long src_id, long long dst_id, double w) { _src.push_back(src_id); _dst.push_back(dst_id); _w.push_back(w); }
+  void ClearConnections() { _src.clear(); _dst.clear(); _w.clear(); }
+  void Initialize() override;
+private:
+  std::vector<long long> _src, _dst;
+  std::vector<double> _w;
 };
 void CalcWeightsFromUniformNums(const double *aVals, double *aWeights, int N);   // src/CommonFunctions.cpp:1845-1853
 

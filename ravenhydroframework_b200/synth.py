@@ -514,6 +514,29 @@ def write_hbv(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUTE_
             f.write(":HRUGroup UpGroup\n  " + " ".join(str(k) for k in range(1, n_hru + 1) if k % 3 != 0) + "\n:EndHRUGroup\n")
             f.write(":HRUGroup LowGroup\n  " + " ".join(str(k) for k in range(1, n_hru + 1) if k % 3 == 0 or k % 5 == 0) + "\n:EndHRUGroup\n")
             f.write(":HRUGroup Sink\n  2\n:EndHRUGroup\n")
+    if variant in ("redistribute", "redistribute_threshold"):
+        # gravitational snow redistribution (reference CmvLatRedistribute): within each subbasin HRU j sheds snow to HRUs j+1 and j+2
+        # (weights 0.6 / 0.4; 1.0 for the last pair) along the :LateralConnections table.  Slopes are steepened (x3.2, up to 64 deg)
+        # so that the threshold method's holding depth is exceeded and its > 60 deg branch is taken.
+        e = ":EndHydrologicProcesses"
+        rvi = rvi.replace(e, "  :SnowRedistribute  %s SNOW %s\n" % (("THRESHOLD", "500.0") if variant.endswith("threshold") else ("CONTINUOUS", "150.0")) + e)
+        lines = open(base + ".rvh").read().split("\n")
+        i0 = [i for i, l in enumerate(lines) if l.startswith(":HRUs")][0] + 3
+        i1 = [i for i, l in enumerate(lines) if l.startswith(":EndHRUs")][0]
+        for i in range(i0, i1):
+            t = lines[i].split(",")
+            t[11] = " %.3f" % (3.2 * float(t[11]))
+            lines[i] = ",".join(t)
+        con = [":LateralConnections SNOW_REDISTRIBUTE"]
+        for p_ in range(n_sb):
+            ks = [p_ * hru_per_sb + j + 1 for j in range(hru_per_sb)]
+            for j in range(len(ks) - 1):
+                if j + 2 < len(ks):
+                    con += ["  %d %d 0.6" % (ks[j], ks[j + 1]), "  %d %d 0.4" % (ks[j], ks[j + 2])]
+                else:
+                    con += ["  %d %d 1.0" % (ks[j], ks[j + 1])]
+        con += [":EndLateralConnections"]
+        open(base + ".rvh", "w").write("\n".join(lines + con) + "\n")
     if variant in ("equilibrate", "equilibrate_interbasin"):
         # lateral mixing (reference CmvLatEquilibrate): the fast reservoirs of the 'MixGroup' HRUs of a subbasin are partially
         # mixed each step; with INTERBASIN the snow packs of the 'Wet' HRUs are mixed across the whole model

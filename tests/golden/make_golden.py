@@ -48,6 +48,9 @@ if hasattr(synth, "write_hbv"):
     # one subbasin (where it does), the latter with an INTERBASIN mixing of the snow packs as well
     CASES["hbv_equil"] = dict(kind="hbv", n_sb=4, hru_per_sb=7, n_days=200, seed=41, routing="ROUTE_MUSKINGUM", season_offset=60, variant="equilibrate")
     CASES["hbv_equil_1sb"] = dict(kind="hbv", n_sb=1, hru_per_sb=9, n_days=200, seed=42, season_offset=20, variant="equilibrate_interbasin")
+    # gravitational snow redistribution along a :LateralConnections table (CmvLatRedistribute), both methods
+    CASES["hbv_redist"] = dict(kind="hbv", n_sb=3, hru_per_sb=6, n_days=240, seed=43, routing="ROUTE_MUSKINGUM", variant="redistribute")
+    CASES["hbv_redist_thresh"] = dict(kind="hbv", n_sb=3, hru_per_sb=6, n_days=240, seed=44, routing="ROUTE_MUSKINGUM", variant="redistribute_threshold")
     CASES["hbv_lateral"] = dict(kind="hbv", n_sb=4, hru_per_sb=7, n_days=250, seed=8, routing="ROUTE_MUSKINGUM", season_offset=40, variant="lateral")
 if hasattr(synth, "write_blended"):
     # Blended multi-model template (BASELINE config 4): weighted process groups, VIC/TOPMODEL/analytic algorithms, SNOBAL_HBV
