@@ -134,7 +134,8 @@ typedef enum {
 /* model-wide method switches; numbering is local to this ABI (the host maps Raven's keywords) */
 typedef enum { RVN_RAINSNOW_DATA = 0, RVN_RAINSNOW_DINGMAN, RVN_RAINSNOW_HBV, RVN_RAINSNOW_UBCWM, RVN_RAINSNOW_THRESHOLD } rvn_rainsnow;
 typedef enum { RVN_POTMELT_NONE = 0, RVN_POTMELT_DATA, RVN_POTMELT_DEGREE_DAY, RVN_POTMELT_HBV, RVN_POTMELT_HMETS } rvn_potmelt;
-typedef enum { RVN_PET_DATA = 0, RVN_PET_FROMMONTHLY, RVN_PET_CONSTANT, RVN_PET_NONE, RVN_PET_HARGREAVES_1985, RVN_PET_OUDIN } rvn_pet;
+typedef enum { RVN_PET_DATA = 0, RVN_PET_FROMMONTHLY, RVN_PET_CONSTANT, RVN_PET_NONE, RVN_PET_HARGREAVES_1985, RVN_PET_OUDIN,
+               RVN_PET_HAMON, RVN_PET_LINEAR_TEMP, RVN_PET_MOHYSE } rvn_pet;   /* CModel::EstimatePET, src/Evaporation.cpp:282-540 */
 typedef enum { RVN_OROCORR_NONE = 0, RVN_OROCORR_SIMPLELAPSE, RVN_OROCORR_HBV } rvn_orocorr;
 typedef enum { RVN_ROUTE_NONE = 0, RVN_ROUTE_MUSKINGUM, RVN_ROUTE_MUSKINGUM_CUNGE, RVN_ROUTE_STORAGECOEFF,
                RVN_ROUTE_PLUG_FLOW, RVN_ROUTE_DIFFUSIVE_WAVE, RVN_ROUTE_HYDROLOGIC } rvn_routing;
@@ -156,7 +157,7 @@ typedef enum {
   RVN_G_PRECIP_LAPSE, RVN_G_RAINSNOW_TEMP, RVN_G_RAINSNOW_DELTA, RVN_G_AVG_ANNUAL_SNOW, RVN_G_SNOW_TEMPERATURE,
   RVN_G_HBVEC_LAPSE_UPPER, RVN_G_HBVEC_LAPSE_RATE, RVN_G_HBVEC_LAPSE_ELEV, RVN_G_AIRSNOW_COEFF,
   RVN_G_AVG_ANNUAL_RUNOFF, RVN_G_MAX_SWE_SURFACE, RVN_G_TOC_MULTIPLIER, RVN_G_TIME_TO_PEAK_MULTIPLIER,
-  RVN_G_GAMMA_SHAPE_MULTIPLIER, RVN_G_GAMMA_SCALE_MULTIPLIER, RVN_G_COUNT
+  RVN_G_GAMMA_SHAPE_MULTIPLIER, RVN_G_GAMMA_SCALE_MULTIPLIER, RVN_G_MOHYSE_PET_COEFF, RVN_G_COUNT
 } rvn_global_field;
 typedef enum {
   RVN_LU_IMPERMEABLE_FRAC = 0, RVN_LU_FOREST_COVERAGE, RVN_LU_FOREST_SPARSENESS, RVN_LU_MELT_FACTOR,
@@ -167,7 +168,7 @@ typedef enum {
   RVN_LU_GLAC_STORAGE_COEFF, RVN_LU_HBV_GLACIER_AG, RVN_LU_DEP_MAX, RVN_LU_LAKE_PET_CORR, RVN_LU_OW_PET_CORR,
   RVN_LU_PARTITION_COEFF, RVN_LU_CC_DECAY_COEFF, RVN_LU_MAX_SAT_AREA_FRAC, RVN_LU_PDM_B, RVN_LU_AET_COEFF,
   RVN_LU_MAX_DEP_AREA_FRAC, RVN_LU_PONDED_EXP, RVN_LU_AWBM_AREAFRAC1, RVN_LU_AWBM_AREAFRAC2, RVN_LU_HYMOD2_G, RVN_LU_HYMOD2_KMAX,
-  RVN_LU_HYMOD2_EXP, RVN_LU_COUNT
+  RVN_LU_HYMOD2_EXP, RVN_LU_PET_LIN_COEFF, RVN_LU_COUNT
 } rvn_landuse_field;
 typedef enum {
   RVN_V_MAX_HEIGHT = 0, RVN_V_MAX_LAI, RVN_V_SAI_HT_RATIO, RVN_V_MAX_CAPACITY, RVN_V_MAX_SNOW_CAPACITY,
@@ -349,6 +350,10 @@ typedef struct rvn_model_desc {
   int32_t nEtRows, pad2_;
   const double *et_radia;
   const int32_t *et_row;      /* [nSteps] */
+  /* day geometry on the same rows (NULL unless a consumed PET needs it): day_length[row][hru] = CRadiation::DayLength(lat, declin)
+   * [d] (src/Radiation.cpp:438-445; F.day_length, src/UpdateForcings.cpp:175) for PET_HAMON, sunset_angle[row][hru] =
+   * acos(-tan(lat)*tan(declin)) [rad] for PET_MOHYSE (src/Evaporation.cpp:476-483) */
+  const double *day_length, *sunset_angle;
   /* lateral exchange processes (reference CLateralExchangeProcessABC; CModel::ApplyLateralProcess, src/Model.cpp:3126-3165,
    * applied by the solver after ALL vertical processes of ALL HRUs and before the routing prep, src/Solvers.cpp:404-443).
    * Only processes that apply (gate of the first source HRU, every participating HRU enabled) are listed, in process order.

@@ -334,6 +334,29 @@ static void update_forcings(const rvn_model_desc *d, const double *ptab, int mem
         PET = omax(0.0, 0.0023 * Ra * sqrt(delT) * (F[RVN_F_TEMP_DAILY_AVE] + 17.8));
       }
     }
+    else if (method == RVN_PET_OUDIN) { /* src/Evaporation.cpp:485-489 */
+      if (d->et_radia) {
+        double ET_radia = d->et_radia[(size_t)d->et_row[step] * d->nHRU + k];
+        PET = omax(ET_radia / O_DENSITY_WATER / 2.501 * O_MM_PER_METER * (F[RVN_F_TEMP_DAILY_AVE] + 5.0) / 100.0, 0.0);
+      }
+    }
+    else if (method == RVN_PET_HAMON) { /* Hamon1961Evap, src/Evaporation.cpp:263-271; GetSaturatedVaporPressure, src/CommonFunctions.cpp:935-949 */
+      if (d->day_length) {
+        double T = F[RVN_F_TEMP_DAILY_AVE], day_length = d->day_length[(size_t)d->et_row[step] * d->nHRU + k];
+        double sat_vap = (T >= 0) ? 0.61078 * exp(17.26939 * T / (T + 237.3)) : 0.61078 * exp(21.87456 * T / (T + 265.5));
+        double abs_hum = 216.7 * (sat_vap * 10) / (T + 273.16);
+        PET = omax(0.0, 0.0055 * 4.0 * abs_hum * day_length * day_length * 25.4);
+      }
+    }
+    else if (method == RVN_PET_LINEAR_TEMP) { /* src/Evaporation.cpp:306-311 */
+      PET = P_LU(&c, RVN_LU_PET_LIN_COEFF) * omax(F[RVN_F_TEMP_DAILY_AVE], 0.0);
+    }
+    else if (method == RVN_PET_MOHYSE) { /* src/Evaporation.cpp:476-483 */
+      if (d->sunset_angle) {
+        double cpet = P_G(&c, RVN_G_MOHYSE_PET_COEFF), ws = d->sunset_angle[(size_t)d->et_row[step] * d->nHRU + k];
+        PET = cpet / 3.1415926535898 * ws * exp((17.3 * F[RVN_F_TEMP_AVE]) / (238 + F[RVN_F_TEMP_AVE]));
+      }
+    }
     else if (method == RVN_PET_FROMMONTHLY) { /* src/Evaporation.cpp:349-355 */
       double peRatio = 1.0 + O_HBV_PET_TEMP_CORR * (temp_ave_unc - temp_month_ave);
       peRatio = omax(0.0, omin(2.0, peRatio));
@@ -348,7 +371,7 @@ static void update_forcings(const rvn_model_desc *d, const double *ptab, int mem
     double factor = O_GLOBAL_PET_CORR * omax(1.0 - O_HBV_PET_ELEV_CORR * (elev - ref_elev_temp), 0.0);
     F[RVN_F_PET] *= factor; F[RVN_F_OW_PET] *= factor;
   }
-  if (d->opt.evaporation == RVN_PET_FROMMONTHLY || d->opt.evaporation == RVN_PET_CONSTANT) /* IsDailyPETmethod, src/Evaporation.cpp:540-556 */
+  if (d->opt.evaporation == RVN_PET_FROMMONTHLY || d->opt.evaporation == RVN_PET_CONSTANT || d->opt.evaporation == RVN_PET_HAMON || d->opt.evaporation == RVN_PET_LINEAR_TEMP) /* IsDailyPETmethod, src/Evaporation.cpp:540-556 */
     F[RVN_F_PET] *= subdaily_corr;
   if (d->opt.snow_suppress_PET) {
     double SWE = 0.0, sc = 1.0;

@@ -356,6 +356,25 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
         delT = dmax(delT, 0.0);
         PET = dmax(0.0, 0.0023 * Ra * sqrt(delT) * (F[RVN_F_TEMP_DAILY_AVE] + 17.8));
       }
+    } else if (method == RVN_PET_OUDIN) {   // src/Evaporation.cpp:485-489
+      if (M.et_radia != nullptr) {
+        const double ET_radia = M.et_radia[(size_t)M.et_row[step] * M.nHp + k];
+        PET = dmax(ET_radia / D_DENSITY_WATER / D_LH_VAPOR * D_MM_PER_METER * (F[RVN_F_TEMP_DAILY_AVE] + 5.0) / 100.0, 0.0);
+      }
+    } else if (method == RVN_PET_HAMON) {   // Hamon1961Evap  src/Evaporation.cpp:263-271; GetSaturatedVaporPressure  src/CommonFunctions.cpp:935-949
+      if (M.day_length != nullptr) {
+        const double T = F[RVN_F_TEMP_DAILY_AVE], day_length = M.day_length[(size_t)M.et_row[step] * M.nHp + k];
+        const double sat_vap = (T >= 0) ? 0.61078 * exp(17.26939 * T / (T + 237.3)) : 0.61078 * exp(21.87456 * T / (T + 265.5));
+        const double abs_hum = 216.7 * (sat_vap * 10) / (T + 273.16);
+        PET = dmax(0.0, 0.0055 * 4.0 * abs_hum * day_length * day_length * 25.4);
+      }
+    } else if (method == RVN_PET_LINEAR_TEMP) {   // src/Evaporation.cpp:306-311
+      PET = c.LU(RVN_LU_PET_LIN_COEFF) * dmax(F[RVN_F_TEMP_DAILY_AVE], 0.0);
+    } else if (method == RVN_PET_MOHYSE) {   // src/Evaporation.cpp:476-483
+      if (M.sunset_angle != nullptr) {
+        const double cpet = c.G(RVN_G_MOHYSE_PET_COEFF), ws = M.sunset_angle[(size_t)M.et_row[step] * M.nHp + k];
+        PET = cpet / D_PI * ws * exp((17.3 * F[RVN_F_TEMP_AVE]) / (238 + F[RVN_F_TEMP_AVE]));
+      }
     } else if (method == RVN_PET_FROMMONTHLY) {
       double peRatio = 1.0 + D_HBV_PET_TEMP_CORR * (temp_ave_unc - temp_month_ave);
       peRatio = dmax(0.0, dmin(2.0, peRatio));
@@ -370,7 +389,8 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
     double factor = D_GLOBAL_PET_CORR * dmax(1.0 - D_HBV_PET_ELEV_CORR * (elev - ref_elev_temp), 0.0);
     F[RVN_F_PET] *= factor; F[RVN_F_OW_PET] *= factor;
   }
-  if (opt.evaporation == RVN_PET_FROMMONTHLY || opt.evaporation == RVN_PET_CONSTANT) F[RVN_F_PET] *= subdaily_corr;
+  if (opt.evaporation == RVN_PET_FROMMONTHLY || opt.evaporation == RVN_PET_CONSTANT || opt.evaporation == RVN_PET_HAMON ||
+      opt.evaporation == RVN_PET_LINEAR_TEMP) F[RVN_F_PET] *= subdaily_corr;   // IsDailyPETmethod, src/Evaporation.cpp:540-556
   if (opt.snow_suppress_PET) {
     double SWE = 0.0, sc = 1.0;
     if (c.iSV(RVN_SV_SNOW) >= 0) SWE = c.old_snow;

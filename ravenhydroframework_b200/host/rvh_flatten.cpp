@@ -256,13 +256,23 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
     bool uses_pet = false, uses_owpet = false;
     for (int j = 0; j < NP; j++) {
       const int op = _f_proc[j].op;
-      if (op == RVN_OP_SOILEVAP_ALL || op == RVN_OP_SOILEVAP_HBV || op == RVN_OP_SOILEVAP_GR4J || op == RVN_OP_CANEVP_ALL || op == RVN_OP_CANSNOWEVP_ALL) uses_pet = true;
-      if (op == RVN_OP_OPEN_WATER_EVAP || op == RVN_OP_LAKE_EVAP_BASIC) uses_owpet = true;
+      if (op == RVN_OP_SOILEVAP_ALL || op == RVN_OP_SOILEVAP_HBV || op == RVN_OP_SOILEVAP_GR4J || op == RVN_OP_SOILEVAP_TOPMODEL ||
+          (op >= RVN_OP_SOILEVAP_LINEAR && op <= RVN_OP_SOILEVAP_AWBM) || op == RVN_OP_CANEVP_ALL || op == RVN_OP_CANSNOWEVP_ALL) uses_pet = true;
+      if (op == RVN_OP_OPEN_WATER_EVAP || op == RVN_OP_LAKE_EVAP_BASIC || op == RVN_OP_SOILEVAP_HYPR) uses_owpet = true;
     }
-    const bool need = (uses_pet && O.evaporation == RVN_PET_HARGREAVES_1985) || (uses_owpet && O.ow_evaporation == RVN_PET_HARGREAVES_1985);
-    if (need) {
+    auto consumed = [&](int method) { return (uses_pet && O.evaporation == method) || (uses_owpet && O.ow_evaporation == method); };
+    const bool need_et = consumed(RVN_PET_HARGREAVES_1985) || consumed(RVN_PET_OUDIN);
+    const bool need_dl = consumed(RVN_PET_HAMON), need_ws = consumed(RVN_PET_MOHYSE);
+    ExitGracefullyIf((consumed(RVN_PET_OUDIN) || need_dl || need_ws || consumed(RVN_PET_LINEAR_TEMP)) && O.timestep < 1.0 - 0.0001,
+                     "CModel::Flatten: PET_OUDIN / PET_HAMON / PET_MOHYSE / PET_LINEAR_TEMP are built for daily steps only in the B200 build");
+    if (consumed(RVN_PET_LINEAR_TEMP))
+      for (size_t c = 0; c < lu_classes.size(); c++)
+        ExitGracefullyIf(lu_classes[c].S.v[RVN_LU_PET_LIN_COEFF] == NOT_SPECIFIED, "CLandUseClass::AutoCalculateLandUseProps: required parameter PET_LIN_COEFF not specified for land use class " + lu_classes[c].tag);
+    ExitGracefullyIf(need_ws && globals.v[RVN_G_MOHYSE_PET_COEFF] == NOT_SPECIFIED, "CModel::Flatten: PET_MOHYSE needs :GlobalParameter MOHYSE_PET_COEFF");
+    d.day_length = NULL; d.sunset_angle = NULL;
+    if (need_et || need_dl || need_ws) {
       _f_et_row.assign(nSteps, 0);
-      _f_et.clear();
+      _f_et.clear(); _f_daylen.clear(); _f_sunset.clear();
       std::map<std::pair<double, double>, int> rows;
       for (int n = 0; n < nSteps; n++) {
         const double t_sol = _f_times[n].julian_day - floor(_f_times[n].julian_day) - 0.5;
@@ -272,12 +282,21 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
           const int r = (int)rows.size();
           rows[key] = r;
           const double declin = SolarDeclination(_f_times[n].day_angle), ecc = EccentricityCorr(_f_times[n].day_angle);
-          for (int k = 0; k < nH; k++)
-            _f_et.push_back(CalcETRadiation2(_f_hru_d[2][k], _f_hru_d[4][k], declin, ecc, _f_hru_d[3][k], t_sol, t_sol + O.timestep, O.timestep >= 1.0));
+          for (int k = 0; k < nH; k++) {
+            if (need_et) _f_et.push_back(CalcETRadiation2(_f_hru_d[2][k], _f_hru_d[4][k], declin, ecc, _f_hru_d[3][k], t_sol, t_sol + O.timestep, O.timestep >= 1.0));
+            if (need_dl) {   // CRadiation::DayLength, src/Radiation.cpp:438-445
+              const double hd = -tan(declin) * tan(_f_hru_d[2][k]);
+              _f_daylen.push_back((hd >= 1.0) ? 0.0 : ((hd <= -1.0) ? 1.0 : acos(hd) / RVH_PI));
+            }
+            if (need_ws) _f_sunset.push_back(acos(-tan(_f_hru_d[2][k]) * tan(declin)));   // src/Evaporation.cpp:481
+          }
           _f_et_row[n] = r;
         } else _f_et_row[n] = it->second;
       }
-      d.nEtRows = (int32_t)rows.size(); d.et_radia = _f_et.data(); d.et_row = _f_et_row.data();
+      d.nEtRows = (int32_t)rows.size(); d.et_row = _f_et_row.data();
+      if (need_et) d.et_radia = _f_et.data();
+      if (need_dl) d.day_length = _f_daylen.data();
+      if (need_ws) d.sunset_angle = _f_sunset.data();
     }
   }
   // ---- gauge series sampled on the model step (src/UpdateForcings.cpp:98-155)

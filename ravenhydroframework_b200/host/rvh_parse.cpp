@@ -70,6 +70,9 @@ static rvn_pet ParsePET(const std::string &s) {
   if (s == "PET_NONE") return RVN_PET_NONE;
   if (s == "PET_HARGREAVES_1985") return RVN_PET_HARGREAVES_1985;
   if (s == "PET_OUDIN") return RVN_PET_OUDIN;
+  if (s == "PET_HAMON") return RVN_PET_HAMON;
+  if (s == "PET_LINEAR_TEMP") return RVN_PET_LINEAR_TEMP;
+  if (s == "PET_MOHYSE") return RVN_PET_MOHYSE;
   ExitGracefully("ParseMainInputFile: evaporation method " + s + " is not implemented in the B200 build");
   return RVN_PET_NONE;
 }

@@ -51,6 +51,13 @@ if hasattr(synth, "write_hbv"):
     # gravitational snow redistribution along a :LateralConnections table (CmvLatRedistribute), both methods
     CASES["hbv_redist"] = dict(kind="hbv", n_sb=3, hru_per_sb=6, n_days=240, seed=43, routing="ROUTE_MUSKINGUM", variant="redistribute")
     CASES["hbv_redist_thresh"] = dict(kind="hbv", n_sb=3, hru_per_sb=6, n_days=240, seed=44, routing="ROUTE_MUSKINGUM", variant="redistribute_threshold")
+    # PET estimated from temperature / day geometry instead of read or monthly (CModel::EstimatePET)
+    CASES["gr4j_pet_oudin"] = dict(kind="gr4j", n_sb=2, hru_per_sb=4, n_days=400, seed=51, pet="PET_OUDIN")
+    CASES["gr4j_pet_hamon"] = dict(kind="gr4j", n_sb=2, hru_per_sb=4, n_days=400, seed=52, pet="PET_HAMON")
+    CASES["hbv_pet_lintemp"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=53, routing="ROUTE_MUSKINGUM", pet="PET_LINEAR_TEMP",
+                                    rvp_extra=":LandUseParameterList\n  :Parameters, PET_LIN_COEFF\n  :Units, mm/d/K\n  [DEFAULT], 0.21\n  LU_OPEN, 0.27\n:EndLandUseParameterList\n")
+    CASES["hbv_pet_mohyse"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=54, routing="ROUTE_MUSKINGUM", pet="PET_MOHYSE",
+                                   rvp_extra=":GlobalParameter MOHYSE_PET_COEFF 1.15\n")
     CASES["hbv_lateral"] = dict(kind="hbv", n_sb=4, hru_per_sb=7, n_days=250, seed=8, routing="ROUTE_MUSKINGUM", season_offset=40, variant="lateral")
 if hasattr(synth, "write_blended"):
     # Blended multi-model template (BASELINE config 4): weighted process groups, VIC/TOPMODEL/analytic algorithms, SNOBAL_HBV
@@ -192,6 +199,8 @@ def make(name, spec):
     member = spec.pop("member", None)
     timestep = spec.pop("timestep", None)     # e.g. "01:00:00": sub-daily model step on the daily forcing series
     method = spec.pop("method", None)         # :Method (numerical method) other than ORDERED_SERIES
+    pet = spec.pop("pet", None)               # :Evaporation method other than the template's
+    rvp_extra = spec.pop("rvp_extra", None)   # lines appended to the .rvp
     d = os.path.join(HERE, name)
     shutil.rmtree(d, ignore_errors=True)
     base = WRITERS[kind](d, name="model", **spec)
@@ -200,6 +209,14 @@ def make(name, spec):
         rvi = open(base + ".rvi").read()
         assert ":Method                ORDERED_SERIES" in rvi
         open(base + ".rvi", "w").write(rvi.replace(":Method                ORDERED_SERIES", ":Method                " + method))
+    if pet is not None:
+        import re
+        rvi = open(base + ".rvi").read()
+        rvi, cnt = re.subn(r":Evaporation\s+\S+", ":Evaporation           " + pet, rvi)
+        assert cnt == 1
+        open(base + ".rvi", "w").write(rvi)
+    if rvp_extra is not None:
+        open(base + ".rvp", "a").write(rvp_extra)
     if timestep is not None:
         rvi = open(base + ".rvi").read()
         assert ":TimeStep              1.0" in rvi
