@@ -133,7 +133,8 @@ typedef enum {
 
 /* model-wide method switches; numbering is local to this ABI (the host maps Raven's keywords) */
 typedef enum { RVN_RAINSNOW_DATA = 0, RVN_RAINSNOW_DINGMAN, RVN_RAINSNOW_HBV, RVN_RAINSNOW_UBCWM, RVN_RAINSNOW_THRESHOLD } rvn_rainsnow;
-typedef enum { RVN_POTMELT_NONE = 0, RVN_POTMELT_DATA, RVN_POTMELT_DEGREE_DAY, RVN_POTMELT_HBV, RVN_POTMELT_HMETS } rvn_potmelt;
+typedef enum { RVN_POTMELT_NONE = 0, RVN_POTMELT_DATA, RVN_POTMELT_DEGREE_DAY, RVN_POTMELT_HBV, RVN_POTMELT_HMETS,
+               RVN_POTMELT_DD_FREEZE, RVN_POTMELT_HBV_ROS } rvn_potmelt;   /* src/PotentialMelt.cpp:20-246 */
 typedef enum { RVN_PET_DATA = 0, RVN_PET_FROMMONTHLY, RVN_PET_CONSTANT, RVN_PET_NONE, RVN_PET_HARGREAVES_1985, RVN_PET_OUDIN,
                RVN_PET_HAMON, RVN_PET_LINEAR_TEMP, RVN_PET_MOHYSE } rvn_pet;   /* CModel::EstimatePET, src/Evaporation.cpp:282-540 */
 typedef enum { RVN_OROCORR_NONE = 0, RVN_OROCORR_SIMPLELAPSE, RVN_OROCORR_HBV } rvn_orocorr;
@@ -168,7 +169,7 @@ typedef enum {
   RVN_LU_GLAC_STORAGE_COEFF, RVN_LU_HBV_GLACIER_AG, RVN_LU_DEP_MAX, RVN_LU_LAKE_PET_CORR, RVN_LU_OW_PET_CORR,
   RVN_LU_PARTITION_COEFF, RVN_LU_CC_DECAY_COEFF, RVN_LU_MAX_SAT_AREA_FRAC, RVN_LU_PDM_B, RVN_LU_AET_COEFF,
   RVN_LU_MAX_DEP_AREA_FRAC, RVN_LU_PONDED_EXP, RVN_LU_AWBM_AREAFRAC1, RVN_LU_AWBM_AREAFRAC2, RVN_LU_HYMOD2_G, RVN_LU_HYMOD2_KMAX,
-  RVN_LU_HYMOD2_EXP, RVN_LU_PET_LIN_COEFF, RVN_LU_COUNT
+  RVN_LU_HYMOD2_EXP, RVN_LU_PET_LIN_COEFF, RVN_LU_RAIN_MELT_MULT, RVN_LU_COUNT
 } rvn_landuse_field;
 typedef enum {
   RVN_V_MAX_HEIGHT = 0, RVN_V_MAX_LAI, RVN_V_SAI_HT_RATIO, RVN_V_MAX_CAPACITY, RVN_V_MAX_SNOW_CAPACITY,

@@ -297,7 +297,7 @@ static void update_forcings(const rvn_model_desc *d, const double *ptab, int mem
     double pm = F[RVN_F_POTENTIAL_MELT];
     if (d->opt.pot_melt == RVN_POTMELT_DEGREE_DAY) {
       pm = P_LU(&c, RVN_LU_MELT_FACTOR) * (F[RVN_F_TEMP_DAILY_AVE] - P_LU(&c, RVN_LU_DD_MELT_TEMP)) * subdaily_corr;
-    } else if (d->opt.pot_melt == RVN_POTMELT_HBV) {
+    } else if (d->opt.pot_melt == RVN_POTMELT_HBV || d->opt.pot_melt == RVN_POTMELT_HBV_ROS) {
       double Ma = P_LU(&c, RVN_LU_MELT_FACTOR), Ma_min = P_LU(&c, RVN_LU_MIN_MELT_FACTOR), AM = P_LU(&c, RVN_LU_HBV_MELT_ASP_CORR);
       double MRF = P_LU(&c, RVN_LU_HBV_MELT_FOR_CORR), Fc = P_LU(&c, RVN_LU_FOREST_COVERAGE), melt_temp = P_LU(&c, RVN_LU_DD_MELT_TEMP);
       double adj = 0, slope_corr;
@@ -306,7 +306,14 @@ static void update_forcings(const rvn_model_desc *d, const double *ptab, int mem
       Ma *= ((1.0 - Fc) * 1.0 + (Fc)*MRF);
       slope_corr = ((1.0 - Fc) * 1.0 + (Fc)*sin(d->hru_slope[k]));
       Ma *= omax(1.0 - AM * slope_corr * cos(d->hru_aspect[k] - adj), 0.0);
-      pm = Ma * (F[RVN_F_TEMP_DAILY_AVE] - melt_temp) * subdaily_corr + 0.0;
+      double rain_energy = 0.0;
+      if (d->opt.pot_melt == RVN_POTMELT_HBV_ROS) /* :77-81 */
+        rain_energy = P_LU(&c, RVN_LU_RAIN_MELT_MULT) * 4.186e-3 / 0.334 * omax(F[RVN_F_TEMP_AVE], 0.0) * (F[RVN_F_PRECIP] * (1.0 - F[RVN_F_SNOW_FRAC]));
+      pm = Ma * (F[RVN_F_TEMP_DAILY_AVE] - melt_temp) * subdaily_corr + rain_energy;
+    } else if (d->opt.pot_melt == RVN_POTMELT_DD_FREEZE) { /* :40-49 */
+      double Ma = P_LU(&c, RVN_LU_MELT_FACTOR), melt_temp = P_LU(&c, RVN_LU_DD_MELT_TEMP), Mf = P_LU(&c, RVN_LU_REFREEZE_FACTOR);
+      if ((Mf > 0) && (F[RVN_F_TEMP_DAILY_AVE] - melt_temp) < 0.0) pm = Mf * (F[RVN_F_TEMP_DAILY_AVE] - melt_temp);
+      else pm = Ma * (F[RVN_F_TEMP_DAILY_AVE] - melt_temp) * subdaily_corr;
     } else if (d->opt.pot_melt == RVN_POTMELT_HMETS) {
       double Ma_min = P_LU(&c, RVN_LU_MIN_MELT_FACTOR), Ma_max = P_LU(&c, RVN_LU_MAX_MELT_FACTOR);
       double melt_temp = P_LU(&c, RVN_LU_DD_MELT_TEMP), Kcum = P_LU(&c, RVN_LU_DD_AGGRADATION);

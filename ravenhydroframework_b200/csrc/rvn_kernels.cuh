@@ -319,7 +319,7 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
     const int method = opt.pot_melt;
     if (method == RVN_POTMELT_DEGREE_DAY) {
       pm = c.LU(RVN_LU_MELT_FACTOR) * (F[RVN_F_TEMP_DAILY_AVE] - c.LU(RVN_LU_DD_MELT_TEMP)) * subdaily_corr;
-    } else if (method == RVN_POTMELT_HBV) {
+    } else if (method == RVN_POTMELT_HBV || method == RVN_POTMELT_HBV_ROS) {
       double Ma = c.LU(RVN_LU_MELT_FACTOR), Ma_min = c.LU(RVN_LU_MIN_MELT_FACTOR), AM = c.LU(RVN_LU_HBV_MELT_ASP_CORR);
       double MRF = c.LU(RVN_LU_HBV_MELT_FOR_CORR), Fc = c.LU(RVN_LU_FOREST_COVERAGE), melt_temp = c.LU(RVN_LU_DD_MELT_TEMP);
       double adj = 0, slope_corr;
@@ -328,7 +328,14 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
       Ma *= ((1.0 - Fc) * 1.0 + (Fc)*MRF);
       slope_corr = ((1.0 - Fc) * 1.0 + (Fc)*sin(c.slope));
       Ma *= dmax(1.0 - AM * slope_corr * cos(c.aspect - adj), 0.0);
-      pm = Ma * (F[RVN_F_TEMP_DAILY_AVE] - melt_temp) * subdaily_corr + 0.0;
+      double rain_energy = 0.0;
+      if (method == RVN_POTMELT_HBV_ROS)   // rain-on-snow energy, src/PotentialMelt.cpp:77-81
+        rain_energy = c.LU(RVN_LU_RAIN_MELT_MULT) * D_SPH_WATER / D_LH_FUSION * dmax(F[RVN_F_TEMP_AVE], 0.0) * (F[RVN_F_PRECIP] * (1.0 - F[RVN_F_SNOW_FRAC]));
+      pm = Ma * (F[RVN_F_TEMP_DAILY_AVE] - melt_temp) * subdaily_corr + rain_energy;
+    } else if (method == RVN_POTMELT_DD_FREEZE) {   // :40-49
+      const double Ma = c.LU(RVN_LU_MELT_FACTOR), melt_temp = c.LU(RVN_LU_DD_MELT_TEMP), Mf = c.LU(RVN_LU_REFREEZE_FACTOR);
+      if ((Mf > 0) && (F[RVN_F_TEMP_DAILY_AVE] - melt_temp) < 0.0) pm = Mf * (F[RVN_F_TEMP_DAILY_AVE] - melt_temp);
+      else pm = Ma * (F[RVN_F_TEMP_DAILY_AVE] - melt_temp) * subdaily_corr;
     } else if (method == RVN_POTMELT_HMETS) {
       double Ma_min = c.LU(RVN_LU_MIN_MELT_FACTOR), Ma_max = c.LU(RVN_LU_MAX_MELT_FACTOR);
       double melt_temp = c.LU(RVN_LU_DD_MELT_TEMP), Kcum = c.LU(RVN_LU_DD_AGGRADATION);

@@ -32,6 +32,8 @@
 #define D_DENSITY_ICE 0.917e3
 #define D_HCP_ICE 1.938
 #define D_LH_VAPOR 2.501
+#define D_SPH_WATER 4.186e-3   // [MJ/kg/K]
+#define D_LH_FUSION 0.334      // [MJ/kg]
 #define D_WINTER_SOLSTICE_ANG 6.111043
 #define D_HBV_PET_ELEV_CORR 0.0005
 #define D_HBV_PET_TEMP_CORR 0.5

@@ -170,6 +170,10 @@ static void ParseMainInputFile(CModel *&pModel, optStruct &Options) {
       else if (s[1] == "POTMELT_HMETS") Options.pot_melt = RVN_POTMELT_HMETS;
       else if (s[1] == "POTMELT_DATA") Options.pot_melt = RVN_POTMELT_DATA;
       else if (s[1] == "POTMELT_NONE") Options.pot_melt = RVN_POTMELT_NONE;
+      else if (s[1] == "POTMELT_DD_FREEZE") Options.pot_melt = RVN_POTMELT_DD_FREEZE;
+      else if (s[1] == "POTMELT_HBV_ROS") Options.pot_melt = RVN_POTMELT_HBV_ROS;
+      else if (s[1] == "POTMELT_DD_RAIN")   // no parameter list in the reference (src/ModelParamCheck.cpp:98-175): DD_MELT_TEMP is then overridden by the -77777.7 "not needed" sentinel
+        ExitGracefully("ParseMainInputFile: POTMELT_DD_RAIN is not supported by the B200 build (the reference evaluates it with an unset DD_MELT_TEMP)");
       else ExitGracefully("ParseMainInputFile: potential melt method " + s[1] + " is not implemented in the B200 build");
       continue;
     }

@@ -58,6 +58,11 @@ if hasattr(synth, "write_hbv"):
                                     rvp_extra=":LandUseParameterList\n  :Parameters, PET_LIN_COEFF\n  :Units, mm/d/K\n  [DEFAULT], 0.21\n  LU_OPEN, 0.27\n:EndLandUseParameterList\n")
     CASES["hbv_pet_mohyse"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=54, routing="ROUTE_MUSKINGUM", pet="PET_MOHYSE",
                                    rvp_extra=":GlobalParameter MOHYSE_PET_COEFF 1.15\n")
+    # potential melt: degree day with refreeze / rain-on-snow variants (CModel::EstimatePotentialMelt)
+    CASES["gr4j_potmelt_ddfreeze"] = dict(kind="gr4j", n_sb=2, hru_per_sb=3, n_days=300, seed=55, potmelt="POTMELT_DD_FREEZE",
+                                          rvp_extra=":LandUseParameterList\n  :Parameters, REFREEZE_FACTOR\n  :Units, mm/d/K\n  [DEFAULT], 1.3\n:EndLandUseParameterList\n")
+    CASES["hbv_potmelt_ros"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=300, seed=57, routing="ROUTE_MUSKINGUM", potmelt="POTMELT_HBV_ROS",
+                                    rvp_extra=":LandUseParameterList\n  :Parameters, RAIN_MELT_MULT\n  :Units, none\n  [DEFAULT], 1.4\n:EndLandUseParameterList\n")
     CASES["hbv_lateral"] = dict(kind="hbv", n_sb=4, hru_per_sb=7, n_days=250, seed=8, routing="ROUTE_MUSKINGUM", season_offset=40, variant="lateral")
 if hasattr(synth, "write_blended"):
     # Blended multi-model template (BASELINE config 4): weighted process groups, VIC/TOPMODEL/analytic algorithms, SNOBAL_HBV
@@ -200,6 +205,7 @@ def make(name, spec):
     timestep = spec.pop("timestep", None)     # e.g. "01:00:00": sub-daily model step on the daily forcing series
     method = spec.pop("method", None)         # :Method (numerical method) other than ORDERED_SERIES
     pet = spec.pop("pet", None)               # :Evaporation method other than the template's
+    potmelt = spec.pop("potmelt", None)       # :PotentialMeltMethod other than the template's
     rvp_extra = spec.pop("rvp_extra", None)   # lines appended to the .rvp
     d = os.path.join(HERE, name)
     shutil.rmtree(d, ignore_errors=True)
@@ -213,6 +219,12 @@ def make(name, spec):
         import re
         rvi = open(base + ".rvi").read()
         rvi, cnt = re.subn(r":Evaporation\s+\S+", ":Evaporation           " + pet, rvi)
+        assert cnt == 1
+        open(base + ".rvi", "w").write(rvi)
+    if potmelt is not None:
+        import re
+        rvi = open(base + ".rvi").read()
+        rvi, cnt = re.subn(r":PotentialMeltMethod\s+\S+", ":PotentialMeltMethod   " + potmelt, rvi)
         assert cnt == 1
         open(base + ".rvi", "w").write(rvi)
     if rvp_extra is not None:
