@@ -135,8 +135,15 @@ typedef enum {
 typedef enum { RVN_RAINSNOW_DATA = 0, RVN_RAINSNOW_DINGMAN, RVN_RAINSNOW_HBV, RVN_RAINSNOW_UBCWM, RVN_RAINSNOW_THRESHOLD } rvn_rainsnow;
 typedef enum { RVN_POTMELT_NONE = 0, RVN_POTMELT_DATA, RVN_POTMELT_DEGREE_DAY, RVN_POTMELT_HBV, RVN_POTMELT_HMETS,
                RVN_POTMELT_DD_FREEZE, RVN_POTMELT_HBV_ROS } rvn_potmelt;   /* src/PotentialMelt.cpp:20-246 */
+/* atmospheric estimators of the forcing chain (reference src/UpdateForcings.cpp:677-731, src/Radiation.cpp:24-57,333-364) */
+typedef enum { RVN_AIRPRESS_BASIC = 0, RVN_AIRPRESS_UBC, RVN_AIRPRESS_CONST } rvn_airpress;
+typedef enum { RVN_RELHUM_CONSTANT = 0, RVN_RELHUM_MINDEWPT } rvn_relhum;
+typedef enum { RVN_SW_RAD_DEFAULT = 0, RVN_SW_RAD_NONE } rvn_sw_rad;
+typedef enum { RVN_SW_CLOUD_CORR_NONE = 0, RVN_SW_CLOUD_CORR_DINGMAN, RVN_SW_CLOUD_CORR_ANNANDALE } rvn_sw_cloudcorr;
 typedef enum { RVN_PET_DATA = 0, RVN_PET_FROMMONTHLY, RVN_PET_CONSTANT, RVN_PET_NONE, RVN_PET_HARGREAVES_1985, RVN_PET_OUDIN,
-               RVN_PET_HAMON, RVN_PET_LINEAR_TEMP, RVN_PET_MOHYSE } rvn_pet;   /* CModel::EstimatePET, src/Evaporation.cpp:282-540 */
+               RVN_PET_HAMON, RVN_PET_LINEAR_TEMP, RVN_PET_MOHYSE,
+               RVN_PET_TURC_1961, RVN_PET_MAKKINK_1957, RVN_PET_PENMAN_SIMPLE33, RVN_PET_PENMAN_SIMPLE39, RVN_PET_VAPDEFICIT, RVN_PET_LINACRE,
+               RVN_PET_HARGREAVES } rvn_pet;   /* CModel::EstimatePET, src/Evaporation.cpp:282-540 */
 typedef enum { RVN_OROCORR_NONE = 0, RVN_OROCORR_SIMPLELAPSE, RVN_OROCORR_HBV } rvn_orocorr;
 typedef enum { RVN_ROUTE_NONE = 0, RVN_ROUTE_MUSKINGUM, RVN_ROUTE_MUSKINGUM_CUNGE, RVN_ROUTE_STORAGECOEFF,
                RVN_ROUTE_PLUG_FLOW, RVN_ROUTE_DIFFUSIVE_WAVE, RVN_ROUTE_HYDROLOGIC } rvn_routing;
@@ -169,7 +176,7 @@ typedef enum {
   RVN_LU_GLAC_STORAGE_COEFF, RVN_LU_HBV_GLACIER_AG, RVN_LU_DEP_MAX, RVN_LU_LAKE_PET_CORR, RVN_LU_OW_PET_CORR,
   RVN_LU_PARTITION_COEFF, RVN_LU_CC_DECAY_COEFF, RVN_LU_MAX_SAT_AREA_FRAC, RVN_LU_PDM_B, RVN_LU_AET_COEFF,
   RVN_LU_MAX_DEP_AREA_FRAC, RVN_LU_PONDED_EXP, RVN_LU_AWBM_AREAFRAC1, RVN_LU_AWBM_AREAFRAC2, RVN_LU_HYMOD2_G, RVN_LU_HYMOD2_KMAX,
-  RVN_LU_HYMOD2_EXP, RVN_LU_PET_LIN_COEFF, RVN_LU_RAIN_MELT_MULT, RVN_LU_COUNT
+  RVN_LU_HYMOD2_EXP, RVN_LU_PET_LIN_COEFF, RVN_LU_RAIN_MELT_MULT, RVN_LU_RELHUM_CORR, RVN_LU_PET_VAP_COEFF, RVN_LU_COUNT
 } rvn_landuse_field;
 typedef enum {
   RVN_V_MAX_HEIGHT = 0, RVN_V_MAX_LAI, RVN_V_SAI_HT_RATIO, RVN_V_MAX_CAPACITY, RVN_V_MAX_SNOW_CAPACITY,
@@ -206,8 +213,11 @@ typedef enum {
 typedef enum {
   RVN_F_PRECIP = 0, RVN_F_SNOW_FRAC, RVN_F_TEMP_AVE, RVN_F_TEMP_DAILY_AVE, RVN_F_TEMP_DAILY_MIN,
   RVN_F_TEMP_DAILY_MAX, RVN_F_PET, RVN_F_OW_PET, RVN_F_POTENTIAL_MELT, RVN_F_TEMP_MONTH_AVE, RVN_F_PET_MONTH_AVE,
+  /* atmospheric forcings: derived only when opt.need_atmos, recorded (rvn_gpu_download_forcings) but not carried through the sweep */
+  RVN_F_AIR_PRES, RVN_F_REL_HUMIDITY, RVN_F_SW_RADIA,
   RVN_F_COUNT
 } rvn_forcing_field;
+#define RVN_F_CARRIED RVN_F_AIR_PRES   /* fields below this index live in the per-thread forcing vector of the sweep */
 
 /* per-step calendar record (reference time_struct, filled by JulianConvert, src/CommonFunctions.cpp:300-380) */
 typedef struct rvn_time {
@@ -265,6 +275,8 @@ typedef struct rvn_options {
   int32_t lake_sv;                /* CModel::GetLakeStorageIndex() */
   int32_t keep_flux_balance;      /* 0: skip per-connection cumulative flux arrays */
   int32_t sol_method;             /* rvn_sol_method: ORDERED_SERIES (default) or EULER (reference src/Solvers.cpp:205-251 / 256-297) */
+  int32_t need_atmos;             /* 1: a consumed PET needs air pressure / relative humidity / shortwave radiation -> derive them */
+  int32_t air_pressure, rel_humidity, sw_radiation, sw_cloudcorr;   /* rvn_airpress, rvn_relhum, rvn_sw_rad, rvn_sw_cloudcorr */
   int32_t pad_[1];
 } rvn_options;
 
@@ -355,6 +367,9 @@ typedef struct rvn_model_desc {
    * [d] (src/Radiation.cpp:438-445; F.day_length, src/UpdateForcings.cpp:175) for PET_HAMON, sunset_angle[row][hru] =
    * acos(-tan(lat)*tan(declin)) [rad] for PET_MOHYSE (src/Evaporation.cpp:476-483) */
   const double *day_length, *sunset_angle;
+  /* clear-sky shortwave pieces on the same rows (NULL unless opt.need_atmos): et_flat = extraterrestrial radiation on a horizontal
+   * surface (F.ET_radia_flat), opt_air_mass = CRadiation::OpticalAirMass (src/Radiation.cpp:909-967) */
+  const double *et_flat, *opt_air_mass;
   /* lateral exchange processes (reference CLateralExchangeProcessABC; CModel::ApplyLateralProcess, src/Model.cpp:3126-3165,
    * applied by the solver after ALL vertical processes of ALL HRUs and before the routing prep, src/Solvers.cpp:404-443).
    * Only processes that apply (gate of the first source HRU, every participating HRU enabled) are listed, in process order.

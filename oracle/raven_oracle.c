@@ -175,6 +175,9 @@ static void apply_forcing_perturbation(const rvn_model_desc *d, int ftype, int m
   }
 }
 
+/* GetSaturatedVaporPressure [kPa], src/CommonFunctions.cpp:935-949; GetDewPointTemp [C], :1131-1139 */
+static double o_sat_vap(double T) { return (T >= 0) ? 0.61078 * exp(17.26939 * T / (T + 237.3)) : 0.61078 * exp(21.87456 * T / (T + 265.5)); }
+static double o_dew_point(double Ta, double rel_hum) { double tmp = (17.27 * Ta / (237.7 + Ta)) + log(rel_hum); return 237.7 * tmp / (17.27 - tmp); }
 /* daily[7]: the HRU's daily forcing items of the previous step (temp_daily_min/max/ave, temp_month_max/min/ave, PET_month_ave), i.e. the
  * part of CHydroUnit::_Forcings that CopyDailyForcingItems (src/Forcings.cpp:72-89) carries through the day on sub-daily steps */
 static void update_forcings(const rvn_model_desc *d, const double *ptab, int member, int k, int step, const double *phi_old, const int *iSV, double *F, double *daily) {
@@ -292,6 +295,32 @@ static void update_forcings(const rvn_model_desc *d, const double *ptab, int mem
     apply_forcing_perturbation(d, RVN_PF_SNOWFALL, member, k, step, F);
   }
   if (d->hru_type[k] == RVN_HRU_MASKED_GLACIER) F[RVN_F_PRECIP] = 0;
+  /* air pressure / relative humidity (EstimateAirPressure, EstimateRelativeHumidity, src/UpdateForcings.cpp:677-731) and incoming
+   * shortwave (CRadiation::EstimateShortwaveRadiation / ClearSkySolarRadiation / SWCloudCoverCorrection, src/Radiation.cpp:24-57,
+   * 992-1038, 333-364); cloud cover is CLOUDCOV_NONE (0).  Date/geometry pieces come from the host tables. */
+  double ET_radia = 0.0;
+  if (d->opt.need_atmos) {
+    const size_t row = (size_t)d->et_row[step] * d->nHRU + k;
+    double relhum = 0.5, cc = 1.0;
+    if (d->opt.air_pressure == RVN_AIRPRESS_BASIC) F[RVN_F_AIR_PRES] = 101.3 * pow(1.0 - 0.0065 * elev / (273.16 + F[RVN_F_TEMP_AVE]), 5.26);
+    else if (d->opt.air_pressure == RVN_AIRPRESS_UBC) F[RVN_F_AIR_PRES] = 101.325 * (1.0 - 0.0001 * elev);
+    else F[RVN_F_AIR_PRES] = 101.3;
+    if (d->opt.rel_humidity == RVN_RELHUM_MINDEWPT) relhum = omin(o_sat_vap(F[RVN_F_TEMP_DAILY_MIN]) / o_sat_vap(F[RVN_F_TEMP_AVE]), 1.0);
+    F[RVN_F_REL_HUMIDITY] = omin(relhum * P_LU(&c, RVN_LU_RELHUM_CORR), 1.0);
+    ET_radia = d->et_radia[row];
+    if (d->opt.sw_radiation == RVN_SW_RAD_DEFAULT) {
+      double dew_pt = o_dew_point(F[RVN_F_TEMP_AVE], F[RVN_F_REL_HUMIDITY]);
+      double Mopt = d->opt_air_mass[row], Ketp = ET_radia, Ket = d->et_flat[row];
+      double wv = 1.12 * exp(0.0614 * dew_pt);                                                         /* Dingman E-10 */
+      double tau = exp((-0.124 - 0.0207 * wv) + (-0.0682 - 0.0248 * wv) * Mopt) - 0.025;               /* E-9, E-11..13 */
+      double tau2 = 0.5 * (1.0 - exp((-0.0363 - 0.0084 * wv) + (-0.0572 - 0.0173 * wv) * Mopt) + 0.025); /* E-15..18 */
+      F[RVN_F_SW_RADIA] = tau * Ketp + tau2 * Ket + tau2 * 0.3 * (tau2 + tau) * Ketp;
+    }
+    if (d->opt.sw_cloudcorr == RVN_SW_CLOUD_CORR_DINGMAN) cc = 0.355 + 0.68 * (1 - 0.0);
+    else if (d->opt.sw_cloudcorr == RVN_SW_CLOUD_CORR_ANNANDALE)
+      cc = (F[RVN_F_TEMP_DAILY_MAX] > F[RVN_F_TEMP_DAILY_MIN]) ? 0.16 * (1.0 + 2.7E-5 * elev) * sqrt(F[RVN_F_TEMP_DAILY_MAX] - F[RVN_F_TEMP_DAILY_MIN]) : 0.0;
+    F[RVN_F_SW_RADIA] *= cc;
+  }
   /* CModel::EstimatePotentialMelt, src/PotentialMelt.cpp:20-246 */
   {
     double pm = F[RVN_F_POTENTIAL_MELT];
@@ -364,6 +393,37 @@ static void update_forcings(const rvn_model_desc *d, const double *ptab, int mem
         PET = cpet / 3.1415926535898 * ws * exp((17.3 * F[RVN_F_TEMP_AVE]) / (238 + F[RVN_F_TEMP_AVE]));
       }
     }
+    else if (method == RVN_PET_TURC_1961) { /* TurcEvap, src/Evaporation.cpp:61-68 */
+      double t = omax(0.0, F[RVN_F_TEMP_DAILY_AVE]);
+      double evp = 0.013 * t / (t + 15) * ((F[RVN_F_SW_RADIA]) * 23.8846 + 50);
+      if (F[RVN_F_REL_HUMIDITY] < 0.5) evp *= (1 + (50 - F[RVN_F_REL_HUMIDITY] * 100) / 70);
+      PET = omax(0.0, evp);
+    }
+    else if (method == RVN_PET_MAKKINK_1957) { /* Makkink1957Evap, src/Evaporation.cpp:32-48; GetSatVapSlope / GetLatentHeatVaporization / GetPsychrometricConstant, src/CommonFunctions.cpp:959-998 */
+      double T = F[RVN_F_TEMP_AVE], sat_vap = o_sat_vap(T);
+      double de_dT = (T > 0) ? 17.26939 * 237.3 / pow(T + 237.3, 2) * sat_vap : 21.87456 * 265.5 / pow(T + 265.5, 2) * sat_vap;
+      double LH_vapor = 2.495 - 0.002361 * T;
+      double gamma = 1.012e-3 / 0.622 * F[RVN_F_AIR_PRES] / LH_vapor;
+      PET = omax(0.0, 0.61 * (de_dT / (de_dT + gamma)) * F[RVN_F_SW_RADIA] * 23.8846 / 58.5 - 0.12);
+    }
+    else if (method == RVN_PET_PENMAN_SIMPLE33) /* Valiantzas (2006) eqn 33, src/Evaporation.cpp:454-463 */
+      PET = 0.047 * F[RVN_F_SW_RADIA] * sqrt(F[RVN_F_TEMP_AVE] + 9.5) - 2.4 * pow(F[RVN_F_SW_RADIA] / ET_radia, 2.0) + 0.09 * (F[RVN_F_TEMP_AVE] + 20) * (1 - F[RVN_F_REL_HUMIDITY]);
+    else if (method == RVN_PET_PENMAN_SIMPLE39) /* eqn 39, :465-474 */
+      PET = 0.038 * F[RVN_F_SW_RADIA] * sqrt(F[RVN_F_TEMP_AVE] + 9.5) - 2.4 * pow(F[RVN_F_SW_RADIA] / ET_radia, 2.0) + 0.075 * (F[RVN_F_TEMP_AVE] + 20) * (1 - F[RVN_F_REL_HUMIDITY]);
+    else if (method == RVN_PET_VAPDEFICIT) { /* src/Evaporation.cpp:506-518 */
+      double e_sat = o_sat_vap(F[RVN_F_TEMP_AVE]), ea = F[RVN_F_REL_HUMIDITY] * e_sat;
+      PET = P_LU(&c, RVN_LU_PET_VAP_COEFF) * (e_sat - ea);
+    }
+    else if (method == RVN_PET_LINACRE) { /* src/Evaporation.cpp:491-504 */
+      double T = F[RVN_F_TEMP_DAILY_AVE], Tdew = o_dew_point(T, F[RVN_F_REL_HUMIDITY]), latit = d->hru_lat_rad[k] * 57.29578951;
+      PET = ((ow ? 700 : 500) * T / (100 - latit) + 15.0 * (T - Tdew)) / (80.0 - T);
+    }
+    else if (method == RVN_PET_HARGREAVES) { /* HargreavesEvap, src/Evaporation.cpp:179-203 */
+      double Ra = ET_radia / (2.501 * O_DENSITY_WATER / O_MM_PER_METER), Ct = 0.125;
+      double delT = (1.8 * temp_month_max + 32.0) - (1.8 * temp_month_min + 32.0);
+      if (F[RVN_F_REL_HUMIDITY] >= 0.54) Ct = 0.035 * pow(100 * (1.0 - F[RVN_F_REL_HUMIDITY]), 0.333);
+      PET = omax(0.0, 0.0075 * Ra * Ct * sqrt(delT) * (1.8 * F[RVN_F_TEMP_DAILY_AVE] + 32.0));
+    }
     else if (method == RVN_PET_FROMMONTHLY) { /* src/Evaporation.cpp:349-355 */
       double peRatio = 1.0 + O_HBV_PET_TEMP_CORR * (temp_ave_unc - temp_month_ave);
       peRatio = omax(0.0, omin(2.0, peRatio));
@@ -378,7 +438,8 @@ static void update_forcings(const rvn_model_desc *d, const double *ptab, int mem
     double factor = O_GLOBAL_PET_CORR * omax(1.0 - O_HBV_PET_ELEV_CORR * (elev - ref_elev_temp), 0.0);
     F[RVN_F_PET] *= factor; F[RVN_F_OW_PET] *= factor;
   }
-  if (d->opt.evaporation == RVN_PET_FROMMONTHLY || d->opt.evaporation == RVN_PET_CONSTANT || d->opt.evaporation == RVN_PET_HAMON || d->opt.evaporation == RVN_PET_LINEAR_TEMP) /* IsDailyPETmethod, src/Evaporation.cpp:540-556 */
+  if (d->opt.evaporation == RVN_PET_FROMMONTHLY || d->opt.evaporation == RVN_PET_CONSTANT || d->opt.evaporation == RVN_PET_HAMON || d->opt.evaporation == RVN_PET_LINEAR_TEMP ||
+      d->opt.evaporation == RVN_PET_TURC_1961 || d->opt.evaporation == RVN_PET_LINACRE) /* IsDailyPETmethod, src/Evaporation.cpp:540-556 */
     F[RVN_F_PET] *= subdaily_corr;
   if (d->opt.snow_suppress_PET) {
     double SWE = 0.0, sc = 1.0;

@@ -70,6 +70,7 @@ struct DevModel {
   int32_t unit_weights;                            // 1: one station, every HRU weight exactly 1.0 (CSR not read)
   const rvn_time *times;
   const double *veg_season;                        // [nSteps][nVeg][2] month-interpolated relative height, relative LAI
+  const double *et_flat, *opt_air_mass;            // [nEtRows][nHp] flat-surface ET radiation and optical air mass (or NULL)
   const double *day_length, *sunset_angle;         // [nEtRows][nHp] day geometry for PET_HAMON / PET_MOHYSE (or NULL)
   const double *et_radia; const int32_t *et_row;   // [nEtRows][nHp] extraterrestrial radiation on the HRU's slope, row of each step (or NULL)
   // network

@@ -35,9 +35,9 @@
 #endif
 #if RVN_F_SMEM
 struct FVec { double *p; RVN_DI double &operator[](int f) const { return p[f * RVN_BS]; } };   // forcing f of this thread at p[f * RVN_BS]
-#define RVN_F_SMEM_DOUBLES (RVN_F_COUNT * RVN_BS)
+#define RVN_F_SMEM_DOUBLES (RVN_F_CARRIED * RVN_BS)
 #else
-struct FVec { double v[RVN_F_COUNT]; RVN_DI double &operator[](int f) { return v[f]; } RVN_DI const double &operator[](int f) const { return v[f]; } };
+struct FVec { double v[RVN_F_CARRIED]; RVN_DI double &operator[](int f) { return v[f]; } RVN_DI const double &operator[](int f) const { return v[f]; } };
 #define RVN_F_SMEM_DOUBLES 0
 #endif
 struct CtxCommon {
@@ -188,6 +188,10 @@ RVN_DI void apply_perturbations(FVec &F, const DevModel &M, const int ftype, con
   }
 }
 
+// GetSaturatedVaporPressure  src/CommonFunctions.cpp:935-949 [kPa]
+RVN_DI double sat_vapor_pressure(const double T) {
+  return (T >= 0) ? 0.61078 * exp(17.26939 * T / (T + 237.3)) : 0.61078 * exp(21.87456 * T / (T + 265.5));
+}
 template <class C>
 RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, int sb) {
   const rvn_options &opt = c.opt();
@@ -197,7 +201,7 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
   FVec &F = c.F;
   double ref_elev_temp = 0.0, ref_elev_precip = 0.0, temp_month_min = 0, temp_month_max = 0, temp_month_ave = 0, PET_month_ave = 0;
 #pragma unroll
-  for (int f = 0; f < RVN_F_COUNT; f++) F[f] = 0.0;
+  for (int f = 0; f < RVN_F_CARRIED; f++) F[f] = 0.0;
   // K3: sparse gather over this HRU's gauges / grid cells (CSR, ascending gauge index = the reference's summation order;
   // omitted zero weights add exact zeros there).  The step's series form one contiguous [forcing][gauge] slab.
   const double *slab = M.gauge_series + (size_t)step * RVN_GF_COUNT * nG;
@@ -314,6 +318,44 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
     apply_perturbations(F, M, RVN_PF_SNOWFALL, e, k, step);
   }
   if (c.type == RVN_HRU_MASKED_GLACIER) F[RVN_F_PRECIP] = 0;
+  // air pressure, relative humidity (src/UpdateForcings.cpp:493-497, 677-731) and incoming shortwave radiation (:591-593;
+  // CRadiation::EstimateShortwaveRadiation / ClearSkySolarRadiation / SWCloudCoverCorrection, src/Radiation.cpp:24-57, 992-1038,
+  // 333-364) -- only when a consumed PET method needs them.  Geometry-only pieces (ET radiation on the slope and on the flat,
+  // optical air mass) come from the host's per-date tables.
+  double air_pres = 0.0, rel_hum = 0.0, SW_radia = 0.0, ET_radia = 0.0;
+  if (opt.need_atmos) {
+    const double Tave = F[RVN_F_TEMP_AVE];
+    if (opt.air_pressure == RVN_AIRPRESS_BASIC) air_pres = D_AMBIENT_AIR_PRESSURE * pow(1.0 - 0.0065 * elev / (D_ZERO_CELSIUS + Tave), 5.26);
+    else if (opt.air_pressure == RVN_AIRPRESS_UBC) air_pres = D_KPA_PER_ATM * (1.0 - 0.0001 * elev);
+    else air_pres = D_AMBIENT_AIR_PRESSURE;
+    double relhum = 0.5;
+    if (opt.rel_humidity == RVN_RELHUM_MINDEWPT) relhum = dmin(sat_vapor_pressure(F[RVN_F_TEMP_DAILY_MIN]) / sat_vapor_pressure(Tave), 1.0);
+    rel_hum = dmin(relhum * c.LU(RVN_LU_RELHUM_CORR), 1.0);
+    const size_t row = (size_t)M.et_row[step] * M.nHp + k;
+    ET_radia = M.et_radia[row];
+    if (opt.sw_radiation == RVN_SW_RAD_DEFAULT) {
+      const double Ketp = ET_radia, Ket = M.et_flat[row], Mopt = M.opt_air_mass[row];
+      double dew_pt;
+      { const double a = 17.27, b = 237.7; const double tmp = (a * Tave / (b + Tave)) + log(rel_hum); dew_pt = b * tmp / (a - tmp); }   // GetDewPointTemp, src/CommonFunctions.cpp:1131-1139
+      const double gamma_dust = 0.025;
+      const double precip_WV = 1.12 * exp(0.0614 * dew_pt);
+      const double tau = exp((-0.124 - 0.0207 * precip_WV) + (-0.0682 - 0.0248 * precip_WV) * Mopt) - gamma_dust;                    // Dingman E-9..E-13
+      const double tau2 = 0.5 * (1.0 - exp((-0.0363 - 0.0084 * precip_WV) + (-0.0572 - 0.0173 * precip_WV) * Mopt) + gamma_dust);    // Dingman E-15..E-18
+      SW_radia = tau * Ketp + tau2 * Ket + tau2 * D_GLOBAL_ALBEDO * (tau2 + tau) * Ketp;
+    }
+    double cc = 1.0;   // cloud cover is 0 (CLOUDCOV_NONE)
+    if (opt.sw_cloudcorr == RVN_SW_CLOUD_CORR_DINGMAN) cc = 0.355 + 0.68 * (1 - 0.0);
+    else if (opt.sw_cloudcorr == RVN_SW_CLOUD_CORR_ANNANDALE) {
+      const double kRs = 0.16;
+      if (F[RVN_F_TEMP_DAILY_MAX] > F[RVN_F_TEMP_DAILY_MIN]) cc = kRs * (1.0 + 2.7E-5 * elev) * sqrt(F[RVN_F_TEMP_DAILY_MAX] - F[RVN_F_TEMP_DAILY_MIN]);
+      else cc = 0.0;
+    }
+    SW_radia *= cc;
+    if (M.record_forcings) {
+      double *gf = M.forc + (size_t)e * RVN_F_COUNT * M.nHp + k;
+      gf[(size_t)RVN_F_AIR_PRES * M.nHp] = air_pres; gf[(size_t)RVN_F_REL_HUMIDITY * M.nHp] = rel_hum; gf[(size_t)RVN_F_SW_RADIA * M.nHp] = SW_radia;
+    }
+  }
   {  // CModel::EstimatePotentialMelt  src/PotentialMelt.cpp:20-246
     double pm = F[RVN_F_POTENTIAL_MELT];
     const int method = opt.pot_melt;
@@ -382,6 +424,39 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
         const double cpet = c.G(RVN_G_MOHYSE_PET_COEFF), ws = M.sunset_angle[(size_t)M.et_row[step] * M.nHp + k];
         PET = cpet / D_PI * ws * exp((17.3 * F[RVN_F_TEMP_AVE]) / (238 + F[RVN_F_TEMP_AVE]));
       }
+    } else if (method == RVN_PET_TURC_1961) {   // TurcEvap  src/Evaporation.cpp:61-68
+      const double t = dmax(0.0, F[RVN_F_TEMP_DAILY_AVE]);
+      double evp = 0.013 * t / (t + 15) * ((SW_radia)*23.8846 + 50);
+      if (rel_hum < 0.5) evp *= (1 + (50 - rel_hum * 100) / 70);
+      PET = dmax(0.0, evp);
+    } else if (method == RVN_PET_MAKKINK_1957) {   // Makkink1957Evap  src/Evaporation.cpp:32-48
+      const double T = F[RVN_F_TEMP_AVE];
+      const double sat_vap = sat_vapor_pressure(T);
+      const double de_dT = (T > 0) ? 17.26939 * 237.3 / pow(T + 237.3, 2) * sat_vap : 21.87456 * 265.5 / pow(T + 265.5, 2) * sat_vap;   // GetSatVapSlope
+      const double LH_vapor = 2.495 - 0.002361 * T;
+      const double gamma = D_SPH_AIR / D_AIR_H20_MW_RAT * air_pres / LH_vapor;
+      PET = dmax(0.0, 0.61 * (de_dT / (de_dT + gamma)) * SW_radia * 23.8846 / 58.5 - 0.12);
+    } else if (method == RVN_PET_PENMAN_SIMPLE33 || method == RVN_PET_PENMAN_SIMPLE39) {   // Valiantzas (2006)  src/Evaporation.cpp:454-474
+      const double Rs = SW_radia, R_et = ET_radia, Tave = F[RVN_F_TEMP_AVE];
+      if (method == RVN_PET_PENMAN_SIMPLE33) PET = 0.047 * Rs * sqrt(Tave + 9.5) - 2.4 * pow(Rs / R_et, 2.0) + 0.09 * (Tave + 20) * (1 - rel_hum);
+      else PET = 0.038 * Rs * sqrt(Tave + 9.5) - 2.4 * pow(Rs / R_et, 2.0) + 0.075 * (Tave + 20) * (1 - rel_hum);
+    } else if (method == RVN_PET_VAPDEFICIT) {   // src/Evaporation.cpp:506-518
+      const double e_sat = sat_vapor_pressure(F[RVN_F_TEMP_AVE]);
+      const double ea = rel_hum * e_sat;
+      PET = c.LU(RVN_LU_PET_VAP_COEFF) * (e_sat - ea);
+    } else if (method == RVN_PET_LINACRE) {   // src/Evaporation.cpp:491-504
+      const double T = F[RVN_F_TEMP_DAILY_AVE];
+      double Tdewpoint;
+      { const double a = 17.27, b = 237.7; const double tmp = (a * T / (b + T)) + log(rel_hum); Tdewpoint = b * tmp / (a - tmp); }
+      const double latit = c.lat * 57.29578951;
+      PET = ((ow ? 700 : 500) * T / (100 - latit) + 15.0 * (T - Tdewpoint)) / (80.0 - T);
+    } else if (method == RVN_PET_HARGREAVES) {   // HargreavesEvap  src/Evaporation.cpp:179-203
+      double Ra = ET_radia;
+      Ra /= (D_LH_VAPOR * D_DENSITY_WATER / D_MM_PER_METER);
+      double Ct = 0.125;
+      if (rel_hum >= 0.54) Ct = 0.035 * pow(100 * (1.0 - rel_hum), 0.333);
+      const double delT = (1.8 * temp_month_max + 32.0) - (1.8 * temp_month_min + 32.0);
+      PET = dmax(0.0, 0.0075 * Ra * Ct * sqrt(delT) * (1.8 * F[RVN_F_TEMP_DAILY_AVE] + 32.0));
     } else if (method == RVN_PET_FROMMONTHLY) {
       double peRatio = 1.0 + D_HBV_PET_TEMP_CORR * (temp_ave_unc - temp_month_ave);
       peRatio = dmax(0.0, dmin(2.0, peRatio));
@@ -397,7 +472,7 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
     F[RVN_F_PET] *= factor; F[RVN_F_OW_PET] *= factor;
   }
   if (opt.evaporation == RVN_PET_FROMMONTHLY || opt.evaporation == RVN_PET_CONSTANT || opt.evaporation == RVN_PET_HAMON ||
-      opt.evaporation == RVN_PET_LINEAR_TEMP) F[RVN_F_PET] *= subdaily_corr;   // IsDailyPETmethod, src/Evaporation.cpp:540-556
+      opt.evaporation == RVN_PET_LINEAR_TEMP || opt.evaporation == RVN_PET_TURC_1961 || opt.evaporation == RVN_PET_LINACRE) F[RVN_F_PET] *= subdaily_corr;   // IsDailyPETmethod, src/Evaporation.cpp:540-556
   if (opt.snow_suppress_PET) {
     double SWE = 0.0, sc = 1.0;
     if (c.iSV(RVN_SV_SNOW) >= 0) SWE = c.old_snow;
@@ -780,7 +855,7 @@ __global__ void __launch_bounds__(RVN_BS, RVN_STATIC_MIN_BLOCKS) hru_sweep_stati
   if (enabled) compute_forcings(c, M, e, k, step, sb);
   else {
 #pragma unroll
-    for (int f = 0; f < RVN_F_COUNT; f++) c.F[f] = 0.0;
+    for (int f = 0; f < RVN_F_CARRIED; f++) c.F[f] = 0.0;
   }
   if (enabled) reboot_diagnostics(c);   // disabled HRUs keep their stored values (the reference never writes them back, :701)
   // ---- ordered-series process sweep on the newest state
@@ -795,7 +870,7 @@ __global__ void __launch_bounds__(RVN_BS, RVN_STATIC_MIN_BLOCKS) hru_sweep_stati
     if (M.record_forcings) {
       double *gf = M.forc + (size_t)e * RVN_F_COUNT * nHp + k;
 #pragma unroll
-      for (int f = 0; f < RVN_F_COUNT; f++) gf[(size_t)f * nHp] = c.F[f];
+      for (int f = 0; f < RVN_F_CARRIED; f++) gf[(size_t)f * nHp] = c.F[f];
     }
   }
   const int par = step & 1;
@@ -853,7 +928,7 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
   c.old_snow_temp = (P->iSV[RVN_SV_SNOW_TEMP] >= 0) ? c.SV(P->iSV[RVN_SV_SNOW_TEMP]) : 0.0;
   load_canopy(c, M, step);
   if (enabled) compute_forcings(c, M, e, k, step, sb);
-  else { for (int f = 0; f < RVN_F_COUNT; f++) c.F[f] = 0.0; }
+  else { for (int f = 0; f < RVN_F_CARRIED; f++) c.F[f] = 0.0; }
   if (enabled) reboot_diagnostics(c);
   if (euler) { for (int s = 0; s < nCore; s++) c.SVW(s) = c.SV(s); }   // aPhinew = aPhi (src/Solvers.cpp:155-200); rates come from aPhi
   const bool unit_dt = (c.tstep == 1.0);
@@ -889,7 +964,7 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
     if (M.record_forcings) {
       double *gf = M.forc + (size_t)e * RVN_F_COUNT * nHp + k;
 #pragma unroll
-      for (int f = 0; f < RVN_F_COUNT; f++) gf[(size_t)f * nHp] = c.F[f];
+      for (int f = 0; f < RVN_F_CARRIED; f++) gf[(size_t)f * nHp] = c.F[f];
     }
   }
   const int par = step & 1;

@@ -34,6 +34,12 @@
 #define D_LH_VAPOR 2.501
 #define D_SPH_WATER 4.186e-3   // [MJ/kg/K]
 #define D_LH_FUSION 0.334      // [MJ/kg]
+#define D_AMBIENT_AIR_PRESSURE 101.3
+#define D_KPA_PER_ATM 101.325
+#define D_ZERO_CELSIUS 273.16
+#define D_GLOBAL_ALBEDO 0.3
+#define D_SPH_AIR 1.012e-3
+#define D_AIR_H20_MW_RAT 0.622
 #define D_WINTER_SOLSTICE_ANG 6.111043
 #define D_HBV_PET_ELEV_CORR 0.0005
 #define D_HBV_PET_TEMP_CORR 0.5

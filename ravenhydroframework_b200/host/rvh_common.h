@@ -82,6 +82,8 @@ struct optStruct {
   rvn_potmelt  pot_melt;
   rvn_pet      evaporation, ow_evaporation, evap_infill, ow_evap_infill;
   rvn_orocorr  orocorr_temp, orocorr_precip, orocorr_PET;
+  int    air_pressure, rel_humidity, SW_radiation, SW_cloudcovercorr;   // rvn_airpress / rvn_relhum / rvn_sw_rad / rvn_sw_cloudcorr
+  std::string unsupported_atmos;   // first atmospheric method command the B200 build cannot honour (fatal only if a consumer needs it)
   rvn_routing  routing;
   catchment_route catchment_routing;
   interp_method interpolation;
@@ -103,6 +105,7 @@ time_struct DateStringToTimeStruct(const std::string &sDate, const std::string &
 double TimeDifference(double jul_day1, int year1, double jul_day2, int year2, int calendar);
 double DayAngle(double julian_day, int year, int calendar);
 double SolarDeclination(double day_angle);                         // src/Radiation.cpp:484-497
+double OpticalAirMass(double latrad, double declin, double day_length, double t_sol, bool avg_daily);   // src/Radiation.cpp:875-967
 double EccentricityCorr(double day_angle);                         // src/Radiation.cpp:505-515
 double CalcETRadiation2(double latrad, double aspect, double declin, double ecc, double slope, double t1, double t2, bool avg_daily);  // src/Radiation.cpp:637-822
 double gamma2(double x);

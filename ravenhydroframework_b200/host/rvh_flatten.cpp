@@ -261,18 +261,31 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
       if (op == RVN_OP_OPEN_WATER_EVAP || op == RVN_OP_LAKE_EVAP_BASIC || op == RVN_OP_SOILEVAP_HYPR) uses_owpet = true;
     }
     auto consumed = [&](int method) { return (uses_pet && O.evaporation == method) || (uses_owpet && O.ow_evaporation == method); };
-    const bool need_et = consumed(RVN_PET_HARGREAVES_1985) || consumed(RVN_PET_OUDIN);
+    bool need_atmos = false;   // PET methods fed by air pressure / humidity / shortwave radiation
+    for (int mth = RVN_PET_TURC_1961; mth <= RVN_PET_HARGREAVES; mth++) if (consumed(mth)) need_atmos = true;
+    ExitGracefullyIf(need_atmos && !O.unsupported_atmos.empty(), "ParseMainInputFile: " + O.unsupported_atmos + " is not implemented in the B200 build");
+    ExitGracefullyIf(need_atmos && O.timestep < 1.0 - 0.0001, "CModel::Flatten: radiation / humidity based PET methods are built for daily steps only in the B200 build");
+    if (consumed(RVN_PET_VAPDEFICIT))
+      for (size_t c = 0; c < lu_classes.size(); c++)
+        ExitGracefullyIf(lu_classes[c].S.v[RVN_LU_PET_VAP_COEFF] == NOT_SPECIFIED, "CLandUseClass::AutoCalculateLandUseProps: required parameter PET_VAP_COEFF not specified for land use class " + lu_classes[c].tag);
+    if (consumed(RVN_PET_HARGREAVES))
+      for (int g = 0; g < nG; g++)
+        ExitGracefullyIf(_pGauges[g]->aMaxTemp[0] == NOT_SPECIFIED || _pGauges[g]->aMinTemp[0] == NOT_SPECIFIED, "PET_HARGREAVES requires minimum and maximum monthly temperatures");
+    d.opt.need_atmos = need_atmos ? 1 : 0;
+    d.opt.air_pressure = O.air_pressure; d.opt.rel_humidity = O.rel_humidity; d.opt.sw_radiation = O.SW_radiation; d.opt.sw_cloudcorr = O.SW_cloudcovercorr;
+    const bool need_et = consumed(RVN_PET_HARGREAVES_1985) || consumed(RVN_PET_OUDIN) || need_atmos;
     const bool need_dl = consumed(RVN_PET_HAMON), need_ws = consumed(RVN_PET_MOHYSE);
+    ExitGracefullyIf(need_et && O.SW_radiation == RVN_SW_RAD_NONE, "CModel::Flatten: :SWRadiationMethod SW_RAD_NONE leaves the extraterrestrial radiation unset; PET methods that read it are not built for that case");
     ExitGracefullyIf((consumed(RVN_PET_OUDIN) || need_dl || need_ws || consumed(RVN_PET_LINEAR_TEMP)) && O.timestep < 1.0 - 0.0001,
                      "CModel::Flatten: PET_OUDIN / PET_HAMON / PET_MOHYSE / PET_LINEAR_TEMP are built for daily steps only in the B200 build");
     if (consumed(RVN_PET_LINEAR_TEMP))
       for (size_t c = 0; c < lu_classes.size(); c++)
         ExitGracefullyIf(lu_classes[c].S.v[RVN_LU_PET_LIN_COEFF] == NOT_SPECIFIED, "CLandUseClass::AutoCalculateLandUseProps: required parameter PET_LIN_COEFF not specified for land use class " + lu_classes[c].tag);
     ExitGracefullyIf(need_ws && globals.v[RVN_G_MOHYSE_PET_COEFF] == NOT_SPECIFIED, "CModel::Flatten: PET_MOHYSE needs :GlobalParameter MOHYSE_PET_COEFF");
-    d.day_length = NULL; d.sunset_angle = NULL;
+    d.day_length = NULL; d.sunset_angle = NULL; d.et_flat = NULL; d.opt_air_mass = NULL;
     if (need_et || need_dl || need_ws) {
       _f_et_row.assign(nSteps, 0);
-      _f_et.clear(); _f_daylen.clear(); _f_sunset.clear();
+      _f_et.clear(); _f_daylen.clear(); _f_sunset.clear(); _f_etflat.clear(); _f_mopt.clear();
       std::map<std::pair<double, double>, int> rows;
       for (int n = 0; n < nSteps; n++) {
         const double t_sol = _f_times[n].julian_day - floor(_f_times[n].julian_day) - 0.5;
@@ -288,6 +301,12 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
               const double hd = -tan(declin) * tan(_f_hru_d[2][k]);
               _f_daylen.push_back((hd >= 1.0) ? 0.0 : ((hd <= -1.0) ? 1.0 : acos(hd) / RVH_PI));
             }
+            if (need_atmos) {   // CRadiation::ClearSkySolarRadiation, src/Radiation.cpp:1015-1032
+              const double hd = -tan(declin) * tan(_f_hru_d[2][k]);
+              const double day_length = (hd >= 1.0) ? 0.0 : ((hd <= -1.0) ? 1.0 : acos(hd) / RVH_PI);
+              _f_etflat.push_back(CalcETRadiation2(_f_hru_d[2][k], _f_hru_d[4][k], declin, ecc, 0.0, t_sol, t_sol + O.timestep, O.timestep >= 1.0));
+              _f_mopt.push_back(OpticalAirMass(_f_hru_d[2][k], declin, day_length, t_sol, O.timestep >= 1.0));
+            }
             if (need_ws) _f_sunset.push_back(acos(-tan(_f_hru_d[2][k]) * tan(declin)));   // src/Evaporation.cpp:481
           }
           _f_et_row[n] = r;
@@ -297,6 +316,7 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
       if (need_et) d.et_radia = _f_et.data();
       if (need_dl) d.day_length = _f_daylen.data();
       if (need_ws) d.sunset_angle = _f_sunset.data();
+      if (need_atmos) { d.et_flat = _f_etflat.data(); d.opt_air_mass = _f_mopt.data(); }
     }
   }
   // ---- gauge series sampled on the model step (src/UpdateForcings.cpp:98-155)

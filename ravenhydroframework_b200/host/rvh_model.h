@@ -320,7 +320,7 @@ private:
   std::vector<rvn_lateral> _f_lat;
   std::vector<int32_t> _f_lat_kfrom, _f_lat_kto, _f_lat_chunk;
   std::vector<int> _f_lat_flag;
-  std::vector<double> _f_daylen, _f_sunset;
+  std::vector<double> _f_daylen, _f_sunset, _f_etflat, _f_mopt;
   std::vector<double> _f_lat_frac, _f_chan_Q, _f_chan_A, _f_sb_Qmult, _f_sb_reach;
   std::vector<int32_t> _f_sb_channel;
   std::vector<double> _f_pert_eps;

@@ -59,8 +59,8 @@ static double ParseIntervalToken(const std::string &t, int calendar) {
 static const char *kIgnoredRVI[] = {":FileType", ":WrittenBy", ":CreationDate", ":Description", ":SilentMode", ":NoisyMode", ":QuietMode",
   ":EvaluationMetrics", ":CustomOutput", ":WriteForcingFunctions", ":WriteMassBalanceFile", ":WriteEnsimFormat", ":WriteNetCDFFormat",
   ":RunName", ":OutputDirectory", ":OutputInterval", ":SuppressOutput", ":DontWriteWatershedStorage", ":SnapshotHydrograph",
-  ":SWRadiationMethod", ":SWCloudCorrect", ":SWCanopyCorrect", ":LWRadiationMethod", ":LWIncomingMethod", ":CloudCoverMethod", ":WindspeedMethod",
-  ":RelativeHumidityMethod", ":AirPressureMethod", ":PavicsMode", ":DebugMode", ":WriteExhaustiveMB", ":HydrologicProcesses", ":EndHydrologicProcesses",
+  ":LWRadiationMethod", ":LWIncomingMethod", ":WindspeedMethod",
+  ":PavicsMode", ":DebugMode", ":WriteExhaustiveMB", ":HydrologicProcesses", ":EndHydrologicProcesses",
   ":WriteSubbasinFile", ":NetCDFAttribute", ":rvh_Filename", NULL};
 
 static rvn_pet ParsePET(const std::string &s) {
@@ -73,6 +73,13 @@ static rvn_pet ParsePET(const std::string &s) {
   if (s == "PET_HAMON") return RVN_PET_HAMON;
   if (s == "PET_LINEAR_TEMP") return RVN_PET_LINEAR_TEMP;
   if (s == "PET_MOHYSE") return RVN_PET_MOHYSE;
+  if (s == "PET_TURC_1961") return RVN_PET_TURC_1961;
+  if (s == "PET_MAKKINK_1957") return RVN_PET_MAKKINK_1957;
+  if (s == "PET_PENMAN_SIMPLE33") return RVN_PET_PENMAN_SIMPLE33;
+  if (s == "PET_PENMAN_SIMPLE39") return RVN_PET_PENMAN_SIMPLE39;
+  if (s == "PET_VAPDEFICIT") return RVN_PET_VAPDEFICIT;
+  if (s == "PET_LINACRE") return RVN_PET_LINACRE;
+  if (s == "PET_HARGREAVES") return RVN_PET_HARGREAVES;
   ExitGracefully("ParseMainInputFile: evaporation method " + s + " is not implemented in the B200 build");
   return RVN_PET_NONE;
 }
@@ -164,6 +171,43 @@ static void ParseMainInputFile(CModel *&pModel, optStruct &Options) {
       else ExitGracefully("ParseMainInputFile: rain/snow method " + s[1] + " is not implemented in the B200 build");
       continue;
     }
+    // atmospheric estimators (src/ParseInput.cpp cases 24, 26, 29, 37, 23, 36): honoured where built; anything else is recorded and
+    // becomes fatal only if a consumed PET method needs the atmospheric chain (the reference derives it for every run, used or not)
+    if (c == ":SWRadiationMethod") {
+      if (Len < 2) continue;
+      if (s[1] == "SW_RAD_DEFAULT") Options.SW_radiation = RVN_SW_RAD_DEFAULT;
+      else if (s[1] == "SW_RAD_NONE") Options.SW_radiation = RVN_SW_RAD_NONE;
+      else if (Options.unsupported_atmos.empty()) Options.unsupported_atmos = c + " " + s[1];
+      continue;
+    }
+    if (c == ":RelativeHumidityMethod") {
+      if (Len < 2) continue;
+      if (s[1] == "CONSTANT" || s[1] == "RELHUM_CONSTANT") Options.rel_humidity = RVN_RELHUM_CONSTANT;
+      else if (s[1] == "MINDEWPT" || s[1] == "RELHUM_MINDEWPT") Options.rel_humidity = RVN_RELHUM_MINDEWPT;
+      else if (Options.unsupported_atmos.empty()) Options.unsupported_atmos = c + " " + s[1];
+      continue;
+    }
+    if (c == ":AirPressureMethod") {
+      if (Len < 2) continue;
+      if (s[1] == "BASIC" || s[1] == "AIRPRESS_BASIC") Options.air_pressure = RVN_AIRPRESS_BASIC;
+      else if (s[1] == "UBC" || s[1] == "AIRPRESS_UBC") Options.air_pressure = RVN_AIRPRESS_UBC;
+      else if (s[1] == "CONSTANT" || s[1] == "AIRPRESS_CONST") Options.air_pressure = RVN_AIRPRESS_CONST;
+      else if (Options.unsupported_atmos.empty()) Options.unsupported_atmos = c + " " + s[1];
+      continue;
+    }
+    if (c == ":SWCloudCorrect") {
+      if (Len < 2) continue;
+      if (s[1] == "SW_CLOUD_CORR_NONE") Options.SW_cloudcovercorr = RVN_SW_CLOUD_CORR_NONE;
+      else if (s[1] == "SW_CLOUD_CORR_DINGMAN") Options.SW_cloudcovercorr = RVN_SW_CLOUD_CORR_DINGMAN;
+      else if (s[1] == "SW_CLOUD_CORR_ANNANDALE") Options.SW_cloudcovercorr = RVN_SW_CLOUD_CORR_ANNANDALE;
+      else if (Options.unsupported_atmos.empty()) Options.unsupported_atmos = c + " " + s[1];
+      continue;
+    }
+    if (c == ":CloudCoverMethod") {
+      if (Len >= 2 && s[1] != "NONE" && s[1] != "CLOUDCOV_NONE" && Options.unsupported_atmos.empty()) Options.unsupported_atmos = c + " " + s[1];
+      continue;
+    }
+    if (c == ":SWCanopyCorrect") { continue; }   // only scales the sub-canopy shortwave, which nothing built here consumes
     if (c == ":PotentialMeltMethod" || c == ":PotentialMelt") {
       if (s[1] == "POTMELT_DEGREE_DAY") Options.pot_melt = RVN_POTMELT_DEGREE_DAY;
       else if (s[1] == "POTMELT_HBV") Options.pot_melt = RVN_POTMELT_HBV;
@@ -514,7 +558,8 @@ static void ParseClassPropertiesFile(CModel *pModel, const optStruct &Options) {
     surface_struct &S = pModel->lu_classes[k].S;
     if (S.v[RVN_LU_FOREST_SPARSENESS] == NOT_SPECIFIED) S.v[RVN_LU_FOREST_SPARSENESS] = 0.0;  // src/LandUseClass.cpp autocalc
     if (S.v[RVN_LU_LAKE_PET_CORR] == NOT_SPECIFIED) S.v[RVN_LU_LAKE_PET_CORR] = 1.0;
-    if (S.v[RVN_LU_MAX_SAT_AREA_FRAC] == NOT_SPECIFIED) S.v[RVN_LU_MAX_SAT_AREA_FRAC] = 1.0;  // src/LandUseClass.cpp:93-98
+    if (S.v[RVN_LU_MAX_SAT_AREA_FRAC] == NOT_SPECIFIED) S.v[RVN_LU_MAX_SAT_AREA_FRAC] = 1.0;
+    if (S.v[RVN_LU_RELHUM_CORR] == NOT_SPECIFIED) S.v[RVN_LU_RELHUM_CORR] = 1.0;   // src/LandUseClass.cpp:264-267  // src/LandUseClass.cpp:93-98
     if (S.v[RVN_LU_OW_PET_CORR] == NOT_SPECIFIED) S.v[RVN_LU_OW_PET_CORR] = 1.0;
     // autogenerated snow parameters (CLandUseClass::AutoCalculateLandUseProps, src/LandUseClass.cpp:100-160)
     if (S.v[RVN_LU_FOREST_COVERAGE] == NOT_SPECIFIED) S.v[RVN_LU_FOREST_COVERAGE] = 0.0;

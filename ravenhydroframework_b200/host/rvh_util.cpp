@@ -24,6 +24,7 @@ optStruct::optStruct()
       rainsnow(RVN_RAINSNOW_DINGMAN), pot_melt(RVN_POTMELT_DEGREE_DAY), evaporation(RVN_PET_HARGREAVES_1985),
       ow_evaporation(RVN_PET_HARGREAVES_1985), evap_infill(RVN_PET_HARGREAVES_1985), ow_evap_infill(RVN_PET_HARGREAVES_1985),
       orocorr_temp(RVN_OROCORR_NONE), orocorr_precip(RVN_OROCORR_NONE), orocorr_PET(RVN_OROCORR_NONE),
+      air_pressure(RVN_AIRPRESS_BASIC), rel_humidity(RVN_RELHUM_CONSTANT), SW_radiation(RVN_SW_RAD_DEFAULT), SW_cloudcovercorr(RVN_SW_CLOUD_CORR_NONE),
       routing(RVN_ROUTE_STORAGECOEFF), catchment_routing(ROUTE_DUMP), interpolation(INTERP_NEAREST_NEIGHBOR),
       month_interp_method(MONTHINT_LINEAR_MID), num_soillayers(-1), suppressCompetitiveET(false), snow_suppressPET(false),
       allow_soil_overfill(false), direct_evap(false), silent(false), noisy(false), benchmarking(false),
@@ -288,6 +289,56 @@ struct BeamGeom {   // Allen et al. (2006) eqn 11 constants + the trigonometric 
   }
 };
 }  // namespace
+// CRadiation::MassFunct / OpticalAirMass (src/Radiation.cpp:875-967; X. Yin 1997): optical air mass averaged over the day or at
+// the step's solar time.  Geometry and date only -> evaluated on the host with the other per-date tables.
+static double MassFunct(double latrad, double declin, double cos_omt, double c1, double c2, double c3, double t) {
+  const double EARTH_ANG_VEL = 6.283185;
+  double a, b, tmp;
+  a = c1 + sin(latrad) * sin(declin);
+  b = cos(latrad) * cos(declin);
+  if (a > b) {
+    tmp = (b + a * cos_omt) / (a + b * cos_omt);
+    return 1.0 / EARTH_ANG_VEL * c2 / sqrt(a * a - b * b) * acos(tmp) + c3 * t;
+  } else if (a < b) {
+    tmp = sqrt(b + a) * sqrt(1.0 + cos_omt) + sqrt(b - a) * sqrt(1.0 - cos_omt);
+    tmp /= (sqrt(b + a) * sqrt(1.0 + cos_omt) - sqrt(b - a) * sqrt(1.0 - cos_omt));
+    return 1.0 / EARTH_ANG_VEL * c2 / sqrt(b * b - a * a) * log(tmp) + c3 * t;
+  } else {
+    return 1.0 / EARTH_ANG_VEL * c2 / a * tan(0.5 * acos(cos_omt)) + c3 * t;
+  }
+}
+double OpticalAirMass(double latrad, double declin, double day_length, double t_sol, bool avg_daily) {
+  const double EARTH_ANG_VEL = 6.283185;
+  const double c1a = 0.00830700, c2a = 1.02129227, c3a = -0.01287829, c1b = 0.03716000, c2b = 1.53832220, c3b = -1.69726057, m90 = 39.7;
+  static const double deg80 = 80.0 / 180.0 * PI;
+  static const double cos80 = cos(deg80);
+  double t1, Zn, Z0, t80;
+  t1 = 0.5 * day_length;
+  if (t1 == 0.0) return m90;
+  Zn = acos(sin(latrad) * sin(declin) - cos(latrad) * cos(declin));
+  if (fabs(latrad + declin) <= 0.5 * PI) Zn = 0.5 * PI;
+  if (avg_daily) {
+    Z0 = 0.5 * PI;
+    if (fabs(latrad - declin) <= 0.5 * PI) Z0 = latrad - declin;
+    t80 = (1.0 / EARTH_ANG_VEL) * acos((cos80 - sin(latrad) * sin(declin)) / (cos(latrad) * cos(declin)));
+    double cos_omt = cos(EARTH_ANG_VEL * t1);
+    if (Zn <= deg80) return MassFunct(latrad, declin, cos_omt, c1a, c2a, c3a, t1) / t1;
+    else if (Z0 >= deg80) return MassFunct(latrad, declin, cos_omt, c1b, c2b, c3b, t1) / t1;
+    else {
+      double cos_omt80 = cos(EARTH_ANG_VEL * t80);
+      double sum = 0;
+      sum += MassFunct(latrad, declin, cos_omt80, c1a, c2a, c3a, t80) / t1;
+      sum += MassFunct(latrad, declin, cos_omt, c1b, c2b, c3b, t1) / t1;
+      sum -= MassFunct(latrad, declin, cos_omt80, c1b, c2b, c3b, t80) / t1;
+      return sum;
+    }
+  } else {
+    double cosZ = sin(latrad) * sin(declin) + cos(latrad) * cos(declin) * cos(EARTH_ANG_VEL * t_sol);
+    if (cosZ < 0) return m90;
+    if (cosZ > cos80) return c2a / (c1a + cosZ) + c3a;
+    else return c2b / (c1b + cosZ) + c3b;
+  }
+}
 double CalcETRadiation2(double latrad, double aspect, double declin, double ecc, double slope, double t1, double t2, bool avg_daily) {
   double revasp = -(aspect + PI);
   if (revasp > 2 * PI) revasp -= 2 * PI;

