@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RVN_ABI_VERSION 5
+#define RVN_ABI_VERSION 6
 #define RVN_DOESNT_EXIST (-1)
 #define RVN_CONV_STORES 50   /* MAX_CONVOL_STORES, reference src/RavenInclude.h / Convolution.cpp:17 */
 #define RVN_MAX_CONN 24      /* max connections of a non-convolution process (Precipitation: 13..19) */
@@ -128,6 +128,7 @@ typedef enum {
   RVN_OP_SOILEVAP_ROOT,        /* CmvSoilEvap             src/SoilEvaporation.cpp:570-596           */
   RVN_OP_SOILEVAP_ROOT_CONSTRAIN, /* CmvSoilEvap          src/SoilEvaporation.cpp:598-622           */
   RVN_OP_SOILEVAP_AWBM,        /* CmvSoilEvap             src/SoilEvaporation.cpp:716-727           */
+  RVN_OP_SUBLIMATION,          /* CmvSublimation          src/Sublimation.cpp:98-243; ia[0] = rvn_sublim */
   RVN_OP_COUNT
 } rvn_opcode;
 
@@ -138,6 +139,9 @@ typedef enum { RVN_POTMELT_NONE = 0, RVN_POTMELT_DATA, RVN_POTMELT_DEGREE_DAY, R
 /* atmospheric estimators of the forcing chain (reference src/UpdateForcings.cpp:677-731, src/Radiation.cpp:24-57,333-364) */
 typedef enum { RVN_AIRPRESS_BASIC = 0, RVN_AIRPRESS_UBC, RVN_AIRPRESS_CONST } rvn_airpress;
 typedef enum { RVN_RELHUM_CONSTANT = 0, RVN_RELHUM_MINDEWPT } rvn_relhum;
+typedef enum { RVN_WINDVEL_CONSTANT = 0, RVN_WINDVEL_UBC_MOD, RVN_WINDVEL_SQRT } rvn_windvel;   /* CModel::EstimateWindVelocity, src/UpdateForcings.cpp:739-790 */
+/* snow sublimation algorithms (reference sublimation_type, src/Sublimation.cpp:98-200); SUBLIM_PBSM is a stub there */
+typedef enum { RVN_SUBLIM_SVERDRUP = 0, RVN_SUBLIM_KUZMIN, RVN_SUBLIM_KUCHMENT_GELFAN, RVN_SUBLIM_BULK_AERO, RVN_SUBLIM_CENTRAL_SIERRA } rvn_sublim;
 typedef enum { RVN_SW_RAD_DEFAULT = 0, RVN_SW_RAD_NONE } rvn_sw_rad;
 typedef enum { RVN_SW_CLOUD_CORR_NONE = 0, RVN_SW_CLOUD_CORR_DINGMAN, RVN_SW_CLOUD_CORR_ANNANDALE } rvn_sw_cloudcorr;
 typedef enum { RVN_PET_DATA = 0, RVN_PET_FROMMONTHLY, RVN_PET_CONSTANT, RVN_PET_NONE, RVN_PET_HARGREAVES_1985, RVN_PET_OUDIN,
@@ -165,7 +169,8 @@ typedef enum {
   RVN_G_PRECIP_LAPSE, RVN_G_RAINSNOW_TEMP, RVN_G_RAINSNOW_DELTA, RVN_G_AVG_ANNUAL_SNOW, RVN_G_SNOW_TEMPERATURE,
   RVN_G_HBVEC_LAPSE_UPPER, RVN_G_HBVEC_LAPSE_RATE, RVN_G_HBVEC_LAPSE_ELEV, RVN_G_AIRSNOW_COEFF,
   RVN_G_AVG_ANNUAL_RUNOFF, RVN_G_MAX_SWE_SURFACE, RVN_G_TOC_MULTIPLIER, RVN_G_TIME_TO_PEAK_MULTIPLIER,
-  RVN_G_GAMMA_SHAPE_MULTIPLIER, RVN_G_GAMMA_SCALE_MULTIPLIER, RVN_G_MOHYSE_PET_COEFF, RVN_G_COUNT
+  RVN_G_GAMMA_SHAPE_MULTIPLIER, RVN_G_GAMMA_SCALE_MULTIPLIER, RVN_G_MOHYSE_PET_COEFF,
+  RVN_G_SNOW_ROUGHNESS, RVN_G_WINDVEL_ICEPT, RVN_G_WINDVEL_SCALE, RVN_G_COUNT
 } rvn_global_field;
 typedef enum {
   RVN_LU_IMPERMEABLE_FRAC = 0, RVN_LU_FOREST_COVERAGE, RVN_LU_FOREST_SPARSENESS, RVN_LU_MELT_FACTOR,
@@ -176,7 +181,8 @@ typedef enum {
   RVN_LU_GLAC_STORAGE_COEFF, RVN_LU_HBV_GLACIER_AG, RVN_LU_DEP_MAX, RVN_LU_LAKE_PET_CORR, RVN_LU_OW_PET_CORR,
   RVN_LU_PARTITION_COEFF, RVN_LU_CC_DECAY_COEFF, RVN_LU_MAX_SAT_AREA_FRAC, RVN_LU_PDM_B, RVN_LU_AET_COEFF,
   RVN_LU_MAX_DEP_AREA_FRAC, RVN_LU_PONDED_EXP, RVN_LU_AWBM_AREAFRAC1, RVN_LU_AWBM_AREAFRAC2, RVN_LU_HYMOD2_G, RVN_LU_HYMOD2_KMAX,
-  RVN_LU_HYMOD2_EXP, RVN_LU_PET_LIN_COEFF, RVN_LU_RAIN_MELT_MULT, RVN_LU_RELHUM_CORR, RVN_LU_PET_VAP_COEFF, RVN_LU_COUNT
+  RVN_LU_HYMOD2_EXP, RVN_LU_PET_LIN_COEFF, RVN_LU_RAIN_MELT_MULT, RVN_LU_RELHUM_CORR, RVN_LU_PET_VAP_COEFF,
+  RVN_LU_MIN_WIND_SPEED, RVN_LU_MAX_WIND_SPEED, RVN_LU_COUNT
 } rvn_landuse_field;
 typedef enum {
   RVN_V_MAX_HEIGHT = 0, RVN_V_MAX_LAI, RVN_V_SAI_HT_RATIO, RVN_V_MAX_CAPACITY, RVN_V_MAX_SNOW_CAPACITY,
@@ -214,7 +220,7 @@ typedef enum {
   RVN_F_PRECIP = 0, RVN_F_SNOW_FRAC, RVN_F_TEMP_AVE, RVN_F_TEMP_DAILY_AVE, RVN_F_TEMP_DAILY_MIN,
   RVN_F_TEMP_DAILY_MAX, RVN_F_PET, RVN_F_OW_PET, RVN_F_POTENTIAL_MELT, RVN_F_TEMP_MONTH_AVE, RVN_F_PET_MONTH_AVE,
   /* atmospheric forcings: derived only when opt.need_atmos, recorded (rvn_gpu_download_forcings) but not carried through the sweep */
-  RVN_F_AIR_PRES, RVN_F_REL_HUMIDITY, RVN_F_SW_RADIA,
+  RVN_F_AIR_PRES, RVN_F_REL_HUMIDITY, RVN_F_SW_RADIA, RVN_F_WIND_VEL,
   RVN_F_COUNT
 } rvn_forcing_field;
 #define RVN_F_CARRIED RVN_F_AIR_PRES   /* fields below this index live in the per-thread forcing vector of the sweep */
@@ -275,9 +281,9 @@ typedef struct rvn_options {
   int32_t lake_sv;                /* CModel::GetLakeStorageIndex() */
   int32_t keep_flux_balance;      /* 0: skip per-connection cumulative flux arrays */
   int32_t sol_method;             /* rvn_sol_method: ORDERED_SERIES (default) or EULER (reference src/Solvers.cpp:205-251 / 256-297) */
-  int32_t need_atmos;             /* 1: a consumed PET needs air pressure / relative humidity / shortwave radiation -> derive them */
+  int32_t need_atmos;             /* 1: a consumed PET or a sublimation process needs air pressure / relative humidity / wind / shortwave radiation -> derive them */
   int32_t air_pressure, rel_humidity, sw_radiation, sw_cloudcorr;   /* rvn_airpress, rvn_relhum, rvn_sw_rad, rvn_sw_cloudcorr */
-  int32_t pad_[1];
+  int32_t wind_velocity;          /* rvn_windvel */
 } rvn_options;
 
 /* Flattened model (all pointers are HOST memory, copied by rvn_gpu_create). */

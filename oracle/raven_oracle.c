@@ -320,6 +320,12 @@ static void update_forcings(const rvn_model_desc *d, const double *ptab, int mem
     else if (d->opt.sw_cloudcorr == RVN_SW_CLOUD_CORR_ANNANDALE)
       cc = (F[RVN_F_TEMP_DAILY_MAX] > F[RVN_F_TEMP_DAILY_MIN]) ? 0.16 * (1.0 + 2.7E-5 * elev) * sqrt(F[RVN_F_TEMP_DAILY_MAX] - F[RVN_F_TEMP_DAILY_MIN]) : 0.0;
     F[RVN_F_SW_RADIA] *= cc;
+    F[RVN_F_WIND_VEL] = 2.0; /* CModel::EstimateWindVelocity, src/UpdateForcings.cpp:739-777 */
+    if (d->opt.wind_velocity == RVN_WINDVEL_UBC_MOD) {
+      double wt = omin(0.04 * (F[RVN_F_TEMP_DAILY_MAX] - F[RVN_F_TEMP_DAILY_MIN]), 1.0);
+      F[RVN_F_WIND_VEL] = omax(0.0, (1 - wt) * P_LU(&c, RVN_LU_MIN_WIND_SPEED) + (wt) * P_LU(&c, RVN_LU_MAX_WIND_SPEED));
+    } else if (d->opt.wind_velocity == RVN_WINDVEL_SQRT)
+      F[RVN_F_WIND_VEL] = omax(0.0, P_G(&c, RVN_G_WINDVEL_SCALE) * (F[RVN_F_TEMP_DAILY_MAX] - F[RVN_F_TEMP_DAILY_MIN]) + P_G(&c, RVN_G_WINDVEL_ICEPT));
   }
   /* CModel::EstimatePotentialMelt, src/PotentialMelt.cpp:20-246 */
   {
@@ -924,6 +930,41 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       if (pr->op == RVN_OP_CANEVP_ALL) rates[0] = omax(rates[0], 0.0);
       rates[0] = omin(rates[0], sv[iFrom[0]] / tstep);
       rates[1] -= (oldRates - rates[0]);
+      break;
+    }
+    case RVN_OP_SUBLIMATION: { /* CmvSublimation, src/Sublimation.cpp:98-243: SublimationRate + depth-change term + ApplyConstraints;
+                                * forcings, snow temperature, SNOW_DEPTH and SWE of the depth term are the HRU's lagged values */
+      const int styp = pr->ia[0];
+      double Ta = F[RVN_F_TEMP_AVE], rel_hum = F[RVN_F_REL_HUMIDITY], wind_vel = F[RVN_F_WIND_VEL], air_pres = F[RVN_F_AIR_PRES];
+      double Tsnow = snow_temperature(c), sublim = 0.0;
+      double air_dens = (air_pres - 0.378 * o_sat_vap(Ta)) / (287.042 * (Ta + 273.16)) * 1000; /* GetAirDensity, src/CommonFunctions.cpp:1039-1043 */
+      if (styp == RVN_SUBLIM_SVERDRUP) {
+        double roughness = P_G(c, RVN_G_SNOW_ROUGHNESS), es = o_sat_vap(Tsnow), ea = o_sat_vap(Ta) * rel_hum;
+        double C_E = 0.42 * 0.42 / (log(8.0 / roughness)) / (log(8.0 / roughness));
+        sublim = air_dens * C_E * wind_vel * 0.623 * (es - ea) / air_pres * O_SEC_PER_DAY / O_DENSITY_WATER * O_MM_PER_METER;
+      } else if (styp == RVN_SUBLIM_KUZMIN) {
+        double ea = o_sat_vap(F[RVN_F_TEMP_DAILY_AVE]) * rel_hum * 10, es = o_sat_vap(Tsnow) * 1.0 * 10;
+        sublim = ((0.18 + 0.098 * wind_vel) * (es - ea));
+      } else if (styp == RVN_SUBLIM_KUCHMENT_GELFAN) {
+        double ea = o_sat_vap(Ta) * rel_hum * 10, es = o_sat_vap(Tsnow) * 1.0 * 10;
+        double Q_E = 32.82 * (0.18 + 0.098 * wind_vel) * (es - ea) * 0.0864;
+        sublim = Q_E / 2.845 / O_DENSITY_WATER * (O_MM_PER_METER);
+      } else if (styp == RVN_SUBLIM_BULK_AERO) {
+        double ea = o_sat_vap(Ta) * rel_hum, es = o_sat_vap(Tsnow) * 1.0;
+        double C_E = (0.42 * 0.42) / (log(2.0 / 0.00005) * log(2.0 / 0.00005));
+        double Q_E = air_dens * 2.845 * C_E * wind_vel * ((0.622 * (es - ea)) / air_pres) * O_SEC_PER_DAY;
+        sublim = Q_E / (2.845 * O_DENSITY_WATER) * O_MM_PER_METER;
+      } else if (styp == RVN_SUBLIM_CENTRAL_SIERRA) {
+        double sat_vap = o_sat_vap(Tsnow) * 10, vap_pres = o_sat_vap(F[RVN_F_TEMP_DAILY_AVE]) * rel_hum * 10;
+        sublim = ((0.0063 * (pow((2.0 * 3.28 * 2.0 * 3.28), (-1 / 6))) * (wind_vel * 2.237) * (sat_vap - vap_pres)) * 25.4); /* (-1/6) == 0 */
+      }
+      rates[0] = sublim;
+      if (pr->nconn == 2) {
+        double SD = c->phi_old[c->iSV[RVN_SV_SNOW_DEPTH]], SWE = c->phi_old[iFrom[0]];
+        if (SWE > 0) rates[1] = rates[0] * SD / SWE;
+      }
+      if (sv[iFrom[0]] <= 0) rates[0] = 0.0;
+      rates[0] = omin(rates[0], sv[iFrom[0]] / tstep);
       break;
     }
     case RVN_OP_OPEN_WATER_EVAP: { /* src/OpenWaterEvap.cpp:113-186 */

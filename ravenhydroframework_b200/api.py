@@ -10,9 +10,9 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-F_COUNT = 14  # RVN_F_COUNT
+F_COUNT = 15  # RVN_F_COUNT
 FORCING_NAMES = ["PRECIP", "SNOW_FRAC", "TEMP_AVE", "TEMP_DAILY_AVE", "TEMP_DAILY_MIN", "TEMP_DAILY_MAX", "PET", "OW_PET",
-                 "POTENTIAL_MELT", "TEMP_MONTH_AVE", "PET_MONTH_AVE", "AIR_PRES", "REL_HUMIDITY", "SW_RADIA"]
+                 "POTENTIAL_MELT", "TEMP_MONTH_AVE", "PET_MONTH_AVE", "AIR_PRES", "REL_HUMIDITY", "SW_RADIA", "WIND_VEL"]
 MAX_RIVER_SEGS = 50
 
 _engine = None

@@ -44,6 +44,7 @@ struct CtxCommon {
   FVec F;                  // derived forcings of this HRU for this step
   // lagged (start-of-step) values (what pHRU->GetStateVarValue returns inside processes)
   double old_snow, old_snow_cover, old_snow_depth, old_snow_temp;
+  double air_pres, rel_hum, wind_vel;   // atmospheric forcings a process may read (only derived when opt.need_atmos)
   double area, elev, lat, slope, aspect;
   double tstep;
   double canopy_cap, canopy_snow_cap;   // veg_var_struct capacity / snow_capacity of this HRU for this step
@@ -323,6 +324,7 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
   // 333-364) -- only when a consumed PET method needs them.  Geometry-only pieces (ET radiation on the slope and on the flat,
   // optical air mass) come from the host's per-date tables.
   double air_pres = 0.0, rel_hum = 0.0, SW_radia = 0.0, ET_radia = 0.0;
+  c.air_pres = 0.0; c.rel_hum = 0.0; c.wind_vel = 0.0;
   if (opt.need_atmos) {
     const double Tave = F[RVN_F_TEMP_AVE];
     if (opt.air_pressure == RVN_AIRPRESS_BASIC) air_pres = D_AMBIENT_AIR_PRESSURE * pow(1.0 - 0.0065 * elev / (D_ZERO_CELSIUS + Tave), 5.26);
@@ -351,7 +353,16 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
       else cc = 0.0;
     }
     SW_radia *= cc;
+    double wind_vel = 2.0;   // CModel::EstimateWindVelocity  src/UpdateForcings.cpp:739-777
+    if (opt.wind_velocity == RVN_WINDVEL_UBC_MOD) {
+      const double wt = dmin(0.04 * (F[RVN_F_TEMP_DAILY_MAX] - F[RVN_F_TEMP_DAILY_MIN]), 1.0);
+      wind_vel = dmax(0.0, (1 - wt) * c.LU(RVN_LU_MIN_WIND_SPEED) + (wt)*c.LU(RVN_LU_MAX_WIND_SPEED));
+    } else if (opt.wind_velocity == RVN_WINDVEL_SQRT) {
+      wind_vel = dmax(0.0, c.G(RVN_G_WINDVEL_SCALE) * (F[RVN_F_TEMP_DAILY_MAX] - F[RVN_F_TEMP_DAILY_MIN]) + c.G(RVN_G_WINDVEL_ICEPT));
+    }
+    c.air_pres = air_pres; c.rel_hum = rel_hum; c.wind_vel = wind_vel;
     if (M.record_forcings) {
+      M.forc[((size_t)e * RVN_F_COUNT + RVN_F_WIND_VEL) * M.nHp + k] = wind_vel;
       double *gf = M.forc + (size_t)e * RVN_F_COUNT * M.nHp + k;
       gf[(size_t)RVN_F_AIR_PRES * M.nHp] = air_pres; gf[(size_t)RVN_F_REL_HUMIDITY * M.nHp] = rel_hum; gf[(size_t)RVN_F_SW_RADIA * M.nHp] = SW_radia;
     }

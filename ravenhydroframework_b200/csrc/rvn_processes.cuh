@@ -222,6 +222,46 @@ template <class C, class PR> RVN_DI void rates_CANSNOWEVP_ALL(C &c, const PR &pr
   c.R(0) = dmin(c.R(0), c.SV(pr.from(0)) / c.tstep);
   c.R(1) -= (oldRates - c.R(0));
 }
+// CmvSublimation  src/Sublimation.cpp:98-243 (SublimationRate, GetRatesOfChange, ApplyConstraints).  Forcings and the snow
+// temperature / depth / SWE of the depth-change term are the HRU's lagged values, as in the reference.
+RVN_DI double SatVap(const double T) { return (T >= 0) ? 0.61078 * exp(17.26939 * T / (T + 237.3)) : 0.61078 * exp(21.87456 * T / (T + 265.5)); }
+template <class C, class PR> RVN_DI void rates_SUBLIMATION(C &c, const PR &pr) {
+  const int type = pr.ia(0);
+  const double Ta = c.F[RVN_F_TEMP_AVE], rel_hum = c.rel_hum, wind_vel = c.wind_vel, Tsnow = SnowTemperature(c);
+  double sub = 0.0;
+  if (type == RVN_SUBLIM_SVERDRUP) {
+    const double roughness = c.G(RVN_G_SNOW_ROUGHNESS), air_pres = c.air_pres;
+    const double air_density = (air_pres - 0.378 * SatVap(Ta)) / (287.042 * (Ta + D_ZERO_CELSIUS)) * 1000;   // GetAirDensity, src/CommonFunctions.cpp:1039-1043
+    const double es = SatVap(Tsnow), ea = SatVap(Ta) * rel_hum;
+    const double C_E = 0.42 * 0.42 / (log(8.0 / roughness)) / (log(8.0 / roughness));
+    sub = air_density * C_E * wind_vel * 0.623 * (es - ea) / air_pres * D_SEC_PER_DAY / D_DENSITY_WATER * D_MM_PER_METER;
+  } else if (type == RVN_SUBLIM_KUZMIN) {
+    const double ea = SatVap(c.F[RVN_F_TEMP_DAILY_AVE]) * rel_hum * 10, es = SatVap(Tsnow) * 1.0 * 10;
+    sub = ((0.18 + 0.098 * wind_vel) * (es - ea));
+  } else if (type == RVN_SUBLIM_KUCHMENT_GELFAN) {
+    const double ea = SatVap(Ta) * rel_hum * 10, es = SatVap(Tsnow) * 1.0 * 10;
+    const double Q_E = 32.82 * (0.18 + 0.098 * wind_vel) * (es - ea) * 0.0864;
+    sub = Q_E / 2.845 / D_DENSITY_WATER * (D_MM_PER_METER);
+  } else if (type == RVN_SUBLIM_BULK_AERO) {
+    const double air_pres = c.air_pres;
+    const double air_dens = (air_pres - 0.378 * SatVap(Ta)) / (287.042 * (Ta + D_ZERO_CELSIUS)) * 1000;
+    const double ea = SatVap(Ta) * rel_hum, es = SatVap(Tsnow) * 1.0;
+    const double z_ref = 2.0, z0 = 0.00005, z0e = 0.00005;
+    const double C_E = (0.42 * 0.42) / (log(z_ref / z0) * log(z_ref / z0e));
+    const double Q_E = air_dens * 2.845 * C_E * wind_vel * ((D_AIR_H20_MW_RAT * (es - ea)) / air_pres) * D_SEC_PER_DAY;
+    sub = Q_E / (2.845 * D_DENSITY_WATER) * D_MM_PER_METER;
+  } else if (type == RVN_SUBLIM_CENTRAL_SIERRA) {
+    const double sat_vap = SatVap(Tsnow) * 10, vap_pres = SatVap(c.F[RVN_F_TEMP_DAILY_AVE]) * rel_hum * 10;
+    const double wind_v = wind_vel * 2.237;
+    sub = ((0.0063 * 1.0 * wind_v * (sat_vap - vap_pres)) * 25.4);   // the height factor pow(h*h, (-1/6)) is pow(.., 0) in the reference (integer division)
+  }
+  c.R(0) = sub;
+  if (pr.nconn() == 2) {   // SNOW_DEPTH simulated: lagged depth and SWE
+    if (c.old_snow > 0) c.R(1) = c.R(0) * c.old_snow_depth / c.old_snow;
+  }
+  if (c.SV(pr.from(0)) <= 0) c.R(0) = 0.0;
+  c.R(0) = dmin(c.R(0), c.SV(pr.from(0)) / c.tstep);   // threshMin(.., .., 0.0)
+}
 // CmvOWEvaporation OPEN_WATER_EVAP  src/OpenWaterEvap.cpp:113-160; ApplyConstraints :170-186
 template <class C, class PR> RVN_DI void rates_OPEN_WATER_EVAP(C &c, const PR &pr) {
   if (c.type == RVN_HRU_MASKED_GLACIER) return;
@@ -635,6 +675,7 @@ template <class C, class PR> RVN_DI void dispatch_rates(C &c, const PR &pr, cons
     case RVN_OP_CANEVP_ALL: rates_CANEVP_ALL(c, pr); break;
     case RVN_OP_CANSNOWEVP_ALL: rates_CANSNOWEVP_ALL(c, pr); break;
     case RVN_OP_OPEN_WATER_EVAP: rates_OPEN_WATER_EVAP(c, pr); break;
+    case RVN_OP_SUBLIMATION: rates_SUBLIMATION(c, pr); break;
     case RVN_OP_LAKE_EVAP_BASIC: rates_LAKE_EVAP_BASIC(c, pr); break;
     case RVN_OP_CAPRISE_HBV: rates_CAPRISE_HBV(c, pr); break;
     case RVN_OP_GLACIERMELT_HBV: rates_GLACIERMELT_HBV(c, pr); break;

@@ -263,8 +263,11 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
     auto consumed = [&](int method) { return (uses_pet && O.evaporation == method) || (uses_owpet && O.ow_evaporation == method); };
     bool need_atmos = false;   // PET methods fed by air pressure / humidity / shortwave radiation
     for (int mth = RVN_PET_TURC_1961; mth <= RVN_PET_HARGREAVES; mth++) if (consumed(mth)) need_atmos = true;
+    for (int j = 0; j < NP; j++) if (_f_proc[j].op == RVN_OP_SUBLIMATION) need_atmos = true;   // reads air pressure, humidity, wind velocity
+    ExitGracefullyIf(need_atmos && O.wind_velocity == RVN_WINDVEL_SQRT && (globals.v[RVN_G_WINDVEL_ICEPT] == NOT_SPECIFIED || globals.v[RVN_G_WINDVEL_SCALE] == NOT_SPECIFIED),
+                     "CGlobalParams::AutoCalculateGlobalParams: required global parameters WINDVEL_ICEPT / WINDVEL_SCALE not specified");
     ExitGracefullyIf(need_atmos && !O.unsupported_atmos.empty(), "ParseMainInputFile: " + O.unsupported_atmos + " is not implemented in the B200 build");
-    ExitGracefullyIf(need_atmos && O.timestep < 1.0 - 0.0001, "CModel::Flatten: radiation / humidity based PET methods are built for daily steps only in the B200 build");
+    ExitGracefullyIf(need_atmos && O.timestep < 1.0 - 0.0001, "CModel::Flatten: radiation / humidity based PET methods and snow sublimation are built for daily steps only in the B200 build");
     if (consumed(RVN_PET_VAPDEFICIT))
       for (size_t c = 0; c < lu_classes.size(); c++)
         ExitGracefullyIf(lu_classes[c].S.v[RVN_LU_PET_VAP_COEFF] == NOT_SPECIFIED, "CLandUseClass::AutoCalculateLandUseProps: required parameter PET_VAP_COEFF not specified for land use class " + lu_classes[c].tag);
@@ -272,7 +275,7 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
       for (int g = 0; g < nG; g++)
         ExitGracefullyIf(_pGauges[g]->aMaxTemp[0] == NOT_SPECIFIED || _pGauges[g]->aMinTemp[0] == NOT_SPECIFIED, "PET_HARGREAVES requires minimum and maximum monthly temperatures");
     d.opt.need_atmos = need_atmos ? 1 : 0;
-    d.opt.air_pressure = O.air_pressure; d.opt.rel_humidity = O.rel_humidity; d.opt.sw_radiation = O.SW_radiation; d.opt.sw_cloudcorr = O.SW_cloudcovercorr;
+    d.opt.air_pressure = O.air_pressure; d.opt.rel_humidity = O.rel_humidity; d.opt.sw_radiation = O.SW_radiation; d.opt.sw_cloudcorr = O.SW_cloudcovercorr; d.opt.wind_velocity = O.wind_velocity;
     const bool need_et = consumed(RVN_PET_HARGREAVES_1985) || consumed(RVN_PET_OUDIN) || need_atmos;
     const bool need_dl = consumed(RVN_PET_HAMON), need_ws = consumed(RVN_PET_MOHYSE);
     ExitGracefullyIf(need_et && O.SW_radiation == RVN_SW_RAD_NONE, "CModel::Flatten: :SWRadiationMethod SW_RAD_NONE leaves the extraterrestrial radiation unset; PET methods that read it are not built for that case");

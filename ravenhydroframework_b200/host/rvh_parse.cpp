@@ -59,7 +59,7 @@ static double ParseIntervalToken(const std::string &t, int calendar) {
 static const char *kIgnoredRVI[] = {":FileType", ":WrittenBy", ":CreationDate", ":Description", ":SilentMode", ":NoisyMode", ":QuietMode",
   ":EvaluationMetrics", ":CustomOutput", ":WriteForcingFunctions", ":WriteMassBalanceFile", ":WriteEnsimFormat", ":WriteNetCDFFormat",
   ":RunName", ":OutputDirectory", ":OutputInterval", ":SuppressOutput", ":DontWriteWatershedStorage", ":SnapshotHydrograph",
-  ":LWRadiationMethod", ":LWIncomingMethod", ":WindspeedMethod",
+  ":LWRadiationMethod", ":LWIncomingMethod",
   ":PavicsMode", ":DebugMode", ":WriteExhaustiveMB", ":HydrologicProcesses", ":EndHydrologicProcesses",
   ":WriteSubbasinFile", ":NetCDFAttribute", ":rvh_Filename", NULL};
 
@@ -200,6 +200,14 @@ static void ParseMainInputFile(CModel *&pModel, optStruct &Options) {
       if (s[1] == "SW_CLOUD_CORR_NONE") Options.SW_cloudcovercorr = RVN_SW_CLOUD_CORR_NONE;
       else if (s[1] == "SW_CLOUD_CORR_DINGMAN") Options.SW_cloudcovercorr = RVN_SW_CLOUD_CORR_DINGMAN;
       else if (s[1] == "SW_CLOUD_CORR_ANNANDALE") Options.SW_cloudcovercorr = RVN_SW_CLOUD_CORR_ANNANDALE;
+      else if (Options.unsupported_atmos.empty()) Options.unsupported_atmos = c + " " + s[1];
+      continue;
+    }
+    if (c == ":WindspeedMethod") {
+      if (Len < 2) continue;
+      if (s[1] == "CONSTANT" || s[1] == "WINDVEL_CONSTANT") Options.wind_velocity = RVN_WINDVEL_CONSTANT;
+      else if (s[1] == "WINDVEL_UBC_MOD") Options.wind_velocity = RVN_WINDVEL_UBC_MOD;
+      else if (s[1] == "WINDVEL_SQRT") Options.wind_velocity = RVN_WINDVEL_SQRT;
       else if (Options.unsupported_atmos.empty()) Options.unsupported_atmos = c + " " + s[1];
       continue;
     }
@@ -561,6 +569,8 @@ static void ParseClassPropertiesFile(CModel *pModel, const optStruct &Options) {
     if (S.v[RVN_LU_MAX_SAT_AREA_FRAC] == NOT_SPECIFIED) S.v[RVN_LU_MAX_SAT_AREA_FRAC] = 1.0;
     if (S.v[RVN_LU_RELHUM_CORR] == NOT_SPECIFIED) S.v[RVN_LU_RELHUM_CORR] = 1.0;   // src/LandUseClass.cpp:264-267  // src/LandUseClass.cpp:93-98
     if (S.v[RVN_LU_OW_PET_CORR] == NOT_SPECIFIED) S.v[RVN_LU_OW_PET_CORR] = 1.0;
+    if (S.v[RVN_LU_MIN_WIND_SPEED] == NOT_SPECIFIED) S.v[RVN_LU_MIN_WIND_SPEED] = 1.0;   // src/LandUseClass.cpp:246-255
+    if (S.v[RVN_LU_MAX_WIND_SPEED] == NOT_SPECIFIED) S.v[RVN_LU_MAX_WIND_SPEED] = 8.0;
     // autogenerated snow parameters (CLandUseClass::AutoCalculateLandUseProps, src/LandUseClass.cpp:100-160)
     if (S.v[RVN_LU_FOREST_COVERAGE] == NOT_SPECIFIED) S.v[RVN_LU_FOREST_COVERAGE] = 0.0;
     if (S.v[RVN_LU_MELT_FACTOR] == NOT_SPECIFIED) S.v[RVN_LU_MELT_FACTOR] = 5.04;
@@ -578,7 +588,7 @@ static void ParseClassPropertiesFile(CModel *pModel, const optStruct &Options) {
     static const struct { int f; double v; } gd[] = {
       {RVN_G_SNOW_SWI, 0.05}, {RVN_G_SNOW_SWI_MIN, 0.05}, {RVN_G_SNOW_SWI_MAX, 0.05}, {RVN_G_SNOW_TEMPERATURE, 0.0}, {RVN_G_RAINSNOW_TEMP, 0.15},
       {RVN_G_RAINSNOW_DELTA, 2.0}, {RVN_G_MAX_SWE_SURFACE, 100.0}, {RVN_G_ADIABATIC_LAPSE, 6.4}, {RVN_G_PRECIP_LAPSE, 0.0},
-      {RVN_G_HBVEC_LAPSE_RATE, 0.08}, {RVN_G_HBVEC_LAPSE_UPPER, 0.0}, {RVN_G_HBVEC_LAPSE_ELEV, 5000.0}};
+      {RVN_G_HBVEC_LAPSE_RATE, 0.08}, {RVN_G_HBVEC_LAPSE_UPPER, 0.0}, {RVN_G_HBVEC_LAPSE_ELEV, 5000.0}, {RVN_G_SNOW_ROUGHNESS, 0.0002}};
     for (size_t i = 0; i < sizeof(gd) / sizeof(gd[0]); i++) if (G.v[gd[i].f] == NOT_SPECIFIED) G.v[gd[i].f] = gd[i].v;
   }
   for (size_t k = 0; k < pModel->veg_classes.size(); k++) {

@@ -598,6 +598,24 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
     p->Connect(pM->GetStateVarIndex(RVN_SV_CANOPY_SNOW), iAtmos); p->Connect(iAET, iAET);
     return p;
   }
+  if (cmd == ":Sublimation") {  // case 210; src/Sublimation.cpp:20-44 (the from/to tokens must be SNOW ATMOSPHERE)
+    need(4);
+    int type = -1;
+    if (s[1] == "SUBLIM_SVERDRUP") type = RVN_SUBLIM_SVERDRUP;
+    else if (s[1] == "SUBLIM_KUZMIN") type = RVN_SUBLIM_KUZMIN;
+    else if (s[1] == "SUBLIM_KUCHMENT_GELFAN") type = RVN_SUBLIM_KUCHMENT_GELFAN;
+    else if (s[1] == "SUBLIM_BULK_AERO") type = RVN_SUBLIM_BULK_AERO;
+    else if (s[1] == "SUBLIM_CENTRAL_SIERRA") type = RVN_SUBLIM_CENTRAL_SIERRA;
+    ExitGracefullyIf(type < 0, "ParseMainInputFile: sublimation algorithm " + s[1] + " is not implemented in the B200 build");
+    ExitGracefullyIf(s[2] != "SNOW" || s[3] != "ATMOSPHERE", "ParseMainInputFile: :Sublimation moves water from SNOW to ATMOSPHERE");
+    AddSVs(pM, {SVL(RVN_SV_SNOW, -1), SVL(RVN_SV_ATMOSPHERE, -1)});
+    CmvGeneric *p = new CmvGeneric("Sublimation", RVN_OP_SUBLIMATION, pM);
+    p->Connect(pM->GetStateVarIndex(RVN_SV_SNOW), iAtmos);
+    const int iSD = pM->GetStateVarIndex(RVN_SV_SNOW_DEPTH);   // depth change is modelled only if SNOW_DEPTH exists when the process is created
+    if (iSD != DOESNT_EXIST) p->Connect(iSD, iSD);
+    p->SetIntArg(0, type);
+    return p;
+  }
   if (cmd == ":OpenWaterEvaporation") {  // case 211; src/OpenWaterEvap.cpp:17-38
     need(4);
     ExitGracefullyIf(s[1] != "OPEN_WATER_EVAP", "ParseMainInputFile: open water evaporation algorithm " + s[1] + " is not implemented in the B200 build");

@@ -77,6 +77,22 @@ if hasattr(synth, "write_hbv"):
                                        rvi_extra=":RelativeHumidityMethod RELHUM_MINDEWPT\n",
                                        gauge_extra="  :MonthlyMinTemperature, -16.9, -13.1, -8.0, -2.6, 2.7, 7.0, 9.3, 8.2, 4.1, -1.0, -7.9, -14.2,\n"
                                                    "  :MonthlyMaxTemperature, -6.2, -1.8, 2.9, 8.6, 14.0, 17.8, 20.1, 19.2, 14.3, 8.1, 0.2, -4.7,\n")
+    # snow sublimation (CmvSublimation), all five algorithms, over the wind-velocity estimators; HBV-EC has no SNOW_TEMP variable (snow
+    # temperature = the SNOW_TEMPERATURE global), GR4J carries SNOW_TEMP as state
+    _hbv_after = r"(    :-->Overflow     RAVEN_DEFAULT      SNOW_LIQ        PONDED_WATER\n)"
+    _gr4j_after = r"( :SnowBalance              SNOBAL_CEMA_NIEGE  SNOW            PONDED_WATER\n)"
+    _sub = "  :Sublimation       %-18s SNOW            ATMOSPHERE\n"
+    CASES["hbv_atm_sub_sverdrup"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=71, routing="ROUTE_MUSKINGUM", proc_after=(_hbv_after, _sub % "SUBLIM_SVERDRUP"),
+                                         rvi_extra=":RelativeHumidityMethod RELHUM_MINDEWPT\n:WindspeedMethod WINDVEL_UBC_MOD\n")
+    CASES["gr4j_atm_sub_kuzmin"] = dict(kind="gr4j", n_sb=2, hru_per_sb=4, n_days=400, seed=72, proc_after=(_gr4j_after, _sub % "SUBLIM_KUZMIN"),
+                                        rvi_extra=":RelativeHumidityMethod RELHUM_MINDEWPT\n:WindspeedMethod WINDVEL_SQRT\n",
+                                        rvp_extra=":GlobalParameter WINDVEL_ICEPT 0.6\n:GlobalParameter WINDVEL_SCALE 0.21\n")
+    CASES["hbv_atm_sub_kuchment"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=73, routing="ROUTE_MUSKINGUM", proc_after=(_hbv_after, _sub % "SUBLIM_KUCHMENT_GELFAN"))
+    CASES["gr4j_atm_sub_bulkaero"] = dict(kind="gr4j", n_sb=2, hru_per_sb=4, n_days=400, seed=74, proc_after=(_gr4j_after, _sub % "SUBLIM_BULK_AERO"),
+                                          rvi_extra=":AirPressureMethod AIRPRESS_UBC\n:RelativeHumidityMethod RELHUM_MINDEWPT\n")
+    CASES["hbv_atm_sub_sierra"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=75, routing="ROUTE_MUSKINGUM", proc_after=(_hbv_after, _sub % "SUBLIM_CENTRAL_SIERRA"),
+                                       rvi_extra=":RelativeHumidityMethod RELHUM_MINDEWPT\n:WindspeedMethod WINDVEL_UBC_MOD\n",
+                                       rvp_extra=":LandUseParameterList\n  :Parameters, MIN_WIND_SPEED, MAX_WIND_SPEED\n  :Units, m/s, m/s\n  [DEFAULT], 0.7, 6.5\n  LU_OPEN, 1.4, 9.0\n:EndLandUseParameterList\n")
     # potential melt: degree day with refreeze / rain-on-snow variants (CModel::EstimatePotentialMelt)
     CASES["gr4j_potmelt_ddfreeze"] = dict(kind="gr4j", n_sb=2, hru_per_sb=3, n_days=300, seed=55, potmelt="POTMELT_DD_FREEZE",
                                           rvp_extra=":LandUseParameterList\n  :Parameters, REFREEZE_FACTOR\n  :Units, mm/d/K\n  [DEFAULT], 1.3\n:EndLandUseParameterList\n")
@@ -227,6 +243,7 @@ def make(name, spec):
     potmelt = spec.pop("potmelt", None)       # :PotentialMeltMethod other than the template's
     rvp_extra = spec.pop("rvp_extra", None)   # lines appended to the .rvp
     rvi_extra = spec.pop("rvi_extra", None)   # option commands inserted at the top of the .rvi
+    proc_after = spec.pop("proc_after", None)   # (regex of a process line, line inserted after it) in the .rvi process list
     gauge_extra = spec.pop("gauge_extra", None)   # lines added to the gauge block of the .rvt (after :MonthlyAveTemperature)
     d = os.path.join(HERE, name)
     shutil.rmtree(d, ignore_errors=True)
@@ -247,6 +264,12 @@ def make(name, spec):
         rvi = open(base + ".rvi").read()
         rvi, cnt = re.subn(r":PotentialMeltMethod\s+\S+", ":PotentialMeltMethod   " + potmelt, rvi)
         assert cnt == 1
+        open(base + ".rvi", "w").write(rvi)
+    if proc_after is not None:
+        import re
+        rvi = open(base + ".rvi").read()
+        rvi, cnt = re.subn(proc_after[0], lambda m: m.group(1) + proc_after[1], rvi)
+        assert cnt == 1, proc_after[0]
         open(base + ".rvi", "w").write(rvi)
     if rvi_extra is not None:
         rvi = open(base + ".rvi").read()

@@ -68,7 +68,7 @@ def test_oracle_matches_golden(case):
     if case.startswith("hmets") or case.startswith("blended"):
         idx.pop("OW_PET")   # :OW_Evaporation defaults to PET_HARGREAVES_1985 there; no HMETS process consumes OW_PET (not derived)
     if "_atm_" in case:   # PET from air pressure / relative humidity / shortwave radiation: the atmospheric chain is derived too
-        idx.update({"AIR_PRES": 18, "REL_HUMIDITY": 19, "SW_RADIA": 24})
+        idx.update({"AIR_PRES": 18, "REL_HUMIDITY": 19, "SW_RADIA": 24, "WIND_VEL": 33})
     for name, j in idx.items():
         mine = o["forc_rec"][steps - 1][:, :, api.FORCING_NAMES.index(name)]
         assert H.rel_err(mine, ref_f[:, :, j]) < TOL, name
