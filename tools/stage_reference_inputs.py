@@ -1,0 +1,49 @@
+"""Pin the host layer + oracle + CUDA path on the reference's OWN shipped input sets (the inputs that pin this path).
+
+Run where /root/reference and oracle/_ref exist (python tools/stage_reference_inputs.py):
+  * runs the unmodified reference (oracle/_ref/ref_dump) on each set and commits only its OUTPUTS as
+    tests/golden/reference_inputs/<set>.npz (FP64 states at selected steps, every hydrograph value, watershed record);
+  * stages the input files, untouched, under tests/_ref_inputs/<set>/ -- git-ignored (the reference's files are not part of this
+    repository's history) but not gpurun-ignored, so that the GPU box, which has no /root/reference, can run the same inputs.
+tests/test_reference_inputs.py reads the inputs from tests/_ref_inputs/ or /root/reference, whichever exists.
+"""
+import glob
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import helpers as H  # noqa: E402
+
+REF_INPUTS = "/root/reference/benchmarking/_InputFiles"
+# set -> number of steps pinned (config 1 of BASELINE.json is the 10-year daily GR4J run)
+SETS = {"Salmon_GR4J": 3653, "Salmon_HMETS": 3653, "Salmon_HBV": 3653, "Salmon_MOHYSE": 3653, "Irondequoit": 366}
+
+
+def main():
+    assert H.have_reference(), "oracle/_ref/ref_dump missing"
+    out_dir = os.path.join(H.GOLDEN, "reference_inputs")
+    stage = os.path.join(ROOT, "tests", "_ref_inputs")
+    os.makedirs(out_dir, exist_ok=True)
+    for name, n in SETS.items():
+        src = os.path.join(REF_INPUTS, name)
+        dst = os.path.join(stage, name)
+        shutil.rmtree(dst, ignore_errors=True)
+        shutil.copytree(src, dst)
+        base = glob.glob(os.path.join(dst, "*.rvi"))[0][:-4]
+        with tempfile.TemporaryDirectory() as td:
+            ref = H.reference_run(base, os.path.join(td, "out"), n)
+        rec = sorted(set([1, 2, 3, 10, 100, 365, 366, 1000, 2000, 3000, n]) & set(range(1, n + 1)))
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), state_steps=np.array(rec), state=ref["state"][rec],
+                            qout=ref["basin"][1:n + 1, :, 0], wshed=ref["wshed"][1:n + 1],
+                            sv_type=np.array([t for t, _ in ref["sv"]]), sv_layer=np.array([l for _, l in ref["sv"]]))
+        print("pinned %-14s nHRU=%d NS=%d NB=%d steps=%d" % (name, ref["nHRU"], ref["NS"], ref["NB"], n))
+
+
+if __name__ == "__main__":
+    main()
