@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RVN_ABI_VERSION 6
+#define RVN_ABI_VERSION 7
 #define RVN_DOESNT_EXIST (-1)
 #define RVN_CONV_STORES 50   /* MAX_CONVOL_STORES, reference src/RavenInclude.h / Convolution.cpp:17 */
 #define RVN_MAX_CONN 24      /* max connections of a non-convolution process (Precipitation: 13..19) */
@@ -129,6 +129,10 @@ typedef enum {
   RVN_OP_SOILEVAP_ROOT_CONSTRAIN, /* CmvSoilEvap          src/SoilEvaporation.cpp:598-622           */
   RVN_OP_SOILEVAP_AWBM,        /* CmvSoilEvap             src/SoilEvaporation.cpp:716-727           */
   RVN_OP_SUBLIMATION,          /* CmvSublimation          src/Sublimation.cpp:98-243; ia[0] = rvn_sublim */
+  RVN_OP_ABSTRACTION,          /* CmvAbstraction          src/Abstraction.cpp:230-256,514-532; ia[0] = rvn_abstraction */
+  RVN_OP_CANEVP_MAXIMUM,       /* CmvCanopyEvap           src/VegetationMovers.cpp:141-145                  */
+  RVN_OP_CANEVP_RUTTER,        /* CmvCanopyEvap           src/VegetationMovers.cpp:133-140 (no TRUNK variable) */
+  RVN_OP_CANSNOWEVP_MAXIMUM,   /* CmvCanopySublimation    src/VegetationMovers.cpp:312-317                  */
   RVN_OP_COUNT
 } rvn_opcode;
 
@@ -139,6 +143,9 @@ typedef enum { RVN_POTMELT_NONE = 0, RVN_POTMELT_DATA, RVN_POTMELT_DEGREE_DAY, R
 /* atmospheric estimators of the forcing chain (reference src/UpdateForcings.cpp:677-731, src/Radiation.cpp:24-57,333-364) */
 typedef enum { RVN_AIRPRESS_BASIC = 0, RVN_AIRPRESS_UBC, RVN_AIRPRESS_CONST } rvn_airpress;
 typedef enum { RVN_RELHUM_CONSTANT = 0, RVN_RELHUM_MINDEWPT } rvn_relhum;
+typedef enum { RVN_ABST_PERCENTAGE = 0, RVN_ABST_FILL } rvn_abstraction;
+/* :PrecipIceptFract (reference precip_icept_method; CVegetationClass::RecalculateCanopyParams, src/VegetationParams.cpp:143-166) */
+typedef enum { RVN_ICEPT_USER = 0, RVN_ICEPT_LAI, RVN_ICEPT_EXPLAI, RVN_ICEPT_NONE } rvn_icept;
 typedef enum { RVN_WINDVEL_CONSTANT = 0, RVN_WINDVEL_UBC_MOD, RVN_WINDVEL_SQRT } rvn_windvel;   /* CModel::EstimateWindVelocity, src/UpdateForcings.cpp:739-790 */
 /* snow sublimation algorithms (reference sublimation_type, src/Sublimation.cpp:98-200); SUBLIM_PBSM is a stub there */
 typedef enum { RVN_SUBLIM_SVERDRUP = 0, RVN_SUBLIM_KUZMIN, RVN_SUBLIM_KUCHMENT_GELFAN, RVN_SUBLIM_BULK_AERO, RVN_SUBLIM_CENTRAL_SIERRA } rvn_sublim;
@@ -182,11 +189,11 @@ typedef enum {
   RVN_LU_PARTITION_COEFF, RVN_LU_CC_DECAY_COEFF, RVN_LU_MAX_SAT_AREA_FRAC, RVN_LU_PDM_B, RVN_LU_AET_COEFF,
   RVN_LU_MAX_DEP_AREA_FRAC, RVN_LU_PONDED_EXP, RVN_LU_AWBM_AREAFRAC1, RVN_LU_AWBM_AREAFRAC2, RVN_LU_HYMOD2_G, RVN_LU_HYMOD2_KMAX,
   RVN_LU_HYMOD2_EXP, RVN_LU_PET_LIN_COEFF, RVN_LU_RAIN_MELT_MULT, RVN_LU_RELHUM_CORR, RVN_LU_PET_VAP_COEFF,
-  RVN_LU_MIN_WIND_SPEED, RVN_LU_MAX_WIND_SPEED, RVN_LU_COUNT
+  RVN_LU_MIN_WIND_SPEED, RVN_LU_MAX_WIND_SPEED, RVN_LU_ABST_PERCENT, RVN_LU_COUNT
 } rvn_landuse_field;
 typedef enum {
   RVN_V_MAX_HEIGHT = 0, RVN_V_MAX_LAI, RVN_V_SAI_HT_RATIO, RVN_V_MAX_CAPACITY, RVN_V_MAX_SNOW_CAPACITY,
-  RVN_V_RAIN_ICEPT_PCT, RVN_V_SNOW_ICEPT_PCT, RVN_V_PET_VEG_CORR,
+  RVN_V_RAIN_ICEPT_PCT, RVN_V_SNOW_ICEPT_PCT, RVN_V_PET_VEG_CORR, RVN_V_RAIN_ICEPT_FACT, RVN_V_SNOW_ICEPT_FACT,
   /* derived canopy variables (reference veg_var_struct; CVegetationClass::RecalculateCanopyParams,
    * src/VegetationParams.cpp:85-200), refreshed by the host for the current step when date-dependent */
   RVN_V_VAR_CAPACITY, RVN_V_VAR_SNOW_CAPACITY, RVN_V_VAR_RAIN_ICEPT_PCT, RVN_V_VAR_SNOW_ICEPT_PCT,
@@ -284,6 +291,8 @@ typedef struct rvn_options {
   int32_t need_atmos;             /* 1: a consumed PET or a sublimation process needs air pressure / relative humidity / wind / shortwave radiation -> derive them */
   int32_t air_pressure, rel_humidity, sw_radiation, sw_cloudcorr;   /* rvn_airpress, rvn_relhum, rvn_sw_rad, rvn_sw_cloudcorr */
   int32_t wind_velocity;          /* rvn_windvel */
+  int32_t interception_factor;    /* rvn_icept */
+  int32_t pad_[1];
 } rvn_options;
 
 /* Flattened model (all pointers are HOST memory, copied by rvn_gpu_create). */

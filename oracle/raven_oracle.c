@@ -46,6 +46,7 @@ typedef struct {
   const double *F;        /* derived forcings of this HRU [RVN_F_COUNT] */
   const double *phi_old;  /* stored (start-of-step) state: what pHRU->GetStateVarValue returns */
   double canopy_cap, canopy_snow_cap; /* veg_var_struct capacity / snow_capacity for this HRU and step */
+  double rain_icept_pct, snow_icept_pct; /* veg_var_struct interception fractions, src/VegetationParams.cpp:143-166 */
   int iSV[RVN_SV_NTYPES]; /* first index of each SV type, or -1 */
 } octx;
 
@@ -492,7 +493,7 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       const int is_lake = (type == RVN_HRU_LAKE);
       if (!is_lake) {
         double Fcan = P_LU(c, RVN_LU_FOREST_COVERAGE);
-        double rain_pct = P_V(c, RVN_V_VAR_RAIN_ICEPT_PCT);
+        double rain_pct = c->rain_icept_pct;
         rain_int = rainfall * rain_pct;
         if (iCan >= 0) {
           double capacity = c->canopy_cap;
@@ -500,7 +501,7 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
           rates[qCan] = Fcan * rain_int;
         } else rates[qAtmos] += Fcan * rain_int;
         rainthru = rainfall - Fcan * rain_int;
-        double snow_pct = P_V(c, RVN_V_VAR_SNOW_ICEPT_PCT);
+        double snow_pct = c->snow_icept_pct;
         snow_int = snowfall * snow_pct;
         if (iSCan >= 0) {
           double snow_capacity = c->canopy_snow_cap;
@@ -932,6 +933,38 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       rates[1] -= (oldRates - rates[0]);
       break;
     }
+    case RVN_OP_CANEVP_MAXIMUM: case RVN_OP_CANEVP_RUTTER: case RVN_OP_CANSNOWEVP_MAXIMUM: { /* src/VegetationMovers.cpp:110-190, 291-346 */
+      if ((type != RVN_HRU_STANDARD) && (type != RVN_HRU_WETLAND)) break;
+      double Fc = P_LU(c, RVN_LU_FOREST_COVERAGE), oldRates;
+      if (Fc != 0) {
+        double PET = omax(F[RVN_F_PET], 0.0), PETused;
+        if (!d->opt.suppress_competitive_ET) { PET -= (sv[c->iSV[RVN_SV_AET]] / tstep); PET = omax(PET, 0.0); }
+        if (pr->op == RVN_OP_CANEVP_RUTTER) { /* trunk fraction forced to 0: no TRUNK state variable */
+          double cap = c->canopy_cap, stor = omin(omax(sv[iFrom[0]], 0.0), cap * Fc), Ft = 0.0;
+          rates[0] = (1.0 - Ft) * Fc * PET * (stor / (cap * Fc));
+        } else rates[0] = Fc * PET;
+        PETused = rates[0];
+        rates[1] = PETused;
+      }
+      oldRates = rates[0];
+      if (pr->op != RVN_OP_CANSNOWEVP_MAXIMUM) rates[0] = omax(rates[0], 0.0);
+      rates[0] = omin(rates[0], sv[iFrom[0]] / tstep);
+      rates[1] -= (oldRates - rates[0]);
+      break;
+    }
+    case RVN_OP_ABSTRACTION: { /* CmvAbstraction ABST_PERCENTAGE / ABST_FILL, src/Abstraction.cpp:230-256, 514-532 */
+      double ponded = sv[iFrom[0]], depression = sv[iTo[0]];
+      if (type != RVN_HRU_STANDARD) break;
+      if (pr->ia[0] == RVN_ABST_PERCENTAGE) rates[0] = P_LU(c, RVN_LU_ABST_PERCENT) * ponded / tstep;
+      else { double dep_space = omax(P_LU(c, RVN_LU_DEP_MAX) - depression, 0.0); rates[0] = omin(dep_space, omax(ponded, 0.0)) / tstep; }
+      {
+        double pond = omax(sv[iFrom[0]], 0.0), stor = omax(sv[iTo[0]], 0.0), max_stor = state_var_max(c, iTo[0], sv), deficit;
+        rates[0] = omin(rates[0], pond / tstep);
+        deficit = omax(max_stor - stor, 0.0);
+        rates[0] = omin(rates[0], deficit / tstep);
+      }
+      break;
+    }
     case RVN_OP_SUBLIMATION: { /* CmvSublimation, src/Sublimation.cpp:98-243: SublimationRate + depth-change term + ApplyConstraints;
                                 * forcings, snow temperature, SNOW_DEPTH and SWE of the depth term are the HRU's lagged values */
       const int styp = pr->ia[0];
@@ -1056,7 +1089,7 @@ static int op_supported(int op) { return op > RVN_OP_NOP && op < RVN_OP_COUNT; }
 static void canopy_capacities(octx *c, int step) {
   const rvn_model_desc *d = c->d;
   c->canopy_cap = c->canopy_snow_cap = 0.0;
-  if (c->iSV[RVN_SV_CANOPY] < 0 && c->iSV[RVN_SV_CANOPY_SNOW] < 0) return;
+  c->rain_icept_pct = c->snow_icept_pct = 0.0; /* PRECIP_ICEPT_NONE */
   int veg = d->hru_veg[c->k];
   double rel_ht = d->veg_season[((size_t)step * d->nVeg + veg) * 2 + 0], rel_LAI = d->veg_season[((size_t)step * d->nVeg + veg) * 2 + 1];
   double max_height = P_V(c, RVN_V_MAX_HEIGHT), sparseness = P_LU(c, RVN_LU_FOREST_SPARSENESS), max_LAI = P_V(c, RVN_V_MAX_LAI);
@@ -1065,6 +1098,12 @@ static void canopy_capacities(octx *c, int step) {
   double height = max_height * rel_ht;
   double LAI = (1.0 - sparseness) * max_LAI * rel_LAI;
   double SAI = (1.0 - sparseness) * (height * SAI_ht_ratio);
+  if (d->opt.interception_factor == RVN_ICEPT_USER) { c->rain_icept_pct = P_V(c, RVN_V_RAIN_ICEPT_PCT); c->snow_icept_pct = P_V(c, RVN_V_SNOW_ICEPT_PCT); }
+  else if (d->opt.interception_factor == RVN_ICEPT_LAI) {
+    c->rain_icept_pct = omin(P_V(c, RVN_V_RAIN_ICEPT_FACT) * (LAI + SAI), 1.0);
+    c->snow_icept_pct = omin(P_V(c, RVN_V_SNOW_ICEPT_FACT) * (LAI + SAI), 1.0);
+  } else if (d->opt.interception_factor == RVN_ICEPT_EXPLAI) c->rain_icept_pct = c->snow_icept_pct = (1.0 - exp(-0.5 * (LAI + SAI)));
+  if (c->iSV[RVN_SV_CANOPY] < 0 && c->iSV[RVN_SV_CANOPY_SNOW] < 0) return;
   if ((max_LAI + max_SAI) > 0) {
     c->canopy_cap = ((LAI + SAI) / (max_LAI + max_SAI)) * P_V(c, RVN_V_MAX_CAPACITY);
     c->canopy_snow_cap = ((LAI + SAI) / (max_LAI + max_SAI)) * P_V(c, RVN_V_MAX_SNOW_CAPACITY);

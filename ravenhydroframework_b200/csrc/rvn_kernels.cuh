@@ -48,6 +48,7 @@ struct CtxCommon {
   double area, elev, lat, slope, aspect;
   double tstep;
   double canopy_cap, canopy_snow_cap;   // veg_var_struct capacity / snow_capacity of this HRU for this step
+  double rain_icept_pct, snow_icept_pct; // veg_var_struct interception fractions (:PrecipIceptFract)
   int type, lu, veg, profile;
   const double *ptab;      // member parameter row (shared memory)
   const rvn_options *popt;
@@ -721,7 +722,10 @@ RVN_DI void load_hru_statics(C &c, const DevModel &M, int k, const double *s_pta
 // host (veg_season[step][veg][2]); everything else is evaluated here in the reference's order.
 template <class C> RVN_DI void load_canopy(C &c, const DevModel &M, int step) {
   c.canopy_cap = 0.0; c.canopy_snow_cap = 0.0;
-  if (c.iSV(RVN_SV_CANOPY) < 0 && c.iSV(RVN_SV_CANOPY_SNOW) < 0) return;
+  const int icept = c.opt().interception_factor;
+  if (icept == RVN_ICEPT_USER) { c.rain_icept_pct = c.VEG(RVN_V_VAR_RAIN_ICEPT_PCT); c.snow_icept_pct = c.VEG(RVN_V_VAR_SNOW_ICEPT_PCT); }
+  else { c.rain_icept_pct = 0.0; c.snow_icept_pct = 0.0; }
+  if (c.iSV(RVN_SV_CANOPY) < 0 && c.iSV(RVN_SV_CANOPY_SNOW) < 0 && (icept == RVN_ICEPT_USER || icept == RVN_ICEPT_NONE)) return;
   const double rel_ht = M.veg_season[((size_t)step * M.nVeg + c.veg) * 2 + 0], rel_LAI = M.veg_season[((size_t)step * M.nVeg + c.veg) * 2 + 1];
   const double max_height = c.VEG(RVN_V_MAX_HEIGHT), sparseness = c.LU(RVN_LU_FOREST_SPARSENESS), max_LAI = c.VEG(RVN_V_MAX_LAI);
   const double SAI_ht_ratio = c.VEG(RVN_V_SAI_HT_RATIO);
@@ -729,6 +733,13 @@ template <class C> RVN_DI void load_canopy(C &c, const DevModel &M, int step) {
   const double height = max_height * rel_ht;
   const double LAI = (1.0 - sparseness) * max_LAI * rel_LAI;
   const double SAI = (1.0 - sparseness) * (height * SAI_ht_ratio);
+  if (icept == RVN_ICEPT_LAI) {          // src/VegetationParams.cpp:145-149
+    c.rain_icept_pct = dmin(c.VEG(RVN_V_RAIN_ICEPT_FACT) * (LAI + SAI), 1.0);
+    c.snow_icept_pct = dmin(c.VEG(RVN_V_SNOW_ICEPT_FACT) * (LAI + SAI), 1.0);
+  } else if (icept == RVN_ICEPT_EXPLAI) {  // :155-159
+    c.rain_icept_pct = (1.0 - exp(-0.5 * (LAI + SAI)));
+    c.snow_icept_pct = (1.0 - exp(-0.5 * (LAI + SAI)));
+  }
   if ((max_LAI + max_SAI) > 0) {
     c.canopy_cap = ((LAI + SAI) / (max_LAI + max_SAI)) * c.VEG(RVN_V_MAX_CAPACITY);
     c.canopy_snow_cap = ((LAI + SAI) / (max_LAI + max_SAI)) * c.VEG(RVN_V_MAX_SNOW_CAPACITY);

@@ -99,14 +99,14 @@ template <class C, class PR> RVN_DI void rates_PRECIPITATION(C &c, const PR &pr)
   const bool is_lake = (c.type == RVN_HRU_LAKE);
   if (!is_lake) {
     const double Fcan = c.LU(RVN_LU_FOREST_COVERAGE);
-    double rain_int = rainfall * c.VEG(RVN_V_VAR_RAIN_ICEPT_PCT);
+    double rain_int = rainfall * c.rain_icept_pct;
     if (iCan >= 0) {
       double capacity = c.canopy_cap;
       rain_int = dmin(rain_int, dmax((capacity - c.SV(iCan)) / tstep, 0.0));
       c.R(qCan) = Fcan * rain_int;
     } else c.R(qAtmos) += Fcan * rain_int;
     rainthru = rainfall - Fcan * rain_int;
-    double snow_int = snowfall * c.VEG(RVN_V_VAR_SNOW_ICEPT_PCT);
+    double snow_int = snowfall * c.snow_icept_pct;
     if (iSCan >= 0) {
       double snow_capacity = c.canopy_snow_cap;
       snow_int = dmax(dmin(snow_int, dmax((snow_capacity - c.SV(iSCan)) / tstep, 0.0)), 0.0);
@@ -209,6 +209,41 @@ template <class C, class PR> RVN_DI void rates_CANEVP_ALL(C &c, const PR &pr) {
   c.R(0) = dmax(c.R(0), 0.0);
   c.R(0) = dmin(c.R(0), c.SV(pr.from(0)) / c.tstep);
   c.R(1) -= (oldRates - c.R(0));
+}
+// CmvCanopyEvap CANEVP_MAXIMUM / CANEVP_RUTTER and CmvCanopySublimation SUBLIM_MAXIMUM: evaporation at (a share of) the PET left
+// by earlier consumers  src/VegetationMovers.cpp:110-190, 291-346.  MODE 0 = MAXIMUM, 1 = RUTTER (Ft = 0: no TRUNK variable), 2 = snow MAXIMUM
+template <int MODE, class C, class PR> RVN_DI void rates_CANEVP_PET(C &c, const PR &pr) {
+  if ((c.type != RVN_HRU_STANDARD) && (c.type != RVN_HRU_WETLAND)) return;
+  const double Fc = c.LU(RVN_LU_FOREST_COVERAGE);
+  if (Fc != 0) {
+    double PET = dmax(c.F[RVN_F_PET], 0.0);
+    if (!c.opt().suppress_competitive_ET) { PET -= (c.SV(c.iSV(RVN_SV_AET)) / c.tstep); PET = dmax(PET, 0.0); }
+    if (MODE == 1) {
+      const double cap = c.canopy_cap;
+      const double stor = dmin(dmax(c.SV(pr.from(0)), 0.0), cap * Fc);
+      c.R(0) = (1.0 - 0.0) * Fc * PET * (stor / (cap * Fc));
+    } else c.R(0) = Fc * PET;
+    c.R(1) = c.R(0);
+  }
+  const double oldRates = c.R(0);
+  if (MODE != 2) c.R(0) = dmax(c.R(0), 0.0);
+  c.R(0) = dmin(c.R(0), c.SV(pr.from(0)) / c.tstep);
+  c.R(1) -= (oldRates - c.R(0));
+}
+// CmvAbstraction ABST_PERCENTAGE / ABST_FILL  src/Abstraction.cpp:230-256; ApplyConstraints :514-532
+template <class C, class PR> RVN_DI void rates_ABSTRACTION(C &c, const PR &pr) {
+  const double ponded = c.SV(pr.from(0)), depression = c.SV(pr.to(0));
+  if (c.type != RVN_HRU_STANDARD) return;
+  if (pr.ia(0) == RVN_ABST_PERCENTAGE) c.R(0) = c.LU(RVN_LU_ABST_PERCENT) * ponded / c.tstep;
+  else {
+    const double dep_space = dmax(c.LU(RVN_LU_DEP_MAX) - depression, 0.0);
+    c.R(0) = dmin(dep_space, dmax(ponded, 0.0)) / c.tstep;
+  }
+  const double pond = dmax(c.SV(pr.from(0)), 0.0);
+  c.R(0) = dmin(c.R(0), pond / c.tstep);
+  const double stor = dmax(c.SV(pr.to(0)), 0.0), max_stor = StateVarMax(c, pr.to(0));
+  const double deficit = dmax(max_stor - stor, 0.0);
+  c.R(0) = dmin(c.R(0), deficit / c.tstep);
 }
 // CmvCanopySublimation SUBLIM_ALL (:CanopySnowEvap CANEVP_ALL)  src/VegetationMovers.cpp:283-346
 template <class C, class PR> RVN_DI void rates_CANSNOWEVP_ALL(C &c, const PR &pr) {
@@ -676,6 +711,10 @@ template <class C, class PR> RVN_DI void dispatch_rates(C &c, const PR &pr, cons
     case RVN_OP_CANSNOWEVP_ALL: rates_CANSNOWEVP_ALL(c, pr); break;
     case RVN_OP_OPEN_WATER_EVAP: rates_OPEN_WATER_EVAP(c, pr); break;
     case RVN_OP_SUBLIMATION: rates_SUBLIMATION(c, pr); break;
+    case RVN_OP_ABSTRACTION: rates_ABSTRACTION(c, pr); break;
+    case RVN_OP_CANEVP_MAXIMUM: rates_CANEVP_PET<0>(c, pr); break;
+    case RVN_OP_CANEVP_RUTTER: rates_CANEVP_PET<1>(c, pr); break;
+    case RVN_OP_CANSNOWEVP_MAXIMUM: rates_CANEVP_PET<2>(c, pr); break;
     case RVN_OP_LAKE_EVAP_BASIC: rates_LAKE_EVAP_BASIC(c, pr); break;
     case RVN_OP_CAPRISE_HBV: rates_CAPRISE_HBV(c, pr); break;
     case RVN_OP_GLACIERMELT_HBV: rates_GLACIERMELT_HBV(c, pr); break;

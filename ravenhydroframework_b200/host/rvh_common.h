@@ -84,6 +84,7 @@ struct optStruct {
   rvn_orocorr  orocorr_temp, orocorr_precip, orocorr_PET;
   int    air_pressure, rel_humidity, SW_radiation, SW_cloudcovercorr;   // rvn_airpress / rvn_relhum / rvn_sw_rad / rvn_sw_cloudcorr
   int    wind_velocity;         // rvn_windvel
+  int    interception_factor;   // rvn_icept
   std::string unsupported_atmos;   // first atmospheric method command the B200 build cannot honour (fatal only if a consumer needs it)
   rvn_routing  routing;
   catchment_route catchment_routing;

@@ -188,6 +188,12 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
       {RVN_OP_SOILEVAP_AWBM, 'L', {RVN_LU_AWBM_AREAFRAC1, RVN_LU_AWBM_AREAFRAC2, -1}},
     };
     for (int r = 0; r < d.nProc; r++)
+      if (d.proc[r].op == RVN_OP_ABSTRACTION) {   // CmvAbstraction::GetParticipatingParamList, src/Abstraction.cpp:100-150
+        const int f = (d.proc[r].ia[0] == RVN_ABST_PERCENTAGE) ? RVN_LU_ABST_PERCENT : RVN_LU_DEP_MAX;
+        for (size_t c = 0; c < lu_classes.size(); c++)
+          ExitGracefullyIf(lu_classes[c].S.v[f] == NOT_SPECIFIED, std::string("CLandUseClass::AutoCalculateLandUseProps: required parameter ") + LandUseFieldName(f) + " not specified for land use class " + lu_classes[c].tag);
+      }
+    for (int r = 0; r < d.nProc; r++)
       for (size_t q = 0; q < sizeof(needs) / sizeof(needs[0]); q++) {
         if (needs[q].op != d.proc[r].op) continue;
         for (int j = 0; j < 5 && needs[q].f[j] >= 0; j++) {
@@ -257,7 +263,8 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
     for (int j = 0; j < NP; j++) {
       const int op = _f_proc[j].op;
       if (op == RVN_OP_SOILEVAP_ALL || op == RVN_OP_SOILEVAP_HBV || op == RVN_OP_SOILEVAP_GR4J || op == RVN_OP_SOILEVAP_TOPMODEL ||
-          (op >= RVN_OP_SOILEVAP_LINEAR && op <= RVN_OP_SOILEVAP_AWBM) || op == RVN_OP_CANEVP_ALL || op == RVN_OP_CANSNOWEVP_ALL) uses_pet = true;
+          (op >= RVN_OP_SOILEVAP_LINEAR && op <= RVN_OP_SOILEVAP_AWBM) || op == RVN_OP_CANEVP_ALL || op == RVN_OP_CANSNOWEVP_ALL ||
+          op == RVN_OP_CANEVP_MAXIMUM || op == RVN_OP_CANEVP_RUTTER || op == RVN_OP_CANSNOWEVP_MAXIMUM) uses_pet = true;
       if (op == RVN_OP_OPEN_WATER_EVAP || op == RVN_OP_LAKE_EVAP_BASIC || op == RVN_OP_SOILEVAP_HYPR) uses_owpet = true;
     }
     auto consumed = [&](int method) { return (uses_pet && O.evaporation == method) || (uses_owpet && O.ow_evaporation == method); };
@@ -275,7 +282,7 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
       for (int g = 0; g < nG; g++)
         ExitGracefullyIf(_pGauges[g]->aMaxTemp[0] == NOT_SPECIFIED || _pGauges[g]->aMinTemp[0] == NOT_SPECIFIED, "PET_HARGREAVES requires minimum and maximum monthly temperatures");
     d.opt.need_atmos = need_atmos ? 1 : 0;
-    d.opt.air_pressure = O.air_pressure; d.opt.rel_humidity = O.rel_humidity; d.opt.sw_radiation = O.SW_radiation; d.opt.sw_cloudcorr = O.SW_cloudcovercorr; d.opt.wind_velocity = O.wind_velocity;
+    d.opt.air_pressure = O.air_pressure; d.opt.rel_humidity = O.rel_humidity; d.opt.sw_radiation = O.SW_radiation; d.opt.sw_cloudcorr = O.SW_cloudcovercorr; d.opt.wind_velocity = O.wind_velocity; d.opt.interception_factor = O.interception_factor;
     const bool need_et = consumed(RVN_PET_HARGREAVES_1985) || consumed(RVN_PET_OUDIN) || need_atmos;
     const bool need_dl = consumed(RVN_PET_HAMON), need_ws = consumed(RVN_PET_MOHYSE);
     ExitGracefullyIf(need_et && O.SW_radiation == RVN_SW_RAD_NONE, "CModel::Flatten: :SWRadiationMethod SW_RAD_NONE leaves the extraterrestrial radiation unset; PET methods that read it are not built for that case");

@@ -15,9 +15,9 @@ static const char *kLUNames[RVN_LU_COUNT] = {"IMPERMEABLE_FRAC", "FOREST_COVERAG
   "HBV_MELT_GLACIER_CORR", "HBV_GLACIER_KMIN", "GLAC_STORAGE_COEFF", "HBV_GLACIER_AG", "DEP_MAX", "LAKE_PET_CORR", "OW_PET_CORR",
   "PARTITION_COEFF", "CC_DECAY_COEFF", "MAX_SAT_AREA_FRAC", "PDM_B", "AET_COEFF", "MAX_DEP_AREA_FRAC", "PONDED_EXP", "AWBM_AREAFRAC1",
   "AWBM_AREAFRAC2", "HYMOD2_G", "HYMOD2_KMAX", "HYMOD2_EXP", "PET_LIN_COEFF", "RAIN_MELT_MULT", "RELHUM_CORR", "PET_VAP_COEFF",
-  "MIN_WIND_SPEED", "MAX_WIND_SPEED"};
+  "MIN_WIND_SPEED", "MAX_WIND_SPEED", "ABST_PERCENT"};
 static const char *kVegNames[RVN_V_COUNT] = {"MAX_HEIGHT", "MAX_LAI", "SAI_HT_RATIO", "MAX_CAPACITY", "MAX_SNOW_CAPACITY", "RAIN_ICEPT_PCT",
-  "SNOW_ICEPT_PCT", "PET_VEG_CORR", "VAR_CAPACITY", "VAR_SNOW_CAPACITY", "VAR_RAIN_ICEPT_PCT", "VAR_SNOW_ICEPT_PCT"};
+  "SNOW_ICEPT_PCT", "PET_VEG_CORR", "RAIN_ICEPT_FACT", "SNOW_ICEPT_FACT", "VAR_CAPACITY", "VAR_SNOW_CAPACITY", "VAR_RAIN_ICEPT_PCT", "VAR_SNOW_ICEPT_PCT"};
 static const char *kGlobalNames[RVN_G_COUNT] = {"SNOW_SWI", "SNOW_SWI_MIN", "SNOW_SWI_MAX", "SWI_REDUCT_COEFF", "ADIABATIC_LAPSE", "PRECIP_LAPSE",
   "RAINSNOW_TEMP", "RAINSNOW_DELTA", "AVG_ANNUAL_SNOW", "SNOW_TEMPERATURE", "HBVEC_LAPSE_UPPER", "HBVEC_LAPSE_RATE", "HBVEC_LAPSE_ELEV",
   "AIRSNOW_COEFF", "AVG_ANNUAL_RUNOFF", "MAX_SWE_SURFACE", "TOC_MULTIPLIER", "TIME_TO_PEAK_MULTIPLIER", "GAMMA_SHAPE_MULTIPLIER",

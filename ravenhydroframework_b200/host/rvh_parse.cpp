@@ -230,7 +230,12 @@ static void ParseMainInputFile(CModel *&pModel, optStruct &Options) {
       continue;
     }
     if (c == ":PrecipIceptFract") {
-      ExitGracefullyIf(s[1] != "PRECIP_ICEPT_USER", "ParseMainInputFile: only PRECIP_ICEPT_USER is implemented in the B200 build"); continue;
+      if (s[1] == "USER_SPECIFIED" || s[1] == "ICEPT_USER" || s[1] == "PRECIP_ICEPT_USER") Options.interception_factor = RVN_ICEPT_USER;
+      else if (s[1] == "LAI_LINEAR" || s[1] == "ICEPT_LAI" || s[1] == "PRECIP_ICEPT_LAI") Options.interception_factor = RVN_ICEPT_LAI;
+      else if (s[1] == "LAI_EXPONENTIAL" || s[1] == "ICEPT_EXPLAI" || s[1] == "PRECIP_ICEPT_EXPLAI") Options.interception_factor = RVN_ICEPT_EXPLAI;
+      else if (s[1] == "PRECIP_ICEPT_NONE") Options.interception_factor = RVN_ICEPT_NONE;
+      else ExitGracefully("ParseMainInputFile: :PrecipIceptFract " + s[1] + " is not implemented in the B200 build");   // HEDSTROM / STICKY read the canopy snow load
+      continue;
     }
     if (c == ":SubdailyMethod" || c == ":SubDailyMethod") {
       ExitGracefullyIf(s[1] != "SUBDAILY_NONE", "ParseMainInputFile: only SUBDAILY_NONE is implemented in the B200 build"); continue;
@@ -598,6 +603,8 @@ static void ParseClassPropertiesFile(CModel *pModel, const optStruct &Options) {
     // CVegetationClass::AutoCalculateVegetationProps (src/VegetationClass.cpp:118-195)
     if (V.v[RVN_V_RAIN_ICEPT_PCT] == NOT_SPECIFIED) V.v[RVN_V_RAIN_ICEPT_PCT] = 0.12;
     if (V.v[RVN_V_SNOW_ICEPT_PCT] == NOT_SPECIFIED) V.v[RVN_V_SNOW_ICEPT_PCT] = 0.10;
+    if (V.v[RVN_V_RAIN_ICEPT_FACT] == NOT_SPECIFIED) V.v[RVN_V_RAIN_ICEPT_FACT] = 0.06;   // src/VegetationClass.cpp:104-116
+    if (V.v[RVN_V_SNOW_ICEPT_FACT] == NOT_SPECIFIED) V.v[RVN_V_SNOW_ICEPT_FACT] = 0.04;
     const double max_LAI = V.v[RVN_V_MAX_LAI], max_SAI = V.v[RVN_V_SAI_HT_RATIO] * V.v[RVN_V_MAX_HEIGHT];
     if (V.v[RVN_V_MAX_CAPACITY] == NOT_SPECIFIED) V.v[RVN_V_MAX_CAPACITY] = 0.15 * (max_LAI + max_SAI);
     if (V.v[RVN_V_MAX_SNOW_CAPACITY] == NOT_SPECIFIED) V.v[RVN_V_MAX_SNOW_CAPACITY] = 0.6 * (max_LAI + max_SAI);

@@ -582,20 +582,38 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
   }
   if (cmd == ":CanopyEvaporation") {  // case 202; src/VegetationMovers.cpp:20-32
     need(4);
-    ExitGracefullyIf(s[1] != "CANEVP_ALL", "ParseMainInputFile: canopy evaporation algorithm " + s[1] + " is not implemented in the B200 build");
+    int op = -1;
+    if (s[1] == "CANEVP_ALL") op = RVN_OP_CANEVP_ALL;
+    else if (s[1] == "CANEVP_MAXIMUM") op = RVN_OP_CANEVP_MAXIMUM;
+    else if (s[1] == "CANEVP_RUTTER") op = RVN_OP_CANEVP_RUTTER;   // trunk fraction is 0 without a TRUNK variable, which nothing built here creates
+    ExitGracefullyIf(op < 0, "ParseMainInputFile: canopy evaporation algorithm " + s[1] + " is not implemented in the B200 build");
     AddSVs(pM, {SVL(RVN_SV_CANOPY, -1), SVL(RVN_SV_ATMOSPHERE, -1), SVL(RVN_SV_AET, -1)});
-    CmvGeneric *p = new CmvGeneric("CanopyEvaporation", RVN_OP_CANEVP_ALL, pM);
+    CmvGeneric *p = new CmvGeneric("CanopyEvaporation", (rvn_opcode)op, pM);
     int iAET = pM->GetStateVarIndex(RVN_SV_AET);
     p->Connect(pM->GetStateVarIndex(RVN_SV_CANOPY), iAtmos); p->Connect(iAET, iAET);
     return p;
   }
   if (cmd == ":CanopySnowEvap" || cmd == ":CanopySnowEvaporation" || cmd == ":CanopySublimation") {  // case 221; src/VegetationMovers.cpp:205-216
     need(4);
-    ExitGracefullyIf(s[1] != "CANEVP_ALL" && s[1] != "SUBLIM_ALL", "ParseMainInputFile: canopy sublimation algorithm " + s[1] + " is not implemented in the B200 build");
+    const bool snow_max = (s[1] == "CANEVP_MAXIMUM" || s[1] == "SUBLIM_MAXIMUM");
+    ExitGracefullyIf(s[1] != "CANEVP_ALL" && s[1] != "SUBLIM_ALL" && !snow_max, "ParseMainInputFile: canopy sublimation algorithm " + s[1] + " is not implemented in the B200 build");
     AddSVs(pM, {SVL(RVN_SV_CANOPY_SNOW, -1), SVL(RVN_SV_ATMOSPHERE, -1), SVL(RVN_SV_AET, -1)});
-    CmvGeneric *p = new CmvGeneric("CanopySublimation", RVN_OP_CANSNOWEVP_ALL, pM);
+    CmvGeneric *p = new CmvGeneric("CanopySublimation", snow_max ? RVN_OP_CANSNOWEVP_MAXIMUM : RVN_OP_CANSNOWEVP_ALL, pM);
     int iAET = pM->GetStateVarIndex(RVN_SV_AET);
     p->Connect(pM->GetStateVarIndex(RVN_SV_CANOPY_SNOW), iAtmos); p->Connect(iAET, iAET);
+    return p;
+  }
+  if (cmd == ":Abstraction") {  // case 225; src/Abstraction.cpp:20-33
+    need(4);
+    int type = -1;
+    if (s[1] == "ABST_PERCENTAGE") type = RVN_ABST_PERCENTAGE;
+    else if (s[1] == "ABST_FILL") type = RVN_ABST_FILL;
+    ExitGracefullyIf(type < 0, "ParseMainInputFile: abstraction algorithm " + s[1] + " is not implemented in the B200 build");
+    ExitGracefullyIf(s[2] != "PONDED_WATER" || s[3] != "DEPRESSION", "ParseMainInputFile: :Abstraction moves water from PONDED_WATER to DEPRESSION");
+    AddSVs(pM, {SVL(RVN_SV_PONDED_WATER, -1), SVL(RVN_SV_DEPRESSION, -1)});
+    CmvGeneric *p = new CmvGeneric("Abstraction", RVN_OP_ABSTRACTION, pM);
+    p->Connect(pM->GetStateVarIndex(RVN_SV_PONDED_WATER), pM->GetStateVarIndex(RVN_SV_DEPRESSION));
+    p->SetIntArg(0, type);
     return p;
   }
   if (cmd == ":Sublimation") {  // case 210; src/Sublimation.cpp:20-44 (the from/to tokens must be SNOW ATMOSPHERE)

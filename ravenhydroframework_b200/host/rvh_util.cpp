@@ -25,7 +25,7 @@ optStruct::optStruct()
       ow_evaporation(RVN_PET_HARGREAVES_1985), evap_infill(RVN_PET_HARGREAVES_1985), ow_evap_infill(RVN_PET_HARGREAVES_1985),
       orocorr_temp(RVN_OROCORR_NONE), orocorr_precip(RVN_OROCORR_NONE), orocorr_PET(RVN_OROCORR_NONE),
       air_pressure(RVN_AIRPRESS_BASIC), rel_humidity(RVN_RELHUM_CONSTANT), SW_radiation(RVN_SW_RAD_DEFAULT), SW_cloudcovercorr(RVN_SW_CLOUD_CORR_NONE),
-      wind_velocity(RVN_WINDVEL_CONSTANT),
+      wind_velocity(RVN_WINDVEL_CONSTANT), interception_factor(RVN_ICEPT_USER),
       routing(RVN_ROUTE_STORAGECOEFF), catchment_routing(ROUTE_DUMP), interpolation(INTERP_NEAREST_NEIGHBOR),
       month_interp_method(MONTHINT_LINEAR_MID), num_soillayers(-1), suppressCompetitiveET(false), snow_suppressPET(false),
       allow_soil_overfill(false), direct_evap(false), silent(false), noisy(false), benchmarking(false),

@@ -93,6 +93,21 @@ if hasattr(synth, "write_hbv"):
     CASES["hbv_atm_sub_sierra"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=75, routing="ROUTE_MUSKINGUM", proc_after=(_hbv_after, _sub % "SUBLIM_CENTRAL_SIERRA"),
                                        rvi_extra=":RelativeHumidityMethod RELHUM_MINDEWPT\n:WindspeedMethod WINDVEL_UBC_MOD\n",
                                        rvp_extra=":LandUseParameterList\n  :Parameters, MIN_WIND_SPEED, MAX_WIND_SPEED\n  :Units, m/s, m/s\n  [DEFAULT], 0.7, 6.5\n  LU_OPEN, 1.4, 9.0\n:EndLandUseParameterList\n")
+    # canopy: interception fractions from LAI (:PrecipIceptFract), evaporation / sublimation at the remaining PET, Rutter; depression abstraction
+    _can = r"  :CanopyEvaporation CANEVP_ALL         CANOPY          ATMOSPHERE\n  :CanopySnowEvap    CANEVP_ALL         CANOPY_SNOW     ATMOSPHERE\n"
+    _can_max = "  :CanopyEvaporation CANEVP_MAXIMUM     CANOPY          ATMOSPHERE\n  :CanopySnowEvap    SUBLIM_MAXIMUM     CANOPY_SNOW     ATMOSPHERE\n"
+    _can_rut = "  :CanopyEvaporation CANEVP_RUTTER      CANOPY          ATMOSPHERE\n  :CanopySnowEvap    CANEVP_MAXIMUM     CANOPY_SNOW     ATMOSPHERE\n"
+    _abst = "  :Abstraction       %-18s PONDED_WATER    DEPRESSION\n  :OpenWaterEvaporation OPEN_WATER_EVAP   DEPRESSION      ATMOSPHERE\n"
+    _dep = ":LandUseParameterList\n  :Parameters, DEP_MAX, ABST_PERCENT\n  :Units, mm, none\n  [DEFAULT], 14.0, 0.22\n  LU_OPEN, 6.5, 0.4\n:EndLandUseParameterList\n"
+    _icf = ":VegetationParameterList\n  :Parameters, RAIN_ICEPT_FACT, SNOW_ICEPT_FACT\n  :Units, none, none\n  [DEFAULT], 0.05, 0.03\n  VEG_LOW, 0.09, 0.07\n:EndVegetationParameterList\n"
+    CASES["hbv_can_icept_lai"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=81, routing="ROUTE_MUSKINGUM", rvi_extra=":PrecipIceptFract PRECIP_ICEPT_LAI\n",
+                                      rvi_sub=[(_can, _can_max)], rvp_extra=_icf)
+    CASES["hbv_can_icept_explai"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=82, routing="ROUTE_MUSKINGUM", rvi_extra=":PrecipIceptFract PRECIP_ICEPT_EXPLAI\n",
+                                         rvi_sub=[(_can, _can_rut)])
+    CASES["hbv_can_icept_none"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=300, seed=83, routing="ROUTE_MUSKINGUM", rvi_extra=":PrecipIceptFract PRECIP_ICEPT_NONE\n")
+    CASES["hbv_abst_fill"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=84, routing="ROUTE_MUSKINGUM", proc_after=(_hbv_after, _abst % "ABST_FILL"), rvp_extra=_dep)
+    CASES["hbv_abst_percentage"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=85, routing="ROUTE_MUSKINGUM", proc_after=(_hbv_after, _abst % "ABST_PERCENTAGE"),
+                                        rvi_sub=[(_can, _can_max)], rvp_extra=_dep)
     # potential melt: degree day with refreeze / rain-on-snow variants (CModel::EstimatePotentialMelt)
     CASES["gr4j_potmelt_ddfreeze"] = dict(kind="gr4j", n_sb=2, hru_per_sb=3, n_days=300, seed=55, potmelt="POTMELT_DD_FREEZE",
                                           rvp_extra=":LandUseParameterList\n  :Parameters, REFREEZE_FACTOR\n  :Units, mm/d/K\n  [DEFAULT], 1.3\n:EndLandUseParameterList\n")
@@ -243,6 +258,7 @@ def make(name, spec):
     potmelt = spec.pop("potmelt", None)       # :PotentialMeltMethod other than the template's
     rvp_extra = spec.pop("rvp_extra", None)   # lines appended to the .rvp
     rvi_extra = spec.pop("rvi_extra", None)   # option commands inserted at the top of the .rvi
+    rvi_sub = spec.pop("rvi_sub", None)   # [(regex, replacement)] applied to the .rvi
     proc_after = spec.pop("proc_after", None)   # (regex of a process line, line inserted after it) in the .rvi process list
     gauge_extra = spec.pop("gauge_extra", None)   # lines added to the gauge block of the .rvt (after :MonthlyAveTemperature)
     d = os.path.join(HERE, name)
@@ -270,6 +286,12 @@ def make(name, spec):
         rvi = open(base + ".rvi").read()
         rvi, cnt = re.subn(proc_after[0], lambda m: m.group(1) + proc_after[1], rvi)
         assert cnt == 1, proc_after[0]
+        open(base + ".rvi", "w").write(rvi)
+    for pat, rep in (rvi_sub or []):
+        import re
+        rvi = open(base + ".rvi").read()
+        rvi, cnt = re.subn(pat, lambda m: rep, rvi)
+        assert cnt == 1, pat
         open(base + ".rvi", "w").write(rvi)
     if rvi_extra is not None:
         rvi = open(base + ".rvi").read()

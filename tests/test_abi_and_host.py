@@ -20,7 +20,7 @@ def test_engine_exports_every_declared_symbol():
     lib = api.engine_lib()
     for n in names:
         assert hasattr(lib, n), "librvn_gpu.so does not export %s" % n
-    assert lib.rvn_gpu_abi_version() == 6
+    assert lib.rvn_gpu_abi_version() == 7
 
 
 def test_engine_is_sm100a_with_specialised_and_interpreter_sweeps():
