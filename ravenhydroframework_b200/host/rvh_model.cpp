@@ -203,6 +203,55 @@ void CChannelXSect::GenerateTrapezoid(double bottom_w, double bottom_elev, doubl
     aQ[i] = sqrt(bedslope) * aXArea[i] * pow(aXArea[i] / aPerim[i], 2.0 / 3.0) / min_mannings;
   }
 }
+// :ChannelProfile: rating curves at 20 equally spaced stages between the lowest and highest survey point; per stage, every survey
+// segment contributes its wetted area / perimeter / top width and its own Manning flow (reference CChannelXSect survey constructor +
+// GenerateRatingCurvesFromProfile + GetPropsFromProfile, src/ChannelXSect.cpp:30-76, 430-527)
+void CChannelXSect::GenerateFromProfile(const std::vector<double> &X, const std::vector<double> &Z, const std::vector<double> &N) {
+  const int nS = (int)X.size();
+  ExitGracefullyIf(nS < 2, "CChannelXSect Constructor: a channel profile needs at least two survey points");
+  ExitGracefullyIf(bedslope < 0.0, "CChannelXSect Constructor: channel profile bedslope must be greater than zero");
+  min_mannings = ALMOST_INF;
+  for (int i = 0; i < nS; i++) {
+    ExitGracefullyIf(N[i] < 0, "CChannelXSect::Constructor: invalid mannings n");
+    if (N[i] < min_mannings) min_mannings = N[i];
+  }
+  mannings_n = min_mannings;
+  double lo = Z[0], hi = Z[0];
+  for (int i = 0; i < nS; i++) { if (Z[i] > hi) hi = Z[i]; if (Z[i] < lo) lo = Z[i]; }
+  ExitGracefullyIf((hi - lo) < REAL_SMALL, "CChannelXSect::GenerateRatingCurvesFromProfile: profile survey points all have same elevation");
+  const int nP = 20;
+  aQ.assign(nP, 0.0); aStage.assign(nP, 0.0); aTopWidth.assign(nP, 0.0); aXArea.assign(nP, 0.0); aPerim.assign(nP, 0.0);
+  const double dz = (hi - lo) / ((int)(nP)-1.0);
+  int r = 0;
+  for (double z = lo; z < hi + 0.5 * dz; z += dz) {   // the reference's floating-point stage loop
+    ExitGracefullyIf(r >= nP, "CChannelXSect::GenerateRatingCurvesFromProfile: stage loop overran the rating table");
+    double A = 0, P = 0, Q = 0, w = 0;
+    for (int i = 0; i < nS - 1; i++) {
+      const double zl = std::min(Z[i], Z[i + 1]), zu = std::max(Z[i], Z[i + 1]), dx = fabs(X[i + 1] - X[i]);
+      double Ai, Pi, wi;
+      if ((z <= zl) || (dx == 0)) { Ai = 0; Pi = 0; wi = 0; }            // dry segment
+      else if (z >= zu) {                                                 // submerged segment (+ vertical banks next to it)
+        wi = dx;
+        Ai = ((z - zu) * dx + 0.5 * dx * (zu - zl));
+        Pi = sqrt(dx * dx + (zu - zl) * (zu - zl));
+        if ((i > 0) && (Z[i - 1] > Z[i]) && (X[i - 1] == X[i])) Pi += (z <= Z[i - 1]) ? (z - Z[i]) : (Z[i - 1] - Z[i]);
+        if ((i < (nS - 2)) && (Z[i + 2] > Z[i + 1]) && (X[i + 2] == X[i + 1])) Pi += (z <= Z[i + 2]) ? (z - Z[i + 1]) : (Z[i + 2] - Z[i + 1]);
+        if (i == 0) Pi += (z - Z[i]);
+        if (i == nS - 2) Pi += (z - Z[i + 1]);
+      } else {                                                            // partly wet segment
+        double ddx = (z - zl) / (zu - zl) * dx;
+        if ((zu - zl) < REAL_SMALL) ddx = 0.0;
+        Ai = 0.5 * (z - zl) * ddx;
+        Pi = sqrt(ddx * ddx + (z - zl) * (z - zl));
+        wi = ddx;
+      }
+      A += Ai; P += Pi; w += wi;
+      if (Ai > 0) Q += pow(bedslope, 0.5) * Ai * pow(Ai / Pi, 2.0 / 3.0) / N[i];
+    }
+    aStage[r] = z; aQ[r] = Q; aTopWidth[r] = w; aXArea[r] = A; aPerim[r] = P;
+    r++;
+  }
+}
 static void FlowCorrections(double bedslope, double min_n, double SB_slope, double SB_n, double &Q_mult) {
   Q_mult = 1.0;
   if (SB_slope != AUTO_COMPUTE) Q_mult = pow(SB_slope / bedslope, 0.5);

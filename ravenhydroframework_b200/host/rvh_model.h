@@ -41,6 +41,8 @@ public:
   double bedslope, mannings_n;
   std::vector<double> aQ, aStage, aTopWidth, aXArea, aPerim;
   void GenerateTrapezoid(double bottom_w, double bottom_elev, double incline_ratio);
+  // surveyed profile (x, bed elevation, Manning's n of the segment to the right of each point) -> 20-point rating curves
+  void GenerateFromProfile(const std::vector<double> &x, const std::vector<double> &elev, const std::vector<double> &mann);
   double GetCelerity(double Q, double SB_slope, double SB_n) const;
   double GetTopWidth(double Q, double SB_slope, double SB_n) const;
   double GetArea(double Q, double SB_slope, double SB_n) const;          // src/ChannelXSect.cpp:297-302

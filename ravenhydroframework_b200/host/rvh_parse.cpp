@@ -358,7 +358,7 @@ static void ParseParameterList(CParser &p, const char *endtok, FieldFn field_of,
   std::vector<int> fields;
   while (p.Tokenize(s)) {
     if (s.empty()) continue;
-    if (s[0] == endtok) return;
+    if (s[0] == endtok || s[0].compare(0, 4, ":End") == 0) return;   // the reference's ParsePropArray stops at any :End... line
     if (s[0] == ":Parameters") {
       fields.clear();
       for (size_t i = 1; i < s.size(); i++) {
@@ -380,7 +380,10 @@ static void ParseParameterList(CParser &p, const char *endtok, FieldFn field_of,
       if (fields[i] < 0) continue;  // recognised but irrelevant to the hot path
       const std::string &v = s[i + 1];
       if (v == "_DEFAULT" || v == "_DEF") continue;
-      ExitGracefullyIf(v == "_AUTO", std::string("ParsePropertyFile: _AUTO values are not supported by the B200 build (") + family + ")");
+      if (v == "_AUTO" || v == "AUTO") {   // AUTO_COMPUTE: the class value is autogenerated even where a [DEFAULT] is given (SetCalculableValue, src/CommonFunctions.cpp:101-116)
+        if (is_default) T.def.erase(fields[i]); else T.cell[std::make_pair(c, fields[i])] = NOT_SPECIFIED;
+        continue;
+      }
       if (is_default) T.def[fields[i]] = s_to_d(v);
       else T.cell[std::make_pair(c, fields[i])] = s_to_d(v);
     }
@@ -405,6 +408,8 @@ static int LUFieldOrIgnore(const std::string &n) {
 static int VegFieldOrIgnore(const std::string &n) {
   if (n == "TFRAIN") return 1000 + RVN_V_RAIN_ICEPT_PCT;   // throughfall fractions: icept = 1 - value (src/ParsePropertyFile.cpp)
   if (n == "TFSNOW") return 1000 + RVN_V_SNOW_ICEPT_PCT;
+  if (n == "RELATIVE_HT") return 2000;    // one value for all twelve months (src/VegetationClass.cpp:388-389); autogenerated 1.0
+  if (n == "RELATIVE_LAI") return 2001;
   int f = VegFieldFromName(n);
   if (f >= 0) return f;
   static const char *ign[] = {"MAX_LEAF_COND", "ALBEDO", "ALBEDO_WET", "SVF_EXTINCTION", "MAX_INTERCEPT_RATE", "RAIN_ICEPT_FACT", "SNOW_ICEPT_FACT", NULL};
@@ -490,8 +495,26 @@ static void ParseClassPropertiesFile(CModel *pModel, const optStruct &Options) {
       continue;
     }
     if (c == ":SoilParameterList") { ParseParameterList(p, ":EndSoilParameterList", SoilFieldOrIgnore, &CModel::FindSoilClass, pModel, Tsoil, "soil"); continue; }
-    if (c == ":LandUseParameterList") { ParseParameterList(p, ":EndLandUseParameterList", LUFieldOrIgnore, &CModel::FindLUClass, pModel, Tlu, "land use"); continue; }
-    if (c == ":VegetationParameterList") { ParseParameterList(p, ":EndVegetationParameterList", VegFieldOrIgnore, &CModel::FindVegClass, pModel, Tveg, "vegetation"); continue; }
+    if (c == ":LandUseParameterList" || c == ":SnowParameterList") {   // :SnowParameterList is the same command (src/ParsePropertyFile.cpp:278)
+      ParseParameterList(p, ":EndLandUseParameterList", LUFieldOrIgnore, &CModel::FindLUClass, pModel, Tlu, "land use"); continue; }
+    if (c == ":VegetationParameterList") {
+      ParseParameterList(p, ":EndVegetationParameterList", VegFieldOrIgnore, &CModel::FindVegClass, pModel, Tveg, "vegetation");
+      for (size_t k = 0; k < pModel->veg_classes.size(); k++)   // RELATIVE_HT / RELATIVE_LAI take effect here so that a later :Seasonal... block overrides them
+        for (int key = 2000; key <= 2001; key++) {
+          std::map<std::pair<int, int>, double>::iterator it = Tveg.cell.find(std::make_pair((int)k, key));
+          double val = NOT_SPECIFIED;
+          if (it != Tveg.cell.end()) val = it->second;
+          else if (Tveg.def.count(key)) val = Tveg.def[key];
+          else continue;
+          if (val == NOT_SPECIFIED) val = 1.0;   // AUTO_COMPUTE -> 1.0 (src/VegetationClass.cpp:205-225)
+          for (int m = 0; m < 12; m++) (key == 2001 ? pModel->veg_classes[k].V.relative_LAI : pModel->veg_classes[k].V.relative_ht)[m] = val;
+        }
+      for (int key = 2000; key <= 2001; key++) {
+        Tveg.def.erase(key);
+        for (size_t k = 0; k < pModel->veg_classes.size(); k++) Tveg.cell.erase(std::make_pair((int)k, key));
+      }
+      continue;
+    }
     if (c == ":GlobalParameter") {
       int f = GlobalFieldFromName(s[1]);
       ExitGracefullyIf(f < 0, "ParseClassPropertiesFile: global parameter " + s[1] + " is not supported by the B200 build");
@@ -505,9 +528,9 @@ static void ParseClassPropertiesFile(CModel *pModel, const optStruct &Options) {
     if (c == ":IrreducibleSnowSaturation") { pModel->globals.v[RVN_G_SNOW_SWI] = s_to_d(s[1]); continue; }
     if (c == ":PrecipitationLapseRate") { pModel->globals.v[RVN_G_PRECIP_LAPSE] = s_to_d(s[1]); continue; }
     if (c == ":AirSnowCoeff") { pModel->globals.v[RVN_G_AIRSNOW_COEFF] = s_to_d(s[1]); continue; }
-    if (c == ":SeasonalRelativeLAI" || c == ":SeasonalRelativeHeight") {
-      const bool lai = (c == ":SeasonalRelativeLAI");
-      const char *endt = lai ? ":EndSeasonalRelativeLAI" : ":EndSeasonalRelativeHeight";
+    if (c == ":SeasonalRelativeLAI" || c == ":SeasonalRelativeHeight" || c == ":SeasonalCanopyLAI" || c == ":SeasonalCanopyHeight") {   // src/ParsePropertyFile.cpp:282-285
+      const bool lai = (c == ":SeasonalRelativeLAI" || c == ":SeasonalCanopyLAI");
+      const std::string endt = ":End" + c.substr(1);
       while (p.Tokenize(s)) {
         if (s.empty() || s[0] == ":Attributes" || s[0] == ":Units") continue;
         if (s[0] == endt) break;
@@ -521,6 +544,45 @@ static void ParseClassPropertiesFile(CModel *pModel, const optStruct &Options) {
           for (int m = 0; m < 12; m++) (lai ? pModel->veg_classes[v].V.relative_LAI : pModel->veg_classes[v].V.relative_ht)[m] = s_to_d(s[1 + m]);
         }
       }
+      continue;
+    }
+    if (c == ":ChannelProfile") {   // src/ParsePropertyFile.cpp:804-915
+      ExitGracefullyIf(s.size() < 2, "ParseClassPropertiesFile: :ChannelProfile needs a name");
+      CChannelXSect *ch = new CChannelXSect();
+      ch->name = s[1]; ch->bedslope = 0.0; ch->mannings_n = 0.0;
+      std::vector<double> x, y, xz, n;
+      int mode = 0;
+      while (p.Tokenize(s)) {
+        if (s.empty()) continue;
+        if (s[0] == ":EndChannelProfile") break;
+        if (s[0] == ":Bedslope" && s.size() == 2) { ch->bedslope = s_to_d(s[1]); continue; }
+        if (s[0] == ":SurveyPoints") { mode = 1; continue; }
+        if (s[0] == ":RoughnessZones") { mode = 2; continue; }
+        if (s[0] == ":EndSurveyPoints" || s[0] == ":EndRoughnessZones") { mode = 0; continue; }
+        ExitGracefullyIf(mode == 0 || s.size() != 2, "ParseClassPropertiesFile: improper format in :ChannelProfile " + ch->name);
+        if (mode == 1) { x.push_back(s_to_d(s[0])); y.push_back(s_to_d(s[1])); }
+        else { xz.push_back(s_to_d(s[0])); n.push_back(s_to_d(s[1])); }
+      }
+      const int nSP = (int)x.size(), nRS = (int)n.size();
+      ExitGracefullyIf(nSP < 2 || nRS < 1, "ParseClassPropertiesFile: :ChannelProfile " + ch->name + " needs survey points and roughness zones");
+      // Manning's n of survey segment i = length-weighted mean of the roughness zones it crosses
+      std::vector<double> nn(nSP, n[nRS - 1]);
+      int j = 0;
+      for (int i = 0; i + 1 < nSP; i++) {
+        if (j == nRS - 1) nn[i] = n[j];
+        else if (xz[j + 1] > x[i + 1]) nn[i] = n[j];
+        else {
+          const double Li = (x[i + 1] - x[i]);
+          nn[i] = (xz[j + 1] - x[i]) / Li * n[j];
+          while ((j < nRS - 1) && (xz[j + 1] < x[i + 1])) {
+            j++;
+            if (j == nRS - 1) nn[i] += (x[i + 1] - xz[j]) / Li * n[j];
+            else nn[i] += (std::min(x[i + 1], xz[j + 1]) - xz[j]) / Li * n[j];
+          }
+        }
+      }
+      ch->GenerateFromProfile(x, y, nn);
+      pModel->channels.push_back(ch);
       continue;
     }
     if (c == ":TrapezoidalChannel") {  // name bot_width bot_elev incline mannings_n bedslope (src/ParsePropertyFile.cpp:982-988)

@@ -108,6 +108,17 @@ if hasattr(synth, "write_hbv"):
     CASES["hbv_abst_fill"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=84, routing="ROUTE_MUSKINGUM", proc_after=(_hbv_after, _abst % "ABST_FILL"), rvp_extra=_dep)
     CASES["hbv_abst_percentage"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=85, routing="ROUTE_MUSKINGUM", proc_after=(_hbv_after, _abst % "ABST_PERCENTAGE"),
                                         rvi_sub=[(_can, _can_max)], rvp_extra=_dep)
+    # surveyed channel cross-section (:ChannelProfile with roughness zones -> 20-point rating curves) under the two routing methods that
+    # read the channel geometry; _AUTO / RELATIVE_LAI / :SeasonalCanopyLAI / :SnowParameterList spellings of the LOTW set-up
+    _prof = (":ChannelProfile CHN\n  :Bedslope 0.0011\n  :SurveyPoints\n    0 103.2\n    6.0 101.1\n    6.0 100.4\n    9.5 100.0\n    16.0 100.15\n    16.001 101.3\n    41.0 102.1\n    60.0 104.0\n  :EndSurveyPoints\n"
+             "  :RoughnessZones\n    0 0.08\n    5.0 0.034\n    17.5 0.061\n    38.0 0.1\n  :EndRoughnessZones\n:EndChannelProfile\n")
+    _lotw_rvp = (":VegetationParameterList\n  :Parameters, RELATIVE_LAI, MAX_CAPACITY\n  :Units, none, mm\n  [DEFAULT], 0.8, _AUTO\n  VEG_LOW, _AUTO, 2.5\n:EndVegetationParameterList\n"
+                 ":SeasonalCanopyLAI\n  VEG_ALL 0.5 0.5 0.5 0.5 0.69 0.88 1.0 1.0 0.75 0.5 0.5 0.5\n:EndSeasonalCanopyLAI\n"
+                 ":SnowParameterList\n  :Parameters, REFREEZE_FACTOR\n  :Units, mm/d/K\n  [DEFAULT], 2.1\n:EndSnowParams\n")
+    CASES["hbv_chanprofile_hydrologic"] = dict(kind="hbv", n_sb=7, hru_per_sb=3, n_days=250, seed=91, routing="ROUTE_HYDROLOGIC", season_offset=50,
+                                               rvp_sub=[(r":TrapezoidalChannel CHN[^\n]*\n", _prof)], rvp_extra=_lotw_rvp)
+    CASES["hbv_chanprofile_muskingum"] = dict(kind="hbv", n_sb=7, hru_per_sb=3, n_days=250, seed=92, routing="ROUTE_MUSKINGUM", season_offset=70,
+                                              rvp_sub=[(r":TrapezoidalChannel CHN[^\n]*\n", _prof)])
     # potential melt: degree day with refreeze / rain-on-snow variants (CModel::EstimatePotentialMelt)
     CASES["gr4j_potmelt_ddfreeze"] = dict(kind="gr4j", n_sb=2, hru_per_sb=3, n_days=300, seed=55, potmelt="POTMELT_DD_FREEZE",
                                           rvp_extra=":LandUseParameterList\n  :Parameters, REFREEZE_FACTOR\n  :Units, mm/d/K\n  [DEFAULT], 1.3\n:EndLandUseParameterList\n")
@@ -259,6 +270,7 @@ def make(name, spec):
     rvp_extra = spec.pop("rvp_extra", None)   # lines appended to the .rvp
     rvi_extra = spec.pop("rvi_extra", None)   # option commands inserted at the top of the .rvi
     rvi_sub = spec.pop("rvi_sub", None)   # [(regex, replacement)] applied to the .rvi
+    rvp_sub = spec.pop("rvp_sub", None)   # [(regex, replacement)] applied to the .rvp
     proc_after = spec.pop("proc_after", None)   # (regex of a process line, line inserted after it) in the .rvi process list
     gauge_extra = spec.pop("gauge_extra", None)   # lines added to the gauge block of the .rvt (after :MonthlyAveTemperature)
     d = os.path.join(HERE, name)
@@ -293,6 +305,12 @@ def make(name, spec):
         rvi, cnt = re.subn(pat, lambda m: rep, rvi)
         assert cnt == 1, pat
         open(base + ".rvi", "w").write(rvi)
+    for pat, rep in (rvp_sub or []):
+        import re
+        rvp = open(base + ".rvp").read()
+        rvp, cnt = re.subn(pat, lambda m: rep, rvp)
+        assert cnt == 1, pat
+        open(base + ".rvp", "w").write(rvp)
     if rvi_extra is not None:
         rvi = open(base + ".rvi").read()
         open(base + ".rvi", "w").write(rvi_extra + rvi)
