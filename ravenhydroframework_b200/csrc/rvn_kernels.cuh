@@ -63,6 +63,7 @@ struct CtxCommon {
 // run-time context of the interpreter: shared-memory columns (column-major over the CTA's threads so that dynamic
 // indexing by state-variable slot is bank-conflict free)
 struct DynCtx : CtxCommon {
+  static constexpr bool kAtmos = true;   // atmospheric forcing chain / non-USER interception compiled in (the engine routes such models here)
   const DevProgram *P;     // program (shared memory)
   double *sv;              // &s_sv[tid]; slot i at sv[i*RVN_BS]  -- the state the processes read: newest (aPhinew[k], ORDERED_SERIES) or
                            //             start-of-step (aPhi[k], EULER)
@@ -103,6 +104,7 @@ struct DynProc {
 #endif
 template <class Prog>
 struct StatCtx : CtxCommon {
+  static constexpr bool kAtmos = false;
 #if RVN_SV_SMEM
   double *svp;   // &s_sv[tid]; slot s at svp[s * RVN_BS] (constant offsets; no register pressure, no local-memory spills)
 #else
@@ -320,13 +322,48 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
     apply_perturbations(F, M, RVN_PF_SNOWFALL, e, k, step);
   }
   if (c.type == RVN_HRU_MASKED_GLACIER) F[RVN_F_PRECIP] = 0;
+  {  // CModel::EstimatePotentialMelt  src/PotentialMelt.cpp:20-246
+    double pm = F[RVN_F_POTENTIAL_MELT];
+    const int method = opt.pot_melt;
+    if (method == RVN_POTMELT_DEGREE_DAY) {
+      pm = c.LU(RVN_LU_MELT_FACTOR) * (F[RVN_F_TEMP_DAILY_AVE] - c.LU(RVN_LU_DD_MELT_TEMP)) * subdaily_corr;
+    } else if (method == RVN_POTMELT_HBV || method == RVN_POTMELT_HBV_ROS) {
+      double Ma = c.LU(RVN_LU_MELT_FACTOR), Ma_min = c.LU(RVN_LU_MIN_MELT_FACTOR), AM = c.LU(RVN_LU_HBV_MELT_ASP_CORR);
+      double MRF = c.LU(RVN_LU_HBV_MELT_FOR_CORR), Fc = c.LU(RVN_LU_FOREST_COVERAGE), melt_temp = c.LU(RVN_LU_DD_MELT_TEMP);
+      double adj = 0, slope_corr;
+      if (c.lat < 0.0) adj = D_PI;
+      Ma = Ma_min + (Ma - Ma_min) * 0.5 * (1.0 - cos(tt.day_angle - D_WINTER_SOLSTICE_ANG - adj));
+      Ma *= ((1.0 - Fc) * 1.0 + (Fc)*MRF);
+      slope_corr = ((1.0 - Fc) * 1.0 + (Fc)*sin(c.slope));
+      Ma *= dmax(1.0 - AM * slope_corr * cos(c.aspect - adj), 0.0);
+      double rain_energy = 0.0;
+      if (method == RVN_POTMELT_HBV_ROS)   // rain-on-snow energy, src/PotentialMelt.cpp:77-81
+        rain_energy = c.LU(RVN_LU_RAIN_MELT_MULT) * D_SPH_WATER / D_LH_FUSION * dmax(F[RVN_F_TEMP_AVE], 0.0) * (F[RVN_F_PRECIP] * (1.0 - F[RVN_F_SNOW_FRAC]));
+      pm = Ma * (F[RVN_F_TEMP_DAILY_AVE] - melt_temp) * subdaily_corr + rain_energy;
+    } else if (method == RVN_POTMELT_DD_FREEZE) {   // :40-49
+      const double Ma = c.LU(RVN_LU_MELT_FACTOR), melt_temp = c.LU(RVN_LU_DD_MELT_TEMP), Mf = c.LU(RVN_LU_REFREEZE_FACTOR);
+      if ((Mf > 0) && (F[RVN_F_TEMP_DAILY_AVE] - melt_temp) < 0.0) pm = Mf * (F[RVN_F_TEMP_DAILY_AVE] - melt_temp);
+      else pm = Ma * (F[RVN_F_TEMP_DAILY_AVE] - melt_temp) * subdaily_corr;
+    } else if (method == RVN_POTMELT_HMETS) {
+      double Ma_min = c.LU(RVN_LU_MIN_MELT_FACTOR), Ma_max = c.LU(RVN_LU_MAX_MELT_FACTOR);
+      double melt_temp = c.LU(RVN_LU_DD_MELT_TEMP), Kcum = c.LU(RVN_LU_DD_AGGRADATION);
+      double cum_melt = 0.0;
+      if (c.iSV(RVN_SV_CUM_SNOWMELT) >= 0) cum_melt = c.SV(c.iSV(RVN_SV_CUM_SNOWMELT));  // still the stored value here
+      double Ma = dmin(Ma_max, Ma_min * (1 + Kcum * cum_melt));
+      pm = Ma * (F[RVN_F_TEMP_DAILY_AVE] - melt_temp) * subdaily_corr;
+    } else if (method == RVN_POTMELT_NONE) {
+      pm = 0.0;
+    }
+    F[RVN_F_POTENTIAL_MELT] = pm;
+  }
+  // (the atmospheric block sits directly in front of the PET estimate that consumes it: its four results are not live across the melt block)
   // air pressure, relative humidity (src/UpdateForcings.cpp:493-497, 677-731) and incoming shortwave radiation (:591-593;
   // CRadiation::EstimateShortwaveRadiation / ClearSkySolarRadiation / SWCloudCoverCorrection, src/Radiation.cpp:24-57, 992-1038,
   // 333-364) -- only when a consumed PET method needs them.  Geometry-only pieces (ET radiation on the slope and on the flat,
   // optical air mass) come from the host's per-date tables.
   double air_pres = 0.0, rel_hum = 0.0, SW_radia = 0.0, ET_radia = 0.0;
   c.air_pres = 0.0; c.rel_hum = 0.0; c.wind_vel = 0.0;
-  if (opt.need_atmos) {
+  if (C::kAtmos && opt.need_atmos) {
     const double Tave = F[RVN_F_TEMP_AVE];
     if (opt.air_pressure == RVN_AIRPRESS_BASIC) air_pres = D_AMBIENT_AIR_PRESSURE * pow(1.0 - 0.0065 * elev / (D_ZERO_CELSIUS + Tave), 5.26);
     else if (opt.air_pressure == RVN_AIRPRESS_UBC) air_pres = D_KPA_PER_ATM * (1.0 - 0.0001 * elev);
@@ -368,40 +405,6 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
       gf[(size_t)RVN_F_AIR_PRES * M.nHp] = air_pres; gf[(size_t)RVN_F_REL_HUMIDITY * M.nHp] = rel_hum; gf[(size_t)RVN_F_SW_RADIA * M.nHp] = SW_radia;
     }
   }
-  {  // CModel::EstimatePotentialMelt  src/PotentialMelt.cpp:20-246
-    double pm = F[RVN_F_POTENTIAL_MELT];
-    const int method = opt.pot_melt;
-    if (method == RVN_POTMELT_DEGREE_DAY) {
-      pm = c.LU(RVN_LU_MELT_FACTOR) * (F[RVN_F_TEMP_DAILY_AVE] - c.LU(RVN_LU_DD_MELT_TEMP)) * subdaily_corr;
-    } else if (method == RVN_POTMELT_HBV || method == RVN_POTMELT_HBV_ROS) {
-      double Ma = c.LU(RVN_LU_MELT_FACTOR), Ma_min = c.LU(RVN_LU_MIN_MELT_FACTOR), AM = c.LU(RVN_LU_HBV_MELT_ASP_CORR);
-      double MRF = c.LU(RVN_LU_HBV_MELT_FOR_CORR), Fc = c.LU(RVN_LU_FOREST_COVERAGE), melt_temp = c.LU(RVN_LU_DD_MELT_TEMP);
-      double adj = 0, slope_corr;
-      if (c.lat < 0.0) adj = D_PI;
-      Ma = Ma_min + (Ma - Ma_min) * 0.5 * (1.0 - cos(tt.day_angle - D_WINTER_SOLSTICE_ANG - adj));
-      Ma *= ((1.0 - Fc) * 1.0 + (Fc)*MRF);
-      slope_corr = ((1.0 - Fc) * 1.0 + (Fc)*sin(c.slope));
-      Ma *= dmax(1.0 - AM * slope_corr * cos(c.aspect - adj), 0.0);
-      double rain_energy = 0.0;
-      if (method == RVN_POTMELT_HBV_ROS)   // rain-on-snow energy, src/PotentialMelt.cpp:77-81
-        rain_energy = c.LU(RVN_LU_RAIN_MELT_MULT) * D_SPH_WATER / D_LH_FUSION * dmax(F[RVN_F_TEMP_AVE], 0.0) * (F[RVN_F_PRECIP] * (1.0 - F[RVN_F_SNOW_FRAC]));
-      pm = Ma * (F[RVN_F_TEMP_DAILY_AVE] - melt_temp) * subdaily_corr + rain_energy;
-    } else if (method == RVN_POTMELT_DD_FREEZE) {   // :40-49
-      const double Ma = c.LU(RVN_LU_MELT_FACTOR), melt_temp = c.LU(RVN_LU_DD_MELT_TEMP), Mf = c.LU(RVN_LU_REFREEZE_FACTOR);
-      if ((Mf > 0) && (F[RVN_F_TEMP_DAILY_AVE] - melt_temp) < 0.0) pm = Mf * (F[RVN_F_TEMP_DAILY_AVE] - melt_temp);
-      else pm = Ma * (F[RVN_F_TEMP_DAILY_AVE] - melt_temp) * subdaily_corr;
-    } else if (method == RVN_POTMELT_HMETS) {
-      double Ma_min = c.LU(RVN_LU_MIN_MELT_FACTOR), Ma_max = c.LU(RVN_LU_MAX_MELT_FACTOR);
-      double melt_temp = c.LU(RVN_LU_DD_MELT_TEMP), Kcum = c.LU(RVN_LU_DD_AGGRADATION);
-      double cum_melt = 0.0;
-      if (c.iSV(RVN_SV_CUM_SNOWMELT) >= 0) cum_melt = c.SV(c.iSV(RVN_SV_CUM_SNOWMELT));  // still the stored value here
-      double Ma = dmin(Ma_max, Ma_min * (1 + Kcum * cum_melt));
-      pm = Ma * (F[RVN_F_TEMP_DAILY_AVE] - melt_temp) * subdaily_corr;
-    } else if (method == RVN_POTMELT_NONE) {
-      pm = 0.0;
-    }
-    F[RVN_F_POTENTIAL_MELT] = pm;
-  }
   // CModel::EstimatePET  src/Evaporation.cpp:282-540
 #pragma unroll
   for (int ow = 0; ow < 2; ow++) {
@@ -436,7 +439,8 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
         const double cpet = c.G(RVN_G_MOHYSE_PET_COEFF), ws = M.sunset_angle[(size_t)M.et_row[step] * M.nHp + k];
         PET = cpet / D_PI * ws * exp((17.3 * F[RVN_F_TEMP_AVE]) / (238 + F[RVN_F_TEMP_AVE]));
       }
-    } else if (method == RVN_PET_TURC_1961) {   // TurcEvap  src/Evaporation.cpp:61-68
+    } else if (C::kAtmos && method >= RVN_PET_TURC_1961 && method <= RVN_PET_HARGREAVES) {
+     if (method == RVN_PET_TURC_1961) {   // TurcEvap  src/Evaporation.cpp:61-68
       const double t = dmax(0.0, F[RVN_F_TEMP_DAILY_AVE]);
       double evp = 0.013 * t / (t + 15) * ((SW_radia)*23.8846 + 50);
       if (rel_hum < 0.5) evp *= (1 + (50 - rel_hum * 100) / 70);
@@ -469,6 +473,7 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
       if (rel_hum >= 0.54) Ct = 0.035 * pow(100 * (1.0 - rel_hum), 0.333);
       const double delT = (1.8 * temp_month_max + 32.0) - (1.8 * temp_month_min + 32.0);
       PET = dmax(0.0, 0.0075 * Ra * Ct * sqrt(delT) * (1.8 * F[RVN_F_TEMP_DAILY_AVE] + 32.0));
+     }
     } else if (method == RVN_PET_FROMMONTHLY) {
       double peRatio = 1.0 + D_HBV_PET_TEMP_CORR * (temp_ave_unc - temp_month_ave);
       peRatio = dmax(0.0, dmin(2.0, peRatio));
@@ -722,7 +727,7 @@ RVN_DI void load_hru_statics(C &c, const DevModel &M, int k, const double *s_pta
 // host (veg_season[step][veg][2]); everything else is evaluated here in the reference's order.
 template <class C> RVN_DI void load_canopy(C &c, const DevModel &M, int step) {
   c.canopy_cap = 0.0; c.canopy_snow_cap = 0.0;
-  const int icept = c.opt().interception_factor;
+  const int icept = C::kAtmos ? c.opt().interception_factor : (int)RVN_ICEPT_USER;
   if (icept == RVN_ICEPT_USER) { c.rain_icept_pct = c.VEG(RVN_V_VAR_RAIN_ICEPT_PCT); c.snow_icept_pct = c.VEG(RVN_V_VAR_SNOW_ICEPT_PCT); }
   else { c.rain_icept_pct = 0.0; c.snow_icept_pct = 0.0; }
   if (c.iSV(RVN_SV_CANOPY) < 0 && c.iSV(RVN_SV_CANOPY_SNOW) < 0 && (icept == RVN_ICEPT_USER || icept == RVN_ICEPT_NONE)) return;
@@ -872,13 +877,13 @@ __global__ void __launch_bounds__(RVN_BS, RVN_STATIC_MIN_BLOCKS) hru_sweep_stati
   c.old_snow_depth = (Prog::iSV(RVN_SV_SNOW_DEPTH) >= 0) ? c.SV(Prog::iSV(RVN_SV_SNOW_DEPTH) >= 0 ? Prog::iSV(RVN_SV_SNOW_DEPTH) : 0) : 0.0;
   c.old_snow_temp = (Prog::iSV(RVN_SV_SNOW_TEMP) >= 0) ? c.SV(Prog::iSV(RVN_SV_SNOW_TEMP) >= 0 ? Prog::iSV(RVN_SV_SNOW_TEMP) : 0) : 0.0;
   __syncthreads();   // parameter row staged
-  load_canopy(c, M, step);
   // ---- forcings (on the stored state)
   if (enabled) compute_forcings(c, M, e, k, step, sb);
   else {
 #pragma unroll
     for (int f = 0; f < RVN_F_CARRIED; f++) c.F[f] = 0.0;
   }
+  load_canopy(c, M, step);   // (class, date) only: placed after the forcing chain so that its results are not live across it
   if (enabled) reboot_diagnostics(c);   // disabled HRUs keep their stored values (the reference never writes them back, :701)
   // ---- ordered-series process sweep on the newest state
   RunProcs<Prog, UNIT_DT, 0>::run(c, M, enabled, mask, e, k, gstate);
@@ -948,9 +953,9 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
   c.old_snow_cover = (P->iSV[RVN_SV_SNOW_COVER] >= 0) ? c.SV(P->iSV[RVN_SV_SNOW_COVER]) : 0.0;
   c.old_snow_depth = (P->iSV[RVN_SV_SNOW_DEPTH] >= 0) ? c.SV(P->iSV[RVN_SV_SNOW_DEPTH]) : 0.0;
   c.old_snow_temp = (P->iSV[RVN_SV_SNOW_TEMP] >= 0) ? c.SV(P->iSV[RVN_SV_SNOW_TEMP]) : 0.0;
-  load_canopy(c, M, step);
   if (enabled) compute_forcings(c, M, e, k, step, sb);
   else { for (int f = 0; f < RVN_F_CARRIED; f++) c.F[f] = 0.0; }
+  load_canopy(c, M, step);
   if (enabled) reboot_diagnostics(c);
   if (euler) { for (int s = 0; s < nCore; s++) c.SVW(s) = c.SV(s); }   // aPhinew = aPhi (src/Solvers.cpp:155-200); rates come from aPhi
   const bool unit_dt = (c.tstep == 1.0);
