@@ -187,6 +187,10 @@ def main():
     if not torch.cuda.is_available():
         sys.stderr.write("bench.py: no CUDA device -- the B200 arm has no CPU fallback\n")
         return 2
+    # stdout carries exactly ONE line (the JSON): library chatter on fd 1 (NCCL prints its version banner there) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
@@ -334,7 +338,8 @@ def main():
         line["ensemble_statistics"] = {"members": stats["n"], "outlet_q_mean_last_step": float(stats["mean"][-1]), "outlet_q_std_last_step": float(stats["std"][-1]),
                                        "ms": 1000.0 * (time.perf_counter() - ts), "backend": "nccl" if world > 1 else "local"}
         if rank == 0:
-            print(json.dumps(line))
+            sys.stdout.flush()
+            os.write(json_fd, (json.dumps(line) + "\n").encode())
         sim.close()
     finally:
         shutil.rmtree(td, ignore_errors=True)
