@@ -430,6 +430,10 @@ int rvn_gpu_device_count(void);
 
 /* build device-resident model; `device` = CUDA ordinal */
 int rvn_gpu_create(const rvn_model_desc *desc, int device, rvn_gpu_model **out);
+/* the same with RVN_CREATE_* flags.  RVN_CREATE_FORCE_INTERPRETER: serve a model whose process list matches a compiled-in
+ * template program with the generic interpreter kernel anyway (both must give bit-identical results; used by the tests) */
+#define RVN_CREATE_FORCE_INTERPRETER 1
+int rvn_gpu_create_ex(const rvn_model_desc *desc, int device, int flags, rvn_gpu_model **out);
 void rvn_gpu_destroy(rvn_gpu_model *m);
 
 /* HRU state, host layout [member][hru][sv] (the reference's aPhi[k][i] per member); device is SoA */
@@ -514,6 +518,11 @@ int rvn_gpu_kernel_variant(rvn_gpu_model *m, char *buf, int buflen);
 /* build tool (no device needed): text of the compile-time program struct for `desc`'s process list, as written into
  * csrc/rvn_static_programs.cuh by tools/gen_static_programs.py */
 int rvn_gpu_emit_static_program(const rvn_model_desc *desc, const char *name, char *buf, int64_t buflen);
+
+/* verification hook (tests/test_glibc_math.py): evaluate the device exp (fn 0) / log (1) / pow (2) the kernels use
+ * (csrc/rvn_glibc_math.h - restatements of the host libm the reference links, src/ calls of exp/log/pow) on n host
+ * arguments x[, y] and return the results in out[n]; these must equal the host libm's bit for bit */
+int rvn_gpu_math_eval(int device, int fn, int64_t n, const double *x, const double *y, double *out);
 
 #ifdef __cplusplus
 }

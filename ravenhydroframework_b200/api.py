@@ -27,13 +27,14 @@ def engine_lib():
     """librvn_gpu.so (C ABI of include/rvn_gpu.h)."""
     global _engine
     if _engine is None:
-        path = os.environ.get("RVN_GPU_LIB") or os.path.join(HERE, "librvn_gpu.so")   # override: kernel-variant experiments
+        path = os.path.join(HERE, "librvn_gpu.so")
         if not os.path.exists(path):
             raise RavenError("librvn_gpu.so is not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
         lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
         lib.rvn_gpu_last_error.restype = C.c_char_p
         vp, i, dp = C.c_void_p, C.c_int, C.c_void_p
         lib.rvn_gpu_create.argtypes = [vp, i, C.POINTER(vp)]
+        lib.rvn_gpu_create_ex.argtypes = [vp, i, i, C.POINTER(vp)]
         lib.rvn_gpu_destroy.argtypes = [vp]
         lib.rvn_gpu_destroy.restype = None
         lib.rvn_gpu_upload_state.argtypes = [vp, dp, i, i]
@@ -64,6 +65,7 @@ def engine_lib():
         lib.rvn_gpu_enkf_pack_host.argtypes = [vp, dp]
         lib.rvn_gpu_enkf_update_host.argtypes = [vp, dp, dp, i, i]
         lib.rvn_gpu_enkf_last_ms.argtypes = [vp, C.POINTER(C.c_double)]
+        lib.rvn_gpu_math_eval.argtypes = [i, i, C.c_int64, dp, dp, dp]
         _engine = lib
     return _engine
 
@@ -299,7 +301,7 @@ class RavenModel:
 class GpuSimulation:
     """Device-resident simulation of all members of a flattened model (rvn_gpu_* C ABI)."""
 
-    def __init__(self, model, n_members=1, device=0, upload_initial=True):
+    def __init__(self, model, n_members=1, device=0, upload_initial=True, force_interpreter=False):
         self.lib = engine_lib()
         self.model = model
         if model.desc is None or model.nMembers != n_members:
@@ -307,7 +309,7 @@ class GpuSimulation:
         self.E, self.nHRU, self.NS, self.nSB = n_members, model.nHRU, model.NS, model.nSB
         self.nSteps = model.nSteps
         h = C.c_void_p()
-        rc = self.lib.rvn_gpu_create(model.desc, int(device), C.byref(h))
+        rc = self.lib.rvn_gpu_create_ex(model.desc, int(device), 1 if force_interpreter else 0, C.byref(h))
         if rc != 0:
             raise RavenError("rvn_gpu_create: %s" % self.lib.rvn_gpu_last_error().decode())
         self.h = h

@@ -194,7 +194,7 @@ RVN_DI void apply_perturbations(FVec &F, const DevModel &M, const int ftype, con
 
 // GetSaturatedVaporPressure  src/CommonFunctions.cpp:935-949 [kPa]
 RVN_DI double sat_vapor_pressure(const double T) {
-  return (T >= 0) ? 0.61078 * exp(17.26939 * T / (T + 237.3)) : 0.61078 * exp(21.87456 * T / (T + 265.5));
+  return (T >= 0) ? 0.61078 * rvn_exp(17.26939 * T / (T + 237.3)) : 0.61078 * rvn_exp(21.87456 * T / (T + 265.5));
 }
 template <class C>
 RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, int sb) {
@@ -365,7 +365,7 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
   c.air_pres = 0.0; c.rel_hum = 0.0; c.wind_vel = 0.0;
   if (C::kAtmos && opt.need_atmos) {
     const double Tave = F[RVN_F_TEMP_AVE];
-    if (opt.air_pressure == RVN_AIRPRESS_BASIC) air_pres = D_AMBIENT_AIR_PRESSURE * pow(1.0 - 0.0065 * elev / (D_ZERO_CELSIUS + Tave), 5.26);
+    if (opt.air_pressure == RVN_AIRPRESS_BASIC) air_pres = D_AMBIENT_AIR_PRESSURE * rvn_pow(1.0 - 0.0065 * elev / (D_ZERO_CELSIUS + Tave), 5.26);
     else if (opt.air_pressure == RVN_AIRPRESS_UBC) air_pres = D_KPA_PER_ATM * (1.0 - 0.0001 * elev);
     else air_pres = D_AMBIENT_AIR_PRESSURE;
     double relhum = 0.5;
@@ -376,11 +376,11 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
     if (opt.sw_radiation == RVN_SW_RAD_DEFAULT) {
       const double Ketp = ET_radia, Ket = M.et_flat[row], Mopt = M.opt_air_mass[row];
       double dew_pt;
-      { const double a = 17.27, b = 237.7; const double tmp = (a * Tave / (b + Tave)) + log(rel_hum); dew_pt = b * tmp / (a - tmp); }   // GetDewPointTemp, src/CommonFunctions.cpp:1131-1139
+      { const double a = 17.27, b = 237.7; const double tmp = (a * Tave / (b + Tave)) + rvn_log(rel_hum); dew_pt = b * tmp / (a - tmp); }   // GetDewPointTemp, src/CommonFunctions.cpp:1131-1139
       const double gamma_dust = 0.025;
-      const double precip_WV = 1.12 * exp(0.0614 * dew_pt);
-      const double tau = exp((-0.124 - 0.0207 * precip_WV) + (-0.0682 - 0.0248 * precip_WV) * Mopt) - gamma_dust;                    // Dingman E-9..E-13
-      const double tau2 = 0.5 * (1.0 - exp((-0.0363 - 0.0084 * precip_WV) + (-0.0572 - 0.0173 * precip_WV) * Mopt) + gamma_dust);    // Dingman E-15..E-18
+      const double precip_WV = 1.12 * rvn_exp(0.0614 * dew_pt);
+      const double tau = rvn_exp((-0.124 - 0.0207 * precip_WV) + (-0.0682 - 0.0248 * precip_WV) * Mopt) - gamma_dust;                    // Dingman E-9..E-13
+      const double tau2 = 0.5 * (1.0 - rvn_exp((-0.0363 - 0.0084 * precip_WV) + (-0.0572 - 0.0173 * precip_WV) * Mopt) + gamma_dust);    // Dingman E-15..E-18
       SW_radia = tau * Ketp + tau2 * Ket + tau2 * D_GLOBAL_ALBEDO * (tau2 + tau) * Ketp;
     }
     double cc = 1.0;   // cloud cover is 0 (CLOUDCOV_NONE)
@@ -428,7 +428,7 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
     } else if (method == RVN_PET_HAMON) {   // Hamon1961Evap  src/Evaporation.cpp:263-271; GetSaturatedVaporPressure  src/CommonFunctions.cpp:935-949
       if (M.day_length != nullptr) {
         const double T = F[RVN_F_TEMP_DAILY_AVE], day_length = M.day_length[(size_t)M.et_row[step] * M.nHp + k];
-        const double sat_vap = (T >= 0) ? 0.61078 * exp(17.26939 * T / (T + 237.3)) : 0.61078 * exp(21.87456 * T / (T + 265.5));
+        const double sat_vap = (T >= 0) ? 0.61078 * rvn_exp(17.26939 * T / (T + 237.3)) : 0.61078 * rvn_exp(21.87456 * T / (T + 265.5));
         const double abs_hum = 216.7 * (sat_vap * 10) / (T + 273.16);
         PET = dmax(0.0, 0.0055 * 4.0 * abs_hum * day_length * day_length * 25.4);
       }
@@ -437,7 +437,7 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
     } else if (method == RVN_PET_MOHYSE) {   // src/Evaporation.cpp:476-483
       if (M.sunset_angle != nullptr) {
         const double cpet = c.G(RVN_G_MOHYSE_PET_COEFF), ws = M.sunset_angle[(size_t)M.et_row[step] * M.nHp + k];
-        PET = cpet / D_PI * ws * exp((17.3 * F[RVN_F_TEMP_AVE]) / (238 + F[RVN_F_TEMP_AVE]));
+        PET = cpet / D_PI * ws * rvn_exp((17.3 * F[RVN_F_TEMP_AVE]) / (238 + F[RVN_F_TEMP_AVE]));
       }
     } else if (C::kAtmos && method >= RVN_PET_TURC_1961 && method <= RVN_PET_HARGREAVES) {
      if (method == RVN_PET_TURC_1961) {   // TurcEvap  src/Evaporation.cpp:61-68
@@ -448,14 +448,14 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
     } else if (method == RVN_PET_MAKKINK_1957) {   // Makkink1957Evap  src/Evaporation.cpp:32-48
       const double T = F[RVN_F_TEMP_AVE];
       const double sat_vap = sat_vapor_pressure(T);
-      const double de_dT = (T > 0) ? 17.26939 * 237.3 / pow(T + 237.3, 2) * sat_vap : 21.87456 * 265.5 / pow(T + 265.5, 2) * sat_vap;   // GetSatVapSlope
+      const double de_dT = (T > 0) ? 17.26939 * 237.3 / rvn_sqr(T + 237.3) * sat_vap : 21.87456 * 265.5 / rvn_sqr(T + 265.5) * sat_vap;   // GetSatVapSlope
       const double LH_vapor = 2.495 - 0.002361 * T;
       const double gamma = D_SPH_AIR / D_AIR_H20_MW_RAT * air_pres / LH_vapor;
       PET = dmax(0.0, 0.61 * (de_dT / (de_dT + gamma)) * SW_radia * 23.8846 / 58.5 - 0.12);
     } else if (method == RVN_PET_PENMAN_SIMPLE33 || method == RVN_PET_PENMAN_SIMPLE39) {   // Valiantzas (2006)  src/Evaporation.cpp:454-474
       const double Rs = SW_radia, R_et = ET_radia, Tave = F[RVN_F_TEMP_AVE];
-      if (method == RVN_PET_PENMAN_SIMPLE33) PET = 0.047 * Rs * sqrt(Tave + 9.5) - 2.4 * pow(Rs / R_et, 2.0) + 0.09 * (Tave + 20) * (1 - rel_hum);
-      else PET = 0.038 * Rs * sqrt(Tave + 9.5) - 2.4 * pow(Rs / R_et, 2.0) + 0.075 * (Tave + 20) * (1 - rel_hum);
+      if (method == RVN_PET_PENMAN_SIMPLE33) PET = 0.047 * Rs * sqrt(Tave + 9.5) - 2.4 * rvn_sqr(Rs / R_et) + 0.09 * (Tave + 20) * (1 - rel_hum);
+      else PET = 0.038 * Rs * sqrt(Tave + 9.5) - 2.4 * rvn_sqr(Rs / R_et) + 0.075 * (Tave + 20) * (1 - rel_hum);
     } else if (method == RVN_PET_VAPDEFICIT) {   // src/Evaporation.cpp:506-518
       const double e_sat = sat_vapor_pressure(F[RVN_F_TEMP_AVE]);
       const double ea = rel_hum * e_sat;
@@ -463,14 +463,14 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
     } else if (method == RVN_PET_LINACRE) {   // src/Evaporation.cpp:491-504
       const double T = F[RVN_F_TEMP_DAILY_AVE];
       double Tdewpoint;
-      { const double a = 17.27, b = 237.7; const double tmp = (a * T / (b + T)) + log(rel_hum); Tdewpoint = b * tmp / (a - tmp); }
+      { const double a = 17.27, b = 237.7; const double tmp = (a * T / (b + T)) + rvn_log(rel_hum); Tdewpoint = b * tmp / (a - tmp); }
       const double latit = c.lat * 57.29578951;
       PET = ((ow ? 700 : 500) * T / (100 - latit) + 15.0 * (T - Tdewpoint)) / (80.0 - T);
     } else if (method == RVN_PET_HARGREAVES) {   // HargreavesEvap  src/Evaporation.cpp:179-203
       double Ra = ET_radia;
       Ra /= (D_LH_VAPOR * D_DENSITY_WATER / D_MM_PER_METER);
       double Ct = 0.125;
-      if (rel_hum >= 0.54) Ct = 0.035 * pow(100 * (1.0 - rel_hum), 0.333);
+      if (rel_hum >= 0.54) Ct = 0.035 * rvn_pow(100 * (1.0 - rel_hum), 0.333);
       const double delT = (1.8 * temp_month_max + 32.0) - (1.8 * temp_month_min + 32.0);
       PET = dmax(0.0, 0.0075 * Ra * Ct * sqrt(delT) * (1.8 * F[RVN_F_TEMP_DAILY_AVE] + 32.0));
      }
@@ -742,8 +742,8 @@ template <class C> RVN_DI void load_canopy(C &c, const DevModel &M, int step) {
     c.rain_icept_pct = dmin(c.VEG(RVN_V_RAIN_ICEPT_FACT) * (LAI + SAI), 1.0);
     c.snow_icept_pct = dmin(c.VEG(RVN_V_SNOW_ICEPT_FACT) * (LAI + SAI), 1.0);
   } else if (icept == RVN_ICEPT_EXPLAI) {  // :155-159
-    c.rain_icept_pct = (1.0 - exp(-0.5 * (LAI + SAI)));
-    c.snow_icept_pct = (1.0 - exp(-0.5 * (LAI + SAI)));
+    c.rain_icept_pct = (1.0 - rvn_exp(-0.5 * (LAI + SAI)));
+    c.snow_icept_pct = (1.0 - rvn_exp(-0.5 * (LAI + SAI)));
   }
   if ((max_LAI + max_SAI) > 0) {
     c.canopy_cap = ((LAI + SAI) / (max_LAI + max_SAI)) * c.VEG(RVN_V_MAX_CAPACITY);

@@ -81,7 +81,7 @@ __global__ void lateral_flush_kernel(const __grid_constant__ DevModel M, const D
         const double snowDepth = snowSWE * SWE_TO_DEPTH_FACTOR;
         double slope_thres = slope_deg;
         if (slope_thres < 10.0) slope_thres = 10.0;
-        const double threshold_snow_height_m = 3178.4 * pow(slope_thres, -1.998);
+        const double threshold_snow_height_m = 3178.4 * rvn_pow(slope_thres, -1.998);
         double threshold_snow_height = threshold_snow_height_m * D_MM_PER_METER;
         if (slope_deg > 60.0) threshold_snow_height = 0.0;
         if (snowDepth > threshold_snow_height) { const double excessSnowDepth = snowDepth - threshold_snow_height; snowMoved = excessSnowDepth / SWE_TO_DEPTH_FACTOR; }

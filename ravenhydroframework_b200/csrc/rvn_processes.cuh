@@ -18,6 +18,7 @@
 #ifndef RVN_PROCESSES_CUH
 #define RVN_PROCESSES_CUH
 #include "rvn_device.cuh"
+#include "rvn_glibc_math.h"   // rvn_exp / rvn_log / rvn_pow: the host libm of the reference build, bit for bit
 
 #define D_ALMOST_INF 1e99
 #define D_REAL_SMALL 1e-12
@@ -50,6 +51,7 @@
 
 RVN_DI double dmax(double r, double l) { return (r >= l) ? r : l; }   // src/RavenInclude.h:1456
 RVN_DI double dmin(double r, double l) { return (r <= l) ? r : l; }   // src/RavenInclude.h:1464
+RVN_DI double rvn_sqr(double x) { return x * x; }   // what g++ -O2 makes of the reference's pow(x, 2) / pow(x, 2.0) (no libm call)
 
 // ---- helpers shared by both context types (CRTP-free: plain function templates over the context) -------------
 // CHydroUnit::GetSoilCapacity (src/HydroUnits.cpp:260-267)
@@ -122,7 +124,7 @@ template <class C, class PR> RVN_DI void rates_PRECIPITATION(C &c, const PR &pr)
       if (iSWE >= 0) {
         c.R(qSnow) = snowthru;
         if (c.iSV(RVN_SV_SNOW_DEPTH) >= 0) {  // CalcFreshSnowDensity, src/SnowParams.cpp:37-47
-          double rho = (air_temp <= D_FREEZING_TEMP) ? 67.92 + 51.25 * exp((air_temp - D_FREEZING_TEMP) / 2.59)
+          double rho = (air_temp <= D_FREEZING_TEMP) ? 67.92 + 51.25 * rvn_exp((air_temp - D_FREEZING_TEMP) / 2.59)
                                                      : dmin((119.17 + 20.0 * (air_temp - D_FREEZING_TEMP)), 200.0);
           c.R(qSnowDepth) = snowthru * D_DENSITY_ICE / rho;
         }
@@ -150,7 +152,7 @@ template <class C, class PR> RVN_DI void rates_SNOBAL_HMETS(C &c, const PR &pr) 
   const double potmelt = dmax(c.F[RVN_F_POTENTIAL_MELT], 0.0);
   const double Tdiurnal = 0.5 * (c.F[RVN_F_TEMP_DAILY_AVE] + c.F[RVN_F_TEMP_DAILY_MIN]);
   SL = dmax(SL, 0.0);
-  double pot_freeze = Kf * pow(dmax(Tbf - Tdiurnal, 0.0), exp_fe);
+  double pot_freeze = Kf * rvn_pow(dmax(Tbf - Tdiurnal, 0.0), exp_fe);
   double freeze = dmin(pot_freeze * tstep, SL);
   SL -= freeze; SWE += freeze;
   double melt = dmin(potmelt * tstep, SWE);
@@ -259,7 +261,7 @@ template <class C, class PR> RVN_DI void rates_CANSNOWEVP_ALL(C &c, const PR &pr
 }
 // CmvSublimation  src/Sublimation.cpp:98-243 (SublimationRate, GetRatesOfChange, ApplyConstraints).  Forcings and the snow
 // temperature / depth / SWE of the depth-change term are the HRU's lagged values, as in the reference.
-RVN_DI double SatVap(const double T) { return (T >= 0) ? 0.61078 * exp(17.26939 * T / (T + 237.3)) : 0.61078 * exp(21.87456 * T / (T + 265.5)); }
+RVN_DI double SatVap(const double T) { return (T >= 0) ? 0.61078 * rvn_exp(17.26939 * T / (T + 237.3)) : 0.61078 * rvn_exp(21.87456 * T / (T + 265.5)); }
 template <class C, class PR> RVN_DI void rates_SUBLIMATION(C &c, const PR &pr) {
   const int type = pr.ia(0);
   const double Ta = c.F[RVN_F_TEMP_AVE], rel_hum = c.rel_hum, wind_vel = c.wind_vel, Tsnow = SnowTemperature(c);
@@ -268,7 +270,7 @@ template <class C, class PR> RVN_DI void rates_SUBLIMATION(C &c, const PR &pr) {
     const double roughness = c.G(RVN_G_SNOW_ROUGHNESS), air_pres = c.air_pres;
     const double air_density = (air_pres - 0.378 * SatVap(Ta)) / (287.042 * (Ta + D_ZERO_CELSIUS)) * 1000;   // GetAirDensity, src/CommonFunctions.cpp:1039-1043
     const double es = SatVap(Tsnow), ea = SatVap(Ta) * rel_hum;
-    const double C_E = 0.42 * 0.42 / (log(8.0 / roughness)) / (log(8.0 / roughness));
+    const double C_E = 0.42 * 0.42 / (rvn_log(8.0 / roughness)) / (rvn_log(8.0 / roughness));
     sub = air_density * C_E * wind_vel * 0.623 * (es - ea) / air_pres * D_SEC_PER_DAY / D_DENSITY_WATER * D_MM_PER_METER;
   } else if (type == RVN_SUBLIM_KUZMIN) {
     const double ea = SatVap(c.F[RVN_F_TEMP_DAILY_AVE]) * rel_hum * 10, es = SatVap(Tsnow) * 1.0 * 10;
@@ -282,13 +284,13 @@ template <class C, class PR> RVN_DI void rates_SUBLIMATION(C &c, const PR &pr) {
     const double air_dens = (air_pres - 0.378 * SatVap(Ta)) / (287.042 * (Ta + D_ZERO_CELSIUS)) * 1000;
     const double ea = SatVap(Ta) * rel_hum, es = SatVap(Tsnow) * 1.0;
     const double z_ref = 2.0, z0 = 0.00005, z0e = 0.00005;
-    const double C_E = (0.42 * 0.42) / (log(z_ref / z0) * log(z_ref / z0e));
+    const double C_E = (0.42 * 0.42) / (rvn_log(z_ref / z0) * rvn_log(z_ref / z0e));
     const double Q_E = air_dens * 2.845 * C_E * wind_vel * ((D_AIR_H20_MW_RAT * (es - ea)) / air_pres) * D_SEC_PER_DAY;
     sub = Q_E / (2.845 * D_DENSITY_WATER) * D_MM_PER_METER;
   } else if (type == RVN_SUBLIM_CENTRAL_SIERRA) {
     const double sat_vap = SatVap(Tsnow) * 10, vap_pres = SatVap(c.F[RVN_F_TEMP_DAILY_AVE]) * rel_hum * 10;
     const double wind_v = wind_vel * 2.237;
-    sub = ((0.0063 * 1.0 * wind_v * (sat_vap - vap_pres)) * 25.4);   // the height factor pow(h*h, (-1/6)) is pow(.., 0) in the reference (integer division)
+    sub = ((0.0063 * 1.0 * wind_v * (sat_vap - vap_pres)) * 25.4);   // the height factor rvn_pow(h*h, (-1/6)) is rvn_pow(.., 0) in the reference (integer division)
   }
   c.R(0) = sub;
   if (pr.nconn() == 2) {   // SNOW_DEPTH simulated: lagged depth and SWE
@@ -334,7 +336,7 @@ template <class C, class PR> RVN_DI void rates_GLACIERRELEASE_HBVEC(C &c, const 
   if (c.type != RVN_HRU_GLACIER) return;
   const double glacier_stor = c.SV(c.iSV(RVN_SV_GLACIER)), snow = c.SV(c.iSV(RVN_SV_SNOW)), liq_snow = c.SV(c.iSV(RVN_SV_SNOW_LIQ));
   const double Kmin = c.LU(RVN_LU_HBV_GLACIER_KMIN), Kmax = c.LU(RVN_LU_GLAC_STORAGE_COEFF), Ag = c.LU(RVN_LU_HBV_GLACIER_AG);
-  const double K = Kmin + (Kmax - Kmin) * exp(-Ag * (snow + liq_snow));
+  const double K = Kmin + (Kmax - Kmin) * rvn_exp(-Ag * (snow + liq_snow));
   c.R(0) = K * glacier_stor;
   if (c.R(0) < 0.0) c.R(0) = 0.0;
   (void)pr;
@@ -355,19 +357,19 @@ template <class C, class PR> RVN_DI void rates_INFILTRATION(C &c, const PR &pr, 
     double direct = Fimp * rainthru;
     double runoff = coef * (sat) * (1.0 - Fimp) * rainthru;
     double infil = (1.0 - Fimp) * rainthru - runoff;
-    double delayed = coef * pow(sat, 2.0) * infil;
+    double delayed = coef * rvn_sqr(sat) * infil;
     infil -= delayed;
     c.R(0) = infil; c.R(1) = direct; c.R(2) = runoff; c.R(3) = delayed;
   } else if (op == RVN_OP_INF_HBV) {
     double stor = c.SV(pr.to(0)), max_stor = SoilCapacity(c, 0), beta = c.SOIL(0, RVN_S_HBV_BETA);
     double sat = dmax(dmin(stor / max_stor, 1.0), 0.0);
-    double runoff = pow(sat, beta) * rainthru;
+    double runoff = rvn_pow(sat, beta) * rainthru;
     runoff = (Fimp)*rainthru + (1 - Fimp) * runoff;
     c.R(0) = rainthru - runoff; c.R(1) = runoff;
   } else if (op == RVN_OP_INF_VIC_ARNO) {   // src/Infiltration.cpp:400-416
     double stor = c.SV(pr.to(0)), max_stor = SoilCapacity(c, 0), b = c.SOIL(0, RVN_S_VIC_B_EXP);
     double sat = dmin(stor / max_stor, 1.0);
-    double sat_area = 1.0 - pow(1.0 - sat, b);
+    double sat_area = 1.0 - rvn_pow(1.0 - sat, b);
     double runoff = sat_area * rainthru;
     runoff = (Fimp)*rainthru + (1 - Fimp) * runoff;
     c.R(0) = rainthru - runoff; c.R(1) = runoff;
@@ -383,9 +385,9 @@ template <class C, class PR> RVN_DI void rates_INFILTRATION(C &c, const PR &pr, 
     double zmax = c.SOIL(0, RVN_S_VIC_ZMAX), zmin = c.SOIL(0, RVN_S_VIC_ZMIN), alpha = c.SOIL(0, RVN_S_VIC_ALPHA);
     double sat = dmin(stor / max_stor, 1.0);
     double gamma = 1.0 / (alpha + 1.0);
-    double K1 = pow((zmax - zmin) * alpha * gamma, -gamma);
+    double K1 = rvn_pow((zmax - zmin) * alpha * gamma, -gamma);
     double Smax = gamma * (alpha * zmax + zmin);
-    double runoff = rainthru * dmax(1.0 - K1 * pow(Smax - sat, gamma), 1.0);   // threshMax(.,1.0,0.0) as written in the reference
+    double runoff = rainthru * dmax(1.0 - K1 * rvn_pow(Smax - sat, gamma), 1.0);   // threshMax(.,1.0,0.0) as written in the reference
     runoff = (Fimp)*rainthru + (1 - Fimp) * runoff;
     c.R(0) = rainthru - runoff; c.R(1) = runoff;
   } else if (op == RVN_OP_INF_PRMS) {   // :418-431
@@ -396,8 +398,8 @@ template <class C, class PR> RVN_DI void rates_INFILTRATION(C &c, const PR &pr, 
   } else if (op == RVN_OP_INF_PDM) {   // :540-563 (Moore 1985)
     double b = c.LU(RVN_LU_PDM_B), stor = c.SV(c.soil_slot(0)), max_stor = SoilCapacity(c, 0);
     double c_max = (b + 1) * max_stor;
-    double c_star = c_max * (1.0 - pow(1.0 - (stor / max_stor), 1.0 / (b + 1.0)));
-    double infil = max_stor * (pow(1.0 - (c_star / c_max), b + 1.0) - pow(1.0 - dmin(c_star + ponded, c_max) / c_max, b + 1.0));
+    double c_star = c_max * (1.0 - rvn_pow(1.0 - (stor / max_stor), 1.0 / (b + 1.0)));
+    double infil = max_stor * (rvn_pow(1.0 - (c_star / c_max), b + 1.0) - rvn_pow(1.0 - dmin(c_star + ponded, c_max) / c_max, b + 1.0));
     infil = dmin(infil, ponded);
     infil = (1.0 - Fimp) * infil / tstep;
     c.R(0) = infil; c.R(1) = rainthru - infil;
@@ -440,12 +442,12 @@ template <class C, class PR> RVN_DI void rates_BASEFLOW(C &c, const PR &pr, cons
     double stor = c.SV(pr.from(0)), max_stor = (m >= 0) ? SoilCapacity(c, m) : 0.0;
     stor = dmin(dmax(stor, 0.0), max_stor);
     if (op == RVN_OP_BASE_LINEAR) c.R(0) = c.SOIL(m, RVN_S_BASEFLOW_COEFF) * stor;
-    else if (op == RVN_OP_BASE_POWER_LAW) c.R(0) = c.SOIL(m, RVN_S_BASEFLOW_COEFF) * pow(stor, c.SOIL(m, RVN_S_BASEFLOW_N));
-    else if (op == RVN_OP_BASE_LINEAR_ANALYTIC) c.R(0) = stor * (1 - exp(-c.SOIL(m, RVN_S_BASEFLOW_COEFF) * c.tstep)) / c.tstep;
-    else if (op == RVN_OP_BASE_VIC) c.R(0) = c.SOIL(m, RVN_S_MAX_BASEFLOW_RATE) * pow(stor / max_stor, c.SOIL(m, RVN_S_BASEFLOW_N));
+    else if (op == RVN_OP_BASE_POWER_LAW) c.R(0) = c.SOIL(m, RVN_S_BASEFLOW_COEFF) * rvn_pow(stor, c.SOIL(m, RVN_S_BASEFLOW_N));
+    else if (op == RVN_OP_BASE_LINEAR_ANALYTIC) c.R(0) = stor * (1 - rvn_exp(-c.SOIL(m, RVN_S_BASEFLOW_COEFF) * c.tstep)) / c.tstep;
+    else if (op == RVN_OP_BASE_VIC) c.R(0) = c.SOIL(m, RVN_S_MAX_BASEFLOW_RATE) * rvn_pow(stor / max_stor, c.SOIL(m, RVN_S_BASEFLOW_N));
     else if (op == RVN_OP_BASE_TOPMODEL) {
       const double K = c.SOIL(m, RVN_S_MAX_BASEFLOW_RATE), n = c.SOIL(m, RVN_S_BASEFLOW_N), lambda = c.TERR(RVN_T_TOPMODEL_LAMBDA);
-      c.R(0) = K * (max_stor / n * pow(lambda, -n)) * pow(stor / max_stor, n);
+      c.R(0) = K * (max_stor / n * rvn_pow(lambda, -n)) * rvn_pow(stor / max_stor, n);
     }
     else if (op == RVN_OP_BASE_LINEAR_CONSTRAIN) {   // src/Baseflow.cpp:188-197
       const double sat = stor / max_stor;
@@ -457,7 +459,7 @@ template <class C, class PR> RVN_DI void rates_BASEFLOW(C &c, const PR &pr, cons
       const double sat = stor / max_stor;
       c.R(0) = 0.0;
       if (sat > tsat) {
-        c.R(0) = K * pow((sat - tsat) / (1.0 - tsat), n);
+        c.R(0) = K * rvn_pow((sat - tsat) / (1.0 - tsat), n);
         c.R(0) = dmin(c.R(0), max_stor * (sat - tsat) / c.tstep);
       }
     }
@@ -468,7 +470,7 @@ template <class C, class PR> RVN_DI void rates_BASEFLOW(C &c, const PR &pr, cons
     }
     else if (op == RVN_OP_BASE_GR4J) {
       const double x3 = c.SOIL(m, RVN_S_GR4J_X3);
-      c.R(0) = stor * (1.0 - pow(1.0 + pow(dmax(stor / x3, 0.0), 4.0), -0.25)) / c.tstep;
+      c.R(0) = stor * (1.0 - rvn_pow(1.0 + rvn_pow(dmax(stor / x3, 0.0), 4.0), -0.25)) / c.tstep;
     }
   }
   c.R(0) = dmin(c.R(0), dmax(c.SV(pr.from(0)), 0.0) / c.tstep);
@@ -484,7 +486,7 @@ template <class C, class PR> RVN_DI void rates_PERCOLATION(C &c, const PR &pr, c
   if (max_stor > 0.0) {
     if (op == RVN_OP_PERC_LINEAR) c.R(0) = c.SOIL(m, RVN_S_PERC_COEFF) * stor;
     else if (op == RVN_OP_PERC_CONSTANT) c.R(0) = c.SOIL(m, RVN_S_MAX_PERC_RATE);
-    else if (op == RVN_OP_PERC_GR4J) c.R(0) = stor * (1.0 - pow(1.0 + pow(4.0 / 9.0 * dmax(stor / max_stor, 0.0), 4.0), -0.25)) / c.tstep;
+    else if (op == RVN_OP_PERC_GR4J) c.R(0) = stor * (1.0 - rvn_pow(1.0 + rvn_pow(4.0 / 9.0 * dmax(stor / max_stor, 0.0), 4.0), -0.25)) / c.tstep;
     else if (op == RVN_OP_PERC_GAWSER) {   // src/Percolation.cpp:204-213
       const double field_cap = c.SOIL(m, RVN_S_FIELD_CAPACITY) * max_stor, max_rate = c.SOIL(m, RVN_S_MAX_PERC_RATE);
       c.R(0) = max_rate * dmax(stor - field_cap, 0.0) / (max_stor - field_cap);
@@ -495,12 +497,12 @@ template <class C, class PR> RVN_DI void rates_PERCOLATION(C &c, const PR &pr, c
         c.R(0) = max_rate * dmax(stor - field_cap, 0.0) / (max_stor - field_cap);
         c.R(0) = dmin(c.R(0), (stor - field_cap) / c.tstep);
       }
-    } else if (op == RVN_OP_PERC_POWER_LAW) c.R(0) = c.SOIL(m, RVN_S_MAX_PERC_RATE) * pow(stor / max_stor, c.SOIL(m, RVN_S_PERC_N));
-    else if (op == RVN_OP_PERC_LINEAR_ANALYTIC) c.R(0) = stor * (1 - exp(-c.SOIL(m, RVN_S_PERC_COEFF) * c.tstep)) / c.tstep;
+    } else if (op == RVN_OP_PERC_POWER_LAW) c.R(0) = c.SOIL(m, RVN_S_MAX_PERC_RATE) * rvn_pow(stor / max_stor, c.SOIL(m, RVN_S_PERC_N));
+    else if (op == RVN_OP_PERC_LINEAR_ANALYTIC) c.R(0) = stor * (1 - rvn_exp(-c.SOIL(m, RVN_S_PERC_COEFF) * c.tstep)) / c.tstep;
     else if (op == RVN_OP_PERC_PRMS) {   // :253-267
       const double tens_stor = SoilTensionCapacity(c, m), max_rate = c.SOIL(m, RVN_S_MAX_PERC_RATE), n = c.SOIL(m, RVN_S_PERC_N);
       const double free_stor = dmax(0.0, stor - tens_stor), free_stor_max = (max_stor - tens_stor);
-      c.R(0) = max_rate * pow(free_stor / free_stor_max, n);
+      c.R(0) = max_rate * rvn_pow(free_stor / free_stor_max, n);
     } else if (op == RVN_OP_PERC_SACRAMENTO) {   // :269-294
       const int m2 = pr.ia(1);
       const double stor2 = c.SV(pr.to(0)), tens_stor = SoilTensionCapacity(c, m);
@@ -508,16 +510,16 @@ template <class C, class PR> RVN_DI void rates_PERCOLATION(C &c, const PR &pr, c
       const double max_stor2 = (m == 0) ? SoilCapacity(c, m2) : D_ALMOST_INF;
       const double free_stor = dmax(0.0, stor - tens_stor), free_stor_max = (max_stor - tens_stor);
       const double max_baseflow = c.SOIL(m, RVN_S_MAX_BASEFLOW_RATE);
-      const double lz_perc = 1.0 + alpha * pow((1 - (stor2 / max_stor2)), psi);
+      const double lz_perc = 1.0 + alpha * rvn_pow((1 - (stor2 / max_stor2)), psi);
       c.R(0) = lz_perc * max_baseflow * (free_stor / free_stor_max);
     } else if (op == RVN_OP_PERC_ASPEN) c.R(0) = c.SOIL(m, RVN_S_PERC_ASPEN);
     else if (op == RVN_OP_PERC_GR4JEXCH) {
       const double x2 = c.SOIL(m, RVN_S_GR4J_X2), x3 = c.SOIL(m, RVN_S_GR4J_X3);
-      c.R(0) = -x2 * pow(dmax(dmin(stor / x3, 1.0), 0.0), 3.5);
+      c.R(0) = -x2 * rvn_pow(dmax(dmin(stor / x3, 1.0), 0.0), 3.5);
     } else if (op == RVN_OP_PERC_GR4JEXCH2) {
       const double x2 = c.SOIL(1, RVN_S_GR4J_X2), x3 = c.SOIL(1, RVN_S_GR4J_X3);
       stor = c.SV(c.soil_slot(1));   // SOIL[1]
-      c.R(0) = -x2 * pow(dmax(dmin(stor / x3, 1.0), 0.0), 3.5);
+      c.R(0) = -x2 * rvn_pow(dmax(dmin(stor / x3, 1.0), 0.0), 3.5);
     }
   }
   c.R(0) = dmin(c.R(0), dmax(c.SV(pr.from(0)) - 0.0, 0.0) / c.tstep);
@@ -558,7 +560,7 @@ template <class C, class PR> RVN_DI void rates_SOILEVAP(C &c, const PR &pr, cons
     const double stor = dmax(c.SV(pr.from(0)), 0.0), tens_stor = SoilTensionCapacity(c, 0);
     c.R(0) = PET * dmin(stor / tens_stor, 1.0);
     const double maxPondedAreaFrac = c.LU(RVN_LU_MAX_DEP_AREA_FRAC), n = c.LU(RVN_LU_PONDED_EXP), dep_max = c.LU(RVN_LU_DEP_MAX);
-    const double area_ponded = maxPondedAreaFrac * pow(dmin(c.SV(c.iSV(RVN_SV_DEPRESSION)) / dep_max, 1.0), n);
+    const double area_ponded = maxPondedAreaFrac * rvn_pow(dmin(c.SV(c.iSV(RVN_SV_DEPRESSION)) / dep_max, 1.0), n);
     c.R(0) = (1.0 - area_ponded) * c.R(0);
     c.R(1) = (area_ponded)*c.F[RVN_F_OW_PET];
     PETused = (c.R(0) + c.R(1)); multi = true;
@@ -567,29 +569,29 @@ template <class C, class PR> RVN_DI void rates_SOILEVAP(C &c, const PR &pr, cons
   } else if (op == RVN_OP_SOILEVAP_PDM || op == RVN_OP_SOILEVAP_HYMOD2) {   // :424-458
     const double stor = c.SV(pr.from(0)), max_stor = SoilCapacity(c, 0), b = c.LU(RVN_LU_PDM_B);
     const double c_max = (b + 1) * max_stor;
-    const double c_star = c_max * (1.0 - pow(1.0 - (stor / max_stor), 1.0 / (b + 1.0)));
+    const double c_star = c_max * (1.0 - rvn_pow(1.0 - (stor / max_stor), 1.0 / (b + 1.0)));
     if (op == RVN_OP_SOILEVAP_PDM) c.R(0) = dmin(c_star, (c_star / c_max) * PET);
     else {
       const double gp = c.LU(RVN_LU_HYMOD2_G), Kmax = c.LU(RVN_LU_HYMOD2_KMAX), ce = c.LU(RVN_LU_HYMOD2_EXP);
-      const double K = Kmax * (gp + (1 - gp) * pow(c_star / c_max, ce));
+      const double K = Kmax * (gp + (1 - gp) * rvn_pow(c_star / c_max, ce));
       c.R(0) = K * dmin(c_star, PET);
     }
   } else if (op == RVN_OP_SOILEVAP_UBC) {   // :470-494 (Quick 1995, RFS emulation)
     const double P0AGEN = c.SOIL(0, RVN_S_UBC_INFIL_SOIL_DEF), P0EGEN = c.SOIL(0, RVN_S_UBC_EVAP_SOIL_DEF);
     const double soil_deficit = dmax(SoilCapacity(c, 0) - c.SV(pr.from(0)), 0.0);
     const double Fimp = c.LU(RVN_LU_IMPERMEABLE_FRAC);
-    const double AET = (PET)*pow(10.0, -soil_deficit / P0EGEN);
+    const double AET = (PET)*rvn_pow(10.0, -soil_deficit / P0EGEN);
     const double total_precip = c.SV(c.iSV(RVN_SV_PONDED_WATER));
     const double soil_deficit_est = dmax(soil_deficit - total_precip + AET * c.tstep, 0.0);
     double b1 = 0.0;
-    if (Fimp < 1.0) b1 = Fimp * pow(10.0, -soil_deficit_est / P0AGEN);
-    c.R(0) = (PET)*pow(10.0, -soil_deficit_est / P0EGEN) * (1.0 - b1);
+    if (Fimp < 1.0) b1 = Fimp * rvn_pow(10.0, -soil_deficit_est / P0AGEN);
+    c.R(0) = (PET)*rvn_pow(10.0, -soil_deficit_est / P0EGEN) * (1.0 - b1);
   } else if (op == RVN_OP_SOILEVAP_VIC) {   // :496-515 (Woods et al. 1992)
     const double stor = c.SV(pr.from(0)), stor_max = SoilCapacity(c, 0);
     const double alpha = c.SOIL(0, RVN_S_VIC_ALPHA), zmax = c.SOIL(0, RVN_S_VIC_ZMAX), zmin = c.SOIL(0, RVN_S_VIC_ZMIN), gamma2 = c.SOIL(0, RVN_S_VIC_EVAP_GAMMA);
     const double Smax = 1.0 / (alpha + 1.0) * (alpha * zmax + zmin);
     const double Sat = stor / stor_max;
-    c.R(0) = PET * (1.0 - pow(1.0 - Sat / Smax, gamma2));
+    c.R(0) = PET * (1.0 - rvn_pow(1.0 - Sat / Smax, gamma2));
   } else if (op == RVN_OP_SOILEVAP_SEQUEN) {   // :553-568
     const double stor_u = dmax(c.SV(pr.from(0)), 0.0), stor_l = dmax(c.SV(pr.from(1)), 0.0);
     const double tens_stor_u = SoilTensionCapacity(c, 0), tens_stor_l = SoilTensionCapacity(c, 1);

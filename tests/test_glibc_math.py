@@ -1,0 +1,106 @@
+"""The device exp / log / pow (csrc/rvn_glibc_math.h) must return what the host libm of the reference build returns, bit for bit:
+the reference's results depend on the last bit of pow() where a store melts out (src/SnowBalance.cpp:507), so "within an ulp" is
+not enough for the 1e-9 contract.  CPU: the restatement compiled for the host (-ffp-contract=off) against the running libm on
+>= 1e8 arguments per function (random bit patterns, hydrological ranges, special-case boundaries).  GPU: the device functions
+through the C ABI against the same libm."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from ravenhydroframework_b200 import api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NAMES = ["exp", "log", "pow"]
+_lib = None
+
+
+def check_lib():
+    global _lib
+    if _lib is None:
+        out = os.path.join(ROOT, "tests", "libglibc_math_check.so")
+        src = os.path.join(ROOT, "tests", "glibc_math_check.c")
+        inc = os.path.join(ROOT, "ravenhydroframework_b200", "csrc")
+        deps = [src, os.path.join(inc, "rvn_glibc_math.h"), os.path.join(inc, "rvn_glibc_tables.h")]
+        if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+            subprocess.check_call(["gcc", "-std=gnu99", "-O2", "-mfma", "-ffp-contract=off", "-fno-builtin", "-fPIC", "-shared",
+                                   "-I" + inc, src, "-o", out, "-lm"])
+        lib = C.CDLL(out)
+        lib.rg_check.restype = C.c_long
+        lib.rg_check.argtypes = [C.c_int, C.c_int, C.c_long, C.c_uint64, C.c_void_p, C.c_int]
+        lib.rg_libm_eval.argtypes = [C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.rg_restated_eval.argtypes = [C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def test_tables_match_the_running_libm():
+    """the committed tables are the ones of this box's libm.so.6 (regenerate with tools/extract_glibc_tables.py otherwise)"""
+    hdr = os.path.join(ROOT, "ravenhydroframework_b200", "csrc", "rvn_glibc_tables.h")
+    before = open(hdr).read()
+    libm = "/lib/x86_64-linux-gnu/libm.so.6"
+    if not os.path.exists(libm):
+        pytest.skip("no x86-64 glibc libm at the usual place")
+    subprocess.check_call(["python", os.path.join(ROOT, "tools", "extract_glibc_tables.py"), libm], stdout=subprocess.DEVNULL)
+    after = open(hdr).read()
+    if after != before:
+        open(hdr, "w").write(before)
+    assert after == before
+
+
+@pytest.mark.parametrize("fn", [0, 1, 2])
+@pytest.mark.parametrize("dist", [0, 1, 2])
+def test_restatement_equals_host_libm(fn, dist):
+    lib = check_lib()
+    bad = np.zeros(2 * 8)
+    n = 40_000_000   # x 3 distributions x several seeds below = 1.2e8 arguments per function
+    nbad = lib.rg_check(fn, dist, n, 1000 + 17 * dist + fn, bad.ctypes.data, 8)
+    assert nbad == 0, "%s: %d of %d arguments differ from libm, first: %s" % (
+        NAMES[fn], nbad, n, [(float(a).hex(), float(b).hex()) for a, b in bad.reshape(-1, 2)[:min(nbad, 8)]])
+
+
+def _arguments(fn, n, seed):
+    rng = np.random.default_rng(seed)
+    third = n // 3
+    raw = rng.integers(0, 2 ** 64, size=third, dtype=np.uint64).view(np.float64)
+    if fn == 0:
+        x = np.concatenate([raw, (rng.random(third) - 0.5) * 60.0, (rng.random(n - 2 * third) - 0.5) * 1500.0])
+        y = np.zeros(n)
+    elif fn == 1:
+        x = np.concatenate([raw, np.exp((rng.random(third) - 0.5) * 80.0), 1.0 + (rng.random(n - 2 * third) - 0.5) * 0.25])
+        y = np.zeros(n)
+    else:
+        x = np.concatenate([raw, rng.random(third) * 4.0, np.exp((rng.random(n - 2 * third) - 0.5) * 40.0)])
+        y = np.concatenate([rng.integers(0, 2 ** 64, size=third, dtype=np.uint64).view(np.float64), rng.random(third) * 8.0 - 2.0,
+                            (rng.random(n - 2 * third) - 0.5) * 60.0])
+    edge = np.array([0.0, -0.0, 1.0, -1.0, 2.0, 0.5, 3.0, -3.0, 1e-320, 2.2250738585072014e-308, 5e-324, 1e308, np.inf, -np.inf, np.nan,
+                     709.78, 709.79, -745.1, -745.2, -708.4, 1024.0, -1075.0, 2.0 ** -54, 2.0 ** -65, 2.0 ** 63, 0.9375, 1.064697265625])
+    k = min(n, 4096)
+    x[:k] = edge[rng.integers(0, len(edge), k)]
+    y[:k] = edge[rng.integers(0, len(edge), k)]
+    return np.ascontiguousarray(x), np.ascontiguousarray(y)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fn", [0, 1, 2])
+def test_device_functions_equal_host_libm(fn):
+    lib = check_lib()
+    eng = api.engine_lib()
+    n = 36_000_000
+    total_bad = 0
+    for seed in (1, 2, 3):   # 1.08e8 arguments per function
+        x, y = _arguments(fn, n, 100 * fn + seed)
+        want = np.empty(n)
+        got = np.empty(n)
+        lib.rg_libm_eval(fn, n, x.ctypes.data, y.ctypes.data, want.ctypes.data)
+        rc = eng.rvn_gpu_math_eval(0, fn, n, x.ctypes.data, y.ctypes.data, got.ctypes.data)
+        assert rc == 0, eng.rvn_gpu_last_error()
+        same = (got.view(np.uint64) == want.view(np.uint64)) | (np.isnan(got) & np.isnan(want))
+        nb = int((~same).sum())
+        if nb:
+            i = np.flatnonzero(~same)[:5]
+            print(NAMES[fn], "mismatch", [(float(x[j]).hex(), float(y[j]).hex(), float(got[j]).hex(), float(want[j]).hex()) for j in i])
+        total_bad += nb
+    assert total_bad == 0

@@ -43,7 +43,6 @@ def test_hmets_tree_ragged_block(tmp_path):
     assert H.rel_err(sim.cumulative()[0], ref["cumul"]) < TOL
     # mass balance closure (MB Error column of WatershedStorage.csv): (S - S0) + (out - in) ~ 0
     w = sim.watershed(0, 400)[:, 0, :]
-    s0 = float((model.initial_state()[:, [5, 6]].sum(axis=1) * 1.0).mean()) if False else None
     assert np.all(np.isfinite(w))
 
 
@@ -217,7 +216,7 @@ def test_gr4j_tree(tmp_path):
 
 
 @pytest.mark.parametrize("kind", ["hmets", "hbv", "gr4j", "blended"])
-def test_specialised_kernel_equals_interpreter(tmp_path, kind, monkeypatch):
+def test_specialised_kernel_equals_interpreter(tmp_path, kind):
     """The compile-time specialisation and the interpreter run the same process functions: results must be bit-identical."""
     base = WRITERS[kind](str(tmp_path), n_sb=5, hru_per_sb=31, n_days=150, seed=17)
     model = api.RavenModel(base)
@@ -226,8 +225,7 @@ def test_specialised_kernel_equals_interpreter(tmp_path, kind, monkeypatch):
     assert a.kernel_variant().startswith("static:")
     a.set_recording(150)
     a.run(150)
-    monkeypatch.setenv("RVN_FORCE_INTERPRETER", "1")
-    b = api.GpuSimulation(model, n_members=2)
+    b = api.GpuSimulation(model, n_members=2, force_interpreter=True)
     assert b.kernel_variant() == "interpreter"
     b.set_recording(150)
     b.run(150)
