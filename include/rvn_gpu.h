@@ -426,6 +426,9 @@ typedef struct rvn_gpu_model rvn_gpu_model; /* opaque */
 /* ---- entry points ------------------------------------------------------------------------------- */
 const char *rvn_gpu_last_error(void);
 int rvn_gpu_abi_version(void);
+/* sha256 of the sources + compiler flags this library was built from (ravenhydroframework_b200/build.py stamps it and rebuilds
+ * on mismatch), "unstamped" for a hand build */
+const char *rvn_gpu_build_digest(void);
 int rvn_gpu_device_count(void);
 
 /* build device-resident model; `device` = CUDA ordinal */

@@ -5,7 +5,7 @@
  * against it on seeded inputs of any size.  Nothing under ravenhydroframework_b200/ may link or call
  * this file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg do.
  *
- * Parity pin: tests/test_oracle_vs_reference.py checks this oracle against in-memory FP64 dumps of the
+ * Parity pin: tests/test_oracle_golden.py and tests/test_reference_inputs.py check this oracle against in-memory FP64 dumps of the
  * unmodified reference (oracle/_ref/ref_dump, built from /root/reference by oracle/build_ref.sh) and
  * against the committed fixtures under tests/golden/ that the same driver generated.
  *
@@ -1471,3 +1471,163 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
   free(F); free(daily); free(phinew); free(phiread); free(aRouted); free(aQinnew);
   return 0;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * EnKF analysis support: x = pinv(P) b for nrhs right-hand sides with singular values below tol * max dropped -- restates the
+ * reference's SVD() (src/Matrix.cpp:144-390, Numerical Recipes' svdcmp + svbksb: Householder bidiagonalisation, accumulation of
+ * the right- and left-hand transformations, implicit-shift QR with at most 30 sweeps per singular value; the reference's
+ * cancellation loop starts at l-1, kept).  P [n][n] row-major; B, X [n][nrhs].  Returns 0, or 1 if the QR iteration did not
+ * converge.  Used by oracle/enkf_oracle.py; pinned on the reference's own analysis by tests/golden/enkf_*.
+ * --------------------------------------------------------------------------------------------------------------------- */
+static double o_sign(double a, double b) { return b >= 0.0 ? (a >= 0.0 ? a : -a) : (a >= 0.0 ? -a : a); }
+static double o_pythag(double a, double b) {
+  double absa = fabs(a), absb = fabs(b);
+  if (absa > absb) return absa * sqrt(1.0 + (absb / absa) * (absb / absa));
+  return (absb == 0.0 ? 0.0 : absb * sqrt(1.0 + (absa / absb) * (absa / absb)));
+}
+#define OA(i, j) A[(size_t)(i) * n + (j)]
+#define OV(i, j) v[(size_t)(i) * n + (j)]
+int rvo_svd_solve(const double *P, int n, double tol, const double *B, int nrhs, double *X) {
+  double *A = (double *)malloc(sizeof(double) * (size_t)n * n), *v = (double *)calloc((size_t)n * n, sizeof(double));
+  double *w = (double *)calloc((size_t)n, sizeof(double)), *rv1 = (double *)calloc((size_t)n, sizeof(double));
+  int i, its, j, jj, k, l = 0, nm = 0, rc = 0;
+  double anorm = 0.0, c, f, g = 0.0, h, s, scale = 0.0, x, y, z;
+  memcpy(A, P, sizeof(double) * (size_t)n * n);
+  for (i = 0; i < n; i++) {
+    l = i + 2;
+    rv1[i] = scale * g;
+    g = s = scale = 0.0;
+    for (k = i; k < n; k++) scale += fabs(OA(k, i));
+    if (scale != 0.0) {
+      for (k = i; k < n; k++) { OA(k, i) /= scale; s += OA(k, i) * OA(k, i); }
+      f = OA(i, i);
+      g = -o_sign(sqrt(s), f);
+      h = f * g - s;
+      OA(i, i) = f - g;
+      for (j = l - 1; j < n; j++) {
+        for (s = 0.0, k = i; k < n; k++) s += OA(k, i) * OA(k, j);
+        f = s / h;
+        for (k = i; k < n; k++) OA(k, j) += f * OA(k, i);
+      }
+      for (k = i; k < n; k++) OA(k, i) *= scale;
+    }
+    w[i] = scale * g;
+    g = s = scale = 0.0;
+    for (k = l - 1; k < n; k++) scale += fabs(OA(i, k));
+    if (scale != 0.0) {
+      for (k = l - 1; k < n; k++) { OA(i, k) /= scale; s += OA(i, k) * OA(i, k); }
+      f = OA(i, l - 1);
+      g = -o_sign(sqrt(s), f);
+      h = f * g - s;
+      OA(i, l - 1) = f - g;
+      for (k = l - 1; k < n; k++) rv1[k] = OA(i, k) / h;
+      for (j = l - 1; j < n; j++) {
+        for (s = 0.0, k = l - 1; k < n; k++) s += OA(j, k) * OA(i, k);
+        for (k = l - 1; k < n; k++) OA(j, k) += s * rv1[k];
+      }
+      for (k = l - 1; k < n; k++) OA(i, k) *= scale;
+    }
+    if (fabs(w[i]) + fabs(rv1[i]) > anorm) anorm = fabs(w[i]) + fabs(rv1[i]);
+  }
+  for (i = n - 1; i >= 0; i--) {
+    if (i < n - 1) {
+      if (g != 0.0) {
+        for (j = l; j < n; j++) OV(j, i) = (OA(i, j) / OA(i, l)) / g;
+        for (j = l; j < n; j++) {
+          for (s = 0.0, k = l; k < n; k++) s += OA(i, k) * OV(k, j);
+          for (k = l; k < n; k++) OV(k, j) += s * OV(k, i);
+        }
+      }
+      for (j = l; j < n; j++) OV(i, j) = OV(j, i) = 0.0;
+    }
+    OV(i, i) = 1.0;
+    g = rv1[i];
+    l = i;
+  }
+  for (i = n - 1; i >= 0; i--) {
+    l = i + 1;
+    g = w[i];
+    for (j = l; j < n; j++) OA(i, j) = 0.0;
+    if (g != 0.0) {
+      g = 1.0 / g;
+      for (j = l; j < n; j++) {
+        for (s = 0.0, k = l; k < n; k++) s += OA(k, i) * OA(k, j);
+        f = (s / OA(i, i)) * g;
+        for (k = i; k < n; k++) OA(k, j) += f * OA(k, i);
+      }
+      for (j = i; j < n; j++) OA(j, i) *= g;
+    } else for (j = i; j < n; j++) OA(j, i) = 0.0;
+    OA(i, i) += 1.0;
+  }
+  for (k = n - 1; k >= 0 && !rc; k--) {
+    for (its = 0; its < 30; its++) {
+      int flag = 1;
+      for (l = k; l >= 0; l--) {
+        nm = l - 1;
+        if (fabs(rv1[l]) + anorm == anorm) { flag = 0; break; }
+        if (fabs(w[nm]) + anorm == anorm) break;
+      }
+      if (flag) {
+        c = 0.0; s = 1.0;
+        for (i = l - 1; i < k + 1; i++) {
+          f = s * rv1[i];
+          rv1[i] *= c;
+          if (fabs(f) + anorm == anorm) break;
+          g = w[i];
+          h = o_pythag(f, g);
+          w[i] = h;
+          h = 1.0 / h;
+          c = g * h;
+          s = -f * h;
+          for (j = 0; j < n; j++) { y = OA(j, nm); z = OA(j, i); OA(j, nm) = y * c + z * s; OA(j, i) = z * c - y * s; }
+        }
+      }
+      z = w[k];
+      if (l == k) {
+        if (z < 0.0) { w[k] = -z; for (j = 0; j < n; j++) OV(j, k) = -OV(j, k); }
+        break;
+      }
+      if (its == 29) { rc = 1; break; }
+      x = w[l]; nm = k - 1; y = w[nm]; g = rv1[nm]; h = rv1[k];
+      f = ((y - z) * (y + z) + (g - h) * (g + h)) / (2.0 * h * y);
+      g = o_pythag(f, 1.0);
+      f = ((x - z) * (x + z) + h * ((y / (f + o_sign(g, f))) - h)) / x;
+      c = s = 1.0;
+      for (j = l; j <= nm; j++) {
+        i = j + 1;
+        g = rv1[i]; y = w[i]; h = s * g; g = c * g;
+        z = o_pythag(f, h);
+        rv1[j] = z;
+        c = f / z; s = h / z;
+        f = x * c + g * s; g = g * c - x * s; h = y * s; y *= c;
+        for (jj = 0; jj < n; jj++) { x = OV(jj, j); z = OV(jj, i); OV(jj, j) = x * c + z * s; OV(jj, i) = z * c - x * s; }
+        z = o_pythag(f, h);
+        w[j] = z;
+        if (z != 0.0) { z = 1.0 / z; c = f * z; s = h * z; }
+        f = c * g + s * y; x = c * y - s * g;
+        for (jj = 0; jj < n; jj++) { y = OA(jj, j); z = OA(jj, i); OA(jj, j) = y * c + z * s; OA(jj, i) = z * c - y * s; }
+      }
+      rv1[l] = 0.0; rv1[k] = f; w[k] = x;
+    }
+  }
+  if (!rc) {
+    double maxw = -O_ALMOST_INF;
+    for (j = 0; j < n; j++) if (w[j] > maxw) maxw = w[j];
+    for (j = 0; j < n; j++) if (fabs(w[j] / maxw) < tol) w[j] = 0.0;
+    for (int r = 0; r < nrhs; r++) {
+      for (j = 0; j < n; j++) {
+        s = 0.0;
+        if (w[j] != 0.0) { for (i = 0; i < n; i++) s += OA(i, j) * B[(size_t)i * nrhs + r]; s /= w[j]; }
+        rv1[j] = s;
+      }
+      for (j = 0; j < n; j++) {
+        for (s = 0.0, jj = 0; jj < n; jj++) s += OV(j, jj) * rv1[jj];
+        X[(size_t)j * nrhs + r] = s;
+      }
+    }
+  }
+  free(A); free(v); free(w); free(rv1);
+  return rc;
+}
+#undef OA
+#undef OV

@@ -100,6 +100,7 @@ def host_lib():
         lib.rvh_desc_info.argtypes = [vp, C.POINTER(C.c_int)]
         lib.rvh_ensemble_begin.argtypes = [vp]
         lib.rvh_ensemble_update_model.argtypes = [vp, C.c_int, vp, C.c_int]
+        lib.rvh_ensemble_update_model_ex.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int]
         lib.rvh_enkf_begin.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int)]
         lib.rvh_enkf_rows.argtypes = [vp, vp]
         lib.rvh_enkf_row_name.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
@@ -214,11 +215,12 @@ class RavenModel:
             raise RavenError(self.lib.rvh_last_error().decode())
         return n
 
-    def ensemble_update_model(self, e):
-        """CEnsemble::UpdateModel(pModel, Options, e): draws member e's parameters from the shared rand() stream and applies
-        them with CModel::UpdateParameter. Members must be visited in order. Returns the sampled values."""
+    def ensemble_update_model(self, e, reparse_ic=True):
+        """CEnsemble::UpdateModel(pModel, Options, e): draws member e's parameters from the shared rand() stream, applies them with
+        CModel::UpdateParameter and (Monte Carlo / DDS, reparse_ic) re-reads the initial conditions under them, as the reference
+        does. Members must be visited in order. Returns the sampled values."""
         vals = np.zeros(256)
-        n = self.lib.rvh_ensemble_update_model(self.h, int(e), vals.ctypes.data, 256)
+        n = self.lib.rvh_ensemble_update_model_ex(self.h, int(e), vals.ctypes.data, 256, 1 if reparse_ic else 0)
         if n < 0:
             raise RavenError(self.lib.rvh_last_error().decode())
         return vals[:n].copy()
@@ -314,8 +316,10 @@ class GpuSimulation:
             raise RavenError("rvn_gpu_create: %s" % self.lib.rvn_gpu_last_error().decode())
         self.h = h
         self.step = 0
+        self._st0 = None
         if upload_initial:
             st = model.initial_state()
+            self._st0 = st
             qin, qlat, qout, scal = model.basin_state()
             for e in range(n_members):
                 self.upload_state(st, e, 1)
@@ -374,9 +378,14 @@ class GpuSimulation:
         m.ensemble_begin()
         samples = []
         for e in range(member0 + self.E):
-            v = m.ensemble_update_model(e)
+            v = m.ensemble_update_model(e, reparse_ic=(e >= member0))
             if e >= member0:
                 self.upload_member_params(e - member0)
+                # the member's initial state is the .rvc re-read under its parameters (clipped to sampled capacities); uploaded only
+                # where it differs from what the handle already holds
+                st = m.initial_state()
+                if self._st0 is None or not np.array_equal(st, self._st0):
+                    self.upload_state(st, e - member0, 1)
                 samples.append(v)
         return np.array(samples)
 

@@ -50,18 +50,20 @@ def run_dds(model, device=0):
     model.flatten(1)
     n_trials = model.ensemble_begin()
     sim = api.GpuSimulation(model, n_members=1, device=device)
-    st0 = model.initial_state()
-    basin0 = model.basin_state()
-    q0 = initial_outflows(model)
     n = model.nSteps
     trials, improvements, nP = [], [], 0
     for e in range(n_trials):
-        vals = model.ensemble_update_model(e)          # CDDSEnsemble::UpdateModel: perturb + CModel::UpdateParameter
+        vals = model.ensemble_update_model(e)          # CDDSEnsemble::UpdateModel: perturb + CModel::UpdateParameter + ParseInitialConditions
         nP = len(vals)
         sim.upload_member_params(0)
-        sim.upload_state(st0, 0, 1)                    # every trial restarts from the .rvc state
+        # every trial restarts from the .rvc state as re-read under the trial's parameters (the reference re-runs
+        # ParseInitialConditions after UpdateParameter, src/DDS.cpp, so stores are clipped to the trial's capacities)
+        st0 = model.initial_state()
+        basin0 = model.basin_state()
+        q0 = initial_outflows(model)
+        sim.upload_state(st0, 0, 1)
         sim._ck(sim.lib.rvn_gpu_upload_basin_state(sim.h, basin0[0].ctypes.data, basin0[1].ctypes.data, basin0[2].ctypes.data, basin0[3].ctypes.data, 0, 1))
-        sim.set_recording(n, hydrographs=True, watershed=False)
+        sim.set_recording(n, hydrographs=True, watershed=False)   # buffers are allocated once and reused (rvn_gpu_set_recording)
         sim.step = 0
         sim.run(n)
         F, Fbest = finish_trial(model, e, sim.hydrographs(0, n)[:, 0, :], q0)

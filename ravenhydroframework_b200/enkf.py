@@ -51,6 +51,9 @@ class EnKFSimulation:
         from . import api
         self.model = model
         self.N = model.num_members
+        if world > self.N:
+            raise ValueError("EnKFSimulation: %d ranks for %d ensemble members - every rank needs at least one member "
+                             "(launch with --nproc-per-node <= %d)" % (world, self.N, self.N))
         self.member0, self.n_local = shard_members(self.N, rank, world)
         model.flatten(self.n_local)
         self.info = model.enkf_begin(self.member0, self.n_local)

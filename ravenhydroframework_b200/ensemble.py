@@ -37,16 +37,20 @@ def ensemble_statistics(values, group=None):
     v = values.to(torch.float64)
     n = torch.tensor([float(v.shape[0])], dtype=torch.float64, device=v.device)
     s = v.sum(dim=0)
-    ss = (v * v).sum(dim=0)
     mn = v.min(dim=0).values if v.shape[0] > 0 else torch.full_like(s, float("inf"))
     mx = v.max(dim=0).values if v.shape[0] > 0 else torch.full_like(s, float("-inf"))
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        packed = torch.cat([s.reshape(-1), ss.reshape(-1), n])
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    if multi:
+        packed = torch.cat([s.reshape(-1), n])
         dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
         k = s.numel()
-        s, ss, n = packed[:k].reshape(s.shape), packed[k:2 * k].reshape(s.shape), packed[2 * k:]
+        s, n = packed[:k].reshape(s.shape), packed[k:]
         dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
     mean = s / n
-    var = torch.clamp(ss / n - mean * mean, min=0.0)
+    d = v - mean
+    m2 = (d * d).sum(dim=0)
+    if multi:
+        dist.all_reduce(m2, op=dist.ReduceOp.SUM, group=group)
+    var = m2 / n
     return dict(mean=mean, std=torch.sqrt(var), min=mn, max=mx, n=int(n.item()))

@@ -18,6 +18,10 @@ static std::string g_err;
 
 extern "C" {
 const char *rvh_last_error() { return g_err.c_str(); }
+#ifndef RVH_BUILD_DIGEST
+#define RVH_BUILD_DIGEST "unstamped"
+#endif
+const char *rvh_build_digest() { return RVH_BUILD_DIGEST; }   // sha256 of sources + flags, stamped by build.py
 
 // base: path prefix of the input set ("dir/name" -> dir/name.rvi, .rvh, .rvp, .rvt, .rvc, .rve), like `Raven.exe base`
 // duration_override > 0 shortens the run (the BMI config 'duration:' does the same, src/Raven_BMI.cpp:341-345)
@@ -51,10 +55,17 @@ int rvh_ensemble_begin(rvh_model *h) {
   return h->pEnsemble->GetNumMembers();
   RVH_CATCH(-1)
 }
-int rvh_ensemble_update_model(rvh_model *h, int e, double *values, int nmax) {
+// reparse_ic != 0: re-read the .rvc under the member's parameters, as CMonteCarloEnsemble / CDDSEnsemble::UpdateModel do after
+// UpdateParameter (src/ModelEnsemble.cpp:259, src/DDS.cpp:197: stores above a sampled capacity are clipped); callers that only
+// replay the rand() stream of members they do not own pass 0.
+int rvh_ensemble_update_model_ex(rvh_model *h, int e, double *values, int nmax, int reparse_ic);
+int rvh_ensemble_update_model(rvh_model *h, int e, double *values, int nmax) { return rvh_ensemble_update_model_ex(h, e, values, nmax, 1); }
+int rvh_ensemble_update_model_ex(rvh_model *h, int e, double *values, int nmax, int reparse_ic) {
   RVH_TRY
   if (!h->pEnsemble) throw RavenError("rvh_ensemble_update_model: call rvh_ensemble_begin first");
   h->pEnsemble->UpdateModel(h->pModel, h->Options, e);
+  if (reparse_ic && (dynamic_cast<const CMonteCarloEnsemble *>(h->pEnsemble) || dynamic_cast<const CDDSEnsemble *>(h->pEnsemble)))
+    ParseInitialConditions(h->pModel, h->Options);
   const CMonteCarloEnsemble *mc = dynamic_cast<const CMonteCarloEnsemble *>(h->pEnsemble);
   const CDDSEnsemble *dds = dynamic_cast<const CDDSEnsemble *>(h->pEnsemble);
   int n = 0;

@@ -322,51 +322,225 @@ void CEnKFEnsemble::HarvestOutputs(const double *qout_rec, const double *qout_in
     }
   }
 }
-// cyclic Jacobi eigen-decomposition of a symmetric matrix (A is destroyed; V's columns are the eigenvectors)
-static void JacobiEigen(std::vector<double> &A, int n, std::vector<double> &w, std::vector<double> &V) {
-  V.assign((size_t)n * n, 0.0);
-  for (int i = 0; i < n; i++) V[(size_t)i * n + i] = 1.0;
-  for (int sweep = 0; sweep < 100; sweep++) {
-    double off = 0.0, diag = 0.0;
-    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) { if (i != j) off += A[(size_t)i * n + j] * A[(size_t)i * n + j]; else diag += A[(size_t)i * n + i] * A[(size_t)i * n + i]; }
-    if (off <= 1e-60 * (diag > 0 ? diag : 1.0) || off == 0.0) break;
-    for (int p = 0; p < n - 1; p++)
-      for (int q = p + 1; q < n; q++) {
-        const double apq = A[(size_t)p * n + q];
-        if (apq == 0.0) continue;
-        const double theta = (A[(size_t)q * n + q] - A[(size_t)p * n + p]) / (2.0 * apq);
-        const double t = ((theta >= 0) ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-        const double c = 1.0 / sqrt(t * t + 1.0), s_ = t * c;
-        for (int k = 0; k < n; k++) {   // columns p,q
-          const double akp = A[(size_t)k * n + p], akq = A[(size_t)k * n + q];
-          A[(size_t)k * n + p] = c * akp - s_ * akq; A[(size_t)k * n + q] = s_ * akp + c * akq;
+// ---------------------------------------------------------------------------------------------------------------------
+// Truncated least-squares solve of P x = b for many right-hand sides, the way the reference does it (SVD(), src/Matrix.cpp:144-390:
+// the Golub-Reinsch singular value decomposition as published in Numerical Recipes' svdcmp/svbksb, singular values below
+// tol * max set to zero).  P of the EnKF analysis is a sample covariance of strongly correlated flows with condition numbers up to
+// the 1e8 cut-off, where two different (individually backward-stable) factorisations agree to ~1e-8 only; the 1e-9 contract of
+// the analysis therefore needs the reference's own sequence of Householder reflections and implicit-shift QR sweeps, which this
+// restates operation by operation (0-based, flat row-major storage; the reference decomposes P once per member with identical
+// results - here once per analysis).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+inline double copysign_nr(double a, double b) { return b >= 0.0 ? (a >= 0.0 ? a : -a) : (a >= 0.0 ? -a : a); }   // SIGN(a,b)
+inline double hypot_nr(double a, double b) {                                                                     // pythag(a,b)
+  const double absa = fabs(a), absb = fabs(b);
+  if (absa > absb) return absa * sqrt(1.0 + (absb / absa) * (absb / absa));
+  return (absb == 0.0) ? 0.0 : absb * sqrt(1.0 + (absa / absb) * (absa / absb));
+}
+struct GolubReinsch {
+  int n;
+  std::vector<double> u, v, w;   // P = u diag(w) v'
+  double &U(int i, int j) { return u[(size_t)i * n + j]; }
+  double &V(int i, int j) { return v[(size_t)i * n + j]; }
+
+  void Decompose(const std::vector<double> &P, int n_) {
+    n = n_;
+    u = P; v.assign((size_t)n * n, 0.0); w.assign(n, 0.0);
+    std::vector<double> e(n, 0.0);   // super-diagonal of the bidiagonal form (the reference's tmp[] / rv1)
+    double g = 0.0, scale = 0.0, anorm = 0.0;
+    int l = 0;
+    // ---- Householder reduction to bidiagonal form
+    for (int i = 0; i < n; i++) {
+      l = i + 2;
+      e[i] = scale * g;
+      g = 0.0; scale = 0.0;
+      double s_ = 0.0;
+      for (int k = i; k < n; k++) scale += fabs(U(k, i));
+      if (scale != 0.0) {
+        for (int k = i; k < n; k++) { U(k, i) /= scale; s_ += U(k, i) * U(k, i); }
+        double f = U(i, i);
+        g = -copysign_nr(sqrt(s_), f);
+        const double h = f * g - s_;
+        U(i, i) = f - g;
+        for (int j = l - 1; j < n; j++) {
+          s_ = 0.0;
+          for (int k = i; k < n; k++) s_ += U(k, i) * U(k, j);
+          f = s_ / h;
+          for (int k = i; k < n; k++) U(k, j) += f * U(k, i);
         }
-        for (int k = 0; k < n; k++) {   // rows p,q
-          const double apk = A[(size_t)p * n + k], aqk = A[(size_t)q * n + k];
-          A[(size_t)p * n + k] = c * apk - s_ * aqk; A[(size_t)q * n + k] = s_ * apk + c * aqk;
-        }
-        for (int k = 0; k < n; k++) {
-          const double vkp = V[(size_t)k * n + p], vkq = V[(size_t)k * n + q];
-          V[(size_t)k * n + p] = c * vkp - s_ * vkq; V[(size_t)k * n + q] = s_ * vkp + c * vkq;
+        for (int k = i; k < n; k++) U(k, i) *= scale;
+      }
+      w[i] = scale * g;
+      g = 0.0; scale = 0.0; s_ = 0.0;
+      {   // row transformation (the reference's guard `i+1<=m && i!=n` always holds for a square matrix)
+        for (int k = l - 1; k < n; k++) scale += fabs(U(i, k));
+        if (scale != 0.0) {
+          for (int k = l - 1; k < n; k++) { U(i, k) /= scale; s_ += U(i, k) * U(i, k); }
+          const double f = U(i, l - 1);
+          g = -copysign_nr(sqrt(s_), f);
+          const double h = f * g - s_;
+          U(i, l - 1) = f - g;
+          for (int k = l - 1; k < n; k++) e[k] = U(i, k) / h;
+          for (int j = l - 1; j < n; j++) {
+            s_ = 0.0;
+            for (int k = l - 1; k < n; k++) s_ += U(j, k) * U(i, k);
+            for (int k = l - 1; k < n; k++) U(j, k) += s_ * e[k];
+          }
+          for (int k = l - 1; k < n; k++) U(i, k) *= scale;
         }
       }
+      const double an = fabs(w[i]) + fabs(e[i]);
+      if (an > anorm) anorm = an;
+    }
+    // ---- accumulation of the right-hand transformations
+    for (int i = n - 1; i >= 0; i--) {
+      if (i < n - 1) {
+        if (g != 0.0) {
+          for (int j = l; j < n; j++) V(j, i) = (U(i, j) / U(i, l)) / g;   // double division avoids underflow
+          for (int j = l; j < n; j++) {
+            double s_ = 0.0;
+            for (int k = l; k < n; k++) s_ += U(i, k) * V(k, j);
+            for (int k = l; k < n; k++) V(k, j) += s_ * V(k, i);
+          }
+        }
+        for (int j = l; j < n; j++) V(i, j) = V(j, i) = 0.0;
+      }
+      V(i, i) = 1.0;
+      g = e[i];
+      l = i;
+    }
+    // ---- accumulation of the left-hand transformations
+    for (int i = n - 1; i >= 0; i--) {
+      l = i + 1;
+      g = w[i];
+      for (int j = l; j < n; j++) U(i, j) = 0.0;
+      if (g != 0.0) {
+        g = 1.0 / g;
+        for (int j = l; j < n; j++) {
+          double s_ = 0.0;
+          for (int k = l; k < n; k++) s_ += U(k, i) * U(k, j);
+          const double f = (s_ / U(i, i)) * g;
+          for (int k = i; k < n; k++) U(k, j) += f * U(k, i);
+        }
+        for (int j = i; j < n; j++) U(j, i) *= g;
+      } else {
+        for (int j = i; j < n; j++) U(j, i) = 0.0;
+      }
+      ++U(i, i);
+    }
+    // ---- diagonalisation of the bidiagonal form: implicit-shift QR, at most 30 sweeps per singular value
+    for (int k = n - 1; k >= 0; k--) {
+      for (int its = 0; its < 30; its++) {
+        bool cancel = true;
+        int nm = 0;
+        for (l = k; l >= 0; l--) {   // test for splitting (e[0] is always zero)
+          nm = l - 1;
+          if (fabs(e[l]) + anorm == anorm) { cancel = false; break; }
+          if (fabs(w[nm]) + anorm == anorm) break;
+        }
+        if (cancel) {   // cancellation of e[l], l > 0
+          double c = 0.0, s_ = 1.0;
+          for (int i = l - 1; i < k + 1; i++) {   // (the reference starts this loop one row early, at i = l-1; kept)
+            const double f = s_ * e[i];
+            e[i] *= c;
+            if (fabs(f) + anorm == anorm) break;
+            g = w[i];
+            double h = hypot_nr(f, g);
+            w[i] = h;
+            h = 1.0 / h;
+            c = g * h;
+            s_ = -f * h;
+            for (int j = 0; j < n; j++) {
+              const double y = U(j, nm), z = U(j, i);
+              U(j, nm) = y * c + z * s_;
+              U(j, i) = z * c - y * s_;
+            }
+          }
+        }
+        double z = w[k];
+        if (l == k) {   // converged: make the singular value non-negative
+          if (z < 0.0) { w[k] = -z; for (int j = 0; j < n; j++) V(j, k) = -V(j, k); }
+          break;
+        }
+        ExitGracefullyIf(its == 29, "Singular Value Decomposition did not converge");
+        double x = w[l];   // shift from the bottom 2x2 minor
+        nm = k - 1;
+        double y = w[nm];
+        g = e[nm];
+        double h = e[k];
+        double f = ((y - z) * (y + z) + (g - h) * (g + h)) / (2.0 * h * y);
+        g = hypot_nr(f, 1.0);
+        f = ((x - z) * (x + z) + h * ((y / (f + copysign_nr(g, f))) - h)) / x;
+        double c = 1.0, s_ = 1.0;
+        for (int j = l; j <= nm; j++) {   // next QR transformation
+          const int i = j + 1;
+          g = e[i];
+          y = w[i];
+          h = s_ * g;
+          g = c * g;
+          z = hypot_nr(f, h);
+          e[j] = z;
+          c = f / z;
+          s_ = h / z;
+          f = x * c + g * s_;
+          g = g * c - x * s_;
+          h = y * s_;
+          y *= c;
+          for (int jj = 0; jj < n; jj++) {
+            x = V(jj, j); z = V(jj, i);
+            V(jj, j) = x * c + z * s_;
+            V(jj, i) = z * c - x * s_;
+          }
+          z = hypot_nr(f, h);
+          w[j] = z;
+          if (z != 0.0) { z = 1.0 / z; c = f * z; s_ = h * z; }   // rotation can be arbitrary if z = 0
+          f = c * g + s_ * y;
+          x = c * y - s_ * g;
+          for (int jj = 0; jj < n; jj++) {
+            y = U(jj, j); z = U(jj, i);
+            U(jj, j) = y * c + z * s_;
+            U(jj, i) = z * c - y * s_;
+          }
+        }
+        e[l] = 0.0;
+        e[k] = f;
+        w[k] = x;
+      }
+    }
   }
-  w.resize(n);
-  for (int i = 0; i < n; i++) w[i] = A[(size_t)i * n + i];
-}
+  // zero the singular values below tol * max, as the reference does before back-substituting
+  void Truncate(double tol) {
+    double maxw = -ALMOST_INF;
+    for (int j = 0; j < n; j++) if (w[j] > maxw) maxw = w[j];
+    for (int j = 0; j < n; j++) if (fabs(w[j] / maxw) < tol) w[j] = 0.0;
+  }
+  // x = V diag(1/w) U' b   (svbksb)
+  void Solve(const double *b, int bstride, double *x, int xstride, std::vector<double> &t) {
+    t.assign(n, 0.0);
+    for (int j = 0; j < n; j++) {
+      double s_ = 0.0;
+      if (w[j] != 0.0) {
+        for (int i = 0; i < n; i++) s_ += U(i, j) * b[(size_t)i * bstride];
+        s_ /= w[j];
+      }
+      t[j] = s_;
+    }
+    for (int j = 0; j < n; j++) {
+      double s_ = 0.0;
+      for (int jj = 0; jj < n; jj++) s_ += V(j, jj) * t[jj];
+      x[(size_t)j * xstride] = s_;
+    }
+  }
+};
+}  // namespace
 void SolveSymmetricTruncated(const std::vector<double> &P, int n, double tol, const std::vector<double> &B, int nrhs, std::vector<double> &X) {
-  std::vector<double> A(P), w, V;
-  JacobiEigen(A, n, w, V);
-  double maxw = 0.0;
-  for (int j = 0; j < n; j++) if (fabs(w[j]) > maxw) maxw = fabs(w[j]);
-  std::vector<double> inv(n, 0.0);
-  for (int j = 0; j < n; j++) if (maxw > 0 && !(fabs(w[j] / maxw) < tol)) inv[j] = 1.0 / w[j];
+  GolubReinsch svd;
+  svd.Decompose(P, n);
+  svd.Truncate(tol);
   X.assign((size_t)n * nrhs, 0.0);
-  std::vector<double> t(n);
-  for (int r = 0; r < nrhs; r++) {   // B, X are [n][nrhs]
-    for (int j = 0; j < n; j++) { double s_ = 0.0; for (int i = 0; i < n; i++) s_ += V[(size_t)i * n + j] * B[(size_t)i * nrhs + r]; t[j] = s_ * inv[j]; }
-    for (int i = 0; i < n; i++) { double s_ = 0.0; for (int j = 0; j < n; j++) s_ += V[(size_t)i * n + j] * t[j]; X[(size_t)i * nrhs + r] = s_; }
-  }
+  std::vector<double> t;
+  for (int r = 0; r < nrhs; r++) svd.Solve(&B[r], nrhs, &X[r], nrhs, t);   // B, X are [n][nrhs]
 }
 bool CEnKFEnsemble::AssimilationCalcs(const double *out_all, std::vector<double> &Z) const {   // src/EnKF.cpp:478-575
   const int N = _nMembers, Nobs = _nObsDatapoints;

@@ -162,6 +162,11 @@ ENKF_CASES = {
                                  perturbations=("PRECIP DIST_NORMAL 0.5 1.0 ADDITIVE", "SNOWFALL DIST_UNIFORM 0.5 1.5 MULTIPLICATIVE",
                                                 "TEMP_AVE DIST_LOGNORMAL 0.0 0.1 MULTIPLICATIVE AssimHRUs"),
                                  obs_error="STREAMFLOW DIST_GAMMA 2.0 0.3 ADDITIVE", obs_level=3.0)),
+    # the config-5 shape at a size the reference finishes in seconds: 64 members, 12 gauged outlets x window 3 (the reference's slot
+    # quirk leaves 24 + 1 distinct observation slots), 31 subbasins -- pins the truncated-SVD solve of an ill-conditioned P
+    "enkf_hbv_n64": dict(kind="hbv", n_sb=31, hru_per_sb=3, n_days=30, seed=29, routing="ROUTE_MUSKINGUM", season_offset=120,
+                         enkf=dict(n_members=64, obs_basins=(1, 2, 3, 4, 5, 6, 7, 9, 11, 13, 17, 23), window=3,
+                                   obs_error="STREAMFLOW DIST_NORMAL 1 0.0002 MULTIPLICATIVE")),
 }
 
 

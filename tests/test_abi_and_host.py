@@ -23,6 +23,17 @@ def test_engine_exports_every_declared_symbol():
     assert lib.rvn_gpu_abi_version() == 7
 
 
+def test_loaded_libraries_were_built_from_the_present_sources():
+    """build() stamps a digest of sources + flags into each library and rebuilds on mismatch: what is loaded is what is in the tree."""
+    from ravenhydroframework_b200 import build as b
+    want = b.source_digests()
+    eng, host = api.engine_lib(), api.host_lib()
+    eng.rvn_gpu_build_digest.restype = C.c_char_p
+    host.rvh_build_digest.restype = C.c_char_p
+    assert eng.rvn_gpu_build_digest().decode() == want["librvn_gpu.so"]
+    assert host.rvh_build_digest().decode() == want["libraven_b200.so"]
+
+
 def test_engine_is_sm100a_with_specialised_and_interpreter_sweeps():
     import shutil
     import subprocess
