@@ -522,8 +522,8 @@ int rvn_gpu_kernel_variant(rvn_gpu_model *m, char *buf, int buflen);
  * csrc/rvn_static_programs.cuh by tools/gen_static_programs.py */
 int rvn_gpu_emit_static_program(const rvn_model_desc *desc, const char *name, char *buf, int64_t buflen);
 
-/* verification hook (tests/test_glibc_math.py): evaluate the device exp (fn 0) / log (1) / pow (2) the kernels use
- * (csrc/rvn_glibc_math.h - restatements of the host libm the reference links, src/ calls of exp/log/pow) on n host
+/* verification hook (tests/test_glibc_math.py): evaluate the device exp (fn 0) / log (1) / pow (2) / expm1 (3) / tanh (4) the kernels use
+ * (csrc/rvn_glibc_math.h - restatements of the host libm the reference links, src/ calls of exp/log/pow/tanh) on n host
  * arguments x[, y] and return the results in out[n]; these must equal the host libm's bit for bit */
 int rvn_gpu_math_eval(int device, int fn, int64_t n, const double *x, const double *y, double *out);
 

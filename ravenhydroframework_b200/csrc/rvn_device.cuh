@@ -69,6 +69,10 @@ struct DevModel {
   const int32_t *wt_ptr, *wt_idx; const double *wt_val;   // CSR gauge/grid-cell weights (rvn_gpu.h)
   int32_t unit_weights;                            // 1: one station, every HRU weight exactly 1.0 (CSR not read)
   const rvn_time *times;
+  // trigonometric factors of POTMELT_HBV (src/PotentialMelt.cpp:60-75) evaluated on the host with the libm the reference links
+  // (CUDA's sin / cos differ from it in the last place now and then): per step cos(day_angle - WINTER_SOLSTICE_ANG - adj) for
+  // adj = 0 (northern) and pi (southern hemisphere) [nSteps][2]; per HRU sin(slope) and cos(aspect - adj)
+  const double *melt_cos; const double *hru_sin_slope, *hru_cos_aspect;
   const double *veg_season;                        // [nSteps][nVeg][2] month-interpolated relative height, relative LAI
   const double *et_flat, *opt_air_mass;            // [nEtRows][nHp] flat-surface ET radiation and optical air mass (or NULL)
   const double *day_length, *sunset_angle;         // [nEtRows][nHp] day geometry for PET_HAMON / PET_MOHYSE (or NULL)

@@ -267,3 +267,98 @@ RG_FN double rvn_pow(double x, double y) {
   const double elo = RG_FMA(y, tail, RG_FMA(hi, y, -ehi));  // y * lo + fma(y, hi, -ehi)
   return rg_exp_core_(ehi, elo, sign_bias, 1);
 }
+
+// ---- expm1 / tanh: fdlibm's s_expm1.c and s_tanh.c as glibc ships them (sysdeps/ieee754/dbl-64), expm1 in the `__expm1_fma`
+// ifunc variant (a*b+c contracted where the compiler chose to; checked against the instruction sequence of this image's libm).
+RG_FN double rg_set_high_(double y, uint32_t hi) { return RG_DBL(((uint64_t)hi << 32) | (RG_BITS(y) & 0xffffffffULL)); }
+RG_FN double rvn_expm1(double x) {
+  const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10, invln2 = 1.44269504088896338700e+00;
+  const double Q1 = -3.33333333333331316428e-02, Q2 = 1.58730158725481460165e-03, Q3 = -7.93650757867487942473e-05,
+               Q4 = 4.00821782732936239552e-06, Q5 = -2.01099218183624371326e-07;
+  const uint64_t ix = RG_BITS(x);
+  uint32_t hx = (uint32_t)(ix >> 32);
+  const uint32_t xsb = hx & 0x80000000u;
+  hx &= 0x7fffffffu;
+  double hi, lo, c = 0.0, t;
+  int k;
+  if (hx >= 0x4043687Au) {                 // |x| >= 56 ln2
+    if (hx >= 0x40862E42u) {               // |x| >= 709.78
+      if (hx >= 0x7ff00000u) {
+        if (((hx & 0xfffffu) | (uint32_t)ix) != 0) return RG_ADD(x, x);   // NaN
+        return (xsb == 0) ? x : -1.0;
+      }
+      if (x > 7.09782712893383973096e+02) return RG_DBL(RG_INF);          // huge * huge
+    }
+    if (xsb != 0) return RG_SUB(1.0e-300, 1.0);                           // tiny - one
+  }
+  if (hx > 0x3fd62e42u) {                  // |x| > 0.5 ln2
+    if (hx < 0x3FF0A2B2u) {                // and |x| < 1.5 ln2
+      if (xsb == 0) { hi = RG_SUB(x, ln2_hi); lo = ln2_lo; k = 1; }
+      else { hi = RG_ADD(x, ln2_hi); lo = -ln2_lo; k = -1; }
+    } else {
+      k = (int)RG_ADD((xsb == 0) ? 0.5 : -0.5, RG_MUL(x, invln2));
+      t = RG_I2D(k);
+      hi = RG_FMA(-t, ln2_hi, x);          // x - t * ln2_hi (the product is exact)
+      lo = RG_MUL(t, ln2_lo);
+    }
+    x = RG_SUB(hi, lo);
+    c = RG_SUB(RG_SUB(hi, x), lo);
+  } else if (hx < 0x3c900000u) {           // |x| < 2^-54
+    return x;
+  } else k = 0;
+  const double hfx = RG_MUL(x, 0.5);
+  const double hxs = RG_MUL(x, hfx);
+  const double R2 = RG_FMA(hxs, Q3, Q2);
+  const double R3 = RG_FMA(hxs, Q5, Q4);
+  const double h2 = RG_MUL(hxs, hxs);
+  const double R1 = RG_FMA(hxs, Q1, 1.0);
+  const double h4 = RG_MUL(h2, h2);
+  const double r1 = RG_FMA(h4, R3, RG_FMA(h2, R2, R1));
+  t = RG_FMA(-r1, hfx, 3.0);                                   // 3.0 - r1 * hfx
+  double e = RG_MUL(RG_DIV(RG_SUB(r1, t), RG_FMA(-x, t, 6.0)), hxs);   // hxs * ((r1 - t) / (6.0 - x * t))
+  if (k == 0) return RG_SUB(x, RG_FMA(e, x, -hxs));            // x - (x * e - hxs)
+  e = RG_FMA(RG_SUB(e, c), x, -c);                             // x * (e - c) - c
+  e = RG_SUB(e, hxs);
+  if (k == -1) return RG_FMA(0.5, RG_SUB(x, e), -0.5);         // 0.5 * (x - e) - 0.5
+  if (k == 1) {
+    if (x < -0.25) return RG_MUL(RG_SUB(e, RG_ADD(x, 0.5)), -2.0);
+    return RG_FMA(RG_SUB(x, e), 2.0, 1.0);                     // one + 2.0 * (x - e)
+  }
+  double y;
+  if (k <= -2 || k > 56) {
+    y = RG_SUB(1.0, RG_SUB(e, x));
+    y = rg_set_high_(y, (uint32_t)(RG_BITS(y) >> 32) + ((uint32_t)k << 20));
+    return RG_SUB(y, 1.0);
+  }
+  if (k < 20) {
+    t = RG_DBL((uint64_t)(0x3ff00000u - (0x200000u >> k)) << 32);   // 1 - 2^-k
+    y = RG_SUB(t, RG_SUB(e, x));
+  } else {
+    t = RG_DBL((uint64_t)((uint32_t)(0x3ff - k) << 20) << 32);      // 2^-k
+    y = RG_SUB(x, RG_ADD(e, t));
+    y = RG_ADD(y, 1.0);
+  }
+  return rg_set_high_(y, (uint32_t)(RG_BITS(y) >> 32) + ((uint32_t)k << 20));
+}
+
+RG_FN double rvn_tanh(double x) {
+  const uint64_t bits = RG_BITS(x);
+  const int32_t jx = (int32_t)(bits >> 32);
+  const uint32_t ix = (uint32_t)jx & 0x7fffffffu;
+  double z;
+  if (ix >= 0x7ff00000u) return (jx >= 0) ? RG_ADD(RG_DIV(1.0, x), 1.0) : RG_SUB(RG_DIV(1.0, x), 1.0);   // inf / NaN
+  if (ix < 0x40360000u) {                          // |x| < 22
+    if ((ix | (uint32_t)bits) == 0) return x;      // +-0
+    if (ix < 0x3c800000u) return RG_MUL(x, RG_ADD(1.0, x));   // |x| < 2^-55
+    const double ax = RG_DBL(bits & 0x7fffffffffffffffULL);
+    if (ix >= 0x3ff00000u) {                       // |x| >= 1
+      const double t = rvn_expm1(RG_ADD(ax, ax));
+      z = RG_SUB(1.0, RG_DIV(2.0, RG_ADD(t, 2.0)));
+    } else {
+      const double t = rvn_expm1(RG_MUL(ax, -2.0));
+      z = RG_DIV(-t, RG_ADD(t, 2.0));
+    }
+  } else z = RG_SUB(1.0, 1.0e-300);                // |x| >= 22
+  return (jx >= 0) ? z : -z;
+}
+

@@ -330,12 +330,12 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
     } else if (method == RVN_POTMELT_HBV || method == RVN_POTMELT_HBV_ROS) {
       double Ma = c.LU(RVN_LU_MELT_FACTOR), Ma_min = c.LU(RVN_LU_MIN_MELT_FACTOR), AM = c.LU(RVN_LU_HBV_MELT_ASP_CORR);
       double MRF = c.LU(RVN_LU_HBV_MELT_FOR_CORR), Fc = c.LU(RVN_LU_FOREST_COVERAGE), melt_temp = c.LU(RVN_LU_DD_MELT_TEMP);
-      double adj = 0, slope_corr;
-      if (c.lat < 0.0) adj = D_PI;
-      Ma = Ma_min + (Ma - Ma_min) * 0.5 * (1.0 - cos(tt.day_angle - D_WINTER_SOLSTICE_ANG - adj));
+      double slope_corr;
+      const int south = (c.lat < 0.0) ? 1 : 0;   // adj = pi
+      Ma = Ma_min + (Ma - Ma_min) * 0.5 * (1.0 - __ldg(M.melt_cos + 2 * step + south));   // cos(day_angle - WINTER_SOLSTICE_ANG - adj), host libm
       Ma *= ((1.0 - Fc) * 1.0 + (Fc)*MRF);
-      slope_corr = ((1.0 - Fc) * 1.0 + (Fc)*sin(c.slope));
-      Ma *= dmax(1.0 - AM * slope_corr * cos(c.aspect - adj), 0.0);
+      slope_corr = ((1.0 - Fc) * 1.0 + (Fc)*__ldg(M.hru_sin_slope + k));                  // sin(slope)
+      Ma *= dmax(1.0 - AM * slope_corr * __ldg(M.hru_cos_aspect + k), 0.0);               // cos(aspect - adj)
       double rain_energy = 0.0;
       if (method == RVN_POTMELT_HBV_ROS)   // rain-on-snow energy, src/PotentialMelt.cpp:77-81
         rain_energy = c.LU(RVN_LU_RAIN_MELT_MULT) * D_SPH_WATER / D_LH_FUSION * dmax(F[RVN_F_TEMP_AVE], 0.0) * (F[RVN_F_PRECIP] * (1.0 - F[RVN_F_SNOW_FRAC]));
@@ -538,35 +538,22 @@ RVN_DI ConvRow ld_row(const ConvRow *__restrict__ tab, int i) {
   return t;
 }
 
-#ifndef RVN_RING
-#define RVN_RING 8   // rows of each convolution's store stream in flight per HRU (ring in shared memory filled by cp.async)
+#ifndef RVN_CONV_R
+#define RVN_CONV_R 4   // rows per register buffer
 #endif
-// The store stream of a convolution (N <= 50 rows of the SoA state, one row = nHp doubles apart) is the bulk of the sweep's HBM
-// traffic.  Every thread keeps RVN_RING rows of its own HRU in flight with 8-byte cp.async copies into a private column of a
-// shared-memory ring: the copies cost no registers, need no CTA-wide barrier (a thread only ever reads what it copied itself,
-// cp.async.wait_group is per thread) and are issued at kernel start, long before the process list reaches the convolution.
-// One group is committed per row, so "all but the RVN_RING-1 most recent groups complete" == "row i has landed" (the prologues
-// of several convolutions are issued in reverse order of use, which keeps that rule valid for each of them).
-RVN_DI uint64_t l2_evict_first_policy() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
-RVN_DI void cp_async8(double *smem_dst, const double *gsrc, const uint64_t policy) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "l"(policy) : "memory");
-}
-RVN_DI void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int NPENDING> RVN_DI void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPENDING) : "memory"); }
-// first RVN_RING rows of a convolution's stores -> this thread's ring column (ring[d * RVN_BS]); always RVN_RING groups
-RVN_DI void conv_ring_prologue(const double *g, const size_t stride, const int N, double *ring, const uint64_t policy) {
+#ifndef RVN_PF_DIST
+#define RVN_PF_DIST 16  // rows of L2 prefetch run-ahead of the store stream (0 = off)
+#endif
+RVN_DI void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// warm L2 with the first rows of a convolution's stores (issued at kernel start, long before they are consumed)
+RVN_DI void conv_prefetch_head(const double *g, const size_t stride) {
 #pragma unroll
-  for (int d = 0; d < RVN_RING; d++) {
-    if (d < N) cp_async8(ring + d * RVN_BS, g + (size_t)d * stride, policy);
-    cp_async_commit();
-  }
+  for (int r = 0; r < RVN_PF_DIST; r++) prefetch_l2(g + (size_t)r * stride);
 }
 
 template <bool UNIT_DT, class C>
 RVN_DI void convolve_direct(C &c, const int iTarget, const int iTS, double *__restrict__ g /*store 0 of this HRU*/, const size_t stride,
-                            const ConvRow *__restrict__ tab, const int N, double *__restrict__ sum_cache, const bool sum_valid,
-                            double *__restrict__ ring /*this thread's column, prologue issued*/, const uint64_t policy) {
+                            const ConvRow *__restrict__ tab, const int N, double *__restrict__ sum_cache, const bool sum_valid) {
   if (N <= 0) return;
   const double tstep = c.tstep;
   // ---- the reference's `sum` of the stores in index order.  The same sum, over the same values in the same order, is
@@ -581,53 +568,82 @@ RVN_DI void convolve_direct(C &c, const int iTarget, const int iTS, double *__re
   const double TS_old = c.SV(iTS);
   const double added = TS_old - sum;
   double target = c.SV(iTarget), nsum = 0.0, TS_new = 0.0;
-  double prev_move = 0.0, prevS = 0.0;
-  double *ps = g;                                          // row being processed (store address)
-  const double *pl = g + (size_t)RVN_RING * stride;        // next row to fetch
-  const int last = N - 1;
-  for (int b = 0; b < N; b += RVN_RING) {
+  {
+    // ---- row 0: receives the new water (connection 0), releases, shifts out unless it is the only store
+    const ConvRow t = ld_row(tab, 0);
+    const double g0 = __ldcs(g);
+    const double r0 = UNIT_DT ? added : added / tstep;                         // rates[0]
+    const double Sin = g0 + added;                                             // local S[0]
+    double act = UNIT_DT ? Sin : g0 + r0 * tstep;                              // store 0 after connection 0
+    const double orig = conv_orig(Sin, t);
+    const double r_ = UNIT_DT ? t.uh * orig : t.uh * orig / tstep;             // rates[1]
+    const double rdt = UNIT_DT ? r_ : r_ * tstep;
+    const double Sloc = Sin - rdt;                                             // local S[0] after release
+    act = act - rdt;                                                           // solver: phinew[store 0] -= r*tstep
+    target += rdt;                                                             // solver: phinew[target]  += r*tstep
+    if (N == 1) {
+      __stcs(g, act);
+      nsum = act;
+    } else {
+      const double mv0 = UNIT_DT ? Sloc : (Sloc / tstep) * tstep;              // m_0*tstep
+      const double fin0 = act - mv0;                                           // connection N+1
+      __stcs(g, fin0);
+      nsum = fin0;
+      double prev_move = mv0, prevS = Sloc;
+      // ---- interior rows 1..N-2: every special case is statically decided; the loads of the next RVN_CONV_R rows are in
+      // flight while the current ones are processed
+      const int end = N - 1;
+      double cur[RVN_CONV_R];
+      double *p = g + stride;
 #pragma unroll
-    for (int d = 0; d < RVN_RING; d++) {
-      const int i = b + d;
-      if (i > last) break;
-      cp_async_wait<RVN_RING - 1>();
-      const double gi = ring[d * RVN_BS];
-      const ConvRow t = ld_row(tab, i);
-      double fin;
-      if (d == 0 && b == 0) {
-        // ---- row 0: receives the new water (connection 0), releases, shifts out unless it is the only store
-        const double r0 = UNIT_DT ? added : added / tstep;                         // rates[0]
-        const double Sin = gi + added;                                             // local S[0]
-        double act = UNIT_DT ? Sin : gi + r0 * tstep;                              // store 0 after connection 0
-        const double orig = conv_orig(Sin, t);
-        const double r_ = UNIT_DT ? t.uh * orig : t.uh * orig / tstep;             // rates[1]
-        const double rdt = UNIT_DT ? r_ : r_ * tstep;
-        const double Sloc = Sin - rdt;                                             // local S[0] after release
-        act = act - rdt;                                                           // solver: phinew[store 0] -= r*tstep
-        target += rdt;                                                             // solver: phinew[target]  += r*tstep
-        const double mv0 = UNIT_DT ? Sloc : (Sloc / tstep) * tstep;                // m_0*tstep
-        fin = (last == 0) ? act : act - mv0;                                       // connection N+1 (not for a single store)
-        prev_move = mv0; prevS = Sloc;
-      } else {
-        // ---- rows 1..N-1: release, receive the shift from row i-1, pass on (except the last row, which keeps what is left)
+      for (int r = 0; r < RVN_CONV_R; r++) cur[r] = (1 + r < end) ? __ldcs(p + (size_t)r * stride) : 0.0;
+      for (int i = 1; i < end; i += RVN_CONV_R) {
+        double nxt[RVN_CONV_R];
+        const double *pn = p + (size_t)RVN_CONV_R * stride;
+#pragma unroll
+        for (int r = 0; r < RVN_CONV_R; r++) nxt[r] = (i + RVN_CONV_R + r < end) ? __ldcs(pn + (size_t)r * stride) : 0.0;
+        if (RVN_PF_DIST > 0) {
+#pragma unroll
+          for (int r = 0; r < RVN_CONV_R; r++) if (i + RVN_PF_DIST + r < N) prefetch_l2(p + (size_t)(RVN_PF_DIST - 1 + r) * stride);
+        }
+#pragma unroll
+        for (int r = 0; r < RVN_CONV_R; r++) {
+          if (i + r < end) {
+            const ConvRow t = ld_row(tab, i + r);
+            const double gi = cur[r];
+            const double orig = conv_orig(gi, t);
+            const double rdt = UNIT_DT ? t.uh * orig : (t.uh * orig / tstep) * tstep;   // rates[i+1]*tstep
+            const double Sloc = gi - rdt;                               // local S[i] after release == store i after release
+            target += rdt;
+            const double mv = UNIT_DT ? Sloc : (Sloc / tstep) * tstep; // m_i*tstep
+            const double fin = (Sloc + prev_move) - mv;                 // connections N+i then N+i+1
+            __stcs(p + (size_t)r * stride, fin);
+            nsum += fin;
+            TS_new += prevS;                                            // local S[i] after the shift loop = S'[i-1]
+            prev_move = mv; prevS = Sloc;
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < RVN_CONV_R; r++) cur[r] = nxt[r];
+        p += (size_t)RVN_CONV_R * stride;
+      }
+      // ---- last row N-1: releases, receives the shift, keeps what is left
+      {
+        double *pl = g + (size_t)(N - 1) * stride;
+        const ConvRow t = ld_row(tab, N - 1);
+        const double gi = __ldcs(pl);
         const double orig = conv_orig(gi, t);
-        const double rdt = UNIT_DT ? t.uh * orig : (t.uh * orig / tstep) * tstep;  // rates[i+1]*tstep
-        const double Sloc = gi - rdt;                                              // local S[i] after release == store i after release
+        const double r_ = UNIT_DT ? t.uh * orig : t.uh * orig / tstep;
+        const double rdt = UNIT_DT ? r_ : r_ * tstep;
+        const double Sloc = gi - rdt;
         target += rdt;
-        const double mv = UNIT_DT ? Sloc : (Sloc / tstep) * tstep;                 // m_i*tstep
-        const double in = Sloc + prev_move;                                        // connection N+i
-        fin = (i == last) ? in : in - mv;                                          // connection N+i+1 (last row: 2N-1 was the final one)
+        const double fin = Sloc + prev_move;                            // connection 2N-1
+        __stcs(pl, fin);
+        nsum += fin;
         // reference TS_new = sum_{j=1..N-1} of the local array after its descending shift loop:
         //   local S[j] = S'[j-1] for j<=N-2 and S'[N-1]+S'[N-2] for j=N-1
-        TS_new += (i == last) ? (Sloc + prevS) : prevS;
-        prev_move = mv; prevS = Sloc;
+        TS_new += (Sloc + prevS);
       }
-      __stcs(ps, fin);
-      nsum += fin;
-      ps += stride;
-      // refill this slot with row i + RVN_RING: program-ordered after the store above, which depends on the value read from it
-      if (i + RVN_RING <= last) { cp_async8(ring + d * RVN_BS, pl, policy); pl += stride; }
-      cp_async_commit();
     }
   }
   *sum_cache = nsum;
@@ -778,17 +794,12 @@ extern __shared__ __align__(16) unsigned char rvn_smem[];
 // ------------------------------------------------------------------------------------------------
 // specialised sweep: the process list is the compile-time program Prog
 // ------------------------------------------------------------------------------------------------
-// cp.async prologues of every convolution of the program, last one first (see conv_ring_prologue)
 template <class Prog, int J>
-struct ConvPrologues {
-  static RVN_DI void run(const DevModel &M, const double *gstate, const int e, const int lu, double *ring0, const uint64_t policy) {
-    if constexpr (J >= 0) {
-      if constexpr (Prog::op(J) == RVN_OP_CONVOLVE) {
-        constexpr int ci = Prog::ia(J, 0);
-        conv_ring_prologue(gstate + (size_t)Prog::ia(J, 2) * M.nHp, (size_t)M.nHp, M.conv_n[((size_t)e * M.nLU + lu) * M.nConv + ci],
-                           ring0 + ci * RVN_RING * RVN_BS, policy);
-      }
-      ConvPrologues<Prog, J - 1>::run(M, gstate, e, lu, ring0, policy);
+struct PrefetchConvs {
+  static RVN_DI void run(const double *gstate, const size_t nHp) {
+    if constexpr (J < Prog::nProc) {
+      if constexpr (Prog::op(J) == RVN_OP_CONVOLVE) conv_prefetch_head(gstate + (size_t)Prog::ia(J, 2) * nHp, nHp);
+      PrefetchConvs<Prog, J + 1>::run(gstate, nHp);
     }
   }
 };
@@ -796,7 +807,7 @@ struct ConvPrologues {
 template <class Prog, bool UNIT_DT, int J>
 struct RunProcs {
   static RVN_DI void run(StatCtx<Prog> &c, const DevModel &M, const bool enabled, const unsigned long long mask, const int e, const int k,
-                         double *gstate, double *ring0, const uint64_t policy) {
+                         double *gstate) {
     if constexpr (J < Prog::nProc) {
       constexpr int op = Prog::op(J);
       const bool apply = enabled && ((mask >> J) & 1ull);   // CModel::ApplyProcess gate (src/Model.cpp:3061)
@@ -806,7 +817,7 @@ struct RunProcs {
           const size_t slot = ((size_t)e * M.nLU + c.lu) * M.nConv + ci;
           convolve_direct<UNIT_DT>(c, Prog::ia(J, 1), Prog::ia(J, 3), gstate + (size_t)Prog::ia(J, 2) * M.nHp, (size_t)M.nHp,
                                    M.conv_tab + slot * RVN_CONV_STORES, M.conv_n[slot], M.conv_sum + ((size_t)e * M.nConv + ci) * M.nHp + k,
-                                   M.conv_sum_valid != 0, ring0 + ci * RVN_RING * RVN_BS, policy);
+                                   M.conv_sum_valid != 0);
         }
       } else {
         if (apply) {
@@ -820,7 +831,7 @@ struct RunProcs {
           }
         }
       }
-      RunProcs<Prog, UNIT_DT, J + 1>::run(c, M, enabled, mask, e, k, gstate, ring0, policy);
+      RunProcs<Prog, UNIT_DT, J + 1>::run(c, M, enabled, mask, e, k, gstate);
     }
   }
 };
@@ -860,10 +871,7 @@ __global__ void __launch_bounds__(RVN_BS, RVN_STATIC_MIN_BLOCKS) hru_sweep_stati
   double *gstate = M.state + (size_t)e * M.NS * nHp + k;
 #pragma unroll
   for (int s = 0; s < Prog::nCore; s++) c.SV(s) = __ldcs(gstate + (size_t)Prog::slot_sv(s) * nHp);
-  // the store streams of the convolutions start now (they depend on the previous step only) and land during the forcing chain
-  const uint64_t policy = l2_evict_first_policy();
-  double *ring0 = s_red + 8 + (RVN_SV_SMEM ? Prog::nCore * RVN_BS : 0) + RVN_F_SMEM_DOUBLES + tid;
-  if (Prog::nConv > 0 && in_range) ConvPrologues<Prog, Prog::nProc - 1>::run(M, gstate, e, c.lu, ring0, policy);
+  if (RVN_PF_DIST > 0 && enabled) PrefetchConvs<Prog, 0>::run(gstate, nHp);
   c.old_snow = (Prog::iSV(RVN_SV_SNOW) >= 0) ? c.SV(Prog::iSV(RVN_SV_SNOW) >= 0 ? Prog::iSV(RVN_SV_SNOW) : 0) : 0.0;
   c.old_snow_cover = (Prog::iSV(RVN_SV_SNOW_COVER) >= 0) ? c.SV(Prog::iSV(RVN_SV_SNOW_COVER) >= 0 ? Prog::iSV(RVN_SV_SNOW_COVER) : 0) : 0.0;
   c.old_snow_depth = (Prog::iSV(RVN_SV_SNOW_DEPTH) >= 0) ? c.SV(Prog::iSV(RVN_SV_SNOW_DEPTH) >= 0 ? Prog::iSV(RVN_SV_SNOW_DEPTH) : 0) : 0.0;
@@ -878,7 +886,7 @@ __global__ void __launch_bounds__(RVN_BS, RVN_STATIC_MIN_BLOCKS) hru_sweep_stati
   load_canopy(c, M, step);   // (class, date) only: placed after the forcing chain so that its results are not live across it
   if (enabled) reboot_diagnostics(c);   // disabled HRUs keep their stored values (the reference never writes them back, :701)
   // ---- ordered-series process sweep on the newest state
-  RunProcs<Prog, UNIT_DT, 0>::run(c, M, enabled, mask, e, k, gstate, ring0, policy);
+  RunProcs<Prog, UNIT_DT, 0>::run(c, M, enabled, mask, e, k, gstate);
   // ---- routing prep, diagnostics, state out + per-HRU part of the output reductions
   double swv = 0.0, stor = 0.0;
   if (enabled) {
@@ -892,7 +900,6 @@ __global__ void __launch_bounds__(RVN_BS, RVN_STATIC_MIN_BLOCKS) hru_sweep_stati
       for (int f = 0; f < RVN_F_CARRIED; f++) gf[(size_t)f * nHp] = c.F[f];
     }
   }
-  cp_async_wait<0>();   // nothing of this thread's ring traffic is left in flight (prologues of convolutions that were not applied)
   const int par = step & 1;
   if (in_range) M.swvol[((size_t)par * M.E + e) * nHp + k] = swv;
   const double pa = enabled ? c.F[RVN_F_PRECIP] * c.area : 0.0;
@@ -946,15 +953,6 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
   c.old_snow_cover = (P->iSV[RVN_SV_SNOW_COVER] >= 0) ? c.SV(P->iSV[RVN_SV_SNOW_COVER]) : 0.0;
   c.old_snow_depth = (P->iSV[RVN_SV_SNOW_DEPTH] >= 0) ? c.SV(P->iSV[RVN_SV_SNOW_DEPTH]) : 0.0;
   c.old_snow_temp = (P->iSV[RVN_SV_SNOW_TEMP] >= 0) ? c.SV(P->iSV[RVN_SV_SNOW_TEMP]) : 0.0;
-  const uint64_t policy = l2_evict_first_policy();
-  double *ring0 = s_red + 8 + RVN_F_SMEM_DOUBLES + tid;
-  if (in_range) {
-    for (int j = P->nProc - 1; j >= 0; j--) {   // cp.async prologues of the convolutions, last one first (conv_ring_prologue)
-      const rvn_process &pr = P->proc[j];
-      if (pr.op != RVN_OP_CONVOLVE) continue;
-      conv_ring_prologue(gstate + (size_t)pr.ia[2] * nHp, nHp, M.conv_n[((size_t)e * M.nLU + c.lu) * M.nConv + pr.ia[0]], ring0 + pr.ia[0] * RVN_RING * RVN_BS, policy);
-    }
-  }
   if (enabled) compute_forcings(c, M, e, k, step, sb);
   else { for (int f = 0; f < RVN_F_CARRIED; f++) c.F[f] = 0.0; }
   load_canopy(c, M, step);
@@ -971,9 +969,8 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
       const size_t slot = ((size_t)e * M.nLU + c.lu) * M.nConv + ci;
       double *g = gstate + (size_t)pr.ia[2] * nHp;
       double *sc = M.conv_sum + ((size_t)e * M.nConv + ci) * nHp + k;
-      double *rg = ring0 + ci * RVN_RING * RVN_BS;
-      if (unit_dt) convolve_direct<true>(c, pr.ia[1], pr.ia[3], g, nHp, M.conv_tab + slot * RVN_CONV_STORES, M.conv_n[slot], sc, M.conv_sum_valid != 0, rg, policy);
-      else convolve_direct<false>(c, pr.ia[1], pr.ia[3], g, nHp, M.conv_tab + slot * RVN_CONV_STORES, M.conv_n[slot], sc, M.conv_sum_valid != 0, rg, policy);
+      if (unit_dt) convolve_direct<true>(c, pr.ia[1], pr.ia[3], g, nHp, M.conv_tab + slot * RVN_CONV_STORES, M.conv_n[slot], sc, M.conv_sum_valid != 0);
+      else convolve_direct<false>(c, pr.ia[1], pr.ia[3], g, nHp, M.conv_tab + slot * RVN_CONV_STORES, M.conv_n[slot], sc, M.conv_sum_valid != 0);
       continue;
     }
     const DynProc dp = {&pr, P};
@@ -997,7 +994,6 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
       for (int f = 0; f < RVN_F_CARRIED; f++) gf[(size_t)f * nHp] = c.F[f];
     }
   }
-  cp_async_wait<0>();
   const int par = step & 1;
   if (in_range && !defer) M.swvol[((size_t)par * M.E + e) * nHp + k] = swv;
   const double pa = enabled ? c.F[RVN_F_PRECIP] * c.area : 0.0;

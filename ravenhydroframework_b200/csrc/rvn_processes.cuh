@@ -18,7 +18,7 @@
 #ifndef RVN_PROCESSES_CUH
 #define RVN_PROCESSES_CUH
 #include "rvn_device.cuh"
-#include "rvn_glibc_math.h"   // rvn_exp / rvn_log / rvn_pow: the host libm of the reference build, bit for bit
+#include "rvn_glibc_math.h"   // rvn_exp / rvn_log / rvn_pow / rvn_tanh: the host libm of the reference build, bit for bit
 
 #define D_ALMOST_INF 1e99
 #define D_REAL_SMALL 1e-12
@@ -406,7 +406,7 @@ template <class C, class PR> RVN_DI void rates_INFILTRATION(C &c, const PR &pr, 
   } else if (op == RVN_OP_INF_GR4J) {
     double x1 = SoilCapacity(c, 0), stor = c.SV(pr.to(0));
     double sat = stor / x1;
-    double tmp = tanh(ponded / x1);
+    double tmp = rvn_tanh(ponded / x1);
     double infil = x1 * (1.0 - (sat * sat)) * tmp / (1.0 + sat * tmp);
     infil = (1.0 - Fimp) * infil;
     c.R(0) = infil; c.R(1) = rainthru - infil;
@@ -554,7 +554,7 @@ template <class C, class PR> RVN_DI void rates_SOILEVAP(C &c, const PR &pr, cons
   } else if (op == RVN_OP_SOILEVAP_GR4J) {
     const double max_stor = SoilCapacity(c, 0), stor = c.SV(pr.from(0));
     const double sat = stor / max_stor;
-    const double tmp = tanh(dmax(PET, 0.0) / max_stor);
+    const double tmp = rvn_tanh(dmax(PET, 0.0) / max_stor);
     c.R(0) = stor * (2.0 - sat) * tmp / (1.0 + (1.0 - sat) * tmp);
   } else if (op == RVN_OP_SOILEVAP_HYPR) {   // src/SoilEvaporation.cpp:385-420 (Ahmed et al. 2020)
     const double stor = dmax(c.SV(pr.from(0)), 0.0), tens_stor = SoilTensionCapacity(c, 0);

@@ -40,11 +40,31 @@ void CModel::FlattenMemberParams(int member) {
 const int32_t *CModel::MemberConvN(int member) const { return _f_conv_n.data() + (size_t)member * lu_classes.size() * _f_nconv; }
 const double *CModel::MemberConvUH(int member) const { return _f_conv_uh.data() + (size_t)member * lu_classes.size() * _f_nconv * RVN_CONV_STORES; }
 
+void CModel::SetCellForcing(int nCells, int nSteps, const double *cell_elev, const double *series, const int32_t *wt_ptr, const int32_t *wt_idx, const double *wt_val) {
+  const int nH = GetNumHRUs();
+  ExitGracefullyIf(nCells < 1 || nSteps < 1 || !cell_elev || !series || !wt_ptr || !wt_idx || !wt_val, "CModel::SetCellForcing: bad arguments");
+  ExitGracefullyIf(wt_ptr[0] != 0, "CModel::SetCellForcing: wt_ptr[0] must be 0");
+  for (int k = 0; k < nH; k++) {
+    ExitGracefullyIf(wt_ptr[k + 1] <= wt_ptr[k], "CModel::SetCellForcing: every HRU needs at least one weighted grid cell");
+    double sum = 0.0;
+    for (int i = wt_ptr[k]; i < wt_ptr[k + 1]; i++) {
+      ExitGracefullyIf(wt_idx[i] < 0 || wt_idx[i] >= nCells, "CModel::SetCellForcing: grid cell index out of range");
+      sum += wt_val[i];
+    }
+    ExitGracefullyIf(fabs(sum - 1.0) > 0.05, "CModel::SetCellForcing: grid weights of an HRU do not sum to 1");   // the reference's CheckWeightArray tolerance
+  }
+  const size_t nnz = (size_t)wt_ptr[nH];
+  _cell_forcing = true; _nCells = nCells;
+  _cell_elev.assign(cell_elev, cell_elev + nCells);
+  _cell_series.assign(series, series + (size_t)RVN_GF_COUNT * nCells * nSteps);
+  _cell_ptr.assign(wt_ptr, wt_ptr + nH + 1); _cell_idx.assign(wt_idx, wt_idx + nnz); _cell_wt.assign(wt_val, wt_val + nnz);
+}
+
 const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
   ExitGracefullyIf(_pOpt == NULL, "CModel::Flatten: model must be initialized first");
   rvn_model_desc &d = _desc;
   memset(&d, 0, sizeof(d));
-  const int nH = GetNumHRUs(), NB = GetNumSubBasins(), NS = GetNumStateVars(), nG = GetNumGauges();
+  const int nH = GetNumHRUs(), NB = GetNumSubBasins(), NS = GetNumStateVars(), nG = _cell_forcing ? _nCells : GetNumGauges();
   d.abi_version = RVN_ABI_VERSION;
   d.nHRU = nH; d.nSB = NB; d.nMembers = nMembers; d.nGauges = nG;
   // ---- options
@@ -278,8 +298,10 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
     if (consumed(RVN_PET_VAPDEFICIT))
       for (size_t c = 0; c < lu_classes.size(); c++)
         ExitGracefullyIf(lu_classes[c].S.v[RVN_LU_PET_VAP_COEFF] == NOT_SPECIFIED, "CLandUseClass::AutoCalculateLandUseProps: required parameter PET_VAP_COEFF not specified for land use class " + lu_classes[c].tag);
+    ExitGracefullyIf(_cell_forcing && (consumed(RVN_PET_HARGREAVES) || consumed(RVN_PET_FROMMONTHLY) || O.evaporation == RVN_PET_FROMMONTHLY),
+                     "CModel::Flatten: PET methods that read monthly station normals are not available with gridded forcing input");
     if (consumed(RVN_PET_HARGREAVES))
-      for (int g = 0; g < nG; g++)
+      for (int g = 0; g < GetNumGauges(); g++)
         ExitGracefullyIf(_pGauges[g]->aMaxTemp[0] == NOT_SPECIFIED || _pGauges[g]->aMinTemp[0] == NOT_SPECIFIED, "PET_HARGREAVES requires minimum and maximum monthly temperatures");
     d.opt.need_atmos = need_atmos ? 1 : 0;
     d.opt.air_pressure = O.air_pressure; d.opt.rel_humidity = O.rel_humidity; d.opt.sw_radiation = O.SW_radiation; d.opt.sw_cloudcorr = O.SW_cloudcovercorr; d.opt.wind_velocity = O.wind_velocity; d.opt.interception_factor = O.interception_factor;
@@ -332,7 +354,16 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
   // ---- gauge series sampled on the model step (src/UpdateForcings.cpp:98-155)
   _f_series.assign((size_t)RVN_GF_COUNT * nG * nSteps, 0.0);
   _f_gconst.assign((size_t)nG * RVN_GC_COUNT, 0.0);
-  for (int g = 0; g < nG; g++) {
+  if (_cell_forcing) {   // one station per grid cell: series as handed over, unit corrections (grid-level :RainCorrection etc. are not built)
+    ExitGracefullyIf(_cell_series.size() != (size_t)RVN_GF_COUNT * nG * nSteps, "CModel::Flatten: the gridded forcing arrays were given for a different number of steps");
+    _f_series = _cell_series;
+    for (int g = 0; g < nG; g++) {
+      double *C = &_f_gconst[(size_t)g * RVN_GC_COUNT];
+      C[RVN_GC_ELEVATION] = _cell_elev[g]; C[RVN_GC_RAIN_CORR] = 1.0; C[RVN_GC_SNOW_CORR] = 1.0; C[RVN_GC_TEMP_CORR] = 0.0;
+      for (int m = 0; m < 48; m++) C[RVN_GC_MONTHLY_AVE_TEMP0 + m] = NOT_SPECIFIED;
+    }
+  }
+  for (int g = 0; g < (_cell_forcing ? 0 : nG); g++) {
     const CGauge *G = _pGauges[g];
     ExitGracefullyIf(!G->GetTimeSeries(F_PRECIP) || !G->GetTimeSeries(F_TEMP_AVE),
                      "CModel::Flatten: every gauge must carry precipitation and temperature series in the B200 build");
@@ -361,13 +392,19 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
   d.gauge_series = _f_series.data(); d.gauge_const = _f_gconst.data();
   // gauge weights -> CSR (the reference keeps three dense [nHRU][nGauges] tables; here they hold the same values)
   _f_wt_ptr.assign(nH + 1, 0); _f_wt_idx.clear(); _f_wt.clear();
-  for (int k = 0; k < nH; k++) {
+  if (_cell_forcing) {
+    _f_wt_ptr = _cell_ptr; _f_wt_idx = _cell_idx;
+    _f_wt.resize(_cell_wt.size() * 3);
+    for (size_t i = 0; i < _cell_wt.size(); i++) _f_wt[3 * i] = _f_wt[3 * i + 1] = _f_wt[3 * i + 2] = _cell_wt[i];
+  }
+  for (int k = 0; k < (_cell_forcing ? 0 : nH); k++) {
     for (int g = 0; g < nG; g++) {
       const double w = _aGaugeWeights[(size_t)k * nG + g];
       if (w != 0.0) { _f_wt_idx.push_back(g); _f_wt.push_back(w); _f_wt.push_back(w); _f_wt.push_back(w); }
     }
     _f_wt_ptr[k + 1] = (int32_t)_f_wt_idx.size();
   }
+  (void)0;
   if (_f_wt_idx.empty()) { _f_wt_idx.push_back(0); _f_wt.assign(3, 0.0); }
   d.wt_ptr = _f_wt_ptr.data(); d.wt_idx = _f_wt_idx.data(); d.wt_val = _f_wt.data();
   // ---- routing network

@@ -254,6 +254,11 @@ public:
   void Initialize(optStruct &Options);
   double GetWatershedArea() const { return _WatershedArea; }
   const std::vector<double> &GetGaugeWeights() const { return _aGaugeWeights; }  // [nHRU][nGauges]
+  // Gridded forcing ingestion (the arithmetic of CForcingGrid::GetWeightedValue, src/ForcingGrid.cpp:1886-1900 = the gauge sum of
+  // src/UpdateForcings.cpp:184-235 over one station per grid cell): cell series already sampled on the model step,
+  // series[RVN_GF_COUNT][nCells][nSteps], reference elevation per cell, CSR weights (wt_ptr[nHRU+1], wt_idx, wt_val; rows sum to 1).
+  // The NetCDF reader of the reference (CForcingGrid::ReadData) is out of scope; callers decode their files and hand the arrays over.
+  void SetCellForcing(int nCells, int nSteps, const double *cell_elev, const double *series, const int32_t *wt_ptr, const int32_t *wt_idx, const double *wt_val);
 
   // ensemble description (.rve)
   std::vector<param_dist> param_dists;
@@ -309,6 +314,11 @@ private:
   std::vector<CGauge *> _pGauges;
   std::vector<int> _aOrderedSBind, _aDownstreamInds, _aSubBasinOrder;
   std::vector<double> _aGaugeWeights;
+  // gridded forcing input (SetCellForcing): one station per grid cell with sparse HRU weights; replaces the :Gauge series at Flatten
+  bool _cell_forcing = false;
+  int _nCells = 0;
+  std::vector<double> _cell_elev, _cell_series, _cell_wt;   // [nCells], [RVN_GF_COUNT][nCells][nSteps], [nnz]
+  std::vector<int32_t> _cell_ptr, _cell_idx;                // CSR over HRUs
   double _WatershedArea;
   const optStruct *_pOpt;
   // flattened storage

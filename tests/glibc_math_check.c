@@ -22,7 +22,7 @@ static int same_(double a, double b) {
   return x == y;
 }
 
-/* mode: 0 exp, 1 log, 2 pow.  dist: 0 = raw bit patterns, 1 = hydrological ranges, 2 = near the special-case boundaries.
+/* mode: 0 exp, 1 log, 2 pow, 3 expm1, 4 tanh.  dist: 0 = raw bit patterns, 1 = hydrological ranges, 2 = near the special-case boundaries.
    Returns the number of mismatches; the first `cap` offending arguments go to bad[2*i], bad[2*i+1]. */
 long rg_check(int mode, int dist, long n, uint64_t seed, double *bad, int cap) {
   long nbad = 0;
@@ -62,6 +62,11 @@ long rg_check(int mode, int dist, long n, uint64_t seed, double *bad, int cap) {
       if (mode == 2 && (next_() & 3) == 0) { x = u01_() * 4; y = -1074.0 / log2(x) * (1 + (u01_() - 0.5) * 0.1); }
       if (mode == 0 && (next_() & 1)) x = (next_() & 1) ? -708.0 - u01_() * 40.0 : 709.0 + u01_() * 1.0;
     }
+    if (mode >= 3) {   /* expm1 / tanh: arguments of every branch */
+      if (dist == 1) x = (u01_() - 0.5) * (i % 4 == 0 ? 0.7 : i % 4 == 1 ? 2.2 : i % 4 == 2 ? 50.0 : 1500.0);
+      if (dist == 2 && (next_() & 1)) x = (u01_() - 0.5) * 4.2;
+      if (mode == 3) { got = rvn_expm1(x); ref = expm1(x); } else { got = rvn_tanh(x); ref = tanh(x); }
+    } else
     if (mode == 0) { got = rvn_exp(x); ref = exp(x); }
     else if (mode == 1) { got = rvn_log(x); ref = log(x); }
     else { got = rvn_pow(x, y); ref = pow(x, y); }
@@ -75,8 +80,8 @@ long rg_check(int mode, int dist, long n, uint64_t seed, double *bad, int cap) {
 
 /* element-wise evaluation through the HOST libm (the thing the device functions must reproduce); used by the GPU test */
 void rg_libm_eval(int mode, long n, const double *x, const double *y, double *out) {
-  for (long i = 0; i < n; i++) out[i] = mode == 0 ? exp(x[i]) : mode == 1 ? log(x[i]) : pow(x[i], y[i]);
+  for (long i = 0; i < n; i++) out[i] = mode == 0 ? exp(x[i]) : mode == 1 ? log(x[i]) : mode == 2 ? pow(x[i], y[i]) : mode == 3 ? expm1(x[i]) : tanh(x[i]);
 }
 void rg_restated_eval(int mode, long n, const double *x, const double *y, double *out) {
-  for (long i = 0; i < n; i++) out[i] = mode == 0 ? rvn_exp(x[i]) : mode == 1 ? rvn_log(x[i]) : rvn_pow(x[i], y[i]);
+  for (long i = 0; i < n; i++) out[i] = mode == 0 ? rvn_exp(x[i]) : mode == 1 ? rvn_log(x[i]) : mode == 2 ? rvn_pow(x[i], y[i]) : mode == 3 ? rvn_expm1(x[i]) : rvn_tanh(x[i]);
 }
