@@ -155,6 +155,30 @@ class RavenModel:
         self.nSteps, self.max_nqin, self.max_nqlat, self.nCore, self.nConvProc, self.ptab_stride = [info[i] for i in range(6)]
         return p
 
+    def gauge_series(self):
+        """Copy of the descriptor's forcing series [RVN_GF_COUNT][nGauges][nSteps] (sampled on the model step)."""
+        self.lib.rvh_desc_gauge_series.restype = C.c_void_p
+        self.lib.rvh_desc_gauge_series.argtypes = [C.c_void_p]
+        self.lib.rvh_desc_num_gauges.argtypes = [C.c_void_p]
+        nG = self.lib.rvh_desc_num_gauges(self.desc)
+        a = np.ctypeslib.as_array((C.c_double * (9 * nG * self.nSteps)).from_address(self.lib.rvh_desc_gauge_series(self.desc)))
+        return a.reshape(9, nG, self.nSteps).copy()
+
+    def set_cell_forcing(self, cell_elev, series, wt_ptr, wt_idx, wt_val):
+        """Gridded forcing input: one station per grid cell.  series [RVN_GF_COUNT][nCells][nSteps] sampled on the model step, CSR weights
+        over the HRUs (the sparse gather of reference CForcingGrid::GetWeightedValue).  Call flatten() afterwards."""
+        series = np.ascontiguousarray(series, dtype=np.float64)
+        cell_elev = np.ascontiguousarray(cell_elev, dtype=np.float64)
+        wt_ptr = np.ascontiguousarray(wt_ptr, dtype=np.int32)
+        wt_idx = np.ascontiguousarray(wt_idx, dtype=np.int32)
+        wt_val = np.ascontiguousarray(wt_val, dtype=np.float64)
+        assert series.ndim == 3 and series.shape[0] == 9 and series.shape[1] == cell_elev.size and wt_ptr.size == self.nHRU + 1
+        self.lib.rvh_model_set_cell_forcing.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5
+        if self.lib.rvh_model_set_cell_forcing(self.h, int(series.shape[1]), int(series.shape[2]), cell_elev.ctypes.data, series.ctypes.data,
+                                               wt_ptr.ctypes.data, wt_idx.ctypes.data, wt_val.ctypes.data):
+            raise RavenError(self.lib.rvh_last_error().decode())
+        self.desc = None
+
     def sv_names(self):
         buf = C.create_string_buffer(64)
         out = []

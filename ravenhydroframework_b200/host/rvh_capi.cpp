@@ -190,6 +190,15 @@ int rvh_desc_info(const rvn_model_desc *d, int *out8) {
   return 0;
 }
 const double *rvh_desc_gauge_series(const rvn_model_desc *d) { return d->gauge_series; }
+int rvh_desc_num_gauges(const rvn_model_desc *d) { return d->nGauges; }
+// gridded forcing ingestion (CModel::SetCellForcing): takes effect at the next rvh_model_flatten
+int rvh_model_set_cell_forcing(rvh_model *h, int nCells, int nSteps, const double *cell_elev, const double *series, const int32_t *wt_ptr,
+                               const int32_t *wt_idx, const double *wt_val) {
+  RVH_TRY
+  h->pModel->SetCellForcing(nCells, nSteps, cell_elev, series, wt_ptr, wt_idx, wt_val);
+  return 0;
+  RVH_CATCH(-1)
+}
 const int32_t *rvh_desc_conv_n(const rvn_model_desc *d) { return d->conv_n; }
 int rvh_desc_sv_table(const rvn_model_desc *d, int32_t *type, int32_t *layer) {
   for (int i = 0; i < d->NS; i++) { type[i] = d->sv_type[i]; layer[i] = d->sv_layer[i]; }

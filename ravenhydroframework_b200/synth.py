@@ -215,6 +215,53 @@ def write_gauge_grid(base, n_gauges, n_days, seed, season_offset, hru_latlon, ex
     return ":InterpolationMethod INTERP_FROM_FILE %s\n" % os.path.basename(wfile)
 
 
+def apply_cell_grid(model, base, nx=200, ny=200, seed=1):
+    """BASELINE config 4's forcing input: a synthetic nx x ny grid over the watershed (values = the single-gauge series of the
+    parsed model x a smooth spatial factor, temperatures + a smooth offset, elevations 700-1200 m), every HRU weighted to its 4 nearest
+    cells with normalised inverse-distance weights (CSR, nnz = 4 nHRU) - handed to the host layer through RavenModel.set_cell_forcing
+    (the arithmetic of CForcingGrid::GetWeightedValue, src/ForcingGrid.cpp:1886-1900).  `model` must be flattened (1 gauge)."""
+    base_series = model.gauge_series()                 # [9][1][nSteps]
+    assert base_series.shape[1] == 1
+    nS = base_series.shape[2]
+    ll = np.array(_hru_latlon(base + ".rvh"))          # [nH][2]
+    la0, la1, lo0, lo1 = ll[:, 0].min(), ll[:, 0].max(), ll[:, 1].min(), ll[:, 1].max()
+    dy, dx = (la1 - la0) / ny + 1e-12, (lo1 - lo0) / nx + 1e-12
+    iy, ix = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+    fac = (1.0 + 0.25 * np.sin(0.13 * ix + 0.4) * np.cos(0.09 * iy - 0.2)).reshape(-1)
+    dT = (2.0 * np.sin(0.07 * ix) - 1.5 * np.cos(0.11 * iy)).reshape(-1)
+    rng = np.random.RandomState(seed + 2000)
+    elev = 700.0 + 500.0 * rng.uniform(0, 1, nx * ny)
+    nC = nx * ny
+    series = np.empty((9, nC, nS))
+    GF = dict(PRECIP=0, SNOW_FRAC=1, TEMP_AVE=2, TEMP_DAILY_AVE=3, TEMP_DAILY_MIN=4, TEMP_DAILY_MAX=5, PET=6, OW_PET=7, POTENTIAL_MELT=8)
+    for name, i in GF.items():
+        b = base_series[i, 0][None, :]
+        if name in ("PRECIP",):
+            series[i] = b * fac[:, None]
+        elif name in ("PET", "OW_PET"):
+            series[i] = b * (2.0 - fac)[:, None]
+        elif name.startswith("TEMP"):
+            series[i] = b + dT[:, None]
+        else:
+            series[i] = np.broadcast_to(b, (nC, nS))
+    # 4 nearest cell centres: the cell containing the HRU and its neighbours towards the HRU's side
+    fy = (ll[:, 0] - la0) / dy - 0.5
+    fx = (ll[:, 1] - lo0) / dx - 0.5
+    y0 = np.clip(np.floor(fy).astype(int), 0, ny - 2)
+    x0 = np.clip(np.floor(fx).astype(int), 0, nx - 2)
+    nH = ll.shape[0]
+    idx = np.stack([y0 * nx + x0, y0 * nx + x0 + 1, (y0 + 1) * nx + x0, (y0 + 1) * nx + x0 + 1], axis=1)   # ascending cell index
+    cy = np.stack([y0, y0, y0 + 1, y0 + 1], axis=1) + 0.5
+    cx = np.stack([x0, x0 + 1, x0, x0 + 1], axis=1) + 0.5
+    d2 = (cy - (fy + 0.5)[:, None]) ** 2 + (cx - (fx + 0.5)[:, None]) ** 2
+    w = 1.0 / (d2 + 1e-6)
+    w = w / w.sum(axis=1, keepdims=True)
+    w[:, 3] = 1.0 - w[:, :3].sum(axis=1)
+    ptr = np.arange(nH + 1, dtype=np.int32) * 4
+    model.set_cell_forcing(elev, series, ptr, idx.reshape(-1).astype(np.int32), w.reshape(-1))
+    return nC
+
+
 def _hru_latlon(rvh_path):
     out, on = [], False
     for line in open(rvh_path):

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import helpers as H
-from ravenhydroframework_b200 import api, synth
+from ravenhydroframework_b200 import api, enkf, synth
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
@@ -88,3 +88,59 @@ def test_config4_blended_distributed_muskingum(tmp_path):
     assert H.rel_err(sim.hydrographs(0, n)[:, 0, :], ref["qout_rec"]) < TOL
     assert H.rel_err(sim.watershed(0, n)[:, 0, :3], ref["wshed_rec"][:, :3]) < TOL
     sim.close()
+
+
+def test_config4_full_size_1m_hrus_50k_subbasins_gridded_hourly(tmp_path):
+    """BASELINE config 4 at its full size: Blended process groups, 1,000,000 HRUs / 50,000 subbasins, forcing on a 200 x 200 grid
+    (40,000 cells, 4 cells per HRU, CSR gather), hourly step, Muskingum routing.  Every HRU storage, every subbasin hydrograph and
+    the watershed balance against the oracle under the strict tolerance - no exception list."""
+    n = 24
+    base = synth.write_blended(str(tmp_path), n_sb=50000, hru_per_sb=20, n_days=1, seed=4, routing="ROUTE_MUSKINGUM", catchment_route="TRIANGULAR_UH",
+                               season_offset=124)
+    rvi = open(base + ".rvi").read()
+    open(base + ".rvi", "w").write(rvi.replace(":TimeStep              1.0", ":TimeStep              01:00:00"))
+    model = api.RavenModel(base)
+    model.flatten(1)
+    assert (model.nHRU, model.nSB, model.nSteps) == (1000000, 50000, n)
+    assert synth.apply_cell_grid(model, base, 200, 200) == 40000
+    model.flatten(1)
+    sim = api.GpuSimulation(model)
+    assert sim.kernel_variant() == "static:BLENDED"
+    sim.set_recording(n)
+    sim.run(n)
+    ref = H.oracle_run(model, n, record_state=False)
+    assert H.rel_err(sim.download_state()[0], ref["state"]) < TOL
+    assert H.rel_err(sim.hydrographs(0, n)[:, 0, :], ref["qout_rec"]) < TOL
+    assert H.rel_err(sim.watershed(0, n)[:, 0, :3], ref["wshed_rec"][:, :3]) < TOL
+    sim.close()
+
+
+def test_config5_enkf_512_members_x_100k_hrus(tmp_path):
+    """BASELINE config 5 at its full size on one GPU: HBV-EC, 100,000 HRUs / 5,000 subbasins, 512 members with forcing perturbations,
+    SOIL[0] + SNOW of every HRU and STREAMFLOW of every subbasin assimilated at 10 gauged outlets.  Forecast: two complete members against
+    the oracle.  Analysis: Z from the host layer equals the oracle's (same Golub-Reinsch SVD), and the device update of a 4,096-row
+    sample of the 310,000-row state matrix equals the oracle's analysis of those rows bit for bit (rows are independent given Z)."""
+    import sys
+    sys.path.insert(0, H.ROOT + "/oracle")
+    import enkf_oracle as EO
+    n_sb, hps, days, N = 5000, 20, 6, 512
+    base = synth.write_hbv(str(tmp_path), n_sb=n_sb, hru_per_sb=hps, n_days=days, seed=31, routing="ROUTE_MUSKINGUM", name="model", season_offset=130)
+    synth.add_enkf(base, n_members=N, n_sb=n_sb, n_hru=n_sb * hps, n_days=days, obs_basins=tuple(range(1, 11)), window=1)
+    model = api.RavenModel(base)
+    sim = enkf.EnKFSimulation(model, device=0)
+    assert (sim.N, model.nHRU, model.nSB) == (N, 100000, 5000)
+    out = sim.forecast()
+    for e in (0, 377):
+        r = H.oracle_run(model, sim.nsteps, member=e, record_state=False)
+        assert H.rel_err(sim.sim.download_state(e, 1)[0], r["state"]) < TOL
+        assert H.rel_err(sim.sim.hydrographs(0, sim.nsteps, e, 1)[:, 0, :], r["qout_rec"]) < TOL
+    obs, noise, _, _ = model.enkf_observations()
+    pre, post = sim.analysis()
+    M = pre.shape[1]
+    assert M == sim.info["M"] and M >= 300000
+    rows = np.random.RandomState(5).choice(M, size=4096, replace=False)
+    Xa, Zo = EO.assimilation_calcs(pre[:, rows], out, obs, noise)
+    assert np.array_equal(model.enkf_compute_Z(out), Zo)
+    assert np.array_equal(post[:, rows], Xa)
+    assert np.array_equal(sim.sim.enkf_pack(), np.maximum(post, 0.0))   # UpdateFromStateMatrix
+    sim.sim.close()
