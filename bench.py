@@ -203,7 +203,7 @@ class Ctx:
 
 
 def _live_stores(model, E):
-    """Mean number of live convolution stores per (member, HRU): sum over convolution processes of N(member, class 0)."""
+    """Mean number of live convolution stores per (member, HRU): sum over convolution processes of N(member, land-use class of the HRU)."""
     import ctypes as C
     import numpy as np
     lib = model.lib
@@ -215,7 +215,11 @@ def _live_stores(model, E):
     if nconv == 0:
         return 0.0
     arr = np.ctypeslib.as_array((C.c_int32 * (E * nLU * nconv)).from_address(lib.rvh_desc_conv_n(model.desc))).reshape(E, nLU, nconv)
-    return float(arr.sum(axis=2).mean())
+    lu = np.zeros(model.nHRU, dtype=np.int32)
+    lib.rvh_desc_hru_lu.argtypes = [C.c_void_p, C.c_void_p]
+    lib.rvh_desc_hru_lu(model.desc, lu.ctypes.data)
+    hrus_per_class = np.bincount(lu, minlength=nLU).astype(np.float64)
+    return float((arr.sum(axis=2) * hrus_per_class[None, :]).sum() / (E * model.nHRU))
 
 
 def resident_pass(cx, sim, W, K, clock_index=None):
@@ -245,8 +249,8 @@ def stream_pass(cx, sim, model, W, K, E, NB):
     nG = model.gauge_series().shape[1]
     series = torch.from_numpy(model.gauge_series())                          # [9][nG][nSteps]
     s0 = sim.step
-    slabs = torch.zeros((W + K, 9, nG), dtype=torch.float64).pin_memory()
-    slabs[:] = series[:, :, s0:s0 + W + K].permute(2, 0, 1)
+    slabs = torch.zeros((W + K, nG, 9), dtype=torch.float64).pin_memory()      # one station-major slab [nGauges][RVN_GF_COUNT] per step
+    slabs[:] = series[:, :, s0:s0 + W + K].permute(2, 1, 0)
     hyd_all = torch.zeros((W + K, E, NB), dtype=torch.float64).pin_memory()
     wsh_all = torch.zeros((W + K, E, 4), dtype=torch.float64).pin_memory()
     sb, hb, wb = slabs.data_ptr(), hyd_all.data_ptr(), wsh_all.data_ptr()

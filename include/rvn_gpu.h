@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RVN_ABI_VERSION 7
+#define RVN_ABI_VERSION 8
 #define RVN_DOESNT_EXIST (-1)
 #define RVN_CONV_STORES 50   /* MAX_CONVOL_STORES, reference src/RavenInclude.h / Convolution.cpp:17 */
 #define RVN_MAX_CONN 24      /* max connections of a non-convolution process (Precipitation: 13..19) */
@@ -404,6 +404,14 @@ typedef struct rvn_model_desc {
    * reference draws nStepsPerDay samples at the start of a day, src/Model.cpp:2829-2847; steps here are daily or longer):
    * pert_eps[member][step][pert].  pert_mask[pert][hru] = 1 where the HRU belongs to the perturbation's HRU group
    * (NULL = every perturbation applies to every HRU). */
+  /* user-specified basin inflows [m3/s] (reference :BasinInflowHydrograph / :BasinInflowHydrograph2, CSubBasin::GetSpecifiedInflow /
+   * GetDownstreamInflow): for the nSpec basins that have one (spec_basin[], ascending index) and every step, spec_in = the value the
+   * solver adds to the basin's inflow from upstream (at t + dt, src/Solvers.cpp:543), spec_down = the value it adds to the outflow of
+   * the last reach segment (at t, :586), spec_cum = the basin's term of CModel::IncrementCumulInput [mm] (src/Model.cpp:2467-2469).
+   * Layout [nSteps][nSpec]; nSpec = 0: none. */
+  int32_t nSpec, pad4_;
+  const int32_t *spec_basin;
+  const double *spec_in, *spec_down, *spec_cum;
   int32_t nPert, pad3_;
   const int32_t *pert_forcing;  /* [nPert] rvn_pert_forcing */
   const int32_t *pert_adj;      /* [nPert] rvn_adjustment */
@@ -461,7 +469,7 @@ int rvn_gpu_upload_forcings(rvn_gpu_model *m, const double *gauge_series, const 
 int rvn_gpu_run(rvn_gpu_model *m, int step0, int nsteps);
 int rvn_gpu_sync(rvn_gpu_model *m);
 /* streaming form of ONE model step for host-side callers (BMI-style drivers that feed forcings and consume hydrographs step by
- * step): nothing waits.  Enqueued, in order: copy of this step's forcing slab forcing_host[RVN_GF_COUNT][nGauges] (pinned host
+ * step): nothing waits.  Enqueued, in order: copy of this step's forcing slab forcing_host[nGauges][RVN_GF_COUNT] (station-major: the layout the sweep gathers from; pinned host
  * memory, may be NULL to keep the uploaded series) to the device; the step; copies of the step's outflows
  * qout_host[nMembers][nSB] and watershed record wshed_host[nMembers][4] (pinned, either may be NULL) back to the host.  The
  * result copies run on the routing stream underneath the next step's sweep.  Host buffers must stay untouched / are valid

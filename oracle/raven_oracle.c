@@ -1417,6 +1417,8 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
       }
       for (int k = 0; k < nH; k++) if (d->hru_enabled[k]) finish_hru(d, k, state + (size_t)k * NS, aRouted, iSW, iRO, iTotalSWE, iGlacierMB);
     }
+    /* ---- user-specified inflows to the upstream end of the reach (src/Solvers.cpp:543): value at t + dt */
+    for (int i = 0; i < d->nSpec; i++) aQinnew[d->spec_basin[i]] += d->spec_in[(size_t)step * d->nSpec + i];
     /* ---- routing, upstream to downstream (src/Solvers.cpp:565-615) */
     for (int pp = 0; pp < NB; pp++) {
       int p = d->sb_order[pp];
@@ -1427,7 +1429,11 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
       for (int n = d->sb_nqlat[p] - 1; n > 0; n--) QlatHist[n] = QlatHist[n - 1]; /* UpdateLateralInflow :1547-1553 */
       QlatHist[0] = aRouted[p] / (tstep * O_SEC_PER_DAY);
       route_water(d, p, &B, aQoutnew);
-      aQoutnew[d->sb_nseg[p] - 1] += 0.0; /* down_Q */
+      {
+        double down_Q = 0.0;   /* GetDownstreamInflow(t) + GetTotalReturnFlow() (src/Solvers.cpp:586) */
+        for (int i = 0; i < d->nSpec; i++) if (d->spec_basin[i] == p) down_Q = d->spec_down[(size_t)step * d->nSpec + i] + 0.0;
+        aQoutnew[d->sb_nseg[p] - 1] += down_Q;
+      }
       update_outflows(d, p, &B, aQoutnew);
       int pTo = d->sb_down[p];
       if (pTo >= 0) aQinnew[pTo] += qout[(size_t)p * RVN_MAX_RIVER_SEGS + d->sb_nseg[p] - 1];
@@ -1439,7 +1445,7 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
       double avg_precip = sum / d->watershed_area;
       cumul[0] += avg_precip * tstep;
       cumul[0] += 0.0 * tstep; /* recharge */
-      for (int p = 0; p < NB; p++) cumul[0] += 0.0 / area * O_MM_PER_METER; /* specified inflows */
+      for (int i = 0; i < d->nSpec; i++) cumul[0] += d->spec_cum[(size_t)step * d->nSpec + i]; /* GetIntegratedSpecInflow of the basins that have one (the others add 0) */
       for (int p = 0; p < NB; p++) {
         int pd = d->sb_down[p];
         if (d->sb_level[p] == 0 || pd < 0) {

@@ -64,7 +64,7 @@ struct DevModel {
   const int32_t *hru_terrain; int32_t terr_off;   // terrain class of each HRU (or NULL) and its block in the parameter table
   const unsigned long long *apply_mask;
   const int32_t *prof_class; const double *prof_thick;
-  const double *gauge_series;                      // [step][RVN_GF_COUNT][nGauges]: one contiguous slab per step
+  const double *gauge_series;                      // [step][nGauges][RVN_GF_COUNT]: one contiguous slab per step, station-major
   const double *gauge_const;
   const int32_t *wt_ptr, *wt_idx; const double *wt_val;   // CSR gauge/grid-cell weights (rvn_gpu.h)
   int32_t unit_weights;                            // 1: one station, every HRU weight exactly 1.0 (CSR not read)
@@ -87,6 +87,8 @@ struct DevModel {
   const double *sb_unit_hydro, *sb_route_hydro;
   const double *chan_Q, *chan_A, *sb_Qmult, *sb_reach_m; const int32_t *sb_channel; int32_t nChanPts;   // ROUTE_HYDROLOGIC rating curves
   double watershed_area;
+  // user-specified basin inflows (rvn_model_desc::spec_*): slot of each basin in the [nSteps][nSpec] tables or -1
+  int32_t nSpec; const int32_t *sb_spec_slot; const double *spec_in, *spec_down, *spec_cum;
   // recording
   double *rec_qout, *rec_wshed;                    // [rec][member][nSB], [rec][member][4]
   int32_t rec_capacity, rec_flags;

@@ -207,9 +207,10 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
 #pragma unroll
   for (int f = 0; f < RVN_F_CARRIED; f++) F[f] = 0.0;
   // K3: sparse gather over this HRU's gauges / grid cells (CSR, ascending gauge index = the reference's summation order;
-  // omitted zero weights add exact zeros there).  The step's series form one contiguous [forcing][gauge] slab.
+  // omitted zero weights add exact zeros there).  The step's series form one contiguous [gauge][forcing] slab: the 9 values of a
+  // station / grid cell are 72 contiguous bytes, so the gather of a scattered HRU touches 2-3 sectors per cell instead of 9.
   const double *slab = M.gauge_series + (size_t)step * RVN_GF_COUNT * nG;
-#define GS(f, g) slab[(size_t)(f) * nG + (g)]
+#define GS(f, g) slab[(size_t)(g) * RVN_GF_COUNT + (f)]
 #define GC(g, f) M.gauge_const[(size_t)(g) * RVN_GC_COUNT + (f)]
   // single-station models (every weight exactly 1.0): no CSR loads at all, the loops below run once with g = 0, wt = 1.0
   const bool uw = (M.unit_weights != 0);
@@ -807,7 +808,7 @@ struct PrefetchConvs {
 template <class Prog, bool UNIT_DT, int J>
 struct RunProcs {
   static RVN_DI void run(StatCtx<Prog> &c, const DevModel &M, const bool enabled, const unsigned long long mask, const int e, const int k,
-                         double *gstate) {
+                         double *gstate, const bool sum_valid) {
     if constexpr (J < Prog::nProc) {
       constexpr int op = Prog::op(J);
       const bool apply = enabled && ((mask >> J) & 1ull);   // CModel::ApplyProcess gate (src/Model.cpp:3061)
@@ -817,7 +818,7 @@ struct RunProcs {
           const size_t slot = ((size_t)e * M.nLU + c.lu) * M.nConv + ci;
           convolve_direct<UNIT_DT>(c, Prog::ia(J, 1), Prog::ia(J, 3), gstate + (size_t)Prog::ia(J, 2) * M.nHp, (size_t)M.nHp,
                                    M.conv_tab + slot * RVN_CONV_STORES, M.conv_n[slot], M.conv_sum + ((size_t)e * M.nConv + ci) * M.nHp + k,
-                                   M.conv_sum_valid != 0);
+                                   sum_valid);
         }
       } else {
         if (apply) {
@@ -831,7 +832,7 @@ struct RunProcs {
           }
         }
       }
-      RunProcs<Prog, UNIT_DT, J + 1>::run(c, M, enabled, mask, e, k, gstate);
+      RunProcs<Prog, UNIT_DT, J + 1>::run(c, M, enabled, mask, e, k, gstate, sum_valid);
     }
   }
 };
@@ -839,8 +840,13 @@ struct RunProcs {
 #ifndef RVN_STATIC_MIN_BLOCKS
 #define RVN_STATIC_MIN_BLOCKS 7   // resident CTAs per SM the specialised sweep is compiled for (caps registers at 72/thread)
 #endif
-template <class Prog, bool UNIT_DT>
-__global__ void __launch_bounds__(RVN_BS, RVN_STATIC_MIN_BLOCKS) hru_sweep_static(const __grid_constant__ DevModel M, const int step) {
+// One launch advances every (member, HRU) pair of the grid by `nsub` consecutive model steps (MULTI; 1 otherwise).  Without lateral
+// exchange an HRU's steps depend on nothing but its own state and the shared forcings, so the state vector stays on chip between
+// the sub-steps (temporal blocking: the core state is read and written once per launch instead of once per step) and only what
+// routing and the balance need per step - the surface-water volume and the block partial sums - goes to the ring slot
+// slot0 + sub-step of the hand-off buffers.
+template <class Prog, bool UNIT_DT, bool MULTI>
+__global__ void __launch_bounds__(RVN_BS, RVN_STATIC_MIN_BLOCKS) hru_sweep_static(const __grid_constant__ DevModel M, const int step0, const int nsub_, const int slot0) {
   double *s_ptab = reinterpret_cast<double *>(rvn_smem);
   double *s_red = s_ptab + ((M.ptab_stride + 1) & ~1);
   const int tid = threadIdx.x, e = blockIdx.y, k = blockIdx.x * RVN_BS + tid;
@@ -872,49 +878,56 @@ __global__ void __launch_bounds__(RVN_BS, RVN_STATIC_MIN_BLOCKS) hru_sweep_stati
 #pragma unroll
   for (int s = 0; s < Prog::nCore; s++) c.SV(s) = __ldcs(gstate + (size_t)Prog::slot_sv(s) * nHp);
   if (RVN_PF_DIST > 0 && enabled) PrefetchConvs<Prog, 0>::run(gstate, nHp);
-  c.old_snow = (Prog::iSV(RVN_SV_SNOW) >= 0) ? c.SV(Prog::iSV(RVN_SV_SNOW) >= 0 ? Prog::iSV(RVN_SV_SNOW) : 0) : 0.0;
-  c.old_snow_cover = (Prog::iSV(RVN_SV_SNOW_COVER) >= 0) ? c.SV(Prog::iSV(RVN_SV_SNOW_COVER) >= 0 ? Prog::iSV(RVN_SV_SNOW_COVER) : 0) : 0.0;
-  c.old_snow_depth = (Prog::iSV(RVN_SV_SNOW_DEPTH) >= 0) ? c.SV(Prog::iSV(RVN_SV_SNOW_DEPTH) >= 0 ? Prog::iSV(RVN_SV_SNOW_DEPTH) : 0) : 0.0;
-  c.old_snow_temp = (Prog::iSV(RVN_SV_SNOW_TEMP) >= 0) ? c.SV(Prog::iSV(RVN_SV_SNOW_TEMP) >= 0 ? Prog::iSV(RVN_SV_SNOW_TEMP) : 0) : 0.0;
   __syncthreads();   // parameter row staged
-  // ---- forcings (on the stored state)
-  if (enabled) compute_forcings(c, M, e, k, step, sb);
-  else {
+  const int nsub = MULTI ? nsub_ : 1;
+#pragma unroll 1
+  for (int ss = 0; ss < nsub; ss++) {
+    const int step = step0 + ss;
+    c.old_snow = (Prog::iSV(RVN_SV_SNOW) >= 0) ? c.SV(Prog::iSV(RVN_SV_SNOW) >= 0 ? Prog::iSV(RVN_SV_SNOW) : 0) : 0.0;
+    c.old_snow_cover = (Prog::iSV(RVN_SV_SNOW_COVER) >= 0) ? c.SV(Prog::iSV(RVN_SV_SNOW_COVER) >= 0 ? Prog::iSV(RVN_SV_SNOW_COVER) : 0) : 0.0;
+    c.old_snow_depth = (Prog::iSV(RVN_SV_SNOW_DEPTH) >= 0) ? c.SV(Prog::iSV(RVN_SV_SNOW_DEPTH) >= 0 ? Prog::iSV(RVN_SV_SNOW_DEPTH) : 0) : 0.0;
+    c.old_snow_temp = (Prog::iSV(RVN_SV_SNOW_TEMP) >= 0) ? c.SV(Prog::iSV(RVN_SV_SNOW_TEMP) >= 0 ? Prog::iSV(RVN_SV_SNOW_TEMP) : 0) : 0.0;
+    // ---- forcings (on the stored state)
+    if (enabled) compute_forcings(c, M, e, k, step, sb);
+    else {
 #pragma unroll
-    for (int f = 0; f < RVN_F_CARRIED; f++) c.F[f] = 0.0;
-  }
-  load_canopy(c, M, step);   // (class, date) only: placed after the forcing chain so that its results are not live across it
-  if (enabled) reboot_diagnostics(c);   // disabled HRUs keep their stored values (the reference never writes them back, :701)
-  // ---- ordered-series process sweep on the newest state
-  RunProcs<Prog, UNIT_DT, 0>::run(c, M, enabled, mask, e, k, gstate);
-  // ---- routing prep, diagnostics, state out + per-HRU part of the output reductions
-  double swv = 0.0, stor = 0.0;
-  if (enabled) {
-    swv = finish_step(c, Prog::nCore);
-    stor = hru_storage(c, Prog::nCore) * c.area;
-#pragma unroll
-    for (int s = 0; s < Prog::nCore; s++) __stcs(gstate + (size_t)Prog::slot_sv(s) * nHp, c.SV(s));
-    if (M.record_forcings) {
-      double *gf = M.forc + (size_t)e * RVN_F_COUNT * nHp + k;
-#pragma unroll
-      for (int f = 0; f < RVN_F_CARRIED; f++) gf[(size_t)f * nHp] = c.F[f];
+      for (int f = 0; f < RVN_F_CARRIED; f++) c.F[f] = 0.0;
     }
-  }
-  const int par = step & 1;
-  if (in_range) M.swvol[((size_t)par * M.E + e) * nHp + k] = swv;
-  const double pa = enabled ? c.F[RVN_F_PRECIP] * c.area : 0.0;
-  const double bp = block_sum(pa, s_red);
-  const double bs = block_sum(stor, s_red);
-  if (tid == 0) {
-    M.part_precip[((size_t)par * M.E + e) * M.nBlocksX + blockIdx.x] = bp;
-    M.part_storage[((size_t)par * M.E + e) * M.nBlocksX + blockIdx.x] = bs;
+    load_canopy(c, M, step);   // (class, date) only: placed after the forcing chain so that its results are not live across it
+    if (enabled) reboot_diagnostics(c);   // disabled HRUs keep their stored values (the reference never writes them back, :701)
+    // ---- ordered-series process sweep on the newest state
+    RunProcs<Prog, UNIT_DT, 0>::run(c, M, enabled, mask, e, k, gstate, (M.conv_sum_valid != 0) || (MULTI && ss > 0));
+    // ---- routing prep, diagnostics + per-HRU part of the output reductions
+    double swv = 0.0, stor = 0.0;
+    if (enabled) {
+      swv = finish_step(c, Prog::nCore);
+      stor = hru_storage(c, Prog::nCore) * c.area;
+      if (!MULTI || ss == nsub - 1) {   // ---- state out
+#pragma unroll
+        for (int s = 0; s < Prog::nCore; s++) __stcs(gstate + (size_t)Prog::slot_sv(s) * nHp, c.SV(s));
+      }
+      if (M.record_forcings) {
+        double *gf = M.forc + (size_t)e * RVN_F_COUNT * nHp + k;
+#pragma unroll
+        for (int f = 0; f < RVN_F_CARRIED; f++) gf[(size_t)f * nHp] = c.F[f];
+      }
+    }
+    const int slot = slot0 + ss;
+    if (in_range) M.swvol[((size_t)slot * M.E + e) * nHp + k] = swv;
+    const double pa = enabled ? c.F[RVN_F_PRECIP] * c.area : 0.0;
+    const double bp = block_sum(pa, s_red);
+    const double bs = block_sum(stor, s_red);
+    if (tid == 0) {
+      M.part_precip[((size_t)slot * M.E + e) * M.nBlocksX + blockIdx.x] = bp;
+      M.part_storage[((size_t)slot * M.E + e) * M.nBlocksX + blockIdx.x] = bs;
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // interpreter sweep: arbitrary process lists (DevProgram), state/rates in shared-memory columns
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant__ DevModel M, const int step) {
+__global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant__ DevModel M, const int step0, const int nsub, const int slot0) {
   // ---- shared memory carve-up
   DevProgram *P = reinterpret_cast<DevProgram *>(rvn_smem);
   double *s_ptab = reinterpret_cast<double *>(rvn_smem + ((sizeof(DevProgram) + 15) & ~size_t(15)));
@@ -949,6 +962,10 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
   const unsigned long long mask = M.apply_mask[k];
   double *gstate = M.state + (size_t)e * M.NS * nHp + k;
   for (int s = 0; s < nCore; s++) c.SV(s) = __ldcs(gstate + (size_t)P->slot_sv[s] * nHp);
+  double *const sv_read = c.sv;
+  for (int ss = 0; ss < nsub; ss++) {   // sub-steps of this launch (see hru_sweep_static); nsub = 1 with lateral processes or EULER
+  const int step = step0 + ss;
+  c.sv = sv_read;
   c.old_snow = (P->iSV[RVN_SV_SNOW] >= 0) ? c.SV(P->iSV[RVN_SV_SNOW]) : 0.0;
   c.old_snow_cover = (P->iSV[RVN_SV_SNOW_COVER] >= 0) ? c.SV(P->iSV[RVN_SV_SNOW_COVER]) : 0.0;
   c.old_snow_depth = (P->iSV[RVN_SV_SNOW_DEPTH] >= 0) ? c.SV(P->iSV[RVN_SV_SNOW_DEPTH]) : 0.0;
@@ -969,8 +986,9 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
       const size_t slot = ((size_t)e * M.nLU + c.lu) * M.nConv + ci;
       double *g = gstate + (size_t)pr.ia[2] * nHp;
       double *sc = M.conv_sum + ((size_t)e * M.nConv + ci) * nHp + k;
-      if (unit_dt) convolve_direct<true>(c, pr.ia[1], pr.ia[3], g, nHp, M.conv_tab + slot * RVN_CONV_STORES, M.conv_n[slot], sc, M.conv_sum_valid != 0);
-      else convolve_direct<false>(c, pr.ia[1], pr.ia[3], g, nHp, M.conv_tab + slot * RVN_CONV_STORES, M.conv_n[slot], sc, M.conv_sum_valid != 0);
+      const bool sum_valid = (M.conv_sum_valid != 0) || ss > 0;
+      if (unit_dt) convolve_direct<true>(c, pr.ia[1], pr.ia[3], g, nHp, M.conv_tab + slot * RVN_CONV_STORES, M.conv_n[slot], sc, sum_valid);
+      else convolve_direct<false>(c, pr.ia[1], pr.ia[3], g, nHp, M.conv_tab + slot * RVN_CONV_STORES, M.conv_n[slot], sc, sum_valid);
       continue;
     }
     const DynProc dp = {&pr, P};
@@ -987,22 +1005,23 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
       swv = finish_step(c, nCore);
       stor = hru_storage(c, nCore) * c.area;
     }
-    for (int s = 0; s < nCore; s++) __stcs(gstate + (size_t)P->slot_sv[s] * nHp, c.SV(s));
+    if (ss == nsub - 1) { for (int s = 0; s < nCore; s++) __stcs(gstate + (size_t)P->slot_sv[s] * nHp, c.SV(s)); }
     if (M.record_forcings) {
       double *gf = M.forc + (size_t)e * RVN_F_COUNT * nHp + k;
 #pragma unroll
       for (int f = 0; f < RVN_F_CARRIED; f++) gf[(size_t)f * nHp] = c.F[f];
     }
   }
-  const int par = step & 1;
-  if (in_range && !defer) M.swvol[((size_t)par * M.E + e) * nHp + k] = swv;
+  const int slot = slot0 + ss;
+  if (in_range && !defer) M.swvol[((size_t)slot * M.E + e) * nHp + k] = swv;
   const double pa = enabled ? c.F[RVN_F_PRECIP] * c.area : 0.0;
   const double bp = block_sum(pa, s_red);
   const double bs = block_sum(stor, s_red);
   if (tid == 0) {
-    M.part_precip[((size_t)par * M.E + e) * M.nBlocksX + blockIdx.x] = bp;
-    if (!defer) M.part_storage[((size_t)par * M.E + e) * M.nBlocksX + blockIdx.x] = bs;
+    M.part_precip[((size_t)slot * M.E + e) * M.nBlocksX + blockIdx.x] = bp;
+    if (!defer) M.part_storage[((size_t)slot * M.E + e) * M.nBlocksX + blockIdx.x] = bs;
   }
+  }   // sub-steps
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1035,7 +1054,7 @@ RVN_DI double channel_area(const DevModel &M, const int p, const double Q) {
 // one basin, one member, one step: HRU -> subbasin aggregation in HRU-index order (src/Solvers.cpp:490-511),
 // CSubBasin::UpdateLateralInflow / UpdateInflow, RouteWater (src/SubBasin.cpp:2584-2863), UpdateOutflows (:2320-2421).
 // `t` = pushes into the histories before this step.
-__device__ void route_one_basin(const DevModel &M, int e, int p, int step, int t) {
+__device__ void route_one_basin(const DevModel &M, int e, int p, int slot, int t, int step) {
   const double tstep = M.opt.timestep;
   const int nSeg = M.sb_nseg[p], nQin = M.sb_nqin[p], nQlat = M.sb_nqlat[p];
   const Ring QinHist(M.qin + ((size_t)e * M.nSB + p) * M.max_nqin, nQin, t + 1);
@@ -1044,14 +1063,15 @@ __device__ void route_one_basin(const DevModel &M, int e, int p, int step, int t
   double *sc = M.scal + ((size_t)e * M.nSB + p) * 8;
   const double *UH = M.sb_unit_hydro + (size_t)p * M.max_nqlat, *RH = M.sb_route_hydro + (size_t)p * M.max_nqin;
   {
-    const double *swvol = M.swvol + ((size_t)(step & 1) * M.E + e) * M.nHp;
+    const double *swvol = M.swvol + ((size_t)slot * M.E + e) * M.nHp;
     double routed = 0.0;
     for (int i = M.sb_hru_ptr[p]; i < M.sb_hru_ptr[p + 1]; i++) routed += swvol[M.sb_hru_idx[i]];
     QlatHist[0] = routed / (tstep * D_SEC_PER_DAY);
   }
   // inflow from upstream basins, accumulated in the reference's processing order (ascending index inside the
   // level above; src/Solvers.cpp:602-606), then CSubBasin::UpdateInflow (src/SubBasin.cpp:1531-1537)
-  double Qin_up = 0.0;
+  const int ispec = (M.nSpec > 0) ? M.sb_spec_slot[p] : -1;
+  double Qin_up = (ispec >= 0) ? 0.0 + M.spec_in[(size_t)step * M.nSpec + ispec] : 0.0;   // user-specified inflow first (src/Solvers.cpp:543)
   for (int u = M.sb_up_ptr[p]; u < M.sb_up_ptr[p + 1]; u++) {
     const int pu = M.sb_up_idx[u];
     Qin_up += M.qout[((size_t)e * M.nSB + pu) * RVN_MAX_RIVER_SEGS + M.sb_nseg[pu] - 1];
@@ -1129,7 +1149,7 @@ __device__ void route_one_basin(const DevModel &M, int e, int p, int step, int t
     aQout[nSeg - 1] = Qin0;
   }
   aQout[nSeg - 1] += Qlat_new;
-  aQout[nSeg - 1] += 0.0;  // down_Q (specified downstream inflows / return flows: none)
+  aQout[nSeg - 1] += (ispec >= 0) ? M.spec_down[(size_t)step * M.nSpec + ispec] + 0.0 : 0.0;  // down_Q = specified downstream inflow + return flows (none)
   // CSubBasin::UpdateOutflows  src/SubBasin.cpp:2320-2421 (no irrigation, diversions or reservoirs)
   sc[0] = QoutLast;
   const double irrQ = dmin(0.0, aQout[nSeg - 1]); aQout[nSeg - 1] -= irrQ;
@@ -1161,29 +1181,30 @@ __device__ void route_one_basin(const DevModel &M, int e, int p, int step, int t
 #ifndef RVN_ROUTE_MINB
 #define RVN_ROUTE_MINB 32
 #endif
-__global__ void __launch_bounds__(RVN_ROUTE_BS, RVN_ROUTE_MINB) route_level_kernel(const __grid_constant__ DevModel M, const int lev0, const int nlev, const int step, const int t) {
+__global__ void __launch_bounds__(RVN_ROUTE_BS, RVN_ROUTE_MINB) route_level_kernel(const __grid_constant__ DevModel M, const int lev0, const int nlev, const int slot, const int t, const int step) {
   const long long idx = (long long)blockIdx.x * RVN_ROUTE_BS + threadIdx.x;
   if (idx >= (long long)M.E * nlev) return;
   const int e = (int)(idx / nlev), i = (int)(idx - (long long)e * nlev);
-  route_one_basin(M, e, M.level_idx[lev0 + i], step, t);
+  route_one_basin(M, e, M.level_idx[lev0 + i], slot, t, step);
 }
-__global__ void __launch_bounds__(RVN_ROUTE_BS, RVN_ROUTE_MINB) balance_kernel(const __grid_constant__ DevModel M, const int step, const int rec) {
-  const int e = blockIdx.x, tid = threadIdx.x, NB = M.nSB;
+// IncrementCumulInput / IncrementCumOutflow (src/Model.cpp:2458-2539) + watershed storage + the step's records for member e; executed
+// by all NT threads of a CTA (s_red: NT/32 x 5 doubles of shared memory)
+template <int NT>
+RVN_DI void balance_member(const DevModel &M, const int e, const int slot, const int rec, const int step, double (*s_red)[5]) {
+  const int tid = threadIdx.x, NB = M.nSB;
   const double tstep = M.opt.timestep;
-  const int par = step & 1;
-  __shared__ double s_red[RVN_ROUTE_BS / 32][5];
   const double area = M.watershed_area * D_M2_PER_KM2;
   double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // outflow, channel storage, rivulet storage, precip partials, storage partials
-  for (int p = tid; p < NB; p += RVN_ROUTE_BS) {
+  for (int p = tid; p < NB; p += NT) {
     const double *sc = M.scal + ((size_t)e * NB + p) * 8;
     const double qo = M.qout[((size_t)e * NB + p) * RVN_MAX_RIVER_SEGS + M.sb_nseg[p] - 1];
     if (M.sb_level[p] == 0 || M.sb_down[p] < 0) v[0] += (0.5 * (qo + sc[0]) * (tstep * D_SEC_PER_DAY)) / area * D_MM_PER_METER;
     v[1] += sc[4]; v[2] += sc[5];
     if ((M.rec_flags & 1) && rec >= 0) M.rec_qout[((size_t)rec * M.E + e) * NB + p] = qo;
   }
-  const double *part_p = M.part_precip + ((size_t)par * M.E + e) * M.nBlocksX, *part_s = M.part_storage + ((size_t)par * M.E + e) * M.nBlocksX;
-  for (int b = tid; b < M.nBlocksX; b += RVN_ROUTE_BS) { v[3] += part_p[b]; v[4] += part_s[b]; }
-  // fixed-shape tree (warp shuffles, then the warp totals in order): deterministic
+  const double *part_p = M.part_precip + ((size_t)slot * M.E + e) * M.nBlocksX, *part_s = M.part_storage + ((size_t)slot * M.E + e) * M.nBlocksX;
+  for (int b = tid; b < M.nBlocksX; b += NT) { v[3] += part_p[b]; v[4] += part_s[b]; }
+  // fixed-shape tree (warp shuffles, then the warp totals in order): deterministic for a given NT
 #pragma unroll
   for (int w = 0; w < 5; w++) {
 #pragma unroll
@@ -1194,16 +1215,47 @@ __global__ void __launch_bounds__(RVN_ROUTE_BS, RVN_ROUTE_MINB) balance_kernel(c
   if (tid == 0) {
     double t[5];
 #pragma unroll
-    for (int w = 0; w < 5; w++) { t[w] = 0.0; for (int i = 0; i < RVN_ROUTE_BS / 32; i++) t[w] += s_red[i][w]; }
+    for (int w = 0; w < 5; w++) { t[w] = 0.0; for (int i = 0; i < NT / 32; i++) t[w] += s_red[i][w]; }
     const double avg_precip = t[3] / M.watershed_area;
     double *cum = M.cumul + (size_t)e * 2;
     cum[0] += avg_precip * tstep;
+    for (int i = 0; i < M.nSpec; i++) cum[0] += M.spec_cum[(size_t)step * M.nSpec + i];   // GetIntegratedSpecInflow, basin after basin (src/Model.cpp:2467-2469)
     cum[1] += t[0];
     if ((M.rec_flags & 2) && rec >= 0) {
       double *w = M.rec_wshed + ((size_t)rec * M.E + e) * 4;
       w[0] = cum[0]; w[1] = cum[1]; w[2] = avg_precip;
       w[3] = t[4] / M.watershed_area + t[1] / area * D_MM_PER_METER + t[2] / area * D_MM_PER_METER;
     }
+  }
+}
+__global__ void __launch_bounds__(RVN_ROUTE_BS, RVN_ROUTE_MINB) balance_kernel(const __grid_constant__ DevModel M, const int slot, const int rec, const int step) {
+  __shared__ double s_red[RVN_ROUTE_BS / 32][5];
+  balance_member<RVN_ROUTE_BS>(M, blockIdx.x, slot, rec, step, s_red);
+}
+
+__global__ void __launch_bounds__(1024) balance_kernel_wide(const __grid_constant__ DevModel M, const int slot, const int rec, const int step) {
+  __shared__ double s_red[1024 / 32][5];
+  balance_member<1024>(M, blockIdx.x, slot, rec, step, s_red);
+}
+
+// ---- small ensembles: one CTA per member routes the whole network - every level in order with a CTA barrier between levels - and
+// closes the balance, for `nsub` consecutive steps in ONE launch (the per-level form needs nLevels + 1 launches per step, which is
+// what a single-member model spends its time on).  The sums of the balance use the same fixed-shape tree as balance_kernel but over
+// RVN_MEMBER_BS threads: their last bits may differ from the per-level path (records are compared at 1e-9).
+#ifndef RVN_MEMBER_BS
+#define RVN_MEMBER_BS 512
+#endif
+__global__ void __launch_bounds__(RVN_MEMBER_BS) route_member_kernel(const __grid_constant__ DevModel M, const int nsub, const int slot0, const int t0, const int rec0, const int step0) {
+  __shared__ double s_red[RVN_MEMBER_BS / 32][5];
+  const int e = blockIdx.x;
+  for (int ss = 0; ss < nsub; ss++) {
+    for (int L = 0; L < M.nLevels; L++) {
+      const int lev0 = M.level_ptr[L], lev1 = M.level_ptr[L + 1];
+      for (int i = lev0 + threadIdx.x; i < lev1; i += RVN_MEMBER_BS) route_one_basin(M, e, M.level_idx[i], slot0 + ss, t0 + ss, step0 + ss);
+      __syncthreads();   // the next level reads this level's outflows
+    }
+    balance_member<RVN_MEMBER_BS>(M, e, slot0 + ss, rec0 >= 0 ? rec0 + ss : -1, step0 + ss, s_red);
+    __syncthreads();
   }
 }
 

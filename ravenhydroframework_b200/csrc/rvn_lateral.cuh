@@ -118,7 +118,7 @@ struct FinCtx {
   RVN_DI int slot_type(int s) const { return P->slot_type[s]; }
   RVN_DI int slot_water(int s) const { return P->slot_water[s]; }
 };
-__global__ void __launch_bounds__(RVN_BS) finish_kernel(const __grid_constant__ DevModel M, const int step) {
+__global__ void __launch_bounds__(RVN_BS) finish_kernel(const __grid_constant__ DevModel M, const int slot) {
   __shared__ double s_red[RVN_BS / 32];
   const DevProgram *P = M.prog;
   const int tid = threadIdx.x, e = blockIdx.y, k = blockIdx.x * RVN_BS + tid;
@@ -135,9 +135,8 @@ __global__ void __launch_bounds__(RVN_BS) finish_kernel(const __grid_constant__ 
     stor = hru_storage(c, nCore) * c.area;
     for (int s = 0; s < nCore; s++) gstate[(size_t)P->slot_sv[s] * nHp] = c.sv[s];
   }
-  const int par = step & 1;
-  if (in_range) M.swvol[((size_t)par * M.E + e) * nHp + k] = swv;
+  if (in_range) M.swvol[((size_t)slot * M.E + e) * nHp + k] = swv;
   const double bs = block_sum(stor, s_red);
-  if (tid == 0) M.part_storage[((size_t)par * M.E + e) * M.nBlocksX + blockIdx.x] = bs;
+  if (tid == 0) M.part_storage[((size_t)slot * M.E + e) * M.nBlocksX + blockIdx.x] = bs;
 }
 #endif

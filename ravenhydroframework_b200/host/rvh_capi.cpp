@@ -191,6 +191,7 @@ int rvh_desc_info(const rvn_model_desc *d, int *out8) {
 }
 const double *rvh_desc_gauge_series(const rvn_model_desc *d) { return d->gauge_series; }
 int rvh_desc_num_gauges(const rvn_model_desc *d) { return d->nGauges; }
+int rvh_desc_hru_lu(const rvn_model_desc *d, int32_t *lu) { for (int k = 0; k < d->nHRU; k++) lu[k] = d->hru_lu[k]; return 0; }
 // gridded forcing ingestion (CModel::SetCellForcing): takes effect at the next rvh_model_flatten
 int rvh_model_set_cell_forcing(rvh_model *h, int nCells, int nSteps, const double *cell_elev, const double *series, const int32_t *wt_ptr,
                                const int32_t *wt_idx, const double *wt_val) {

@@ -246,6 +246,8 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
   // ---- calendar: replay the reference time loop  for(t=0; t<duration-TIME_CORRECTION; t+=timestep)  (src/RavenMain.cpp:145)
   _f_times.clear();
   _f_veg_season.clear();
+  _f_spec_basin.clear(); _f_spec_in.clear(); _f_spec_down.clear(); _f_spec_cum.clear();
+  for (int p = 0; p < NB; p++) if (_pSubBasins[p]->pInflowHydro || _pSubBasins[p]->pInflowHydro2) _f_spec_basin.push_back(p);
   {
     time_struct tt;
     JulianConvert(0.0, O.julian_start_day, O.julian_start_year, O.calendar, tt);
@@ -261,6 +263,16 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
       }
       r.day_angle = last_angle;
       _f_times.push_back(r);
+      for (size_t i = 0; i < _f_spec_basin.size(); i++) {   // user-specified basin inflows of this step (src/Solvers.cpp:543,586; src/SubBasin.cpp:950-957)
+        const CSubBasin *b = _pSubBasins[_f_spec_basin[i]];
+        const double area = _WatershedArea * M2_PER_KM2;
+        _f_spec_in.push_back(b->GetSpecifiedInflow(t + O.timestep));
+        _f_spec_down.push_back(b->GetDownstreamInflow(t));
+        double sum = 0.0;
+        sum += 0.5 * (b->GetSpecifiedInflow(tt.model_time) + b->GetSpecifiedInflow(tt.model_time + O.timestep)) * (O.timestep * SEC_PER_DAY);
+        sum += b->GetDownstreamInflow(tt.model_time) * (O.timestep * SEC_PER_DAY);
+        _f_spec_cum.push_back(sum / area * MM_PER_METER);
+      }
       // month-interpolated relative vegetation height / LAI (CVegetationClass::RecalculateCanopyParams, src/VegetationParams.cpp:102-107;
       // the reference repeats this per HRU per step although it depends on (vegetation class, date) only)
       for (size_t v = 0; v < veg_classes.size(); v++) {
@@ -440,6 +452,9 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
   d.sb_musk_K = _f_sb_d[4].data(); d.sb_musk_X = _f_sb_d[5].data(); d.sb_K_reach = _f_sb_d[6].data();
   d.max_nqin = maxqin; d.max_nqlat = maxqlat; d.sb_unit_hydro = _f_uh.data(); d.sb_route_hydro = _f_rh.data();
   d.watershed_area = _WatershedArea;
+  d.nSpec = (int32_t)_f_spec_basin.size();
+  d.spec_basin = d.nSpec ? _f_spec_basin.data() : NULL; d.spec_in = d.nSpec ? _f_spec_in.data() : NULL;
+  d.spec_down = d.nSpec ? _f_spec_down.data() : NULL; d.spec_cum = d.nSpec ? _f_spec_cum.data() : NULL;
   // ---- ROUTE_HYDROLOGIC: rating curves flow -> cross-section area
   d.nChannels = 0; d.nChanPts = 0; d.chan_Q = d.chan_A = NULL; d.sb_channel = NULL; d.sb_Qmult = d.sb_reach_m = NULL;
   if (O.routing == RVN_ROUTE_HYDROLOGIC) {

@@ -50,6 +50,12 @@ int CTimeSeries::GetTimeIndex(double t_loc) const {
   return (n <= last) ? n : last;
 }
 double CTimeSeries::GetValue(double t) const { return _aVal[GetTimeIndex(t + _t_corr)]; }
+double CTimeSeries::GetValueInterp(double t) const {
+  const double t_loc = t + _t_corr;
+  const int n = GetTimeIndex(t_loc), nP = (int)_aVal.size();
+  if (n == nP - 1) return _aVal[n];
+  return _aVal[n] + (t_loc - (double)(n)*_interval) / (_interval) * (_aVal[n + 1] - _aVal[n]);
+}
 double CTimeSeries::GetAvgValue(double t, double tstep) const {
   // pulse-type series only (all forcing series of the supported subset): reference src/TimeSeries.cpp:343-405
   double t_loc = t + _t_corr;
@@ -302,7 +308,7 @@ CSubBasin::CSubBasin()
       nSegments(1), basin_area(0), drainage_area(0), t_conc(AUTO_COMPUTE), t_peak(AUTO_COMPUTE), t_lag(AUTO_COMPUTE),
       gamma_shape(AUTO_COMPUTE), gamma_scale(AUTO_COMPUTE), Q_ref(AUTO_COMPUTE), c_ref(AUTO_COMPUTE), w_ref(AUTO_COMPUTE),
       mannings_n(AUTO_COMPUTE), slope(AUTO_COMPUTE), rain_corr(1.0), snow_corr(1.0), temperature_corr(0.0), QoutLast(0), QlatLast(0),
-      Qlocal(0), QlocLast(0), channel_storage(0), rivulet_storage(0) { aQout.assign(1, AUTO_COMPUTE); }
+      Qlocal(0), QlocLast(0), channel_storage(0), rivulet_storage(0), pInflowHydro(NULL), pInflowHydro2(NULL) { aQout.assign(1, AUTO_COMPUTE); }
 
 bool CSubBasin::SetBasinProperties(const std::string &label_in, double value) {
   std::string l = StringToUppercase(label_in);
@@ -433,6 +439,7 @@ void CSubBasin::InitializeFlowStates(double Qin_avg, double Qlat_avg, const optS
 void CSubBasin::Initialize(double Qin_avg, double Qlat_avg, double total_drain_area, const CModel *pModel, const optStruct &O) {
   ExitGracefullyIf((pChannel == NULL) && (O.routing != RVN_ROUTE_NONE),
                    "CSubBasin::Initialize: channel profile for basin " + std::to_string(ID) + " may only be 'NONE' if Routing=ROUTE_NONE or ROUTE_EXTERNAL");
+  if (pInflowHydro != NULL) is_headwater = false;   // src/SubBasin.cpp:1797
   drainage_area = total_drain_area;
   if (disabled) return;
   const global_struct *G = pModel->GetGlobalParams();
@@ -457,6 +464,8 @@ void CSubBasin::Initialize(double Qin_avg, double Qlat_avg, double total_drain_a
   GenerateCatchmentHydrograph(Qlat_avg, O);
   GenerateRoutingHydrograph(Qin_avg, O);
   InitializeFlowStates(Qin_avg, Qlat_avg, O);
+  if (pInflowHydro) pInflowHydro->Initialize(O.julian_start_day, O.julian_start_year, O.duration, O.timestep, O.calendar);      // src/SubBasin.cpp:1899-1904
+  if (pInflowHydro2) pInflowHydro2->Initialize(O.julian_start_day, O.julian_start_year, O.duration, O.timestep, O.calendar);
 }
 void CSubBasin::SetQout(double Q) {
   for (int i = 0; i < nSegments; i++) aQout[i] = Q;
@@ -642,7 +651,10 @@ void CModel::InitializeBasins(const optStruct &O) {
     aSBArea[p] = _pSubBasins[p]->GetBasinArea();
     if (globals.v[RVN_G_AVG_ANNUAL_RUNOFF] > 0) runoff_est = globals.v[RVN_G_AVG_ANNUAL_RUNOFF] / DAYS_PER_YEAR;
     aSBQlat[p] = runoff_est / MM_PER_METER * (aSBArea[p] * M2_PER_KM2) / SEC_PER_DAY;
-    aSBQin[p] = 0.0;
+    // specified inflows at "t = 0" (src/ModelInitialize.cpp:663-665): asked before the series are initialised, i.e. with a zero time
+    // offset - the first value of the series whatever its start date
+    aSBQlat[p] += _pSubBasins[p]->pInflowHydro2 ? _pSubBasins[p]->pInflowHydro2->FirstValue() : 0.0;
+    aSBQin[p] = _pSubBasins[p]->pInflowHydro ? _pSubBasins[p]->pInflowHydro->FirstValue() : 0.0;
   }
   for (int pp = 0; pp < NB; pp++) {
     int p = GetOrderedSubBasinIndex(pp);

@@ -61,6 +61,8 @@ public:
   // is_observation: no overlap QA, one extra sample for the last period-ending value (src/TimeSeries.cpp:214-262)
   void   Initialize(double model_start_day, int model_start_year, double model_duration, double timestep, int calendar, bool is_observation = false);
   double GetValue(double t) const;                  // pulse-type point value at model time t
+  double GetValueInterp(double t) const;            // point value of a series parsed as not pulse-based (src/TimeSeries.cpp:320-334)
+  double FirstValue() const { return _aVal[0]; }
   double GetAvgValue(double t, double tstep) const;
   double GetSampledValue(int nn) const;
   int    GetNumSampledValues() const { return (int)_aSampVal.size(); }
@@ -136,6 +138,10 @@ public:
   // routing arrays (reference _aUnitHydro/_aRouteHydro/_aQlatHist/_aQinHist/_aQout)
   std::vector<double> aUnitHydro, aRouteHydro, aQlatHist, aQinHist, aQout;
   double QoutLast, QlatLast, Qlocal, QlocLast, channel_storage, rivulet_storage;
+  // user-specified inflows [m3/s]: :BasinInflowHydrograph (upstream end of the reach) and :BasinInflowHydrograph2 (downstream end)
+  CTimeSeries *pInflowHydro, *pInflowHydro2;
+  double GetSpecifiedInflow(double t) const { return pInflowHydro ? pInflowHydro->GetValueInterp(t) : 0.0; }     // src/SubBasin.cpp:478-482
+  double GetDownstreamInflow(double t) const { return pInflowHydro2 ? pInflowHydro2->GetValueInterp(t) : 0.0; }  // :488-492
   // reference-surface accessors
   long long GetID() const { return ID; }
   double GetBasinArea() const { return basin_area; }
@@ -327,7 +333,8 @@ private:
   std::vector<rvn_process> _f_proc;
   std::vector<uint64_t> _f_mask;
   std::vector<double> _f_hru_d[5], _f_prof_thick, _f_ptab, _f_conv_uh, _f_series, _f_gconst, _f_wt, _f_sb_d[7], _f_uh, _f_rh, _f_veg_season, _f_et;
-  std::vector<int32_t> _f_et_row, _f_wt_ptr, _f_wt_idx, _f_pert_forcing, _f_pert_adj, _f_hru_terr;
+  std::vector<int32_t> _f_et_row, _f_wt_ptr, _f_wt_idx, _f_pert_forcing, _f_pert_adj, _f_hru_terr, _f_spec_basin;
+  std::vector<double> _f_spec_in, _f_spec_down, _f_spec_cum;
   std::vector<uint8_t> _f_pert_mask;
   std::vector<rvn_lateral> _f_lat;
   std::vector<int32_t> _f_lat_kfrom, _f_lat_kto, _f_lat_chunk;

@@ -964,6 +964,28 @@ static void ParseTimeSeriesFile(CModel *pModel, const optStruct &Options, const 
       pModel->observed.push_back(o);
       continue;
     }
+    if (c == ":BasinInflowHydrograph" || c == ":BasinInflowHydrograph2") {   // src/ParseTimeSeriesFile.cpp:582-628 (series parsed as not pulse-based)
+      ExitGracefullyIf(s.size() < 2, "ParseTimeSeriesFile: " + c + " needs a subbasin ID");
+      const long long SBID = s_to_ll(s[1]);
+      const std::string endtag = (c == ":BasinInflowHydrograph") ? ":EndBasinInflowHydrograph" : ":EndBasinInflowHydrograph2";
+      double start_day, interval; int start_yr, n;
+      ReadSeriesHeader(p, Options, start_day, start_yr, interval, n);
+      std::vector<double> v; v.reserve(n);
+      std::vector<std::string> t;
+      while (p.Tokenize(t)) {
+        if (t.empty()) continue;
+        if (t[0] == endtag) break;
+        for (size_t i = 0; i < t.size(); i++) v.push_back(ts_s_to_d(t[i].c_str()));
+      }
+      ExitGracefullyIf((int)v.size() != n, "CTimeSeries::Parse: wrong number of data points in " + c + " block. File: " + p.filename());
+      const int pb = pModel->GetSubBasinIndex(SBID);
+      if (pb < 0) { WriteWarning(c + " Subbasin " + std::to_string(SBID) + " not in model, cannot set inflow hydrograph"); continue; }
+      CTimeSeries *ts = new CTimeSeries("Inflow_Hydrograph_" + std::to_string(SBID), start_day, start_yr, interval, v);
+      CSubBasin *pSB = pModel->GetSubBasin(pb);
+      if (c == ":BasinInflowHydrograph") { delete pSB->pInflowHydro; pSB->pInflowHydro = ts; }
+      else { delete pSB->pInflowHydro2; pSB->pInflowHydro2 = ts; }
+      continue;
+    }
     if (c == ":AssimilateStreamflow") {   // src/ParseTimeSeriesFile.cpp:1225-1248
       AssimilateStreamflowCommand(pModel, s);
       continue;

@@ -35,8 +35,12 @@ bool CHydroProcessABC::ShouldApply(const CHydroUnit *pHRU) const {
       const std::string &nm = pModel->veg_classes[pHRU->veg_class].tag;
       if ((c.data != nm) && (c.compare_method == COMPARE_IS_EQUAL)) return false;
       if ((c.data == nm) && (c.compare_method == COMPARE_NOT_EQUAL)) return false;
-    } else {
-      ExitGracefully("CHydroProcessABC::ShouldApply: HRU_GROUP conditions are not supported by the B200 build yet");
+    } else {   // BASIS_HRU_GROUP: CModel::IsInHRUGroup (src/Model.cpp:465-477; an unknown group name means "not in the group")
+      bool is_in_group = false;
+      for (size_t g = 0; g < pModel->hru_groups.size(); g++)
+        if (pModel->hru_groups[g].name == c.data) { is_in_group = pModel->hru_groups[g].IsInGroup(pHRU->global_k); break; }
+      if ((!is_in_group) && (c.compare_method == COMPARE_IS_EQUAL)) return false;
+      if ((is_in_group) && (c.compare_method == COMPARE_NOT_EQUAL)) return false;
     }
   }
   return true;

@@ -97,7 +97,7 @@ def test_streaming_steps_equal_batched(tmp_path):
     model.lib.rvh_desc_gauge_series.argtypes = [C.c_void_p]
     nG = model.nGauges
     series = np.ctypeslib.as_array((C.c_double * (9 * nG * model.nSteps)).from_address(model.lib.rvh_desc_gauge_series(model.desc))).reshape(9, nG, model.nSteps)
-    slabs = torch.from_numpy(np.ascontiguousarray(series.transpose(2, 0, 1))).pin_memory()
+    slabs = torch.from_numpy(np.ascontiguousarray(series.transpose(2, 1, 0))).pin_memory()   # per step: [nGauges][RVN_GF_COUNT]
     b = api.GpuSimulation(model, n_members=3)
     b.upload_forcings(np.zeros((9, nG, model.nSteps)), 0, model.nSteps)        # the device copy is wiped: every step must bring its own slab
     q = torch.zeros((60, 3, model.nSB), dtype=torch.float64).pin_memory()

@@ -24,10 +24,9 @@ REF_INPUTS = "/root/reference/benchmarking/_InputFiles"
 # set -> number of steps pinned (config 1 of BASELINE.json is the 10-year daily GR4J run)
 SETS = {"Salmon_GR4J": 3653, "Salmon_HMETS": 3653, "Salmon_HBV": 3653, "Salmon_MOHYSE": 3653, "Irondequoit": 366,
         "York_nongridded_m_daily_i_daily": 1461}
-# York (7 subbasins, ROUTE_HYDROLOGIC on surveyed :ChannelProfile sections, LAI interception, depression abstraction) is staged with ONE
-# line dropped from its .rvt: the :RedirectToFile to the :BasinInflowHydrograph series (user-specified inflow to subbasin 6), which the
-# B200 build does not implement yet.  The reference runs the same edited copy, so both sides see identical inputs.
-DROP_LINES = {"York_nongridded_m_daily_i_daily": "York_BancroftInflows_daily.rvt"}
+# York (7 subbasins, ROUTE_HYDROLOGIC on surveyed :ChannelProfile sections, LAI interception, depression abstraction, a user-specified
+# :BasinInflowHydrograph into subbasin 6) is read as shipped.
+DROP_LINES = {}
 
 
 def main():
