@@ -164,7 +164,7 @@ typedef enum { RVN_ROUTE_NONE = 0, RVN_ROUTE_MUSKINGUM, RVN_ROUTE_MUSKINGUM_CUNG
 typedef enum { RVN_PF_PRECIP = 0, RVN_PF_RAINFALL, RVN_PF_SNOWFALL, RVN_PF_TEMP_AVE } rvn_pert_forcing;
 typedef enum { RVN_ADJ_ADDITIVE = 0, RVN_ADJ_MULTIPLICATIVE, RVN_ADJ_REPLACE } rvn_adjustment;
 #define RVN_MAX_PERT 8
-typedef enum { RVN_SOL_ORDERED_SERIES = 0, RVN_SOL_EULER = 1 } rvn_sol_method;
+typedef enum { RVN_SOL_ORDERED_SERIES = 0, RVN_SOL_EULER = 1, RVN_SOL_ITERATED_HEUN = 2 } rvn_sol_method;
 typedef enum { RVN_CONVOL_GR4J_1 = 0, RVN_CONVOL_GR4J_2, RVN_CONVOL_GAMMA, RVN_CONVOL_GAMMA_2 } rvn_convol_type;
 
 /* ---- per-member parameter table ------------------------------------------------------------------
@@ -287,12 +287,13 @@ typedef struct rvn_options {
   int32_t routing, suppress_competitive_ET, snow_suppress_PET, allow_soil_overfill, direct_evap;
   int32_t lake_sv;                /* CModel::GetLakeStorageIndex() */
   int32_t keep_flux_balance;      /* 0: skip per-connection cumulative flux arrays */
-  int32_t sol_method;             /* rvn_sol_method: ORDERED_SERIES (default) or EULER (reference src/Solvers.cpp:205-251 / 256-297) */
+  int32_t sol_method;             /* rvn_sol_method: ORDERED_SERIES (default), EULER or ITERATED_HEUN (reference src/Solvers.cpp:205-251 / 256-297 / 304-397) */
   int32_t need_atmos;             /* 1: a consumed PET or a sublimation process needs air pressure / relative humidity / wind / shortwave radiation -> derive them */
   int32_t air_pressure, rel_humidity, sw_radiation, sw_cloudcorr;   /* rvn_airpress, rvn_relhum, rvn_sw_rad, rvn_sw_cloudcorr */
   int32_t wind_velocity;          /* rvn_windvel */
   int32_t interception_factor;    /* rvn_icept */
-  int32_t pad_[1];
+  int32_t max_iterations;         /* ITERATED_HEUN: Options.max_iterations (30) */
+  double  convergence_crit;       /* ITERATED_HEUN: Options.convergence_crit (0.01) */
 } rvn_options;
 
 /* Flattened model (all pointers are HOST memory, copied by rvn_gpu_create). */

@@ -1258,6 +1258,10 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
   const double tstep = d->opt.timestep;
   for (int j = 0; j < NP; j++) if (!op_supported(d->proc[j].op)) return -1;
   if (d->opt.sol_method == RVN_SOL_EULER && d->nConvProc > 0) return -1; /* the reference's Euler branch mishandles convolution stores (:279-282) */
+  if (d->opt.sol_method == RVN_SOL_ITERATED_HEUN) {   /* restated for plain process lists only */
+    if (d->nConvProc > 0) return -1;
+    for (int j = 0; j < d->nProc; j++) if (d->proc[j].group != 0) return -1;
+  }
   octx c; memset(&c, 0, sizeof(c));
   c.d = d; c.member = member; c.ptab = d->ptab + (size_t)member * d->ptab_stride;
   for (int t = 0; t < RVN_SV_NTYPES; t++) c.iSV[t] = sv_index(d, t, -1);
@@ -1287,6 +1291,44 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
       const int euler = (d->opt.sol_method == RVN_SOL_EULER);
       if (euler) memcpy(phiread, phinew, sizeof(double) * NS);
       const double *phisee = euler ? phiread : phinew;
+      if (d->hru_enabled[k] && d->opt.sol_method == RVN_SOL_ITERATED_HEUN) {
+        /* ITERATED_HEUN (src/Solvers.cpp:304-397): rate1 from aPhi, rate2 from the previous iterate, the iterate rebuilt from aPhi with
+         * the mean rate (water from ATMOS_PRECIP keeps rate1) until mean |change| <= convergence_crit or max_iterations */
+        double *phiprev = (double *)malloc(sizeof(double) * NS), *phi0 = (double *)malloc(sizeof(double) * NS);
+        double rate2[O_MAXCONN];
+        c.k = k; c.F = F + (size_t)k * RVN_F_COUNT; c.phi_old = phi_old;
+        canopy_capacities(&c, step);
+        memcpy(phi0, phinew, sizeof(double) * NS);
+        const int iAtm = c.iSV[RVN_SV_ATMOS_PRECIP];
+        int iter = 0, converg = 0;
+        do {
+          iter++;
+          for (int i = 0; i < NS; i++) { phiprev[i] = phinew[i]; phinew[i] = phi0[i]; }
+          for (int j = 0; j < NP; j++) {
+            const rvn_process *pr = &d->proc[j];
+            if (!((d->apply_mask[k] >> j) & 1ull)) continue;
+            const int nconn = pr->nconn;
+            for (int q = 0; q < nconn; q++) { cf[q] = d->conn_from[pr->conn0 + q]; ct[q] = d->conn_to[pr->conn0 + q]; rates[q] = 0.0; rate2[q] = 0.0; }
+            op_rates(&c, pr, cf, ct, phi0, rates);
+            op_rates(&c, pr, cf, ct, phiprev, rate2);
+            for (int q = 0; q < nconn; q++) {
+              int typ = d->sv_type[cf[q]];
+              double rg = 0.5 * (rates[q] + rate2[q]);
+              if (cf[q] == iAtm) rg = rates[q];
+              if (ct[q] != cf[q]) { phinew[cf[q]] -= rg * tstep; phinew[ct[q]] += rg * tstep; }
+              else if (is_water_storage(typ) && (typ != RVN_SV_CONVOLUTION)) { phinew[ct[q]] += 0.0; }
+              else phinew[ct[q]] += rg * tstep;
+            }
+          }
+          double check = 0.0;
+          for (int i = 0; i < NS; i++) check += (fabs(phinew[i] - phiprev[i]) / NS);
+          converg = (check <= d->opt.convergence_crit) || (iter == d->opt.max_iterations);
+        } while (!converg);
+        free(phiprev); free(phi0);
+        if (d->nLat > 0) { memcpy(phi_old, phinew, sizeof(double) * NS); continue; }
+        finish_hru(d, k, phinew, aRouted, iSW, iRO, iTotalSWE, iGlacierMB);
+        memcpy(phi_old, phinew, sizeof(double) * NS);
+      } else
       if (d->hru_enabled[k]) {
         c.k = k; c.F = F + (size_t)k * RVN_F_COUNT; c.phi_old = phi_old;
         canopy_capacities(&c, step);

@@ -528,6 +528,14 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
 // such store) gives 0 like the division.  Outside 1e-290 < |S| < 1e290 the sequence is only faithful, not correctly
 // rounded -- storages are O(1e-12..1e5) mm.
 // ------------------------------------------------------------------------------------------------
+// x / y for a divisor that is fixed over a loop (the model time step): with yr = RN(1 / y) the same Markstein sequence as conv_orig
+// returns the correctly rounded quotient (tests/test_glibc_math.py::test_division_by_constant_is_exact checks it against IEEE
+// division for the step lengths in use) in 3 dependent operations instead of the ~25 instructions of a double-precision division.
+RVN_DI double div_by(const double x, const double y, const double yr) {
+  const double q = __dmul_rn(x, yr);
+  const double r = __fma_rn(-y, q, x);
+  return __fma_rn(r, yr, q);
+}
 RVN_DI double conv_orig(const double S, const ConvRow &t) {
   const double q = __dmul_rn(S, t.rcp);
   const double r = __fma_rn(-t.sumrem, q, S);
@@ -557,6 +565,7 @@ RVN_DI void convolve_direct(C &c, const int iTarget, const int iTS, double *__re
                             const ConvRow *__restrict__ tab, const int N, double *__restrict__ sum_cache, const bool sum_valid) {
   if (N <= 0) return;
   const double tstep = c.tstep;
+  const double rstep = UNIT_DT ? 1.0 : 1.0 / tstep;   // correctly rounded reciprocal of the step for div_by
   // ---- the reference's `sum` of the stores in index order.  The same sum, over the same values in the same order, is
   // accumulated while the stores are written at the end of the previous step, so it is normally read back from a
   // one-double-per-HRU cache; only after the state was replaced from outside is it recomputed.
@@ -573,11 +582,11 @@ RVN_DI void convolve_direct(C &c, const int iTarget, const int iTS, double *__re
     // ---- row 0: receives the new water (connection 0), releases, shifts out unless it is the only store
     const ConvRow t = ld_row(tab, 0);
     const double g0 = __ldcs(g);
-    const double r0 = UNIT_DT ? added : added / tstep;                         // rates[0]
+    const double r0 = UNIT_DT ? added : div_by(added, tstep, rstep);                         // rates[0]
     const double Sin = g0 + added;                                             // local S[0]
     double act = UNIT_DT ? Sin : g0 + r0 * tstep;                              // store 0 after connection 0
     const double orig = conv_orig(Sin, t);
-    const double r_ = UNIT_DT ? t.uh * orig : t.uh * orig / tstep;             // rates[1]
+    const double r_ = UNIT_DT ? t.uh * orig : div_by(t.uh * orig, tstep, rstep);             // rates[1]
     const double rdt = UNIT_DT ? r_ : r_ * tstep;
     const double Sloc = Sin - rdt;                                             // local S[0] after release
     act = act - rdt;                                                           // solver: phinew[store 0] -= r*tstep
@@ -586,7 +595,7 @@ RVN_DI void convolve_direct(C &c, const int iTarget, const int iTS, double *__re
       __stcs(g, act);
       nsum = act;
     } else {
-      const double mv0 = UNIT_DT ? Sloc : (Sloc / tstep) * tstep;              // m_0*tstep
+      const double mv0 = UNIT_DT ? Sloc : div_by(Sloc, tstep, rstep) * tstep;              // m_0*tstep
       const double fin0 = act - mv0;                                           // connection N+1
       __stcs(g, fin0);
       nsum = fin0;
@@ -613,10 +622,10 @@ RVN_DI void convolve_direct(C &c, const int iTarget, const int iTS, double *__re
             const ConvRow t = ld_row(tab, i + r);
             const double gi = cur[r];
             const double orig = conv_orig(gi, t);
-            const double rdt = UNIT_DT ? t.uh * orig : (t.uh * orig / tstep) * tstep;   // rates[i+1]*tstep
+            const double rdt = UNIT_DT ? t.uh * orig : (div_by(t.uh * orig, tstep, rstep)) * tstep;   // rates[i+1]*tstep
             const double Sloc = gi - rdt;                               // local S[i] after release == store i after release
             target += rdt;
-            const double mv = UNIT_DT ? Sloc : (Sloc / tstep) * tstep; // m_i*tstep
+            const double mv = UNIT_DT ? Sloc : div_by(Sloc, tstep, rstep) * tstep; // m_i*tstep
             const double fin = (Sloc + prev_move) - mv;                 // connections N+i then N+i+1
             __stcs(p + (size_t)r * stride, fin);
             nsum += fin;
@@ -634,7 +643,7 @@ RVN_DI void convolve_direct(C &c, const int iTarget, const int iTS, double *__re
         const ConvRow t = ld_row(tab, N - 1);
         const double gi = __ldcs(pl);
         const double orig = conv_orig(gi, t);
-        const double r_ = UNIT_DT ? t.uh * orig : t.uh * orig / tstep;
+        const double r_ = UNIT_DT ? t.uh * orig : div_by(t.uh * orig, tstep, rstep);
         const double rdt = UNIT_DT ? r_ : r_ * tstep;
         const double Sloc = gi - rdt;
         target += rdt;
@@ -649,7 +658,7 @@ RVN_DI void convolve_direct(C &c, const int iTarget, const int iTS, double *__re
   }
   *sum_cache = nsum;
   c.SV(iTarget) = target;
-  const double rTS = UNIT_DT ? (TS_new - TS_old) : (TS_new - TS_old) / tstep;   // rates[2N]
+  const double rTS = UNIT_DT ? (TS_new - TS_old) : div_by(TS_new - TS_old, tstep, rstep);   // rates[2N]
   c.SV(iTS) += UNIT_DT ? rTS : rTS * tstep;                                     // CONVOLUTION[c]: iTo==iFrom, updated in place
 }
 
@@ -936,7 +945,10 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
   double *s_grt = s_rt + (size_t)M.maxConn * RVN_BS;
   double *s_svw = s_grt + (size_t)M.maxGroupConn * RVN_BS;                       // EULER only: aPhinew columns
   const bool euler = (M.opt.sol_method == RVN_SOL_EULER);
-  double *s_red = s_svw + (euler ? (size_t)M.nCore * RVN_BS : 0);
+  const bool heun = (M.opt.sol_method == RVN_SOL_ITERATED_HEUN);   // columns: s_svw = aPhinew, then aPhiPrevIter and rate1
+  double *s_prev = s_svw + ((euler || heun) ? (size_t)M.nCore * RVN_BS : 0);
+  double *s_r1 = s_prev + (heun ? (size_t)M.nCore * RVN_BS : 0);
+  double *s_red = s_r1 + (heun ? (size_t)M.maxConn * RVN_BS : 0);
   const int tid = threadIdx.x, e = blockIdx.y, k = blockIdx.x * RVN_BS + tid;
   {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(M.prog);
@@ -953,7 +965,7 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
   DynCtx c;
   load_hru_statics(c, M, k, s_ptab);
   c.P = P; c.sv = s_sv + tid; c.rt = s_rt + tid; c.grt = s_grt + tid;
-  c.svw = euler ? (s_svw + tid) : c.sv;
+  c.svw = (euler || heun) ? (s_svw + tid) : c.sv;
 #if RVN_F_SMEM
   c.F.p = s_red + 8 + tid;
 #endif
@@ -974,10 +986,48 @@ __global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant
   else { for (int f = 0; f < RVN_F_CARRIED; f++) c.F[f] = 0.0; }
   load_canopy(c, M, step);
   if (enabled) reboot_diagnostics(c);
-  if (euler) { for (int s = 0; s < nCore; s++) c.SVW(s) = c.SV(s); }   // aPhinew = aPhi (src/Solvers.cpp:155-200); rates come from aPhi
+  if (euler || heun) { for (int s = 0; s < nCore; s++) c.SVW(s) = c.SV(s); }   // aPhinew = aPhi (src/Solvers.cpp:155-200); rates come from aPhi
   const bool unit_dt = (c.tstep == 1.0);
   const int nProc = P->nProc;
-  for (int j = 0; j < nProc; j++) {
+  if (heun && enabled) {
+    // ITERATED_HEUN (src/Solvers.cpp:304-397): every process is evaluated on the start-of-step vector aPhi (rate1) and on the previous
+    // iterate aPhiPrevIter (rate2), the iterate aPhinew is rebuilt from aPhi with the mean rate (precipitation keeps rate1), until the
+    // mean absolute change of the state variables falls below Options.convergence_crit or max_iterations is reached
+    double *phi = c.sv, *nw = c.svw, *pv = s_prev + tid, *r1 = s_r1 + tid;
+    const int iAtm = P->iSV[RVN_SV_ATMOS_PRECIP];
+    const double tstep = c.tstep;
+    int iter = 0;
+    bool converg;
+    do {
+      iter++;
+      for (int s = 0; s < nCore; s++) { pv[s * RVN_BS] = nw[s * RVN_BS]; nw[s * RVN_BS] = phi[s * RVN_BS]; }
+      for (int j = 0; j < nProc; j++) {
+        const rvn_process &pr = P->proc[j];
+        if (!((mask >> j) & 1ull)) continue;
+        const DynProc dp = {&pr, P};
+        c.sv = phi;
+        for (int q = 0; q < pr.nconn; q++) c.R(q) = 0.0;
+        dispatch_rates(c, dp, pr.op);
+        for (int q = 0; q < pr.nconn; q++) r1[q * RVN_BS] = c.R(q);
+        c.sv = pv;
+        for (int q = 0; q < pr.nconn; q++) c.R(q) = 0.0;
+        dispatch_rates(c, dp, pr.op);
+        for (int q = 0; q < pr.nconn; q++) {
+          const int from = dp.from(q), to = dp.to(q);
+          double rg = 0.5 * (r1[q * RVN_BS] + c.R(q));
+          if (from == iAtm) rg = r1[q * RVN_BS];
+          if (to != from) { nw[from * RVN_BS] -= rg * tstep; nw[to * RVN_BS] += rg * tstep; }
+          else if (c.slot_water(from) == 1) { nw[to * RVN_BS] += 0.0; }
+          else nw[to * RVN_BS] += rg * tstep;
+        }
+      }
+      double check = 0.0;
+      for (int s = 0; s < nCore; s++) check += (fabs(nw[s * RVN_BS] - pv[s * RVN_BS]) / nCore);
+      converg = (check <= M.opt.convergence_crit) || (iter == M.opt.max_iterations);
+    } while (!converg);
+    c.sv = phi;
+  }
+  for (int j = 0; j < (heun ? 0 : nProc); j++) {
     const rvn_process &pr = P->proc[j];
     const bool apply = enabled && ((mask >> j) & 1ull);   // CModel::ApplyProcess gate (src/Model.cpp:3061)
     if (!apply) continue;
@@ -1054,7 +1104,29 @@ RVN_DI double channel_area(const DevModel &M, const int p, const double Q) {
 // one basin, one member, one step: HRU -> subbasin aggregation in HRU-index order (src/Solvers.cpp:490-511),
 // CSubBasin::UpdateLateralInflow / UpdateInflow, RouteWater (src/SubBasin.cpp:2584-2863), UpdateOutflows (:2320-2421).
 // `t` = pushes into the histories before this step.
-__device__ void route_one_basin(const DevModel &M, int e, int p, int slot, int t, int step) {
+// HRU -> subbasin aggregation of one basin (src/Solvers.cpp:490-511) and CSubBasin::UpdateLateralInflow: independent of the routing
+// order, so callers may run it for all basins at once.  The surface-water volumes are summed in HRU-index order (bit-identical to
+// the reference's loop); the loads of a batch are issued together so that their latencies overlap.
+__device__ void basin_lateral_inflow(const DevModel &M, int e, int p, int slot, int t) {
+  const double tstep = M.opt.timestep;
+  const Ring QlatHist(M.qlat + ((size_t)e * M.nSB + p) * M.max_nqlat, M.sb_nqlat[p], t + 1);
+  const double *swvol = M.swvol + ((size_t)slot * M.E + e) * M.nHp;
+  double routed = 0.0;
+  const int i1 = M.sb_hru_ptr[p + 1];
+  int i = M.sb_hru_ptr[p];
+  for (; i + 8 <= i1; i += 8) {
+    double v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = swvol[M.sb_hru_idx[i + j]];
+#pragma unroll
+    for (int j = 0; j < 8; j++) routed += v[j];
+  }
+  for (; i < i1; i++) routed += swvol[M.sb_hru_idx[i]];
+  QlatHist[0] = routed / (tstep * D_SEC_PER_DAY);
+}
+// the ordered part: CSubBasin::UpdateInflow, RouteWater (src/SubBasin.cpp:2584-2863), UpdateOutflows (:2320-2421); needs the lateral
+// inflow of this step (basin_lateral_inflow) and the outflows of the basins above.  `t` = pushes into the histories before this step.
+__device__ void basin_route(const DevModel &M, int e, int p, int t, int step) {
   const double tstep = M.opt.timestep;
   const int nSeg = M.sb_nseg[p], nQin = M.sb_nqin[p], nQlat = M.sb_nqlat[p];
   const Ring QinHist(M.qin + ((size_t)e * M.nSB + p) * M.max_nqin, nQin, t + 1);
@@ -1062,12 +1134,6 @@ __device__ void route_one_basin(const DevModel &M, int e, int p, int slot, int t
   double *aQout = M.qout + ((size_t)e * M.nSB + p) * RVN_MAX_RIVER_SEGS;
   double *sc = M.scal + ((size_t)e * M.nSB + p) * 8;
   const double *UH = M.sb_unit_hydro + (size_t)p * M.max_nqlat, *RH = M.sb_route_hydro + (size_t)p * M.max_nqin;
-  {
-    const double *swvol = M.swvol + ((size_t)slot * M.E + e) * M.nHp;
-    double routed = 0.0;
-    for (int i = M.sb_hru_ptr[p]; i < M.sb_hru_ptr[p + 1]; i++) routed += swvol[M.sb_hru_idx[i]];
-    QlatHist[0] = routed / (tstep * D_SEC_PER_DAY);
-  }
   // inflow from upstream basins, accumulated in the reference's processing order (ascending index inside the
   // level above; src/Solvers.cpp:602-606), then CSubBasin::UpdateInflow (src/SubBasin.cpp:1531-1537)
   const int ispec = (M.nSpec > 0) ? M.sb_spec_slot[p] : -1;
@@ -1091,10 +1157,14 @@ __device__ void route_one_basin(const DevModel &M, int e, int p, int slot, int t
     double dt = dmin(K, tstep);
     // aQout[] is advanced in place over the local sub-steps; the reference restores the stored array and then
     // overwrites it with the final values in UpdateOutflows, which is the same end state.
+    double dt_c = -1.0, c1 = 0.0, c2 = 0.0, c3 = 0.0, c4 = 0.0;   // the coefficients change only when dt does (the last, shorter sub-step)
     for (double tt = 0; tt < tstep; tt += dt) {
       if (dt > (tstep - tt)) dt = tstep - tt;
-      const double denom = (2 * K * (1.0 - X) + dt);
-      const double c1 = (dt - 2 * K * (X)) / denom, c2 = (dt + 2 * K * (X)) / denom, c3 = (-dt + 2 * K * (1 - X)) / denom, c4 = (dt) / denom;
+      if (dt != dt_c) {
+        const double denom = (2 * K * (1.0 - X) + dt);
+        c1 = (dt - 2 * K * (X)) / denom; c2 = (dt + 2 * K * (X)) / denom; c3 = (-dt + 2 * K * (1 - X)) / denom; c4 = (dt) / denom;
+        dt_c = dt;
+      }
       double Qin = Qin1 + ((tt) / tstep) * (Qin0 - Qin1);
       double Qin_new = Qin1 + ((tt + dt) / tstep) * (Qin0 - Qin1);
       for (int s = 0; s < nSeg; s++) {
@@ -1185,7 +1255,9 @@ __global__ void __launch_bounds__(RVN_ROUTE_BS, RVN_ROUTE_MINB) route_level_kern
   const long long idx = (long long)blockIdx.x * RVN_ROUTE_BS + threadIdx.x;
   if (idx >= (long long)M.E * nlev) return;
   const int e = (int)(idx / nlev), i = (int)(idx - (long long)e * nlev);
-  route_one_basin(M, e, M.level_idx[lev0 + i], slot, t, step);
+  const int p = M.level_idx[lev0 + i];
+  basin_lateral_inflow(M, e, p, slot, t);
+  basin_route(M, e, p, t, step);
 }
 // IncrementCumulInput / IncrementCumOutflow (src/Model.cpp:2458-2539) + watershed storage + the step's records for member e; executed
 // by all NT threads of a CTA (s_red: NT/32 x 5 doubles of shared memory)
@@ -1249,9 +1321,11 @@ __global__ void __launch_bounds__(RVN_MEMBER_BS) route_member_kernel(const __gri
   __shared__ double s_red[RVN_MEMBER_BS / 32][5];
   const int e = blockIdx.x;
   for (int ss = 0; ss < nsub; ss++) {
+    for (int p = threadIdx.x; p < M.nSB; p += RVN_MEMBER_BS) basin_lateral_inflow(M, e, p, slot0 + ss, t0 + ss);   // no order among basins
+    __syncthreads();
     for (int L = 0; L < M.nLevels; L++) {
       const int lev0 = M.level_ptr[L], lev1 = M.level_ptr[L + 1];
-      for (int i = lev0 + threadIdx.x; i < lev1; i += RVN_MEMBER_BS) route_one_basin(M, e, M.level_idx[i], slot0 + ss, t0 + ss, step0 + ss);
+      for (int i = lev0 + threadIdx.x; i < lev1; i += RVN_MEMBER_BS) basin_route(M, e, M.level_idx[i], t0 + ss, step0 + ss);
       __syncthreads();   // the next level reads this level's outflows
     }
     balance_member<RVN_MEMBER_BS>(M, e, slot0 + ss, rec0 >= 0 ? rec0 + ss : -1, step0 + ss, s_red);

@@ -77,7 +77,8 @@ struct optStruct {
   int    calendar;
   std::string rvi_filename, rvh_filename, rvp_filename, rvt_filename, rvc_filename, rve_filename;
   std::string output_dir, main_output_dir, run_name, working_dir;
-  int    sol_method;            // rvn_sol_method: ORDERED_SERIES (0) or EULER (1)
+  int    sol_method;            // rvn_sol_method: ORDERED_SERIES (0), EULER (1) or ITERATED_HEUN (2)
+  double convergence_crit = 0.01; int max_iterations = 30;   // ITERATED_HEUN (src/ParseInput.cpp:242-243, 744-745)
   rvn_rainsnow rainsnow;
   rvn_potmelt  pot_melt;
   rvn_pet      evaporation, ow_evaporation, evap_infill, ow_evap_infill;

@@ -126,7 +126,12 @@ static void ParseMainInputFile(CModel *&pModel, optStruct &Options) {
     if (c == ":Method" || c == ":NumericalMethod") {
       if (s[1] == "ORDERED_SERIES" || s[1] == "STANDARD") Options.sol_method = RVN_SOL_ORDERED_SERIES;
       else if (s[1] == "EULER") Options.sol_method = RVN_SOL_EULER;
-      else ExitGracefully("ParseMainInputFile: only :Method ORDERED_SERIES and EULER are implemented in the B200 build");
+      else if (s[1] == "ITER_HEUN") {   // src/ParseInput.cpp:742-746: the keyword is ITER_HEUN and both numbers are read unconditionally
+        ExitGracefullyIf(Len < 4, "ParseMainInputFile: :Method ITER_HEUN needs [convergence criterion] [max iterations] (the reference reads both without checking)");
+        Options.sol_method = RVN_SOL_ITERATED_HEUN;
+        Options.convergence_crit = s_to_d(s[2]); Options.max_iterations = (int)s_to_d(s[3]);
+      }
+      else ExitGracefully("ParseMainInputFile: only :Method ORDERED_SERIES, EULER and ITER_HEUN are implemented in the B200 build");
       continue;
     }
     if (c == ":SoilModel") {

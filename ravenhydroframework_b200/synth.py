@@ -142,11 +142,14 @@ def _write(path, text):
         f.write(text)
 
 
+TOPOLOGY = "tree"   # "tree": heap-ordered binary tree down(p) = p // 2; "chain": down(p) = p - 1, as deep as the network can be
+
+
 def write_network(f, n_sb, hru_per_sb, rng, profile, lu_classes, veg_classes, soil_profiles, gauged_all=False, paired_profiles=False,
                   terrain_classes=None):
     f.write(":SubBasins\n  :Attributes NAME DOWNSTREAM_ID PROFILE REACH_LENGTH GAUGED\n  :Units none none none km none\n")
     for p in range(1, n_sb + 1):
-        down = -1 if p == 1 else p // 2
+        down = -1 if p == 1 else (p // 2 if TOPOLOGY == "tree" else p - 1)
         reach = "_AUTO" if profile == "NONE" else "%.4f" % rng.uniform(5, 15)
         f.write("  %d, sb%d, %d, %s, %s, %d\n" % (p, p, down, profile, reach, 1 if (p == 1 or gauged_all) else 0))
     f.write(":EndSubBasins\n:HRUs\n  :Attributes AREA ELEVATION LATITUDE LONGITUDE BASIN_ID LAND_USE_CLASS VEG_CLASS SOIL_PROFILE AQUIFER_PROFILE TERRAIN_CLASS SLOPE ASPECT\n")
@@ -546,6 +549,21 @@ def write_hbv(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUTE_
             swap("  :Baseflow          BASE_POWER_LAW     FAST_RESERVOIR  SURFACE_WATER\n", "  :Baseflow          %s FAST_RESERVOIR SURFACE_WATER\n" % algo["base_fast"])
         if "base_slow" in algo:
             swap("  :Baseflow          BASE_LINEAR        SLOW_RESERVOIR  SURFACE_WATER\n", "  :Baseflow          %s SLOW_RESERVOIR SURFACE_WATER\n" % algo["base_slow"])
+    if variant == "hrugroup_cond":
+        # process conditions on HRU groups (reference CHydroProcessABC::ShouldApply, BASIS_HRU_GROUP): capillary rise only inside
+        # 'Wetted', the slow baseflow everywhere except 'Sealed'
+        a = ":HydrologicProcesses\n"
+        rvi = rvi.replace(a, ":DefineHRUGroups Wetted Sealed\n" + a)
+        x = "  :CapillaryRise     RISE_HBV           FAST_RESERVOIR  SOIL[0]\n"
+        assert x in rvi
+        rvi = rvi.replace(x, x + "    :-->Conditional HRU_GROUP IS Wetted\n")
+        x = "  :Baseflow          BASE_LINEAR        SLOW_RESERVOIR  SURFACE_WATER\n"
+        assert x in rvi
+        rvi = rvi.replace(x, x + "    :-->Conditional HRU_GROUP IS_NOT Sealed\n")
+        n_hru = n_sb * hru_per_sb
+        with open(base + ".rvh", "a") as f:
+            f.write(":HRUGroup Wetted\n  " + " ".join(str(k) for k in range(1, n_hru + 1) if k % 2 == 0) + "\n:EndHRUGroup\n")
+            f.write(":HRUGroup Sealed\n  " + " ".join(str(k) for k in range(1, n_hru + 1) if k % 3 == 0) + "\n:EndHRUGroup\n")
     if variant == "lateral":
         # lateral exchange (reference CmvLatFlush): surface water of the 'UpGroup' HRUs is flushed into the fast reservoir of the
         # 'LowGroup' HRUs of the same subbasin (limited by the room left there); one more flush moves ponded water to one single

@@ -85,3 +85,19 @@ void rg_libm_eval(int mode, long n, const double *x, const double *y, double *ou
 void rg_restated_eval(int mode, long n, const double *x, const double *y, double *out) {
   for (long i = 0; i < n; i++) out[i] = mode == 0 ? rvn_exp(x[i]) : mode == 1 ? rvn_log(x[i]) : mode == 2 ? rvn_pow(x[i], y[i]) : mode == 3 ? rvn_expm1(x[i]) : rvn_tanh(x[i]);
 }
+
+/* x / y against the reciprocal-multiply + one Markstein correction the sweep uses for divisions by the model time step
+   (csrc/rvn_kernels.cuh div_by): number of mismatches over n pseudo-random x spanning `decades` decades around 1 */
+long rg_check_div(double y, long n, uint64_t seed, int decades, double *bad, int cap) {
+  long nbad = 0;
+  s_[0] = seed * 0x9E3779B97F4A7C15ULL + 7; s_[1] = seed ^ 0xA24BAED4963EE407ULL;
+  for (int w = 0; w < 16; w++) next_();
+  const double yr = 1.0 / y;
+  for (long i = 0; i < n; i++) {
+    double x = (u01_() - 0.3) * pow(10.0, (u01_() - 0.5) * 2.0 * decades);
+    if (i % 97 == 0) x = 0.0;
+    const double q = x * yr, r = __builtin_fma(-y, q, x), got = __builtin_fma(r, yr, q), ref = x / y;
+    if (!same_(got, ref)) { if (nbad < cap) { bad[2 * nbad] = x; bad[2 * nbad + 1] = y; } nbad++; }
+  }
+  return nbad;
+}

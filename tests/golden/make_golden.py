@@ -124,6 +124,13 @@ if hasattr(synth, "write_hbv"):
                                           rvp_extra=":LandUseParameterList\n  :Parameters, REFREEZE_FACTOR\n  :Units, mm/d/K\n  [DEFAULT], 1.3\n:EndLandUseParameterList\n")
     CASES["hbv_potmelt_ros"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=300, seed=57, routing="ROUTE_MUSKINGUM", potmelt="POTMELT_HBV_ROS",
                                     rvp_extra=":LandUseParameterList\n  :Parameters, RAIN_MELT_MULT\n  :Units, none\n  [DEFAULT], 1.4\n:EndLandUseParameterList\n")
+    # ITER_HEUN (src/Solvers.cpp:304-397).  The reference executable only survives the FIRST step of such a run: its rate1 / rate2 scratch
+    # arrays are sized with a per-call `maxConns` that is computed on the first call only (src/Solvers.cpp:30,116-118,313-314), so the
+    # second step writes past zero-length allocations and glibc aborts.  The cases therefore pin one step each, from different seasons.
+    for _i, (_crit, _so) in enumerate([("0.01 30", 150), ("1e-7 6", 130), ("0.001 30", 200), ("0.05 3", 100)]):
+        CASES["hbv_heun_%d" % _i] = dict(kind="hbv", n_sb=3, hru_per_sb=6, n_days=1, seed=14 + _i, routing="ROUTE_MUSKINGUM", season_offset=_so,
+                                         rvi_sub=[(r":Method\s+ORDERED_SERIES", ":Method                ITER_HEUN " + _crit)])
+    CASES["hbv_hrugroup_cond"] = dict(kind="hbv", n_sb=3, hru_per_sb=5, n_days=250, seed=12, routing="ROUTE_MUSKINGUM", season_offset=40, variant="hrugroup_cond")
     CASES["hbv_lateral"] = dict(kind="hbv", n_sb=4, hru_per_sb=7, n_days=250, seed=8, routing="ROUTE_MUSKINGUM", season_offset=40, variant="lateral")
 if hasattr(synth, "write_blended"):
     # Blended multi-model template (BASELINE config 4): weighted process groups, VIC/TOPMODEL/analytic algorithms, SNOBAL_HBV

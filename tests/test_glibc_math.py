@@ -61,6 +61,17 @@ def test_restatement_equals_host_libm(fn, dist):
         NAMES[fn], nbad, n, [(float(a).hex(), float(b).hex()) for a, b in bad.reshape(-1, 2)[:min(nbad, 8)]])
 
 
+@pytest.mark.parametrize("tstep", [1.0 / 24.0, 1.0 / 48.0, 1.0 / 8.0, 0.25, 1.0 / 3.0, 0.5, 1.0 / 1440.0, 2.0, 7.0])
+def test_division_by_constant_is_exact(tstep):
+    """the sweep divides by the model time step with a tabulated reciprocal + one correction step (div_by): same bits as IEEE division"""
+    lib = check_lib()
+    lib.rg_check_div.restype = C.c_long
+    lib.rg_check_div.argtypes = [C.c_double, C.c_long, C.c_uint64, C.c_int, C.c_void_p, C.c_int]
+    bad = np.zeros(16)
+    nbad = lib.rg_check_div(tstep, 4_000_000, 5, 140, bad.ctypes.data, 8)
+    assert nbad == 0, [float(x).hex() for x in bad[:2 * min(nbad, 8):2]]
+
+
 def _arguments(fn, n, seed):
     rng = np.random.default_rng(seed)
     third = n // 3

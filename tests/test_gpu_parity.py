@@ -234,6 +234,26 @@ def test_specialised_kernel_equals_interpreter(tmp_path, kind):
     assert np.array_equal(a.watershed(0, 150), b.watershed(0, 150))
 
 
+def test_iterated_heun_many_steps_equals_oracle(tmp_path):
+    """:Method ITER_HEUN over a whole season: the reference executable aborts after its first step (tests/golden/hbv_heun_* pin that
+    step on it), the oracle restates src/Solvers.cpp:304-397 and the interpreter sweep must follow it bit for bit."""
+    base = synth.write_hbv(str(tmp_path), n_sb=5, hru_per_sb=13, n_days=200, seed=21, routing="ROUTE_MUSKINGUM", season_offset=60)
+    rvi = open(base + ".rvi").read()
+    assert ":Method                ORDERED_SERIES" in rvi
+    open(base + ".rvi", "w").write(rvi.replace(":Method                ORDERED_SERIES", ":Method                ITER_HEUN 0.002 12"))
+    model = api.RavenModel(base)
+    model.flatten(2)
+    sim = api.GpuSimulation(model, n_members=2)
+    assert sim.kernel_variant() == "interpreter"
+    sim.set_recording(200)
+    sim.run(200)
+    ref = H.oracle_run(model, 200)
+    st = sim.download_state()
+    assert H.rel_err(st[0], ref["state"]) < TOL and np.array_equal(st[0], st[1])
+    assert H.rel_err(sim.hydrographs(0, 200)[:, 0, :], ref["qout_rec"]) < TOL
+    assert H.rel_err(sim.watershed(0, 200)[:, 0, :3], ref["wshed_rec"][:, :3]) < TOL
+
+
 def test_blended_weights_are_runtime_data(tmp_path):
     """Different :EndProcessGroup weights keep the specialised Blended kernel (weights are not part of the compiled program) and
     change the result; both runs equal the oracle."""

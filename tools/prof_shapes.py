@@ -16,13 +16,20 @@ elif kind == "hbv":
     base = synth.write_hbv(td, n_sb=n_sb, hru_per_sb=20, n_days=steps, seed=2, routing="ROUTE_MUSKINGUM", season_offset=100)
 elif kind == "gr4j":
     base = synth.write_gr4j(td, n_sb=n_sb, hru_per_sb=20, n_days=steps, seed=3, season_offset=100)
-elif kind == "blended":
-    base = synth.write_blended(td, n_sb=n_sb, hru_per_sb=20, n_days=steps, seed=4, routing="ROUTE_MUSKINGUM", catchment_route="TRIANGULAR_UH", season_offset=124)
+elif kind.startswith("blended"):
+    hourly = "hourly" in kind
+    base = synth.write_blended(td, n_sb=n_sb, hru_per_sb=20, n_days=((steps + 23) // 24 if hourly else steps), seed=4, routing="ROUTE_MUSKINGUM", catchment_route="TRIANGULAR_UH", season_offset=124)
+    if hourly:
+        rvi = open(base + ".rvi").read()
+        open(base + ".rvi", "w").write(rvi.replace(":TimeStep              1.0", ":TimeStep              01:00:00"))
 else:
     base = synth.write_hmets(td, n_sb=n_sb, hru_per_sb=20, n_days=steps, seed=1, single_class=True, season_offset=105)
     force = True
 model = api.RavenModel(base)
 model.flatten(E)
+if "grid" in kind:
+    synth.apply_cell_grid(model, base, 200, 200)
+    model.flatten(E)
 sim = api.GpuSimulation(model, n_members=E, force_interpreter=force)
 sim.set_kernel_timing(True)
 sim.run(steps)
