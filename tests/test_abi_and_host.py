@@ -92,8 +92,11 @@ def test_unsupported_commands_fail_loudly(tmp_path):
     open(base + ".rvi", "w").write(rvi + ":ReservoirDemandAllocation X\n")
     with pytest.raises(api.RavenError, match="not supported"):
         api.RavenModel(base)
-    open(base + ".rvi", "w").write(rvi.replace(":Method                ORDERED_SERIES", ":Method ITER_HEUN 0.01 30"))
+    open(base + ".rvi", "w").write(rvi.replace(":Method                ORDERED_SERIES", ":Method RUNGE_KUTTA_4"))
     with pytest.raises(api.RavenError, match="ORDERED_SERIES"):
+        api.RavenModel(base)
+    open(base + ".rvi", "w").write(rvi.replace(":Method                ORDERED_SERIES", ":Method ITER_HEUN"))   # the reference reads two numbers unchecked
+    with pytest.raises(api.RavenError, match="ITER_HEUN needs"):
         api.RavenModel(base)
 
 
