@@ -531,6 +531,18 @@ int rvn_gpu_kernel_variant(rvn_gpu_model *m, char *buf, int buflen);
  * csrc/rvn_static_programs.cuh by tools/gen_static_programs.py */
 int rvn_gpu_emit_static_program(const rvn_model_desc *desc, const char *name, char *buf, int64_t buflen);
 
+/* ---- model diagnostics on the device (reference CalculateDiagnostic, src/Diagnostics.cpp, as called by CModel::GetObjFuncVal,
+ * src/StandardOutput.cpp:3282-3322): for every member of the range the diagnostic of the recorded hydrograph of subbasin `basin`
+ * against an observation series, so that a calibration trial never copies its hydrograph back.  The modelled series is the one the
+ * reference compares with a HYDROGRAPH observation: mod[0] = qout_initial[member], mod[nn] = 0.5 * (Q[nn-1] + Q[nn-2]) * dt / dt of
+ * the recorded outflows (CModel::UpdateDiagnostics, src/Model.cpp:2929-2936); obs[nobs] (host) is the observation series sampled on
+ * the model step (RVN_BLANK where missing); samples nnstart <= nn < nnend count.  Sums run in the reference's order (one thread per
+ * member, sequential over time), so the value is the host layer's bit for bit.  type: 0 NASH_SUTCLIFFE, 1 RMSE, 2 KLING_GUPTA.
+ * out[nmembers] (host); -1e99 where the reference returns -ALMOST_INF. */
+#define RVN_BLANK (-1.2345)
+int rvn_gpu_diagnostic(rvn_gpu_model *m, int type, int basin, const double *obs, int nobs, int nnstart, int nnend,
+                       const double *qout_initial, int member0, int nmembers, double *out);
+
 /* verification hook (tests/test_glibc_math.py): evaluate the device exp (fn 0) / log (1) / pow (2) / expm1 (3) / tanh (4) the kernels use
  * (csrc/rvn_glibc_math.h - restatements of the host libm the reference links, src/ calls of exp/log/pow/tanh) on n host
  * arguments x[, y] and return the results in out[n]; these must equal the host libm's bit for bit */

@@ -66,6 +66,7 @@ def engine_lib():
         lib.rvn_gpu_enkf_update_host.argtypes = [vp, dp, dp, i, i]
         lib.rvn_gpu_enkf_last_ms.argtypes = [vp, C.POINTER(C.c_double)]
         lib.rvn_gpu_math_eval.argtypes = [i, i, C.c_int64, dp, dp, dp]
+        lib.rvn_gpu_diagnostic.argtypes = [vp, i, i, dp, i, i, i, dp, i, i, dp]
         _engine = lib
     return _engine
 
@@ -513,6 +514,15 @@ class GpuSimulation:
         v = C.c_double()
         self._ck(self.lib.rvn_gpu_enkf_last_ms(self.h, C.byref(v)))
         return v.value
+
+    def diagnostic(self, kind, basin, obs, nnstart, nnend, qout_initial, member0=0, nmembers=None):
+        """NASH_SUTCLIFFE (0) / RMSE (1) / KLING_GUPTA (2) of the recorded hydrograph of `basin` against obs, per member, on the device."""
+        nmembers = self.E - member0 if nmembers is None else nmembers
+        obs = np.ascontiguousarray(obs, dtype=np.float64)
+        q0 = np.ascontiguousarray(np.broadcast_to(np.asarray(qout_initial, dtype=np.float64), (nmembers,)))
+        out = np.zeros(nmembers)
+        self._ck(self.lib.rvn_gpu_diagnostic(self.h, int(kind), int(basin), obs.ctypes.data, obs.size, int(nnstart), int(nnend), q0.ctypes.data, member0, nmembers, out.ctypes.data))
+        return out
 
     def kernel_variant(self):
         """'static:<PROGRAM>' or 'interpreter' (which HRU-sweep kernel serves this model)."""

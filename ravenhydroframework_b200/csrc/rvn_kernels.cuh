@@ -1333,6 +1333,51 @@ __global__ void __launch_bounds__(RVN_MEMBER_BS) route_member_kernel(const __gri
   }
 }
 
+// CalculateDiagnostic (src/Diagnostics.cpp) of the recorded hydrograph of one basin, one thread per member, sums in the reference's order
+__global__ void diagnostic_kernel(const __grid_constant__ DevModel M, const int type, const int basin, const double *__restrict__ obs, const int nobs,
+                                  const int nnstart, const int nnend, const double *__restrict__ q0, const int member0, const int nmembers,
+                                  const int nrec, double *__restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nmembers) return;
+  const int e = member0 + i, NB = M.nSB, nmod = nrec + 1;
+  const double dts = M.opt.timestep * D_SEC_PER_DAY;
+  auto modv = [&](int nn) -> double {   // period-averaged outflow at sample nn
+    if (nn == 0) return q0[i];
+    const double Q = M.rec_qout[((size_t)(nn - 1) * M.E + e) * NB + basin];
+    const double Ql = (nn >= 2) ? M.rec_qout[((size_t)(nn - 2) * M.E + e) * NB + basin] : q0[i];
+    return (0.5 * (Q + Ql) * dts) / dts;
+  };
+  auto wt = [&](int nn) -> double { return (obs[nn] == RVN_BLANK || nn >= nmod) ? 0.0 : 1.0; };
+  auto mv = [&](int nn) -> double { return (nn < nmod) ? modv(nn) : 0.0; };
+  double N = 0.0, res = -D_ALMOST_INF;
+  if (type == 0) {
+    double avgobs = 0.0;
+    for (int nn = nnstart; nn < nnend; nn++) { avgobs += wt(nn) * obs[nn]; N += wt(nn); }
+    if (N > 0.0) avgobs /= N;
+    double sum1 = 0.0, sum2 = 0.0;
+    for (int nn = nnstart; nn < nnend; nn++) { const double w = wt(nn), m = mv(nn); sum1 += w * rvn_sqr(obs[nn] - m); sum2 += w * rvn_sqr(obs[nn] - avgobs); }
+    if (N > 0) res = 1.0 - (sum1 / sum2);
+  } else if (type == 1) {
+    double sum = 0.0;
+    for (int nn = nnstart; nn < nnend; nn++) { const double w = wt(nn); sum += w * rvn_sqr(obs[nn] - mv(nn)); N += w; }
+    if (N > 0.0) res = sqrt(sum / N);
+  } else {
+    double ObsSum = 0, ModSum = 0, ObsStd = 0, ModStd = 0, Cov = 0;
+    for (int nn = nnstart; nn < nnend; nn++) { const double w = wt(nn); ObsSum += obs[nn] * w; ModSum += mv(nn) * w; N += w; }
+    const double ObsAvg = ObsSum / N, ModAvg = ModSum / N;
+    for (int nn = nnstart; nn < nnend; nn++) {
+      const double w = wt(nn), m = mv(nn);
+      ObsStd += rvn_sqr(obs[nn] - ObsAvg) * w;
+      ModStd += rvn_sqr(m - ModAvg) * w;
+      Cov += (obs[nn] - ObsAvg) * (m - ModAvg) * w;
+    }
+    ObsStd = sqrt(ObsStd / N); ModStd = sqrt(ModStd / N); Cov /= N;
+    const double r = Cov / ObsStd / ModStd, Beta = ModAvg / ObsAvg, Alpha = ModStd / ObsStd;
+    if ((N > 0) && ((ObsAvg != 0.0) || (Beta == 1.0)) && (ObsStd != 0.0) && (ModStd != 0.0)) res = 1.0 - sqrt(rvn_sqr(r - 1) + rvn_sqr(Alpha - 1) + rvn_sqr(Beta - 1));
+  }
+  out[i] = res;
+}
+
 // area-weighted watershed average of every state variable (CModel::GetAvgStateVar, src/Model.cpp:1159-1174)
 __global__ void avg_state_kernel(const __grid_constant__ DevModel M, double *out, int member0) {
   const int e = member0 + blockIdx.y, i = blockIdx.x, tid = threadIdx.x;

@@ -35,6 +35,31 @@ def finish_trial(model, e, qout_rec, qout_initial):
     return F, fb.value
 
 
+def objective_inputs(model):
+    """(basin index, diagnostic type, nnstart, nnend, observations sampled on the model step) of the DDS calibration target."""
+    lib = model.lib
+    lib.rvh_dds_objective_inputs.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4 + [C.c_void_p, C.c_int]
+    b, t, a, e = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    n = lib.rvh_dds_objective_inputs(model.h, C.byref(b), C.byref(t), C.byref(a), C.byref(e), None, 0)
+    if n < 0:
+        raise api.RavenError(lib.rvh_last_error().decode())
+    obs = np.zeros(n)
+    lib.rvh_dds_objective_inputs(model.h, C.byref(b), C.byref(t), C.byref(a), C.byref(e), obs.ctypes.data, n)
+    return b.value, t.value, a.value, e.value, obs
+
+
+def finish_trial_value(model, e, diagnostic):
+    """CDDSEnsemble::FinishEnsembleRun(e) for a trial whose diagnostic was evaluated on the device; returns (Ftest, Fbest)."""
+    lib = model.lib
+    lib.rvh_dds_finish_value.restype = C.c_double
+    lib.rvh_dds_finish_value.argtypes = [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_double)]
+    fb = C.c_double()
+    F = lib.rvh_dds_finish_value(model.h, int(e), float(diagnostic), C.byref(fb))
+    if F <= -1e299:
+        raise api.RavenError(lib.rvh_last_error().decode())
+    return F, fb.value
+
+
 def best_parameters(model, n):
     _decl(model.lib)
     out = np.zeros(n)
@@ -44,9 +69,10 @@ def best_parameters(model, n):
     return out[:k]
 
 
-def run_dds(model, device=0):
+def run_dds(model, device=0, device_objective=True):
     """The reference's member loop for ENSEMBLE_DDS (src/RavenMain.cpp:115-196): returns dict(trials=[(e+1, Ftest, Fbest)],
-    best=parameter vector, improvements=[(trial, Fbest)] = the rows of DDSOutput.csv)."""
+    best=parameter vector, improvements=[(trial, Fbest)] = the rows of DDSOutput.csv).  device_objective: the trial's diagnostic is
+    evaluated on the device (rvn_gpu_diagnostic, same sums in the same order) and only one double comes back per trial."""
     model.flatten(1)
     n_trials = model.ensemble_begin()
     sim = api.GpuSimulation(model, n_members=1, device=device)
@@ -66,7 +92,11 @@ def run_dds(model, device=0):
         sim.set_recording(n, hydrographs=True, watershed=False)   # buffers are allocated once and reused (rvn_gpu_set_recording)
         sim.step = 0
         sim.run(n)
-        F, Fbest = finish_trial(model, e, sim.hydrographs(0, n)[:, 0, :], q0)
+        if device_objective:
+            basin, kind, nn0, nn1, obs = objective_inputs(model)
+            F, Fbest = finish_trial_value(model, e, sim.diagnostic(kind, basin, obs, nn0, nn1, q0[basin], 0, 1)[0])
+        else:
+            F, Fbest = finish_trial(model, e, sim.hydrographs(0, n)[:, 0, :], q0)
         if F <= Fbest:                                 # accepted: this trial is the new best (a row of DDSOutput.csv)
             improvements.append((e + 1, Fbest))
         trials.append((e + 1, F, Fbest))

@@ -95,6 +95,30 @@ double rvh_dds_finish_run(rvh_model *h, int e, const double *qout_rec, const dou
   return F;
   RVH_CATCH(-1e300)
 }
+// device-side objective: the inputs of rvn_gpu_diagnostic (obs may be NULL to query its length), and the bookkeeping of a trial
+// whose diagnostic value came back from the device (sign convention of CModel::GetObjFuncVal applied here)
+int rvh_dds_objective_inputs(rvh_model *h, int *basin, int *type, int *nnstart, int *nnend, double *obs, int nmax) {
+  RVH_TRY
+  CDDSEnsemble *dds = dynamic_cast<CDDSEnsemble *>(h->pEnsemble);
+  if (!dds) throw RavenError("rvh_dds_objective_inputs: not a DDS ensemble");
+  std::vector<double> o;
+  dds->ObjectiveInputs(h->pModel, h->Options, *basin, *type, *nnstart, *nnend, o);
+  if (obs) for (int i = 0; i < (int)o.size() && i < nmax; i++) obs[i] = o[i];
+  return (int)o.size();
+  RVH_CATCH(-1)
+}
+double rvh_dds_finish_value(rvh_model *h, int e, double diagnostic, double *Fbest) {
+  RVH_TRY
+  CDDSEnsemble *dds = dynamic_cast<CDDSEnsemble *>(h->pEnsemble);
+  if (!dds) throw RavenError("rvh_dds_finish_value: not a DDS ensemble");
+  int basin, type, a, b; std::vector<double> o;
+  dds->ObjectiveInputs(h->pModel, h->Options, basin, type, a, b, o);
+  const double F = (type == 1) ? diagnostic : -1.0 * diagnostic;   // NSE / KGE are maximised: objval *= -1
+  dds->FinishEnsembleRun(F, e);
+  if (Fbest) *Fbest = dds->BestObjective();
+  return F;
+  RVH_CATCH(-1e300)
+}
 int rvh_dds_best(rvh_model *h, double *best, int nmax) {
   RVH_TRY
   CDDSEnsemble *dds = dynamic_cast<CDDSEnsemble *>(h->pEnsemble);

@@ -188,6 +188,24 @@ double CDDSEnsemble::ObjectiveFromHydrograph(const CModel *pModel, const optStru
   return objval;
 }
 
+void CDDSEnsemble::ObjectiveInputs(const CModel *pModel, const optStruct &Options, int &basin, int &type, int &nnstart, int &nnend, std::vector<double> &obs) const {
+  double starttime = 0.0, endtime = 0.0;
+  for (size_t d = 0; d < pModel->diag_periods.size(); d++)
+    if (pModel->diag_periods[d].name == _calib_Period) { starttime = pModel->diag_periods[d].t_start; endtime = pModel->diag_periods[d].t_end; }
+  const observed_ts *pObs = NULL;
+  for (size_t i = 0; i < pModel->observed.size(); i++) if (pModel->observed[i].name == "HYDROGRAPH" && pModel->observed[i].loc_ID == _calib_SBID) pObs = &pModel->observed[i];
+  ExitGracefullyIf(pObs == NULL, "GetObjFuncVal: unable to find calibration target time series (hydrograph in basin :CalibrationSBID)");
+  ExitGracefullyIf(endtime == 0.0, "GetObjFuncVal: unable to find calibration period with this name ");
+  basin = pModel->GetSubBasinIndex(_calib_SBID);
+  type = (_calib_Obj == DIAG_NASH_SUTCLIFFE) ? 0 : (_calib_Obj == DIAG_RMSE) ? 1 : 2;
+  obs.resize(pObs->pTS->GetNumSampledValues());
+  for (size_t nn = 0; nn < obs.size(); nn++) obs[nn] = pObs->pTS->GetSampledValue((int)nn);
+  const int nSampVal = (int)obs.size();
+  auto index_of = [&](double t_mod) { int i = (int)(rvh_max(floor((t_mod + TIME_CORRECTION) / Options.timestep), 0.0)); return (i < nSampVal - 1) ? i : nSampVal - 1; };
+  nnstart = index_of(starttime) + 1;   // averaged hydrographs: the value at index 0 is not a period average
+  nnend = index_of(endtime) + 1;
+}
+
 // ---------------------------------------------------------------------------------------------------------------- EnKF
 CEnKFEnsemble::CEnKFEnsemble(int num_members, const optStruct &Options)
     : CEnsemble(num_members, Options), _EnKF_mode(ENKF_UNSPECIFIED), _window_size(1), _nTimeSteps(0), _nObsDatapoints(0), _member0(0), _nLocal(num_members) {

@@ -68,6 +68,8 @@ public:
   // the reference signature reads the objective from the model; here the caller hands over the modelled series of the trial
   void FinishEnsembleRun(double Ftest, int e);
   double ObjectiveFromHydrograph(const CModel *pModel, const optStruct &Options, const double *qout_rec, const double *qout_initial, int nsteps, int nSB) const;
+  // what rvn_gpu_diagnostic needs to evaluate the same objective on the device: basin index, diagnostic, sample window, observations
+  void ObjectiveInputs(const CModel *pModel, const optStruct &Options, int &basin, int &type, int &nnstart, int &nnend, std::vector<double> &obs) const;
   const std::vector<double> &TestParams() const { return _TestParams; }
   const std::vector<double> &BestParams() const { return _BestParams; }
   double BestObjective() const { return _Fbest; }

@@ -47,6 +47,50 @@ def test_dds_host_logic_matches_reference_executable():
 
 @pytest.mark.gpu
 def test_dds_on_gpu_matches_reference_executable():
+    """objective evaluated on the device (rvn_gpu_diagnostic): only one double per trial comes back"""
     ref = json.load(open(os.path.join(CASE, "reference_dds.json")))
     model = api.RavenModel(os.path.join(CASE, "model"))
-    _check(dds.run_dds(model), ref)
+    on_device = dds.run_dds(model, device_objective=True)
+    _check(on_device, ref)
+    model2 = api.RavenModel(os.path.join(CASE, "model"))
+    on_host = dds.run_dds(model2, device_objective=False)       # hydrographs copied back, host CalculateDiagnostic
+    assert on_device["trials"] == on_host["trials"]             # same sums in the same order: identical bits
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_device_diagnostics_equal_host_formulas(kind, tmp_path):
+    """NSE / RMSE / KGE of every member's hydrograph on the device against a numpy restatement of src/Diagnostics.cpp, with blanks."""
+    from ravenhydroframework_b200 import synth
+    base = synth.write_hbv(str(tmp_path), n_sb=5, hru_per_sb=4, n_days=120, seed=5, routing="ROUTE_MUSKINGUM", season_offset=90)
+    model = api.RavenModel(base)
+    model.flatten(4)
+    sim = api.GpuSimulation(model, n_members=4)
+    sim.set_recording(120)
+    sim.run(120)
+    q = sim.hydrographs(0, 120)[:, :, 2]                        # [step][member]
+    q0 = dds.initial_outflows(model)[2]
+    rng = np.random.RandomState(kind)
+    obs = np.abs(q[:, 0].mean() * (1 + 0.3 * rng.normal(size=121)))
+    obs[rng.choice(121, 9, replace=False)] = -1.2345            # RAV_BLANK_DATA
+    got = sim.diagnostic(kind, 2, obs, 1, 121, q0)
+    for e in range(4):
+        mod = np.empty(121)
+        mod[0] = q0
+        for nn in range(1, 121):
+            ql = q[nn - 2, e] if nn >= 2 else q0
+            mod[nn] = (0.5 * (q[nn - 1, e] + ql) * 86400.0) / 86400.0
+        w = (obs != -1.2345).astype(float)
+        w[0] = 0.0
+        N = w.sum()
+        if kind == 0:
+            avg = (w * obs).sum() / N
+            want = 1.0 - (w * (obs - mod) ** 2).sum() / (w * (obs - avg) ** 2).sum()
+        elif kind == 1:
+            want = np.sqrt((w * (obs - mod) ** 2).sum() / N)
+        else:
+            oa, ma = (obs * w).sum() / N, (mod * w).sum() / N
+            os_, ms_ = np.sqrt(((obs - oa) ** 2 * w).sum() / N), np.sqrt(((mod - ma) ** 2 * w).sum() / N)
+            r = ((obs - oa) * (mod - ma) * w).sum() / N / os_ / ms_
+            want = 1.0 - np.sqrt((r - 1) ** 2 + (ms_ / os_ - 1) ** 2 + (ma / oa - 1) ** 2)
+        assert abs(got[e] - want) <= 1e-12 * max(1.0, abs(want))
