@@ -936,7 +936,10 @@ __global__ void __launch_bounds__(RVN_BS, RVN_STATIC_MIN_BLOCKS) hru_sweep_stati
 // ------------------------------------------------------------------------------------------------
 // interpreter sweep: arbitrary process lists (DevProgram), state/rates in shared-memory columns
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RVN_BS) hru_sweep_interp(const __grid_constant__ DevModel M, const int step0, const int nsub, const int slot0) {
+#ifndef RVN_INTERP_MIN_BLOCKS
+#define RVN_INTERP_MIN_BLOCKS 4   // caps the interpreter at 128 registers/thread (uncapped it compiles to 253 = 2 resident CTAs/SM; measured on 128 members x 10k HRUs HMETS: 1.47 ms uncapped, 1.11 ms at 3, 0.98 ms at 4)
+#endif
+__global__ void __launch_bounds__(RVN_BS, RVN_INTERP_MIN_BLOCKS) hru_sweep_interp(const __grid_constant__ DevModel M, const int step0, const int nsub, const int slot0) {
   // ---- shared memory carve-up
   DevProgram *P = reinterpret_cast<DevProgram *>(rvn_smem);
   double *s_ptab = reinterpret_cast<double *>(rvn_smem + ((sizeof(DevProgram) + 15) & ~size_t(15)));
@@ -1104,6 +1107,16 @@ RVN_DI double channel_area(const DevModel &M, const int p, const double Q) {
 // one basin, one member, one step: HRU -> subbasin aggregation in HRU-index order (src/Solvers.cpp:490-511),
 // CSubBasin::UpdateLateralInflow / UpdateInflow, RouteWater (src/SubBasin.cpp:2584-2863), UpdateOutflows (:2320-2421).
 // `t` = pushes into the histories before this step.
+// the per-basin tables the ordered part of routing chases (global memory, or the member kernel's shared-memory copies)
+struct RouteTabs {
+  const int32_t *nseg, *nqin, *nqlat, *headwater, *up_ptr, *up_idx;
+  const double *musk_K, *musk_X;
+  RVN_DI void from_model(const DevModel &M) {
+    nseg = M.sb_nseg; nqin = M.sb_nqin; nqlat = M.sb_nqlat; headwater = M.sb_headwater; up_ptr = M.sb_up_ptr; up_idx = M.sb_up_idx;
+    musk_K = M.sb_musk_K; musk_X = M.sb_musk_X;
+  }
+};
+
 // HRU -> subbasin aggregation of one basin (src/Solvers.cpp:490-511) and CSubBasin::UpdateLateralInflow: independent of the routing
 // order, so callers may run it for all basins at once.  The surface-water volumes are summed in HRU-index order (bit-identical to
 // the reference's loop); the loads of a batch are issued together so that their latencies overlap.
@@ -1126,9 +1139,9 @@ __device__ void basin_lateral_inflow(const DevModel &M, int e, int p, int slot, 
 }
 // the ordered part: CSubBasin::UpdateInflow, RouteWater (src/SubBasin.cpp:2584-2863), UpdateOutflows (:2320-2421); needs the lateral
 // inflow of this step (basin_lateral_inflow) and the outflows of the basins above.  `t` = pushes into the histories before this step.
-__device__ void basin_route(const DevModel &M, int e, int p, int t, int step) {
+__device__ void basin_route(const DevModel &M, const RouteTabs &T, int e, int p, int t, int step) {
   const double tstep = M.opt.timestep;
-  const int nSeg = M.sb_nseg[p], nQin = M.sb_nqin[p], nQlat = M.sb_nqlat[p];
+  const int nSeg = T.nseg[p], nQin = T.nqin[p], nQlat = T.nqlat[p];
   const Ring QinHist(M.qin + ((size_t)e * M.nSB + p) * M.max_nqin, nQin, t + 1);
   const Ring QlatHist(M.qlat + ((size_t)e * M.nSB + p) * M.max_nqlat, nQlat, t + 1);
   double *aQout = M.qout + ((size_t)e * M.nSB + p) * RVN_MAX_RIVER_SEGS;
@@ -1138,9 +1151,9 @@ __device__ void basin_route(const DevModel &M, int e, int p, int t, int step) {
   // level above; src/Solvers.cpp:602-606), then CSubBasin::UpdateInflow (src/SubBasin.cpp:1531-1537)
   const int ispec = (M.nSpec > 0) ? M.sb_spec_slot[p] : -1;
   double Qin_up = (ispec >= 0) ? 0.0 + M.spec_in[(size_t)step * M.nSpec + ispec] : 0.0;   // user-specified inflow first (src/Solvers.cpp:543)
-  for (int u = M.sb_up_ptr[p]; u < M.sb_up_ptr[p + 1]; u++) {
-    const int pu = M.sb_up_idx[u];
-    Qin_up += M.qout[((size_t)e * M.nSB + pu) * RVN_MAX_RIVER_SEGS + M.sb_nseg[pu] - 1];
+  for (int u = T.up_ptr[p]; u < T.up_ptr[p + 1]; u++) {
+    const int pu = T.up_idx[u];
+    Qin_up += M.qout[((size_t)e * M.nSB + pu) * RVN_MAX_RIVER_SEGS + T.nseg[pu] - 1];
   }
   QinHist[0] = Qin_up;
   const double Qin0 = Qin_up, Qin1 = QinHist[1], Qlat0 = QlatHist[0];
@@ -1148,11 +1161,11 @@ __device__ void basin_route(const DevModel &M, int e, int p, int t, int step) {
   double Qlat_new = 0.0;
   for (int n = 0; n < nQlat; n++) Qlat_new += UH[n] * QlatHist[n];
   int method = M.opt.routing;
-  if (M.sb_headwater[p]) method = RVN_ROUTE_NONE;
+  if (T.headwater[p]) method = RVN_ROUTE_NONE;
   const double seg_fraction = 1.0 / (double)(nSeg);
   const double QoutLast = aQout[nSeg - 1];
   if (method == RVN_ROUTE_MUSKINGUM || method == RVN_ROUTE_MUSKINGUM_CUNGE) {
-    const double K = M.sb_musk_K[p], X = M.sb_musk_X[p];
+    const double K = T.musk_K[p], X = T.musk_X[p];
     const double cunge = (method == RVN_ROUTE_MUSKINGUM_CUNGE) ? 1.0 : 0.0;
     double dt = dmin(K, tstep);
     // aQout[] is advanced in place over the local sub-steps; the reference restores the stored array and then
@@ -1256,8 +1269,9 @@ __global__ void __launch_bounds__(RVN_ROUTE_BS, RVN_ROUTE_MINB) route_level_kern
   if (idx >= (long long)M.E * nlev) return;
   const int e = (int)(idx / nlev), i = (int)(idx - (long long)e * nlev);
   const int p = M.level_idx[lev0 + i];
+  RouteTabs T; T.from_model(M);
   basin_lateral_inflow(M, e, p, slot, t);
-  basin_route(M, e, p, t, step);
+  basin_route(M, T, e, p, t, step);
 }
 // IncrementCumulInput / IncrementCumOutflow (src/Model.cpp:2458-2539) + watershed storage + the step's records for member e; executed
 // by all NT threads of a CTA (s_red: NT/32 x 5 doubles of shared memory)
@@ -1317,15 +1331,36 @@ __global__ void __launch_bounds__(1024) balance_kernel_wide(const __grid_constan
 #ifndef RVN_MEMBER_BS
 #define RVN_MEMBER_BS 512
 #endif
+#ifndef RVN_MEMBER_STAGE
+#define RVN_MEMBER_STAGE 1024
+#endif
 __global__ void __launch_bounds__(RVN_MEMBER_BS) route_member_kernel(const __grid_constant__ DevModel M, const int nsub, const int slot0, const int t0, const int rec0, const int step0) {
   __shared__ double s_red[RVN_MEMBER_BS / 32][5];
-  const int e = blockIdx.x;
+  // networks of up to RVN_MEMBER_STAGE basins: the index / parameter tables the level loop chases are staged in shared memory once
+  // per launch (a level of a deep network is a chain of dependent loads; from global memory that is ~8 L2 round trips per level)
+  __shared__ int32_t s_i[7][RVN_MEMBER_STAGE + 1];
+  __shared__ double s_d[2][RVN_MEMBER_STAGE];
+  const int e = blockIdx.x, NB = M.nSB;
+  RouteTabs T; T.from_model(M);
+  const int32_t *level_idx = M.level_idx;
+  if (NB <= RVN_MEMBER_STAGE) {
+    for (int p = threadIdx.x; p < NB; p += RVN_MEMBER_BS) {
+      s_i[0][p] = M.sb_nseg[p]; s_i[1][p] = M.sb_nqin[p]; s_i[2][p] = M.sb_nqlat[p]; s_i[3][p] = M.sb_headwater[p]; s_i[6][p] = M.level_idx[p];
+      s_d[0][p] = M.sb_musk_K ? M.sb_musk_K[p] : 0.0; s_d[1][p] = M.sb_musk_X ? M.sb_musk_X[p] : 0.0;
+    }
+    for (int p = threadIdx.x; p <= NB; p += RVN_MEMBER_BS) s_i[4][p] = M.sb_up_ptr[p];
+    const int nup = M.sb_up_ptr[NB];   // <= NB - 1 edges in a tree
+    for (int u = threadIdx.x; u < nup; u += RVN_MEMBER_BS) s_i[5][u] = M.sb_up_idx[u];
+    __syncthreads();
+    T.nseg = s_i[0]; T.nqin = s_i[1]; T.nqlat = s_i[2]; T.headwater = s_i[3]; T.up_ptr = s_i[4]; T.up_idx = s_i[5]; T.musk_K = s_d[0]; T.musk_X = s_d[1];
+    level_idx = s_i[6];
+  }
   for (int ss = 0; ss < nsub; ss++) {
-    for (int p = threadIdx.x; p < M.nSB; p += RVN_MEMBER_BS) basin_lateral_inflow(M, e, p, slot0 + ss, t0 + ss);   // no order among basins
+    for (int p = threadIdx.x; p < NB; p += RVN_MEMBER_BS) basin_lateral_inflow(M, e, p, slot0 + ss, t0 + ss);   // no order among basins
     __syncthreads();
     for (int L = 0; L < M.nLevels; L++) {
       const int lev0 = M.level_ptr[L], lev1 = M.level_ptr[L + 1];
-      for (int i = lev0 + threadIdx.x; i < lev1; i += RVN_MEMBER_BS) basin_route(M, e, M.level_idx[i], t0 + ss, step0 + ss);
+      for (int i = lev0 + threadIdx.x; i < lev1; i += RVN_MEMBER_BS) basin_route(M, T, e, level_idx[i], t0 + ss, step0 + ss);
       __syncthreads();   // the next level reads this level's outflows
     }
     balance_member<RVN_MEMBER_BS>(M, e, slot0 + ss, rec0 >= 0 ? rec0 + ss : -1, step0 + ss, s_red);
