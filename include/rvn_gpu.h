@@ -22,12 +22,14 @@
 extern "C" {
 #endif
 
-#define RVN_ABI_VERSION 8
+#define RVN_ABI_VERSION 9
 #define RVN_DOESNT_EXIST (-1)
 #define RVN_CONV_STORES 50   /* MAX_CONVOL_STORES, reference src/RavenInclude.h / Convolution.cpp:17 */
 #define RVN_MAX_CONN 24      /* max connections of a non-convolution process (Precipitation: 13..19) */
 #define RVN_MAX_SOIL_LAYERS 8
 #define RVN_MAX_RIVER_SEGS 50 /* MAX_RIVER_SEGS, reference src/SubBasin.h */
+#define RVN_RES_CURVES 5      /* stage [m], weir/curve outflow Q, underflow Q [m3/s], area [m2], volume [m3] */
+#define RVN_RES_STATE 8       /* doubles of state per (member, reservoir) */
 
 typedef enum {
   RVN_OK = 0, RVN_ERR_NO_DEVICE = -1, RVN_ERR_BAD_ARG = -2, RVN_ERR_CUDA = -3, RVN_ERR_UNSUPPORTED = -4,
@@ -413,6 +415,19 @@ typedef struct rvn_model_desc {
   int32_t nSpec, pad4_;
   const int32_t *spec_basin;
   const double *spec_in, *spec_down, *spec_cum;
+  /* reservoirs / lakes at subbasin outlets (reference CReservoir, src/Reservoir.cpp; level-pool routing CReservoir::RouteWater
+   * :1532-1853 called from the solver after the reach is routed, src/Solvers.cpp:591-596).  Reservoir r sits in basin res_basin[r]
+   * (ascending basin index) and is linked to HRU res_hru[r] (-1: none; a linked HRU's surface water becomes precipitation on the
+   * reservoir, its open-water PET x LAKE_PET_CORR the reservoir evaporation, and its AET state variable receives CReservoir::GetAET,
+   * src/Solvers.cpp:502-503,608-612).  Curves (the reference's _aStage/_aQ/_aQunder/_aArea/_aVolume, built by the host exactly like the
+   * CReservoir constructors) are stored [nRes][RVN_RES_CURVES][nResPts] with res_np[r] valid points each.  res_min_stage = _min_stage
+   * (returned for a reservoir that dried out).  res_extract[nSteps][nRes] = demand of the reservoir's :ReservoirExtraction series for the
+   * step [m3/s] (CDemand::UpdateDemand, src/WaterDemands.cpp:204-216; at most one series per reservoir), 0 without one.
+   * res_state0[nRes][RVN_RES_STATE] = initial {stage, stage_last, Qout, Qout_last, precip m3, MB losses m3, AET m3, 0} of every member.
+   * Supported: no control structures, DZTR, seepage, stage / flow constraint series or stage assimilation. */
+  int32_t nRes, nResPts;
+  const int32_t *res_basin, *res_hru, *res_np;   /* [nRes] */
+  const double *res_curves, *res_min_stage, *res_extract, *res_state0;
   int32_t nPert, pad3_;
   const int32_t *pert_forcing;  /* [nPert] rvn_pert_forcing */
   const int32_t *pert_adj;      /* [nPert] rvn_adjustment */
@@ -457,6 +472,9 @@ int rvn_gpu_upload_basin_state(rvn_gpu_model *m, const double *qin_hist, const d
                                const double *qout, const double *scalars, int member0, int nmembers);
 int rvn_gpu_download_basin_state(rvn_gpu_model *m, double *qin_hist, double *qlat_hist, double *qout,
                                  double *scalars, int member0, int nmembers);
+/* reservoir state, host layout [member][nRes][RVN_RES_STATE] (see rvn_model_desc::res_state0); no-ops for a model without reservoirs */
+int rvn_gpu_upload_reservoir_state(rvn_gpu_model *m, const double *res, int member0, int nmembers);
+int rvn_gpu_download_reservoir_state(rvn_gpu_model *m, double *res, int member0, int nmembers);
 /* replace parameter tables / convolution UHs of a member range (ensemble UpdateModel) */
 int rvn_gpu_upload_params(rvn_gpu_model *m, const double *ptab, const int32_t *conv_n, const double *conv_uh,
                           int member0, int nmembers);

@@ -50,6 +50,11 @@ typedef struct {
   int iSV[RVN_SV_NTYPES]; /* first index of each SV type, or -1 */
 } octx;
 
+/* CHydroUnit::IsLinkedToReservoir (src/HydroUnits.cpp:194; set in src/ModelInitialize.cpp:165-175) */
+static int hru_linked(const rvn_model_desc *d, int k) {
+  for (int r = 0; r < d->nRes; r++) if (d->res_hru[r] == k) return 1;
+  return 0;
+}
 static int sv_index(const rvn_model_desc *d, int type, int layer) {
   for (int i = 0; i < d->NS; i++) if (d->sv_type[i] == type && (layer < 0 || d->sv_layer[i] == layer)) return i;
   return -1;
@@ -510,7 +515,7 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
         } else rates[qAtmos] += Fcan * snow_int;
         snowthru = snowfall - Fcan * snow_int;
       } else { snowthru = snowfall; rainthru = rainfall; }
-      if (is_lake) rates[qLake] = snowthru + rainthru;
+      if (is_lake) { if (hru_linked(d, c->k)) rates[qSW] = snowthru + rainthru; else rates[qLake] = snowthru + rainthru; } /* src/PartitionPrecip.cpp:258-265 */
       else if (type == RVN_HRU_WETLAND) rates[qDep] = snowthru + rainthru;
       else if (type == RVN_HRU_WATER) rates[qSW] = snowthru + rainthru;
       else {
@@ -1002,6 +1007,7 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
     }
     case RVN_OP_OPEN_WATER_EVAP: { /* src/OpenWaterEvap.cpp:113-186 */
       if (type == RVN_HRU_MASKED_GLACIER) break;
+      if (hru_linked(d, c->k)) break; /* :124 reservoir-linked HRUs handle ET via the reservoir mass balance */
       double OWPET = F[RVN_F_OW_PET];
       if (!d->opt.suppress_competitive_ET) { OWPET -= (sv[c->iSV[RVN_SV_AET]] / tstep); OWPET = omax(OWPET, 0.0); }
       rates[0] = P_LU(c, RVN_LU_OW_PET_CORR) * OWPET;
@@ -1014,7 +1020,7 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       break;
     }
     case RVN_OP_LAKE_EVAP_BASIC: { /* src/OpenWaterEvap.cpp:269-314 */
-      if ((type == RVN_HRU_LAKE) || (d->opt.lake_sv == iFrom[0])) {
+      if (((type == RVN_HRU_LAKE) || (d->opt.lake_sv == iFrom[0])) && !hru_linked(d, c->k)) { /* :279 */
         rates[0] = P_LU(c, RVN_LU_LAKE_PET_CORR) * F[RVN_F_OW_PET];
         rates[pr->nconn - 1] = rates[0];
       }
@@ -1198,7 +1204,88 @@ static void route_water(const rvn_model_desc *d, int p, const obasin *B, double 
   }
   aQout_new[nSeg - 1] += Qlat_new;
 }
-/* CSubBasin::UpdateOutflows, src/SubBasin.cpp:2320-2421 (no irrigation/diversion/reservoir) */
+/* ---- reservoirs: CReservoir (src/Reservoir.cpp) without control structures, DZTR, seepage, constraint series, stage assimilation */
+static double interpolate_curve(double x, const double *xx, const double *y, int N, int extrapbottom) { /* src/CommonFunctions.cpp:1982-2004 */
+  if (x <= xx[0]) {
+    if (extrapbottom) return y[0] + (y[1] - y[0]) / (xx[1] - xx[0]) * (x - xx[0]);
+    return y[0];
+  } else if (x >= xx[N - 1]) return y[N - 1] + (y[N - 1] - y[N - 2]) / (xx[N - 1] - xx[N - 2]) * (x - xx[N - 1]);
+  int i = 0;
+  while (!((x >= xx[i]) && (x < xx[i + 1]))) i++;
+  if (fabs(xx[i + 1] - xx[i]) < O_REAL_SMALL) return (y[i] + y[i + 1]) / 2;
+  return y[i] + (y[i + 1] - y[i]) / (xx[i + 1] - xx[i]) * (x - xx[i]);
+}
+static const double *res_curve(const rvn_model_desc *d, int r, int c) { return d->res_curves + ((size_t)r * RVN_RES_CURVES + c) * d->nResPts; }
+static double res_volume(const rvn_model_desc *d, int r, double ht) { return interpolate_curve(ht, res_curve(d, r, 0), res_curve(d, r, 4), d->res_np[r], 1); } /* :1871 */
+static double res_area(const rvn_model_desc *d, int r, double ht) { return interpolate_curve(ht, res_curve(d, r, 0), res_curve(d, r, 3), d->res_np[r], 0); }   /* :1880 */
+static double res_weir_outflow(const rvn_model_desc *d, int r, double ht) { /* :1890-1894, weir adjustment 0 */
+  double underflow = interpolate_curve(ht, res_curve(d, r, 0), res_curve(d, r, 2), d->res_np[r], 0);
+  return interpolate_curve(ht - 0.0, res_curve(d, r, 0), res_curve(d, r, 1), d->res_np[r], 0) + underflow;
+}
+/* CReservoir::RouteWater (:1532-1853); rs = {stage, stage_last, Qout, Qout_last, Precip, MB_losses, AET m3, -}; OW_PET / lake_PET_corr of the
+ * linked HRU (ignored without one).  Returns the new stage, *res_outflow the outflow at the end of the step. */
+static double reservoir_route_water(const rvn_model_desc *d, int r, const double *rs, double Qin_old, double Qin_new, double OW_PET, double lake_PET_corr,
+                                    double demand, double *res_outflow) {
+  const double RES_TOLERANCE = 0.0001; const int RES_MAXITER = 100;
+  const double tstep = d->opt.timestep, _stage = rs[0], _Qout = rs[2];
+  double stage_new = 0.0, Qmin = 0.0, Qmax = 1e99;
+  double dh = 0.001, V_old = res_volume(d, r, _stage), A_old = res_area(d, r, _stage), h_guess = _stage;
+  int iter = 0;
+  double change = 0, f, dfdh, out, out2, ET = 0.0, precip = 0.0, ext_old = 0.0, ext_new = 0.0, seep_old = 0.0;
+  const double _seepage_const = 0.0, _local_GW_head = 0.0;
+  if (d->res_hru[r] >= 0) {
+    ET = OW_PET / O_SEC_PER_DAY / O_MM_PER_METER;
+    ET *= lake_PET_corr;
+    precip = rs[4] / d->opt.timestep / O_SEC_PER_DAY;
+  }
+  ext_new = ext_old = 0.0;
+  ext_old = demand; ext_new = demand; /* one demand series (or none: demand = 0) */
+  double gamma = V_old + ((Qin_old + Qin_new) - _Qout + 2.0 * precip - ET * A_old - seep_old - (ext_old + ext_new)) / 2.0 * (tstep * O_SEC_PER_DAY);
+  if (gamma < 0) { *res_outflow = 0.0; return d->res_min_stage[r]; }
+  double relax = 1.0;
+  do {
+    out = out2 = 0.0;
+    out = res_weir_outflow(d, r, h_guess);
+    out2 = res_weir_outflow(d, r, h_guess + dh);
+    out += ET * res_area(d, r, h_guess) + _seepage_const * (h_guess - _local_GW_head);
+    out2 += ET * res_area(d, r, h_guess + dh) + _seepage_const * (h_guess + dh - _local_GW_head);
+    f = (res_volume(d, r, h_guess) + out / 2.0 * (tstep * O_SEC_PER_DAY));
+    dfdh = ((res_volume(d, r, h_guess + dh) + out2 / 2.0 * (tstep * O_SEC_PER_DAY)) - f) / dh;
+    change = -(f - gamma) / dfdh;
+    if (dfdh == 0) change = 1e-7;
+    if (iter > 3) relax *= 0.98;
+    h_guess += relax * change;
+    iter++;
+  } while ((iter < RES_MAXITER) && (fabs(change / relax) > RES_TOLERANCE));
+  stage_new = h_guess;
+  *res_outflow = res_weir_outflow(d, r, stage_new);
+  if ((*res_outflow < Qmin) || (*res_outflow > Qmax)) { /* :1775-1803 */
+    if (*res_outflow < Qmin) *res_outflow = Qmin;
+    if (*res_outflow > Qmax) *res_outflow = Qmax;
+    double A_guess = A_old, A_last, V_new, seep_guess = seep_old;
+    do {
+      V_new = V_old + ((Qin_old + Qin_new) - (_Qout + *res_outflow) + 2.0 * precip - ET * (A_old + A_guess) - (seep_old + seep_guess) - (ext_old + ext_new)) / 2.0 * (tstep * O_SEC_PER_DAY);
+      if (V_new < 0) {
+        V_new = 0;
+        *res_outflow = -2.0 * (V_new - V_old) / (tstep * O_SEC_PER_DAY) + (-_Qout + 2.0 * precip + (Qin_old + Qin_new) - ET * (A_old + 0.0) - (ext_old + ext_new));
+      }
+      stage_new = interpolate_curve(V_new, res_curve(d, r, 4), res_curve(d, r, 0), d->res_np[r], 0);
+      A_last = A_guess;
+      A_guess = res_area(d, r, stage_new);
+      seep_guess = _seepage_const * (stage_new - _local_GW_head);
+    } while (fabs(1.0 - A_guess / A_last) > 0.00001);
+  }
+  return stage_new;
+}
+/* CReservoir::GetAET [mm/d] (:1283-1292) */
+static double reservoir_aet(const rvn_model_desc *d, int r, const double *rs, double OW_PET, double lake_PET_corr) {
+  if (d->res_hru[r] < 0) return 0.0;
+  double Evap = OW_PET;
+  Evap *= lake_PET_corr;
+  return Evap * 0.5 * (res_area(d, r, rs[0]) + res_area(d, r, rs[1])) / (d->hru_area[d->res_hru[r]] * O_M2_PER_KM2);
+}
+
+/* CSubBasin::UpdateOutflows, src/SubBasin.cpp:2320-2421 (no irrigation/diversion; the reservoir part is in the caller) */
 static void update_outflows(const rvn_model_desc *d, int p, const obasin *B, const double *aQo) {
   const int nSeg = d->sb_nseg[p], nQlat = d->sb_nqlat[p];
   double *aQout = &B->qout[(size_t)p * RVN_MAX_RIVER_SEGS], *sc = &B->scal[(size_t)p * 8];
@@ -1224,13 +1311,16 @@ static void update_outflows(const rvn_model_desc *d, int p, const obasin *B, con
   sc[1] = Qlat_new; /* _QlatLast */
 }
 
+/* reservoir state of the member being run [nRes][RVN_RES_STATE] (set by rvo_run_member_res; the oracle is single-threaded test infrastructure) */
+static double *g_res_state = NULL;
 /* ======================================================================== one member, n steps === */
 /* routing prep (src/Solvers.cpp:495-511) and diagnostics of the write-back (:697-729) for one HRU's newest state vector */
 static void finish_hru(const rvn_model_desc *d, int k, double *phinew, double *aRouted, int iSW, int iRO, int iTotalSWE, int iGlacierMB) {
   const int NS = d->NS;
   int p = d->hru_sb[k];
   double SWvol = (phinew[iSW] / O_MM_PER_METER) * (d->hru_area[k] * O_M2_PER_KM2);
-  aRouted[p] += SWvol;
+  if (hru_linked(d, k)) { for (int r = 0; r < d->nRes; r++) if (d->res_hru[r] == k) g_res_state[(size_t)r * RVN_RES_STATE + 4] = SWvol; } /* SetPrecip, src/Solvers.cpp:502-503 */
+  else aRouted[p] += SWvol;
   phinew[iRO] = phinew[iSW];
   phinew[iSW] = 0.0;
   if (iTotalSWE >= 0) {
@@ -1252,8 +1342,22 @@ static void finish_hru(const rvn_model_desc *d, int k, double *phinew, double *a
  * optional records (NULL to skip): qout_rec[nsteps][nSB], wshed_rec[nsteps][4], state_rec[nsteps][nHRU][NS],
  *                                  forc_rec[nsteps][nHRU][RVN_F_COUNT]
  * returns 0, or -1 if the model uses an op the oracle does not implement. */
+int rvo_run_member_res(const rvn_model_desc *d, int member, double *state, double *qin, double *qlat, double *qout, double *scal, double *cumul,
+                       int step0, int nsteps, double *qout_rec, double *wshed_rec, double *state_rec, double *forc_rec, double *res_state);
+/* the same for a model without reservoirs, or with reservoirs started from the descriptor's initial reservoir state */
 int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *qin, double *qlat, double *qout, double *scal, double *cumul,
                    int step0, int nsteps, double *qout_rec, double *wshed_rec, double *state_rec, double *forc_rec) {
+  double *rs = NULL;
+  if (d->nRes > 0) { rs = (double *)malloc(sizeof(double) * (size_t)d->nRes * RVN_RES_STATE); memcpy(rs, d->res_state0, sizeof(double) * (size_t)d->nRes * RVN_RES_STATE); }
+  int rc = rvo_run_member_res(d, member, state, qin, qlat, qout, scal, cumul, step0, nsteps, qout_rec, wshed_rec, state_rec, forc_rec, rs);
+  free(rs);
+  return rc;
+}
+/* res_state [nRes][RVN_RES_STATE] in/out (NULL without reservoirs) */
+int rvo_run_member_res(const rvn_model_desc *d, int member, double *state, double *qin, double *qlat, double *qout, double *scal, double *cumul,
+                       int step0, int nsteps, double *qout_rec, double *wshed_rec, double *state_rec, double *forc_rec, double *res_state) {
+  g_res_state = res_state;
+  if (d->nRes > 0 && (!res_state || d->opt.sol_method != RVN_SOL_ORDERED_SERIES)) return -1;
   const int nH = d->nHRU, NS = d->NS, NB = d->nSB, NP = d->nProc;
   const double tstep = d->opt.timestep;
   for (int j = 0; j < NP; j++) if (!op_supported(d->proc[j].op)) return -1;
@@ -1476,9 +1580,30 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
         for (int i = 0; i < d->nSpec; i++) if (d->spec_basin[i] == p) down_Q = d->spec_down[(size_t)step * d->nSpec + i] + 0.0;
         aQoutnew[d->sb_nseg[p] - 1] += down_Q;
       }
+      int r = -1;
+      for (int i = 0; i < d->nRes; i++) if (d->res_basin[i] == p) r = i;
+      double res_ht = 0.0, res_outflow = 0.0, owpet = 0.0, lpc = 0.0;
+      if (r >= 0) { /* src/Solvers.cpp:589-596 */
+        double *rs = res_state + (size_t)r * RVN_RES_STATE;
+        const int kr = d->res_hru[r];
+        if (kr >= 0) { owpet = F[(size_t)kr * RVN_F_COUNT + RVN_F_OW_PET]; lpc = c.ptab[d->lu_off + d->hru_lu[kr] * RVN_LU_COUNT + RVN_LU_LAKE_PET_CORR]; }
+        double res_inflow_last = qout[(size_t)p * RVN_MAX_RIVER_SEGS + d->sb_nseg[p] - 1];
+        double res_inflow = omax((aQoutnew[d->sb_nseg[p] - 1] - 0.0 - 0.0), 0.0);
+        res_ht = reservoir_route_water(d, r, rs, res_inflow_last, res_inflow, owpet, lpc, d->res_extract[(size_t)step * d->nRes + r], &res_outflow);
+      }
       update_outflows(d, p, &B, aQoutnew);
+      if (r >= 0) { /* CReservoir::UpdateStage + UpdateMassBalance (src/Reservoir.cpp:1264-1323), called from UpdateOutflows */
+        double *rs = res_state + (size_t)r * RVN_RES_STATE;
+        rs[1] = rs[0]; rs[0] = res_ht; rs[3] = rs[2]; rs[2] = res_outflow;
+        rs[5] = 0.0; rs[6] = 0.0;
+        if (d->res_hru[r] >= 0) rs[6] = reservoir_aet(d, r, rs, owpet, lpc) * (d->hru_area[d->res_hru[r]] * O_M2_PER_KM2) / O_MM_PER_METER * tstep;
+        rs[5] += rs[6];
+        rs[5] += d->res_extract[(size_t)step * d->nRes + r] * O_SEC_PER_DAY * tstep;
+      }
       int pTo = d->sb_down[p];
-      if (pTo >= 0) aQinnew[pTo] += qout[(size_t)p * RVN_MAX_RIVER_SEGS + d->sb_nseg[p] - 1];
+      if (pTo >= 0) aQinnew[pTo] += (r >= 0) ? res_state[(size_t)r * RVN_RES_STATE + 2] : qout[(size_t)p * RVN_MAX_RIVER_SEGS + d->sb_nseg[p] - 1]; /* GetOutflowRate */
+      if (r >= 0 && d->res_hru[r] >= 0 && iAET >= 0) /* :608-612 */
+        state[(size_t)d->res_hru[r] * NS + iAET] = reservoir_aet(d, r, res_state + (size_t)r * RVN_RES_STATE, owpet, lpc);
     }
     /* ---- IncrementCumulInput / IncrementCumOutflow (src/Model.cpp:2458-2539) */
     {
@@ -1490,11 +1615,15 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
       for (int i = 0; i < d->nSpec; i++) cumul[0] += d->spec_cum[(size_t)step * d->nSpec + i]; /* GetIntegratedSpecInflow of the basins that have one (the others add 0) */
       for (int p = 0; p < NB; p++) {
         int pd = d->sb_down[p];
+        int r = -1;
+        for (int i = 0; i < d->nRes; i++) if (d->res_basin[i] == p) r = i;
         if (d->sb_level[p] == 0 || pd < 0) {
           double integ = 0.5 * (qout[(size_t)p * RVN_MAX_RIVER_SEGS + d->sb_nseg[p] - 1] + scal[(size_t)p * 8 + 0]) * (tstep * O_SEC_PER_DAY);
+          if (r >= 0) integ = 0.5 * (omax(res_state[(size_t)r * RVN_RES_STATE + 2] + 0.0, 0.0) + omax(res_state[(size_t)r * RVN_RES_STATE + 3] + 0.0, 0.0)) * (tstep * O_SEC_PER_DAY); /* CReservoir::GetIntegratedOutflow */
           cumul[1] += integ / area * O_MM_PER_METER;
         }
-        cumul[1] += 0.0 / area * O_MM_PER_METER; cumul[1] += 0.0 / area * O_MM_PER_METER; cumul[1] += 0.0 / area * O_MM_PER_METER;
+        cumul[1] += ((r >= 0) ? res_state[(size_t)r * RVN_RES_STATE + 5] : 0.0) / area * O_MM_PER_METER; /* GetReservoirLosses */
+        cumul[1] += 0.0 / area * O_MM_PER_METER; cumul[1] += 0.0 / area * O_MM_PER_METER;
       }
       if (wshed_rec) {
         double *w = wshed_rec + (size_t)s * 4;
@@ -1509,11 +1638,16 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
         }
         double ch = 0, rv = 0;
         for (int p = 0; p < NB; p++) { ch += scal[(size_t)p * 8 + 4]; rv += scal[(size_t)p * 8 + 5]; }
-        tot += ch / (d->watershed_area * O_M2_PER_KM2) * O_MM_PER_METER + rv / (d->watershed_area * O_M2_PER_KM2) * O_MM_PER_METER + 0.0;
+        double rsv = 0.0;
+        for (int r = 0; r < d->nRes; r++) rsv += res_volume(d, r, res_state[(size_t)r * RVN_RES_STATE + 0]); /* GetTotalReservoirStorage */
+        tot += ch / (d->watershed_area * O_M2_PER_KM2) * O_MM_PER_METER + rv / (d->watershed_area * O_M2_PER_KM2) * O_MM_PER_METER + rsv / (d->watershed_area * O_M2_PER_KM2) * O_MM_PER_METER;
         w[3] = tot;
       }
     }
-    if (qout_rec) for (int p = 0; p < NB; p++) qout_rec[(size_t)s * NB + p] = qout[(size_t)p * RVN_MAX_RIVER_SEGS + d->sb_nseg[p] - 1];
+    if (qout_rec) {
+      for (int p = 0; p < NB; p++) qout_rec[(size_t)s * NB + p] = qout[(size_t)p * RVN_MAX_RIVER_SEGS + d->sb_nseg[p] - 1];
+      for (int r = 0; r < d->nRes; r++) qout_rec[(size_t)s * NB + d->res_basin[r]] = res_state[(size_t)r * RVN_RES_STATE + 2]; /* GetOutflowRate */
+    }
     if (state_rec) memcpy(state_rec + (size_t)s * nH * NS, state, sizeof(double) * (size_t)nH * NS);
   }
   free(F); free(daily); free(phinew); free(phiread); free(aRouted); free(aQinnew);

@@ -11,6 +11,7 @@
 //     <out>/forc.f64    [nsteps+1][nHRU][43]   force_struct (all doubles), as used for the step
 //     <out>/basin.f64   [nsteps+1][NB][6]      Qout, Qlocal, channel stor, rivulet stor, Qin[0], Qlat[0]
 //     <out>/wshed.f64   [nsteps+1][3]          _CumulInput, _CumulOutput, GetAveragePrecip
+//     <out>/res.f64     [nsteps+1][NB][4]      reservoir stage, outflow, losses of the step [m3], storage [m3] (zeros for basins without one)
 //     <out>/meta.txt    integer tables: SV catalogue, process connections, routing order, UH arrays
 // Row 0 is the initial condition (after the t=0 forcing update), row n the state after step n.
 //
@@ -166,7 +167,8 @@ int main(int argc, char **argv)
   FILE *ff = fopen((outdir + "forc.f64").c_str(), "wb");
   FILE *fb = fopen((outdir + "basin.f64").c_str(), "wb");
   FILE *fw = fopen((outdir + "wshed.f64").c_str(), "wb");
-  if (!fs || !ff || !fb || !fw) { perror("open dump"); return 3; }
+  FILE *fr = fopen((outdir + "res.f64").c_str(), "wb");
+  if (!fs || !ff || !fb || !fw || !fr) { perror("open dump"); return 3; }
 
   std::vector<double> row(NS);
   auto dump_state = [&]() {
@@ -180,6 +182,12 @@ int main(int argc, char **argv)
       double v[6] = { b->GetOutflowRate(), b->GetLocalOutflowRate(), b->GetChannelStorage(), b->GetRivuletStorage(),
                       b->GetInflowHistory()[0], b->GetLatHistory()[0] };
       wr(fb, v, 6);
+    }
+    for (int p = 0; p < NB; p++) {
+      const CReservoir *r = pModel->GetSubBasin(p)->GetReservoir();
+      double v[4] = { 0.0, 0.0, 0.0, 0.0 };
+      if (r != NULL) { v[0] = r->GetResStage(); v[1] = r->GetOutflowRate(false); v[2] = r->GetReservoirLosses(Options.timestep); v[3] = r->GetStorage(); }
+      wr(fr, v, 4);
     }
     double w[3] = { pModel->_CumulInput, pModel->_CumulOutput, pModel->GetAveragePrecip() };
     wr(fw, w, 3);
@@ -210,7 +218,7 @@ int main(int argc, char **argv)
     dump_forc();  // row step+1 = forcings that drove step `step`
     step++;
   }
-  fclose(fs); fclose(ff); fclose(fb); fclose(fw);
+  fclose(fs); fclose(ff); fclose(fb); fclose(fw); fclose(fr);
   {
     std::ofstream M((outdir + "meta.txt").c_str(), std::ios::app);
     M << "nsteps " << step << "\n";

@@ -14,6 +14,7 @@ F_COUNT = 15  # RVN_F_COUNT
 FORCING_NAMES = ["PRECIP", "SNOW_FRAC", "TEMP_AVE", "TEMP_DAILY_AVE", "TEMP_DAILY_MIN", "TEMP_DAILY_MAX", "PET", "OW_PET",
                  "POTENTIAL_MELT", "TEMP_MONTH_AVE", "PET_MONTH_AVE", "AIR_PRES", "REL_HUMIDITY", "SW_RADIA", "WIND_VEL"]
 MAX_RIVER_SEGS = 50
+RES_STATE = 8  # RVN_RES_STATE
 
 _engine = None
 _host = None
@@ -41,6 +42,8 @@ def engine_lib():
         lib.rvn_gpu_download_state.argtypes = [vp, dp, i, i]
         lib.rvn_gpu_upload_basin_state.argtypes = [vp, dp, dp, dp, dp, i, i]
         lib.rvn_gpu_download_basin_state.argtypes = [vp, dp, dp, dp, dp, i, i]
+        lib.rvn_gpu_upload_reservoir_state.argtypes = [vp, dp, i, i]
+        lib.rvn_gpu_download_reservoir_state.argtypes = [vp, dp, i, i]
         lib.rvn_gpu_upload_params.argtypes = [vp, dp, dp, dp, i, i]
         lib.rvn_gpu_upload_forcings.argtypes = [vp, dp, dp, i, i]
         lib.rvn_gpu_run.argtypes = [vp, i, i]
@@ -111,7 +114,10 @@ def host_lib():
         lib.rvh_enkf_harvest_outputs.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp]
         lib.rvh_enkf_compute_Z.argtypes = [vp, vp, vp]
         lib.rvh_desc_nseg.argtypes = [vp, vp]
+        lib.rvh_desc_num_reservoirs.argtypes = [vp]
+        lib.rvh_desc_reservoir_state.argtypes = [vp, vp, vp]
         lib.rvh_model_write_solution.argtypes = [vp, C.c_char_p, C.c_double, vp, vp, vp, vp, vp, C.c_int]
+        lib.rvh_model_write_solution_res.argtypes = [vp, C.c_char_p, C.c_double, vp, vp, vp, vp, vp, C.c_int, vp]
         _host = lib
     return _host
 
@@ -214,11 +220,24 @@ class RavenModel:
             raise RavenError(self.lib.rvh_last_error().decode())
         return qin, qlat, qout, scal
 
-    def write_solution(self, filename, model_time, state, qin, qlat, qout, scal, full_precision=True):
+    def reservoir_state(self):
+        """Initial reservoir state [nRes][8] = {stage, stage_last, Qout, Qout_last, precip m3, losses m3, AET m3, 0} and the basin index of
+        each reservoir (rvn_model_desc::res_state0 / res_basin)."""
+        assert self.desc, "flatten() first"
+        n = self.lib.rvh_desc_num_reservoirs(self.desc)
+        st = np.zeros((n, RES_STATE)); sb = np.zeros(n, dtype=np.int32)
+        if n:
+            self.lib.rvh_desc_reservoir_state(self.desc, st.ctypes.data, sb.ctypes.data)
+        return st, sb
+
+    def write_solution(self, filename, model_time, state, qin, qlat, qout, scal, full_precision=True, res=None):
         """Checkpoint of one member in the reference's solution.rvc format (CModel::WriteMajorOutput): state [nHRU][NS], basin arrays
-        as returned by GpuSimulation.download_basin_state() for that member.  full_precision writes %.17g so a restart is bit-exact."""
+        as returned by GpuSimulation.download_basin_state() for that member, res = its reservoir state [nRes][8] (models with reservoirs).
+        full_precision writes %.17g so a restart is bit-exact."""
         a = [np.ascontiguousarray(x, dtype=np.float64) for x in (state, qin, qlat, qout, scal)]
-        if self.lib.rvh_model_write_solution(self.h, str(filename).encode(), float(model_time), *[x.ctypes.data for x in a], 1 if full_precision else 0):
+        r = np.ascontiguousarray(res, dtype=np.float64) if res is not None and np.size(res) else None
+        if self.lib.rvh_model_write_solution_res(self.h, str(filename).encode(), float(model_time), *[x.ctypes.data for x in a], 1 if full_precision else 0,
+                                                 r.ctypes.data if r is not None else None):
             raise RavenError(self.lib.rvh_last_error().decode())
 
     def update_parameter(self, class_type, pname, cname, value):
@@ -386,11 +405,25 @@ class GpuSimulation:
         self._ck(self.lib.rvn_gpu_download_basin_state(self.h, qin.ctypes.data, qlat.ctypes.data, qout.ctypes.data, scal.ctypes.data, member0, nmembers))
         return qin, qlat, qout, scal
 
+    def download_reservoir_state(self, member0=0, nmembers=None):
+        nmembers = self.E - member0 if nmembers is None else nmembers
+        n = self.model.reservoir_state()[0].shape[0]
+        res = np.zeros((nmembers, n, RES_STATE))
+        if n:
+            self._ck(self.lib.rvn_gpu_download_reservoir_state(self.h, res.ctypes.data, member0, nmembers))
+        return res
+
+    def upload_reservoir_state(self, res, member0=0, nmembers=None):
+        res = np.ascontiguousarray(res, dtype=np.float64)
+        nmembers = (res.shape[0] if res.ndim == 3 else 1) if nmembers is None else nmembers
+        if res.size:
+            self._ck(self.lib.rvn_gpu_upload_reservoir_state(self.h, res.ctypes.data, member0, nmembers))
+
     def write_solution(self, filename, member=0, full_precision=True):
         """solution.rvc of `member` at the current step, straight from the device buffers."""
         st = self.download_state(member, 1)[0]
         qin, qlat, qout, scal = [a[0] for a in self.download_basin_state(member, 1)]
-        self.model.write_solution(filename, self.step * self.model.timestep, st, qin, qlat, qout, scal, full_precision)
+        self.model.write_solution(filename, self.step * self.model.timestep, st, qin, qlat, qout, scal, full_precision, res=self.download_reservoir_state(member, 1)[0])
 
     def upload_member_params(self, member):
         a, b, c = self.model.flatten_member(member)

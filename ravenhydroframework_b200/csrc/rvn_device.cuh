@@ -44,6 +44,7 @@ struct DevProgram {
   int32_t maxConn, nConn, nConv, maxGroupConn;
 };
 
+#define RVN_DEV_RES_LINKED 0x100   // device-side flag in DevModel::hru_type[]: the HRU is linked to a reservoir (CHydroUnit::IsLinkedToReservoir)
 struct DevModel {
   int32_t nH, nHp, nSB, E, NS, nCore, maxConn, maxGroupConn;
   rvn_options opt;
@@ -89,6 +90,10 @@ struct DevModel {
   double watershed_area;
   // user-specified basin inflows (rvn_model_desc::spec_*): slot of each basin in the [nSteps][nSpec] tables or -1
   int32_t nSpec; const int32_t *sb_spec_slot; const double *spec_in, *spec_down, *spec_cum;
+  // reservoirs (rvn_model_desc::res_*): hru_type[] carries RVN_DEV_RES_LINKED for a reservoir-linked HRU, hru_res[k] = its reservoir or -1;
+  // res_state [member][nRes][RVN_RES_STATE]; res_force [slot][member][nRes][2] = {OW_PET, LAKE_PET_CORR} of the linked HRU, written by the sweep
+  int32_t nRes, nResPts; const int32_t *sb_res, *res_hru, *res_np, *hru_res; const double *res_curves, *res_min_stage, *res_extract;
+  double *res_state, *res_force; int32_t iAET;
   // recording
   double *rec_qout, *rec_wshed;                    // [rec][member][nSB], [rec][member][4]
   int32_t rec_capacity, rec_flags;

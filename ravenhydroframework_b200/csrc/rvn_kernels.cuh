@@ -50,6 +50,7 @@ struct CtxCommon {
   double canopy_cap, canopy_snow_cap;   // veg_var_struct capacity / snow_capacity of this HRU for this step
   double rain_icept_pct, snow_icept_pct; // veg_var_struct interception fractions (:PrecipIceptFract)
   int type, lu, veg, profile;
+  bool linked;   // HRU linked to a reservoir (CHydroUnit::IsLinkedToReservoir)
   const double *ptab;      // member parameter row (shared memory)
   const rvn_options *popt;
   int glob_off, lu_base, veg_base, soil_off, terr_base;
@@ -603,8 +604,8 @@ RVN_DI void convolve_direct(C &c, const int iTarget, const int iTS, double *__re
       // ---- interior rows 1..N-2: every special case is statically decided; the loads of the next RVN_CONV_R rows are in
       // flight while the current ones are processed
       const int end = N - 1;
-      double cur[RVN_CONV_R];
       double *p = g + stride;
+      double cur[RVN_CONV_R];
 #pragma unroll
       for (int r = 0; r < RVN_CONV_R; r++) cur[r] = (1 + r < end) ? __ldcs(p + (size_t)r * stride) : 0.0;
       for (int i = 1; i < end; i += RVN_CONV_R) {
@@ -724,7 +725,8 @@ RVN_DI void load_hru_statics(C &c, const DevModel &M, int k, const double *s_pta
   c.ptab = s_ptab; c.popt = &M.opt;
   c.tstep = M.opt.timestep;
   c.area = M.hru_area[k]; c.elev = M.hru_elev[k]; c.lat = M.hru_lat[k]; c.slope = M.hru_slope[k]; c.aspect = M.hru_aspect[k];
-  c.type = M.hru_type[k]; c.lu = M.hru_lu[k]; c.veg = M.hru_veg[k]; c.profile = M.hru_profile[k];
+  { const int t = M.hru_type[k]; c.type = t & 0xff; c.linked = (t & RVN_DEV_RES_LINKED) != 0; }
+  c.lu = M.hru_lu[k]; c.veg = M.hru_veg[k]; c.profile = M.hru_profile[k];
   c.glob_off = M.glob_off; c.lu_base = M.lu_off + c.lu * RVN_LU_COUNT; c.veg_base = M.veg_off + c.veg * RVN_V_COUNT; c.soil_off = M.soil_off;
   {
     const int terr = (M.hru_terrain != nullptr) ? M.hru_terrain[k] : -1;
@@ -761,6 +763,12 @@ template <class C> RVN_DI void load_canopy(C &c, const DevModel &M, int step) {
   }
 }
 
+// open-water PET and its lake correction factor of a reservoir-linked HRU for this step: what CReservoir::RouteWater / GetAET read through
+// _pHRU (src/Reservoir.cpp:1632-1636,1283-1292), handed to the routing kernels in ring slot `slot`
+template <class C> RVN_DI void export_reservoir_forcing(C &c, const DevModel &M, const int e, const int k, const int slot) {
+  double *rf = M.res_force + (((size_t)slot * M.E + e) * M.nRes + M.hru_res[k]) * 2;
+  rf[0] = c.F[RVN_F_OW_PET]; rf[1] = c.LU(RVN_LU_LAKE_PET_CORR);
+}
 // AET / RUNOFF / GROUNDWATER reboot (src/Solvers.cpp:171-200)
 template <class C> RVN_DI void reboot_diagnostics(C &c) {
   if (c.iSV(RVN_SV_AET) >= 0) c.SV(c.iSV(RVN_SV_AET)) = 0.0;
@@ -898,7 +906,8 @@ __global__ void __launch_bounds__(RVN_BS, RVN_STATIC_MIN_BLOCKS) hru_sweep_stati
     c.old_snow_temp = (Prog::iSV(RVN_SV_SNOW_TEMP) >= 0) ? c.SV(Prog::iSV(RVN_SV_SNOW_TEMP) >= 0 ? Prog::iSV(RVN_SV_SNOW_TEMP) : 0) : 0.0;
     // ---- forcings (on the stored state)
     if (enabled) compute_forcings(c, M, e, k, step, sb);
-    else {
+    if (M.nRes > 0 && enabled && c.linked) export_reservoir_forcing(c, M, e, k, slot0 + ss);
+    if (!enabled) {
 #pragma unroll
       for (int f = 0; f < RVN_F_CARRIED; f++) c.F[f] = 0.0;
     }
@@ -987,6 +996,7 @@ __global__ void __launch_bounds__(RVN_BS, RVN_INTERP_MIN_BLOCKS) hru_sweep_inter
   c.old_snow_temp = (P->iSV[RVN_SV_SNOW_TEMP] >= 0) ? c.SV(P->iSV[RVN_SV_SNOW_TEMP]) : 0.0;
   if (enabled) compute_forcings(c, M, e, k, step, sb);
   else { for (int f = 0; f < RVN_F_CARRIED; f++) c.F[f] = 0.0; }
+  if (M.nRes > 0 && enabled && c.linked) export_reservoir_forcing(c, M, e, k, slot0 + ss);
   load_canopy(c, M, step);
   if (enabled) reboot_diagnostics(c);
   if (euler || heun) { for (int s = 0; s < nCore; s++) c.SVW(s) = c.SV(s); }   // aPhinew = aPhi (src/Solvers.cpp:155-200); rates come from aPhi
@@ -1127,19 +1137,122 @@ __device__ void basin_lateral_inflow(const DevModel &M, int e, int p, int slot, 
   double routed = 0.0;
   const int i1 = M.sb_hru_ptr[p + 1];
   int i = M.sb_hru_ptr[p];
+  // a reservoir-linked HRU does not drain into the catchment: its surface water is precipitation on the reservoir (src/Solvers.cpp:502-507);
+  // here it contributes an exact zero to the sum
+  const int r = (M.nRes > 0) ? M.sb_res[p] : -1;
+  const int kres = (r >= 0) ? M.res_hru[r] : -1;
   for (; i + 8 <= i1; i += 8) {
     double v[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) v[j] = swvol[M.sb_hru_idx[i + j]];
+    for (int j = 0; j < 8; j++) { const int k = M.sb_hru_idx[i + j]; v[j] = (k == kres) ? 0.0 : swvol[k]; }
 #pragma unroll
     for (int j = 0; j < 8; j++) routed += v[j];
   }
-  for (; i < i1; i++) routed += swvol[M.sb_hru_idx[i]];
+  for (; i < i1; i++) { const int k = M.sb_hru_idx[i]; routed += (k == kres) ? 0.0 : swvol[k]; }
   QlatHist[0] = routed / (tstep * D_SEC_PER_DAY);
+  if (kres >= 0 && M.hru_enabled[kres]) M.res_state[((size_t)e * M.nRes + r) * RVN_RES_STATE + 4] = swvol[kres];   // CReservoir::SetPrecip [m3]
+}
+
+// InterpolateCurve (src/CommonFunctions.cpp:1982-2004) on one curve of reservoir r; the interval is the one with xx[i] <= x < xx[i+1]
+RVN_DI double res_interp(const double x, const double *xx, const double *y, const int N, const bool extrapbottom) {
+  if (x <= xx[0]) {
+    if (extrapbottom) return y[0] + (y[1] - y[0]) / (xx[1] - xx[0]) * (x - xx[0]);
+    return y[0];
+  }
+  if (x >= xx[N - 1]) return y[N - 1] + (y[N - 1] - y[N - 2]) / (xx[N - 1] - xx[N - 2]) * (x - xx[N - 1]);
+  int lo = 0, hi = N - 1;   // invariant: xx[lo] <= x < xx[hi]
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (x >= xx[mid]) lo = mid; else hi = mid; }
+  if (fabs(xx[lo + 1] - xx[lo]) < D_REAL_SMALL) return (y[lo] + y[lo + 1]) / 2;
+  return y[lo] + (y[lo + 1] - y[lo]) / (xx[lo + 1] - xx[lo]) * (x - xx[lo]);
+}
+struct ResCurves {
+  const double *stage, *Q, *Qunder, *area, *volume; int N;
+  RVN_DI ResCurves(const DevModel &M, const int r) {
+    stage = M.res_curves + (size_t)r * RVN_RES_CURVES * M.nResPts; Q = stage + M.nResPts; Qunder = Q + M.nResPts; area = Qunder + M.nResPts; volume = area + M.nResPts;
+    N = M.res_np[r];
+  }
+  RVN_DI double GetVolume(const double ht) const { return res_interp(ht, stage, volume, N, true); }      // src/Reservoir.cpp:1871-1874
+  RVN_DI double GetArea(const double ht) const { return res_interp(ht, stage, area, N, false); }          // :1880-1883
+  RVN_DI double GetWeirOutflow(const double ht) const {                                                    // :1890-1894 (no weir-height series: adj = 0)
+    const double underflow = res_interp(ht, stage, Qunder, N, false);
+    return res_interp(ht - 0.0, stage, Q, N, false) + underflow;
+  }
+};
+// CReservoir::RouteWater (src/Reservoir.cpp:1532-1853) for a reservoir without control structures, DZTR, seepage, constraint series or stage
+// assimilation, then UpdateStage + UpdateMassBalance (:1264-1323) and the AET hand-back to the linked HRU (src/Solvers.cpp:608-612).
+// Level-pool mass balance over the step solved for the new stage with Newton's method on a finite-difference derivative.
+__device__ void reservoir_route(const DevModel &M, const int e, const int r, const int slot, const int step, const double Qin_old, const double Qin_new) {
+  const ResCurves C(M, r);
+  double *rs = M.res_state + ((size_t)e * M.nRes + r) * RVN_RES_STATE;   // stage, stage_last, Qout, Qout_last, precip, MB losses, AET
+  const double tstep = M.opt.timestep;
+  const double stage = rs[0], Qout = rs[2];
+  const int k = M.res_hru[r];
+  const double dh = 0.001;
+  const double V_old = C.GetVolume(stage), A_old = C.GetArea(stage);
+  double ET = 0.0, precip = 0.0, Evap = 0.0;
+  if (k >= 0) {
+    const double *rf = M.res_force + (((size_t)slot * M.E + e) * M.nRes + r) * 2;
+    ET = rf[0] / D_SEC_PER_DAY / D_MM_PER_METER;
+    ET *= rf[1];
+    Evap = rf[0]; Evap *= rf[1];
+    precip = rs[4] / M.opt.timestep / D_SEC_PER_DAY;
+  }
+  const double seep_old = 0.0;
+  const double demand = M.res_extract[(size_t)step * M.nRes + r];
+  const double ext_old = demand, ext_new = demand;
+  double stage_new, res_outflow;
+  const double gamma = V_old + ((Qin_old + Qin_new) - Qout + 2.0 * precip - ET * A_old - seep_old - (ext_old + ext_new)) / 2.0 * (tstep * D_SEC_PER_DAY);
+  if (gamma < 0) {   // reservoir dried out
+    res_outflow = 0.0; stage_new = M.res_min_stage[r];
+  } else {
+    double h_guess = stage, relax = 1.0, change;
+    int iter = 0;
+    do {
+      double out = C.GetWeirOutflow(h_guess), out2 = C.GetWeirOutflow(h_guess + dh);
+      out += ET * C.GetArea(h_guess) + 0.0 * (h_guess - 0.0);
+      out2 += ET * C.GetArea(h_guess + dh) + 0.0 * (h_guess + dh - 0.0);
+      const double f = (C.GetVolume(h_guess) + out / 2.0 * (tstep * D_SEC_PER_DAY));
+      const double dfdh = ((C.GetVolume(h_guess + dh) + out2 / 2.0 * (tstep * D_SEC_PER_DAY)) - f) / dh;
+      change = -(f - gamma) / dfdh;
+      if (dfdh == 0) change = 1e-7;
+      if (iter > 3) relax *= 0.98;
+      h_guess += relax * change;
+      iter++;
+    } while ((iter < 100) && (fabs(change / relax) > 0.0001));
+    stage_new = h_guess;
+    res_outflow = C.GetWeirOutflow(stage_new);
+    if ((res_outflow < 0.0) || (res_outflow > D_ALMOST_INF)) {   // minimum (0) / maximum flow violated: fix the flow, recompute the volume (:1775-1803)
+      if (res_outflow < 0.0) res_outflow = 0.0;
+      if (res_outflow > D_ALMOST_INF) res_outflow = D_ALMOST_INF;
+      double A_guess = A_old, A_last;
+      do {
+        double V_new = V_old + ((Qin_old + Qin_new) - (Qout + res_outflow) + 2.0 * precip - ET * (A_old + A_guess) - (seep_old + 0.0) - (ext_old + ext_new)) / 2.0 * (tstep * D_SEC_PER_DAY);
+        if (V_new < 0) {
+          V_new = 0;
+          res_outflow = -2.0 * (V_new - V_old) / (tstep * D_SEC_PER_DAY) + (-Qout + 2.0 * precip + (Qin_old + Qin_new) - ET * (A_old + 0.0) - (ext_old + ext_new));
+        }
+        stage_new = res_interp(V_new, C.volume, C.stage, C.N, false);
+        A_last = A_guess;
+        A_guess = C.GetArea(stage_new);
+      } while (fabs(1.0 - A_guess / A_last) > 0.00001);
+    }
+  }
+  // UpdateStage / UpdateMassBalance
+  rs[1] = stage; rs[0] = stage_new; rs[3] = Qout; rs[2] = res_outflow;
+  double losses = 0.0, AET_m3 = 0.0;
+  if (k >= 0) {
+    const double harea = M.hru_area[k] * D_M2_PER_KM2;
+    const double aet = Evap * 0.5 * (C.GetArea(stage_new) + C.GetArea(stage)) / harea;   // CReservoir::GetAET [mm/d], normalised to the HRU area
+    AET_m3 = aet * harea / D_MM_PER_METER * tstep;
+    if (M.iAET >= 0) M.state[((size_t)e * M.NS + M.iAET) * M.nHp + k] = aet;
+  }
+  losses += AET_m3;
+  losses += demand * D_SEC_PER_DAY * tstep;   // no series: an exact zero
+  rs[5] = losses; rs[6] = AET_m3;
 }
 // the ordered part: CSubBasin::UpdateInflow, RouteWater (src/SubBasin.cpp:2584-2863), UpdateOutflows (:2320-2421); needs the lateral
 // inflow of this step (basin_lateral_inflow) and the outflows of the basins above.  `t` = pushes into the histories before this step.
-__device__ void basin_route(const DevModel &M, const RouteTabs &T, int e, int p, int t, int step) {
+__device__ void basin_route(const DevModel &M, const RouteTabs &T, int e, int p, int t, int step, int slot) {
   const double tstep = M.opt.timestep;
   const int nSeg = T.nseg[p], nQin = T.nqin[p], nQlat = T.nqlat[p];
   const Ring QinHist(M.qin + ((size_t)e * M.nSB + p) * M.max_nqin, nQin, t + 1);
@@ -1153,7 +1266,8 @@ __device__ void basin_route(const DevModel &M, const RouteTabs &T, int e, int p,
   double Qin_up = (ispec >= 0) ? 0.0 + M.spec_in[(size_t)step * M.nSpec + ispec] : 0.0;   // user-specified inflow first (src/Solvers.cpp:543)
   for (int u = T.up_ptr[p]; u < T.up_ptr[p + 1]; u++) {
     const int pu = T.up_idx[u];
-    Qin_up += M.qout[((size_t)e * M.nSB + pu) * RVN_MAX_RIVER_SEGS + T.nseg[pu] - 1];
+    const int ru = (M.nRes > 0) ? M.sb_res[pu] : -1;   // CSubBasin::GetOutflowRate: the reservoir's outflow where there is one (src/SubBasin.cpp:844-848)
+    Qin_up += (ru >= 0) ? M.res_state[((size_t)e * M.nRes + ru) * RVN_RES_STATE + 2] : M.qout[((size_t)e * M.nSB + pu) * RVN_MAX_RIVER_SEGS + T.nseg[pu] - 1];
   }
   QinHist[0] = Qin_up;
   const double Qin0 = Qin_up, Qin1 = QinHist[1], Qlat0 = QlatHist[0];
@@ -1233,7 +1347,9 @@ __device__ void basin_route(const DevModel &M, const RouteTabs &T, int e, int p,
   }
   aQout[nSeg - 1] += Qlat_new;
   aQout[nSeg - 1] += (ispec >= 0) ? M.spec_down[(size_t)step * M.nSpec + ispec] + 0.0 : 0.0;  // down_Q = specified downstream inflow + return flows (none)
-  // CSubBasin::UpdateOutflows  src/SubBasin.cpp:2320-2421 (no irrigation, diversions or reservoirs)
+  if (M.nRes > 0 && M.sb_res[p] >= 0)   // src/Solvers.cpp:591-596: inflow to the reservoir = channel outflow at the start and at the end of the step
+    reservoir_route(M, e, M.sb_res[p], slot, step, QoutLast, dmax((aQout[nSeg - 1] - 0.0 - 0.0), 0.0));
+  // CSubBasin::UpdateOutflows  src/SubBasin.cpp:2320-2421 (no irrigation or diversions)
   sc[0] = QoutLast;
   const double irrQ = dmin(0.0, aQout[nSeg - 1]); aQout[nSeg - 1] -= irrQ;
   const double divQ = dmin(0.0, aQout[nSeg - 1]); aQout[nSeg - 1] -= divQ;
@@ -1271,7 +1387,7 @@ __global__ void __launch_bounds__(RVN_ROUTE_BS, RVN_ROUTE_MINB) route_level_kern
   const int p = M.level_idx[lev0 + i];
   RouteTabs T; T.from_model(M);
   basin_lateral_inflow(M, e, p, slot, t);
-  basin_route(M, T, e, p, t, step);
+  basin_route(M, T, e, p, t, step, slot);
 }
 // IncrementCumulInput / IncrementCumOutflow (src/Model.cpp:2458-2539) + watershed storage + the step's records for member e; executed
 // by all NT threads of a CTA (s_red: NT/32 x 5 doubles of shared memory)
@@ -1283,8 +1399,15 @@ RVN_DI void balance_member(const DevModel &M, const int e, const int slot, const
   double v[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // outflow, channel storage, rivulet storage, precip partials, storage partials
   for (int p = tid; p < NB; p += NT) {
     const double *sc = M.scal + ((size_t)e * NB + p) * 8;
-    const double qo = M.qout[((size_t)e * NB + p) * RVN_MAX_RIVER_SEGS + M.sb_nseg[p] - 1];
-    if (M.sb_level[p] == 0 || M.sb_down[p] < 0) v[0] += (0.5 * (qo + sc[0]) * (tstep * D_SEC_PER_DAY)) / area * D_MM_PER_METER;
+    double qo = M.qout[((size_t)e * NB + p) * RVN_MAX_RIVER_SEGS + M.sb_nseg[p] - 1];
+    const int r = (M.nRes > 0) ? M.sb_res[p] : -1;
+    if (r >= 0) {   // CSubBasin::GetOutflowRate / GetIntegratedOutflow / GetReservoirLosses / GetReservoirStorage with a reservoir (src/SubBasin.cpp:803-807,844-848,902-906,929-934)
+      const double *rs = M.res_state + ((size_t)e * M.nRes + r) * RVN_RES_STATE;
+      qo = rs[2];
+      if (M.sb_level[p] == 0 || M.sb_down[p] < 0) v[0] += (0.5 * (dmax(rs[2] + 0.0, 0.0) + dmax(rs[3] + 0.0, 0.0)) * (tstep * D_SEC_PER_DAY)) / area * D_MM_PER_METER;
+      v[0] += rs[5] / area * D_MM_PER_METER;
+      v[1] += ResCurves(M, r).GetVolume(rs[0]);   // reservoir storage rides with the channel storage in the watershed record
+    } else if (M.sb_level[p] == 0 || M.sb_down[p] < 0) v[0] += (0.5 * (qo + sc[0]) * (tstep * D_SEC_PER_DAY)) / area * D_MM_PER_METER;
     v[1] += sc[4]; v[2] += sc[5];
     if ((M.rec_flags & 1) && rec >= 0) M.rec_qout[((size_t)rec * M.E + e) * NB + p] = qo;
   }
@@ -1360,7 +1483,7 @@ __global__ void __launch_bounds__(RVN_MEMBER_BS) route_member_kernel(const __gri
     __syncthreads();
     for (int L = 0; L < M.nLevels; L++) {
       const int lev0 = M.level_ptr[L], lev1 = M.level_ptr[L + 1];
-      for (int i = lev0 + threadIdx.x; i < lev1; i += RVN_MEMBER_BS) basin_route(M, T, e, level_idx[i], t0 + ss, step0 + ss);
+      for (int i = lev0 + threadIdx.x; i < lev1; i += RVN_MEMBER_BS) basin_route(M, T, e, level_idx[i], t0 + ss, step0 + ss, slot0 + ss);
       __syncthreads();   // the next level reads this level's outflows
     }
     balance_member<RVN_MEMBER_BS>(M, e, slot0 + ss, rec0 >= 0 ? rec0 + ss : -1, step0 + ss, s_red);

@@ -116,7 +116,7 @@ template <class C, class PR> RVN_DI void rates_PRECIPITATION(C &c, const PR &pr)
     } else c.R(qAtmos) += Fcan * snow_int;
     snowthru = snowfall - Fcan * snow_int;
   } else { snowthru = snowfall; rainthru = rainfall; }
-  if (is_lake) c.R(qLake) = snowthru + rainthru;
+  if (is_lake) { if (c.linked) c.R(qSW) = snowthru + rainthru; else c.R(qLake) = snowthru + rainthru; }   // src/PartitionPrecip.cpp:258-265
   else if (c.type == RVN_HRU_WETLAND) c.R(qDep) = snowthru + rainthru;
   else if (c.type == RVN_HRU_WATER) c.R(qSW) = snowthru + rainthru;
   else {
@@ -302,6 +302,7 @@ template <class C, class PR> RVN_DI void rates_SUBLIMATION(C &c, const PR &pr) {
 // CmvOWEvaporation OPEN_WATER_EVAP  src/OpenWaterEvap.cpp:113-160; ApplyConstraints :170-186
 template <class C, class PR> RVN_DI void rates_OPEN_WATER_EVAP(C &c, const PR &pr) {
   if (c.type == RVN_HRU_MASKED_GLACIER) return;
+  if (c.linked) return;   // reservoir-linked HRUs handle ET via the reservoir mass balance (src/OpenWaterEvap.cpp:124)
   double OWPET = c.F[RVN_F_OW_PET];
   if (!c.opt().suppress_competitive_ET) { OWPET -= (c.SV(c.iSV(RVN_SV_AET)) / c.tstep); OWPET = dmax(OWPET, 0.0); }
   c.R(0) = c.LU(RVN_LU_OW_PET_CORR) * OWPET;
@@ -315,7 +316,7 @@ template <class C, class PR> RVN_DI void rates_OPEN_WATER_EVAP(C &c, const PR &p
 // CmvLakeEvaporation LAKE_EVAP_BASIC  src/OpenWaterEvap.cpp:269-290; ApplyConstraints :300-314.  ia(0) = 1 when the
 // source is the :LakeStorage variable (then the process applies to every HRU type, not only lakes)
 template <class C, class PR> RVN_DI void rates_LAKE_EVAP_BASIC(C &c, const PR &pr) {
-  if ((c.type == RVN_HRU_LAKE) || (pr.ia(0) == 1)) {
+  if (((c.type == RVN_HRU_LAKE) || (pr.ia(0) == 1)) && !c.linked) {   // reservoir-linked HRUs: ET via the reservoir mass balance (:279)
     c.R(0) = c.LU(RVN_LU_LAKE_PET_CORR) * c.F[RVN_F_OW_PET];
     c.R(pr.nconn() - 1) = c.R(0);
   }

@@ -82,6 +82,14 @@ int rvh_model_write_solution(rvh_model *h, const char *filename, double model_ti
   return 0;
   RVH_CATCH(-1)
 }
+// the same with the reservoir state [nRes][RVN_RES_STATE] of the member (:ResFlow / :ResStage lines)
+int rvh_model_write_solution_res(rvh_model *h, const char *filename, double model_time, const double *state, const double *qin, const double *qlat,
+                                 const double *qout, const double *scal, int full_precision, const double *res_state) {
+  RVH_TRY
+  h->pModel->WriteSolutionFile(filename, h->Options, model_time, state, qin, qlat, qout, scal, full_precision != 0, res_state);
+  return 0;
+  RVH_CATCH(-1)
+}
 // ---- DDS (CDDSEnsemble): rvh_ensemble_begin + rvh_ensemble_update_model(e) perturb the best-so-far vector (the sampled values
 // returned are the trial's parameters); after the trial's GPU run rvh_dds_finish_run(e, hydrographs) evaluates the objective
 // function and updates the best solution.  qout_rec[nsteps][nSB] = CSubBasin::GetOutflowRate after every step of the single member.
@@ -211,6 +219,13 @@ int rvh_desc_info(const rvn_model_desc *d, int *out8) {
   for (int i = 0; i < d->NS; i++) if (d->sv_type[i] != RVN_SV_CONV_STOR) ncore++;
   out8[0] = d->nSteps; out8[1] = d->max_nqin; out8[2] = d->max_nqlat; out8[3] = ncore; out8[4] = d->nConvProc; out8[5] = d->ptab_stride;
   out8[6] = d->nMembers; out8[7] = d->nLU;
+  return 0;
+}
+// reservoirs of the flattened model: count, and the initial state [nRes][RVN_RES_STATE] + basin index of each
+int rvh_desc_num_reservoirs(const rvn_model_desc *d) { return d->nRes; }
+int rvh_desc_reservoir_state(const rvn_model_desc *d, double *res_state, int32_t *res_basin) {
+  for (int i = 0; i < d->nRes * RVN_RES_STATE; i++) res_state[i] = d->res_state0[i];
+  if (res_basin) for (int r = 0; r < d->nRes; r++) res_basin[r] = d->res_basin[r];
   return 0;
 }
 const double *rvh_desc_gauge_series(const rvn_model_desc *d) { return d->gauge_series; }

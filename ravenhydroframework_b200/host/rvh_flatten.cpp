@@ -248,6 +248,19 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
   _f_veg_season.clear();
   _f_spec_basin.clear(); _f_spec_in.clear(); _f_spec_down.clear(); _f_spec_cum.clear();
   for (int p = 0; p < NB; p++) if (_pSubBasins[p]->pInflowHydro || _pSubBasins[p]->pInflowHydro2) _f_spec_basin.push_back(p);
+  // reservoirs: curves padded to the longest, initial state, linked HRU (src/ModelInitialize.cpp:165-175)
+  _f_res_basin.clear(); _f_res_hru.clear(); _f_res_np.clear(); _f_res_curves.clear(); _f_res_min_stage.clear(); _f_res_extract.clear(); _f_res_state0.clear();
+  int nResPts = 0;
+  for (int p = 0; p < NB; p++) if (_pSubBasins[p]->pReservoir) { _f_res_basin.push_back(p); nResPts = std::max(nResPts, (int)_pSubBasins[p]->pReservoir->_aStage.size()); }
+  for (size_t r = 0; r < _f_res_basin.size(); r++) {
+    const CReservoir *R = _pSubBasins[_f_res_basin[r]]->pReservoir;
+    const int np = (int)R->_aStage.size();
+    _f_res_hru.push_back(R->_hru_k); _f_res_np.push_back(np); _f_res_min_stage.push_back(R->_min_stage);
+    const std::vector<double> *cv[RVN_RES_CURVES] = {&R->_aStage, &R->_aQ, &R->_aQunder, &R->_aArea, &R->_aVolume};
+    for (int c = 0; c < RVN_RES_CURVES; c++) for (int i = 0; i < nResPts; i++) _f_res_curves.push_back(i < np ? (*cv[c])[i] : (*cv[c])[np - 1]);
+    const double st0[RVN_RES_STATE] = {R->_stage, R->_stage_last, R->_Qout, R->_Qout_last, 0.0, 0.0, 0.0, 0.0};
+    _f_res_state0.insert(_f_res_state0.end(), st0, st0 + RVN_RES_STATE);
+  }
   {
     time_struct tt;
     JulianConvert(0.0, O.julian_start_day, O.julian_start_year, O.calendar, tt);
@@ -272,6 +285,12 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
         sum += 0.5 * (b->GetSpecifiedInflow(tt.model_time) + b->GetSpecifiedInflow(tt.model_time + O.timestep)) * (O.timestep * SEC_PER_DAY);
         sum += b->GetDownstreamInflow(tt.model_time) * (O.timestep * SEC_PER_DAY);
         _f_spec_cum.push_back(sum / area * MM_PER_METER);
+      }
+      for (size_t r = 0; r < _f_res_basin.size(); r++) {   // CDemand::UpdateDemand (src/WaterDemands.cpp:204-216): sampled value of the step, blank = 0
+        const CReservoir *R = _pSubBasins[_f_res_basin[r]]->pReservoir;
+        double Qirr = 0.0;
+        if (R->_pDemandTS) { Qirr = R->_pDemandTS->GetSampledValue((int)((tt.model_time + TIME_CORRECTION) / O.timestep)); if (Qirr == RAV_BLANK_DATA) Qirr = 0.0; Qirr = 1.0 * Qirr; }
+        _f_res_extract.push_back(Qirr);
       }
       // month-interpolated relative vegetation height / LAI (CVegetationClass::RecalculateCanopyParams, src/VegetationParams.cpp:102-107;
       // the reference repeats this per HRU per step although it depends on (vegetation class, date) only)
@@ -299,6 +318,7 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
           op == RVN_OP_CANEVP_MAXIMUM || op == RVN_OP_CANEVP_RUTTER || op == RVN_OP_CANSNOWEVP_MAXIMUM) uses_pet = true;
       if (op == RVN_OP_OPEN_WATER_EVAP || op == RVN_OP_LAKE_EVAP_BASIC || op == RVN_OP_SOILEVAP_HYPR) uses_owpet = true;
     }
+    for (int p = 0; p < NB; p++) if (_pSubBasins[p]->pReservoir && _pSubBasins[p]->pReservoir->_hru_k >= 0) uses_owpet = true;   // reservoir evaporation reads OW_PET of the linked HRU (src/Reservoir.cpp:1634)
     auto consumed = [&](int method) { return (uses_pet && O.evaporation == method) || (uses_owpet && O.ow_evaporation == method); };
     bool need_atmos = false;   // PET methods fed by air pressure / humidity / shortwave radiation
     for (int mth = RVN_PET_TURC_1961; mth <= RVN_PET_HARGREAVES; mth++) if (consumed(mth)) need_atmos = true;
@@ -452,6 +472,10 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
   d.sb_musk_K = _f_sb_d[4].data(); d.sb_musk_X = _f_sb_d[5].data(); d.sb_K_reach = _f_sb_d[6].data();
   d.max_nqin = maxqin; d.max_nqlat = maxqlat; d.sb_unit_hydro = _f_uh.data(); d.sb_route_hydro = _f_rh.data();
   d.watershed_area = _WatershedArea;
+  d.nRes = (int32_t)_f_res_basin.size(); d.nResPts = nResPts;
+  d.res_basin = d.nRes ? _f_res_basin.data() : NULL; d.res_hru = d.nRes ? _f_res_hru.data() : NULL; d.res_np = d.nRes ? _f_res_np.data() : NULL;
+  d.res_curves = d.nRes ? _f_res_curves.data() : NULL; d.res_min_stage = d.nRes ? _f_res_min_stage.data() : NULL;
+  d.res_extract = d.nRes ? _f_res_extract.data() : NULL; d.res_state0 = d.nRes ? _f_res_state0.data() : NULL;
   d.nSpec = (int32_t)_f_spec_basin.size();
   d.spec_basin = d.nSpec ? _f_spec_basin.data() : NULL; d.spec_in = d.nSpec ? _f_spec_in.data() : NULL;
   d.spec_down = d.nSpec ? _f_spec_down.data() : NULL; d.spec_cum = d.nSpec ? _f_spec_cum.data() : NULL;
@@ -536,7 +560,7 @@ static std::string DecDaysToHours(double dec_date) {   // src/CommonFunctions.cp
   return b;
 }
 void CModel::WriteSolutionFile(const std::string &filename, const optStruct &O, double model_time, const double *state, const double *qin, const double *qlat,
-                               const double *qout, const double *scal, bool full_precision) const {
+                               const double *qout, const double *scal, bool full_precision, const double *res_state) const {
   FILE *f = fopen(filename.c_str(), "w");
   ExitGracefullyIf(f == NULL, "CModel::WriteMajorOutput: Unable to open output file " + filename + " for writing.");
   const char *fmt_s = full_precision ? "%.17g" : "%.5f";   // HRU table: std::fixed, precision 5
@@ -578,6 +602,13 @@ void CModel::WriteSolutionFile(const std::string &filename, const optStruct &O, 
     fprintf(f, "    :Qin ,%d", b->GetInflowHistorySize());
     for (int i = 0; i < b->GetInflowHistorySize(); i++) { fprintf(f, ","); fprintf(f, fmt_b, qin[(size_t)p * _desc.max_nqin + i]); if (i % 200 == 199) fprintf(f, "\n    "); }
     fprintf(f, "\n");
+    if (b->pReservoir != NULL && res_state != NULL) {   // CReservoir::WriteToSolutionFile (src/Reservoir.cpp:1855-1863)
+      int r = 0;
+      for (int q = 0; q < p; q++) if (_pSubBasins[q]->pReservoir) r++;
+      const double *rs = res_state + (size_t)r * RVN_RES_STATE;
+      fprintf(f, "    :ResFlow, "); fprintf(f, fmt_b, rs[2]); fprintf(f, ","); fprintf(f, fmt_b, rs[3]); fprintf(f, "\n");
+      fprintf(f, "    :ResStage, "); fprintf(f, fmt_b, rs[0]); fprintf(f, ","); fprintf(f, fmt_b, rs[1]); fprintf(f, "\n");
+    }
   }
   fprintf(f, ":EndBasinStateVariables\n");
   fclose(f);

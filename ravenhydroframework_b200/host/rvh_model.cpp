@@ -295,6 +295,135 @@ double CChannelXSect::GetArea(double Qin, double SB_slope, double SB_n) const {
   return y[i] + (y[i + 1] - y[i]) / (xx[i + 1] - xx[i]) * (x - xx[i]);
 }
 
+// ---------------------------------------------------------------------------------- reservoirs
+// InterpolateCurve, src/CommonFunctions.cpp:1982-2004 (the interval is the one with xx[i] <= x < xx[i+1])
+static double InterpolateCurve(double x, const double *xx, const double *y, int N, bool extrapbottom) {
+  if (x <= xx[0]) {
+    if (extrapbottom) return y[0] + (y[1] - y[0]) / (xx[1] - xx[0]) * (x - xx[0]);
+    return y[0];
+  }
+  if (x >= xx[N - 1]) return y[N - 1] + (y[N - 1] - y[N - 2]) / (xx[N - 1] - xx[N - 2]) * (x - xx[N - 1]);
+  int i = 0; while ((i < N - 1) && !((x >= xx[i]) && (x < xx[i + 1]))) i++;
+  ExitGracefullyIf(i >= N - 1, "InterpolateCurve::mis-ordered list or infinite x");   // e.g. NaN from a diverged Newton iteration (src/CommonFunctions.cpp:1999)
+  if (fabs(xx[i + 1] - xx[i]) < REAL_SMALL) return (y[i] + y[i + 1]) / 2;
+  return y[i] + (y[i + 1] - y[i]) / (xx[i + 1] - xx[i]) * (x - xx[i]);
+}
+static const double RES_GRAVITY = 9.80616;   // src/RavenInclude.h:118
+void CReservoir::SetPowerLaw(double a_V, double b_V, double a_Q, double b_Q, double a_A, double b_A, double crestht, double depth) {   // src/Reservoir.cpp:122-163
+  const int Np = 100;
+  _aStage.assign(Np, 0.0); _aQ.assign(Np, 0.0); _aQunder.assign(Np, 0.0); _aArea.assign(Np, 0.0); _aVolume.assign(Np, 0.0);
+  double aA = a_A, bA = b_A;
+  if (aA == AUTO_COMPUTE) aA = a_V / depth * b_V;
+  if (bA == AUTO_COMPUTE) bA = b_V - 1.0;
+  _crest_ht = crestht; _min_stage = _crest_ht - depth; _max_stage = _crest_ht + 6.0;
+  const double dh = (_max_stage - _min_stage) / (double)(Np - 1);
+  for (int i = 0; i < Np; i++) {
+    double ht = _min_stage + (double)(i) * dh;
+    if (((ht + dh) - _crest_ht) * (ht - _crest_ht) < 0.0) ht = _crest_ht;
+    const double ht_above_bottom = ht - _min_stage;
+    _aStage[i] = ht;
+    _aQ[i] = a_Q * pow(std::max(ht - _crest_ht, 0.0), b_Q);
+    _aArea[i] = aA * pow(ht_above_bottom / depth, bA);
+    _aVolume[i] = a_V * pow(ht_above_bottom / depth, b_V);
+    _aQunder[i] = 0.0;
+  }
+  _max_capacity = _aVolume[Np - 1];
+}
+void CReservoir::SetLookup(const std::vector<double> &ht, const std::vector<double> &Q, const std::vector<double> &Qund, const std::vector<double> &A,
+                           const std::vector<double> &V) {   // src/Reservoir.cpp:173-226
+  const int Np = (int)ht.size();
+  ExitGracefullyIf(Np < 2, "CReservoir::constructor: must have more than 1 data point in stage relations");
+  _min_stage = ALMOST_INF; _max_stage = -ALMOST_INF;
+  _aStage = ht; _aQ = Q; _aArea = A; _aVolume = V; _aQunder = Qund.empty() ? std::vector<double>(Np, 0.0) : Qund;
+  for (int i = 0; i < Np; i++) {
+    if (_aStage[i] < _min_stage) _min_stage = _aStage[i];
+    if (_aStage[i] > _max_stage) _max_stage = _aStage[i];
+    if (_aQ[i] == 0.0) _crest_ht = _aStage[i];
+    const std::string id = " [bad reservoir: " + _name + " " + std::to_string(_SBID) + "]";
+    ExitGracefullyIf((i > 0) && ((_aStage[i] - _aStage[i - 1]) < 0), "CReservoir::constructor: stage relations must be specified in order of increasing stage." + id);
+    ExitGracefullyIf((i > 0) && ((_aVolume[i] - _aVolume[i - 1]) <= -REAL_SMALL), "CReservoir::constructor: volume-stage relationships must be monotonically increasing for all stages." + id);
+    ExitGracefullyIf((i > 0) && ((_aQ[i] - _aQ[i - 1]) < -REAL_SMALL), "CReservoir::constructor: stage-discharge relationships must be increasing or flat for all stages." + id);
+    ExitGracefullyIf((i > 0) && ((_aQunder[i] - _aQunder[i - 1]) < -REAL_SMALL), "CReservoir::constructor: stage-discharge (underflow) relationships must be increasing or flat for all stages." + id);
+  }
+  _max_capacity = _aVolume[Np - 1];
+}
+void CReservoir::SetLake(double weircoeff, double crestw, double crestht, double A, double depth) {   // src/Reservoir.cpp:311-358
+  _crest_width = crestw; _crest_ht = crestht; _min_stage = -depth + _crest_ht; _max_stage = 5.0 + _crest_ht;
+  ExitGracefullyIf(depth <= 0, "CReservoir::Constructor (Lake): cannot have negative maximum lake depth");
+  ExitGracefullyIf(A <= 0, "CReservoir::Constructor (Lake): cannot have negative or zero lake area");
+  ExitGracefullyIf(crestw <= 0, "CReservoir::Constructor (Lake): cannot have negative or zero crest width");
+  ExitGracefullyIf(weircoeff <= 0, "CReservoir::Constructor (Lake): cannot have negative or zero weir discharge coefficient");
+  const int Np = 102;
+  _aStage.assign(Np, 0.0); _aQ.assign(Np, 0.0); _aQunder.assign(Np, 0.0); _aArea.assign(Np, 0.0); _aVolume.assign(Np, 0.0);
+  const double dh = (_max_stage - _crest_ht) / (Np - 2);
+  _aStage[0] = _min_stage; _aQ[0] = 0.0; _aQunder[0] = 0.0; _aArea[0] = A; _aVolume[0] = 0.0;
+  for (int i = 1; i < Np; i++) {
+    _aStage[i] = _crest_ht + (i - 1) * dh;
+    _aQ[i] = 2.0 / 3.0 * weircoeff * sqrt(2 * RES_GRAVITY) * crestw * pow((_aStage[i] - _crest_ht), 1.5);
+    _aQunder[i] = 0.0;
+    _aArea[i] = A;
+    _aVolume[i] = A * (_aStage[i] - _min_stage);
+  }
+  _max_capacity = _aVolume[Np - 1];
+}
+void CReservoir::SetVolumeStageCurve(const std::vector<double> &a_ht, const std::vector<double> &a_V, double weircoeff, double crestwidth) {   // src/Reservoir.cpp:1068-1116
+  const int nPoints = (int)a_ht.size(), Np = (int)_aStage.size();
+  const std::string id = " [bad reservoir: " + _name + " " + std::to_string(_SBID) + "]";
+  for (int i = 1; i < nPoints; i++)
+    ExitGracefullyIf(((a_ht[i] - a_ht[i - 1]) <= REAL_SMALL) || ((a_V[i] - a_V[i - 1]) <= REAL_SMALL), "CReservoir::SetVolumeStageCurve: volume-stage relationships must be monotonically increasing for all stages." + id);
+  ExitGracefullyIf(a_V[0] != 0.0, "CReservoir::SetVolumeStageCurve: volume-stage relationships must start with volume of zero." + id);
+  _min_stage = a_ht[0]; _max_stage = a_ht[nPoints - 1];
+  const double dh = (_max_stage - _min_stage) / (Np - 1);
+  _aStage[0] = _min_stage; _aQ[0] = 0.0; _aQunder[0] = 0.0;
+  _aArea[0] = (InterpolateCurve(_aStage[0] + dh, a_ht.data(), a_V.data(), nPoints, false)) / dh;
+  _aVolume[0] = 0.0;
+  for (int i = 1; i < Np; i++) {
+    _aStage[i] = _min_stage + i * dh;
+    _aQ[i] = 0.0;
+    if ((_aStage[i] - _crest_ht) > 0.0) _aQ[i] = 2.0 / 3.0 * weircoeff * sqrt(2 * RES_GRAVITY) * crestwidth * pow((_aStage[i] - _crest_ht), 1.5);
+    if (((_aStage[i] - _crest_ht) < dh) && ((_aStage[i] - _crest_ht) >= 0.0)) { _aStage[i] = _crest_ht; _aQ[i] = 0.0; }
+    _aQunder[i] = 0.0;
+    _aVolume[i] = InterpolateCurve(_aStage[i], a_ht.data(), a_V.data(), nPoints, false);
+    _aArea[i] = (InterpolateCurve(_aStage[i] + dh, a_ht.data(), a_V.data(), nPoints, false) - _aVolume[i]) / dh;
+  }
+  _max_capacity = _aVolume[Np - 1];
+}
+void CReservoir::SetAreaStageCurve(const std::vector<double> &a_ht, const std::vector<double> &a_A) {   // src/Reservoir.cpp:1124-1134
+  const int Np = (int)_aStage.size();
+  for (int i = 0; i < Np; i++) {
+    _aArea[i] = InterpolateCurve(_aStage[i], a_ht.data(), a_A.data(), (int)a_ht.size(), false);
+    ExitGracefullyIf((i > 0) && ((_aArea[i] - _aArea[i - 1]) <= -REAL_SMALL) && (_aArea[i] != 0.0),
+                     "CReservoir::SetAreaStageCurve: area-stage relationships must be monotonically increasing for all stages. [bad reservoir: " + _name + " " + std::to_string(_SBID) + "]");
+  }
+}
+double CReservoir::GetVolume(double ht) const { return InterpolateCurve(ht, _aStage.data(), _aVolume.data(), (int)_aStage.size(), true); }
+double CReservoir::GetArea(double ht) const { return InterpolateCurve(ht, _aStage.data(), _aArea.data(), (int)_aStage.size(), false); }
+double CReservoir::GetWeirOutflow(double ht) const {   // src/Reservoir.cpp:1890-1894, weir adjustment 0
+  const double underflow = InterpolateCurve(ht, _aStage.data(), _aQunder.data(), (int)_aStage.size(), false);
+  return InterpolateCurve(ht - 0.0, _aStage.data(), _aQ.data(), (int)_aStage.size(), false) + underflow;
+}
+void CReservoir::SetInitialFlow(double initQ, double initQlast, bool justFlow) {   // src/Reservoir.cpp:1413-1485 (no control structures / DZTR)
+  if ((initQ == 0.0) || justFlow) { _Qout = initQ; _Qout_last = initQlast; return; }
+  const double RES_TOLERANCE = 0.001; const int RES_MAXITER = 20;
+  const double dh = 0.0001;
+  double h_guess = 0.1;
+  const int Np = (int)_aStage.size();
+  for (int i = 0; i < Np; i++)
+    if (_aQ[i] > 0.0) { h_guess = _min_stage + (double)(i) / (double)(Np) * (_max_stage - _min_stage); break; }
+  int iter = 0; double change = 0, Q, dQdh;
+  do {
+    Q = GetWeirOutflow(h_guess);
+    dQdh = (GetWeirOutflow(h_guess + dh) - Q) / dh;
+    change = -(Q - initQ) / dQdh;
+    h_guess += change;
+    iter++;
+  } while ((iter < RES_MAXITER) && (fabs(change) > RES_TOLERANCE));
+  if (iter == RES_MAXITER) WriteWarning("CReservoir::SetInitialFlow did not converge after " + std::to_string(RES_MAXITER) + "  iterations for basin " + std::to_string(_SBID));
+  _stage = h_guess;
+  _Qout = GetWeirOutflow(_stage);
+  _stage_last = _stage; _Qout_last = _Qout;
+}
+
 // ---------------------------------------------------------------------------------- HRU / subbasin
 // the reference converts with the rounded literal DEGREES_TO_RADIANS = 0.017453293 (src/RavenInclude.h:166; src/ParseHRUFile.cpp:327-328,
 // src/HydroUnits.cpp:95), not with PI/180
@@ -308,7 +437,7 @@ CSubBasin::CSubBasin()
       nSegments(1), basin_area(0), drainage_area(0), t_conc(AUTO_COMPUTE), t_peak(AUTO_COMPUTE), t_lag(AUTO_COMPUTE),
       gamma_shape(AUTO_COMPUTE), gamma_scale(AUTO_COMPUTE), Q_ref(AUTO_COMPUTE), c_ref(AUTO_COMPUTE), w_ref(AUTO_COMPUTE),
       mannings_n(AUTO_COMPUTE), slope(AUTO_COMPUTE), rain_corr(1.0), snow_corr(1.0), temperature_corr(0.0), QoutLast(0), QlatLast(0),
-      Qlocal(0), QlocLast(0), channel_storage(0), rivulet_storage(0), pInflowHydro(NULL), pInflowHydro2(NULL) { aQout.assign(1, AUTO_COMPUTE); }
+      Qlocal(0), QlocLast(0), channel_storage(0), rivulet_storage(0), pInflowHydro(NULL), pInflowHydro2(NULL), pReservoir(NULL) { aQout.assign(1, AUTO_COMPUTE); }
 
 bool CSubBasin::SetBasinProperties(const std::string &label_in, double value) {
   std::string l = StringToUppercase(label_in);
@@ -466,6 +595,7 @@ void CSubBasin::Initialize(double Qin_avg, double Qlat_avg, double total_drain_a
   InitializeFlowStates(Qin_avg, Qlat_avg, O);
   if (pInflowHydro) pInflowHydro->Initialize(O.julian_start_day, O.julian_start_year, O.duration, O.timestep, O.calendar);      // src/SubBasin.cpp:1899-1904
   if (pInflowHydro2) pInflowHydro2->Initialize(O.julian_start_day, O.julian_start_year, O.duration, O.timestep, O.calendar);
+  if (pReservoir && pReservoir->_pDemandTS) pReservoir->_pDemandTS->Initialize(O.julian_start_day, O.julian_start_year, O.duration, O.timestep, O.calendar);   // CDemand::Initialize, src/WaterDemands.cpp:190-198
 }
 void CSubBasin::SetQout(double Q) {
   for (int i = 0; i < nSegments; i++) aQout[i] = Q;
@@ -585,7 +715,11 @@ int CModel::FindVegClass(const std::string &t) const { for (size_t i = 0; i < ve
 int CModel::FindLUClass(const std::string &t) const { for (size_t i = 0; i < lu_classes.size(); i++) if (lu_classes[i].tag == t) return (int)i; return -1; }
 int CModel::FindTerrainClass(const std::string &t) const { for (size_t i = 0; i < terrain_classes.size(); i++) if (terrain_classes[i].tag == t) return (int)i; return -1; }
 int CModel::FindSoilProfile(const std::string &t) const { for (size_t i = 0; i < soil_profiles.size(); i++) if (soil_profiles[i].tag == t) return (int)i; return -1; }
-const CChannelXSect *CModel::FindChannel(const std::string &t) const { for (size_t i = 0; i < channels.size(); i++) if (channels[i]->name == t) return channels[i]; return NULL; }
+const CChannelXSect *CModel::FindChannel(const std::string &t) const {   // case-insensitive like CModel::StringToChannelXSect (src/Model.cpp:2256)
+  const std::string up = StringToUppercase(t);
+  for (size_t i = 0; i < channels.size(); i++) if (StringToUppercase(channels[i]->name) == up) return channels[i];
+  return NULL;
+}
 int CModel::GetSubBasinIndex(long long SBID) const {
   if (SBID < 0) return DOESNT_EXIST;
   for (size_t p = 0; p < _pSubBasins.size(); p++) if (_pSubBasins[p]->ID == SBID) return (int)p;

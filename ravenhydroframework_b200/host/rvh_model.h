@@ -122,6 +122,34 @@ public:
   bool   IsEnabled() const { return enabled; }
 };
 
+// ---- reservoir / lake at a subbasin outlet (reference CReservoir, src/Reservoir.h) --------------------------------------------
+// Host half only: the curves (built like the reference's constructors) and the initial state; the level-pool routing itself
+// (CReservoir::RouteWater, src/Reservoir.cpp:1532-1853) runs on the device.  Not built: control structures, DZTR, seepage,
+// stage / flow constraint time series, stage assimilation, :VaryingStageRelations -- the parser rejects them.
+class CReservoir {
+public:
+  CReservoir(const std::string &name, long long SBID) : _name(name), _SBID(SBID), _HRUID(DOESNT_EXIST), _hru_k(DOESNT_EXIST), _stage(0), _stage_last(0),
+      _min_stage(0), _max_stage(0), _Qout(0), _Qout_last(0), _crest_ht(0), _crest_width(DOESNT_EXIST), _max_capacity(0), _pDemandTS(NULL), _demand_mult(1.0) {}
+  ~CReservoir() { delete _pDemandTS; }
+  // power-law curves (src/Reservoir.cpp:130-180), lookup tables :StageRelations (:190-237), prismatic lake behind a weir (:311-358)
+  void SetPowerLaw(double a_V, double b_V, double a_Q, double b_Q, double a_A, double b_A, double crestht, double depth);
+  void SetLookup(const std::vector<double> &ht, const std::vector<double> &Q, const std::vector<double> &Qund, const std::vector<double> &A, const std::vector<double> &V);
+  void SetLake(double weircoeff, double crestw, double crestht, double A, double depth);
+  void SetVolumeStageCurve(const std::vector<double> &ht, const std::vector<double> &V, double weircoeff, double crestwidth);   // :1068-1116
+  void SetAreaStageCurve(const std::vector<double> &ht, const std::vector<double> &A);                                           // :1124-1134
+  void SetInitialFlow(double initQ, double initQlast, bool justFlow);                                                           // :1413-1485
+  void SetReservoirStage(double ht, double ht_last) { if (ht_last != RAV_BLANK_DATA) _stage_last = ht_last; _stage = ht; }      // :1509-1513
+  double GetVolume(double ht) const;        // InterpolateCurve(ht, _aStage, _aVolume, _Np, true)
+  double GetArea(double ht) const;          // ... (_aArea, false)
+  double GetWeirOutflow(double ht) const;   // underflow + curve outflow, no weir-height adjustment series
+  long long GetSubbasinID() const { return _SBID; }
+  std::string _name; long long _SBID, _HRUID; int _hru_k;
+  double _stage, _stage_last, _min_stage, _max_stage, _Qout, _Qout_last, _crest_ht, _crest_width, _max_capacity;
+  std::vector<double> _aStage, _aQ, _aQunder, _aArea, _aVolume;
+  CTimeSeries *_pDemandTS;   // :ReservoirExtraction / :ReservoirDemand (one per reservoir)
+  double _demand_mult;
+};
+
 class CSubBasin {
 public:
   CSubBasin();
@@ -140,6 +168,7 @@ public:
   double QoutLast, QlatLast, Qlocal, QlocLast, channel_storage, rivulet_storage;
   // user-specified inflows [m3/s]: :BasinInflowHydrograph (upstream end of the reach) and :BasinInflowHydrograph2 (downstream end)
   CTimeSeries *pInflowHydro, *pInflowHydro2;
+  CReservoir *pReservoir;   // NULL: none (CSubBasin::AddReservoir, src/SubBasin.cpp:1122-1132)
   double GetSpecifiedInflow(double t) const { return pInflowHydro ? pInflowHydro->GetValueInterp(t) : 0.0; }     // src/SubBasin.cpp:478-482
   double GetDownstreamInflow(double t) const { return pInflowHydro2 ? pInflowHydro2->GetValueInterp(t) : 0.0; }  // :488-492
   // reference-surface accessors
@@ -151,7 +180,7 @@ public:
   int    GetInflowHistorySize() const { return (int)aQinHist.size(); }
   const double *GetUnitHydrograph() const { return aUnitHydro.data(); }
   const double *GetRoutingHydrograph() const { return aRouteHydro.data(); }
-  double GetOutflowRate() const { return aQout[nSegments - 1]; }
+  double GetOutflowRate() const { return pReservoir ? pReservoir->_Qout : aQout[nSegments - 1]; }   // src/SubBasin.cpp:844-848
   double GetMuskingumK(double dx) const;    // src/SubBasin.cpp:2429-2437
   double GetMuskingumX(double dx) const;    // src/SubBasin.cpp:2443-2452
   bool   SetBasinProperties(const std::string &label, double value);  // src/SubBasin.cpp SetBasinProperties
@@ -302,7 +331,7 @@ public:
   // rvn_gpu_download_state / rvn_gpu_download_basin_state.  full_precision: %.17g instead of the reference's 5 fixed decimals
   // (6 significant digits for the basin block), so that a restart continues bit-identically.
   void WriteSolutionFile(const std::string &filename, const optStruct &Options, double model_time, const double *state, const double *qin,
-                         const double *qlat, const double *qout, const double *scal, bool full_precision) const;
+                         const double *qlat, const double *qout, const double *scal, bool full_precision, const double *res_state = NULL) const;
   // initial basin routing state in the layout of rvn_gpu_upload_basin_state (one member)
   void PackBasinState(std::vector<double> &qin, std::vector<double> &qlat, std::vector<double> &qout, std::vector<double> &scal) const;
 
@@ -334,6 +363,8 @@ private:
   std::vector<uint64_t> _f_mask;
   std::vector<double> _f_hru_d[5], _f_prof_thick, _f_ptab, _f_conv_uh, _f_series, _f_gconst, _f_wt, _f_sb_d[7], _f_uh, _f_rh, _f_veg_season, _f_et;
   std::vector<int32_t> _f_et_row, _f_wt_ptr, _f_wt_idx, _f_pert_forcing, _f_pert_adj, _f_hru_terr, _f_spec_basin;
+  std::vector<int32_t> _f_res_basin, _f_res_hru, _f_res_np;
+  std::vector<double> _f_res_curves, _f_res_min_stage, _f_res_extract, _f_res_state0;
   std::vector<double> _f_spec_in, _f_spec_down, _f_spec_cum;
   std::vector<uint8_t> _f_pert_mask;
   std::vector<rvn_lateral> _f_lat;

@@ -679,14 +679,103 @@ static void ParseClassPropertiesFile(CModel *pModel, const optStruct &Options) {
 }
 
 // ================================================================================================ .rvh
-static void ParseHRUPropsFile(CModel *pModel, const optStruct &Options) {
-  CParser p(Options.rvh_filename);
-  ExitGracefullyIf(!p.ok(), "ParseHRUPropsFile: cannot open " + Options.rvh_filename);
+// :Reservoir [name] ... :EndReservoir (ReservoirParse, src/ParseHRUFile.cpp:1312-2119).  The formats whose routing the device implements:
+// lake type (:WeirCoefficient / :CrestWidth / :MaxDepth / :LakeArea [/ :AbsoluteCrestHeight], optional LOOKUP_TABLE :VolumeStageRelation /
+// :AreaStageRelation overrides), :StageRelations lookup tables, POWER_LAW / LINEAR relations.  Everything else fails loudly.
+static void ReservoirParse(CParser &p, const std::string &name, CModel *pModel) {
+  enum { CURVE_POWERLAW, CURVE_LINEAR, CURVE_DATA, CURVE_LAKE } type = CURVE_POWERLAW;
+  long long SBID = DOESNT_EXIST, HRUID = DOESNT_EXIST;
+  double a_V = 1000.0, b_V = 1.0, a_Q = 10.0, b_Q = 1.0, a_A = AUTO_COMPUTE, b_A = AUTO_COMPUTE;
+  double cwidth = DOESNT_EXIST, max_depth = DOESNT_EXIST, weircoeff = DOESNT_EXIST, lakearea = DOESNT_EXIST, crestht = 0.0, max_capacity = 0, demand_mult = 1.0;
+  std::vector<double> aQ, aQ_ht, aV, aV_ht, aA, aA_ht, aQund;
+  std::vector<std::string> s;
+  auto next = [&]() { do { ExitGracefullyIf(!p.Tokenize(s), "ReservoirParse: unexpected end of file inside :Reservoir block"); } while (s.empty()); };
+  auto table = [&](std::vector<double> &x, std::vector<double> &y) {
+    next(); const int n = s_to_i(s[0]);
+    x.clear(); y.clear();
+    for (int i = 0; i < n; i++) { next(); ExitGracefullyIf(s.size() < 2, "ReservoirParse: lookup table rows need two columns"); x.push_back(s_to_d(s[0])); y.push_back(s_to_d(s[1])); }
+    next();   // :End...Relation
+  };
+  for (;;) {
+    next();
+    const std::string c = s[0];
+    if (c == ":EndReservoir") break;
+    else if (c == ":SubBasinID") SBID = s_to_ll(s[1]);
+    else if (c == ":HRUID") HRUID = s_to_ll(s[1]);
+    else if (c == ":Type") {}
+    else if (c == ":CrestWidth") { cwidth = s_to_d(s[1]); type = CURVE_LAKE; }
+    else if (c == ":MaxCapacity") max_capacity = s_to_d(s[1]);
+    else if (c == ":WeirCoefficient") { weircoeff = s_to_d(s[1]); type = CURVE_LAKE; }
+    else if (c == ":MaxDepth") { max_depth = s_to_d(s[1]); type = CURVE_LAKE; }
+    else if (c == ":LakeArea") { lakearea = s_to_d(s[1]); type = CURVE_LAKE; }
+    else if (c == ":AbsoluteCrestHeight") { crestht = s_to_d(s[1]); type = CURVE_LAKE; }
+    else if (c == ":DemandMultiplier") demand_mult = s_to_d(s[1]);
+    else if (c == ":LakebedThickness" || c == ":LakebedThermalConductivity" || c == ":LakeConvectionCoeff") {}   // thermal properties: transport only
+    else if (c == ":VolumeStageRelation") {
+      ExitGracefullyIf(s.size() < 2, "VolumeStageRelation : Must specify whether LOOKUP_TABLE or POWER_LAW");
+      if (s[1] == "POWER_LAW") { type = CURVE_POWERLAW; next(); if (s.size() >= 2) { a_V = s_to_d(s[0]); b_V = s_to_d(s[1]); } next(); }
+      else if (s[1] == "LINEAR") { next(); if (s.size() >= 1) { a_V = s_to_d(s[0]); b_V = 1.0; } next(); }
+      else if (s[1] == "LOOKUP_TABLE") table(aV_ht, aV);
+    } else if (c == ":AreaStageRelation") {
+      ExitGracefullyIf(s.size() < 2, "AreaStageRelation : Must specify whether LOOKUP_TABLE or POWER_LAW");
+      if (s[1] == "POWER_LAW") { type = CURVE_POWERLAW; next(); if (s.size() >= 2) { a_A = s_to_d(s[0]); b_A = s_to_d(s[1]); } next(); }
+      else if (s[1] == "CONSTANT") { type = CURVE_LINEAR; next(); if (s.size() >= 1) { a_A = s_to_d(s[0]); b_A = 0.0; } next(); }
+      else if (s[1] == "LINEAR") { type = CURVE_LINEAR; next(); if (s.size() >= 1) { a_A = s_to_d(s[0]); b_A = 1.0; } next(); }
+      else if (s[1] == "LOOKUP_TABLE") table(aA_ht, aA);
+    } else if (c == ":OutflowStageRelation") {
+      ExitGracefullyIf(s.size() < 2, "OutflowStageRelation : Must specify whether LOOKUP_TABLE or POWER_LAW");
+      if (s[1] == "POWER_LAW") { type = CURVE_POWERLAW; next(); if (s.size() >= 2) { a_Q = s_to_d(s[0]); b_Q = s_to_d(s[1]); } next(); }
+      else if (s[1] == "LINEAR") { type = CURVE_LINEAR; next(); if (s.size() >= 1) { a_Q = s_to_d(s[0]); b_Q = 1.0; } next(); }
+      // the reference tests s[0] (not s[1]) against LOOKUP_TABLE here (src/ParseHRUFile.cpp:1663), so that branch is never taken
+    } else if (c == ":StageRelations") {
+      type = CURVE_DATA;
+      next(); const int n = s_to_i(s[0]);
+      for (int i = 0; i < n; i++) {
+        next();
+        ExitGracefullyIf(s.size() < 4, "Incorrect line length (<4) in :Reservoir :StageRelations command");
+        aQ_ht.push_back(s_to_d(s[0])); aQ.push_back(s_to_d(s[1])); aV.push_back(s_to_d(s[2])); aA.push_back(s_to_d(s[3]));
+        aQund.push_back(s.size() >= 5 ? s_to_d(s[4]) : 0.0);
+      }
+      next();   // :EndStageRelations
+    } else if (c == ":EndStageRelations") {}
+    else ExitGracefully("ReservoirParse: command " + c + " in :Reservoir block (line " + std::to_string(p.line()) + ") is not supported by the B200 build");
+  }
+  CReservoir *pRes = new CReservoir(name, SBID);
+  if (type == CURVE_POWERLAW || type == CURVE_LINEAR) {
+    ExitGracefullyIf(max_depth == DOESNT_EXIST, "ReservoirParse: :MaxDepth must be given for POWER_LAW / LINEAR stage relations");
+    pRes->SetPowerLaw(a_V, b_V, a_Q, b_Q, a_A, b_A, crestht, max_depth);
+  } else if (type == CURVE_DATA) pRes->SetLookup(aQ_ht, aQ, aQund, aA, aV);
+  else {
+    ExitGracefullyIf(weircoeff == DOESNT_EXIST, "CReservoir::Parse: :WeirCoefficient must be specified for lake-type reservoirs");
+    ExitGracefullyIf(cwidth == DOESNT_EXIST, "CReservoir::Parse: :CrestWidth must be specified for lake-type reservoirs");
+    ExitGracefullyIf(lakearea == DOESNT_EXIST, "CReservoir::Parse: :LakeArea  must be specified for lake-type reservoirs");
+    ExitGracefullyIf(max_depth == DOESNT_EXIST, "CReservoir::Parse: :LakeDepth must be specified for lake-type reservoirs");
+    pRes->SetLake(weircoeff, cwidth, crestht, lakearea, max_depth);
+  }
+  if (max_capacity != 0) pRes->_max_capacity = max_capacity;
+  if ((type == CURVE_LAKE) && !aV.empty() && !aV_ht.empty()) pRes->SetVolumeStageCurve(aV_ht, aV, weircoeff, cwidth);
+  if ((type == CURVE_LAKE) && !aA.empty() && !aA_ht.empty()) pRes->SetAreaStageCurve(aA_ht, aA);
+  pRes->_demand_mult = demand_mult;
+  const int pb = pModel->GetSubBasinIndex(pRes->GetSubbasinID());
+  ExitGracefullyIf(pb < 0, "ParseHRUProps: Bad Sub-basin index in :Reservoir command");
+  if (HRUID != DOESNT_EXIST)
+    for (int k = 0; k < pModel->GetNumHRUs(); k++) if (pModel->GetHydroUnit(k)->ID == HRUID) { pRes->_HRUID = HRUID; pRes->_hru_k = k; break; }
+  ExitGracefullyIf(pModel->GetSubBasin(pb)->pReservoir != NULL, "CSubBasin::AddReservoir: only one inflow reservoir may be specified per basin");
+  pModel->GetSubBasin(pb)->pReservoir = pRes;
+}
+
+static void ParseHRUPropsFileInner(CModel *pModel, const optStruct &Options, const std::string &filename);
+static void ParseHRUPropsFile(CModel *pModel, const optStruct &Options) { ParseHRUPropsFileInner(pModel, Options, Options.rvh_filename); }
+static void ParseHRUPropsFileInner(CModel *pModel, const optStruct &Options, const std::string &filename) {
+  CParser p(filename);
+  ExitGracefullyIf(!p.ok(), "ParseHRUPropsFile: cannot open " + filename);
   std::vector<std::string> s;
   while (p.Tokenize(s)) {
     if (s.empty()) continue;
     const std::string &c = s[0];
     if (c == ":FileType" || c == ":WrittenBy" || c == ":CreationDate") continue;
+    if (c == ":RedirectToFile") { ExitGracefullyIf(s.size() < 2, "ParseHRUPropsFile: :RedirectToFile needs a file name"); ParseHRUPropsFileInner(pModel, Options, CorrectForRelativePath(s[1], filename)); continue; }
+    if (c == ":Reservoir") { ExitGracefullyIf(s.size() < 2, "ParseHRUProps: No reservoir name provided in :Reservoir command "); const std::string nm = s[1]; ReservoirParse(p, nm, pModel); continue; }
     if (c == ":SubBasins") {
       while (p.Tokenize(s)) {
         if (s.empty() || s[0] == ":Attributes" || s[0] == ":Units") continue;
@@ -991,6 +1080,36 @@ static void ParseTimeSeriesFile(CModel *pModel, const optStruct &Options, const 
       else { delete pSB->pInflowHydro2; pSB->pInflowHydro2 = ts; }
       continue;
     }
+    if (c == ":ReservoirExtraction" || c == ":ReservoirDemand") {   // src/ParseTimeSeriesFile.cpp:627-667 (pulse-based series, [m3/s])
+      ExitGracefullyIf(s.size() < 2, "ParseTimeSeriesFile: " + c + " needs a subbasin ID");
+      const long long SBID = s_to_ll(s[1]);
+      const std::string endtag = (c == ":ReservoirExtraction") ? ":EndReservoirExtraction" : ":EndReservoirDemand";
+      double start_day, interval; int start_yr, n;
+      ReadSeriesHeader(p, Options, start_day, start_yr, interval, n);
+      std::vector<double> v; v.reserve(n);
+      std::vector<std::string> t;
+      // CTimeSeries::Parse (src/TimeSeries.cpp:700-760) reads lines until it has n values and then one more line as the :End command,
+      // whatever that line says (LOTW's extraction files end with a run-together ":EndObservationData:EndReservoirExtraction")
+      while ((int)v.size() < n && p.Tokenize(t)) {
+        if (t.empty()) continue;
+        ExitGracefullyIf(t[0][0] == ':', "CTimeSeries::Parse: wrong number of data points in " + c + " block. File: " + p.filename());
+        for (size_t i = 0; i < t.size(); i++) v.push_back(ts_s_to_d(t[i].c_str()));
+      }
+      ExitGracefullyIf((int)v.size() != n, "CTimeSeries::Parse: wrong number of data points in " + c + " block. File: " + p.filename());
+      do { if (!p.Tokenize(t)) break; } while (t.empty());   // the :End... line
+      (void)endtag;
+      const int pb = pModel->GetSubBasinIndex(SBID);
+      if (pb < 0 || pModel->GetSubBasin(pb)->pReservoir == NULL) {
+        WriteWarning(":ReservoirDemand Subbasin " + std::to_string(SBID) + " not in model or doesn't have reservoir, cannot set Reservoir Demand");
+        continue;
+      }
+      CReservoir *pRes = pModel->GetSubBasin(pb)->pReservoir;
+      // the reference keeps a list; its RouteWater uses the LAST demand only while the mass balance adds all of them (src/Reservoir.cpp:1643-1652,
+      // 1316-1323) -- one series per reservoir is what is supported here
+      ExitGracefullyIf(pRes->_pDemandTS != NULL, "ParseTimeSeriesFile: more than one :ReservoirExtraction series for subbasin " + std::to_string(SBID) + " is not supported by the B200 build");
+      pRes->_pDemandTS = new CTimeSeries("ResDemand_" + std::to_string(SBID), start_day, start_yr, interval, v);
+      continue;
+    }
     if (c == ":AssimilateStreamflow") {   // src/ParseTimeSeriesFile.cpp:1225-1248
       AssimilateStreamflowCommand(pModel, s);
       continue;
@@ -1205,10 +1324,28 @@ bool ParseInitialConditions(CModel *&pModel, const optStruct &Options) {
               for (int i = 0; i < m; i++) pBasin->aQinHist[i] = v[i];
             }
           }
-        } else if (s[0] == ":ResStage" || s[0] == ":ResFlow") {
-          WriteWarning("ParseInitialConditionsFile: reservoir initial conditions for basin without reservoir will be ignored.");
+        } else if (s[0] == ":ResStage") {   // src/ParseInitialConditionFile.cpp:628-637
+          if (s.size() >= 3) {
+            if (pBasin->pReservoir == NULL) WriteWarning("ParseInitialConditionsFile: reservoir initial conditions for basin without reservoir will be ignored.");
+            else pBasin->pReservoir->SetReservoirStage(s_to_d(s[1]), s_to_d(s[2]));
+          }
+        } else if (s[0] == ":ResFlow") {    // :638-646
+          if (s.size() >= 3) {
+            if (pBasin->pReservoir == NULL) WriteWarning("ParseInitialConditionsFile: reservoir initial conditions for basin without reservoir will be ignored.");
+            else pBasin->pReservoir->SetInitialFlow(s_to_d(s[1]), s_to_d(s[2]), true);
+          }
         } else ExitGracefully("ParseInitialConditionsFile: command " + s[0] + " inside :BasinStateVariables is not supported by the B200 build");
       }
+      continue;
+    }
+    if (c == ":InitialReservoirFlow" || c == ":InitialReservoirStage") {   // src/ParseInitialConditionFile.cpp:668-699
+      ExitGracefullyIf(s.size() < 3, "ParseInitialConditionsFile: " + c + " needs [SBID] [value]");
+      const int pb = pModel->GetSubBasinIndex(s_to_ll(s[1]));
+      ExitGracefullyIf(pb < 0, "ParseInitialConditionsFile: bad basin index in " + c + " command (.rvc file)");
+      CReservoir *pRes = pModel->GetSubBasin(pb)->pReservoir;
+      if (pRes == NULL) { WriteWarning("ParseInitialConditionsFile: bad basin index in " + c + " command (.rvc file), no reservoir exists in basin " + s[1] + ". Command will be ignored."); continue; }
+      if (c == ":InitialReservoirFlow") pRes->SetInitialFlow(s_to_d(s[2]), s_to_d(s[2]), false);
+      else pRes->SetReservoirStage(s_to_d(s[2]), s_to_d(s[2]));
       continue;
     }
     if (c == ":UniformInitialConditions") {

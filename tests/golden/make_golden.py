@@ -130,6 +130,23 @@ if hasattr(synth, "write_hbv"):
     for _i, (_crit, _so) in enumerate([("0.01 30", 150), ("1e-7 6", 130), ("0.001 30", 200), ("0.05 3", 100)]):
         CASES["hbv_heun_%d" % _i] = dict(kind="hbv", n_sb=3, hru_per_sb=6, n_days=1, seed=14 + _i, routing="ROUTE_MUSKINGUM", season_offset=_so,
                                          rvi_sub=[(r":Method\s+ORDERED_SERIES", ":Method                ITER_HEUN " + _crit)])
+    # reservoirs at subbasin outlets (CReservoir level-pool routing): lake type behind a weir with a linked HRU (its surface water is
+    # precipitation on the lake, its open-water PET the lake evaporation) + an extraction series + an initial stage; lookup-table
+    # (:StageRelations), power-law and volume / area-curve-overridden lake reservoirs, one of them at the outlet
+    _ext = ":ReservoirExtraction 5\n  2000-01-01 00:00:00 1.0 %d\n" % 260 + "".join("  %.3f\n" % (0.05 + 0.04 * ((i * 7) % 11) / 11.0) for i in range(260)) + ":EndReservoirExtraction\n"
+    CASES["hbv_res_lake"] = dict(kind="hbv", n_sb=7, hru_per_sb=3, n_days=260, seed=95, routing="ROUTE_MUSKINGUM", season_offset=60,
+                                 rvh_extra=":Reservoir LakeA\n  :SubBasinID 2\n  :HRUID 5\n  :WeirCoefficient 0.6\n  :CrestWidth 4.5\n  :MaxDepth 6\n  :LakeArea 1.4e6\n:EndReservoir\n"
+                                           ":Reservoir LakeB\n  :SubBasinID 5\n  :HRUID 13\n  :WeirCoefficient 0.55\n  :CrestWidth 2.0\n  :MaxDepth 4\n  :LakeArea 0.9e6\n  :AbsoluteCrestHeight 312.5\n:EndReservoir\n",
+                                 rvt_extra=_ext, rvc_extra=":InitialReservoirStage 5 312.9\n:InitialReservoirStage 2 0.35\n")
+    CASES["hbv_res_tables"] = dict(kind="hbv", n_sb=7, hru_per_sb=3, n_days=260, seed=96, routing="ROUTE_DIFFUSIVE_WAVE", season_offset=90,
+                                   rvh_extra=":Reservoir Tab\n  :SubBasinID 3\n  :StageRelations\n    6\n    100.0 0.0 0.0 4.0e5\n    101.0 0.0 4.2e5 4.4e5\n    102.0 1.5 8.8e5 4.8e5\n"
+                                             "    103.0 6.0 1.38e6 5.2e5 \n    104.0 15.0 1.92e6 5.6e5\n    106.0 50.0 3.1e6 6.2e5\n  :EndStageRelations\n:EndReservoir\n"
+                                             ":Reservoir Pow\n  :SubBasinID 1\n  :MaxDepth 8\n  :VolumeStageRelation POWER_LAW\n    2.4e6 1.6\n  :EndVolumeStageRelation\n"
+                                             "  :OutflowStageRelation POWER_LAW\n    7.5 1.5\n  :EndOutflowStageRelation\n:EndReservoir\n"
+                                             ":Reservoir Over\n  :SubBasinID 6\n  :HRUID 16\n  :WeirCoefficient 0.7\n  :CrestWidth 3.0\n  :MaxDepth 5\n  :LakeArea 1.1e6\n"
+                                             "  :VolumeStageRelation LOOKUP_TABLE\n    4\n    -5.0 0.0\n    -2.0 2.0e6\n    0.0 4.1e6\n    5.0 1.02e7\n  :EndVolumeStageRelation\n"
+                                             "  :AreaStageRelation LOOKUP_TABLE\n    3\n    -5.0 5.0e5\n    0.0 1.1e6\n    5.0 1.3e6\n  :EndAreaStageRelation\n:EndReservoir\n",
+                                   rvc_extra=":InitialReservoirStage 3 101.6\n")
     CASES["hbv_hrugroup_cond"] = dict(kind="hbv", n_sb=3, hru_per_sb=5, n_days=250, seed=12, routing="ROUTE_MUSKINGUM", season_offset=40, variant="hrugroup_cond")
     CASES["hbv_lateral"] = dict(kind="hbv", n_sb=4, hru_per_sb=7, n_days=250, seed=8, routing="ROUTE_MUSKINGUM", season_offset=40, variant="lateral")
 if hasattr(synth, "write_blended"):
@@ -285,6 +302,9 @@ def make(name, spec):
     rvp_sub = spec.pop("rvp_sub", None)   # [(regex, replacement)] applied to the .rvp
     proc_after = spec.pop("proc_after", None)   # (regex of a process line, line inserted after it) in the .rvi process list
     gauge_extra = spec.pop("gauge_extra", None)   # lines added to the gauge block of the .rvt (after :MonthlyAveTemperature)
+    rvh_extra = spec.pop("rvh_extra", None)   # lines appended to the .rvh / .rvt / .rvc
+    rvt_extra = spec.pop("rvt_extra", None)
+    rvc_extra = spec.pop("rvc_extra", None)
     d = os.path.join(HERE, name)
     shutil.rmtree(d, ignore_errors=True)
     base = WRITERS[kind](d, name="model", **spec)
@@ -334,6 +354,9 @@ def make(name, spec):
         open(base + ".rvt", "w").write(rvt)
     if rvp_extra is not None:
         open(base + ".rvp", "a").write(rvp_extra)
+    for ext, txt in ((".rvh", rvh_extra), (".rvt", rvt_extra), (".rvc", rvc_extra)):
+        if txt is not None:
+            open(base + ext, "a").write(txt)
     if timestep is not None:
         rvi = open(base + ".rvi").read()
         assert ":TimeStep              1.0" in rvi
@@ -353,7 +376,8 @@ def make(name, spec):
                         basin_last=ref["basin"][n], wshed=ref["wshed"][1:n + 1], forc_steps=np.array(rec), forc=ref["forc"][rec],
                         sv_type=np.array([t for t, _ in ref["sv"]]), sv_layer=np.array([l for _, l in ref["sv"]]),
                         order=np.array(ref["order"]), proc=np.array([" ".join(p) for p in ref["proc"]]),
-                        param=np.array([" ".join(p) for p in ref["param"]]))
+                        param=np.array([" ".join(p) for p in ref["param"]]),
+                        **({"res_stage": ref["res"][rec][:, :, 0], "res_losses": ref["res"][rec][:, :, 2]} if np.any(ref["res"][:, :, 3] != 0.0) else {}))
     shutil.rmtree(out, ignore_errors=True)
     print("golden %-18s nHRU=%d NS=%d NB=%d steps=%d" % (name, ref["nHRU"], ref["NS"], ref["NB"], n))
 

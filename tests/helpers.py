@@ -26,6 +26,7 @@ def oracle_lib():
         lib = C.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
         vp, i = C.c_void_p, C.c_int
         lib.rvo_run_member.argtypes = [vp, i] + [vp] * 6 + [i, i] + [vp] * 4
+        lib.rvo_run_member_res.argtypes = [vp, i] + [vp] * 6 + [i, i] + [vp] * 5
         _oracle = lib
     return _oracle
 
@@ -44,12 +45,14 @@ def oracle_run(model, nsteps, member=0, state=None, record_state=True, record_fo
     wrec = np.zeros((nsteps, 4))
     srec = np.zeros((nsteps, model.nHRU, model.NS)) if record_state else None
     frec = np.zeros((nsteps, model.nHRU, api.F_COUNT)) if record_forcings else None
-    rc = lib.rvo_run_member(model.desc, member, st.ctypes.data, qin.ctypes.data, qlat.ctypes.data, qout.ctypes.data, scal.ctypes.data,
-                            cumul.ctypes.data, 0, nsteps, qrec.ctypes.data, wrec.ctypes.data,
-                            srec.ctypes.data if record_state else None, frec.ctypes.data if record_forcings else None)
+    res = model.reservoir_state()[0].copy()   # [nRes][8]: stage, stage_last, Qout, Qout_last, precip, losses, AET (empty without reservoirs)
+    rc = lib.rvo_run_member_res(model.desc, member, st.ctypes.data, qin.ctypes.data, qlat.ctypes.data, qout.ctypes.data, scal.ctypes.data,
+                                cumul.ctypes.data, 0, nsteps, qrec.ctypes.data, wrec.ctypes.data,
+                                srec.ctypes.data if record_state else None, frec.ctypes.data if record_forcings else None,
+                                res.ctypes.data if res.size else None)
     if rc != 0:
         raise RuntimeError("oracle does not implement one of the model's processes (rc=%d)" % rc)
-    return dict(state=st, qin=qin, qlat=qlat, qout=qout, scal=scal, cumul=cumul, qout_rec=qrec, wshed_rec=wrec, state_rec=srec, forc_rec=frec)
+    return dict(state=st, qin=qin, qlat=qlat, qout=qout, scal=scal, cumul=cumul, qout_rec=qrec, wshed_rec=wrec, state_rec=srec, forc_rec=frec, res=res)
 
 
 def reference_run(base, outdir, nsteps=-1):
@@ -75,6 +78,8 @@ def load_reference_dump(outdir):
     out["forc"] = np.fromfile(outdir + "forc.f64").reshape(-1, nH, NF)
     out["basin"] = np.fromfile(outdir + "basin.f64").reshape(-1, NB, 6)
     out["wshed"] = np.fromfile(outdir + "wshed.f64").reshape(-1, 3)
+    if os.path.exists(outdir + "res.f64"):   # reservoir stage, outflow, losses, storage per basin (zeros without a reservoir)
+        out["res"] = np.fromfile(outdir + "res.f64").reshape(-1, NB, 4)
     out["sv"] = [(int(l.split()[2]), int(l.split()[3])) for l in meta if l.startswith("SV ")]
     out["order"] = [int(l.split()[2]) for l in meta if l.startswith("ORDER ")]
     out["proc"] = [l.split()[1:] for l in meta if l.startswith("PROC ")]

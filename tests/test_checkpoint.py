@@ -16,8 +16,15 @@ from ravenhydroframework_b200 import api, synth
 N1, N2 = 90, 60
 
 
-def _inputs(tmp_path):
+RESERVOIRS = (":Reservoir LakeA\n  :SubBasinID 2\n  :HRUID 6\n  :WeirCoefficient 0.6\n  :CrestWidth 4.5\n  :MaxDepth 6\n  :LakeArea 1.4e6\n:EndReservoir\n"
+              ":Reservoir Out\n  :SubBasinID 1\n  :MaxDepth 8\n  :VolumeStageRelation POWER_LAW\n    2.4e6 1.6\n  :EndVolumeStageRelation\n"
+              "  :OutflowStageRelation POWER_LAW\n    7.5 1.5\n  :EndOutflowStageRelation\n:EndReservoir\n")
+
+
+def _inputs(tmp_path, reservoirs=False):
     base = synth.write_hbv(str(tmp_path / "full"), n_sb=7, hru_per_sb=4, n_days=N1 + N2, seed=31, routing="ROUTE_MUSKINGUM", name="model", season_offset=40)
+    if reservoirs:   # :ResFlow / :ResStage lines of the checkpoint (CReservoir::WriteToSolutionFile)
+        open(base + ".rvh", "a").write(RESERVOIRS)
     return base
 
 
@@ -38,23 +45,25 @@ def _comparable(model):
     return np.array([n not in skip for n in model.sv_names()])
 
 
-def test_oracle_run_survives_write_and_reload(tmp_path):
-    base = _inputs(tmp_path)
+@pytest.mark.parametrize("reservoirs", [False, True])
+def test_oracle_run_survives_write_and_reload(tmp_path, reservoirs):
+    base = _inputs(tmp_path, reservoirs)
     model = api.RavenModel(base)
     model.flatten(1)
     full = H.oracle_run(model, N1 + N2)
     part = H.oracle_run(model, N1)
     rvc = str(tmp_path / "ckpt.rvc")
-    model.write_solution(rvc, N1 * model.timestep, part["state"], part["qin"], part["qlat"], part["qout"], part["scal"], full_precision=True)
+    model.write_solution(rvc, N1 * model.timestep, part["state"], part["qin"], part["qlat"], part["qout"], part["scal"], full_precision=True, res=part["res"])
     warm = api.RavenModel(_restart_inputs(tmp_path, base, rvc))
     warm.flatten(1)
     cont = H.oracle_run(warm, N2)
     keep = _comparable(model)
     assert np.array_equal(cont["state"][:, keep], full["state"][:, keep])
     assert np.array_equal(cont["qout_rec"], full["qout_rec"][N1:])
+    assert np.array_equal(cont["res"][:, :4], full["res"][:, :4]) and (cont["res"].shape[0] == (2 if reservoirs else 0))
     # the reference's own precision: 5 decimals
     rvc5 = str(tmp_path / "ckpt5.rvc")
-    model.write_solution(rvc5, N1 * model.timestep, part["state"], part["qin"], part["qlat"], part["qout"], part["scal"], full_precision=False)
+    model.write_solution(rvc5, N1 * model.timestep, part["state"], part["qin"], part["qlat"], part["qout"], part["scal"], full_precision=False, res=part["res"])
     warm5 = api.RavenModel(_restart_inputs(tmp_path / "b", base, rvc5))
     warm5.flatten(1)
     cont5 = H.oracle_run(warm5, N2)
@@ -62,8 +71,9 @@ def test_oracle_run_survives_write_and_reload(tmp_path):
 
 
 @pytest.mark.gpu
-def test_gpu_run_survives_write_and_reload(tmp_path):
-    base = _inputs(tmp_path)
+@pytest.mark.parametrize("reservoirs", [False, True])
+def test_gpu_run_survives_write_and_reload(tmp_path, reservoirs):
+    base = _inputs(tmp_path, reservoirs)
     model = api.RavenModel(base)
     model.flatten(2)
     sim = api.GpuSimulation(model, n_members=2)
@@ -81,3 +91,4 @@ def test_gpu_run_survives_write_and_reload(tmp_path):
     keep = _comparable(model)
     assert np.array_equal(b.download_state()[0][:, keep], full_state[:, keep])
     assert np.array_equal(b.hydrographs(0, N2)[:, 0, :], full_q)
+    assert np.array_equal(b.download_reservoir_state()[0][:, :4], sim.download_reservoir_state()[1][:, :4])

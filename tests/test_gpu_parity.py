@@ -138,10 +138,16 @@ def test_gpu_matches_reference_golden(case):
     sim.enable_forcing_output(True)
     steps = list(g["state_steps"])
     got = []
+    res = []
     for s in steps:                      # stop at every recorded step and read the state back
         sim.run(int(s) - sim.step)
         got.append(sim.download_state()[1])
+        res.append(sim.download_reservoir_state()[1])
     assert H.rel_err(np.array(got), g["state"]) < TOL
+    if "res_stage" in g:                 # reservoirs: stage and mass-balance losses of every reservoir at the recorded steps
+        _, sb = model.reservoir_state()
+        assert H.rel_err(np.array(res)[:, :, 0], g["res_stage"][:, sb]) < TOL
+        assert H.rel_err(np.array(res)[:, :, 5], g["res_losses"][:, sb]) < TOL
     if "_atm_" in case:                  # derived atmospheric forcings of the last step (reference force_struct columns)
         f = sim.forcings()[1]
         for name, j in {"AIR_PRES": 18, "REL_HUMIDITY": 19, "SW_RADIA": 24, "WIND_VEL": 33, "PET": 34, "OW_PET": 35}.items():

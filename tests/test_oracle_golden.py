@@ -61,6 +61,9 @@ def test_oracle_matches_golden(case):
     assert H.rel_err(o["state_rec"][steps - 1], g["state"]) < TOL
     assert H.rel_err(o["qout_rec"], g["qout"]) < TOL
     assert H.rel_err(o["wshed_rec"][:, :3], g["wshed"]) < TOL
+    if "res_stage" in g:   # reservoirs: stage and losses after the last step (the last recorded step)
+        _, sb = model.reservoir_state()
+        assert steps[-1] == n and H.rel_err(o["res"][:, 0], g["res_stage"][-1][sb]) < TOL and H.rel_err(o["res"][:, 5], g["res_losses"][-1][sb]) < TOL
     # derived forcings the oracle keeps (subset of the reference force_struct; indices from src/RavenInclude.h:1294-1343)
     ref_f = g["forc"]
     idx = {"PRECIP": 0, "SNOW_FRAC": 3, "TEMP_AVE": 7, "TEMP_DAILY_MIN": 8, "TEMP_DAILY_MAX": 9, "TEMP_DAILY_AVE": 10,

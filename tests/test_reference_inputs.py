@@ -29,7 +29,7 @@ def _base(name):
 
 
 def test_sets_are_pinned():
-    assert {"Salmon_GR4J", "Salmon_HMETS", "Salmon_HBV", "Salmon_MOHYSE", "Irondequoit", "York_nongridded_m_daily_i_daily"} <= set(SETS)
+    assert {"Salmon_GR4J", "Salmon_HMETS", "Salmon_HBV", "Salmon_MOHYSE", "Irondequoit", "York_nongridded_m_daily_i_daily", "LOTW"} <= set(SETS)
 
 
 @pytest.mark.parametrize("name", SETS)
@@ -47,6 +47,9 @@ def test_oracle_on_reference_inputs(name):
     assert H.rel_err(o["state_rec"][g["state_steps"] - 1], g["state"]) < TOL
     assert H.rel_err(o["qout_rec"], g["qout"]) < TOL
     assert H.rel_err(o["wshed_rec"][:, :3], g["wshed"]) < TOL
+    if "res_stage" in g:   # reservoir stages at the end of the run (the last recorded step is the last step)
+        _, sb = model.reservoir_state()
+        assert g["state_steps"][-1] == n and H.rel_err(o["res"][:, 0], g["res_stage"][-1][sb]) < TOL
 
 
 @pytest.mark.gpu
@@ -65,4 +68,7 @@ def test_gpu_on_reference_inputs(name):
     assert H.rel_err(np.array(got), g["state"]) < TOL
     assert H.rel_err(sim.hydrographs(0, n)[:, 1, :], g["qout"]) < TOL
     assert H.rel_err(sim.watershed(0, n)[:, 1, :3], g["wshed"]) < TOL
+    if "res_stage" in g:
+        _, sb = model.reservoir_state()
+        assert H.rel_err(sim.download_reservoir_state()[1][:, 0], g["res_stage"][-1][sb]) < TOL
     sim.close()

@@ -23,9 +23,12 @@ import helpers as H  # noqa: E402
 REF_INPUTS = "/root/reference/benchmarking/_InputFiles"
 # set -> number of steps pinned (config 1 of BASELINE.json is the 10-year daily GR4J run)
 SETS = {"Salmon_GR4J": 3653, "Salmon_HMETS": 3653, "Salmon_HBV": 3653, "Salmon_MOHYSE": 3653, "Irondequoit": 366,
-        "York_nongridded_m_daily_i_daily": 1461}
+        "York_nongridded_m_daily_i_daily": 1461, "LOTW": 2192}
 # York (7 subbasins, ROUTE_HYDROLOGIC on surveyed :ChannelProfile sections, LAI interception, depression abstraction, a user-specified
 # :BasinInflowHydrograph into subbasin 6) is read as shipped.
+# LOTW (Lake of the Woods / Rainy River: 374 HRUs in 73 subbasins, 32 lake-type reservoirs behind weirs with linked lake HRUs, three
+# :ReservoirExtraction series, two :BasinInflowHydrograph series, ROUTE_HYDROLOGIC, 45-gauge INTERP_FROM_FILE weights; the reference's own
+# 151,912 HRU-steps/s benchmarking case) is read as shipped; its npz also carries the reservoir stages.
 DROP_LINES = {}
 
 
@@ -48,9 +51,12 @@ def main():
         with tempfile.TemporaryDirectory() as td:
             ref = H.reference_run(base, os.path.join(td, "out"), n)
         rec = sorted(set([1, 2, 3, 10, 100, 365, 366, 1000, 2000, 3000, n]) & set(range(1, n + 1)))
+        extra = {}
+        if np.any(ref["res"][:, :, 3] != 0.0):   # reservoirs: stage of every basin that has one, at the recorded steps
+            extra["res_stage"] = ref["res"][rec][:, :, 0]
         np.savez_compressed(os.path.join(out_dir, name + ".npz"), state_steps=np.array(rec), state=ref["state"][rec],
                             qout=ref["basin"][1:n + 1, :, 0], wshed=ref["wshed"][1:n + 1],
-                            sv_type=np.array([t for t, _ in ref["sv"]]), sv_layer=np.array([l for _, l in ref["sv"]]))
+                            sv_type=np.array([t for t, _ in ref["sv"]]), sv_layer=np.array([l for _, l in ref["sv"]]), **extra)
         print("pinned %-14s nHRU=%d NS=%d NB=%d steps=%d" % (name, ref["nHRU"], ref["NS"], ref["NB"], n))
 
 
