@@ -159,7 +159,7 @@ typedef enum { RVN_PET_DATA = 0, RVN_PET_FROMMONTHLY, RVN_PET_CONSTANT, RVN_PET_
                RVN_PET_HARGREAVES } rvn_pet;   /* CModel::EstimatePET, src/Evaporation.cpp:282-540 */
 typedef enum { RVN_OROCORR_NONE = 0, RVN_OROCORR_SIMPLELAPSE, RVN_OROCORR_HBV } rvn_orocorr;
 typedef enum { RVN_ROUTE_NONE = 0, RVN_ROUTE_MUSKINGUM, RVN_ROUTE_MUSKINGUM_CUNGE, RVN_ROUTE_STORAGECOEFF,
-               RVN_ROUTE_PLUG_FLOW, RVN_ROUTE_DIFFUSIVE_WAVE, RVN_ROUTE_HYDROLOGIC } rvn_routing;
+               RVN_ROUTE_PLUG_FLOW, RVN_ROUTE_DIFFUSIVE_WAVE, RVN_ROUTE_HYDROLOGIC, RVN_ROUTE_DIFFUSIVE_VARY } rvn_routing;
 /* forcing perturbations of the EnKF members (reference forcing_type / adjustment, src/RavenInclude.h; applied by
  * CModel::ApplyForcingPerturbation, src/Model.cpp:2856-2879, in the order the reference calls it from
  * UpdateHRUForcingFunctions: TEMP_AVE after the temperature lapse, then PRECIP, RAINFALL, SNOWFALL after the precipitation lapse) */
@@ -372,6 +372,11 @@ typedef struct rvn_model_desc {
   const double *chan_Q, *chan_A;   /* [nChannels][nChanPts] */
   const int32_t *sb_channel;       /* [nSB] */
   const double *sb_Qmult, *sb_reach_m; /* [nSB] */
+  /* ROUTE_DIFFUSIVE_VARY (reference CSubBasin::UpdateRoutingHydro, src/SubBasin.cpp:2521-2572): the routing hydrograph of every basin is
+   * rebuilt each step from a history of celerities read off the channel rating curve at the latest inflow.  Uses chan_Q / chan_A /
+   * sb_channel / sb_Qmult / sb_reach_m above plus, per basin, the reference celerity c_ref [m/s] and alpha = D_ref / 2 [m2/d] with D_ref
+   * the diffusivity at the reference flow.  NULL otherwise. */
+  const double *sb_c_ref, *sb_diff_alpha; /* [nSB] */
   /* month-interpolated relative vegetation height / LAI of every vegetation class at every step
    * (InterpolateMo(relative_ht|relative_LAI, tt), reference src/VegetationParams.cpp:102-107): [nSteps][nVeg][2] */
   const double *veg_season;

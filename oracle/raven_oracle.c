@@ -18,6 +18,7 @@
 
 #define O_ALMOST_INF 1e99
 #define O_REAL_SMALL 1e-12
+#define O_TIME_CORRECTION 0.0001
 #define O_PI 3.1415926535898
 #define O_SEC_PER_DAY 86400.0
 #define O_MM_PER_METER 1000.0
@@ -1133,12 +1134,72 @@ static double channel_get_area(const rvn_model_desc *d, int p, double Q) {
   return y[i] + (y[i + 1] - y[i]) / (xx[i + 1] - xx[i]) * (x - xx[i]);
 }
 
+/* ROUTE_DIFFUSIVE_VARY: routing hydrographs [nSB][max_nqin] and celerity histories [nSB][max_nqin + 1] of the member being run */
+static double *g_route_hydro = NULL, *g_c_hist = NULL;
+/* rvn_erfc, src/CommonFunctions.cpp:1487-1512 (rational approximation / asymptotic series, not libm's erfc) */
+static double o_erfc(double x) {
+  double tmp = fabs(x), fun, f1, tmp2, tmp3;
+  if (tmp > 3.0) {
+    f1 = (1.0 - 1.0 / (2.0 * tmp * tmp) + 3.0 / (4.0 * pow(tmp, 4)) - 5.0 / (6.0 * pow(tmp, 6)));
+    fun = f1 * exp(-tmp * tmp) / (tmp * sqrt(O_PI));
+  } else {
+    tmp2 = 1.0 / (1.0 + (0.3275911 * tmp));
+    tmp3 = 0.254829592 * tmp2 - (0.284496736 * tmp2 * tmp2) + (1.421413741 * pow(tmp2, 3)) - (1.453152027 * pow(tmp2, 4)) + (1.061405429 * pow(tmp2, 5));
+    fun = tmp3 * exp(-tmp * tmp);
+  }
+  if (tmp == x) return fun;
+  return (2 - fun);
+}
+/* TimeVaryingADRCumDist, src/CommonFunctions.cpp:1819-1836 */
+static double o_tv_adr_cum_dist(double t, double L, const double *v, double D, double dt) {
+  int i = (int)(floor((t + O_TIME_CORRECTION) / dt));
+  double tstar = v[i] / v[0] * (t - (double)(i)*dt);
+  for (int j = 0; j < i; j++) tstar += dt * v[j] / v[0];
+  double F = 0;
+  if (t <= 0) return 0.0;
+  if (L < 500 * (D / v[0])) F = 0.5 * (exp((v[0] * L) / D) * o_erfc((L + v[0] * tstar) / sqrt(4.0 * D * tstar)));
+  F += 0.5 * (o_erfc((L - v[0] * tstar) / sqrt(4.0 * D * tstar)));
+  return F;
+}
+/* CChannelXSect::GetCelerity, src/ChannelXSect.cpp (flow -> wave celerity off the rating curve of basin p's channel) */
+static double channel_get_celerity(const rvn_model_desc *d, int p, double Q) {
+  const int N = d->nChanPts;
+  const double *aQ = d->chan_Q + (size_t)d->sb_channel[p] * N, *aA = d->chan_A + (size_t)d->sb_channel[p] * N;
+  const double Q_mult = d->sb_Qmult[p];
+  if (Q < 0) return 0.0;
+  int i = 0;
+  while ((Q > Q_mult * aQ[i + 1]) && (i < (N - 2))) i++;
+  return Q_mult * (aQ[i + 1] - aQ[i]) / (aA[i + 1] - aA[i]);
+}
+/* CSubBasin::UpdateRoutingHydro (src/SubBasin.cpp:2521-2572), ROUTE_DIFFUSIVE_VARY: called for every basin before the routing loop
+ * (src/Solvers.cpp:552), i.e. _aQinHist[0] is still the inflow of the previous step.  c_hist [max_nqin + 1], rh [max_nqin] of basin p. */
+static void update_routing_hydro(const rvn_model_desc *d, int p, const double *QinHist, double *c_hist, double *rh) {
+  const int nQ = d->sb_nqin[p];
+  const double tstep = d->opt.timestep, L = d->sb_reach_m[p];
+  double Q = QinHist[0];
+  double cc = channel_get_celerity(d, p, Q) * O_SEC_PER_DAY;
+  for (int n = nQ; n > 0; n--) c_hist[n] = c_hist[n - 1];
+  c_hist[0] = cc;
+  double sum = 0, alpha = d->sb_diff_alpha[p];
+  for (int n = 0; n < nQ; n++) {
+    rh[n] = omax(o_tv_adr_cum_dist((n)*tstep, L, c_hist, alpha, tstep) - sum, 0.0);
+    sum += rh[n];
+  }
+  for (int n = 0; n < nQ; n++) rh[n] /= sum;
+  double travel_time = L / d->sb_c_ref[p];   /* [s] compared with a step in days, as the reference does */
+  if (travel_time < tstep) {
+    rh[0] = 1.0 - travel_time / tstep;
+    rh[1] = travel_time / tstep;
+    for (int n = 2; n < nQ; n++) rh[n] = 0.0;
+  }
+}
 static void route_water(const rvn_model_desc *d, int p, const obasin *B, double *aQout_new) {
   const int nSeg = d->sb_nseg[p], nQin = d->sb_nqin[p], nQlat = d->sb_nqlat[p];
   const double tstep = d->opt.timestep;
   const double *QinHist = &B->qin[(size_t)p * d->max_nqin], *QlatHist = &B->qlat[(size_t)p * d->max_nqlat];
   double *aQout = &B->qout[(size_t)p * RVN_MAX_RIVER_SEGS];
-  const double *UH = &d->sb_unit_hydro[(size_t)p * d->max_nqlat], *RH = &d->sb_route_hydro[(size_t)p * d->max_nqin];
+  const double *UH = &d->sb_unit_hydro[(size_t)p * d->max_nqlat];
+  const double *RH = &d->sb_route_hydro[(size_t)p * d->max_nqin];
   const double seg_fraction = 1.0 / (double)(nSeg);
   double Qlat_new = 0.0;
   for (int n = 0; n < nQlat; n++) Qlat_new += UH[n] * QlatHist[n];
@@ -1195,7 +1256,8 @@ static void route_water(const rvn_model_desc *d, int p, const obasin *B, double 
     } while ((iter < ROUTE_MAXITER) && (fabs(change) > ROUTE_TOLERANCE));
     for (int s = 0; s < nSeg; s++) aQout_new[s] = aQout[s];
     aQout_new[nSeg - 1] = Q_guess;
-  } else if (method == RVN_ROUTE_PLUG_FLOW || method == RVN_ROUTE_DIFFUSIVE_WAVE) {
+  } else if (method == RVN_ROUTE_PLUG_FLOW || method == RVN_ROUTE_DIFFUSIVE_WAVE || method == RVN_ROUTE_DIFFUSIVE_VARY) {
+    if (method == RVN_ROUTE_DIFFUSIVE_VARY) RH = g_route_hydro + (size_t)p * d->max_nqin;   /* this step's hydrograph (update_routing_hydro) */
     aQout_new[nSeg - 1] = 0.0;
     for (int n = 0; n < nQin; n++) aQout_new[nSeg - 1] += RH[n] * QinHist[n];
   } else { /* ROUTE_NONE */
@@ -1357,6 +1419,16 @@ int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *q
 int rvo_run_member_res(const rvn_model_desc *d, int member, double *state, double *qin, double *qlat, double *qout, double *scal, double *cumul,
                        int step0, int nsteps, double *qout_rec, double *wshed_rec, double *state_rec, double *forc_rec, double *res_state) {
   g_res_state = res_state;
+  free(g_route_hydro); free(g_c_hist); g_route_hydro = g_c_hist = NULL;
+  if (d->opt.routing == RVN_ROUTE_DIFFUSIVE_VARY) {
+    /* the celerity history is not part of the model state the reference saves or the C ABI carries: every call starts from the initial
+     * history (c_ref everywhere) and the dump hydrograph, like a fresh run of the reference (src/SubBasin.cpp:2138-2148) */
+    if (step0 != 0) return -1;
+    g_route_hydro = (double *)malloc(sizeof(double) * (size_t)d->nSB * d->max_nqin);
+    g_c_hist = (double *)malloc(sizeof(double) * (size_t)d->nSB * (d->max_nqin + 1));
+    memcpy(g_route_hydro, d->sb_route_hydro, sizeof(double) * (size_t)d->nSB * d->max_nqin);
+    for (int p = 0; p < d->nSB; p++) for (int n = 0; n <= d->max_nqin; n++) g_c_hist[(size_t)p * (d->max_nqin + 1) + n] = d->sb_c_ref[p] * O_SEC_PER_DAY;
+  }
   if (d->nRes > 0 && (!res_state || d->opt.sol_method != RVN_SOL_ORDERED_SERIES)) return -1;
   const int nH = d->nHRU, NS = d->NS, NB = d->nSB, NP = d->nProc;
   const double tstep = d->opt.timestep;
@@ -1565,6 +1637,8 @@ int rvo_run_member_res(const rvn_model_desc *d, int member, double *state, doubl
     }
     /* ---- user-specified inflows to the upstream end of the reach (src/Solvers.cpp:543): value at t + dt */
     for (int i = 0; i < d->nSpec; i++) aQinnew[d->spec_basin[i]] += d->spec_in[(size_t)step * d->nSpec + i];
+    if (d->opt.routing == RVN_ROUTE_DIFFUSIVE_VARY) /* CSubBasin::UpdateSubBasin for every basin, before any of them is routed (src/Solvers.cpp:552) */
+      for (int p = 0; p < NB; p++) update_routing_hydro(d, p, &qin[(size_t)p * d->max_nqin], g_c_hist + (size_t)p * (d->max_nqin + 1), g_route_hydro + (size_t)p * d->max_nqin);
     /* ---- routing, upstream to downstream (src/Solvers.cpp:565-615) */
     for (int pp = 0; pp < NB; pp++) {
       int p = d->sb_order[pp];

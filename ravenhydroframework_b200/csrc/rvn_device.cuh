@@ -87,6 +87,8 @@ struct DevModel {
   const double *sb_area, *sb_rain_corr, *sb_snow_corr, *sb_temp_corr, *sb_musk_K, *sb_musk_X, *sb_K_reach;
   const double *sb_unit_hydro, *sb_route_hydro;
   const double *chan_Q, *chan_A, *sb_Qmult, *sb_reach_m; const int32_t *sb_channel; int32_t nChanPts;   // ROUTE_HYDROLOGIC rating curves
+  // ROUTE_DIFFUSIVE_VARY: per-member routing hydrographs [member][nSB][max_nqin] and celerity histories [member][nSB][max_nqin] rebuilt every step
+  const double *sb_c_ref, *sb_diff_alpha; double *route_hydro_m, *c_hist;
   double watershed_area;
   // user-specified basin inflows (rvn_model_desc::spec_*): slot of each basin in the [nSteps][nSpec] tables or -1
   int32_t nSpec; const int32_t *sb_spec_slot; const double *spec_in, *spec_down, *spec_cum;

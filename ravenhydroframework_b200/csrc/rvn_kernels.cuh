@@ -1114,6 +1114,64 @@ RVN_DI double channel_area(const DevModel &M, const int p, const double Q) {
   return y[lo] + (y[lo + 1] - y[lo]) / (xx[lo + 1] - xx[lo]) * (x - xx[lo]);
 }
 
+// ---- ROUTE_DIFFUSIVE_VARY (CSubBasin::UpdateRoutingHydro, src/SubBasin.cpp:2521-2572)
+// rvn_erfc of the reference (src/CommonFunctions.cpp:1487-1512): its own rational approximation / asymptotic series, not libm's erfc
+RVN_DI double raven_erfc(const double x) {
+  const double tmp = fabs(x);
+  double fun;
+  if (tmp > 3.0) {
+    const double f1 = (1.0 - 1.0 / (2.0 * tmp * tmp) + 3.0 / (4.0 * rvn_pow(tmp, 4.0)) - 5.0 / (6.0 * rvn_pow(tmp, 6.0)));
+    fun = f1 * rvn_exp(-tmp * tmp) / (tmp * sqrt(D_PI));
+  } else {
+    const double tmp2 = 1.0 / (1.0 + (0.3275911 * tmp));
+    const double tmp3 = 0.254829592 * tmp2 - (0.284496736 * tmp2 * tmp2) + (1.421413741 * rvn_pow(tmp2, 3.0)) - (1.453152027 * rvn_pow(tmp2, 4.0)) + (1.061405429 * rvn_pow(tmp2, 5.0));
+    fun = tmp3 * rvn_exp(-tmp * tmp);
+  }
+  if (tmp == x) return fun;
+  return (2 - fun);
+}
+// TimeVaryingADRCumDist (src/CommonFunctions.cpp:1819-1836): cumulative arrival at distance L of a pulse advected with the celerity history v[]
+RVN_DI double tv_adr_cum_dist(const double t, const double L, const double *v, const double D, const double dt) {
+  const int i = (int)(floor((t + 0.0001) / dt));
+  double tstar = v[i] / v[0] * (t - (double)(i)*dt);
+  for (int j = 0; j < i; j++) tstar += dt * v[j] / v[0];
+  double F = 0;
+  if (t <= 0) return 0.0;
+  if (L < 500 * (D / v[0])) F = 0.5 * (rvn_exp((v[0] * L) / D) * raven_erfc((L + v[0] * tstar) / sqrt(4.0 * D * tstar)));
+  F += 0.5 * (raven_erfc((L - v[0] * tstar) / sqrt(4.0 * D * tstar)));
+  return F;
+}
+// this step's routing hydrograph of basin p, member e: celerity at the latest inflow Q off the rating curve (CChannelXSect::GetCelerity), pushed
+// into the celerity history; rh[n] = increments of the time-varying advection-diffusion arrival curve, normalised
+__device__ __noinline__ void update_routing_hydro(const DevModel &M, const int e, const int p, const int nQ, const double Q) {
+  const double tstep = M.opt.timestep, L = M.sb_reach_m[p];
+  double *c_hist = M.c_hist + ((size_t)e * M.nSB + p) * M.max_nqin, *rh = M.route_hydro_m + ((size_t)e * M.nSB + p) * M.max_nqin;
+  double cel = 0.0;
+  if (!(Q < 0)) {
+    const int N = M.nChanPts;
+    const double *aQ = M.chan_Q + (size_t)M.sb_channel[p] * N, *aA = M.chan_A + (size_t)M.sb_channel[p] * N;
+    const double Q_mult = M.sb_Qmult[p];
+    int i = 0;
+    while ((Q > Q_mult * aQ[i + 1]) && (i < (N - 2))) i++;
+    cel = Q_mult * (aQ[i + 1] - aQ[i]) / (aA[i + 1] - aA[i]);
+  }
+  for (int n = nQ - 1; n > 0; n--) c_hist[n] = c_hist[n - 1];   // the reference also writes one slot past the end, which nothing reads
+  c_hist[0] = cel * D_SEC_PER_DAY;
+  double sum = 0;
+  const double alpha = M.sb_diff_alpha[p];
+  for (int n = 0; n < nQ; n++) {
+    rh[n] = dmax(tv_adr_cum_dist((n)*tstep, L, c_hist, alpha, tstep) - sum, 0.0);
+    sum += rh[n];
+  }
+  for (int n = 0; n < nQ; n++) rh[n] /= sum;
+  const double travel_time = L / M.sb_c_ref[p];   // [s] against a step in [d]: the reference's comparison, kept
+  if (travel_time < tstep) {
+    rh[0] = 1.0 - travel_time / tstep;
+    rh[1] = travel_time / tstep;
+    for (int n = 2; n < nQ; n++) rh[n] = 0.0;
+  }
+}
+
 // one basin, one member, one step: HRU -> subbasin aggregation in HRU-index order (src/Solvers.cpp:490-511),
 // CSubBasin::UpdateLateralInflow / UpdateInflow, RouteWater (src/SubBasin.cpp:2584-2863), UpdateOutflows (:2320-2421).
 // `t` = pushes into the histories before this step.
@@ -1181,7 +1239,7 @@ struct ResCurves {
 // CReservoir::RouteWater (src/Reservoir.cpp:1532-1853) for a reservoir without control structures, DZTR, seepage, constraint series or stage
 // assimilation, then UpdateStage + UpdateMassBalance (:1264-1323) and the AET hand-back to the linked HRU (src/Solvers.cpp:608-612).
 // Level-pool mass balance over the step solved for the new stage with Newton's method on a finite-difference derivative.
-__device__ void reservoir_route(const DevModel &M, const int e, const int r, const int slot, const int step, const double Qin_old, const double Qin_new) {
+__device__ __noinline__ void reservoir_route(const DevModel &M, const int e, const int r, const int slot, const int step, const double Qin_old, const double Qin_new) {
   const ResCurves C(M, r);
   double *rs = M.res_state + ((size_t)e * M.nRes + r) * RVN_RES_STATE;   // stage, stage_last, Qout, Qout_last, precip, MB losses, AET
   const double tstep = M.opt.timestep;
@@ -1337,6 +1395,13 @@ __device__ void basin_route(const DevModel &M, const RouteTabs &T, int e, int p,
       if (iter > 10) relax = 0.7;
     } while ((iter < 20) && (fabs(change) > 0.0001));
     aQout[nSeg - 1] = Q_guess;
+  } else if (method == RVN_ROUTE_DIFFUSIVE_VARY) {
+    // CSubBasin::UpdateSubBasin runs before any basin is routed (src/Solvers.cpp:552): the celerity comes from the inflow of the previous step
+    update_routing_hydro(M, e, p, nQin, Qin1);
+    const double *rh = M.route_hydro_m + ((size_t)e * M.nSB + p) * M.max_nqin;
+    double q = 0.0;
+    for (int n = 0; n < nQin; n++) q += rh[n] * QinHist[n];
+    aQout[nSeg - 1] = q;
   } else if (method == RVN_ROUTE_PLUG_FLOW || method == RVN_ROUTE_DIFFUSIVE_WAVE) {
     double q = 0.0;
     for (int n = 0; n < nQin; n++) q += RH[n] * QinHist[n];

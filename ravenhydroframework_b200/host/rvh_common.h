@@ -64,7 +64,7 @@ struct time_struct {
 };
 
 enum catchment_route { ROUTE_DUMP, ROUTE_TRI_CONVOLUTION, ROUTE_GAMMA_CONVOLUTION, ROUTE_DELAYED_FIRST_ORDER };
-enum interp_method { INTERP_NEAREST_NEIGHBOR, INTERP_AVERAGE_ALL, INTERP_INVERSE_DISTANCE, INTERP_FROM_FILE };
+enum interp_method { INTERP_NEAREST_NEIGHBOR, INTERP_AVERAGE_ALL, INTERP_INVERSE_DISTANCE, INTERP_FROM_FILE, INTERP_INVERSE_DISTANCE_ELEVATION };
 enum month_interp { MONTHINT_UNIFORM, MONTHINT_LINEAR_FOM, MONTHINT_LINEAR_MID, MONTHINT_LINEAR_21 };
 enum ensemble_type { ENSEMBLE_NONE, ENSEMBLE_MONTECARLO, ENSEMBLE_DDS, ENSEMBLE_ENKF };
 
@@ -128,6 +128,7 @@ public:
   bool ok() const { return _ok; }
   // returns false at EOF; empty/comment lines yield an empty token list
   bool Tokenize(std::vector<std::string> &tokens);
+  bool Include(const std::string &filename);   // splice another file in at the current position (:RedirectToFile)
   int  line() const { return _line; }
   const std::string &filename() const { return _filename; }
 private:
@@ -139,6 +140,7 @@ private:
 };
 std::string DirName(const std::string &path);
 std::string CorrectForRelativePath(const std::string &filename, const std::string &relfile);
+void LatLonToUTMXY(double lat_deg, double lon_deg, int zone, double &x, double &y);   // src/UTM_to_LatLong.cpp:216-227
 std::string StringToUppercase(const std::string &s);
 bool   IsComment(const std::string &tok);
 double s_to_d(const std::string &s);

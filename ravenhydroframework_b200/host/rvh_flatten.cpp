@@ -481,7 +481,8 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
   d.spec_down = d.nSpec ? _f_spec_down.data() : NULL; d.spec_cum = d.nSpec ? _f_spec_cum.data() : NULL;
   // ---- ROUTE_HYDROLOGIC: rating curves flow -> cross-section area
   d.nChannels = 0; d.nChanPts = 0; d.chan_Q = d.chan_A = NULL; d.sb_channel = NULL; d.sb_Qmult = d.sb_reach_m = NULL;
-  if (O.routing == RVN_ROUTE_HYDROLOGIC) {
+  d.sb_c_ref = d.sb_diff_alpha = NULL;
+  if (O.routing == RVN_ROUTE_HYDROLOGIC || O.routing == RVN_ROUTE_DIFFUSIVE_VARY) {
     int npts = 0;
     for (size_t c = 0; c < channels.size(); c++) npts = std::max(npts, (int)channels[c]->aQ.size());
     d.nChannels = (int32_t)channels.size(); d.nChanPts = npts;
@@ -497,6 +498,11 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
       for (size_t c = 0; c < channels.size(); c++) if (channels[c] == b->pChannel) _f_sb_channel[p] = (int32_t)c;
       if (b->pChannel) _f_sb_Qmult[p] = b->pChannel->GetFlowMultiplier(b->slope, b->mannings_n);
       _f_sb_reach[p] = b->reach_length;
+    }
+    if (O.routing == RVN_ROUTE_DIFFUSIVE_VARY) {
+      _f_sb_cref.assign(NB, 0.0); _f_sb_alpha.assign(NB, 0.0);
+      for (int p = 0; p < NB; p++) { _f_sb_cref[p] = _pSubBasins[p]->c_ref; _f_sb_alpha[p] = _pSubBasins[p]->diff_alpha; }
+      d.sb_c_ref = _f_sb_cref.data(); d.sb_diff_alpha = _f_sb_alpha.data();
     }
     d.chan_Q = _f_chan_Q.data(); d.chan_A = _f_chan_A.data(); d.sb_channel = _f_sb_channel.data(); d.sb_Qmult = _f_sb_Qmult.data(); d.sb_reach_m = _f_sb_reach.data();
   }

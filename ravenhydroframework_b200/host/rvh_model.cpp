@@ -437,7 +437,7 @@ CSubBasin::CSubBasin()
       nSegments(1), basin_area(0), drainage_area(0), t_conc(AUTO_COMPUTE), t_peak(AUTO_COMPUTE), t_lag(AUTO_COMPUTE),
       gamma_shape(AUTO_COMPUTE), gamma_scale(AUTO_COMPUTE), Q_ref(AUTO_COMPUTE), c_ref(AUTO_COMPUTE), w_ref(AUTO_COMPUTE),
       mannings_n(AUTO_COMPUTE), slope(AUTO_COMPUTE), rain_corr(1.0), snow_corr(1.0), temperature_corr(0.0), QoutLast(0), QlatLast(0),
-      Qlocal(0), QlocLast(0), channel_storage(0), rivulet_storage(0), pInflowHydro(NULL), pInflowHydro2(NULL), pReservoir(NULL) { aQout.assign(1, AUTO_COMPUTE); }
+      Qlocal(0), QlocLast(0), channel_storage(0), rivulet_storage(0), pInflowHydro(NULL), pInflowHydro2(NULL), pReservoir(NULL) { aQout.assign(1, AUTO_COMPUTE); diff_alpha = 0.0; }
 
 bool CSubBasin::SetBasinProperties(const std::string &label_in, double value) {
   std::string l = StringToUppercase(label_in);
@@ -516,6 +516,7 @@ void CSubBasin::GenerateRoutingHydrograph(double Qin_avg, const optStruct &O) {
   int nQin;
   if (O.routing == RVN_ROUTE_PLUG_FLOW) nQin = (int)(ceil(travel_time / tstep)) + 2;
   else if (O.routing == RVN_ROUTE_DIFFUSIVE_WAVE) nQin = (int)(ceil(2 * travel_time / tstep)) + 2;
+  else if (O.routing == RVN_ROUTE_DIFFUSIVE_VARY) nQin = (int)(ceil(2.5 * travel_time / tstep)) + 2;   // src/SubBasin.cpp:2078-2081
   else if (O.routing == RVN_ROUTE_HYDROLOGIC) nQin = 2;
   else nQin = 20;
   aQinHist.assign(nQin, Qin_avg);
@@ -533,6 +534,12 @@ void CSubBasin::GenerateRoutingHydrograph(double Qin_avg, const optStruct &O) {
     const double diff_ref = 0.5 * (Q_ref) / pChannel->GetTopWidth(Q_ref, slope, mannings_n) / (slope_mult * pChannel->bedslope);
     const double cc = c_ref * SEC_PER_DAY, diffusivity = diff_ref * SEC_PER_DAY;   // [m/d], [m2/d]
     for (int n = 0; n < nQin; n++) aRouteHydro[n] = DiffusiveWaveUH(n, reach_length, cc, diffusivity, tstep);
+  } else if (O.routing == RVN_ROUTE_DIFFUSIVE_VARY) {   // src/SubBasin.cpp:2138-2148: a dump hydrograph until the first UpdateRoutingHydro
+    ExitGracefullyIf(nSegments > 1, "ROUTE_DIFFUSIVE_VARY only valid for single-segment rivers");
+    ExitGracefullyIf(Q_ref <= 0, "CChannelXSect::GetDiffusivity: Invalid channel flowrate");
+    aRouteHydro[0] = 1.0;
+    const double slope_mult = (slope != AUTO_COMPUTE) ? (slope / pChannel->bedslope) : 1.0;
+    diff_alpha = (0.5 * (Q_ref) / pChannel->GetTopWidth(Q_ref, slope, mannings_n) / (slope_mult * pChannel->bedslope)) * SEC_PER_DAY / 2;   // D_ref / 2 of UpdateRoutingHydro (:2539,2556)
   } else {
     aRouteHydro[0] = 1.0;
   }
@@ -825,9 +832,48 @@ void CModel::GenerateGaugeWeights(const optStruct &O) {
   } else if (O.interpolation == INTERP_AVERAGE_ALL) {
     for (int k = 0; k < nH; k++) for (int g = 0; g < nG; g++) _aGaugeWeights[(size_t)k * nG + g] = 1.0 / (double)(nG);
   } else {
-    ExitGracefullyIf(nG != 1, "GenerateGaugeWeights: distance-based gauge interpolation with several gauges needs the UTM projection, which the "
-                              "B200 build does not implement yet; use INTERP_FROM_FILE or INTERP_AVERAGE_ALL");
-    for (int k = 0; k < nH; k++) _aGaugeWeights[k] = 1.0;
+    // distance-based interpolation (src/ModelInitialize.cpp:868-975) in the UTM zone of the area-weighted mean HRU longitude (:108-124).
+    // One weight table serves all forcings: every gauge must carry the same series (the reference builds a table per forcing from the gauges
+    // that have it).
+    for (int g = 1; g < nG; g++)
+      for (int f = 0; f < F_NTYPES; f++)
+        ExitGracefullyIf((_pGauges[g]->GetTimeSeries((forcing_type)f) != NULL) != (_pGauges[0]->GetTimeSeries((forcing_type)f) != NULL),
+                         "GenerateGaugeWeights: gauges carrying different forcing series are not supported by the B200 build with distance-based interpolation");
+    double cen_long = 0, area_tot = 0;
+    for (int k = 0; k < nH; k++) { area_tot += _pHydroUnits[k]->GetArea(); cen_long += _pHydroUnits[k]->longitude * (_pHydroUnits[k]->GetArea()); }
+    cen_long /= area_tot;
+    const int zone = (int)(floor((cen_long + 180.0) / 6) + 1);
+    std::vector<double> gx(nG), gy(nG);
+    for (int g = 0; g < nG; g++) LatLonToUTMXY(_pGauges[g]->latitude, _pGauges[g]->longitude, zone, gx[g], gy[g]);
+    const double IDW_POWER = 2.0;
+    for (int k = 0; k < nH; k++) {
+      double hx, hy;
+      LatLonToUTMXY(_pHydroUnits[k]->latitude, _pHydroUnits[k]->longitude, zone, hx, hy);
+      double *w = &_aGaugeWeights[(size_t)k * nG];
+      if (O.interpolation == INTERP_NEAREST_NEIGHBOR) {
+        int g_min = 0; double distmin = ALMOST_INF;
+        for (int g = 0; g < nG; g++) {
+          const double dist = pow(hx - gx[g], 2) + pow(hy - gy[g], 2);
+          if (dist < distmin) { distmin = dist; g_min = g; }
+          w[g] = 0.0;
+        }
+        w[g_min] = 1.0;
+      } else {
+        const bool by_elev = (O.interpolation == INTERP_INVERSE_DISTANCE_ELEVATION);
+        int atop_gauge = DOESNT_EXIST; double denomsum = 0;
+        std::vector<double> dist(nG);
+        for (int g = 0; g < nG; g++) {
+          dist[g] = by_elev ? fabs(_pHydroUnits[k]->GetElevation() - _pGauges[g]->elevation) : sqrt(pow(hx - gx[g], 2) + pow(hy - gy[g], 2));
+          denomsum += pow(dist[g], -IDW_POWER);
+          if (dist[g] < REAL_SMALL) atop_gauge = g;
+        }
+        for (int g = 0; g < nG; g++) {
+          w[g] = 0.0;
+          if (atop_gauge != DOESNT_EXIST) { w[g] = 0.0; w[atop_gauge] = 1.0; }
+          else w[g] = pow(dist[g], -IDW_POWER) / denomsum;
+        }
+      }
+    }
   }
 }
 void CModel::Initialize(optStruct &O) {

@@ -166,6 +166,7 @@ public:
   // routing arrays (reference _aUnitHydro/_aRouteHydro/_aQlatHist/_aQinHist/_aQout)
   std::vector<double> aUnitHydro, aRouteHydro, aQlatHist, aQinHist, aQout;
   double QoutLast, QlatLast, Qlocal, QlocLast, channel_storage, rivulet_storage;
+  double diff_alpha;        // ROUTE_DIFFUSIVE_VARY: half the diffusivity at the reference flow [m2/d]
   // user-specified inflows [m3/s]: :BasinInflowHydrograph (upstream end of the reach) and :BasinInflowHydrograph2 (downstream end)
   CTimeSeries *pInflowHydro, *pInflowHydro2;
   CReservoir *pReservoir;   // NULL: none (CSubBasin::AddReservoir, src/SubBasin.cpp:1122-1132)
@@ -365,6 +366,7 @@ private:
   std::vector<int32_t> _f_et_row, _f_wt_ptr, _f_wt_idx, _f_pert_forcing, _f_pert_adj, _f_hru_terr, _f_spec_basin;
   std::vector<int32_t> _f_res_basin, _f_res_hru, _f_res_np;
   std::vector<double> _f_res_curves, _f_res_min_stage, _f_res_extract, _f_res_state0;
+  std::vector<double> _f_sb_cref, _f_sb_alpha;
   std::vector<double> _f_spec_in, _f_spec_down, _f_spec_cum;
   std::vector<uint8_t> _f_pert_mask;
   std::vector<rvn_lateral> _f_lat;

@@ -61,7 +61,7 @@ static const char *kIgnoredRVI[] = {":FileType", ":WrittenBy", ":CreationDate", 
   ":RunName", ":OutputDirectory", ":OutputInterval", ":SuppressOutput", ":DontWriteWatershedStorage", ":SnapshotHydrograph",
   ":LWRadiationMethod", ":LWIncomingMethod",
   ":PavicsMode", ":DebugMode", ":WriteExhaustiveMB", ":HydrologicProcesses", ":EndHydrologicProcesses",
-  ":WriteSubbasinFile", ":NetCDFAttribute", ":rvh_Filename", NULL};
+  ":WriteSubbasinFile", ":NetCDFAttribute", ":rvh_Filename", ":AggregatedVariable", ":BenchmarkingMode", NULL};
 
 static rvn_pet ParsePET(const std::string &s) {
   if (s == "PET_DATA") return RVN_PET_DATA;
@@ -151,6 +151,7 @@ static void ParseMainInputFile(CModel *&pModel, optStruct &Options) {
       else if (s[1] == "ROUTE_PLUG_FLOW") Options.routing = RVN_ROUTE_PLUG_FLOW;
       else if (s[1] == "ROUTE_HYDROLOGIC") Options.routing = RVN_ROUTE_HYDROLOGIC;
       else if (s[1] == "ROUTE_DIFFUSIVE_WAVE") Options.routing = RVN_ROUTE_DIFFUSIVE_WAVE;
+      else if (s[1] == "ROUTE_DIFFUSIVE_VARY") Options.routing = RVN_ROUTE_DIFFUSIVE_VARY;
       else ExitGracefully("ParseMainInputFile: routing method " + s[1] + " is not implemented in the B200 build (SURVEY 8f)");
       continue;
     }
@@ -257,6 +258,7 @@ static void ParseMainInputFile(CModel *&pModel, optStruct &Options) {
       if (s[1] == "NEAREST_NEIGHBOR" || s[1] == "INTERP_NEAREST_NEIGHBOR") Options.interpolation = INTERP_NEAREST_NEIGHBOR;
       else if (s[1] == "AVERAGE_ALL" || s[1] == "INTERP_AVERAGE_ALL") Options.interpolation = INTERP_AVERAGE_ALL;
       else if (s[1] == "INVERSE_DISTANCE" || s[1] == "INTERP_INVERSE_DISTANCE") Options.interpolation = INTERP_INVERSE_DISTANCE;
+      else if (s[1] == "INVERSE_DISTANCE_ELEVATION" || s[1] == "INTERP_INVERSE_DISTANCE_ELEVATION") Options.interpolation = INTERP_INVERSE_DISTANCE_ELEVATION;
       else if (s[1] == "INTERP_FROM_FILE") { Options.interpolation = INTERP_FROM_FILE; Options.interp_file = CorrectForRelativePath(s[2], Options.rvi_filename); }
       else ExitGracefully("ParseMainInputFile: Unrecognized interpolation method");
       continue;
@@ -598,7 +600,12 @@ static void ParseClassPropertiesFile(CModel *pModel, const optStruct &Options) {
       pModel->channels.push_back(ch);
       continue;
     }
-    if (c == ":RedirectToFile") ExitGracefully("ParseClassPropertiesFile: :RedirectToFile inside .rvp is not supported by the B200 build");
+    if (c == ":RedirectToFile") {   // src/ParseClassPropertiesFile.cpp: the redirect file is parsed in place
+      ExitGracefullyIf(s.size() < 2, "ParseClassPropertiesFile: :RedirectToFile needs a file name");
+      const std::string f = CorrectForRelativePath(s[1], Options.rvp_filename);
+      ExitGracefullyIf(!p.Include(f), "ParseClassPropertiesFile: cannot open redirect file " + f);
+      continue;
+    }
     ExitGracefully("ParseClassPropertiesFile: command " + c + " (line " + std::to_string(p.line()) + ") is not supported by the B200 build");
   }
   // resolve [DEFAULT] rows into the classes

@@ -57,6 +57,15 @@ CParser::CParser(const std::string &filename) : _pos(0), _line(0), _ok(false), _
   std::string l;
   while (std::getline(in, l)) _lines.push_back(l);
 }
+bool CParser::Include(const std::string &filename) {   // :RedirectToFile: the lines of `filename` are read next, then the rest of this file
+  std::ifstream in(filename.c_str());
+  if (!in.good()) return false;
+  std::vector<std::string> add;
+  std::string l;
+  while (std::getline(in, l)) add.push_back(l);
+  _lines.insert(_lines.begin() + _pos, add.begin(), add.end());
+  return true;
+}
 bool CParser::Tokenize(std::vector<std::string> &tokens) {
   tokens.clear();
   if (_pos >= _lines.size()) return false;
@@ -471,4 +480,38 @@ double DiffusiveWaveUH(int n, double L, double v, double D, double dt) {
   double UH = 1.0 / dt * (2 * G_integral(n * dt, L, v, D) - G_integral((n - 1) * dt, L, v, D) - G_integral((n + 1) * dt, L, v, D));
   UH += -(2 * n) * ADRCumDist(n * dt, L, v, D) + (n - 1) * ADRCumDist((n - 1) * dt, L, v, D) + (n + 1) * ADRCumDist((n + 1) * dt, L, v, D);
   return UH;
+}
+
+// ---- geographic -> UTM coordinates of HRU centroids and gauges, as the reference projects them for distance-based gauge interpolation
+// (LatLonToUTMXY / MapLatLonToXY / ArcLengthOfMeridian, src/UTM_to_LatLong.cpp:20-37,88-129,216-227: the transverse-Mercator series of
+// Hoffmann-Wellenhof et al. on the WGS84 ellipsoid).  The operation order is the reference's so that inverse-distance weights are identical.
+void LatLonToUTMXY(double lat_deg, double lon_deg, int zone, double &x, double &y) {
+  const double a = 6378137.0, b = 6356752.314, k0 = 0.9996, DEGREES_TO_RADIANS = 0.017453293;   // the rounded literal of src/RavenInclude.h:166
+  const double phi = lat_deg * DEGREES_TO_RADIANS, lambda = lon_deg * DEGREES_TO_RADIANS, lambda0 = (-183.0 + (zone * 6.0)) * DEGREES_TO_RADIANS;
+  // meridian arc from the equator to phi
+  const double n = (a - b) / (a + b);
+  const double alpha = ((a + b) / 2.0) * (1.0 + (pow(n, 2.0) / 4.0) + (pow(n, 4.0) / 64.0));
+  const double beta = (-3.0 * n / 2.0) + (9.0 * pow(n, 3.0) / 16.0) + (-3.0 * pow(n, 5.0) / 32.0);
+  const double gamma = (15.0 * pow(n, 2.0) / 16.0) + (-15.0 * pow(n, 4.0) / 32.0);
+  const double delta = (-35.0 * pow(n, 3.0) / 48.0) + (105.0 * pow(n, 5.0) / 256.0);
+  const double epsilon = (315.0 * pow(n, 4.0) / 512.0);
+  const double arc = alpha * (phi + (beta * sin(2.0 * phi)) + (gamma * sin(4.0 * phi)) + (delta * sin(6.0 * phi)) + (epsilon * sin(8.0 * phi)));
+  // transverse Mercator
+  const double ep2 = (pow(a, 2.0) - pow(b, 2.0)) / pow(b, 2.0);
+  const double nu2 = ep2 * pow(cos(phi), 2.0);
+  const double N = pow(a, 2.0) / (b * sqrt(1 + nu2));
+  const double t = tan(phi), t2 = t * t, l = lambda - lambda0;
+  const double c3 = 1.0 - t2 + nu2;
+  const double c4 = 5.0 - t2 + 9 * nu2 + 4.0 * (nu2 * nu2);
+  const double c5 = 5.0 - 18.0 * t2 + (t2 * t2) + 14.0 * nu2 - 58.0 * t2 * nu2;
+  const double c6 = 61.0 - 58.0 * t2 + (t2 * t2) + 270.0 * nu2 - 330.0 * t2 * nu2;
+  const double c7 = 61.0 - 479.0 * t2 + 179.0 * (t2 * t2) - (t2 * t2 * t2);
+  const double c8 = 1385.0 - 3111.0 * t2 + 543.0 * (t2 * t2) - (t2 * t2 * t2);
+  x = N * cos(phi) * l + (N / 6.0 * pow(cos(phi), 3.0) * c3 * pow(l, 3.0)) + (N / 120.0 * pow(cos(phi), 5.0) * c5 * pow(l, 5.0)) +
+      (N / 5040.0 * pow(cos(phi), 7.0) * c7 * pow(l, 7.0));
+  y = arc + (t / 2.0 * N * pow(cos(phi), 2.0) * pow(l, 2.0)) + (t / 24.0 * N * pow(cos(phi), 4.0) * c4 * pow(l, 4.0)) +
+      (t / 720.0 * N * pow(cos(phi), 6.0) * c6 * pow(l, 6.0)) + (t / 40320.0 * N * pow(cos(phi), 8.0) * c8 * pow(l, 8.0));
+  x = x * k0 + 500000.0;
+  y = y * k0;
+  if (y < 0.0) y = y + 10000000.0;
 }

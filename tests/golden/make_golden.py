@@ -147,6 +147,8 @@ if hasattr(synth, "write_hbv"):
                                              "  :VolumeStageRelation LOOKUP_TABLE\n    4\n    -5.0 0.0\n    -2.0 2.0e6\n    0.0 4.1e6\n    5.0 1.02e7\n  :EndVolumeStageRelation\n"
                                              "  :AreaStageRelation LOOKUP_TABLE\n    3\n    -5.0 5.0e5\n    0.0 1.1e6\n    5.0 1.3e6\n  :EndAreaStageRelation\n:EndReservoir\n",
                                    rvc_extra=":InitialReservoirStage 3 101.6\n")
+    # ROUTE_DIFFUSIVE_VARY: the routing hydrograph of every reach is rebuilt each step from a history of flow-dependent celerities
+    CASES["hbv_diffusive_vary"] = dict(kind="hbv", n_sb=15, hru_per_sb=4, n_days=260, seed=97, routing="ROUTE_DIFFUSIVE_VARY", season_offset=70)
     CASES["hbv_hrugroup_cond"] = dict(kind="hbv", n_sb=3, hru_per_sb=5, n_days=250, seed=12, routing="ROUTE_MUSKINGUM", season_offset=40, variant="hrugroup_cond")
     CASES["hbv_lateral"] = dict(kind="hbv", n_sb=4, hru_per_sb=7, n_days=250, seed=8, routing="ROUTE_MUSKINGUM", season_offset=40, variant="lateral")
 if hasattr(synth, "write_blended"):

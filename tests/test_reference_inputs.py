@@ -29,7 +29,7 @@ def _base(name):
 
 
 def test_sets_are_pinned():
-    assert {"Salmon_GR4J", "Salmon_HMETS", "Salmon_HBV", "Salmon_MOHYSE", "Irondequoit", "York_nongridded_m_daily_i_daily", "LOTW"} <= set(SETS)
+    assert {"Salmon_GR4J", "Salmon_HMETS", "Salmon_HBV", "Salmon_MOHYSE", "Irondequoit", "York_nongridded_m_daily_i_daily", "LOTW", "Nith"} <= set(SETS)
 
 
 @pytest.mark.parametrize("name", SETS)

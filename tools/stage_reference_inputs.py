@@ -23,12 +23,14 @@ import helpers as H  # noqa: E402
 REF_INPUTS = "/root/reference/benchmarking/_InputFiles"
 # set -> number of steps pinned (config 1 of BASELINE.json is the 10-year daily GR4J run)
 SETS = {"Salmon_GR4J": 3653, "Salmon_HMETS": 3653, "Salmon_HBV": 3653, "Salmon_MOHYSE": 3653, "Irondequoit": 366,
-        "York_nongridded_m_daily_i_daily": 1461, "LOTW": 2192}
+        "York_nongridded_m_daily_i_daily": 1461, "LOTW": 2192, "Nith": 730}
 # York (7 subbasins, ROUTE_HYDROLOGIC on surveyed :ChannelProfile sections, LAI interception, depression abstraction, a user-specified
 # :BasinInflowHydrograph into subbasin 6) is read as shipped.
 # LOTW (Lake of the Woods / Rainy River: 374 HRUs in 73 subbasins, 32 lake-type reservoirs behind weirs with linked lake HRUs, three
 # :ReservoirExtraction series, two :BasinInflowHydrograph series, ROUTE_HYDROLOGIC, 45-gauge INTERP_FROM_FILE weights; the reference's own
 # 151,912 HRU-steps/s benchmarking case) is read as shipped; its npz also carries the reservoir stages.
+# Nith (32 HRUs / 4 subbasins, three climate stations with INTERP_NEAREST_NEIGHBOR in UTM coordinates, ROUTE_HYDROLOGIC on surveyed sections
+# read through a :RedirectToFile inside the .rvp, :LakeStorage) is read as shipped.
 DROP_LINES = {}
 
 
