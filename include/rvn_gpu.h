@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RVN_ABI_VERSION 9
+#define RVN_ABI_VERSION 10
 #define RVN_DOESNT_EXIST (-1)
 #define RVN_CONV_STORES 50   /* MAX_CONVOL_STORES, reference src/RavenInclude.h / Convolution.cpp:17 */
 #define RVN_MAX_CONN 24      /* max connections of a non-convolution process (Precipitation: 13..19) */
@@ -433,6 +433,18 @@ typedef struct rvn_model_desc {
   int32_t nRes, nResPts;
   const int32_t *res_basin, *res_hru, *res_np;   /* [nRes] */
   const double *res_curves, *res_min_stage, *res_extract, *res_state0;
+  /* direct-insertion streamflow assimilation (reference src/Assimilate.cpp, :AssimilateStreamflow; DA_ECCC).  Everything the reference's
+   * PrepareAssimilation derives from the observations and the network alone is tabulated by the host per step, [nSteps][nSB]:
+   * da_override = 1 where a gauged basin has a valid observation for the step (its outflow is overridden, CModel::AssimilationOverride
+   * :67-118), da_obsQ / da_obsQ2 the observation at the end of this and the next step (-1.2345 = blank), and for the upstream propagation
+   * of the correction (AssimilationBackPropagate :283-339) da_decay = exp(-distfact * _aDAlength[p]) and da_wt = the drainage-area weight
+   * ECCCwt.  Per basin: sb_drain_area [km2] and sb_da_corr = exp(-distfact * reach length) of CSubBasin::AdjustAllFlows.
+   * assimilation_fact = the ASSIMILATION_FACT global.  assimilate_flow = 0: none (pointers NULL).  Not with reservoirs. */
+  int32_t assimilate_flow, pad5_;
+  double assimilation_fact;
+  const uint8_t *da_override;
+  const double *da_obsQ, *da_obsQ2, *da_decay, *da_wt;
+  const double *sb_drain_area, *sb_da_corr;
   int32_t nPert, pad3_;
   const int32_t *pert_forcing;  /* [nPert] rvn_pert_forcing */
   const int32_t *pert_adj;      /* [nPert] rvn_adjustment */

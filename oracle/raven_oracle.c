@@ -1449,6 +1449,7 @@ int rvo_run_member_res(const rvn_model_desc *d, int member, double *state, doubl
   double *aRouted = (double *)malloc(sizeof(double) * NB), *aQinnew = (double *)malloc(sizeof(double) * NB);
   double rates[O_MAXCONN]; int cf[O_MAXCONN], ct[O_MAXCONN];
   obasin B; B.qin = qin; B.qlat = qlat; B.qout = qout; B.scal = scal;
+  double *DAQadjust = (double *)calloc((size_t)NB, sizeof(double)); /* _aDAQadjust: persists between steps */
   for (int s = 0; s < nsteps; s++) {
     const int step = step0 + s;
     /* ---- UpdateHRUForcingFunctions (all HRUs, on the stored state) */
@@ -1674,10 +1675,58 @@ int rvo_run_member_res(const rvn_model_desc *d, int member, double *state, doubl
         rs[5] += rs[6];
         rs[5] += d->res_extract[(size_t)step * d->nRes + r] * O_SEC_PER_DAY * tstep;
       }
+      if (d->assimilate_flow) { /* CModel::AssimilationOverride, src/Assimilate.cpp:67-118 (DA_ECCC) */
+        const size_t ix = (size_t)step * NB + p;
+        if (d->da_override[ix]) {
+          double Qobs = d->da_obsQ[ix], Qobs2 = d->da_obsQ2[ix], alpha = d->assimilation_fact;
+          double Qmod = qout[(size_t)p * RVN_MAX_RIVER_SEGS + d->sb_nseg[p] - 1];
+          if ((Qmod > 1e-8) && (Qobs != -1.2345)) {
+            if (Qobs2 == -1.2345) DAQadjust[p] = alpha * (Qobs - Qmod);
+            else DAQadjust[p] = alpha * (0.5 * (Qobs2 + Qobs) - Qmod);
+          } else DAQadjust[p] = 0.0;
+          /* CSubBasin::AdjustAllFlows(adjust, overriding = true, assimsite = true), src/SubBasin.cpp:1572-1616 */
+          double va = 0.0;
+          for (int i = 0; i < d->sb_nseg[p]; i++) {
+            double *q = &qout[(size_t)p * RVN_MAX_RIVER_SEGS + i];
+            *q += DAQadjust[p]; if (*q < 0.0) *q = 0.0;
+            va += DAQadjust[p] * tstep * O_SEC_PER_DAY;
+          }
+          if (va > 0.0) cumul[0] += va / (d->watershed_area * O_M2_PER_KM2) * O_MM_PER_METER;
+          else cumul[1] -= va / (d->watershed_area * O_M2_PER_KM2) * O_MM_PER_METER;
+        } else {
+          cumul[1] -= 0.0 / (d->watershed_area * O_M2_PER_KM2) * O_MM_PER_METER;
+        }
+      }
       int pTo = d->sb_down[p];
       if (pTo >= 0) aQinnew[pTo] += (r >= 0) ? res_state[(size_t)r * RVN_RES_STATE + 2] : qout[(size_t)p * RVN_MAX_RIVER_SEGS + d->sb_nseg[p] - 1]; /* GetOutflowRate */
       if (r >= 0 && d->res_hru[r] >= 0 && iAET >= 0) /* :608-612 */
         state[(size_t)d->res_hru[r] * NS + iAET] = reservoir_aet(d, r, res_state + (size_t)r * RVN_RES_STATE, owpet, lpc);
+    }
+    if (d->assimilate_flow) { /* CModel::AssimilationBackPropagate, src/Assimilate.cpp:283-339 */
+      for (int pp = NB - 1; pp >= 0; pp--) { /* downstream to upstream */
+        int p = d->sb_order[pp], pdown = d->sb_down[p];
+        if (!d->da_override[(size_t)step * NB + p]) {
+          if (pdown >= 0) DAQadjust[p] = DAQadjust[pdown] * (d->sb_drain_area[p] / d->sb_drain_area[pdown]);
+          else DAQadjust[p] = 0.0;
+        }
+      }
+      for (int p = 0; p < NB; p++) {
+        const size_t ix = (size_t)step * NB + p;
+        if (!d->da_override[ix]) {
+          if (d->sb_down[p] >= 0) DAQadjust[p] *= d->da_decay[ix];
+          DAQadjust[p] = DAQadjust[p] * d->da_wt[ix];
+        }
+      }
+      for (int p = 0; p < NB; p++) { /* AdjustAllFlows(adjust, overriding = false, assimsite = override) */
+        const double adjust = DAQadjust[p];
+        double *QinHist = &qin[(size_t)p * d->max_nqin];
+        for (int n = 1; n < d->sb_nqin[p]; n++) {
+          QinHist[n] += adjust * (d->sb_drain_area[p] - d->sb_area[p]) / d->sb_drain_area[p] * d->sb_da_corr[p];
+          if (QinHist[n] < 0.0) QinHist[n] = 0.0;
+        }
+        if (!d->da_override[(size_t)step * NB + p])
+          for (int i = 0; i < d->sb_nseg[p]; i++) { double *q = &qout[(size_t)p * RVN_MAX_RIVER_SEGS + i]; *q += adjust; if (*q < 0.0) *q = 0.0; }
+      }
     }
     /* ---- IncrementCumulInput / IncrementCumOutflow (src/Model.cpp:2458-2539) */
     {
@@ -1724,7 +1773,7 @@ int rvo_run_member_res(const rvn_model_desc *d, int member, double *state, doubl
     }
     if (state_rec) memcpy(state_rec + (size_t)s * nH * NS, state, sizeof(double) * (size_t)nH * NS);
   }
-  free(F); free(daily); free(phinew); free(phiread); free(aRouted); free(aQinnew);
+  free(F); free(daily); free(phinew); free(phiread); free(aRouted); free(aQinnew); free(DAQadjust);
   return 0;
 }
 

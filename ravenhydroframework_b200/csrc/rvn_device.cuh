@@ -96,6 +96,11 @@ struct DevModel {
   // res_state [member][nRes][RVN_RES_STATE]; res_force [slot][member][nRes][2] = {OW_PET, LAKE_PET_CORR} of the linked HRU, written by the sweep
   int32_t nRes, nResPts; const int32_t *sb_res, *res_hru, *res_np, *hru_res; const double *res_curves, *res_min_stage, *res_extract;
   double *res_state, *res_force; int32_t iAET;
+  // direct-insertion streamflow assimilation (rvn_model_desc::da_*): da_adjust [member][nSB] = _aDAQadjust, da_mass [member][nSB] = volume the
+  // override added to basin p this step [m3] (booked by the balance)
+  int32_t assimilate_flow; double assimilation_fact;
+  const uint8_t *da_override; const double *da_obsQ, *da_obsQ2, *da_decay, *da_wt, *sb_drain_area, *sb_da_corr;
+  double *da_adjust, *da_mass;
   // recording
   double *rec_qout, *rec_wshed;                    // [rec][member][nSB], [rec][member][4]
   int32_t rec_capacity, rec_flags;

@@ -1432,6 +1432,57 @@ __device__ void basin_route(const DevModel &M, const RouteTabs &T, int e, int p,
   dV -= 0.5 * (Qlat_new + sc[1]) * dts;
   sc[5] += dV;
   sc[1] = Qlat_new;
+  if (M.assimilate_flow) {   // CModel::AssimilationOverride (src/Assimilate.cpp:67-118, DA_ECCC): the gauge's outflow is nudged onto the observation
+    const size_t ix = (size_t)step * M.nSB + p;
+    double va = 0.0;
+    if (M.da_override[ix]) {
+      const double Qobs = M.da_obsQ[ix], Qobs2 = M.da_obsQ2[ix], alpha = M.assimilation_fact;
+      const double Qmod = aQout[nSeg - 1];
+      double adj = 0.0;
+      if ((Qmod > 1e-8) && (Qobs != -1.2345)) adj = (Qobs2 == -1.2345) ? alpha * (Qobs - Qmod) : alpha * (0.5 * (Qobs2 + Qobs) - Qmod);
+      M.da_adjust[(size_t)e * M.nSB + p] = adj;
+      for (int i = 0; i < nSeg; i++) {   // CSubBasin::AdjustAllFlows(adjust, overriding, assimsite), src/SubBasin.cpp:1604-1611
+        double q = aQout[i] + adj;
+        if (q < 0.0) q = 0.0;
+        aQout[i] = q;
+        va += adj * tstep * D_SEC_PER_DAY;
+      }
+    }
+    M.da_mass[(size_t)e * M.nSB + p] = va;
+  }
+}
+// CModel::AssimilationBackPropagate (src/Assimilate.cpp:283-339), first loop: a basin without a valid observation takes the correction of the
+// basin below scaled by the ratio of drainage areas; downstream to upstream, i.e. level after level starting at the outlets
+RVN_DI void da_propagate(const DevModel &M, const int e, const int p, const int step) {
+  if (M.da_override[(size_t)step * M.nSB + p]) return;
+  const int pdown = M.sb_down[p];
+  double *adj = M.da_adjust + (size_t)e * M.nSB;
+  adj[p] = (pdown >= 0) ? adj[pdown] * (M.sb_drain_area[p] / M.sb_drain_area[pdown]) : 0.0;
+}
+// second and third loop: distance decay and drainage-area weight of the propagated correction, then CSubBasin::AdjustAllFlows(adjust, false, override)
+// (src/SubBasin.cpp:1585-1603): the inflow history (all but the newest entry) and, away from the gauges, the reach outflows move by the correction
+__device__ void da_apply(const DevModel &M, const int e, const int p, const int step, const int t) {
+  const size_t ix = (size_t)step * M.nSB + p;
+  double *padj = M.da_adjust + (size_t)e * M.nSB + p;
+  const bool site = M.da_override[ix] != 0;
+  if (!site) {
+    double a = *padj;
+    if (M.sb_down[p] >= 0) a *= M.da_decay[ix];
+    a = a * M.da_wt[ix];
+    *padj = a;
+  }
+  const double adjust = *padj;
+  const int nQin = M.sb_nqin[p], nSeg = M.sb_nseg[p];
+  const Ring QinHist(M.qin + ((size_t)e * M.nSB + p) * M.max_nqin, nQin, t + 1);
+  for (int n = 1; n < nQin; n++) {
+    double q = QinHist[n] + adjust * (M.sb_drain_area[p] - M.sb_area[p]) / M.sb_drain_area[p] * M.sb_da_corr[p];
+    if (q < 0.0) q = 0.0;
+    QinHist[n] = q;
+  }
+  if (!site) {
+    double *aQout = M.qout + ((size_t)e * M.nSB + p) * RVN_MAX_RIVER_SEGS;
+    for (int i = 0; i < nSeg; i++) { double q = aQout[i] + adjust; if (q < 0.0) q = 0.0; aQout[i] = q; }
+  }
 }
 
 // ---- routing runs as a short sequence of small kernels on its own stream (one thread per (member, basin)):
@@ -1453,6 +1504,18 @@ __global__ void __launch_bounds__(RVN_ROUTE_BS, RVN_ROUTE_MINB) route_level_kern
   RouteTabs T; T.from_model(M);
   basin_lateral_inflow(M, e, p, slot, t);
   basin_route(M, T, e, p, t, step, slot);
+}
+__global__ void __launch_bounds__(RVN_ROUTE_BS) da_propagate_kernel(const __grid_constant__ DevModel M, const int lev0, const int nlev, const int step) {
+  const long long idx = (long long)blockIdx.x * RVN_ROUTE_BS + threadIdx.x;
+  if (idx >= (long long)M.E * nlev) return;
+  const int e = (int)(idx / nlev), i = (int)(idx - (long long)e * nlev);
+  da_propagate(M, e, M.level_idx[lev0 + i], step);
+}
+__global__ void __launch_bounds__(RVN_ROUTE_BS) da_apply_kernel(const __grid_constant__ DevModel M, const int step, const int t) {
+  const long long idx = (long long)blockIdx.x * RVN_ROUTE_BS + threadIdx.x;
+  if (idx >= (long long)M.E * M.nSB) return;
+  const int e = (int)(idx / M.nSB), p = (int)(idx - (long long)e * M.nSB);
+  da_apply(M, e, p, step, t);
 }
 // IncrementCumulInput / IncrementCumOutflow (src/Model.cpp:2458-2539) + watershed storage + the step's records for member e; executed
 // by all NT threads of a CTA (s_red: NT/32 x 5 doubles of shared memory)
@@ -1495,6 +1558,12 @@ RVN_DI void balance_member(const DevModel &M, const int e, const int slot, const
     cum[0] += avg_precip * tstep;
     for (int i = 0; i < M.nSpec; i++) cum[0] += M.spec_cum[(size_t)step * M.nSpec + i];   // GetIntegratedSpecInflow, basin after basin (src/Model.cpp:2467-2469)
     cum[1] += t[0];
+    if (M.assimilate_flow) {   // volume the overrides added (src/Assimilate.cpp:115-116): input when positive, negative output otherwise; few gauges, one thread
+      for (int p = 0; p < NB; p++) {
+        const double va = M.da_mass[(size_t)e * NB + p];
+        if (va > 0.0) cum[0] += va / area * D_MM_PER_METER; else cum[1] -= va / area * D_MM_PER_METER;
+      }
+    }
     if ((M.rec_flags & 2) && rec >= 0) {
       double *w = M.rec_wshed + ((size_t)rec * M.E + e) * 4;
       w[0] = cum[0]; w[1] = cum[1]; w[2] = avg_precip;
@@ -1550,6 +1619,15 @@ __global__ void __launch_bounds__(RVN_MEMBER_BS) route_member_kernel(const __gri
       const int lev0 = M.level_ptr[L], lev1 = M.level_ptr[L + 1];
       for (int i = lev0 + threadIdx.x; i < lev1; i += RVN_MEMBER_BS) basin_route(M, T, e, level_idx[i], t0 + ss, step0 + ss, slot0 + ss);
       __syncthreads();   // the next level reads this level's outflows
+    }
+    if (M.assimilate_flow) {   // AssimilationBackPropagate: outlets first, one level at a time, then the corrections are applied everywhere
+      for (int L = M.nLevels - 1; L >= 0; L--) {
+        const int lev0 = M.level_ptr[L], lev1 = M.level_ptr[L + 1];
+        for (int i = lev0 + threadIdx.x; i < lev1; i += RVN_MEMBER_BS) da_propagate(M, e, level_idx[i], step0 + ss);
+        __syncthreads();
+      }
+      for (int p = threadIdx.x; p < NB; p += RVN_MEMBER_BS) da_apply(M, e, p, step0 + ss, t0 + ss);
+      __syncthreads();
     }
     balance_member<RVN_MEMBER_BS>(M, e, slot0 + ss, rec0 >= 0 ? rec0 + ss : -1, step0 + ss, s_red);
     __syncthreads();

@@ -39,6 +39,7 @@ rvh_model *rvh_model_load(const char *base, double duration_override) {
     }
     h->pModel->Initialize(h->Options);
     ParseInitialConditions(h->pModel, h->Options);
+    h->pModel->ApplyInitialAssimilation(h->Options);
   } catch (...) { delete h->pModel; delete h; throw; }
   return h;
   RVH_CATCH(NULL)

@@ -95,6 +95,8 @@ struct optStruct {
   int    num_soillayers;
   bool   suppressCompetitiveET, snow_suppressPET, allow_soil_overfill, direct_evap;
   bool   silent, noisy, benchmarking;
+  bool   assimilate_flow = false; double assimilation_start = -1.0;   // :AssimilateStreamflow / :AssimilationStartTime (src/ParseInput.cpp:335-339,1795-1818)
+  double assimilation_fact = 1.0, assim_upstream_decay = 0.0, assim_time_decay = 0.2;   // globals ASSIMILATION_FACT / ASSIM_UPSTREAM_DECAY [1/km] / ASSIM_TIME_DECAY (src/GlobalParams.cpp:388-390)
   ensemble_type ensemble;
   unsigned int random_seed;
   bool   random_seed_set;

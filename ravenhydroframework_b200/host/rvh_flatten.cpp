@@ -248,6 +248,11 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
   _f_veg_season.clear();
   _f_spec_basin.clear(); _f_spec_in.clear(); _f_spec_down.clear(); _f_spec_cum.clear();
   for (int p = 0; p < NB; p++) if (_pSubBasins[p]->pInflowHydro || _pSubBasins[p]->pInflowHydro2) _f_spec_basin.push_back(p);
+  // direct-insertion assimilation: CModel::PrepareAssimilation (src/Assimilate.cpp:125-275) replayed over the run; its arrays persist from step to step
+  _f_da_override.clear(); _f_da_obsQ.clear(); _f_da_obsQ2.clear(); _f_da_decay.clear(); _f_da_wt.clear();
+  std::vector<double> DAlength(NB, 0.0), DAtimesince(NB, 0.0), DAobsQ(NB, 0.0), DAobsQ2(NB, 0.0), DADrainSum(NB, 0.0), DADownSum(NB, 0.0);
+  std::vector<char> DAoverride(NB, 0);
+  if (O.assimilate_flow) for (int p = 0; p < NB; p++) ExitGracefullyIf(_pSubBasins[p]->pReservoir != NULL, "CModel::Flatten: streamflow assimilation in a model with reservoirs is not supported by the B200 build");
   // reservoirs: curves padded to the longest, initial state, linked HRU (src/ModelInitialize.cpp:165-175)
   _f_res_basin.clear(); _f_res_hru.clear(); _f_res_np.clear(); _f_res_curves.clear(); _f_res_min_stage.clear(); _f_res_extract.clear(); _f_res_state0.clear();
   int nResPts = 0;
@@ -285,6 +290,54 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
         sum += 0.5 * (b->GetSpecifiedInflow(tt.model_time) + b->GetSpecifiedInflow(tt.model_time + O.timestep)) * (O.timestep * SEC_PER_DAY);
         sum += b->GetDownstreamInflow(tt.model_time) * (O.timestep * SEC_PER_DAY);
         _f_spec_cum.push_back(sum / area * MM_PER_METER);
+      }
+      if (O.assimilate_flow) {
+        if (!(tt.model_time < (O.assimilation_start - O.timestep / 2.0))) {
+          int p = 0, pdown;
+          double Qobs = 0, Qobs2 = 0;
+          for (p = 0; p < NB; p++) { DADrainSum[p] = 0.0; DAlength[p] = 0.0; }
+          const int nn = (int)((tt.model_time + TIME_CORRECTION) / O.timestep) + 1;   // end-of-step index
+          for (int pp = NB - 1; pp >= 0; pp--) {   // downstream to upstream
+            p = _aOrderedSBind[pp];
+            pdown = _aDownstreamInds[p];
+            bool ObsExists = false;
+            if (_pSubBasins[p]->assimilate) {
+              const CTimeSeries *obs = FlowObservation(_pSubBasins[p]);
+              if (obs != NULL) { Qobs = obs->GetSampledValue(nn); Qobs2 = obs->GetSampledValue(nn + 1); ObsExists = true; }
+            }
+            if (ObsExists) {
+              if (Qobs != RAV_BLANK_DATA) {
+                DAlength[p] = 0.0; DAtimesince[p] = 0.0; DAoverride[p] = 1; DAobsQ[p] = Qobs; DAobsQ2[p] = Qobs2;
+              } else {
+                if (pdown != DOESNT_EXIST) DAlength[p] += _pSubBasins[pdown]->GetReachLength(); else DAlength[p] = 0;
+                DAtimesince[p] += O.timestep; DAoverride[p] = 0; DAobsQ[p] = 0.0; DAobsQ2[p] = 0.0;
+              }
+            } else {
+              if ((pdown != DOESNT_EXIST) && (!DAoverride[p]) && (!_pSubBasins[p]->disabled) && (!_pSubBasins[pdown]->disabled)) {
+                DAlength[p] += _pSubBasins[pdown]->GetReachLength(); DAtimesince[p] = DAtimesince[pdown]; DAoverride[p] = 0;
+              } else { DAlength[p] = 0.0; DAtimesince[p] = 0.0; DAoverride[p] = 0; }
+            }
+          }
+          for (int pp = 0; pp < NB; pp++) { DADrainSum[p] = 0.0; DADownSum[p] = 0.0; }   // the reference's loop: p is not advanced (:238-242)
+          for (int pp = 0; pp < NB; pp++) {   // upstream to downstream
+            p = _aOrderedSBind[pp]; pdown = _aDownstreamInds[p];
+            if (DAoverride[p]) DADrainSum[p] = _pSubBasins[p]->drainage_area;
+            else if (pdown != DOESNT_EXIST) DADrainSum[pdown] += DADrainSum[p];
+          }
+          for (int pp = NB - 1; pp >= 0; pp--) {   // downstream to upstream
+            p = _aOrderedSBind[pp]; pdown = _aDownstreamInds[p];
+            if (DAoverride[p]) DADownSum[p] = _pSubBasins[p]->drainage_area;
+            else if (pdown != DOESNT_EXIST) DADownSum[p] = DADownSum[pdown];
+          }
+        }
+        const double distfact = O.assim_upstream_decay / M_PER_KM;   // [1/km] -> [1/m]
+        for (int p = 0; p < NB; p++) {   // what AssimilationOverride / AssimilationBackPropagate (:67-118, 283-339) read this step
+          _f_da_override.push_back(DAoverride[p] ? 1 : 0); _f_da_obsQ.push_back(DAobsQ[p]); _f_da_obsQ2.push_back(DAobsQ2[p]);
+          _f_da_decay.push_back((_aDownstreamInds[p] != DOESNT_EXIST) ? exp(-distfact * DAlength[p]) : 1.0);
+          double ECCCwt = 1.0;
+          if (DADrainSum[p] != 0.0) ECCCwt = (_pSubBasins[p]->drainage_area - DADrainSum[p]) / (DADownSum[p] - DADrainSum[p]);
+          _f_da_wt.push_back(ECCCwt);
+        }
       }
       for (size_t r = 0; r < _f_res_basin.size(); r++) {   // CDemand::UpdateDemand (src/WaterDemands.cpp:204-216): sampled value of the step, blank = 0
         const CReservoir *R = _pSubBasins[_f_res_basin[r]]->pReservoir;
@@ -476,6 +529,15 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
   d.res_basin = d.nRes ? _f_res_basin.data() : NULL; d.res_hru = d.nRes ? _f_res_hru.data() : NULL; d.res_np = d.nRes ? _f_res_np.data() : NULL;
   d.res_curves = d.nRes ? _f_res_curves.data() : NULL; d.res_min_stage = d.nRes ? _f_res_min_stage.data() : NULL;
   d.res_extract = d.nRes ? _f_res_extract.data() : NULL; d.res_state0 = d.nRes ? _f_res_state0.data() : NULL;
+  d.assimilate_flow = O.assimilate_flow ? 1 : 0; d.assimilation_fact = O.assimilation_fact;
+  d.da_override = NULL; d.da_obsQ = d.da_obsQ2 = d.da_decay = d.da_wt = d.sb_drain_area = d.sb_da_corr = NULL;
+  if (O.assimilate_flow) {
+    const double distfact = O.assim_upstream_decay / M_PER_KM;
+    _f_sb_drain.assign(NB, 0.0); _f_sb_dacorr.assign(NB, 1.0);
+    for (int p = 0; p < NB; p++) { _f_sb_drain[p] = _pSubBasins[p]->drainage_area; _f_sb_dacorr[p] = exp(-distfact * _pSubBasins[p]->reach_length); }
+    d.da_override = _f_da_override.data(); d.da_obsQ = _f_da_obsQ.data(); d.da_obsQ2 = _f_da_obsQ2.data(); d.da_decay = _f_da_decay.data(); d.da_wt = _f_da_wt.data();
+    d.sb_drain_area = _f_sb_drain.data(); d.sb_da_corr = _f_sb_dacorr.data();
+  }
   d.nSpec = (int32_t)_f_spec_basin.size();
   d.spec_basin = d.nSpec ? _f_spec_basin.data() : NULL; d.spec_in = d.nSpec ? _f_spec_in.data() : NULL;
   d.spec_down = d.nSpec ? _f_spec_down.data() : NULL; d.spec_cum = d.nSpec ? _f_spec_cum.data() : NULL;
@@ -556,6 +618,27 @@ void CModel::PackBasinState(std::vector<double> &qin, std::vector<double> &qlat,
     for (int sgm = 0; sgm < b->nSegments; sgm++) qout[(size_t)p * RVN_MAX_RIVER_SEGS + sgm] = b->aQout[sgm];
     double *s = &scal[(size_t)p * 8];
     s[0] = b->QoutLast; s[1] = b->QlatLast; s[2] = b->Qlocal; s[3] = b->QlocLast; s[4] = b->channel_storage; s[5] = b->rivulet_storage;
+  }
+}
+
+// ---- direct-insertion streamflow assimilation (src/Assimilate.cpp) -----------------------------------------------------------
+const CTimeSeries *CModel::FlowObservation(const CSubBasin *b) const {   // IsContinuousFlowObs2 (:12-19): first HYDROGRAPH series of the basin
+  for (size_t i = 0; i < observed.size(); i++) if (observed[i].pTS != NULL && observed[i].loc_ID == b->ID && observed[i].name == "HYDROGRAPH") return observed[i].pTS;
+  return NULL;
+}
+void CModel::ApplyInitialAssimilation(const optStruct &O) {
+  if (!O.assimilate_flow) return;
+  if (0.0 < (O.assimilation_start - O.timestep / 2.0)) return;   // PrepareAssimilation returns before the assimilation start (:128)
+  for (int p = 0; p < GetNumSubBasins(); p++) {
+    CSubBasin *b = _pSubBasins[p];
+    if (!b->assimilate) continue;
+    const CTimeSeries *obs = FlowObservation(b);
+    if (obs == NULL) continue;
+    const double Qobs = obs->GetSampledValue(1);   // nn == 1: the end of the first step
+    if (Qobs == RAV_BLANK_DATA) continue;
+    ExitGracefullyIf(b->pReservoir != NULL, "ApplyInitialAssimilation: streamflow assimilation at a reservoir outlet is not supported by the B200 build");
+    b->SetQout(Qobs);
+    for (size_t n = 0; n < b->aQinHist.size(); n++) b->aQinHist[n] = Qobs;   // SetQinHist with a constant history
   }
 }
 

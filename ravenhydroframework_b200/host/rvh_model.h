@@ -331,6 +331,10 @@ public:
   // CSubBasin::WriteToSolutionFile, src/SubBasin.cpp:2869-2880) for ONE member, from arrays in the layouts of
   // rvn_gpu_download_state / rvn_gpu_download_basin_state.  full_precision: %.17g instead of the reference's 5 fixed decimals
   // (6 significant digits for the basin block), so that a restart continues bit-identically.
+  // direct-insertion assimilation: the reference's first PrepareAssimilation call also overwrites the initial flows of gauged basins with the
+  // first observation (src/Assimilate.cpp:160-178); call after the initial conditions were read
+  void ApplyInitialAssimilation(const optStruct &Options);
+  const CTimeSeries *FlowObservation(const CSubBasin *b) const;   // the continuous HYDROGRAPH series linked to the basin, or NULL
   void WriteSolutionFile(const std::string &filename, const optStruct &Options, double model_time, const double *state, const double *qin,
                          const double *qlat, const double *qout, const double *scal, bool full_precision, const double *res_state = NULL) const;
   // initial basin routing state in the layout of rvn_gpu_upload_basin_state (one member)
@@ -367,6 +371,8 @@ private:
   std::vector<int32_t> _f_res_basin, _f_res_hru, _f_res_np;
   std::vector<double> _f_res_curves, _f_res_min_stage, _f_res_extract, _f_res_state0;
   std::vector<double> _f_sb_cref, _f_sb_alpha;
+  std::vector<uint8_t> _f_da_override;
+  std::vector<double> _f_da_obsQ, _f_da_obsQ2, _f_da_decay, _f_da_wt, _f_sb_drain, _f_sb_dacorr;
   std::vector<double> _f_spec_in, _f_spec_down, _f_spec_cum;
   std::vector<uint8_t> _f_pert_mask;
   std::vector<rvn_lateral> _f_lat;

@@ -143,6 +143,15 @@ static void ParseMainInputFile(CModel *&pModel, optStruct &Options) {
       for (size_t i = 0; i < pending_alias.size(); i++) pModel->AddAlias(pending_alias[i].first, pending_alias[i].second);
       continue;
     }
+    if (c == ":AssimilateStreamflow") { Options.assimilate_flow = true; continue; }   // src/ParseInput.cpp:1813-1818 (the per-gauge command of the .rvt has the same name)
+    if (c == ":AssimilationStartTime") {   // :1795-1812
+      ExitGracefullyIf(s.size() < 3, "ParseMainInputFile: :AssimilationStartTime needs [yyyy-mm-dd] [hh:mm:ss]");
+      time_struct tt = DateStringToTimeStruct(s[1], s[2], Options.calendar);
+      Options.assimilation_start = TimeDifference(Options.julian_start_day, Options.julian_start_year, tt.julian_day, tt.year, Options.calendar);
+      if (Options.assimilation_start > Options.duration) WriteWarning("Data assimilation start date is after model simulation end. No data assimilation will be applied.");
+      continue;
+    }
+    if (c == ":AssimilationMethod") { ExitGracefullyIf(s.size() >= 2 && s[1] != "DA_ECCC", "ParseMainInputFile: only :AssimilationMethod DA_ECCC is supported"); continue; }
     if (c == ":Routing") {
       if (s[1] == "ROUTE_NONE") Options.routing = RVN_ROUTE_NONE;
       else if (s[1] == "ROUTE_MUSKINGUM") Options.routing = RVN_ROUTE_MUSKINGUM;
@@ -520,6 +529,14 @@ static void ParseClassPropertiesFile(CModel *pModel, const optStruct &Options) {
         Tveg.def.erase(key);
         for (size_t k = 0; k < pModel->veg_classes.size(); k++) Tveg.cell.erase(std::make_pair((int)k, key));
       }
+      continue;
+    }
+    if (c == ":GlobalParameter" && s.size() >= 3 && (s[1] == "ASSIMILATION_FACT" || s[1] == "ASSIM_UPSTREAM_DECAY" || s[1] == "ASSIM_TIME_DECAY")) {
+      // streamflow-assimilation globals: host-side only (they shape the per-step tables of CModel::Flatten)
+      optStruct &Ow = const_cast<optStruct &>(Options);
+      if (s[1] == "ASSIMILATION_FACT") Ow.assimilation_fact = s_to_d(s[2]);
+      else if (s[1] == "ASSIM_UPSTREAM_DECAY") Ow.assim_upstream_decay = s_to_d(s[2]);
+      else Ow.assim_time_decay = s_to_d(s[2]);
       continue;
     }
     if (c == ":GlobalParameter") {

@@ -149,6 +149,18 @@ if hasattr(synth, "write_hbv"):
                                    rvc_extra=":InitialReservoirStage 3 101.6\n")
     # ROUTE_DIFFUSIVE_VARY: the routing hydrograph of every reach is rebuilt each step from a history of flow-dependent celerities
     CASES["hbv_diffusive_vary"] = dict(kind="hbv", n_sb=15, hru_per_sb=4, n_days=260, seed=97, routing="ROUTE_DIFFUSIVE_VARY", season_offset=70)
+    # direct-insertion streamflow assimilation (src/Assimilate.cpp): gauges at the outlet and at an interior basin, blanks in both series,
+    # corrections propagated upstream with a distance decay; the second case starts assimilating mid-run
+    def _obs(sb, n, seed, blanks):
+        r = np.random.RandomState(seed)
+        v = ["-1.2345" if (i in blanks) else "%.4f" % (0.6 + 2.5 * abs(np.sin(i / 17.0 + seed)) + 0.3 * r.rand()) for i in range(n + 1)]
+        return ":ObservationData HYDROGRAPH %d m3/s\n  2000-01-01 00:00:00 1.0 %d\n  " % (sb, n + 1) + "\n  ".join(v) + "\n:EndObservationData\n:AssimilateStreamflow %d\n" % sb
+    CASES["hbv_assim"] = dict(kind="hbv", n_sb=7, hru_per_sb=3, n_days=200, seed=98, routing="ROUTE_MUSKINGUM", season_offset=60,
+                              rvi_extra=":AssimilateStreamflow\n", rvp_extra=":GlobalParameter ASSIM_UPSTREAM_DECAY 0.04\n:GlobalParameter ASSIMILATION_FACT 0.8\n",
+                              rvt_extra=_obs(1, 200, 1, set(range(40, 55)) | {120}) + _obs(3, 200, 2, set(range(0, 5)) | set(range(90, 140))))
+    CASES["hbv_assim_late"] = dict(kind="hbv", n_sb=15, hru_per_sb=2, n_days=150, seed=99, routing="ROUTE_DIFFUSIVE_WAVE", season_offset=100,
+                                   rvi_extra=":AssimilateStreamflow\n:AssimilationStartTime 2000-02-10 00:00:00\n",
+                                   rvt_extra=_obs(2, 150, 3, {60, 61}) + _obs(5, 150, 4, set()) + _obs(1, 150, 5, set(range(100, 151))))
     CASES["hbv_hrugroup_cond"] = dict(kind="hbv", n_sb=3, hru_per_sb=5, n_days=250, seed=12, routing="ROUTE_MUSKINGUM", season_offset=40, variant="hrugroup_cond")
     CASES["hbv_lateral"] = dict(kind="hbv", n_sb=4, hru_per_sb=7, n_days=250, seed=8, routing="ROUTE_MUSKINGUM", season_offset=40, variant="lateral")
 if hasattr(synth, "write_blended"):

@@ -20,7 +20,7 @@ def test_engine_exports_every_declared_symbol():
     lib = api.engine_lib()
     for n in names:
         assert hasattr(lib, n), "librvn_gpu.so does not export %s" % n
-    assert lib.rvn_gpu_abi_version() == 9
+    assert lib.rvn_gpu_abi_version() == 10
 
 
 def test_loaded_libraries_were_built_from_the_present_sources():

@@ -156,6 +156,27 @@ def test_gpu_matches_reference_golden(case):
     assert H.rel_err(sim.watershed(0, n)[:, 1, :3], g["wshed"]) < TOL
 
 
+@pytest.mark.parametrize("case", ["hbv_res_lake", "hbv_res_tables", "hbv_assim", "hbv_assim_late", "hbv_diffusive_vary", "hbv_chanprofile_hydrologic"])
+def test_level_routing_path_matches_reference_golden(case):
+    """Ensembles of more than 16 members route with one launch per network level (route_level_kernel, da_propagate_kernel, ...) instead
+    of the one-CTA-per-member kernel the two-member golden runs take: the same fixtures through that path."""
+    g = np.load(os.path.join(H.GOLDEN, case, "reference.npz"))
+    model = api.RavenModel(os.path.join(H.GOLDEN, case, "model"))
+    E = 20
+    model.flatten(E)
+    n = g["qout"].shape[0]
+    sim = api.GpuSimulation(model, n_members=E)
+    sim.set_recording(n)
+    sim.run(n)
+    assert H.rel_err(sim.download_state()[E - 1], g["state"][-1]) < TOL
+    q = sim.hydrographs(0, n)
+    assert H.rel_err(q[:, E - 1, :], g["qout"]) < TOL and H.rel_err(q[:, 7, :], g["qout"]) < TOL
+    assert H.rel_err(sim.watershed(0, n)[:, E - 1, :3], g["wshed"]) < TOL
+    if "res_stage" in g:
+        _, sb = model.reservoir_state()
+        assert H.rel_err(sim.download_reservoir_state()[E - 1][:, 0], g["res_stage"][-1][sb]) < TOL
+
+
 def test_state_upload_mid_run_invalidates_cached_sums(tmp_path):
     """Replacing the state from the host (EnKF update, restart) must give the same result as a fresh simulation."""
     base = synth.write_hmets(str(tmp_path), n_sb=3, hru_per_sb=5, n_days=260, seed=12, season_offset=100)
