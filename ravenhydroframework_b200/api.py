@@ -117,6 +117,7 @@ def host_lib():
         lib.rvh_desc_num_reservoirs.argtypes = [vp]
         lib.rvh_desc_reservoir_state.argtypes = [vp, vp, vp]
         lib.rvh_model_write_solution.argtypes = [vp, C.c_char_p, C.c_double, vp, vp, vp, vp, vp, C.c_int]
+        lib.rvh_model_write_hydrographs.argtypes = [vp, C.c_char_p, vp, vp, vp, vp, C.c_int]
         lib.rvh_model_write_solution_res.argtypes = [vp, C.c_char_p, C.c_double, vp, vp, vp, vp, vp, C.c_int, vp]
         _host = lib
     return _host
@@ -219,6 +220,21 @@ class RavenModel:
         if self.lib.rvh_model_basin_state(self.h, qin.ctypes.data, qlat.ctypes.data, qout.ctypes.data, scal.ctypes.data):
             raise RavenError(self.lib.rvh_last_error().decode())
         return qin, qlat, qout, scal
+
+    def write_hydrographs(self, filename, qout_rec, precip, qout0=None, qout0_last=None):
+        """Hydrographs.csv in the reference's format (period-ending stamps, step-averaged flows, observed series beside the modelled ones,
+        6 significant digits) from recorded hydrographs qout_rec [nsteps][nSB] and watershed-average precipitation precip [nsteps]."""
+        q = np.ascontiguousarray(qout_rec, dtype=np.float64); pr = np.ascontiguousarray(precip, dtype=np.float64)
+        if qout0 is None:
+            _, _, qo, sc = self.basin_state()
+            nseg = np.zeros(self.nSB, dtype=np.int32); self.lib.rvh_desc_nseg(self.desc, nseg.ctypes.data)
+            qout0 = qo[np.arange(self.nSB), nseg - 1].copy(); qout0_last = sc[:, 0].copy()
+            res, sb = self.reservoir_state()
+            if len(sb):
+                qout0[sb] = res[:, 2]; qout0_last[sb] = res[:, 3]
+        q0 = np.ascontiguousarray(qout0, dtype=np.float64); q0l = np.ascontiguousarray(qout0_last, dtype=np.float64)
+        if self.lib.rvh_model_write_hydrographs(self.h, str(filename).encode(), q.ctypes.data, q0.ctypes.data, q0l.ctypes.data, pr.ctypes.data, int(q.shape[0])):
+            raise RavenError(self.lib.rvh_last_error().decode())
 
     def reservoir_state(self):
         """Initial reservoir state [nRes][8] = {stage, stage_last, Qout, Qout_last, precip m3, losses m3, AET m3, 0} and the basin index of

@@ -91,6 +91,14 @@ int rvh_model_write_solution_res(rvh_model *h, const char *filename, double mode
   return 0;
   RVH_CATCH(-1)
 }
+// Hydrographs.csv of one member from the recorded hydrographs qout_rec[nsteps][nSB], the initial outflows q0 / q0last [nSB] and the recorded
+// watershed-average precipitation precip[nsteps] (CModel::WriteMinorOutput, src/StandardOutput.cpp:790-836)
+int rvh_model_write_hydrographs(rvh_model *h, const char *filename, const double *qout_rec, const double *q0, const double *q0last, const double *precip, int nsteps) {
+  RVH_TRY
+  h->pModel->WriteHydrographsFile(filename, h->Options, qout_rec, q0, q0last, precip, nsteps);
+  return 0;
+  RVH_CATCH(-1)
+}
 // ---- DDS (CDDSEnsemble): rvh_ensemble_begin + rvh_ensemble_update_model(e) perturb the best-so-far vector (the sampled values
 // returned are the trial's parameters); after the trial's GPU run rvh_dds_finish_run(e, hydrographs) evaluates the objective
 // function and updates the best solution.  qout_rec[nsteps][nSB] = CSubBasin::GetOutflowRate after every step of the single member.

@@ -627,6 +627,7 @@ const CTimeSeries *CModel::FlowObservation(const CSubBasin *b) const {   // IsCo
   return NULL;
 }
 void CModel::ApplyInitialAssimilation(const optStruct &O) {
+  _pre_assim_q0.clear(); _pre_assim_q0last.clear();
   if (!O.assimilate_flow) return;
   if (0.0 < (O.assimilation_start - O.timestep / 2.0)) return;   // PrepareAssimilation returns before the assimilation start (:128)
   for (int p = 0; p < GetNumSubBasins(); p++) {
@@ -637,15 +638,20 @@ void CModel::ApplyInitialAssimilation(const optStruct &O) {
     const double Qobs = obs->GetSampledValue(1);   // nn == 1: the end of the first step
     if (Qobs == RAV_BLANK_DATA) continue;
     ExitGracefullyIf(b->pReservoir != NULL, "ApplyInitialAssimilation: streamflow assimilation at a reservoir outlet is not supported by the B200 build");
+    if (_pre_assim_q0.empty()) { _pre_assim_q0.assign(GetNumSubBasins(), 0.0); _pre_assim_q0last.assign(GetNumSubBasins(), 0.0); for (int q = 0; q < GetNumSubBasins(); q++) { _pre_assim_q0[q] = _pSubBasins[q]->GetOutflowRate(); _pre_assim_q0last[q] = _pSubBasins[q]->QoutLast; } }
     b->SetQout(Qobs);
     for (size_t n = 0; n < b->aQinHist.size(); n++) b->aQinHist[n] = Qobs;   // SetQinHist with a constant history
   }
 }
 
-static std::string DecDaysToHours(double dec_date) {   // src/CommonFunctions.cpp DecDaysToHours: hh:mm:ss.sss of the fractional day
-  double hours = (dec_date - floor(dec_date)) * 24.0 + 1e-9;
-  int h = (int)floor(hours); double mins = (hours - h) * 60.0; int mi = (int)floor(mins); double sec = (mins - mi) * 60.0;
-  char b[32]; snprintf(b, sizeof b, "%02d:%02d:%06.3f", h, mi, sec < 0 ? 0.0 : sec);
+static std::string DecDaysToHours(double dec_date) {   // src/CommonFunctions.cpp:385-402 (not truncated): hh:mm:ss.ss of the fractional day
+  const double hours = (dec_date - floor(dec_date)) * 24.0, mind = (hours - floor(hours)) * 60.0;
+  double sec = (mind - floor(mind)) * 60.0;
+  int hr = (int)(floor(hours)), min = (int)(floor(mind));
+  if (sec >= 59.995) { min++; sec = 0.0; }
+  if (min == 60) { hr++; min = 0; }
+  if (hr == 24) hr = 0;
+  char b[32]; snprintf(b, sizeof b, "%2.2d:%2.2d:%05.2f", hr, min, sec);
   return b;
 }
 void CModel::WriteSolutionFile(const std::string &filename, const optStruct &O, double model_time, const double *state, const double *qin, const double *qlat,
@@ -700,5 +706,54 @@ void CModel::WriteSolutionFile(const std::string &filename, const optStruct &O, 
     }
   }
   fprintf(f, ":EndBasinStateVariables\n");
+  fclose(f);
+}
+
+// ---- Hydrographs.csv (reference CModel::WriteOutputFileHeaders / WriteMinorOutput, src/StandardOutput.cpp:199-243,790-836) ----------------
+// Written after the run from what the device recorded: qout_rec[nsteps][NB] = CSubBasin::GetOutflowRate after every step, q0[NB] the outflow
+// and q0last[NB] the _QoutLast of the initial condition, precip[nsteps] = GetAveragePrecip.  Default options of the reference: period-ending
+// time stamps, step-averaged hydrographs (0.5 * (Qout + QoutLast)), observed series next to the modelled one, 6 significant digits.
+static std::string StreamDouble(double v) { char b[64]; snprintf(b, sizeof b, "%g", v); return b; }   // operator<<(double) of a default ostream
+void CModel::WriteHydrographsFile(const std::string &filename, const optStruct &O, const double *qout_rec, const double *q0, const double *q0last,
+                                  const double *precip, int nsteps) const {
+  FILE *f = fopen(filename.c_str(), "w");
+  ExitGracefullyIf(f == NULL, "CModel::WriteOutputFileHeaders: Unable to open output file " + filename + " for writing.");
+  const int NB = GetNumSubBasins();
+  for (int p = 0; p < NB; p++)
+    ExitGracefullyIf(_pSubBasins[p]->gauged && !_pSubBasins[p]->disabled && _pSubBasins[p]->pReservoir != NULL,
+                     "CModel::WriteHydrographsFile: the reservoir-inflow columns of gauged reservoir basins are not written by the B200 build");
+  fprintf(f, "time,date,hour,precip [mm/day]");
+  for (int p = 0; p < NB; p++) {
+    const CSubBasin *b = _pSubBasins[p];
+    if (!(b->gauged && !b->disabled)) continue;
+    if (b->name == "") fprintf(f, ",ID=%lld [m3/s]", b->ID); else fprintf(f, ",%s [m3/s]", b->name.c_str());
+    for (size_t i = 0; i < observed.size(); i++)
+      if (observed[i].pTS != NULL && observed[i].loc_ID == b->ID && observed[i].name == "HYDROGRAPH") {
+        if (b->name == "") fprintf(f, ",ID=%lld (observed) [m3/s]", b->ID); else fprintf(f, ",%s (observed) [m3/s]", b->name.c_str());
+      }
+  }
+  fprintf(f, "\n");
+  for (int n = 0; n <= nsteps; n++) {   // row 0 = the initial condition (WriteMinorOutput at t = 0), row n = the end of step n
+    const double t = n * O.timestep;
+    time_struct tt;
+    JulianConvert(t, O.julian_start_day, O.julian_start_year, O.calendar, tt);
+    fprintf(f, "%s,%s,%s", StreamDouble(tt.model_time).c_str(), tt.date_string.c_str(), DecDaysToHours(tt.julian_day).c_str());
+    if (n != 0) fprintf(f, ",%s", StreamDouble(precip[n - 1]).c_str()); else fprintf(f, ",---");
+    for (int p = 0; p < NB; p++) {
+      const CSubBasin *b = _pSubBasins[p];
+      if (!(b->gauged && !b->disabled)) continue;
+      // row 0 is written before the first PrepareAssimilation call replaces the initial flows of the gauges by their first observation
+      const double Qnow = (n == 0) ? (_pre_assim_q0.empty() ? q0[p] : _pre_assim_q0[p]) : qout_rec[(size_t)(n - 1) * NB + p];
+      const double Qlast = (n == 0) ? (_pre_assim_q0.empty() ? q0last[p] : _pre_assim_q0last[p]) : ((n == 1) ? q0[p] : qout_rec[(size_t)(n - 2) * NB + p]);
+      // CSubBasin::GetIntegratedOutflow(tstep) / (tstep * SEC_PER_DAY), src/SubBasin.cpp:929-934
+      fprintf(f, ",%s", StreamDouble(0.5 * (Qnow + Qlast) * (O.timestep * SEC_PER_DAY) / (O.timestep * SEC_PER_DAY)).c_str());
+      for (size_t i = 0; i < observed.size(); i++)
+        if (observed[i].pTS != NULL && observed[i].loc_ID == b->ID && observed[i].name == "HYDROGRAPH") {
+          const double val = observed[i].pTS->GetAvgValue(tt.model_time, O.timestep);
+          if ((val != RAV_BLANK_DATA) && (tt.model_time > 0)) fprintf(f, ",%s", StreamDouble(val).c_str()); else fprintf(f, ",");
+        }
+    }
+    fprintf(f, "\n");
+  }
   fclose(f);
 }

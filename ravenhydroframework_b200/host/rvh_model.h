@@ -333,6 +333,8 @@ public:
   // (6 significant digits for the basin block), so that a restart continues bit-identically.
   // direct-insertion assimilation: the reference's first PrepareAssimilation call also overwrites the initial flows of gauged basins with the
   // first observation (src/Assimilate.cpp:160-178); call after the initial conditions were read
+  void WriteHydrographsFile(const std::string &filename, const optStruct &Options, const double *qout_rec, const double *q0, const double *q0last,
+                            const double *precip, int nsteps) const;   // Hydrographs.csv from the device's per-step records
   void ApplyInitialAssimilation(const optStruct &Options);
   const CTimeSeries *FlowObservation(const CSubBasin *b) const;   // the continuous HYDROGRAPH series linked to the basin, or NULL
   void WriteSolutionFile(const std::string &filename, const optStruct &Options, double model_time, const double *state, const double *qin,
@@ -371,6 +373,7 @@ private:
   std::vector<int32_t> _f_res_basin, _f_res_hru, _f_res_np;
   std::vector<double> _f_res_curves, _f_res_min_stage, _f_res_extract, _f_res_state0;
   std::vector<double> _f_sb_cref, _f_sb_alpha;
+  std::vector<double> _pre_assim_q0, _pre_assim_q0last;   // outflows of the initial condition before ApplyInitialAssimilation (row 0 of Hydrographs.csv)
   std::vector<uint8_t> _f_da_override;
   std::vector<double> _f_da_obsQ, _f_da_obsQ2, _f_da_decay, _f_da_wt, _f_sb_drain, _f_sb_dacorr;
   std::vector<double> _f_spec_in, _f_spec_down, _f_spec_cum;

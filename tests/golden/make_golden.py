@@ -302,6 +302,21 @@ def make_dds(name="dds_hmets"):
     print("golden %-18s trials=%d improvements=%d" % (name, len(trials), len(rows)))
 
 
+HYDROGRAPH_CASES = ("hbv_assim", "hbv_muskingum", "hmets_tree")
+
+
+def make_hydrographs(name):
+    """Hydrographs.csv as the reference EXECUTABLE writes it for an existing fixture's inputs (text, 6 significant digits)."""
+    import subprocess
+    d = os.path.join(HERE, name)
+    out = os.path.join(d, "_exe") + "/"
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "Raven.exe"), "model", "-o", out], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert os.path.exists(out + "Hydrographs.csv"), r.stdout[-2000:]
+    shutil.copy(out + "Hydrographs.csv", os.path.join(d, "reference_Hydrographs.csv"))
+    shutil.rmtree(out, ignore_errors=True)
+    print("golden %-18s Hydrographs.csv (%d lines)" % (name, len(open(os.path.join(d, "reference_Hydrographs.csv")).readlines())))
+
+
 def make(name, spec):
     spec = dict(spec)
     kind = spec.pop("kind")
@@ -403,6 +418,9 @@ if __name__ == "__main__":
         if only and name not in only:
             continue
         make(name, spec)
+    for name in HYDROGRAPH_CASES:
+        if not only or name in only:
+            make_hydrographs(name)
     if not only or "dds_hmets" in only:
         make_dds()
     if not only or "hbv_restart" in only:

@@ -177,6 +177,21 @@ def test_level_routing_path_matches_reference_golden(case):
         assert H.rel_err(sim.download_reservoir_state()[E - 1][:, 0], g["res_stage"][-1][sb]) < TOL
 
 
+@pytest.mark.parametrize("case", sorted(os.path.basename(os.path.dirname(p)) for p in glob.glob(os.path.join(H.GOLDEN, "*", "reference_Hydrographs.csv"))))
+def test_gpu_hydrographs_csv_equals_the_reference_executables(case, tmp_path):
+    """Hydrographs.csv formatted from the device's per-step records = the text file of the reference executable."""
+    model = api.RavenModel(os.path.join(H.GOLDEN, case, "model"))
+    model.flatten(1)
+    ref = open(os.path.join(H.GOLDEN, case, "reference_Hydrographs.csv")).read().split("\n")
+    n = len([l for l in ref if l.strip()]) - 2
+    sim = api.GpuSimulation(model)
+    sim.set_recording(n)
+    sim.run(n)
+    out = str(tmp_path / "Hydrographs.csv")
+    model.write_hydrographs(out, sim.hydrographs(0, n)[:, 0, :], sim.watershed(0, n)[:, 0, 2])
+    assert open(out).read().split("\n") == ref
+
+
 def test_state_upload_mid_run_invalidates_cached_sums(tmp_path):
     """Replacing the state from the host (EnKF update, restart) must give the same result as a fresh simulation."""
     base = synth.write_hmets(str(tmp_path), n_sb=3, hru_per_sb=5, n_days=260, seed=12, season_offset=100)

@@ -179,3 +179,19 @@ def test_monte_carlo_member_matches_reference_golden():
     assert H.rel_err(o["qout_rec"], g["qout"]) < TOL
     other = H.oracle_run(model, n, member=1)
     assert H.rel_err(other["qout_rec"], g["qout"]) > 1e-3     # members really differ
+
+
+HYDRO_CASES = sorted(os.path.basename(os.path.dirname(p)) for p in glob.glob(os.path.join(H.GOLDEN, "*", "reference_Hydrographs.csv")))
+
+
+@pytest.mark.parametrize("case", HYDRO_CASES)
+def test_hydrographs_csv_equals_the_reference_executables(case, tmp_path):
+    """Output path: Hydrographs.csv written by the host layer from per-step records (here the oracle's) is the same TEXT the reference
+    executable writes for the same inputs (step-averaged flows, observed columns with blanks, 6 significant digits, date / hour stamps)."""
+    _, model = _load(case)
+    ref = open(os.path.join(H.GOLDEN, case, "reference_Hydrographs.csv")).read().split("\n")
+    n = len([l for l in ref if l.strip()]) - 2   # header + initial row
+    o = H.oracle_run(model, n)
+    out = str(tmp_path / "Hydrographs.csv")
+    model.write_hydrographs(out, o["qout_rec"], o["wshed_rec"][:, 2])
+    assert open(out).read().split("\n") == ref
