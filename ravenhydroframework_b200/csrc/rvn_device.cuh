@@ -87,20 +87,9 @@ struct DevModel {
   const double *sb_area, *sb_rain_corr, *sb_snow_corr, *sb_temp_corr, *sb_musk_K, *sb_musk_X, *sb_K_reach;
   const double *sb_unit_hydro, *sb_route_hydro;
   const double *chan_Q, *chan_A, *sb_Qmult, *sb_reach_m; const int32_t *sb_channel; int32_t nChanPts;   // ROUTE_HYDROLOGIC rating curves
-  // ROUTE_DIFFUSIVE_VARY: per-member routing hydrographs [member][nSB][max_nqin] and celerity histories [member][nSB][max_nqin] rebuilt every step
-  const double *sb_c_ref, *sb_diff_alpha; double *route_hydro_m, *c_hist;
   double watershed_area;
   // user-specified basin inflows (rvn_model_desc::spec_*): slot of each basin in the [nSteps][nSpec] tables or -1
   int32_t nSpec; const int32_t *sb_spec_slot; const double *spec_in, *spec_down, *spec_cum;
-  // reservoirs (rvn_model_desc::res_*): hru_type[] carries RVN_DEV_RES_LINKED for a reservoir-linked HRU, hru_res[k] = its reservoir or -1;
-  // res_state [member][nRes][RVN_RES_STATE]; res_force [slot][member][nRes][2] = {OW_PET, LAKE_PET_CORR} of the linked HRU, written by the sweep
-  int32_t nRes, nResPts; const int32_t *sb_res, *res_hru, *res_np, *hru_res; const double *res_curves, *res_min_stage, *res_extract;
-  double *res_state, *res_force; int32_t iAET;
-  // direct-insertion streamflow assimilation (rvn_model_desc::da_*): da_adjust [member][nSB] = _aDAQadjust, da_mass [member][nSB] = volume the
-  // override added to basin p this step [m3] (booked by the balance)
-  int32_t assimilate_flow; double assimilation_fact;
-  const uint8_t *da_override; const double *da_obsQ, *da_obsQ2, *da_decay, *da_wt, *sb_drain_area, *sb_da_corr;
-  double *da_adjust, *da_mass;
   // recording
   double *rec_qout, *rec_wshed;                    // [rec][member][nSB], [rec][member][4]
   int32_t rec_capacity, rec_flags;
@@ -113,5 +102,18 @@ struct DevModel {
   int32_t pert_forcing[RVN_MAX_PERT], pert_adj[RVN_MAX_PERT];
   const uint8_t *pert_mask;                        // [nPert][nHp] or NULL
   const double *pert_eps;                          // [member][nSteps][nPert]
+  // ---- fields only the routing kernels read are kept behind everything the sweeps read: the sweeps' constant-bank offsets do not move when
+  // routing features are added (a 5 % difference of the headline sweep was measured between two layouts, profiles/r02/devmodel_layout.md)
+  // ROUTE_DIFFUSIVE_VARY: per-member routing hydrographs [member][nSB][max_nqin] and celerity histories [member][nSB][max_nqin] rebuilt every step
+  const double *sb_c_ref, *sb_diff_alpha; double *route_hydro_m, *c_hist;
+  // reservoirs (rvn_model_desc::res_*): hru_type[] carries RVN_DEV_RES_LINKED for a reservoir-linked HRU, hru_res[k] = its reservoir or -1;
+  // res_state [member][nRes][RVN_RES_STATE]; res_force [slot][member][nRes][2] = {OW_PET, LAKE_PET_CORR} of the linked HRU, written by the sweep
+  int32_t nRes, nResPts; const int32_t *sb_res, *res_hru, *res_np, *hru_res; const double *res_curves, *res_min_stage, *res_extract;
+  double *res_state, *res_force; int32_t iAET;
+  // direct-insertion streamflow assimilation (rvn_model_desc::da_*): da_adjust [member][nSB] = _aDAQadjust, da_mass [member][nSB] = volume the
+  // override added to basin p this step [m3] (booked by the balance)
+  int32_t assimilate_flow; double assimilation_fact;
+  const uint8_t *da_override; const double *da_obsQ, *da_obsQ2, *da_decay, *da_wt, *sb_drain_area, *sb_da_corr;
+  double *da_adjust, *da_mass;
 };
 #endif

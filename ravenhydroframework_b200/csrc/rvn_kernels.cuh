@@ -556,9 +556,12 @@ RVN_DI ConvRow ld_row(const ConvRow *__restrict__ tab, int i) {
 #endif
 RVN_DI void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // warm L2 with the first rows of a convolution's stores (issued at kernel start, long before they are consumed)
-RVN_DI void conv_prefetch_head(const double *g, const size_t stride) {
+#ifndef RVN_PF_HEAD
+#define RVN_PF_HEAD RVN_PF_DIST   // rows of each convolution warmed at kernel start
+#endif
+RVN_DI void conv_prefetch_head(const double *g, const size_t stride, const int n) {
 #pragma unroll
-  for (int r = 0; r < RVN_PF_DIST; r++) prefetch_l2(g + (size_t)r * stride);
+  for (int r = 0; r < RVN_PF_HEAD; r++) if (RVN_PF_HEAD <= RVN_PF_DIST || r < n) prefetch_l2(g + (size_t)r * stride);
 }
 
 template <bool UNIT_DT, class C>
@@ -814,10 +817,10 @@ extern __shared__ __align__(16) unsigned char rvn_smem[];
 // ------------------------------------------------------------------------------------------------
 template <class Prog, int J>
 struct PrefetchConvs {
-  static RVN_DI void run(const double *gstate, const size_t nHp) {
+  static RVN_DI void run(const double *gstate, const size_t nHp, const int32_t *conv_n) {
     if constexpr (J < Prog::nProc) {
-      if constexpr (Prog::op(J) == RVN_OP_CONVOLVE) conv_prefetch_head(gstate + (size_t)Prog::ia(J, 2) * nHp, nHp);
-      PrefetchConvs<Prog, J + 1>::run(gstate, nHp);
+      if constexpr (Prog::op(J) == RVN_OP_CONVOLVE) conv_prefetch_head(gstate + (size_t)Prog::ia(J, 2) * nHp, nHp, (RVN_PF_HEAD > RVN_PF_DIST) ? conv_n[Prog::ia(J, 0)] : 0);
+      PrefetchConvs<Prog, J + 1>::run(gstate, nHp, conv_n);
     }
   }
 };
@@ -894,7 +897,7 @@ __global__ void __launch_bounds__(RVN_BS, RVN_STATIC_MIN_BLOCKS) hru_sweep_stati
   double *gstate = M.state + (size_t)e * M.NS * nHp + k;
 #pragma unroll
   for (int s = 0; s < Prog::nCore; s++) c.SV(s) = __ldcs(gstate + (size_t)Prog::slot_sv(s) * nHp);
-  if (RVN_PF_DIST > 0 && enabled) PrefetchConvs<Prog, 0>::run(gstate, nHp);
+  if (RVN_PF_DIST > 0 && enabled) PrefetchConvs<Prog, 0>::run(gstate, nHp, M.conv_n + ((size_t)e * M.nLU + c.lu) * M.nConv);
   __syncthreads();   // parameter row staged
   const int nsub = MULTI ? nsub_ : 1;
 #pragma unroll 1

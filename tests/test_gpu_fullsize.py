@@ -14,7 +14,7 @@ TOL = 1e-9
 
 def test_config3_share_hmets_512_members_x_10k_hrus(tmp_path):
     """BASELINE config 3, the per-GPU share: HMETS, 10,000 HRUs / 500 subbasins, 512 members, Monte-Carlo parameters."""
-    n = 12
+    n = 1461   # four years of the configuration's daily steps: long-run drift of the convolution stores and the snow pack is part of the check
     base = synth.write_hmets(str(tmp_path), n_sb=500, hru_per_sb=20, n_days=n + 1, seed=1, single_class=True, ensemble_members=512, season_offset=105)
     model = api.RavenModel(base)
     E = 512
@@ -26,19 +26,21 @@ def test_config3_share_hmets_512_members_x_10k_hrus(tmp_path):
     st0 = model.initial_state()
     sim.set_recording(n)
     sim.run(n)
-    # one complete member against the oracle (member 37: its own sampled parameters)
-    ref = H.oracle_run(model, n, member=37)
-    st = sim.download_state(37, 1)[0]
-    assert H.rel_err(st, ref["state"]) < TOL
-    assert H.rel_err(sim.hydrographs(0, n, 37, 1)[:, 0, :], ref["qout_rec"]) < TOL
-    assert H.rel_err(sim.watershed(0, n, 37, 1)[:, 0, :3], ref["wshed_rec"][:, :3]) < TOL
+    # complete members against the oracle over the whole run (their own sampled parameters): every storage of every HRU at the end, every
+    # hydrograph value and the watershed balance of every step
+    for mem in (37, 0, 511):
+        ref = H.oracle_run(model, n, member=mem, record_state=False)
+        st = sim.download_state(mem, 1)[0]
+        assert H.rel_err(st, ref["state"]) < TOL
+        assert H.rel_err(sim.hydrographs(0, n, mem, 1)[:, 0, :], ref["qout_rec"]) < TOL
+        assert H.rel_err(sim.watershed(0, n, mem, 1)[:, 0, :3], ref["wshed_rec"][:, :3]) < TOL
     # every member: finite, different from its neighbours, balance closed
     w = sim.watershed(0, n)                               # [n][E][4]
     assert np.all(np.isfinite(w))
     s_init = ref["wshed_rec"][0, 3] - (ref["wshed_rec"][0, 0] - ref["wshed_rec"][0, 1])   # S0 of a member = S1 - (in1 - out1); same initial state for all
     mb = (w[:, :, 3] - s_init) + (w[:, :, 1] - w[:, :, 0])
     assert np.abs(mb).max() < 1e-7 * max(1.0, np.abs(w[:, :, 3]).max()), np.abs(mb).max()
-    q = sim.hydrographs(0, n)[:, :, 0]
+    q = sim.hydrographs(n - 1, 1)[:, :, 0]
     assert len(np.unique(q[-1])) > 500
     sim.close()
     assert st0.shape == (10000, model.NS)
@@ -47,7 +49,7 @@ def test_config3_share_hmets_512_members_x_10k_hrus(tmp_path):
 def test_config2_hbvec_10k_hrus_500_subbasins_muskingum(tmp_path):
     """BASELINE config 2: HBV-EC semi-distributed, 10,000 HRUs / 500 subbasins, Muskingum routing -- complete comparison with the
     oracle (every HRU storage, every subbasin hydrograph), plus identical replicas."""
-    n = 60
+    n = 7305   # the configuration's full 20 years of daily steps
     base = synth.write_hbv(str(tmp_path), n_sb=500, hru_per_sb=20, n_days=n, seed=2, routing="ROUTE_MUSKINGUM", season_offset=100)
     model = api.RavenModel(base)
     model.flatten(3)
@@ -55,7 +57,7 @@ def test_config2_hbvec_10k_hrus_500_subbasins_muskingum(tmp_path):
     assert sim.kernel_variant() == "static:HBVEC"
     sim.set_recording(n)
     sim.run(n)
-    ref = H.oracle_run(model, n)
+    ref = H.oracle_run(model, n, record_state=False)
     st = sim.download_state()
     assert H.rel_err(st[0], ref["state"]) < TOL
     assert np.array_equal(st[0], st[1]) and np.array_equal(st[0], st[2])
