@@ -141,7 +141,7 @@ typedef enum {
 /* model-wide method switches; numbering is local to this ABI (the host maps Raven's keywords) */
 typedef enum { RVN_RAINSNOW_DATA = 0, RVN_RAINSNOW_DINGMAN, RVN_RAINSNOW_HBV, RVN_RAINSNOW_UBCWM, RVN_RAINSNOW_THRESHOLD } rvn_rainsnow;
 typedef enum { RVN_POTMELT_NONE = 0, RVN_POTMELT_DATA, RVN_POTMELT_DEGREE_DAY, RVN_POTMELT_HBV, RVN_POTMELT_HMETS,
-               RVN_POTMELT_DD_FREEZE, RVN_POTMELT_HBV_ROS } rvn_potmelt;   /* src/PotentialMelt.cpp:20-246 */
+               RVN_POTMELT_DD_FREEZE, RVN_POTMELT_HBV_ROS, RVN_POTMELT_EB, RVN_POTMELT_RESTRICTED } rvn_potmelt;   /* src/PotentialMelt.cpp:20-246 */
 /* atmospheric estimators of the forcing chain (reference src/UpdateForcings.cpp:677-731, src/Radiation.cpp:24-57,333-364) */
 typedef enum { RVN_AIRPRESS_BASIC = 0, RVN_AIRPRESS_UBC, RVN_AIRPRESS_CONST } rvn_airpress;
 typedef enum { RVN_RELHUM_CONSTANT = 0, RVN_RELHUM_MINDEWPT } rvn_relhum;
@@ -156,7 +156,7 @@ typedef enum { RVN_SW_CLOUD_CORR_NONE = 0, RVN_SW_CLOUD_CORR_DINGMAN, RVN_SW_CLO
 typedef enum { RVN_PET_DATA = 0, RVN_PET_FROMMONTHLY, RVN_PET_CONSTANT, RVN_PET_NONE, RVN_PET_HARGREAVES_1985, RVN_PET_OUDIN,
                RVN_PET_HAMON, RVN_PET_LINEAR_TEMP, RVN_PET_MOHYSE,
                RVN_PET_TURC_1961, RVN_PET_MAKKINK_1957, RVN_PET_PENMAN_SIMPLE33, RVN_PET_PENMAN_SIMPLE39, RVN_PET_VAPDEFICIT, RVN_PET_LINACRE,
-               RVN_PET_HARGREAVES } rvn_pet;   /* CModel::EstimatePET, src/Evaporation.cpp:282-540 */
+               RVN_PET_HARGREAVES, RVN_PET_PRIESTLEY_TAYLOR, RVN_PET_PENMAN_COMBINATION } rvn_pet;   /* CModel::EstimatePET, src/Evaporation.cpp:282-540 */
 typedef enum { RVN_OROCORR_NONE = 0, RVN_OROCORR_SIMPLELAPSE, RVN_OROCORR_HBV } rvn_orocorr;
 typedef enum { RVN_ROUTE_NONE = 0, RVN_ROUTE_MUSKINGUM, RVN_ROUTE_MUSKINGUM_CUNGE, RVN_ROUTE_STORAGECOEFF,
                RVN_ROUTE_PLUG_FLOW, RVN_ROUTE_DIFFUSIVE_WAVE, RVN_ROUTE_HYDROLOGIC, RVN_ROUTE_DIFFUSIVE_VARY } rvn_routing;
@@ -191,11 +191,11 @@ typedef enum {
   RVN_LU_PARTITION_COEFF, RVN_LU_CC_DECAY_COEFF, RVN_LU_MAX_SAT_AREA_FRAC, RVN_LU_PDM_B, RVN_LU_AET_COEFF,
   RVN_LU_MAX_DEP_AREA_FRAC, RVN_LU_PONDED_EXP, RVN_LU_AWBM_AREAFRAC1, RVN_LU_AWBM_AREAFRAC2, RVN_LU_HYMOD2_G, RVN_LU_HYMOD2_KMAX,
   RVN_LU_HYMOD2_EXP, RVN_LU_PET_LIN_COEFF, RVN_LU_RAIN_MELT_MULT, RVN_LU_RELHUM_CORR, RVN_LU_PET_VAP_COEFF,
-  RVN_LU_MIN_WIND_SPEED, RVN_LU_MAX_WIND_SPEED, RVN_LU_ABST_PERCENT, RVN_LU_COUNT
+  RVN_LU_MIN_WIND_SPEED, RVN_LU_MAX_WIND_SPEED, RVN_LU_ABST_PERCENT, RVN_LU_ROUGHNESS, RVN_LU_PRIESTLEYTAYLOR_COEFF, RVN_LU_COUNT
 } rvn_landuse_field;
 typedef enum {
   RVN_V_MAX_HEIGHT = 0, RVN_V_MAX_LAI, RVN_V_SAI_HT_RATIO, RVN_V_MAX_CAPACITY, RVN_V_MAX_SNOW_CAPACITY,
-  RVN_V_RAIN_ICEPT_PCT, RVN_V_SNOW_ICEPT_PCT, RVN_V_PET_VEG_CORR, RVN_V_RAIN_ICEPT_FACT, RVN_V_SNOW_ICEPT_FACT,
+  RVN_V_RAIN_ICEPT_PCT, RVN_V_SNOW_ICEPT_PCT, RVN_V_PET_VEG_CORR, RVN_V_RAIN_ICEPT_FACT, RVN_V_SNOW_ICEPT_FACT, RVN_V_ALBEDO, RVN_V_SVF_EXTINCTION,
   /* derived canopy variables (reference veg_var_struct; CVegetationClass::RecalculateCanopyParams,
    * src/VegetationParams.cpp:85-200), refreshed by the host for the current step when date-dependent */
   RVN_V_VAR_CAPACITY, RVN_V_VAR_SNOW_CAPACITY, RVN_V_VAR_RAIN_ICEPT_PCT, RVN_V_VAR_SNOW_ICEPT_PCT,
@@ -207,7 +207,7 @@ typedef enum {
   RVN_S_MAX_PERC_RATE, RVN_S_GR4J_X2, RVN_S_GR4J_X3, RVN_S_VIC_B_EXP, RVN_S_MAX_BASEFLOW_RATE, RVN_S_MAX_INTERFLOW_RATE,
   RVN_S_PERC_N, RVN_S_SAC_PERC_ALPHA, RVN_S_SAC_PERC_EXPON, RVN_S_PERC_ASPEN, RVN_S_BASEFLOW_THRESH, RVN_S_BASEFLOW_COEFF2,
   RVN_S_STORAGE_THRESHOLD, RVN_S_VIC_ZMIN, RVN_S_VIC_ZMAX, RVN_S_VIC_ALPHA, RVN_S_VIC_EVAP_GAMMA, RVN_S_UBC_EVAP_SOIL_DEF,
-  RVN_S_UBC_INFIL_SOIL_DEF, RVN_S_COUNT
+  RVN_S_UBC_INFIL_SOIL_DEF, RVN_S_ALBEDO_WET, RVN_S_ALBEDO_DRY, RVN_S_COUNT
 } rvn_soil_field;
 typedef enum { RVN_T_TOPMODEL_LAMBDA = 0, RVN_T_COUNT } rvn_terrain_field;   /* reference terrain_struct, src/Properties.h */
 
@@ -230,6 +230,8 @@ typedef enum {
   RVN_F_TEMP_DAILY_MAX, RVN_F_PET, RVN_F_OW_PET, RVN_F_POTENTIAL_MELT, RVN_F_TEMP_MONTH_AVE, RVN_F_PET_MONTH_AVE,
   /* atmospheric forcings: derived only when opt.need_atmos, recorded (rvn_gpu_download_forcings) but not carried through the sweep */
   RVN_F_AIR_PRES, RVN_F_REL_HUMIDITY, RVN_F_SW_RADIA, RVN_F_WIND_VEL,
+  /* net radiation (opt.need_radiation): shortwave above the canopy x (1 - total albedo), net longwave */
+  RVN_F_SW_RADIA_NET, RVN_F_LW_RADIA_NET,
   RVN_F_COUNT
 } rvn_forcing_field;
 #define RVN_F_CARRIED RVN_F_AIR_PRES   /* fields below this index live in the per-thread forcing vector of the sweep */
@@ -293,6 +295,10 @@ typedef struct rvn_options {
   int32_t need_atmos;             /* 1: a consumed PET or a sublimation process needs air pressure / relative humidity / wind / shortwave radiation -> derive them */
   int32_t air_pressure, rel_humidity, sw_radiation, sw_cloudcorr;   /* rvn_airpress, rvn_relhum, rvn_sw_rad, rvn_sw_cloudcorr */
   int32_t wind_velocity;          /* rvn_windvel */
+  int32_t need_radiation;         /* 1: a consumed PET or potential-melt method needs net shortwave / longwave radiation (implies need_atmos) */
+  int32_t lw_radiation;           /* 0 LW_RAD_DEFAULT (Dingman clear-sky emissivity with LW_INC_DEFAULT, src/Radiation.cpp:210-231), 1 LW_RAD_NONE */
+  int32_t sw_canopycorr;          /* 0 SW_CANOPY_CORR_NONE, 1 SW_CANOPY_CORR_STATIC (src/Radiation.cpp:377-415) */
+  int32_t pad_opt_;
   int32_t interception_factor;    /* rvn_icept */
   int32_t max_iterations;         /* ITERATED_HEUN: Options.max_iterations (30) */
   double  convergence_crit;       /* ITERATED_HEUN: Options.convergence_crit (0.01) */
@@ -554,7 +560,9 @@ int rvn_gpu_enkf_update_host(rvn_gpu_model *m, double *Xall_host, const double *
 /* CUDA-event time [ms] of the last rvn_gpu_enkf_update's update kernel */
 int rvn_gpu_enkf_last_ms(rvn_gpu_model *m, double *update_ms);
 
-/* raw device pointers for zero-copy callers that already live on the GPU (bench, NCCL EnKF gather) */
+/* raw device pointer of the state for zero-copy callers that already live on the GPU.  The state is tiled: element (member e, state
+ * variable i, HRU k) lies at ((e * nTiles + k / 128) * NS + i) * 128 + k % 128 doubles, nTiles = ceil(nHRU / 128); member_stride = NS * 128 *
+ * nTiles, sv_stride = 128 (the stride between state variables inside a tile) */
 int rvn_gpu_device_state_ptr(rvn_gpu_model *m, void **dptr, int64_t *member_stride, int64_t *sv_stride);
 /* CUDA-event time (ms) spent in kernels of the last rvn_gpu_run, and number of kernel launches it made */
 int rvn_gpu_last_run_stats(rvn_gpu_model *m, double *sweep_ms, double *total_ms, int64_t *launches);

@@ -184,6 +184,7 @@ static void apply_forcing_perturbation(const rvn_model_desc *d, int ftype, int m
 
 /* GetSaturatedVaporPressure [kPa], src/CommonFunctions.cpp:935-949; GetDewPointTemp [C], :1131-1139 */
 static double o_sat_vap(double T) { return (T >= 0) ? 0.61078 * exp(17.26939 * T / (T + 237.3)) : 0.61078 * exp(21.87456 * T / (T + 265.5)); }
+static double o_dew_point_vp(double e) { double numer = log(e) + 0.4926, denom = 0.0708 - 0.00421 * log(e); return numer / denom; } /* GetDewPointTemp(e), src/CommonFunctions.cpp:1148-1156 */
 static double o_dew_point(double Ta, double rel_hum) { double tmp = (17.27 * Ta / (237.7 + Ta)) + log(rel_hum); return 237.7 * tmp / (17.27 - tmp); }
 /* daily[7]: the HRU's daily forcing items of the previous step (temp_daily_min/max/ave, temp_month_max/min/ave, PET_month_ave), i.e. the
  * part of CHydroUnit::_Forcings that CopyDailyForcingItems (src/Forcings.cpp:72-89) carries through the day on sub-daily steps */
@@ -334,6 +335,55 @@ static void update_forcings(const rvn_model_desc *d, const double *ptab, int mem
     } else if (d->opt.wind_velocity == RVN_WINDVEL_SQRT)
       F[RVN_F_WIND_VEL] = omax(0.0, P_G(&c, RVN_G_WINDVEL_SCALE) * (F[RVN_F_TEMP_DAILY_MAX] - F[RVN_F_TEMP_DAILY_MIN]) + P_G(&c, RVN_G_WINDVEL_ICEPT));
   }
+  /* net radiation (src/UpdateForcings.cpp:591-606): sub-canopy shortwave (CRadiation::SWCanopyCorrection, src/Radiation.cpp:377-415), total albedo
+   * above and below the canopy (CHydroUnit::GetTotalAlbedo, src/HydroUnits.cpp:728-781; snow albedo = DEFAULT_SNOW_ALBEDO), net longwave
+   * LW_RAD_DEFAULT with LW_INC_DEFAULT (src/Radiation.cpp:210-231), cloud cover 0.  Canopy variables of this step as
+   * CVegetationClass::RecalculateCanopyParams / RecalculateRootParams (src/VegetationParams.cpp:85-142,236-262) derive them. */
+  double SW_subcan_net = 0.0, veg_height = 0.0, veg_LAI = 0.0, veg_SAI = 0.0;
+  if (d->opt.need_radiation) {
+    const int veg = d->hru_veg[k];
+    const double rel_ht = d->veg_season[((size_t)step * d->nVeg + veg) * 2 + 0], rel_LAI = d->veg_season[((size_t)step * d->nVeg + veg) * 2 + 1];
+    const double max_height = P_V(&c, RVN_V_MAX_HEIGHT), sparseness = P_LU(&c, RVN_LU_FOREST_SPARSENESS), max_LAI = P_V(&c, RVN_V_MAX_LAI);
+    const double SAI_ht_ratio = P_V(&c, RVN_V_SAI_HT_RATIO), extinction = P_V(&c, RVN_V_SVF_EXTINCTION), Fc = P_LU(&c, RVN_LU_FOREST_COVERAGE);
+    veg_height = max_height * rel_ht;
+    veg_LAI = (1.0 - sparseness) * max_LAI * rel_LAI;
+    veg_SAI = (1.0 - sparseness) * (veg_height * SAI_ht_ratio);
+    double svf = exp(-extinction * (veg_LAI + veg_SAI));
+    double canopy_corr = 1.0;
+    if (d->opt.sw_canopycorr == 1) canopy_corr = (1.0 - Fc) * 1.0 + Fc * exp(-extinction * (veg_LAI + veg_SAI));
+    const double SW_subcan = F[RVN_F_SW_RADIA] * canopy_corr;
+    /* GetTotalAlbedo */
+    double land_albedo = 0.0;
+    const double snow_albedo = 0.8, snow_cov = snow_cover(&c);
+    const int type = d->hru_type[k];
+    if (type == RVN_HRU_STANDARD) {
+      const int iTop = sv_index(d, RVN_SV_SOIL, 0);
+      double soil_sat = omax(omin(phi_old[iTop] / soil_capacity(&c, 0), 1.0), 0.0);
+      land_albedo = (soil_sat)*P_S(&c, 0, RVN_S_ALBEDO_WET) + (1.0 - soil_sat) * P_S(&c, 0, RVN_S_ALBEDO_DRY);
+    } else if (type == RVN_HRU_GLACIER || type == RVN_HRU_MASKED_GLACIER) land_albedo = 0.4;
+    else if (type == RVN_HRU_LAKE) land_albedo = 0.1;
+    else if (type == RVN_HRU_WATER) land_albedo = 0.1;
+    else if (type == RVN_HRU_ROCK) land_albedo = 0.35;
+    else if (type == RVN_HRU_WETLAND) land_albedo = 0.15;
+    land_albedo = (snow_cov)*snow_albedo + (1.0 - snow_cov) * land_albedo;
+    double veg_albedo = P_V(&c, RVN_V_ALBEDO), svf2 = svf, land2 = land_albedo;
+    if (veg_albedo < 0) veg_albedo = 0.14;
+    if (svf2 > 1.0) svf2 = 0.0;
+    if (land2 < 0) land2 = 0.3;
+    const double albedo_above = (1.0 - svf2) * (Fc)*veg_albedo + ((svf2) * (Fc) + (1.0 - Fc)) * land2;
+    F[RVN_F_SW_RADIA_NET] = F[RVN_F_SW_RADIA] * (1 - albedo_above);
+    SW_subcan_net = SW_subcan * (1 - land_albedo);
+    if (d->opt.lw_radiation == 1) F[RVN_F_LW_RADIA_NET] = 0.0;
+    else {
+      const double emissivity = 0.99, Tair = F[RVN_F_TEMP_AVE] + 273.16, Tsurf = F[RVN_F_TEMP_AVE] + 273.16;
+      double ea = F[RVN_F_REL_HUMIDITY] * o_sat_vap(F[RVN_F_TEMP_AVE]);
+      double emiss_eff = 1.72 * pow(ea / Tair, 1 / 7.0);
+      double eps_at = emiss_eff * (1.0 + 0.22 * 0.0 * 0.0);
+      eps_at = (1 - Fc) * eps_at + (Fc)*1.0;
+      double LW_incoming = 4.90e-9 * eps_at * pow(Tair, 4);
+      F[RVN_F_LW_RADIA_NET] = LW_incoming - 4.90e-9 * emissivity * pow(Tsurf, 4);
+    }
+  }
   /* CModel::EstimatePotentialMelt, src/PotentialMelt.cpp:20-246 */
   {
     double pm = F[RVN_F_POTENTIAL_MELT];
@@ -363,6 +413,30 @@ static void update_forcings(const rvn_model_desc *d, const double *ptab, int mem
       if (iSV[RVN_SV_CUM_SNOWMELT] >= 0) cum_melt = phi_old[iSV[RVN_SV_CUM_SNOWMELT]];
       Ma = omin(Ma_max, Ma_min * (1 + Kcum * cum_melt));
       pm = Ma * (F[RVN_F_TEMP_DAILY_AVE] - melt_temp) * subdaily_corr;
+    } else if (d->opt.pot_melt == RVN_POTMELT_EB) { /* :103-124; GetSensibleHeatSnow / GetLatentHeatSnow / GetRainHeatInput, src/SnowParams.cpp:111-190 */
+      const double rainfall = F[RVN_F_PRECIP] * (1 - F[RVN_F_SNOW_FRAC]) + 0.0;
+      const double air_temp = F[RVN_F_TEMP_AVE], air_pres = F[RVN_F_AIR_PRES], rel_humid = F[RVN_F_REL_HUMIDITY], wind_vel = F[RVN_F_WIND_VEL];
+      const double ref_ht = 2.0, roughness = P_LU(&c, RVN_LU_ROUGHNESS), surf_temp = snow_temperature(&c);
+      const double K = SW_subcan_net, L = F[RVN_F_LW_RADIA_NET];
+      double temp_var = pow(0.42 / log(ref_ht / roughness), 2);
+      const double H = 1.2466 * 1.012e-3 * temp_var * wind_vel * O_SEC_PER_DAY * (air_temp - surf_temp);
+      double vap_pres = o_sat_vap(air_temp) * rel_humid, surf_pres = o_sat_vap(surf_temp) * 1.0;
+      double CE = pow(0.42, 2) / pow(log(ref_ht / roughness), 2);
+      temp_var = 0.622 * 1.2466 * CE / air_pres;
+      const double LH = 2.845 * temp_var * wind_vel * O_SEC_PER_DAY * (vap_pres - surf_pres);
+      double R = 0, rain_temp;
+      rain_temp = o_dew_point_vp(o_sat_vap(air_temp) * rel_humid);
+      if (surf_temp < O_FREEZING_TEMP) R = O_DENSITY_WATER * (rainfall / O_MM_PER_METER) * (4.186e-3 * (rain_temp - O_FREEZING_TEMP) + 0.334);
+      if (surf_temp >= O_FREEZING_TEMP) R = O_DENSITY_WATER * (rainfall / O_MM_PER_METER) * (4.186e-3 * (rain_temp - O_FREEZING_TEMP));
+      double S = K + L + H + LH + R;
+      S *= (O_MM_PER_METER / O_DENSITY_WATER / 0.334);
+      pm = S;
+    } else if (d->opt.pot_melt == RVN_POTMELT_RESTRICTED) { /* :127-136 */
+      const double melt_temp = P_LU(&c, RVN_LU_DD_MELT_TEMP), Ma = P_LU(&c, RVN_LU_MELT_FACTOR);
+      const double tmp_rate = omax(Ma * (F[RVN_F_TEMP_DAILY_AVE] - melt_temp), 0.0);
+      const double rad = (SW_subcan_net + F[RVN_F_LW_RADIA_NET]);
+      const double convert = O_MM_PER_METER / O_DENSITY_WATER / 0.334;
+      pm = tmp_rate * subdaily_corr + omax(rad * convert, 0.0);
     } else if (d->opt.pot_melt == RVN_POTMELT_NONE) {
       pm = 0.0;
     }
@@ -430,6 +504,44 @@ static void update_forcings(const rvn_model_desc *d, const double *ptab, int mem
     else if (method == RVN_PET_LINACRE) { /* src/Evaporation.cpp:491-504 */
       double T = F[RVN_F_TEMP_DAILY_AVE], Tdew = o_dew_point(T, F[RVN_F_REL_HUMIDITY]), latit = d->hru_lat_rad[k] * 57.29578951;
       PET = ((ow ? 700 : 500) * T / (100 - latit) + 15.0 * (T - Tdew)) / (80.0 - T);
+    }
+    else if (method == RVN_PET_PRIESTLEY_TAYLOR) { /* PriestleyTaylorEvap, src/Evaporation.cpp:155-168 */
+      double T = F[RVN_F_TEMP_AVE], sat_vap = o_sat_vap(T);
+      double de_dT = (T > 0) ? 17.26939 * 237.3 / pow(T + 237.3, 2) * sat_vap : 21.87456 * 265.5 / pow(T + 265.5, 2) * sat_vap;
+      double LH_vapor = 2.495 - 0.002361 * T;
+      double gamma = 1.012e-3 / 0.622 * F[RVN_F_AIR_PRES] / LH_vapor;
+      PET = P_LU(&c, RVN_LU_PRIESTLEYTAYLOR_COEFF) * (de_dT / (de_dT + gamma)) * omax(F[RVN_F_SW_RADIA_NET] + F[RVN_F_LW_RADIA_NET], 0.0) / LH_vapor / O_DENSITY_WATER * O_MM_PER_METER;
+    }
+    else if (method == RVN_PET_PENMAN_COMBINATION) { /* :404-416, PenmanCombinationEvap :119-144, GetVerticalTransportEfficiency src/CommonFunctions.cpp:1083-1094 */
+      /* canopy roughness of this step (Brook90 ROUGH, src/VegetationParams.cpp:236-262) */
+      const double SAI_ht_ratio = P_V(&c, RVN_V_SAI_HT_RATIO), lu_rough = P_LU(&c, RVN_LU_ROUGHNESS);
+      double closed_roughness, closed_zerodisp, zero_pl, z0, ratio, xx;
+      if (veg_height >= 10.0) closed_roughness = 0.05 * veg_height;
+      else if (veg_height <= 1.0) closed_roughness = 0.13 * veg_height;
+      else { closed_roughness = 0.13 * 1.0; closed_roughness += (0.05 * 10.0 - 0.13 * 1.0) * (veg_height - 1.0) / (10.0 - 1.0); }
+      closed_zerodisp = veg_height - closed_roughness / 0.3;
+      if (lu_rough > closed_roughness) closed_roughness = lu_rough;
+      ratio = (veg_LAI + veg_SAI) / (4.0 + SAI_ht_ratio * veg_height);
+      if (ratio >= 1.0) { zero_pl = closed_zerodisp; z0 = closed_roughness; }
+      else {
+        xx = 0.0;
+        if (veg_height > O_REAL_SMALL) xx = ratio * pow(-1.0 + exp(0.909 - 3.03 * closed_zerodisp / veg_height), 4);
+        zero_pl = 1.1 * veg_height * log(1.0 + pow(xx, 0.25));
+        z0 = omin(0.3 * (veg_height - zero_pl), lu_rough + 0.3 * veg_height * sqrt(xx));
+      }
+      double ref_ht = veg_height + 2.0;
+      double numer = 0.622 * 1.2466;
+      double denom = F[RVN_F_AIR_PRES] * O_DENSITY_WATER * (1.0 / pow(0.42, 2) * (pow((log((ref_ht - zero_pl) / z0)), 2)));
+      const double vert_trans = numer / denom;
+      double T = F[RVN_F_TEMP_AVE], sat_vap = o_sat_vap(T);
+      double de_dT = (T > 0) ? 17.26939 * 237.3 / pow(T + 237.3, 2) * sat_vap : 21.87456 * 265.5 / pow(T + 265.5, 2) * sat_vap;
+      double LH_vapor = 2.495 - 0.002361 * T;
+      double gamma = 1.012e-3 / 0.622 * F[RVN_F_AIR_PRES] / LH_vapor;
+      double vapor_def = sat_vap * (1.0 - (F[RVN_F_REL_HUMIDITY]));
+      numer = de_dT * omax((F[RVN_F_SW_RADIA_NET]) + (F[RVN_F_LW_RADIA_NET]), 0.0);
+      numer += gamma * vert_trans * O_DENSITY_WATER * LH_vapor * (F[RVN_F_WIND_VEL]) * vapor_def;
+      denom = O_DENSITY_WATER * LH_vapor * (de_dT + gamma);
+      PET = omax(0.0, (numer / denom)) * O_MM_PER_METER;
     }
     else if (method == RVN_PET_HARGREAVES) { /* HargreavesEvap, src/Evaporation.cpp:179-203 */
       double Ra = ET_radia / (2.501 * O_DENSITY_WATER / O_MM_PER_METER), Ct = 0.125;

@@ -10,9 +10,9 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-F_COUNT = 15  # RVN_F_COUNT
+F_COUNT = 17  # RVN_F_COUNT
 FORCING_NAMES = ["PRECIP", "SNOW_FRAC", "TEMP_AVE", "TEMP_DAILY_AVE", "TEMP_DAILY_MIN", "TEMP_DAILY_MAX", "PET", "OW_PET",
-                 "POTENTIAL_MELT", "TEMP_MONTH_AVE", "PET_MONTH_AVE", "AIR_PRES", "REL_HUMIDITY", "SW_RADIA", "WIND_VEL"]
+                 "POTENTIAL_MELT", "TEMP_MONTH_AVE", "PET_MONTH_AVE", "AIR_PRES", "REL_HUMIDITY", "SW_RADIA", "WIND_VEL", "SW_RADIA_NET", "LW_RADIA_NET"]
 MAX_RIVER_SEGS = 50
 RES_STATE = 8  # RVN_RES_STATE
 

@@ -44,14 +44,20 @@ struct DevProgram {
   int32_t maxConn, nConn, nConv, maxGroupConn;
 };
 
+// State layout in HBM: tiles of RVN_TILE (= one sweep CTA's) HRUs, state[member][tile][sv][RVN_TILE].  A CTA's rows are consecutive 1 KB
+// lines, the row stride is a compile-time constant (row addresses of the specialised sweeps become immediate offsets), and the store
+// stream of a CTA stays inside one ~100 KB region instead of touching one 2 MB page per row when a member has a million HRUs (with rows
+// [sv][nHp] the stride of BASELINE config 4 was 8 MB: the sweep ran at 0.25 of the HBM peak, TLB / DRAM-page bound).
+#define RVN_TILE RVN_BS
+#define RVN_STATE_OFF(M, e, sv, k) ((((size_t)(e) * (M).nTiles + (size_t)((k) / RVN_TILE)) * (M).NS + (size_t)(sv)) * RVN_TILE + (size_t)((k) % RVN_TILE))
 #define RVN_DEV_RES_LINKED 0x100   // device-side flag in DevModel::hru_type[]: the HRU is linked to a reservoir (CHydroUnit::IsLinkedToReservoir)
 struct DevModel {
-  int32_t nH, nHp, nSB, E, NS, nCore, maxConn, maxGroupConn;
+  int32_t nH, nHp, nTiles, nSB, E, NS, nCore, maxConn, maxGroupConn;   // nHp = nTiles * RVN_TILE
   rvn_options opt;
   int32_t glob_off, lu_off, veg_off, soil_off, ptab_stride;
   int32_t nLU, nVeg, nConv, nGauges, nSteps, record_forcings;
   // per-member arrays
-  double *state, *swvol, *forc, *ptab;
+  double *state, *swvol, *forc, *ptab;             // state: tiled, see RVN_STATE_OFF
   ConvRow *conv_tab;
   int32_t *conv_n;
   double *conv_sum;                               // [member][nConv][nHp] sum of each HRU's live convolution stores

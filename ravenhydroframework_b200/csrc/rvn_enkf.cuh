@@ -25,7 +25,7 @@ struct EnkfMap {
 
 RVN_DI double *enkf_locate(const DevModel &Mo, const EnkfMap &mp, const int e, const long long r) {
   const rvn_enkf_row row = mp.rows[r];
-  if (row.kind == RVN_XROW_HRU_SV) return Mo.state + ((size_t)e * Mo.NS + row.sub) * Mo.nHp + row.index;
+  if (row.kind == RVN_XROW_HRU_SV) return Mo.state + RVN_STATE_OFF(Mo, e, row.sub, row.index);
   const int p = row.index;
   if (row.kind == RVN_XROW_QIN_HIST) {
     const int nQ = Mo.sb_nqin[p];

@@ -548,6 +548,9 @@ RVN_DI ConvRow ld_row(const ConvRow *__restrict__ tab, int i) {
   return t;
 }
 
+#ifndef RVN_DA_ON
+#define RVN_DA_ON 1   // 0 compiles the streamflow-assimilation code out of the routing kernels (layout experiments only)
+#endif
 #ifndef RVN_CONV_R
 #define RVN_CONV_R 4   // rows per register buffer
 #endif
@@ -817,10 +820,10 @@ extern __shared__ __align__(16) unsigned char rvn_smem[];
 // ------------------------------------------------------------------------------------------------
 template <class Prog, int J>
 struct PrefetchConvs {
-  static RVN_DI void run(const double *gstate, const size_t nHp, const int32_t *conv_n) {
+  static RVN_DI void run(const double *gstate, const size_t stride, const int32_t *conv_n) {
     if constexpr (J < Prog::nProc) {
-      if constexpr (Prog::op(J) == RVN_OP_CONVOLVE) conv_prefetch_head(gstate + (size_t)Prog::ia(J, 2) * nHp, nHp, (RVN_PF_HEAD > RVN_PF_DIST) ? conv_n[Prog::ia(J, 0)] : 0);
-      PrefetchConvs<Prog, J + 1>::run(gstate, nHp, conv_n);
+      if constexpr (Prog::op(J) == RVN_OP_CONVOLVE) conv_prefetch_head(gstate + (size_t)Prog::ia(J, 2) * stride, stride, (RVN_PF_HEAD > RVN_PF_DIST) ? conv_n[Prog::ia(J, 0)] : 0);
+      PrefetchConvs<Prog, J + 1>::run(gstate, stride, conv_n);
     }
   }
 };
@@ -836,7 +839,7 @@ struct RunProcs {
         if (apply) {
           constexpr int ci = Prog::ia(J, 0);
           const size_t slot = ((size_t)e * M.nLU + c.lu) * M.nConv + ci;
-          convolve_direct<UNIT_DT>(c, Prog::ia(J, 1), Prog::ia(J, 3), gstate + (size_t)Prog::ia(J, 2) * M.nHp, (size_t)M.nHp,
+          convolve_direct<UNIT_DT>(c, Prog::ia(J, 1), Prog::ia(J, 3), gstate + (size_t)Prog::ia(J, 2) * RVN_TILE, (size_t)RVN_TILE,
                                    M.conv_tab + slot * RVN_CONV_STORES, M.conv_n[slot], M.conv_sum + ((size_t)e * M.nConv + ci) * M.nHp + k,
                                    sum_valid);
         }
@@ -894,10 +897,10 @@ __global__ void __launch_bounds__(RVN_BS, RVN_STATIC_MIN_BLOCKS) hru_sweep_stati
   const int sb = M.hru_sb[k];
   const unsigned long long mask = M.apply_mask[k];
   // ---- state in: coalesced over k for every state variable (aPhi[k][i] = pHRU->GetStateVarValue(i))
-  double *gstate = M.state + (size_t)e * M.NS * nHp + k;
+  double *gstate = M.state + RVN_STATE_OFF(M, e, 0, k);   // this thread's column of its tile: state variable i at gstate[i * RVN_TILE]
 #pragma unroll
-  for (int s = 0; s < Prog::nCore; s++) c.SV(s) = __ldcs(gstate + (size_t)Prog::slot_sv(s) * nHp);
-  if (RVN_PF_DIST > 0 && enabled) PrefetchConvs<Prog, 0>::run(gstate, nHp, M.conv_n + ((size_t)e * M.nLU + c.lu) * M.nConv);
+  for (int s = 0; s < Prog::nCore; s++) c.SV(s) = __ldcs(gstate + (size_t)Prog::slot_sv(s) * RVN_TILE);
+  if (RVN_PF_DIST > 0 && enabled) PrefetchConvs<Prog, 0>::run(gstate, (size_t)RVN_TILE, M.conv_n + ((size_t)e * M.nLU + c.lu) * M.nConv);
   __syncthreads();   // parameter row staged
   const int nsub = MULTI ? nsub_ : 1;
 #pragma unroll 1
@@ -925,7 +928,7 @@ __global__ void __launch_bounds__(RVN_BS, RVN_STATIC_MIN_BLOCKS) hru_sweep_stati
       stor = hru_storage(c, Prog::nCore) * c.area;
       if (!MULTI || ss == nsub - 1) {   // ---- state out
 #pragma unroll
-        for (int s = 0; s < Prog::nCore; s++) __stcs(gstate + (size_t)Prog::slot_sv(s) * nHp, c.SV(s));
+        for (int s = 0; s < Prog::nCore; s++) __stcs(gstate + (size_t)Prog::slot_sv(s) * RVN_TILE, c.SV(s));
       }
       if (M.record_forcings) {
         double *gf = M.forc + (size_t)e * RVN_F_COUNT * nHp + k;
@@ -987,8 +990,8 @@ __global__ void __launch_bounds__(RVN_BS, RVN_INTERP_MIN_BLOCKS) hru_sweep_inter
   c.prof_class = M.prof_class + c.profile * RVN_MAX_SOIL_LAYERS; c.prof_thick = M.prof_thick + c.profile * RVN_MAX_SOIL_LAYERS;
   const int sb = M.hru_sb[k];
   const unsigned long long mask = M.apply_mask[k];
-  double *gstate = M.state + (size_t)e * M.NS * nHp + k;
-  for (int s = 0; s < nCore; s++) c.SV(s) = __ldcs(gstate + (size_t)P->slot_sv[s] * nHp);
+  double *gstate = M.state + RVN_STATE_OFF(M, e, 0, k);
+  for (int s = 0; s < nCore; s++) c.SV(s) = __ldcs(gstate + (size_t)P->slot_sv[s] * RVN_TILE);
   double *const sv_read = c.sv;
   for (int ss = 0; ss < nsub; ss++) {   // sub-steps of this launch (see hru_sweep_static); nsub = 1 with lateral processes or EULER
   const int step = step0 + ss;
@@ -1050,11 +1053,11 @@ __global__ void __launch_bounds__(RVN_BS, RVN_INTERP_MIN_BLOCKS) hru_sweep_inter
     if (pr.op == RVN_OP_CONVOLVE) {
       const int ci = pr.ia[0];
       const size_t slot = ((size_t)e * M.nLU + c.lu) * M.nConv + ci;
-      double *g = gstate + (size_t)pr.ia[2] * nHp;
+      double *g = gstate + (size_t)pr.ia[2] * RVN_TILE;
       double *sc = M.conv_sum + ((size_t)e * M.nConv + ci) * nHp + k;
       const bool sum_valid = (M.conv_sum_valid != 0) || ss > 0;
-      if (unit_dt) convolve_direct<true>(c, pr.ia[1], pr.ia[3], g, nHp, M.conv_tab + slot * RVN_CONV_STORES, M.conv_n[slot], sc, sum_valid);
-      else convolve_direct<false>(c, pr.ia[1], pr.ia[3], g, nHp, M.conv_tab + slot * RVN_CONV_STORES, M.conv_n[slot], sc, sum_valid);
+      if (unit_dt) convolve_direct<true>(c, pr.ia[1], pr.ia[3], g, (size_t)RVN_TILE, M.conv_tab + slot * RVN_CONV_STORES, M.conv_n[slot], sc, sum_valid);
+      else convolve_direct<false>(c, pr.ia[1], pr.ia[3], g, (size_t)RVN_TILE, M.conv_tab + slot * RVN_CONV_STORES, M.conv_n[slot], sc, sum_valid);
       continue;
     }
     const DynProc dp = {&pr, P};
@@ -1071,7 +1074,7 @@ __global__ void __launch_bounds__(RVN_BS, RVN_INTERP_MIN_BLOCKS) hru_sweep_inter
       swv = finish_step(c, nCore);
       stor = hru_storage(c, nCore) * c.area;
     }
-    if (ss == nsub - 1) { for (int s = 0; s < nCore; s++) __stcs(gstate + (size_t)P->slot_sv[s] * nHp, c.SV(s)); }
+    if (ss == nsub - 1) { for (int s = 0; s < nCore; s++) __stcs(gstate + (size_t)P->slot_sv[s] * RVN_TILE, c.SV(s)); }
     if (M.record_forcings) {
       double *gf = M.forc + (size_t)e * RVN_F_COUNT * nHp + k;
 #pragma unroll
@@ -1305,11 +1308,32 @@ __device__ __noinline__ void reservoir_route(const DevModel &M, const int e, con
     const double harea = M.hru_area[k] * D_M2_PER_KM2;
     const double aet = Evap * 0.5 * (C.GetArea(stage_new) + C.GetArea(stage)) / harea;   // CReservoir::GetAET [mm/d], normalised to the HRU area
     AET_m3 = aet * harea / D_MM_PER_METER * tstep;
-    if (M.iAET >= 0) M.state[((size_t)e * M.NS + M.iAET) * M.nHp + k] = aet;
+    if (M.iAET >= 0) M.state[RVN_STATE_OFF(M, e, M.iAET, k)] = aet;
   }
   losses += AET_m3;
   losses += demand * D_SEC_PER_DAY * tstep;   // no series: an exact zero
   rs[5] = losses; rs[6] = AET_m3;
+}
+// CModel::AssimilationOverride (src/Assimilate.cpp:67-118, DA_ECCC): the gauge's outflow is nudged onto the observation.  Kept out of line so
+// that models without assimilation (every benchmark shape) route with the register allocation they had before this existed.
+__device__ __noinline__ void da_override(const DevModel &M, const int e, const int p, const int step, double *aQout, const int nSeg) {
+  const double tstep = M.opt.timestep;
+  const size_t ix = (size_t)step * M.nSB + p;
+  double va = 0.0;
+  if (M.da_override[ix]) {
+    const double Qobs = M.da_obsQ[ix], Qobs2 = M.da_obsQ2[ix], alpha = M.assimilation_fact;
+    const double Qmod = aQout[nSeg - 1];
+    double adj = 0.0;
+    if ((Qmod > 1e-8) && (Qobs != -1.2345)) adj = (Qobs2 == -1.2345) ? alpha * (Qobs - Qmod) : alpha * (0.5 * (Qobs2 + Qobs) - Qmod);
+    M.da_adjust[(size_t)e * M.nSB + p] = adj;
+    for (int i = 0; i < nSeg; i++) {   // CSubBasin::AdjustAllFlows(adjust, overriding, assimsite), src/SubBasin.cpp:1604-1611
+      double q = aQout[i] + adj;
+      if (q < 0.0) q = 0.0;
+      aQout[i] = q;
+      va += adj * tstep * D_SEC_PER_DAY;
+    }
+  }
+  M.da_mass[(size_t)e * M.nSB + p] = va;
 }
 // the ordered part: CSubBasin::UpdateInflow, RouteWater (src/SubBasin.cpp:2584-2863), UpdateOutflows (:2320-2421); needs the lateral
 // inflow of this step (basin_lateral_inflow) and the outflows of the basins above.  `t` = pushes into the histories before this step.
@@ -1435,24 +1459,7 @@ __device__ void basin_route(const DevModel &M, const RouteTabs &T, int e, int p,
   dV -= 0.5 * (Qlat_new + sc[1]) * dts;
   sc[5] += dV;
   sc[1] = Qlat_new;
-  if (M.assimilate_flow) {   // CModel::AssimilationOverride (src/Assimilate.cpp:67-118, DA_ECCC): the gauge's outflow is nudged onto the observation
-    const size_t ix = (size_t)step * M.nSB + p;
-    double va = 0.0;
-    if (M.da_override[ix]) {
-      const double Qobs = M.da_obsQ[ix], Qobs2 = M.da_obsQ2[ix], alpha = M.assimilation_fact;
-      const double Qmod = aQout[nSeg - 1];
-      double adj = 0.0;
-      if ((Qmod > 1e-8) && (Qobs != -1.2345)) adj = (Qobs2 == -1.2345) ? alpha * (Qobs - Qmod) : alpha * (0.5 * (Qobs2 + Qobs) - Qmod);
-      M.da_adjust[(size_t)e * M.nSB + p] = adj;
-      for (int i = 0; i < nSeg; i++) {   // CSubBasin::AdjustAllFlows(adjust, overriding, assimsite), src/SubBasin.cpp:1604-1611
-        double q = aQout[i] + adj;
-        if (q < 0.0) q = 0.0;
-        aQout[i] = q;
-        va += adj * tstep * D_SEC_PER_DAY;
-      }
-    }
-    M.da_mass[(size_t)e * M.nSB + p] = va;
-  }
+  if (RVN_DA_ON && M.assimilate_flow) da_override(M, e, p, step, aQout, nSeg);
 }
 // CModel::AssimilationBackPropagate (src/Assimilate.cpp:283-339), first loop: a basin without a valid observation takes the correction of the
 // basin below scaled by the ratio of drainage areas; downstream to upstream, i.e. level after level starting at the outlets
@@ -1499,14 +1506,37 @@ __device__ void da_apply(const DevModel &M, const int e, const int p, const int 
 #ifndef RVN_ROUTE_MINB
 #define RVN_ROUTE_MINB 32
 #endif
+// HRU -> subbasin aggregation + lateral inflow of every (member, basin): no order among basins, one full-width launch per step, so that the
+// per-level launches below carry only the ordered part of the chain
+__global__ void __launch_bounds__(RVN_ROUTE_BS, RVN_ROUTE_MINB) lateral_all_kernel(const __grid_constant__ DevModel M, const int slot, const int t) {
+  const long long idx = (long long)blockIdx.x * RVN_ROUTE_BS + threadIdx.x;
+  if (idx >= (long long)M.E * M.nSB) return;
+  const int e = (int)(idx / M.nSB), p = (int)(idx - (long long)e * M.nSB);
+  basin_lateral_inflow(M, e, p, slot, t);
+}
 __global__ void __launch_bounds__(RVN_ROUTE_BS, RVN_ROUTE_MINB) route_level_kernel(const __grid_constant__ DevModel M, const int lev0, const int nlev, const int slot, const int t, const int step) {
   const long long idx = (long long)blockIdx.x * RVN_ROUTE_BS + threadIdx.x;
   if (idx >= (long long)M.E * nlev) return;
   const int e = (int)(idx / nlev), i = (int)(idx - (long long)e * nlev);
   const int p = M.level_idx[lev0 + i];
   RouteTabs T; T.from_model(M);
-  basin_lateral_inflow(M, e, p, slot, t);
   basin_route(M, T, e, p, t, step, slot);
+}
+// the narrow levels towards the outlets (at most RVN_TAIL_MAX (member, basin) pairs each) in ONE launch: one CTA per member walks them in order with a CTA
+// barrier in between.  A level of a handful of basins costs a full kernel's latency chain when it is launched on its own; a 50 000-basin
+// tree has 11 such levels out of 16.
+#ifndef RVN_TAIL_MAX
+#define RVN_TAIL_MAX 2048
+#endif
+#define RVN_TAIL_BS 256
+__global__ void __launch_bounds__(RVN_TAIL_BS, 4) route_tail_kernel(const __grid_constant__ DevModel M, const int L0, const int slot, const int t, const int step) {
+  const int e = blockIdx.x;
+  RouteTabs T; T.from_model(M);
+  for (int L = L0; L < M.nLevels; L++) {
+    const int lev0 = M.level_ptr[L], lev1 = M.level_ptr[L + 1];
+    for (int i = lev0 + threadIdx.x; i < lev1; i += RVN_TAIL_BS) basin_route(M, T, e, M.level_idx[i], t, step, slot);
+    __syncthreads();   // the next level reads this level's outflows (global memory, same CTA)
+  }
 }
 __global__ void __launch_bounds__(RVN_ROUTE_BS) da_propagate_kernel(const __grid_constant__ DevModel M, const int lev0, const int nlev, const int step) {
   const long long idx = (long long)blockIdx.x * RVN_ROUTE_BS + threadIdx.x;
@@ -1519,6 +1549,13 @@ __global__ void __launch_bounds__(RVN_ROUTE_BS) da_apply_kernel(const __grid_con
   if (idx >= (long long)M.E * M.nSB) return;
   const int e = (int)(idx / M.nSB), p = (int)(idx - (long long)e * M.nSB);
   da_apply(M, e, p, step, t);
+}
+// volume the assimilation overrides added (src/Assimilate.cpp:115-116): input when positive, negative output otherwise; few gauges, one thread
+__device__ __noinline__ void da_book_mass(const DevModel &M, const int e, double *cum, const double area) {
+  for (int p = 0; p < M.nSB; p++) {
+    const double va = M.da_mass[(size_t)e * M.nSB + p];
+    if (va > 0.0) cum[0] += va / area * D_MM_PER_METER; else cum[1] -= va / area * D_MM_PER_METER;
+  }
 }
 // IncrementCumulInput / IncrementCumOutflow (src/Model.cpp:2458-2539) + watershed storage + the step's records for member e; executed
 // by all NT threads of a CTA (s_red: NT/32 x 5 doubles of shared memory)
@@ -1561,12 +1598,7 @@ RVN_DI void balance_member(const DevModel &M, const int e, const int slot, const
     cum[0] += avg_precip * tstep;
     for (int i = 0; i < M.nSpec; i++) cum[0] += M.spec_cum[(size_t)step * M.nSpec + i];   // GetIntegratedSpecInflow, basin after basin (src/Model.cpp:2467-2469)
     cum[1] += t[0];
-    if (M.assimilate_flow) {   // volume the overrides added (src/Assimilate.cpp:115-116): input when positive, negative output otherwise; few gauges, one thread
-      for (int p = 0; p < NB; p++) {
-        const double va = M.da_mass[(size_t)e * NB + p];
-        if (va > 0.0) cum[0] += va / area * D_MM_PER_METER; else cum[1] -= va / area * D_MM_PER_METER;
-      }
-    }
+    if (RVN_DA_ON && M.assimilate_flow) da_book_mass(M, e, cum, area);
     if ((M.rec_flags & 2) && rec >= 0) {
       double *w = M.rec_wshed + ((size_t)rec * M.E + e) * 4;
       w[0] = cum[0]; w[1] = cum[1]; w[2] = avg_precip;
@@ -1623,7 +1655,7 @@ __global__ void __launch_bounds__(RVN_MEMBER_BS) route_member_kernel(const __gri
       for (int i = lev0 + threadIdx.x; i < lev1; i += RVN_MEMBER_BS) basin_route(M, T, e, level_idx[i], t0 + ss, step0 + ss, slot0 + ss);
       __syncthreads();   // the next level reads this level's outflows
     }
-    if (M.assimilate_flow) {   // AssimilationBackPropagate: outlets first, one level at a time, then the corrections are applied everywhere
+    if (RVN_DA_ON && M.assimilate_flow) {   // AssimilationBackPropagate: outlets first, one level at a time, then the corrections are applied everywhere
       for (int L = M.nLevels - 1; L >= 0; L--) {
         const int lev0 = M.level_ptr[L], lev1 = M.level_ptr[L + 1];
         for (int i = lev0 + threadIdx.x; i < lev1; i += RVN_MEMBER_BS) da_propagate(M, e, level_idx[i], step0 + ss);
@@ -1686,24 +1718,29 @@ __global__ void diagnostic_kernel(const __grid_constant__ DevModel M, const int 
 __global__ void avg_state_kernel(const __grid_constant__ DevModel M, double *out, int member0) {
   const int e = member0 + blockIdx.y, i = blockIdx.x, tid = threadIdx.x;
   __shared__ double s_red[256];
-  const double *row = M.state + ((size_t)e * M.NS + i) * M.nHp;
   double v = 0.0;
-  for (int k = tid; k < M.nH; k += 256) if (M.hru_enabled[k]) v += row[k] * M.hru_area[k];
+  for (int k = tid; k < M.nH; k += 256) if (M.hru_enabled[k]) v += M.state[RVN_STATE_OFF(M, e, i, k)] * M.hru_area[k];
   s_red[tid] = v;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) { if (tid < o) s_red[tid] += s_red[tid + o]; __syncthreads(); }
   if (tid == 0) out[(size_t)blockIdx.y * M.NS + i] = s_red[0] / M.watershed_area;
 }
 
-// [member][hru][sv] (host order) <-> [member][sv][nHp] (device order)
-__global__ void transpose_in_kernel(const double *__restrict__ src, double *__restrict__ dst, int nH, int nHp, int NS) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x, e = blockIdx.y;
-  if (k >= nH) return;
-  for (int i = 0; i < NS; i++) dst[((size_t)e * NS + i) * nHp + k] = src[((size_t)e * nH + k) * NS + i];
-}
-__global__ void transpose_out_kernel(const double *__restrict__ src, double *__restrict__ dst, int nH, int nHp, int NS) {
+// plain [member][field][nHp] rows (the recorded forcings) -> [member][hru][field] (host order)
+__global__ void transpose_rows_out_kernel(const double *__restrict__ src, double *__restrict__ dst, int nH, int nHp, int NS) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x, e = blockIdx.y;
   if (k >= nH) return;
   for (int i = 0; i < NS; i++) dst[((size_t)e * nH + k) * NS + i] = src[((size_t)e * NS + i) * nHp + k];
+}
+// [member][hru][sv] (host order) <-> the tiled device order (RVN_STATE_OFF) of members member0 + blockIdx.y
+__global__ void transpose_in_kernel(const double *__restrict__ src, const __grid_constant__ DevModel M, const int member0) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x, e = blockIdx.y;
+  if (k >= M.nH) return;
+  for (int i = 0; i < M.NS; i++) M.state[RVN_STATE_OFF(M, member0 + e, i, k)] = src[((size_t)e * M.nH + k) * M.NS + i];
+}
+__global__ void transpose_out_kernel(const __grid_constant__ DevModel M, double *__restrict__ dst, const int member0) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x, e = blockIdx.y;
+  if (k >= M.nH) return;
+  for (int i = 0; i < M.NS; i++) dst[((size_t)e * M.nH + k) * M.NS + i] = M.state[RVN_STATE_OFF(M, member0 + e, i, k)];
 }
 #endif

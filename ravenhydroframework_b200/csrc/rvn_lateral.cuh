@@ -40,16 +40,21 @@ RVN_DI double lateral_max_storage(const DevModel &M, const DevLateral &L, const 
   }
   if (L.to_type == RVN_SV_DEPRESSION) { const double dm = ptab[M.lu_off + M.hru_lu[k] * RVN_LU_COUNT + RVN_LU_DEP_MAX]; return (dm >= 0) ? dm : D_ALMOST_INF; }
   if (L.to_type == RVN_SV_SNOW_COVER) return 1.0;
-  if (L.to_type == RVN_SV_SNOW_LIQ) return ptab[M.glob_off + RVN_G_SNOW_SWI] * M.state[((size_t)e * M.NS + L.sv_snow) * M.nHp + k];
+  if (L.to_type == RVN_SV_SNOW_LIQ) return ptab[M.glob_off + RVN_G_SNOW_SWI] * M.state[RVN_STATE_OFF(M, e, L.sv_snow, k)];
   return D_ALMOST_INF;
 }
 
+// one state variable of one member across HRUs in the tiled state layout
+struct TiledRow {
+  double *base; const DevModel *M; int e, sv;
+  RVN_DI double &operator[](const int k) const { return base[RVN_STATE_OFF(*M, e, sv, k)]; }
+};
 __global__ void lateral_flush_kernel(const __grid_constant__ DevModel M, const DevLateral L) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)M.E * L.nchunks) return;
   const int e = (int)(idx / L.nchunks), c = (int)(idx - (long long)e * L.nchunks);
   const double tstep = M.opt.timestep;
-  double *from_row = M.state + ((size_t)e * M.NS + L.sv_from) * M.nHp, *to_row = M.state + ((size_t)e * M.NS + L.sv_to) * M.nHp;
+  const TiledRow from_row{M.state, &M, e, L.sv_from}, to_row{M.state, &M, e, L.sv_to};   // row[k] = state variable of HRU k (tiled layout)
   double *rates = L.rates + (size_t)e * L.nconn;
   const int q0 = L.chunk_ptr[c], q1 = L.chunk_ptr[c + 1];
   if (L.kind == RVN_LAT_EQUILIBRATE) {   // CmvLatEquilibrate::GetLateralExchange, src/LatEquilibrate.cpp:168-212; one chunk = one subbasin's pool
@@ -129,11 +134,11 @@ __global__ void __launch_bounds__(RVN_BS) finish_kernel(const __grid_constant__ 
   double swv = 0.0, stor = 0.0;
   if (enabled) {
     FinCtx c; c.P = P; c.area = M.hru_area[k];
-    double *gstate = M.state + (size_t)e * M.NS * nHp + k;
-    for (int s = 0; s < nCore; s++) c.sv[s] = gstate[(size_t)P->slot_sv[s] * nHp];
+    double *gstate = M.state + RVN_STATE_OFF(M, e, 0, k);
+    for (int s = 0; s < nCore; s++) c.sv[s] = gstate[(size_t)P->slot_sv[s] * RVN_TILE];
     swv = finish_step(c, nCore);
     stor = hru_storage(c, nCore) * c.area;
-    for (int s = 0; s < nCore; s++) gstate[(size_t)P->slot_sv[s] * nHp] = c.sv[s];
+    for (int s = 0; s < nCore; s++) gstate[(size_t)P->slot_sv[s] * RVN_TILE] = c.sv[s];
   }
   if (in_range) M.swvol[((size_t)slot * M.E + e) * nHp + k] = swv;
   const double bs = block_sum(stor, s_red);

@@ -6,7 +6,7 @@
 
 static const char *kForcingNames[RVN_F_COUNT] = {"PRECIP", "SNOW_FRAC", "TEMP_AVE", "TEMP_DAILY_AVE", "TEMP_DAILY_MIN", "TEMP_DAILY_MAX",
                                                  "PET", "OW_PET", "POTENTIAL_MELT", "TEMP_MONTH_AVE", "PET_MONTH_AVE",
-                                                 "AIR_PRES", "REL_HUMIDITY", "SW_RADIA", "WIND_VEL"};
+                                                 "AIR_PRES", "REL_HUMIDITY", "SW_RADIA", "WIND_VEL", "SW_RADIA_NET", "LW_RADIA_NET"};
 static_assert(sizeof(kForcingNames) / sizeof(kForcingNames[0]) == RVN_F_COUNT, "one name per rvn_forcing_field");
 
 CRavenBMI::CRavenBMI() : pModel(NULL), _sim(NULL), _duration(0.0) {}

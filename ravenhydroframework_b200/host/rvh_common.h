@@ -86,6 +86,8 @@ struct optStruct {
   int    air_pressure, rel_humidity, SW_radiation, SW_cloudcovercorr;   // rvn_airpress / rvn_relhum / rvn_sw_rad / rvn_sw_cloudcorr
   int    wind_velocity;         // rvn_windvel
   int    interception_factor;   // rvn_icept
+  int    LW_radiation = 0, SW_canopycorr = 0;   // rvn_options::lw_radiation / sw_canopycorr
+  std::string unsupported_radiation;   // first radiation method command the B200 build cannot honour (fatal only if net radiation is consumed)
   std::string unsupported_atmos;   // first atmospheric method command the B200 build cannot honour (fatal only if a consumer needs it)
   rvn_routing  routing;
   catchment_route catchment_routing;

@@ -374,7 +374,13 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
     for (int p = 0; p < NB; p++) if (_pSubBasins[p]->pReservoir && _pSubBasins[p]->pReservoir->_hru_k >= 0) uses_owpet = true;   // reservoir evaporation reads OW_PET of the linked HRU (src/Reservoir.cpp:1634)
     auto consumed = [&](int method) { return (uses_pet && O.evaporation == method) || (uses_owpet && O.ow_evaporation == method); };
     bool need_atmos = false;   // PET methods fed by air pressure / humidity / shortwave radiation
-    for (int mth = RVN_PET_TURC_1961; mth <= RVN_PET_HARGREAVES; mth++) if (consumed(mth)) need_atmos = true;
+    for (int mth = RVN_PET_TURC_1961; mth <= RVN_PET_PENMAN_COMBINATION; mth++) if (consumed(mth)) need_atmos = true;
+    // net shortwave / longwave radiation (src/UpdateForcings.cpp:591-606): energy-balance PET and potential-melt methods
+    const bool need_radiation = consumed(RVN_PET_PRIESTLEY_TAYLOR) || consumed(RVN_PET_PENMAN_COMBINATION) || O.pot_melt == RVN_POTMELT_EB || O.pot_melt == RVN_POTMELT_RESTRICTED;
+    if (need_radiation) need_atmos = true;
+    ExitGracefullyIf(need_radiation && !O.unsupported_radiation.empty(), "ParseMainInputFile: " + O.unsupported_radiation + " is not implemented in the B200 build");
+    ExitGracefullyIf(need_radiation && GetStateVarIndex(RVN_SV_SNOW_ALBEDO) != DOESNT_EXIST, "CModel::Flatten: net radiation with an evolving SNOW_ALBEDO state variable is not built (the default snow albedo 0.8 is)");
+    d.opt.need_radiation = need_radiation ? 1 : 0; d.opt.lw_radiation = O.LW_radiation; d.opt.sw_canopycorr = O.SW_canopycorr; d.opt.pad_opt_ = 0;
     for (int j = 0; j < NP; j++) if (_f_proc[j].op == RVN_OP_SUBLIMATION) need_atmos = true;   // reads air pressure, humidity, wind velocity
     ExitGracefullyIf(need_atmos && O.wind_velocity == RVN_WINDVEL_SQRT && (globals.v[RVN_G_WINDVEL_ICEPT] == NOT_SPECIFIED || globals.v[RVN_G_WINDVEL_SCALE] == NOT_SPECIFIED),
                      "CGlobalParams::AutoCalculateGlobalParams: required global parameters WINDVEL_ICEPT / WINDVEL_SCALE not specified");

@@ -8,16 +8,16 @@
 static const char *kSoilNames[RVN_S_COUNT] = {"POROSITY", "CAP_RATIO", "PERC_COEFF", "PET_CORRECTION", "BASEFLOW_COEFF", "BASEFLOW_N",
   "FIELD_CAPACITY", "SAT_WILT", "HBV_BETA", "MAX_CAP_RISE_RATE", "MAX_PERC_RATE", "GR4J_X2", "GR4J_X3", "VIC_B_EXP", "MAX_BASEFLOW_RATE", "MAX_INTERFLOW_RATE",
   "PERC_N", "SAC_PERC_ALPHA", "SAC_PERC_EXPON", "PERC_ASPEN", "BASEFLOW_THRESH", "BASEFLOW_COEFF2", "STORAGE_THRESHOLD", "VIC_ZMIN", "VIC_ZMAX",
-  "VIC_ALPHA", "VIC_EVAP_GAMMA", "UBC_EVAP_SOIL_DEF", "UBC_INFIL_SOIL_DEF"};
+  "VIC_ALPHA", "VIC_EVAP_GAMMA", "UBC_EVAP_SOIL_DEF", "UBC_INFIL_SOIL_DEF", "ALBEDO_WET", "ALBEDO_DRY"};
 static const char *kLUNames[RVN_LU_COUNT] = {"IMPERMEABLE_FRAC", "FOREST_COVERAGE", "FOREST_SPARSENESS", "MELT_FACTOR", "MIN_MELT_FACTOR",
   "MAX_MELT_FACTOR", "DD_MELT_TEMP", "DD_AGGRADATION", "REFREEZE_FACTOR", "DD_REFREEZE_TEMP", "REFREEZE_EXP", "HMETS_RUNOFF_COEFF",
   "GAMMA_SHAPE", "GAMMA_SCALE", "GAMMA_SHAPE2", "GAMMA_SCALE2", "GR4J_X4", "HBV_MELT_FOR_CORR", "HBV_MELT_ASP_CORR",
   "HBV_MELT_GLACIER_CORR", "HBV_GLACIER_KMIN", "GLAC_STORAGE_COEFF", "HBV_GLACIER_AG", "DEP_MAX", "LAKE_PET_CORR", "OW_PET_CORR",
   "PARTITION_COEFF", "CC_DECAY_COEFF", "MAX_SAT_AREA_FRAC", "PDM_B", "AET_COEFF", "MAX_DEP_AREA_FRAC", "PONDED_EXP", "AWBM_AREAFRAC1",
   "AWBM_AREAFRAC2", "HYMOD2_G", "HYMOD2_KMAX", "HYMOD2_EXP", "PET_LIN_COEFF", "RAIN_MELT_MULT", "RELHUM_CORR", "PET_VAP_COEFF",
-  "MIN_WIND_SPEED", "MAX_WIND_SPEED", "ABST_PERCENT"};
+  "MIN_WIND_SPEED", "MAX_WIND_SPEED", "ABST_PERCENT", "ROUGHNESS", "PRIESTLEYTAYLOR_COEFF"};
 static const char *kVegNames[RVN_V_COUNT] = {"MAX_HEIGHT", "MAX_LAI", "SAI_HT_RATIO", "MAX_CAPACITY", "MAX_SNOW_CAPACITY", "RAIN_ICEPT_PCT",
-  "SNOW_ICEPT_PCT", "PET_VEG_CORR", "RAIN_ICEPT_FACT", "SNOW_ICEPT_FACT", "VAR_CAPACITY", "VAR_SNOW_CAPACITY", "VAR_RAIN_ICEPT_PCT", "VAR_SNOW_ICEPT_PCT"};
+  "SNOW_ICEPT_PCT", "PET_VEG_CORR", "RAIN_ICEPT_FACT", "SNOW_ICEPT_FACT", "ALBEDO", "SVF_EXTINCTION", "VAR_CAPACITY", "VAR_SNOW_CAPACITY", "VAR_RAIN_ICEPT_PCT", "VAR_SNOW_ICEPT_PCT"};
 static const char *kGlobalNames[RVN_G_COUNT] = {"SNOW_SWI", "SNOW_SWI_MIN", "SNOW_SWI_MAX", "SWI_REDUCT_COEFF", "ADIABATIC_LAPSE", "PRECIP_LAPSE",
   "RAINSNOW_TEMP", "RAINSNOW_DELTA", "AVG_ANNUAL_SNOW", "SNOW_TEMPERATURE", "HBVEC_LAPSE_UPPER", "HBVEC_LAPSE_RATE", "HBVEC_LAPSE_ELEV",
   "AIRSNOW_COEFF", "AVG_ANNUAL_RUNOFF", "MAX_SWE_SURFACE", "TOC_MULTIPLIER", "TIME_TO_PEAK_MULTIPLIER", "GAMMA_SHAPE_MULTIPLIER",

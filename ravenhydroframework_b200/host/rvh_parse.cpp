@@ -59,7 +59,6 @@ static double ParseIntervalToken(const std::string &t, int calendar) {
 static const char *kIgnoredRVI[] = {":FileType", ":WrittenBy", ":CreationDate", ":Description", ":SilentMode", ":NoisyMode", ":QuietMode",
   ":EvaluationMetrics", ":CustomOutput", ":WriteForcingFunctions", ":WriteMassBalanceFile", ":WriteEnsimFormat", ":WriteNetCDFFormat",
   ":RunName", ":OutputDirectory", ":OutputInterval", ":SuppressOutput", ":DontWriteWatershedStorage", ":SnapshotHydrograph",
-  ":LWRadiationMethod", ":LWIncomingMethod",
   ":PavicsMode", ":DebugMode", ":WriteExhaustiveMB", ":HydrologicProcesses", ":EndHydrologicProcesses",
   ":WriteSubbasinFile", ":NetCDFAttribute", ":rvh_Filename", ":AggregatedVariable", ":BenchmarkingMode", NULL};
 
@@ -80,6 +79,8 @@ static rvn_pet ParsePET(const std::string &s) {
   if (s == "PET_VAPDEFICIT") return RVN_PET_VAPDEFICIT;
   if (s == "PET_LINACRE") return RVN_PET_LINACRE;
   if (s == "PET_HARGREAVES") return RVN_PET_HARGREAVES;
+  if (s == "PET_PRIESTLEY_TAYLOR") return RVN_PET_PRIESTLEY_TAYLOR;
+  if (s == "PET_PENMAN_COMBINATION") return RVN_PET_PENMAN_COMBINATION;
   ExitGracefully("ParseMainInputFile: evaporation method " + s + " is not implemented in the B200 build");
   return RVN_PET_NONE;
 }
@@ -230,7 +231,22 @@ static void ParseMainInputFile(CModel *&pModel, optStruct &Options) {
       if (Len >= 2 && s[1] != "NONE" && s[1] != "CLOUDCOV_NONE" && Options.unsupported_atmos.empty()) Options.unsupported_atmos = c + " " + s[1];
       continue;
     }
-    if (c == ":SWCanopyCorrect") { continue; }   // only scales the sub-canopy shortwave, which nothing built here consumes
+    if (c == ":SWCanopyCorrect") {   // src/ParseInput.cpp; CRadiation::SWCanopyCorrection (src/Radiation.cpp:377-415)
+      if (Len >= 2 && (s[1] == "SW_CANOPY_CORR_NONE" || s[1] == "NONE")) Options.SW_canopycorr = 0;
+      else if (Len >= 2 && (s[1] == "SW_CANOPY_CORR_STATIC" || s[1] == "STATIC")) Options.SW_canopycorr = 1;
+      else if (Options.unsupported_radiation.empty()) Options.unsupported_radiation = c + " " + (Len >= 2 ? s[1] : std::string());
+      continue;
+    }
+    if (c == ":LWRadiationMethod") {
+      if (Len >= 2 && (s[1] == "LW_RAD_DEFAULT" || s[1] == "DEFAULT")) Options.LW_radiation = 0;
+      else if (Len >= 2 && (s[1] == "LW_RAD_NONE" || s[1] == "NONE")) Options.LW_radiation = 1;
+      else if (Options.unsupported_radiation.empty()) Options.unsupported_radiation = c + " " + (Len >= 2 ? s[1] : std::string());
+      continue;
+    }
+    if (c == ":LWIncomingMethod") {
+      if (!(Len >= 2 && (s[1] == "LW_INC_DEFAULT" || s[1] == "DEFAULT")) && Options.unsupported_radiation.empty()) Options.unsupported_radiation = c + " " + (Len >= 2 ? s[1] : std::string());
+      continue;
+    }
     if (c == ":PotentialMeltMethod" || c == ":PotentialMelt") {
       if (s[1] == "POTMELT_DEGREE_DAY") Options.pot_melt = RVN_POTMELT_DEGREE_DAY;
       else if (s[1] == "POTMELT_HBV") Options.pot_melt = RVN_POTMELT_HBV;
@@ -239,6 +255,8 @@ static void ParseMainInputFile(CModel *&pModel, optStruct &Options) {
       else if (s[1] == "POTMELT_NONE") Options.pot_melt = RVN_POTMELT_NONE;
       else if (s[1] == "POTMELT_DD_FREEZE") Options.pot_melt = RVN_POTMELT_DD_FREEZE;
       else if (s[1] == "POTMELT_HBV_ROS") Options.pot_melt = RVN_POTMELT_HBV_ROS;
+      else if (s[1] == "POTMELT_EB") Options.pot_melt = RVN_POTMELT_EB;
+      else if (s[1] == "POTMELT_RESTRICTED") Options.pot_melt = RVN_POTMELT_RESTRICTED;
       else if (s[1] == "POTMELT_DD_RAIN")   // no parameter list in the reference (src/ModelParamCheck.cpp:98-175): DD_MELT_TEMP is then overridden by the -77777.7 "not needed" sentinel
         ExitGracefully("ParseMainInputFile: POTMELT_DD_RAIN is not supported by the B200 build (the reference evaluates it with an unset DD_MELT_TEMP)");
       else ExitGracefully("ParseMainInputFile: potential melt method " + s[1] + " is not implemented in the B200 build");
@@ -410,14 +428,14 @@ static void ParseParameterList(CParser &p, const char *endtok, FieldFn field_of,
 static int SoilFieldOrIgnore(const std::string &n) {
   int f = SoilFieldFromName(n);
   if (f >= 0) return f;
-  static const char *ign[] = {"SAND_CON", "CLAY_CON", "SILT_CON", "ORG_CON", "STONE_FRAC", "BULK_DENSITY", "HYDRAUL_COND", "ALBEDO_WET", "ALBEDO_DRY", NULL};
+  static const char *ign[] = {"SAND_CON", "CLAY_CON", "SILT_CON", "ORG_CON", "STONE_FRAC", "BULK_DENSITY", "HYDRAUL_COND", NULL};
   for (int i = 0; ign[i]; i++) if (n == ign[i]) return -1;
   return -2;
 }
 static int LUFieldOrIgnore(const std::string &n) {
   int f = LandUseFieldFromName(n);
   if (f >= 0) return f;
-  static const char *ign[] = {"ROUGHNESS", "FOREST_PET_CORR", "PDMROF_B", NULL};
+  static const char *ign[] = {"FOREST_PET_CORR", "PDMROF_B", NULL};
   for (int i = 0; ign[i]; i++) if (n == ign[i]) return -1;
   return -2;
 }
@@ -428,7 +446,7 @@ static int VegFieldOrIgnore(const std::string &n) {
   if (n == "RELATIVE_LAI") return 2001;
   int f = VegFieldFromName(n);
   if (f >= 0) return f;
-  static const char *ign[] = {"MAX_LEAF_COND", "ALBEDO", "ALBEDO_WET", "SVF_EXTINCTION", "MAX_INTERCEPT_RATE", "RAIN_ICEPT_FACT", "SNOW_ICEPT_FACT", NULL};
+  static const char *ign[] = {"MAX_LEAF_COND", "ALBEDO_WET", "MAX_INTERCEPT_RATE", NULL};
   for (int i = 0; ign[i]; i++) if (n == ign[i]) return -1;
   return -2;
 }
@@ -657,6 +675,10 @@ static void ParseClassPropertiesFile(CModel *pModel, const optStruct &Options) {
     if (S.v[RVN_S_POROSITY] == NOT_SPECIFIED) S.v[RVN_S_POROSITY] = 1.0;
     S.v[RVN_S_CAP_RATIO] = S.v[RVN_S_POROSITY] * (1.0 - 0.0);  // stone_frac autogenerates to 0 (src/SoilClass.cpp:93-99,113)
     if (S.v[RVN_S_PET_CORRECTION] == NOT_SPECIFIED) S.v[RVN_S_PET_CORRECTION] = 1.0;  // src/SoilClass.cpp PET_CORRECTION default
+    // bare-soil albedo: the reference initialises every soil class with 0.16 / 0.24 (CSoilClass::InitializeSoilProperties, src/SoilClass.cpp:397-398),
+    // so its sand-content autogeneration (:312-327) only runs for an explicit _AUTO
+    if (S.v[RVN_S_ALBEDO_WET] == NOT_SPECIFIED) S.v[RVN_S_ALBEDO_WET] = 0.16;
+    if (S.v[RVN_S_ALBEDO_DRY] == NOT_SPECIFIED) S.v[RVN_S_ALBEDO_DRY] = 0.24;
   }
   for (size_t k = 0; k < pModel->lu_classes.size(); k++) {
     surface_struct &S = pModel->lu_classes[k].S;
@@ -667,6 +689,8 @@ static void ParseClassPropertiesFile(CModel *pModel, const optStruct &Options) {
     if (S.v[RVN_LU_OW_PET_CORR] == NOT_SPECIFIED) S.v[RVN_LU_OW_PET_CORR] = 1.0;
     if (S.v[RVN_LU_MIN_WIND_SPEED] == NOT_SPECIFIED) S.v[RVN_LU_MIN_WIND_SPEED] = 1.0;   // src/LandUseClass.cpp:246-255
     if (S.v[RVN_LU_MAX_WIND_SPEED] == NOT_SPECIFIED) S.v[RVN_LU_MAX_WIND_SPEED] = 8.0;
+    if (S.v[RVN_LU_ROUGHNESS] == NOT_SPECIFIED) S.v[RVN_LU_ROUGHNESS] = 0.0;   // src/LandUseClass.cpp:85-91
+    if (S.v[RVN_LU_PRIESTLEYTAYLOR_COEFF] == NOT_SPECIFIED) S.v[RVN_LU_PRIESTLEYTAYLOR_COEFF] = 1.26;   // :190-194
     // autogenerated snow parameters (CLandUseClass::AutoCalculateLandUseProps, src/LandUseClass.cpp:100-160)
     if (S.v[RVN_LU_FOREST_COVERAGE] == NOT_SPECIFIED) S.v[RVN_LU_FOREST_COVERAGE] = 0.0;
     if (S.v[RVN_LU_MELT_FACTOR] == NOT_SPECIFIED) S.v[RVN_LU_MELT_FACTOR] = 5.04;
@@ -696,6 +720,8 @@ static void ParseClassPropertiesFile(CModel *pModel, const optStruct &Options) {
     if (V.v[RVN_V_SNOW_ICEPT_PCT] == NOT_SPECIFIED) V.v[RVN_V_SNOW_ICEPT_PCT] = 0.10;
     if (V.v[RVN_V_RAIN_ICEPT_FACT] == NOT_SPECIFIED) V.v[RVN_V_RAIN_ICEPT_FACT] = 0.06;   // src/VegetationClass.cpp:104-116
     if (V.v[RVN_V_SNOW_ICEPT_FACT] == NOT_SPECIFIED) V.v[RVN_V_SNOW_ICEPT_FACT] = 0.04;
+    if (V.v[RVN_V_SVF_EXTINCTION] == NOT_SPECIFIED) V.v[RVN_V_SVF_EXTINCTION] = 0.5;   // src/VegetationClass.cpp:79-86
+    if (V.v[RVN_V_ALBEDO] == NOT_SPECIFIED) V.v[RVN_V_ALBEDO] = 0.14;                  // :88-95
     const double max_LAI = V.v[RVN_V_MAX_LAI], max_SAI = V.v[RVN_V_SAI_HT_RATIO] * V.v[RVN_V_MAX_HEIGHT];
     if (V.v[RVN_V_MAX_CAPACITY] == NOT_SPECIFIED) V.v[RVN_V_MAX_CAPACITY] = 0.15 * (max_LAI + max_SAI);
     if (V.v[RVN_V_MAX_SNOW_CAPACITY] == NOT_SPECIFIED) V.v[RVN_V_MAX_SNOW_CAPACITY] = 0.6 * (max_LAI + max_SAI);
