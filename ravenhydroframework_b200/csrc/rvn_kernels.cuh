@@ -364,6 +364,7 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
   // 333-364) -- only when a consumed PET method needs them.  Geometry-only pieces (ET radiation on the slope and on the flat,
   // optical air mass) come from the host's per-date tables.
   double air_pres = 0.0, rel_hum = 0.0, SW_radia = 0.0, ET_radia = 0.0;
+  double SW_radia_net = 0.0, LW_radia_net = 0.0, veg_height = 0.0, veg_LAI = 0.0, veg_SAI = 0.0;   // net radiation and the canopy state behind it (opt.need_radiation)
   c.air_pres = 0.0; c.rel_hum = 0.0; c.wind_vel = 0.0;
   if (C::kAtmos && opt.need_atmos) {
     const double Tave = F[RVN_F_TEMP_AVE];
@@ -401,6 +402,80 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
       wind_vel = dmax(0.0, c.G(RVN_G_WINDVEL_SCALE) * (F[RVN_F_TEMP_DAILY_MAX] - F[RVN_F_TEMP_DAILY_MIN]) + c.G(RVN_G_WINDVEL_ICEPT));
     }
     c.air_pres = air_pres; c.rel_hum = rel_hum; c.wind_vel = wind_vel;
+    // net radiation (src/UpdateForcings.cpp:591-606): sub-canopy shortwave (CRadiation::SWCanopyCorrection, src/Radiation.cpp:377-415), total
+    // albedo above and below the canopy (CHydroUnit::GetTotalAlbedo, src/HydroUnits.cpp:728-781; snow albedo = DEFAULT_SNOW_ALBEDO), net
+    // longwave LW_RAD_DEFAULT with LW_INC_DEFAULT (src/Radiation.cpp:210-231), cloud cover 0; canopy variables of this step as
+    // CVegetationClass::RecalculateCanopyParams derives them (src/VegetationParams.cpp:85-142)
+    if (opt.need_radiation) {
+      const double rel_ht = M.veg_season[((size_t)step * M.nVeg + c.veg) * 2 + 0], rel_LAI = M.veg_season[((size_t)step * M.nVeg + c.veg) * 2 + 1];
+      const double max_height = c.VEG(RVN_V_MAX_HEIGHT), sparseness = c.LU(RVN_LU_FOREST_SPARSENESS), max_LAI = c.VEG(RVN_V_MAX_LAI);
+      const double SAI_ht_ratio = c.VEG(RVN_V_SAI_HT_RATIO), extinction = c.VEG(RVN_V_SVF_EXTINCTION), Fc = c.LU(RVN_LU_FOREST_COVERAGE);
+      veg_height = max_height * rel_ht;
+      veg_LAI = (1.0 - sparseness) * max_LAI * rel_LAI;
+      veg_SAI = (1.0 - sparseness) * (veg_height * SAI_ht_ratio);
+      const double svf = rvn_exp(-extinction * (veg_LAI + veg_SAI));
+      double canopy_corr = 1.0;
+      if (opt.sw_canopycorr == 1) canopy_corr = (1.0 - Fc) * 1.0 + Fc * rvn_exp(-extinction * (veg_LAI + veg_SAI));
+      const double SW_subcan = SW_radia * canopy_corr;
+      double land_albedo = 0.0;
+      const double snow_albedo = 0.8, snow_cov = SnowCover(c);
+      if (c.type == RVN_HRU_STANDARD) {
+        const double soil_sat = dmax(dmin(c.SV(c.soil_slot(0)) / SoilCapacity(c, 0), 1.0), 0.0);   // the stored state: nothing has moved yet this step
+        land_albedo = (soil_sat)*c.SOIL(0, RVN_S_ALBEDO_WET) + (1.0 - soil_sat) * c.SOIL(0, RVN_S_ALBEDO_DRY);
+      } else if (c.type == RVN_HRU_GLACIER || c.type == RVN_HRU_MASKED_GLACIER) land_albedo = 0.4;
+      else if (c.type == RVN_HRU_LAKE) land_albedo = 0.1;
+      else if (c.type == RVN_HRU_WATER) land_albedo = 0.1;
+      else if (c.type == RVN_HRU_ROCK) land_albedo = 0.35;
+      else if (c.type == RVN_HRU_WETLAND) land_albedo = 0.15;
+      land_albedo = (snow_cov)*snow_albedo + (1.0 - snow_cov) * land_albedo;
+      double veg_albedo = c.VEG(RVN_V_ALBEDO), svf2 = svf, land2 = land_albedo;
+      if (veg_albedo < 0) veg_albedo = 0.14;
+      if (svf2 > 1.0) svf2 = 0.0;
+      if (land2 < 0) land2 = 0.3;
+      const double albedo_above = (1.0 - svf2) * (Fc)*veg_albedo + ((svf2) * (Fc) + (1.0 - Fc)) * land2;
+      SW_radia_net = SW_radia * (1 - albedo_above);
+      const double SW_subcan_net = SW_subcan * (1 - land_albedo);
+      if (opt.lw_radiation == 1) LW_radia_net = 0.0;
+      else {
+        const double emissivity = 0.99, Tair = Tave + D_ZERO_CELSIUS, Tsurf = Tave + D_ZERO_CELSIUS;
+        const double ea = rel_hum * sat_vapor_pressure(Tave);
+        const double emiss_eff = 1.72 * rvn_pow(ea / Tair, 1 / 7.0);
+        double eps_at = emiss_eff * (1.0 + 0.22 * 0.0 * 0.0);
+        eps_at = (1 - Fc) * eps_at + (Fc)*1.0;
+        const double LW_incoming = 4.90e-9 * eps_at * rvn_pow(Tair, 4.0);
+        LW_radia_net = LW_incoming - 4.90e-9 * emissivity * rvn_pow(Tsurf, 4.0);
+      }
+      // potential melt from the energy balance (CModel::EstimatePotentialMelt, src/PotentialMelt.cpp:103-136; the reference evaluates it after
+      // the radiation terms, which is why these two methods sit here and not in the melt block above)
+      if (opt.pot_melt == RVN_POTMELT_EB) {   // GetSensibleHeatSnow / GetLatentHeatSnow / GetRainHeatInput, src/SnowParams.cpp:111-190
+        const double rainfall = F[RVN_F_PRECIP] * (1 - F[RVN_F_SNOW_FRAC]) + 0.0;
+        const double ref_ht = 2.0, roughness = c.LU(RVN_LU_ROUGHNESS), surf_temp = SnowTemperature(c);
+        double temp_var = rvn_pow(0.42 / rvn_log(ref_ht / roughness), 2.0);
+        const double H = 1.2466 * D_SPH_AIR * temp_var * wind_vel * D_SEC_PER_DAY * (Tave - surf_temp);
+        const double vap_pres = sat_vapor_pressure(Tave) * rel_hum, surf_pres = sat_vapor_pressure(surf_temp) * 1.0;
+        const double CE = rvn_pow(0.42, 2.0) / rvn_pow(rvn_log(ref_ht / roughness), 2.0);
+        temp_var = D_AIR_H20_MW_RAT * 1.2466 * CE / air_pres;
+        const double LH = 2.845 * temp_var * wind_vel * D_SEC_PER_DAY * (vap_pres - surf_pres);
+        double R = 0;
+        const double le = rvn_log(sat_vapor_pressure(Tave) * rel_hum);
+        const double rain_temp = (le + 0.4926) / (0.0708 - 0.00421 * le);   // GetDewPointTemp(e), src/CommonFunctions.cpp:1148-1156
+        if (surf_temp < D_FREEZING_TEMP) R = D_DENSITY_WATER * (rainfall / D_MM_PER_METER) * (D_SPH_WATER * (rain_temp - D_FREEZING_TEMP) + D_LH_FUSION);
+        if (surf_temp >= D_FREEZING_TEMP) R = D_DENSITY_WATER * (rainfall / D_MM_PER_METER) * (D_SPH_WATER * (rain_temp - D_FREEZING_TEMP));
+        double S = SW_subcan_net + LW_radia_net + H + LH + R;
+        S *= (D_MM_PER_METER / D_DENSITY_WATER / D_LH_FUSION);
+        F[RVN_F_POTENTIAL_MELT] = S;
+      } else if (opt.pot_melt == RVN_POTMELT_RESTRICTED) {
+        const double tmp_rate = dmax(c.LU(RVN_LU_MELT_FACTOR) * (F[RVN_F_TEMP_DAILY_AVE] - c.LU(RVN_LU_DD_MELT_TEMP)), 0.0);
+        const double rad = (SW_subcan_net + LW_radia_net);
+        const double convert = D_MM_PER_METER / D_DENSITY_WATER / D_LH_FUSION;
+        F[RVN_F_POTENTIAL_MELT] = tmp_rate * subdaily_corr + dmax(rad * convert, 0.0);
+      }
+      if (M.record_forcings) {
+        double *gf = M.forc + (size_t)e * RVN_F_COUNT * M.nHp + k;
+        gf[(size_t)RVN_F_SW_RADIA_NET * M.nHp] = SW_radia_net; gf[(size_t)RVN_F_LW_RADIA_NET * M.nHp] = LW_radia_net;
+        gf[(size_t)RVN_F_POTENTIAL_MELT * M.nHp] = F[RVN_F_POTENTIAL_MELT];
+      }
+    }
     if (M.record_forcings) {
       M.forc[((size_t)e * RVN_F_COUNT + RVN_F_WIND_VEL) * M.nHp + k] = wind_vel;
       double *gf = M.forc + (size_t)e * RVN_F_COUNT * M.nHp + k;
@@ -440,6 +515,40 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
       if (M.sunset_angle != nullptr) {
         const double cpet = c.G(RVN_G_MOHYSE_PET_COEFF), ws = M.sunset_angle[(size_t)M.et_row[step] * M.nHp + k];
         PET = cpet / D_PI * ws * rvn_exp((17.3 * F[RVN_F_TEMP_AVE]) / (238 + F[RVN_F_TEMP_AVE]));
+      }
+    } else if (C::kAtmos && (method == RVN_PET_PRIESTLEY_TAYLOR || method == RVN_PET_PENMAN_COMBINATION)) {
+      const double T = F[RVN_F_TEMP_AVE];
+      const double sat_vap = sat_vapor_pressure(T);
+      const double de_dT = (T > 0) ? 17.26939 * 237.3 / rvn_sqr(T + 237.3) * sat_vap : 21.87456 * 265.5 / rvn_sqr(T + 265.5) * sat_vap;   // GetSatVapSlope
+      const double LH_vapor = 2.495 - 0.002361 * T;
+      const double gamma = D_SPH_AIR / D_AIR_H20_MW_RAT * air_pres / LH_vapor;
+      if (method == RVN_PET_PRIESTLEY_TAYLOR) {   // PriestleyTaylorEvap  src/Evaporation.cpp:155-168
+        PET = c.LU(RVN_LU_PRIESTLEYTAYLOR_COEFF) * (de_dT / (de_dT + gamma)) * dmax(SW_radia_net + LW_radia_net, 0.0) / LH_vapor / D_DENSITY_WATER * D_MM_PER_METER;
+      } else {   // PET_PENMAN_COMBINATION  :404-416, PenmanCombinationEvap :119-144, canopy roughness after Brook90 ROUGH (src/VegetationParams.cpp:236-262)
+        const double SAI_ht_ratio = c.VEG(RVN_V_SAI_HT_RATIO), lu_rough = c.LU(RVN_LU_ROUGHNESS);
+        double closed_roughness, zero_pl, z0;
+        if (veg_height >= 10.0) closed_roughness = 0.05 * veg_height;
+        else if (veg_height <= 1.0) closed_roughness = 0.13 * veg_height;
+        else { closed_roughness = 0.13 * 1.0; closed_roughness += (0.05 * 10.0 - 0.13 * 1.0) * (veg_height - 1.0) / (10.0 - 1.0); }
+        const double closed_zerodisp = veg_height - closed_roughness / 0.3;
+        if (lu_rough > closed_roughness) closed_roughness = lu_rough;
+        const double ratio = (veg_LAI + veg_SAI) / (4.0 + SAI_ht_ratio * veg_height);
+        if (ratio >= 1.0) { zero_pl = closed_zerodisp; z0 = closed_roughness; }
+        else {
+          double xx = 0.0;
+          if (veg_height > D_REAL_SMALL) xx = ratio * rvn_pow(-1.0 + rvn_exp(0.909 - 3.03 * closed_zerodisp / veg_height), 4.0);
+          zero_pl = 1.1 * veg_height * rvn_log(1.0 + rvn_pow(xx, 0.25));
+          z0 = dmin(0.3 * (veg_height - zero_pl), lu_rough + 0.3 * veg_height * sqrt(xx));
+        }
+        const double ref_ht = veg_height + 2.0;
+        double numer = D_AIR_H20_MW_RAT * 1.2466;
+        double denom = air_pres * D_DENSITY_WATER * (1.0 / rvn_pow(0.42, 2.0) * (rvn_pow((rvn_log((ref_ht - zero_pl) / z0)), 2.0)));
+        const double vert_trans = numer / denom;   // GetVerticalTransportEfficiency  src/CommonFunctions.cpp:1083-1094
+        const double vapor_def = sat_vap * (1.0 - (rel_hum));
+        numer = de_dT * dmax((SW_radia_net) + (LW_radia_net), 0.0);
+        numer += gamma * vert_trans * D_DENSITY_WATER * LH_vapor * (c.wind_vel) * vapor_def;
+        denom = D_DENSITY_WATER * LH_vapor * (de_dT + gamma);
+        PET = dmax(0.0, (numer / denom)) * D_MM_PER_METER;
       }
     } else if (C::kAtmos && method >= RVN_PET_TURC_1961 && method <= RVN_PET_HARGREAVES) {
      if (method == RVN_PET_TURC_1961) {   // TurcEvap  src/Evaporation.cpp:61-68

@@ -384,6 +384,7 @@ static void ParseMainInputFile(CModel *&pModel, optStruct &Options) {
 struct ParamTable {  // [DEFAULT] row + per-class explicit cells for one class family
   std::map<int, double> def;                              // field -> default
   std::map<std::pair<int, int>, double> cell;             // (class, field) -> explicit value
+  std::set<int> no_default;                               // fields whose [DEFAULT] row the reference never applies (its class structs start from a literal)
 };
 template <class FieldFn>
 static void ParseParameterList(CParser &p, const char *endtok, FieldFn field_of, int (CModel::*find)(const std::string &) const,
@@ -418,7 +419,7 @@ static void ParseParameterList(CParser &p, const char *endtok, FieldFn field_of,
         if (is_default) T.def.erase(fields[i]); else T.cell[std::make_pair(c, fields[i])] = NOT_SPECIFIED;
         continue;
       }
-      if (is_default) T.def[fields[i]] = s_to_d(v);
+      if (is_default) { if (!T.no_default.count(fields[i])) T.def[fields[i]] = s_to_d(v); }
       else T.cell[std::make_pair(c, fields[i])] = s_to_d(v);
     }
   }
@@ -456,6 +457,9 @@ static void ParseClassPropertiesFile(CModel *pModel, const optStruct &Options) {
   ExitGracefullyIf(!p.ok(), "ParseClassPropertiesFile: cannot open " + Options.rvp_filename);
   std::vector<std::string> s;
   ParamTable Tsoil, Tlu, Tveg;
+  // ALBEDO_WET / ALBEDO_DRY of a soil class start at 0.16 / 0.24 (src/SoilClass.cpp:397-398), i.e. count as specified: SetCalculableValue never
+  // consults the [DEFAULT] template for them
+  Tsoil.no_default.insert(RVN_S_ALBEDO_WET); Tsoil.no_default.insert(RVN_S_ALBEDO_DRY);
   for (int f = 0; f < RVN_G_COUNT; f++) pModel->globals.v[f] = NOT_SPECIFIED;
   pModel->globals.v[RVN_G_TOC_MULTIPLIER] = pModel->globals.v[RVN_G_TIME_TO_PEAK_MULTIPLIER] = 1.0;
   pModel->globals.v[RVN_G_GAMMA_SHAPE_MULTIPLIER] = pModel->globals.v[RVN_G_GAMMA_SCALE_MULTIPLIER] = 1.0;

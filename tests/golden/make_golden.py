@@ -77,6 +77,22 @@ if hasattr(synth, "write_hbv"):
                                        rvi_extra=":RelativeHumidityMethod RELHUM_MINDEWPT\n",
                                        gauge_extra="  :MonthlyMinTemperature, -16.9, -13.1, -8.0, -2.6, 2.7, 7.0, 9.3, 8.2, 4.1, -1.0, -7.9, -14.2,\n"
                                                    "  :MonthlyMaxTemperature, -6.2, -1.8, 2.9, 8.6, 14.0, 17.8, 20.1, 19.2, 14.3, 8.1, 0.2, -4.7,\n")
+    # net radiation: total albedo above / below the canopy, default longwave, static canopy correction of shortwave, and the energy-balance PET
+    # and potential-melt methods on them.  PENMAN_COMBINATION is given every parameter it reads: the reference leaves those missing from its
+    # required-parameter list at the "not needed" marker instead of autogenerating them (src/ModelParamCheck.cpp:50-54)
+    _rad_rvp = (":VegetationParameterList\n  :Parameters, SAI_HT_RATIO, RELATIVE_LAI, RELATIVE_HT, SVF_EXTINCTION, ALBEDO\n  :Units, none, none, none, none, none\n"
+                "  [DEFAULT], 0.3, 0.9, 1.0, 0.45, 0.13\n  VEG_LOW, 0.1, 0.7, 0.8, 0.6, 0.18\n:EndVegetationParameterList\n"
+                ":LandUseParameterList\n  :Parameters, ROUGHNESS, FOREST_SPARSENESS, PRIESTLEYTAYLOR_COEFF\n  :Units, m, none, none\n  [DEFAULT], 0.02, 0.1, 1.26\n  LU_OPEN, 0.005, 0.3, 1.31\n:EndLandUseParameterList\n"
+                ":SoilParameterList\n  :Parameters, ALBEDO_WET, ALBEDO_DRY\n  :Units, none, none\n  [DEFAULT], 0.12, 0.27\n  TOPSOIL, 0.11, 0.29\n:EndSoilParameterList\n")
+    CASES["hbv_atm_priestley"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=101, routing="ROUTE_MUSKINGUM", pet="PET_PRIESTLEY_TAYLOR",
+                                      rvi_extra=":RelativeHumidityMethod RELHUM_MINDEWPT\n:OW_Evaporation PET_PRIESTLEY_TAYLOR\n")
+    CASES["hbv_atm_penmancomb"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=102, routing="ROUTE_MUSKINGUM", pet="PET_PENMAN_COMBINATION",
+                                       rvi_extra=":SWCanopyCorrect SW_CANOPY_CORR_STATIC\n:WindspeedMethod WINDVEL_UBC_MOD\n", rvp_extra=_rad_rvp)
+    CASES["gr4j_atm_potmelt_eb"] = dict(kind="gr4j", n_sb=2, hru_per_sb=4, n_days=400, seed=103, potmelt="POTMELT_EB", pet="PET_PRIESTLEY_TAYLOR",
+                                        rvi_extra=":SWCanopyCorrect SW_CANOPY_CORR_STATIC\n:RelativeHumidityMethod RELHUM_MINDEWPT\n:WindspeedMethod WINDVEL_UBC_MOD\n",
+                                        rvp_extra=":LandUseParameterList\n  :Parameters, ROUGHNESS\n  :Units, m\n  [DEFAULT], 0.003\n:EndLandUseParameterList\n")
+    CASES["hbv_atm_potmelt_restricted"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=104, routing="ROUTE_MUSKINGUM", potmelt="POTMELT_RESTRICTED",
+                                               pet="PET_PRIESTLEY_TAYLOR", rvi_extra=":LWRadiationMethod LW_RAD_DEFAULT\n")
     # snow sublimation (CmvSublimation), all five algorithms, over the wind-velocity estimators; HBV-EC has no SNOW_TEMP variable (snow
     # temperature = the SNOW_TEMPERATURE global), GR4J carries SNOW_TEMP as state
     _hbv_after = r"(    :-->Overflow     RAVEN_DEFAULT      SNOW_LIQ        PONDED_WATER\n)"

@@ -150,7 +150,10 @@ def test_gpu_matches_reference_golden(case):
         assert H.rel_err(np.array(res)[:, :, 5], g["res_losses"][:, sb]) < TOL
     if "_atm_" in case:                  # derived atmospheric forcings of the last step (reference force_struct columns)
         f = sim.forcings()[1]
-        for name, j in {"AIR_PRES": 18, "REL_HUMIDITY": 19, "SW_RADIA": 24, "WIND_VEL": 33, "PET": 34, "OW_PET": 35}.items():
+        cols = {"AIR_PRES": 18, "REL_HUMIDITY": 19, "SW_RADIA": 24, "WIND_VEL": 33, "PET": 34, "OW_PET": 35}
+        if case in ("hbv_atm_priestley", "hbv_atm_penmancomb", "gr4j_atm_potmelt_eb", "hbv_atm_potmelt_restricted"):   # net radiation and the melt on it
+            cols.update({"SW_RADIA_NET": 25, "LW_RADIA_NET": 28, "POTENTIAL_MELT": 32})
+        for name, j in cols.items():
             assert H.rel_err(f[:, api.FORCING_NAMES.index(name)], g["forc"][-1][:, j]) < TOL, name
     assert H.rel_err(sim.hydrographs(0, n)[:, 1, :], g["qout"]) < TOL
     assert H.rel_err(sim.watershed(0, n)[:, 1, :3], g["wshed"]) < TOL

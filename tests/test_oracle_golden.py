@@ -72,6 +72,8 @@ def test_oracle_matches_golden(case):
         idx.pop("OW_PET")   # :OW_Evaporation defaults to PET_HARGREAVES_1985 there; no HMETS process consumes OW_PET (not derived)
     if "_atm_" in case:   # PET from air pressure / relative humidity / shortwave radiation: the atmospheric chain is derived too
         idx.update({"AIR_PRES": 18, "REL_HUMIDITY": 19, "SW_RADIA": 24, "WIND_VEL": 33})
+    if case in ("hbv_atm_priestley", "hbv_atm_penmancomb", "gr4j_atm_potmelt_eb", "hbv_atm_potmelt_restricted"):   # net radiation consumed by the PET method
+        idx.update({"SW_RADIA_NET": 25, "LW_RADIA_NET": 28})
     for name, j in idx.items():
         mine = o["forc_rec"][steps - 1][:, :, api.FORCING_NAMES.index(name)]
         assert H.rel_err(mine, ref_f[:, :, j]) < TOL, name
