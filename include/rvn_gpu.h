@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RVN_ABI_VERSION 10
+#define RVN_ABI_VERSION 11
 #define RVN_DOESNT_EXIST (-1)
 #define RVN_CONV_STORES 50   /* MAX_CONVOL_STORES, reference src/RavenInclude.h / Convolution.cpp:17 */
 #define RVN_MAX_CONN 24      /* max connections of a non-convolution process (Precipitation: 13..19) */
@@ -135,6 +135,8 @@ typedef enum {
   RVN_OP_CANEVP_MAXIMUM,       /* CmvCanopyEvap           src/VegetationMovers.cpp:141-145                  */
   RVN_OP_CANEVP_RUTTER,        /* CmvCanopyEvap           src/VegetationMovers.cpp:133-140 (no TRUNK variable) */
   RVN_OP_CANSNOWEVP_MAXIMUM,   /* CmvCanopySublimation    src/VegetationMovers.cpp:312-317                  */
+  RVN_OP_INF_GREEN_AMPT,       /* CmvInfiltration         src/GreenAmpt.cpp:26-52,65-175; LambertN src/CommonFunctions.cpp:1572-1579 */
+  RVN_OP_INF_GA_SIMPLE,        /* CmvInfiltration         src/GreenAmpt.cpp:65-175 (event memory in CUM_INFIL / GA_MOISTURE_INIT, connections src/Infiltration.cpp:25-33) */
   RVN_OP_COUNT
 } rvn_opcode;
 
@@ -207,7 +209,7 @@ typedef enum {
   RVN_S_MAX_PERC_RATE, RVN_S_GR4J_X2, RVN_S_GR4J_X3, RVN_S_VIC_B_EXP, RVN_S_MAX_BASEFLOW_RATE, RVN_S_MAX_INTERFLOW_RATE,
   RVN_S_PERC_N, RVN_S_SAC_PERC_ALPHA, RVN_S_SAC_PERC_EXPON, RVN_S_PERC_ASPEN, RVN_S_BASEFLOW_THRESH, RVN_S_BASEFLOW_COEFF2,
   RVN_S_STORAGE_THRESHOLD, RVN_S_VIC_ZMIN, RVN_S_VIC_ZMAX, RVN_S_VIC_ALPHA, RVN_S_VIC_EVAP_GAMMA, RVN_S_UBC_EVAP_SOIL_DEF,
-  RVN_S_UBC_INFIL_SOIL_DEF, RVN_S_ALBEDO_WET, RVN_S_ALBEDO_DRY, RVN_S_COUNT
+  RVN_S_UBC_INFIL_SOIL_DEF, RVN_S_ALBEDO_WET, RVN_S_ALBEDO_DRY, RVN_S_HYDRAUL_COND, RVN_S_WETTING_FRONT_PSI, RVN_S_COUNT
 } rvn_soil_field;
 typedef enum { RVN_T_TOPMODEL_LAMBDA = 0, RVN_T_COUNT } rvn_terrain_field;   /* reference terrain_struct, src/Properties.h */
 

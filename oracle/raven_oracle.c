@@ -68,6 +68,27 @@ static double P_S(const octx *c, int m, int f) {
   return c->ptab[c->d->soil_off + cls * RVN_S_COUNT + f];
 }
 /* CHydroUnit::GetSoilCapacity, src/HydroUnits.cpp:260-267 */
+/* LambertN, src/CommonFunctions.cpp:1572-1579 */
+static double o_lambert_n(double x, int N) {
+  double sigma, tmp;
+  sigma = pow(-2.0 - 2.0 * log(-x), 0.5);
+  if (N <= 2) tmp = -1.0 - 0.5 * sigma * sigma - sigma / (1.0 + sigma / 6.3);
+  else tmp = o_lambert_n(x, N - 1);
+  return (1 + log(-x) - log(-tmp)) * tmp / (1 + tmp);
+}
+/* CmvInfiltration::GreenAmptCumInf, src/GreenAmpt.cpp:26-52 */
+static double o_green_ampt_cum_inf(double t, double alpha, double Ks, double w) {
+  if (Ks == 0) return 0.0;
+  if (w == 0) return 0.0;
+  if (alpha == 0) return 0.0;
+  double tp = alpha * Ks / w / (w - Ks);
+  if ((t < tp) || (w < Ks)) return w * t;
+  double tstar, x;
+  double Fp = w * tp;
+  tstar = Ks / alpha * (t - tp);
+  x = -(1.0 + Fp / alpha) * exp(-(1.0 + tstar + Fp / alpha));
+  return alpha * (-1.0 - o_lambert_n(x, 3));
+}
 static double soil_capacity(const octx *c, int m) {
   double thick = c->d->prof_thick[c->d->hru_profile[c->k] * RVN_MAX_SOIL_LAYERS + m];
   return thick * O_MM_PER_METER * P_S(c, m, RVN_S_CAP_RATIO);
@@ -679,7 +700,7 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       break;
     }
     case RVN_OP_INF_HMETS: case RVN_OP_INF_HBV: case RVN_OP_INF_GR4J: case RVN_OP_INF_VIC_ARNO: case RVN_OP_INF_RATIONAL:
-    case RVN_OP_INF_ALL_INFILTRATES: case RVN_OP_INF_VIC: case RVN_OP_INF_PRMS: case RVN_OP_INF_PDM: { /* src/Infiltration.cpp:304-330,384-398,477-489,491-514 + constraints :605-626 */
+    case RVN_OP_INF_ALL_INFILTRATES: case RVN_OP_INF_VIC: case RVN_OP_INF_PRMS: case RVN_OP_INF_PDM: case RVN_OP_INF_GREEN_AMPT: case RVN_OP_INF_GA_SIMPLE: { /* src/Infiltration.cpp:304-330,384-398,477-489,491-514 + constraints :605-626 */
       if (type != RVN_HRU_STANDARD && type != RVN_HRU_ROCK && type != RVN_HRU_MASKED_GLACIER) break;
       double Fimp = P_LU(c, RVN_LU_IMPERMEABLE_FRAC);
       double ponded = omax(sv[c->iSV[RVN_SV_PONDED_WATER]], 0.0);
@@ -740,6 +761,47 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
         infil = omin(infil, ponded);
         infil = (1.0 - Fimp) * infil / tstep;
         rates[0] = infil; rates[1] = rainthru - infil;
+      } else if (pr->op == RVN_OP_INF_GREEN_AMPT || pr->op == RVN_OP_INF_GA_SIMPLE) { /* CmvInfiltration::GetGreenAmptRunoff, src/GreenAmpt.cpp:65-175 */
+        double finf, cumInf = 0, Keff, alpha, deficit, runoff;
+        double Ksat = P_S(c, 0, RVN_S_HYDRAUL_COND), psi_wf = P_S(c, 0, RVN_S_WETTING_FRONT_PSI), poro = P_S(c, 0, RVN_S_POROSITY);
+        double stor = sv[iTo[0]], max_stor = soil_capacity(c, 0), initStor = 0;
+        int simple = (pr->op == RVN_OP_INF_GA_SIMPLE);
+        Keff = Ksat;
+        if (simple) {
+          cumInf = sv[iFrom[2]];
+          initStor = sv[iFrom[3]];
+          if (rainthru <= Keff) {
+            if (cumInf <= 0) { cumInf = 0; initStor = 0; }
+            else {
+              double distribution_rate = omax(cumInf * 2 / 3, Keff);
+              cumInf -= distribution_rate * tstep;
+              initStor += distribution_rate * tstep;
+              initStor = omin(initStor, stor);
+              if (cumInf <= 0) { cumInf = 0; initStor = 0; }
+            }
+            rates[2] = (cumInf - sv[iFrom[2]]) / tstep;
+            rates[3] = (initStor - sv[iFrom[3]]) / tstep;
+          }
+        }
+        if (rainthru <= O_REAL_SMALL) { rates[0] = 0; rates[1] = 0; }
+        else {
+          deficit = (1.0 - stor / max_stor) * poro;
+          alpha = psi_wf * deficit;
+          if (!simple) cumInf = o_green_ampt_cum_inf(tstep, alpha, Keff, rainthru);
+          else {
+            if (cumInf <= 0) { cumInf = o_green_ampt_cum_inf(tstep, alpha, Keff, rainthru); initStor = stor; }
+            else { deficit = (1.0 - initStor / max_stor) * poro; alpha = psi_wf * deficit; }
+          }
+          if (cumInf > 0) finf = Keff * (1.0 + alpha / cumInf); else finf = 0.0;
+          runoff = omax(rainthru - finf, 0.0);
+          runoff = (Fimp)*rainthru + (1 - Fimp) * runoff;
+          if (simple) {
+            cumInf += (rainthru - runoff) * tstep;
+            rates[2] = (cumInf - sv[iFrom[2]]) / tstep;
+            rates[3] = (initStor - sv[iFrom[3]]) / tstep;
+          }
+          rates[0] = rainthru - runoff; rates[1] = runoff;
+        }
       } else {
         double x1 = soil_capacity(c, 0), stor = sv[iTo[0]];
         double sat = stor / x1;

@@ -1615,15 +1615,16 @@ __device__ void da_apply(const DevModel &M, const int e, const int p, const int 
 #ifndef RVN_ROUTE_MINB
 #define RVN_ROUTE_MINB 32
 #endif
+#define RVN_ROUTE_LB ((RVN_ROUTE_BS) < 64 ? 64 : (RVN_ROUTE_BS))   // register budget of a 64-thread CTA (<= 32 registers) also when CTAs of one warp are launched
 // HRU -> subbasin aggregation + lateral inflow of every (member, basin): no order among basins, one full-width launch per step, so that the
 // per-level launches below carry only the ordered part of the chain
-__global__ void __launch_bounds__(RVN_ROUTE_BS, RVN_ROUTE_MINB) lateral_all_kernel(const __grid_constant__ DevModel M, const int slot, const int t) {
+__global__ void __launch_bounds__(RVN_ROUTE_LB, RVN_ROUTE_MINB) lateral_all_kernel(const __grid_constant__ DevModel M, const int slot, const int t) {
   const long long idx = (long long)blockIdx.x * RVN_ROUTE_BS + threadIdx.x;
   if (idx >= (long long)M.E * M.nSB) return;
   const int e = (int)(idx / M.nSB), p = (int)(idx - (long long)e * M.nSB);
   basin_lateral_inflow(M, e, p, slot, t);
 }
-__global__ void __launch_bounds__(RVN_ROUTE_BS, RVN_ROUTE_MINB) route_level_kernel(const __grid_constant__ DevModel M, const int lev0, const int nlev, const int slot, const int t, const int step) {
+__global__ void __launch_bounds__(RVN_ROUTE_LB, RVN_ROUTE_MINB) route_level_kernel(const __grid_constant__ DevModel M, const int lev0, const int nlev, const int slot, const int t, const int step) {
   const long long idx = (long long)blockIdx.x * RVN_ROUTE_BS + threadIdx.x;
   if (idx >= (long long)M.E * nlev) return;
   const int e = (int)(idx / nlev), i = (int)(idx - (long long)e * nlev);
@@ -1638,12 +1639,16 @@ __global__ void __launch_bounds__(RVN_ROUTE_BS, RVN_ROUTE_MINB) route_level_kern
 #define RVN_TAIL_MAX 2048
 #endif
 #define RVN_TAIL_BS 256
-__global__ void __launch_bounds__(RVN_TAIL_BS, 4) route_tail_kernel(const __grid_constant__ DevModel M, const int L0, const int slot, const int t, const int step) {
+#ifndef RVN_TAIL_BS_NARROW
+#define RVN_TAIL_BS_NARROW 32   // large ensembles: every tail level has a handful of basins per member - one warp per member, 32 registers (see RVN_ROUTE_BS)
+#endif
+template <int BS>
+__global__ void __launch_bounds__(BS < 64 ? 64 : BS, BS < 64 ? 32 : 4) route_tail_kernel(const __grid_constant__ DevModel M, const int L0, const int slot, const int t, const int step) {
   const int e = blockIdx.x;
   RouteTabs T; T.from_model(M);
   for (int L = L0; L < M.nLevels; L++) {
     const int lev0 = M.level_ptr[L], lev1 = M.level_ptr[L + 1];
-    for (int i = lev0 + threadIdx.x; i < lev1; i += RVN_TAIL_BS) basin_route(M, T, e, M.level_idx[i], t, step, slot);
+    for (int i = lev0 + threadIdx.x; i < lev1; i += BS) basin_route(M, T, e, M.level_idx[i], t, step, slot);
     __syncthreads();   // the next level reads this level's outflows (global memory, same CTA)
   }
 }
@@ -1715,7 +1720,7 @@ RVN_DI void balance_member(const DevModel &M, const int e, const int slot, const
     }
   }
 }
-__global__ void __launch_bounds__(RVN_ROUTE_BS, RVN_ROUTE_MINB) balance_kernel(const __grid_constant__ DevModel M, const int slot, const int rec, const int step) {
+__global__ void __launch_bounds__(RVN_ROUTE_LB, RVN_ROUTE_MINB) balance_kernel(const __grid_constant__ DevModel M, const int slot, const int rec, const int step) {
   __shared__ double s_red[RVN_ROUTE_BS / 32][5];
   balance_member<RVN_ROUTE_BS>(M, blockIdx.x, slot, rec, step, s_red);
 }

@@ -343,6 +343,26 @@ template <class C, class PR> RVN_DI void rates_GLACIERRELEASE_HBVEC(C &c, const 
   (void)pr;
 }
 
+// LambertN (src/CommonFunctions.cpp:1572-1579), N = 3: the recursion of the reference unrolled (sigma is the same at every depth)
+RVN_DI double lambert_n3(const double x) {
+  const double lx = rvn_log(-x);
+  const double sigma = rvn_pow(-2.0 - 2.0 * lx, 0.5);
+  double tmp = -1.0 - 0.5 * sigma * sigma - sigma / (1.0 + sigma / 6.3);
+  tmp = (1 + lx - rvn_log(-tmp)) * tmp / (1 + tmp);            // LambertN(x, 2)
+  return (1 + lx - rvn_log(-tmp)) * tmp / (1 + tmp);           // LambertN(x, 3)
+}
+// CmvInfiltration::GreenAmptCumInf  src/GreenAmpt.cpp:26-52
+RVN_DI double green_ampt_cum_inf(const double t, const double alpha, const double Ks, const double w) {
+  if (Ks == 0) return 0.0;
+  if (w == 0) return 0.0;
+  if (alpha == 0) return 0.0;
+  const double tp = alpha * Ks / w / (w - Ks);
+  if ((t < tp) || (w < Ks)) return w * t;
+  const double Fp = w * tp;
+  const double tstar = Ks / alpha * (t - tp);
+  const double x = -(1.0 + Fp / alpha) * rvn_exp(-(1.0 + tstar + Fp / alpha));
+  return alpha * (-1.0 - lambert_n3(x));
+}
 // CmvInfiltration INF_HMETS / INF_HBV / INF_GR4J  src/Infiltration.cpp:304-330, 384-398, 477-489, 491-514; ApplyConstraints :605-626
 template <class C, class PR> RVN_DI void rates_INFILTRATION(C &c, const PR &pr, const int op) {
   const double tstep = c.tstep;
@@ -404,6 +424,45 @@ template <class C, class PR> RVN_DI void rates_INFILTRATION(C &c, const PR &pr, 
     infil = dmin(infil, ponded);
     infil = (1.0 - Fimp) * infil / tstep;
     c.R(0) = infil; c.R(1) = rainthru - infil;
+  } else if (op == RVN_OP_INF_GREEN_AMPT || op == RVN_OP_INF_GA_SIMPLE) {   // src/GreenAmpt.cpp:65-175
+    const double Ksat = c.SOIL(0, RVN_S_HYDRAUL_COND), psi_wf = c.SOIL(0, RVN_S_WETTING_FRONT_PSI), poro = c.SOIL(0, RVN_S_POROSITY);
+    const double stor = c.SV(pr.to(0)), max_stor = SoilCapacity(c, 0);
+    const double Keff = Ksat;
+    double cumInf = 0, initStor = 0;
+    if (op == RVN_OP_INF_GA_SIMPLE) {   // rainfall-event memory: cumulative infiltration and the storage at the start of the event
+      const double cum0 = c.SV(pr.from(2)), init0 = c.SV(pr.from(3));
+      cumInf = cum0; initStor = init0;
+      if (rainthru <= Keff) {   // redistribution during periods of low rainfall
+        if (cumInf <= 0) { cumInf = 0; initStor = 0; }
+        else {
+          const double distribution_rate = dmax(cumInf * 2 / 3, Keff);
+          cumInf -= distribution_rate * tstep;
+          initStor += distribution_rate * tstep;
+          initStor = dmin(initStor, stor);
+          if (cumInf <= 0) { cumInf = 0; initStor = 0; }
+        }
+        c.R(2) = (cumInf - cum0) / tstep;
+        c.R(3) = (initStor - init0) / tstep;
+      }
+    }
+    if (rainthru <= D_REAL_SMALL) { c.R(0) = 0; c.R(1) = 0; }
+    else {
+      double deficit = (1.0 - stor / max_stor) * poro;
+      double alpha = psi_wf * deficit;
+      if (op == RVN_OP_INF_GREEN_AMPT) cumInf = green_ampt_cum_inf(tstep, alpha, Keff, rainthru);
+      else if (cumInf <= 0) { cumInf = green_ampt_cum_inf(tstep, alpha, Keff, rainthru); initStor = stor; }   // first step of a rainfall event
+      else { deficit = (1.0 - initStor / max_stor) * poro; alpha = psi_wf * deficit; }
+      double finf = 0.0;
+      if (cumInf > 0) finf = Keff * (1.0 + alpha / cumInf);
+      double runoff = dmax(rainthru - finf, 0.0);
+      runoff = (Fimp)*rainthru + (1 - Fimp) * runoff;
+      if (op == RVN_OP_INF_GA_SIMPLE) {
+        cumInf += (rainthru - runoff) * tstep;
+        c.R(2) = (cumInf - c.SV(pr.from(2))) / tstep;
+        c.R(3) = (initStor - c.SV(pr.from(3))) / tstep;
+      }
+      c.R(0) = rainthru - runoff; c.R(1) = runoff;
+    }
   } else if (op == RVN_OP_INF_GR4J) {
     double x1 = SoilCapacity(c, 0), stor = c.SV(pr.to(0));
     double sat = stor / x1;
@@ -692,7 +751,7 @@ template <class C, class PR> RVN_DI void dispatch_rates(C &c, const PR &pr, cons
     case RVN_OP_SNOWREFREEZE_DD: rates_SNOWREFREEZE_DD(c, pr); break;
     case RVN_OP_SNOTEMP_NEWTONS: rates_SNOTEMP_NEWTONS(c, pr); break;
     case RVN_OP_INF_HMETS: case RVN_OP_INF_HBV: case RVN_OP_INF_GR4J: case RVN_OP_INF_VIC_ARNO: case RVN_OP_INF_RATIONAL:
-    case RVN_OP_INF_ALL_INFILTRATES: case RVN_OP_INF_VIC: case RVN_OP_INF_PRMS: case RVN_OP_INF_PDM: rates_INFILTRATION(c, pr, op); break;
+    case RVN_OP_INF_ALL_INFILTRATES: case RVN_OP_INF_VIC: case RVN_OP_INF_PRMS: case RVN_OP_INF_PDM: case RVN_OP_INF_GREEN_AMPT: case RVN_OP_INF_GA_SIMPLE: rates_INFILTRATION(c, pr, op); break;
     case RVN_OP_SNOBAL_HBV: rates_SNOBAL_HBV(c, pr); break;
     case RVN_OP_INTERFLOW_PRMS: rates_INTERFLOW_PRMS(c, pr); break;
     case RVN_OP_SNOWMELT_POTMELT: rates_SNOWMELT_POTMELT(c, pr); break;

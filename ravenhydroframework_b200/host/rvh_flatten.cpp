@@ -206,6 +206,8 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
       {RVN_OP_SOILEVAP_SEQUEN, 'S', {RVN_S_FIELD_CAPACITY, RVN_S_SAT_WILT, -1}}, {RVN_OP_SOILEVAP_ROOT, 'S', {RVN_S_FIELD_CAPACITY, RVN_S_SAT_WILT, -1}},
       {RVN_OP_SOILEVAP_ROOT_CONSTRAIN, 'S', {RVN_S_FIELD_CAPACITY, RVN_S_SAT_WILT, -1}},
       {RVN_OP_SOILEVAP_AWBM, 'L', {RVN_LU_AWBM_AREAFRAC1, RVN_LU_AWBM_AREAFRAC2, -1}},
+      {RVN_OP_INF_GREEN_AMPT, 'S', {RVN_S_HYDRAUL_COND, RVN_S_WETTING_FRONT_PSI, -1}},
+      {RVN_OP_INF_GA_SIMPLE, 'S', {RVN_S_HYDRAUL_COND, RVN_S_WETTING_FRONT_PSI, -1}},
     };
     for (int r = 0; r < d.nProc; r++)
       if (d.proc[r].op == RVN_OP_ABSTRACTION) {   // CmvAbstraction::GetParticipatingParamList, src/Abstraction.cpp:100-150

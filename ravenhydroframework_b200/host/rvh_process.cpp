@@ -405,6 +405,15 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
                           : (s[1] == "INF_PRMS") ? RVN_OP_INF_PRMS : (s[1] == "INF_PDM") ? RVN_OP_INF_PDM : RVN_OP_INF_RATIONAL;
       p = new CmvGeneric("Infiltration", op, pM);
       p->Connect(iPond, iTop); p->Connect(iPond, iSW);
+    } else if (s[1] == "INF_GREEN_AMPT") {   // src/Infiltration.cpp:20-23 (the two default connections), src/GreenAmpt.cpp
+      p = new CmvGeneric("Infiltration", RVN_OP_INF_GREEN_AMPT, pM);
+      p->Connect(iPond, iTop); p->Connect(iPond, iSW);
+    } else if (s[1] == "INF_GA_SIMPLE") {   // src/Infiltration.cpp:25-33,244-249: tracks the cumulative infiltration of the running rainfall event
+      AddSVs(pM, {SVL(RVN_SV_CUM_INFIL, -1), SVL(RVN_SV_GA_MOISTURE_INIT, -1)});
+      p = new CmvGeneric("Infiltration", RVN_OP_INF_GA_SIMPLE, pM);
+      p->Connect(iPond, iTop); p->Connect(iPond, iSW);
+      const int iCum = pM->GetStateVarIndex(RVN_SV_CUM_INFIL), iGA = pM->GetStateVarIndex(RVN_SV_GA_MOISTURE_INIT);
+      p->Connect(iCum, iCum); p->Connect(iGA, iGA);
     } else {
       ExitGracefully("ParseMainInputFile: infiltration algorithm " + s[1] + " is not implemented in the B200 build");
     }

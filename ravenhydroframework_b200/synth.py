@@ -458,6 +458,20 @@ ALGO_SETS = {
     "h": dict(sevap="SOILEVAP_AWBM", inf="INF_PDM"),
     "i": dict(sevap="SOILEVAP_UBC"),
     "j": dict(sevap="SOILEVAP_HYPR", depression=True),
+    "k": dict(inf="INF_GREEN_AMPT", rvp=""":SoilParameterList
+  :Parameters, HYDRAUL_COND, WETTING_FRONT_PSI
+  :Units     ,         mm/d,               -mm
+    [DEFAULT],          4.5,             110.0
+     FAST_RES,         22.0,              75.0
+:EndSoilParameterList
+"""),
+    "l": dict(inf="INF_GA_SIMPLE", rvp=""":SoilParameterList
+  :Parameters, HYDRAUL_COND, WETTING_FRONT_PSI
+  :Units     ,         mm/d,               -mm
+    [DEFAULT],          4.5,             110.0
+     FAST_RES,         22.0,              75.0
+:EndSoilParameterList
+"""),
 }
 ALGO_RVP = """:SoilParameterList
   :Parameters, PERC_N, SAC_PERC_ALPHA, SAC_PERC_EXPON, PERC_ASPEN, BASEFLOW_THRESH, BASEFLOW_COEFF2, STORAGE_THRESHOLD, MAX_BASEFLOW_RATE, PERC_COEFF
@@ -502,7 +516,7 @@ def write_hbv(dirpath, n_sb=1, hru_per_sb=1, n_days=365, seed=1, routing="ROUTE_
         extra_rvp += ":SoilParameterList\n  :Parameters, MAX_INTERFLOW_RATE\n  :Units, mm/d\n  [DEFAULT], 0.0\n  FAST_RES, 7.25\n:EndSoilParameterList\n"
     algo = ALGO_SETS[variant[5:]] if (variant or "").startswith("algo:") else None
     if algo is not None:
-        extra_rvp += ALGO_RVP
+        extra_rvp += ALGO_RVP + algo.get("rvp", "")
     _write(base + ".rvp", HBV_RVP.format(extra=extra_rvp))
     with open(base + ".rvh", "w") as f:
         if single_class:

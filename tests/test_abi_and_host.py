@@ -20,7 +20,7 @@ def test_engine_exports_every_declared_symbol():
     lib = api.engine_lib()
     for n in names:
         assert hasattr(lib, n), "librvn_gpu.so does not export %s" % n
-    assert lib.rvn_gpu_abi_version() == 10
+    assert lib.rvn_gpu_abi_version() == 11
 
 
 def test_loaded_libraries_were_built_from_the_present_sources():
@@ -86,7 +86,7 @@ def test_product_path_does_not_touch_the_oracle():
 def test_unsupported_commands_fail_loudly(tmp_path):
     base = synth.write_hmets(str(tmp_path), n_sb=1, hru_per_sb=1, n_days=10)
     rvi = open(base + ".rvi").read()
-    open(base + ".rvi", "w").write(rvi.replace("INF_HMETS", "INF_GREEN_AMPT"))
+    open(base + ".rvi", "w").write(rvi.replace("INF_HMETS", "INF_SCS"))
     with pytest.raises(api.RavenError, match="not implemented"):
         api.RavenModel(base)
     open(base + ".rvi", "w").write(rvi + ":ReservoirDemandAllocation X\n")
