@@ -137,6 +137,7 @@ typedef enum {
   RVN_OP_CANSNOWEVP_MAXIMUM,   /* CmvCanopySublimation    src/VegetationMovers.cpp:312-317                  */
   RVN_OP_INF_GREEN_AMPT,       /* CmvInfiltration         src/GreenAmpt.cpp:26-52,65-175; LambertN src/CommonFunctions.cpp:1572-1579 */
   RVN_OP_INF_GA_SIMPLE,        /* CmvInfiltration         src/GreenAmpt.cpp:65-175 (event memory in CUM_INFIL / GA_MOISTURE_INIT, connections src/Infiltration.cpp:25-33) */
+  RVN_OP_INF_UBC,              /* CmvInfiltration         src/Infiltration.cpp:685-759 (GetUBCWMRunoff; connections :34-43; needs 4 soil layers) */
   RVN_OP_COUNT
 } rvn_opcode;
 
@@ -181,7 +182,7 @@ typedef enum {
   RVN_G_HBVEC_LAPSE_UPPER, RVN_G_HBVEC_LAPSE_RATE, RVN_G_HBVEC_LAPSE_ELEV, RVN_G_AIRSNOW_COEFF,
   RVN_G_AVG_ANNUAL_RUNOFF, RVN_G_MAX_SWE_SURFACE, RVN_G_TOC_MULTIPLIER, RVN_G_TIME_TO_PEAK_MULTIPLIER,
   RVN_G_GAMMA_SHAPE_MULTIPLIER, RVN_G_GAMMA_SCALE_MULTIPLIER, RVN_G_MOHYSE_PET_COEFF,
-  RVN_G_SNOW_ROUGHNESS, RVN_G_WINDVEL_ICEPT, RVN_G_WINDVEL_SCALE, RVN_G_COUNT
+  RVN_G_SNOW_ROUGHNESS, RVN_G_WINDVEL_ICEPT, RVN_G_WINDVEL_SCALE, RVN_G_UBC_GW_SPLIT, RVN_G_UBC_FLASH_PONDING, RVN_G_COUNT
 } rvn_global_field;
 typedef enum {
   RVN_LU_IMPERMEABLE_FRAC = 0, RVN_LU_FOREST_COVERAGE, RVN_LU_FOREST_SPARSENESS, RVN_LU_MELT_FACTOR,

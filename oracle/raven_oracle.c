@@ -700,7 +700,7 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       break;
     }
     case RVN_OP_INF_HMETS: case RVN_OP_INF_HBV: case RVN_OP_INF_GR4J: case RVN_OP_INF_VIC_ARNO: case RVN_OP_INF_RATIONAL:
-    case RVN_OP_INF_ALL_INFILTRATES: case RVN_OP_INF_VIC: case RVN_OP_INF_PRMS: case RVN_OP_INF_PDM: case RVN_OP_INF_GREEN_AMPT: case RVN_OP_INF_GA_SIMPLE: { /* src/Infiltration.cpp:304-330,384-398,477-489,491-514 + constraints :605-626 */
+    case RVN_OP_INF_ALL_INFILTRATES: case RVN_OP_INF_VIC: case RVN_OP_INF_PRMS: case RVN_OP_INF_PDM: case RVN_OP_INF_GREEN_AMPT: case RVN_OP_INF_GA_SIMPLE: case RVN_OP_INF_UBC: { /* src/Infiltration.cpp:304-330,384-398,477-489,491-514 + constraints :605-626 */
       if (type != RVN_HRU_STANDARD && type != RVN_HRU_ROCK && type != RVN_HRU_MASKED_GLACIER) break;
       double Fimp = P_LU(c, RVN_LU_IMPERMEABLE_FRAC);
       double ponded = omax(sv[c->iSV[RVN_SV_PONDED_WATER]], 0.0);
@@ -802,6 +802,25 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
           }
           rates[0] = rainthru - runoff; rates[1] = runoff;
         }
+      } else if (pr->op == RVN_OP_INF_UBC) { /* CmvInfiltration::GetUBCWMRunoff, src/Infiltration.cpp:685-759 */
+        const double V0FLAX = 1800.0;
+        double infil, to_GW, to_interflow, runoff, flash_factor, b1, b2;
+        double soil_deficit = omax(0.0, soil_capacity(c, 0) - sv[iTo[0]]);
+        double max_perc_rate = P_S(c, 1, RVN_S_MAX_PERC_RATE), P0AGEN = P_S(c, 0, RVN_S_UBC_INFIL_SOIL_DEF);
+        double P0DSH = P_G(c, RVN_G_UBC_GW_SPLIT), V0FLAS = P_G(c, RVN_G_UBC_FLASH_PONDING);
+        b1 = 1.0;
+        if (Fimp < 1.0) b1 = Fimp * pow(10.0, -soil_deficit / P0AGEN);
+        flash_factor = 0.0;
+        if (rainthru > V0FLAS) flash_factor = (1.0 + log(rainthru / V0FLAX) / log(V0FLAX / V0FLAS));
+        if (1.0 < flash_factor) flash_factor = 1.0; /* lowerswap */
+        if (0.0 > flash_factor) flash_factor = 0.0; /* upperswap */
+        b2 = (b1) * (1.0) + (1.0 - b1) * flash_factor;
+        infil = omin(soil_deficit / tstep, rainthru);
+        to_GW = omin(max_perc_rate, rainthru - infil);
+        to_interflow = (rainthru - infil - to_GW);
+        infil *= 1 - b2; to_GW *= 1 - b2; to_interflow *= 1 - b2;
+        runoff = rainthru - infil - to_GW - to_interflow;
+        rates[0] = infil; rates[1] = runoff; rates[2] = to_interflow; rates[3] = (1.0 - P0DSH) * to_GW; rates[4] = (P0DSH)*to_GW;
       } else {
         double x1 = soil_capacity(c, 0), stor = sv[iTo[0]];
         double sat = stor / x1;

@@ -463,6 +463,24 @@ template <class C, class PR> RVN_DI void rates_INFILTRATION(C &c, const PR &pr, 
       }
       c.R(0) = rainthru - runoff; c.R(1) = runoff;
     }
+  } else if (op == RVN_OP_INF_UBC) {   // GetUBCWMRunoff, src/Infiltration.cpp:685-759 (Quick 1995): topsoil deficit, groundwater and interflow shares, flash-flood factor
+    const double V0FLAX = 1800.0;
+    const double soil_deficit = dmax(0.0, SoilCapacity(c, 0) - c.SV(pr.to(0)));
+    const double max_perc_rate = c.SOIL(1, RVN_S_MAX_PERC_RATE), P0AGEN = c.SOIL(0, RVN_S_UBC_INFIL_SOIL_DEF);
+    const double P0DSH = c.G(RVN_G_UBC_GW_SPLIT), V0FLAS = c.G(RVN_G_UBC_FLASH_PONDING);
+    double b1 = 1.0;
+    if (Fimp < 1.0) b1 = Fimp * rvn_pow(10.0, -soil_deficit / P0AGEN);
+    double flash_factor = 0.0;
+    if (rainthru > V0FLAS) flash_factor = (1.0 + rvn_log(rainthru / V0FLAX) / rvn_log(V0FLAX / V0FLAS));
+    if (1.0 < flash_factor) flash_factor = 1.0;
+    if (0.0 > flash_factor) flash_factor = 0.0;
+    const double b2 = (b1) * (1.0) + (1.0 - b1) * flash_factor;
+    double infil = dmin(soil_deficit / tstep, rainthru);
+    double to_GW = dmin(max_perc_rate, rainthru - infil);
+    double to_interflow = (rainthru - infil - to_GW);
+    infil *= 1 - b2; to_GW *= 1 - b2; to_interflow *= 1 - b2;
+    const double runoff = rainthru - infil - to_GW - to_interflow;
+    c.R(0) = infil; c.R(1) = runoff; c.R(2) = to_interflow; c.R(3) = (1.0 - P0DSH) * to_GW; c.R(4) = (P0DSH)*to_GW;
   } else if (op == RVN_OP_INF_GR4J) {
     double x1 = SoilCapacity(c, 0), stor = c.SV(pr.to(0));
     double sat = stor / x1;
@@ -751,7 +769,7 @@ template <class C, class PR> RVN_DI void dispatch_rates(C &c, const PR &pr, cons
     case RVN_OP_SNOWREFREEZE_DD: rates_SNOWREFREEZE_DD(c, pr); break;
     case RVN_OP_SNOTEMP_NEWTONS: rates_SNOTEMP_NEWTONS(c, pr); break;
     case RVN_OP_INF_HMETS: case RVN_OP_INF_HBV: case RVN_OP_INF_GR4J: case RVN_OP_INF_VIC_ARNO: case RVN_OP_INF_RATIONAL:
-    case RVN_OP_INF_ALL_INFILTRATES: case RVN_OP_INF_VIC: case RVN_OP_INF_PRMS: case RVN_OP_INF_PDM: case RVN_OP_INF_GREEN_AMPT: case RVN_OP_INF_GA_SIMPLE: rates_INFILTRATION(c, pr, op); break;
+    case RVN_OP_INF_ALL_INFILTRATES: case RVN_OP_INF_VIC: case RVN_OP_INF_PRMS: case RVN_OP_INF_PDM: case RVN_OP_INF_GREEN_AMPT: case RVN_OP_INF_GA_SIMPLE: case RVN_OP_INF_UBC: rates_INFILTRATION(c, pr, op); break;
     case RVN_OP_SNOBAL_HBV: rates_SNOBAL_HBV(c, pr); break;
     case RVN_OP_INTERFLOW_PRMS: rates_INTERFLOW_PRMS(c, pr); break;
     case RVN_OP_SNOWMELT_POTMELT: rates_SNOWMELT_POTMELT(c, pr); break;

@@ -210,6 +210,13 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
       {RVN_OP_INF_GA_SIMPLE, 'S', {RVN_S_HYDRAUL_COND, RVN_S_WETTING_FRONT_PSI, -1}},
     };
     for (int r = 0; r < d.nProc; r++)
+      if (d.proc[r].op == RVN_OP_INF_UBC) {   // CmvInfiltration::GetParticipatingParamList, src/Infiltration.cpp:181-190 (UBC_FLASH_PONDING is autogenerated)
+        ExitGracefullyIf(globals.v[RVN_G_UBC_GW_SPLIT] == NOT_SPECIFIED, "CGlobalParams::AutoCalculateGlobalParams: required global parameter UBC_GW_SPLIT not specified");
+        for (size_t c = 0; c < soil_classes.size(); c++)
+          ExitGracefullyIf(soil_classes[c].S.v[RVN_S_MAX_PERC_RATE] == NOT_SPECIFIED || soil_classes[c].S.v[RVN_S_UBC_INFIL_SOIL_DEF] == NOT_SPECIFIED,
+                           "CSoilClass::AutoCalculateSoilProps: required parameter MAX_PERC_RATE / UBC_INFIL_SOIL_DEF not specified for soil class " + soil_classes[c].tag);
+      }
+    for (int r = 0; r < d.nProc; r++)
       if (d.proc[r].op == RVN_OP_ABSTRACTION) {   // CmvAbstraction::GetParticipatingParamList, src/Abstraction.cpp:100-150
         const int f = (d.proc[r].ia[0] == RVN_ABST_PERCENTAGE) ? RVN_LU_ABST_PERCENT : RVN_LU_DEP_MAX;
         for (size_t c = 0; c < lu_classes.size(); c++)

@@ -22,7 +22,8 @@ static const char *kVegNames[RVN_V_COUNT] = {"MAX_HEIGHT", "MAX_LAI", "SAI_HT_RA
 static const char *kGlobalNames[RVN_G_COUNT] = {"SNOW_SWI", "SNOW_SWI_MIN", "SNOW_SWI_MAX", "SWI_REDUCT_COEFF", "ADIABATIC_LAPSE", "PRECIP_LAPSE",
   "RAINSNOW_TEMP", "RAINSNOW_DELTA", "AVG_ANNUAL_SNOW", "SNOW_TEMPERATURE", "HBVEC_LAPSE_UPPER", "HBVEC_LAPSE_RATE", "HBVEC_LAPSE_ELEV",
   "AIRSNOW_COEFF", "AVG_ANNUAL_RUNOFF", "MAX_SWE_SURFACE", "TOC_MULTIPLIER", "TIME_TO_PEAK_MULTIPLIER", "GAMMA_SHAPE_MULTIPLIER",
-  "GAMMA_SCALE_MULTIPLIER", "MOHYSE_PET_COEFF", "SNOW_ROUGHNESS", "WINDVEL_ICEPT", "WINDVEL_SCALE"};
+  "GAMMA_SCALE_MULTIPLIER", "MOHYSE_PET_COEFF", "SNOW_ROUGHNESS", "WINDVEL_ICEPT", "WINDVEL_SCALE",
+  "UBC_GW_SPLIT", "UBC_FLASH_PONDING"};
 static int FindName(const char *const *tab, int n, const std::string &name) {
   for (int i = 0; i < n; i++) if (name == tab[i]) return i;
   return -1;

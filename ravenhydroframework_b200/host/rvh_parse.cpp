@@ -712,7 +712,8 @@ static void ParseClassPropertiesFile(CModel *pModel, const optStruct &Options) {
     static const struct { int f; double v; } gd[] = {
       {RVN_G_SNOW_SWI, 0.05}, {RVN_G_SNOW_SWI_MIN, 0.05}, {RVN_G_SNOW_SWI_MAX, 0.05}, {RVN_G_SNOW_TEMPERATURE, 0.0}, {RVN_G_RAINSNOW_TEMP, 0.15},
       {RVN_G_RAINSNOW_DELTA, 2.0}, {RVN_G_MAX_SWE_SURFACE, 100.0}, {RVN_G_ADIABATIC_LAPSE, 6.4}, {RVN_G_PRECIP_LAPSE, 0.0},
-      {RVN_G_HBVEC_LAPSE_RATE, 0.08}, {RVN_G_HBVEC_LAPSE_UPPER, 0.0}, {RVN_G_HBVEC_LAPSE_ELEV, 5000.0}, {RVN_G_SNOW_ROUGHNESS, 0.0002}};
+      {RVN_G_HBVEC_LAPSE_RATE, 0.08}, {RVN_G_HBVEC_LAPSE_UPPER, 0.0}, {RVN_G_HBVEC_LAPSE_ELEV, 5000.0}, {RVN_G_SNOW_ROUGHNESS, 0.0002},
+      {RVN_G_UBC_FLASH_PONDING, 36.0}};
     for (size_t i = 0; i < sizeof(gd) / sizeof(gd[0]); i++) if (G.v[gd[i].f] == NOT_SPECIFIED) G.v[gd[i].f] = gd[i].v;
   }
   for (size_t k = 0; k < pModel->veg_classes.size(); k++) {

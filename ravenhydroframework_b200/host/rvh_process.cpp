@@ -408,6 +408,12 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
     } else if (s[1] == "INF_GREEN_AMPT") {   // src/Infiltration.cpp:20-23 (the two default connections), src/GreenAmpt.cpp
       p = new CmvGeneric("Infiltration", RVN_OP_INF_GREEN_AMPT, pM);
       p->Connect(iPond, iTop); p->Connect(iPond, iSW);
+    } else if (s[1] == "INF_UBC") {   // src/Infiltration.cpp:34-43,250-256: topsoil, interflow, upper and lower groundwater stores
+      ExitGracefullyIf(pM->GetNumSoilLayers() < 4, "INF_UBCWM infiltration algorithm requires at least 4 soil layers to operate. Please use a different :SoilModel or replace this infiltration algorithm.");
+      AddSVs(pM, {SVL(RVN_SV_SOIL, 1), SVL(RVN_SV_SOIL, 2), SVL(RVN_SV_SOIL, 3)});
+      p = new CmvGeneric("Infiltration", RVN_OP_INF_UBC, pM);
+      p->Connect(iPond, iTop); p->Connect(iPond, iSW);
+      for (int m = 1; m <= 3; m++) p->Connect(iPond, pM->GetStateVarIndex(RVN_SV_SOIL, m));
     } else if (s[1] == "INF_GA_SIMPLE") {   // src/Infiltration.cpp:25-33,244-249: tracks the cumulative infiltration of the running rainfall event
       AddSVs(pM, {SVL(RVN_SV_CUM_INFIL, -1), SVL(RVN_SV_GA_MOISTURE_INIT, -1)});
       p = new CmvGeneric("Infiltration", RVN_OP_INF_GA_SIMPLE, pM);

@@ -52,6 +52,10 @@ if hasattr(synth, "write_hbv"):
     CASES["hbv_redist"] = dict(kind="hbv", n_sb=3, hru_per_sb=6, n_days=240, seed=43, routing="ROUTE_MUSKINGUM", variant="redistribute")
     CASES["hbv_redist_thresh"] = dict(kind="hbv", n_sb=3, hru_per_sb=6, n_days=240, seed=44, routing="ROUTE_MUSKINGUM", variant="redistribute_threshold")
     # PET estimated from temperature / day geometry instead of read or monthly (CModel::EstimatePET)
+    # INF_UBC (UBCWM infiltration: topsoil deficit, interflow, upper / lower groundwater shares, flash-flood factor) on the four soil stores of GR4J
+    CASES["gr4j_inf_ubc"] = dict(kind="gr4j", n_sb=2, hru_per_sb=4, n_days=400, seed=57, rvi_sub=[(r"INF_GR4J ", "INF_UBC  ")],
+                                 rvp_extra=":GlobalParameter UBC_GW_SPLIT 0.35\n:GlobalParameter UBC_FLASH_PONDING 12.0\n"
+                                           ":SoilParameterList\n  :Parameters, MAX_PERC_RATE, UBC_INFIL_SOIL_DEF\n  :Units, mm/d, mm\n  [DEFAULT], 6.5, 210.0\n:EndSoilParameterList\n")
     CASES["gr4j_pet_oudin"] = dict(kind="gr4j", n_sb=2, hru_per_sb=4, n_days=400, seed=51, pet="PET_OUDIN")
     CASES["gr4j_pet_hamon"] = dict(kind="gr4j", n_sb=2, hru_per_sb=4, n_days=400, seed=52, pet="PET_HAMON")
     CASES["hbv_pet_lintemp"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=53, routing="ROUTE_MUSKINGUM", pet="PET_LINEAR_TEMP",
