@@ -138,6 +138,7 @@ typedef enum {
   RVN_OP_INF_GREEN_AMPT,       /* CmvInfiltration         src/GreenAmpt.cpp:26-52,65-175; LambertN src/CommonFunctions.cpp:1572-1579 */
   RVN_OP_INF_GA_SIMPLE,        /* CmvInfiltration         src/GreenAmpt.cpp:65-175 (event memory in CUM_INFIL / GA_MOISTURE_INIT, connections src/Infiltration.cpp:25-33) */
   RVN_OP_INF_UBC,              /* CmvInfiltration         src/Infiltration.cpp:685-759 (GetUBCWMRunoff; connections :34-43; needs 4 soil layers) */
+  RVN_OP_SNOBAL_COLD_CONTENT,  /* CmvSnowBalance          src/SnowBalance.cpp:732-835 (ColdContentBalance, Brook90 SNOENRGY / SNOPACK; connections :41-55); needs day_length */
   RVN_OP_COUNT
 } rvn_opcode;
 

@@ -48,6 +48,7 @@ typedef struct {
   const double *phi_old;  /* stored (start-of-step) state: what pHRU->GetStateVarValue returns */
   double canopy_cap, canopy_snow_cap; /* veg_var_struct capacity / snow_capacity for this HRU and step */
   double rain_icept_pct, snow_icept_pct; /* veg_var_struct interception fractions, src/VegetationParams.cpp:143-166 */
+  double veg_LAI, veg_SAI, day_length;   /* veg_var_struct LAI / SAI and force_struct day_length of this HRU and step (SNOBAL_COLD_CONTENT) */
   int iSV[RVN_SV_NTYPES]; /* first index of each SV type, or -1 */
 } octx;
 
@@ -1050,6 +1051,56 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       rates[pr->nconn - 1] -= corr;
       break;
     }
+    case RVN_OP_SNOBAL_COLD_CONTENT: { /* CmvSnowBalance::ColdContentBalance, src/SnowBalance.cpp:732-835 */
+      const double CCFAC = 0.3, MELT_FAC = 1.5, LAIMLT = 0.2, SAIMLT = 0.5, LH_FUSION = 0.334, SPH_ICE = 2.100e-3, SPH_WATER = 4.186e-3;
+      const double SWI = P_G(c, RVN_G_SNOW_SWI);
+      double Ta = F[RVN_F_TEMP_DAILY_AVE], day_length = c->day_length;
+      double CC = sv[iFrom[0]], SL = sv[iFrom[1]], S = sv[iFrom[3]];
+      double LAI = c->veg_LAI, SAI = c->veg_SAI;
+      double incoming_snow_en, pot_melt, CC_air, liq_snow_cap, rainthru = 0.0, Tsnow, instant_refreeze;
+      double refreeze, cooling, warming, melt_to_liq, melt_to_SW, shrinking_poro, eq_en_avail;
+      if (S == 0) break;
+      if ((CC > 0) && (SL > 0)) {
+        instant_refreeze = omin(SL / tstep, CC / LH_FUSION / tstep);
+        rates[1] += instant_refreeze;
+        rates[0] -= instant_refreeze * LH_FUSION;
+        SL -= rates[1] * tstep;
+      }
+      Tsnow = O_FREEZING_TEMP - CC / S / SPH_ICE;
+      if (Ta <= O_FREEZING_TEMP) incoming_snow_en = CCFAC * 2.0 * day_length * (Ta - Tsnow);
+      else incoming_snow_en = MELT_FAC * 2.0 * day_length * (Ta - O_FREEZING_TEMP) * exp(-SAIMLT * SAI) * exp(-LAIMLT * LAI);
+      incoming_snow_en += rainthru * omax(Ta - O_FREEZING_TEMP, 0.0) * SPH_WATER * O_DENSITY_WATER / O_MM_PER_METER;
+      pot_melt = incoming_snow_en * (1.0 / O_DENSITY_WATER / LH_FUSION * O_MM_PER_METER);
+      CC_air = (O_FREEZING_TEMP - Ta) * SPH_ICE * S;
+      liq_snow_cap = SWI * S; /* CalculateSnowLiquidCapacity, src/SnowParams.cpp:79-88 */
+      if (pot_melt <= 0) {
+        refreeze = omin(SL / tstep, -pot_melt);
+        rates[1] += refreeze;
+        pot_melt += refreeze;
+        cooling = omin(-pot_melt, 0.0) * LH_FUSION;
+        cooling = omin(cooling, (CC_air - CC) / tstep);
+        rates[2] += cooling;
+      } else {
+        if ((pot_melt * LH_FUSION < CC / tstep) || (Ta < O_FREEZING_TEMP)) {
+          warming = pot_melt * LH_FUSION;
+          warming = omin(warming, -(CC - CC_air) / tstep);
+          rates[0] -= warming;
+        } else {
+          eq_en_avail = pot_melt;
+          warming = CC / tstep;
+          rates[0] += warming;
+          eq_en_avail -= warming / LH_FUSION;
+          melt_to_liq = omin(eq_en_avail, (liq_snow_cap - SL) / tstep);
+          rates[1] -= melt_to_liq;
+          eq_en_avail -= melt_to_liq;
+          melt_to_SW = omin(eq_en_avail, S / tstep - melt_to_liq);
+          rates[3] += melt_to_SW;
+          shrinking_poro = melt_to_SW * SWI;
+          rates[4] += shrinking_poro;
+        }
+      }
+      break;
+    }
     case RVN_OP_SNOBAL_HBV: { /* src/SnowBalance.cpp:430-465; liquid capacity src/SnowParams.cpp:79-88 */
       double Ka = P_LU(c, RVN_LU_REFREEZE_FACTOR), Ta = F[RVN_F_TEMP_DAILY_AVE];
       double melt, refreeze, liq_cap, to_liq, overflow;
@@ -1298,6 +1349,8 @@ static void canopy_capacities(octx *c, int step) {
   double height = max_height * rel_ht;
   double LAI = (1.0 - sparseness) * max_LAI * rel_LAI;
   double SAI = (1.0 - sparseness) * (height * SAI_ht_ratio);
+  c->veg_LAI = LAI; c->veg_SAI = SAI;
+  c->day_length = d->day_length ? d->day_length[(size_t)d->et_row[step] * d->nHRU + c->k] : 0.0;
   if (d->opt.interception_factor == RVN_ICEPT_USER) { c->rain_icept_pct = P_V(c, RVN_V_RAIN_ICEPT_PCT); c->snow_icept_pct = P_V(c, RVN_V_SNOW_ICEPT_PCT); }
   else if (d->opt.interception_factor == RVN_ICEPT_LAI) {
     c->rain_icept_pct = omin(P_V(c, RVN_V_RAIN_ICEPT_FACT) * (LAI + SAI), 1.0);

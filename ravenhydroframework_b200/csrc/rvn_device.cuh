@@ -121,5 +121,6 @@ struct DevModel {
   int32_t assimilate_flow; double assimilation_fact;
   const uint8_t *da_override; const double *da_obsQ, *da_obsQ2, *da_decay, *da_wt, *sb_drain_area, *sb_da_corr;
   double *da_adjust, *da_mass;
+  int need_cc;   // the process list holds SNOBAL_COLD_CONTENT: the sweep derives LAI / SAI / day length of every HRU (CtxCommon::veg_LAI ...)
 };
 #endif

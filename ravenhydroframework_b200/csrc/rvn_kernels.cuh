@@ -49,6 +49,7 @@ struct CtxCommon {
   double tstep;
   double canopy_cap, canopy_snow_cap;   // veg_var_struct capacity / snow_capacity of this HRU for this step
   double rain_icept_pct, snow_icept_pct; // veg_var_struct interception fractions (:PrecipIceptFract)
+  double veg_LAI, veg_SAI, day_length;   // veg_var_struct LAI / SAI and force_struct day_length of this HRU and step: set when the process list holds SNOBAL_COLD_CONTENT (M.need_cc)
   int type, lu, veg, profile;
   bool linked;   // HRU linked to a reservoir (CHydroUnit::IsLinkedToReservoir)
   const double *ptab;      // member parameter row (shared memory)
@@ -852,8 +853,15 @@ RVN_DI void load_hru_statics(C &c, const DevModel &M, int k, const double *s_pta
 // canopy storage capacities of this HRU for this step: CVegetationClass::RecalculateCanopyParams (src/VegetationParams.cpp:85-135).
 // The month-interpolated relative height / LAI of each vegetation class depend on the date only and are hoisted to the
 // host (veg_season[step][veg][2]); everything else is evaluated here in the reference's order.
-template <class C> RVN_DI void load_canopy(C &c, const DevModel &M, int step) {
+template <class C> RVN_DI void load_canopy(C &c, const DevModel &M, int step, int k) {
   c.canopy_cap = 0.0; c.canopy_snow_cap = 0.0;
+  if (C::kAtmos && M.need_cc) {   // what ColdContentBalance reads from the HRU (src/SnowBalance.cpp:745-753)
+    const double rel_ht = M.veg_season[((size_t)step * M.nVeg + c.veg) * 2 + 0], rel_LAI = M.veg_season[((size_t)step * M.nVeg + c.veg) * 2 + 1];
+    const double sparseness = c.LU(RVN_LU_FOREST_SPARSENESS);
+    c.veg_LAI = (1.0 - sparseness) * c.VEG(RVN_V_MAX_LAI) * rel_LAI;
+    c.veg_SAI = (1.0 - sparseness) * ((c.VEG(RVN_V_MAX_HEIGHT) * rel_ht) * c.VEG(RVN_V_SAI_HT_RATIO));
+    c.day_length = M.day_length[(size_t)M.et_row[step] * M.nHp + k];
+  }
   const int icept = C::kAtmos ? c.opt().interception_factor : (int)RVN_ICEPT_USER;
   if (icept == RVN_ICEPT_USER) { c.rain_icept_pct = c.VEG(RVN_V_VAR_RAIN_ICEPT_PCT); c.snow_icept_pct = c.VEG(RVN_V_VAR_SNOW_ICEPT_PCT); }
   else { c.rain_icept_pct = 0.0; c.snow_icept_pct = 0.0; }
@@ -1026,7 +1034,7 @@ __global__ void __launch_bounds__(RVN_BS, RVN_STATIC_MIN_BLOCKS) hru_sweep_stati
 #pragma unroll
       for (int f = 0; f < RVN_F_CARRIED; f++) c.F[f] = 0.0;
     }
-    load_canopy(c, M, step);   // (class, date) only: placed after the forcing chain so that its results are not live across it
+    load_canopy(c, M, step, k);   // (class, date) only: placed after the forcing chain so that its results are not live across it
     if (enabled) reboot_diagnostics(c);   // disabled HRUs keep their stored values (the reference never writes them back, :701)
     // ---- ordered-series process sweep on the newest state
     RunProcs<Prog, UNIT_DT, 0>::run(c, M, enabled, mask, e, k, gstate, (M.conv_sum_valid != 0) || (MULTI && ss > 0));
@@ -1112,7 +1120,7 @@ __global__ void __launch_bounds__(RVN_BS, RVN_INTERP_MIN_BLOCKS) hru_sweep_inter
   if (enabled) compute_forcings(c, M, e, k, step, sb);
   else { for (int f = 0; f < RVN_F_CARRIED; f++) c.F[f] = 0.0; }
   if (M.nRes > 0 && enabled && c.linked) export_reservoir_forcing(c, M, e, k, slot0 + ss);
-  load_canopy(c, M, step);
+  load_canopy(c, M, step, k);
   if (enabled) reboot_diagnostics(c);
   if (euler || heun) { for (int s = 0; s < nCore; s++) c.SVW(s) = c.SV(s); }   // aPhinew = aPhi (src/Solvers.cpp:155-200); rates come from aPhi
   const bool unit_dt = (c.tstep == 1.0);

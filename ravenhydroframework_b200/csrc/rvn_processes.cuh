@@ -714,6 +714,55 @@ template <class C, class PR> RVN_DI void rates_SOILEVAP(C &c, const PR &pr, cons
   c.R(last) -= corr;
 }
 
+// CmvSnowBalance SNOBAL_COLD_CONTENT  src/SnowBalance.cpp:732-835 (ColdContentBalance, adapted there from Brook90 SNOENRGY / SNOPACK);
+// connections :41-55: COLD_CONTENT -> ENERGY_LOSSES, SNOW_LIQ -> SNOW, ENERGY_LOSSES -> COLD_CONTENT, SNOW -> PONDED, SNOW_LIQ -> PONDED
+template <class C, class PR> RVN_DI void rates_SNOBAL_COLD_CONTENT(C &c, const PR &pr) {
+  const double CCFAC = 0.3, MELT_FAC = 1.5, LAIMLT = 0.2, SAIMLT = 0.5, SPH_ICE = 2.100e-3;
+  const double SWI = c.G(RVN_G_SNOW_SWI), tstep = c.tstep;
+  const double Ta = c.F[RVN_F_TEMP_DAILY_AVE], day_length = c.day_length;
+  const double CC = c.SV(pr.from(0)), S = c.SV(pr.from(3));
+  double SL = c.SV(pr.from(1));
+  const double rainthru = 0.0;
+  if (S == 0) return;
+  if ((CC > 0) && (SL > 0)) {   // instant equilibrium of cold content and liquid water
+    const double instant_refreeze = dmin(SL / tstep, CC / D_LH_FUSION / tstep);
+    c.R(1) += instant_refreeze;
+    c.R(0) -= instant_refreeze * D_LH_FUSION;
+    SL -= c.R(1) * tstep;
+  }
+  const double Tsnow = D_FREEZING_TEMP - CC / S / SPH_ICE;
+  double incoming_snow_en;
+  if (Ta <= D_FREEZING_TEMP) incoming_snow_en = CCFAC * 2.0 * day_length * (Ta - Tsnow);
+  else incoming_snow_en = MELT_FAC * 2.0 * day_length * (Ta - D_FREEZING_TEMP) * rvn_exp(-SAIMLT * c.veg_SAI) * rvn_exp(-LAIMLT * c.veg_LAI);
+  incoming_snow_en += rainthru * dmax(Ta - D_FREEZING_TEMP, 0.0) * D_SPH_WATER * D_DENSITY_WATER / D_MM_PER_METER;
+  double pot_melt = incoming_snow_en * (1.0 / D_DENSITY_WATER / D_LH_FUSION * D_MM_PER_METER);
+  const double CC_air = (D_FREEZING_TEMP - Ta) * SPH_ICE * S;
+  const double liq_snow_cap = SWI * S;   // CalculateSnowLiquidCapacity, src/SnowParams.cpp:79-88
+  if (pot_melt <= 0) {   // negative energy balance: refreeze, then cool (not below the air temperature)
+    const double refreeze = dmin(SL / tstep, -pot_melt);
+    c.R(1) += refreeze;
+    pot_melt += refreeze;
+    double cooling = dmin(-pot_melt, 0.0) * D_LH_FUSION;
+    cooling = dmin(cooling, (CC_air - CC) / tstep);
+    c.R(2) += cooling;
+  } else if ((pot_melt * D_LH_FUSION < CC / tstep) || (Ta < D_FREEZING_TEMP)) {   // energy only reduces the cold content
+    double warming = pot_melt * D_LH_FUSION;
+    warming = dmin(warming, -(CC - CC_air) / tstep);
+    c.R(0) -= warming;
+  } else {   // all cold content lost, the rest melts: into the pack's liquid capacity first, then out
+    double eq_en_avail = pot_melt;
+    const double warming = CC / tstep;
+    c.R(0) += warming;
+    eq_en_avail -= warming / D_LH_FUSION;
+    const double melt_to_liq = dmin(eq_en_avail, (liq_snow_cap - SL) / tstep);
+    c.R(1) -= melt_to_liq;
+    eq_en_avail -= melt_to_liq;
+    const double melt_to_SW = dmin(eq_en_avail, S / tstep - melt_to_liq);
+    c.R(3) += melt_to_SW;
+    c.R(4) += melt_to_SW * SWI;
+  }
+}
+
 // CmvSnowBalance SNOBAL_HBV  src/SnowBalance.cpp:430-465 (connections :56-70; CalculateSnowLiquidCapacity src/SnowParams.cpp:79-88)
 template <class C, class PR> RVN_DI void rates_SNOBAL_HBV(C &c, const PR &pr) {
   const double Ka = c.LU(RVN_LU_REFREEZE_FACTOR), Ta = c.F[RVN_F_TEMP_DAILY_AVE], tstep = c.tstep;
@@ -764,6 +813,7 @@ template <class C, class PR> RVN_DI void dispatch_rates(C &c, const PR &pr, cons
   switch (op) {   // uniform across the CTA: every thread runs the same process at the same time
     case RVN_OP_PRECIPITATION: rates_PRECIPITATION(c, pr); break;
     case RVN_OP_SNOBAL_HMETS: rates_SNOBAL_HMETS(c, pr); break;
+    case RVN_OP_SNOBAL_COLD_CONTENT: rates_SNOBAL_COLD_CONTENT(c, pr); break;
     case RVN_OP_SNOBAL_SIMPLE_MELT: rates_SNOBAL_SIMPLE_MELT(c, pr); break;
     case RVN_OP_SNOBAL_CEMA_NEIGE: rates_SNOBAL_CEMA_NEIGE(c, pr); break;
     case RVN_OP_SNOWREFREEZE_DD: rates_SNOWREFREEZE_DD(c, pr); break;

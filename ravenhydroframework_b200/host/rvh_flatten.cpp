@@ -406,7 +406,9 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
     d.opt.need_atmos = need_atmos ? 1 : 0;
     d.opt.air_pressure = O.air_pressure; d.opt.rel_humidity = O.rel_humidity; d.opt.sw_radiation = O.SW_radiation; d.opt.sw_cloudcorr = O.SW_cloudcovercorr; d.opt.wind_velocity = O.wind_velocity; d.opt.interception_factor = O.interception_factor;
     const bool need_et = consumed(RVN_PET_HARGREAVES_1985) || consumed(RVN_PET_OUDIN) || need_atmos;
-    const bool need_dl = consumed(RVN_PET_HAMON), need_ws = consumed(RVN_PET_MOHYSE);
+    bool uses_cc = false;   // ColdContentBalance reads force_struct::day_length (src/SnowBalance.cpp:746)
+    for (int j = 0; j < NP; j++) if (_f_proc[j].op == RVN_OP_SNOBAL_COLD_CONTENT) uses_cc = true;
+    const bool need_dl = consumed(RVN_PET_HAMON) || uses_cc, need_ws = consumed(RVN_PET_MOHYSE);
     ExitGracefullyIf(need_et && O.SW_radiation == RVN_SW_RAD_NONE, "CModel::Flatten: :SWRadiationMethod SW_RAD_NONE leaves the extraterrestrial radiation unset; PET methods that read it are not built for that case");
     ExitGracefullyIf((consumed(RVN_PET_OUDIN) || need_dl || need_ws || consumed(RVN_PET_LINEAR_TEMP)) && O.timestep < 1.0 - 0.0001,
                      "CModel::Flatten: PET_OUDIN / PET_HAMON / PET_MOHYSE / PET_LINEAR_TEMP are built for daily steps only in the B200 build");

@@ -377,6 +377,12 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
       int iSnow = pM->GetStateVarIndex(RVN_SV_SNOW), iSL = pM->GetStateVarIndex(RVN_SV_SNOW_LIQ), iSoil = pM->GetStateVarIndex(RVN_SV_SOIL, 0);
       p = new CmvGeneric("SnowBalance", RVN_OP_SNOBAL_HBV, pM);
       p->Connect(iSnow, iSL); p->Connect(iSnow, iSoil); p->Connect(iSL, iSoil); p->Connect(iSnow, iPond); p->Connect(iSL, iPond);
+    } else if (s[1] == "SNOBAL_COLD_CONTENT") {   // src/SnowBalance.cpp:41-55 (connections), :287-295 (state variables, in this order)
+      AddSVs(pM, {SVL(RVN_SV_SNOW_LIQ, -1), SVL(RVN_SV_COLD_CONTENT, -1), SVL(RVN_SV_ENERGY_LOSSES, -1), SVL(RVN_SV_SURFACE_WATER, -1), SVL(RVN_SV_SNOW, -1)});
+      const int iSnow = pM->GetStateVarIndex(RVN_SV_SNOW), iSL = pM->GetStateVarIndex(RVN_SV_SNOW_LIQ);
+      const int iCC = pM->GetStateVarIndex(RVN_SV_COLD_CONTENT), iEn = pM->GetStateVarIndex(RVN_SV_ENERGY_LOSSES);
+      p = new CmvGeneric("SnowBalance", RVN_OP_SNOBAL_COLD_CONTENT, pM);
+      p->Connect(iCC, iEn); p->Connect(iSL, iSnow); p->Connect(iEn, iCC); p->Connect(iSnow, iPond); p->Connect(iSL, iPond);
     } else if (s[1] == "SNOBAL_CEMA_NIEGE" || s[1] == "SNOBAL_CEMA_NEIGE") {
       AddSVs(pM, {SVL(RVN_SV_SNOW, -1), SVL(RVN_SV_PONDED_WATER, -1), SVL(RVN_SV_SNOW_COVER, -1)});
       int iSnow = pM->GetStateVarIndex(RVN_SV_SNOW), iSC = pM->GetStateVarIndex(RVN_SV_SNOW_COVER);

@@ -56,6 +56,11 @@ if hasattr(synth, "write_hbv"):
     CASES["gr4j_inf_ubc"] = dict(kind="gr4j", n_sb=2, hru_per_sb=4, n_days=400, seed=57, rvi_sub=[(r"INF_GR4J ", "INF_UBC  ")],
                                  rvp_extra=":GlobalParameter UBC_GW_SPLIT 0.35\n:GlobalParameter UBC_FLASH_PONDING 12.0\n"
                                            ":SoilParameterList\n  :Parameters, MAX_PERC_RATE, UBC_INFIL_SOIL_DEF\n  :Units, mm/d, mm\n  [DEFAULT], 6.5, 210.0\n:EndSoilParameterList\n")
+    # SNOBAL_COLD_CONTENT (Brook90-style energy balance of the pack: cold content, refreeze, liquid holding capacity) with the cold content of
+    # new snow added by the precipitation partition; reads day length and the canopy LAI / SAI
+    CASES["hbv_snobal_coldcontent"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=58, routing="ROUTE_MUSKINGUM",
+                                           rvi_sub=[(r"  :SnowBalance       SNOBAL_SIMPLE_MELT SNOW            SNOW_LIQ\n    :-->Overflow     RAVEN_DEFAULT      SNOW_LIQ        PONDED_WATER\n",
+                                                     "  :SnowBalance       SNOBAL_COLD_CONTENT SNOW           PONDED_WATER\n")])
     CASES["gr4j_pet_oudin"] = dict(kind="gr4j", n_sb=2, hru_per_sb=4, n_days=400, seed=51, pet="PET_OUDIN")
     CASES["gr4j_pet_hamon"] = dict(kind="gr4j", n_sb=2, hru_per_sb=4, n_days=400, seed=52, pet="PET_HAMON")
     CASES["hbv_pet_lintemp"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=53, routing="ROUTE_MUSKINGUM", pet="PET_LINEAR_TEMP",
