@@ -139,6 +139,8 @@ typedef enum {
   RVN_OP_INF_GA_SIMPLE,        /* CmvInfiltration         src/GreenAmpt.cpp:65-175 (event memory in CUM_INFIL / GA_MOISTURE_INIT, connections src/Infiltration.cpp:25-33) */
   RVN_OP_INF_UBC,              /* CmvInfiltration         src/Infiltration.cpp:685-759 (GetUBCWMRunoff; connections :34-43; needs 4 soil layers) */
   RVN_OP_SNOBAL_COLD_CONTENT,  /* CmvSnowBalance          src/SnowBalance.cpp:732-835 (ColdContentBalance, Brook90 SNOENRGY / SNOPACK; connections :41-55); needs day_length */
+  RVN_OP_SNOBAL_GAWSER,        /* CmvSnowBalance          src/SnowBalance.cpp:1098-1201 (GawserBalance: refreeze, density-based compaction, fixed sublimation; connections :123-145) */
+  RVN_OP_SNOBAL_CRHM_EBSM,     /* CmvSnowBalance          src/SnowBalance.cpp:1214-1291 (CRHMSnowBalance, Marks et al. energy budget; connections :146-158) */
   RVN_OP_COUNT
 } rvn_opcode;
 

@@ -1051,6 +1051,80 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       rates[pr->nconn - 1] -= corr;
       break;
     }
+    case RVN_OP_SNOBAL_GAWSER: { /* CmvSnowBalance::GawserBalance, src/SnowBalance.cpp:1098-1201 */
+      double SWC = sv[iFrom[0]], rainthru = sv[iFrom[1]], snow_liq = sv[iFrom[2]], snow_depth = sv[iFrom[3]], newSnow = sv[iFrom[6]];
+      double KF = P_LU(c, RVN_LU_REFREEZE_FACTOR), KM = P_LU(c, RVN_LU_MELT_FACTOR), SWI = P_G(c, RVN_G_SNOW_SWI);
+      double RHOICE = O_DENSITY_ICE / O_DENSITY_WATER, MRHO = 0.35, a = 0.1, b = 96, NEWDEN = 0.1;
+      double TEMPs = F[RVN_F_TEMP_AVE], TBAS = 0;
+      double MELTP = 0, REFRZP = 0;
+      if (TEMPs < TBAS) { REFRZP = tstep * KF * (TBAS - TEMPs); }
+      if (TEMPs > TBAS) { MELTP = tstep * KM * (TEMPs - TBAS); }
+      double RHO = 0;
+      if (SWC > 0) { RHO = omin(MRHO, SWC / snow_depth); }
+      double POR = 1 - RHO / RHOICE;
+      double snow_liqAP = POR * snow_depth * SWI;
+      double RAIN_IN_1 = 0, MELT_1 = 0, MELT_2 = 0, EXCESS_snow_liq = 0;
+      double REFRZ = 0;
+      if (TBAS > TEMPs) { REFRZ = omin(REFRZP, snow_liq); }
+      double SWC2 = SWC + REFRZ;
+      double RHO2 = omin(MRHO, SWC2 / snow_depth);
+      double snow_liq2 = snow_liq - REFRZ;
+      if (snow_liq2 >= snow_liqAP) { EXCESS_snow_liq = snow_liq2 - snow_liqAP; MELT_2 = omin(MELTP, SWC); }
+      else { MELT_1 = omin(MELTP, SWC); RAIN_IN_1 = rainthru; }
+      double KC = b * exp(-1 * a * TEMPs);
+      double TRHO = (RHO2 * MRHO) / (RHO2 + (MRHO - RHO2) * exp(-1 * tstep * 24 / KC));
+      double compaction = 0;
+      if (SWC2 > 0) { compaction = snow_depth - SWC2 / TRHO; }
+      double snowmelt = 0;
+      if (SWC2 > 0) { snowmelt = (MELT_1 + MELT_2) / TRHO; }
+      double SUBLIM = 0;
+      if (TEMPs < 0) { SUBLIM = 2.4 * tstep; }
+      if (SWC2 - MELT_1 - MELT_2 < SUBLIM) { SUBLIM = omax(omin(SUBLIM, SWC2 - MELT_1 - MELT_2), 0.0); }
+      double SUBLIM_snow_depth = 0;
+      if (SWC2 > 0) { SUBLIM_snow_depth = SUBLIM / TRHO; }
+      rates[0] = MELT_1 / tstep;
+      rates[1] = RAIN_IN_1 / tstep;
+      rates[2] = REFRZ / tstep;
+      rates[3] = -compaction / tstep;
+      rates[4] = -(snowmelt + SUBLIM_snow_depth) / tstep;
+      rates[5] = newSnow / NEWDEN / tstep;
+      rates[6] = newSnow / tstep;
+      rates[7] = SUBLIM / tstep;
+      rates[8] = EXCESS_snow_liq / tstep;
+      rates[9] = MELT_2 / tstep;
+      break;
+    }
+    case RVN_OP_SNOBAL_CRHM_EBSM: { /* CmvSnowBalance::CRHMSnowBalance, src/SnowBalance.cpp:1214-1291 */
+      const double LH_FUSION = 0.334;
+      double snow_liq = sv[c->iSV[RVN_SV_SNOW_LIQ]], SWE = sv[c->iSV[RVN_SV_SNOW]], snow_energy = -sv[c->iSV[RVN_SV_COLD_CONTENT]];
+      double snow_energy_old = snow_energy;
+      if (SWE <= 0.0) break;
+      double pot_melt = F[RVN_F_POTENTIAL_MELT], T_min = F[RVN_F_TEMP_DAILY_MIN];
+      pot_melt *= LH_FUSION * O_DENSITY_WATER / O_MM_PER_METER * tstep;
+      double snoliq_max = P_G(c, RVN_G_SNOW_SWI) * SWE;
+      double t_minus = omin(T_min, 0.0);
+      double Umin = SWE * (2.115 + 0.00779 * t_minus) * t_minus;
+      double refreeze = 0.0, snowmelt0 = 0.0, snowmelt1 = 0.0, snowmelt2 = 0.0;
+      snow_energy += pot_melt;
+      snow_energy = omax(Umin, snow_energy);
+      if (snow_energy > 0.0) {
+        double B = 0.95;
+        double melt = snow_energy / LH_FUSION / O_DENSITY_WATER * O_MM_PER_METER / B;
+        if (melt > (snoliq_max - snow_liq)) {
+          if (SWE > melt) { snowmelt0 = snoliq_max - snow_liq; snowmelt1 = melt - (snoliq_max - snow_liq); snowmelt2 = 0.0; }
+          else { snowmelt0 = 0; snowmelt1 = SWE; snowmelt2 = snow_liq; }
+        } else { snowmelt0 = melt; snowmelt1 = 0; snowmelt2 = 0; }
+        snow_energy = 0.0;
+      } else {
+        snowmelt0 = snowmelt1 = snowmelt2 = 0;
+        refreeze = -snow_energy / LH_FUSION / O_DENSITY_WATER * O_MM_PER_METER;
+        if (snow_liq > refreeze) { snow_energy = 0.0; }
+        else { snow_energy += snow_liq * LH_FUSION * O_DENSITY_WATER / O_MM_PER_METER; refreeze = snow_liq; }
+      }
+      rates[0] = snowmelt0; rates[1] = snowmelt1; rates[2] = snowmelt2; rates[3] = refreeze;
+      rates[4] = -(snow_energy - snow_energy_old) / tstep;
+      break;
+    }
     case RVN_OP_SNOBAL_COLD_CONTENT: { /* CmvSnowBalance::ColdContentBalance, src/SnowBalance.cpp:732-835 */
       const double CCFAC = 0.3, MELT_FAC = 1.5, LAIMLT = 0.2, SAIMLT = 0.5, LH_FUSION = 0.334, SPH_ICE = 2.100e-3, SPH_WATER = 4.186e-3;
       const double SWI = P_G(c, RVN_G_SNOW_SWI);

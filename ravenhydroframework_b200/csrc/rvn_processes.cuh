@@ -763,6 +763,82 @@ template <class C, class PR> RVN_DI void rates_SNOBAL_COLD_CONTENT(C &c, const P
   }
 }
 
+// CmvSnowBalance SNOBAL_GAWSER  src/SnowBalance.cpp:1098-1201 (GawserBalance); connections :123-145: SNOW -> SNOW_LIQ, PONDED -> SNOW_LIQ, SNOW_LIQ -> SNOW,
+// three SNOW_DEPTH self-connections (compaction, melt + sublimation, snowfall), NEW_SNOW -> SNOW, SNOW -> ATMOSPHERE, SNOW_LIQ -> PONDED, SNOW -> PONDED
+template <class C, class PR> RVN_DI void rates_SNOBAL_GAWSER(C &c, const PR &pr) {
+  const double tstep = c.tstep;
+  const double SWC = c.SV(pr.from(0)), rainthru = c.SV(pr.from(1)), snow_liq = c.SV(pr.from(2)), snow_depth = c.SV(pr.from(3)), newSnow = c.SV(pr.from(6));
+  const double KF = c.LU(RVN_LU_REFREEZE_FACTOR), KM = c.LU(RVN_LU_MELT_FACTOR), SWI = c.G(RVN_G_SNOW_SWI);
+  const double RHOICE = D_DENSITY_ICE / D_DENSITY_WATER, MRHO = 0.35, a = 0.1, b = 96, NEWDEN = 0.1;
+  const double TEMPs = c.F[RVN_F_TEMP_AVE], TBAS = 0;
+  double MELTP = 0, REFRZP = 0;
+  if (TEMPs < TBAS) REFRZP = tstep * KF * (TBAS - TEMPs);
+  if (TEMPs > TBAS) MELTP = tstep * KM * (TEMPs - TBAS);
+  double RHO = 0;
+  if (SWC > 0) RHO = dmin(MRHO, SWC / snow_depth);
+  const double POR = 1 - RHO / RHOICE;
+  const double snow_liqAP = POR * snow_depth * SWI;
+  double RAIN_IN_1 = 0, MELT_1 = 0, MELT_2 = 0, EXCESS_snow_liq = 0, REFRZ = 0;
+  if (TBAS > TEMPs) REFRZ = dmin(REFRZP, snow_liq);
+  const double SWC2 = SWC + REFRZ;
+  const double RHO2 = dmin(MRHO, SWC2 / snow_depth);
+  const double snow_liq2 = snow_liq - REFRZ;
+  if (snow_liq2 >= snow_liqAP) { EXCESS_snow_liq = snow_liq2 - snow_liqAP; MELT_2 = dmin(MELTP, SWC); }
+  else { MELT_1 = dmin(MELTP, SWC); RAIN_IN_1 = rainthru; }
+  const double KC = b * rvn_exp(-1 * a * TEMPs);
+  const double TRHO = (RHO2 * MRHO) / (RHO2 + (MRHO - RHO2) * rvn_exp(-1 * tstep * 24 / KC));
+  double compaction = 0, snowmelt = 0, SUBLIM = 0, SUBLIM_snow_depth = 0;
+  if (SWC2 > 0) compaction = snow_depth - SWC2 / TRHO;
+  if (SWC2 > 0) snowmelt = (MELT_1 + MELT_2) / TRHO;
+  if (TEMPs < 0) SUBLIM = 2.4 * tstep;
+  if (SWC2 - MELT_1 - MELT_2 < SUBLIM) SUBLIM = dmax(dmin(SUBLIM, SWC2 - MELT_1 - MELT_2), 0.0);
+  if (SWC2 > 0) SUBLIM_snow_depth = SUBLIM / TRHO;
+  c.R(0) = MELT_1 / tstep;
+  c.R(1) = RAIN_IN_1 / tstep;
+  c.R(2) = REFRZ / tstep;
+  c.R(3) = -compaction / tstep;
+  c.R(4) = -(snowmelt + SUBLIM_snow_depth) / tstep;
+  c.R(5) = newSnow / NEWDEN / tstep;
+  c.R(6) = newSnow / tstep;
+  c.R(7) = SUBLIM / tstep;
+  c.R(8) = EXCESS_snow_liq / tstep;
+  c.R(9) = MELT_2 / tstep;
+}
+
+// CmvSnowBalance SNOBAL_CRHM_EBSM  src/SnowBalance.cpp:1214-1291 (CRHMSnowBalance; amounts per step are handed over as rates exactly as written there);
+// connections :146-158: SNOW -> SNOW_LIQ, SNOW -> PONDED, SNOW_LIQ -> PONDED, SNOW_LIQ -> SNOW, COLD_CONTENT self-connection
+template <class C, class PR> RVN_DI void rates_SNOBAL_CRHM_EBSM(C &c, const PR &pr) {
+  const double snow_liq = c.SV(c.iSV(RVN_SV_SNOW_LIQ)), SWE = c.SV(c.iSV(RVN_SV_SNOW));
+  double snow_energy = -c.SV(c.iSV(RVN_SV_COLD_CONTENT));
+  const double snow_energy_old = snow_energy;
+  if (SWE <= 0.0) return;
+  double pot_melt = c.F[RVN_F_POTENTIAL_MELT];
+  const double T_min = c.F[RVN_F_TEMP_DAILY_MIN];
+  pot_melt *= D_LH_FUSION * D_DENSITY_WATER / D_MM_PER_METER * c.tstep;
+  const double snoliq_max = c.G(RVN_G_SNOW_SWI) * SWE;
+  const double t_minus = dmin(T_min, 0.0);
+  const double Umin = SWE * (2.115 + 0.00779 * t_minus) * t_minus;
+  double refreeze = 0.0, snowmelt0 = 0.0, snowmelt1 = 0.0, snowmelt2 = 0.0;
+  snow_energy += pot_melt;
+  snow_energy = dmax(Umin, snow_energy);
+  if (snow_energy > 0.0) {
+    const double B = 0.95;
+    const double melt = snow_energy / D_LH_FUSION / D_DENSITY_WATER * D_MM_PER_METER / B;
+    if (melt > (snoliq_max - snow_liq)) {
+      if (SWE > melt) { snowmelt0 = snoliq_max - snow_liq; snowmelt1 = melt - (snoliq_max - snow_liq); snowmelt2 = 0.0; }
+      else { snowmelt0 = 0; snowmelt1 = SWE; snowmelt2 = snow_liq; }
+    } else { snowmelt0 = melt; snowmelt1 = 0; snowmelt2 = 0; }
+    snow_energy = 0.0;
+  } else {
+    refreeze = -snow_energy / D_LH_FUSION / D_DENSITY_WATER * D_MM_PER_METER;
+    if (snow_liq > refreeze) snow_energy = 0.0;
+    else { snow_energy += snow_liq * D_LH_FUSION * D_DENSITY_WATER / D_MM_PER_METER; refreeze = snow_liq; }
+  }
+  c.R(0) = snowmelt0; c.R(1) = snowmelt1; c.R(2) = snowmelt2; c.R(3) = refreeze;
+  c.R(4) = -(snow_energy - snow_energy_old) / c.tstep;
+  (void)pr;
+}
+
 // CmvSnowBalance SNOBAL_HBV  src/SnowBalance.cpp:430-465 (connections :56-70; CalculateSnowLiquidCapacity src/SnowParams.cpp:79-88)
 template <class C, class PR> RVN_DI void rates_SNOBAL_HBV(C &c, const PR &pr) {
   const double Ka = c.LU(RVN_LU_REFREEZE_FACTOR), Ta = c.F[RVN_F_TEMP_DAILY_AVE], tstep = c.tstep;
@@ -814,6 +890,8 @@ template <class C, class PR> RVN_DI void dispatch_rates(C &c, const PR &pr, cons
     case RVN_OP_PRECIPITATION: rates_PRECIPITATION(c, pr); break;
     case RVN_OP_SNOBAL_HMETS: rates_SNOBAL_HMETS(c, pr); break;
     case RVN_OP_SNOBAL_COLD_CONTENT: rates_SNOBAL_COLD_CONTENT(c, pr); break;
+    case RVN_OP_SNOBAL_GAWSER: rates_SNOBAL_GAWSER(c, pr); break;
+    case RVN_OP_SNOBAL_CRHM_EBSM: rates_SNOBAL_CRHM_EBSM(c, pr); break;
     case RVN_OP_SNOBAL_SIMPLE_MELT: rates_SNOBAL_SIMPLE_MELT(c, pr); break;
     case RVN_OP_SNOBAL_CEMA_NEIGE: rates_SNOBAL_CEMA_NEIGE(c, pr); break;
     case RVN_OP_SNOWREFREEZE_DD: rates_SNOWREFREEZE_DD(c, pr); break;

@@ -377,6 +377,18 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
       int iSnow = pM->GetStateVarIndex(RVN_SV_SNOW), iSL = pM->GetStateVarIndex(RVN_SV_SNOW_LIQ), iSoil = pM->GetStateVarIndex(RVN_SV_SOIL, 0);
       p = new CmvGeneric("SnowBalance", RVN_OP_SNOBAL_HBV, pM);
       p->Connect(iSnow, iSL); p->Connect(iSnow, iSoil); p->Connect(iSL, iSoil); p->Connect(iSnow, iPond); p->Connect(iSL, iPond);
+    } else if (s[1] == "SNOBAL_GAWSER") {   // src/SnowBalance.cpp:123-145 (connections), :336-344 (state variables, in this order)
+      AddSVs(pM, {SVL(RVN_SV_NEW_SNOW, -1), SVL(RVN_SV_SNOW, -1), SVL(RVN_SV_SNOW_LIQ, -1), SVL(RVN_SV_SNOW_DEPTH, -1), SVL(RVN_SV_PONDED_WATER, -1)});
+      const int iNew = pM->GetStateVarIndex(RVN_SV_NEW_SNOW), iSWC = pM->GetStateVarIndex(RVN_SV_SNOW), iSD = pM->GetStateVarIndex(RVN_SV_SNOW_DEPTH);
+      const int iLWC = pM->GetStateVarIndex(RVN_SV_SNOW_LIQ);
+      p = new CmvGeneric("SnowBalance", RVN_OP_SNOBAL_GAWSER, pM);
+      p->Connect(iSWC, iLWC); p->Connect(iPond, iLWC); p->Connect(iLWC, iSWC); p->Connect(iSD, iSD); p->Connect(iSD, iSD); p->Connect(iSD, iSD);
+      p->Connect(iNew, iSWC); p->Connect(iSWC, iAtmos); p->Connect(iLWC, iPond); p->Connect(iSWC, iPond);
+    } else if (s[1] == "SNOBAL_CRHM_EBSM") {   // src/SnowBalance.cpp:146-158 (connections), :345-352 (state variables)
+      AddSVs(pM, {SVL(RVN_SV_SNOW, -1), SVL(RVN_SV_SNOW_LIQ, -1), SVL(RVN_SV_PONDED_WATER, -1), SVL(RVN_SV_COLD_CONTENT, -1)});
+      const int iSnow = pM->GetStateVarIndex(RVN_SV_SNOW), iSL = pM->GetStateVarIndex(RVN_SV_SNOW_LIQ), iCC = pM->GetStateVarIndex(RVN_SV_COLD_CONTENT);
+      p = new CmvGeneric("SnowBalance", RVN_OP_SNOBAL_CRHM_EBSM, pM);
+      p->Connect(iSnow, iSL); p->Connect(iSnow, iPond); p->Connect(iSL, iPond); p->Connect(iSL, iSnow); p->Connect(iCC, iCC);
     } else if (s[1] == "SNOBAL_COLD_CONTENT") {   // src/SnowBalance.cpp:41-55 (connections), :287-295 (state variables, in this order)
       AddSVs(pM, {SVL(RVN_SV_SNOW_LIQ, -1), SVL(RVN_SV_COLD_CONTENT, -1), SVL(RVN_SV_ENERGY_LOSSES, -1), SVL(RVN_SV_SURFACE_WATER, -1), SVL(RVN_SV_SNOW, -1)});
       const int iSnow = pM->GetStateVarIndex(RVN_SV_SNOW), iSL = pM->GetStateVarIndex(RVN_SV_SNOW_LIQ);

@@ -61,6 +61,14 @@ if hasattr(synth, "write_hbv"):
     CASES["hbv_snobal_coldcontent"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=58, routing="ROUTE_MUSKINGUM",
                                            rvi_sub=[(r"  :SnowBalance       SNOBAL_SIMPLE_MELT SNOW            SNOW_LIQ\n    :-->Overflow     RAVEN_DEFAULT      SNOW_LIQ        PONDED_WATER\n",
                                                      "  :SnowBalance       SNOBAL_COLD_CONTENT SNOW           PONDED_WATER\n")])
+    # SNOBAL_GAWSER (Hinckley et al. 1996): snowfall through NEW_SNOW, refreeze, density-based compaction of SNOW_DEPTH, fixed sublimation
+    CASES["hbv_snobal_gawser"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=59, routing="ROUTE_MUSKINGUM",
+                                      rvi_sub=[(r"  :SnowBalance       SNOBAL_SIMPLE_MELT SNOW            SNOW_LIQ\n    :-->Overflow     RAVEN_DEFAULT      SNOW_LIQ        PONDED_WATER\n",
+                                                "  :SnowBalance       SNOBAL_GAWSER      SNOW            PONDED_WATER\n")])
+    # SNOBAL_CRHM_EBSM (energy-budget melt with a minimum snow energy from the daily minimum temperature)
+    CASES["hbv_snobal_crhm"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=60, routing="ROUTE_MUSKINGUM",
+                                    rvi_sub=[(r"  :SnowBalance       SNOBAL_SIMPLE_MELT SNOW            SNOW_LIQ\n    :-->Overflow     RAVEN_DEFAULT      SNOW_LIQ        PONDED_WATER\n",
+                                              "  :SnowBalance       SNOBAL_CRHM_EBSM   SNOW            PONDED_WATER\n")])
     CASES["gr4j_pet_oudin"] = dict(kind="gr4j", n_sb=2, hru_per_sb=4, n_days=400, seed=51, pet="PET_OUDIN")
     CASES["gr4j_pet_hamon"] = dict(kind="gr4j", n_sb=2, hru_per_sb=4, n_days=400, seed=52, pet="PET_HAMON")
     CASES["hbv_pet_lintemp"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=53, routing="ROUTE_MUSKINGUM", pet="PET_LINEAR_TEMP",
