@@ -1,3 +1,3 @@
 #!/usr/bin/env bash
-# full GPU suite on the current tree
-python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+# GPU parity of the new process algorithms + the complete golden suite
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -8
