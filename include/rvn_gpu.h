@@ -141,6 +141,8 @@ typedef enum {
   RVN_OP_SNOBAL_COLD_CONTENT,  /* CmvSnowBalance          src/SnowBalance.cpp:732-835 (ColdContentBalance, Brook90 SNOENRGY / SNOPACK; connections :41-55); needs day_length */
   RVN_OP_SNOBAL_GAWSER,        /* CmvSnowBalance          src/SnowBalance.cpp:1098-1201 (GawserBalance: refreeze, density-based compaction, fixed sublimation; connections :123-145) */
   RVN_OP_SNOBAL_CRHM_EBSM,     /* CmvSnowBalance          src/SnowBalance.cpp:1214-1291 (CRHMSnowBalance, Marks et al. energy budget; connections :146-158) */
+  RVN_OP_INF_SCS,              /* CmvInfiltration         src/Infiltration.cpp:338-343,638-680 (GetSCSRunoff: curve number with antecedent-moisture classes from the 5-day precipitation) */
+  RVN_OP_INF_SCS_NOABSTRACTION,/* CmvInfiltration         same, Ia = 0 (src/Infiltration.cpp:668-677) */
   RVN_OP_COUNT
 } rvn_opcode;
 
@@ -197,7 +199,7 @@ typedef enum {
   RVN_LU_PARTITION_COEFF, RVN_LU_CC_DECAY_COEFF, RVN_LU_MAX_SAT_AREA_FRAC, RVN_LU_PDM_B, RVN_LU_AET_COEFF,
   RVN_LU_MAX_DEP_AREA_FRAC, RVN_LU_PONDED_EXP, RVN_LU_AWBM_AREAFRAC1, RVN_LU_AWBM_AREAFRAC2, RVN_LU_HYMOD2_G, RVN_LU_HYMOD2_KMAX,
   RVN_LU_HYMOD2_EXP, RVN_LU_PET_LIN_COEFF, RVN_LU_RAIN_MELT_MULT, RVN_LU_RELHUM_CORR, RVN_LU_PET_VAP_COEFF,
-  RVN_LU_MIN_WIND_SPEED, RVN_LU_MAX_WIND_SPEED, RVN_LU_ABST_PERCENT, RVN_LU_ROUGHNESS, RVN_LU_PRIESTLEYTAYLOR_COEFF, RVN_LU_COUNT
+  RVN_LU_MIN_WIND_SPEED, RVN_LU_MAX_WIND_SPEED, RVN_LU_ABST_PERCENT, RVN_LU_ROUGHNESS, RVN_LU_PRIESTLEYTAYLOR_COEFF, RVN_LU_SCS_CN, RVN_LU_SCS_IA_FRACTION, RVN_LU_COUNT
 } rvn_landuse_field;
 typedef enum {
   RVN_V_MAX_HEIGHT = 0, RVN_V_MAX_LAI, RVN_V_SAI_HT_RATIO, RVN_V_MAX_CAPACITY, RVN_V_MAX_SNOW_CAPACITY,
@@ -462,6 +464,10 @@ typedef struct rvn_model_desc {
   const int32_t *pert_adj;      /* [nPert] rvn_adjustment */
   const uint8_t *pert_mask;     /* [nPert][nHRU] or NULL */
   const double  *pert_eps;      /* [nMembers][nSteps][nPert] */
+  /* 5-day antecedent precipitation of every gauge at every step, or NULL when no process reads force_struct::precip_5day:
+   * CGauge::GetForcingValue(F_PRECIP, t - 5, 5) * 5 (src/UpdateForcings.cpp:107; blank value before the series starts).  The sweep applies the
+   * precipitation weights, gauge / basin corrections and the orographic correction to it exactly as to the precipitation (:525, src/OrographicCorrections.cpp:229,244) */
+  const double *gauge_precip5;  /* [nGauges][nSteps] */
 } rvn_model_desc;
 
 /* ---- EnKF state matrix (reference CEnKFEnsemble::AddToStateMatrix / UpdateFromStateMatrix, src/EnKF.cpp:602-747) ------

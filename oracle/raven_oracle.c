@@ -36,6 +36,7 @@
 #define O_MAXCONN 256
 
 /* src/RavenInclude.h:1456-1464 -- ties return the FIRST argument */
+static double *g_precip5 = 0; /* [nHRU] force_struct::precip_5day of the current step (update_forcings -> INF_SCS) */
 static double omax(double r, double l) { return (r >= l) ? r : l; }
 static double omin(double r, double l) { return (r <= l) ? r : l; }
 
@@ -44,6 +45,7 @@ typedef struct {
   int member;
   const double *ptab;     /* this member's parameter row */
   int k;                  /* HRU */
+  int step;               /* model step (calendar record d->times[step]) */
   const double *F;        /* derived forcings of this HRU [RVN_F_COUNT] */
   const double *phi_old;  /* stored (start-of-step) state: what pHRU->GetStateVarValue returns */
   double canopy_cap, canopy_snow_cap; /* veg_var_struct capacity / snow_capacity for this HRU and step */
@@ -298,6 +300,7 @@ static void update_forcings(const rvn_model_desc *d, const double *ptab, int mem
     }
     F[RVN_F_SNOW_FRAC] = sf;
   }
+  double p5 = 0.0; /* precip_5day (src/UpdateForcings.cpp:107,525) */
   { /* precip gauge corrections :507-527 */
     double rc = d->sb_rain_corr[p], sc = d->sb_snow_corr[p];
     F[RVN_F_PRECIP] = 0.0;
@@ -306,25 +309,28 @@ static void update_forcings(const rvn_model_desc *d, const double *ptab, int mem
       double gauge_corr = F[RVN_F_SNOW_FRAC] * sc * GC(g, RVN_GC_SNOW_CORR) + (1.0 - F[RVN_F_SNOW_FRAC]) * rc * GC(g, RVN_GC_RAIN_CORR);
       double wt = d->wt_val[3 * (size_t)i + 0];
       F[RVN_F_PRECIP] += wt * gauge_corr * GS(RVN_GF_PRECIP, g);
+      if (d->gauge_precip5) p5 += wt * gauge_corr * d->gauge_precip5[(size_t)g * d->nSteps + step];
     }
   }
   /* CModel::CorrectPrecip, src/OrographicCorrections.cpp:213-245 */
   if (d->opt.orocorr_precip == RVN_OROCORR_SIMPLELAPSE) {
     double lapse = P_G(&c, RVN_G_PRECIP_LAPSE);
     lapse /= 1000;
-    if (F[RVN_F_PRECIP] > O_REAL_SMALL) F[RVN_F_PRECIP] = omax(F[RVN_F_PRECIP] + lapse * (elev - ref_elev_precip), 0.0);
+    if (F[RVN_F_PRECIP] > O_REAL_SMALL) { F[RVN_F_PRECIP] = omax(F[RVN_F_PRECIP] + lapse * (elev - ref_elev_precip), 0.0); p5 = omax(p5 + lapse * (elev - ref_elev_precip), 0.0); }
   } else if (d->opt.orocorr_precip == RVN_OROCORR_HBV) {
     double corr_upper = P_G(&c, RVN_G_HBVEC_LAPSE_UPPER) / 1000.0, corr = P_G(&c, RVN_G_HBVEC_LAPSE_RATE) / 1000.0;
     double lapse_elev = P_G(&c, RVN_G_HBVEC_LAPSE_ELEV), add = 0.0;
     if (elev > lapse_elev) add = (corr_upper - corr) * (elev - lapse_elev);
     F[RVN_F_PRECIP] *= omax(1.0 + corr * (elev - ref_elev_precip) + add, 0.0);
+    p5 *= omax(1.0 + corr * (elev - ref_elev_precip) + add, 0.0);
   }
   if (d->nPert > 0) { /* src/UpdateForcings.cpp:558-560 */
     apply_forcing_perturbation(d, RVN_PF_PRECIP, member, k, step, F);
     apply_forcing_perturbation(d, RVN_PF_RAINFALL, member, k, step, F);
     apply_forcing_perturbation(d, RVN_PF_SNOWFALL, member, k, step, F);
   }
-  if (d->hru_type[k] == RVN_HRU_MASKED_GLACIER) F[RVN_F_PRECIP] = 0;
+  if (d->hru_type[k] == RVN_HRU_MASKED_GLACIER) { F[RVN_F_PRECIP] = 0; p5 = 0; }
+  if (g_precip5) g_precip5[k] = p5;
   /* air pressure / relative humidity (EstimateAirPressure, EstimateRelativeHumidity, src/UpdateForcings.cpp:677-731) and incoming
    * shortwave (CRadiation::EstimateShortwaveRadiation / ClearSkySolarRadiation / SWCloudCoverCorrection, src/Radiation.cpp:24-57,
    * 992-1038, 333-364); cloud cover is CLOUDCOV_NONE (0).  Date/geometry pieces come from the host tables. */
@@ -701,7 +707,7 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       break;
     }
     case RVN_OP_INF_HMETS: case RVN_OP_INF_HBV: case RVN_OP_INF_GR4J: case RVN_OP_INF_VIC_ARNO: case RVN_OP_INF_RATIONAL:
-    case RVN_OP_INF_ALL_INFILTRATES: case RVN_OP_INF_VIC: case RVN_OP_INF_PRMS: case RVN_OP_INF_PDM: case RVN_OP_INF_GREEN_AMPT: case RVN_OP_INF_GA_SIMPLE: case RVN_OP_INF_UBC: { /* src/Infiltration.cpp:304-330,384-398,477-489,491-514 + constraints :605-626 */
+    case RVN_OP_INF_ALL_INFILTRATES: case RVN_OP_INF_VIC: case RVN_OP_INF_PRMS: case RVN_OP_INF_PDM: case RVN_OP_INF_GREEN_AMPT: case RVN_OP_INF_GA_SIMPLE: case RVN_OP_INF_UBC: case RVN_OP_INF_SCS: case RVN_OP_INF_SCS_NOABSTRACTION: { /* src/Infiltration.cpp:304-330,384-398,477-489,491-514 + constraints :605-626 */
       if (type != RVN_HRU_STANDARD && type != RVN_HRU_ROCK && type != RVN_HRU_MASKED_GLACIER) break;
       double Fimp = P_LU(c, RVN_LU_IMPERMEABLE_FRAC);
       double ponded = omax(sv[c->iSV[RVN_SV_PONDED_WATER]], 0.0);
@@ -803,6 +809,24 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
           }
           rates[0] = rainthru - runoff; rates[1] = runoff;
         }
+      } else if (pr->op == RVN_OP_INF_SCS || pr->op == RVN_OP_INF_SCS_NOABSTRACTION) { /* src/Infiltration.cpp:338-343; GetSCSRunoff :638-680 */
+        int condition = 2;
+        double S, CN, W, Weff, TR, Ia;
+        TR = g_precip5[c->k] / 25.4;
+        CN = P_LU(c, RVN_LU_SCS_CN);
+        int month = d->times[c->step].month;
+        if ((month > 4) && (month < 9)) { if (TR < 1.4) { condition = 1; } else if (TR > 2.1) { condition = 3; } }
+        else { if (TR < 0.5) { condition = 1; } else if (TR > 1.1) { condition = 3; } }
+        if (condition == 1) { CN = 5E-05 * pow(CN, 3) + 0.0008 * pow(CN, 2) + 0.4431 * CN; }
+        else if (condition == 3) { CN = 7E-05 * pow(CN, 3) - 0.0185 * pow(CN, 2) + 2.1586 * CN; }
+        CN = omin(CN, 100.0);
+        S = 25.4 * (1000.0 / CN - 10.0);
+        W = rainthru * tstep;
+        if (pr->op == RVN_OP_INF_SCS) Ia = (P_LU(c, RVN_LU_SCS_IA_FRACTION)) * S; else Ia = 0.0;
+        Weff = pow(omax(W - Ia, 0.0), 2) / (W + (S - Ia));
+        if (W + (S - Ia) == 0.0) { Weff = 0.0; }
+        double runoff = Weff / tstep;
+        rates[0] = rainthru - runoff; rates[1] = runoff;
       } else if (pr->op == RVN_OP_INF_UBC) { /* CmvInfiltration::GetUBCWMRunoff, src/Infiltration.cpp:685-759 */
         const double V0FLAX = 1800.0;
         double infil, to_GW, to_interflow, runoff, flash_factor, b1, b2;
@@ -1764,6 +1788,7 @@ int rvo_run_member_res(const rvn_model_desc *d, int member, double *state, doubl
   const int iSW = c.iSV[RVN_SV_SURFACE_WATER], iAET = c.iSV[RVN_SV_AET], iRO = c.iSV[RVN_SV_RUNOFF], iGW = c.iSV[RVN_SV_GROUNDWATER];
   const int iTotalSWE = c.iSV[RVN_SV_TOTAL_SWE], iGlacierMB = c.iSV[RVN_SV_GLACIER_MB];
   double *F = (double *)malloc(sizeof(double) * (size_t)nH * RVN_F_COUNT);
+  g_precip5 = d->gauge_precip5 ? (double *)calloc((size_t)nH, sizeof(double)) : 0;
   double *daily = (double *)calloc((size_t)nH * 7, sizeof(double)); /* valid from the first step of a day on: runs must start at a day boundary */
   double *phinew = (double *)malloc(sizeof(double) * NS), *phiread = (double *)malloc(sizeof(double) * NS);
   double *aRouted = (double *)malloc(sizeof(double) * NB), *aQinnew = (double *)malloc(sizeof(double) * NB);
@@ -1793,7 +1818,7 @@ int rvo_run_member_res(const rvn_model_desc *d, int member, double *state, doubl
          * the mean rate (water from ATMOS_PRECIP keeps rate1) until mean |change| <= convergence_crit or max_iterations */
         double *phiprev = (double *)malloc(sizeof(double) * NS), *phi0 = (double *)malloc(sizeof(double) * NS);
         double rate2[O_MAXCONN];
-        c.k = k; c.F = F + (size_t)k * RVN_F_COUNT; c.phi_old = phi_old;
+        c.k = k; c.step = step; c.F = F + (size_t)k * RVN_F_COUNT; c.phi_old = phi_old;
         canopy_capacities(&c, step);
         memcpy(phi0, phinew, sizeof(double) * NS);
         const int iAtm = c.iSV[RVN_SV_ATMOS_PRECIP];
@@ -1827,7 +1852,7 @@ int rvo_run_member_res(const rvn_model_desc *d, int member, double *state, doubl
         memcpy(phi_old, phinew, sizeof(double) * NS);
       } else
       if (d->hru_enabled[k]) {
-        c.k = k; c.F = F + (size_t)k * RVN_F_COUNT; c.phi_old = phi_old;
+        c.k = k; c.step = step; c.F = F + (size_t)k * RVN_F_COUNT; c.phi_old = phi_old;
         canopy_capacities(&c, step);
         for (int j = 0; j < NP; j++) {
           const rvn_process *pr = &d->proc[j];
@@ -2093,6 +2118,7 @@ int rvo_run_member_res(const rvn_model_desc *d, int member, double *state, doubl
     }
     if (state_rec) memcpy(state_rec + (size_t)s * nH * NS, state, sizeof(double) * (size_t)nH * NS);
   }
+  free(g_precip5); g_precip5 = 0;
   free(F); free(daily); free(phinew); free(phiread); free(aRouted); free(aQinnew); free(DAQadjust);
   return 0;
 }

@@ -49,6 +49,7 @@ struct CtxCommon {
   double tstep;
   double canopy_cap, canopy_snow_cap;   // veg_var_struct capacity / snow_capacity of this HRU for this step
   double rain_icept_pct, snow_icept_pct; // veg_var_struct interception fractions (:PrecipIceptFract)
+  double precip_5day; int month;          // force_struct::precip_5day and the calendar month of the step (INF_SCS; derived when M.gauge_p5 is given)
   double veg_LAI, veg_SAI, day_length;   // veg_var_struct LAI / SAI and force_struct day_length of this HRU and step: set when the process list holds SNOBAL_COLD_CONTENT (M.need_cc)
   int type, lu, veg, profile;
   bool linked;   // HRU linked to a reservoir (CHydroUnit::IsLinkedToReservoir)
@@ -298,33 +299,37 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
     }
     F[RVN_F_SNOW_FRAC] = sf;
   }
+  double p5 = 0.0;   // precip_5day: everything that happens to the precipitation happens to it (only kept when a process reads it)
   {  // precipitation gauge+basin corrections (:507-527)
     const double rc = M.sb_rain_corr[sb], sc = M.sb_snow_corr[sb];
-    F[RVN_F_PRECIP] = 0.0;
+    F[RVN_F_PRECIP] = 0.0; p5 = 0.0;
     for (int i = w0; i < w1; i++) {
       const int g = WG(i);
       double gauge_corr = F[RVN_F_SNOW_FRAC] * sc * GC(g, RVN_GC_SNOW_CORR) + (1.0 - F[RVN_F_SNOW_FRAC]) * rc * GC(g, RVN_GC_RAIN_CORR);
       double wt = WT(i, 0);
       F[RVN_F_PRECIP] += wt * gauge_corr * GS(RVN_GF_PRECIP, g);
+      if (C::kAtmos && M.gauge_p5 != nullptr) p5 += wt * gauge_corr * M.gauge_p5[(size_t)g * M.nSteps + step];
     }
   }
   // CModel::CorrectPrecip  src/OrographicCorrections.cpp:213-245
   if (opt.orocorr_precip == RVN_OROCORR_SIMPLELAPSE) {
     double lapse = c.G(RVN_G_PRECIP_LAPSE);
     lapse /= 1000;
-    if (F[RVN_F_PRECIP] > D_REAL_SMALL) F[RVN_F_PRECIP] = dmax(F[RVN_F_PRECIP] + lapse * (elev - ref_elev_precip), 0.0);
+    if (F[RVN_F_PRECIP] > D_REAL_SMALL) { F[RVN_F_PRECIP] = dmax(F[RVN_F_PRECIP] + lapse * (elev - ref_elev_precip), 0.0); p5 = dmax(p5 + lapse * (elev - ref_elev_precip), 0.0); }
   } else if (opt.orocorr_precip == RVN_OROCORR_HBV) {
     double corr_upper = c.G(RVN_G_HBVEC_LAPSE_UPPER) / 1000.0, corr = c.G(RVN_G_HBVEC_LAPSE_RATE) / 1000.0;
     double lapse_elev = c.G(RVN_G_HBVEC_LAPSE_ELEV), add = 0.0;
     if (elev > lapse_elev) add = (corr_upper - corr) * (elev - lapse_elev);
     F[RVN_F_PRECIP] *= dmax(1.0 + corr * (elev - ref_elev_precip) + add, 0.0);
+    p5 *= dmax(1.0 + corr * (elev - ref_elev_precip) + add, 0.0);
   }
   if (M.nPert > 0) {   // src/UpdateForcings.cpp:558-560
     apply_perturbations(F, M, RVN_PF_PRECIP, e, k, step);
     apply_perturbations(F, M, RVN_PF_RAINFALL, e, k, step);
     apply_perturbations(F, M, RVN_PF_SNOWFALL, e, k, step);
   }
-  if (c.type == RVN_HRU_MASKED_GLACIER) F[RVN_F_PRECIP] = 0;
+  if (c.type == RVN_HRU_MASKED_GLACIER) { F[RVN_F_PRECIP] = 0; p5 = 0; }
+  if (C::kAtmos && M.gauge_p5 != nullptr) { c.precip_5day = p5; c.month = mo; }
   {  // CModel::EstimatePotentialMelt  src/PotentialMelt.cpp:20-246
     double pm = F[RVN_F_POTENTIAL_MELT];
     const int method = opt.pot_melt;

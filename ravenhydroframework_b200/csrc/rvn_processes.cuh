@@ -397,6 +397,22 @@ template <class C, class PR> RVN_DI void rates_INFILTRATION(C &c, const PR &pr, 
   } else if (op == RVN_OP_INF_RATIONAL) {   // src/Infiltration.cpp:333-338 (no impermeable-fraction correction in the reference)
     double runoff = c.LU(RVN_LU_PARTITION_COEFF) * rainthru;
     c.R(0) = rainthru - runoff; c.R(1) = runoff;
+  } else if (op == RVN_OP_INF_SCS || op == RVN_OP_INF_SCS_NOABSTRACTION) {   // :338-343 + GetSCSRunoff :638-680
+    int condition = 2;   // antecedent moisture condition
+    const double TR = c.precip_5day / 25.4;   // [in] (MM_PER_INCH)
+    double CN = c.LU(RVN_LU_SCS_CN);
+    if ((c.month > 4) && (c.month < 9)) { if (TR < 1.4) condition = 1; else if (TR > 2.1) condition = 3; }
+    else { if (TR < 0.5) condition = 1; else if (TR > 1.1) condition = 3; }
+    if (condition == 1) CN = 5E-05 * rvn_pow(CN, 3) + 0.0008 * rvn_pow(CN, 2) + 0.4431 * CN;
+    else if (condition == 3) CN = 7E-05 * rvn_pow(CN, 3) - 0.0185 * rvn_pow(CN, 2) + 2.1586 * CN;
+    CN = dmin(CN, 100.0);
+    const double S = 25.4 * (1000.0 / CN - 10.0);
+    const double W = rainthru * tstep;
+    const double Ia = (op == RVN_OP_INF_SCS) ? (c.LU(RVN_LU_SCS_IA_FRACTION)) * S : 0.0;
+    double Weff = rvn_pow(dmax(W - Ia, 0.0), 2) / (W + (S - Ia));
+    if (W + (S - Ia) == 0.0) Weff = 0.0;
+    const double runoff = Weff / tstep;
+    c.R(0) = rainthru - runoff; c.R(1) = runoff;
   } else if (op == RVN_OP_INF_ALL_INFILTRATES) {   // :347-353
     double runoff = 0.0;
     runoff = (Fimp)*rainthru + (1 - Fimp) * runoff;
@@ -897,7 +913,7 @@ template <class C, class PR> RVN_DI void dispatch_rates(C &c, const PR &pr, cons
     case RVN_OP_SNOWREFREEZE_DD: rates_SNOWREFREEZE_DD(c, pr); break;
     case RVN_OP_SNOTEMP_NEWTONS: rates_SNOTEMP_NEWTONS(c, pr); break;
     case RVN_OP_INF_HMETS: case RVN_OP_INF_HBV: case RVN_OP_INF_GR4J: case RVN_OP_INF_VIC_ARNO: case RVN_OP_INF_RATIONAL:
-    case RVN_OP_INF_ALL_INFILTRATES: case RVN_OP_INF_VIC: case RVN_OP_INF_PRMS: case RVN_OP_INF_PDM: case RVN_OP_INF_GREEN_AMPT: case RVN_OP_INF_GA_SIMPLE: case RVN_OP_INF_UBC: rates_INFILTRATION(c, pr, op); break;
+    case RVN_OP_INF_ALL_INFILTRATES: case RVN_OP_INF_VIC: case RVN_OP_INF_PRMS: case RVN_OP_INF_PDM: case RVN_OP_INF_GREEN_AMPT: case RVN_OP_INF_GA_SIMPLE: case RVN_OP_INF_UBC: case RVN_OP_INF_SCS: case RVN_OP_INF_SCS_NOABSTRACTION: rates_INFILTRATION(c, pr, op); break;
     case RVN_OP_SNOBAL_HBV: rates_SNOBAL_HBV(c, pr); break;
     case RVN_OP_INTERFLOW_PRMS: rates_INTERFLOW_PRMS(c, pr); break;
     case RVN_OP_SNOWMELT_POTMELT: rates_SNOWMELT_POTMELT(c, pr); break;

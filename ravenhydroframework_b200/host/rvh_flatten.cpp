@@ -207,6 +207,7 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
       {RVN_OP_SOILEVAP_ROOT_CONSTRAIN, 'S', {RVN_S_FIELD_CAPACITY, RVN_S_SAT_WILT, -1}},
       {RVN_OP_SOILEVAP_AWBM, 'L', {RVN_LU_AWBM_AREAFRAC1, RVN_LU_AWBM_AREAFRAC2, -1}},
       {RVN_OP_INF_GREEN_AMPT, 'S', {RVN_S_HYDRAUL_COND, RVN_S_WETTING_FRONT_PSI, -1}},
+      {RVN_OP_INF_SCS, 'L', {RVN_LU_SCS_CN, -1}}, {RVN_OP_INF_SCS_NOABSTRACTION, 'L', {RVN_LU_SCS_CN, -1}},
       {RVN_OP_INF_GA_SIMPLE, 'S', {RVN_S_HYDRAUL_COND, RVN_S_WETTING_FRONT_PSI, -1}},
     };
     for (int r = 0; r < d.nProc; r++)
@@ -492,6 +493,18 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
     }
   }
   d.gauge_series = _f_series.data(); d.gauge_const = _f_gconst.data();
+  {   // force_struct::precip_5day of the gauges (src/UpdateForcings.cpp:107), only when a process reads it
+    bool uses_p5 = false;
+    for (int j = 0; j < NP; j++) if (_f_proc[j].op == RVN_OP_INF_SCS || _f_proc[j].op == RVN_OP_INF_SCS_NOABSTRACTION) uses_p5 = true;
+    d.gauge_precip5 = NULL;
+    if (uses_p5) {
+      ExitGracefullyIf(_cell_forcing, "CModel::Flatten: INF_SCS needs gauge precipitation series (the 5-day antecedent precipitation is not derived from gridded input in the B200 build)");
+      _f_p5.assign((size_t)nG * nSteps, 0.0);
+      for (int g = 0; g < nG; g++)
+        for (int n = 0; n < nSteps; n++) _f_p5[(size_t)g * nSteps + n] = _pGauges[g]->GetTimeSeries(F_PRECIP)->GetAvgValue(_f_times[n].model_time - 5.0, 5.0) * 5.0;
+      d.gauge_precip5 = _f_p5.data();
+    }
+  }
   // gauge weights -> CSR (the reference keeps three dense [nHRU][nGauges] tables; here they hold the same values)
   _f_wt_ptr.assign(nH + 1, 0); _f_wt_idx.clear(); _f_wt.clear();
   if (_cell_forcing) {

@@ -703,6 +703,7 @@ static void ParseClassPropertiesFile(CModel *pModel, const optStruct &Options) {
     if (S.v[RVN_LU_REFREEZE_FACTOR] == NOT_SPECIFIED) S.v[RVN_LU_REFREEZE_FACTOR] = 5.04;
     if (S.v[RVN_LU_DD_REFREEZE_TEMP] == NOT_SPECIFIED) S.v[RVN_LU_DD_REFREEZE_TEMP] = 0.0;
     if (S.v[RVN_LU_REFREEZE_EXP] == NOT_SPECIFIED) S.v[RVN_LU_REFREEZE_EXP] = 1.0;
+    if (S.v[RVN_LU_SCS_IA_FRACTION] == NOT_SPECIFIED) S.v[RVN_LU_SCS_IA_FRACTION] = 0.2;   // src/LandUseClass.cpp:195-199
     if (S.v[RVN_LU_HBV_MELT_FOR_CORR] == NOT_SPECIFIED) S.v[RVN_LU_HBV_MELT_FOR_CORR] = 1.0;
     if (S.v[RVN_LU_HBV_MELT_ASP_CORR] == NOT_SPECIFIED) S.v[RVN_LU_HBV_MELT_ASP_CORR] = 0.0;
     if (S.v[RVN_LU_HBV_MELT_GLACIER_CORR] == NOT_SPECIFIED) S.v[RVN_LU_HBV_MELT_GLACIER_CORR] = 1.0;

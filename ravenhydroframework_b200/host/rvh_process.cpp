@@ -426,6 +426,9 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
     } else if (s[1] == "INF_GREEN_AMPT") {   // src/Infiltration.cpp:20-23 (the two default connections), src/GreenAmpt.cpp
       p = new CmvGeneric("Infiltration", RVN_OP_INF_GREEN_AMPT, pM);
       p->Connect(iPond, iTop); p->Connect(iPond, iSW);
+    } else if (s[1] == "INF_SCS" || s[1] == "INF_SCS_NOABSTRACTION") {   // src/Infiltration.cpp:20-23, GetSCSRunoff :638-680
+      p = new CmvGeneric("Infiltration", s[1] == "INF_SCS" ? RVN_OP_INF_SCS : RVN_OP_INF_SCS_NOABSTRACTION, pM);
+      p->Connect(iPond, iTop); p->Connect(iPond, iSW);
     } else if (s[1] == "INF_UBC") {   // src/Infiltration.cpp:34-43,250-256: topsoil, interflow, upper and lower groundwater stores
       ExitGracefullyIf(pM->GetNumSoilLayers() < 4, "INF_UBCWM infiltration algorithm requires at least 4 soil layers to operate. Please use a different :SoilModel or replace this infiltration algorithm.");
       AddSVs(pM, {SVL(RVN_SV_SOIL, 1), SVL(RVN_SV_SOIL, 2), SVL(RVN_SV_SOIL, 3)});

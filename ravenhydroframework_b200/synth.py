@@ -472,6 +472,20 @@ ALGO_SETS = {
      FAST_RES,         22.0,              75.0
 :EndSoilParameterList
 """),
+    "m": dict(inf="INF_SCS", rvp=""":LandUseParameterList
+  :Parameters, SCS_CN, SCS_IA_FRACTION
+  :Units     ,   none,            none
+    [DEFAULT],   71.0,            0.18
+    LU_OPEN,     83.0,            0.20
+:EndLandUseParameterList
+"""),
+    "n": dict(inf="INF_SCS_NOABSTRACTION", rvp=""":LandUseParameterList
+  :Parameters, SCS_CN
+  :Units     ,   none
+    [DEFAULT],   64.0
+    LU_OPEN,     78.0
+:EndLandUseParameterList
+"""),
 }
 ALGO_RVP = """:SoilParameterList
   :Parameters, PERC_N, SAC_PERC_ALPHA, SAC_PERC_EXPON, PERC_ASPEN, BASEFLOW_THRESH, BASEFLOW_COEFF2, STORAGE_THRESHOLD, MAX_BASEFLOW_RATE, PERC_COEFF

@@ -41,7 +41,7 @@ if hasattr(synth, "write_hbv"):
     # process classes outside the three templates: :SnowMelt, :SnowSqueeze, :Interflow
     CASES["hbv_meltsqueeze"] = dict(kind="hbv", n_sb=3, hru_per_sb=5, n_days=300, seed=14, routing="ROUTE_MUSKINGUM", variant="melt_squeeze_interflow")
     # lateral exchange between HRUs (CmvLatFlush): within-subbasin flush limited by the recipient's room + an INTERBASIN flush
-    for _k in "abcdefghijkl":   # other members of the infiltration / soil evaporation / percolation / baseflow process classes
+    for _k in "abcdefghijklmn":   # other members of the infiltration / soil evaporation / percolation / baseflow process classes
         CASES["hbv_algo_" + _k] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=220, seed=30 + ord(_k), routing="ROUTE_MUSKINGUM", season_offset=80,
                                        variant="algo:" + _k)
     # lateral mixing (CmvLatEquilibrate): several subbasins (where the reference's pool bookkeeping never reaches its hand-back step) and

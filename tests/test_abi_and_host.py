@@ -86,7 +86,7 @@ def test_product_path_does_not_touch_the_oracle():
 def test_unsupported_commands_fail_loudly(tmp_path):
     base = synth.write_hmets(str(tmp_path), n_sb=1, hru_per_sb=1, n_days=10)
     rvi = open(base + ".rvi").read()
-    open(base + ".rvi", "w").write(rvi.replace("INF_HMETS", "INF_SCS"))
+    open(base + ".rvi", "w").write(rvi.replace("INF_HMETS", "INF_UPSCALED_GREEN_AMPT"))
     with pytest.raises(api.RavenError, match="not implemented"):
         api.RavenModel(base)
     open(base + ".rvi", "w").write(rvi + ":ReservoirDemandAllocation X\n")
