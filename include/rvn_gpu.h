@@ -153,7 +153,7 @@ typedef enum { RVN_POTMELT_NONE = 0, RVN_POTMELT_DATA, RVN_POTMELT_DEGREE_DAY, R
 /* atmospheric estimators of the forcing chain (reference src/UpdateForcings.cpp:677-731, src/Radiation.cpp:24-57,333-364) */
 typedef enum { RVN_AIRPRESS_BASIC = 0, RVN_AIRPRESS_UBC, RVN_AIRPRESS_CONST } rvn_airpress;
 typedef enum { RVN_RELHUM_CONSTANT = 0, RVN_RELHUM_MINDEWPT } rvn_relhum;
-typedef enum { RVN_ABST_PERCENTAGE = 0, RVN_ABST_FILL } rvn_abstraction;
+typedef enum { RVN_ABST_PERCENTAGE = 0, RVN_ABST_FILL, RVN_ABST_SCS, RVN_ABST_PDMROF } rvn_abstraction;   /* src/Abstraction.cpp:243-309 */
 /* :PrecipIceptFract (reference precip_icept_method; CVegetationClass::RecalculateCanopyParams, src/VegetationParams.cpp:143-166) */
 typedef enum { RVN_ICEPT_USER = 0, RVN_ICEPT_LAI, RVN_ICEPT_EXPLAI, RVN_ICEPT_NONE } rvn_icept;
 typedef enum { RVN_WINDVEL_CONSTANT = 0, RVN_WINDVEL_UBC_MOD, RVN_WINDVEL_SQRT } rvn_windvel;   /* CModel::EstimateWindVelocity, src/UpdateForcings.cpp:739-790 */
@@ -199,7 +199,7 @@ typedef enum {
   RVN_LU_PARTITION_COEFF, RVN_LU_CC_DECAY_COEFF, RVN_LU_MAX_SAT_AREA_FRAC, RVN_LU_PDM_B, RVN_LU_AET_COEFF,
   RVN_LU_MAX_DEP_AREA_FRAC, RVN_LU_PONDED_EXP, RVN_LU_AWBM_AREAFRAC1, RVN_LU_AWBM_AREAFRAC2, RVN_LU_HYMOD2_G, RVN_LU_HYMOD2_KMAX,
   RVN_LU_HYMOD2_EXP, RVN_LU_PET_LIN_COEFF, RVN_LU_RAIN_MELT_MULT, RVN_LU_RELHUM_CORR, RVN_LU_PET_VAP_COEFF,
-  RVN_LU_MIN_WIND_SPEED, RVN_LU_MAX_WIND_SPEED, RVN_LU_ABST_PERCENT, RVN_LU_ROUGHNESS, RVN_LU_PRIESTLEYTAYLOR_COEFF, RVN_LU_SCS_CN, RVN_LU_SCS_IA_FRACTION, RVN_LU_COUNT
+  RVN_LU_MIN_WIND_SPEED, RVN_LU_MAX_WIND_SPEED, RVN_LU_ABST_PERCENT, RVN_LU_ROUGHNESS, RVN_LU_PRIESTLEYTAYLOR_COEFF, RVN_LU_SCS_CN, RVN_LU_SCS_IA_FRACTION, RVN_LU_PDMROF_B, RVN_LU_COUNT
 } rvn_landuse_field;
 typedef enum {
   RVN_V_MAX_HEIGHT = 0, RVN_V_MAX_LAI, RVN_V_SAI_HT_RATIO, RVN_V_MAX_CAPACITY, RVN_V_MAX_SNOW_CAPACITY,

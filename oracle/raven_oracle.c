@@ -1304,7 +1304,27 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       double ponded = sv[iFrom[0]], depression = sv[iTo[0]];
       if (type != RVN_HRU_STANDARD) break;
       if (pr->ia[0] == RVN_ABST_PERCENTAGE) rates[0] = P_LU(c, RVN_LU_ABST_PERCENT) * ponded / tstep;
-      else { double dep_space = omax(P_LU(c, RVN_LU_DEP_MAX) - depression, 0.0); rates[0] = omin(dep_space, omax(ponded, 0.0)) / tstep; }
+      else if (pr->ia[0] == RVN_ABST_SCS) { /* src/Abstraction.cpp:257-285 */
+        double S, CN, TR, Ia;
+        int condition = 2, month = d->times[c->step].month;
+        TR = g_precip5[c->k] / 25.4;
+        CN = P_LU(c, RVN_LU_SCS_CN);
+        if ((month > 4) && (month < 9)) { if (TR < 1.4) { condition = 1; } else if (TR > 2.1) { condition = 3; } }
+        else { if (TR < 0.5) { condition = 1; } else if (TR > 1.1) { condition = 3; } }
+        if (condition == 1) { CN = 5E-05 * pow(CN, 3) + 0.0008 * pow(CN, 2) + 0.4431 * CN; }
+        else if (condition == 3) { CN = 0.0003 * pow(CN, 3) - 0.0185 * pow(CN, 2) + 2.1586 * CN; }
+        S = 25.4 * (1000 / CN - 10);
+        Ia = (P_LU(c, RVN_LU_SCS_IA_FRACTION)) * S;
+        rates[0] = omax(Ia, ponded) / tstep;
+      } else if (pr->ia[0] == RVN_ABST_PDMROF) { /* :287-309 */
+        double dep_max = P_LU(c, RVN_LU_DEP_MAX), b = P_LU(c, RVN_LU_PDMROF_B);
+        double c_max = (b + 1) * dep_max;
+        double c_star = c_max * (1.0 - pow(1.0 - (depression / dep_max), 1.0 / (b + 1.0)));
+        double abstracted = dep_max * (pow(1.0 - (c_star / c_max), b + 1.0) - pow(1.0 - omin(c_star + ponded, c_max) / c_max, b + 1.0));
+        abstracted = omin(abstracted, ponded);
+        rates[0] = (abstracted) / tstep;
+        rates[1] = (ponded - abstracted) / tstep;
+      } else { double dep_space = omax(P_LU(c, RVN_LU_DEP_MAX) - depression, 0.0); rates[0] = omin(dep_space, omax(ponded, 0.0)) / tstep; }
       {
         double pond = omax(sv[iFrom[0]], 0.0), stor = omax(sv[iTo[0]], 0.0), max_stor = state_var_max(c, iTo[0], sv), deficit;
         rates[0] = omin(rates[0], pond / tstep);

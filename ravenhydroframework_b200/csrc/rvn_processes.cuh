@@ -237,7 +237,26 @@ template <class C, class PR> RVN_DI void rates_ABSTRACTION(C &c, const PR &pr) {
   const double ponded = c.SV(pr.from(0)), depression = c.SV(pr.to(0));
   if (c.type != RVN_HRU_STANDARD) return;
   if (pr.ia(0) == RVN_ABST_PERCENTAGE) c.R(0) = c.LU(RVN_LU_ABST_PERCENT) * ponded / c.tstep;
-  else {
+  else if (pr.ia(0) == RVN_ABST_SCS) {   // src/Abstraction.cpp:257-285: initial abstraction of the curve-number method (condition-3 polynomial as written there)
+    int condition = 2;
+    const double TR = c.precip_5day / 25.4;
+    double CN = c.LU(RVN_LU_SCS_CN);
+    if ((c.month > 4) && (c.month < 9)) { if (TR < 1.4) condition = 1; else if (TR > 2.1) condition = 3; }
+    else { if (TR < 0.5) condition = 1; else if (TR > 1.1) condition = 3; }
+    if (condition == 1) CN = 5E-05 * rvn_pow(CN, 3) + 0.0008 * rvn_pow(CN, 2) + 0.4431 * CN;
+    else if (condition == 3) CN = 0.0003 * rvn_pow(CN, 3) - 0.0185 * rvn_pow(CN, 2) + 2.1586 * CN;
+    const double S = 25.4 * (1000 / CN - 10);
+    const double Ia = (c.LU(RVN_LU_SCS_IA_FRACTION)) * S;
+    c.R(0) = dmax(Ia, ponded) / c.tstep;
+  } else if (pr.ia(0) == RVN_ABST_PDMROF) {   // :287-309 (Mekonnen et al. 2014): Pareto-distributed depression capacity, the rest runs off
+    const double dep_max = c.LU(RVN_LU_DEP_MAX), b = c.LU(RVN_LU_PDMROF_B);
+    const double c_max = (b + 1) * dep_max;
+    const double c_star = c_max * (1.0 - rvn_pow(1.0 - (depression / dep_max), 1.0 / (b + 1.0)));
+    double abstracted = dep_max * (rvn_pow(1.0 - (c_star / c_max), b + 1.0) - rvn_pow(1.0 - dmin(c_star + ponded, c_max) / c_max, b + 1.0));
+    abstracted = dmin(abstracted, ponded);
+    c.R(0) = (abstracted) / c.tstep;
+    c.R(1) = (ponded - abstracted) / c.tstep;
+  } else {
     const double dep_space = dmax(c.LU(RVN_LU_DEP_MAX) - depression, 0.0);
     c.R(0) = dmin(dep_space, dmax(ponded, 0.0)) / c.tstep;
   }

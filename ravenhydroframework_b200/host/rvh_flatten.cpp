@@ -219,7 +219,8 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
       }
     for (int r = 0; r < d.nProc; r++)
       if (d.proc[r].op == RVN_OP_ABSTRACTION) {   // CmvAbstraction::GetParticipatingParamList, src/Abstraction.cpp:100-150
-        const int f = (d.proc[r].ia[0] == RVN_ABST_PERCENTAGE) ? RVN_LU_ABST_PERCENT : RVN_LU_DEP_MAX;
+        const int a = d.proc[r].ia[0];
+        const int f = (a == RVN_ABST_PERCENTAGE) ? RVN_LU_ABST_PERCENT : (a == RVN_ABST_SCS) ? RVN_LU_SCS_CN : RVN_LU_DEP_MAX;
         for (size_t c = 0; c < lu_classes.size(); c++)
           ExitGracefullyIf(lu_classes[c].S.v[f] == NOT_SPECIFIED, std::string("CLandUseClass::AutoCalculateLandUseProps: required parameter ") + LandUseFieldName(f) + " not specified for land use class " + lu_classes[c].tag);
       }
@@ -495,7 +496,8 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
   d.gauge_series = _f_series.data(); d.gauge_const = _f_gconst.data();
   {   // force_struct::precip_5day of the gauges (src/UpdateForcings.cpp:107), only when a process reads it
     bool uses_p5 = false;
-    for (int j = 0; j < NP; j++) if (_f_proc[j].op == RVN_OP_INF_SCS || _f_proc[j].op == RVN_OP_INF_SCS_NOABSTRACTION) uses_p5 = true;
+    for (int j = 0; j < NP; j++)
+      if (_f_proc[j].op == RVN_OP_INF_SCS || _f_proc[j].op == RVN_OP_INF_SCS_NOABSTRACTION || (_f_proc[j].op == RVN_OP_ABSTRACTION && _f_proc[j].ia[0] == RVN_ABST_SCS)) uses_p5 = true;
     d.gauge_precip5 = NULL;
     if (uses_p5) {
       ExitGracefullyIf(_cell_forcing, "CModel::Flatten: INF_SCS needs gauge precipitation series (the 5-day antecedent precipitation is not derived from gridded input in the B200 build)");

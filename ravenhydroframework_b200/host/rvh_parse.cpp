@@ -436,7 +436,7 @@ static int SoilFieldOrIgnore(const std::string &n) {
 static int LUFieldOrIgnore(const std::string &n) {
   int f = LandUseFieldFromName(n);
   if (f >= 0) return f;
-  static const char *ign[] = {"FOREST_PET_CORR", "PDMROF_B", NULL};
+  static const char *ign[] = {"FOREST_PET_CORR", NULL};
   for (int i = 0; ign[i]; i++) if (n == ign[i]) return -1;
   return -2;
 }

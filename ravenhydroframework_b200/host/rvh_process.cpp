@@ -648,11 +648,14 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
     int type = -1;
     if (s[1] == "ABST_PERCENTAGE") type = RVN_ABST_PERCENTAGE;
     else if (s[1] == "ABST_FILL") type = RVN_ABST_FILL;
+    else if (s[1] == "ABST_SCS") type = RVN_ABST_SCS;
+    else if (s[1] == "ABST_PDMROF") type = RVN_ABST_PDMROF;
     ExitGracefullyIf(type < 0, "ParseMainInputFile: abstraction algorithm " + s[1] + " is not implemented in the B200 build");
     ExitGracefullyIf(s[2] != "PONDED_WATER" || s[3] != "DEPRESSION", "ParseMainInputFile: :Abstraction moves water from PONDED_WATER to DEPRESSION");
     AddSVs(pM, {SVL(RVN_SV_PONDED_WATER, -1), SVL(RVN_SV_DEPRESSION, -1)});
     CmvGeneric *p = new CmvGeneric("Abstraction", RVN_OP_ABSTRACTION, pM);
     p->Connect(pM->GetStateVarIndex(RVN_SV_PONDED_WATER), pM->GetStateVarIndex(RVN_SV_DEPRESSION));
+    if (type == RVN_ABST_PDMROF) p->Connect(pM->GetStateVarIndex(RVN_SV_PONDED_WATER), iSW);   // runoff of what the depressions shed (src/Abstraction.cpp:33-41)
     p->SetIntArg(0, type);
     return p;
   }

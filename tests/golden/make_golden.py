@@ -139,6 +139,10 @@ if hasattr(synth, "write_hbv"):
                                          rvi_sub=[(_can, _can_rut)])
     CASES["hbv_can_icept_none"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=300, seed=83, routing="ROUTE_MUSKINGUM", rvi_extra=":PrecipIceptFract PRECIP_ICEPT_NONE\n")
     CASES["hbv_abst_fill"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=84, routing="ROUTE_MUSKINGUM", proc_after=(_hbv_after, _abst % "ABST_FILL"), rvp_extra=_dep)
+    CASES["hbv_abst_scs"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=86, routing="ROUTE_MUSKINGUM", proc_after=(_hbv_after, _abst % "ABST_SCS"),
+                                 rvp_extra=_dep + ":LandUseParameterList\n  :Parameters, SCS_CN, SCS_IA_FRACTION\n  :Units, none, none\n  [DEFAULT], 74.0, 0.05\n  LU_OPEN, 86.0, 0.08\n:EndLandUseParameterList\n")
+    CASES["hbv_abst_pdmrof"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=87, routing="ROUTE_MUSKINGUM", proc_after=(_hbv_after, _abst % "ABST_PDMROF"),
+                                    rvp_extra=_dep + ":LandUseParameterList\n  :Parameters, PDMROF_B\n  :Units, none\n  [DEFAULT], 0.7\n  LU_OPEN, 1.6\n:EndLandUseParameterList\n")
     CASES["hbv_abst_percentage"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=85, routing="ROUTE_MUSKINGUM", proc_after=(_hbv_after, _abst % "ABST_PERCENTAGE"),
                                         rvi_sub=[(_can, _can_max)], rvp_extra=_dep)
     # surveyed channel cross-section (:ChannelProfile with roughness zones -> 20-point rating curves) under the two routing methods that
