@@ -468,6 +468,10 @@ typedef struct rvn_model_desc {
    * CGauge::GetForcingValue(F_PRECIP, t - 5, 5) * 5 (src/UpdateForcings.cpp:107; blank value before the series starts).  The sweep applies the
    * precipitation weights, gauge / basin corrections and the orographic correction to it exactly as to the precipitation (:525, src/OrographicCorrections.cpp:229,244) */
   const double *gauge_precip5;  /* [nGauges][nSteps] */
+  /* force_struct::subdaily_corr of every HRU for every distinct (date, time of day) row of et_row, or NULL (= 1: daily steps or SUBDAILY_NONE).
+   * SUBDAILY_SIMPLE (CModel::CalculateSubDailyCorrection, src/UpdateForcings.cpp:964-982): the share of the day's half-sine between dawn and dusk
+   * that falls into the step, from the HRU's day length; multiplies the daily PET estimators and the degree-day potential melt */
+  const double *subdaily_corr;  /* [nEtRows][nHRU] */
 } rvn_model_desc;
 
 /* ---- EnKF state matrix (reference CEnKFEnsemble::AddToStateMatrix / UpdateFromStateMatrix, src/EnKF.cpp:602-747) ------

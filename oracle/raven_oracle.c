@@ -280,7 +280,7 @@ static void update_forcings(const rvn_model_desc *d, const double *ptab, int mem
   daily[0] = F[RVN_F_TEMP_DAILY_MIN]; daily[1] = F[RVN_F_TEMP_DAILY_MAX]; daily[2] = F[RVN_F_TEMP_DAILY_AVE];
   daily[3] = temp_month_max; daily[4] = temp_month_min; daily[5] = temp_month_ave; daily[6] = PET_month_ave;
   F[RVN_F_TEMP_MONTH_AVE] = temp_month_ave; F[RVN_F_PET_MONTH_AVE] = PET_month_ave;
-  const double subdaily_corr = 1.0;
+  const double subdaily_corr = d->subdaily_corr ? d->subdaily_corr[(size_t)d->et_row[step] * d->nHRU + k] : 1.0; /* CalculateSubDailyCorrection, host-tabulated */
   /* CModel::EstimateSnowFraction, src/UpdateForcings.cpp:1068-1197 */
   {
     double sf = F[RVN_F_SNOW_FRAC];

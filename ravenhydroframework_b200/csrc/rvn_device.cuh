@@ -121,6 +121,7 @@ struct DevModel {
   int32_t assimilate_flow; double assimilation_fact;
   const uint8_t *da_override; const double *da_obsQ, *da_obsQ2, *da_decay, *da_wt, *sb_drain_area, *sb_da_corr;
   double *da_adjust, *da_mass;
+  const double *subdaily;   // [nEtRows][nHp] force_struct::subdaily_corr (rvn_model_desc::subdaily_corr) or NULL (= 1)
   const double *gauge_p5;   // [nGauges][nSteps] 5-day antecedent precipitation of the gauges (rvn_model_desc::gauge_precip5) or NULL
   int need_cc;   // the process list holds SNOBAL_COLD_CONTENT: the sweep derives LAI / SAI / day length of every HRU (CtxCommon::veg_LAI ...)
 };

@@ -279,7 +279,8 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
     }
   }
   F[RVN_F_TEMP_MONTH_AVE] = temp_month_ave; F[RVN_F_PET_MONTH_AVE] = PET_month_ave;
-  const double subdaily_corr = 1.0;  // CalculateSubDailyCorrection: timestep>=1 (src/UpdateForcings.cpp:949-958)
+  // CalculateSubDailyCorrection (src/UpdateForcings.cpp:949-1024): 1 for daily steps / SUBDAILY_NONE, else the host-tabulated SUBDAILY_SIMPLE share (interpreter sweep only)
+  const double subdaily_corr = (C::kAtmos && M.subdaily != nullptr) ? M.subdaily[(size_t)M.et_row[step] * M.nHp + k] : 1.0;
   {  // CModel::EstimateSnowFraction  src/UpdateForcings.cpp:1068-1197
     double sf = F[RVN_F_SNOW_FRAC];
     const int method = opt.rainsnow;

@@ -419,9 +419,11 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
         ExitGracefullyIf(lu_classes[c].S.v[RVN_LU_PET_LIN_COEFF] == NOT_SPECIFIED, "CLandUseClass::AutoCalculateLandUseProps: required parameter PET_LIN_COEFF not specified for land use class " + lu_classes[c].tag);
     ExitGracefullyIf(need_ws && globals.v[RVN_G_MOHYSE_PET_COEFF] == NOT_SPECIFIED, "CModel::Flatten: PET_MOHYSE needs :GlobalParameter MOHYSE_PET_COEFF");
     d.day_length = NULL; d.sunset_angle = NULL; d.et_flat = NULL; d.opt_air_mass = NULL;
-    if (need_et || need_dl || need_ws) {
+    const bool need_sd = (O.subdaily == 1) && (O.timestep < 1.0);   // SUBDAILY_SIMPLE (CalculateSubDailyCorrection returns 1 for daily steps)
+    d.subdaily_corr = NULL;
+    if (need_et || need_dl || need_ws || need_sd) {
       _f_et_row.assign(nSteps, 0);
-      _f_et.clear(); _f_daylen.clear(); _f_sunset.clear(); _f_etflat.clear(); _f_mopt.clear();
+      _f_et.clear(); _f_daylen.clear(); _f_sunset.clear(); _f_etflat.clear(); _f_mopt.clear(); _f_subdaily.clear();
       std::map<std::pair<double, double>, int> rows;
       for (int n = 0; n < nSteps; n++) {
         const double t_sol = _f_times[n].julian_day - floor(_f_times[n].julian_day) - 0.5;
@@ -444,6 +446,17 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
               _f_mopt.push_back(OpticalAirMass(_f_hru_d[2][k], declin, day_length, t_sol, O.timestep >= 1.0));
             }
             if (need_ws) _f_sunset.push_back(acos(-tan(_f_hru_d[2][k]) * tan(declin)));   // src/Evaporation.cpp:481
+            if (need_sd) {   // CModel::CalculateSubDailyCorrection, SUBDAILY_SIMPLE (src/UpdateForcings.cpp:964-982); F.day_length is the day's (:174-175)
+              const double hd = -tan(declin) * tan(_f_hru_d[2][k]);
+              const double DL = (hd >= 1.0) ? 0.0 : ((hd <= -1.0) ? 1.0 : acos(hd) / RVH_PI);
+              const double dawn = 0.5 - 0.5 * DL, dusk = 0.5 + 0.5 * DL;
+              const double t = _f_times[n].julian_day - floor(_f_times[n].julian_day), dt = O.timestep;
+              double corr = 0.0;
+              if ((t > dawn) && (t + dt <= dusk)) corr = -0.5 * (cos(RVH_PI * (t + dt - dawn) / DL) - cos(RVH_PI * (t - dawn) / DL)) / O.timestep;
+              else if ((t < dawn) && (t + dt >= dawn)) corr = -0.5 * (cos(RVH_PI * (t + dt - dawn) / DL) - 1) / O.timestep;
+              else if ((t < dusk) && (t + dt >= dusk)) corr = -0.5 * (-1 - cos(RVH_PI * (t - dawn) / DL)) / O.timestep;
+              _f_subdaily.push_back(corr);
+            }
           }
           _f_et_row[n] = r;
         } else _f_et_row[n] = it->second;
@@ -452,6 +465,7 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
       if (need_et) d.et_radia = _f_et.data();
       if (need_dl) d.day_length = _f_daylen.data();
       if (need_ws) d.sunset_angle = _f_sunset.data();
+      if (need_sd) d.subdaily_corr = _f_subdaily.data();
       if (need_atmos) { d.et_flat = _f_etflat.data(); d.opt_air_mass = _f_mopt.data(); }
     }
   }

@@ -359,6 +359,7 @@ private:
   // gridded forcing input (SetCellForcing): one station per grid cell with sparse HRU weights; replaces the :Gauge series at Flatten
   bool _cell_forcing = false;
   int _nCells = 0;
+  std::vector<double> _f_subdaily;   // [nEtRows][nHRU] SUBDAILY_SIMPLE correction factors
   std::vector<double> _f_p5;   // [nGauges][nSteps] 5-day antecedent precipitation of the gauges (INF_SCS)
   std::vector<double> _cell_elev, _cell_series, _cell_wt;   // [nCells], [RVN_GF_COUNT][nCells][nSteps], [nnz]
   std::vector<int32_t> _cell_ptr, _cell_idx;                // CSR over HRUs

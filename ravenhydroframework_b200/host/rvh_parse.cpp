@@ -271,7 +271,10 @@ static void ParseMainInputFile(CModel *&pModel, optStruct &Options) {
       continue;
     }
     if (c == ":SubdailyMethod" || c == ":SubDailyMethod") {
-      ExitGracefullyIf(s[1] != "SUBDAILY_NONE", "ParseMainInputFile: only SUBDAILY_NONE is implemented in the B200 build"); continue;
+      if (s[1] == "NONE" || s[1] == "SUBDAILY_NONE") Options.subdaily = 0;
+      else if (s[1] == "SIMPLE" || s[1] == "SUBDAILY_SIMPLE") Options.subdaily = 1;   // src/ParseInput.cpp:1186-1191
+      else ExitGracefully("ParseMainInputFile: :SubdailyMethod " + s[1] + " is not implemented in the B200 build (SUBDAILY_UBC re-derives every temperature of the day per step)");
+      continue;
     }
     if (c == ":MonthlyInterpolationMethod") {
       if (s[1] == "UNIFORM") Options.month_interp_method = MONTHINT_UNIFORM;

@@ -214,6 +214,9 @@ if hasattr(synth, "write_blended"):
     CASES["hbv_diffusive"] = dict(kind="hbv", n_sb=7, hru_per_sb=3, n_days=200, seed=22, routing="ROUTE_DIFFUSIVE_WAVE", season_offset=70)
     CASES["hbv_hydrologic"] = dict(kind="hbv", n_sb=7, hru_per_sb=3, n_days=250, seed=24, routing="ROUTE_HYDROLOGIC", season_offset=50)
     CASES["hbv_euler"] = dict(kind="hbv", n_sb=4, hru_per_sb=5, n_days=300, seed=9, routing="ROUTE_MUSKINGUM", season_offset=30, method="EULER")
+    # SUBDAILY_SIMPLE: the day's PET (daily estimators) and degree-day melt distributed over the steps by a half-sine between dawn and dusk
+    CASES["hbv_3hourly_subdaily"] = dict(kind="hbv", n_sb=3, hru_per_sb=4, n_days=90, seed=21, routing="ROUTE_MUSKINGUM", season_offset=70, timestep="03:00:00",
+                                         rvi_extra=":SubdailyMethod SUBDAILY_SIMPLE\n")
     CASES["hmets_3hourly"] = dict(kind="hmets", n_sb=3, hru_per_sb=4, n_days=60, seed=20, season_offset=90, timestep="03:00:00")
 if hasattr(synth, "write_gr4j"):
     WRITERS["gr4j"] = synth.write_gr4j
