@@ -143,6 +143,7 @@ typedef enum {
   RVN_OP_SNOBAL_CRHM_EBSM,     /* CmvSnowBalance          src/SnowBalance.cpp:1214-1291 (CRHMSnowBalance, Marks et al. energy budget; connections :146-158) */
   RVN_OP_INF_SCS,              /* CmvInfiltration         src/Infiltration.cpp:338-343,638-680 (GetSCSRunoff: curve number with antecedent-moisture classes from the 5-day precipitation) */
   RVN_OP_INF_SCS_NOABSTRACTION,/* CmvInfiltration         same, Ia = 0 (src/Infiltration.cpp:668-677) */
+  RVN_OP_SOILEVAP_SACSMA,      /* CmvSoilEvap             src/SoilEvaporation.cpp:652-715 (Sacramento soil accounting: six stores; connections :86-97) */
   RVN_OP_COUNT
 } rvn_opcode;
 
@@ -215,7 +216,7 @@ typedef enum {
   RVN_S_MAX_PERC_RATE, RVN_S_GR4J_X2, RVN_S_GR4J_X3, RVN_S_VIC_B_EXP, RVN_S_MAX_BASEFLOW_RATE, RVN_S_MAX_INTERFLOW_RATE,
   RVN_S_PERC_N, RVN_S_SAC_PERC_ALPHA, RVN_S_SAC_PERC_EXPON, RVN_S_PERC_ASPEN, RVN_S_BASEFLOW_THRESH, RVN_S_BASEFLOW_COEFF2,
   RVN_S_STORAGE_THRESHOLD, RVN_S_VIC_ZMIN, RVN_S_VIC_ZMAX, RVN_S_VIC_ALPHA, RVN_S_VIC_EVAP_GAMMA, RVN_S_UBC_EVAP_SOIL_DEF,
-  RVN_S_UBC_INFIL_SOIL_DEF, RVN_S_ALBEDO_WET, RVN_S_ALBEDO_DRY, RVN_S_HYDRAUL_COND, RVN_S_WETTING_FRONT_PSI, RVN_S_COUNT
+  RVN_S_UBC_INFIL_SOIL_DEF, RVN_S_ALBEDO_WET, RVN_S_ALBEDO_DRY, RVN_S_HYDRAUL_COND, RVN_S_WETTING_FRONT_PSI, RVN_S_UNAVAIL_FRAC, RVN_S_COUNT
 } rvn_soil_field;
 typedef enum { RVN_T_TOPMODEL_LAMBDA = 0, RVN_T_COUNT } rvn_terrain_field;   /* reference terrain_struct, src/Properties.h */
 

@@ -976,7 +976,7 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
     }
     case RVN_OP_SOILEVAP_ALL: case RVN_OP_SOILEVAP_HBV: case RVN_OP_SOILEVAP_GR4J: case RVN_OP_SOILEVAP_TOPMODEL:
     case RVN_OP_SOILEVAP_LINEAR: case RVN_OP_SOILEVAP_PDM: case RVN_OP_SOILEVAP_HYMOD2: case RVN_OP_SOILEVAP_UBC: case RVN_OP_SOILEVAP_VIC:
-    case RVN_OP_SOILEVAP_HYPR: case RVN_OP_SOILEVAP_SEQUEN: case RVN_OP_SOILEVAP_ROOT: case RVN_OP_SOILEVAP_ROOT_CONSTRAIN: case RVN_OP_SOILEVAP_AWBM: { /* src/SoilEvaporation.cpp:325-343,379-405,640-650 + :767-783 */
+    case RVN_OP_SOILEVAP_HYPR: case RVN_OP_SOILEVAP_SEQUEN: case RVN_OP_SOILEVAP_ROOT: case RVN_OP_SOILEVAP_ROOT_CONSTRAIN: case RVN_OP_SOILEVAP_AWBM: case RVN_OP_SOILEVAP_SACSMA: { /* src/SoilEvaporation.cpp:325-343,379-405,640-650 + :767-783 */
       if (type != RVN_HRU_STANDARD) break;
       double PET = F[RVN_F_PET];
       if (!d->opt.suppress_competitive_ET) { PET -= (sv[c->iSV[RVN_SV_AET]] / tstep); PET = omax(PET, 0.0); }
@@ -1057,6 +1057,45 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
         double rootfrac_l = 1.0 - rootfrac_u;
         rates[1] = PET * rootfrac_l * 1;
         PETused = rates[0] + rates[1]; multi = 1;
+      } else if (pr->op == RVN_OP_SOILEVAP_SACSMA) { /* :652-715 */
+        double red, e1, e2, e3, e5;
+        double Adimp = P_LU(c, RVN_LU_MAX_SAT_AREA_FRAC), Aimp = P_LU(c, RVN_LU_IMPERMEABLE_FRAC), rserv = P_S(c, 3, RVN_S_UNAVAIL_FRAC);
+        double Aperv = 1.0 - Adimp - Aimp;
+        double uzt_stor_max = soil_capacity(c, 0), uzf_stor_max = soil_capacity(c, 1), lzt_stor_max = soil_capacity(c, 2);
+        double lzfp_stor_max = soil_capacity(c, 3), lzfs_stor_max = soil_capacity(c, 4);
+        double uzt_stor = sv[sv_index(d, RVN_SV_SOIL, 0)] / Aperv, uzf_stor = sv[sv_index(d, RVN_SV_SOIL, 1)] / Aperv;
+        double lzt_stor = sv[sv_index(d, RVN_SV_SOIL, 2)] / Aperv, lzfp_stor = sv[sv_index(d, RVN_SV_SOIL, 3)] / Aperv;
+        double lzfs_stor = sv[sv_index(d, RVN_SV_SOIL, 4)] / Aperv, adimc_stor = sv[sv_index(d, RVN_SV_SOIL, 5)] / Adimp;
+        if (Adimp == 0) { adimc_stor = 0; }
+        e1 = omin(PET * (uzt_stor / uzt_stor_max), uzt_stor);
+        red = PET - e1;
+        uzt_stor -= e1;
+        rates[0] = e1 * Aperv / tstep;
+        e2 = omin(red, uzf_stor);
+        red -= e2;
+        uzf_stor -= e2;
+        rates[1] = e2 * Aperv / tstep;
+        if ((uzt_stor / uzt_stor_max) < (uzf_stor / uzf_stor_max)) {
+          double delta = uzt_stor_max * (uzt_stor + uzf_stor) / (uzt_stor_max + uzf_stor_max) - uzt_stor;
+          uzt_stor += delta;
+          uzf_stor -= delta;
+          rates[2] = delta * Aperv / tstep;
+        }
+        e3 = omin(red * (lzt_stor / (uzt_stor_max + lzt_stor_max)), lzt_stor);
+        lzt_stor -= e3;
+        rates[3] = e3 * Aperv / tstep;
+        double ratlzt = lzt_stor / lzt_stor_max;
+        double saved = rserv * (lzfp_stor_max + lzfs_stor_max);
+        double ratlz = (lzt_stor + lzfp_stor + lzfs_stor - saved) / (lzt_stor_max + lzfp_stor_max + lzfs_stor_max - saved);
+        if (ratlzt < ratlz) {
+          double del = omin((ratlz - ratlzt) * lzt_stor_max, lzfs_stor);
+          lzt_stor += del;
+          lzfs_stor -= del;
+        }
+        e5 = omin(e1 + (red + e2) * (adimc_stor - uzt_stor - e1) / (uzt_stor_max + lzt_stor_max), adimc_stor);
+        adimc_stor -= e5;
+        rates[5] = e5 * Adimp / tstep;
+        PETused = (e1 + e2 + e3) * Aperv + e5 * Adimp; multi = 1;
       } else if (pr->op == RVN_OP_SOILEVAP_AWBM) { /* :716-727 */
         double a1 = P_LU(c, RVN_LU_AWBM_AREAFRAC1), a2 = P_LU(c, RVN_LU_AWBM_AREAFRAC2);
         double a3 = 1.0 - a1 - a2;

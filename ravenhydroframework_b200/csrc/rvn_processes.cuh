@@ -729,6 +729,44 @@ template <class C, class PR> RVN_DI void rates_SOILEVAP(C &c, const PR &pr, cons
     const double rootfrac_l = 1.0 - rootfrac_u;
     c.R(1) = PET * rootfrac_l * 1;
     PETused = c.R(0) + c.R(1); multi = true;
+  } else if (op == RVN_OP_SOILEVAP_SACSMA) {   // :652-715 (Sacramento soil moisture accounting): UZT, UZF, LZT, LZFP, LZFS, ADIMC = SOIL[0..5], depths over the pervious area
+    const double Adimp = c.LU(RVN_LU_MAX_SAT_AREA_FRAC), Aimp = c.LU(RVN_LU_IMPERMEABLE_FRAC), rserv = c.SOIL(3, RVN_S_UNAVAIL_FRAC);
+    const double Aperv = 1.0 - Adimp - Aimp;
+    const double uzt_stor_max = SoilCapacity(c, 0), uzf_stor_max = SoilCapacity(c, 1), lzt_stor_max = SoilCapacity(c, 2);
+    const double lzfp_stor_max = SoilCapacity(c, 3), lzfs_stor_max = SoilCapacity(c, 4);
+    double uzt_stor = c.SV(c.soil_slot(0)) / Aperv, uzf_stor = c.SV(c.soil_slot(1)) / Aperv, lzt_stor = c.SV(c.soil_slot(2)) / Aperv;
+    const double lzfp_stor = c.SV(c.soil_slot(3)) / Aperv;
+    double lzfs_stor = c.SV(c.soil_slot(4)) / Aperv, adimc_stor = c.SV(c.soil_slot(5)) / Adimp;
+    if (Adimp == 0) adimc_stor = 0;
+    const double e1 = dmin(PET * (uzt_stor / uzt_stor_max), uzt_stor);
+    double red = PET - e1;
+    uzt_stor -= e1;
+    c.R(0) = e1 * Aperv / c.tstep;
+    const double e2 = dmin(red, uzf_stor);
+    red -= e2;
+    uzf_stor -= e2;
+    c.R(1) = e2 * Aperv / c.tstep;
+    if ((uzt_stor / uzt_stor_max) < (uzf_stor / uzf_stor_max)) {   // equilibrate the storage ratios of the upper zone
+      const double delta = uzt_stor_max * (uzt_stor + uzf_stor) / (uzt_stor_max + uzf_stor_max) - uzt_stor;
+      uzt_stor += delta;
+      uzf_stor -= delta;
+      c.R(2) = delta * Aperv / c.tstep;
+    }
+    const double e3 = dmin(red * (lzt_stor / (uzt_stor_max + lzt_stor_max)), lzt_stor);
+    lzt_stor -= e3;
+    c.R(3) = e3 * Aperv / c.tstep;
+    const double ratlzt = lzt_stor / lzt_stor_max;
+    const double saved = rserv * (lzfp_stor_max + lzfs_stor_max);
+    const double ratlz = (lzt_stor + lzfp_stor + lzfs_stor - saved) / (lzt_stor_max + lzfp_stor_max + lzfs_stor_max - saved);
+    if (ratlzt < ratlz) {   // resupply of the lower-zone tension water: bookkeeping only in the reference (its rates[4] stays 0)
+      const double del = dmin((ratlz - ratlzt) * lzt_stor_max, lzfs_stor);
+      lzt_stor += del;
+      lzfs_stor -= del;
+    }
+    const double e5 = dmin(e1 + (red + e2) * (adimc_stor - uzt_stor - e1) / (uzt_stor_max + lzt_stor_max), adimc_stor);
+    adimc_stor -= e5;
+    c.R(5) = e5 * Adimp / c.tstep;
+    PETused = (e1 + e2 + e3) * Aperv + e5 * Adimp; multi = true;
   } else if (op == RVN_OP_SOILEVAP_AWBM) {   // :716-727 (Boughton 2004)
     const double a1 = c.LU(RVN_LU_AWBM_AREAFRAC1), a2 = c.LU(RVN_LU_AWBM_AREAFRAC2);
     const double a3 = 1.0 - a1 - a2;
@@ -948,7 +986,7 @@ template <class C, class PR> RVN_DI void dispatch_rates(C &c, const PR &pr, cons
     case RVN_OP_PERC_SACRAMENTO: case RVN_OP_PERC_ASPEN: rates_PERCOLATION(c, pr, op); break;
     case RVN_OP_SOILEVAP_ALL: case RVN_OP_SOILEVAP_HBV: case RVN_OP_SOILEVAP_GR4J: case RVN_OP_SOILEVAP_TOPMODEL:
     case RVN_OP_SOILEVAP_LINEAR: case RVN_OP_SOILEVAP_PDM: case RVN_OP_SOILEVAP_HYMOD2: case RVN_OP_SOILEVAP_UBC: case RVN_OP_SOILEVAP_VIC:
-    case RVN_OP_SOILEVAP_HYPR: case RVN_OP_SOILEVAP_SEQUEN: case RVN_OP_SOILEVAP_ROOT: case RVN_OP_SOILEVAP_ROOT_CONSTRAIN: case RVN_OP_SOILEVAP_AWBM:
+    case RVN_OP_SOILEVAP_HYPR: case RVN_OP_SOILEVAP_SEQUEN: case RVN_OP_SOILEVAP_ROOT: case RVN_OP_SOILEVAP_ROOT_CONSTRAIN: case RVN_OP_SOILEVAP_AWBM: case RVN_OP_SOILEVAP_SACSMA:
       rates_SOILEVAP(c, pr, op); break;
     case RVN_OP_CANEVP_ALL: rates_CANEVP_ALL(c, pr); break;
     case RVN_OP_CANSNOWEVP_ALL: rates_CANSNOWEVP_ALL(c, pr); break;

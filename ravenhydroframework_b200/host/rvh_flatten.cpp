@@ -207,6 +207,7 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
       {RVN_OP_SOILEVAP_ROOT_CONSTRAIN, 'S', {RVN_S_FIELD_CAPACITY, RVN_S_SAT_WILT, -1}},
       {RVN_OP_SOILEVAP_AWBM, 'L', {RVN_LU_AWBM_AREAFRAC1, RVN_LU_AWBM_AREAFRAC2, -1}},
       {RVN_OP_INF_GREEN_AMPT, 'S', {RVN_S_HYDRAUL_COND, RVN_S_WETTING_FRONT_PSI, -1}},
+      {RVN_OP_SOILEVAP_SACSMA, 'S', {RVN_S_UNAVAIL_FRAC, -1}},
       {RVN_OP_INF_SCS, 'L', {RVN_LU_SCS_CN, -1}}, {RVN_OP_INF_SCS_NOABSTRACTION, 'L', {RVN_LU_SCS_CN, -1}},
       {RVN_OP_INF_GA_SIMPLE, 'S', {RVN_S_HYDRAUL_COND, RVN_S_WETTING_FRONT_PSI, -1}},
     };
@@ -378,7 +379,7 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
     for (int j = 0; j < NP; j++) {
       const int op = _f_proc[j].op;
       if (op == RVN_OP_SOILEVAP_ALL || op == RVN_OP_SOILEVAP_HBV || op == RVN_OP_SOILEVAP_GR4J || op == RVN_OP_SOILEVAP_TOPMODEL ||
-          (op >= RVN_OP_SOILEVAP_LINEAR && op <= RVN_OP_SOILEVAP_AWBM) || op == RVN_OP_CANEVP_ALL || op == RVN_OP_CANSNOWEVP_ALL ||
+          (op >= RVN_OP_SOILEVAP_LINEAR && op <= RVN_OP_SOILEVAP_AWBM) || op == RVN_OP_SOILEVAP_SACSMA || op == RVN_OP_CANEVP_ALL || op == RVN_OP_CANSNOWEVP_ALL ||
           op == RVN_OP_CANEVP_MAXIMUM || op == RVN_OP_CANEVP_RUTTER || op == RVN_OP_CANSNOWEVP_MAXIMUM) uses_pet = true;
       if (op == RVN_OP_OPEN_WATER_EVAP || op == RVN_OP_LAKE_EVAP_BASIC || op == RVN_OP_SOILEVAP_HYPR) uses_owpet = true;
     }

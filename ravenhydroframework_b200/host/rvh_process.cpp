@@ -531,8 +531,20 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
     else if (s[1] == "SOILEVAP_ROOT") op = RVN_OP_SOILEVAP_ROOT;
     else if (s[1] == "SOILEVAP_ROOT_CONSTRAIN") op = RVN_OP_SOILEVAP_ROOT_CONSTRAIN;
     else if (s[1] == "SOILEVAP_AWBM") op = RVN_OP_SOILEVAP_AWBM;
+    else if (s[1] == "SOILEVAP_SACSMA") op = RVN_OP_SOILEVAP_SACSMA;
     else ExitGracefully("ParseMainInputFile: soil evaporation algorithm " + s[1] + " is not implemented in the B200 build");
     // state variables and connections: src/SoilEvaporation.cpp:21-100 and :244-313
+    if (op == RVN_OP_SOILEVAP_SACSMA) {   // :86-97, :294-301: UZT, UZF, LZT, LZFP, LZFS, ADIMC = SOIL[0..5]
+      ExitGracefullyIf(pM->GetNumSoilLayers() < 6, "SOILEVAP_SACSMA needs the six Sacramento soil stores (:SoilModel SOIL_MULTILAYER 6)");
+      for (int m = 0; m <= 5; m++) AddSV1(pM, RVN_SV_SOIL, m);
+      AddSV1(pM, RVN_SV_ATMOSPHERE); AddSV1(pM, RVN_SV_AET);
+      CmvGeneric *p = new CmvGeneric("SoilEvaporation", op, pM);
+      const int iAET = pM->GetStateVarIndex(RVN_SV_AET);
+      auto S = [&](int m) { return pM->GetStateVarIndex(RVN_SV_SOIL, m); };
+      p->Connect(S(0), iAtmos); p->Connect(S(1), iAtmos); p->Connect(S(1), S(0)); p->Connect(S(2), iAtmos); p->Connect(S(4), S(2)); p->Connect(S(5), iAtmos);
+      p->Connect(iAET, iAET);
+      return p;
+    }
     const bool two = (op == RVN_OP_SOILEVAP_SEQUEN || op == RVN_OP_SOILEVAP_ROOT || op == RVN_OP_SOILEVAP_ROOT_CONSTRAIN);
     AddSV1(pM, RVN_SV_SOIL, 0);
     if (two || op == RVN_OP_SOILEVAP_AWBM) AddSV1(pM, RVN_SV_SOIL, 1);

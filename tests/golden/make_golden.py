@@ -69,6 +69,17 @@ if hasattr(synth, "write_hbv"):
     CASES["hbv_snobal_crhm"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=60, routing="ROUTE_MUSKINGUM",
                                     rvi_sub=[(r"  :SnowBalance       SNOBAL_SIMPLE_MELT SNOW            SNOW_LIQ\n    :-->Overflow     RAVEN_DEFAULT      SNOW_LIQ        PONDED_WATER\n",
                                               "  :SnowBalance       SNOBAL_CRHM_EBSM   SNOW            PONDED_WATER\n")])
+    # SOILEVAP_SACSMA (Sacramento soil accounting, six soil stores) on a six-layer variant of the GR4J set-up
+    CASES["gr4j_sevap_sacsma"] = dict(kind="gr4j", n_sb=2, hru_per_sb=4, n_days=400, seed=63,
+                                      rvi_sub=[(r"SOIL_MULTILAYER  4", "SOIL_MULTILAYER  6"), (r"SOILEVAP_GR4J      PRODUCT_STORE", "SOILEVAP_SACSMA    PRODUCT_STORE")],
+                                      rvp_sub=[(r"   SOIL_GW\n:EndSoilClasses", "   SOIL_GW\n   SOIL_LZFS\n   SOIL_ADIMC\n:EndSoilClasses"),
+                                               (r"DEFAULT_P,  4, SOIL_PROD, 0.529, SOIL_ROUT, 0.300, SOIL_TEMP, 1.000, SOIL_GW, 1.000,",
+                                                "DEFAULT_P,  6, SOIL_PROD, 0.529, SOIL_ROUT, 0.300, SOIL_TEMP, 1.000, SOIL_GW, 1.000, SOIL_LZFS, 0.400, SOIL_ADIMC, 0.250,"),
+                                               (r"THIN_P,     4, SOIL_PROD, 0.310, SOIL_ROUT, 0.300, SOIL_TEMP, 1.000, SOIL_GW, 1.000,",
+                                                "THIN_P,     6, SOIL_PROD, 0.310, SOIL_ROUT, 0.300, SOIL_TEMP, 1.000, SOIL_GW, 1.000, SOIL_LZFS, 0.300, SOIL_ADIMC, 0.200,")],
+                                      rvp_extra=":SoilParameterList\n  :Parameters, UNAVAIL_FRAC\n  :Units, none\n  [DEFAULT], 0.22\n:EndSoilParameterList\n"
+                                                ":LandUseParameterList\n  :Parameters, MAX_SAT_AREA_FRAC\n  :Units, none\n  [DEFAULT], 0.12\n  LU_TOWN, 0.07\n:EndLandUseParameterList\n",
+                                      rvc_extra=":UniformInitialConditions SOIL[2] 120.0\n:UniformInitialConditions SOIL[3] 90.0\n:UniformInitialConditions SOIL[4] 55.0\n:UniformInitialConditions SOIL[5] 35.0\n")
     CASES["gr4j_pet_oudin"] = dict(kind="gr4j", n_sb=2, hru_per_sb=4, n_days=400, seed=51, pet="PET_OUDIN")
     CASES["gr4j_pet_hamon"] = dict(kind="gr4j", n_sb=2, hru_per_sb=4, n_days=400, seed=52, pet="PET_HAMON")
     CASES["hbv_pet_lintemp"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=53, routing="ROUTE_MUSKINGUM", pet="PET_LINEAR_TEMP",
