@@ -50,7 +50,7 @@ typedef enum {
   RVN_SV_SOIL_TEMP = 35, RVN_SV_CANOPY_TEMP = 36, RVN_SV_SOIL_PCT_FROZ = 37, RVN_SV_SNOW_DEPTH = 38,
   RVN_SV_FIRN_GRAVITY = 39, RVN_SV_PERMAFROST_DEPTH = 40, RVN_SV_THAW_DEPTH = 41, RVN_SV_SNOW_DEPTH_STDDEV = 42,
   RVN_SV_SNOW_COVER = 43, RVN_SV_GLACIER_CC = 44, RVN_SV_SNOW_DEFICIT = 45, RVN_SV_SNOW_AGE = 46,
-  RVN_SV_SNODRIFT_TEMP = 47, RVN_SV_SNOW_DRIFT = 48, RVN_SV_ICE_THICKNESS = 49, RVN_SV_SNOW_ALBEDO = 50,
+  RVN_SV_SNODRIFT_TEMP = 47, RVN_SV_SNOW_DRIFT = 48, RVN_SV_ICE_THICKNESS = 49, RVN_SV_SNOW_ALBEDO = 50, RVN_SV_CROP_HEAT_UNITS = 51,
   RVN_SV_NTYPES = 64
 } rvn_sv_type;
 
@@ -144,6 +144,8 @@ typedef enum {
   RVN_OP_INF_SCS,              /* CmvInfiltration         src/Infiltration.cpp:338-343,638-680 (GetSCSRunoff: curve number with antecedent-moisture classes from the 5-day precipitation) */
   RVN_OP_INF_SCS_NOABSTRACTION,/* CmvInfiltration         same, Ia = 0 (src/Infiltration.cpp:668-677) */
   RVN_OP_SOILEVAP_SACSMA,      /* CmvSoilEvap             src/SoilEvaporation.cpp:652-715 (Sacramento soil accounting: six stores; connections :86-97) */
+  RVN_OP_SOILEVAP_CHU,         /* CmvSoilEvap             src/SoilEvaporation.cpp:460-468 (Ontario crop-heat-unit method) */
+  RVN_OP_CHU_ONTARIO,          /* CmvCropHeatUnitEvolve   src/CropGrowth.cpp:91-136 (CROP_HEAT_UNITS self-connection) */
   RVN_OP_COUNT
 } rvn_opcode;
 
@@ -204,7 +206,7 @@ typedef enum {
 } rvn_landuse_field;
 typedef enum {
   RVN_V_MAX_HEIGHT = 0, RVN_V_MAX_LAI, RVN_V_SAI_HT_RATIO, RVN_V_MAX_CAPACITY, RVN_V_MAX_SNOW_CAPACITY,
-  RVN_V_RAIN_ICEPT_PCT, RVN_V_SNOW_ICEPT_PCT, RVN_V_PET_VEG_CORR, RVN_V_RAIN_ICEPT_FACT, RVN_V_SNOW_ICEPT_FACT, RVN_V_ALBEDO, RVN_V_SVF_EXTINCTION,
+  RVN_V_RAIN_ICEPT_PCT, RVN_V_SNOW_ICEPT_PCT, RVN_V_PET_VEG_CORR, RVN_V_RAIN_ICEPT_FACT, RVN_V_SNOW_ICEPT_FACT, RVN_V_ALBEDO, RVN_V_SVF_EXTINCTION, RVN_V_CHU_MATURITY,
   /* derived canopy variables (reference veg_var_struct; CVegetationClass::RecalculateCanopyParams,
    * src/VegetationParams.cpp:85-200), refreshed by the host for the current step when date-dependent */
   RVN_V_VAR_CAPACITY, RVN_V_VAR_SNOW_CAPACITY, RVN_V_VAR_RAIN_ICEPT_PCT, RVN_V_VAR_SNOW_ICEPT_PCT,

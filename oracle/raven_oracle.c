@@ -976,7 +976,7 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
     }
     case RVN_OP_SOILEVAP_ALL: case RVN_OP_SOILEVAP_HBV: case RVN_OP_SOILEVAP_GR4J: case RVN_OP_SOILEVAP_TOPMODEL:
     case RVN_OP_SOILEVAP_LINEAR: case RVN_OP_SOILEVAP_PDM: case RVN_OP_SOILEVAP_HYMOD2: case RVN_OP_SOILEVAP_UBC: case RVN_OP_SOILEVAP_VIC:
-    case RVN_OP_SOILEVAP_HYPR: case RVN_OP_SOILEVAP_SEQUEN: case RVN_OP_SOILEVAP_ROOT: case RVN_OP_SOILEVAP_ROOT_CONSTRAIN: case RVN_OP_SOILEVAP_AWBM: case RVN_OP_SOILEVAP_SACSMA: { /* src/SoilEvaporation.cpp:325-343,379-405,640-650 + :767-783 */
+    case RVN_OP_SOILEVAP_HYPR: case RVN_OP_SOILEVAP_SEQUEN: case RVN_OP_SOILEVAP_ROOT: case RVN_OP_SOILEVAP_ROOT_CONSTRAIN: case RVN_OP_SOILEVAP_AWBM: case RVN_OP_SOILEVAP_SACSMA: case RVN_OP_SOILEVAP_CHU: { /* src/SoilEvaporation.cpp:325-343,379-405,640-650 + :767-783 */
       if (type != RVN_HRU_STANDARD) break;
       double PET = F[RVN_F_PET];
       if (!d->opt.suppress_competitive_ET) { PET -= (sv[c->iSV[RVN_SV_AET]] / tstep); PET = omax(PET, 0.0); }
@@ -1004,6 +1004,9 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
         rates[0] = (1.0 - area_ponded) * rates[0];
         rates[1] = (area_ponded)*F[RVN_F_OW_PET];
         PETused = (rates[0] + rates[1]); multi = 1;
+      } else if (pr->op == RVN_OP_SOILEVAP_CHU) { /* :460-468 */
+        double CHU = omax(sv[c->iSV[RVN_SV_CROP_HEAT_UNITS]], 0.0);
+        rates[0] = PET * omin(CHU / P_V(c, RVN_V_CHU_MATURITY), 1.0);
       } else if (pr->op == RVN_OP_SOILEVAP_LINEAR) { /* :370-377 */
         double stor = sv[iFrom[0]], alpha = P_LU(c, RVN_LU_AET_COEFF);
         rates[0] = omin(alpha * stor, PET);
@@ -1112,6 +1115,22 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
         corr += oldrate - rates[q];
       }
       rates[pr->nconn - 1] -= corr;
+      break;
+    }
+    case RVN_OP_CHU_ONTARIO: { /* CmvCropHeatUnitEvolve, src/CropGrowth.cpp:91-136 */
+      if (type != RVN_HRU_STANDARD) break;
+      double CHU = sv[iFrom[0]], old_CHU = CHU, CHU_day, CHU_night;
+      double temp_ave = F[RVN_F_TEMP_DAILY_AVE], temp_max = F[RVN_F_TEMP_DAILY_MAX], temp_min = F[RVN_F_TEMP_DAILY_MIN];
+      int growing_season = (CHU > -0.5);
+      if (!growing_season) { if (temp_ave > 12.8) { CHU = 0.0; } }
+      else {
+        CHU_day = omax(3.33 * (temp_max - 10) - 0.084 * pow(temp_max - 10.0, 2.0), 0.0);
+        CHU_night = omax(1.8 * (temp_min - 4.4), 0.0);
+        CHU += 0.5 * (CHU_day + CHU_night);
+        if (temp_ave < -2.0) { CHU = -1.0; }
+        if (d->times[c->step].month > 9) { CHU = -1.0; }
+      }
+      rates[0] = (CHU - old_CHU) / tstep;
       break;
     }
     case RVN_OP_SNOBAL_GAWSER: { /* CmvSnowBalance::GawserBalance, src/SnowBalance.cpp:1098-1201 */

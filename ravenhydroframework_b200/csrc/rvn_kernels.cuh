@@ -330,7 +330,7 @@ RVN_DI void compute_forcings(C &c, const DevModel &M, int e, int k, int step, in
     apply_perturbations(F, M, RVN_PF_SNOWFALL, e, k, step);
   }
   if (c.type == RVN_HRU_MASKED_GLACIER) { F[RVN_F_PRECIP] = 0; p5 = 0; }
-  if (C::kAtmos && M.gauge_p5 != nullptr) { c.precip_5day = p5; c.month = mo; }
+  if (C::kAtmos) { c.precip_5day = p5; c.month = mo; }   // interpreter only: INF_SCS / ABST_SCS / CHU_ONTARIO read them
   {  // CModel::EstimatePotentialMelt  src/PotentialMelt.cpp:20-246
     double pm = F[RVN_F_POTENTIAL_MELT];
     const int method = opt.pot_melt;

@@ -677,6 +677,9 @@ template <class C, class PR> RVN_DI void rates_SOILEVAP(C &c, const PR &pr, cons
     c.R(0) = (1.0 - area_ponded) * c.R(0);
     c.R(1) = (area_ponded)*c.F[RVN_F_OW_PET];
     PETused = (c.R(0) + c.R(1)); multi = true;
+  } else if (op == RVN_OP_SOILEVAP_CHU) {   // :460-468: evaporation scaled by the crop heat units accumulated towards maturity
+    const double CHU = dmax(c.SV(c.iSV(RVN_SV_CROP_HEAT_UNITS)), 0.0);
+    c.R(0) = PET * dmin(CHU / c.VEG(RVN_V_CHU_MATURITY), 1.0);
   } else if (op == RVN_OP_SOILEVAP_LINEAR) {   // :370-377
     c.R(0) = dmin(c.LU(RVN_LU_AET_COEFF) * c.SV(pr.from(0)), PET);
   } else if (op == RVN_OP_SOILEVAP_PDM || op == RVN_OP_SOILEVAP_HYMOD2) {   // :424-458
@@ -836,6 +839,23 @@ template <class C, class PR> RVN_DI void rates_SNOBAL_COLD_CONTENT(C &c, const P
   }
 }
 
+// CmvCropHeatUnitEvolve CHU_ONTARIO  src/CropGrowth.cpp:91-136: -1 outside the growing season, reset to 0 when the daily mean exceeds 12.8 C, then daily day / night increments
+template <class C, class PR> RVN_DI void rates_CHU_ONTARIO(C &c, const PR &pr) {
+  if (c.type != RVN_HRU_STANDARD) return;
+  double CHU = c.SV(pr.from(0));
+  const double old_CHU = CHU;
+  const double temp_ave = c.F[RVN_F_TEMP_DAILY_AVE], temp_max = c.F[RVN_F_TEMP_DAILY_MAX], temp_min = c.F[RVN_F_TEMP_DAILY_MIN];
+  const bool growing_season = (CHU > -0.5);
+  if (!growing_season) { if (temp_ave > 12.8) CHU = 0.0; }
+  else {
+    const double CHU_day = dmax(3.33 * (temp_max - 10) - 0.084 * rvn_pow(temp_max - 10.0, 2.0), 0.0);
+    const double CHU_night = dmax(1.8 * (temp_min - 4.4), 0.0);
+    CHU += 0.5 * (CHU_day + CHU_night);
+    if (temp_ave < -2.0) CHU = -1.0;
+    if (c.month > 9) CHU = -1.0;
+  }
+  c.R(0) = (CHU - old_CHU) / c.tstep;
+}
 // CmvSnowBalance SNOBAL_GAWSER  src/SnowBalance.cpp:1098-1201 (GawserBalance); connections :123-145: SNOW -> SNOW_LIQ, PONDED -> SNOW_LIQ, SNOW_LIQ -> SNOW,
 // three SNOW_DEPTH self-connections (compaction, melt + sublimation, snowfall), NEW_SNOW -> SNOW, SNOW -> ATMOSPHERE, SNOW_LIQ -> PONDED, SNOW -> PONDED
 template <class C, class PR> RVN_DI void rates_SNOBAL_GAWSER(C &c, const PR &pr) {
@@ -964,6 +984,7 @@ template <class C, class PR> RVN_DI void dispatch_rates(C &c, const PR &pr, cons
     case RVN_OP_SNOBAL_HMETS: rates_SNOBAL_HMETS(c, pr); break;
     case RVN_OP_SNOBAL_COLD_CONTENT: rates_SNOBAL_COLD_CONTENT(c, pr); break;
     case RVN_OP_SNOBAL_GAWSER: rates_SNOBAL_GAWSER(c, pr); break;
+    case RVN_OP_CHU_ONTARIO: rates_CHU_ONTARIO(c, pr); break;
     case RVN_OP_SNOBAL_CRHM_EBSM: rates_SNOBAL_CRHM_EBSM(c, pr); break;
     case RVN_OP_SNOBAL_SIMPLE_MELT: rates_SNOBAL_SIMPLE_MELT(c, pr); break;
     case RVN_OP_SNOBAL_CEMA_NEIGE: rates_SNOBAL_CEMA_NEIGE(c, pr); break;
@@ -986,7 +1007,7 @@ template <class C, class PR> RVN_DI void dispatch_rates(C &c, const PR &pr, cons
     case RVN_OP_PERC_SACRAMENTO: case RVN_OP_PERC_ASPEN: rates_PERCOLATION(c, pr, op); break;
     case RVN_OP_SOILEVAP_ALL: case RVN_OP_SOILEVAP_HBV: case RVN_OP_SOILEVAP_GR4J: case RVN_OP_SOILEVAP_TOPMODEL:
     case RVN_OP_SOILEVAP_LINEAR: case RVN_OP_SOILEVAP_PDM: case RVN_OP_SOILEVAP_HYMOD2: case RVN_OP_SOILEVAP_UBC: case RVN_OP_SOILEVAP_VIC:
-    case RVN_OP_SOILEVAP_HYPR: case RVN_OP_SOILEVAP_SEQUEN: case RVN_OP_SOILEVAP_ROOT: case RVN_OP_SOILEVAP_ROOT_CONSTRAIN: case RVN_OP_SOILEVAP_AWBM: case RVN_OP_SOILEVAP_SACSMA:
+    case RVN_OP_SOILEVAP_HYPR: case RVN_OP_SOILEVAP_SEQUEN: case RVN_OP_SOILEVAP_ROOT: case RVN_OP_SOILEVAP_ROOT_CONSTRAIN: case RVN_OP_SOILEVAP_AWBM: case RVN_OP_SOILEVAP_SACSMA: case RVN_OP_SOILEVAP_CHU:
       rates_SOILEVAP(c, pr, op); break;
     case RVN_OP_CANEVP_ALL: rates_CANEVP_ALL(c, pr); break;
     case RVN_OP_CANSNOWEVP_ALL: rates_CANSNOWEVP_ALL(c, pr); break;

@@ -212,6 +212,10 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
       {RVN_OP_INF_GA_SIMPLE, 'S', {RVN_S_HYDRAUL_COND, RVN_S_WETTING_FRONT_PSI, -1}},
     };
     for (int r = 0; r < d.nProc; r++)
+      if (d.proc[r].op == RVN_OP_SOILEVAP_CHU)   // src/SoilEvaporation.cpp:189-193
+        for (size_t c = 0; c < veg_classes.size(); c++)
+          ExitGracefullyIf(veg_classes[c].V.v[RVN_V_CHU_MATURITY] == NOT_SPECIFIED, "CVegetationClass::AutoCalculateVegetationProps: required parameter CHU_MATURITY not specified for vegetation class " + veg_classes[c].tag);
+    for (int r = 0; r < d.nProc; r++)
       if (d.proc[r].op == RVN_OP_INF_UBC) {   // CmvInfiltration::GetParticipatingParamList, src/Infiltration.cpp:181-190 (UBC_FLASH_PONDING is autogenerated)
         ExitGracefullyIf(globals.v[RVN_G_UBC_GW_SPLIT] == NOT_SPECIFIED, "CGlobalParams::AutoCalculateGlobalParams: required global parameter UBC_GW_SPLIT not specified");
         for (size_t c = 0; c < soil_classes.size(); c++)
@@ -379,7 +383,7 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
     for (int j = 0; j < NP; j++) {
       const int op = _f_proc[j].op;
       if (op == RVN_OP_SOILEVAP_ALL || op == RVN_OP_SOILEVAP_HBV || op == RVN_OP_SOILEVAP_GR4J || op == RVN_OP_SOILEVAP_TOPMODEL ||
-          (op >= RVN_OP_SOILEVAP_LINEAR && op <= RVN_OP_SOILEVAP_AWBM) || op == RVN_OP_SOILEVAP_SACSMA || op == RVN_OP_CANEVP_ALL || op == RVN_OP_CANSNOWEVP_ALL ||
+          (op >= RVN_OP_SOILEVAP_LINEAR && op <= RVN_OP_SOILEVAP_AWBM) || op == RVN_OP_SOILEVAP_SACSMA || op == RVN_OP_SOILEVAP_CHU || op == RVN_OP_CANEVP_ALL || op == RVN_OP_CANSNOWEVP_ALL ||
           op == RVN_OP_CANEVP_MAXIMUM || op == RVN_OP_CANEVP_RUTTER || op == RVN_OP_CANSNOWEVP_MAXIMUM) uses_pet = true;
       if (op == RVN_OP_OPEN_WATER_EVAP || op == RVN_OP_LAKE_EVAP_BASIC || op == RVN_OP_SOILEVAP_HYPR) uses_owpet = true;
     }

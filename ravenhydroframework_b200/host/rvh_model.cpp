@@ -18,7 +18,7 @@ static const char *kLUNames[RVN_LU_COUNT] = {"IMPERMEABLE_FRAC", "FOREST_COVERAG
   "AWBM_AREAFRAC2", "HYMOD2_G", "HYMOD2_KMAX", "HYMOD2_EXP", "PET_LIN_COEFF", "RAIN_MELT_MULT", "RELHUM_CORR", "PET_VAP_COEFF",
   "MIN_WIND_SPEED", "MAX_WIND_SPEED", "ABST_PERCENT", "ROUGHNESS", "PRIESTLEYTAYLOR_COEFF", "SCS_CN", "SCS_IA_FRACTION", "PDMROF_B"};
 static const char *kVegNames[RVN_V_COUNT] = {"MAX_HEIGHT", "MAX_LAI", "SAI_HT_RATIO", "MAX_CAPACITY", "MAX_SNOW_CAPACITY", "RAIN_ICEPT_PCT",
-  "SNOW_ICEPT_PCT", "PET_VEG_CORR", "RAIN_ICEPT_FACT", "SNOW_ICEPT_FACT", "ALBEDO", "SVF_EXTINCTION", "VAR_CAPACITY", "VAR_SNOW_CAPACITY", "VAR_RAIN_ICEPT_PCT", "VAR_SNOW_ICEPT_PCT"};
+  "SNOW_ICEPT_PCT", "PET_VEG_CORR", "RAIN_ICEPT_FACT", "SNOW_ICEPT_FACT", "ALBEDO", "SVF_EXTINCTION", "CHU_MATURITY", "VAR_CAPACITY", "VAR_SNOW_CAPACITY", "VAR_RAIN_ICEPT_PCT", "VAR_SNOW_ICEPT_PCT"};
 static const char *kGlobalNames[RVN_G_COUNT] = {"SNOW_SWI", "SNOW_SWI_MIN", "SNOW_SWI_MAX", "SWI_REDUCT_COEFF", "ADIABATIC_LAPSE", "PRECIP_LAPSE",
   "RAINSNOW_TEMP", "RAINSNOW_DELTA", "AVG_ANNUAL_SNOW", "SNOW_TEMPERATURE", "HBVEC_LAPSE_UPPER", "HBVEC_LAPSE_RATE", "HBVEC_LAPSE_ELEV",
   "AIRSNOW_COEFF", "AVG_ANNUAL_RUNOFF", "MAX_SWE_SURFACE", "TOC_MULTIPLIER", "TIME_TO_PEAK_MULTIPLIER", "GAMMA_SHAPE_MULTIPLIER",
@@ -687,7 +687,7 @@ static const struct { const char *name; sv_type t; } kSVNames[] = {
   {"CONVOLUTION", RVN_SV_CONVOLUTION}, {"CONV_STOR", RVN_SV_CONV_STOR}, {"CUM_INFIL", RVN_SV_CUM_INFIL}, {"CUM_SNOWMELT", RVN_SV_CUM_SNOWMELT},
   {"AET", RVN_SV_AET}, {"RUNOFF", RVN_SV_RUNOFF}, {"SNOW_TEMP", RVN_SV_SNOW_TEMP}, {"COLD_CONTENT", RVN_SV_COLD_CONTENT},
   {"SNOW_DEPTH", RVN_SV_SNOW_DEPTH}, {"SNOW_COVER", RVN_SV_SNOW_COVER}, {"SNOW_DEFICIT", RVN_SV_SNOW_DEFICIT}, {"SNOW_AGE", RVN_SV_SNOW_AGE},
-  {"SNOW_ALBEDO", RVN_SV_SNOW_ALBEDO}, {"ICE_THICKNESS", RVN_SV_ICE_THICKNESS}, {NULL, RVN_SV_NTYPES}};
+  {"SNOW_ALBEDO", RVN_SV_SNOW_ALBEDO}, {"CROP_HEAT_UNITS", RVN_SV_CROP_HEAT_UNITS}, {"ICE_THICKNESS", RVN_SV_ICE_THICKNESS}, {NULL, RVN_SV_NTYPES}};
 sv_type CModel::StringToSVType(const std::string &sin, int &layer, bool strict) const {
   std::string s = sin;
   std::map<std::string, std::string>::const_iterator it = _aliases.find(s);

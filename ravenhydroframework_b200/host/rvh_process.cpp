@@ -532,6 +532,7 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
     else if (s[1] == "SOILEVAP_ROOT_CONSTRAIN") op = RVN_OP_SOILEVAP_ROOT_CONSTRAIN;
     else if (s[1] == "SOILEVAP_AWBM") op = RVN_OP_SOILEVAP_AWBM;
     else if (s[1] == "SOILEVAP_SACSMA") op = RVN_OP_SOILEVAP_SACSMA;
+    else if (s[1] == "SOILEVAP_CHU") op = RVN_OP_SOILEVAP_CHU;
     else ExitGracefully("ParseMainInputFile: soil evaporation algorithm " + s[1] + " is not implemented in the B200 build");
     // state variables and connections: src/SoilEvaporation.cpp:21-100 and :244-313
     if (op == RVN_OP_SOILEVAP_SACSMA) {   // :86-97, :294-301: UZT, UZF, LZT, LZFP, LZFS, ADIMC = SOIL[0..5]
@@ -552,6 +553,7 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
     AddSV1(pM, RVN_SV_ATMOSPHERE);
     if (op == RVN_OP_SOILEVAP_HYPR) AddSV1(pM, RVN_SV_DEPRESSION);
     if (op == RVN_OP_SOILEVAP_UBC) AddSV1(pM, RVN_SV_SNOW);
+    if (op == RVN_OP_SOILEVAP_CHU) AddSV1(pM, RVN_SV_CROP_HEAT_UNITS);   // src/SoilEvaporation.cpp:271-276
     AddSV1(pM, RVN_SV_AET);
     CmvGeneric *p = new CmvGeneric("SoilEvaporation", op, pM);
     int iAET = pM->GetStateVarIndex(RVN_SV_AET);
@@ -653,6 +655,15 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
     CmvGeneric *p = new CmvGeneric("CanopySublimation", snow_max ? RVN_OP_CANSNOWEVP_MAXIMUM : RVN_OP_CANSNOWEVP_ALL, pM);
     int iAET = pM->GetStateVarIndex(RVN_SV_AET);
     p->Connect(pM->GetStateVarIndex(RVN_SV_CANOPY_SNOW), iAtmos); p->Connect(iAET, iAET);
+    return p;
+  }
+  if (cmd == ":CropHeatUnitEvolve") {  // case 224; src/CropGrowth.cpp:15-33,76-84
+    need(2);
+    ExitGracefullyIf(s[1] != "CHU_ONTARIO", "ParseMainInputFile: Unrecognized crop heat evolution algorithm");
+    AddSV1(pM, RVN_SV_CROP_HEAT_UNITS);
+    CmvGeneric *p = new CmvGeneric("CropHeatUnitEvolve", RVN_OP_CHU_ONTARIO, pM);
+    const int iCHU = pM->GetStateVarIndex(RVN_SV_CROP_HEAT_UNITS);
+    p->Connect(iCHU, iCHU);
     return p;
   }
   if (cmd == ":Abstraction") {  // case 225; src/Abstraction.cpp:20-33

@@ -154,6 +154,12 @@ if hasattr(synth, "write_hbv"):
                                  rvp_extra=_dep + ":LandUseParameterList\n  :Parameters, SCS_CN, SCS_IA_FRACTION\n  :Units, none, none\n  [DEFAULT], 74.0, 0.05\n  LU_OPEN, 86.0, 0.08\n:EndLandUseParameterList\n")
     CASES["hbv_abst_pdmrof"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=87, routing="ROUTE_MUSKINGUM", proc_after=(_hbv_after, _abst % "ABST_PDMROF"),
                                     rvp_extra=_dep + ":LandUseParameterList\n  :Parameters, PDMROF_B\n  :Units, none\n  [DEFAULT], 0.7\n  LU_OPEN, 1.6\n:EndLandUseParameterList\n")
+    # Ontario crop heat units: CHU_ONTARIO evolves CROP_HEAT_UNITS (-1 outside the growing season), SOILEVAP_CHU scales PET by CHU / CHU_MATURITY
+    CASES["hbv_chu_ontario"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=500, seed=88, routing="ROUTE_MUSKINGUM",
+                                    proc_after=(_hbv_after, "  :CropHeatUnitEvolve CHU_ONTARIO\n"),
+                                    rvi_sub=[(r"  :SoilEvaporation   SOILEVAP_HBV       SOIL\[0\]         ATMOSPHERE\n", "  :SoilEvaporation   SOILEVAP_CHU       SOIL[0]         ATMOSPHERE\n")],
+                                    rvp_extra=":VegetationParameterList\n  :Parameters, CHU_MATURITY\n  :Units, none\n  [DEFAULT], 2600.0\n  VEG_LOW, 1900.0\n:EndVegetationParameterList\n",
+                                    rvc_extra=":UniformInitialConditions CROP_HEAT_UNITS -1.0\n")
     CASES["hbv_abst_percentage"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=85, routing="ROUTE_MUSKINGUM", proc_after=(_hbv_after, _abst % "ABST_PERCENTAGE"),
                                         rvi_sub=[(_can, _can_max)], rvp_extra=_dep)
     # surveyed channel cross-section (:ChannelProfile with roughness zones -> 20-point rating curves) under the two routing methods that
