@@ -146,6 +146,7 @@ typedef enum {
   RVN_OP_SOILEVAP_SACSMA,      /* CmvSoilEvap             src/SoilEvaporation.cpp:652-715 (Sacramento soil accounting: six stores; connections :86-97) */
   RVN_OP_SOILEVAP_CHU,         /* CmvSoilEvap             src/SoilEvaporation.cpp:460-468 (Ontario crop-heat-unit method) */
   RVN_OP_CHU_ONTARIO,          /* CmvCropHeatUnitEvolve   src/CropGrowth.cpp:91-136 (CROP_HEAT_UNITS self-connection) */
+  RVN_OP_EXCHANGE_FLOW,        /* CmvExchangeFlow         src/Flush.cpp:296-308,358-368: two soil stores swap EXCHANGE_FLOW [mm/d] in both directions; ia[0] = soil layer of the 'from' store */
   RVN_OP_COUNT
 } rvn_opcode;
 
@@ -218,7 +219,7 @@ typedef enum {
   RVN_S_MAX_PERC_RATE, RVN_S_GR4J_X2, RVN_S_GR4J_X3, RVN_S_VIC_B_EXP, RVN_S_MAX_BASEFLOW_RATE, RVN_S_MAX_INTERFLOW_RATE,
   RVN_S_PERC_N, RVN_S_SAC_PERC_ALPHA, RVN_S_SAC_PERC_EXPON, RVN_S_PERC_ASPEN, RVN_S_BASEFLOW_THRESH, RVN_S_BASEFLOW_COEFF2,
   RVN_S_STORAGE_THRESHOLD, RVN_S_VIC_ZMIN, RVN_S_VIC_ZMAX, RVN_S_VIC_ALPHA, RVN_S_VIC_EVAP_GAMMA, RVN_S_UBC_EVAP_SOIL_DEF,
-  RVN_S_UBC_INFIL_SOIL_DEF, RVN_S_ALBEDO_WET, RVN_S_ALBEDO_DRY, RVN_S_HYDRAUL_COND, RVN_S_WETTING_FRONT_PSI, RVN_S_UNAVAIL_FRAC, RVN_S_COUNT
+  RVN_S_UBC_INFIL_SOIL_DEF, RVN_S_ALBEDO_WET, RVN_S_ALBEDO_DRY, RVN_S_HYDRAUL_COND, RVN_S_WETTING_FRONT_PSI, RVN_S_UNAVAIL_FRAC, RVN_S_EXCHANGE_FLOW, RVN_S_COUNT
 } rvn_soil_field;
 typedef enum { RVN_T_TOPMODEL_LAMBDA = 0, RVN_T_COUNT } rvn_terrain_field;   /* reference terrain_struct, src/Properties.h */
 

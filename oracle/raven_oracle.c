@@ -1117,6 +1117,11 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       rates[pr->nconn - 1] -= corr;
       break;
     }
+    case RVN_OP_EXCHANGE_FLOW: { /* CmvExchangeFlow, src/Flush.cpp:358-368 */
+      rates[0] = P_S(c, pr->ia[0], RVN_S_EXCHANGE_FLOW);
+      rates[1] = P_S(c, pr->ia[0], RVN_S_EXCHANGE_FLOW);
+      break;
+    }
     case RVN_OP_CHU_ONTARIO: { /* CmvCropHeatUnitEvolve, src/CropGrowth.cpp:91-136 */
       if (type != RVN_HRU_STANDARD) break;
       double CHU = sv[iFrom[0]], old_CHU = CHU, CHU_day, CHU_night;

@@ -540,6 +540,11 @@ template <class C, class PR> RVN_DI void rates_OVERFLOW(C &c, const PR &pr) {
   double max_storage = dmax(StateVarMax(c, pr.from(0)), 0.0);
   c.R(0) = dmax(c.SV(pr.from(0)) - max_storage, 0.0) / c.tstep;
 }
+// CmvExchangeFlow  src/Flush.cpp:358-368 (no constraints, :380-388)
+template <class C, class PR> RVN_DI void rates_EXCHANGE_FLOW(C &c, const PR &pr) {
+  const double q = c.SOIL(pr.ia(0), RVN_S_EXCHANGE_FLOW);
+  c.R(0) = q; c.R(1) = q;
+}
 // CmvFlush  src/Flush.cpp:75-86
 template <class C, class PR> RVN_DI void rates_FLUSH(C &c, const PR &pr) { c.R(0) = pr.da(0) * c.SV(pr.from(0)) / c.tstep; }
 // CmvSplit  src/Flush.cpp:178-186
@@ -985,6 +990,7 @@ template <class C, class PR> RVN_DI void dispatch_rates(C &c, const PR &pr, cons
     case RVN_OP_SNOBAL_COLD_CONTENT: rates_SNOBAL_COLD_CONTENT(c, pr); break;
     case RVN_OP_SNOBAL_GAWSER: rates_SNOBAL_GAWSER(c, pr); break;
     case RVN_OP_CHU_ONTARIO: rates_CHU_ONTARIO(c, pr); break;
+    case RVN_OP_EXCHANGE_FLOW: rates_EXCHANGE_FLOW(c, pr); break;
     case RVN_OP_SNOBAL_CRHM_EBSM: rates_SNOBAL_CRHM_EBSM(c, pr); break;
     case RVN_OP_SNOBAL_SIMPLE_MELT: rates_SNOBAL_SIMPLE_MELT(c, pr); break;
     case RVN_OP_SNOBAL_CEMA_NEIGE: rates_SNOBAL_CEMA_NEIGE(c, pr); break;

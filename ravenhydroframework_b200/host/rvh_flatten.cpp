@@ -208,6 +208,7 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
       {RVN_OP_SOILEVAP_AWBM, 'L', {RVN_LU_AWBM_AREAFRAC1, RVN_LU_AWBM_AREAFRAC2, -1}},
       {RVN_OP_INF_GREEN_AMPT, 'S', {RVN_S_HYDRAUL_COND, RVN_S_WETTING_FRONT_PSI, -1}},
       {RVN_OP_SOILEVAP_SACSMA, 'S', {RVN_S_UNAVAIL_FRAC, -1}},
+      {RVN_OP_EXCHANGE_FLOW, 'S', {RVN_S_EXCHANGE_FLOW, -1}},
       {RVN_OP_INF_SCS, 'L', {RVN_LU_SCS_CN, -1}}, {RVN_OP_INF_SCS_NOABSTRACTION, 'L', {RVN_LU_SCS_CN, -1}},
       {RVN_OP_INF_GA_SIMPLE, 'S', {RVN_S_HYDRAUL_COND, RVN_S_WETTING_FRONT_PSI, -1}},
     };

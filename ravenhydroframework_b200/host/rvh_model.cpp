@@ -9,7 +9,7 @@ static const char *kSoilNames[RVN_S_COUNT] = {"POROSITY", "CAP_RATIO", "PERC_COE
   "FIELD_CAPACITY", "SAT_WILT", "HBV_BETA", "MAX_CAP_RISE_RATE", "MAX_PERC_RATE", "GR4J_X2", "GR4J_X3", "VIC_B_EXP", "MAX_BASEFLOW_RATE", "MAX_INTERFLOW_RATE",
   "PERC_N", "SAC_PERC_ALPHA", "SAC_PERC_EXPON", "PERC_ASPEN", "BASEFLOW_THRESH", "BASEFLOW_COEFF2", "STORAGE_THRESHOLD", "VIC_ZMIN", "VIC_ZMAX",
   "VIC_ALPHA", "VIC_EVAP_GAMMA", "UBC_EVAP_SOIL_DEF", "UBC_INFIL_SOIL_DEF", "ALBEDO_WET", "ALBEDO_DRY",
-  "HYDRAUL_COND", "WETTING_FRONT_PSI", "UNAVAIL_FRAC"};
+  "HYDRAUL_COND", "WETTING_FRONT_PSI", "UNAVAIL_FRAC", "EXCHANGE_FLOW"};
 static const char *kLUNames[RVN_LU_COUNT] = {"IMPERMEABLE_FRAC", "FOREST_COVERAGE", "FOREST_SPARSENESS", "MELT_FACTOR", "MIN_MELT_FACTOR",
   "MAX_MELT_FACTOR", "DD_MELT_TEMP", "DD_AGGRADATION", "REFREEZE_FACTOR", "DD_REFREEZE_TEMP", "REFREEZE_EXP", "HMETS_RUNOFF_COEFF",
   "GAMMA_SHAPE", "GAMMA_SCALE", "GAMMA_SHAPE2", "GAMMA_SCALE2", "GR4J_X4", "HBV_MELT_FOR_CORR", "HBV_MELT_ASP_CORR",

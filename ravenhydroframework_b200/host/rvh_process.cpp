@@ -454,6 +454,15 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
     p->SetIntArg(0, SoilLayerOf(pM, from));
     return p;
   }
+  if (cmd == ":ExchangeFlow") {  // case 231: :ExchangeFlow RAVEN_DEFAULT [from] [mixing zone]; src/Flush.cpp:296-326
+    need(4);
+    int from = pM->ParseSVTypeIndex(s[2]), to = pM->ParseSVTypeIndex(s[3]);
+    ExitGracefullyIf(SoilLayerOf(pM, from) < 0 || SoilLayerOf(pM, to) < 0, "CmvExchangeFlow::Initialize: exchange flow  must be between two soil units");
+    CmvGeneric *p = new CmvGeneric("ExchangeFlow", RVN_OP_EXCHANGE_FLOW, pM);
+    p->Connect(from, to); p->Connect(to, from);
+    p->SetIntArg(0, SoilLayerOf(pM, from));
+    return p;
+  }
   if (cmd == ":Flush") {  // case 221
     need(4);
     int from = pM->ParseSVTypeIndex(s[2]), to = pM->ParseSVTypeIndex(s[3]);

@@ -160,6 +160,10 @@ if hasattr(synth, "write_hbv"):
                                     rvi_sub=[(r"  :SoilEvaporation   SOILEVAP_HBV       SOIL\[0\]         ATMOSPHERE\n", "  :SoilEvaporation   SOILEVAP_CHU       SOIL[0]         ATMOSPHERE\n")],
                                     rvp_extra=":VegetationParameterList\n  :Parameters, CHU_MATURITY\n  :Units, none\n  [DEFAULT], 2600.0\n  VEG_LOW, 1900.0\n:EndVegetationParameterList\n",
                                     rvc_extra=":UniformInitialConditions CROP_HEAT_UNITS -1.0\n")
+    # :ExchangeFlow between the fast and the slow reservoir (constant two-way mixing flux)
+    CASES["hbv_exchangeflow"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=300, seed=89, routing="ROUTE_MUSKINGUM",
+                                     proc_after=(r"(  :CapillaryRise     RISE_HBV           FAST_RESERVOIR  SOIL\[0\]\n)", "  :ExchangeFlow      RAVEN_DEFAULT      FAST_RESERVOIR  SLOW_RESERVOIR\n"),
+                                     rvp_extra=":SoilParameterList\n  :Parameters, EXCHANGE_FLOW\n  :Units, mm/d\n  [DEFAULT], 0.0\n  FAST_RES, 0.35\n:EndSoilParameterList\n")
     CASES["hbv_abst_percentage"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=85, routing="ROUTE_MUSKINGUM", proc_after=(_hbv_after, _abst % "ABST_PERCENTAGE"),
                                         rvi_sub=[(_can, _can_max)], rvp_extra=_dep)
     # surveyed channel cross-section (:ChannelProfile with roughness zones -> 20-point rating curves) under the two routing methods that
