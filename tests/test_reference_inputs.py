@@ -21,22 +21,35 @@ def _base(name):
     roots = [os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref_inputs")]
     if not name.startswith("York"):   # York is pinned on a copy with one line dropped (tools/stage_reference_inputs.py): staged copy only
         roots.append("/root/reference/benchmarking/_InputFiles")
+    folder, _, stem = name.partition("__")   # "dir__basename": several set-ups in one folder (York_nc)
     for root in roots:
-        rvi = glob.glob(os.path.join(root, name, "*.rvi"))
+        rvi = glob.glob(os.path.join(root, folder, (stem or "*") + ".rvi"))
         if rvi:
             return rvi[0][:-4]
     pytest.skip("reference input set %s not staged here (tools/stage_reference_inputs.py)" % name)
 
 
+def _duration_days(base, n):
+    """n model steps in days, from the :TimeStep of the .rvi (daily unless hh:mm:ss)."""
+    for line in open(base + ".rvi"):
+        t = line.split()
+        if len(t) >= 2 and t[0] == ":TimeStep" and ":" in t[1]:
+            h, m, sec = (float(x) for x in t[1].split(":"))
+            return n * (h / 24.0 + m / 1440.0 + sec / 86400.0)
+    return n
+
+
 def test_sets_are_pinned():
-    assert {"Salmon_GR4J", "Salmon_HMETS", "Salmon_HBV", "Salmon_MOHYSE", "Irondequoit", "York_nongridded_m_daily_i_daily", "LOTW", "Nith"} <= set(SETS)
+    assert {"Salmon_GR4J", "Salmon_HMETS", "Salmon_HBV", "Salmon_MOHYSE", "Irondequoit", "York_nongridded_m_daily_i_daily", "LOTW", "Nith",
+            "York_nc__York_nongridded_m_subdaily_i_subdaily", "York_nc__York_nongridded_m_subdaily_i_daily", "York_nc__York_nongridded_m_daily_i_subdaily", "York_nc__York"} <= set(SETS)
 
 
 @pytest.mark.parametrize("name", SETS)
 def test_oracle_on_reference_inputs(name):
     g = np.load(os.path.join(OUT, name + ".npz"))
     n = g["qout"].shape[0]
-    model = api.RavenModel(_base(name), duration=n)
+    base = _base(name)
+    model = api.RavenModel(base, duration=_duration_days(base, n))
     model.flatten(1)
     import ctypes as C
     model.lib.rvh_desc_sv_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -57,7 +70,8 @@ def test_oracle_on_reference_inputs(name):
 def test_gpu_on_reference_inputs(name):
     g = np.load(os.path.join(OUT, name + ".npz"))
     n = g["qout"].shape[0]
-    model = api.RavenModel(_base(name), duration=n)
+    base = _base(name)
+    model = api.RavenModel(base, duration=_duration_days(base, n))
     model.flatten(2)
     sim = api.GpuSimulation(model, n_members=2)
     sim.set_recording(n)

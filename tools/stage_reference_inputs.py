@@ -23,7 +23,11 @@ import helpers as H  # noqa: E402
 REF_INPUTS = "/root/reference/benchmarking/_InputFiles"
 # set -> number of steps pinned (config 1 of BASELINE.json is the 10-year daily GR4J run)
 SETS = {"Salmon_GR4J": 3653, "Salmon_HMETS": 3653, "Salmon_HBV": 3653, "Salmon_MOHYSE": 3653, "Irondequoit": 366,
-        "York_nongridded_m_daily_i_daily": 1461, "LOTW": 2192, "Nith": 730}
+        "York_nongridded_m_daily_i_daily": 1461, "LOTW": 2192, "Nith": 730,
+        # York_nc holds several set-ups side by side ("dir__basename"): hourly model steps and / or hourly station inputs (ASCII station files; the gridded
+        # variants of the same folder need NetCDF)
+        "York_nc__York_nongridded_m_subdaily_i_subdaily": 35064, "York_nc__York_nongridded_m_subdaily_i_daily": 35064,
+        "York_nc__York_nongridded_m_daily_i_subdaily": 1461, "York_nc__York": 35064}
 # York (7 subbasins, ROUTE_HYDROLOGIC on surveyed :ChannelProfile sections, LAI interception, depression abstraction, a user-specified
 # :BasinInflowHydrograph into subbasin 6) is read as shipped.
 # LOTW (Lake of the Woods / Rainy River: 374 HRUs in 73 subbasins, 32 lake-type reservoirs behind weirs with linked lake HRUs, three
@@ -39,12 +43,16 @@ def main():
     out_dir = os.path.join(H.GOLDEN, "reference_inputs")
     stage = os.path.join(ROOT, "tests", "_ref_inputs")
     os.makedirs(out_dir, exist_ok=True)
+    only = sys.argv[1:]
     for name, n in SETS.items():
-        src = os.path.join(REF_INPUTS, name)
-        dst = os.path.join(stage, name)
+        folder, _, stem = name.partition("__")
+        src = os.path.join(REF_INPUTS, folder)
+        dst = os.path.join(stage, folder)
+        if only and name not in only:
+            continue
         shutil.rmtree(dst, ignore_errors=True)
-        shutil.copytree(src, dst)
-        base = glob.glob(os.path.join(dst, "*.rvi"))[0][:-4]
+        shutil.copytree(src, dst, ignore=shutil.ignore_patterns("*.nc"))
+        base = os.path.join(dst, stem) if stem else glob.glob(os.path.join(dst, "*.rvi"))[0][:-4]
         if name in DROP_LINES:
             lines = open(base + ".rvt").read().split("\n")
             kept = [l for l in lines if DROP_LINES[name] not in l]
