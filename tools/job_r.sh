@@ -1,3 +1,2 @@
 #!/usr/bin/env bash
-# GPU parity of the new process algorithms + the complete golden suite
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -8
+python -m pytest tests/test_reference_inputs.py tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -8
