@@ -1,3 +1,3 @@
 #!/usr/bin/env bash
-# footprint of the routing CTAs next to the sweep: tail kernel one warp per member, 32 / 64 / 128-thread routing CTAs
-bash tools/run_variants.sh q2 --skip-other
+# depth of the sweep -> routing hand-off ring and priority of the routing stream on the headline workload
+bash tools/run_variants.sh q3 --skip-other
