@@ -302,7 +302,10 @@ typedef struct rvn_options {
   int32_t orocorr_temp, orocorr_precip, orocorr_pet;
   int32_t routing, suppress_competitive_ET, snow_suppress_PET, allow_soil_overfill, direct_evap;
   int32_t lake_sv;                /* CModel::GetLakeStorageIndex() */
-  int32_t keep_flux_balance;      /* 0: skip per-connection cumulative flux arrays */
+  int32_t keep_flux_balance;      /* 1: keep CModel::_aCumulativeBal (src/Model.cpp:2428-2436) on the device: the cumulative amount moved through every process
+                                   * connection of every HRU, [member][nConn][nHRU], read with rvn_gpu_download_flux_balance.  Interpreter sweep, ORDERED_SERIES,
+                                   * process lists without :Convolve (whose 2N+1 internal connections per process are not tabulated in conn_from/conn_to).
+                                   * 0 (default): not kept - the array is larger than the state and nothing on the hot path reads it */
   int32_t sol_method;             /* rvn_sol_method: ORDERED_SERIES (default), EULER or ITERATED_HEUN (reference src/Solvers.cpp:205-251 / 256-297 / 304-397) */
   int32_t need_atmos;             /* 1: a consumed PET or a sublimation process needs air pressure / relative humidity / wind / shortwave radiation -> derive them */
   int32_t air_pressure, rel_humidity, sw_radiation, sw_cloudcorr;   /* rvn_airpress, rvn_relhum, rvn_sw_rad, rvn_sw_cloudcorr */
@@ -522,6 +525,10 @@ int rvn_gpu_download_reservoir_state(rvn_gpu_model *m, double *res, int member0,
 int rvn_gpu_upload_params(rvn_gpu_model *m, const double *ptab, const int32_t *conv_n, const double *conv_uh,
                           int member0, int nmembers);
 /* replace forcing series (streaming long runs / BMI SetValue): same layout as desc, nsteps samples from step0 */
+/* CModel::GetCumulativeFlux / GetCumulFluxBetween source data (src/Model.cpp:902-965): cumulative [mm] moved through connection q (conn_from[q] -> conn_to[q],
+ * process-list order; members of a :ProcessGroup: the group's weighted connections) of HRU k, for members member0 .. member0+nmembers-1: cum[member][nConn][nHRU].
+ * Needs opt.keep_flux_balance = 1 at create. */
+int rvn_gpu_download_flux_balance(rvn_gpu_model *m, double *cum, int member0, int nmembers);
 int rvn_gpu_upload_forcings(rvn_gpu_model *m, const double *gauge_series, const rvn_time *times, int step0, int nsteps);
 
 /* advance all members by nsteps model steps starting at step index `step0`:

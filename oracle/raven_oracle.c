@@ -36,6 +36,7 @@
 #define O_MAXCONN 256
 
 /* src/RavenInclude.h:1456-1464 -- ties return the FIRST argument */
+static double *g_cum_flux = 0; /* optional [nConn][nHRU] cumulative amount moved through every process connection (CModel::IncrementBalance, src/Model.cpp:2428-2436); rvo_set_flux_buffer */
 static double *g_precip5 = 0; /* [nHRU] force_struct::precip_5day of the current step (update_forcings -> INF_SCS) */
 static double omax(double r, double l) { return (r >= l) ? r : l; }
 static double omin(double r, double l) { return (r <= l) ? r : l; }
@@ -1834,6 +1835,8 @@ static void finish_hru(const rvn_model_desc *d, int k, double *phinew, double *a
 int rvo_run_member_res(const rvn_model_desc *d, int member, double *state, double *qin, double *qlat, double *qout, double *scal, double *cumul,
                        int step0, int nsteps, double *qout_rec, double *wshed_rec, double *state_rec, double *forc_rec, double *res_state);
 /* the same for a model without reservoirs, or with reservoirs started from the descriptor's initial reservoir state */
+/* test hook: cumulative per-connection fluxes of the following rvo_run_member* calls are added into buf[nConn][nHRU] (NULL switches it off) */
+void rvo_set_flux_buffer(double *buf) { g_cum_flux = buf; }
 int rvo_run_member(const rvn_model_desc *d, int member, double *state, double *qin, double *qlat, double *qout, double *scal, double *cumul,
                    int step0, int nsteps, double *qout_rec, double *wshed_rec, double *state_rec, double *forc_rec) {
   double *rs = NULL;
@@ -1982,6 +1985,10 @@ int rvo_run_member_res(const rvn_model_desc *d, int member, double *state, doubl
             if (ct[q] != cf[q]) { phinew[cf[q]] -= rates[q] * tstep; phinew[ct[q]] += rates[q] * tstep; }
             else if (is_water_storage(typ) && (typ != RVN_SV_CONVOLUTION) && (typ != RVN_SV_CONV_STOR)) { rates[q] = 0.0; phinew[ct[q]] += 0.0; }
             else phinew[ct[q]] += rates[q] * tstep;
+          }
+          if (g_cum_flux && pr->op != RVN_OP_CONVOLVE) { /* pModel->IncrementBalance(qs, k, rates_of_change[q] * tstep), src/Solvers.cpp:234 */
+            const int q0 = (pr->group != 0) ? pr->gconn0 : pr->conn0;
+            for (int q = 0; q < nconn; q++) g_cum_flux[(size_t)(q0 + q) * nH + k] += rates[q] * tstep;
           }
         }
         if (d->nLat > 0) { memcpy(phi_old, phinew, sizeof(double) * NS); continue; } /* lateral exchange first: the row now holds aPhinew[k] */

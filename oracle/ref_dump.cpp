@@ -11,6 +11,7 @@
 //     <out>/forc.f64    [nsteps+1][nHRU][43]   force_struct (all doubles), as used for the step
 //     <out>/basin.f64   [nsteps+1][NB][6]      Qout, Qlocal, channel stor, rivulet stor, Qin[0], Qlat[0]
 //     <out>/wshed.f64   [nsteps+1][3]          _CumulInput, _CumulOutput, GetAveragePrecip
+//     <out>/cumflux.f64 [nHRU][NS][2]          CModel::GetCumulativeFlux(k, i, to / from) at the end of the run
 //     <out>/res.f64     [nsteps+1][NB][4]      reservoir stage, outflow, losses of the step [m3], storage [m3] (zeros for basins without one)
 //     <out>/meta.txt    integer tables: SV catalogue, process connections, routing order, UH arrays
 // Row 0 is the initial condition (after the t=0 forcing update), row n the state after step n.
@@ -219,6 +220,15 @@ int main(int argc, char **argv)
     step++;
   }
   fclose(fs); fclose(ff); fclose(fb); fclose(fw); fclose(fr);
+  {  // CModel::GetCumulativeFlux(k, i, to): cumulative [mm] moved into (to = true) / out of (to = false) state variable i of HRU k by all processes
+    FILE *fc = fopen((outdir + "cumflux.f64").c_str(), "wb");
+    std::vector<double> row((size_t)NS * 2);
+    for (int k = 0; k < nH; k++) {
+      for (int i = 0; i < NS; i++) { row[2 * i] = pModel->GetCumulativeFlux(k, i, true); row[2 * i + 1] = pModel->GetCumulativeFlux(k, i, false); }
+      wr(fc, row.data(), row.size());
+    }
+    fclose(fc);
+  }
   {
     std::ofstream M((outdir + "meta.txt").c_str(), std::ios::app);
     M << "nsteps " << step << "\n";

@@ -187,6 +187,22 @@ class RavenModel:
             raise RavenError(self.lib.rvh_last_error().decode())
         self.desc = None
 
+    def set_flux_balance(self, on=True):
+        """Keep the per-connection cumulative fluxes (reference CModel::_aCumulativeBal) on the device; call flatten() afterwards."""
+        self.lib.rvh_model_set_flux_balance.argtypes = [C.c_void_p, C.c_int]
+        if self.lib.rvh_model_set_flux_balance(self.h, 1 if on else 0):
+            raise RavenError(self.lib.rvh_last_error().decode())
+        self.desc = None
+
+    def connections(self):
+        """(from, to) state-variable indices of every tabulated process connection, in process-list order."""
+        self.lib.rvh_desc_num_connections.argtypes = [C.c_void_p]
+        n = self.lib.rvh_desc_num_connections(self.desc)
+        f = np.zeros(n, dtype=np.int32); t = np.zeros(n, dtype=np.int32)
+        self.lib.rvh_desc_connections.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self.lib.rvh_desc_connections(self.desc, f.ctypes.data, t.ctypes.data)
+        return f, t
+
     def sv_names(self):
         buf = C.create_string_buffer(64)
         out = []
@@ -428,6 +444,15 @@ class GpuSimulation:
         if n:
             self._ck(self.lib.rvn_gpu_download_reservoir_state(self.h, res.ctypes.data, member0, nmembers))
         return res
+
+    def download_flux_balance(self, member0=0, nmembers=None):
+        """[member][connection][HRU] cumulative amount moved through every process connection (needs RavenModel.set_flux_balance)."""
+        nmembers = self.E - member0 if nmembers is None else nmembers
+        f, _ = self.model.connections()
+        cum = np.zeros((nmembers, f.size, self.model.nHRU))
+        self.lib.rvn_gpu_download_flux_balance.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        self._ck(self.lib.rvn_gpu_download_flux_balance(self.h, cum.ctypes.data, member0, nmembers))
+        return cum
 
     def upload_reservoir_state(self, res, member0=0, nmembers=None):
         res = np.ascontiguousarray(res, dtype=np.float64)

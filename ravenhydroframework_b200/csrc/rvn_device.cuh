@@ -123,6 +123,7 @@ struct DevModel {
   double *da_adjust, *da_mass;
   const double *subdaily;   // [nEtRows][nHp] force_struct::subdaily_corr (rvn_model_desc::subdaily_corr) or NULL (= 1)
   const double *gauge_p5;   // [nGauges][nSteps] 5-day antecedent precipitation of the gauges (rvn_model_desc::gauge_precip5) or NULL
+  double *cum_flux; int nFlux;   // [member][nFlux = nConn][nHp] cumulative per-connection fluxes (opt.keep_flux_balance) or NULL
   int need_cc;   // the process list holds SNOBAL_COLD_CONTENT: the sweep derives LAI / SAI / day length of every HRU (CtxCommon::veg_LAI ...)
 };
 #endif

@@ -1184,10 +1184,27 @@ __global__ void __launch_bounds__(RVN_BS, RVN_INTERP_MIN_BLOCKS) hru_sweep_inter
       continue;
     }
     const DynProc dp = {&pr, P};
-    if (pr.group != 0) { run_group_member(c, dp, pr.op, pr.group, P->maxConn); continue; }
+    if (pr.group != 0) {
+      run_group_member(c, dp, pr.op, pr.group, P->maxConn);
+      if (M.cum_flux != nullptr && (pr.group & RVN_GRP_LAST)) {   // IncrementBalance over the group's weighted connections (src/Solvers.cpp:234)
+        for (int q = 0; q < pr.gnconn; q++) {
+          const int from = dp.gfrom(q), to = dp.gto(q);
+          const double r = (to == from && c.slot_water(from) == 1) ? 0.0 : c.GR(q);
+          M.cum_flux[((size_t)e * M.nFlux + pr.gconn0 + q) * nHp + k] += r * c.tstep;
+        }
+      }
+      continue;
+    }
     for (int q = 0; q < pr.nconn; q++) c.R(q) = 0.0;          // src/Model.cpp:3066-3071
     dispatch_rates(c, dp, pr.op);
     apply_connections(c, dp);
+    if (M.cum_flux != nullptr) {   // pModel->IncrementBalance(qs, k, rates_of_change[q] * tstep): a redirect-to-self of a water store counts zero (src/Solvers.cpp:227-234)
+      for (int q = 0; q < pr.nconn; q++) {
+        const int from = dp.from(q), to = dp.to(q);
+        const double r = (to == from && c.slot_water(from) == 1) ? 0.0 : c.R(q);
+        M.cum_flux[((size_t)e * M.nFlux + pr.conn0 + q) * nHp + k] += r * c.tstep;
+      }
+    }
   }
   c.sv = c.svw;   // from here on "the state" is the updated vector aPhinew
   double swv = 0.0, stor = 0.0;

@@ -248,6 +248,15 @@ int rvh_model_set_cell_forcing(rvh_model *h, int nCells, int nSteps, const doubl
   return 0;
   RVH_CATCH(-1)
 }
+// per-connection cumulative flux arrays (reference CModel::IncrementBalance): off by default, takes effect at the next rvh_model_flatten
+int rvh_model_set_flux_balance(rvh_model *h, int on) {
+  RVH_TRY
+  h->Options.keep_flux_balance = (on != 0);   // the model reads its options through a pointer to this struct
+  return 0;
+  RVH_CATCH(-1)
+}
+int rvh_desc_num_connections(const rvn_model_desc *d) { return d->nConn; }
+int rvh_desc_connections(const rvn_model_desc *d, int32_t *from, int32_t *to) { for (int q = 0; q < d->nConn; q++) { from[q] = d->conn_from[q]; to[q] = d->conn_to[q]; } return 0; }
 const int32_t *rvh_desc_conv_n(const rvn_model_desc *d) { return d->conv_n; }
 int rvh_desc_sv_table(const rvn_model_desc *d, int32_t *type, int32_t *layer) {
   for (int i = 0; i < d->NS; i++) { type[i] = d->sv_type[i]; layer[i] = d->sv_layer[i]; }

@@ -88,6 +88,7 @@ struct optStruct {
   int    interception_factor;   // rvn_icept
   int    LW_radiation = 0, SW_canopycorr = 0;   // rvn_options::lw_radiation / sw_canopycorr
   std::string unsupported_radiation;   // first radiation method command the B200 build cannot honour (fatal only if net radiation is consumed)
+  bool keep_flux_balance = false;   // keep the per-connection cumulative fluxes (CModel::_aCumulativeBal) on the device: rvn_options::keep_flux_balance
   int subdaily = 0;   // :SubdailyMethod: 0 SUBDAILY_NONE, 1 SUBDAILY_SIMPLE
   std::string unsupported_atmos;   // first atmospheric method command the B200 build cannot honour (fatal only if a consumer needs it)
   rvn_routing  routing;

@@ -72,7 +72,7 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
   d.opt.rainsnow = O.rainsnow; d.opt.pot_melt = O.pot_melt; d.opt.evaporation = O.evaporation; d.opt.ow_evaporation = O.ow_evaporation;
   d.opt.orocorr_temp = O.orocorr_temp; d.opt.orocorr_precip = O.orocorr_precip; d.opt.orocorr_pet = O.orocorr_PET;
   d.opt.routing = O.routing; d.opt.suppress_competitive_ET = O.suppressCompetitiveET; d.opt.snow_suppress_PET = O.snow_suppressPET;
-  d.opt.allow_soil_overfill = O.allow_soil_overfill; d.opt.direct_evap = O.direct_evap; d.opt.lake_sv = _lake_sv; d.opt.keep_flux_balance = 0; d.opt.sol_method = O.sol_method; d.opt.max_iterations = O.max_iterations; d.opt.convergence_crit = O.convergence_crit;
+  d.opt.allow_soil_overfill = O.allow_soil_overfill; d.opt.direct_evap = O.direct_evap; d.opt.lake_sv = _lake_sv; d.opt.keep_flux_balance = O.keep_flux_balance ? 1 : 0; d.opt.sol_method = O.sol_method; d.opt.max_iterations = O.max_iterations; d.opt.convergence_crit = O.convergence_crit;
   // ---- state variables
   d.NS = NS; d.nSoilLayers = _nSoilVars;
   _f_svtype.resize(NS); _f_svlayer.resize(NS);

@@ -378,6 +378,20 @@ def make_hydrographs(name):
     print("golden %-18s Hydrographs.csv (%d lines)" % (name, len(open(os.path.join(d, "reference_Hydrographs.csv")).readlines())))
 
 
+FLUX_CASES = ("hbv_muskingum", "hbv_algo_d", "hbv_hrugroup_cond", "hbv_snobal_crhm")   # no :Convolve
+
+
+def make_cumflux(name):
+    """reference_cumflux.npz: CModel::GetCumulativeFlux of every (HRU, state variable) at the end of the golden case's run."""
+    d = os.path.join(HERE, name)
+    n = int(np.load(os.path.join(d, "reference.npz"))["qout"].shape[0])
+    out = os.path.join(d, "_refout")
+    ref = H.reference_run(os.path.join(d, "model"), out, n)
+    np.savez_compressed(os.path.join(d, "reference_cumflux.npz"), cumflux=ref["cumflux"], nsteps=np.array(n))
+    shutil.rmtree(out, ignore_errors=True)
+    print("golden %-18s cumulative fluxes of %d steps" % (name, n))
+
+
 def make(name, spec):
     spec = dict(spec)
     kind = spec.pop("kind")
@@ -482,6 +496,9 @@ if __name__ == "__main__":
     for name in HYDROGRAPH_CASES:
         if not only or name in only:
             make_hydrographs(name)
+    for name in FLUX_CASES:
+        if not only or name in only or "cumflux" in only:
+            make_cumflux(name)
     if not only or "dds_hmets" in only:
         make_dds()
     if not only or "hbv_restart" in only:

@@ -55,6 +55,30 @@ def oracle_run(model, nsteps, member=0, state=None, record_state=True, record_fo
     return dict(state=st, qin=qin, qlat=qlat, qout=qout, scal=scal, cumul=cumul, qout_rec=qrec, wshed_rec=wrec, state_rec=srec, forc_rec=frec, res=res)
 
 
+def oracle_flux_balance(model, nsteps, member=0):
+    """Cumulative per-connection fluxes [nConn][nHRU] of an oracle run (reference CModel::IncrementBalance)."""
+    lib = oracle_lib()
+    f, _ = model.connections()
+    buf = np.zeros((f.size, model.nHRU))
+    lib.rvo_set_flux_buffer.argtypes = [C.c_void_p]
+    lib.rvo_set_flux_buffer(buf.ctypes.data)
+    try:
+        oracle_run(model, nsteps, member=member, record_state=False)
+    finally:
+        lib.rvo_set_flux_buffer(None)
+    return buf
+
+
+def flux_by_state_variable(model, cum):
+    """[nHRU][NS][2]: what CModel::GetCumulativeFlux(k, i, to=True / False) sums (src/Model.cpp:902-923) from per-connection arrays cum[nConn][nHRU]."""
+    f, t = model.connections()
+    out = np.zeros((model.nHRU, model.NS, 2))
+    for q in range(f.size):   # process-list order, as the reference's loop
+        out[:, t[q], 0] += cum[q]
+        out[:, f[q], 1] += cum[q]
+    return out
+
+
 def reference_run(base, outdir, nsteps=-1):
     """Run the unmodified reference on <base>.rv* and load its in-memory FP64 dumps."""
     os.makedirs(outdir, exist_ok=True)
@@ -80,6 +104,8 @@ def load_reference_dump(outdir):
     out["wshed"] = np.fromfile(outdir + "wshed.f64").reshape(-1, 3)
     if os.path.exists(outdir + "res.f64"):   # reservoir stage, outflow, losses, storage per basin (zeros without a reservoir)
         out["res"] = np.fromfile(outdir + "res.f64").reshape(-1, NB, 4)
+    if os.path.exists(outdir + "cumflux.f64"):   # CModel::GetCumulativeFlux(k, i, to / from) at the end of the run
+        out["cumflux"] = np.fromfile(outdir + "cumflux.f64").reshape(nH, NS, 2)
     out["sv"] = [(int(l.split()[2]), int(l.split()[3])) for l in meta if l.startswith("SV ")]
     out["order"] = [int(l.split()[2]) for l in meta if l.startswith("ORDER ")]
     out["proc"] = [l.split()[1:] for l in meta if l.startswith("PROC ")]

@@ -358,3 +358,34 @@ def test_sparse_station_interpolation(tmp_path):
     sums of a gridded forcing -- with elevation-dependent corrections from the weighted station elevations."""
     _gpu_vs_oracle(tmp_path, "hbv", 120, members=2, n_sb=9, hru_per_sb=17, seed=31, routing="ROUTE_MUSKINGUM", n_gauges=25)
     _gpu_vs_oracle(tmp_path / "b", "hmets", 120, n_sb=3, hru_per_sb=50, seed=32, n_gauges=16)
+
+
+FLUX_CASES = sorted(os.path.basename(os.path.dirname(p)) for p in glob.glob(os.path.join(H.GOLDEN, "*", "reference_cumflux.npz")))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", FLUX_CASES)
+def test_gpu_flux_balance_matches_oracle_and_reference(case):
+    """Optional per-connection cumulative flux arrays (rvn_options::keep_flux_balance, reference CModel::_aCumulativeBal): every connection of
+    every HRU against the oracle, and summed by state variable against the reference's GetCumulativeFlux; a model created without the option
+    refuses the download."""
+    g = np.load(os.path.join(H.GOLDEN, case, "reference_cumflux.npz"))
+    n = int(g["nsteps"])
+    model = api.RavenModel(os.path.join(H.GOLDEN, case, "model"))
+    model.set_flux_balance(True)
+    model.flatten(2)
+    want = H.oracle_flux_balance(model, n)
+    sim = api.GpuSimulation(model, n_members=2)
+    assert sim.kernel_variant() == "interpreter"
+    sim.run(n)
+    got = sim.download_flux_balance()
+    assert H.rel_err(got[0], want) < TOL and np.array_equal(got[0], got[1])
+    assert H.rel_err(H.flux_by_state_variable(model, got[1]), g["cumflux"]) < TOL
+    sim.close()
+    model.set_flux_balance(False)
+    model.flatten(1)
+    sim = api.GpuSimulation(model, n_members=1)
+    sim.run(2)
+    with pytest.raises(api.RavenError):
+        sim.download_flux_balance()
+    sim.close()

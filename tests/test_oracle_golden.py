@@ -197,3 +197,18 @@ def test_hydrographs_csv_equals_the_reference_executables(case, tmp_path):
     out = str(tmp_path / "Hydrographs.csv")
     model.write_hydrographs(out, o["qout_rec"], o["wshed_rec"][:, 2])
     assert open(out).read().split("\n") == ref
+
+
+FLUX_CASES = sorted(os.path.basename(os.path.dirname(p)) for p in glob.glob(os.path.join(H.GOLDEN, "*", "reference_cumflux.npz")))
+
+
+@pytest.mark.parametrize("case", FLUX_CASES)
+def test_cumulative_connection_fluxes_match_reference(case):
+    """SURVEY 8a row a11, the optional arrays: per-connection cumulative fluxes (CModel::IncrementBalance, src/Model.cpp:2428-2436) of the oracle,
+    summed the way CModel::GetCumulativeFlux does (src/Model.cpp:902-923), against the reference's GetCumulativeFlux for every HRU and state variable."""
+    g = np.load(os.path.join(H.GOLDEN, case, "reference_cumflux.npz"))
+    model = api.RavenModel(os.path.join(H.GOLDEN, case, "model"))
+    model.flatten(1)
+    cum = H.oracle_flux_balance(model, int(g["nsteps"]))
+    assert np.abs(cum).sum() > 0.0
+    assert H.rel_err(H.flux_by_state_variable(model, cum), g["cumflux"]) < TOL
