@@ -147,6 +147,9 @@ typedef enum {
   RVN_OP_SOILEVAP_CHU,         /* CmvSoilEvap             src/SoilEvaporation.cpp:460-468 (Ontario crop-heat-unit method) */
   RVN_OP_CHU_ONTARIO,          /* CmvCropHeatUnitEvolve   src/CropGrowth.cpp:91-136 (CROP_HEAT_UNITS self-connection) */
   RVN_OP_EXCHANGE_FLOW,        /* CmvExchangeFlow         src/Flush.cpp:296-308,358-368: two soil stores swap EXCHANGE_FLOW [mm/d] in both directions; ia[0] = soil layer of the 'from' store */
+  RVN_OP_GLACIERMELT_SIMPLE,   /* CmvGlacierMelt          GMELT_SIMPLE_MELT src/GlacierProcesses.cpp:126-129 */
+  RVN_OP_GLACIERMELT_UBC,      /* CmvGlacierMelt          GMELT_UBC :139-166 (GLACIER_ICE -> PONDED_WATER, GLACIER_CC self-connection :29-36) */
+  RVN_OP_GLACIERRELEASE_LINEAR,/* CmvGlacierRelease       GRELEASE_LINEAR / GRELEASE_LINEAR_ANALYTIC :317-327; ia[0] = 1 for the analytic form */
   RVN_OP_COUNT
 } rvn_opcode;
 

@@ -1472,6 +1472,32 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       if (!(sv[c->iSV[RVN_SV_SNOW]] > O_REAL_SMALL)) rates[0] = P_LU(c, RVN_LU_HBV_MELT_GLACIER_CORR) * omax(F[RVN_F_POTENTIAL_MELT], 0.0);
       if (rates[0] < 0.0) rates[0] = 0.0;
       break;
+    case RVN_OP_GLACIERMELT_SIMPLE: /* GMELT_SIMPLE_MELT, src/GlacierProcesses.cpp:126-129 + :170-186 */
+      if (type != RVN_HRU_GLACIER) break;
+      rates[0] = F[RVN_F_POTENTIAL_MELT];
+      if (rates[0] < 0.0) rates[0] = 0.0;
+      break;
+    case RVN_OP_GLACIERMELT_UBC: { /* GMELT_UBC, :139-166 */
+      if (type != RVN_HRU_GLACIER) break;
+      double CC = sv[iFrom[1]], snow_coverage = snow_cover(c), pot_melt = F[RVN_F_POTENTIAL_MELT];
+      if (pot_melt > 0.0) { pot_melt *= (1.0 - snow_coverage); } else { pot_melt = 0.0; }
+      if (CC > pot_melt * tstep) { CC -= pot_melt * tstep; pot_melt = 0; }
+      else { pot_melt -= CC / tstep; CC = 0.0; }
+      double P0CTKG = 0.0;
+      CC *= (1 - (1 / (1 + P0CTKG)));
+      rates[0] = pot_melt;
+      rates[1] = (CC - sv[iFrom[1]]) / tstep;
+      if (rates[0] < 0.0) rates[0] = 0.0;
+      break;
+    }
+    case RVN_OP_GLACIERRELEASE_LINEAR: { /* GRELEASE_LINEAR / _ANALYTIC, :317-327 + :340-350 */
+      if (type != RVN_HRU_GLACIER) break;
+      double glacier_stor = sv[c->iSV[RVN_SV_GLACIER]], K = P_LU(c, RVN_LU_GLAC_STORAGE_COEFF);
+      if (pr->ia[0] == 0) rates[0] = K * glacier_stor;
+      else rates[0] = glacier_stor * (1 - exp(-K * tstep)) / tstep;
+      if (rates[0] < 0.0) rates[0] = 0.0;
+      break;
+    }
     case RVN_OP_GLACIERRELEASE_HBVEC: { /* src/GlacierProcesses.cpp:292-350 */
       if (type != RVN_HRU_GLACIER) break;
       double glacier_stor = sv[c->iSV[RVN_SV_GLACIER]], snow = sv[c->iSV[RVN_SV_SNOW]], liq_snow = sv[c->iSV[RVN_SV_SNOW_LIQ]];

@@ -351,6 +351,36 @@ template <class C, class PR> RVN_DI void rates_GLACIERMELT_HBV(C &c, const PR &p
   if (c.R(0) < 0.0) c.R(0) = 0.0;
   (void)pr;
 }
+// CmvGlacierMelt GMELT_SIMPLE_MELT / GMELT_UBC  src/GlacierProcesses.cpp:126-129,139-166; ApplyConstraints :170-186 (glacier_model_on off)
+template <class C, class PR> RVN_DI void rates_GLACIERMELT_SIMPLE(C &c, const PR &pr) {
+  if (c.type != RVN_HRU_GLACIER) return;
+  c.R(0) = c.F[RVN_F_POTENTIAL_MELT];
+  if (c.R(0) < 0.0) c.R(0) = 0.0;
+  (void)pr;
+}
+template <class C, class PR> RVN_DI void rates_GLACIERMELT_UBC(C &c, const PR &pr) {
+  if (c.type != RVN_HRU_GLACIER) return;
+  double CC = c.SV(pr.from(1));
+  const double snow_coverage = SnowCover(c);
+  double pot_melt = c.F[RVN_F_POTENTIAL_MELT];
+  if (pot_melt > 0.0) pot_melt *= (1.0 - snow_coverage);   // no glacier melt under snow
+  else pot_melt = 0.0;
+  if (CC > pot_melt * c.tstep) { CC -= pot_melt * c.tstep; pot_melt = 0; }
+  else { pot_melt -= CC / c.tstep; CC = 0.0; }
+  const double P0CTKG = 0.0;
+  CC *= (1 - (1 / (1 + P0CTKG)));
+  c.R(0) = pot_melt;
+  c.R(1) = (CC - c.SV(pr.from(1))) / c.tstep;
+  if (c.R(0) < 0.0) c.R(0) = 0.0;
+}
+// CmvGlacierRelease GRELEASE_LINEAR / GRELEASE_LINEAR_ANALYTIC  src/GlacierProcesses.cpp:317-327; ApplyConstraints :340-350
+template <class C, class PR> RVN_DI void rates_GLACIERRELEASE_LINEAR(C &c, const PR &pr) {
+  if (c.type != RVN_HRU_GLACIER) return;
+  const double glacier_stor = c.SV(c.iSV(RVN_SV_GLACIER)), K = c.LU(RVN_LU_GLAC_STORAGE_COEFF);
+  if (pr.ia(0) == 0) c.R(0) = K * glacier_stor;
+  else c.R(0) = glacier_stor * (1 - rvn_exp(-K * c.tstep)) / c.tstep;
+  if (c.R(0) < 0.0) c.R(0) = 0.0;
+}
 // CmvGlacierRelease GRELEASE_HBV_EC  src/GlacierProcesses.cpp:292-325; ApplyConstraints :340-350
 template <class C, class PR> RVN_DI void rates_GLACIERRELEASE_HBVEC(C &c, const PR &pr) {
   if (c.type != RVN_HRU_GLACIER) return;
@@ -1026,6 +1056,9 @@ template <class C, class PR> RVN_DI void dispatch_rates(C &c, const PR &pr, cons
     case RVN_OP_LAKE_EVAP_BASIC: rates_LAKE_EVAP_BASIC(c, pr); break;
     case RVN_OP_CAPRISE_HBV: rates_CAPRISE_HBV(c, pr); break;
     case RVN_OP_GLACIERMELT_HBV: rates_GLACIERMELT_HBV(c, pr); break;
+    case RVN_OP_GLACIERMELT_SIMPLE: rates_GLACIERMELT_SIMPLE(c, pr); break;
+    case RVN_OP_GLACIERMELT_UBC: rates_GLACIERMELT_UBC(c, pr); break;
+    case RVN_OP_GLACIERRELEASE_LINEAR: rates_GLACIERRELEASE_LINEAR(c, pr); break;
     case RVN_OP_GLACIERRELEASE_HBVEC: rates_GLACIERRELEASE_HBVEC(c, pr); break;
     default: break;
   }

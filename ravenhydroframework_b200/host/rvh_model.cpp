@@ -687,7 +687,7 @@ static const struct { const char *name; sv_type t; } kSVNames[] = {
   {"CONVOLUTION", RVN_SV_CONVOLUTION}, {"CONV_STOR", RVN_SV_CONV_STOR}, {"CUM_INFIL", RVN_SV_CUM_INFIL}, {"CUM_SNOWMELT", RVN_SV_CUM_SNOWMELT},
   {"AET", RVN_SV_AET}, {"RUNOFF", RVN_SV_RUNOFF}, {"SNOW_TEMP", RVN_SV_SNOW_TEMP}, {"COLD_CONTENT", RVN_SV_COLD_CONTENT},
   {"SNOW_DEPTH", RVN_SV_SNOW_DEPTH}, {"SNOW_COVER", RVN_SV_SNOW_COVER}, {"SNOW_DEFICIT", RVN_SV_SNOW_DEFICIT}, {"SNOW_AGE", RVN_SV_SNOW_AGE},
-  {"SNOW_ALBEDO", RVN_SV_SNOW_ALBEDO}, {"CROP_HEAT_UNITS", RVN_SV_CROP_HEAT_UNITS}, {"ICE_THICKNESS", RVN_SV_ICE_THICKNESS}, {NULL, RVN_SV_NTYPES}};
+  {"SNOW_ALBEDO", RVN_SV_SNOW_ALBEDO}, {"CROP_HEAT_UNITS", RVN_SV_CROP_HEAT_UNITS}, {"GLACIER_CC", RVN_SV_GLACIER_CC}, {"ICE_THICKNESS", RVN_SV_ICE_THICKNESS}, {NULL, RVN_SV_NTYPES}};
 sv_type CModel::StringToSVType(const std::string &sin, int &layer, bool strict) const {
   std::string s = sin;
   std::map<std::string, std::string>::const_iterator it = _aliases.find(s);

@@ -733,18 +733,29 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
   }
   if (cmd == ":GlacierMelt") {  // case 219; src/GlacierProcesses.cpp:17-36
     need(4);
-    ExitGracefullyIf(s[1] != "GMELT_HBV" && s[1] != "HBV", "ParseMainInputFile: glacier melt algorithm " + s[1] + " is not implemented in the B200 build");
+    rvn_opcode op = RVN_OP_NOP;
+    if (s[1] == "GMELT_HBV" || s[1] == "HBV") op = RVN_OP_GLACIERMELT_HBV;
+    else if (s[1] == "GMELT_SIMPLE_MELT" || s[1] == "SIMPLE") op = RVN_OP_GLACIERMELT_SIMPLE;
+    else if (s[1] == "GMELT_UBC" || s[1] == "UBC") op = RVN_OP_GLACIERMELT_UBC;
+    else ExitGracefully("ParseMainInputFile: glacier melt algorithm " + s[1] + " is not implemented in the B200 build");
     AddSVs(pM, {SVL(RVN_SV_GLACIER_ICE, -1), SVL(RVN_SV_GLACIER, -1)});
-    CmvGeneric *p = new CmvGeneric("GlacierMelt", RVN_OP_GLACIERMELT_HBV, pM);
-    p->Connect(pM->GetStateVarIndex(RVN_SV_GLACIER_ICE), pM->GetStateVarIndex(RVN_SV_GLACIER));
+    if (op == RVN_OP_GLACIERMELT_UBC) AddSV1(pM, RVN_SV_GLACIER_CC);   // src/GlacierProcesses.cpp:95-103
+    CmvGeneric *p = new CmvGeneric("GlacierMelt", op, pM);
+    if (op == RVN_OP_GLACIERMELT_UBC) {   // :29-36: melt goes to PONDED_WATER, cold content of the ice is a self-connection
+      const int iCC = pM->GetStateVarIndex(RVN_SV_GLACIER_CC);
+      p->Connect(pM->GetStateVarIndex(RVN_SV_GLACIER_ICE), iPond); p->Connect(iCC, iCC);
+    } else p->Connect(pM->GetStateVarIndex(RVN_SV_GLACIER_ICE), pM->GetStateVarIndex(RVN_SV_GLACIER));
     return p;
   }
   if (cmd == ":GlacierRelease") {  // case 220; src/GlacierProcesses.cpp:200-211,240-251
     need(4);
-    ExitGracefullyIf(s[1] != "GRELEASE_HBV_EC" && s[1] != "HBV_EC", "ParseMainInputFile: glacier release algorithm " + s[1] + " is not implemented in the B200 build");
-    AddSVs(pM, {SVL(RVN_SV_GLACIER, -1), SVL(RVN_SV_SNOW, -1), SVL(RVN_SV_SNOW_LIQ, -1)});
-    CmvGeneric *p = new CmvGeneric("GlacierRelease", RVN_OP_GLACIERRELEASE_HBVEC, pM);
+    const bool hbvec = (s[1] == "GRELEASE_HBV_EC" || s[1] == "HBV_EC"), lin = (s[1] == "GRELEASE_LINEAR" || s[1] == "LINEAR_STORAGE"), ana = (s[1] == "GRELEASE_LINEAR_ANALYTIC");
+    ExitGracefullyIf(!hbvec && !lin && !ana, "ParseMainInputFile: glacier release algorithm " + s[1] + " is not implemented in the B200 build");
+    if (hbvec) AddSVs(pM, {SVL(RVN_SV_GLACIER, -1), SVL(RVN_SV_SNOW, -1), SVL(RVN_SV_SNOW_LIQ, -1)});
+    else AddSV1(pM, RVN_SV_GLACIER);
+    CmvGeneric *p = new CmvGeneric("GlacierRelease", hbvec ? RVN_OP_GLACIERRELEASE_HBVEC : RVN_OP_GLACIERRELEASE_LINEAR, pM);
     p->Connect(pM->GetStateVarIndex(RVN_SV_GLACIER), iSW);
+    if (!hbvec) p->SetIntArg(0, ana ? 1 : 0);
     return p;
   }
   if (cmd == ":CapillaryRise") {  // case 216; src/CapillaryRise.cpp:20-35

@@ -164,6 +164,14 @@ if hasattr(synth, "write_hbv"):
     CASES["hbv_exchangeflow"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=300, seed=89, routing="ROUTE_MUSKINGUM",
                                      proc_after=(r"(  :CapillaryRise     RISE_HBV           FAST_RESERVOIR  SOIL\[0\]\n)", "  :ExchangeFlow      RAVEN_DEFAULT      FAST_RESERVOIR  SLOW_RESERVOIR\n"),
                                      rvp_extra=":SoilParameterList\n  :Parameters, EXCHANGE_FLOW\n  :Units, mm/d\n  [DEFAULT], 0.0\n  FAST_RES, 0.35\n:EndSoilParameterList\n")
+    # the other glacier algorithms: potential melt passed on unchanged + linear glacier storage; UBC melt (GLACIER_CC, no melt under snow) + analytic release
+    CASES["hbv_glacier_simple"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=90, routing="ROUTE_MUSKINGUM",
+                                       rvi_sub=[(r"GMELT_HBV          GLACIER_ICE     GLACIER", "GMELT_SIMPLE_MELT  GLACIER_ICE     GLACIER"),
+                                                (r"GRELEASE_HBV_EC    GLACIER", "GRELEASE_LINEAR    GLACIER")])
+    CASES["hbv_glacier_ubc"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=91, routing="ROUTE_MUSKINGUM",
+                                    rvi_sub=[(r"GMELT_HBV          GLACIER_ICE     GLACIER", "GMELT_UBC          GLACIER_ICE     PONDED_WATER"),
+                                             (r"GRELEASE_HBV_EC    GLACIER", "GRELEASE_LINEAR_ANALYTIC GLACIER")],
+                                    rvc_extra=":UniformInitialConditions GLACIER_CC 6.0\n")
     CASES["hbv_abst_percentage"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=85, routing="ROUTE_MUSKINGUM", proc_after=(_hbv_after, _abst % "ABST_PERCENTAGE"),
                                         rvi_sub=[(_can, _can_max)], rvp_extra=_dep)
     # surveyed channel cross-section (:ChannelProfile with roughness zones -> 20-point rating curves) under the two routing methods that
