@@ -1118,6 +1118,31 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       rates[pr->nconn - 1] -= corr;
       break;
     }
+    case RVN_OP_DEPRESSION_OVERFLOW: { /* CmvDepressionOverflow, src/DepressionProcesses.cpp:106-165 */
+      double stor = sv[iFrom[0]], thresh_stor = P_LU(c, RVN_LU_DEP_THRESHOLD);
+      if (pr->ia[0] == 0) {
+        double max_flow = P_LU(c, RVN_LU_DEP_MAX_FLOW), n = P_LU(c, RVN_LU_DEP_N), max_stor = P_LU(c, RVN_LU_DEP_MAX);
+        if (max_stor < thresh_stor) rates[0] = max_flow;
+        else rates[0] = max_flow * pow(omax((stor - thresh_stor) / (max_stor - thresh_stor), 0.0), n);
+      } else if (pr->ia[0] == 1) {
+        double dep_k = P_LU(c, RVN_LU_DEP_K);
+        rates[0] = omax(stor - thresh_stor, 0.0) * (1 - exp(-dep_k * tstep)) / tstep;
+      } else {
+        double dep_rat = P_LU(c, RVN_LU_DEP_CRESTRATIO), area = d->hru_area[c->k];
+        double cw = dep_rat * sqrt(area);
+        rates[0] = 0.666 * cw / area * sqrt(2 * 9.80616) * pow(omax(stor - thresh_stor, 0.0), 1.5);
+      }
+      rates[0] = omin(rates[0], omax(sv[iFrom[0]] / tstep, 0.0));
+      break;
+    }
+    case RVN_OP_SEEPAGE: { /* CmvSeepage SEEP_LINEAR, src/DepressionProcesses.cpp:254-298 */
+      double stor = sv[iFrom[0]], dep_k = P_LU(c, RVN_LU_DEP_SEEP_K), room;
+      rates[0] = omax(stor, 0.0) * (1 - exp(-dep_k * tstep)) / tstep;
+      rates[0] = omin(rates[0], omax(sv[iFrom[0]] / tstep, 0.0));
+      room = omax(state_var_max(c, iTo[0], sv) - sv[iTo[0]], 0.0);
+      rates[0] = omin(rates[0], room / tstep);
+      break;
+    }
     case RVN_OP_EXCHANGE_FLOW: { /* CmvExchangeFlow, src/Flush.cpp:358-368 */
       rates[0] = P_S(c, pr->ia[0], RVN_S_EXCHANGE_FLOW);
       rates[1] = P_S(c, pr->ia[0], RVN_S_EXCHANGE_FLOW);

@@ -575,6 +575,29 @@ template <class C, class PR> RVN_DI void rates_EXCHANGE_FLOW(C &c, const PR &pr)
   const double q = c.SOIL(pr.ia(0), RVN_S_EXCHANGE_FLOW);
   c.R(0) = q; c.R(1) = q;
 }
+// CmvDepressionOverflow  src/DepressionProcesses.cpp:106-165 (DEPRESSION -> SURFACE_WATER)
+template <class C, class PR> RVN_DI void rates_DEPRESSION_OVERFLOW(C &c, const PR &pr) {
+  const double stor = c.SV(pr.from(0)), thresh_stor = c.LU(RVN_LU_DEP_THRESHOLD);
+  if (pr.ia(0) == 0) {   // DFLOW_THRESHPOW
+    const double max_flow = c.LU(RVN_LU_DEP_MAX_FLOW), n = c.LU(RVN_LU_DEP_N), max_stor = c.LU(RVN_LU_DEP_MAX);
+    if (max_stor < thresh_stor) c.R(0) = max_flow;
+    else c.R(0) = max_flow * rvn_pow(dmax((stor - thresh_stor) / (max_stor - thresh_stor), 0.0), n);
+  } else if (pr.ia(0) == 1) {   // DFLOW_LINEAR (analytical)
+    c.R(0) = dmax(stor - thresh_stor, 0.0) * (1 - rvn_exp(-c.LU(RVN_LU_DEP_K) * c.tstep)) / c.tstep;
+  } else {   // DFLOW_WEIR
+    const double cw = c.LU(RVN_LU_DEP_CRESTRATIO) * sqrt(c.area);
+    c.R(0) = 0.666 * cw / c.area * sqrt(2 * 9.80616) * rvn_pow(dmax(stor - thresh_stor, 0.0), 1.5);
+  }
+  c.R(0) = dmin(c.R(0), dmax(c.SV(pr.from(0)) / c.tstep, 0.0));
+}
+// CmvSeepage SEEP_LINEAR  src/DepressionProcesses.cpp:254-298
+template <class C, class PR> RVN_DI void rates_SEEPAGE(C &c, const PR &pr) {
+  const double stor = c.SV(pr.from(0));
+  c.R(0) = dmax(stor, 0.0) * (1 - rvn_exp(-c.LU(RVN_LU_DEP_SEEP_K) * c.tstep)) / c.tstep;
+  c.R(0) = dmin(c.R(0), dmax(c.SV(pr.from(0)) / c.tstep, 0.0));
+  const double room = dmax(StateVarMax(c, pr.to(0)) - c.SV(pr.to(0)), 0.0);
+  c.R(0) = dmin(c.R(0), room / c.tstep);
+}
 // CmvFlush  src/Flush.cpp:75-86
 template <class C, class PR> RVN_DI void rates_FLUSH(C &c, const PR &pr) { c.R(0) = pr.da(0) * c.SV(pr.from(0)) / c.tstep; }
 // CmvSplit  src/Flush.cpp:178-186
@@ -1021,6 +1044,8 @@ template <class C, class PR> RVN_DI void dispatch_rates(C &c, const PR &pr, cons
     case RVN_OP_SNOBAL_GAWSER: rates_SNOBAL_GAWSER(c, pr); break;
     case RVN_OP_CHU_ONTARIO: rates_CHU_ONTARIO(c, pr); break;
     case RVN_OP_EXCHANGE_FLOW: rates_EXCHANGE_FLOW(c, pr); break;
+    case RVN_OP_DEPRESSION_OVERFLOW: rates_DEPRESSION_OVERFLOW(c, pr); break;
+    case RVN_OP_SEEPAGE: rates_SEEPAGE(c, pr); break;
     case RVN_OP_SNOBAL_CRHM_EBSM: rates_SNOBAL_CRHM_EBSM(c, pr); break;
     case RVN_OP_SNOBAL_SIMPLE_MELT: rates_SNOBAL_SIMPLE_MELT(c, pr); break;
     case RVN_OP_SNOBAL_CEMA_NEIGE: rates_SNOBAL_CEMA_NEIGE(c, pr); break;

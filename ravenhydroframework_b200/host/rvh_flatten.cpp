@@ -213,6 +213,15 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
       {RVN_OP_INF_GA_SIMPLE, 'S', {RVN_S_HYDRAUL_COND, RVN_S_WETTING_FRONT_PSI, -1}},
     };
     for (int r = 0; r < d.nProc; r++)
+      if (d.proc[r].op == RVN_OP_DEPRESSION_OVERFLOW || d.proc[r].op == RVN_OP_SEEPAGE) {   // src/DepressionProcesses.cpp:44-75,215-222
+        static const int need_f[4][5] = {{RVN_LU_DEP_THRESHOLD, RVN_LU_DEP_N, RVN_LU_DEP_MAX_FLOW, RVN_LU_DEP_MAX, -1}, {RVN_LU_DEP_THRESHOLD, RVN_LU_DEP_K, -1, -1, -1},
+                                         {RVN_LU_DEP_THRESHOLD, RVN_LU_DEP_CRESTRATIO, -1, -1, -1}, {RVN_LU_DEP_SEEP_K, -1, -1, -1, -1}};
+        const int row = (d.proc[r].op == RVN_OP_SEEPAGE) ? 3 : d.proc[r].ia[0];
+        for (int j = 0; j < 5 && need_f[row][j] >= 0; j++)
+          for (size_t c = 0; c < lu_classes.size(); c++)
+            ExitGracefullyIf(lu_classes[c].S.v[need_f[row][j]] == NOT_SPECIFIED, std::string("CLandUseClass::AutoCalculateLandUseProps: required parameter ") + LandUseFieldName(need_f[row][j]) + " not specified for land use class " + lu_classes[c].tag);
+      }
+    for (int r = 0; r < d.nProc; r++)
       if (d.proc[r].op == RVN_OP_SOILEVAP_CHU)   // src/SoilEvaporation.cpp:189-193
         for (size_t c = 0; c < veg_classes.size(); c++)
           ExitGracefullyIf(veg_classes[c].V.v[RVN_V_CHU_MATURITY] == NOT_SPECIFIED, "CVegetationClass::AutoCalculateVegetationProps: required parameter CHU_MATURITY not specified for vegetation class " + veg_classes[c].tag);

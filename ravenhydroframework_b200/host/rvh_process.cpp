@@ -454,6 +454,28 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
     p->SetIntArg(0, SoilLayerOf(pM, from));
     return p;
   }
+  if (cmd == ":DepressionOverflow") {  // case 230; src/DepressionProcesses.cpp:20-33,90-98
+    need(4);
+    int type = -1;
+    if (s[1] == "DFLOW_THRESHPOW") type = 0; else if (s[1] == "DFLOW_LINEAR") type = 1; else if (s[1] == "DFLOW_WEIR") type = 2;
+    ExitGracefullyIf(type < 0, "ParseMainInputFile: Unrecognized depression overflow algorithm");
+    AddSVs(pM, {SVL(RVN_SV_DEPRESSION, -1), SVL(RVN_SV_SURFACE_WATER, -1)});
+    CmvGeneric *p = new CmvGeneric("DepressionOverflow", RVN_OP_DEPRESSION_OVERFLOW, pM);
+    p->Connect(pM->GetStateVarIndex(RVN_SV_DEPRESSION), iSW);
+    p->SetIntArg(0, type);
+    return p;
+  }
+  if (cmd == ":Seepage") {  // case 233; src/DepressionProcesses.cpp:180-214
+    need(4);
+    ExitGracefullyIf(s[1] != "SEEP_LINEAR", "ParseMainInputFile: Unrecognized seepage algorithm");
+    AddSV1(pM, RVN_SV_DEPRESSION);
+    const int to = pM->ParseSVTypeIndex(s[3]);
+    ExitGracefullyIf(pM->GetStateVarType(to) != RVN_SV_SOIL && pM->GetStateVarType(to) != RVN_SV_GROUNDWATER, "CmvSeepage::Initialize: seepage must move water to soil or groundwater unit");
+    CmvGeneric *p = new CmvGeneric("Seepage", RVN_OP_SEEPAGE, pM);
+    p->Connect(pM->GetStateVarIndex(RVN_SV_DEPRESSION), to);
+    p->SetIntArg(0, SoilLayerOf(pM, to));
+    return p;
+  }
   if (cmd == ":ExchangeFlow") {  // case 231: :ExchangeFlow RAVEN_DEFAULT [from] [mixing zone]; src/Flush.cpp:296-326
     need(4);
     int from = pM->ParseSVTypeIndex(s[2]), to = pM->ParseSVTypeIndex(s[3]);

@@ -172,6 +172,12 @@ if hasattr(synth, "write_hbv"):
                                     rvi_sub=[(r"GMELT_HBV          GLACIER_ICE     GLACIER", "GMELT_UBC          GLACIER_ICE     PONDED_WATER"),
                                              (r"GRELEASE_HBV_EC    GLACIER", "GRELEASE_LINEAR_ANALYTIC GLACIER")],
                                     rvc_extra=":UniformInitialConditions GLACIER_CC 6.0\n")
+    # what leaves the depressions again: threshold-power / linear / weir overflow to surface water, linear seepage to the fast reservoir
+    _dpar = ":LandUseParameterList\n  :Parameters, DEP_THRESHOLD, DEP_N, DEP_MAX_FLOW, DEP_K, DEP_CRESTRATIO, DEP_SEEP_K\n  :Units, mm, none, mm/d, 1/d, none, 1/d\n  [DEFAULT], 4.0, 1.6, 9.0, 0.18, 0.02, 0.035\n  LU_OPEN, 2.0, 2.1, 14.0, 0.3, 0.05, 0.06\n:EndLandUseParameterList\n"
+    for _i, _d in enumerate(("DFLOW_THRESHPOW", "DFLOW_LINEAR", "DFLOW_WEIR")):
+        CASES["hbv_depflow_" + _d[6:].lower()] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=92 + _i, routing="ROUTE_MUSKINGUM",
+            proc_after=(_hbv_after, _abst % "ABST_PERCENTAGE" + "  :DepressionOverflow %-16s DEPRESSION      SURFACE_WATER\n" % _d + ("  :Seepage           SEEP_LINEAR        DEPRESSION      FAST_RESERVOIR\n" if _i == 1 else "")),
+            rvp_extra=_dep + _dpar)
     CASES["hbv_abst_percentage"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=85, routing="ROUTE_MUSKINGUM", proc_after=(_hbv_after, _abst % "ABST_PERCENTAGE"),
                                         rvi_sub=[(_can, _can_max)], rvp_extra=_dep)
     # surveyed channel cross-section (:ChannelProfile with roughness zones -> 20-point rating curves) under the two routing methods that
