@@ -152,6 +152,7 @@ typedef enum {
   RVN_OP_GLACIERRELEASE_LINEAR,/* CmvGlacierRelease       GRELEASE_LINEAR / GRELEASE_LINEAR_ANALYTIC :317-327; ia[0] = 1 for the analytic form */
   RVN_OP_DEPRESSION_OVERFLOW,  /* CmvDepressionOverflow   src/DepressionProcesses.cpp:106-165; ia[0] = 0 DFLOW_THRESHPOW, 1 DFLOW_LINEAR, 2 DFLOW_WEIR */
   RVN_OP_SEEPAGE,              /* CmvSeepage SEEP_LINEAR  src/DepressionProcesses.cpp:254-298 (DEPRESSION -> soil / groundwater store) */
+  RVN_OP_OPEN_WATER_RIPARIAN,  /* CmvOWEvaporation        OPEN_WATER_RIPARIAN src/OpenWaterEvap.cpp:137-141 (x STREAM_FRACTION) */
   RVN_OP_COUNT
 } rvn_opcode;
 
@@ -209,7 +210,7 @@ typedef enum {
   RVN_LU_MAX_DEP_AREA_FRAC, RVN_LU_PONDED_EXP, RVN_LU_AWBM_AREAFRAC1, RVN_LU_AWBM_AREAFRAC2, RVN_LU_HYMOD2_G, RVN_LU_HYMOD2_KMAX,
   RVN_LU_HYMOD2_EXP, RVN_LU_PET_LIN_COEFF, RVN_LU_RAIN_MELT_MULT, RVN_LU_RELHUM_CORR, RVN_LU_PET_VAP_COEFF,
   RVN_LU_MIN_WIND_SPEED, RVN_LU_MAX_WIND_SPEED, RVN_LU_ABST_PERCENT, RVN_LU_ROUGHNESS, RVN_LU_PRIESTLEYTAYLOR_COEFF, RVN_LU_SCS_CN, RVN_LU_SCS_IA_FRACTION, RVN_LU_PDMROF_B,
-  RVN_LU_DEP_THRESHOLD, RVN_LU_DEP_N, RVN_LU_DEP_MAX_FLOW, RVN_LU_DEP_K, RVN_LU_DEP_CRESTRATIO, RVN_LU_DEP_SEEP_K, RVN_LU_COUNT
+  RVN_LU_DEP_THRESHOLD, RVN_LU_DEP_N, RVN_LU_DEP_MAX_FLOW, RVN_LU_DEP_K, RVN_LU_DEP_CRESTRATIO, RVN_LU_DEP_SEEP_K, RVN_LU_STREAM_FRACTION, RVN_LU_COUNT
 } rvn_landuse_field;
 typedef enum {
   RVN_V_MAX_HEIGHT = 0, RVN_V_MAX_LAI, RVN_V_SAI_HT_RATIO, RVN_V_MAX_CAPACITY, RVN_V_MAX_SNOW_CAPACITY,

@@ -1457,12 +1457,14 @@ static void op_rates(const octx *c, const rvn_process *pr, const int *iFrom, con
       rates[0] = omin(rates[0], sv[iFrom[0]] / tstep);
       break;
     }
+    case RVN_OP_OPEN_WATER_RIPARIAN: /* :137-141 */
     case RVN_OP_OPEN_WATER_EVAP: { /* src/OpenWaterEvap.cpp:113-186 */
       if (type == RVN_HRU_MASKED_GLACIER) break;
       if (hru_linked(d, c->k)) break; /* :124 reservoir-linked HRUs handle ET via the reservoir mass balance */
       double OWPET = F[RVN_F_OW_PET];
       if (!d->opt.suppress_competitive_ET) { OWPET -= (sv[c->iSV[RVN_SV_AET]] / tstep); OWPET = omax(OWPET, 0.0); }
-      rates[0] = P_LU(c, RVN_LU_OW_PET_CORR) * OWPET;
+      if (pr->op == RVN_OP_OPEN_WATER_RIPARIAN) rates[0] = P_LU(c, RVN_LU_OW_PET_CORR) * P_LU(c, RVN_LU_STREAM_FRACTION) * OWPET;
+      else rates[0] = P_LU(c, RVN_LU_OW_PET_CORR) * OWPET;
       if (rates[0] < 0) rates[0] = 0.0;
       if (iFrom[0] != c->iSV[RVN_SV_SURFACE_WATER]) {
         rates[0] = omin(rates[0], sv[iFrom[0]] / tstep);

@@ -319,12 +319,13 @@ template <class C, class PR> RVN_DI void rates_SUBLIMATION(C &c, const PR &pr) {
   c.R(0) = dmin(c.R(0), c.SV(pr.from(0)) / c.tstep);   // threshMin(.., .., 0.0)
 }
 // CmvOWEvaporation OPEN_WATER_EVAP  src/OpenWaterEvap.cpp:113-160; ApplyConstraints :170-186
-template <class C, class PR> RVN_DI void rates_OPEN_WATER_EVAP(C &c, const PR &pr) {
+template <bool RIPARIAN = false, class C, class PR> RVN_DI void rates_OPEN_WATER_EVAP(C &c, const PR &pr) {   // RIPARIAN: OPEN_WATER_RIPARIAN (:137-141), evaporation from the stream fraction of the HRU
   if (c.type == RVN_HRU_MASKED_GLACIER) return;
   if (c.linked) return;   // reservoir-linked HRUs handle ET via the reservoir mass balance (src/OpenWaterEvap.cpp:124)
   double OWPET = c.F[RVN_F_OW_PET];
   if (!c.opt().suppress_competitive_ET) { OWPET -= (c.SV(c.iSV(RVN_SV_AET)) / c.tstep); OWPET = dmax(OWPET, 0.0); }
-  c.R(0) = c.LU(RVN_LU_OW_PET_CORR) * OWPET;
+  if (RIPARIAN) c.R(0) = c.LU(RVN_LU_OW_PET_CORR) * c.LU(RVN_LU_STREAM_FRACTION) * OWPET;
+  else c.R(0) = c.LU(RVN_LU_OW_PET_CORR) * OWPET;
   if (c.R(0) < 0) c.R(0) = 0.0;
   if (pr.from(0) != c.iSV(RVN_SV_SURFACE_WATER)) {
     c.R(0) = dmin(c.R(0), c.SV(pr.from(0)) / c.tstep);
@@ -1073,6 +1074,7 @@ template <class C, class PR> RVN_DI void dispatch_rates(C &c, const PR &pr, cons
     case RVN_OP_CANEVP_ALL: rates_CANEVP_ALL(c, pr); break;
     case RVN_OP_CANSNOWEVP_ALL: rates_CANSNOWEVP_ALL(c, pr); break;
     case RVN_OP_OPEN_WATER_EVAP: rates_OPEN_WATER_EVAP(c, pr); break;
+    case RVN_OP_OPEN_WATER_RIPARIAN: rates_OPEN_WATER_EVAP<true>(c, pr); break;
     case RVN_OP_SUBLIMATION: rates_SUBLIMATION(c, pr); break;
     case RVN_OP_ABSTRACTION: rates_ABSTRACTION(c, pr); break;
     case RVN_OP_CANEVP_MAXIMUM: rates_CANEVP_PET<0>(c, pr); break;

@@ -209,6 +209,7 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
       {RVN_OP_INF_GREEN_AMPT, 'S', {RVN_S_HYDRAUL_COND, RVN_S_WETTING_FRONT_PSI, -1}},
       {RVN_OP_SOILEVAP_SACSMA, 'S', {RVN_S_UNAVAIL_FRAC, -1}},
       {RVN_OP_EXCHANGE_FLOW, 'S', {RVN_S_EXCHANGE_FLOW, -1}},
+      {RVN_OP_OPEN_WATER_RIPARIAN, 'L', {RVN_LU_STREAM_FRACTION, -1}},
       {RVN_OP_INF_SCS, 'L', {RVN_LU_SCS_CN, -1}}, {RVN_OP_INF_SCS_NOABSTRACTION, 'L', {RVN_LU_SCS_CN, -1}},
       {RVN_OP_INF_GA_SIMPLE, 'S', {RVN_S_HYDRAUL_COND, RVN_S_WETTING_FRONT_PSI, -1}},
     };
@@ -395,7 +396,7 @@ const rvn_model_desc *CModel::Flatten(const optStruct &O, int nMembers) {
       if (op == RVN_OP_SOILEVAP_ALL || op == RVN_OP_SOILEVAP_HBV || op == RVN_OP_SOILEVAP_GR4J || op == RVN_OP_SOILEVAP_TOPMODEL ||
           (op >= RVN_OP_SOILEVAP_LINEAR && op <= RVN_OP_SOILEVAP_AWBM) || op == RVN_OP_SOILEVAP_SACSMA || op == RVN_OP_SOILEVAP_CHU || op == RVN_OP_CANEVP_ALL || op == RVN_OP_CANSNOWEVP_ALL ||
           op == RVN_OP_CANEVP_MAXIMUM || op == RVN_OP_CANEVP_RUTTER || op == RVN_OP_CANSNOWEVP_MAXIMUM) uses_pet = true;
-      if (op == RVN_OP_OPEN_WATER_EVAP || op == RVN_OP_LAKE_EVAP_BASIC || op == RVN_OP_SOILEVAP_HYPR) uses_owpet = true;
+      if (op == RVN_OP_OPEN_WATER_EVAP || op == RVN_OP_OPEN_WATER_RIPARIAN || op == RVN_OP_LAKE_EVAP_BASIC || op == RVN_OP_SOILEVAP_HYPR) uses_owpet = true;
     }
     for (int p = 0; p < NB; p++) if (_pSubBasins[p]->pReservoir && _pSubBasins[p]->pReservoir->_hru_k >= 0) uses_owpet = true;   // reservoir evaporation reads OW_PET of the linked HRU (src/Reservoir.cpp:1634)
     auto consumed = [&](int method) { return (uses_pet && O.evaporation == method) || (uses_owpet && O.ow_evaporation == method); };

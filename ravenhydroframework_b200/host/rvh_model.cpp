@@ -16,7 +16,7 @@ static const char *kLUNames[RVN_LU_COUNT] = {"IMPERMEABLE_FRAC", "FOREST_COVERAG
   "HBV_MELT_GLACIER_CORR", "HBV_GLACIER_KMIN", "GLAC_STORAGE_COEFF", "HBV_GLACIER_AG", "DEP_MAX", "LAKE_PET_CORR", "OW_PET_CORR",
   "PARTITION_COEFF", "CC_DECAY_COEFF", "MAX_SAT_AREA_FRAC", "PDM_B", "AET_COEFF", "MAX_DEP_AREA_FRAC", "PONDED_EXP", "AWBM_AREAFRAC1",
   "AWBM_AREAFRAC2", "HYMOD2_G", "HYMOD2_KMAX", "HYMOD2_EXP", "PET_LIN_COEFF", "RAIN_MELT_MULT", "RELHUM_CORR", "PET_VAP_COEFF",
-  "MIN_WIND_SPEED", "MAX_WIND_SPEED", "ABST_PERCENT", "ROUGHNESS", "PRIESTLEYTAYLOR_COEFF", "SCS_CN", "SCS_IA_FRACTION", "PDMROF_B", "DEP_THRESHOLD", "DEP_N", "DEP_MAX_FLOW", "DEP_K", "DEP_CRESTRATIO", "DEP_SEEP_K"};
+  "MIN_WIND_SPEED", "MAX_WIND_SPEED", "ABST_PERCENT", "ROUGHNESS", "PRIESTLEYTAYLOR_COEFF", "SCS_CN", "SCS_IA_FRACTION", "PDMROF_B", "DEP_THRESHOLD", "DEP_N", "DEP_MAX_FLOW", "DEP_K", "DEP_CRESTRATIO", "DEP_SEEP_K", "STREAM_FRACTION"};
 static const char *kVegNames[RVN_V_COUNT] = {"MAX_HEIGHT", "MAX_LAI", "SAI_HT_RATIO", "MAX_CAPACITY", "MAX_SNOW_CAPACITY", "RAIN_ICEPT_PCT",
   "SNOW_ICEPT_PCT", "PET_VEG_CORR", "RAIN_ICEPT_FACT", "SNOW_ICEPT_FACT", "ALBEDO", "SVF_EXTINCTION", "CHU_MATURITY", "VAR_CAPACITY", "VAR_SNOW_CAPACITY", "VAR_RAIN_ICEPT_PCT", "VAR_SNOW_ICEPT_PCT"};
 static const char *kGlobalNames[RVN_G_COUNT] = {"SNOW_SWI", "SNOW_SWI_MIN", "SNOW_SWI_MAX", "SWI_REDUCT_COEFF", "ADIABATIC_LAPSE", "PRECIP_LAPSE",

@@ -733,10 +733,10 @@ CHydroProcessABC *CreateProcessFromRVI(const std::vector<std::string> &s, CModel
   }
   if (cmd == ":OpenWaterEvaporation") {  // case 211; src/OpenWaterEvap.cpp:17-38
     need(4);
-    ExitGracefullyIf(s[1] != "OPEN_WATER_EVAP", "ParseMainInputFile: open water evaporation algorithm " + s[1] + " is not implemented in the B200 build");
+    ExitGracefullyIf(s[1] != "OPEN_WATER_EVAP" && s[1] != "OPEN_WATER_RIPARIAN", "ParseMainInputFile: open water evaporation algorithm " + s[1] + " is not implemented in the B200 build");
     AddSVs(pM, {SVL(RVN_SV_ATMOSPHERE, -1), SVL(RVN_SV_AET, -1)});
     int from = pM->ParseSVTypeIndex(s[2]);
-    CmvGeneric *p = new CmvGeneric("OpenWaterEvaporation", RVN_OP_OPEN_WATER_EVAP, pM);
+    CmvGeneric *p = new CmvGeneric("OpenWaterEvaporation", s[1] == "OPEN_WATER_RIPARIAN" ? RVN_OP_OPEN_WATER_RIPARIAN : RVN_OP_OPEN_WATER_EVAP, pM);
     int iAET = pM->GetStateVarIndex(RVN_SV_AET);
     p->Connect(from, iAtmos); p->Connect(iAET, iAET);
     return p;

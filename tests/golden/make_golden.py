@@ -178,6 +178,10 @@ if hasattr(synth, "write_hbv"):
         CASES["hbv_depflow_" + _d[6:].lower()] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=92 + _i, routing="ROUTE_MUSKINGUM",
             proc_after=(_hbv_after, _abst % "ABST_PERCENTAGE" + "  :DepressionOverflow %-16s DEPRESSION      SURFACE_WATER\n" % _d + ("  :Seepage           SEEP_LINEAR        DEPRESSION      FAST_RESERVOIR\n" if _i == 1 else "")),
             rvp_extra=_dep + _dpar)
+    # OPEN_WATER_RIPARIAN: evaporation from the stream fraction of the HRU (here from the depressions filled by ABST_FILL)
+    CASES["hbv_ow_riparian"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=95, routing="ROUTE_MUSKINGUM",
+                                    proc_after=(_hbv_after, (_abst % "ABST_FILL").replace("OPEN_WATER_EVAP  ", "OPEN_WATER_RIPARIAN")),
+                                    rvp_extra=_dep + ":LandUseParameterList\n  :Parameters, STREAM_FRACTION\n  :Units, none\n  [DEFAULT], 0.35\n  LU_OPEN, 0.6\n:EndLandUseParameterList\n")
     CASES["hbv_abst_percentage"] = dict(kind="hbv", n_sb=2, hru_per_sb=4, n_days=400, seed=85, routing="ROUTE_MUSKINGUM", proc_after=(_hbv_after, _abst % "ABST_PERCENTAGE"),
                                         rvi_sub=[(_can, _can_max)], rvp_extra=_dep)
     # surveyed channel cross-section (:ChannelProfile with roughness zones -> 20-point rating curves) under the two routing methods that
