@@ -1,4 +1,4 @@
 #!/usr/bin/env bash
-# the driver's 2-GPU command on the current tree (both arms)
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 50 --warmup 5 > gpurun_out/r2_bench_2gpu.json 2> gpurun_out/r2_bench_2gpu.err
-echo "rc=$?"; tail -c 1500 gpurun_out/r2_bench_2gpu.json; tail -5 gpurun_out/r2_bench_2gpu.err
+# the driver's 8-GPU command on the final tree
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 8 --steps 50 --warmup 5 > gpurun_out/r2_bench_8gpu.json 2> gpurun_out/r2_bench_8gpu.err
+echo "rc=$?"; head -c 600 gpurun_out/r2_bench_8gpu.json; tail -3 gpurun_out/r2_bench_8gpu.err
